@@ -1,0 +1,158 @@
+/*
+ * v2m_b200 -- C ABI of the B200-native (sm_100a) kernels for the Affective Multimodal
+ * Transformer hot path of khangklj/Video2Music.
+ *
+ * The reference has no FFI boundary: its hot path is a set of PyTorch nn.Modules calling ATen
+ * (SURVEY.md section 8b).  This header is therefore the boundary a maintainer of the reference
+ * would bind (ctypes / cffi / a 20-line torch extension) to replace the ATen op sequences listed
+ * next to each entry point; INTEGRATION.md shows that binding.  Conventions:
+ *   - plain C, raw DEVICE pointers, explicit sizes/strides, caller-owned outputs and workspaces;
+ *   - no allocation, no global state, re-entrant per stream; `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success or a V2M_* status; v2m_last_error() gives the text
+ *     (thread-local); the Python host turns it into RuntimeError like the reference's asserts /
+ *     raises (rpr.py:242-247, grouped_query_attention.py:58-66);
+ *   - dtype codes: 0 = float32, 1 = bfloat16.
+ * Paths relative to the reference root are cited as file:line.
+ */
+#ifndef V2M_B200_H_
+#define V2M_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2M_OK 0
+#define V2M_BAD_ARG 1
+#define V2M_CUDA_ERROR 2
+#define V2M_UNSUPPORTED 3
+#define V2M_NO_DEVICE 4
+
+#define V2M_F32 0
+#define V2M_BF16 1
+
+int v2m_abi_version(void);
+const char* v2m_last_error(void);
+/* sizeof() of the ABI structs as compiled: 0 v2m_epilogue, 1 v2m_attn, 2 v2m_dec_layer, 3 v2m_decode (binding self-check). */
+int64_t v2m_struct_size(int32_t which);
+/* 1 if the current CUDA device is compute capability 10.x (the only target), else 0. */
+int v2m_device_ok(void);
+
+/* ---- dense linear layers ---------------------------------------------------------------------
+ * C[M,N] = epilogue(A[M,K] * W[N,K]^T); replaces torch.nn.functional.linear at
+ * model/rpr.py:253,263,277,417, model/rpr.py:67 (FFN), model/video_music_transformer.py:1001,1022,1042
+ * and the stock nn.TransformerEncoderLayer linears created at video_music_transformer.py:967-971.
+ * Epilogue, in order: +bias[n]; *alpha for n < alpha_cols (q scaling, rpr.py:328); ReLU (rpr.py:67);
+ * + row_scale[m]*col_vec[n] (key column of Linear_chord, video_music_transformer.py:991-1001);
+ * + residual[(m % res_mod)*ldr + n] (residual add rpr.py:59-68 or positional encoding
+ * positional_encoding.py:22 when res_mod = sequence length).
+ * head_scatter != 0 writes element (m,n) into the head-major KV cache layout
+ * [part][batch][head][cap][dh] (see kernels.h) instead of C[m*ldc+n].                              */
+typedef struct v2m_epilogue {
+  const float* bias;
+  const void* residual;     /* fp32, or bf16 when residual_bf16 */
+  int32_t ldr, res_mod;
+  const float* row_scale;
+  const float* col_vec;
+  float alpha;
+  int32_t alpha_cols;
+  int32_t relu;
+  int32_t residual_bf16;
+  int32_t head_scatter, S, H, dh, cap, pos0;
+  int64_t part_stride;
+} v2m_epilogue;
+
+/* fp32 SIMT GEMM (exact path, batch-invariant summation order). */
+int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float* C, int32_t ldc,
+                 int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream);
+/* bf16 tcgen05/TMEM/TMA GEMM; C is bf16 (out_dtype 1) or fp32 (0); lda, ldw multiples of 8. */
+int v2m_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
+                  int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream);
+
+/* ---- attention ---------------------------------------------------------------------------------
+ * out = softmax(q k^T + skew(q Er^T) + causal mask) v for every (batch, head); replaces
+ * model/rpr.py:387-414 (bmm, einsum with Er, _skew :439-455, mask, softmax, bmm), the stock
+ * nn.MultiheadAttention cores (rpr.py:62, encoder layers) when Er == NULL, and
+ * scaled_dot_product_gqa (model/grouped_query_attention.py:122-156) when Hkv < Hq.
+ * Element (b,l,h,d) of q is q[b*q_sb + l*q_sl + h*dh + d] (same for k, v, o).
+ * lse (optional) [B*Hq, Lq]; p_out (optional) [B*Hq, Lq, Lk] = the probabilities (need_weights).  */
+typedef struct v2m_attn {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl;
+  int32_t B, Hq, Hkv, Lq, Lk, dh;
+  int32_t causal;
+  const void* Er; int32_t er_len;
+  float q_scale;
+  float* lse; float* p_out;
+} v2m_attn;
+int v2m_attn_fwd(const v2m_attn* p, int32_t dtype, void* stream);
+
+/* ---- residual + LayerNorm (rpr.py:59-69; nn.LayerNorm eps) ------------------------------------ */
+int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma,
+                  const float* beta, void* y, int32_t y_dtype, void* y2, int32_t y2_dtype, int32_t M, int32_t D,
+                  float eps, void* stream);
+
+/* ---- input staging (video_music_transformer.py:984-1018) -------------------------------------- */
+int v2m_embed_sum(const int64_t* idx_a, const float* table_a, const int64_t* idx_b, const float* table_b, void* out,
+                  int32_t out_dtype, int32_t ld_out, int32_t rows, int32_t D, void* stream);
+int v2m_concat_features(const float* sem, int32_t sem_dim, const float* scene, const float* motion, int32_t motion_dim,
+                        const float* emotion, int32_t emo_dim, void* out, int32_t out_dtype, int32_t ld_out,
+                        int32_t rows, void* stream);
+int v2m_cast_2d(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
+                int32_t rows, int32_t cols, int32_t zero_pad, void* stream);
+
+/* mode 0: out = a * silu(b) (GLUExpert gating, moe.py:47); mode 1: out = a + alpha*b (shared expert, moe.py:301) */
+int v2m_binary_f32(const float* a, const float* b, float* out, int64_t n, int32_t mode, float alpha, void* stream);
+
+/* ---- KV-cached greedy decode (replaces the re-forward loop of VideoMusicTransformer.generate,
+ * video_music_transformer.py:1069-1084 with beam=1).  All pointers are device pointers owned by the
+ * caller; caches are head-major [B][H][cap|S][64] in `dtype`.                                      */
+#define V2M_MAX_DEC_LAYERS 8
+typedef struct v2m_dec_layer {
+  const void* w_qkv; const float* b_qkv;
+  const void* w_so;  const float* b_so;
+  const void* w_cq;  const float* b_cq;
+  const void* w_co;  const float* b_co;
+  const void* w_f1;  const float* b_f1;
+  const void* w_f2;  const float* b_f2;
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;
+  const float* ln3_g; const float* ln3_b;
+  const void* er;
+  void* self_k; void* self_v;
+  const void* cross_k; const void* cross_v;
+} v2m_dec_layer;
+typedef struct v2m_decode {
+  int32_t dtype;
+  int32_t B, H, E, FF, S, cap, n_layers, er_len, vocab, vocab_limit, primer_len, chord_embed;
+  v2m_dec_layer layer[V2M_MAX_DEC_LAYERS];
+  const float* lnf_g; const float* lnf_b;
+  const void* w_out; const float* b_out;
+  const float* emb_root; const float* emb_attr; const float* emb_chord;
+  const void* w_chord; const float* wc_key; const float* b_chord;
+  const float* pe;
+  const float* key;
+  int64_t* gen; int64_t* gen_root; int64_t* gen_attr;
+  int32_t* step;
+  float* h; void* r; float* qbuf; void* ctx; void* ff; float* logits; float* logits_all;
+} v2m_decode;
+int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void* stream);
+int64_t v2m_decode_launches_per_step(const v2m_decode* p);
+
+/* ---- selective scan, model/pscan.py:154-226: H[t] = A[t]*H[t-1] + X[t] over (B,L,D,N) fp32 ---- */
+int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream);
+int v2m_pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float* gX, int32_t B, int32_t L,
+                  int32_t D, int32_t N, void* stream);
+
+/* ---- MoE router, model/moe.py:180-190 / 244-288: gate GEMV + top-k + softmax + histogram ------
+ * sel = (x Wg^T + bg) * inv_t_pre (+ sel_bias for selection only, moe.py:260-268);
+ * weights = softmax(gathered logits * inv_t_post) in fp32 (moe.py:190,288).                        */
+int v2m_moe_route(const float* x, const float* wg, const float* bg, const float* sel_bias, float inv_t_pre,
+                  float inv_t_post, int32_t tokens, int32_t d, int32_t n_experts, int32_t k, int64_t* idx_out,
+                  float* w_out, float* logits_out, int32_t* hist_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2M_B200_H_ */

@@ -1,0 +1,401 @@
+"""CPU restatement (torch fp32, functional) of the reference's AMT hot path.
+
+TEST INFRASTRUCTURE ONLY -- this file is the *checker*, never the product.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import it.  video2music_b200/ must not.
+
+Parity pin: the reference (khangklj/Video2Music) ships no tests, golden
+vectors or checkpoints, so this restatement is pinned by
+(1) tests/test_oracle_vs_reference.py, which runs the unmodified reference
+live through oracle/ref_shim.py whenever /root/reference is mounted, and
+(2) the fixtures under tests/golden/ that oracle/make_golden.py produced from
+the unmodified reference in that same container.
+
+Every function cites the reference lines it restates (paths relative to the
+reference root).  Weights are passed as a plain dict with the reference's
+state_dict keys.
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+CHORD_END, CHORD_PAD, CHORD_SIZE = 157, 158, 159      # utilities/constants.py:50-52
+CHORD_ROOT_PAD, CHORD_ATTR_PAD = 14, 15               # utilities/constants.py:55-62
+
+SD = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------
+# RPR attention (model/rpr.py)
+# --------------------------------------------------------------------------
+def get_valid_embedding(Er: torch.Tensor, len_q: int) -> torch.Tensor:
+    """model/rpr.py:426-437."""
+    return Er[max(0, Er.shape[0] - len_q):, :]
+
+
+def skew_literal(qe: torch.Tensor) -> torch.Tensor:
+    """model/rpr.py:439-455, step by step (mask, pad one column, reshape, drop row)."""
+    sz = qe.shape[1]
+    mask = (torch.triu(torch.ones(sz, sz)) == 1).float().flip(0)
+    qe = mask * qe
+    qe = F.pad(qe, (1, 0, 0, 0, 0, 0))
+    qe = torch.reshape(qe, (qe.shape[0], qe.shape[2], qe.shape[1]))
+    return qe[:, 1:, :]
+
+
+def skew_closed_form(q: torch.Tensor, Er_valid: torch.Tensor) -> torch.Tensor:
+    """Closed form of rpr.py:393-395: Srel[h,i,j] = q[h,i] . Er_valid[Lv-1-(i-j)] for
+    j <= i and 0 for j > i (what the CUDA kernels implement)."""
+    H, L, _ = q.shape
+    Lv = Er_valid.shape[0]
+    i = torch.arange(L).view(L, 1)
+    j = torch.arange(L).view(1, L)
+    idx = (Lv - 1 - (i - j)).clamp(0, Lv - 1)
+    e = Er_valid[idx]                                    # (L, L, dh)
+    s = torch.einsum("hid,ijd->hij", q, e)
+    return s * (j <= i).float()
+
+
+def mha_forward(query: torch.Tensor, key: torch.Tensor, in_w: torch.Tensor, in_b: torch.Tensor,
+                out_w: torch.Tensor, out_b: torch.Tensor, num_heads: int,
+                Er: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None,
+                need_weights: bool = False):
+    """multi_head_attention_forward_rpr, model/rpr.py:201-424 (eval mode, no
+    bias_kv / zero_attn / padding mask), which for Er=None is also the arithmetic of
+    the stock nn.MultiheadAttention used for cross attention (rpr.py:42,62) and of
+    the stock encoder layers.  query (L,B,E), key=value (S,B,E)."""
+    L, B, E = query.shape
+    S = key.shape[0]
+    dh = E // num_heads
+    scaling = float(dh) ** -0.5
+    q = F.linear(query, in_w[:E], in_b[:E])                       # rpr.py:253 / :263
+    k, v = F.linear(key, in_w[E:], in_b[E:]).chunk(2, dim=-1)     # rpr.py:277
+    q = q * scaling                                               # rpr.py:328
+    q = q.contiguous().view(L, B * num_heads, dh).transpose(0, 1)  # rpr.py:349-353
+    k = k.contiguous().view(S, B * num_heads, dh).transpose(0, 1)
+    v = v.contiguous().view(S, B * num_heads, dh).transpose(0, 1)
+    w = torch.bmm(q, k.transpose(1, 2))                           # rpr.py:387
+    if Er is not None:                                            # rpr.py:391-395
+        Erv = get_valid_embedding(Er, L)
+        qe = torch.einsum("hld,md->hlm", q, Erv)
+        w = w + skew_literal(qe)
+    if attn_mask is not None:                                     # rpr.py:397-399
+        w = w + attn_mask.unsqueeze(0)
+    w = torch.softmax(w, dim=-1)                                  # rpr.py:409
+    o = torch.bmm(w, v)                                           # rpr.py:414
+    o = o.transpose(0, 1).contiguous().view(L, B, E)
+    o = F.linear(o, out_w, out_b)                                 # rpr.py:417
+    if need_weights:
+        return o, w.view(B, num_heads, L, S).sum(dim=1) / num_heads   # rpr.py:419-422
+    return o, None
+
+
+def _ln(x, sd, prefix):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], 1e-5)
+
+
+def encoder_layer(x: torch.Tensor, sd: SD, p: str, H: int) -> torch.Tensor:
+    """Stock nn.TransformerEncoderLayer as instantiated by nn.Transformer at
+    video_music_transformer.py:967-971 (post-norm, ReLU, eps 1e-5)."""
+    a, _ = mha_forward(x, x, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
+                       sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], H)
+    x = _ln(x + a, sd, p + "norm1")
+    f = F.linear(F.relu(F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                 sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    return _ln(x + f, sd, p + "norm2")
+
+
+def decoder_layer_rpr(tgt: torch.Tensor, memory: torch.Tensor, sd: SD, p: str, H: int,
+                      tgt_mask: Optional[torch.Tensor]) -> torch.Tensor:
+    """TransformerDecoderLayerRPR.forward, model/rpr.py:55-70 (eval: dropouts are identity)."""
+    a, _ = mha_forward(tgt, tgt, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"],
+                       sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], H,
+                       Er=sd.get(p + "self_attn.Er"), attn_mask=tgt_mask)
+    tgt = _ln(tgt + a, sd, p + "norm1")
+    c, _ = mha_forward(tgt, memory, sd[p + "multihead_attn.in_proj_weight"], sd[p + "multihead_attn.in_proj_bias"],
+                       sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"], H)
+    tgt = _ln(tgt + c, sd, p + "norm2")
+    f = F.linear(F.relu(F.linear(tgt, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                 sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    return _ln(tgt + f, sd, p + "norm3")
+
+
+def sinusoid_pe(max_len: int, d_model: int) -> torch.Tensor:
+    """model/positional_encoding.py:13-19 -> (max_len, d_model)."""
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def count_layers(sd: SD, prefix: str) -> int:
+    n = 0
+    while (prefix + "%d.linear1.weight" % n) in sd:
+        n += 1
+    return n
+
+
+def video_features(sem, scene, motion, emotion) -> torch.Tensor:
+    """video_music_transformer.py:1003-1018: concat semantic | scene offset | motion | emotion."""
+    vf = torch.cat([sem.float(), scene.unsqueeze(-1).float()], dim=-1)
+    if motion.dim() == 2:
+        vf = torch.cat([vf, motion.unsqueeze(-1).float()], dim=-1)
+    else:
+        vf = torch.cat([vf, motion], dim=-1)
+    return torch.cat([vf, emotion.float()], dim=-1)
+
+
+def chord_inputs(sd: SD, x, x_root, x_attr, feature_key, chord_embed: bool) -> torch.Tensor:
+    """video_music_transformer.py:984-1001 -> Linear_chord([embed | key])  (B,T,d)."""
+    if not chord_embed:
+        e = F.embedding(x_root, sd["embedding_root.weight"]) + F.embedding(x_attr, sd["embedding_attr.weight"])
+    else:
+        e = F.embedding(x, sd["chord_embedding_model.weight"])
+    B, T = e.shape[0], e.shape[1]
+    key = feature_key.reshape(B, 1, 1).float().expand(B, T, 1)
+    return F.linear(torch.cat([e, key], dim=-1), sd["Linear_chord.weight"], sd["Linear_chord.bias"])
+
+
+def encode_memory(sd: SD, sem, scene, motion, emotion, num_heads: int = 8) -> torch.Tensor:
+    """Encoder half of VideoMusicTransformer.forward (video_music_transformer.py:1003-1033):
+    Linear_vis, + PE, 6 stock encoder layers, final LayerNorm -> memory (S,B,d)."""
+    vf = F.linear(video_features(sem, scene, motion, emotion), sd["Linear_vis.weight"], sd["Linear_vis.bias"])
+    vf = vf.permute(1, 0, 2)
+    d = vf.shape[-1]
+    vf = vf + sinusoid_pe(max(300, vf.shape[0]), d)[: vf.shape[0]].unsqueeze(1)
+    nl = count_layers(sd, "transformer.encoder.layers.")
+    for l in range(nl):
+        vf = encoder_layer(vf, sd, "transformer.encoder.layers.%d." % l, num_heads)
+    return _ln(vf, sd, "transformer.encoder.norm")
+
+
+def amt_forward(sd: SD, x, x_root, x_attr, sem, key, scene, motion, emotion,
+                num_heads: int = 8, chord_embed: bool = False, mask: bool = True) -> torch.Tensor:
+    """VideoMusicTransformer.forward, video_music_transformer.py:978-1044 (IS_SEPERATED=False)."""
+    T = x.shape[1]
+    tgt_mask = torch.triu(torch.full((T, T), float("-inf")), diagonal=1) if mask else None  # :980
+    xf = chord_inputs(sd, x, x_root, x_attr, key, chord_embed).permute(1, 0, 2)
+    d = xf.shape[-1]
+    xf = xf + sinusoid_pe(max(300, T), d)[:T].unsqueeze(1)                                # :1029
+    memory = encode_memory(sd, sem, scene, motion, emotion, num_heads)
+    nl = count_layers(sd, "transformer.decoder.layers.")
+    out = xf
+    for l in range(nl):                                                                    # rpr.py:24-35
+        out = decoder_layer_rpr(out, memory, sd, "transformer.decoder.layers.%d." % l, num_heads, tgt_mask)
+    out = _ln(out, sd, "transformer.decoder.norm")
+    return F.linear(out.permute(1, 0, 2), sd["Wout.weight"], sd["Wout.bias"])           # :1042
+
+
+def generate_greedy_literal(sd: SD, sem, key, scene, motion, emotion, primer, primer_root, primer_attr,
+                            target_seq_length: int = 300, num_heads: int = 8, chord_embed: bool = False,
+                            return_margins: bool = False):
+    """VideoMusicTransformer.generate with beam=1, beam_chance=1.0
+    (video_music_transformer.py:1046-1084,1129-1132): batch 1, the whole model is
+    re-run on the growing prefix every step, the next token is the arg-max of
+    softmax(logits)[..., :CHORD_END] at the last position; gen_seq_root / gen_seq_attr
+    are NOT updated in this branch (they stay PAD for generated positions)."""
+    gen = torch.full((1, target_seq_length), CHORD_PAD, dtype=torch.int64)
+    gen_root = torch.full((1, target_seq_length), CHORD_ROOT_PAD, dtype=torch.int64)
+    gen_attr = torch.full((1, target_seq_length), CHORD_ATTR_PAD, dtype=torch.int64)
+    n = len(primer)
+    gen[..., :n] = primer
+    gen_root[..., :n] = primer_root
+    gen_attr[..., :n] = primer_attr
+    margins = []
+    cur = n
+    while cur < target_seq_length:
+        y = torch.softmax(amt_forward(sd, gen[..., :cur], gen_root[..., :cur], gen_attr[..., :cur],
+                                      sem, key, scene, motion, emotion, num_heads, chord_embed), dim=-1)[..., :CHORD_END]
+        probs = y[:, cur - 1, :].flatten()
+        top, idx = torch.topk(probs, 2)
+        gen[..., cur] = idx[0] % CHORD_SIZE
+        margins.append(float(top[0] - top[1]))
+        cur += 1
+    if return_margins:
+        return gen[:, :cur], torch.tensor(margins)
+    return gen[:, :cur]
+
+
+def generate_greedy_cached(sd: SD, sem, key, scene, motion, emotion, primer, primer_root, primer_attr,
+                           target_seq_length: int = 300, num_heads: int = 8, chord_embed: bool = False,
+                           return_logits: bool = False):
+    """KV-cached, batched restatement of the same greedy loop (what the decode
+    kernels implement).  Mathematically identical to generate_greedy_literal because
+    the decoder is causal: row t of the prefix forward depends only on rows <= t, and
+    Srel[t,j] = q_t . Er[er_len-1-(t-j)] does not depend on the prefix length
+    (rpr.py:426-455).  primer* are (B,P) or (P,).  Returns (B, target_seq_length)."""
+    B = sem.shape[0]
+    E = sd["Linear_chord.weight"].shape[0]
+    H = num_heads
+    dh = E // H
+    if primer.dim() == 1:
+        primer, primer_root, primer_attr = (t.unsqueeze(0).expand(B, -1) for t in (primer, primer_root, primer_attr))
+    P = primer.shape[1]
+    gen = torch.full((B, target_seq_length), CHORD_PAD, dtype=torch.int64)
+    gen_root = torch.full((B, target_seq_length), CHORD_ROOT_PAD, dtype=torch.int64)
+    gen_attr = torch.full((B, target_seq_length), CHORD_ATTR_PAD, dtype=torch.int64)
+    gen[:, :P], gen_root[:, :P], gen_attr[:, :P] = primer, primer_root, primer_attr
+    memory = encode_memory(sd, sem, scene, motion, emotion, H)            # (S,B,E)
+    S = memory.shape[0]
+    nl = count_layers(sd, "transformer.decoder.layers.")
+    pe = sinusoid_pe(max(300, target_seq_length), E)
+    scaling = float(dh) ** -0.5
+    ck, cv, sk, sv = [], [], [], []
+    for l in range(nl):
+        p = "transformer.decoder.layers.%d.multihead_attn." % l
+        k, v = F.linear(memory, sd[p + "in_proj_weight"][E:], sd[p + "in_proj_bias"][E:]).chunk(2, dim=-1)
+        ck.append(k.view(S, B, H, dh).permute(1, 2, 0, 3))                # (B,H,S,dh)
+        cv.append(v.view(S, B, H, dh).permute(1, 2, 0, 3))
+        sk.append(torch.zeros(B, H, target_seq_length, dh))
+        sv.append(torch.zeros(B, H, target_seq_length, dh))
+    all_logits = []
+    for t in range(target_seq_length - 1):
+        xt = chord_inputs(sd, gen[:, t:t + 1], gen_root[:, t:t + 1], gen_attr[:, t:t + 1], key, chord_embed)[:, 0]
+        h = xt + pe[t]
+        for l in range(nl):
+            p = "transformer.decoder.layers.%d." % l
+            qkv = F.linear(h, sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"])
+            q, k, v = qkv.chunk(3, dim=-1)
+            q = (q * scaling).view(B, H, dh)
+            sk[l][:, :, t] = k.view(B, H, dh)
+            sv[l][:, :, t] = v.view(B, H, dh)
+            s = torch.einsum("bhd,bhjd->bhj", q, sk[l][:, :, :t + 1])
+            Er = sd[p + "self_attn.Er"]
+            er_rows = Er[Er.shape[0] - 1 - (t - torch.arange(t + 1))]     # Er[er_len-1-(t-j)]
+            s = s + torch.einsum("bhd,jd->bhj", q, er_rows)
+            a = torch.einsum("bhj,bhjd->bhd", torch.softmax(s, dim=-1), sv[l][:, :, :t + 1]).reshape(B, E)
+            a = F.linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+            h = _ln(h + a, sd, p + "norm1")
+            q = (F.linear(h, sd[p + "multihead_attn.in_proj_weight"][:E], sd[p + "multihead_attn.in_proj_bias"][:E])
+                 * scaling).view(B, H, dh)
+            s = torch.einsum("bhd,bhjd->bhj", q, ck[l])
+            c = torch.einsum("bhj,bhjd->bhd", torch.softmax(s, dim=-1), cv[l]).reshape(B, E)
+            c = F.linear(c, sd[p + "multihead_attn.out_proj.weight"], sd[p + "multihead_attn.out_proj.bias"])
+            h = _ln(h + c, sd, p + "norm2")
+            f = F.linear(F.relu(F.linear(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"])),
+                         sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+            h = _ln(h + f, sd, p + "norm3")
+        h = _ln(h, sd, "transformer.decoder.norm")
+        logits = F.linear(h, sd["Wout.weight"], sd["Wout.bias"])
+        if return_logits:
+            all_logits.append(logits)
+        if t + 1 >= P:
+            gen[:, t + 1] = torch.argmax(logits[:, :CHORD_END], dim=-1)
+    if return_logits:
+        return gen, torch.stack(all_logits, dim=1)
+    return gen
+
+
+# --------------------------------------------------------------------------
+# MoE (model/moe.py)
+# --------------------------------------------------------------------------
+def glu_expert(x: torch.Tensor, sd: SD, p: str) -> torch.Tensor:
+    """GLUExpert.forward, model/moe.py:44-49 (eval)."""
+    x_ff = F.linear(x, sd[p + "linear1.weight"], sd[p + "linear1.bias"])
+    x_g = F.linear(x, sd[p + "gate.weight"], sd[p + "gate.bias"])
+    return F.linear(x_ff * F.silu(x_g), sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+
+
+def moe_route(x: torch.Tensor, gate_w: torch.Tensor, gate_b: torch.Tensor, k: int, t: float = 1.0,
+              divide_before_topk: bool = True):
+    """MoELayer: gate_logits = gate(x)/t; topk; softmax(fp32) (moe.py:180-190);
+    SharedMoELayer (non-balancing): topk(gate(x)); softmax(weights/t) (moe.py:244-247,288)."""
+    logits = F.linear(x, gate_w, gate_b)
+    if divide_before_topk:
+        logits = logits / t
+    w, idx = torch.topk(logits, k)
+    if not divide_before_topk:
+        w = w / t
+    return torch.softmax(w, dim=-1, dtype=torch.float), idx, logits
+
+
+def moe_layer(x: torch.Tensor, sd: SD, p: str, n_experts: int, k: int, shared: bool = False,
+              t: float = 1.0):
+    """MoELayer.forward (moe.py:167-200) / SharedMoELayer.forward non-balancing
+    (moe.py:231-302), eval mode.  x (L,B,d).  Returns (out, selected_experts, weights)."""
+    w, idx, _ = moe_route(x, sd[p + "gate.weight"], sd[p + "gate.bias"], k, t, divide_before_topk=not shared)
+    out = torch.zeros_like(x)
+    for i in range(n_experts):
+        ti, bi, ki = torch.where(idx == i)
+        if ti.shape[0] == 0:
+            continue
+        out[ti, bi] += w[ti, bi, ki].unsqueeze(1) * glu_expert(x[ti, bi], sd, p + "experts.%d." % i)
+    if shared:
+        out = out + (1.0 / k) * glu_expert(x, sd, p + "shared_expert.")
+    return out, idx, w
+
+
+# --------------------------------------------------------------------------
+# Grouped-query attention (model/grouped_query_attention.py)
+# --------------------------------------------------------------------------
+def sdp_gqa(query, key, value, is_causal: bool = False, scale: Optional[float] = None):
+    """scaled_dot_product_gqa, grouped_query_attention.py:19-170 without dropout/masks.
+    query (b,n,hq,d), key/value (b,s,hk,d) -> out (n,b,hq,d)  [sic: the reference
+    returns sequence-first, :159].  Query head index = h*g + gi where h is the kv head."""
+    b, n, hq, d = query.shape
+    s, hk = key.shape[1], key.shape[2]
+    g = hq // hk
+    if scale is None:
+        scale = d ** 0.5
+    q = (query / scale).permute(0, 2, 1, 3).reshape(b, hk, g, n, d)         # (b,h,g,n,d)
+    k = key.permute(0, 2, 1, 3)
+    v = value.permute(0, 2, 1, 3)
+    sim = torch.einsum("bhgnd,bhsd->bhgns", q, k)
+    if is_causal:
+        m = torch.ones(n, s, dtype=torch.bool).tril_()
+        sim = sim.masked_fill(~m, torch.finfo(sim.dtype).min)                  # :149
+    att = torch.softmax(sim, dim=-1)
+    out = torch.einsum("bhgns,bhsd->bhgnd", att, v)                           # (b,h,g,n,d)
+    return out.reshape(b, hq, n, d).permute(2, 0, 1, 3).contiguous()           # (n,b,(h g),d)
+
+
+def mhgqa_forward(query, key, value, sd: SD, p: str, query_heads: int, kv_heads: int,
+                  is_causal: bool = False, layer_norm: bool = True):
+    """MultiheadGQA.forward, grouped_query_attention.py:285-358 (RoPE=None), including its
+    literal `.view` reinterpretation of the (L,B,E) projections as (B,L,E) (:316-326)."""
+    q = F.linear(query, sd[p + "q_proj.weight"], sd[p + "q_proj.bias"])
+    k = F.linear(key, sd[p + "k_proj.weight"], sd[p + "k_proj.bias"])
+    v = F.linear(value, sd[p + "v_proj.weight"], sd[p + "v_proj.bias"])
+    tgt_len, bsz = q.shape[0], q.shape[1]
+    src_len = k.shape[0]
+    dh = q.shape[-1] // query_heads
+    q = q.contiguous().view(bsz, tgt_len, query_heads, dh)
+    k = k.contiguous().view(bsz, src_len, kv_heads, dh)
+    v = v.contiguous().view(bsz, src_len, kv_heads, dh)
+    x = sdp_gqa(q, k, v, is_causal=is_causal)              # (n,b,h,d) labelled "b n h d" by the caller (:343)
+    x = x.reshape(x.shape[0], x.shape[1], query_heads * dh)
+    if layer_norm:
+        x = F.layer_norm(x, (x.shape[-1],), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    return F.linear(x, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+
+
+# --------------------------------------------------------------------------
+# Selective scan (model/pscan.py)
+# --------------------------------------------------------------------------
+def pscan_forward(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    """What PScan.forward computes (pscan.py:154-188): H[t] = A[t]*H[t-1] + X[t], H[-1]=0,
+    along dim 1 of (B,L,D,N).  Sequential restatement (cf. selective_scan_seq, mamba.py:353-383)."""
+    H = torch.empty_like(X)
+    h = torch.zeros_like(X[:, 0])
+    for t in range(X.shape[1]):
+        h = A[:, t] * h + X[:, t]
+        H[:, t] = h
+    return H
+
+
+def pscan_backward(A: torch.Tensor, H: torch.Tensor, gH: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """PScan.backward (pscan.py:191-226): gX[t] = gH[t] + A[t+1]*gX[t+1] (reverse scan with A
+    shifted by one, :218-221), gA[t] = H[t-1]*gX[t] with gA[0]=0 (:223-224)."""
+    L = A.shape[1]
+    gX = torch.empty_like(gH)
+    g = torch.zeros_like(gH[:, 0])
+    for t in range(L - 1, -1, -1):
+        g = gH[:, t] + (A[:, t + 1] * g if t + 1 < L else 0)
+        gX[:, t] = g
+    gA = torch.zeros_like(A)
+    gA[:, 1:] = H[:, :-1] * gX[:, 1:]
+    return gA, gX

@@ -1,0 +1,272 @@
+"""Regenerates tests/golden/*.pt from the UNMODIFIED reference (/root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Run in a container that has the reference mounted:
+
+    python oracle/make_golden.py [--only NAME] [--gen-videos 4]
+
+The reference has no golden vectors of its own, so these
+fixtures are the pin: inputs and weights are regenerated from the seeds stored in
+each fixture (video2music_b200/synthetic.py), only the reference's OUTPUTS are
+stored.  `weights_checksum` lets a consumer prove it rebuilt the same weights.
+"""
+import argparse
+import contextlib
+import io
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.ref_shim import load_reference, reference_cwd  # noqa: E402
+from video2music_b200 import synthetic as syn  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _save(name, obj):
+    path = os.path.join(GOLD, name)
+    torch.save(obj, path)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024))
+
+
+def _load_weights(module, seed, wout_gain=1.0):
+    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    sd = syn.fill_like_reference_init(shapes, seed=seed, wout_gain=wout_gain)
+    module.load_state_dict(sd, strict=False)
+    return sd
+
+
+def _amt(ref, vf, chord_embed=False, seed=0, wout_gain=1.0, **kw):
+    with contextlib.redirect_stdout(io.StringIO()), reference_cwd():
+        m = ref.vmt.VideoMusicTransformer(total_vf_dim=vf, rpr=True, chord_embed=chord_embed, **kw).eval()
+    sd = _load_weights(m, seed, wout_gain)
+    return m, sd
+
+
+def golden_forward(ref):
+    """BASELINE config 1: base AMT forward, B=4, T=299, S=300, eval, fp32 CPU."""
+    spec = dict(batch=4, tgt_len=299, src_len=300, motion_type=0, input_seed=1234, weight_seed=0)
+    m, sd = _amt(ref, syn.vf_dim(0), seed=spec["weight_seed"])
+    inp = syn.make_inputs(spec["batch"], spec["input_seed"], spec["tgt_len"], spec["src_len"], 0)
+    with torch.no_grad():
+        y = m(inp["x"], inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"],
+              inp["feature_scene_offset"], inp["feature_motion"], inp["feature_emotion"])
+    _save("amt_forward_cfg1.pt", dict(spec=spec, weights_checksum=syn.checksum(sd), logits=y.contiguous()))
+    # a ragged/short case (T=37, S=120, B=3, motion_type 1 -> vf 1287) and the no-mask path
+    spec2 = dict(batch=3, tgt_len=37, src_len=120, motion_type=1, input_seed=99, weight_seed=5)
+    m2, sd2 = _amt(ref, syn.vf_dim(1), seed=5)
+    inp = syn.make_inputs(3, 99, 37, 120, 1)
+    with torch.no_grad():
+        y2 = m2(inp["x"], inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"],
+                inp["feature_scene_offset"], inp["feature_motion"], inp["feature_emotion"])
+    _save("amt_forward_small.pt", dict(spec=spec2, weights_checksum=syn.checksum(sd2), logits=y2.contiguous()))
+
+
+def golden_train(ref):
+    """One training step's loss and gradients (run_model_vevo.py:84-121), dropout 0, fp32 CPU."""
+    spec = dict(batch=2, tgt_len=64, src_len=300, motion_type=0, input_seed=4321, weight_seed=3)
+    with contextlib.redirect_stdout(io.StringIO()), reference_cwd():
+        m = ref.vmt.VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0).train()
+    sd = _load_weights(m, 3)
+    inp = syn.make_inputs(2, 4321, 64, 300, 0)
+    y = m(inp["x"], inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"],
+          inp["feature_scene_offset"], inp["feature_motion"], inp["feature_emotion"])
+    ce = torch.nn.CrossEntropyLoss(ignore_index=158, label_smoothing=0.1)          # train.py:222
+    bce = torch.nn.BCEWithLogitsLoss()                                             # train.py:233
+    loss_chord = ce(y.permute(0, 2, 1), inp["tgt"])                                 # run_model_vevo.py:101
+    loss_emotion = bce(y.permute(0, 2, 1), inp["tgt_emotion"].permute(0, 2, 1))     # :102
+    total = 0.4 * loss_chord + 0.6 * loss_emotion                                   # :119, LOSS_LAMBDA
+    total.backward()
+    grads = {}
+    norms = {}
+    keep = ("transformer.decoder.layers.0.self_attn.Er", "transformer.decoder.layers.5.self_attn.Er",
+            "Wout.bias", "transformer.decoder.layers.3.norm2.weight", "embedding_root.weight",
+            "transformer.encoder.layers.0.self_attn.in_proj_bias", "Linear_chord.bias")
+    for n, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        norms[n] = float(p.grad.double().norm())
+        if n in keep:
+            grads[n] = p.grad.clone()
+    _save("amt_train_step.pt", dict(spec=spec, weights_checksum=syn.checksum(sd), logits=y.detach().clone(),
+                                    loss=float(total), loss_chord=float(loss_chord), loss_emotion=float(loss_emotion),
+                                    grad_norms=norms, grads=grads))
+
+
+def golden_generate(ref, n_videos):
+    """BASELINE config 2 oracle: reference generate(beam=1) run video by video (batch 1)."""
+    out = {}
+    for chord_embed in (False, True):
+        spec = dict(n_videos=n_videos, target_seq_length=300, motion_type=0, input_seed=2024, weight_seed=1,
+                    chord_embed=chord_embed, primer=[1], primer_root=[1], primer_attr=[0], wout_gain=4.0)
+        m, sd = _amt(ref, syn.vf_dim(0), chord_embed=chord_embed, seed=1, wout_gain=4.0)
+        inp = syn.make_inputs(n_videos, 2024, 299, 300, 0)
+        prim, pr, pa = (torch.tensor(spec[k]) for k in ("primer", "primer_root", "primer_attr"))
+        seqs = []
+        t0 = time.time()
+        for b in range(n_videos):
+            with torch.no_grad(), reference_cwd(), contextlib.redirect_stdout(io.StringIO()):
+                g = m.generate(inp["feature_semantic_list"][b:b + 1], inp["feature_key"][b],
+                               inp["feature_scene_offset"][b:b + 1], inp["feature_motion"][b:b + 1],
+                               inp["feature_emotion"][b:b + 1], primer=prim, primer_root=pr, primer_attr=pa,
+                               target_seq_length=300, beam=1, beam_chance=1.0)
+            seqs.append(g[0].clone())
+            print("generate chord_embed=%s video %d: %.1fs" % (chord_embed, b, time.time() - t0), flush=True)
+        extra = {}
+        if chord_embed:
+            extra["chord_embedding_weight_checksum"] = float(m.chord_embedding_model.weight.double().abs().sum())
+        out["chord_embed_%s" % chord_embed] = dict(spec=spec, weights_checksum=syn.checksum(sd),
+                                                   tokens=torch.stack(seqs), seconds=time.time() - t0, **extra)
+    _save("amt_generate_greedy.pt", out)
+
+
+def golden_generate_primed(ref, n_videos=2):
+    """Same loop with a 120-chord random primer (teacher-forced prefix makes every cached K/V row distinct)."""
+    out = {}
+    for chord_embed in (False, True):
+        spec = dict(n_videos=n_videos, target_seq_length=300, motion_type=0, input_seed=777, weight_seed=2,
+                    chord_embed=chord_embed, primer_len=120, wout_gain=4.0)
+        m, sd = _amt(ref, syn.vf_dim(0), chord_embed=chord_embed, seed=2, wout_gain=4.0)
+        inp = syn.make_inputs(n_videos, 777, 299, 300, 0)
+        seqs = []
+        t0 = time.time()
+        for b in range(n_videos):
+            prim, pr, pa = inp["x"][b, :120], inp["x_root"][b, :120], inp["x_attr"][b, :120]
+            with torch.no_grad(), reference_cwd(), contextlib.redirect_stdout(io.StringIO()):
+                g = m.generate(inp["feature_semantic_list"][b:b + 1], inp["feature_key"][b],
+                               inp["feature_scene_offset"][b:b + 1], inp["feature_motion"][b:b + 1],
+                               inp["feature_emotion"][b:b + 1], primer=prim, primer_root=pr, primer_attr=pa,
+                               target_seq_length=300, beam=1, beam_chance=1.0)
+            seqs.append(g[0].clone())
+            print("primed generate chord_embed=%s video %d: %.1fs" % (chord_embed, b, time.time() - t0), flush=True)
+        out["chord_embed_%s" % chord_embed] = dict(spec=spec, weights_checksum=syn.checksum(sd), tokens=torch.stack(seqs))
+    _save("amt_generate_primed.pt", out)
+
+
+def golden_rpr(ref):
+    """MultiheadAttentionRPR module (rpr.py:112-424) on ragged shapes, incl. returned weights."""
+    cases = []
+    for (L, B, E, H, er_len, seed) in [(37, 3, 128, 4, 64, 11), (299, 1, 512, 8, 300, 12), (150, 2, 512, 8, 300, 13),
+                                       (1, 2, 128, 2, 16, 14)]:
+        torch.manual_seed(0)
+        mod = ref.rpr.MultiheadAttentionRPR(E, H, dropout=0.0, er_len=er_len).eval()
+        sd = _load_weights(mod, seed)
+        g = syn._gen(seed, "x")
+        x = syn.unit_uniform((L, B, E), g)
+        mask = torch.triu(torch.full((L, L), float("-inf")), diagonal=1)
+        x.requires_grad_(True)
+        out, w = mod(x, x, x, attn_mask=mask)
+        gy = syn.unit_uniform((L, B, E), syn._gen(seed, "gy"))
+        (out * gy).sum().backward()
+        cases.append(dict(spec=dict(L=L, B=B, E=E, H=H, er_len=er_len, seed=seed), weights_checksum=syn.checksum(sd),
+                          out=out.detach().clone(), weights_mean=w.detach().clone() if L <= 64 else None,
+                          grad_x=x.grad.clone(), grad_Er=mod.Er.grad.clone(),
+                          grad_in_proj_weight_norm=float(mod.in_proj_weight.grad.double().norm()),
+                          grad_in_proj_bias=mod.in_proj_bias.grad.clone()))
+    # decoder layer (rpr.py:37-70)
+    torch.manual_seed(0)
+    layer = ref.rpr.TransformerDecoderLayerRPR(256, 4, 512, 0.0, er_len=80).eval()
+    sd = _load_weights(layer, 21)
+    tgt = syn.unit_uniform((50, 3, 256), syn._gen(21, "tgt"))
+    mem = syn.unit_uniform((70, 3, 256), syn._gen(21, "mem"))
+    mask = torch.triu(torch.full((50, 50), float("-inf")), diagonal=1)
+    with torch.no_grad():
+        y = layer(tgt, mem, tgt_mask=mask)
+    _save("rpr_attention.pt", dict(cases=cases, layer=dict(spec=dict(T=50, S=70, B=3, E=256, H=4, ff=512, er_len=80, seed=21),
+                                                          weights_checksum=syn.checksum(sd), out=y.clone())))
+
+
+def golden_moe(ref):
+    """MoELayer / SharedMoELayer (moe.py:150-302) with GLUExpert(512,1024), 6 experts, top-2, eval."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    for shared in (False, True):
+        torch.manual_seed(0)
+        exp = ref.moe.GLUExpert(512, 1024, 0.0)
+        cls = ref.moe.SharedMoELayer if shared else ref.moe.MoELayer
+        mod = cls(exp, 512, n_experts=6, n_experts_per_token=2, dropout=0.0).eval()
+        sd = _load_weights(mod, 31 + shared)
+        x = syn.unit_uniform((75, 4, 512), syn._gen(31, "x"))
+        with torch.no_grad():
+            y = mod(x)
+            logits = mod.gate(x)
+            w, idx = torch.topk(logits, 2)
+        top3 = torch.topk(logits, 3).values
+        out["shared_%s" % shared] = dict(spec=dict(L=75, B=4, d=512, ff=1024, n_experts=6, k=2, seed=31 + shared, x_seed=31),
+                                         weights_checksum=syn.checksum(sd), out=y.clone(), selected_experts=idx.clone(),
+                                         gate_logits=logits.clone(), min_rank_gap=float((top3[..., :-1] - top3[..., 1:]).min()))
+    _save("moe.pt", out)
+
+
+def golden_gqa(ref):
+    """scaled_dot_product_gqa (grouped_query_attention.py:19-170) and MultiheadGQA (:172-358)."""
+    out = {}
+    fn_cases = []
+    for (b, n, s, hq, hk, d, causal, seed) in [(2, 33, 33, 8, 2, 64, True, 41), (3, 20, 45, 8, 4, 64, False, 42),
+                                               (1, 300, 300, 8, 1, 64, True, 43)]:
+        q = syn.unit_uniform((b, n, hq, d), syn._gen(seed, "q"))
+        k = syn.unit_uniform((b, s, hk, d), syn._gen(seed, "k"))
+        v = syn.unit_uniform((b, s, hk, d), syn._gen(seed, "v"))
+        with torch.no_grad():
+            o, _ = ref.gqa.scaled_dot_product_gqa(q, k, v, num_heads=hq, is_causal=True if causal else None)
+        fn_cases.append(dict(spec=dict(b=b, n=n, s=s, hq=hq, hk=hk, d=d, causal=causal, seed=seed), out=o.clone()))
+    out["function"] = fn_cases
+    mod_cases = []
+    for (L, S, B, seed) in [(40, 40, 1, 51), (24, 36, 3, 52)]:
+        torch.manual_seed(0)
+        mod = ref.gqa.MultiheadGQA(512, 8, 2, dropout=0.0).eval()
+        sd = _load_weights(mod, seed)
+        xq = syn.unit_uniform((L, B, 512), syn._gen(seed, "xq"))
+        xk = syn.unit_uniform((S, B, 512), syn._gen(seed, "xk"))
+        with torch.no_grad():
+            y, _ = mod(xq, xk, xk)
+        mod_cases.append(dict(spec=dict(L=L, S=S, B=B, E=512, hq=8, hk=2, seed=seed), weights_checksum=syn.checksum(sd),
+                              out=y.clone()))
+    out["module"] = mod_cases
+    _save("gqa.pt", out)
+
+
+def golden_pscan(ref):
+    """pscan forward/backward (pscan.py:154-226) incl. a non power-of-two length."""
+    cases = []
+    for (B, L, D, N, seed) in [(2, 300, 8, 16, 7), (1, 1024, 4, 16, 8), (3, 5, 2, 16, 9), (1, 1, 2, 16, 10)]:
+        A = torch.rand((B, L, D, N), generator=syn._gen(seed, "A")) * 0.99
+        X = syn.unit_uniform((B, L, D, N), syn._gen(seed, "X"))
+        gH = syn.unit_uniform((B, L, D, N), syn._gen(seed, "gH"))
+        A.requires_grad_(True)
+        X.requires_grad_(True)
+        if L >= 2:
+            H = ref.pscan.pscan(A, X)
+            (H * gH).sum().backward()
+            cases.append(dict(spec=dict(B=B, L=L, D=D, N=N, seed=seed), H=H.detach().clone(), gA=A.grad.clone(), gX=X.grad.clone()))
+        else:
+            cases.append(dict(spec=dict(B=B, L=L, D=D, N=N, seed=seed), H=X.detach().clone(), gA=torch.zeros_like(A), gX=gH.clone()))
+    _save("pscan.pt", dict(cases=cases))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--gen-videos", type=int, default=4)
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    ref = load_reference()
+    torch.set_num_threads(os.cpu_count())
+    jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
+                moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
+                generate=lambda: golden_generate(ref, args.gen_videos),
+                primed=lambda: golden_generate_primed(ref))
+    for name, fn in jobs.items():
+        if args.only and args.only != name:
+            continue
+        t0 = time.time()
+        fn()
+        print("%s done in %.1fs" % (name, time.time() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,144 @@
+"""CPU: the oracle (oracle/amt_oracle.py) against the golden vectors produced by the UNMODIFIED reference
+(tests/golden/*.pt, generator: oracle/make_golden.py).  This is what pins the oracle."""
+import pytest
+import torch
+
+from conftest import amt_state_dict, load_golden, rel_err
+from oracle import amt_oracle as O
+from video2music_b200 import synthetic as syn
+
+
+def _inputs(spec):
+    return syn.make_inputs(spec["batch"], spec["input_seed"], spec["tgt_len"], spec["src_len"], spec["motion_type"])
+
+
+def _fwd(sd, inp, **kw):
+    with torch.no_grad():
+        return O.amt_forward(sd, inp["x"], inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"],
+                             inp["feature_scene_offset"], inp["feature_motion"], inp["feature_emotion"], **kw)
+
+
+def test_weights_regenerate_bit_identically():
+    g = load_golden("amt_forward_cfg1.pt")
+    _, sd = amt_state_dict(syn.vf_dim(0), g["spec"]["weight_seed"])
+    assert syn.checksum({k: v for k, v in sd.items() if not k.endswith(".pe")}) == g["weights_checksum"]
+
+
+@pytest.mark.parametrize("name", ["amt_forward_small.pt", "amt_forward_cfg1.pt"])
+def test_forward_matches_reference_golden(name):
+    g = load_golden(name)
+    spec = g["spec"]
+    _, sd = amt_state_dict(syn.vf_dim(spec["motion_type"]), spec["weight_seed"])
+    y = _fwd(sd, _inputs(spec))
+    assert y.shape == g["logits"].shape
+    assert rel_err(y, g["logits"]) < 2e-5
+
+
+def test_skew_closed_form_equals_literal():
+    torch.manual_seed(0)
+    q = torch.randn(3, 17, 8)
+    Er = torch.randn(17, 8)
+    lit = O.skew_literal(torch.einsum("hld,md->hlm", q, Er))
+    assert torch.allclose(lit, O.skew_closed_form(q, Er), atol=1e-5)
+
+
+@pytest.mark.parametrize("chord_embed", [False, True])
+def test_cached_greedy_equals_reference_generate(chord_embed):
+    g = load_golden("amt_generate_greedy.pt")["chord_embed_%s" % chord_embed]
+    spec = g["spec"]
+    _, sd = amt_state_dict(syn.vf_dim(0), spec["weight_seed"], chord_embed=chord_embed, wout_gain=spec["wout_gain"])
+    inp = syn.make_inputs(spec["n_videos"], spec["input_seed"], 299, 300, 0)
+    prim, pr, pa = (torch.tensor(spec[k]) for k in ("primer", "primer_root", "primer_attr"))
+    with torch.no_grad():
+        gen = O.generate_greedy_cached(sd, inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+                                       inp["feature_motion"], inp["feature_emotion"], prim, pr, pa, 300,
+                                       chord_embed=chord_embed)
+    assert torch.equal(gen, g["tokens"])
+
+
+@pytest.mark.parametrize("chord_embed", [False, True])
+def test_cached_greedy_primed_equals_reference_generate(chord_embed):
+    g = load_golden("amt_generate_primed.pt")["chord_embed_%s" % chord_embed]
+    spec = g["spec"]
+    _, sd = amt_state_dict(syn.vf_dim(0), spec["weight_seed"], chord_embed=chord_embed, wout_gain=spec["wout_gain"])
+    inp = syn.make_inputs(spec["n_videos"], spec["input_seed"], 299, 300, 0)
+    P = spec["primer_len"]
+    with torch.no_grad():
+        gen = O.generate_greedy_cached(sd, inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+                                       inp["feature_motion"], inp["feature_emotion"], inp["x"][:, :P], inp["x_root"][:, :P],
+                                       inp["x_attr"][:, :P], 300, chord_embed=chord_embed)
+    assert torch.equal(gen, g["tokens"])
+
+
+def test_rpr_module_golden():
+    g = load_golden("rpr_attention.pt")
+    for case in g["cases"]:
+        s = case["spec"]
+        shapes = {"in_proj_weight": (3 * s["E"], s["E"]), "in_proj_bias": (3 * s["E"],), "out_proj.weight": (s["E"], s["E"]),
+                  "out_proj.bias": (s["E"],), "Er": (s["er_len"], s["E"] // s["H"])}
+        sd = syn.fill_like_reference_init(shapes, seed=s["seed"])
+        assert syn.checksum(sd) == case["weights_checksum"]
+        x = syn.unit_uniform((s["L"], s["B"], s["E"]), syn._gen(s["seed"], "x"))
+        mask = torch.triu(torch.full((s["L"], s["L"]), float("-inf")), diagonal=1)
+        out, w = O.mha_forward(x, x, sd["in_proj_weight"], sd["in_proj_bias"], sd["out_proj.weight"], sd["out_proj.bias"],
+                               s["H"], Er=sd["Er"], attn_mask=mask, need_weights=True)
+        assert rel_err(out, case["out"]) < 2e-5
+        if case["weights_mean"] is not None:
+            assert rel_err(w, case["weights_mean"]) < 2e-5
+
+
+def _moe_sd(spec, shared):
+    shapes = {"gate.weight": (spec["n_experts"], spec["d"]), "gate.bias": (spec["n_experts"],)}
+    names = ["experts.%d." % i for i in range(spec["n_experts"])] + (["shared_expert."] if shared else [])
+    for p in names:
+        shapes.update({p + "linear1.weight": (spec["ff"], spec["d"]), p + "linear1.bias": (spec["ff"],),
+                       p + "gate.weight": (spec["ff"], spec["d"]), p + "gate.bias": (spec["ff"],),
+                       p + "linear2.weight": (spec["d"], spec["ff"]), p + "linear2.bias": (spec["d"],)})
+    return syn.fill_like_reference_init(shapes, seed=spec["seed"])
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_moe_golden(shared):
+    g = load_golden("moe.pt")["shared_%s" % shared]
+    spec = g["spec"]
+    sd = _moe_sd(spec, shared)
+    assert syn.checksum(sd) == g["weights_checksum"]
+    x = syn.unit_uniform((spec["L"], spec["B"], spec["d"]), syn._gen(spec["x_seed"], "x"))
+    out, idx, _ = O.moe_layer(x, sd, "", spec["n_experts"], spec["k"], shared=shared)
+    assert torch.equal(idx, g["selected_experts"])
+    assert rel_err(out, g["out"]) < 2e-5
+
+
+def test_gqa_golden():
+    g = load_golden("gqa.pt")
+    for case in g["function"]:
+        s = case["spec"]
+        q = syn.unit_uniform((s["b"], s["n"], s["hq"], s["d"]), syn._gen(s["seed"], "q"))
+        k = syn.unit_uniform((s["b"], s["s"], s["hk"], s["d"]), syn._gen(s["seed"], "k"))
+        v = syn.unit_uniform((s["b"], s["s"], s["hk"], s["d"]), syn._gen(s["seed"], "v"))
+        assert rel_err(O.sdp_gqa(q, k, v, is_causal=s["causal"]), case["out"]) < 2e-5
+    for case in g["module"]:
+        s = case["spec"]
+        kv = s["E"] // s["hq"] * s["hk"]
+        shapes = {"q_proj.weight": (s["E"], s["E"]), "q_proj.bias": (s["E"],), "k_proj.weight": (kv, s["E"]),
+                  "k_proj.bias": (kv,), "v_proj.weight": (kv, s["E"]), "v_proj.bias": (kv,), "norm.weight": (s["E"],),
+                  "norm.bias": (s["E"],), "out_proj.weight": (s["E"], s["E"]), "out_proj.bias": (s["E"],)}
+        sd = syn.fill_like_reference_init(shapes, seed=s["seed"])
+        assert syn.checksum(sd) == case["weights_checksum"]
+        xq = syn.unit_uniform((s["L"], s["B"], s["E"]), syn._gen(s["seed"], "xq"))
+        xk = syn.unit_uniform((s["S"], s["B"], s["E"]), syn._gen(s["seed"], "xk"))
+        y = O.mhgqa_forward(xq, xk, xk, sd, "", s["hq"], s["hk"])
+        assert rel_err(y, case["out"]) < 2e-5
+
+
+def test_pscan_golden():
+    for case in load_golden("pscan.pt")["cases"]:
+        s = case["spec"]
+        A = torch.rand((s["B"], s["L"], s["D"], s["N"]), generator=syn._gen(s["seed"], "A")) * 0.99
+        X = syn.unit_uniform((s["B"], s["L"], s["D"], s["N"]), syn._gen(s["seed"], "X"))
+        gH = syn.unit_uniform((s["B"], s["L"], s["D"], s["N"]), syn._gen(s["seed"], "gH"))
+        H = O.pscan_forward(A, X)
+        assert rel_err(H, case["H"]) < 1e-5
+        gA, gX = O.pscan_backward(A, H, gH)
+        assert rel_err(gX, case["gX"]) < 1e-5
+        assert rel_err(gA, case["gA"]) < 1e-5 or float(case["gA"].abs().max()) == 0.0

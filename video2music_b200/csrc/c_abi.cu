@@ -1,0 +1,155 @@
+// extern "C" entry points declared in include/v2m_b200.h + error plumbing.
+#include "common.cuh"
+#include "kernels.h"
+#include "../../include/v2m_b200.h"
+#include <stdarg.h>
+#include <string.h>
+
+namespace v2m {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return kCudaError;
+  }
+  return kOk;
+}
+
+static GemmEpilogue to_ep(const v2m_epilogue* e) {
+  GemmEpilogue g;
+  if (!e) return g;
+  g.bias = e->bias;
+  g.residual = static_cast<const float*>(e->residual);
+  g.ldr = e->ldr; g.res_mod = e->res_mod;
+  g.row_scale = e->row_scale; g.col_vec = e->col_vec;
+  g.alpha = e->alpha; g.alpha_cols = e->alpha_cols; g.relu = e->relu; g.residual_bf16 = e->residual_bf16;
+  g.head_scatter = e->head_scatter; g.S = e->S; g.H = e->H; g.dh = e->dh; g.cap = e->cap; g.pos0 = e->pos0;
+  g.part_stride = e->part_stride;
+  return g;
+}
+
+static_assert(sizeof(v2m_dec_layer) == sizeof(DecLayer), "v2m_dec_layer must mirror DecLayer");
+static_assert(sizeof(v2m_decode) == sizeof(DecodeParams), "v2m_decode must mirror DecodeParams");
+
+}  // namespace v2m
+
+using namespace v2m;
+
+extern "C" {
+
+int v2m_abi_version(void) { return 1; }
+const char* v2m_last_error(void) { return g_err; }
+
+int64_t v2m_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(v2m_epilogue);
+    case 1: return sizeof(v2m_attn);
+    case 2: return sizeof(v2m_dec_layer);
+    case 3: return sizeof(v2m_decode);
+    default: return -1;
+  }
+}
+
+int v2m_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float* C, int32_t ldc, int32_t M, int32_t N,
+                 int32_t K, const v2m_epilogue* ep, void* stream) {
+  GemmEpilogue g = to_ep(ep);
+  V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32: bf16 residual not supported on the fp32 path");
+  return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
+                  int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
+  return gemm_bf16_tc(A, lda, W, ldw, C, ldc, out_dtype == V2M_BF16, M, N, K, to_ep(ep), static_cast<cudaStream_t>(stream));
+}
+
+int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {
+  V2M_REQUIRE(a != nullptr, "v2m_attn_fwd: null params");
+  AttnParams p;
+  p.q = a->q; p.k = a->k; p.v = a->v; p.o = a->o;
+  p.q_sb = a->q_sb; p.q_sl = a->q_sl; p.k_sb = a->k_sb; p.k_sl = a->k_sl;
+  p.v_sb = a->v_sb; p.v_sl = a->v_sl; p.o_sb = a->o_sb; p.o_sl = a->o_sl;
+  p.B = a->B; p.Hq = a->Hq; p.Hkv = a->Hkv; p.Lq = a->Lq; p.Lk = a->Lk; p.dh = a->dh;
+  p.causal = a->causal; p.Er = a->Er; p.er_len = a->er_len; p.q_scale = a->q_scale;
+  p.lse = a->lse; p.p_out = a->p_out;
+  if (dtype == V2M_F32) return attn_fwd_f32(p, static_cast<cudaStream_t>(stream));
+  if (dtype == V2M_BF16) return attn_fwd_bf16_tc(p, static_cast<cudaStream_t>(stream));
+  set_last_error("v2m_attn_fwd: dtype %d unsupported", dtype);
+  return kUnsupported;
+}
+
+int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma, const float* beta,
+                  void* y, int32_t y_dtype, void* y2, int32_t y2_dtype, int32_t M, int32_t D, float eps, void* stream) {
+  return layernorm(x, x_dtype, res, res_dtype, gamma, beta, y, y_dtype, y2, y2_dtype, M, D, eps,
+                   static_cast<cudaStream_t>(stream));
+}
+
+int v2m_embed_sum(const int64_t* idx_a, const float* table_a, const int64_t* idx_b, const float* table_b, void* out,
+                  int32_t out_dtype, int32_t ld_out, int32_t rows, int32_t D, void* stream) {
+  return embed_sum(reinterpret_cast<const long long*>(idx_a), table_a, reinterpret_cast<const long long*>(idx_b), table_b,
+                   out, out_dtype, ld_out, rows, D, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_concat_features(const float* sem, int32_t sem_dim, const float* scene, const float* motion, int32_t motion_dim,
+                        const float* emotion, int32_t emo_dim, void* out, int32_t out_dtype, int32_t ld_out, int32_t rows,
+                        void* stream) {
+  return concat_features(sem, sem_dim, scene, motion, motion_dim, emotion, emo_dim, out, out_dtype, ld_out, rows,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int v2m_cast_2d(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
+                int32_t rows, int32_t cols, int32_t zero_pad, void* stream) {
+  return cast_copy_2d(src, src_dtype, ld_src, dst, dst_dtype, ld_dst, rows, cols, zero_pad,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int v2m_binary_f32(const float* a, const float* b, float* out, int64_t n, int32_t mode, float alpha, void* stream) {
+  return binary_op(a, b, out, n, mode, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void* stream) {
+  V2M_REQUIRE(p != nullptr, "v2m_decode_run: null params");
+  DecodeParams d;
+  memcpy(&d, p, sizeof(d));
+  return decode_run(d, n_steps, use_graph, static_cast<cudaStream_t>(stream));
+}
+
+int64_t v2m_decode_launches_per_step(const v2m_decode* p) {
+  DecodeParams d;
+  memcpy(&d, p, sizeof(d));
+  return decode_kernel_launches_per_step(d);
+}
+
+int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream) {
+  return pscan_fwd(A, X, H, B, L, D, N, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float* gX, int32_t B, int32_t L, int32_t D,
+                  int32_t N, void* stream) {
+  return pscan_bwd(A, H, gH, gA, gX, B, L, D, N, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_moe_route(const float* x, const float* wg, const float* bg, const float* sel_bias, float inv_t_pre, float inv_t_post,
+                  int32_t tokens, int32_t d, int32_t n_experts, int32_t k, int64_t* idx_out, float* w_out, float* logits_out,
+                  int32_t* hist_out, void* stream) {
+  return moe_route(x, wg, bg, sel_bias, inv_t_pre, inv_t_post, tokens, d, n_experts, k,
+                   reinterpret_cast<long long*>(idx_out), w_out, logits_out, hist_out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,563 @@
+// KV-cached single-token decode for chord generation (BASELINE config 2).
+//
+// The reference has no such path: VideoMusicTransformer.generate re-runs the whole model on
+// the growing prefix every step (model/video_music_transformer.py:1069-1071).  Because the
+// decoder is causal, row t of that forward depends only on positions <= t, so one step here
+// computes exactly that row for all B videos at once from cached keys/values:
+//   x_t   = Linear_chord([emb | key]) + pe[t]                         (:984-1001,1029)
+//   6 x   TransformerDecoderLayerRPR on the single row                  (model/rpr.py:55-70)
+//         self-attention logits  q.k_j + q.Er[er_len-1-(t-j)], j <= t   (rpr.py:387-395,439-455)
+//   y_t   = Wout(LayerNorm(x))  ->  argmax over [:CHORD_END]            (:1042,1070-1084, beam=1)
+//
+// Two kinds of kernels, both HBM/L2-bandwidth bound (arithmetic intensity < 64 flop/B):
+//   * skinny GEMM  [B<=64 rows] x [N,K]^T : every CTA owns 8 output features, streams its weight
+//     rows once with 16-byte loads issued before the activation prologue, keeps the activation
+//     tile in shared memory (LayerNorm of the previous sub-layer is applied while staging it) and
+//     splits K over its 8 warps (mma.sync m16n8k16 for bf16, FFMA for fp32; tcgen05 needs M>=64
+//     *per tile* and buys nothing at 16 flop/B).
+//   * attention over the cache: one CTA per (video, head); K and V blocks are contiguous in the
+//     head-major cache layout [B][H][pos][64] and are pulled into shared memory with one bulk
+//     async copy each (TMA engine, mbarrier completion).
+#include "common.cuh"
+#include "kernels.h"
+#include <type_traits>
+
+namespace v2m {
+
+enum AMode { A_PLAIN_T = 0, A_PLAIN_F32 = 1, A_LN = 2, A_LN2 = 3, A_EMBED = 4 };
+enum EMode { E_QKV = 0, E_RESID = 1, E_Q = 2, E_RELU = 3, E_EMBED = 4, E_LOGITS = 5 };
+
+struct SkinnyArgs {
+  const void* W; const float* bias; int N, K;
+  int amode; const void* a_src;
+  const float* ln_g; const float* ln_b; const float* ln2_g; const float* ln2_b;
+  int emode; int layer;
+};
+
+constexpr int MT = 64;        // rows (videos) per tile
+constexpr int NT = 8;         // output features per CTA
+constexpr int SK_THREADS = 256;
+constexpr int F32_KCHUNK = 512;
+
+template <typename T> struct SkinnyCfg;
+template <> struct SkinnyCfg<bf16> {
+  static __host__ __device__ int a_stride(int K) { return K + 32; }                 // elements; 64 B pad -> conflict-free LDS.128
+  static size_t smem(int K) { return (size_t)MT * a_stride(K) * 2 + 8 * MT * NT * 4; }
+};
+template <> struct SkinnyCfg<float> {
+  static __host__ __device__ int a_stride(int) { return F32_KCHUNK + 1; }
+  static size_t smem(int) { return (size_t)MT * (F32_KCHUNK + 1) * 4; }
+};
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Stage the activation tile rows [row0, row0+MT) x columns [kc0, kc0+kc) into shared memory as T,
+// applying the A-mode transform.  One warp per row; LayerNorm modes always have K == E == kc.
+template <typename T>
+__device__ void stage_a(const DecodeParams& p, const SkinnyArgs& a, T* As, int a_stride, int row0, int kc0, int kc, int t,
+                        bool write_h) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < MT; r += SK_THREADS / 32) {
+    const int row = row0 + r;
+    T* dst = As + (size_t)r * a_stride;
+    if (row >= p.B) {
+      for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(0.f);
+      continue;
+    }
+    if (a.amode == A_PLAIN_T) {
+      const T* src = static_cast<const T*>(a.a_src) + (size_t)row * a.K + kc0;
+      for (int k = lane; k < kc; k += 32) dst[k] = src[k];
+    } else if (a.amode == A_PLAIN_F32) {
+      const float* src = static_cast<const float*>(a.a_src) + (size_t)row * a.K + kc0;
+      for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(src[k]);
+    } else if (a.amode == A_EMBED) {
+      // video_music_transformer.py:984-989
+      if (p.chord_embed) {
+        const float* e = p.emb_chord + (size_t)p.gen[(size_t)row * p.cap + t] * p.E + kc0;
+        for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(e[k]);
+      } else {
+        const float* e0 = p.emb_root + (size_t)p.gen_root[(size_t)row * p.cap + t] * p.E + kc0;
+        const float* e1 = p.emb_attr + (size_t)p.gen_attr[(size_t)row * p.cap + t] * p.E + kc0;
+        for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(e0[k] + e1[k]);
+      }
+    } else {  // A_LN / A_LN2 : x = LayerNorm(r) ; K == E <= 1024
+      const T* src = static_cast<const T*>(a.a_src) + (size_t)row * a.K;
+      float vals[32];
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = lane + 32 * c;
+        vals[c] = (k < a.K) ? to_f32(src[k]) : 0.f;
+        sum += vals[c];
+      }
+      float mean = warp_sum(sum) / (float)a.K;
+      float sq = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = lane + 32 * c;
+        if (k < a.K) { const float d = vals[c] - mean; sq = fmaf(d, d, sq); }
+      }
+      float rstd = rsqrtf(warp_sum(sq) / (float)a.K + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = lane + 32 * c;
+        if (k < a.K) vals[c] = (vals[c] - mean) * rstd * a.ln_g[k] + a.ln_b[k];
+      }
+      if (write_h) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int k = lane + 32 * c;
+          if (k < a.K) p.h[(size_t)row * p.E + k] = vals[c];
+        }
+      }
+      if (a.amode == A_LN2) {   // decoder final norm on top of the last layer's norm3 (rpr.py:32-33)
+        sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) sum += (lane + 32 * c < a.K) ? vals[c] : 0.f;
+        mean = warp_sum(sum) / (float)a.K;
+        sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int k = lane + 32 * c;
+          if (k < a.K) { const float d = vals[c] - mean; sq = fmaf(d, d, sq); }
+        }
+        rstd = rsqrtf(warp_sum(sq) / (float)a.K + 1e-5f);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int k = lane + 32 * c;
+          if (k < a.K) vals[c] = (vals[c] - mean) * rstd * a.ln2_g[k] + a.ln2_b[k];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int k = lane + 32 * c;
+        if (k >= kc0 && k < kc0 + kc) dst[k - kc0] = from_f32<T>(vals[c]);
+      }
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void skinny_epilogue(const DecodeParams& p, const SkinnyArgs& a, int row, int n, float v, int t) {
+  if (row >= p.B || n >= a.N) return;
+  v += a.bias[n];
+  const float scaling = 1.0f / sqrtf((float)(p.E / p.H));   // float(head_dim) ** -0.5, rpr.py:251
+  switch (a.emode) {
+    case E_QKV: {
+      const DecLayer& L = p.layer[a.layer];
+      const int dh = p.E / p.H;
+      if (n < p.E) {
+        p.qbuf[(size_t)row * 3 * p.E + n] = v * scaling;               // rpr.py:328
+      } else {
+        const int m = (n - p.E) % p.E, hh = m / dh, d = m % dh;
+        T* dst = static_cast<T*>(n < 2 * p.E ? L.self_k : L.self_v);
+        dst[(((size_t)row * p.H + hh) * p.cap + t) * dh + d] = from_f32<T>(v);
+      }
+      break;
+    }
+    case E_Q:
+      p.qbuf[(size_t)row * 3 * p.E + n] = v * scaling;
+      break;
+    case E_RESID:
+      static_cast<T*>(p.r)[(size_t)row * p.E + n] = from_f32<T>(v + p.h[(size_t)row * p.E + n]);
+      break;
+    case E_RELU:
+      static_cast<T*>(p.ff)[(size_t)row * p.FF + n] = from_f32<T>(fmaxf(v, 0.f));
+      break;
+    case E_EMBED:
+      p.h[(size_t)row * p.E + n] = v + p.key[row] * p.wc_key[n] + p.pe[(size_t)t * p.E + n];
+      break;
+    case E_LOGITS:
+      p.logits[(size_t)row * p.vocab + n] = v;
+      if (p.logits_all) p.logits_all[((size_t)row * p.cap + t) * p.vocab + n] = v;
+      break;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_constant__ DecodeParams p,
+                                                                 const __grid_constant__ SkinnyArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * NT, row0 = blockIdx.y * MT;
+  const int t = *p.step;
+  const int K = a.K;
+  const bool write_h = (blockIdx.x == 0) && (a.amode == A_LN);
+
+  if constexpr (std::is_same<T, bf16>::value) {
+    bf16* As = reinterpret_cast<bf16*>(smem_raw);
+    const int AS = SkinnyCfg<bf16>::a_stride(K);
+    float* red = reinterpret_cast<float*>(smem_raw + (size_t)MT * AS * 2);
+    const int g = lane >> 2, q = lane & 3;
+    const int kw = K / 8, kbase = warp * kw, nch = kw / 32;          // nch in {2, 4}
+    // weight stream first: its HBM latency overlaps the activation staging below
+    const bf16* wrow = static_cast<const bf16*>(a.W) + (size_t)min(n0 + g, a.N - 1) * K + kbase + q * 8;
+    uint4 wv[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+      if (ch < nch) wv[ch] = ld_nc_v4(wrow + ch * 32);
+    stage_a<bf16>(p, a, As, AS, row0, 0, K, t, write_h);
+    __syncthreads();
+    float c[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[mt][i] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < nch) {
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const bf16* ar = As + (size_t)(mt * 16 + g) * AS + kbase + ch * 32 + q * 8;
+          const uint4 lo = *reinterpret_cast<const uint4*>(ar);
+          const uint4 hi = *reinterpret_cast<const uint4*>(ar + 8 * AS);
+          // k-permutation: a thread's 8 contiguous k values feed two MMAs (see decode notes in DESIGN.md)
+          mma_bf16_16816(c[mt], lo.x, hi.x, lo.y, hi.y, wv[ch].x, wv[ch].y);
+          mma_bf16_16816(c[mt], lo.z, hi.z, lo.w, hi.w, wv[ch].z, wv[ch].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      float* r0 = red + ((size_t)warp * MT + mt * 16 + g) * NT + 2 * q;
+      r0[0] = c[mt][0]; r0[1] = c[mt][1];
+      r0[8 * NT] = c[mt][2]; r0[8 * NT + 1] = c[mt][3];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = tid; o < MT * NT; o += SK_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[(size_t)w * MT * NT + o];
+      skinny_epilogue<T>(p, a, row0 + o / NT, n0 + o % NT, s, t);
+    }
+  } else {
+    float* As = reinterpret_cast<float*>(smem_raw);
+    const int AS = F32_KCHUNK + 1;
+    const int row = tid & 63, cp = tid >> 6;
+    const float* w0 = static_cast<const float*>(a.W) + (size_t)min(n0 + 2 * cp, a.N - 1) * K;
+    const float* w1 = static_cast<const float*>(a.W) + (size_t)min(n0 + 2 * cp + 1, a.N - 1) * K;
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int kc0 = 0; kc0 < K; kc0 += F32_KCHUNK) {
+      const int kc = min(F32_KCHUNK, K - kc0);
+      if (kc0 > 0) __syncthreads();
+      stage_a<float>(p, a, As, AS, row0, kc0, kc, t, write_h && kc0 == 0);
+      __syncthreads();
+      const float* ar = As + (size_t)row * AS;
+      for (int k = 0; k < kc; k += 4) {
+        const float4 x0 = __ldg(reinterpret_cast<const float4*>(w0 + kc0 + k));
+        const float4 x1 = __ldg(reinterpret_cast<const float4*>(w1 + kc0 + k));
+        const float a0 = ar[k], a1 = ar[k + 1], a2 = ar[k + 2], a3 = ar[k + 3];
+        acc0 = fmaf(a0, x0.x, acc0); acc1 = fmaf(a0, x1.x, acc1);
+        acc0 = fmaf(a1, x0.y, acc0); acc1 = fmaf(a1, x1.y, acc1);
+        acc0 = fmaf(a2, x0.z, acc0); acc1 = fmaf(a2, x1.z, acc1);
+        acc0 = fmaf(a3, x0.w, acc0); acc1 = fmaf(a3, x1.w, acc1);
+      }
+    }
+    skinny_epilogue<T>(p, a, row0 + row, n0 + 2 * cp, acc0, t);
+    skinny_epilogue<T>(p, a, row0 + row, n0 + 2 * cp + 1, acc1, t);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Attention of the single query row over the cached keys/values of one (video, head).
+constexpr int DA_THREADS = 256;
+
+template <typename T> struct DecAttnCfg;
+template <> struct DecAttnCfg<bf16> { static constexpr int kVec = 8; };   // elements per 16 B
+template <> struct DecAttnCfg<float> { static constexpr int kVec = 4; };
+
+template <typename T>
+__device__ __forceinline__ void load_vec_f32(const T* p, float* out);
+template <>
+__device__ __forceinline__ void load_vec_f32<bf16>(const bf16* p, float* out) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = bf16x2_to_f2(u.x); out[0] = f.x; out[1] = f.y;
+  f = bf16x2_to_f2(u.y); out[2] = f.x; out[3] = f.y;
+  f = bf16x2_to_f2(u.z); out[4] = f.x; out[5] = f.y;
+  f = bf16x2_to_f2(u.w); out[6] = f.x; out[7] = f.y;
+}
+template <>
+__device__ __forceinline__ void load_vec_f32<float>(const float* p, float* out) {
+  const float4 u = *reinterpret_cast<const float4*>(p);
+  out[0] = u.x; out[1] = u.y; out[2] = u.z; out[3] = u.w;
+}
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(DA_THREADS) dec_attn_kernel(const __grid_constant__ DecodeParams p, int layer,
+                                                              int is_cross, int n_max, int e_rows) {
+  constexpr int VEC = DecAttnCfg<T>::kVec;
+  constexpr int NCH = DH / VEC;                 // 16-byte chunks per row
+  constexpr int JG = DA_THREADS / NCH;          // row groups in the PV pass
+  extern __shared__ __align__(128) unsigned char dec_attn_smem[];
+  T* Ks = reinterpret_cast<T*>(dec_attn_smem);
+  T* Vs = Ks + (size_t)n_max * DH;
+  T* Es = Vs + (size_t)n_max * DH;              // bf16 self-attention only
+  const bool es_in_smem = e_rows > 0;           // Er rows staged in shared memory (bf16 self-attention)
+  float* qs = reinterpret_cast<float*>(Es + (size_t)e_rows * DH);
+  float* sc = qs + DH;                          // [n_max]
+  float* red = sc + ((n_max + 3) & ~3);         // [JG][DH]
+  float* stat = red + JG * DH;                  // [16]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stat + 16);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int t = *p.step;
+  const DecLayer& L = p.layer[layer];
+  const int n = is_cross ? p.S : t + 1;
+  const int kv_cap = is_cross ? p.S : p.cap;
+  const T* kg = static_cast<const T*>(is_cross ? L.cross_k : L.self_k) + ((size_t)b * p.H + h) * kv_cap * DH;
+  const T* vg = static_cast<const T*>(is_cross ? L.cross_v : L.self_v) + ((size_t)b * p.H + h) * kv_cap * DH;
+  const T* eg = static_cast<const T*>(L.er) + (size_t)(p.er_len - 1 - t) * DH;   // rows for j = 0..t
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    const uint32_t bytes = (uint32_t)(n * DH * sizeof(T));
+    const bool want_e = !is_cross && es_in_smem;
+    mbar_arrive_expect_tx(bar, bytes * (want_e ? 3 : 2));
+    bulk_g2s(Ks, kg, bytes, bar);
+    bulk_g2s(Vs, vg, bytes, bar);
+    if (want_e) bulk_g2s(Es, eg, bytes, bar);
+  }
+  if (tid < DH) qs[tid] = p.qbuf[(size_t)b * 3 * p.E + h * DH + tid];
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  // ---- scores: thread <-> key j; 16-byte chunks visited in an order rotated by j (conflict-free)
+  float lmax = -INFINITY;
+  for (int j = tid; j < n; j += DA_THREADS) {
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int cc = (c + j) & (NCH - 1);
+      float kv[VEC];
+      load_vec_f32<T>(Ks + (size_t)j * DH + cc * VEC, kv);
+      if (!is_cross) {
+        float ev[VEC];
+        if (es_in_smem) load_vec_f32<T>(Es + (size_t)j * DH + cc * VEC, ev);
+        else load_vec_f32<T>(eg + (size_t)j * DH + cc * VEC, ev);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) kv[e] += ev[e];
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) dot = fmaf(qs[cc * VEC + e], kv[e], dot);
+    }
+    sc[j] = dot;
+    lmax = fmaxf(lmax, dot);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) stat[warp] = lmax;
+  __syncthreads();
+  float mx = stat[0];
+#pragma unroll
+  for (int w = 1; w < DA_THREADS / 32; ++w) mx = fmaxf(mx, stat[w]);
+  float lsum = 0.f;
+  for (int j = tid; j < n; j += DA_THREADS) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) stat[8 + warp] = lsum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < DA_THREADS / 32; ++w) tot += stat[8 + w];
+
+  // ---- out = P V : thread <-> (row group jg, 16-byte chunk dc)
+  const int jg = tid / NCH, dc = tid % NCH;
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+  for (int j = jg; j < n; j += JG) {
+    float vv[VEC];
+    load_vec_f32<T>(Vs + (size_t)j * DH + dc * VEC, vv);
+    const float pj = sc[j];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = fmaf(pj, vv[e], acc[e]);
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) red[jg * DH + dc * VEC + e] = acc[e];
+  __syncthreads();
+  if (tid < DH) {
+    float o = 0.f;
+#pragma unroll 8
+    for (int g2 = 0; g2 < JG; ++g2) o += red[g2 * DH + tid];
+    static_cast<T*>(p.ctx)[(size_t)b * p.E + h * DH + tid] = from_f32<T>(o / tot);
+  }
+}
+
+// arg-max over logits[:, :vocab_limit] (softmax is monotone: video_music_transformer.py:1070-1084 with beam=1),
+// first index wins on exact ties; writes gen[:, t+1] and advances the step counter.
+__global__ void __launch_bounds__(256) argmax_advance_kernel(const __grid_constant__ DecodeParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = *p.step;
+  for (int b = warp; b < p.B; b += 8) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int n = lane; n < p.vocab_limit; n += 32) {
+      const float v = p.logits[(size_t)b * p.vocab + n];
+      if (v > best) { best = v; bi = n; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0 && t + 1 >= p.primer_len && t + 1 < p.cap) p.gen[(size_t)b * p.cap + t + 1] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *p.step = t + 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_skinny(const DecodeParams& p, const SkinnyArgs& a, cudaStream_t s) {
+  const size_t smem = SkinnyCfg<T>::smem(a.K);
+  dim3 grid((a.N + NT - 1) / NT, (p.B + MT - 1) / MT);
+  skinny_gemm_kernel<T><<<grid, SK_THREADS, smem, s>>>(p, a);
+  return check_launch("decode skinny gemm");
+}
+
+template <typename T>
+static int launch_attn(const DecodeParams& p, int layer, int is_cross, cudaStream_t s) {
+  const int n_max = p.S > p.cap ? p.S : p.cap;
+  const int dh = p.E / p.H;
+  const int e_rows = (std::is_same<T, bf16>::value && !is_cross) ? n_max : 0;
+  constexpr int VEC = DecAttnCfg<T>::kVec;
+  const size_t smem = (size_t)(2 * n_max + e_rows) * dh * sizeof(T) +
+                      sizeof(float) * (dh + ((n_max + 3) & ~3) + (DA_THREADS / (dh / VEC)) * dh + 16) + 16;
+  dec_attn_kernel<T, 64><<<p.B * p.H, DA_THREADS, smem, s>>>(p, layer, is_cross, n_max, e_rows);
+  return check_launch("decode attention");
+}
+
+template <typename T>
+static int enqueue_step(const DecodeParams& p, cudaStream_t s) {
+  int rc;
+  SkinnyArgs a{};
+#define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
+  // x_t = Linear_chord([emb | key]) + pe[t]
+  a = SkinnyArgs{p.w_chord, p.b_chord, p.E, p.E, A_EMBED, nullptr, nullptr, nullptr, nullptr, nullptr, E_EMBED, 0};
+  RUN(launch_skinny<T>(p, a, s));
+  for (int l = 0; l < p.n_layers; ++l) {
+    const DecLayer& L = p.layer[l];
+    const DecLayer* P = l > 0 ? &p.layer[l - 1] : nullptr;
+    // self-attention block
+    a = SkinnyArgs{L.w_qkv, L.b_qkv, 3 * p.E, p.E, l == 0 ? A_PLAIN_F32 : A_LN, l == 0 ? (const void*)p.h : (const void*)p.r,
+                   P ? P->ln3_g : nullptr, P ? P->ln3_b : nullptr, nullptr, nullptr, E_QKV, l};
+    RUN(launch_skinny<T>(p, a, s));
+    RUN(launch_attn<T>(p, l, 0, s));
+    a = SkinnyArgs{L.w_so, L.b_so, p.E, p.E, A_PLAIN_T, p.ctx, nullptr, nullptr, nullptr, nullptr, E_RESID, l};
+    RUN(launch_skinny<T>(p, a, s));
+    // cross-attention block
+    a = SkinnyArgs{L.w_cq, L.b_cq, p.E, p.E, A_LN, p.r, L.ln1_g, L.ln1_b, nullptr, nullptr, E_Q, l};
+    RUN(launch_skinny<T>(p, a, s));
+    RUN(launch_attn<T>(p, l, 1, s));
+    a = SkinnyArgs{L.w_co, L.b_co, p.E, p.E, A_PLAIN_T, p.ctx, nullptr, nullptr, nullptr, nullptr, E_RESID, l};
+    RUN(launch_skinny<T>(p, a, s));
+    // feed-forward block
+    a = SkinnyArgs{L.w_f1, L.b_f1, p.FF, p.E, A_LN, p.r, L.ln2_g, L.ln2_b, nullptr, nullptr, E_RELU, l};
+    RUN(launch_skinny<T>(p, a, s));
+    a = SkinnyArgs{L.w_f2, L.b_f2, p.E, p.FF, A_PLAIN_T, p.ff, nullptr, nullptr, nullptr, nullptr, E_RESID, l};
+    RUN(launch_skinny<T>(p, a, s));
+  }
+  const DecLayer& LL = p.layer[p.n_layers - 1];
+  a = SkinnyArgs{p.w_out, p.b_out, p.vocab, p.E, A_LN2, p.r, LL.ln3_g, LL.ln3_b, p.lnf_g, p.lnf_b, E_LOGITS, 0};
+  RUN(launch_skinny<T>(p, a, s));
+  argmax_advance_kernel<<<1, 256, 0, s>>>(p);
+  RUN(check_launch("decode argmax"));
+#undef RUN
+  return kOk;
+}
+
+long long decode_kernel_launches_per_step(const DecodeParams& p) { return 1 + 8LL * p.n_layers + 2; }
+
+template <typename T>
+static int set_attrs() {
+  static bool done = false;
+  if (done) return kOk;
+  cudaError_t e = cudaFuncSetAttribute(skinny_gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(dec_attn_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    set_last_error("decode: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    return kCudaError;
+  }
+  done = true;
+  return kOk;
+}
+
+template <typename T>
+static int decode_run_t(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream) {
+  int rc = set_attrs<T>();
+  if (rc) return rc;
+  if (!use_graph) {
+    for (int i = 0; i < n_steps; ++i) {
+      rc = enqueue_step<T>(p, stream);
+      if (rc) return rc;
+    }
+    return kOk;
+  }
+  // One step is captured once and replayed: every kernel reads the position from *p.step.
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t cs = stream;
+  cudaStream_t own = nullptr;
+  if (cs == nullptr || cs == cudaStreamLegacy) {   // the legacy default stream cannot be captured
+    if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) {
+      set_last_error("decode: cudaStreamCreate failed");
+      return kCudaError;
+    }
+    cudaStreamSynchronize(stream);
+    cs = own;
+  }
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { set_last_error("decode: begin capture: %s", cudaGetErrorString(e)); return kCudaError; }
+  rc = enqueue_step<T>(p, cs);
+  e = cudaStreamEndCapture(cs, &graph);
+  if (rc || e != cudaSuccess) {
+    if (!rc) set_last_error("decode: end capture: %s", cudaGetErrorString(e));
+    if (graph) cudaGraphDestroy(graph);
+    if (own) cudaStreamDestroy(own);
+    return rc ? rc : kCudaError;
+  }
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  if (e != cudaSuccess) {
+    set_last_error("decode: graph instantiate: %s", cudaGetErrorString(e));
+    cudaGraphDestroy(graph);
+    if (own) cudaStreamDestroy(own);
+    return kCudaError;
+  }
+  for (int i = 0; i < n_steps && e == cudaSuccess; ++i) e = cudaGraphLaunch(exec, cs);
+  if (own) {
+    cudaStreamSynchronize(own);
+    cudaStreamDestroy(own);
+  }
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { set_last_error("decode: graph launch: %s", cudaGetErrorString(e)); return kCudaError; }
+  return kOk;
+}
+
+int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream) {
+  V2M_REQUIRE(p.n_layers >= 1 && p.n_layers <= kMaxDecLayers, "decode: n_layers %d out of range", p.n_layers);
+  V2M_REQUIRE(p.E % p.H == 0 && p.E / p.H == 64, "decode: head_dim must be 64 (E=%d H=%d)", p.E, p.H);
+  V2M_REQUIRE(p.E % 256 == 0 && p.FF % 256 == 0 && p.E <= 1024, "decode: E=%d FF=%d must be multiples of 256, E<=1024", p.E, p.FF);
+  V2M_REQUIRE(p.cap <= p.er_len, "decode: cap %d exceeds er_len %d (rpr.py:426-450 fails for L > er_len)", p.cap, p.er_len);
+  V2M_REQUIRE(p.B >= 1 && n_steps >= 0, "decode: bad B=%d n_steps=%d", p.B, n_steps);
+  if (p.dtype == 0) return decode_run_t<float>(p, n_steps, use_graph, stream);
+  if (p.dtype == 1) return decode_run_t<bf16>(p, n_steps, use_graph, stream);
+  set_last_error("decode: dtype %d unsupported", p.dtype);
+  return kUnsupported;
+}
+
+}  // namespace v2m

@@ -1,0 +1,158 @@
+// Bandwidth-bound helpers: residual + LayerNorm, embedding gather, feature concat, casts.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace v2m {
+
+__device__ __forceinline__ float load_any(const void* p, int dtype, size_t i) {
+  return dtype == 0 ? static_cast<const float*>(p)[i] : __bfloat162float(static_cast<const bf16*>(p)[i]);
+}
+__device__ __forceinline__ void store_any(void* p, int dtype, size_t i, float v) {
+  if (dtype == 0) static_cast<float*>(p)[i] = v;
+  else static_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// One warp per row; the row lives in registers (D <= 32 * kMaxPerLane).  Two-pass mean / variance in fp32,
+// the arithmetic of nn.LayerNorm (rpr.py:59-69: tgt = norm(tgt + dropout(tgt2))).
+constexpr int kMaxPerLane = 32;
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, int x_dtype,
+                                                        const void* __restrict__ res, int res_dtype,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        void* __restrict__ y, int y_dtype, void* __restrict__ y2, int y2_dtype,
+                                                        int M, int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const size_t base = (size_t)warp * D;
+  float vals[kMaxPerLane];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxPerLane; ++c) {
+    const int d = lane + 32 * c;
+    float v = 0.f;
+    if (d < D) {
+      v = load_any(x, x_dtype, base + d);
+      if (res) v += load_any(res, res_dtype, base + d);
+    }
+    vals[c] = v;
+    sum += v;
+  }
+  const float mean = warp_sum(sum) / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxPerLane; ++c) {
+    const int d = lane + 32 * c;
+    if (d < D) {
+      const float t = vals[c] - mean;
+      sq = fmaf(t, t, sq);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+#pragma unroll
+  for (int c = 0; c < kMaxPerLane; ++c) {
+    const int d = lane + 32 * c;
+    if (d < D) {
+      const float o = (vals[c] - mean) * rstd * gamma[d] + beta[d];
+      store_any(y, y_dtype, base + d, o);
+      if (y2) store_any(y2, y2_dtype, base + d, o);
+    }
+  }
+}
+
+int layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const float* gamma, const float* beta,
+              void* y, int y_dtype, void* y2, int y2_dtype, int M, int D, float eps, cudaStream_t stream) {
+  V2M_REQUIRE(D > 0 && D <= 32 * kMaxPerLane, "layernorm: D=%d unsupported (<= %d)", D, 32 * kMaxPerLane);
+  if (M == 0) return kOk;
+  const int rows_per_block = 8;
+  layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
+      x, x_dtype, res, res_dtype, gamma, beta, y, y_dtype, y2, y2_dtype, M, D, eps);
+  return check_launch("layernorm");
+}
+
+__global__ void embed_sum_kernel(const long long* __restrict__ idx_a, const float* __restrict__ table_a,
+                                 const long long* __restrict__ idx_b, const float* __restrict__ table_b,
+                                 void* __restrict__ out, int out_dtype, int ld_out, int rows, int D) {
+  const int row = blockIdx.x;
+  const long long ia = idx_a[row];
+  const long long ib = idx_b ? idx_b[row] : 0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v = table_a[ia * D + d];
+    if (idx_b) v += table_b[ib * D + d];
+    store_any(out, out_dtype, (size_t)row * ld_out + d, v);
+  }
+}
+
+int embed_sum(const long long* idx_a, const float* table_a, const long long* idx_b, const float* table_b,
+              void* out, int out_dtype, int ld_out, int rows, int D, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  embed_sum_kernel<<<rows, 128, 0, stream>>>(idx_a, table_a, idx_b, table_b, out, out_dtype, ld_out, rows, D);
+  return check_launch("embed_sum");
+}
+
+__global__ void concat_features_kernel(const float* __restrict__ sem, int sem_dim, const float* __restrict__ scene,
+                                       const float* __restrict__ motion, int motion_dim,
+                                       const float* __restrict__ emotion, int emo_dim, void* __restrict__ out,
+                                       int out_dtype, int ld_out, int rows) {
+  const int row = blockIdx.x;
+  const int o_scene = sem_dim, o_motion = sem_dim + 1, o_emo = o_motion + motion_dim, total = o_emo + emo_dim;
+  for (int c = threadIdx.x; c < ld_out; c += blockDim.x) {
+    float v = 0.f;
+    if (c < o_scene) v = sem[(size_t)row * sem_dim + c];
+    else if (c < o_motion) v = scene[row];
+    else if (c < o_emo) v = motion[(size_t)row * motion_dim + (c - o_motion)];
+    else if (c < total) v = emotion[(size_t)row * emo_dim + (c - o_emo)];
+    store_any(out, out_dtype, (size_t)row * ld_out + c, v);
+  }
+}
+
+int concat_features(const float* sem, int sem_dim, const float* scene, const float* motion, int motion_dim,
+                    const float* emotion, int emo_dim, void* out, int out_dtype, int ld_out, int rows, cudaStream_t stream) {
+  V2M_REQUIRE(ld_out >= sem_dim + 1 + motion_dim + emo_dim, "concat_features: ld_out %d too small", ld_out);
+  if (rows == 0) return kOk;
+  concat_features_kernel<<<rows, 256, 0, stream>>>(sem, sem_dim, scene, motion, motion_dim, emotion, emo_dim, out,
+                                                   out_dtype, ld_out, rows);
+  return check_launch("concat_features");
+}
+
+__global__ void cast_copy_2d_kernel(const void* __restrict__ src, int src_dtype, long long ld_src, void* __restrict__ dst,
+                                    int dst_dtype, long long ld_dst, int rows, int cols, int width) {
+  const long long total = (long long)rows * width;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / width), c = (int)(i % width);
+    const float v = c < cols ? load_any(src, src_dtype, (size_t)(r * ld_src + c)) : 0.f;
+    store_any(dst, dst_dtype, (size_t)(r * ld_dst + c), v);
+  }
+}
+
+int cast_copy_2d(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
+                 int rows, int cols, int zero_pad, cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return kOk;
+  const int width = zero_pad ? (int)ld_dst : cols;
+  const long long total = (long long)rows * width;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  cast_copy_2d_kernel<<<blocks, 256, 0, stream>>>(src, src_dtype, ld_src, dst, dst_dtype, ld_dst, rows, cols, width);
+  return check_launch("cast_copy_2d");
+}
+
+int cast_copy(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t stream) {
+  if (n == 0) return kOk;
+  return cast_copy_2d(src, src_dtype, n, dst, dst_dtype, n, 1, (int)n, 0, stream);
+}
+
+// mode 0: out = a * silu(b)   (GLUExpert, moe.py:47);  mode 1: out = a + alpha * b  (shared expert, moe.py:301)
+__global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                              long long n, int mode, float alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = a[i], y = b[i];
+    out[i] = mode == 0 ? x * (y / (1.f + expf(-y))) : fmaf(alpha, y, x);
+  }
+}
+
+int binary_op(const float* a, const float* b, float* out, long long n, int mode, float alpha, cudaStream_t stream) {
+  if (n == 0) return kOk;
+  const long long want = (n + 255) / 256;
+  const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  binary_kernel<<<blocks, 256, 0, stream>>>(a, b, out, n, mode, alpha);
+  return check_launch("binary_op");
+}
+
+}  // namespace v2m

@@ -1,0 +1,259 @@
+// bf16 tensor-core GEMM  C[M,N] = epi(A[M,K] * W[N,K]^T)  on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Replaces every nn.Linear of the AMT on the bf16 path: QKV / out projections
+// (model/rpr.py:253,277,417 and the stock encoder layers), FFN (rpr.py:67), Linear_vis /
+// Linear_chord / Wout (model/video_music_transformer.py:1001,1022,1042) with the bias, q-scaling,
+// ReLU, residual(+positional encoding) and KV-cache scatter fused into the epilogue.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0     TMA producer   : cp.async.bulk.tensor 2-D tiles (128B swizzle) into a kStages ring
+//   warp 1     MMA issuer     : one lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//                               accumulators in TMEM, 2 accumulator stages (2*BN columns)
+//   warp 2     TMEM allocator
+//   warps 4-7  epilogue       : tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// Ragged edges: TMA zero-fills out-of-bounds rows/columns (M, N, K tails), stores are guarded.
+#include "common.cuh"
+#include "kernels.h"
+#include <cuda.h>
+
+namespace v2m {
+
+constexpr int GM = 128, GK = 64;
+constexpr int kGemmThreads = 256;
+
+template <int BN> struct GemmCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = GM * GK * 2;
+  static constexpr int kBBytes = BN * GK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;      // two accumulator stages
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns, 128B swizzle.
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return kCudaError; }
+  V2M_REQUIRE((ld * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(base) % 16 == 0,
+              "TMA needs 16-byte aligned base and row pitch (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
+  return kOk;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
+                    int ldc, int out_bf16, int M, int N, int K, const __grid_constant__ GemmEpilogue ep) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + GM - 1) / GM, n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + GK - 1) / GK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+          tma_load_2d(sa, &tmA, kb * GK, m_blk * GM, full_bar + stage);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, kb * GK, n_blk * BN, full_bar + stage);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = make_idesc_bf16(GM, BN, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < GK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss(tmem_base + acc * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);                    // frees the smem slot when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar + acc);  // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int m = m_blk * GM + quad * 32 + lane;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const bool row_ok = m < M;
+      const float rs = (row_ok && ep.row_scale) ? ep.row_scale[m] : 0.f;
+      const size_t res_row = ep.residual ? (size_t)(ep.res_mod > 0 ? m % ep.res_mod : m) * ep.ldr : 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (row_ok && n0 < N) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = n0 + i;
+            float x = __uint_as_float(r[i]);
+            if (n < N) {
+              if (ep.bias) x += __ldg(ep.bias + n);
+              if (n < ep.alpha_cols) x *= ep.alpha;
+              if (ep.relu) x = fmaxf(x, 0.f);
+              if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
+              if (ep.residual) {
+                x += ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
+                                      : __ldg(ep.residual + res_row + n);
+              }
+            }
+            v[i] = x;
+          }
+          // 8-element groups stay inside one head / one row: vector store when aligned and in range
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int n = n0 + g8 * 8;
+            if (n >= N) break;
+            const long long o = epi_out_index(ep, m, n, ldc);
+            if (out_bf16) {
+              bf16* dst = static_cast<bf16*>(C) + o;
+              if (n + 8 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                uint4 pk;
+                pk.x = f2_to_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
+                pk.y = f2_to_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
+                pk.z = f2_to_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
+                pk.w = f2_to_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
+                *reinterpret_cast<uint4*>(dst) = pk;
+              } else {
+                for (int i = 0; i < 8 && n + i < N; ++i)
+                  static_cast<bf16*>(C)[epi_out_index(ep, m, n + i, ldc)] = __float2bfloat16_rn(v[g8 * 8 + i]);
+              }
+            } else {
+              float* dst = static_cast<float*>(C) + o;
+              if (n + 8 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                reinterpret_cast<float4*>(dst)[0] = make_float4(v[g8 * 8 + 0], v[g8 * 8 + 1], v[g8 * 8 + 2], v[g8 * 8 + 3]);
+                reinterpret_cast<float4*>(dst)[1] = make_float4(v[g8 * 8 + 4], v[g8 * 8 + 5], v[g8 * 8 + 6], v[g8 * 8 + 7]);
+              } else {
+                for (int i = 0; i < 8 && n + i < N; ++i)
+                  static_cast<float*>(C)[epi_out_index(ep, m, n + i, ldc)] = v[g8 * 8 + i];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int M, int N, int K,
+                       const GemmEpilogue& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
+    attr = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  gemm_bf16_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, M, N, K, ep);
+  return check_launch("gemm_bf16_tc");
+}
+
+int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream) {
+  V2M_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_bf16_tc: bad dims M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return kOk;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, GM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, W, N, K, ldw, bn);
+  if (rc) return rc;
+  return bn == 256 ? launch_gemm<256>(tmA, tmB, C, ldc, out_bf16, M, N, K, ep, stream)
+                   : launch_gemm<128>(tmA, tmB, C, ldc, out_bf16, M, N, K, ep, stream);
+}
+
+}  // namespace v2m

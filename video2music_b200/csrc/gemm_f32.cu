@@ -1,0 +1,112 @@
+// fp32 SIMT GEMM  C[M,N] = epi(A[M,K] * W[N,K]^T)  -- the exact-precision path.
+//
+// Replaces the F.linear calls of the reference on the fp32 parity path
+// (model/rpr.py:253,277,417; model/video_music_transformer.py:1001,1022,1042; stock
+// nn.TransformerEncoderLayer linears).  Plain FFMA with a fixed k order, so each output row is
+// bit-identical whatever the batch size (batch invariance, needed for greedy-token parity).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace v2m {
+
+constexpr int BM = 128, BN = 128, BK = 16, PAD = 4;
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda,
+                                                       const float* __restrict__ W, int ldw,
+                                                       float* __restrict__ C, int ldc, int M, int N, int K,
+                                                       GemmEpilogue ep) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int lrow = tid >> 2;         // 0..63
+  const int lk = (tid & 3) * 4;      // 0,4,8,12
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = lrow + 64 * i;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + lk;
+      if (ALIGNED) {
+        if (gm < M && gk < K) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk));
+        if (gn < N && gk < K) vb = __ldg(reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk));
+      } else {
+        if (gm < M) {
+          const float* p = A + (size_t)gm * lda + gk;
+          if (gk + 0 < K) va.x = __ldg(p + 0);
+          if (gk + 1 < K) va.y = __ldg(p + 1);
+          if (gk + 2 < K) va.z = __ldg(p + 2);
+          if (gk + 3 < K) va.w = __ldg(p + 3);
+        }
+        if (gn < N) {
+          const float* p = W + (size_t)gn * ldw + gk;
+          if (gk + 0 < K) vb.x = __ldg(p + 0);
+          if (gk + 1 < K) vb.y = __ldg(p + 1);
+          if (gk + 2 < K) vb.z = __ldg(p + 2);
+          if (gk + 3 < K) vb.w = __ldg(p + 3);
+        }
+      }
+      As[lk + 0][r] = va.x; As[lk + 1][r] = va.y; As[lk + 2][r] = va.z; As[lk + 3][r] = va.w;
+      Bs[lk + 0][r] = vb.x; Bs[lk + 1][r] = vb.y; Bs[lk + 2][r] = vb.z; Bs[lk + 3][r] = vb.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+    const float rs = ep.row_scale ? ep.row_scale[m] : 0.f;
+    const float* res = ep.residual ? ep.residual + (size_t)(ep.res_mod > 0 ? m % ep.res_mod : m) * ep.ldr : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (ep.bias) v += ep.bias[n];
+      if (n < ep.alpha_cols) v *= ep.alpha;
+      if (ep.relu) v = fmaxf(v, 0.f);
+      if (ep.row_scale) v = fmaf(rs, ep.col_vec[n], v);
+      if (res) v += res[n];  // fp32 path: residual is always fp32
+      C[epi_out_index(ep, m, n, ldc)] = v;
+    }
+  }
+}
+
+int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+             const GemmEpilogue& ep, cudaStream_t stream) {
+  V2M_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_f32: bad dims M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return kOk;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  const bool aligned = (lda % 4 == 0) && (ldw % 4 == 0) && (K % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(W) % 16 == 0);
+  if (aligned)
+    gemm_f32_kernel<true><<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
+  else
+    gemm_f32_kernel<false><<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
+  return check_launch("gemm_f32");
+}
+
+}  // namespace v2m

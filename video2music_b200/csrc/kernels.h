@@ -1,0 +1,135 @@
+// Internal C++ interface between the kernel translation units and the C ABI (c_abi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace v2m {
+
+// Epilogue shared by the fp32 SIMT GEMM and the bf16 tcgen05 GEMM.  Applied in this order:
+//   v = acc + bias[n];  if (n < alpha_cols) v *= alpha;  if (relu) v = max(v, 0);
+//   v += row_scale[m] * col_vec[n];  v += residual[(m % res_mod) * ldr + n]
+struct GemmEpilogue {
+  const float* bias = nullptr;
+  const float* residual = nullptr;   // fp32 (or bf16 when residual_bf16 != 0)
+  int ldr = 0;
+  int res_mod = 0;                    // 0: residual row = m
+  const float* row_scale = nullptr;  // [M]
+  const float* col_vec = nullptr;    // [N]
+  float alpha = 1.f;
+  int alpha_cols = 0;
+  int relu = 0;
+  int residual_bf16 = 0;
+  // Output addressing.  head_scatter == 0: C[m*ldc + n].  Otherwise the (m, n) element goes to
+  // the head-major KV-cache layout  C + (n / (H*dh)) * part_stride + (((m / S)*H + h)*cap + (m % S) + pos0)*dh + d
+  // with h = (n % (H*dh)) / dh, d = n % dh  (used for the cross-attention K|V projection of memory).
+  int head_scatter = 0;
+  int S = 0, H = 0, dh = 0, cap = 0, pos0 = 0;
+  long long part_stride = 0;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ long long epi_out_index(const GemmEpilogue& ep, int m, int n, int ldc) {
+  if (!ep.head_scatter) return (long long)m * ldc + n;
+  const int hd = ep.H * ep.dh;
+  const int part = n / hd, rem = n - part * hd;
+  const int h = rem / ep.dh, d = rem - h * ep.dh;
+  const int b = m / ep.S, s = m - b * ep.S;
+  return (long long)part * ep.part_stride + (((long long)b * ep.H + h) * ep.cap + s + ep.pos0) * ep.dh + d;
+}
+#endif
+
+int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+             const GemmEpilogue& ep, cudaStream_t stream);
+
+// bf16 tensor-core GEMM (tcgen05/TMEM/TMA).  A [M,K] bf16 row-major (lda), W [N,K] bf16 row-major (ldw).
+// out_bf16: C is bf16, else fp32.
+int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream);
+
+// Attention, one (batch, head) problem per blockIdx.y.  Element (b, l, h, d) of q lives at
+// q + b*q_sb + l*q_sl + h*dh + d (same for k, v, o).  kv head of query head hq is hq / (Hq / Hkv).
+struct AttnParams {
+  const void* q; const void* k; const void* v; void* o;
+  long long q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl;
+  int B, Hq, Hkv, Lq, Lk, dh;
+  int causal;              // keys j <= i only
+  const void* Er;          // [er_len, dh] or null; adds q_i . Er[er_len-1-(i-j)] for j <= i (rpr.py:391-395,439-455)
+  int er_len;
+  float q_scale;           // multiplies q on load (1.0 when the projection epilogue already scaled it)
+  float* lse;              // optional [B*Hq, Lq] log-sum-exp (for backward)
+  float* p_out;            // optional [B*Hq, Lq, Lk] probabilities (need_weights=True)
+};
+int attn_fwd_f32(const AttnParams& p, cudaStream_t stream);
+int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream);
+
+// y = LayerNorm(x (+ res)) * gamma + beta over the last dim D (eps 1e-5 like nn.LayerNorm).
+// dtype codes: 0 = fp32, 1 = bf16.  y2 (optional) receives a second copy in dtype y2_dtype.
+int layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const float* gamma, const float* beta,
+              void* y, int y_dtype, void* y2, int y2_dtype, int M, int D, float eps, cudaStream_t stream);
+
+// out[row, :] = table_a[idx_a[row]] (+ table_b[idx_b[row]]);  tables fp32 [*, D]; out dtype 0/1, ld_out elements.
+int embed_sum(const long long* idx_a, const float* table_a, const long long* idx_b, const float* table_b,
+              void* out, int out_dtype, int ld_out, int rows, int D, cudaStream_t stream);
+
+// Video feature concat (video_music_transformer.py:1003-1018): out[row] = [sem(768) | scene | motion(md) | emotion(6) | 0-pad]
+int concat_features(const float* sem, int sem_dim, const float* scene, const float* motion, int motion_dim,
+                    const float* emotion, int emo_dim, void* out, int out_dtype, int ld_out, int rows, cudaStream_t stream);
+
+int cast_copy(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, cudaStream_t stream);
+// dst[r, 0:cols] = src[r, 0:cols] with independent leading dims and dtypes, zero-filling dst columns [cols, ld_dst).
+int cast_copy_2d(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
+                 int rows, int cols, int zero_pad, cudaStream_t stream);
+
+int binary_op(const float* a, const float* b, float* out, long long n, int mode, float alpha, cudaStream_t stream);
+
+// ------------------------------------------------------------------ KV-cached decode (decode.cu)
+constexpr int kMaxDecLayers = 8;
+struct DecLayer {
+  const void* w_qkv; const float* b_qkv;
+  const void* w_so;  const float* b_so;
+  const void* w_cq;  const float* b_cq;
+  const void* w_co;  const float* b_co;
+  const void* w_f1;  const float* b_f1;
+  const void* w_f2;  const float* b_f2;
+  const float* ln1_g; const float* ln1_b;
+  const float* ln2_g; const float* ln2_b;
+  const float* ln3_g; const float* ln3_b;
+  const void* er;                 // [er_len, dh] in the compute dtype
+  void* self_k; void* self_v;     // [B, H, cap, dh]
+  const void* cross_k; const void* cross_v;  // [B, H, S, dh]
+};
+struct DecodeParams {
+  int dtype;                      // 0 fp32, 1 bf16: type of weights, KV caches and the T scratch buffers
+  int B, H, E, FF, S, cap, n_layers, er_len, vocab, vocab_limit, primer_len, chord_embed;
+  DecLayer layer[kMaxDecLayers];
+  const float* lnf_g; const float* lnf_b;
+  const void* w_out; const float* b_out;        // [vocab, E]
+  const float* emb_root; const float* emb_attr; const float* emb_chord;  // fp32 tables
+  const void* w_chord; const float* wc_key; const float* b_chord;        // Linear_chord split: [E,E] | [E] | [E]
+  const float* pe;                // [cap, E]
+  const float* key;               // [B]
+  long long* gen; long long* gen_root; long long* gen_attr;  // [B, cap] token buffers (int64 like the reference)
+  int* step;                      // device scalar: position t being processed
+  float* h;                       // [B, E]  residual stream (post-LN), fp32
+  void* r;                        // [B, E]  pre-LN sum, dtype T
+  float* qbuf;                    // [B, 3E] fp32 (q only is used)
+  void* ctx;                      // [B, E]  attention output, dtype T
+  void* ff;                       // [B, FF] dtype T
+  float* logits;                  // [B, vocab]
+  float* logits_all;              // optional [B, cap, vocab] (tests): row t receives the step-t logits
+};
+// Runs `n_steps` decode steps starting at *step (device).  use_graph: capture one step into a CUDA graph and replay.
+int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream);
+long long decode_kernel_launches_per_step(const DecodeParams& p);
+
+// ------------------------------------------------------------------ selective scan (pscan.cu)
+int pscan_fwd(const float* A, const float* X, float* H, int B, int L, int D, int N, cudaStream_t stream);
+int pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float* gX, int B, int L, int D, int N,
+              cudaStream_t stream);
+
+// ------------------------------------------------------------------ MoE (moe.cu)
+int moe_route(const float* x, const float* wg, const float* bg, const float* sel_bias, float inv_t_pre, float inv_t_post,
+              int tokens, int d, int n_experts, int k, long long* idx_out, float* w_out, float* logits_out,
+              int* hist_out, cudaStream_t stream);
+
+}  // namespace v2m

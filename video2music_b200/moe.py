@@ -1,0 +1,195 @@
+"""Drop-in for the MoE FFN of model/moe.py: GLUExpert (:36-49), MoELayer (:150-200), SharedMoELayer
+(:202-302), TopKScheduler (:66-82), TemperatureScheduler (:84-97) -- same constructor signatures and
+parameter names (`experts.N.{linear1,linear2,gate}`, `gate`, `shared_expert`, buffer `bias`).
+
+Routing (gate GEMV + top-k + fp32 softmax + expert histogram) is one fused kernel; tokens are then
+grouped by expert and every expert runs as GEMMs over its contiguous token group with the SwiGLU
+gating fused between them (see `_experts_forward`).  The reference's per-expert Python loop with
+`torch.where` host syncs (moe.py:192-199) is gone; the logging side channels
+(third_party/log_experts.py, log_maxvio.py) are kept as optional callables (`on_route`).
+"""
+import copy
+from typing import Callable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .rpr import _get_clones
+
+
+class GLUExpert(nn.Module):
+    def __init__(self, d_model, d_ff=2048, dropout=0.1):
+        super().__init__()
+        self.linear1 = nn.Linear(d_model, d_ff)
+        self.linear2 = nn.Linear(d_ff, d_model)
+        self.gate = nn.Linear(d_model, d_ff)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        """x (..., d) -> linear2((linear1 x) * silu(gate x))  (moe.py:44-49), eval semantics."""
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not built yet")
+        shp = x.shape
+        x2 = x.detach().reshape(-1, shp[-1]).float().contiguous()
+        return _glu(self, x2).view(shp[:-1] + (self.linear2.out_features,))
+
+
+def _glu(e: GLUExpert, x2: torch.Tensor) -> torch.Tensor:
+    d = x2.shape[1]
+    a = ops.linear(x2, e.linear1.weight.detach(), e.linear1.bias.detach(), k=d)
+    g = ops.linear(x2, e.gate.weight.detach(), e.gate.bias.detach(), k=d)
+    h = ops.swiglu(a, g)
+    return ops.linear(h, e.linear2.weight.detach(), e.linear2.bias.detach(), k=h.shape[1])
+
+
+class TopKScheduler(nn.Module):
+    def __init__(self, n_experts=8, min_n_experts_per_token=2, update_step=16):
+        super().__init__()
+        self.n_experts = n_experts
+        self.min_n_experts_per_token = min_n_experts_per_token
+        self.k = n_experts
+        self.update_step = update_step
+        self.counting_step = 0
+
+    def step(self):
+        self.counting_step += 1
+        if self.counting_step % self.update_step == 0:
+            self.k = max(self.min_n_experts_per_token, self.k - 1)
+
+    def getK(self):
+        return self.k
+
+
+class TemperatureScheduler(nn.Module):
+    def __init__(self, temperature_min=0.8, temperature_max=1.1, temperature_step=0.0005):
+        super().__init__()
+        self.temperature_min = temperature_min
+        self.temperature_max = temperature_max
+        self.temperature_step = temperature_step
+        self.t = self.temperature_min
+
+    def step(self):
+        self.t += self.temperature_step
+        self.t = min(self.t, self.temperature_max)
+
+    def getT(self):
+        return self.t
+
+
+def _experts_forward(experts, x2: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor) -> torch.Tensor:
+    """out[t] = sum_r w[t,r] * expert_{idx[t,r]}(x[t])  (moe.py:191-199).
+    Tokens are permuted into expert-contiguous order (stable counting sort by expert), every expert
+    processes its slice, and the weighted results are combined per token in rank order (deterministic)."""
+    T, k = idx.shape
+    d = x2.shape[1]
+    flat = idx.reshape(-1)
+    order = torch.argsort(flat, stable=True)                 # TODO(round 2): fused permute kernel
+    tok = order // k
+    xp = x2.index_select(0, tok)
+    counts = hist.tolist()
+    yp = torch.empty((T * k, experts[0].linear2.out_features), device=x2.device, dtype=torch.float32)
+    start = 0
+    for i, e in enumerate(experts):
+        n = counts[i]
+        if n:
+            yp[start:start + n] = _glu(e, xp[start:start + n])
+        start += n
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(order.numel(), device=order.device)
+    y = yp.index_select(0, inv).view(T, k, -1)
+    return (y * w.unsqueeze(-1)).sum(dim=1)
+
+
+class MoELayer(nn.Module):
+    def __init__(self, expert, d_model, n_experts=8, n_experts_per_token=2, dropout=0.1, topk_scheduler=None,
+                 temperature_scheduler=None):
+        super().__init__()
+        self.n_experts = n_experts
+        self.n_experts_per_token = n_experts_per_token
+        self.d_model = d_model
+        self.dropout = nn.Dropout(dropout)
+        self.experts = _get_clones(expert, n_experts)
+        self.gate = nn.Linear(d_model, n_experts)
+        if topk_scheduler is not None:
+            self.topk_scheduler = topk_scheduler
+        if temperature_scheduler is not None:
+            self.temperature_scheduler = temperature_scheduler
+        self.on_route: Optional[Callable] = None      # hook(selected_experts, histogram, training)
+        self.last_selected_experts = None
+
+    def forward(self, x):
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not built yet")
+        if hasattr(self, "topk_scheduler") and self.training:            # moe.py:168-172
+            self.topk_scheduler.step()
+            k = self.topk_scheduler.getK()
+        else:
+            k = self.n_experts_per_token
+        if hasattr(self, "temperature_scheduler") and self.training:     # moe.py:174-178
+            self.temperature_scheduler.step()
+            t = self.temperature_scheduler.getT()
+        else:
+            t = 1.0
+        shp = x.shape
+        x2 = x.detach().reshape(-1, shp[-1]).float().contiguous()
+        idx, w, hist, _ = ops.moe_route(x2, self.gate.weight.detach(), self.gate.bias.detach(), k, inv_t_pre=1.0 / t)
+        self.last_selected_experts = idx.view(shp[:-1] + (k,))
+        if self.on_route is not None:
+            self.on_route(self.last_selected_experts, hist, self.training)
+        return _experts_forward(self.experts, x2, idx, w, hist).view(shp)
+
+
+class SharedMoELayer(nn.Module):
+    def __init__(self, expert, d_model, n_experts=8, n_experts_per_token=2, dropout=0.1, balancing=False,
+                 topk_scheduler=None, temperature_scheduler=None, use_KAN=False):
+        super().__init__()
+        if use_KAN:
+            raise NotImplementedError("KAN gate needs efficient_kan (out of scope, SURVEY.md 8c)")
+        self.n_experts = n_experts
+        self.n_experts_per_token = n_experts_per_token
+        self.d_model = d_model
+        self.dropout = nn.Dropout(dropout)
+        self.experts = _get_clones(expert, n_experts)
+        self.balancing = balancing
+        if topk_scheduler is not None:
+            self.topk_scheduler = topk_scheduler
+        if temperature_scheduler is not None:
+            self.temperature_scheduler = temperature_scheduler
+        self.gate = nn.Linear(d_model, n_experts)
+        if self.balancing:
+            self.register_buffer("bias", torch.zeros((n_experts, 1)))
+            self.update_rate = 0.001
+        self.shared_expert = _get_clones(expert, 1)[0]
+        self.on_route: Optional[Callable] = None
+        self.last_selected_experts = None
+
+    def forward(self, x):
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not built yet")
+        if hasattr(self, "topk_scheduler") and self.training:            # moe.py:232-236
+            self.topk_scheduler.step()
+            k = self.topk_scheduler.getK()
+        else:
+            k = self.n_experts_per_token
+        if hasattr(self, "temperature_scheduler"):                       # moe.py:238-242 (steps in eval too)
+            self.temperature_scheduler.step()
+            t = self.temperature_scheduler.getT()
+        else:
+            t = 1.0
+        shp = x.shape
+        x2 = x.detach().reshape(-1, shp[-1]).float().contiguous()
+        sel_bias = None
+        if self.balancing and self.training:                             # moe.py:258-268
+            sel_bias = self.bias.detach().reshape(-1).float().contiguous()
+        idx, w, hist, _ = ops.moe_route(x2, self.gate.weight.detach(), self.gate.bias.detach(), k, sel_bias=sel_bias,
+                                        inv_t_post=1.0 / t)
+        if self.balancing and self.training:                             # moe.py:270-279
+            c = hist.to(self.bias.dtype)
+            self.bias += self.update_rate * (c.mean() - c).unsqueeze(1)
+        self.last_selected_experts = idx.view(shp[:-1] + (k,))
+        if self.on_route is not None:
+            self.on_route(self.last_selected_experts, hist, self.training)
+        out = _experts_forward(self.experts, x2, idx, w, hist)
+        shared = _glu(self.shared_expert, x2)                            # moe.py:301
+        return ops.axpy(out, shared, 1.0 / k).view(shp[:-1] + (self.d_model,))

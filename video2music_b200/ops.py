@@ -1,0 +1,198 @@
+"""Thin functional wrappers: torch CUDA tensors in, kernels of libv2m_b200.so out.
+
+torch is used for device memory and the current stream only; every arithmetic
+op below is one of our kernels.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, Attn, Epilogue, check, dtype_code, load, ptr, require_device, stream
+
+
+def _rows(t: torch.Tensor) -> int:
+    return t.numel() // t.shape[-1]
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, k: Optional[int] = None,
+           relu: bool = False, alpha: float = 1.0, alpha_cols: int = 0,
+           residual: Optional[torch.Tensor] = None, res_mod: int = 0,
+           row_scale: Optional[torch.Tensor] = None, col_vec: Optional[torch.Tensor] = None,
+           out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
+           head_scatter: Optional[dict] = None) -> torch.Tensor:
+    """y = epilogue(x @ w[:, :k].T).  x (M, >=k) and w (N, >=k) are row-major 2-D tensors of the same
+    dtype (fp32 -> SIMT exact GEMM, bf16 -> tcgen05 GEMM); leading dims are taken from the strides."""
+    require_device(x)
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
+    assert x.dtype == w.dtype, (x.dtype, w.dtype)
+    M, N = x.shape[0], w.shape[0]
+    K = k if k is not None else min(x.shape[1], w.shape[1])
+    lda, ldw = x.stride(0), w.stride(0)
+    if out_dtype is None:
+        out_dtype = x.dtype
+    ep = Epilogue()
+    ep.bias = ptr(bias)
+    ep.alpha, ep.alpha_cols, ep.relu = alpha, alpha_cols, int(relu)
+    if residual is not None:
+        assert residual.stride(-1) == 1
+        ep.residual, ep.ldr, ep.res_mod = ptr(residual), residual.stride(-2), res_mod
+        ep.residual_bf16 = int(residual.dtype == torch.bfloat16)
+    if row_scale is not None:
+        ep.row_scale, ep.col_vec = ptr(row_scale), ptr(col_vec)
+    if head_scatter is not None:
+        assert out is not None
+        ep.head_scatter = 1
+        for f in ("S", "H", "dh", "cap", "pos0", "part_stride"):
+            setattr(ep, f, head_scatter[f])
+        ldc = 0
+    else:
+        if out is None:
+            out = torch.empty((M, N), device=x.device, dtype=out_dtype)
+        ldc = out.stride(0)
+    lib = load()
+    if x.dtype == torch.float32:
+        assert out.dtype == torch.float32
+        check(lib.v2m_gemm_f32(ptr(x), lda, ptr(w), ldw, ptr(out), ldc, M, N, K, C.byref(ep), stream()))
+    else:
+        check(lib.v2m_gemm_bf16(ptr(x), lda, ptr(w), ldw, ptr(out), ldc, dtype_code(out.dtype), M, N, K,
+                                C.byref(ep), stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, Hq: int, Hkv: int,
+              Lq: int, Lk: int, dh: int, q_strides, k_strides, v_strides, o_strides, causal: bool,
+              Er: Optional[torch.Tensor] = None, q_scale: float = 1.0, lse: Optional[torch.Tensor] = None,
+              p_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T + skew(q Er^T) + causal) v.  *_strides = (batch stride, row stride) in elements;
+    q/k/v/out may be column slices of wider matrices (head h starts at column h*dh of the given pointer)."""
+    require_device(q)
+    a = Attn()
+    a.q, a.k, a.v, a.o = ptr(q), ptr(k), ptr(v), ptr(out)
+    a.q_sb, a.q_sl = q_strides
+    a.k_sb, a.k_sl = k_strides
+    a.v_sb, a.v_sl = v_strides
+    a.o_sb, a.o_sl = o_strides
+    a.B, a.Hq, a.Hkv, a.Lq, a.Lk, a.dh = B, Hq, Hkv, Lq, Lk, dh
+    a.causal = int(causal)
+    if Er is not None:
+        assert Er.dtype == q.dtype and Er.is_contiguous()
+        a.Er, a.er_len = ptr(Er), Er.shape[0]
+    a.q_scale = q_scale
+    a.lse, a.p_out = ptr(lse), ptr(p_out)
+    check(load().v2m_attn_fwd(C.byref(a), dtype_code(q.dtype), stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, res: Optional[torch.Tensor] = None,
+              out_dtype: Optional[torch.dtype] = None, eps: float = 1e-5) -> torch.Tensor:
+    require_device(x)
+    assert x.is_contiguous()
+    D = x.shape[-1]
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    check(load().v2m_layernorm(ptr(x), dtype_code(x.dtype), ptr(res), dtype_code(res.dtype) if res is not None else 0,
+                               ptr(gamma), ptr(beta), ptr(y), dtype_code(y.dtype), None, 0, _rows(x), D, eps, stream()))
+    _lib.count_launches(1)
+    return y
+
+
+def embed_sum(idx_a: torch.Tensor, table_a: torch.Tensor, idx_b: Optional[torch.Tensor],
+              table_b: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+    require_device(table_a)
+    rows, D = idx_a.numel(), table_a.shape[1]
+    idx_a = idx_a.contiguous()
+    if idx_b is not None:
+        idx_b = idx_b.contiguous()
+    out = torch.empty((rows, D), device=table_a.device, dtype=out_dtype)
+    check(load().v2m_embed_sum(ptr(idx_a), ptr(table_a), ptr(idx_b), ptr(table_b), ptr(out), dtype_code(out_dtype), D,
+                               rows, D, stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def concat_features(sem: torch.Tensor, scene: torch.Tensor, motion: torch.Tensor, emotion: torch.Tensor,
+                    out_dtype: torch.dtype, ld_out: int) -> torch.Tensor:
+    """[semantic | scene offset | motion | emotion | zero pad] per (video, second), video_music_transformer.py:1003-1018."""
+    require_device(sem)
+    rows = sem.shape[0] * sem.shape[1]
+    sem, scene, motion, emotion = (t.float().contiguous() for t in (sem, scene, motion, emotion))
+    motion_dim = 1 if motion.dim() == 2 else motion.shape[-1]
+    out = torch.empty((rows, ld_out), device=sem.device, dtype=out_dtype)
+    check(load().v2m_concat_features(ptr(sem), sem.shape[-1], ptr(scene), ptr(motion), motion_dim, ptr(emotion),
+                                     emotion.shape[-1], ptr(out), dtype_code(out_dtype), ld_out, rows, stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def cast_2d(src: torch.Tensor, dst_dtype: torch.dtype, ld_dst: Optional[int] = None) -> torch.Tensor:
+    """Row-major 2-D copy with dtype conversion and optional zero padding of the leading dimension."""
+    require_device(src)
+    assert src.dim() == 2 and src.stride(1) == 1
+    rows, cols = src.shape
+    ld = ld_dst or cols
+    dst = torch.empty((rows, ld), device=src.device, dtype=dst_dtype)
+    check(load().v2m_cast_2d(ptr(src), dtype_code(src.dtype), src.stride(0), ptr(dst), dtype_code(dst_dtype), ld, rows,
+                             cols, int(ld != cols), stream()))
+    _lib.count_launches(1)
+    return dst
+
+
+def _binary(a: torch.Tensor, b: torch.Tensor, mode: int, alpha: float) -> torch.Tensor:
+    require_device(a)
+    a, b = a.contiguous(), b.contiguous()
+    assert a.shape == b.shape and a.dtype == b.dtype == torch.float32
+    out = torch.empty_like(a)
+    check(load().v2m_binary_f32(ptr(a), ptr(b), ptr(out), a.numel(), mode, alpha, stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def swiglu(a: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """a * silu(g)  (moe.py:47)."""
+    return _binary(a, g, 0, 0.0)
+
+
+def axpy(a: torch.Tensor, b: torch.Tensor, alpha: float) -> torch.Tensor:
+    """a + alpha * b  (moe.py:301)."""
+    return _binary(a, b, 1, alpha)
+
+
+def pscan_fwd(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+    require_device(A)
+    A, X = A.contiguous(), X.contiguous()
+    B, L, D, N = A.shape
+    H = torch.empty_like(X)
+    check(load().v2m_pscan_fwd(ptr(A), ptr(X), ptr(H), B, L, D, N, stream()))
+    _lib.count_launches(1)
+    return H
+
+
+def pscan_bwd(A: torch.Tensor, H: torch.Tensor, gH: torch.Tensor):
+    require_device(A)
+    A, H, gH = A.contiguous(), H.contiguous(), gH.contiguous()
+    B, L, D, N = A.shape
+    gA, gX = torch.empty_like(A), torch.empty_like(A)
+    check(load().v2m_pscan_bwd(ptr(A), ptr(H), ptr(gH), ptr(gA), ptr(gX), B, L, D, N, stream()))
+    _lib.count_launches(1)
+    return gA, gX
+
+
+def moe_route(x: torch.Tensor, wg: torch.Tensor, bg: torch.Tensor, k: int, *, sel_bias: Optional[torch.Tensor] = None,
+              inv_t_pre: float = 1.0, inv_t_post: float = 1.0, want_logits: bool = False):
+    """x (..., d) fp32 -> (selected_experts int64 (..., k), weights fp32 (..., k), histogram int32 (E,), logits?)."""
+    require_device(x)
+    x = x.contiguous()
+    d = x.shape[-1]
+    tokens = x.numel() // d
+    E = wg.shape[0]
+    idx = torch.empty(x.shape[:-1] + (k,), device=x.device, dtype=torch.int64)
+    w = torch.empty(x.shape[:-1] + (k,), device=x.device, dtype=torch.float32)
+    hist = torch.zeros((E,), device=x.device, dtype=torch.int32)
+    logits = torch.empty(x.shape[:-1] + (E,), device=x.device, dtype=torch.float32) if want_logits else None
+    check(load().v2m_moe_route(ptr(x), ptr(wg.contiguous()), ptr(bg.contiguous()), ptr(sel_bias), inv_t_pre, inv_t_post,
+                               tokens, d, E, k, ptr(idx), ptr(w), ptr(logits), ptr(hist), stream()))
+    _lib.count_launches(1)
+    return idx, w, hist, logits
