@@ -28,6 +28,11 @@ def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
 
 
+def same_checksum(a: float, b: float) -> bool:
+    """Weight fingerprints are float64 sums; the reduction order of torch.sum differs between CPUs (SIMD width)."""
+    return abs(a - b) <= 1e-9 * max(abs(a), abs(b), 1.0)
+
+
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     """max |a-b| relative to the largest magnitude of the reference tensor b."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()

@@ -1,0 +1,309 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) exactly like the product."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, same_checksum
+from oracle import amt_oracle as O
+from video2music_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _u(shape, seed, name="t"):
+    return syn.unit_uniform(shape, syn._gen(seed, name))
+
+
+# ---------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(1, 8, 4), (111, 159, 512), (300, 512, 776), (257, 1536, 512), (64, 512, 1287), (0, 16, 16)])
+def test_gemm_f32(M, N, K):
+    from video2music_b200 import ops
+    a, w, b = _u((M, K), 1, "a"), _u((N, K), 1, "w") * 0.1, _u((N,), 1, "b")
+    res = _u((max(M, 1), N), 1, "r")[:M]
+    y = ops.linear(a.to(DEV), w.to(DEV), b.to(DEV), relu=True, alpha=0.5, alpha_cols=N // 2, residual=res.to(DEV))
+    ref = a.double() @ w.double().T + b.double()
+    ref[:, : N // 2] *= 0.5
+    ref = torch.relu(ref) + res.double()
+    assert y.shape == (M, N)
+    if M:
+        assert rel_err(y, ref) < 1e-5
+
+
+def test_gemm_f32_rowscale_resmod_and_batch_invariance():
+    from video2music_b200 import ops
+    M, N, K, T = 90, 512, 512, 30
+    a, w = _u((M, K), 2, "a").to(DEV), (_u((N, K), 2, "w") * 0.1).to(DEV)
+    rs, cv, pe = _u((M,), 2, "rs").to(DEV), _u((N,), 2, "cv").to(DEV), _u((T, N), 2, "pe").to(DEV)
+    y = ops.linear(a, w, None, row_scale=rs, col_vec=cv, residual=pe, res_mod=T)
+    ref = a.double() @ w.double().T + rs.double()[:, None] * cv.double()[None] + pe.double().repeat(M // T, 1)
+    assert rel_err(y, ref) < 1e-5
+    y1 = ops.linear(a[7:8].contiguous(), w, None)
+    yb = ops.linear(a, w, None)
+    assert torch.equal(y1[0], yb[7])              # same bits whatever the batch
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 512), (300, 512, 776), (1000, 1536, 512), (19200, 512, 1024),
+                                   (77, 159, 512), (64, 1024, 1288)])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_gemm_bf16_tcgen05(M, N, K, out_bf16):
+    from video2music_b200 import ops
+    a = _u((M, K), 3, "a").to(DEV).to(torch.bfloat16)
+    w = (_u((N, K), 3, "w") * 0.1).to(DEV).to(torch.bfloat16)
+    b = _u((N,), 3, "b").to(DEV)
+    res = _u((M, N), 3, "r").to(DEV)
+    y = ops.linear(a, w, b, alpha=0.25, alpha_cols=64, relu=False, residual=res,
+                   out_dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    ref = a.double() @ w.double().T + b.double()
+    ref[:, :64] *= 0.25
+    ref = ref + res.double()
+    tol = 1.2e-2 if out_bf16 else 2e-3
+    assert rel_err(y.float(), ref) < tol, "tcgen05 GEMM mismatch"
+
+
+def test_gemm_bf16_exact_small_integers():
+    """Integer-valued inputs make the bf16 tensor-core result exact: catches any descriptor / swizzle slip."""
+    from video2music_b200 import ops
+    M, N, K = 256, 256, 192
+    g = syn._gen(5, "ints")
+    a = torch.randint(-3, 4, (M, K), generator=g).float()
+    w = torch.randint(-3, 4, (N, K), generator=g).float()
+    y = ops.linear(a.to(DEV).to(torch.bfloat16), w.to(DEV).to(torch.bfloat16), None, out_dtype=torch.float32)
+    assert torch.equal(y.cpu(), a @ w.T)
+
+
+def test_gemm_head_scatter():
+    from video2music_b200 import ops
+    B, S, H, dh, E = 3, 50, 4, 64, 256
+    x, w, b = _u((B * S, E), 6, "x"), _u((2 * H * dh, E), 6, "w") * 0.1, _u((2 * H * dh,), 6, "b")
+    ref = (x.double() @ w.double().T + b.double()).view(B, S, 2, H, dh).permute(2, 0, 3, 1, 4)
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1.2e-2)):
+        out = torch.zeros((2, B, H, S, dh), device=DEV, dtype=dt)
+        ops.linear(x.to(DEV).to(dt), w.to(DEV).to(dt), b.to(DEV), out=out,
+                   head_scatter=dict(S=S, H=H, dh=dh, cap=S, pos0=0, part_stride=B * H * S * dh))
+        assert rel_err(out.float(), ref) < tol
+
+
+# ---------------------------------------------------------------- attention (fp32)
+def _attn_ref(q, k, v, Er, causal):
+    """q (B,H,L,dh) already scaled; oracle arithmetic of rpr.py:387-414 with the literal _skew."""
+    B, H, L, dh = q.shape
+    S = k.shape[2]
+    w = torch.einsum("bhld,bhsd->bhls", q, k)
+    if Er is not None:
+        qe = torch.einsum("hld,md->hlm", q.reshape(B * H, L, dh), O.get_valid_embedding(Er, L))
+        w = w + O.skew_literal(qe).view(B, H, L, L)
+    if causal:
+        w = w + torch.triu(torch.full((L, S), float("-inf")), diagonal=1 + S - L)
+    p = torch.softmax(w, dim=-1)
+    return torch.einsum("bhls,bhsd->bhld", p, v), p
+
+
+@pytest.mark.parametrize("B,H,L,S,dh,er_len,causal", [(2, 8, 299, 299, 64, 300, True), (3, 4, 37, 37, 32, 64, True),
+                                                      (2, 8, 299, 300, 64, 0, False), (1, 2, 1, 1, 64, 16, True),
+                                                      (2, 4, 33, 33, 64, 40, False), (1, 8, 300, 300, 64, 300, True)])
+def test_attention_f32(B, H, L, S, dh, er_len, causal):
+    from video2music_b200 import ops
+    q, k, v = _u((B, L, H, dh), 7, "q") * 0.3, _u((B, S, H, dh), 7, "k"), _u((B, S, H, dh), 7, "v")
+    Er = _u((er_len, dh), 7, "er") if er_len else None
+    ref, pref = _attn_ref(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), Er, causal)
+    out = torch.empty((B, L, H, dh), device=DEV)
+    p_out = torch.empty((B * H, L, S), device=DEV)
+    ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), out, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh,
+                  q_strides=(L * H * dh, H * dh), k_strides=(S * H * dh, H * dh), v_strides=(S * H * dh, H * dh),
+                  o_strides=(L * H * dh, H * dh), causal=causal, Er=Er.to(DEV) if er_len else None, p_out=p_out)
+    assert rel_err(out.permute(0, 2, 1, 3), ref) < 2e-5
+    assert rel_err(p_out.view(B, H, L, S), pref) < 2e-5
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,L,S,er_len,causal,seq_first", [
+    (2, 8, 8, 299, 299, 300, True, False),      # decoder RPR self-attention, BASELINE shape
+    (1, 8, 8, 300, 300, 300, True, False),
+    (2, 8, 8, 300, 300, 0, False, False),       # encoder self-attention
+    (2, 8, 8, 299, 300, 0, False, False),       # decoder cross-attention
+    (3, 4, 4, 37, 37, 64, True, False),         # single tile, tiny band
+    (2, 4, 4, 200, 200, 300, True, True),       # sequence-first (L, B, E) layout of the module API, QE half B in use
+    (2, 4, 4, 150, 150, 160, False, False),     # RPR without a mask (mask=False path)
+    (2, 8, 2, 130, 170, 0, False, False),       # grouped-query (Hkv < Hq), ragged
+    (2, 8, 8, 1, 1, 300, True, False),
+])
+def test_attention_bf16_tcgen05(B, Hq, Hkv, L, S, er_len, causal, seq_first):
+    from video2music_b200 import ops
+    dh = 64
+    bf = torch.bfloat16
+    q = (_u((B, L, Hq, dh), 9, "q") * 0.3).to(bf)
+    k, v = _u((B, S, Hkv, dh), 9, "k").to(bf), _u((B, S, Hkv, dh), 9, "v").to(bf)
+    Er = _u((er_len, dh), 9, "er").to(bf) if er_len else None
+    g = Hq // Hkv
+    kx = k.float().repeat_interleave(g, dim=2)
+    vx = v.float().repeat_interleave(g, dim=2)
+    ref, _ = _attn_ref(q.float().permute(0, 2, 1, 3), kx.permute(0, 2, 1, 3), vx.permute(0, 2, 1, 3),
+                       Er.float() if er_len else None, causal)
+    ref = ref.permute(0, 2, 1, 3)                                                  # (B, L, H, dh)
+    if seq_first:
+        qd, kd, vd = (t.permute(1, 0, 2, 3).contiguous().to(DEV) for t in (q, k, v))  # (L, B, H, dh)
+        out = torch.zeros((L, B, Hq, dh), device=DEV, dtype=bf)
+        qs, ks, os_ = (Hq * dh, B * Hq * dh), (Hkv * dh, B * Hkv * dh), (Hq * dh, B * Hq * dh)
+    else:
+        qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+        out = torch.zeros((B, L, Hq, dh), device=DEV, dtype=bf)
+        qs, ks, os_ = (L * Hq * dh, Hq * dh), (S * Hkv * dh, Hkv * dh), (L * Hq * dh, Hq * dh)
+    lse = torch.zeros((B * Hq, L), device=DEV)
+    ops.attention(qd, kd, vd, out, B=B, Hq=Hq, Hkv=Hkv, Lq=L, Lk=S, dh=dh, q_strides=qs, k_strides=ks, v_strides=ks,
+                  o_strides=os_, causal=causal, Er=Er.to(DEV) if er_len else None, lse=lse)
+    got = out.float().cpu()
+    if seq_first:
+        got = got.permute(1, 0, 2, 3)
+    err = rel_err(got, ref)
+    print("bf16 attention rel err", err)
+    assert err < 1.5e-2
+    assert torch.isfinite(lse).all()
+
+
+def test_rpr_module_golden_gpu():
+    from video2music_b200 import MultiheadAttentionRPR
+    g = load_golden("rpr_attention.pt")
+    for case in g["cases"]:
+        s = case["spec"]
+        mod = MultiheadAttentionRPR(s["E"], s["H"], dropout=0.0, er_len=s["er_len"]).eval()
+        shapes = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+        mod.load_state_dict(syn.fill_like_reference_init(shapes, seed=s["seed"]))
+        mod = mod.to(DEV)
+        x = _u((s["L"], s["B"], s["E"]), s["seed"], "x").to(DEV)
+        mask = torch.triu(torch.full((s["L"], s["L"]), float("-inf"), device=DEV), diagonal=1)
+        with torch.no_grad():
+            out, w = mod(x, x, x, attn_mask=mask)
+        assert rel_err(out, case["out"]) < 1e-4
+        if case["weights_mean"] is not None:
+            assert rel_err(w, case["weights_mean"]) < 1e-4
+
+
+def test_decoder_layer_golden_gpu():
+    from video2music_b200 import TransformerDecoderLayerRPR
+    g = load_golden("rpr_attention.pt")["layer"]
+    s = g["spec"]
+    layer = TransformerDecoderLayerRPR(s["E"], s["H"], s["ff"], 0.0, er_len=s["er_len"]).eval()
+    shapes = {k: tuple(v.shape) for k, v in layer.state_dict().items()}
+    sd = syn.fill_like_reference_init(shapes, seed=s["seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    layer.load_state_dict(sd)
+    layer = layer.to(DEV)
+    tgt, mem = _u((s["T"], s["B"], s["E"]), s["seed"], "tgt").to(DEV), _u((s["S"], s["B"], s["E"]), s["seed"], "mem").to(DEV)
+    mask = torch.triu(torch.full((s["T"], s["T"]), float("-inf"), device=DEV), diagonal=1)
+    with torch.no_grad():
+        y = layer(tgt, mem, tgt_mask=mask)
+    assert rel_err(y, g["out"]) < 1e-4
+
+
+# ---------------------------------------------------------------- layernorm
+@pytest.mark.parametrize("M,D", [(1, 128), (77, 512), (300, 1024), (5, 96)])
+def test_layernorm(M, D):
+    from video2music_b200 import ops
+    x, r, g, b = _u((M, D), 8, "x"), _u((M, D), 8, "r"), 1 + 0.1 * _u((D,), 8, "g"), _u((D,), 8, "b")
+    y = ops.layernorm(x.to(DEV), g.to(DEV), b.to(DEV), res=r.to(DEV))
+    ref = torch.nn.functional.layer_norm((x + r).double(), (D,), g.double(), b.double(), 1e-5)
+    assert rel_err(y, ref) < 1e-5
+    yb = ops.layernorm(x.to(DEV).to(torch.bfloat16), g.to(DEV), b.to(DEV))
+    ref = torch.nn.functional.layer_norm(x.to(torch.bfloat16).double(), (D,), g.double(), b.double(), 1e-5)
+    assert rel_err(yb.float(), ref) < 1e-2
+
+
+# ---------------------------------------------------------------- pscan
+def test_pscan_golden_gpu():
+    from video2music_b200 import pscan
+    for case in load_golden("pscan.pt")["cases"]:
+        s = case["spec"]
+        shp = (s["B"], s["L"], s["D"], s["N"])
+        A = (torch.rand(shp, generator=syn._gen(s["seed"], "A")) * 0.99).to(DEV).requires_grad_(True)
+        X = _u(shp, s["seed"], "X").to(DEV).requires_grad_(True)
+        gH = _u(shp, s["seed"], "gH").to(DEV)
+        A0, X0 = A.detach().clone(), X.detach().clone()
+        H = pscan(A, X)
+        (H * gH).sum().backward()
+        assert torch.equal(A.detach(), A0) and torch.equal(X.detach(), X0)       # inputs untouched
+        assert rel_err(H, case["H"]) < 1e-5
+        assert rel_err(X.grad, case["gX"]) < 1e-5
+        if float(case["gA"].abs().max()) > 0:
+            assert rel_err(A.grad, case["gA"]) < 1e-5
+
+
+@pytest.mark.parametrize("B,L,D,N", [(64, 300, 256, 16), (1, 4096, 256, 16), (8, 4096, 256, 16), (2, 700, 4, 16), (2, 1500, 8, 16)])
+def test_pscan_full_size_properties(B, L, D, N):
+    """Full BASELINE sizes: recurrence residual H[t] - A[t]*H[t-1] - X[t] == 0 (size-independent property),
+    a sampled channel against the sequential oracle, and linearity in X."""
+    from video2music_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(7)
+    A = (torch.rand((B, L, D, N), generator=g) * 0.99).to(DEV)
+    X = syn.unit_uniform((B, L, D, N), g).to(DEV)
+    H = ops.pscan_fwd(A, X)
+    resid = H[:, 1:] - (A[:, 1:] * H[:, :-1] + X[:, 1:])
+    assert float(resid.abs().max()) < 1e-4 * float(H.abs().max())
+    assert torch.allclose(H[:, 0], X[:, 0])
+    Hs = O.pscan_forward(A[:1, :, :2].cpu(), X[:1, :, :2].cpu())
+    assert rel_err(H[:1, :, :2], Hs) < 1e-5
+    H2 = ops.pscan_fwd(A, 2.0 * X)
+    assert rel_err(H2, 2.0 * H) < 1e-6
+    gH = syn.unit_uniform((B, L, D, N), g).to(DEV)
+    gA, gX = ops.pscan_bwd(A, H, gH)
+    gAs, gXs = O.pscan_backward(A[:1, :, :2].cpu(), Hs, gH[:1, :, :2].cpu())
+    assert rel_err(gX[:1, :, :2], gXs) < 1e-5 and rel_err(gA[:1, :, :2], gAs) < 1e-5
+
+
+# ---------------------------------------------------------------- MoE
+@pytest.mark.parametrize("shared", [False, True])
+def test_moe_golden_gpu(shared):
+    from video2music_b200 import GLUExpert, MoELayer, SharedMoELayer
+    g = load_golden("moe.pt")["shared_%s" % shared]
+    s = g["spec"]
+    cls = SharedMoELayer if shared else MoELayer
+    mod = cls(GLUExpert(s["d"], s["ff"], 0.0), s["d"], n_experts=s["n_experts"], n_experts_per_token=s["k"], dropout=0.0).eval()
+    shapes = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+    sd = syn.fill_like_reference_init(shapes, seed=s["seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    x = _u((s["L"], s["B"], s["d"]), s["x_seed"], "x").to(DEV)
+    with torch.no_grad():
+        y = mod(x)
+    assert g["min_rank_gap"] > 1e-4                                        # no near-tie in the reference's own logits
+    assert torch.equal(mod.last_selected_experts.cpu(), g["selected_experts"])   # routing indices bit-exact
+    assert rel_err(y, g["out"]) < 1e-4
+
+
+def test_moe_route_ties_and_bias():
+    from video2music_b200 import ops
+    x = torch.zeros((5, 64), device=DEV)
+    wg = torch.zeros((6, 64), device=DEV)
+    bg = torch.tensor([0.5, 0.5, 0.1, 0.9, 0.9, 0.0], device=DEV)
+    idx, w, hist, _ = ops.moe_route(x, wg, bg, 3)
+    assert idx[0].tolist() == [3, 4, 0]                                     # lowest index first on exact ties
+    assert hist.tolist() == [5, 0, 0, 5, 5, 0]
+    assert torch.allclose(w.sum(-1), torch.ones(5, device=DEV))
+    idx2, w2, _, _ = ops.moe_route(x, wg, bg, 2, sel_bias=torch.tensor([0., 0., 5., 0., 0., 0.], device=DEV))
+    assert idx2[0].tolist() == [2, 3]
+    assert torch.allclose(w2[0], torch.softmax(torch.tensor([0.1, 0.9]), 0).to(DEV))    # weights from un-biased logits
+
+
+# ---------------------------------------------------------------- GQA
+def test_gqa_golden_gpu():
+    from video2music_b200 import MultiheadGQA, scaled_dot_product_gqa
+    g = load_golden("gqa.pt")
+    for case in g["function"]:
+        s = case["spec"]
+        q, k, v = (_u(shp, s["seed"], n).to(DEV) for shp, n in (((s["b"], s["n"], s["hq"], s["d"]), "q"),
+                                                               ((s["b"], s["s"], s["hk"], s["d"]), "k"),
+                                                               ((s["b"], s["s"], s["hk"], s["d"]), "v")))
+        out, _ = scaled_dot_product_gqa(q, k, v, num_heads=s["hq"], is_causal=True if s["causal"] else None)
+        assert rel_err(out, case["out"]) < 2e-5
+    for case in g["module"]:
+        s = case["spec"]
+        mod = MultiheadGQA(s["E"], s["hq"], s["hk"], dropout=0.0).eval()
+        shapes = {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+        mod.load_state_dict(syn.fill_like_reference_init(shapes, seed=s["seed"]))
+        mod = mod.to(DEV)
+        xq, xk = _u((s["L"], s["B"], s["E"]), s["seed"], "xq").to(DEV), _u((s["S"], s["B"], s["E"]), s["seed"], "xk").to(DEV)
+        with torch.no_grad():
+            y, _ = mod(xq, xk, xk)
+        assert rel_err(y, case["out"]) < 1e-4
+    with pytest.raises(ValueError):
+        scaled_dot_product_gqa(torch.zeros(1, 2, 3, 8, device=DEV), torch.zeros(1, 2, 2, 8, device=DEV),
+                               torch.zeros(1, 2, 2, 8, device=DEV))

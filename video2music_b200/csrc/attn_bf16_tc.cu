@@ -1,9 +1,320 @@
-// placeholder, replaced below by the tcgen05 attention kernel
+// Fused RPR attention forward on tcgen05 / TMEM / TMA (bf16 operands, fp32 accumulate, sm_100a).
+//
+//   O = softmax(Q K^T + skew(Q Er^T) + causal) V      one CTA = one (video, head) x 128 query rows
+//
+// Replaces model/rpr.py:387-414 of the reference (bmm, einsum("hld,md->hlm", q, Er), _skew :439-455,
+// + mask, softmax, bmm) -- three materialised (B*H, L, L) fp32 tensors and ~10 ATen kernels -- and,
+// with Er == null, the stock attention cores (encoder self-attention, decoder cross-attention,
+// grouped-query attention with Hkv < Hq).
+//
+// Because L <= 320 the whole score row of a query fits in tensor memory, so the softmax is exact
+// (two passes over TMEM, no online rescaling):
+//   TMEM columns [0,320)    S = Q K^T (fp32), later overwritten in place by P (packed bf16 pairs)
+//   TMEM columns [320,512)  QE = Q Er_band^T, 192 columns at a time (two overlapping halves), later O
+// The relative term needs, for query row i and key j, column c = j - i + imax of QE (imax = last row
+// of the tile): a per-row shift.  tcgen05.ld addresses are warp-uniform, so each softmax warp pulls a
+// 64-column window of QE into registers, parks it in its private shared-memory scratch rows and
+// reads it back at the row-dependent offset -- the skew is a shifted read of shared memory
+// (conflict-free: row pitch 68 words).
+//
+// Warp roles (160 threads): warp 0 = TMA producer + single-thread MMA issuer + TMEM allocator,
+// warps 1-4 = softmax/epilogue, one TMEM lane quadrant (32 query rows) each.
 #include "common.cuh"
 #include "kernels.h"
+#include <cuda.h>
+
 namespace v2m {
+
+constexpr int AT_M = 128;            // query rows per CTA
+constexpr int AT_DH = 64;            // head dim (128-byte swizzled rows)
+constexpr int AT_MAXK = 320;         // keys per row that fit the TMEM plan
+constexpr int AT_QE_COLS = 192;      // width of one QE half
+constexpr int AT_QE_OVERLAP = 128;   // half B starts at band column 128
+constexpr int AT_THREADS = 160;
+constexpr int AT_SCR_PITCH = 68;     // floats; 68 % 32 == 4 -> conflict-free STS.128 and shifted LDS.32
+
+constexpr int AT_SMEM_Q = AT_M * 128;
+constexpr int AT_SMEM_K = AT_MAXK * 128;
+constexpr int AT_SMEM_SCR = 4 * 32 * AT_SCR_PITCH * 4;
+constexpr size_t AT_SMEM = 1024 + AT_SMEM_Q + 3 * AT_SMEM_K + AT_SMEM_SCR + 256;
+
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch,
+                      long long row_pitch, long long batch_pitch, int box_rows, int swap);
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows);
+
+struct AttnTcArgs {
+  void* o; long long o_sb, o_sl;
+  float* lse;
+  int B, Hq, Hkv, Lq, Lk, causal, has_er, er_len;
+  int swap;   // tensor maps are (col, batch, row) instead of (col, row, batch): sequence-first layouts
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
+                    const __grid_constant__ AttnTcArgs a) {
+  extern __shared__ unsigned char at_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sK = sQ + AT_SMEM_Q;
+  unsigned char* sV = sK + AT_SMEM_K;
+  unsigned char* sE = sV + AT_SMEM_K;
+  float* scr = reinterpret_cast<float*>(sE + AT_SMEM_K);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scr) + AT_SMEM_SCR);
+  uint64_t* bar_qk = bars + 0;     // Q and K tiles landed
+  uint64_t* bar_e = bars + 1;      // Er band landed
+  uint64_t* bar_v = bars + 2;      // V tile landed
+  uint64_t* bar_s = bars + 3;      // S = Q K^T complete
+  uint64_t* bar_qa = bars + 4;     // QE half A complete
+  uint64_t* bar_qa_free = bars + 5;  // all softmax warps are done with half A (count 4)
+  uint64_t* bar_qb = bars + 6;     // QE half B complete
+  uint64_t* bar_p = bars + 7;      // P written to TMEM by all softmax warps (count 4)
+  uint64_t* bar_o = bars + 8;      // O = P V complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  auto tma3 = [&](void* dst, const CUtensorMap* tm, int col, int row, int batch, uint64_t* bar) {
+    if (a.swap) tma_load_3d(dst, tm, col, batch, row, bar);
+    else tma_load_3d(dst, tm, col, row, batch, bar);
+  };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / a.Hq, hq = bh % a.Hq, hkv = hq / (a.Hq / a.Hkv);
+  const int i0 = blockIdx.x * AT_M;
+  const int imax = min(i0 + AT_M - 1, a.Lq - 1);
+  const int coff = a.Lk - a.Lq;
+  const int nk = a.causal ? min(a.Lk, imax + coff + 1) : a.Lk;         // keys this tile needs
+  const int nk16 = (nk + 15) & ~15;
+  const int nk64 = (nk + 63) & ~63;
+  // band column c <-> Er row e_base + c, needed c in [0, imax]
+  const int e_base = a.er_len - 1 - imax;
+  const bool need_b = a.has_er && (imax >= AT_QE_COLS);               // widest window start is clamped to 128 in half A
+  const int qe_rows = need_b ? AT_QE_OVERLAP + AT_QE_COLS : AT_QE_COLS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 9; ++i) mbar_init(bars + i, (i == 5 || i == 7) ? 4u : 1u);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    if (a.has_er) tma_prefetch_desc(&tmE);
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t T_S = tmem, T_QE = tmem + AT_MAXK, T_O = tmem + AT_MAXK, T_P = tmem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA: Q + K, Er band, V (64-row boxes) ----------------
+      mbar_arrive_expect_tx(bar_qk, AT_SMEM_Q + nk64 * 128);
+      tma3(sQ, &tmQ, hq * AT_DH, i0, b, bar_qk);
+      tma3(sQ + 64 * 128, &tmQ, hq * AT_DH, i0 + 64, b, bar_qk);
+      for (int r = 0; r < nk64; r += 64) tma3(sK + r * 128, &tmK, hkv * AT_DH, r, b, bar_qk);
+      if (a.has_er) {
+        mbar_arrive_expect_tx(bar_e, qe_rows * 128);
+        for (int r = 0; r < qe_rows; r += 64) tma_load_2d(sE + r * 128, &tmE, 0, e_base + r, bar_e);
+      }
+      mbar_arrive_expect_tx(bar_v, nk64 * 128);
+      for (int r = 0; r < nk64; r += 64) tma3(sV + r * 128, &tmV, hkv * AT_DH, r, b, bar_v);
+
+      // ---------------- MMA issue ----------------
+      const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), e_addr = smem_u32(sE);
+      mbar_wait(bar_qk, 0);
+      tc_fence_after();
+      for (int n0 = 0; n0 < nk16; n0 += 256) {                         // S[:, n0:n0+n] = Q K[n0:n0+n]^T
+        const int n = min(256, nk16 - n0);
+        const uint32_t idesc = make_idesc_bf16(AT_M, n, 0, 0);
+#pragma unroll
+        for (int k = 0; k < AT_DH / 16; ++k)
+          umma_bf16_ss(T_S + n0, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + n0 * 128 + k * 32, 16, 1024), idesc, k != 0);
+      }
+      umma_commit(bar_s);
+      if (a.has_er) {
+        const uint32_t idesc = make_idesc_bf16(AT_M, AT_QE_COLS, 0, 0);
+        mbar_wait(bar_e, 0);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AT_DH / 16; ++k)
+          umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(bar_qa);
+        if (need_b) {
+          mbar_wait(bar_qa_free, 0);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < AT_DH / 16; ++k)
+            umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         make_smem_desc_sw128(e_addr + AT_QE_OVERLAP * 128 + k * 32, 16, 1024), idesc, k != 0);
+          umma_commit(bar_qb);
+        }
+      }
+      // O = P V : A = P from TMEM (bf16 pairs, 8 columns per k16), B = V (d contiguous -> MN-major)
+      mbar_wait(bar_v, 0);
+      mbar_wait(bar_p, 0);
+      tc_fence_after();
+      {
+        const uint32_t idesc = make_idesc_bf16(AT_M, AT_DH, 0, 1);
+        for (int k = 0; k < nk16 / 16; ++k)
+          umma_bf16_ts(T_O, T_P + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc, k != 0);
+      }
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax / epilogue warps =================
+    const int quad = warp & 3;                                   // TMEM lane quadrant of this warp
+    const int u = lane;
+    const int i = i0 + quad * 32 + u;                            // my query row
+    const bool row_ok = i < a.Lq;
+    const int jlim = row_ok ? (a.causal ? min(a.Lk, i + coff + 1) : a.Lk) : 0;   // keys [0, jlim) are visible
+    const int wlast = min(imax, i0 + quad * 32 + 31);            // last valid row of this warp
+    const int wjlim = (i0 + quad * 32 <= imax) ? (a.causal ? min(a.Lk, wlast + coff + 1) : a.Lk) : 0;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float* my_scr = scr + (size_t)(quad * 32 + u) * AT_SCR_PITCH;
+    const int nchunks = (nk16 + 31) / 32;
+    const int base_w = imax - i0 - quad * 32 - 31;               // window start (band column) for key chunk j0 is j0 + base_w
+    const float LOG2E = 1.4426950408889634f;
+
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+    // ---- pass A: s = S + Srel, mask, running max, s written back to TMEM
+    for (int phase = 0; phase < 2; ++phase) {
+      if (phase == 0 && a.has_er) { mbar_wait(bar_qa, 0); tc_fence_after(); }
+      if (phase == 1) {
+        if (!need_b) break;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_qa_free);
+        mbar_wait(bar_qb, 0);
+        tc_fence_after();
+      }
+      for (int c = 0; c < nchunks; ++c) {
+        const int j0 = c * 32;
+        const int start = j0 + base_w;                           // un-clamped window start
+        const bool rel_chunk = a.has_er && (j0 < wjlim) && (j0 <= wlast);   // chunk holds some (i, j<=i) of this warp
+        const bool in_a = !need_b || !rel_chunk || start <= AT_QE_OVERLAP;
+        if ((phase == 0) != in_a) continue;
+        uint32_t r[32];
+        tmem_ld_32x32(T_S + lane_off + j0, r);
+        if (rel_chunk) {
+          const int cs = in_a ? max(0, min(start, AT_QE_COLS - 64)) : max(AT_QE_OVERLAP, min(start, AT_QE_OVERLAP + AT_QE_COLS - 64));
+          const int tcol = in_a ? cs : cs - AT_QE_OVERLAP;      // column inside the resident half
+          uint32_t w[64];
+          tmem_ld_32x32(T_QE + lane_off + tcol, w);
+          tmem_ld_32x32(T_QE + lane_off + tcol + 32, w + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 16; ++q4)
+            *reinterpret_cast<uint4*>(my_scr + q4 * 4) = make_uint4(w[q4 * 4], w[q4 * 4 + 1], w[q4 * 4 + 2], w[q4 * 4 + 3]);
+          // band column of (i, j) is j - i + imax; offset inside the window = that - cs
+          const int off = j0 - i + imax - cs;                    // in [0, 63 - k] for every (i, j <= i) that is needed
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float rel = my_scr[min(max(off + k, 0), 63)];  // clamped reads only hit masked / invalid entries
+            if (j0 + k <= i) r[k] = __float_as_uint(__uint_as_float(r[k]) + rel);
+          }
+        } else {
+          tmem_ld_wait();
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          float s = __uint_as_float(r[k]);
+          s = (j0 + k < jlim) ? s : -INFINITY;
+          mx = fmaxf(mx, s);
+          r[k] = __float_as_uint(s);
+        }
+        tmem_st_32x32(T_S + lane_off + j0, r);
+      }
+    }
+    tmem_st_wait();
+    // ---- pass B: p = exp(s - max), row sum, P (bf16 pairs) written over S
+    const float mneg = (mx == -INFINITY) ? 0.f : mx * LOG2E;
+    float sum = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+      const int j0 = c * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(T_S + lane_off + j0, r);
+      tmem_ld_wait();
+      uint32_t pk[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float p0 = exp2f(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
+        const float p1 = exp2f(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
+        sum += p0 + p1;
+        pk[k] = f2_to_bf16x2(p0, p1);
+      }
+      tmem_st_32x16(T_P + lane_off + c * 16, pk);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
+    // ---- epilogue: O / sum -> bf16 -> global
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    uint32_t o[64];
+    tmem_ld_32x32(T_O + lane_off, o);
+    tmem_ld_32x32(T_O + lane_off + 32, o + 32);
+    tmem_ld_wait();
+    if (row_ok) {
+      const float inv = 1.f / sum;
+      bf16* dst = static_cast<bf16*>(a.o) + (size_t)b * a.o_sb + (size_t)i * a.o_sl + (size_t)hq * AT_DH;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) {
+        uint4 v;
+        v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]) * inv, __uint_as_float(o[g8 * 8 + 1]) * inv);
+        v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]) * inv, __uint_as_float(o[g8 * 8 + 3]) * inv);
+        v.z = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 4]) * inv, __uint_as_float(o[g8 * 8 + 5]) * inv);
+        v.w = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 6]) * inv, __uint_as_float(o[g8 * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + g8 * 8) = v;
+      }
+      if (a.lse) a.lse[(size_t)bh * a.Lq + i] = mx + logf(sum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
-  set_last_error("attn_fwd_bf16_tc: not built yet");
-  return kUnsupported;
+  V2M_REQUIRE(p.dh == AT_DH, "attn_fwd_bf16_tc: head_dim %d unsupported (64)", p.dh);
+  V2M_REQUIRE(p.B > 0 && p.Hq > 0 && p.Hkv > 0 && p.Hq % p.Hkv == 0, "attn_fwd_bf16_tc: bad heads %d/%d", p.Hq, p.Hkv);
+  V2M_REQUIRE(p.Lq > 0 && p.Lk > 0 && p.Lk <= AT_MAXK, "attn_fwd_bf16_tc: Lk=%d unsupported (1..%d)", p.Lk, AT_MAXK);
+  V2M_REQUIRE(!p.Er || (p.Lq == p.Lk && p.Lq <= p.er_len), "attn_fwd_bf16_tc: RPR needs Lq == Lk <= er_len (%d, %d, %d)",
+              p.Lq, p.Lk, p.er_len);
+  V2M_REQUIRE(!p.causal || p.Lk >= p.Lq, "attn_fwd_bf16_tc: causal needs Lk >= Lq");
+  V2M_REQUIRE(p.q_scale == 1.0f, "attn_fwd_bf16_tc: q must be pre-scaled (fold the scale into the projection epilogue)");
+  V2M_REQUIRE(p.p_out == nullptr, "attn_fwd_bf16_tc: need_weights output is only available on the fp32 path");
+  V2M_REQUIRE(p.o_sl % 8 == 0 && p.o_sb % 8 == 0 && reinterpret_cast<uintptr_t>(p.o) % 16 == 0,
+              "attn_fwd_bf16_tc: output must be 16-byte aligned");
+  CUtensorMap tmQ, tmK, tmV, tmE;
+  int rc;
+  // TMA wants ascending strides: sequence-first tensors (row pitch > batch pitch) get (col, batch, row) maps
+  const int swap = p.B > 1 && p.q_sl > p.q_sb;
+  V2M_REQUIRE(p.B == 1 || ((p.k_sl > p.k_sb) == (swap != 0) && (p.v_sl > p.v_sb) == (swap != 0)),
+              "attn_fwd_bf16_tc: q, k, v must share one layout family (batch-first or sequence-first)");
+  if ((rc = make_tmap_3d_bf16(&tmQ, p.q, (long long)p.Hq * AT_DH, p.Lq, p.B, p.q_sl, p.q_sb, 64, swap))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tmK, p.k, (long long)p.Hkv * AT_DH, p.Lk, p.B, p.k_sl, p.k_sb, 64, swap))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tmV, p.v, (long long)p.Hkv * AT_DH, p.Lk, p.B, p.v_sl, p.v_sb, 64, swap))) return rc;
+  if (p.Er) {
+    if ((rc = make_tmap_2d_bf16(&tmE, p.Er, p.er_len, AT_DH, AT_DH, 64))) return rc;
+  } else {
+    tmE = tmQ;
+  }
+  AttnTcArgs a;
+  a.o = p.o; a.o_sb = p.o_sb; a.o_sl = p.o_sl; a.lse = p.lse;
+  a.B = p.B; a.Hq = p.Hq; a.Hkv = p.Hkv; a.Lq = p.Lq; a.Lk = p.Lk; a.causal = p.causal;
+  a.has_er = p.Er != nullptr; a.er_len = p.er_len; a.swap = swap;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
+    if (e != cudaSuccess) { set_last_error("attn_fwd_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
+    attr = true;
+  }
+  dim3 grid((p.Lq + AT_M - 1) / AT_M, p.B * p.Hq);
+  attn_bf16_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, tmE, a);
+  return check_launch("attn_fwd_bf16_tc");
 }
-}
+
+}  // namespace v2m

@@ -85,8 +85,9 @@ __global__ void __launch_bounds__(NW * 32) attn_f32_kernel(AttnParams p, int lk_
   __syncwarp();
   // ---- pass 2: relative-position term, skewed into place -----------------------------------
   if (Er) {
-    const int imax = i0 + r0 + RPW - 1;          // largest row of this warp -> largest distance
-    for (int rel = lane; rel <= imax && rel < p.er_len; rel += 32) {
+    // largest distance this warp needs; only distances [0, i0 + nrows) were staged in Es
+    const int rel_end = min(min(i0 + r0 + RPW, i0 + nrows), p.er_len);
+    for (int rel = lane; rel < rel_end; rel += 32) {
       float acc[RPW];
 #pragma unroll
       for (int r = 0; r < RPW; ++r) acc[r] = 0.f;

@@ -20,7 +20,7 @@
 namespace v2m {
 
 constexpr int GM = 128, GK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;   // 4 control warps + 8 epilogue warps
 
 template <int BN> struct GemmCfg {
   static constexpr int kStages = BN == 256 ? 4 : 6;
@@ -64,10 +64,36 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, long lo
   return kOk;
 }
 
+// 3-D bf16 view (cols, rows, batch) of a strided matrix stack; box = 64 columns x box_rows rows x 1 batch,
+// 128B swizzle.  swap != 0 orders the map (cols, batch, rows) for sequence-first tensors (ascending strides).
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch,
+                      long long row_pitch, long long batch_pitch, int box_rows, int swap) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return kCudaError; }
+  if (batch == 1) batch_pitch = row_pitch * rows;      // any valid pitch will do
+  V2M_REQUIRE((row_pitch * 2) % 16 == 0 && (batch_pitch * 2) % 16 == 0 && reinterpret_cast<uintptr_t>(base) % 16 == 0,
+              "TMA needs 16-byte aligned base and pitches (row %lld, batch %lld elements)", row_pitch, batch_pitch);
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1u, 1u, 1u};
+  dims[0] = (cuuint64_t)cols; box[0] = 64u;
+  if (!swap) {
+    dims[1] = (cuuint64_t)rows;  strides[0] = (cuuint64_t)row_pitch * 2;   box[1] = (cuuint32_t)box_rows;
+    dims[2] = (cuuint64_t)batch; strides[1] = (cuuint64_t)batch_pitch * 2; box[2] = 1u;
+  } else {
+    dims[1] = (cuuint64_t)batch; strides[0] = (cuuint64_t)batch_pitch * 2; box[1] = 1u;
+    dims[2] = (cuuint64_t)rows;  strides[1] = (cuuint64_t)row_pitch * 2;   box[2] = (cuuint32_t)box_rows;
+  }
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return kCudaError; }
+  return kOk;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
-                    int ldc, int out_bf16, int M, int N, int K, const __grid_constant__ GemmEpilogue ep) {
+                    int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -88,7 +114,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -142,8 +168,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
+    // ================= epilogue: 8 warps, two per TMEM lane quadrant, alternating 32-column chunks ============
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;          // which chunks of the tile this warp drains
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -154,58 +181,97 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float rs = (row_ok && ep.row_scale) ? ep.row_scale[m] : 0.f;
       const size_t res_row = ep.residual ? (size_t)(ep.res_mod > 0 ? m % ep.res_mod : m) * ep.ldr : 0;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
         tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
-        if (row_ok && n0 < N) {
-          float v[32];
+        if (!row_ok || n0 >= N) continue;
+        float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int n = n0 + i;
-            float x = __uint_as_float(r[i]);
-            if (n < N) {
-              if (ep.bias) x += __ldg(ep.bias + n);
-              if (n < ep.alpha_cols) x *= ep.alpha;
-              if (ep.relu) x = fmaxf(x, 0.f);
-              if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
-              if (ep.residual) {
-                x += ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
-                                      : __ldg(ep.residual + res_row + n);
-              }
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (vec_ok && n0 + 32 <= N) {
+          // ---- fast path: whole chunk in range, every pointer 16-byte aligned -> 128-bit loads / stores only
+          if (ep.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(bp + q);
+              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
             }
-            v[i] = x;
           }
-          // 8-element groups stay inside one head / one row: vector store when aligned and in range
+          if (n0 < ep.alpha_cols) {
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int n = n0 + g8 * 8;
-            if (n >= N) break;
-            const long long o = epi_out_index(ep, m, n, ldc);
-            if (out_bf16) {
-              bf16* dst = static_cast<bf16*>(C) + o;
-              if (n + 8 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                uint4 pk;
-                pk.x = f2_to_bf16x2(v[g8 * 8 + 0], v[g8 * 8 + 1]);
-                pk.y = f2_to_bf16x2(v[g8 * 8 + 2], v[g8 * 8 + 3]);
-                pk.z = f2_to_bf16x2(v[g8 * 8 + 4], v[g8 * 8 + 5]);
-                pk.w = f2_to_bf16x2(v[g8 * 8 + 6], v[g8 * 8 + 7]);
-                *reinterpret_cast<uint4*>(dst) = pk;
-              } else {
-                for (int i = 0; i < 8 && n + i < N; ++i)
-                  static_cast<bf16*>(C)[epi_out_index(ep, m, n + i, ldc)] = __float2bfloat16_rn(v[g8 * 8 + i]);
+            for (int i = 0; i < 32; ++i) v[i] = (n0 + i < ep.alpha_cols) ? v[i] * ep.alpha : v[i];
+          }
+          if (ep.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (ep.row_scale) {
+            const float4* cp = reinterpret_cast<const float4*>(ep.col_vec + n0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(cp + q);
+              v[4 * q] = fmaf(rs, t.x, v[4 * q]); v[4 * q + 1] = fmaf(rs, t.y, v[4 * q + 1]);
+              v[4 * q + 2] = fmaf(rs, t.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs, t.w, v[4 * q + 3]);
+            }
+          }
+          if (ep.residual) {
+            if (ep.residual_bf16) {
+              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.residual) + res_row + n0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 t = __ldg(rp + q);
+                float2 f;
+                f = bf16x2_to_f2(t.x); v[8 * q] += f.x; v[8 * q + 1] += f.y;
+                f = bf16x2_to_f2(t.y); v[8 * q + 2] += f.x; v[8 * q + 3] += f.y;
+                f = bf16x2_to_f2(t.z); v[8 * q + 4] += f.x; v[8 * q + 5] += f.y;
+                f = bf16x2_to_f2(t.w); v[8 * q + 6] += f.x; v[8 * q + 7] += f.y;
               }
             } else {
-              float* dst = static_cast<float*>(C) + o;
-              if (n + 8 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                reinterpret_cast<float4*>(dst)[0] = make_float4(v[g8 * 8 + 0], v[g8 * 8 + 1], v[g8 * 8 + 2], v[g8 * 8 + 3]);
-                reinterpret_cast<float4*>(dst)[1] = make_float4(v[g8 * 8 + 4], v[g8 * 8 + 5], v[g8 * 8 + 6], v[g8 * 8 + 7]);
-              } else {
-                for (int i = 0; i < 8 && n + i < N; ++i)
-                  static_cast<float*>(C)[epi_out_index(ep, m, n + i, ldc)] = v[g8 * 8 + i];
+              const float4* rp = reinterpret_cast<const float4*>(ep.residual + res_row + n0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t = __ldg(rp + q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
               }
             }
+          }
+          const long long o = epi_out_index(ep, m, n0, ldc);     // 32 columns never straddle a head (dh % 32 == 0)
+          if (out_bf16) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<bf16*>(C) + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 pk;
+              pk.x = f2_to_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+              pk.y = f2_to_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+              pk.z = f2_to_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+              pk.w = f2_to_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              dst[q] = pk;
+            }
+          } else {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(C) + o);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        } else {
+          // ---- edge path (N tail or unaligned operands): scalar, guarded
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i) {
+            const int n = n0 + i;
+            if (n >= N) break;
+            float x = v[i];
+            if (ep.bias) x += __ldg(ep.bias + n);
+            if (n < ep.alpha_cols) x *= ep.alpha;
+            if (ep.relu) x = fmaxf(x, 0.f);
+            if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
+            if (ep.residual)
+              x += ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
+                                    : __ldg(ep.residual + res_row + n);
+            const long long o = epi_out_index(ep, m, n, ldc);
+            if (out_bf16) static_cast<bf16*>(C)[o] = __float2bfloat16_rn(x);
+            else static_cast<float*>(C)[o] = x;
           }
         }
       }
@@ -221,7 +287,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int M, int N, int K,
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
                        const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
@@ -238,7 +304,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   }
   const int tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, M, N, K, ep);
+  gemm_bf16_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep);
   return check_launch("gemm_bf16_tc");
 }
 
@@ -252,8 +318,15 @@ int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ld
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tmB, W, N, K, ldw, bn);
   if (rc) return rc;
-  return bn == 256 ? launch_gemm<256>(tmA, tmB, C, ldc, out_bf16, M, N, K, ep, stream)
-                   : launch_gemm<128>(tmA, tmB, C, ldc, out_bf16, M, N, K, ep, stream);
+  // 128-bit epilogue accesses need 16-byte aligned vectors, residual rows and output rows
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const int osz = out_bf16 ? 2 : 4;
+  bool vec_ok = al16(ep.bias) && al16(ep.col_vec) && al16(ep.residual) && al16(C);
+  vec_ok = vec_ok && (!ep.residual || ((long long)ep.ldr * (ep.residual_bf16 ? 2 : 4)) % 16 == 0);
+  if (ep.head_scatter) vec_ok = vec_ok && ep.dh % 32 == 0 && ((long long)ep.part_stride * osz) % 16 == 0;
+  else vec_ok = vec_ok && ((long long)ldc * osz) % 16 == 0;
+  return bn == 256 ? launch_gemm<256>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream)
+                   : launch_gemm<128>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream);
 }
 
 }  // namespace v2m
