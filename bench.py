@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the AMT hot path (BASELINE.json): KV-cached greedy chord generation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype bf16|fp32]
+
+One "step" = one full generation pass over a batch of 64 synthetic videos per GPU (BASELINE config 2:
+encoder over 300 video seconds, cross-attention K/V caches, 299 greedy decode steps with a KV cache).
+Prints ONE JSON line (rank 0).  `value` is whole-job chord-tokens/s with the inputs resident in HBM,
+`e2e` is the same metric through the public API (`VideoMusicTransformer.generate`) from pinned host
+buffers (H2D of the features and D2H of the tokens inside the timed region).
+
+`--impl reference` times the reference's own algorithm -- batch 1, no KV cache, the whole model re-run
+on the growing prefix every step (video_music_transformer.py:1046-1084) -- on the host cores, using the
+CPU restatement in oracle/ (the reference is pure Python and /root/reference does not exist on the
+GPU box; the restatement is pinned to it by tests/golden).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64                 # videos per GPU (BASELINE config 2)
+SEQ = 300                  # target_seq_length -> 299 generated chord tokens per video
+METRIC = "generate_chord_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(B, S, T, E, H, FF, NL, vocab, esz):
+    """bytes one whole decode run must touch (each weight once per step, each cached K/V element
+    once per step)."""
+    w = NL * (3 * E * E + E * E + E * E + E * E + 2 * E * FF + 300 * (E // H)) + E * vocab + (E + 1) * E
+    per_step_w = w * esz
+    cross = NL * 2 * S * E * B * esz
+    steps = T - 1
+    self_kv = sum(NL * 2 * (t + 1) * E * B * esz for t in range(steps))
+    return steps * (per_step_w + cross) + self_kv, NL * 0 + 2 * S * E * B * esz   # (whole run, one cross-attention launch)
+
+
+def make_model(dtype, device, seed=1):
+    from video2music_b200 import VideoMusicTransformer
+    from video2music_b200 import synthetic as syn
+    m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, chord_embed=True)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(syn.fill_like_reference_init(shapes, seed=seed, wout_gain=4.0), strict=False)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    if device is not None:
+        m = m.to(device)
+    return m.eval().set_compute_dtype(dtype), sd
+
+
+def reference_arm(args):
+    """The reference's algorithm on the host cores (oracle port, literal re-forward loop, batch 1)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import amt_oracle as O
+    from video2music_b200 import synthetic as syn
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, sd = make_model(torch.float32, None)
+    inp = syn.make_inputs(1, 1234, SEQ - 1, 300, 0)
+    prim, pr, pa = torch.tensor([1]), torch.tensor([1]), torch.tensor([0])
+
+    def run(n):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.generate_greedy_literal(sd, inp["feature_semantic_list"], inp["feature_key"][0], inp["feature_scene_offset"],
+                                      inp["feature_motion"], inp["feature_emotion"], prim, pr, pa, n, chord_embed=True)
+        return time.perf_counter() - t0
+
+    # bounded sample: the longest prefix for which (steps + warmup) passes fit in ~150 s
+    t_probe = run(24)
+    seq = SEQ
+    total = args.steps + args.warmup
+    for cand in (300, 200, 128, 64, 32):
+        est = t_probe * (cand / 24.0) ** 1.6
+        seq = cand
+        if est * total <= 150.0:
+            break
+    for _ in range(args.warmup):
+        run(seq)
+    times = [run(seq) for _ in range(args.steps)]
+    tokens = seq - 1
+    val = tokens / (sum(times) / len(times))
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "AMT greedy chord generation, reference algorithm (batch 1, no KV cache, full re-forward per token)",
+                      "videos": 1, "target_seq_length": seq},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": "1 video x %d greedy tokens, literal re-forward loop" % tokens},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch.distributed as dist
+    from video2music_b200 import _lib, engine
+    from video2music_b200 import synthetic as syn
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model, sd = make_model(dtype, dev)
+    # videos are sharded over ranks (no collective on the data path): rank r owns videos [r*64, (r+1)*64)
+    inp = syn.make_inputs(BATCH, 1234 + rank, SEQ - 1, 300, 0)
+    keys = ("feature_semantic_list", "feature_key", "feature_scene_offset", "feature_motion", "feature_emotion")
+    host = {k: inp[k].pin_memory() for k in keys}
+    devt = {k: inp[k].to(dev) for k in keys}
+    prim, pr, pa = torch.tensor([1]), torch.tensor([1]), torch.tensor([0])
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def gen(src):
+        return model.generate(src["feature_semantic_list"], src["feature_key"], src["feature_scene_offset"],
+                              src["feature_motion"], src["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa,
+                              target_seq_length=SEQ, beam=1, beam_chance=1.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed (untimed) between steps."""
+        ms = []
+        for _ in range(steps):
+            l2_flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return ms
+
+    def e2e_step():
+        d = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        toks = gen(d)
+        return toks.to("cpu", non_blocking=False)
+
+    for _ in range(args.warmup):
+        gen(devt)
+        e2e_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launches()
+    barrier()
+    ms = timed(lambda: gen(devt), args.steps)
+    barrier()
+    launches = _lib.launches()
+    ms_e2e = timed(e2e_step, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- dominant kernel: decode cross-attention over the video K/V cache, timed alone on the launching stream
+    st = engine.build_decode(model._w(), model._cfg(), devt["feature_semantic_list"], devt["feature_key"].reshape(-1),
+                             devt["feature_scene_offset"], devt["feature_motion"], devt["feature_emotion"],
+                             prim, pr, pa, SEQ)
+    engine.run_decode(st, 8, use_graph=False)
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l2_flush.fill_(1)
+    e0.record()
+    engine.probe_decode_kernel(st, kind=1, reps=reps)          # kind 1 = cross-attention, cycles through the layers
+    e1.record()
+    e1.synchronize()
+    n_l = model.nlayers
+    kern_ms = e0.elapsed_time(e1) / (reps * n_l)
+
+    t_step = sum(ms) / len(ms)
+    t_e2e = sum(ms_e2e) / len(ms_e2e)
+    if world > 1:
+        t = torch.tensor([t_step, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                # device-timed, max over ranks
+        t_step, t_e2e = float(t[0]), float(t[1])
+    tokens = world * BATCH * (SEQ - 1)
+    esz = 2 if dtype == torch.bfloat16 else 4
+    run_bytes, kern_bytes = algorithmic_bytes(BATCH, 300, SEQ, 512, 8, 1024, 6, 159, esz)
+    peak, peak_src = peaks()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+    out = {
+        "metric": METRIC, "value": tokens / (t_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "AMT greedy chord generation with KV cache: 64 videos/GPU x 300 positions (299 decoded tokens), "
+                               "6+6 layers, d_model 512, 8 heads, RPR, vf 776, primer length 1, chord_embed",
+                   "videos_per_gpu": BATCH, "target_seq_length": SEQ, "sharding": "independent videos per rank, no collective",
+                   "l2": "256 MiB written between timed steps (L2 flush); per-step working set 386 MB > L2"},
+        "e2e": {"value": tokens / (t_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": BATCH * SEQ * 8, "ms_per_step": t_e2e},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "dec_attn_kernel<%s> (cross-attention over the cached video K/V)" % args.dtype, "bound": "hbm",
+                     "achieved": kern_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": kern_bytes, "us_per_launch": kern_ms * 1e3},
+        "generate_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": run_bytes,
+                              "achieved": run_bytes / (sum(ms) / len(ms) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": run_bytes / (sum(ms) / len(ms) * 1e-3) / 1e9 / peak,
+                              "note": "whole generate call (prefill + 299 decode steps) against the decode byte floor"},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import amt_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        one = {k: inp[k][:1] for k in keys}
+        n_tok = 64
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.generate_greedy_literal(sd, one["feature_semantic_list"], one["feature_key"][0], one["feature_scene_offset"],
+                                      one["feature_motion"], one["feature_emotion"], prim, pr, pa, n_tok, chord_embed=True)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (n_tok - 1) / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                               "sample": "1 video x %d greedy tokens of the reference algorithm (batch 1, no KV cache, "
+                                         "full re-forward per token) on the host" % (n_tok - 1)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
