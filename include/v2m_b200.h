@@ -139,6 +139,9 @@ typedef struct v2m_decode {
 } v2m_decode;
 int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void* stream);
 int64_t v2m_decode_launches_per_step(const v2m_decode* p);
+/* Measurement aid: launches one decode kernel kind (0 self-attention, 1 cross-attention, 2 QKV GEMM, 3 FFN1 GEMM)
+ * `reps` rounds over all layers on `stream`, reading the current step from *p->step. */
+int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stream);
 
 /* ---- selective scan, model/pscan.py:154-226: H[t] = A[t]*H[t-1] + X[t] over (B,L,D,N) fp32 ---- */
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream);

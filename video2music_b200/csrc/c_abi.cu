@@ -130,6 +130,13 @@ int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void
   return decode_run(d, n_steps, use_graph, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stream) {
+  V2M_REQUIRE(p != nullptr, "v2m_decode_probe: null params");
+  DecodeParams d;
+  memcpy(&d, p, sizeof(d));
+  return decode_probe(d, kind, reps, static_cast<cudaStream_t>(stream));
+}
+
 int64_t v2m_decode_launches_per_step(const v2m_decode* p) {
   DecodeParams d;
   memcpy(&d, p, sizeof(d));

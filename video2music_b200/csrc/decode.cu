@@ -57,88 +57,122 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Stage the activation tile rows [row0, row0+MT) x columns [kc0, kc0+kc) into shared memory as T,
-// applying the A-mode transform.  One warp per row; LayerNorm modes always have K == E == kc.
-template <typename T>
-__device__ void stage_a(const DecodeParams& p, const SkinnyArgs& a, T* As, int a_stride, int row0, int kc0, int kc, int t,
-                        bool write_h) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < MT; r += SK_THREADS / 32) {
-    const int row = row0 + r;
-    T* dst = As + (size_t)r * a_stride;
-    if (row >= p.B) {
-      for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(0.f);
-      continue;
+// Row I/O of the activation staging.  A lane owns 16 of the 512 elements of a row segment:
+//   bf16: 16 consecutive elements (two 16-byte loads / stores per row),
+//   fp32: elements lane + 32*e (coalesced scalar loads, conflict-free stores into the 513-word pitch).
+template <typename T> struct RowIO;
+template <> struct RowIO<bf16> {
+  static __device__ __forceinline__ int kidx(int lane, int e) { return lane * 16 + e; }
+  static __device__ __forceinline__ void load_T(const bf16* seg, int lane, float* v) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(seg + lane * 16));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(seg + lane * 16 + 8));
+    float2 f;
+    f = bf16x2_to_f2(a.x); v[0] = f.x; v[1] = f.y;   f = bf16x2_to_f2(a.y); v[2] = f.x; v[3] = f.y;
+    f = bf16x2_to_f2(a.z); v[4] = f.x; v[5] = f.y;   f = bf16x2_to_f2(a.w); v[6] = f.x; v[7] = f.y;
+    f = bf16x2_to_f2(b.x); v[8] = f.x; v[9] = f.y;   f = bf16x2_to_f2(b.y); v[10] = f.x; v[11] = f.y;
+    f = bf16x2_to_f2(b.z); v[12] = f.x; v[13] = f.y; f = bf16x2_to_f2(b.w); v[14] = f.x; v[15] = f.y;
+  }
+  static __device__ __forceinline__ void load_f32(const float* seg, int lane, float* v) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(seg + lane * 16) + q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
     }
-    if (a.amode == A_PLAIN_T) {
-      const T* src = static_cast<const T*>(a.a_src) + (size_t)row * a.K + kc0;
-      for (int k = lane; k < kc; k += 32) dst[k] = src[k];
-    } else if (a.amode == A_PLAIN_F32) {
-      const float* src = static_cast<const float*>(a.a_src) + (size_t)row * a.K + kc0;
-      for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(src[k]);
-    } else if (a.amode == A_EMBED) {
-      // video_music_transformer.py:984-989
-      if (p.chord_embed) {
-        const float* e = p.emb_chord + (size_t)p.gen[(size_t)row * p.cap + t] * p.E + kc0;
-        for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(e[k]);
-      } else {
-        const float* e0 = p.emb_root + (size_t)p.gen_root[(size_t)row * p.cap + t] * p.E + kc0;
-        const float* e1 = p.emb_attr + (size_t)p.gen_attr[(size_t)row * p.cap + t] * p.E + kc0;
-        for (int k = lane; k < kc; k += 32) dst[k] = from_f32<T>(e0[k] + e1[k]);
-      }
-    } else {  // A_LN / A_LN2 : x = LayerNorm(r) ; K == E <= 1024
-      const T* src = static_cast<const T*>(a.a_src) + (size_t)row * a.K;
-      float vals[32];
-      float sum = 0.f;
+  }
+  static __device__ __forceinline__ void store_f32(float* seg, int lane, const float* v) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int k = lane + 32 * c;
-        vals[c] = (k < a.K) ? to_f32(src[k]) : 0.f;
-        sum += vals[c];
-      }
-      float mean = warp_sum(sum) / (float)a.K;
-      float sq = 0.f;
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(seg + lane * 16)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  static __device__ __forceinline__ void store_smem(bf16* seg, int lane, const float* v) {
+    uint4 a, b;
+    a.x = f2_to_bf16x2(v[0], v[1]);   a.y = f2_to_bf16x2(v[2], v[3]);   a.z = f2_to_bf16x2(v[4], v[5]);   a.w = f2_to_bf16x2(v[6], v[7]);
+    b.x = f2_to_bf16x2(v[8], v[9]);   b.y = f2_to_bf16x2(v[10], v[11]); b.z = f2_to_bf16x2(v[12], v[13]); b.w = f2_to_bf16x2(v[14], v[15]);
+    *reinterpret_cast<uint4*>(seg + lane * 16) = a;
+    *reinterpret_cast<uint4*>(seg + lane * 16 + 8) = b;
+  }
+};
+template <> struct RowIO<float> {
+  static __device__ __forceinline__ int kidx(int lane, int e) { return lane + 32 * e; }
+  static __device__ __forceinline__ void load_T(const float* seg, int lane, float* v) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int k = lane + 32 * c;
-        if (k < a.K) { const float d = vals[c] - mean; sq = fmaf(d, d, sq); }
-      }
-      float rstd = rsqrtf(warp_sum(sq) / (float)a.K + 1e-5f);
+    for (int e = 0; e < 16; ++e) v[e] = __ldg(seg + lane + 32 * e);
+  }
+  static __device__ __forceinline__ void load_f32(const float* seg, int lane, float* v) { load_T(seg, lane, v); }
+  static __device__ __forceinline__ void store_f32(float* seg, int lane, const float* v) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int k = lane + 32 * c;
-        if (k < a.K) vals[c] = (vals[c] - mean) * rstd * a.ln_g[k] + a.ln_b[k];
-      }
-      if (write_h) {
+    for (int e = 0; e < 16; ++e) seg[lane + 32 * e] = v[e];
+  }
+  static __device__ __forceinline__ void store_smem(float* seg, int lane, const float* v) { store_f32(seg, lane, v); }
+};
+
+__device__ __forceinline__ void ln16(float* v, const float* g, const float* b, int K) {
+  float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int k = lane + 32 * c;
-          if (k < a.K) p.h[(size_t)row * p.E + k] = vals[c];
+  for (int e = 0; e < 16; ++e) sum += v[e];
+  const float mean = warp_sum(sum) / (float)K;
+  float sq = 0.f;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) { const float d = v[e] - mean; sq = fmaf(d, d, sq); }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)K + 1e-5f);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = (v[e] - mean) * rstd * g[e] + b[e];
+}
+
+// Stage the activation tile rows [row0, row0+MT) x columns [kc0, kc0+512) into shared memory as T, applying the
+// A-mode transform.  Every warp owns 8 rows and moves them 4 at a time with all global loads of a batch in flight
+// together (this prologue is pure latency otherwise).  LayerNorm modes require K == 512 (one segment == one row).
+template <typename T>
+__device__ void stage_a(const DecodeParams& p, const SkinnyArgs& a, T* As, int a_stride, int row0, int kc0, int t,
+                        bool write_h) {
+  typedef RowIO<T> IO;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool is_ln = (a.amode == A_LN || a.amode == A_LN2);
+  float g1[16], b1[16], g2[16], b2[16];
+  if (is_ln) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { g1[e] = __ldg(a.ln_g + IO::kidx(lane, e)); b1[e] = __ldg(a.ln_b + IO::kidx(lane, e)); }
+    if (a.amode == A_LN2) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { g2[e] = __ldg(a.ln2_g + IO::kidx(lane, e)); b2[e] = __ldg(a.ln2_b + IO::kidx(lane, e)); }
+    }
+  }
+#pragma unroll 1
+  for (int rb = 0; rb < 8; rb += 4) {
+    float v[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp * 8 + rb + i, row = row0 + r;
+      if (row >= p.B) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[i][e] = 0.f;
+        continue;
+      }
+      if (a.amode == A_PLAIN_T || is_ln) {
+        IO::load_T(static_cast<const T*>(a.a_src) + (size_t)row * a.K + kc0, lane, v[i]);
+      } else if (a.amode == A_PLAIN_F32) {
+        IO::load_f32(static_cast<const float*>(a.a_src) + (size_t)row * a.K + kc0, lane, v[i]);
+      } else {  // A_EMBED, video_music_transformer.py:984-989
+        if (p.chord_embed) {
+          IO::load_f32(p.emb_chord + (size_t)p.gen[(size_t)row * p.cap + t] * p.E + kc0, lane, v[i]);
+        } else {
+          float w[16];
+          IO::load_f32(p.emb_root + (size_t)p.gen_root[(size_t)row * p.cap + t] * p.E + kc0, lane, v[i]);
+          IO::load_f32(p.emb_attr + (size_t)p.gen_attr[(size_t)row * p.cap + t] * p.E + kc0, lane, w);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[i][e] += w[e];
         }
       }
-      if (a.amode == A_LN2) {   // decoder final norm on top of the last layer's norm3 (rpr.py:32-33)
-        sum = 0.f;
+    }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) sum += (lane + 32 * c < a.K) ? vals[c] : 0.f;
-        mean = warp_sum(sum) / (float)a.K;
-        sq = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int k = lane + 32 * c;
-          if (k < a.K) { const float d = vals[c] - mean; sq = fmaf(d, d, sq); }
-        }
-        rstd = rsqrtf(warp_sum(sq) / (float)a.K + 1e-5f);
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int k = lane + 32 * c;
-          if (k < a.K) vals[c] = (vals[c] - mean) * rstd * a.ln2_g[k] + a.ln2_b[k];
-        }
+    for (int i = 0; i < 4; ++i) {
+      const int r = warp * 8 + rb + i, row = row0 + r;
+      if (is_ln && row < p.B) {
+        ln16(v[i], g1, b1, a.K);                                   // x = LayerNorm(r)   (rpr.py:59,66,69)
+        if (write_h) IO::store_f32(p.h + (size_t)row * p.E, lane, v[i]);
+        if (a.amode == A_LN2) ln16(v[i], g2, b2, a.K);             // decoder final norm on top (rpr.py:32-33)
       }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int k = lane + 32 * c;
-        if (k >= kc0 && k < kc0 + kc) dst[k - kc0] = from_f32<T>(vals[c]);
-      }
+      IO::store_smem(As + (size_t)r * a_stride, lane, v[i]);
     }
   }
 }
@@ -202,7 +236,7 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_co
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
       if (ch < nch) wv[ch] = ld_nc_v4(wrow + ch * 32);
-    stage_a<bf16>(p, a, As, AS, row0, 0, K, t, write_h);
+    for (int kc0 = 0; kc0 < K; kc0 += 512) stage_a<bf16>(p, a, As + kc0, AS, row0, kc0, t, write_h);
     __syncthreads();
     float c[4][4];
 #pragma unroll
@@ -247,7 +281,7 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_co
     for (int kc0 = 0; kc0 < K; kc0 += F32_KCHUNK) {
       const int kc = min(F32_KCHUNK, K - kc0);
       if (kc0 > 0) __syncthreads();
-      stage_a<float>(p, a, As, AS, row0, kc0, kc, t, write_h && kc0 == 0);
+      stage_a<float>(p, a, As, AS, row0, kc0, t, write_h && kc0 == 0);
       __syncthreads();
       const float* ar = As + (size_t)row * AS;
       for (int k = 0; k < kc; k += 4) {
@@ -548,10 +582,37 @@ static int decode_run_t(const DecodeParams& p, int n_steps, int use_graph, cudaS
   return kOk;
 }
 
+// Launches one decode kernel kind `reps` rounds over all layers (bench.py times it with CUDA events for the roofline
+// line).  kind 0: self-attention, 1: cross-attention, 2: QKV skinny GEMM, 3: FFN1 skinny GEMM.
+template <typename T>
+static int decode_probe_t(const DecodeParams& p, int kind, int reps, cudaStream_t s) {
+  int rc = set_attrs<T>();
+  if (rc) return rc;
+  for (int r = 0; r < reps; ++r)
+    for (int l = 0; l < p.n_layers; ++l) {
+      const DecLayer& L = p.layer[l];
+      if (kind == 0 || kind == 1) rc = launch_attn<T>(p, l, kind, s);
+      else if (kind == 2) {
+        SkinnyArgs a{L.w_qkv, L.b_qkv, 3 * p.E, p.E, A_PLAIN_F32, p.h, nullptr, nullptr, nullptr, nullptr, E_Q, l};
+        rc = launch_skinny<T>(p, a, s);
+      } else {
+        SkinnyArgs a{L.w_f1, L.b_f1, p.FF, p.E, A_PLAIN_F32, p.h, nullptr, nullptr, nullptr, nullptr, E_RELU, l};
+        rc = launch_skinny<T>(p, a, s);
+      }
+      if (rc) return rc;
+    }
+  return kOk;
+}
+
+int decode_probe(const DecodeParams& p, int kind, int reps, cudaStream_t stream) {
+  V2M_REQUIRE(kind >= 0 && kind <= 3 && reps >= 1, "decode_probe: bad kind/reps");
+  return p.dtype == 0 ? decode_probe_t<float>(p, kind, reps, stream) : decode_probe_t<bf16>(p, kind, reps, stream);
+}
+
 int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream) {
   V2M_REQUIRE(p.n_layers >= 1 && p.n_layers <= kMaxDecLayers, "decode: n_layers %d out of range", p.n_layers);
   V2M_REQUIRE(p.E % p.H == 0 && p.E / p.H == 64, "decode: head_dim must be 64 (E=%d H=%d)", p.E, p.H);
-  V2M_REQUIRE(p.E % 256 == 0 && p.FF % 256 == 0 && p.E <= 1024, "decode: E=%d FF=%d must be multiples of 256, E<=1024", p.E, p.FF);
+  V2M_REQUIRE(p.E == 512 && p.FF % 512 == 0 && p.FF <= 2048, "decode: d_model must be 512 and dim_feedforward a multiple of 512 (E=%d FF=%d)", p.E, p.FF);
   V2M_REQUIRE(p.cap <= p.er_len, "decode: cap %d exceeds er_len %d (rpr.py:426-450 fails for L > er_len)", p.cap, p.er_len);
   V2M_REQUIRE(p.B >= 1 && n_steps >= 0, "decode: bad B=%d n_steps=%d", p.B, n_steps);
   if (p.dtype == 0) return decode_run_t<float>(p, n_steps, use_graph, stream);

@@ -121,6 +121,7 @@ struct DecodeParams {
 // Runs `n_steps` decode steps starting at *step (device).  use_graph: capture one step into a CUDA graph and replay.
 int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream);
 long long decode_kernel_launches_per_step(const DecodeParams& p);
+int decode_probe(const DecodeParams& p, int kind, int reps, cudaStream_t stream);
 
 // ------------------------------------------------------------------ selective scan (pscan.cu)
 int pscan_fwd(const float* A, const float* X, float* H, int B, int L, int D, int N, cudaStream_t stream);

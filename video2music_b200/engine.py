@@ -291,3 +291,9 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
 def run_decode(st: DecodeState, n_steps: int, use_graph: bool = True) -> None:
     check(load().v2m_decode_run(C.byref(st.params), n_steps, int(use_graph), stream()))
     _lib.count_launches(n_steps * st.launches_per_step)
+
+
+def probe_decode_kernel(st: DecodeState, kind: int, reps: int) -> None:
+    """Measurement aid for bench.py: `reps` rounds of one decode kernel kind over all layers (see v2m_decode_probe)."""
+    check(load().v2m_decode_probe(C.byref(st.params), kind, reps, stream()))
+    _lib.count_launches(reps * st.params.n_layers)
