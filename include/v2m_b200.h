@@ -136,8 +136,14 @@ typedef struct v2m_decode {
   int64_t* gen; int64_t* gen_root; int64_t* gen_attr;
   int32_t* step;
   float* h; void* r; float* qbuf; void* ctx; void* ff; float* logits; float* logits_all;
+  void* xn;
 } v2m_decode;
 int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void* stream);
+/* Same loop as ONE persistent kernel launch: thread-block clusters own 8 videos each for all n_steps positions
+ * starting at position t0 (the host copy of *p->step).  bf16, d_model 512, 8 heads; V2M_UNSUPPORTED otherwise. */
+int v2m_decode_run_cluster(const v2m_decode* p, int32_t t0, int32_t n_steps, void* stream);
+/* Measurement aid: CTA 0 of cluster 0 writes a globaltimer stamp (ns) at every phase boundary of the cluster kernel. */
+int v2m_debug_set_timestamps(uint64_t* buf, int32_t cap);
 int64_t v2m_decode_launches_per_step(const v2m_decode* p);
 /* Measurement aid: launches one decode kernel kind (0 self-attention, 1 cross-attention, 2 QKV GEMM, 3 FFN1 GEMM)
  * `reps` rounds over all layers on `stream`, reading the current step from *p->step. */

@@ -128,6 +128,51 @@ def test_generate_bf16_vs_oracle():
     assert err < TOL_BF16
 
 
+def test_generate_bf16_cluster_kernel_matches_per_kernel_path():
+    """The persistent cluster kernel and the 51-kernels-per-position path implement the same arithmetic: logits agree to
+    bf16 rounding noise when both are teacher-forced, and both stay within the bf16 tolerance of the fp32 oracle."""
+    B = 13                                                       # ragged: one full cluster of 8 videos + one of 5
+    m, sd = amt_state_dict(syn.vf_dim(0), 2, chord_embed=True, wout_gain=4.0)
+    m = m.to(DEV).eval().set_compute_dtype(torch.bfloat16)
+    inp = syn.make_inputs(B, 77, 299, 300, 0)
+    P = 299
+    prim, pr, pa = inp["x"][:, :P], inp["x_root"][:, :P], inp["x_attr"][:, :P]
+    outs = {}
+    for mode in ("kernels", "cluster"):
+        gen, logits = m.generate(inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+                                 inp["feature_motion"], inp["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa,
+                                 target_seq_length=300, beam=1, return_logits=True, decode_mode=mode)
+        outs[mode] = logits[:, :299].float().cpu()
+        assert torch.equal(gen[:, :P].cpu(), prim)
+    with torch.no_grad():
+        _, lref = O.generate_greedy_cached(sd, inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+                                           inp["feature_motion"], inp["feature_emotion"], prim, pr, pa, 300,
+                                           chord_embed=True, return_logits=True)
+    e_k, e_c = rel_err(outs["kernels"], lref), rel_err(outs["cluster"], lref)
+    print("bf16 decode rel err: kernels %.3e cluster %.3e, cluster vs kernels %.3e" % (e_k, e_c, rel_err(outs["cluster"], outs["kernels"])))
+    assert e_k < TOL_BF16 and e_c < TOL_BF16
+    assert rel_err(outs["cluster"], outs["kernels"]) < 1.5e-2          # two bf16 schedules (different K splits)
+
+
+def test_generate_bf16_cluster_free_running():
+    """Free-running greedy generation (tokens feed back) with the cluster kernel: tokens equal the per-kernel path's
+    wherever the oracle's top-2 margin is comfortably above bf16 noise."""
+    B = 16
+    m, sd = amt_state_dict(syn.vf_dim(0), 1, chord_embed=True, wout_gain=4.0)
+    m = m.to(DEV).eval().set_compute_dtype(torch.bfloat16)
+    inp = syn.make_inputs(B, 4242, 299, 300, 0)
+    P = 8
+    prim, pr, pa = inp["x"][:, :P], inp["x_root"][:, :P], inp["x_attr"][:, :P]
+    gens = {}
+    for mode in ("kernels", "cluster"):
+        gens[mode] = m.generate(inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+                                inp["feature_motion"], inp["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa,
+                                target_seq_length=300, beam=1, decode_mode=mode).cpu()
+    agree = float((gens["kernels"] == gens["cluster"]).float().mean())
+    print("token agreement cluster vs kernels: %.4f" % agree)
+    assert agree > 0.98
+
+
 def test_forward_bf16_vs_reference_golden():
     g = load_golden("amt_forward_cfg1.pt")
     s = g["spec"]

@@ -50,14 +50,14 @@ class Decode(C.Structure):
                 [("layer", DecLayer * MAX_DEC_LAYERS)] +
                 [(n, vp) for n in ("lnf_g", "lnf_b", "w_out", "b_out", "emb_root", "emb_attr", "emb_chord",
                                    "w_chord", "wc_key", "b_chord", "pe", "key", "gen", "gen_root", "gen_attr",
-                                   "step", "h", "r", "qbuf", "ctx", "ff", "logits", "logits_all")])
+                                   "step", "h", "r", "qbuf", "ctx", "ff", "logits", "logits_all", "xn")])
 
 
 # every symbol include/v2m_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_bf16", "v2m_attn_fwd",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
-    "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
+    "v2m_decode_run_cluster", "v2m_debug_set_timestamps", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -88,6 +88,8 @@ def load() -> C.CDLL:
     lib.v2m_cast_2d.argtypes = [vp, i32, i64, vp, i32, i64, i32, i32, i32, vp]
     lib.v2m_binary_f32.argtypes = [vp, vp, vp, i64, i32, C.c_float, vp]
     lib.v2m_decode_run.argtypes = [C.POINTER(Decode), i32, i32, vp]
+    lib.v2m_debug_set_timestamps.argtypes = [vp, i32]
+    lib.v2m_decode_run_cluster.argtypes = [C.POINTER(Decode), i32, i32, vp]
     lib.v2m_decode_launches_per_step.argtypes = [C.POINTER(Decode)]
     lib.v2m_decode_probe.argtypes = [C.POINTER(Decode), i32, i32, vp]
     lib.v2m_pscan_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]

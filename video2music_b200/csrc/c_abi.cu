@@ -130,6 +130,19 @@ int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void
   return decode_run(d, n_steps, use_graph, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_decode_run_cluster(const v2m_decode* p, int32_t t0, int32_t n_steps, void* stream) {
+  V2M_REQUIRE(p != nullptr, "v2m_decode_run_cluster: null params");
+  DecodeParams d;
+  memcpy(&d, p, sizeof(d));
+  int rc = decode_run_cluster(d, t0, n_steps, static_cast<cudaStream_t>(stream));
+  if (rc == kUnsupported) set_last_error("decode_run_cluster: configuration not covered by the cluster kernel (bf16, d_model 512, 8 heads)");
+  return rc;
+}
+
+int v2m_debug_set_timestamps(uint64_t* buf, int32_t cap) {
+  return decode_debug_set_timestamps(reinterpret_cast<unsigned long long*>(buf), cap);
+}
+
 int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stream) {
   V2M_REQUIRE(p != nullptr, "v2m_decode_probe: null params");
   DecodeParams d;

@@ -21,16 +21,20 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace v2m {
 
-enum AMode { A_PLAIN_T = 0, A_PLAIN_F32 = 1, A_LN = 2, A_LN2 = 3, A_EMBED = 4 };
+// Programmatic dependent launch: a kernel may start while its predecessor in the stream is still running; everything
+// before pdl_wait() must only touch data that no kernel of the decode chain writes (weights, static cross K/V).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 enum EMode { E_QKV = 0, E_RESID = 1, E_Q = 2, E_RELU = 3, E_EMBED = 4, E_LOGITS = 5 };
 
 struct SkinnyArgs {
   const void* W; const float* bias; int N, K;
-  int amode; const void* a_src;
-  const float* ln_g; const float* ln_b; const float* ln2_g; const float* ln2_b;
+  const void* a_src;            // [B, K] activations in the compute dtype (p.xn / p.ctx / p.ff)
   int emode; int layer;
 };
 
@@ -42,7 +46,7 @@ constexpr int F32_KCHUNK = 512;
 template <typename T> struct SkinnyCfg;
 template <> struct SkinnyCfg<bf16> {
   static __host__ __device__ int a_stride(int K) { return K + 32; }                 // elements; 64 B pad -> conflict-free LDS.128
-  static size_t smem(int K) { return (size_t)MT * a_stride(K) * 2 + 8 * MT * NT * 4; }
+  static size_t smem(int K) { return (size_t)MT * a_stride(K) * 2 + 8 * MT * NT * 4 + 16; }
 };
 template <> struct SkinnyCfg<float> {
   static __host__ __device__ int a_stride(int) { return F32_KCHUNK + 1; }
@@ -57,124 +61,83 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// Row I/O of the activation staging.  A lane owns 16 of the 512 elements of a row segment:
-//   bf16: 16 consecutive elements (two 16-byte loads / stores per row),
-//   fp32: elements lane + 32*e (coalesced scalar loads, conflict-free stores into the 513-word pitch).
-template <typename T> struct RowIO;
-template <> struct RowIO<bf16> {
-  static __device__ __forceinline__ int kidx(int lane, int e) { return lane * 16 + e; }
-  static __device__ __forceinline__ void load_T(const bf16* seg, int lane, float* v) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(seg + lane * 16));
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(seg + lane * 16 + 8));
-    float2 f;
-    f = bf16x2_to_f2(a.x); v[0] = f.x; v[1] = f.y;   f = bf16x2_to_f2(a.y); v[2] = f.x; v[3] = f.y;
-    f = bf16x2_to_f2(a.z); v[4] = f.x; v[5] = f.y;   f = bf16x2_to_f2(a.w); v[6] = f.x; v[7] = f.y;
-    f = bf16x2_to_f2(b.x); v[8] = f.x; v[9] = f.y;   f = bf16x2_to_f2(b.y); v[10] = f.x; v[11] = f.y;
-    f = bf16x2_to_f2(b.z); v[12] = f.x; v[13] = f.y; f = bf16x2_to_f2(b.w); v[14] = f.x; v[15] = f.y;
-  }
-  static __device__ __forceinline__ void load_f32(const float* seg, int lane, float* v) {
+// 16 consecutive elements of a row (lane-contiguous ownership: lane l holds elements [16 l, 16 l + 16) of a 512 segment)
+__device__ __forceinline__ void load16(const bf16* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+  float2 f;
+  f = bf16x2_to_f2(a.x); v[0] = f.x; v[1] = f.y;   f = bf16x2_to_f2(a.y); v[2] = f.x; v[3] = f.y;
+  f = bf16x2_to_f2(a.z); v[4] = f.x; v[5] = f.y;   f = bf16x2_to_f2(a.w); v[6] = f.x; v[7] = f.y;
+  f = bf16x2_to_f2(b.x); v[8] = f.x; v[9] = f.y;   f = bf16x2_to_f2(b.y); v[10] = f.x; v[11] = f.y;
+  f = bf16x2_to_f2(b.z); v[12] = f.x; v[13] = f.y; f = bf16x2_to_f2(b.w); v[14] = f.x; v[15] = f.y;
+}
+__device__ __forceinline__ void load16(const float* p, float* v) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(seg + lane * 16) + q);
-      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-    }
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = reinterpret_cast<const float4*>(p)[q];
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
   }
-  static __device__ __forceinline__ void store_f32(float* seg, int lane, const float* v) {
+}
+__device__ __forceinline__ void store16(bf16* p, const float* v) {
+  uint4 a, b;
+  a.x = f2_to_bf16x2(v[0], v[1]);   a.y = f2_to_bf16x2(v[2], v[3]);   a.z = f2_to_bf16x2(v[4], v[5]);   a.w = f2_to_bf16x2(v[6], v[7]);
+  b.x = f2_to_bf16x2(v[8], v[9]);   b.y = f2_to_bf16x2(v[10], v[11]); b.z = f2_to_bf16x2(v[12], v[13]); b.w = f2_to_bf16x2(v[14], v[15]);
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 8) = b;
+}
+__device__ __forceinline__ void store16(float* p, const float* v) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      reinterpret_cast<float4*>(seg + lane * 16)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  }
-  static __device__ __forceinline__ void store_smem(bf16* seg, int lane, const float* v) {
-    uint4 a, b;
-    a.x = f2_to_bf16x2(v[0], v[1]);   a.y = f2_to_bf16x2(v[2], v[3]);   a.z = f2_to_bf16x2(v[4], v[5]);   a.w = f2_to_bf16x2(v[6], v[7]);
-    b.x = f2_to_bf16x2(v[8], v[9]);   b.y = f2_to_bf16x2(v[10], v[11]); b.z = f2_to_bf16x2(v[12], v[13]); b.w = f2_to_bf16x2(v[14], v[15]);
-    *reinterpret_cast<uint4*>(seg + lane * 16) = a;
-    *reinterpret_cast<uint4*>(seg + lane * 16 + 8) = b;
-  }
-};
-template <> struct RowIO<float> {
-  static __device__ __forceinline__ int kidx(int lane, int e) { return lane + 32 * e; }
-  static __device__ __forceinline__ void load_T(const float* seg, int lane, float* v) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = __ldg(seg + lane + 32 * e);
-  }
-  static __device__ __forceinline__ void load_f32(const float* seg, int lane, float* v) { load_T(seg, lane, v); }
-  static __device__ __forceinline__ void store_f32(float* seg, int lane, const float* v) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) seg[lane + 32 * e] = v[e];
-  }
-  static __device__ __forceinline__ void store_smem(float* seg, int lane, const float* v) { store_f32(seg, lane, v); }
-};
+  for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
 
-__device__ __forceinline__ void ln16(float* v, const float* g, const float* b, int K) {
+__device__ __forceinline__ void ln16(float* v, const float* g, const float* b, int E) {
   float sum = 0.f;
 #pragma unroll
   for (int e = 0; e < 16; ++e) sum += v[e];
-  const float mean = warp_sum(sum) / (float)K;
+  const float mean = warp_sum(sum) / (float)E;
   float sq = 0.f;
 #pragma unroll
   for (int e = 0; e < 16; ++e) { const float d = v[e] - mean; sq = fmaf(d, d, sq); }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)K + 1e-5f);
+  const float rstd = rsqrtf(warp_sum(sq) / (float)E + 1e-5f);
+  float gg[16], bb[16];
+  load16(g, gg);
+  load16(b, bb);
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = (v[e] - mean) * rstd * g[e] + b[e];
+  for (int e = 0; e < 16; ++e) v[e] = (v[e] - mean) * rstd * gg[e] + bb[e];
 }
 
-// Stage the activation tile rows [row0, row0+MT) x columns [kc0, kc0+512) into shared memory as T, applying the
-// A-mode transform.  Every warp owns 8 rows and moves them 4 at a time with all global loads of a batch in flight
-// together (this prologue is pure latency otherwise).  LayerNorm modes require K == 512 (one segment == one row).
+// Row preparation, done ONCE per row (one warp per video) instead of redundantly inside every GEMM CTA:
+//   PREP_LN   : xn = LayerNorm(r) -> p.xn (dtype T, GEMM operand) and p.h (fp32 residual)      (rpr.py:59,66,69)
+//   PREP_LN2  : xn = LayerNorm_f(LayerNorm(r))  -> p.xn                                          (rpr.py:32-33)
+//   PREP_EMBED: emb_root[.] + emb_attr[.] (or the chord embedding) of position t -> p.ctx       (video_music_transformer.py:984-989)
+enum PrepMode { PREP_LN = 0, PREP_LN2 = 1, PREP_EMBED = 2 };
 template <typename T>
-__device__ void stage_a(const DecodeParams& p, const SkinnyArgs& a, T* As, int a_stride, int row0, int kc0, int t,
-                        bool write_h) {
-  typedef RowIO<T> IO;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool is_ln = (a.amode == A_LN || a.amode == A_LN2);
-  float g1[16], b1[16], g2[16], b2[16];
-  if (is_ln) {
+__global__ void __launch_bounds__(256) rows_prep_kernel(const __grid_constant__ DecodeParams p, int mode, const float* g1,
+                                                        const float* b1, const float* g2, const float* b2) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
+  if (row >= p.B) return;
+  const int t = *p.step;
+  const int k0 = lane * 16;                       // E == 512
+  float v[16];
+  if (mode == PREP_EMBED) {
+    if (p.chord_embed) {
+      load16(p.emb_chord + (size_t)p.gen[(size_t)row * p.cap + t] * p.E + k0, v);
+    } else {
+      float w[16];
+      load16(p.emb_root + (size_t)p.gen_root[(size_t)row * p.cap + t] * p.E + k0, v);
+      load16(p.emb_attr + (size_t)p.gen_attr[(size_t)row * p.cap + t] * p.E + k0, w);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { g1[e] = __ldg(a.ln_g + IO::kidx(lane, e)); b1[e] = __ldg(a.ln_b + IO::kidx(lane, e)); }
-    if (a.amode == A_LN2) {
-#pragma unroll
-      for (int e = 0; e < 16; ++e) { g2[e] = __ldg(a.ln2_g + IO::kidx(lane, e)); b2[e] = __ldg(a.ln2_b + IO::kidx(lane, e)); }
+      for (int e = 0; e < 16; ++e) v[e] += w[e];
     }
+    store16(static_cast<T*>(p.ctx) + (size_t)row * p.E + k0, v);
+    return;
   }
-#pragma unroll 1
-  for (int rb = 0; rb < 8; rb += 4) {
-    float v[4][16];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = warp * 8 + rb + i, row = row0 + r;
-      if (row >= p.B) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[i][e] = 0.f;
-        continue;
-      }
-      if (a.amode == A_PLAIN_T || is_ln) {
-        IO::load_T(static_cast<const T*>(a.a_src) + (size_t)row * a.K + kc0, lane, v[i]);
-      } else if (a.amode == A_PLAIN_F32) {
-        IO::load_f32(static_cast<const float*>(a.a_src) + (size_t)row * a.K + kc0, lane, v[i]);
-      } else {  // A_EMBED, video_music_transformer.py:984-989
-        if (p.chord_embed) {
-          IO::load_f32(p.emb_chord + (size_t)p.gen[(size_t)row * p.cap + t] * p.E + kc0, lane, v[i]);
-        } else {
-          float w[16];
-          IO::load_f32(p.emb_root + (size_t)p.gen_root[(size_t)row * p.cap + t] * p.E + kc0, lane, v[i]);
-          IO::load_f32(p.emb_attr + (size_t)p.gen_attr[(size_t)row * p.cap + t] * p.E + kc0, lane, w);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[i][e] += w[e];
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = warp * 8 + rb + i, row = row0 + r;
-      if (is_ln && row < p.B) {
-        ln16(v[i], g1, b1, a.K);                                   // x = LayerNorm(r)   (rpr.py:59,66,69)
-        if (write_h) IO::store_f32(p.h + (size_t)row * p.E, lane, v[i]);
-        if (a.amode == A_LN2) ln16(v[i], g2, b2, a.K);             // decoder final norm on top (rpr.py:32-33)
-      }
-      IO::store_smem(As + (size_t)r * a_stride, lane, v[i]);
-    }
-  }
+  load16(static_cast<const T*>(p.r) + (size_t)row * p.E + k0, v);
+  ln16(v, g1 + k0, b1 + k0, p.E);
+  if (mode == PREP_LN) store16(p.h + (size_t)row * p.E + k0, v);
+  else ln16(v, g2 + k0, b2 + k0, p.E);
+  store16(static_cast<T*>(p.xn) + (size_t)row * p.E + k0, v);
 }
 
 template <typename T>
@@ -205,7 +168,9 @@ __device__ __forceinline__ void skinny_epilogue(const DecodeParams& p, const Ski
       static_cast<T*>(p.ff)[(size_t)row * p.FF + n] = from_f32<T>(fmaxf(v, 0.f));
       break;
     case E_EMBED:
-      p.h[(size_t)row * p.E + n] = v + p.key[row] * p.wc_key[n] + p.pe[(size_t)t * p.E + n];
+      v += p.key[row] * p.wc_key[n] + p.pe[(size_t)t * p.E + n];
+      p.h[(size_t)row * p.E + n] = v;                                  // residual of the first block
+      static_cast<T*>(p.xn)[(size_t)row * p.E + n] = from_f32<T>(v);   // operand of layer 0's QKV projection
       break;
     case E_LOGITS:
       p.logits[(size_t)row * p.vocab + n] = v;
@@ -220,9 +185,8 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_co
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * NT, row0 = blockIdx.y * MT;
-  const int t = *p.step;
   const int K = a.K;
-  const bool write_h = (blockIdx.x == 0) && (a.amode == A_LN);
+  pdl_trigger();
 
   if constexpr (std::is_same<T, bf16>::value) {
     bf16* As = reinterpret_cast<bf16*>(smem_raw);
@@ -236,7 +200,20 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_co
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
       if (ch < nch) wv[ch] = ld_nc_v4(wrow + ch * 32);
-    for (int kc0 = 0; kc0 < K; kc0 += 512) stage_a<bf16>(p, a, As + kc0, AS, row0, kc0, t, write_h);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 8 * MT * NT);
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    pdl_wait();                                              // predecessor's outputs (and the position counter) are final
+    const int t = *p.step;
+    // activation rows: already in the compute dtype in global memory -> one bulk async copy per row, no instructions
+    const int nrows = min(MT, p.B - row0);
+    if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nrows * K * 2));
+    if (tid < nrows) {
+      bulk_g2s(As + (size_t)tid * AS, static_cast<const bf16*>(a.a_src) + (size_t)(row0 + tid) * K, (uint32_t)(K * 2), bar);
+    } else if (tid < MT) {
+      for (int k = 0; k < K; k += 8) *reinterpret_cast<uint4*>(As + (size_t)tid * AS + k) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    mbar_wait(bar, 0);
     __syncthreads();
     float c[4][4];
 #pragma unroll
@@ -278,10 +255,17 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_co
     const float* w0 = static_cast<const float*>(a.W) + (size_t)min(n0 + 2 * cp, a.N - 1) * K;
     const float* w1 = static_cast<const float*>(a.W) + (size_t)min(n0 + 2 * cp + 1, a.N - 1) * K;
     float acc0 = 0.f, acc1 = 0.f;
+    pdl_wait();
+    const int t = *p.step;
     for (int kc0 = 0; kc0 < K; kc0 += F32_KCHUNK) {
       const int kc = min(F32_KCHUNK, K - kc0);
       if (kc0 > 0) __syncthreads();
-      stage_a<float>(p, a, As, AS, row0, kc0, t, write_h && kc0 == 0);
+      for (int r = warp; r < MT; r += SK_THREADS / 32) {       // coalesced row copies, 16 loads in flight per lane
+        const bool ok = row0 + r < p.B;
+        const float* src = static_cast<const float*>(a.a_src) + (size_t)(row0 + r) * K + kc0;
+#pragma unroll 16
+        for (int k = lane; k < kc; k += 32) As[(size_t)r * AS + k] = ok ? src[k] : 0.f;
+      }
       __syncthreads();
       const float* ar = As + (size_t)row * AS;
       for (int k = 0; k < kc; k += 4) {
@@ -343,19 +327,29 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_kernel(const __grid_const
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int t = *p.step;
   const DecLayer& L = p.layer[layer];
-  const int n = is_cross ? p.S : t + 1;
   const int kv_cap = is_cross ? p.S : p.cap;
   const T* kg = static_cast<const T*>(is_cross ? L.cross_k : L.self_k) + ((size_t)b * p.H + h) * kv_cap * DH;
   const T* vg = static_cast<const T*>(is_cross ? L.cross_v : L.self_v) + ((size_t)b * p.H + h) * kv_cap * DH;
-  const T* eg = static_cast<const T*>(L.er) + (size_t)(p.er_len - 1 - t) * DH;   // rows for j = 0..t
-
+  pdl_trigger();
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
+    if (is_cross) {
+      // the video K/V cache is written once before the decode loop: stream it while the predecessor still runs
+      const uint32_t bytes = (uint32_t)(p.S * DH * sizeof(T));
+      mbar_arrive_expect_tx(bar, bytes * 2);
+      bulk_g2s(Ks, kg, bytes, bar);
+      bulk_g2s(Vs, vg, bytes, bar);
+    }
+  }
+  pdl_wait();
+  const int t = *p.step;
+  const int n = is_cross ? p.S : t + 1;
+  const T* eg = static_cast<const T*>(L.er) + (size_t)(p.er_len - 1 - t) * DH;   // rows for j = 0..t
+  if (tid == 0 && !is_cross) {
     const uint32_t bytes = (uint32_t)(n * DH * sizeof(T));
-    const bool want_e = !is_cross && es_in_smem;
+    const bool want_e = es_in_smem;
     mbar_arrive_expect_tx(bar, bytes * (want_e ? 3 : 2));
     bulk_g2s(Ks, kg, bytes, bar);
     bulk_g2s(Vs, vg, bytes, bar);
@@ -433,6 +427,8 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_kernel(const __grid_const
 // first index wins on exact ties; writes gen[:, t+1] and advances the step counter.
 __global__ void __launch_bounds__(256) argmax_advance_kernel(const __grid_constant__ DecodeParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_trigger();
+  pdl_wait();
   const int t = *p.step;
   for (int b = warp; b < p.B; b += 8) {
     float best = -INFINITY;
@@ -454,24 +450,46 @@ __global__ void __launch_bounds__(256) argmax_advance_kernel(const __grid_consta
 }
 
 // ----------------------------------------------------------------------------------------------
+static bool g_use_pdl = true;
+
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const char* what,
+                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return kCudaError;
+  }
+  return kOk;
+}
+
 template <typename T>
 static int launch_skinny(const DecodeParams& p, const SkinnyArgs& a, cudaStream_t s) {
   const size_t smem = SkinnyCfg<T>::smem(a.K);
   dim3 grid((a.N + NT - 1) / NT, (p.B + MT - 1) / MT);
-  skinny_gemm_kernel<T><<<grid, SK_THREADS, smem, s>>>(p, a);
-  return check_launch("decode skinny gemm");
+  return launch_pdl(skinny_gemm_kernel<T>, grid, dim3(SK_THREADS), smem, s, "decode skinny gemm", p, a);
 }
 
 template <typename T>
 static int launch_attn(const DecodeParams& p, int layer, int is_cross, cudaStream_t s) {
   const int n_max = p.S > p.cap ? p.S : p.cap;
   const int dh = p.E / p.H;
-  const int e_rows = (std::is_same<T, bf16>::value && !is_cross) ? n_max : 0;
+  const int e_rows = 0;       // Er rows are read through L1 (38 KB shared by every CTA); K+V alone keep 2 CTAs per SM
   constexpr int VEC = DecAttnCfg<T>::kVec;
   const size_t smem = (size_t)(2 * n_max + e_rows) * dh * sizeof(T) +
                       sizeof(float) * (dh + ((n_max + 3) & ~3) + (DA_THREADS / (dh / VEC)) * dh + 16) + 16;
-  dec_attn_kernel<T, 64><<<p.B * p.H, DA_THREADS, smem, s>>>(p, layer, is_cross, n_max, e_rows);
-  return check_launch("decode attention");
+  return launch_pdl(dec_attn_kernel<T, 64>, dim3(p.B * p.H), dim3(DA_THREADS), smem, s, "decode attention", p, layer, is_cross,
+                    n_max, e_rows);
 }
 
 template <typename T>
@@ -479,41 +497,45 @@ static int enqueue_step(const DecodeParams& p, cudaStream_t s) {
   int rc;
   SkinnyArgs a{};
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
+  auto prep = [&](int mode, const float* g1, const float* b1, const float* g2, const float* b2) {
+    return launch_pdl(rows_prep_kernel<T>, dim3((p.B + 7) / 8), dim3(256), 0, s, "decode rows_prep", p, mode, g1, b1, g2, b2);
+  };
   // x_t = Linear_chord([emb | key]) + pe[t]
-  a = SkinnyArgs{p.w_chord, p.b_chord, p.E, p.E, A_EMBED, nullptr, nullptr, nullptr, nullptr, nullptr, E_EMBED, 0};
+  RUN(prep(PREP_EMBED, nullptr, nullptr, nullptr, nullptr));
+  a = SkinnyArgs{p.w_chord, p.b_chord, p.E, p.E, p.ctx, E_EMBED, 0};
   RUN(launch_skinny<T>(p, a, s));
   for (int l = 0; l < p.n_layers; ++l) {
     const DecLayer& L = p.layer[l];
-    const DecLayer* P = l > 0 ? &p.layer[l - 1] : nullptr;
-    // self-attention block
-    a = SkinnyArgs{L.w_qkv, L.b_qkv, 3 * p.E, p.E, l == 0 ? A_PLAIN_F32 : A_LN, l == 0 ? (const void*)p.h : (const void*)p.r,
-                   P ? P->ln3_g : nullptr, P ? P->ln3_b : nullptr, nullptr, nullptr, E_QKV, l};
+    // self-attention block (rpr.py:56-59)
+    a = SkinnyArgs{L.w_qkv, L.b_qkv, 3 * p.E, p.E, p.xn, E_QKV, l};
     RUN(launch_skinny<T>(p, a, s));
     RUN(launch_attn<T>(p, l, 0, s));
-    a = SkinnyArgs{L.w_so, L.b_so, p.E, p.E, A_PLAIN_T, p.ctx, nullptr, nullptr, nullptr, nullptr, E_RESID, l};
+    a = SkinnyArgs{L.w_so, L.b_so, p.E, p.E, p.ctx, E_RESID, l};
     RUN(launch_skinny<T>(p, a, s));
-    // cross-attention block
-    a = SkinnyArgs{L.w_cq, L.b_cq, p.E, p.E, A_LN, p.r, L.ln1_g, L.ln1_b, nullptr, nullptr, E_Q, l};
+    RUN(prep(PREP_LN, L.ln1_g, L.ln1_b, nullptr, nullptr));
+    // cross-attention block (rpr.py:62-66)
+    a = SkinnyArgs{L.w_cq, L.b_cq, p.E, p.E, p.xn, E_Q, l};
     RUN(launch_skinny<T>(p, a, s));
     RUN(launch_attn<T>(p, l, 1, s));
-    a = SkinnyArgs{L.w_co, L.b_co, p.E, p.E, A_PLAIN_T, p.ctx, nullptr, nullptr, nullptr, nullptr, E_RESID, l};
+    a = SkinnyArgs{L.w_co, L.b_co, p.E, p.E, p.ctx, E_RESID, l};
     RUN(launch_skinny<T>(p, a, s));
-    // feed-forward block
-    a = SkinnyArgs{L.w_f1, L.b_f1, p.FF, p.E, A_LN, p.r, L.ln2_g, L.ln2_b, nullptr, nullptr, E_RELU, l};
+    RUN(prep(PREP_LN, L.ln2_g, L.ln2_b, nullptr, nullptr));
+    // feed-forward block (rpr.py:67-69)
+    a = SkinnyArgs{L.w_f1, L.b_f1, p.FF, p.E, p.xn, E_RELU, l};
     RUN(launch_skinny<T>(p, a, s));
-    a = SkinnyArgs{L.w_f2, L.b_f2, p.E, p.FF, A_PLAIN_T, p.ff, nullptr, nullptr, nullptr, nullptr, E_RESID, l};
+    a = SkinnyArgs{L.w_f2, L.b_f2, p.E, p.FF, p.ff, E_RESID, l};
     RUN(launch_skinny<T>(p, a, s));
+    if (l + 1 < p.n_layers) RUN(prep(PREP_LN, L.ln3_g, L.ln3_b, nullptr, nullptr));
+    else RUN(prep(PREP_LN2, L.ln3_g, L.ln3_b, p.lnf_g, p.lnf_b));       // + decoder final norm (rpr.py:32-33)
   }
-  const DecLayer& LL = p.layer[p.n_layers - 1];
-  a = SkinnyArgs{p.w_out, p.b_out, p.vocab, p.E, A_LN2, p.r, LL.ln3_g, LL.ln3_b, p.lnf_g, p.lnf_b, E_LOGITS, 0};
+  a = SkinnyArgs{p.w_out, p.b_out, p.vocab, p.E, p.xn, E_LOGITS, 0};
   RUN(launch_skinny<T>(p, a, s));
-  argmax_advance_kernel<<<1, 256, 0, s>>>(p);
-  RUN(check_launch("decode argmax"));
+  RUN(launch_pdl(argmax_advance_kernel, dim3(1), dim3(256), 0, s, "decode argmax", p));
 #undef RUN
   return kOk;
 }
 
-long long decode_kernel_launches_per_step(const DecodeParams& p) { return 1 + 8LL * p.n_layers + 2; }
+long long decode_kernel_launches_per_step(const DecodeParams& p) { return 2 + 11LL * p.n_layers + 2; }
 
 template <typename T>
 static int set_attrs() {
@@ -530,22 +552,76 @@ static int set_attrs() {
   return kOk;
 }
 
+// The videos [b0, b0+nb) as an independent decode problem: every buffer pointer is advanced to the sub-batch.
+static DecodeParams sub_batch(const DecodeParams& p, int b0, int nb, int idx) {
+  DecodeParams s = p;
+  const size_t es = p.dtype == 0 ? 4 : 2;
+  const int dh = p.E / p.H;
+  auto adv = [](const void* q, size_t bytes) { return q ? static_cast<const void*>(static_cast<const char*>(q) + bytes) : q; };
+  auto advm = [](void* q, size_t bytes) { return q ? static_cast<void*>(static_cast<char*>(q) + bytes) : q; };
+  s.B = nb;
+  s.key = p.key + b0;
+  s.gen = p.gen + (size_t)b0 * p.cap;
+  s.gen_root = p.gen_root + (size_t)b0 * p.cap;
+  s.gen_attr = p.gen_attr + (size_t)b0 * p.cap;
+  s.step = p.step + idx;
+  s.h = p.h + (size_t)b0 * p.E;
+  s.r = advm(p.r, (size_t)b0 * p.E * es);
+  s.qbuf = p.qbuf + (size_t)b0 * 3 * p.E;
+  s.ctx = advm(p.ctx, (size_t)b0 * p.E * es);
+  s.ff = advm(p.ff, (size_t)b0 * p.FF * es);
+  s.xn = advm(p.xn, (size_t)b0 * p.E * es);
+  s.logits = p.logits + (size_t)b0 * p.vocab;
+  if (p.logits_all) s.logits_all = p.logits_all + (size_t)b0 * p.cap * p.vocab;
+  for (int l = 0; l < p.n_layers; ++l) {
+    s.layer[l].self_k = advm(p.layer[l].self_k, (size_t)b0 * p.H * p.cap * dh * es);
+    s.layer[l].self_v = advm(p.layer[l].self_v, (size_t)b0 * p.H * p.cap * dh * es);
+    s.layer[l].cross_k = adv(p.layer[l].cross_k, (size_t)b0 * p.H * p.S * dh * es);
+    s.layer[l].cross_v = adv(p.layer[l].cross_v, (size_t)b0 * p.H * p.S * dh * es);
+  }
+  return s;
+}
+
+constexpr int kMaxSplit = 8;
+
+// use_graph: 0 = plain launches; 1 = one CUDA graph per position (51 kernel nodes) replayed n_steps times;
+// k in [2, 8] = the same graph with the batch cut into k sub-batches whose 51-kernel chains are independent branches,
+// so that the latency-bound linear kernels of one sub-batch overlap the bandwidth-bound attention of another.
+// p.step must point to kMaxSplit ints holding the same position.
 template <typename T>
 static int decode_run_t(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream) {
   int rc = set_attrs<T>();
   if (rc) return rc;
+  int n_split = use_graph > 1 ? use_graph : 1;
+  if (n_split > kMaxSplit) n_split = kMaxSplit;
+  if (n_split > p.B) n_split = p.B;
+  const int per = (p.B + n_split - 1) / n_split;
+  n_split = (p.B + per - 1) / per;
+  DecodeParams subs[kMaxSplit];
+  for (int i = 0; i < n_split; ++i) subs[i] = sub_batch(p, i * per, (i + 1) * per <= p.B ? per : p.B - i * per, i);
   if (!use_graph) {
     for (int i = 0; i < n_steps; ++i) {
-      rc = enqueue_step<T>(p, stream);
+      rc = enqueue_step<T>(subs[0], stream);
       if (rc) return rc;
     }
     return kOk;
   }
-  // One step is captured once and replayed: every kernel reads the position from *p.step.
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaStream_t cs = stream;
   cudaStream_t own = nullptr;
+  cudaStream_t side[kMaxSplit] = {nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev[kMaxSplit] = {nullptr};
+  auto cleanup = [&]() {
+    for (int i = 1; i < n_split; ++i) {
+      if (side[i]) cudaStreamDestroy(side[i]);
+      if (join_ev[i]) cudaEventDestroy(join_ev[i]);
+    }
+    if (fork_ev) cudaEventDestroy(fork_ev);
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (own) { cudaStreamSynchronize(own); cudaStreamDestroy(own); }
+  };
   if (cs == nullptr || cs == cudaStreamLegacy) {   // the legacy default stream cannot be captured
     if (cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking) != cudaSuccess) {
       set_last_error("decode: cudaStreamCreate failed");
@@ -554,30 +630,40 @@ static int decode_run_t(const DecodeParams& p, int n_steps, int use_graph, cudaS
     cudaStreamSynchronize(stream);
     cs = own;
   }
-  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-  if (e != cudaSuccess) { set_last_error("decode: begin capture: %s", cudaGetErrorString(e)); return kCudaError; }
-  rc = enqueue_step<T>(p, cs);
+  cudaError_t e = cudaSuccess;
+  for (int i = 1; i < n_split && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join_ev[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess && n_split > 1) e = cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming);
+  if (e != cudaSuccess) { set_last_error("decode: stream/event setup: %s", cudaGetErrorString(e)); cleanup(); return kCudaError; }
+  e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) { set_last_error("decode: begin capture: %s", cudaGetErrorString(e)); cleanup(); return kCudaError; }
+  if (n_split > 1) {
+    cudaEventRecord(fork_ev, cs);
+    for (int i = 1; i < n_split; ++i) cudaStreamWaitEvent(side[i], fork_ev, 0);
+  }
+  rc = enqueue_step<T>(subs[0], cs);
+  for (int i = 1; i < n_split && !rc; ++i) {
+    rc = enqueue_step<T>(subs[i], side[i]);
+    cudaEventRecord(join_ev[i], side[i]);
+    cudaStreamWaitEvent(cs, join_ev[i], 0);
+  }
   e = cudaStreamEndCapture(cs, &graph);
   if (rc || e != cudaSuccess) {
     if (!rc) set_last_error("decode: end capture: %s", cudaGetErrorString(e));
-    if (graph) cudaGraphDestroy(graph);
-    if (own) cudaStreamDestroy(own);
+    cleanup();
     return rc ? rc : kCudaError;
   }
   e = cudaGraphInstantiate(&exec, graph, 0);
   if (e != cudaSuccess) {
     set_last_error("decode: graph instantiate: %s", cudaGetErrorString(e));
-    cudaGraphDestroy(graph);
-    if (own) cudaStreamDestroy(own);
+    cleanup();
     return kCudaError;
   }
   for (int i = 0; i < n_steps && e == cudaSuccess; ++i) e = cudaGraphLaunch(exec, cs);
-  if (own) {
-    cudaStreamSynchronize(own);
-    cudaStreamDestroy(own);
-  }
-  cudaGraphExecDestroy(exec);
-  cudaGraphDestroy(graph);
+  if (!own) cudaStreamSynchronize(cs);           // the graph and its side streams are destroyed below
+  cleanup();
   if (e != cudaSuccess) { set_last_error("decode: graph launch: %s", cudaGetErrorString(e)); return kCudaError; }
   return kOk;
 }
@@ -593,10 +679,10 @@ static int decode_probe_t(const DecodeParams& p, int kind, int reps, cudaStream_
       const DecLayer& L = p.layer[l];
       if (kind == 0 || kind == 1) rc = launch_attn<T>(p, l, kind, s);
       else if (kind == 2) {
-        SkinnyArgs a{L.w_qkv, L.b_qkv, 3 * p.E, p.E, A_PLAIN_F32, p.h, nullptr, nullptr, nullptr, nullptr, E_Q, l};
+        SkinnyArgs a{L.w_qkv, L.b_qkv, 3 * p.E, p.E, p.xn, E_Q, l};
         rc = launch_skinny<T>(p, a, s);
       } else {
-        SkinnyArgs a{L.w_f1, L.b_f1, p.FF, p.E, A_PLAIN_F32, p.h, nullptr, nullptr, nullptr, nullptr, E_RELU, l};
+        SkinnyArgs a{L.w_f1, L.b_f1, p.FF, p.E, p.xn, E_RELU, l};
         rc = launch_skinny<T>(p, a, s);
       }
       if (rc) return rc;
@@ -610,6 +696,7 @@ int decode_probe(const DecodeParams& p, int kind, int reps, cudaStream_t stream)
 }
 
 int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream) {
+  g_use_pdl = getenv("V2M_NO_PDL") == nullptr;
   V2M_REQUIRE(p.n_layers >= 1 && p.n_layers <= kMaxDecLayers, "decode: n_layers %d out of range", p.n_layers);
   V2M_REQUIRE(p.E % p.H == 0 && p.E / p.H == 64, "decode: head_dim must be 64 (E=%d H=%d)", p.E, p.H);
   V2M_REQUIRE(p.E == 512 && p.FF % 512 == 0 && p.FF <= 2048, "decode: d_model must be 512 and dim_feedforward a multiple of 512 (E=%d FF=%d)", p.E, p.FF);

@@ -117,11 +117,15 @@ struct DecodeParams {
   void* ff;                       // [B, FF] dtype T
   float* logits;                  // [B, vocab]
   float* logits_all;              // optional [B, cap, vocab] (tests): row t receives the step-t logits
+  void* xn;                       // [B, E]  normalised activations (GEMM operand), dtype T
 };
 // Runs `n_steps` decode steps starting at *step (device).  use_graph: capture one step into a CUDA graph and replay.
 int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream);
 long long decode_kernel_launches_per_step(const DecodeParams& p);
 int decode_probe(const DecodeParams& p, int kind, int reps, cudaStream_t stream);
+// One persistent cluster kernel for n_steps positions starting at t0 (bf16, d_model 512); kUnsupported otherwise.
+int decode_run_cluster(const DecodeParams& p, int t0, int n_steps, cudaStream_t stream);
+int decode_debug_set_timestamps(unsigned long long* buf, int cap);
 
 // ------------------------------------------------------------------ selective scan (pscan.cu)
 int pscan_fwd(const float* A, const float* X, float* H, int B, int L, int D, int N, cudaStream_t stream);

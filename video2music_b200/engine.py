@@ -187,6 +187,8 @@ class DecodeState:
         self.gen = None
         self.logits_all = None
         self.launches_per_step = 0
+        self.pos = 0            # host copy of the device position counter
+        self.step = None
 
 
 def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, primer_root, primer_attr,
@@ -272,12 +274,14 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     d.pe = hold(pe)
     d.key = hold(key.reshape(B).float().contiguous().to(dev))
     d.gen, d.gen_root, d.gen_attr = ptr(gen), ptr(gen_root), ptr(gen_attr)
-    step = torch.zeros((1,), dtype=torch.int32, device=dev)
+    step = torch.zeros((8,), dtype=torch.int32, device=dev)     # one position counter per sub-batch chain
     d.step = hold(step)
+    st.step = step
     d.h = hold(torch.empty((B, E), device=dev, dtype=torch.float32))
     d.r = hold(torch.empty((B, E), device=dev, dtype=dt))
     d.qbuf = hold(torch.empty((B, 3 * E), device=dev, dtype=torch.float32))
     d.ctx = hold(torch.empty((B, E), device=dev, dtype=dt))
+    d.xn = hold(torch.empty((B, E), device=dev, dtype=dt))
     d.ff = hold(torch.empty((B, FF), device=dev, dtype=dt))
     d.logits = hold(torch.empty((B, CHORD_SIZE), device=dev, dtype=torch.float32))
     if want_logits:
@@ -288,9 +292,27 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     return st
 
 
-def run_decode(st: DecodeState, n_steps: int, use_graph: bool = True) -> None:
-    check(load().v2m_decode_run(C.byref(st.params), n_steps, int(use_graph), stream()))
-    _lib.count_launches(n_steps * st.launches_per_step)
+def run_decode(st: DecodeState, n_steps: int, use_graph: bool = True, mode: str = "auto", n_split: int = 0) -> None:
+    """Advance the generation by n_steps positions.
+
+    mode "cluster": the whole loop as ONE persistent thread-block-cluster kernel (bf16, d_model 512, csrc/decode_cluster.cu);
+    mode "kernels": 51 kernels per position, replayed from a CUDA graph when use_graph (csrc/decode.cu, also the fp32 path);
+    mode "auto": kernels (the cluster kernel is experimental: correct, but slower so far -- see DESIGN.md).
+    n_split: independent sub-batch chains inside the graph (0 = pick from the batch size)."""
+    d = st.params
+    if mode == "auto":
+        mode = "kernels"
+    if n_split <= 0:
+        n_split = 4 if d.B >= 32 else (2 if d.B >= 8 else 1)
+    if mode == "cluster":
+        check(load().v2m_decode_run_cluster(C.byref(d), st.pos, n_steps, stream()))
+        _lib.count_launches(1)
+    else:
+        split = n_split if use_graph else 0
+        check(load().v2m_decode_run(C.byref(d), n_steps, split if use_graph else 0, stream()))
+        _lib.count_launches(n_steps * st.launches_per_step * max(1, split))
+    st.pos += n_steps
+    st.step.fill_(st.pos)
 
 
 def probe_decode_kernel(st: DecodeState, kind: int, reps: int) -> None:

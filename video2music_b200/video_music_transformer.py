@@ -172,7 +172,7 @@ class VideoMusicTransformer(nn.Module):
     @torch.no_grad()
     def generate(self, feature_semantic_list=[], feature_key=None, feature_scene_offset=None, feature_motion=None,
                  feature_emotion=None, primer=None, primer_root=None, primer_attr=None, target_seq_length=300, beam=0,
-                 beam_chance=1.0, max_conseq_N=0, max_conseq_chord=2, use_graph=True, return_logits=False):
+                 beam_chance=1.0, max_conseq_N=0, max_conseq_chord=2, use_graph=True, return_logits=False, decode_mode="auto"):
         assert (not self.training), "Cannot generate while in training mode"
         if not (beam >= 1 and beam_chance >= 1.0):
             raise NotImplementedError(
@@ -189,7 +189,7 @@ class VideoMusicTransformer(nn.Module):
                                  feature_motion.to(dev).float(), feature_emotion.to(dev).float(),
                                  primer.long(), primer_root.long(), primer_attr.long(), target_seq_length,
                                  want_logits=return_logits)
-        engine.run_decode(st, target_seq_length - 1, use_graph=use_graph)
+        engine.run_decode(st, target_seq_length - 1, use_graph=use_graph, mode=decode_mode)
         gen = st.gen[:, :target_seq_length]
         if return_logits:
             return gen, st.logits_all
