@@ -88,6 +88,38 @@ typedef struct v2m_attn {
 } v2m_attn;
 int v2m_attn_fwd(const v2m_attn* p, int32_t dtype, void* stream);
 
+/* fp32 GEMM with explicit element strides: A(m,k) = A[m*a_rs + k*a_cs], W(n,k) = W[n*w_rs + k*w_cs]; used by the
+ * backward pass (dX = dY W, dW = dY^T X) without materialising transposes.                                        */
+int v2m_gemm_f32_strided(const float* A, int32_t a_rs, int32_t a_cs, const float* W, int32_t w_rs, int32_t w_cs, float* C,
+                         int32_t ldc, int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream);
+
+/* ---- backward pass of the training step (run_model_vevo.py:84-124; the reference relies on torch autograd) ------
+ * v2m_attn_bwd: dQ, dK, dV, dEr of v2m_attn_fwd (needs its lse).  dk / dv / dEr are caller-zeroed fp32 accumulators
+ * (dk, dv addressed as [b*dkv_sb + j*dkv_sl + hkv*dh + d]); dq has the dtype of q.                                */
+typedef struct v2m_attn_bwd_t {
+  const void* q; const void* k; const void* v; const void* o; const void* dO; const float* lse; const void* Er;
+  void* dq; float* dk; float* dv; float* dEr;
+  int64_t q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl, do_sb, do_sl, dq_sb, dq_sl, dkv_sb, dkv_sl;
+  int32_t B, Hq, Hkv, Lq, Lk, dh, causal, er_len, dtype;
+  float q_scale;
+} v2m_attn_bwd_t;
+int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);
+/* dz = dy * relu'(y) * (n < alpha_cols ? alpha : 1), db[n] += sum_m dz[m][n]: gradient of the fused linear epilogue. */
+int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
+                float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
+                void* stream);
+int v2m_layernorm_bwd(const void* x, int32_t x_dtype, const float* gamma, const void* dy, int32_t dy_dtype, void* dx,
+                      int32_t dx_dtype, float* dgamma, float* dbeta, int32_t M, int32_t D, float eps, void* stream);
+int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld_d, float* dtable, int32_t rows, int32_t D,
+                  void* stream);
+/* 0.4*CrossEntropy(label_smoothing, ignore_index) + 0.6*BCEWithLogits (run_model_vevo.py:101-119, train.py:222,233):
+ * scratch3 = [sum CE over valid rows, sum BCE over elements, #valid rows]; dlogits = d(total loss)/d(logits).      */
+int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
+                 float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream);
+/* torch.optim.Adam step on flat fp32 buffers (train.py:238). grad_scale multiplies g first (1/world_size after all-reduce). */
+int v2m_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
+                  float grad_scale, void* stream);
+
 /* ---- residual + LayerNorm (rpr.py:59-69; nn.LayerNorm eps) ------------------------------------ */
 int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma,
                   const float* beta, void* y, int32_t y_dtype, void* y2, int32_t y2_dtype, int32_t M, int32_t D,

@@ -1,0 +1,56 @@
+"""GPU parity of the training step (forward + loss + backward) against the reference's own autograd
+(tests/golden/amt_train_step.pt: run_model_vevo.py:84-121 on the unmodified reference, fp32, dropout 0)."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, same_checksum
+from video2music_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(seed, dtype):
+    from video2music_b200 import VideoMusicTransformer
+    m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = syn.fill_like_reference_init(shapes, seed=seed)
+    m.load_state_dict(sd, strict=False)
+    return m.to(DEV).train().set_compute_dtype(dtype), sd
+
+
+def _step(m, inp):
+    from video2music_b200.autograd import AmtLossFn
+    args = [inp[k].to(DEV) for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                                      "feature_motion", "feature_emotion")]
+    y = m(*args)
+    loss = AmtLossFn.apply(y, inp["tgt"].to(DEV), inp["tgt_emotion"].to(DEV), 0.1, 0.4, 0.6)
+    loss.backward()
+    return y, loss
+
+
+def test_train_step_fp32_vs_reference_golden():
+    g = load_golden("amt_train_step.pt")
+    s = g["spec"]
+    m, sd = _model(s["weight_seed"], torch.float32)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    inp = syn.make_inputs(s["batch"], s["input_seed"], s["tgt_len"], s["src_len"], s["motion_type"])
+    y, loss = _step(m, inp)
+    assert rel_err(y, g["logits"]) < 1e-4
+    assert abs(float(loss) - g["loss"]) < 2e-5 * abs(g["loss"])
+    params = dict(m.named_parameters())
+    worst = 0.0
+    for name, gn in g["grad_norms"].items():
+        p = params[name]
+        assert p.grad is not None, name
+        got = float(p.grad.double().norm())
+        worst = max(worst, abs(got - gn) / max(gn, 1e-12))
+    print("worst relative gradient-norm error over %d parameters: %.2e" % (len(g["grad_norms"]), worst))
+    assert worst < 2e-3
+    for name, gref in g["grads"].items():
+        e = rel_err(params[name].grad, gref)
+        print("grad %-60s rel err %.2e" % (name, e))
+        assert e < 2e-3, name
+    # parameters that the forward never touches get no gradient in the reference either
+    for name, p in params.items():
+        assert (p.grad is not None) == (name in g["grad_norms"]), name

@@ -37,6 +37,14 @@ class Attn(C.Structure):
                 ("lse", vp), ("p_out", vp)]
 
 
+class AttnBwd(C.Structure):
+    _fields_ = ([(n, vp) for n in ("q", "k", "v", "o", "dO", "lse", "Er", "dq", "dk", "dv", "dEr")] +
+                [(n, i64) for n in ("q_sb", "q_sl", "k_sb", "k_sl", "v_sb", "v_sl", "o_sb", "o_sl", "do_sb", "do_sl",
+                                    "dq_sb", "dq_sl", "dkv_sb", "dkv_sl")] +
+                [(n, i32) for n in ("B", "Hq", "Hkv", "Lq", "Lk", "dh", "causal", "er_len", "dtype")] +
+                [("q_scale", C.c_float)])
+
+
 class DecLayer(C.Structure):
     _fields_ = [(n, vp) for n in (
         "w_qkv", "b_qkv", "w_so", "b_so", "w_cq", "b_cq", "w_co", "b_co", "w_f1", "b_f1", "w_f2", "b_f2",
@@ -55,7 +63,8 @@ class Decode(C.Structure):
 
 # every symbol include/v2m_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_bf16", "v2m_attn_fwd",
+    "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_dy_prep",
+    "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
     "v2m_decode_run_cluster", "v2m_debug_set_timestamps", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
 ]
@@ -82,6 +91,13 @@ def load() -> C.CDLL:
     lib.v2m_gemm_f32.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_gemm_bf16.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_attn_fwd.argtypes = [C.POINTER(Attn), i32, vp]
+    lib.v2m_gemm_f32_strided.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
+    lib.v2m_attn_bwd.argtypes = [C.POINTER(AttnBwd), vp]
+    lib.v2m_dy_prep.argtypes = [vp, i32, i64, vp, i32, i64, i32, C.c_float, i32, vp, i32, i64, vp, i32, i32, vp]
+    lib.v2m_layernorm_bwd.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, C.c_float, vp]
+    lib.v2m_embed_bwd.argtypes = [vp, vp, i32, i64, vp, i32, i32, vp]
+    lib.v2m_amt_loss.argtypes = [vp, vp, vp, i32, i32, i64, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    lib.v2m_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp]
     lib.v2m_layernorm.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, C.c_float, vp]
     lib.v2m_embed_sum.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.v2m_concat_features.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp]

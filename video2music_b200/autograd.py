@@ -1,0 +1,277 @@
+"""Training path: the AMT forward as a chain of torch.autograd.Functions whose forward AND backward are our
+kernels (torch.autograd only does the graph bookkeeping; the reference gets its gradients from autograd over ATen ops,
+utilities/run_model_vevo.py:84-121).
+
+Functions:  LinearFn (GEMM + fused bias / q-scale / ReLU / residual, backward = dy_prep + 2 GEMMs),
+AttnSelfFn / AttnCrossFn (fused attention forward with lse, backward = attn_bwd: dQ, dK, dV, dEr), LayerNormFn,
+EmbedKeyFn (embedding sums + key column), AmtLossFn (0.4 CE + 0.6 BCE with the gradient produced in the same pass).
+"""
+from typing import Optional
+
+import torch
+
+from . import engine, ops
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------------------------- GEMM helpers
+def _gemm_dx(dz: torch.Tensor, w: torch.Tensor, K: int) -> torch.Tensor:
+    """dX[M,K] = dz[M,N] @ W[N,K]   (W read as the transposed operand in place)."""
+    M, N = dz.shape
+    if dz.dtype == F32:
+        return ops.gemm_strided(dz, dz.stride(0), 1, w, 1, w.stride(0), M, K, N)
+    return ops.linear_general(dz, w, a_mn=False, b_mn=True, M=M, N=K, K=N, out_dtype=BF16)
+
+
+def _gemm_dw(dz: torch.Tensor, x: torch.Tensor, K: int) -> torch.Tensor:
+    """dW[N,K] = dz[M,N]^T @ x[M,K]   (both operands read transposed in place), fp32 result."""
+    M, N = dz.shape
+    if dz.dtype == F32:
+        return ops.gemm_strided(dz, 1, dz.stride(0), x, 1, x.stride(0), N, K, M)
+    return ops.linear_general(dz, x, a_mn=True, b_mn=True, M=N, N=K, K=M, out_dtype=F32)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = relu?((x @ w[:, :K].T + b) * alpha_n) + residual.   x (M, >=K) compute dtype; w, b fp32 masters."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype):
+        y = ops.linear(x, wc, b, k=K, relu=relu, alpha=alpha, alpha_cols=alpha_cols, residual=residual, res_mod=res_mod,
+                       out_dtype=out_dtype)
+        ctx.save_for_backward(x, wc, y if relu else None)
+        ctx.meta = (K, relu, alpha, alpha_cols, residual is not None and res_mod == 0, b is not None, tuple(w.shape), x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wc, y = ctx.saved_tensors
+        K, relu, alpha, alpha_cols, res_grad, has_b, wshape, cdt = ctx.meta
+        dy = dy.contiguous()
+        plain = (not relu) and alpha_cols == 0 and dy.dtype == cdt
+        dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain)
+        if plain:
+            dz = dy
+        dx = _gemm_dx(dz, wc, K) if ctx.needs_input_grad[0] else None
+        if dx is not None and dx.shape[1] != x.shape[1]:                     # x carries zero padding columns
+            full = torch.zeros_like(x)
+            full[:, :K] = dx
+            dx = full
+        dw = _gemm_dw(dz, x, K)
+        if dw.shape[1] != wshape[1]:
+            dw = dw[:, :wshape[1]].contiguous()
+        dres = dy if res_grad else None
+        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None
+
+
+class AttnSelfFn(torch.autograd.Function):
+    """ctx[M,E] = attention over the fused qkv [M, 3E] (q pre-scaled by the projection epilogue), optional Er, causal."""
+
+    @staticmethod
+    def forward(ctx, qkv, er, erc, B, L, H, causal):
+        E = qkv.shape[1] // 3
+        dh = E // H
+        out = torch.empty((B * L, E), device=qkv.device, dtype=qkv.dtype)
+        lse = torch.empty((B * H, L), device=qkv.device, dtype=F32)
+        ld = qkv.stride(0)
+        ops.attention(qkv, qkv[:, E:], qkv[:, 2 * E:], out, B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh,
+                      q_strides=(L * ld, ld), k_strides=(L * ld, ld), v_strides=(L * ld, ld), o_strides=(L * E, E),
+                      causal=causal, Er=erc, lse=lse)
+        ctx.save_for_backward(qkv, out, lse, erc)
+        ctx.meta = (B, L, H, causal, er is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, erc = ctx.saved_tensors
+        B, L, H, causal, has_er = ctx.meta
+        E = qkv.shape[1] // 3
+        dh = E // H
+        dout = dout.contiguous()
+        ld = qkv.stride(0)
+        dkv32 = torch.zeros((B * L, 2 * E), device=qkv.device, dtype=F32)
+        dqkv = torch.empty_like(qkv)
+        der = torch.zeros(erc.shape, device=qkv.device, dtype=F32) if has_er else None
+        ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dkv32, dkv32[:, E:], der,
+                          B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=(L * ld, ld), k_strides=(L * ld, ld),
+                          v_strides=(L * ld, ld), o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld),
+                          dkv_strides=(L * 2 * E, 2 * E), causal=causal)
+        dqkv[:, E:] = dkv32                                               # fp32 accumulators -> gradient dtype
+        return dqkv, der, None, None, None, None, None
+
+
+class AttnCrossFn(torch.autograd.Function):
+    """ctx[Mq,E] = attention of q [B*T, E] (pre-scaled) over kv [B*S, 2E] (non-causal, no Er)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, B, T, S, H):
+        E = q.shape[1]
+        dh = E // H
+        out = torch.empty((B * T, E), device=q.device, dtype=q.dtype)
+        lse = torch.empty((B * H, T), device=q.device, dtype=F32)
+        ops.attention(q, kv, kv[:, E:], out, B=B, Hq=H, Hkv=H, Lq=T, Lk=S, dh=dh, q_strides=(T * E, E),
+                      k_strides=(S * 2 * E, 2 * E), v_strides=(S * 2 * E, 2 * E), o_strides=(T * E, E), causal=False, lse=lse)
+        ctx.save_for_backward(q, kv, out, lse)
+        ctx.meta = (B, T, S, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv, out, lse = ctx.saved_tensors
+        B, T, S, H = ctx.meta
+        E = q.shape[1]
+        dh = E // H
+        dout = dout.contiguous()
+        dq = torch.empty_like(q)
+        dkv32 = torch.zeros((B * S, 2 * E), device=q.device, dtype=F32)
+        ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv32, dkv32[:, E:], None, B=B, Hq=H, Hkv=H, Lq=T, Lk=S,
+                          dh=dh, q_strides=(T * E, E), k_strides=(S * 2 * E, 2 * E), v_strides=(S * 2 * E, 2 * E),
+                          o_strides=(T * E, E), do_strides=(T * E, E), dq_strides=(T * E, E), dkv_strides=(S * 2 * E, 2 * E),
+                          causal=False)
+        return dq, dkv32.to(kv.dtype) if kv.dtype != F32 else dkv32, None, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y = ops.layernorm(x, gamma, beta, eps=eps)
+        ctx.save_for_backward(x, gamma)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(x, gamma, dy, ctx.eps)
+        return dx, dg, db, None
+
+
+class EmbedKeyFn(torch.autograd.Function):
+    """[emb_a[idx_a] (+ emb_b[idx_b]) | key | 0-pad] as a (rows, pad8(D+1)) matrix in the compute dtype
+    (video_music_transformer.py:984-999)."""
+
+    @staticmethod
+    def forward(ctx, idx_a, table_a, idx_b, table_b, key_rows, dtype):
+        rows, D = idx_a.numel(), table_a.shape[1]
+        ld = _pad8(D + 1)
+        out = torch.zeros((rows, ld), device=table_a.device, dtype=dtype)
+        e = ops.embed_sum(idx_a, table_a, idx_b, table_b, dtype)
+        out[:, :D] = e
+        out[:, D] = key_rows.to(dtype)
+        ctx.save_for_backward(idx_a, idx_b)
+        ctx.meta = (table_a.shape[0], table_b.shape[0] if table_b is not None else 0, D,
+                    table_a.requires_grad, table_b is not None and table_b.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        idx_a, idx_b = ctx.saved_tensors
+        na, nb, D, ga, gb = ctx.meta
+        dout = dout.contiguous()
+        da = ops.embed_bwd(idx_a, dout, na, D) if ga else None
+        db = ops.embed_bwd(idx_b, dout, nb, D) if gb else None
+        return None, da, None, db, None, None
+
+
+class AmtLossFn(torch.autograd.Function):
+    """total = 0.4 * CE(label_smoothing 0.1, ignore 158) + 0.6 * BCEWithLogits  (run_model_vevo.py:101-119)."""
+
+    @staticmethod
+    def forward(ctx, logits, tgt, tgt_emotion, smooth, w_ce, w_bce):
+        scratch, dl = ops.amt_loss(logits, tgt, tgt_emotion, 158, smooth, w_ce, w_bce)
+        R = logits.numel() // logits.shape[-1]
+        ce = scratch[0] / scratch[2].clamp_min(1.0)
+        bce = scratch[1] / float(R * logits.shape[-1])
+        ctx.save_for_backward(dl)
+        ctx.parts = (ce.detach(), bce.detach())
+        return w_ce * ce + w_bce * bce
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------- model forward
+def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, residual=None, res_mod=0, rows=None,
+         out_dtype=None):
+    w = W._sd[wname]
+    b = W._sd[bname] if bname is not None else None
+    if rows is not None:
+        w_v, b_v = w[rows], (b[rows] if b is not None else None)
+    else:
+        w_v, b_v = w, b
+    wc = W.w(wname, rows=rows)
+    K = K if K is not None else w.shape[1]
+    return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype)
+
+
+def _ln(W, name, x):
+    return LayerNormFn.apply(x, W._sd[name + ".weight"], W._sd[name + ".bias"], 1e-5)
+
+
+def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emotion, mask: bool = True) -> torch.Tensor:
+    """Differentiable VideoMusicTransformer.forward (video_music_transformer.py:978-1044), dropout-free."""
+    W = model._w()
+    W.refresh()
+    cfg = model._cfg()
+    dt = W.dtype
+    B, T = x.shape
+    S = sem.shape[1]
+    E, H, NL = cfg["d_model"], cfg["nhead"], cfg["n_layers"]
+    dh = E // H
+    scal = float(dh) ** -0.5
+    sd = W._sd
+    # ---- video stream
+    vf_dim = sd["Linear_vis.weight"].shape[1]
+    vin = ops.concat_features(sem, scene, motion, emotion, dt, vf_dim if dt == F32 else _pad8(vf_dim))
+    pe_v = sd["positional_encoding_video.pe"].view(-1, E)
+    xv = _lin(W, vin, "Linear_vis.weight", "Linear_vis.bias", K=vf_dim, residual=pe_v, res_mod=S)
+    for l in range(NL):
+        p = "transformer.encoder.layers.%d." % l
+        qkv = _lin(W, xv, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E)
+        a = AttnSelfFn.apply(qkv, None, None, B, S, H, False)
+        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv)
+        xv = _ln(W, p + "norm1", r)
+        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True)
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv)
+        xv = _ln(W, p + "norm2", r)
+    mem = _ln(W, "transformer.encoder.norm", xv)
+    # ---- chord stream
+    key_rows = key.reshape(B, 1).float().expand(B, T).reshape(-1)
+    if cfg["chord_embed"]:
+        xin = EmbedKeyFn.apply(x.reshape(-1), sd["chord_embedding_model.weight"], None, None, key_rows, dt)
+    else:
+        xin = EmbedKeyFn.apply(x_root.reshape(-1), sd["embedding_root.weight"], x_attr.reshape(-1), sd["embedding_attr.weight"],
+                               key_rows, dt)
+    pe_c = sd["positional_encoding.pe"].view(-1, E)
+    xf = _lin(W, xin, "Linear_chord.weight", "Linear_chord.bias", K=E + 1, residual=pe_c, res_mod=T)
+    for l in range(NL):
+        p = "transformer.decoder.layers.%d." % l
+        er = sd.get(p + "self_attn.Er")
+        erc = W.table(p + "self_attn.Er") if er is not None else None
+        qkv = _lin(W, xf, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E)
+        a = AttnSelfFn.apply(qkv, er, erc, B, T, H, bool(mask))
+        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xf)
+        xf = _ln(W, p + "norm1", r)
+        q = _lin(W, xf, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(0, E), alpha=scal,
+                 alpha_cols=E)
+        kv = _lin(W, mem, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(E, 3 * E))
+        a = AttnCrossFn.apply(q, kv, B, T, S, H)
+        r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf)
+        xf = _ln(W, p + "norm2", r)
+        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True)
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf)
+        xf = _ln(W, p + "norm3", r)
+    xf = _ln(W, "transformer.decoder.norm", xf)
+    y = _lin(W, xf, "Wout.weight", "Wout.bias", out_dtype=F32)
+    return y.view(B, T, -1)
+
+
+def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
+    raise NotImplementedError("module-level autograd for MultiheadAttentionRPR: train through VideoMusicTransformer "
+                              "(video2music_b200.autograd.amt_forward_autograd) or call under torch.no_grad()")

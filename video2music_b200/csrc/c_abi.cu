@@ -74,6 +74,13 @@ int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float
   return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_gemm_f32_strided(const float* A, int32_t a_rs, int32_t a_cs, const float* W, int32_t w_rs, int32_t w_cs, float* C,
+                         int32_t ldc, int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
+  GemmEpilogue g = to_ep(ep);
+  V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32_strided: bf16 residual not supported on the fp32 path");
+  return gemm_f32(A, a_rs, W, w_rs, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream), a_cs, w_cs);
+}
+
 int v2m_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
                   int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
   return gemm_bf16_tc(A, lda, W, ldw, C, ldc, out_dtype == V2M_BF16, M, N, K, to_ep(ep), static_cast<cudaStream_t>(stream));
@@ -92,6 +99,42 @@ int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {
   if (dtype == V2M_BF16) return attn_fwd_bf16_tc(p, static_cast<cudaStream_t>(stream));
   set_last_error("v2m_attn_fwd: dtype %d unsupported", dtype);
   return kUnsupported;
+}
+
+int v2m_attn_bwd(const v2m_attn_bwd_t* a, void* stream) {
+  V2M_REQUIRE(a != nullptr, "v2m_attn_bwd: null params");
+  static_assert(sizeof(v2m_attn_bwd_t) == sizeof(AttnBwdParams), "v2m_attn_bwd_t must mirror AttnBwdParams");
+  AttnBwdParams p;
+  memcpy(&p, a, sizeof(p));
+  return attn_bwd(p, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
+                float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
+                void* stream) {
+  return dy_prep(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz, db, M, N,
+                 static_cast<cudaStream_t>(stream));
+}
+
+int v2m_layernorm_bwd(const void* x, int32_t x_dtype, const float* gamma, const void* dy, int32_t dy_dtype, void* dx,
+                      int32_t dx_dtype, float* dgamma, float* dbeta, int32_t M, int32_t D, float eps, void* stream) {
+  return layernorm_bwd(x, x_dtype, gamma, dy, dy_dtype, dx, dx_dtype, dgamma, dbeta, M, D, eps, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld_d, float* dtable, int32_t rows, int32_t D,
+                  void* stream) {
+  return embed_bwd(reinterpret_cast<const long long*>(idx), d, d_dtype, ld_d, dtable, rows, D, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
+                 float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream) {
+  return amt_loss(logits, reinterpret_cast<const long long*>(tgt), tgt_emotion, R, Cn, ignore, smooth, w_ce, w_bce, scratch3,
+                  dlogits, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
+                  float grad_scale, void* stream) {
+  return adam_step(p, g, m, v, n, lr, b1, b2, eps, step, grad_scale, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma, const float* beta,

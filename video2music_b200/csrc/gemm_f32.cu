@@ -15,7 +15,7 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda,
                                                        const float* __restrict__ W, int ldw,
                                                        float* __restrict__ C, int ldc, int M, int N, int K,
-                                                       GemmEpilogue ep) {
+                                                       GemmEpilogue ep, int a_cs, int w_cs) {
   __shared__ __align__(16) float As[BK][BM + PAD];
   __shared__ __align__(16) float Bs[BK][BN + PAD];
   const int tid = threadIdx.x;
@@ -40,18 +40,18 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
         if (gn < N && gk < K) vb = __ldg(reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk));
       } else {
         if (gm < M) {
-          const float* p = A + (size_t)gm * lda + gk;
-          if (gk + 0 < K) va.x = __ldg(p + 0);
-          if (gk + 1 < K) va.y = __ldg(p + 1);
-          if (gk + 2 < K) va.z = __ldg(p + 2);
-          if (gk + 3 < K) va.w = __ldg(p + 3);
+          const float* p = A + (size_t)gm * lda + (size_t)gk * a_cs;      // element (m, k) at m*lda + k*a_cs
+          if (gk + 0 < K) va.x = __ldg(p);
+          if (gk + 1 < K) va.y = __ldg(p + (size_t)a_cs);
+          if (gk + 2 < K) va.z = __ldg(p + 2 * (size_t)a_cs);
+          if (gk + 3 < K) va.w = __ldg(p + 3 * (size_t)a_cs);
         }
         if (gn < N) {
-          const float* p = W + (size_t)gn * ldw + gk;
-          if (gk + 0 < K) vb.x = __ldg(p + 0);
-          if (gk + 1 < K) vb.y = __ldg(p + 1);
-          if (gk + 2 < K) vb.z = __ldg(p + 2);
-          if (gk + 3 < K) vb.w = __ldg(p + 3);
+          const float* p = W + (size_t)gn * ldw + (size_t)gk * w_cs;
+          if (gk + 0 < K) vb.x = __ldg(p);
+          if (gk + 1 < K) vb.y = __ldg(p + (size_t)w_cs);
+          if (gk + 2 < K) vb.z = __ldg(p + 2 * (size_t)w_cs);
+          if (gk + 3 < K) vb.w = __ldg(p + 3 * (size_t)w_cs);
         }
       }
       As[lk + 0][r] = va.x; As[lk + 1][r] = va.y; As[lk + 2][r] = va.z; As[lk + 3][r] = va.w;
@@ -96,16 +96,16 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 }
 
 int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
-             const GemmEpilogue& ep, cudaStream_t stream) {
+             const GemmEpilogue& ep, cudaStream_t stream, int a_cs, int w_cs) {
   V2M_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_f32: bad dims M=%d N=%d K=%d", M, N, K);
   if (M == 0) return kOk;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  const bool aligned = (lda % 4 == 0) && (ldw % 4 == 0) && (K % 4 == 0) &&
+  const bool aligned = (a_cs == 1) && (w_cs == 1) && (lda % 4 == 0) && (ldw % 4 == 0) && (K % 4 == 0) &&
                        (reinterpret_cast<uintptr_t>(A) % 16 == 0) && (reinterpret_cast<uintptr_t>(W) % 16 == 0);
   if (aligned)
-    gemm_f32_kernel<true><<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
+    gemm_f32_kernel<true><<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, ep, 1, 1);
   else
-    gemm_f32_kernel<false><<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, ep);
+    gemm_f32_kernel<false><<<grid, 256, 0, stream>>>(A, lda, W, ldw, C, ldc, M, N, K, ep, a_cs, w_cs);
   return check_launch("gemm_f32");
 }
 

@@ -38,8 +38,9 @@ __device__ __forceinline__ long long epi_out_index(const GemmEpilogue& ep, int m
 }
 #endif
 
+// a_cs / w_cs: element stride along K (1 = row-major operands; lda = 1 with a_cs = ld reads a transposed operand).
 int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
-             const GemmEpilogue& ep, cudaStream_t stream);
+             const GemmEpilogue& ep, cudaStream_t stream, int a_cs = 1, int w_cs = 1);
 
 // bf16 tensor-core GEMM (tcgen05/TMEM/TMA).  A [M,K] bf16 row-major (lda), W [N,K] bf16 row-major (ldw).
 // out_bf16: C is bf16, else fp32.
@@ -61,6 +62,26 @@ struct AttnParams {
 };
 int attn_fwd_f32(const AttnParams& p, cudaStream_t stream);
 int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream);
+
+struct AttnBwdParams {
+  const void* q; const void* k; const void* v; const void* o; const void* dO; const float* lse; const void* Er;
+  void* dq; float* dk; float* dv; float* dEr;
+  long long q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl, do_sb, do_sl, dq_sb, dq_sl, dkv_sb, dkv_sl;
+  int B, Hq, Hkv, Lq, Lk, dh, causal, er_len, dtype;
+  float q_scale;
+};
+int attn_bwd(const AttnBwdParams& p, cudaStream_t stream);
+
+int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
+            int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, cudaStream_t stream);
+int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy, int dy_dtype, void* dx, int dx_dtype,
+                  float* dgamma, float* dbeta, int M, int D, float eps, cudaStream_t stream);
+int embed_bwd(const long long* idx, const void* d, int d_dtype, long long ld_d, float* dtable, int rows, int D,
+              cudaStream_t stream);
+int amt_loss(const float* logits, const long long* tgt, const float* tgt_emotion, int R, int Cn, long long ignore, float smooth,
+             float w_ce, float w_bce, float* scratch3, float* dlogits, cudaStream_t stream);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+              float grad_scale, cudaStream_t stream);
 
 // y = LayerNorm(x (+ res)) * gamma + beta over the last dim D (eps 1e-5 like nn.LayerNorm).
 // dtype codes: 0 = fp32, 1 = bf16.  y2 (optional) receives a second copy in dtype y2_dtype.

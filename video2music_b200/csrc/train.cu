@@ -1,0 +1,243 @@
+// Backward-pass and optimiser kernels of the AMT training step (run_model_vevo.py:84-124 of the reference:
+// forward, 0.4*CE(label_smoothing 0.1, ignore PAD) + 0.6*BCEWithLogits, backward, Adam).
+// The heavy contractions reuse the GEMM kernels (dX = dY W, dW = dY^T X) and attn_bwd.cu; this file
+// holds the bandwidth-bound pieces.  dtype codes: 0 = fp32, 1 = bf16.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace v2m {
+
+__device__ __forceinline__ float ld_any(const void* p, int dtype, size_t i) {
+  return dtype == 0 ? static_cast<const float*>(p)[i] : __bfloat162float(static_cast<const bf16*>(p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
+  if (dtype == 0) static_cast<float*>(p)[i] = v;
+  else static_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// ---- gradient of the fused linear epilogue --------------------------------------------------------------------
+// dz = dy * (relu ? y > 0 : 1) * (n < alpha_cols ? alpha : 1);  db[n] = sum_m dz[m][n]
+// (the epilogue computed y = relu((x W^T + b) * alpha_n); residual terms pass dy through unchanged.)
+// Block = 32 columns x 8 row-lanes; rows strided over the grid; db via shared partial sums + one atomic per column.
+__global__ void __launch_bounds__(256) dy_prep_kernel(const void* __restrict__ dy, int dy_dtype, long long ld_dy,
+                                                      const void* __restrict__ y, int y_dtype, long long ld_y, int relu,
+                                                      float alpha, int alpha_cols, void* __restrict__ dz, int dz_dtype,
+                                                      long long ld_dz, float* __restrict__ db, int M, int N) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (n < N) {
+    const float sc = n < alpha_cols ? alpha : 1.f;
+    for (int m = blockIdx.y * 8 + ty; m < M; m += gridDim.y * 8) {
+      float g = ld_any(dy, dy_dtype, (size_t)m * ld_dy + n);
+      if (relu && !(ld_any(y, y_dtype, (size_t)m * ld_y + n) > 0.f)) g = 0.f;
+      g *= sc;
+      if (dz) st_any(dz, dz_dtype, (size_t)m * ld_dz + n, g);
+      acc += g;
+    }
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N && db) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][tx];
+    atomicAdd(db + n, s);
+  }
+}
+
+int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
+            int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, cudaStream_t stream) {
+  if (M == 0 || N == 0) return kOk;
+  int gy = (M + 7) / 8;
+  if (gy > 148 * 2) gy = 148 * 2;
+  dim3 grid((N + 31) / 32, gy);
+  dy_prep_kernel<<<grid, 256, 0, stream>>>(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz,
+                                          db, M, N);
+  return check_launch("dy_prep");
+}
+
+// ---- LayerNorm backward ---------------------------------------------------------------------------------------
+// y = LN(x) * g + b with x the pre-norm sum.  dx = rstd * (dxh - mean(dxh) - xh * mean(dxh * xh)), dxh = dy * g;
+// dg[d] += dy * xh, db[d] += dy.  One warp per row; a CTA accumulates its 8 rows' dg/db in shared memory first.
+constexpr int LNB_MAX = 32;
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ gamma,
+                                                            const void* __restrict__ dy, int dy_dtype, void* __restrict__ dx,
+                                                            int dx_dtype, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int M, int D, float eps) {
+  extern __shared__ float sacc[];                 // [2][D]
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int row = blockIdx.x * 8 + warp; row < M; row += gridDim.x * 8) {
+    const size_t base = (size_t)row * D;
+    float xv[LNB_MAX], gv[LNB_MAX];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNB_MAX; ++c) {
+      const int d = lane + 32 * c;
+      xv[c] = d < D ? ld_any(x, x_dtype, base + d) : 0.f;
+      sum += xv[c];
+    }
+    const float mean = warp_sum(sum) / (float)D;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNB_MAX; ++c) {
+      const int d = lane + 32 * c;
+      if (d < D) { const float t = xv[c] - mean; sq = fmaf(t, t, sq); }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNB_MAX; ++c) {
+      const int d = lane + 32 * c;
+      if (d < D) {
+        const float xh = (xv[c] - mean) * rstd;
+        const float g = ld_any(dy, dy_dtype, base + d);
+        atomicAdd(&sacc[d], g * xh);
+        atomicAdd(&sacc[D + d], g);
+        const float dxh = g * gamma[d];
+        xv[c] = xh;
+        gv[c] = dxh;
+        s1 += dxh;
+        s2 = fmaf(dxh, xh, s2);
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int c = 0; c < LNB_MAX; ++c) {
+      const int d = lane + 32 * c;
+      if (d < D) st_any(dx, dx_dtype, base + d, rstd * (gv[c] - s1 - xv[c] * s2));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(dgamma + i, sacc[i]);
+    atomicAdd(dbeta + i, sacc[D + i]);
+  }
+}
+
+int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy, int dy_dtype, void* dx, int dx_dtype,
+                  float* dgamma, float* dbeta, int M, int D, float eps, cudaStream_t stream) {
+  V2M_REQUIRE(D > 0 && D <= 32 * LNB_MAX, "layernorm_bwd: D=%d unsupported", D);
+  if (M == 0) return kOk;
+  int grid = (M + 7) / 8;
+  if (grid > 148 * 4) grid = 148 * 4;
+  layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), stream>>>(x, x_dtype, gamma, dy, dy_dtype, dx, dx_dtype, dgamma,
+                                                                     dbeta, M, D, eps);
+  return check_launch("layernorm_bwd");
+}
+
+// ---- embedding backward: dtable[idx[row]] += d[row] ----------------------------------------------------------
+__global__ void embed_bwd_kernel(const long long* __restrict__ idx, const void* __restrict__ d, int d_dtype, long long ld_d,
+                                 float* __restrict__ dtable, int rows, int D) {
+  const int row = blockIdx.x;
+  const long long i = idx[row];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) atomicAdd(dtable + i * D + c, ld_any(d, d_dtype, (size_t)row * ld_d + c));
+}
+
+int embed_bwd(const long long* idx, const void* d, int d_dtype, long long ld_d, float* dtable, int rows, int D,
+              cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  embed_bwd_kernel<<<rows, 128, 0, stream>>>(idx, d, d_dtype, ld_d, dtable, rows, D);
+  return check_launch("embed_bwd");
+}
+
+// ---- loss: 0.4 * CrossEntropy(label_smoothing eps, ignore_index) + 0.6 * BCEWithLogits, and d(loss)/d(logits) ----
+// run_model_vevo.py:101-119 with train.py:222,233.  logits [R, C] fp32 (R = B*T), tgt [R] int64, tgt_emotion [R, C] fp32.
+// One warp per row.  out[0] += CE row sum (valid rows), out[1] += BCE element sum; n_valid is a device scalar
+// (count of tgt != ignore) produced by count_valid_kernel.  dlogits gets the already weighted and normalised gradient.
+__global__ void count_valid_kernel(const long long* __restrict__ tgt, int R, long long ignore, float* __restrict__ n_valid) {
+  int c = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) c += (tgt[i] != ignore);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_valid, (float)c);
+}
+
+__global__ void __launch_bounds__(256) amt_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt,
+                                                       const float* __restrict__ tgt_emotion, int R, int Cn, long long ignore,
+                                                       float smooth, float w_ce, float w_bce, const float* __restrict__ n_valid,
+                                                       float* __restrict__ out, float* __restrict__ dlogits) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= R) return;
+  const float* x = logits + (size_t)row * Cn;
+  const float* e = tgt_emotion + (size_t)row * Cn;
+  const long long t = tgt[row];
+  const bool valid = t != ignore;
+  float mx = -INFINITY;
+  for (int c = lane; c < Cn; c += 32) mx = fmaxf(mx, x[c]);
+  mx = warp_max(mx);
+  float se = 0.f, sx = 0.f, bce = 0.f;
+  for (int c = lane; c < Cn; c += 32) {
+    const float v = x[c];
+    se += expf(v - mx);
+    sx += v;
+    bce += fmaxf(v, 0.f) - v * e[c] + log1pf(expf(-fabsf(v)));        // BCEWithLogits, numerically stable form
+  }
+  se = warp_sum(se);
+  sx = warp_sum(sx);
+  bce = warp_sum(bce);
+  const float lse = mx + logf(se);
+  const float nv = fmaxf(*n_valid, 1.f);
+  const float inv_bce = 1.f / ((float)R * (float)Cn);
+  if (lane == 0) {
+    if (valid) {
+      const float nll = lse - x[t];
+      const float smooth_term = lse - sx / (float)Cn;                  // mean_c(-log p_c)
+      atomicAdd(out + 0, (1.f - smooth) * nll + smooth * smooth_term);
+    }
+    atomicAdd(out + 1, bce);
+  }
+  if (dlogits) {
+    for (int c = lane; c < Cn; c += 32) {
+      const float v = x[c];
+      float g = w_bce * inv_bce * (1.f / (1.f + expf(-v)) - e[c]);
+      if (valid) {
+        const float p = expf(v - lse);
+        const float q = (1.f - smooth) * (c == t ? 1.f : 0.f) + smooth / (float)Cn;
+        g += w_ce * (p - q) / nv;
+      }
+      dlogits[(size_t)row * Cn + c] = g;
+    }
+  }
+}
+
+int amt_loss(const float* logits, const long long* tgt, const float* tgt_emotion, int R, int Cn, long long ignore, float smooth,
+             float w_ce, float w_bce, float* scratch3, float* dlogits, cudaStream_t stream) {
+  // scratch3: [ce_sum, bce_sum, n_valid] (device, zeroed here)
+  if (R == 0) return kOk;
+  cudaError_t e = cudaMemsetAsync(scratch3, 0, 3 * sizeof(float), stream);
+  if (e != cudaSuccess) { set_last_error("amt_loss: memset: %s", cudaGetErrorString(e)); return kCudaError; }
+  count_valid_kernel<<<(R + 255) / 256 < 296 ? (R + 255) / 256 : 296, 256, 0, stream>>>(tgt, R, ignore, scratch3 + 2);
+  amt_loss_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, tgt, tgt_emotion, R, Cn, ignore, smooth, w_ce, w_bce, scratch3 + 2,
+                                                   scratch3, dlogits);
+  return check_launch("amt_loss");
+}
+
+// ---- Adam (train.py:238: betas (0.9, 0.98), eps 1e-9 per constants.py:89-91; torch.optim.Adam semantics) --------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  }
+}
+
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+              float grad_scale, cudaStream_t stream) {
+  if (n == 0) return kOk;
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  const long long want = (n + 255) / 256;
+  adam_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  return check_launch("adam_step");
+}
+
+}  // namespace v2m

@@ -196,3 +196,97 @@ def moe_route(x: torch.Tensor, wg: torch.Tensor, bg: torch.Tensor, k: int, *, se
                                tokens, d, E, k, ptr(idx), ptr(w), ptr(logits), ptr(hist), stream()))
     _lib.count_launches(1)
     return idx, w, hist, logits
+
+
+# ----------------------------------------------------------------------------- backward-pass kernels
+def gemm_strided(a: torch.Tensor, a_rs: int, a_cs: int, w: torch.Tensor, w_rs: int, w_cs: int, M: int, N: int, K: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 C[M,N] = sum_k A(m,k) W(n,k) with A(m,k) = a[m*a_rs + k*a_cs], W(n,k) = w[n*w_rs + k*w_cs]."""
+    require_device(a)
+    assert a.dtype == w.dtype == torch.float32
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    ep = Epilogue()
+    check(load().v2m_gemm_f32_strided(ptr(a), a_rs, a_cs, ptr(w), w_rs, w_cs, ptr(out), out.stride(0), M, N, K, C.byref(ep),
+                                      stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: float, alpha_cols: int, out_dtype: torch.dtype,
+            want_dz: bool = True):
+    """dz = dy * relu'(y) * alpha_n ; db = column sums of dz.  Returns (dz or None, db fp32 [N])."""
+    require_device(dy)
+    assert dy.dim() == 2 and dy.stride(1) == 1
+    M, N = dy.shape
+    dz = torch.empty((M, N), device=dy.device, dtype=out_dtype) if want_dz else None
+    db = torch.zeros((N,), device=dy.device, dtype=torch.float32)
+    check(load().v2m_dy_prep(ptr(dy), dtype_code(dy.dtype), dy.stride(0), ptr(y), dtype_code(y.dtype) if y is not None else 0,
+                             y.stride(0) if y is not None else 0, int(relu), alpha, alpha_cols, ptr(dz),
+                             dtype_code(out_dtype), N, ptr(db), M, N, stream()))
+    _lib.count_launches(1)
+    return dz, db
+
+
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5):
+    require_device(x)
+    x, dy = x.contiguous(), dy.contiguous()
+    D = x.shape[-1]
+    M = x.numel() // D
+    dx = torch.empty_like(x)
+    dg = torch.zeros((D,), device=x.device, dtype=torch.float32)
+    db = torch.zeros((D,), device=x.device, dtype=torch.float32)
+    check(load().v2m_layernorm_bwd(ptr(x), dtype_code(x.dtype), ptr(gamma), ptr(dy), dtype_code(dy.dtype), ptr(dx),
+                                   dtype_code(dx.dtype), ptr(dg), ptr(db), M, D, eps, stream()))
+    _lib.count_launches(1)
+    return dx, dg, db
+
+
+def embed_bwd(idx: torch.Tensor, d: torch.Tensor, n_rows_table: int, D: int) -> torch.Tensor:
+    require_device(d)
+    idx = idx.contiguous().view(-1)
+    dt = torch.zeros((n_rows_table, D), device=d.device, dtype=torch.float32)
+    check(load().v2m_embed_bwd(ptr(idx), ptr(d), dtype_code(d.dtype), d.stride(0), ptr(dt), idx.numel(), D, stream()))
+    _lib.count_launches(1)
+    return dt
+
+
+def amt_loss(logits: torch.Tensor, tgt: torch.Tensor, tgt_emotion: torch.Tensor, ignore: int = 158, smooth: float = 0.1,
+             w_ce: float = 0.4, w_bce: float = 0.6, want_grad: bool = True):
+    """Returns (scratch [ce_sum, bce_sum, n_valid] on device, dlogits or None)."""
+    require_device(logits)
+    logits = logits.contiguous()
+    Cn = logits.shape[-1]
+    R = logits.numel() // Cn
+    tgt = tgt.contiguous().view(-1)
+    tgt_emotion = tgt_emotion.contiguous().float()
+    scratch = torch.empty((3,), device=logits.device, dtype=torch.float32)
+    dl = torch.empty_like(logits) if want_grad else None
+    check(load().v2m_amt_loss(ptr(logits), ptr(tgt), ptr(tgt_emotion), R, Cn, ignore, smooth, w_ce, w_bce, ptr(scratch), ptr(dl),
+                              stream()))
+    _lib.count_launches(2)
+    return scratch, dl
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, b1: float, b2: float, eps: float,
+              step: int, grad_scale: float = 1.0) -> None:
+    require_device(p)
+    assert p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32
+    check(load().v2m_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, b1, b2, eps, step, grad_scale, stream()))
+    _lib.count_launches(1)
+
+
+def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_strides,
+                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0):
+    require_device(q)
+    a = _lib.AttnBwd()
+    a.q, a.k, a.v, a.o, a.dO, a.lse, a.Er = ptr(q), ptr(k), ptr(v), ptr(o), ptr(dO), ptr(lse), ptr(Er)
+    a.dq, a.dk, a.dv, a.dEr = ptr(dq), ptr(dk), ptr(dv), ptr(dEr)
+    (a.q_sb, a.q_sl), (a.k_sb, a.k_sl), (a.v_sb, a.v_sl) = q_strides, k_strides, v_strides
+    (a.o_sb, a.o_sl), (a.do_sb, a.do_sl), (a.dq_sb, a.dq_sl), (a.dkv_sb, a.dkv_sl) = o_strides, do_strides, dq_strides, dkv_strides
+    a.B, a.Hq, a.Hkv, a.Lq, a.Lk, a.dh, a.causal = B, Hq, Hkv, Lq, Lk, dh, int(causal)
+    a.er_len = Er.shape[0] if Er is not None else 0
+    a.dtype = dtype_code(q.dtype)
+    a.q_scale = q_scale
+    check(load().v2m_attn_bwd(C.byref(a), stream()))
+    _lib.count_launches(1)
