@@ -34,7 +34,7 @@ extern "C" {
 
 int v2m_abi_version(void);
 const char* v2m_last_error(void);
-/* sizeof() of the ABI structs as compiled: 0 v2m_epilogue, 1 v2m_attn, 2 v2m_dec_layer, 3 v2m_decode (binding self-check). */
+/* sizeof() of the ABI structs as compiled: 0 v2m_epilogue, 1 v2m_attn, 2 v2m_dec_layer, 3 v2m_decode, 4 v2m_attn_bwd_t (binding self-check). */
 int64_t v2m_struct_size(int32_t which);
 /* 1 if the current CUDA device is compute capability 10.x (the only target), else 0. */
 int v2m_device_ok(void);
@@ -69,6 +69,11 @@ int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float
 /* bf16 tcgen05/TMEM/TMA GEMM; C is bf16 (out_dtype 1) or fp32 (0); lda, ldw multiples of 8. */
 int v2m_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
                   int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream);
+
+/* General tcgen05 GEMM: a_mn / b_mn != 0 mean the operand is stored transposed ([K, M] resp. [K, N] row-major) and is fed
+ * to the tensor core as an MN-major operand -- backward pass: dX = dY W (b_mn), dW = dY^T X (a_mn, b_mn).           */
+int v2m_gemm_bf16_general(const void* A, int32_t lda, int32_t a_mn, const void* W, int32_t ldw, int32_t b_mn, void* C, int32_t ldc,
+                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream);
 
 /* ---- attention ---------------------------------------------------------------------------------
  * out = softmax(q k^T + skew(q Er^T) + causal mask) v for every (batch, head); replaces

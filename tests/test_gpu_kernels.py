@@ -71,6 +71,22 @@ def test_gemm_bf16_exact_small_integers():
     assert torch.equal(y.cpu(), a @ w.T)
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 192), (300, 512, 130), (159, 512, 128), (1536, 512, 600)])
+def test_gemm_bf16_transposed_operands_exact(M, N, K, a_mn, b_mn):
+    """MN-major (transposed-storage) operands of the tcgen05 GEMM, as used by dX = dY W and dW = dY^T X:
+    small-integer inputs make the result exact."""
+    from video2music_b200 import ops
+    g = syn._gen(15, "ints2")
+    a = torch.randint(-3, 4, (M, K), generator=g).float()
+    b = torch.randint(-3, 4, (N, K), generator=g).float()
+    pad = lambda t: torch.nn.functional.pad(t, (0, (-t.shape[1]) % 8)).to(DEV).to(torch.bfloat16)[:, :t.shape[1]]
+    ad = pad(a.t().contiguous()) if a_mn else pad(a)
+    bd = pad(b.t().contiguous()) if b_mn else pad(b)
+    y = ops.linear_general(ad, bd, a_mn=a_mn, b_mn=b_mn, M=M, N=N, K=K, out_dtype=torch.float32)
+    assert torch.equal(y.cpu(), a @ b.T)
+
+
 def test_gemm_head_scatter():
     from video2music_b200 import ops
     B, S, H, dh, E = 3, 50, 4, 64, 256

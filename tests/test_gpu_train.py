@@ -54,3 +54,25 @@ def test_train_step_fp32_vs_reference_golden():
     # parameters that the forward never touches get no gradient in the reference either
     for name, p in params.items():
         assert (p.grad is not None) == (name in g["grad_norms"]), name
+
+
+def test_train_step_bf16_close_to_reference():
+    """bf16 tensor-core training step (tcgen05 GEMMs forward and backward, bf16 activations, fp32 master weights and
+    gradients): loss within 2e-2 and gradients close to the reference's fp32 autograd."""
+    g = load_golden("amt_train_step.pt")
+    s = g["spec"]
+    m, _ = _model(s["weight_seed"], torch.bfloat16)
+    inp = syn.make_inputs(s["batch"], s["input_seed"], s["tgt_len"], s["src_len"], s["motion_type"])
+    y, loss = _step(m, inp)
+    assert rel_err(y, g["logits"]) < 2e-2
+    assert abs(float(loss.detach()) - g["loss"]) < 2e-2 * abs(g["loss"])
+    params = dict(m.named_parameters())
+    errs = {n: abs(float(params[n].grad.double().norm()) - gn) / max(gn, 1e-12) for n, gn in g["grad_norms"].items()}
+    worst = max(errs, key=errs.get)
+    print("bf16 worst gradient-norm error: %.3f (%s); median %.4f" % (errs[worst], worst, sorted(errs.values())[len(errs) // 2]))
+    assert sorted(errs.values())[len(errs) // 2] < 3e-2
+    assert errs[worst] < 0.25
+    for name, gref in g["grads"].items():
+        e = rel_err(params[name].grad, gref)
+        print("bf16 grad %-55s rel err %.3e" % (name, e))
+        assert e < 0.15, name

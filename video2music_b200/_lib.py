@@ -63,7 +63,7 @@ class Decode(C.Structure):
 
 # every symbol include/v2m_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_dy_prep",
+    "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_dy_prep",
     "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
     "v2m_decode_run_cluster", "v2m_debug_set_timestamps", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
     lib.v2m_gemm_f32.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_gemm_bf16.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_attn_fwd.argtypes = [C.POINTER(Attn), i32, vp]
+    lib.v2m_gemm_bf16_general.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_gemm_f32_strided.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_attn_bwd.argtypes = [C.POINTER(AttnBwd), vp]
     lib.v2m_dy_prep.argtypes = [vp, i32, i64, vp, i32, i64, i32, C.c_float, i32, vp, i32, i64, vp, i32, i32, vp]
@@ -111,7 +112,7 @@ def load() -> C.CDLL:
     lib.v2m_pscan_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.v2m_pscan_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.v2m_moe_route.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, i32, i32, i32, i32, vp, vp, vp, vp, vp]
-    for which, cls in enumerate((Epilogue, Attn, DecLayer, Decode)):
+    for which, cls in enumerate((Epilogue, Attn, DecLayer, Decode, AttnBwd)):
         if lib.v2m_struct_size(which) != C.sizeof(cls):
             raise ImportError("ctypes layout of %s (%d B) differs from the C ABI (%d B)"
                               % (cls.__name__, C.sizeof(cls), lib.v2m_struct_size(which)))

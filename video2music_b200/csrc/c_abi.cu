@@ -56,6 +56,7 @@ int64_t v2m_struct_size(int32_t which) {
     case 1: return sizeof(v2m_attn);
     case 2: return sizeof(v2m_dec_layer);
     case 3: return sizeof(v2m_decode);
+    case 4: return sizeof(v2m_attn_bwd_t);
     default: return -1;
   }
 }
@@ -84,6 +85,12 @@ int v2m_gemm_f32_strided(const float* A, int32_t a_rs, int32_t a_cs, const float
 int v2m_gemm_bf16(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
                   int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
   return gemm_bf16_tc(A, lda, W, ldw, C, ldc, out_dtype == V2M_BF16, M, N, K, to_ep(ep), static_cast<cudaStream_t>(stream));
+}
+
+int v2m_gemm_bf16_general(const void* A, int32_t lda, int32_t a_mn, const void* W, int32_t ldw, int32_t b_mn, void* C, int32_t ldc,
+                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
+  return gemm_bf16_tc_general(A, lda, a_mn, W, ldw, b_mn, C, ldc, out_dtype == V2M_BF16, M, N, K, to_ep(ep),
+                              static_cast<cudaStream_t>(stream));
 }
 
 int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {

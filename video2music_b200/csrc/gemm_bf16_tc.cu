@@ -90,7 +90,10 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long lo
   return kOk;
 }
 
-template <int BN>
+// A_MN / B_MN: the operand is stored transposed ([K, M] resp. [K, N] row-major, "MN-major" for the tensor core):
+// TMA fetches 64(k) x 64(m|n) boxes, the smem descriptor walks 8-k-row groups (SBO 1024 B) and 64-wide chunks (LBO 8 KB).
+// This is what lets the backward pass compute dX = dY W and dW = dY^T X without materialising a transpose.
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
                     int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep) {
@@ -133,15 +136,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(empty_bar + stage, phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
-          tma_load_2d(sa, &tmA, kb * GK, m_blk * GM, full_bar + stage);
-          tma_load_2d(sa + Cfg::kABytes, &tmB, kb * GK, n_blk * BN, full_bar + stage);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < GM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m_blk * GM + c * 64, kb * GK, full_bar + stage);
+          } else {
+            tma_load_2d(sa, &tmA, kb * GK, m_blk * GM, full_bar + stage);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sa + Cfg::kABytes + c * 8192, &tmB, n_blk * BN + c * 64, kb * GK, full_bar + stage);
+          } else {
+            tma_load_2d(sa + Cfg::kABytes, &tmB, kb * GK, n_blk * BN, full_bar + stage);
+          }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_bf16(GM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(GM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -155,8 +169,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < GK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
             umma_bf16_ss(tmem_base + acc * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar + stage);                    // frees the smem slot when these MMAs retire
@@ -286,13 +302,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
-template <int BN>
+template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
                        const GemmEpilogue& ep, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
     attr = true;
   }
@@ -304,19 +320,20 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   }
   const int tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tc_kernel<BN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep);
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep);
   return check_launch("gemm_bf16_tc");
 }
 
-int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,
-                 const GemmEpilogue& ep, cudaStream_t stream) {
+int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ldw, int b_mn, void* C, int ldc, int out_bf16,
+                         int M, int N, int K, const GemmEpilogue& ep, cudaStream_t stream) {
   V2M_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_bf16_tc: bad dims M=%d N=%d K=%d", M, N, K);
   if (M == 0) return kOk;
   const int bn = (N % 256 == 0) ? 256 : 128;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, GM);
+  // K-major operand: [rows = M|N, cols = K], box (rows x 64 k);  MN-major operand: [rows = K, cols = M|N], box (64 k x 64)
+  int rc = a_mn ? make_tmap_2d_bf16(&tmA, A, K, M, lda, 64) : make_tmap_2d_bf16(&tmA, A, M, K, lda, GM);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tmB, W, N, K, ldw, bn);
+  rc = b_mn ? make_tmap_2d_bf16(&tmB, W, K, N, ldw, 64) : make_tmap_2d_bf16(&tmB, W, N, K, ldw, bn);
   if (rc) return rc;
   // 128-bit epilogue accesses need 16-byte aligned vectors, residual rows and output rows
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
@@ -325,8 +342,23 @@ int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ld
   vec_ok = vec_ok && (!ep.residual || ((long long)ep.ldr * (ep.residual_bf16 ? 2 : 4)) % 16 == 0);
   if (ep.head_scatter) vec_ok = vec_ok && ep.dh % 32 == 0 && ((long long)ep.part_stride * osz) % 16 == 0;
   else vec_ok = vec_ok && ((long long)ldc * osz) % 16 == 0;
-  return bn == 256 ? launch_gemm<256>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream)
-                   : launch_gemm<128>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream);
+#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream)
+  if (bn == 256) {
+    if (!a_mn && !b_mn) return V2M_GO(256, false, false);
+    if (!a_mn && b_mn) return V2M_GO(256, false, true);
+    if (a_mn && b_mn) return V2M_GO(256, true, true);
+    return V2M_GO(256, true, false);
+  }
+  if (!a_mn && !b_mn) return V2M_GO(128, false, false);
+  if (!a_mn && b_mn) return V2M_GO(128, false, true);
+  if (a_mn && b_mn) return V2M_GO(128, true, true);
+  return V2M_GO(128, true, false);
+#undef V2M_GO
+}
+
+int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,
+                 const GemmEpilogue& ep, cudaStream_t stream) {
+  return gemm_bf16_tc_general(A, lda, 0, W, ldw, 0, C, ldc, out_bf16, M, N, K, ep, stream);
 }
 
 }  // namespace v2m

@@ -47,6 +47,10 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream);
 
+// General form: a_mn / b_mn != 0 means the operand is stored transposed ([K, M] resp. [K, N] row-major).
+int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ldw, int b_mn, void* C, int ldc, int out_bf16,
+                         int M, int N, int K, const GemmEpilogue& ep, cudaStream_t stream);
+
 // Attention, one (batch, head) problem per blockIdx.y.  Element (b, l, h, d) of q lives at
 // q + b*q_sb + l*q_sl + h*dh + d (same for k, v, o).  kv head of query head hq is hq / (Hq / Hkv).
 struct AttnParams {

@@ -219,13 +219,16 @@ def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: floa
     require_device(dy)
     assert dy.dim() == 2 and dy.stride(1) == 1
     M, N = dy.shape
-    dz = torch.empty((M, N), device=dy.device, dtype=out_dtype) if want_dz else None
+    ld = N if out_dtype == torch.float32 else (N + 7) // 8 * 8        # TMA operands need a 16-byte row pitch
+    dz = None
+    if want_dz:
+        dz = torch.zeros((M, ld), device=dy.device, dtype=out_dtype) if ld != N else torch.empty((M, N), device=dy.device, dtype=out_dtype)
     db = torch.zeros((N,), device=dy.device, dtype=torch.float32)
     check(load().v2m_dy_prep(ptr(dy), dtype_code(dy.dtype), dy.stride(0), ptr(y), dtype_code(y.dtype) if y is not None else 0,
                              y.stride(0) if y is not None else 0, int(relu), alpha, alpha_cols, ptr(dz),
-                             dtype_code(out_dtype), N, ptr(db), M, N, stream()))
+                             dtype_code(out_dtype), ld, ptr(db), M, N, stream()))
     _lib.count_launches(1)
-    return dz, db
+    return (dz[:, :N] if (dz is not None and ld != N) else dz), db
 
 
 def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5):
@@ -290,3 +293,17 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
     a.q_scale = q_scale
     check(load().v2m_attn_bwd(C.byref(a), stream()))
     _lib.count_launches(1)
+
+
+def linear_general(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool, b_mn: bool, M: int, N: int, K: int,
+                   out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """bf16 tcgen05 GEMM C[M,N] = A B^T-style with optionally transposed storage: a is [M,K] (or [K,M] when a_mn),
+    b is [N,K] (or [K,N] when b_mn), both row-major 2-D bf16 tensors (leading dims from the strides)."""
+    require_device(a)
+    assert a.dtype == b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
+    out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    ep = Epilogue()
+    check(load().v2m_gemm_bf16_general(ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0),
+                                       dtype_code(out_dtype), M, N, K, C.byref(ep), stream()))
+    _lib.count_launches(1)
+    return out
