@@ -1,0 +1,95 @@
+"""Data-parallel training step for the AMT (replaces the body of train_epoch, utilities/run_model_vevo.py:84-124).
+
+One process per GPU (the reference hard-codes cuda:0, utilities/device.py:8-9, so each process sees its GPU as
+device 0 or sets the device explicitly), replicated weights, the global batch cut into equal per-rank shards, and ONE
+exchange step per iteration: an all-reduce (NCCL over NVLink / NVSwitch on GPUs, gloo in the CPU tests) of the flat
+fp32 gradient buffer (32.5 M parameters = 130 MB).  Parameters, gradients and the Adam moments live in flat buffers so
+that the optimiser is one kernel launch and the collective one call.
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def noam_lr(step: int, d_model: int = 512, warmup: int = 4000, start: float = 1.0) -> float:
+    """LrStepTracker.step (utilities/lr_scheduling.py:28-45): Noam / 'Attention is all you need' schedule."""
+    step = max(step, 1)
+    return start * (d_model ** -0.5) * min(step ** -0.5, step * warmup ** -1.5)
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced [begin, end) slice of n items for `rank` (videos for generation, samples for training)."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    n = next(iter(batch.values())).shape[0]
+    b, e = shard_range(n, rank, world)
+    return {k: v[b:e] for k, v in batch.items()}
+
+
+def allreduce_mean_(flat: torch.Tensor, group=None) -> float:
+    """Sum-all-reduce of the flat gradient buffer; returns the scale (1/world) the optimiser applies."""
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
+    return 1.0
+
+
+class FlatParams:
+    """Re-homes every parameter of `model` into one contiguous fp32 buffer (and its gradient into another)."""
+
+    def __init__(self, model: torch.nn.Module):
+        params = [p for p in model.parameters() if p.requires_grad]
+        self.params = params
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + k].view(p.shape)
+            p.grad = self.flat_g[off:off + k].view(p.shape)
+            off += k
+        self.numel = n
+
+
+class Trainer:
+    def __init__(self, model, lr: Optional[float] = None, betas=(0.9, 0.98), eps: float = 1e-9, warmup: int = 4000,
+                 group=None):
+        from .autograd import AmtLossFn  # noqa: F401  (fail early if the extension is missing)
+        self.model = model
+        self.flat = FlatParams(model)
+        self.m = torch.zeros_like(self.flat.flat_p)
+        self.v = torch.zeros_like(self.flat.flat_p)
+        self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
+        self.group = group
+        self.step_no = 0
+        self.last_parts = None
+
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """batch: this rank's shard with the keys of synthetic.make_inputs (run_model_vevo.py:31-45)."""
+        from . import ops
+        from .autograd import AmtLossFn
+        m = self.model
+        dev = self.flat.flat_p.device
+        b = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+        y = m(b["x"], b["x_root"], b["x_attr"], b["feature_semantic_list"], b["feature_key"], b["feature_scene_offset"],
+              b["feature_motion"], b["feature_emotion"])
+        loss = AmtLossFn.apply(y, b["tgt"], b["tgt_emotion"], 0.1, 0.4, 0.6)          # run_model_vevo.py:101-119
+        loss.backward()                                                                  # accumulates into flat_g views
+        scale = allreduce_mean_(self.flat.flat_g, self.group)                            # the one exchange step
+        self.step_no += 1
+        lr = self.lr if self.lr is not None else noam_lr(self.step_no, m.d_model, self.warmup)
+        ops.adam_step(self.flat.flat_p, self.flat.flat_g, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps,
+                      self.step_no, grad_scale=scale)
+        self.flat.flat_g.zero_()
+        return loss.detach()
