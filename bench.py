@@ -224,7 +224,7 @@ def main():
     # ---- dominant kernel: decode cross-attention over the video K/V cache, timed alone on the launching stream
     st = engine.build_decode(model._w(), model._cfg(), devt["feature_semantic_list"], devt["feature_key"].reshape(-1),
                              devt["feature_scene_offset"], devt["feature_motion"], devt["feature_emotion"],
-                             prim, pr, pa, SEQ)
+                             prim, pr, pa, SEQ, mode="kernels")
     engine.run_decode(st, 8, use_graph=False)
     torch.cuda.synchronize()
     reps = 20

@@ -157,6 +157,7 @@ typedef struct v2m_dec_layer {
   const float* ln2_g; const float* ln2_b;
   const float* ln3_g; const float* ln3_b;
   const void* er;
+  const void* er_sw;   /* v2m_decode_run_stream only: 8 swizzled copies of Er, see below */
   void* self_k; void* self_v;
   const void* cross_k; const void* cross_v;
 } v2m_dec_layer;
@@ -176,11 +177,18 @@ typedef struct v2m_decode {
   void* xn;
 } v2m_decode;
 int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void* stream);
-/* Same loop as ONE persistent kernel launch: thread-block clusters own 8 videos each for all n_steps positions
- * starting at position t0 (the host copy of *p->step).  bf16, d_model 512, 8 heads; V2M_UNSUPPORTED otherwise. */
-int v2m_decode_run_cluster(const v2m_decode* p, int32_t t0, int32_t n_steps, void* stream);
-/* Measurement aid: CTA 0 of cluster 0 writes a globaltimer stamp (ns) at every phase boundary of the cluster kernel. */
-int v2m_debug_set_timestamps(uint64_t* buf, int32_t cap);
+/* Same loop as ONE persistent kernel launch (csrc/decode_stream.cu): a cluster of 8 CTAs (one per head) owns up to 8
+ * videos for all n_steps positions starting at t0 (the host copy of *p->step).  *p is a SEPARATE parameter block:
+ *  - the matrix pointers (w_qkv, w_so, w_cq, w_co, w_f1, w_f2, w_chord, w_out) reference FRAGMENT-PACKED bf16 copies:
+ *    tiles of 16 output rows x 16 k in mma.m16n8k16 A-fragment order, [N/16][K/16][32 lanes][8], rows zero-padded to 16;
+ *  - self_k / cross_k reference caches of 256-byte rows [K(64) | V(64)] per (video, head, position) whose 16-byte chunks
+ *    sit at chunk position c ^ (position & 7) (v2m_kv_interleave builds the cross cache); self_v / cross_v are unused;
+ *  - er_sw references 8 copies of Er, copy s storing row r with its chunks at c ^ ((r - s) & 7).
+ * bf16, d_model 512, 8 heads, dim_feedforward 1024; V2M_UNSUPPORTED otherwise (callers then use v2m_decode_run).
+ * timestamps (optional, device, ts_cap entries): globaltimer (ns) at every phase boundary of CTA 0 (measurement aid). */
+int v2m_decode_run_stream(const v2m_decode* p, int32_t t0, int32_t n_steps, uint64_t* timestamps, int32_t ts_cap, void* stream);
+/* out[row] = [k[row] | v[row]] (2 x 64 bf16) with the XOR swizzle above, row = (video*H + head)*S + position. */
+int v2m_kv_interleave(const void* k, const void* v, void* out, int64_t rows, int32_t S, void* stream);
 int64_t v2m_decode_launches_per_step(const v2m_decode* p);
 /* Measurement aid: launches one decode kernel kind (0 self-attention, 1 cross-attention, 2 QKV GEMM, 3 FFN1 GEMM)
  * `reps` rounds over all layers on `stream`, reading the current step from *p->step. */

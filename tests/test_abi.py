@@ -32,7 +32,7 @@ def test_struct_sizes_match_c_layout():
     lib = _lib.load()
     for which, cls in enumerate((_lib.Epilogue, _lib.Attn, _lib.DecLayer, _lib.Decode)):
         assert lib.v2m_struct_size(which) == ctypes.sizeof(cls), cls.__name__
-    assert ctypes.sizeof(_lib.DecLayer) == 23 * 8
+    assert ctypes.sizeof(_lib.DecLayer) == 24 * 8
 
 
 def test_no_cpu_fallback():

@@ -128,17 +128,20 @@ def test_generate_bf16_vs_oracle():
     assert err < TOL_BF16
 
 
-def test_generate_bf16_cluster_kernel_matches_per_kernel_path():
-    """The persistent cluster kernel and the 51-kernels-per-position path implement the same arithmetic: logits agree to
-    bf16 rounding noise when both are teacher-forced, and both stay within the bf16 tolerance of the fp32 oracle."""
-    B = 13                                                       # ragged: one full cluster of 8 videos + one of 5
-    m, sd = amt_state_dict(syn.vf_dim(0), 2, chord_embed=True, wout_gain=4.0)
+@pytest.mark.parametrize("rows,B,chord_embed", [(0, 13, True), (1, 3, True), (5, 13, False), (8, 16, True), (3, 7, True)])
+def test_generate_bf16_stream_kernel_matches_per_kernel_path(rows, B, chord_embed, monkeypatch):
+    """The streamed cluster kernel (one launch for the whole loop) and the 70-kernels-per-position path implement the same
+    arithmetic: logits agree to bf16 rounding noise when both are teacher-forced, and both stay within the bf16 tolerance
+    of the fp32 oracle.  rows = videos per cluster (0: chosen by the library); B not a multiple of rows = ragged last cluster."""
+    if rows:
+        monkeypatch.setenv("V2M_STREAM_ROWS", str(rows))
+    m, sd = amt_state_dict(syn.vf_dim(0), 2, chord_embed=chord_embed, wout_gain=4.0)
     m = m.to(DEV).eval().set_compute_dtype(torch.bfloat16)
     inp = syn.make_inputs(B, 77, 299, 300, 0)
     P = 299
     prim, pr, pa = inp["x"][:, :P], inp["x_root"][:, :P], inp["x_attr"][:, :P]
     outs = {}
-    for mode in ("kernels", "cluster"):
+    for mode in ("kernels", "stream"):
         gen, logits = m.generate(inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
                                  inp["feature_motion"], inp["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa,
                                  target_seq_length=300, beam=1, return_logits=True, decode_mode=mode)
@@ -147,16 +150,16 @@ def test_generate_bf16_cluster_kernel_matches_per_kernel_path():
     with torch.no_grad():
         _, lref = O.generate_greedy_cached(sd, inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
                                            inp["feature_motion"], inp["feature_emotion"], prim, pr, pa, 300,
-                                           chord_embed=True, return_logits=True)
-    e_k, e_c = rel_err(outs["kernels"], lref), rel_err(outs["cluster"], lref)
-    print("bf16 decode rel err: kernels %.3e cluster %.3e, cluster vs kernels %.3e" % (e_k, e_c, rel_err(outs["cluster"], outs["kernels"])))
+                                           chord_embed=chord_embed, return_logits=True)
+    e_k, e_c = rel_err(outs["kernels"], lref), rel_err(outs["stream"], lref)
+    print("bf16 decode rel err: kernels %.3e stream %.3e, stream vs kernels %.3e" % (e_k, e_c, rel_err(outs["stream"], outs["kernels"])))
     assert e_k < TOL_BF16 and e_c < TOL_BF16
-    assert rel_err(outs["cluster"], outs["kernels"]) < 1.5e-2          # two bf16 schedules (different K splits)
+    assert rel_err(outs["stream"], outs["kernels"]) < 1.5e-2           # two bf16 schedules (different K splits)
 
 
-def test_generate_bf16_cluster_free_running():
-    """Free-running greedy generation (tokens feed back) with the cluster kernel: tokens equal the per-kernel path's
-    wherever the oracle's top-2 margin is comfortably above bf16 noise."""
+def test_generate_bf16_stream_free_running():
+    """Free-running greedy generation (tokens feed back) with the streamed kernel: tokens equal the per-kernel path's
+    wherever the oracle's top-2 margin is comfortably above bf16 noise; short sequences and resumed runs included."""
     B = 16
     m, sd = amt_state_dict(syn.vf_dim(0), 1, chord_embed=True, wout_gain=4.0)
     m = m.to(DEV).eval().set_compute_dtype(torch.bfloat16)
@@ -164,13 +167,21 @@ def test_generate_bf16_cluster_free_running():
     P = 8
     prim, pr, pa = inp["x"][:, :P], inp["x_root"][:, :P], inp["x_attr"][:, :P]
     gens = {}
-    for mode in ("kernels", "cluster"):
+    for mode in ("kernels", "stream"):
         gens[mode] = m.generate(inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
                                 inp["feature_motion"], inp["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa,
                                 target_seq_length=300, beam=1, decode_mode=mode).cpu()
-    agree = float((gens["kernels"] == gens["cluster"]).float().mean())
-    print("token agreement cluster vs kernels: %.4f" % agree)
+    agree = float((gens["kernels"] == gens["stream"]).float().mean())
+    print("token agreement stream vs kernels: %.4f" % agree)
     assert agree > 0.98
+    # the same run cut into two launches (positions [0,100) then [100,299)) reproduces the single-launch tokens exactly
+    from video2music_b200 import engine
+    d = {k: v.to(DEV) for k, v in inp.items()}
+    st = engine.build_decode(m._w(), m._cfg(), d["feature_semantic_list"], d["feature_key"].reshape(-1), d["feature_scene_offset"],
+                             d["feature_motion"], d["feature_emotion"], prim, pr, pa, 300, mode="stream")
+    engine.run_decode(st, 100, mode="stream")
+    engine.run_decode(st, 199, mode="stream")
+    assert torch.equal(st.gen.cpu(), gens["stream"])
 
 
 def test_forward_bf16_vs_reference_golden():

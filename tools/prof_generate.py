@@ -14,7 +14,8 @@ inp = syn.make_inputs(64, 1234, 299, 300, 0)
 d = {k: v.to(dev) for k, v in inp.items()}
 prim, pr, pa = torch.tensor([1]), torch.tensor([1]), torch.tensor([0])
 st = engine.build_decode(model._w(), model._cfg(), d["feature_semantic_list"], d["feature_key"].reshape(-1),
-                         d["feature_scene_offset"], d["feature_motion"], d["feature_emotion"], prim, pr, pa, seq)
+                         d["feature_scene_offset"], d["feature_motion"], d["feature_emotion"], prim, pr, pa, seq,
+                         mode=(sys.argv[5] if len(sys.argv) > 5 else 'kernels'))
 torch.cuda.synchronize()
 st.keep[-1]  # noqa
 # jump to a mid-sequence position: the caches hold zeros there, which costs the same bytes

@@ -48,7 +48,7 @@ class AttnBwd(C.Structure):
 class DecLayer(C.Structure):
     _fields_ = [(n, vp) for n in (
         "w_qkv", "b_qkv", "w_so", "b_so", "w_cq", "b_cq", "w_co", "b_co", "w_f1", "b_f1", "w_f2", "b_f2",
-        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "ln3_g", "ln3_b", "er", "self_k", "self_v", "cross_k", "cross_v")]
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "ln3_g", "ln3_b", "er", "er_sw", "self_k", "self_v", "cross_k", "cross_v")]
 
 
 class Decode(C.Structure):
@@ -66,7 +66,7 @@ EXPORTS = [
     "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_dy_prep",
     "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
-    "v2m_decode_run_cluster", "v2m_debug_set_timestamps", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
+    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -105,8 +105,8 @@ def load() -> C.CDLL:
     lib.v2m_cast_2d.argtypes = [vp, i32, i64, vp, i32, i64, i32, i32, i32, vp]
     lib.v2m_binary_f32.argtypes = [vp, vp, vp, i64, i32, C.c_float, vp]
     lib.v2m_decode_run.argtypes = [C.POINTER(Decode), i32, i32, vp]
-    lib.v2m_debug_set_timestamps.argtypes = [vp, i32]
-    lib.v2m_decode_run_cluster.argtypes = [C.POINTER(Decode), i32, i32, vp]
+    lib.v2m_decode_run_stream.argtypes = [C.POINTER(Decode), i32, i32, vp, i32, vp]
+    lib.v2m_kv_interleave.argtypes = [vp, vp, vp, i64, i32, vp]
     lib.v2m_decode_launches_per_step.argtypes = [C.POINTER(Decode)]
     lib.v2m_decode_probe.argtypes = [C.POINTER(Decode), i32, i32, vp]
     lib.v2m_pscan_fwd.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]

@@ -180,17 +180,20 @@ int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void
   return decode_run(d, n_steps, use_graph, static_cast<cudaStream_t>(stream));
 }
 
-int v2m_decode_run_cluster(const v2m_decode* p, int32_t t0, int32_t n_steps, void* stream) {
-  V2M_REQUIRE(p != nullptr, "v2m_decode_run_cluster: null params");
+int v2m_decode_run_stream(const v2m_decode* p, int32_t t0, int32_t n_steps, uint64_t* timestamps, int32_t ts_cap, void* stream) {
+  V2M_REQUIRE(p != nullptr, "v2m_decode_run_stream: null params");
   DecodeParams d;
   memcpy(&d, p, sizeof(d));
-  int rc = decode_run_cluster(d, t0, n_steps, static_cast<cudaStream_t>(stream));
-  if (rc == kUnsupported) set_last_error("decode_run_cluster: configuration not covered by the cluster kernel (bf16, d_model 512, 8 heads)");
+  int rc = decode_run_stream(d, t0, n_steps, reinterpret_cast<unsigned long long*>(timestamps), ts_cap, static_cast<cudaStream_t>(stream));
+  if (rc == kUnsupported)
+    set_last_error("decode_run_stream: configuration not covered by the streamed cluster kernel (bf16, d_model 512, 8 heads, "
+                   "dim_feedforward 1024, all clusters co-resident)");
   return rc;
 }
 
-int v2m_debug_set_timestamps(uint64_t* buf, int32_t cap) {
-  return decode_debug_set_timestamps(reinterpret_cast<unsigned long long*>(buf), cap);
+int v2m_kv_interleave(const void* k, const void* v, void* out, int64_t rows, int32_t S, void* stream) {
+  V2M_REQUIRE(k && v && out, "v2m_kv_interleave: null pointer");
+  return kv_interleave(k, v, out, rows, S, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stream) {

@@ -138,6 +138,28 @@ int cast_copy(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
   return cast_copy_2d(src, src_dtype, n, dst, dst_dtype, n, 1, (int)n, 0, stream);
 }
 
+// Cache layout of the streamed decode kernel: out[row] = [K(64) | V(64)] bf16 with the eight 16-byte chunks of each half
+// stored at chunk position (c ^ (pos & 7)), pos = row % S  (row = (video * H + head) * S + pos).
+__global__ void kv_interleave_kernel(const uint4* __restrict__ k, const uint4* __restrict__ v, uint4* __restrict__ out,
+                                     long long rows, int S) {
+  const long long total = rows * 16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i >> 4;
+    const int part = (int)(i >> 3) & 1, c = (int)i & 7, pos = (int)(row % S);
+    out[row * 16 + part * 8 + (c ^ (pos & 7))] = (part ? v : k)[row * 8 + c];
+  }
+}
+
+int kv_interleave(const void* k, const void* v, void* out, long long rows, int S, cudaStream_t stream) {
+  if (rows == 0) return kOk;
+  V2M_REQUIRE(S > 0, "kv_interleave: S must be positive");
+  const long long want = (rows * 16 + 255) / 256;
+  const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  kv_interleave_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(k), static_cast<const uint4*>(v),
+                                                    static_cast<uint4*>(out), rows, S);
+  return check_launch("kv_interleave");
+}
+
 // mode 0: out = a * silu(b)   (GLUExpert, moe.py:47);  mode 1: out = a + alpha * b  (shared expert, moe.py:301)
 __global__ void binary_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                               long long n, int mode, float alpha) {

@@ -105,6 +105,9 @@ int cast_copy(const void* src, int src_dtype, void* dst, int dst_dtype, long lon
 int cast_copy_2d(const void* src, int src_dtype, long long ld_src, void* dst, int dst_dtype, long long ld_dst,
                  int rows, int cols, int zero_pad, cudaStream_t stream);
 
+// out[row] = [K | V] (2 x 64 bf16) with 16-byte chunks XOR-swizzled by (row % S) & 7: cache layout of decode_stream.cu
+int kv_interleave(const void* k, const void* v, void* out, long long rows, int S, cudaStream_t stream);
+
 int binary_op(const float* a, const float* b, float* out, long long n, int mode, float alpha, cudaStream_t stream);
 
 // ------------------------------------------------------------------ KV-cached decode (decode.cu)
@@ -120,6 +123,8 @@ struct DecLayer {
   const float* ln2_g; const float* ln2_b;
   const float* ln3_g; const float* ln3_b;
   const void* er;                 // [er_len, dh] in the compute dtype
+  const void* er_sw;              // stream path only: [8][er_len, dh] bf16, copy s holds row r with its 16-byte chunks at
+                                  // position c ^ ((r - s) & 7)  (conflict-free ldmatrix for slices starting at rows = s mod 8)
   void* self_k; void* self_v;     // [B, H, cap, dh]
   const void* cross_k; const void* cross_v;  // [B, H, S, dh]
 };
@@ -148,9 +153,9 @@ struct DecodeParams {
 int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream);
 long long decode_kernel_launches_per_step(const DecodeParams& p);
 int decode_probe(const DecodeParams& p, int kind, int reps, cudaStream_t stream);
-// One persistent cluster kernel for n_steps positions starting at t0 (bf16, d_model 512); kUnsupported otherwise.
-int decode_run_cluster(const DecodeParams& p, int t0, int n_steps, cudaStream_t stream);
-int decode_debug_set_timestamps(unsigned long long* buf, int cap);
+// One persistent cluster kernel for n_steps positions starting at t0 (bf16, d_model 512, 8 heads, FF 1024); the weight
+// pointers of p reference fragment-packed matrices (decode_stream.cu).  kUnsupported otherwise.
+int decode_run_stream(const DecodeParams& p, int t0, int n_steps, unsigned long long* ts, int ts_cap, cudaStream_t stream);
 
 // ------------------------------------------------------------------ selective scan (pscan.cu)
 int pscan_fwd(const float* A, const float* X, float* H, int B, int L, int D, int N, cudaStream_t stream);

@@ -178,12 +178,28 @@ def amt_forward(W: AMTWeights, cfg, x, x_root, x_attr, sem, key, scene, motion, 
     return y.view(B, T, -1)
 
 
+def pack_fragments(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] bf16 matrix -> tiles of 16 rows x 16 k in mma.m16n8k16 A-fragment order, [ceil(N/16)][K/16][32 lanes][8]
+    (rows zero-padded to a multiple of 16).  One 16-row x 512-k tile is then 16 KB of contiguous memory that the streamed
+    decode kernel (csrc/decode_stream.cu) fetches with a single bulk copy and reads with conflict-free 16-byte loads.
+    Lane l = 4*g + q holds rows (g, g+8) x columns (2q, 2q+1, 2q+8, 2q+9) of a tile: [k-half][row-half][pair]."""
+    assert w.dim() == 2 and w.dtype == torch.bfloat16 and w.shape[1] % 16 == 0
+    N, K = w.shape
+    Np = (N + 15) // 16 * 16
+    if Np != N:
+        w = torch.cat([w, w.new_zeros((Np - N, K))], 0)
+    v = w.contiguous().view(Np // 16, 2, 8, K // 16, 2, 4, 2)          # n16, row-half, g, k16, k-half, q, pair
+    return v.permute(0, 3, 2, 5, 4, 1, 6).contiguous().view(Np // 16, K // 16, 32, 8)
+
+
 class DecodeState:
     """Device buffers of one batched KV-cached generation run (kept alive while kernels are in flight)."""
 
     def __init__(self):
         self.keep = []
         self.params: Optional[Decode] = None
+        self.packed: Optional[Decode] = None      # same buffers, fragment-packed matrices (streamed cluster kernel)
+        self.mode = "kernels"
         self.gen = None
         self.logits_all = None
         self.launches_per_step = 0
@@ -191,10 +207,31 @@ class DecodeState:
         self.step = None
 
 
+def swizzled_er_copies(er: torch.Tensor) -> torch.Tensor:
+    """[er_len, 64] bf16 -> [8, er_len, 64]: copy s stores row r with its eight 16-byte chunks at position c ^ ((r - s) & 7),
+    so that a bulk copy of rows [start, start + n) taken from copy (start & 7) lands in shared memory with the XOR swizzle
+    (slice row & 7) that ldmatrix reads without bank conflicts (csrc/decode_stream.cu)."""
+    n = er.shape[0]
+    rows = torch.arange(n, device=er.device)
+    chunks = torch.arange(8, device=er.device)
+    v = er.contiguous().view(n, 8, 8)
+    out = torch.empty((8, n, 8, 8), device=er.device, dtype=er.dtype)
+    for s_ in range(8):
+        src_chunk = chunks[None, :] ^ ((rows[:, None] - s_) & 7)          # position p holds chunk p ^ key (XOR is an involution)
+        out[s_] = torch.gather(v, 1, src_chunk[:, :, None].expand(n, 8, 8))
+    return out.view(8, n, 64)
+
+
+def stream_config_ok(dt, E, H, FF, B) -> bool:
+    """Configurations the streamed cluster kernel covers (all clusters co-resident: <= 8 videos per 8-SM cluster)."""
+    return dt == torch.bfloat16 and E == 512 and H == 8 and FF == 1024 and B <= 8 * 13
+
+
 def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, primer_root, primer_attr,
-                 target_seq_length: int, want_logits: bool = False) -> DecodeState:
+                 target_seq_length: int, want_logits: bool = False, mode: str = "auto") -> DecodeState:
     """Encoder pass + cross-attention K/V caches + decode buffers.
-    Replaces the per-step re-forward of generate() (video_music_transformer.py:1069-1071)."""
+    Replaces the per-step re-forward of generate() (video_music_transformer.py:1069-1071).
+    mode "stream" / "kernels" / "auto" picks the decode path (see run_decode); the caches are built for that path only."""
     W.refresh()
     dev = sem.device
     B, S = sem.shape[0], sem.shape[1]
@@ -203,6 +240,11 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     cap = target_seq_length
     dt = W.dtype
     st = DecodeState()
+    if mode == "auto":
+        mode = "stream" if stream_config_ok(dt, E, H, FF, B) else "kernels"
+    if mode == "stream" and not stream_config_ok(dt, E, H, FF, B):
+        raise RuntimeError("streamed decode needs bf16, d_model 512, 8 heads, dim_feedforward 1024, batch <= 104")
+    st.mode = mode
     mem = encode_memory(W, cfg, sem, scene, motion, emotion)
 
     d = Decode()
@@ -221,10 +263,17 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     gen[:, :P] = primer.to(dev)                                                             # :1063-1066
     gen_root[:, :P] = primer_root.to(dev)
     gen_attr[:, :P] = primer_attr.to(dev)
-    self_kv = torch.zeros((NL, 2, B, H, cap, dh), device=dev, dtype=dt)
-    cross_kv = torch.empty((NL, 2, B, H, S, dh), device=dev, dtype=dt)
+    if mode == "stream":
+        # 256-byte rows [K | V] per (video, head, position), chunks XOR-swizzled by position (decode_stream.cu)
+        self_kv = torch.zeros((NL, B, H, cap, 2 * dh), device=dev, dtype=dt)
+        cross_sw = torch.empty((NL, B, H, S, 2 * dh), device=dev, dtype=dt)
+        cross_kv = torch.empty((1, 2, B, H, S, dh), device=dev, dtype=dt)      # staging of one layer (GEMM output layout)
+    else:
+        self_kv = torch.zeros((NL, 2, B, H, cap, dh), device=dev, dtype=dt)
+        cross_kv = torch.empty((NL, 2, B, H, S, dh), device=dev, dtype=dt)
+        cross_sw = None
     keep = st.keep
-    keep += [mem, gen, gen_root, gen_attr, self_kv, cross_kv]
+    keep += [mem, gen, gen_root, gen_attr, self_kv, cross_kv, cross_sw]
 
     def hold(t):
         keep.append(t)
@@ -234,9 +283,13 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
         p = "transformer.decoder.layers.%d." % l
         L = d.layer[l]
         # K|V of the video memory once per sequence (the reference recomputes them every layer AND every step, rpr.py:62)
+        ckv = cross_kv[0 if mode == "stream" else l]
         ops.linear(mem, W.w(p + "multihead_attn.in_proj_weight", rows=slice(E, 3 * E)),
-                   W.f(p + "multihead_attn.in_proj_bias")[E:], k=E, out=cross_kv[l],
+                   W.f(p + "multihead_attn.in_proj_bias")[E:], k=E, out=ckv,
                    head_scatter=dict(S=S, H=H, dh=dh, cap=S, pos0=0, part_stride=B * H * S * dh))
+        if mode == "stream":
+            check(load().v2m_kv_interleave(ptr(ckv[0]), ptr(ckv[1]), ptr(cross_sw[l]), B * H * S, S, stream()))
+            _lib.count_launches(1)
         L.w_qkv = hold(W.w(p + "self_attn.in_proj_weight"))
         L.b_qkv = hold(W.f(p + "self_attn.in_proj_bias"))
         L.w_so, L.b_so = hold(W.w(p + "self_attn.out_proj.weight")), hold(W.f(p + "self_attn.out_proj.bias"))
@@ -252,8 +305,15 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
         er = W.table(p + "self_attn.Er")
         d.er_len = er.shape[0]
         L.er = hold(er)
-        L.self_k, L.self_v = ptr(self_kv[l, 0]), ptr(self_kv[l, 1])
-        L.cross_k, L.cross_v = ptr(cross_kv[l, 0]), ptr(cross_kv[l, 1])
+        if mode == "stream":
+            L.self_k, L.cross_k = ptr(self_kv[l]), ptr(cross_sw[l])
+            key_sw = p + "self_attn.Er|sw8"
+            if key_sw not in W._cache:
+                W._cache[key_sw] = swizzled_er_copies(er)
+            L.er_sw = hold(W._cache[key_sw])
+        else:
+            L.self_k, L.self_v = ptr(self_kv[l, 0]), ptr(self_kv[l, 1])
+            L.cross_k, L.cross_v = ptr(cross_kv[l, 0]), ptr(cross_kv[l, 1])
     # the skinny decode GEMMs need dense [N, K] weights (K == leading dimension)
     for l in range(NL):
         p = "transformer.decoder.layers.%d." % l
@@ -289,23 +349,57 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
         d.logits_all = ptr(st.logits_all)
     st.params, st.gen = d, gen
     st.launches_per_step = int(load().v2m_decode_launches_per_step(C.byref(d)))
+    if mode == "stream":
+        # fragment-packed copies of the matrices for the streamed cluster kernel (cached with the bf16 weights)
+        def packed(name, rows=None, cols=None):
+            key = "%s|%s|%s|frag" % (name, rows, cols)
+            t = W._cache.get(key)
+            if t is None:
+                src = W.w(name, rows=rows, cols=cols)
+                t = pack_fragments(src[:, :src.shape[1] // 16 * 16] if src.shape[1] % 16 else src)
+                W._cache[key] = t
+            return hold(t)
+        dp = Decode()
+        C.memmove(C.byref(dp), C.byref(d), C.sizeof(Decode))
+        for l in range(NL):
+            p = "transformer.decoder.layers.%d." % l
+            L = dp.layer[l]
+            L.w_qkv = packed(p + "self_attn.in_proj_weight")
+            L.w_so = packed(p + "self_attn.out_proj.weight")
+            L.w_cq = packed(p + "multihead_attn.in_proj_weight", rows=slice(0, E))
+            L.w_co = packed(p + "multihead_attn.out_proj.weight")
+            L.w_f1 = packed(p + "linear1.weight")
+            L.w_f2 = packed(p + "linear2.weight")
+        dp.w_out = packed("Wout.weight")
+        b_out = W.f("Wout.bias")
+        dp.b_out = hold(torch.cat([b_out, b_out.new_zeros((-b_out.numel()) % 16)]))     # tiles of 16 rows read whole
+        dp.w_chord = packed("Linear_chord.weight", cols=E)
+        st.packed = dp
     return st
 
 
-def run_decode(st: DecodeState, n_steps: int, use_graph: bool = True, mode: str = "auto", n_split: int = 0) -> None:
+def run_decode(st: DecodeState, n_steps: int, use_graph: bool = True, mode: str = "auto", n_split: int = 0,
+               timestamps: Optional[torch.Tensor] = None) -> None:
     """Advance the generation by n_steps positions.
 
-    mode "cluster": the whole loop as ONE persistent thread-block-cluster kernel (bf16, d_model 512, csrc/decode_cluster.cu);
-    mode "kernels": 51 kernels per position, replayed from a CUDA graph when use_graph (csrc/decode.cu, also the fp32 path);
-    mode "auto": kernels (the cluster kernel is experimental: correct, but slower so far -- see DESIGN.md).
+    mode "stream": the whole loop as ONE persistent thread-block-cluster kernel (bf16, d_model 512, 8 heads,
+                   csrc/decode_stream.cu);
+    mode "kernels": 70 kernels per position, replayed from a CUDA graph when use_graph (csrc/decode.cu, also the fp32 path);
+    mode "auto": whatever build_decode chose.  The caches are laid out for one path, so mode must match build_decode's.
     n_split: independent sub-batch chains inside the graph (0 = pick from the batch size)."""
     d = st.params
     if mode == "auto":
-        mode = "kernels"
+        mode = st.mode
+    if mode != st.mode:
+        raise RuntimeError("decode state was built for mode %r, not %r" % (st.mode, mode))
     if n_split <= 0:
-        n_split = 4 if d.B >= 32 else (2 if d.B >= 8 else 1)
-    if mode == "cluster":
-        check(load().v2m_decode_run_cluster(C.byref(d), st.pos, n_steps, stream()))
+        n_split = 2 if d.B >= 32 else 1
+    if mode == "stream":
+        if st.packed is None:
+            raise RuntimeError("streamed decode needs bf16, d_model 512, 8 heads, dim_feedforward 1024")
+        tsp = ptr(timestamps) if timestamps is not None else None
+        check(load().v2m_decode_run_stream(C.byref(st.packed), st.pos, n_steps, tsp,
+                                           0 if timestamps is None else timestamps.numel(), stream()))
         _lib.count_launches(1)
     else:
         split = n_split if use_graph else 0

@@ -188,8 +188,8 @@ class VideoMusicTransformer(nn.Module):
         st = engine.build_decode(self._w(), self._cfg(), sem, key.to(dev), feature_scene_offset.to(dev).float(),
                                  feature_motion.to(dev).float(), feature_emotion.to(dev).float(),
                                  primer.long(), primer_root.long(), primer_attr.long(), target_seq_length,
-                                 want_logits=return_logits)
-        engine.run_decode(st, target_seq_length - 1, use_graph=use_graph, mode=decode_mode)
+                                 want_logits=return_logits, mode=decode_mode)
+        engine.run_decode(st, target_seq_length - 1, use_graph=use_graph)
         gen = st.gen[:, :target_seq_length]
         if return_logits:
             return gen, st.logits_all
