@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 64                 # videos per GPU (BASELINE config 2)
+TRAIN_GLOBAL_BATCH = 512   # BASELINE config 3 (split over the ranks: strong scaling)
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture, per launch)
+NCU_TRAFFIC_BYTES = {"stream": 116703284000 + 257316352}   # profiles/r01_decode_stream_ncu_full_details.txt
 SEQ = 300                  # target_seq_length -> 299 generated chord tokens per video
 METRIC = "generate_chord_tokens_per_s"
 UNIT = "tokens/s"
@@ -99,6 +102,47 @@ def make_model(dtype, device, seed=1):
     return m.eval().set_compute_dtype(dtype), sd
 
 
+def train_leg(args, dev, rank, world, dtype):
+    """BASELINE config 3: training step (forward + loss + backward + all-reduce + Adam), global batch 512 split over the
+    ranks, bf16 operands / fp32 master weights.  Returned as the extra key "train" of the JSON line."""
+    import torch.distributed as dist
+    from video2music_b200 import VideoMusicTransformer, _lib
+    from video2music_b200 import synthetic as syn
+    from video2music_b200.trainer import Trainer, shard_range
+    m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(syn.fill_like_reference_init(shapes, seed=1), strict=False)
+    m = m.to(dev).train().set_compute_dtype(dtype)
+    tr = Trainer(m)
+    b0, b1 = shard_range(TRAIN_GLOBAL_BATCH, rank, world)
+    inp = syn.make_inputs(b1 - b0, 4321 + rank, SEQ - 1, 300, 0)
+    host = {k: v.pin_memory() for k, v in inp.items()}
+    for _ in range(2):
+        tr.train_step(host)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    _lib.reset_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.train_steps):
+        loss = tr.train_step(host)                      # H2D of the batch inside the timed region
+    lossv = float(loss)                                 # D2H of the loss
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / args.train_steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    flops = 69.4e9 * TRAIN_GLOBAL_BATCH                 # SURVEY 8d: 3 x 23.14 GF per sample
+    return {"metric": "train_samples_per_s", "value": TRAIN_GLOBAL_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+            "global_batch": TRAIN_GLOBAL_BATCH, "per_gpu_batch": b1 - b0, "scaling": "strong", "steps": args.train_steps,
+            "loss": lossv, "tflops": flops / (ms * 1e-3) / 1e12, "launches_per_step": _lib.launches() // args.train_steps,
+            "collective": "NCCL all-reduce of the flat fp32 gradient buffer (130 MB)" if world > 1 else "none (1 rank)",
+            "timed": "e2e: pinned-host batch -> device inside the step, loss read back at the end"}
+
+
 def reference_arm(args):
     """The reference's algorithm on the host cores (oracle port, literal re-forward loop, batch 1)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -152,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE config 3)")
+    ap.add_argument("--train-steps", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -221,33 +267,39 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- dominant kernel: decode cross-attention over the video K/V cache, timed alone on the launching stream
-    st = engine.build_decode(model._w(), model._cfg(), devt["feature_semantic_list"], devt["feature_key"].reshape(-1),
-                             devt["feature_scene_offset"], devt["feature_motion"], devt["feature_emotion"],
-                             prim, pr, pa, SEQ, mode="kernels")
-    engine.run_decode(st, 8, use_graph=False)
-    torch.cuda.synchronize()
-    reps = 20
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l2_flush.fill_(1)
-    e0.record()
-    engine.probe_decode_kernel(st, kind=1, reps=reps)          # kind 1 = cross-attention, cycles through the layers
-    e1.record()
-    e1.synchronize()
-    n_l = model.nlayers
-    kern_ms = e0.elapsed_time(e1) / (reps * n_l)
+    # ---- dominant kernel: the streamed cluster decode kernel (ONE launch = all 299 positions of the rank's 64 videos),
+    # timed alone with CUDA events on the stream it is launched on (torch's current stream)
+    kern_ms = []
+    for _ in range(3):
+        st = engine.build_decode(model._w(), model._cfg(), devt["feature_semantic_list"], devt["feature_key"].reshape(-1),
+                                 devt["feature_scene_offset"], devt["feature_motion"], devt["feature_emotion"],
+                                 prim, pr, pa, SEQ)
+        torch.cuda.synchronize()
+        l2_flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        engine.run_decode(st, SEQ - 1)
+        e1.record()
+        e1.synchronize()
+        kern_ms.append(e0.elapsed_time(e1))
+        decode_mode = st.mode
+        del st
+    kern_ms = sorted(kern_ms)[1]
 
     t_step = sum(ms) / len(ms)
     t_e2e = sum(ms_e2e) / len(ms_e2e)
+    train = train_leg(args, dev, rank, world, dtype) if not args.no_train else None
     if world > 1:
-        t = torch.tensor([t_step, t_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([t_step, t_e2e, kern_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)                # device-timed, max over ranks
-        t_step, t_e2e = float(t[0]), float(t[1])
+        t_step, t_e2e, kern_ms = float(t[0]), float(t[1]), float(t[2])
     tokens = world * BATCH * (SEQ - 1)
     esz = 2 if dtype == torch.bfloat16 else 4
-    run_bytes, kern_bytes = algorithmic_bytes(BATCH, 300, SEQ, 512, 8, 1024, 6, 159, esz)
+    run_bytes, _ = algorithmic_bytes(BATCH, 300, SEQ, 512, 8, 1024, 6, 159, esz)
     peak, peak_src = peaks()
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
+    kname = "decode_stream_kernel (one launch: 299 positions x 64 videos, 6 layers)" if decode_mode == "stream" else \
+        "decode step kernels (skinny_gemm / dec_attn, 70 launches per position)"
     out = {
         "metric": METRIC, "value": tokens / (t_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -260,20 +312,20 @@ def main():
                 "d2h_bytes_per_step": BATCH * SEQ * 8, "ms_per_step": t_e2e},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "dec_attn_kernel<%s> (cross-attention over the cached video K/V)" % args.dtype, "bound": "hbm",
-                     "achieved": kern_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_launch": kern_bytes, "us_per_launch": kern_ms * 1e3},
-        "generate_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": run_bytes,
-                              "achieved": run_bytes / (sum(ms) / len(ms) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": run_bytes / (sum(ms) / len(ms) * 1e-3) / 1e9 / peak,
-                              "note": "whole generate call (prefill + 299 decode steps) against the decode byte floor"},
+        "roofline": {"kernel": kname, "bound": "hbm", "achieved": run_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": run_bytes / (kern_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC_BYTES.get(decode_mode),
+                     "peak_source": peak_src, "bytes_per_launch": run_bytes, "us_per_launch": kern_ms * 1e3,
+                     "note": "algorithmic bytes = SURVEY 8d decode byte floor (weights once per position + every cached K/V "
+                             "element once per position) for the 299 positions one launch processes"},
+        "share_of_step": kern_ms / t_step,
     }
+    if train is not None:
+        out["train"] = train
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import amt_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)
         one = {k: inp[k][:1] for k in keys}
-        n_tok = 64
+        n_tok = 200
         t0 = time.perf_counter()
         with torch.no_grad():
             O.generate_greedy_literal(sd, one["feature_semantic_list"], one["feature_key"][0], one["feature_scene_offset"],
