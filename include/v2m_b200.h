@@ -109,6 +109,12 @@ typedef struct v2m_attn_bwd_t {
   float q_scale;
 } v2m_attn_bwd_t;
 int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);
+/* Tensor-core attention backward (bf16, head_dim 64, q pre-scaled: q_scale must be 1): same gradients as v2m_attn_bwd from
+ * mma.sync kernels (csrc/attn_bwd_tc.cu).  Here a->dk / a->dv are BF16 outputs (strides dkv_sb / dkv_sl in elements) that
+ * are written once -- no zeroing, no accumulation; a->dEr (fp32 [er_len, 64]) must be zeroed by the caller.
+ * ws: v2m_attn_bwd_tc_workspace(B, Hq, Lq, Lk, has_er) bytes of device scratch (P, dS and skewed dS tiles, bf16). */
+int64_t v2m_attn_bwd_tc_workspace(int32_t B, int32_t Hq, int32_t Lq, int32_t Lk, int32_t has_er);
+int v2m_attn_bwd_tc(const v2m_attn_bwd_t* a, void* ws, int64_t ws_bytes, void* stream);
 /* dz = dy * relu'(y) * (n < alpha_cols ? alpha : 1), db[n] += sum_m dz[m][n]: gradient of the fused linear epilogue. */
 int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
                 float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,

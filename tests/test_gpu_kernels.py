@@ -131,6 +131,52 @@ def test_attention_f32(B, H, L, S, dh, er_len, causal):
     assert rel_err(p_out.view(B, H, L, S), pref) < 2e-5
 
 
+@pytest.mark.parametrize("B,Hq,Hkv,L,S,er_len,causal", [
+    (2, 8, 8, 299, 299, 300, True),      # decoder RPR self-attention, BASELINE shape
+    (2, 8, 8, 300, 300, 0, False),       # encoder self-attention
+    (2, 8, 8, 299, 300, 0, False),       # decoder cross-attention
+    (3, 4, 4, 37, 37, 64, True),         # single tile, tiny band
+    (2, 4, 4, 150, 150, 160, False),     # RPR without a mask
+    (2, 8, 2, 130, 170, 0, False),       # grouped-query (Hkv < Hq), ragged
+    (1, 2, 2, 1, 1, 16, True),
+])
+def test_attention_bwd_tensor_core(B, Hq, Hkv, L, S, er_len, causal):
+    """mma.sync attention backward (csrc/attn_bwd_tc.cu) against torch autograd over the oracle's arithmetic (the
+    reference's gradients come from autograd over the same ops, rpr.py:387-414) on the same bf16-rounded inputs."""
+    from video2music_b200 import ops
+    dh, bf = 64, torch.bfloat16
+    q = (_u((B, L, Hq, dh), 11, "q") * 0.3).to(bf)
+    k, v = _u((B, S, Hkv, dh), 11, "k").to(bf), _u((B, S, Hkv, dh), 11, "v").to(bf)
+    dO = _u((B, L, Hq, dh), 11, "do").to(bf)
+    Er = _u((er_len, dh), 11, "er").to(bf) if er_len else None
+    g = Hq // Hkv
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    erf = Er.float().requires_grad_(True) if er_len else None
+    ref, _ = _attn_ref(qf.permute(0, 2, 1, 3), kf.repeat_interleave(g, dim=2).permute(0, 2, 1, 3),
+                       vf.repeat_interleave(g, dim=2).permute(0, 2, 1, 3), erf, causal)
+    ref = ref.permute(0, 2, 1, 3)
+    ref.backward(dO.float())
+    qd, kd, vd, dOd = q.to(DEV), k.to(DEV), v.to(DEV), dO.to(DEV)
+    out = torch.zeros((B, L, Hq, dh), device=DEV, dtype=bf)
+    lse = torch.zeros((B * Hq, L), device=DEV)
+    qs, ks = (L * Hq * dh, Hq * dh), (S * Hkv * dh, Hkv * dh)
+    ops.attention(qd, kd, vd, out, B=B, Hq=Hq, Hkv=Hkv, Lq=L, Lk=S, dh=dh, q_strides=qs, k_strides=ks, v_strides=ks,
+                  o_strides=qs, causal=causal, Er=Er.to(DEV) if er_len else None, lse=lse)
+    dq = torch.full_like(qd, float("nan"))
+    dk, dv = torch.full_like(kd, float("nan")), torch.full_like(vd, float("nan"))
+    der = torch.zeros((er_len, dh), device=DEV) if er_len else None
+    ops.attention_bwd(qd, kd, vd, out, dOd, lse, Er.to(DEV) if er_len else None, dq, dk, dv, der, B=B, Hq=Hq, Hkv=Hkv, Lq=L,
+                      Lk=S, dh=dh, q_strides=qs, k_strides=ks, v_strides=ks, o_strides=qs, do_strides=qs, dq_strides=qs,
+                      dkv_strides=ks, causal=causal, tensor_core=True)
+    errs = {"dq": rel_err(dq.float().cpu(), qf.grad), "dk": rel_err(dk.float().cpu(), kf.grad),
+            "dv": rel_err(dv.float().cpu(), vf.grad)}
+    if er_len:
+        errs["dEr"] = rel_err(der.cpu(), erf.grad)
+    print("attention backward (tensor core) rel errs", {n: "%.2e" % e for n, e in errs.items()})
+    for n, e in errs.items():
+        assert e < 2e-2, n
+
+
 @pytest.mark.parametrize("B,Hq,Hkv,L,S,er_len,causal,seq_first", [
     (2, 8, 8, 299, 299, 300, True, False),      # decoder RPR self-attention, BASELINE shape
     (1, 8, 8, 300, 300, 300, True, False),

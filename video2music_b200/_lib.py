@@ -63,7 +63,7 @@ class Decode(C.Structure):
 
 # every symbol include/v2m_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
-    "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_dy_prep",
+    "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_attn_bwd_tc", "v2m_attn_bwd_tc_workspace", "v2m_dy_prep",
     "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
     "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route",
@@ -94,6 +94,9 @@ def load() -> C.CDLL:
     lib.v2m_gemm_bf16_general.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_gemm_f32_strided.argtypes = [vp, i32, i32, vp, i32, i32, vp, i32, i32, i32, i32, C.POINTER(Epilogue), vp]
     lib.v2m_attn_bwd.argtypes = [C.POINTER(AttnBwd), vp]
+    lib.v2m_attn_bwd_tc.argtypes = [C.POINTER(AttnBwd), vp, i64, vp]
+    lib.v2m_attn_bwd_tc_workspace.argtypes = [i32, i32, i32, i32, i32]
+    lib.v2m_attn_bwd_tc_workspace.restype = i64
     lib.v2m_dy_prep.argtypes = [vp, i32, i64, vp, i32, i64, i32, C.c_float, i32, vp, i32, i64, vp, i32, i32, vp]
     lib.v2m_layernorm_bwd.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, C.c_float, vp]
     lib.v2m_embed_bwd.argtypes = [vp, vp, i32, i64, vp, i32, i32, vp]

@@ -93,14 +93,19 @@ class AttnSelfFn(torch.autograd.Function):
         dh = E // H
         dout = dout.contiguous()
         ld = qkv.stride(0)
-        dkv32 = torch.zeros((B * L, 2 * E), device=qkv.device, dtype=F32)
         dqkv = torch.empty_like(qkv)
         der = torch.zeros(erc.shape, device=qkv.device, dtype=F32) if has_er else None
-        ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dkv32, dkv32[:, E:], der,
-                          B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=(L * ld, ld), k_strides=(L * ld, ld),
-                          v_strides=(L * ld, ld), o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld),
-                          dkv_strides=(L * 2 * E, 2 * E), causal=causal)
-        dqkv[:, E:] = dkv32                                               # fp32 accumulators -> gradient dtype
+        common = dict(B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=(L * ld, ld), k_strides=(L * ld, ld), v_strides=(L * ld, ld),
+                      o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld), causal=causal)
+        if qkv.dtype == BF16 and dh == 64:
+            # tensor-core kernels write dK / dV straight into the fused gradient (bf16), no fp32 staging
+            ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dqkv[:, E:],
+                              dqkv[:, 2 * E:], der, dkv_strides=(L * ld, ld), tensor_core=True, **common)
+        else:
+            dkv32 = torch.zeros((B * L, 2 * E), device=qkv.device, dtype=F32)
+            ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dkv32, dkv32[:, E:],
+                              der, dkv_strides=(L * 2 * E, 2 * E), **common)
+            dqkv[:, E:] = dkv32                                           # fp32 accumulators -> gradient dtype
         return dqkv, der, None, None, None, None, None
 
 
@@ -127,11 +132,15 @@ class AttnCrossFn(torch.autograd.Function):
         dh = E // H
         dout = dout.contiguous()
         dq = torch.empty_like(q)
+        common = dict(B=B, Hq=H, Hkv=H, Lq=T, Lk=S, dh=dh, q_strides=(T * E, E), k_strides=(S * 2 * E, 2 * E),
+                      v_strides=(S * 2 * E, 2 * E), o_strides=(T * E, E), do_strides=(T * E, E), dq_strides=(T * E, E),
+                      dkv_strides=(S * 2 * E, 2 * E), causal=False)
+        if q.dtype == BF16 and dh == 64:
+            dkv = torch.empty_like(kv)
+            ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv, dkv[:, E:], None, tensor_core=True, **common)
+            return dq, dkv, None, None, None, None
         dkv32 = torch.zeros((B * S, 2 * E), device=q.device, dtype=F32)
-        ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv32, dkv32[:, E:], None, B=B, Hq=H, Hkv=H, Lq=T, Lk=S,
-                          dh=dh, q_strides=(T * E, E), k_strides=(S * 2 * E, 2 * E), v_strides=(S * 2 * E, 2 * E),
-                          o_strides=(T * E, E), do_strides=(T * E, E), dq_strides=(T * E, E), dkv_strides=(S * 2 * E, 2 * E),
-                          causal=False)
+        ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv32, dkv32[:, E:], None, **common)
         return dq, dkv32.to(kv.dtype) if kv.dtype != F32 else dkv32, None, None, None, None
 
 

@@ -1,0 +1,402 @@
+// Attention backward on the tensor cores (bf16 operands, fp32 accumulation): dQ, dK, dV and dEr of
+//   O = softmax(Q K^T + skew(Q Er^T) + causal) V        (model/rpr.py:387-414, _skew :439-455)
+// which the reference obtains from autograd over the materialised (B*H, L, L) tensors.  Same math as the exact SIMT
+// kernel in attn_bwd.cu (see the formulas there); three kernels, no atomics except the final dEr reduction:
+//   rows kernel : one CTA = (batch, head) x 64 query rows, one warp = 16 rows (P and dS never leave the registers of the
+//                 warp that owns the rows).  Recomputes S = Q K^T (+ Srel read from a per-CTA Q Er_rev^T table), P, dP = dO V^T,
+//                 dS = P o (dP - D); accumulates dQ = dS K (+ dQE Er_rev) in registers; writes the P and dS tiles (bf16) and,
+//                 for RPR, the skewed dS rows dQE[i][d] = dS[i][i-d] to a workspace.
+//   cols kernel : one CTA = (batch, kv head) x 64 keys: dV = P^T dO, dK = dS^T Q from the workspace tiles (operands
+//                 transposed on the fly by ldmatrix.trans), summed over the query heads of the group (GQA).
+//   dEr kernel  : dEr[er_len-1-d] = sum_{b,h,i} dQE[i][d] q_i, split over (batch, head) groups, one fp32 atomic per output.
+// Shared-memory tiles are 64 x 64 bf16 with a pitch of 72 elements: ldmatrix and 32-bit fragment loads are conflict-free.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace v2m {
+
+namespace abt {
+
+constexpr int TP = 72;                 // tile pitch (bf16 elements)
+constexpr int TILE = 64 * TP;          // elements per tile
+constexpr int THREADS = 128;
+
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_t(const bf16* p, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ uint32_t lds32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// 64 rows x 64 bf16 from global (row stride `ld` elements, rows >= n_valid zero-filled) into a pitch-72 tile
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long ld, int n_valid) {
+  for (int idx = threadIdx.x; idx < 64 * 8; idx += THREADS) {
+    const int r = idx >> 3, c = idx & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < n_valid) v = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8);
+    *reinterpret_cast<uint4*>(dst + r * TP + c * 8) = v;
+  }
+}
+
+// A fragment (rows r0+g, r0+g+8; k-step ks) of a row-major tile
+__device__ __forceinline__ void frag_a(const bf16* t, int r0, int ks, int g, int q, uint32_t* a) {
+  const bf16* p = t + (r0 + g) * TP + ks * 16 + 2 * q;
+  a[0] = lds32(p); a[1] = lds32(p + 8 * TP); a[2] = lds32(p + 8); a[3] = lds32(p + 8 * TP + 8);
+}
+
+// acc[8][4] (16 x 64, n over the 64 columns of `t`) += A(16 x 64, from four k-steps of a_frag) * T  where T is row-major
+// [k = 64 rows][n = 64 cols] in shared memory (operand transposed by ldmatrix.trans)
+__device__ __forceinline__ void mma_a_times_rowmajor(float acc[8][4], const uint32_t a[4][4], const bf16* t, int lane) {
+  const int ri = lane & 7, mi = lane >> 3;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int ntp = 0; ntp < 4; ++ntp) {
+      uint32_t r0, r1, r2, r3;
+      ldsm_x4_t(t + (kk * 16 + (mi & 1) * 8 + ri) * TP + (2 * ntp + (mi >> 1)) * 8, r0, r1, r2, r3);
+      mma16816(acc[2 * ntp], a[kk], r0, r1);
+      mma16816(acc[2 * ntp + 1], a[kk], r2, r3);
+    }
+  }
+}
+
+struct Ws {          // workspace views (bf16), padded to multiples of 64 in both dims
+  bf16* P; bf16* dS; bf16* dQE;
+  int Lqp, Lkp;
+};
+
+// ------------------------------------------------------------------------------------------------ rows kernel
+template <bool HAS_ER>
+__global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
+  extern __shared__ __align__(16) unsigned char abt_smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(abt_smem);
+  bf16* sdO = sQ + TILE;
+  bf16* sK = sdO + TILE;                // first holds the O tile
+  bf16* sV = sK + TILE;
+  // RPR only: Er_rev rows (d -> Er[er_len-1-d]), the Q Er_rev^T table (fp32) and the skewed dS rows (bf16)
+  const int QP = ws.Lkp + 4, DP = ws.Lkp + 8;
+  bf16* sEr = sV + TILE;                                   // [Lkp][TP]
+  float* sQE = reinterpret_cast<float*>(sEr + (HAS_ER ? ws.Lkp * TP : 0));   // [64][QP]
+  bf16* sdQE = reinterpret_cast<bf16*>(sQE + (HAS_ER ? 64 * QP : 0));        // [64][DP]
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int bh = blockIdx.y, b = bh / p.Hq, hq = bh % p.Hq, hkv = hq / (p.Hq / p.Hkv);
+  const int I0 = blockIdx.x * 64;
+  const int coff = p.Lk - p.Lq;
+  const bf16* Qg = static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64;
+  const bf16* Kg = static_cast<const bf16*>(p.k) + (long long)b * p.k_sb + (long long)hkv * 64;
+  const bf16* Vg = static_cast<const bf16*>(p.v) + (long long)b * p.v_sb + (long long)hkv * 64;
+  const bf16* Og = static_cast<const bf16*>(p.o) + (long long)b * p.o_sb + (long long)hq * 64;
+  const bf16* dOg = static_cast<const bf16*>(p.dO) + (long long)b * p.do_sb + (long long)hq * 64;
+  const int nq = max(0, min(64, p.Lq - I0));
+  load_tile(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
+  load_tile(sdO, dOg + (long long)I0 * p.do_sl, p.do_sl, nq);
+  load_tile(sK, Og + (long long)I0 * p.o_sl, p.o_sl, nq);
+  const int dmax = min(ws.Lkp, I0 + 64);                   // distances d = i - j < dmax are needed (multiple of 64)
+  if (HAS_ER) {
+    const bf16* Er = static_cast<const bf16*>(p.Er);
+    for (int idx = tid; idx < dmax * 8; idx += THREADS) {
+      const int d = idx >> 3, c = idx & 7;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (d < p.er_len && d < p.Lq) v = *reinterpret_cast<const uint4*>(Er + (long long)(p.er_len - 1 - d) * 64 + c * 8);
+      *reinterpret_cast<uint4*>(sEr + d * TP + c * 8) = v;
+    }
+    for (int idx = tid; idx < 64 * DP / 8; idx += THREADS) reinterpret_cast<uint4*>(sdQE)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+
+  const int r0 = w * 16;
+  uint32_t qa[4][4], doa[4][4];
+  float Dlo = 0.f, Dhi = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    frag_a(sQ, r0, ks, g, q, qa[ks]);
+    frag_a(sdO, r0, ks, g, q, doa[ks]);
+    uint32_t oa[4];
+    frag_a(sK, r0, ks, g, q, oa);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = bf16x2_to_f2(doa[ks][e]), y = bf16x2_to_f2(oa[e]);
+      const float s = x.x * y.x + x.y * y.y;
+      if (e & 1) Dhi += s; else Dlo += s;
+    }
+  }
+  Dlo += __shfl_xor_sync(0xffffffffu, Dlo, 1); Dlo += __shfl_xor_sync(0xffffffffu, Dlo, 2);
+  Dhi += __shfl_xor_sync(0xffffffffu, Dhi, 1); Dhi += __shfl_xor_sync(0xffffffffu, Dhi, 2);
+  const int ilo = I0 + r0 + g, ihi = ilo + 8;
+  const float lse_lo = ilo < p.Lq ? p.lse[(long long)bh * p.Lq + ilo] : 0.f;
+  const float lse_hi = ihi < p.Lq ? p.lse[(long long)bh * p.Lq + ihi] : 0.f;
+
+  if (HAS_ER) {
+    // QE[i][d] = q_i . Er_rev[d] for this warp's 16 rows (only the warp itself reads them back)
+    for (int nt = 0; nt < dmax / 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const bf16* bp = sEr + (nt * 8 + g) * TP + ks * 16 + 2 * q;
+        mma16816(c, qa[ks], lds32(bp), lds32(bp + 8));
+      }
+      float* dst = sQE + (r0 + g) * QP + nt * 8 + 2 * q;
+      dst[0] = c[0]; dst[1] = c[1];
+      dst[8 * QP] = c[2]; dst[8 * QP + 1] = c[3];
+    }
+  }
+  __syncthreads();                                         // the O tile is no longer needed: K / V tiles go there
+
+  float dq[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dq[nt][e] = 0.f;
+  const int n_jt = p.causal ? min(ws.Lkp / 64, (I0 + 63 + coff) / 64 + 1) : ws.Lkp / 64;
+  bf16* Pw = ws.P + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
+  bf16* dSw = ws.dS + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
+  for (int jt = 0; jt < n_jt; ++jt) {
+    const int J0 = jt * 64;
+    const int nk = max(0, min(64, p.Lk - J0));
+    load_tile(sK, Kg + (long long)J0 * p.k_sl, p.k_sl, nk);
+    load_tile(sV, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s[nt][e] = 0.f; dp[nt][e] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const bf16* kp = sK + (nt * 8 + g) * TP + ks * 16 + 2 * q;
+        mma16816(s[nt], qa[ks], lds32(kp), lds32(kp + 8));
+        const bf16* vp = sV + (nt * 8 + g) * TP + ks * 16 + 2 * q;
+        mma16816(dp[nt], doa[ks], lds32(vp), lds32(vp + 8));
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int hi = e >> 1, i = hi ? ihi : ilo, j = J0 + nt * 8 + 2 * q + (e & 1);
+        const bool valid = i < p.Lq && j < p.Lk && (!p.causal || j <= i + coff);
+        float sc = s[nt][e];
+        const bool rel = HAS_ER && valid && j <= i;            // _skew contributes only for j <= i (rpr.py:439-455)
+        if (rel) sc += sQE[(r0 + g + hi * 8) * QP + (i - j)];
+        const float pv = valid ? __expf(sc - (hi ? lse_hi : lse_lo)) : 0.f;
+        const float dsv = pv * (dp[nt][e] - (hi ? Dhi : Dlo));
+        s[nt][e] = pv;
+        dp[nt][e] = dsv;
+        if (rel) sdQE[(r0 + g + hi * 8) * DP + (i - j)] = __float2bfloat16_rn(dsv);
+      }
+      // P and dS tiles for the cols kernel
+      const long long o_lo = (long long)g * ws.Lkp + J0 + nt * 8 + 2 * q, o_hi = o_lo + 8LL * ws.Lkp;
+      *reinterpret_cast<uint32_t*>(Pw + o_lo) = f2_to_bf16x2(s[nt][0], s[nt][1]);
+      *reinterpret_cast<uint32_t*>(Pw + o_hi) = f2_to_bf16x2(s[nt][2], s[nt][3]);
+      *reinterpret_cast<uint32_t*>(dSw + o_lo) = f2_to_bf16x2(dp[nt][0], dp[nt][1]);
+      *reinterpret_cast<uint32_t*>(dSw + o_hi) = f2_to_bf16x2(dp[nt][2], dp[nt][3]);
+    }
+    // dQ += dS K_J : the C fragments of two adjacent key tiles form the A fragment of one k-step
+    uint32_t a[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      a[kk][0] = f2_to_bf16x2(dp[2 * kk][0], dp[2 * kk][1]);
+      a[kk][1] = f2_to_bf16x2(dp[2 * kk][2], dp[2 * kk][3]);
+      a[kk][2] = f2_to_bf16x2(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      a[kk][3] = f2_to_bf16x2(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+    }
+    mma_a_times_rowmajor(dq, a, sK, lane);
+    __syncthreads();
+  }
+  if (HAS_ER) {
+    __syncwarp();
+    // skewed dS rows of this warp -> workspace (for the dEr kernel), then dQ += dQE Er_rev
+    bf16* dQEw = ws.dQE + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
+    for (int idx = lane; idx < 16 * (ws.Lkp / 8); idx += 32) {
+      const int r = idx / (ws.Lkp / 8), c = idx % (ws.Lkp / 8);
+      *reinterpret_cast<uint4*>(dQEw + (long long)r * ws.Lkp + c * 8) = *reinterpret_cast<const uint4*>(sdQE + (r0 + r) * DP + c * 8);
+    }
+    const int ri = lane & 7, mi = lane >> 3;
+    for (int ks = 0; ks < dmax / 16; ++ks) {
+      uint32_t af[4];
+      const bf16* ap = sdQE + (r0 + g) * DP + ks * 16 + 2 * q;
+      af[0] = lds32(ap); af[1] = lds32(ap + 8 * DP); af[2] = lds32(ap + 8); af[3] = lds32(ap + 8 * DP + 8);
+#pragma unroll
+      for (int ntp = 0; ntp < 4; ++ntp) {
+        uint32_t x0, x1, x2, x3;
+        ldsm_x4_t(sEr + (ks * 16 + (mi & 1) * 8 + ri) * TP + (2 * ntp + (mi >> 1)) * 8, x0, x1, x2, x3);
+        mma16816(dq[2 * ntp], af, x0, x1);
+        mma16816(dq[2 * ntp + 1], af, x2, x3);
+      }
+    }
+  }
+  bf16* dQg = static_cast<bf16*>(p.dq) + (long long)b * p.dq_sb + (long long)hq * 64;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (ilo < p.Lq) *reinterpret_cast<uint32_t*>(dQg + (long long)ilo * p.dq_sl + nt * 8 + 2 * q) = f2_to_bf16x2(dq[nt][0] * p.q_scale, dq[nt][1] * p.q_scale);
+    if (ihi < p.Lq) *reinterpret_cast<uint32_t*>(dQg + (long long)ihi * p.dq_sl + nt * 8 + 2 * q) = f2_to_bf16x2(dq[nt][2] * p.q_scale, dq[nt][3] * p.q_scale);
+  }
+}
+
+// A fragments (m = column c0.. of the tile, k = its rows): acc += T^T-style products.  a[kk] = A(16 m x 16 k) with
+// A[m][k] = t[kk*16 + k][c0 + m]
+__device__ __forceinline__ void frag_a_transposed(const bf16* t, int c0, int lane, uint32_t a[4][4]) {
+  const int ri = lane & 7, mi = lane >> 3;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    ldsm_x4_t(t + (kk * 16 + (mi >> 1) * 8 + ri) * TP + c0 + (mi & 1) * 8, a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+}
+
+// ------------------------------------------------------------------------------------------------ cols kernel
+__global__ void __launch_bounds__(THREADS) attn_bwd_cols_kernel(AttnBwdParams p, Ws ws) {
+  extern __shared__ __align__(16) unsigned char abt_smem[];
+  bf16* sP = reinterpret_cast<bf16*>(abt_smem);
+  bf16* sdS = sP + TILE;
+  bf16* sdO = sdS + TILE;
+  bf16* sQ = sdO + TILE;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int b = blockIdx.y / p.Hkv, hkv = blockIdx.y % p.Hkv, grp = p.Hq / p.Hkv;
+  const int J0 = blockIdx.x * 64, jt = blockIdx.x;
+  const int coff = p.Lk - p.Lq;
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
+  for (int hh = 0; hh < grp; ++hh) {
+    const int hq = hkv * grp + hh, bh = b * p.Hq + hq;
+    const bf16* Qg = static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64;
+    const bf16* dOg = static_cast<const bf16*>(p.dO) + (long long)b * p.do_sb + (long long)hq * 64;
+    for (int it = 0; it < ws.Lqp / 64; ++it) {
+      const int I0 = it * 64;
+      if (p.causal && jt > (I0 + 63 + coff) / 64) continue;           // tile never written by the rows kernel (all masked)
+      const int nq = max(0, min(64, p.Lq - I0));
+      load_tile(sP, ws.P + ((long long)bh * ws.Lqp + I0) * ws.Lkp + J0, ws.Lkp, 64);
+      load_tile(sdS, ws.dS + ((long long)bh * ws.Lqp + I0) * ws.Lkp + J0, ws.Lkp, 64);
+      load_tile(sdO, dOg + (long long)I0 * p.do_sl, p.do_sl, nq);
+      load_tile(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
+      __syncthreads();
+      uint32_t a[4][4];
+      frag_a_transposed(sP, w * 16, lane, a);                         // A[m = key][k = query] = P[query][key]
+      mma_a_times_rowmajor(dv, a, sdO, lane);
+      frag_a_transposed(sdS, w * 16, lane, a);
+      mma_a_times_rowmajor(dk, a, sQ, lane);
+      __syncthreads();
+    }
+  }
+  const int jlo = J0 + w * 16 + g, jhi = jlo + 8;
+  bf16* dKg = reinterpret_cast<bf16*>(p.dk) + (long long)b * p.dkv_sb + (long long)hkv * 64;
+  bf16* dVg = reinterpret_cast<bf16*>(p.dv) + (long long)b * p.dkv_sb + (long long)hkv * 64;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * q;
+    if (jlo < p.Lk) {
+      *reinterpret_cast<uint32_t*>(dKg + (long long)jlo * p.dkv_sl + c) = f2_to_bf16x2(dk[nt][0], dk[nt][1]);
+      *reinterpret_cast<uint32_t*>(dVg + (long long)jlo * p.dkv_sl + c) = f2_to_bf16x2(dv[nt][0], dv[nt][1]);
+    }
+    if (jhi < p.Lk) {
+      *reinterpret_cast<uint32_t*>(dKg + (long long)jhi * p.dkv_sl + c) = f2_to_bf16x2(dk[nt][2], dk[nt][3]);
+      *reinterpret_cast<uint32_t*>(dVg + (long long)jhi * p.dkv_sl + c) = f2_to_bf16x2(dv[nt][2], dv[nt][3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dEr kernel
+__global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, Ws ws, int n_split) {
+  extern __shared__ __align__(16) unsigned char abt_smem[];
+  bf16* sE = reinterpret_cast<bf16*>(abt_smem);          // dQE tile [64 i][64 d]
+  bf16* sQ = sE + TILE;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int D0 = blockIdx.x * 64;
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  for (int bh = blockIdx.y; bh < p.B * p.Hq; bh += n_split) {
+    const int b = bh / p.Hq, hq = bh % p.Hq;
+    const bf16* Qg = static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64;
+    for (int it = D0 / 64; it < ws.Lqp / 64; ++it) {       // rows i >= d only
+      const int I0 = it * 64;
+      const int nq = max(0, min(64, p.Lq - I0));
+      load_tile(sE, ws.dQE + ((long long)bh * ws.Lqp + I0) * ws.Lkp + D0, ws.Lkp, 64);
+      load_tile(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
+      __syncthreads();
+      uint32_t a[4][4];
+      frag_a_transposed(sE, w * 16, lane, a);               // A[m = d][k = i] = dQE[i][d]
+      mma_a_times_rowmajor(acc, a, sQ, lane);
+      __syncthreads();
+    }
+  }
+  const int dlo = D0 + w * 16 + g, dhi = dlo + 8;
+  const int dlim = min(p.Lq, p.er_len);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int c = nt * 8 + 2 * q;
+    if (dlo < dlim) {
+      atomicAdd(p.dEr + (long long)(p.er_len - 1 - dlo) * 64 + c, acc[nt][0] * p.q_scale);
+      atomicAdd(p.dEr + (long long)(p.er_len - 1 - dlo) * 64 + c + 1, acc[nt][1] * p.q_scale);
+    }
+    if (dhi < dlim) {
+      atomicAdd(p.dEr + (long long)(p.er_len - 1 - dhi) * 64 + c, acc[nt][2] * p.q_scale);
+      atomicAdd(p.dEr + (long long)(p.er_len - 1 - dhi) * 64 + c + 1, acc[nt][3] * p.q_scale);
+    }
+  }
+}
+
+}  // namespace abt
+
+// Workspace bytes attn_bwd_tc needs for these dimensions.
+long long attn_bwd_tc_workspace(int B, int Hq, int Lq, int Lk, int has_er) {
+  const long long Lqp = (Lq + 63) / 64 * 64, Lkp = (Lk + 63) / 64 * 64;
+  return (long long)B * Hq * Lqp * Lkp * 2 * (has_er ? 3 : 2);
+}
+
+// bf16 only, head_dim 64.  p.dk / p.dv are BF16 outputs here (written once, no accumulation; strides dkv_sb / dkv_sl in
+// elements), p.dEr fp32 [er_len, 64] must be zeroed by the caller.  ws: attn_bwd_tc_workspace() bytes of device memory.
+int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaStream_t stream) {
+  V2M_REQUIRE(p.dtype == 1 && p.dh == 64, "attn_bwd_tc: bf16 with head_dim 64 only (dtype %d, dh %d)", p.dtype, p.dh);
+  V2M_REQUIRE(p.B > 0 && p.Hq > 0 && p.Hkv > 0 && p.Hq % p.Hkv == 0, "attn_bwd_tc: bad heads %d/%d", p.Hq, p.Hkv);
+  V2M_REQUIRE(p.Lq > 0 && p.Lk > 0, "attn_bwd_tc: empty sequence");
+  V2M_REQUIRE(p.q_scale == 1.0f, "attn_bwd_tc: q must be pre-scaled (q_scale 1)");
+  const bool has_er = p.Er != nullptr;
+  V2M_REQUIRE(!has_er || (p.Lq == p.Lk && p.Lq <= p.er_len && p.dEr), "attn_bwd_tc: RPR needs Lq == Lk <= er_len and a dEr buffer");
+  V2M_REQUIRE(p.q_sl % 8 == 0 && p.k_sl % 8 == 0 && p.v_sl % 8 == 0 && p.o_sl % 8 == 0 && p.do_sl % 8 == 0 && p.q_sb % 8 == 0 &&
+              p.k_sb % 8 == 0 && p.v_sb % 8 == 0 && p.o_sb % 8 == 0 && p.do_sb % 8 == 0,
+              "attn_bwd_tc: operand strides must be multiples of 8 elements (16-byte rows)");
+  V2M_REQUIRE(p.dq_sl % 2 == 0 && p.dkv_sl % 2 == 0 && p.dq_sb % 2 == 0 && p.dkv_sb % 2 == 0, "attn_bwd_tc: odd gradient strides");
+  const long long need = attn_bwd_tc_workspace(p.B, p.Hq, p.Lq, p.Lk, has_er);
+  V2M_REQUIRE(ws_ptr && ws_bytes >= need, "attn_bwd_tc: workspace of %lld B needed, %lld given", need, ws_bytes);
+  abt::Ws ws;
+  ws.Lqp = (p.Lq + 63) / 64 * 64;
+  ws.Lkp = (p.Lk + 63) / 64 * 64;
+  const long long plane = (long long)p.B * p.Hq * ws.Lqp * ws.Lkp;
+  ws.P = static_cast<bf16*>(ws_ptr);
+  ws.dS = ws.P + plane;
+  ws.dQE = has_er ? ws.dS + plane : nullptr;
+  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16);
+  const size_t smem_er = tiles4 + (size_t)ws.Lkp * abt::TP * 2 + (size_t)64 * (ws.Lkp + 4) * 4 + (size_t)64 * (ws.Lkp + 8) * 2;
+  V2M_REQUIRE(!has_er || smem_er <= 227 * 1024, "attn_bwd_tc: L=%d needs %zu B of shared memory with RPR (> 227 KB)", p.Lk, smem_er);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles4);
+    attr_set = true;
+  }
+  dim3 grid_r(ws.Lqp / 64, p.B * p.Hq);
+  if (has_er) abt::attn_bwd_rows_kernel<true><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
+  else abt::attn_bwd_rows_kernel<false><<<grid_r, abt::THREADS, tiles4, stream>>>(p, ws);
+  int rc = check_launch("attn_bwd_rows");
+  if (rc) return rc;
+  dim3 grid_c(ws.Lkp / 64, p.B * p.Hkv);
+  abt::attn_bwd_cols_kernel<<<grid_c, abt::THREADS, tiles4, stream>>>(p, ws);
+  rc = check_launch("attn_bwd_cols");
+  if (rc || !has_er) return rc;
+  const int n_split = p.B * p.Hq < 64 ? p.B * p.Hq : 64;
+  dim3 grid_e(ws.Lkp / 64, n_split);
+  abt::attn_bwd_der_kernel<<<grid_e, abt::THREADS, 2 * abt::TILE * sizeof(bf16), stream>>>(p, ws, n_split);
+  return check_launch("attn_bwd_der");
+}
+
+}  // namespace v2m

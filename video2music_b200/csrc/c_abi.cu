@@ -116,6 +116,17 @@ int v2m_attn_bwd(const v2m_attn_bwd_t* a, void* stream) {
   return attn_bwd(p, static_cast<cudaStream_t>(stream));
 }
 
+int64_t v2m_attn_bwd_tc_workspace(int32_t B, int32_t Hq, int32_t Lq, int32_t Lk, int32_t has_er) {
+  return attn_bwd_tc_workspace(B, Hq, Lq, Lk, has_er);
+}
+
+int v2m_attn_bwd_tc(const v2m_attn_bwd_t* a, void* ws, int64_t ws_bytes, void* stream) {
+  V2M_REQUIRE(a != nullptr, "v2m_attn_bwd_tc: null params");
+  AttnBwdParams p;
+  memcpy(&p, a, sizeof(p));
+  return attn_bwd_tc(p, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
                 float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
                 void* stream) {

@@ -75,6 +75,10 @@ struct AttnBwdParams {
   float q_scale;
 };
 int attn_bwd(const AttnBwdParams& p, cudaStream_t stream);
+// Tensor-core variant (bf16, head_dim 64, q pre-scaled): p.dk / p.dv are BF16 outputs written once (no accumulation),
+// p.dEr fp32 zeroed by the caller; ws = attn_bwd_tc_workspace() bytes of device scratch (P, dS and skewed-dS tiles).
+long long attn_bwd_tc_workspace(int B, int Hq, int Lq, int Lk, int has_er);
+int attn_bwd_tc(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStream_t stream);
 
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
             int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, cudaStream_t stream);

@@ -280,7 +280,9 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 
 
 def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_strides,
-                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0):
+                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False):
+    """tensor_core=True (bf16, head_dim 64): dk / dv are bf16 outputs written once by the mma.sync kernels of
+    csrc/attn_bwd_tc.cu; otherwise dk / dv are zeroed fp32 buffers the exact SIMT kernel accumulates into."""
     require_device(q)
     a = _lib.AttnBwd()
     a.q, a.k, a.v, a.o, a.dO, a.lse, a.Er = ptr(q), ptr(k), ptr(v), ptr(o), ptr(dO), ptr(lse), ptr(Er)
@@ -291,6 +293,12 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
     a.er_len = Er.shape[0] if Er is not None else 0
     a.dtype = dtype_code(q.dtype)
     a.q_scale = q_scale
+    if tensor_core:
+        n = int(load().v2m_attn_bwd_tc_workspace(B, Hq, Lq, Lk, int(Er is not None)))
+        ws = torch.empty(n, dtype=torch.uint8, device=q.device)
+        check(load().v2m_attn_bwd_tc(C.byref(a), ptr(ws), n, stream()))
+        _lib.count_launches(3 if Er is not None else 2)
+        return
     check(load().v2m_attn_bwd(C.byref(a), stream()))
     _lib.count_launches(1)
 
