@@ -58,10 +58,83 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   }
 }
 
+// D == 512 fast path: a lane owns 16 contiguous columns (128-bit loads / stores), a warp walks rows grid-stride with
+// gamma / beta in registers.  Same two-pass arithmetic as the generic kernel.
+__device__ __forceinline__ void ld16(const bf16* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+  float2 f;
+  f = bf16x2_to_f2(a.x); v[0] = f.x; v[1] = f.y;   f = bf16x2_to_f2(a.y); v[2] = f.x; v[3] = f.y;
+  f = bf16x2_to_f2(a.z); v[4] = f.x; v[5] = f.y;   f = bf16x2_to_f2(a.w); v[6] = f.x; v[7] = f.y;
+  f = bf16x2_to_f2(b.x); v[8] = f.x; v[9] = f.y;   f = bf16x2_to_f2(b.y); v[10] = f.x; v[11] = f.y;
+  f = bf16x2_to_f2(b.z); v[12] = f.x; v[13] = f.y; f = bf16x2_to_f2(b.w); v[14] = f.x; v[15] = f.y;
+}
+__device__ __forceinline__ void ld16(const float* p, float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = reinterpret_cast<const float4*>(p)[q];
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void st16(bf16* p, const float* v) {
+  uint4 a, b;
+  a.x = f2_to_bf16x2(v[0], v[1]);   a.y = f2_to_bf16x2(v[2], v[3]);   a.z = f2_to_bf16x2(v[4], v[5]);   a.w = f2_to_bf16x2(v[6], v[7]);
+  b.x = f2_to_bf16x2(v[8], v[9]);   b.y = f2_to_bf16x2(v[10], v[11]); b.z = f2_to_bf16x2(v[12], v[13]); b.w = f2_to_bf16x2(v[14], v[15]);
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 8) = b;
+}
+__device__ __forceinline__ void st16(float* p, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm512_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           T* __restrict__ y, int M, float eps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = gridDim.x * 8;
+  float g[16], b[16];
+  ld16(gamma + lane * 16, g);
+  ld16(beta + lane * 16, b);
+  for (int row = blockIdx.x * 8 + warp; row < M; row += nw) {
+    float v[16];
+    ld16(x + (size_t)row * 512 + lane * 16, v);
+    if (res) {
+      float r[16];
+      ld16(res + (size_t)row * 512 + lane * 16, r);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] += r[e];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) sum += v[e];
+    const float mean = warp_sum(sum) * (1.f / 512.f);
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const float t = v[e] - mean; sq = fmaf(t, t, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.f / 512.f) + eps);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = (v[e] - mean) * rstd * g[e] + b[e];
+    st16(y + (size_t)row * 512 + lane * 16, v);
+  }
+}
+
 int layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const float* gamma, const float* beta,
               void* y, int y_dtype, void* y2, int y2_dtype, int M, int D, float eps, cudaStream_t stream) {
   V2M_REQUIRE(D > 0 && D <= 32 * kMaxPerLane, "layernorm: D=%d unsupported (<= %d)", D, 32 * kMaxPerLane);
   if (M == 0) return kOk;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (D == 512 && !y2 && x_dtype == y_dtype && (!res || res_dtype == x_dtype) && al16(x) && al16(res) && al16(y) && al16(gamma) &&
+      al16(beta)) {
+    int grid = (M + 7) / 8;
+    if (grid > 148 * 8) grid = 148 * 8;
+    if (x_dtype == 0)
+      layernorm512_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<const float*>(res), gamma, beta,
+                                                           static_cast<float*>(y), M, eps);
+    else
+      layernorm512_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(res), gamma, beta,
+                                                          static_cast<bf16*>(y), M, eps);
+    return check_launch("layernorm512");
+  }
   const int rows_per_block = 8;
   layernorm_kernel<<<(M + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, stream>>>(
       x, x_dtype, res, res_dtype, gamma, beta, y, y_dtype, y2, y2_dtype, M, D, eps);

@@ -96,7 +96,9 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long lo
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
-                    int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep) {
+                    int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split) {
+  // k_split > 1: a work item is (output tile, K slice); partial sums are added to the zero-initialised fp32 C with
+  // red.global (small outputs with a long K, e.g. dW = dY^T X over all tokens, would otherwise keep a handful of SMs busy)
   using Cfg = GemmCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,8 +110,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + GM - 1) / GM, n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + GK - 1) / GK;
+  const int num_tiles = m_tiles * n_tiles * k_split;       // work items
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -130,9 +132,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+        const int tile = item / k_split, ks = item - tile * k_split;
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
           mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
@@ -158,10 +162,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     constexpr uint32_t idesc = make_idesc_bf16(GM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int ks = item % k_split;
+      const int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
       mbar_wait(tempty_bar + acc, acc_phase ^ 1);
       tc_fence_after();
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar + stage, phase);
         tc_fence_after();
         if (lane == 0) {
@@ -173,10 +179,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                      : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_base + acc * BN, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_base + acc * BN, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar + stage);                    // frees the smem slot when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar + acc);  // accumulator ready for the epilogue
+          if (kb == kb1 - 1) umma_commit(tfull_bar + acc);     // accumulator ready for the epilogue
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -188,7 +194,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;          // which chunks of the tile this warp drains
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      const int tile = item / k_split;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m = m_blk * GM + quad * 32 + lane;
       mbar_wait(tfull_bar + acc, acc_phase);
@@ -206,6 +213,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (k_split > 1) {                                   // partial sum of one K slice (plain fp32 output, no epilogue ops)
+          float* dst = static_cast<float*>(C) + (size_t)m * ldc + n0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n0 + i < N) atomicAdd(dst + i, v[i]);
+          continue;
+        }
         if (vec_ok && n0 + 32 <= N) {
           // ---- fast path: whole chunk in range, every pointer 16-byte aligned -> 128-bit loads / stores only
           if (ep.bias) {
@@ -304,7 +318,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
-                       const GemmEpilogue& ep, cudaStream_t stream) {
+                       const GemmEpilogue& ep, cudaStream_t stream, bool allow_split) {
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -319,8 +333,20 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int tiles = ((M + GM - 1) / GM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep);
+  int k_split = 1;
+  const int num_kb = (K + GK - 1) / GK;
+  if (allow_split && tiles * 2 <= num_sms && num_kb >= 16) {
+    k_split = num_sms / tiles;
+    if (k_split > num_kb / 4) k_split = num_kb / 4;           // at least 4 k-blocks per slice
+    if (k_split < 1) k_split = 1;
+  }
+  if (k_split > 1) {
+    cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+    if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: clearing the split-K output failed: %s", cudaGetErrorString(e)); return kCudaError; }
+  }
+  const int items = tiles * k_split;
+  const int grid = items < num_sms ? items : num_sms;
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split);
   return check_launch("gemm_bf16_tc");
 }
 
@@ -342,7 +368,9 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
   vec_ok = vec_ok && (!ep.residual || ((long long)ep.ldr * (ep.residual_bf16 ? 2 : 4)) % 16 == 0);
   if (ep.head_scatter) vec_ok = vec_ok && ep.dh % 32 == 0 && ((long long)ep.part_stride * osz) % 16 == 0;
   else vec_ok = vec_ok && ((long long)ldc * osz) % 16 == 0;
-#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream)
+  // split-K only for plain fp32 outputs (no epilogue operation commutes with partial sums except the identity)
+  const bool allow_split = !out_bf16 && !ep.bias && !ep.residual && !ep.row_scale && !ep.relu && ep.alpha_cols == 0 && !ep.head_scatter;
+#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split)
   if (bn == 256) {
     if (!a_mn && !b_mn) return V2M_GO(256, false, false);
     if (!a_mn && b_mn) return V2M_GO(256, false, true);

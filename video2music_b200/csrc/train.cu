@@ -119,10 +119,105 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
   }
 }
 
+// D == 512 fast path: a lane owns 16 contiguous columns (128-bit accesses), dgamma / dbeta partials live in registers over
+// all rows a warp visits, are combined per CTA in shared memory and leave with one global atomic per column and CTA.
+__device__ __forceinline__ void lnb_ld16(const bf16* p, float* v) {
+  const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + 8);
+  float2 f;
+  f = bf16x2_to_f2(a.x); v[0] = f.x; v[1] = f.y;   f = bf16x2_to_f2(a.y); v[2] = f.x; v[3] = f.y;
+  f = bf16x2_to_f2(a.z); v[4] = f.x; v[5] = f.y;   f = bf16x2_to_f2(a.w); v[6] = f.x; v[7] = f.y;
+  f = bf16x2_to_f2(b.x); v[8] = f.x; v[9] = f.y;   f = bf16x2_to_f2(b.y); v[10] = f.x; v[11] = f.y;
+  f = bf16x2_to_f2(b.z); v[12] = f.x; v[13] = f.y; f = bf16x2_to_f2(b.w); v[14] = f.x; v[15] = f.y;
+}
+__device__ __forceinline__ void lnb_ld16(const float* p, float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 t = reinterpret_cast<const float4*>(p)[q];
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void lnb_st16(bf16* p, const float* v) {
+  uint4 a, b;
+  a.x = f2_to_bf16x2(v[0], v[1]);   a.y = f2_to_bf16x2(v[2], v[3]);   a.z = f2_to_bf16x2(v[4], v[5]);   a.w = f2_to_bf16x2(v[6], v[7]);
+  b.x = f2_to_bf16x2(v[8], v[9]);   b.y = f2_to_bf16x2(v[10], v[11]); b.z = f2_to_bf16x2(v[12], v[13]); b.w = f2_to_bf16x2(v[14], v[15]);
+  *reinterpret_cast<uint4*>(p) = a;
+  *reinterpret_cast<uint4*>(p + 8) = b;
+}
+__device__ __forceinline__ void lnb_st16(float* p, const float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm512_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                               const T* __restrict__ dy, T* __restrict__ dx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta, int M, float eps) {
+  __shared__ float sacc[2 * 512];
+  for (int i = threadIdx.x; i < 2 * 512; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = gridDim.x * 8;
+  float gm[16], dg[16], db[16];
+  lnb_ld16(gamma + lane * 16, gm);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) { dg[e] = 0.f; db[e] = 0.f; }
+  for (int row = blockIdx.x * 8 + warp; row < M; row += nw) {
+    float xv[16], gv[16];
+    lnb_ld16(x + (size_t)row * 512 + lane * 16, xv);
+    lnb_ld16(dy + (size_t)row * 512 + lane * 16, gv);
+    float sum = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) sum += xv[e];
+    const float mean = warp_sum(sum) * (1.f / 512.f);
+    float sq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { const float t = xv[e] - mean; sq = fmaf(t, t, sq); }
+    const float rstd = rsqrtf(warp_sum(sq) * (1.f / 512.f) + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const float xh = (xv[e] - mean) * rstd;
+      dg[e] = fmaf(gv[e], xh, dg[e]);
+      db[e] += gv[e];
+      const float dxh = gv[e] * gm[e];
+      xv[e] = xh;
+      gv[e] = dxh;
+      s1 += dxh;
+      s2 = fmaf(dxh, xh, s2);
+    }
+    s1 = warp_sum(s1) * (1.f / 512.f);
+    s2 = warp_sum(s2) * (1.f / 512.f);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) gv[e] = rstd * (gv[e] - s1 - xv[e] * s2);
+    lnb_st16(dx + (size_t)row * 512 + lane * 16, gv);
+  }
+#pragma unroll
+  for (int e = 0; e < 16; ++e) {
+    atomicAdd(&sacc[lane * 16 + e], dg[e]);
+    atomicAdd(&sacc[512 + lane * 16 + e], db[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += 256) {
+    atomicAdd(dgamma + i, sacc[i]);
+    atomicAdd(dbeta + i, sacc[512 + i]);
+  }
+}
+
 int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy, int dy_dtype, void* dx, int dx_dtype,
                   float* dgamma, float* dbeta, int M, int D, float eps, cudaStream_t stream) {
   V2M_REQUIRE(D > 0 && D <= 32 * LNB_MAX, "layernorm_bwd: D=%d unsupported", D);
   if (M == 0) return kOk;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (D == 512 && x_dtype == dy_dtype && x_dtype == dx_dtype && al16(x) && al16(dy) && al16(dx) && al16(gamma)) {
+    int g2 = (M + 7) / 8;
+    if (g2 > 148 * 2) g2 = 148 * 2;
+    if (x_dtype == 0)
+      layernorm512_bwd_kernel<float><<<g2, 256, 0, stream>>>(static_cast<const float*>(x), gamma, static_cast<const float*>(dy),
+                                                             static_cast<float*>(dx), dgamma, dbeta, M, eps);
+    else
+      layernorm512_bwd_kernel<bf16><<<g2, 256, 0, stream>>>(static_cast<const bf16*>(x), gamma, static_cast<const bf16*>(dy),
+                                                            static_cast<bf16*>(dx), dgamma, dbeta, M, eps);
+    return check_launch("layernorm512_bwd");
+  }
   int grid = (M + 7) / 8;
   if (grid > 148 * 4) grid = 148 * 4;
   layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), stream>>>(x, x_dtype, gamma, dy, dy_dtype, dx, dx_dtype, dgamma,
