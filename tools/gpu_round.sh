@@ -1,5 +1,4 @@
 set -x
-timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py -x -q 2>&1 | tail -5
-timeout 100 python tools/train_time.py 64 bf16 5 2>&1 | tail -1
-timeout 100 python tools/train_time.py 64 fp32 3 2>&1 | tail -1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2400 --csv --log-file gpurun_out/s13_train_launches.csv python tools/train_time.py 64 bf16 1 > gpurun_out/s13_ncu.log 2>&1
+timeout 500 python bench.py > gpurun_out/s14_bench.json 2> gpurun_out/s14_bench.err; tail -3 gpurun_out/s14_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/s14_bench.json')); print({k:d[k] for k in ('value','ms_per_step','share_of_step','gpu_launches')}); print(d['roofline']['frac']); print(d.get('train'))"
+nvidia-smi --query-gpu=memory.used,memory.total --format=csv
