@@ -1,4 +1,4 @@
 set -x
-timeout 500 python bench.py > gpurun_out/s14_bench.json 2> gpurun_out/s14_bench.err; tail -3 gpurun_out/s14_bench.err; python -c "
-import json; d=json.load(open('gpurun_out/s14_bench.json')); print({k:d[k] for k in ('value','ms_per_step','share_of_step','gpu_launches')}); print(d['roofline']['frac']); print(d.get('train'))"
-nvidia-smi --query-gpu=memory.used,memory.total --format=csv
+timeout 40 python tools/stream_debug.py 13 140 3 5 > gpurun_out/s15_dbg.log 2>&1; grep -v "^[0-9]* \[" gpurun_out/s15_dbg.log | cut -c1-160 | tail -4
+timeout 150 python -m pytest tests/test_gpu_amt.py -x -q -k "stream" 2>&1 | tail -3
+timeout 100 python tools/probe_decode.py > gpurun_out/s15_probe.log 2>&1; grep "bfloat16 decode step mode=stream" gpurun_out/s15_probe.log

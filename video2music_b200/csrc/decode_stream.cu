@@ -22,8 +22,10 @@
 //     conflicts, so q.K^T and P.V run on the tensor cores (mma.sync m16n8k16, keys / dims as the M operand).
 //     A chunk (128 positions of one video) is processed by the warp whose index equals its ring slot: it produces a partial softmax
 //     (max, sum, unnormalised output) for it; the partials of a video are combined once per phase (split softmax).
-//   * the cluster barrier between phases is an mbarrier per CTA on which one thread of every CTA of the cluster
-//     arrives remotely (release.cluster) -- consumers only, so the producers are not throttled by it.
+//   * an all-gather IS its barrier: every CTA stages its slice in shared memory and sends it to each of the 8 CTAs with
+//     one cp.async.bulk (shared::cta -> shared::cluster) that completes on the RECEIVER's mbarrier; a CTA waits on its own
+//     barrier for the 8 slices.  No fence, no separate arrive, producers not involved.  (The one remaining plain cluster
+//     barrier per position, for the logits in global memory, is an mbarrier with remote arrives.)
 #include "common.cuh"
 #include "kernels.h"
 #include <stdlib.h>
@@ -42,7 +44,10 @@ constexpr int NPROD = 2;              // producer warps (one issuing lane each):
 constexpr int THREADS = NCONS + 32 * NPROD;
 constexpr int DH = 64, E = 512, FF = 1024;
 constexpr int XP = E + 8;             // pitch (bf16) of 512-wide operand rows: conflict-free B-fragment loads
-constexpr int HP = FF + 8;
+// gathered operands are slice-major: [8 source CTAs][R rows][slice pitch]; one source CTA's block is contiguous
+constexpr int CP = 72;                // pitch (bf16) of a 64-wide attention-context slice row
+constexpr int HSP = 136;              // pitch (bf16) of a 128-wide FFN-hidden slice row
+constexpr int YP = 64;                // pitch (fp32) of a 64-wide pre-LayerNorm slice row
 constexpr int KCH = 128;              // cache positions per ring slot (256 B each)
 constexpr int ECH = 256;              // Er rows per ring slot (128 B each)
 constexpr int SMEM_MAX = 227 * 1024;
@@ -51,19 +56,21 @@ constexpr int CW = 68;                // floats per softmax partial: m, l, pad, 
 struct Layout {
   uint32_t ring, bars, bias, xn, ctxg, hg, yg, resid, stage, qs, knew, vnew, srel, comb, snew, tok, total;
   int srel_pitch, nslot, nch_max;
+  uint32_t stage_bytes;
 };
 __host__ __device__ inline Layout make_layout(int R, int cap) {
   Layout L;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 127u) & ~127u; return r; };
-  L.bars = take(128);                 // full[MAX_SLOTS] empty[MAX_SLOTS] cbar
+  L.bars = take(128);                 // full[MAX_SLOTS] empty[MAX_SLOTS] cbar gbar[3]
   L.bias = take(kMaxDecLayers * 576 * 4);   // this CTA's bias slices of every layer: q k v so cq co (64 each) f1 (128) f2 (64)
   L.xn = take(R * XP * 2);
-  L.ctxg = take(R * XP * 2);
-  L.hg = take(R * HP * 2);
-  L.yg = take(R * E * 4);
+  L.ctxg = take(CS * R * CP * 2);
+  L.hg = take(CS * R * HSP * 2);
+  L.yg = take(CS * R * YP * 4);
   L.resid = take(R * DH * 4);
-  L.stage = take(R * 128 * 4);
+  L.stage_bytes = (uint32_t)((R * HSP * 2 + 127) & ~127);      // largest slice block (FFN hidden)
+  L.stage = take(2 * L.stage_bytes);                            // two staging buffers, used alternately
   L.qs = take(R * DH * 4);
   L.knew = take(R * DH * 2);
   L.vnew = take(R * DH * 2);
@@ -185,6 +192,10 @@ struct Ctx {
   Ring rg;
   uint64_t* cbar;
   uint32_t cphase;
+  uint64_t* gbar;       // [3] gather barriers: 0 attention context, 1 pre-LayerNorm rows, 2 FFN hidden
+  uint32_t gphase;      // bit i: parity of the next use of gbar[i]
+  uint32_t n_gather;    // gathers issued so far (selects the staging buffer)
+  __device__ __forceinline__ unsigned char* stage_buf() const { return sm + L.stage + (n_gather & 1u) * L.stage_bytes; }
   int c;          // CTA rank in the cluster == head
   int row0, R;    // videos [row0, row0 + R)
   int t;
@@ -222,8 +233,10 @@ __device__ __forceinline__ void cluster_sync_cons(Ctx& cx) {
 // epi(tile, c): c (bias already added): c[0] = (feature g, video 2q), c[1] = (g, 2q+1), c[2] = (g+8, 2q), c[3] = (g+8, 2q+1)
 // bias_of(tile): pointer to the tile's 16 biases, loaded BEFORE the wait on the ring (global latency off the critical path)
 template <class BiasOf, class Epi>
-__device__ __forceinline__ void gemm_phase(Ctx& cx, int n_tiles, int K, bool single, uint32_t x_off, int pitch, BiasOf bias_of,
-                                           Epi epi) {
+// Operand rows: element k of row r lives at x_off + ((k >> slice_log2) * R + r) * pitch + (k & (slice - 1))  (slice-major
+// gathered buffers; slice_log2 >= log2(K) for a plain row-major operand).
+__device__ __forceinline__ void gemm_phase(Ctx& cx, int n_tiles, int K, bool single, uint32_t x_off, int pitch, int slice_log2,
+                                           BiasOf bias_of, Epi epi) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
   cons_sync();                                   // operand rows written by other warps
   ++cx.ph; mark(cx.ph * 1000 + 100 + n_tiles);
@@ -243,6 +256,7 @@ __device__ __forceinline__ void gemm_phase(Ctx& cx, int n_tiles, int K, bool sin
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bf16* xr = cx.at<bf16>(x_off) + (size_t)min(g, cx.R - 1) * pitch + 2 * q;
+    const int slice_stride = cx.R * pitch, slice_mask = (1 << slice_log2) - 1;
     const float* bp = bias_of(warp);
     const float blo = bp[g], bhi = bp[g + 8];
     cx.rg.wait_full(my_slot, my_par);
@@ -252,8 +266,9 @@ __device__ __forceinline__ void gemm_phase(Ctx& cx, int n_tiles, int K, bool sin
 #pragma unroll 8
     for (int ks = 0; ks < nks; ++ks) {
       const uint4 a = ap[ks * 32];
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(xr + ks * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(xr + ks * 16 + 8);
+      const bf16* xk = xr + ((ks * 16) >> slice_log2) * slice_stride + ((ks * 16) & slice_mask);
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(xk);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(xk + 8);
       mma_bf16_16816(acc[ks & 3], a.x, a.y, a.z, a.w, b0, b1);
     }
     __syncwarp();
@@ -270,19 +285,31 @@ __device__ __forceinline__ void gemm_phase(Ctx& cx, int n_tiles, int K, bool sin
   FSTAMP(cx);
 }
 
-// ---- all-gather: every CTA copies its R rows of `row_bytes` (multiple of 16) from local `src_off` (row pitch
-// src_pitch bytes) to offset dst_off + r * dst_pitch + c * row_bytes in ALL 8 CTAs of the cluster -------------------------
-__device__ __forceinline__ void all_gather(const Ctx& cx, uint32_t src_off, int src_pitch, int row_bytes, uint32_t dst_off,
-                                           int dst_pitch) {
-  const int vec_per_row = row_bytes >> 4;
-  const int items = cx.R * vec_per_row;
-  const uint32_t base = smem_u32(cx.sm);
-  for (int i = threadIdx.x; i < items * CS; i += NCONS) {
-    const int peer = i / items, it = i - peer * items;
-    const int r = it / vec_per_row, v = it - r * vec_per_row;
-    const uint4 val = *reinterpret_cast<const uint4*>(cx.sm + src_off + (size_t)r * src_pitch + v * 16);
-    st_cluster_v4(mapa(base + dst_off + r * dst_pitch + cx.c * row_bytes + v * 16, peer), val);
+// ---- all-gather with the barrier built in.  The caller has written this CTA's slice block (R rows, `block_bytes`
+// contiguous bytes, a multiple of 16) to cx.stage_buf().  Warp w sends it to CTA w of the cluster with one bulk copy that
+// completes (complete_tx) on the receiver's gather barrier `which`; everybody then waits for the 8 blocks addressed to
+// this CTA.  dst_off: offset of the gathered buffer; block c of it belongs to source CTA c.
+// Staging buffers alternate: buffer k is rewritten at gather k+2, after the wait of gather k+1 -- which every peer can
+// only have sent after receiving block k from this CTA, i.e. after this CTA's copy k has completed.
+__device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster_addr, const void* src, uint32_t bytes, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_cluster_addr), "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void gather(Ctx& cx, int which, uint32_t dst_off, uint32_t block_bytes) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows (generic proxy) -> bulk copy (async proxy)
+  cons_sync();
+  uint64_t* bar = cx.gbar + which;
+  if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, CS * block_bytes);
+  if (lane == 0) {
+    const uint32_t base = smem_u32(cx.sm);
+    bulk_s2c(mapa(base + dst_off + cx.c * block_bytes, warp), cx.stage_buf(), block_bytes, mapa(smem_u32(bar), warp));
   }
+  ++cx.n_gather;
+  mbar_wait(bar, (cx.gphase >> which) & 1u);
+  cx.gphase ^= 1u << which;
+  FSTAMP(cx);
 }
 
 // LayerNorm affine parameters of this lane's 16 columns, fetched BEFORE the cluster barrier (global latency hidden)
@@ -315,7 +342,7 @@ __device__ __forceinline__ void rows_norm(const Ctx& cx, int n_ln, const LnP& p1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < cx.R) {
     float v[16];
-    const float* y = cx.at<float>(cx.L.yg) + (size_t)warp * E + lane * 16;
+    const float* y = cx.at<float>(cx.L.yg) + ((size_t)(lane >> 2) * cx.R + warp) * YP + (lane & 3) * 16;
 #pragma unroll
     for (int q4 = 0; q4 < 4; ++q4) {
       const float4 t4 = reinterpret_cast<const float4*>(y)[q4];
@@ -497,7 +524,7 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
   FSTAMP(cx);
   mark(cx.ph * 1000 + (is_self ? 240 : 340));
   // ---- combine the chunk partials of every video (and, for self-attention, the new key / value): thread <-> (video, dim)
-  bf16* st = cx.at<bf16>(cx.L.stage);
+  bf16* st = reinterpret_cast<bf16*>(cx.stage_buf());
   for (int i = threadIdx.x; i < cx.R * DH; i += NCONS) {
     const int r = i >> 6, d = i & 63;
     const float* cb = comb + (size_t)r * cx.L.nch_max * CW;
@@ -514,10 +541,9 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
       Lt = fmaf(cb[ci * CW + 1], f, Lt);
       ov = fmaf(cb[ci * CW + 4 + d], f, ov);
     }
-    st[r * DH + d] = __float2bfloat16_rn(ov / Lt);
+    st[r * CP + d] = __float2bfloat16_rn(ov / Lt);
   }
-  cons_sync();
-  all_gather(cx, cx.L.stage, DH * 2, DH * 2, cx.L.ctxg, XP * 2); FSTAMP(cx);
+  gather(cx, 0, cx.L.ctxg, (uint32_t)cx.R * CP * 2);
   mark(cx.ph * 1000 + (is_self ? 250 : 350));
 }
 
@@ -544,6 +570,9 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
   cx.rg = Ring{bars, bars + MAX_SLOTS, ds_smem + cx.L.ring, 0u, 0, cx.L.nslot};
   cx.cbar = bars + 2 * MAX_SLOTS;
   cx.cphase = 0u;
+  cx.gbar = cx.cbar + 1;
+  cx.gphase = 0u;
+  cx.n_gather = 0u;
   cx.ph = 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   if (cx.R <= 0) return;                                 // uniform over the cluster
@@ -553,6 +582,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
   if (tid == 0) {
     for (int i = 0; i < cx.L.nslot; ++i) { mbar_init(cx.rg.full + i, 1); mbar_init(cx.rg.empty + i, 8); }
     mbar_init(cx.cbar, CS);
+    for (int i = 0; i < 3; ++i) mbar_init(cx.gbar + i, 1);
     fence_barrier_init();
   }
   // stale ring rows (beyond the valid positions of a chunk) reach the tensor cores multiplied by p = 0: they must be finite
@@ -657,19 +687,16 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
       dst[0] = a;
       dst[1] = bb;
     }
-    float* stf = cx.at<float>(cx.L.stage);
     const float* resid = cx.at<float>(cx.L.resid);
-    gemm_phase(cx, 4, 512, false, cx.L.xn, XP, [&](int tl) { return p.b_chord + c * DH + tl * 16; }, [&](int tl, const float* cc) {
+    gemm_phase(cx, 4, 512, false, cx.L.xn, XP, 10, [&](int tl) { return p.b_chord + c * DH + tl * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int nl = tl * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1), n = c * DH + nl;
         if (vid < cx.R)
-          stf[vid * DH + nl] = cc[i] + __ldg(p.key + cx.row0 + vid) * __ldg(p.wc_key + n) + __ldg(p.pe + (size_t)t * E + n);
+          reinterpret_cast<float*>(cx.stage_buf())[vid * YP + nl] = cc[i] + __ldg(p.key + cx.row0 + vid) * __ldg(p.wc_key + n) + __ldg(p.pe + (size_t)t * E + n);
       }
     });
-    cons_sync();
-    all_gather(cx, cx.L.stage, DH * 4, DH * 4, cx.L.yg, E * 4); FSTAMP(cx);
-    cluster_sync_cons(cx);
+    gather(cx, 1, cx.L.yg, (uint32_t)cx.R * YP * 4);
     LnP lp1, lp2;
     rows_norm(cx, 0, lp1, lp2);
     stamp(cx);
@@ -681,7 +708,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
       float* qsm = cx.at<float>(cx.L.qs);
       bf16* knew = cx.at<bf16>(cx.L.knew);
       bf16* vnew = cx.at<bf16>(cx.L.vnew);
-      gemm_phase(cx, 8, 512, false, cx.L.xn, XP, [&](int tl) { return bl + tl * 16; },
+      gemm_phase(cx, 8, 512, false, cx.L.xn, XP, 10, [&](int tl) { return bl + tl * 16; },
                  [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -692,7 +719,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
           }
         }
       });
-      gemm_phase(cx, 4, 512, false, cx.L.xn, XP, [&](int tl) { return bl + 128 + tl * 16; },
+      gemm_phase(cx, 4, 512, false, cx.L.xn, XP, 10, [&](int tl) { return bl + 128 + tl * 16; },
                  [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -710,24 +737,21 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
       }
       stamp(cx);
       attention_phase(cx, p, l, true);
-      cluster_sync_cons(cx);
       stamp(cx);
       // ---- out-proj + residual -> LayerNorm  (rpr.py:417,58-59)
-      gemm_phase(cx, 4, 512, false, cx.L.ctxg, XP, [&](int tl) { return bl + 192 + tl * 16; }, [&](int tl, const float* cc) {
+      gemm_phase(cx, 4, 512, false, cx.L.ctxg, CP, 6, [&](int tl) { return bl + 192 + tl * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int nl = tl * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1);
-          if (vid < cx.R) stf[vid * DH + nl] = cc[i] + resid[vid * DH + nl];
+          if (vid < cx.R) reinterpret_cast<float*>(cx.stage_buf())[vid * YP + nl] = cc[i] + resid[vid * DH + nl];
         }
       });
-      cons_sync();
-      all_gather(cx, cx.L.stage, DH * 4, DH * 4, cx.L.yg, E * 4); FSTAMP(cx);
       if (warp < cx.R) ln_load(lp1, Ld.ln1_g, Ld.ln1_b);
-      cluster_sync_cons(cx);
+      gather(cx, 1, cx.L.yg, (uint32_t)cx.R * YP * 4);
       rows_norm(cx, 1, lp1, lp2);
       stamp(cx);
       // ---- cross-attention over the video memory  (rpr.py:62-66)
-      gemm_phase(cx, 4, 512, false, cx.L.xn, XP, [&](int tl) { return bl + 256 + tl * 16; }, [&](int tl, const float* cc) {
+      gemm_phase(cx, 4, 512, false, cx.L.xn, XP, 10, [&](int tl) { return bl + 256 + tl * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int nl = tl * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1);
@@ -736,54 +760,46 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
       });
       stamp(cx);
       attention_phase(cx, p, l, false);
-      cluster_sync_cons(cx);
       stamp(cx);
-      gemm_phase(cx, 4, 512, false, cx.L.ctxg, XP, [&](int tl) { return bl + 320 + tl * 16; }, [&](int tl, const float* cc) {
+      gemm_phase(cx, 4, 512, false, cx.L.ctxg, CP, 6, [&](int tl) { return bl + 320 + tl * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int nl = tl * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1);
-          if (vid < cx.R) stf[vid * DH + nl] = cc[i] + resid[vid * DH + nl];
+          if (vid < cx.R) reinterpret_cast<float*>(cx.stage_buf())[vid * YP + nl] = cc[i] + resid[vid * DH + nl];
         }
       });
-      cons_sync();
-      all_gather(cx, cx.L.stage, DH * 4, DH * 4, cx.L.yg, E * 4); FSTAMP(cx);
       if (warp < cx.R) ln_load(lp1, Ld.ln2_g, Ld.ln2_b);
-      cluster_sync_cons(cx);
+      gather(cx, 1, cx.L.yg, (uint32_t)cx.R * YP * 4);
       rows_norm(cx, 1, lp1, lp2);
       stamp(cx);
       // ---- feed-forward  (rpr.py:67-69): hidden features [128c, 128c+128), then output features [64c, 64c+64)
-      bf16* sth = cx.at<bf16>(cx.L.stage);
-      gemm_phase(cx, 8, 512, false, cx.L.xn, XP, [&](int tl) { return bl + 384 + tl * 16; }, [&](int tl, const float* cc) {
+      gemm_phase(cx, 8, 512, false, cx.L.xn, XP, 10, [&](int tl) { return bl + 384 + tl * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int nl = tl * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1);
-          if (vid < cx.R) sth[vid * 128 + nl] = __float2bfloat16_rn(fmaxf(cc[i], 0.f));
+          if (vid < cx.R) reinterpret_cast<bf16*>(cx.stage_buf())[vid * HSP + nl] = __float2bfloat16_rn(fmaxf(cc[i], 0.f));
         }
       });
-      cons_sync();
-      all_gather(cx, cx.L.stage, 128 * 2, 128 * 2, cx.L.hg, HP * 2); FSTAMP(cx);
-      cluster_sync_cons(cx);
+      gather(cx, 2, cx.L.hg, (uint32_t)cx.R * HSP * 2);
       stamp(cx);
-      gemm_phase(cx, 4, 1024, false, cx.L.hg, HP, [&](int tl) { return bl + 512 + tl * 16; }, [&](int tl, const float* cc) {
+      gemm_phase(cx, 4, 1024, false, cx.L.hg, HSP, 7, [&](int tl) { return bl + 512 + tl * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int nl = tl * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1);
-          if (vid < cx.R) stf[vid * DH + nl] = cc[i] + resid[vid * DH + nl];
+          if (vid < cx.R) reinterpret_cast<float*>(cx.stage_buf())[vid * YP + nl] = cc[i] + resid[vid * DH + nl];
         }
       });
-      cons_sync();
-      all_gather(cx, cx.L.stage, DH * 4, DH * 4, cx.L.yg, E * 4); FSTAMP(cx);
       if (warp < cx.R) {
         ln_load(lp1, Ld.ln3_g, Ld.ln3_b);
         if (l + 1 == NL) ln_load(lp2, p.lnf_g, p.lnf_b);                     // + decoder final norm (rpr.py:32-33)
       }
-      cluster_sync_cons(cx);
+      gather(cx, 1, cx.L.yg, (uint32_t)cx.R * YP * 4);
       rows_norm(cx, l + 1 < NL ? 1 : 2, lp1, lp2);
       stamp(cx);
     }
     // ---- logits: vocabulary tiles c, c + 8  (video_music_transformer.py:1042)
     const int my_vt = c < n_vt ? (n_vt - c + CS - 1) / CS : 0;
-    gemm_phase(cx, my_vt, 512, true, cx.L.xn, XP, [&](int tl) { return p.b_out + (c + tl * CS) * 16; }, [&](int tl, const float* cc) {
+    gemm_phase(cx, my_vt, 512, true, cx.L.xn, XP, 10, [&](int tl) { return p.b_out + (c + tl * CS) * 16; }, [&](int tl, const float* cc) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int n = (c + tl * CS) * 16 + g + (i >> 1) * 8, vid = 2 * q + (i & 1);
