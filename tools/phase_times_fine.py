@@ -17,12 +17,12 @@ st = engine.build_decode(model._w(), model._cfg(), d["feature_semantic_list"], d
 st.step.fill_(pos); st.pos = pos
 engine.run_decode(st, 2, mode="stream")
 torch.cuda.synchronize()
-layer = (["qk mma", "v mma", "kv write"] + ["self: Er pass", "self: chunks", "self: combine+gather", "self: barrier", "self: -"] +
-         ["so mma", "so gather", "so barrier", "so LN"] + ["cq mma", "cq -"] +
-         ["cross: chunks", "cross: combine+gather", "cross: barrier", "cross: -"] +
-         ["co mma", "co gather", "co barrier", "co LN"] + ["f1 mma", "f1 gather", "f1 barrier", "f1 -"] +
-         ["f2 mma", "f2 gather", "f2 barrier", "f2 LN"])
-labels = ["embed mma", "embed gather", "embed barrier", "embed conv"] + sum([["L%d %s" % (l, x) for x in layer] for l in range(6)], []) + \
+layer = (["qk mma", "v mma", "kv write"] + ["self: Er pass", "self: chunks", "self: combine+gather", "self: -"] +
+         ["so mma", "so gather", "so LN"] + ["cq mma", "cq -"] +
+         ["cross: chunks", "cross: combine+gather", "cross: -"] +
+         ["co mma", "co gather", "co LN"] + ["f1 mma", "f1 gather", "f1 -"] +
+         ["f2 mma", "f2 gather", "f2 LN"])
+labels = ["embed mma", "embed gather", "embed conv"] + sum([["L%d %s" % (l, x) for x in layer] for l in range(6)], []) + \
          ["logits mma", "logits barrier", "argmax"]
 per_step = len(labels)
 ts = torch.zeros(1 + 3 * per_step, dtype=torch.int64, device=dev)

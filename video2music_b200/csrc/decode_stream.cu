@@ -152,6 +152,11 @@ __device__ __forceinline__ void mark(int) {}
 #else
 #define FSTAMP(cx)
 #endif
+#ifdef V2M_CHUNK_STAMPS
+#define CSTAMP(cx) stamp(cx)
+#else
+#define CSTAMP(cx)
+#endif
 
 // One ring of 32 KB slots: every use of a slot flips its parity bit; slots are taken round-robin.  Producer and
 // consumers walk the same static schedule, so both sides derive (slot, parity) of every copy without communication.
@@ -451,7 +456,9 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
         qb[ks][1] = f2_to_bf16x2(hi.x, hi.y);
       }
     }
+    CSTAMP(cx);
     cx.rg.wait_full(my_slot, my_par);
+    CSTAMP(cx);
     mark(cx.ph * 1000 + (is_self ? 210 : 310) + ci);
     const uint32_t base = smem_u32(cx.rg.slot(my_slot));
     // ---- scores of 16 keys per tile: lane (g, q) ends up with key g (c0 == c1) and key g + 8 (c2 == c3)
@@ -512,6 +519,7 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_cnt(cx.rg.empty + my_slot, 8);
+    CSTAMP(cx);
     mark(cx.ph * 1000 + (is_self ? 220 : 320) + ci);
     float* cb = comb + ((size_t)r * cx.L.nch_max + ci) * CW;
     if (lane == 0) { cb[0] = m; cb[1] = l; }
