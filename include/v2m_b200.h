@@ -200,6 +200,18 @@ int64_t v2m_decode_launches_per_step(const v2m_decode* p);
  * `reps` rounds over all layers on `stream`, reading the current step from *p->step. */
 int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stream);
 
+/* ---- Mamba block, model/mamba.py:259-351 (fp32).  Row-major (B, L, ld) views with explicit leading dimensions. ----
+ * conv: y = silu(conv1d(x, w, bias, groups=ED, padding=KW-1)[:, :, :L])  (mamba.py:270-276).
+ * scan: delta = softplus(delta_raw + dt_bias); h = exp(delta A) h + delta B x; y = h.C + D x; out = y silu(z)
+ *       (+ x (1 - sigmoid(silu z)) when plus != 0, mamba.py:283-287) -- the (B, L, ED, N) tensors of mamba.py:333-351 are
+ *       never materialised.  rmsnorm: mamba.py:483-489. */
+int v2m_mamba_conv_silu(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int32_t B, int32_t L,
+                        int32_t ED, int32_t KW, void* stream);
+int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
+                           const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz, float* out,
+                           int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, void* stream);
+int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, float eps, void* stream);
+
 /* ---- selective scan, model/pscan.py:154-226: H[t] = A[t]*H[t-1] + X[t] over (B,L,D,N) fp32 ---- */
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream);
 int v2m_pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float* gX, int32_t B, int32_t L,

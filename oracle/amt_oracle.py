@@ -399,3 +399,62 @@ def pscan_backward(A: torch.Tensor, H: torch.Tensor, gH: torch.Tensor) -> Tuple[
     gA = torch.zeros_like(A)
     gA[:, 1:] = H[:, :-1] * gX[:, 1:]
     return gA, gX
+
+
+# --------------------------------------------------------------------------
+# Mamba block (model/mamba.py, model/bimamba.py)
+# --------------------------------------------------------------------------
+def rmsnorm(x: torch.Tensor, weight, eps: float = 1e-5) -> torch.Tensor:
+    """RMSNorm.forward (mamba.py:483-489)."""
+    out = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)
+    return out * weight if weight is not None else out
+
+
+def mamba_block_forward(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, dt_rank: int, d_state: int = 16,
+                        use_version: int = 0) -> torch.Tensor:
+    """MambaBlock.forward + ssm + selective_scan (mamba.py:259-351) with the scan stated sequentially
+    (selective_scan_seq, :353-383, equals pscan mode).  x (B, L, D); sd[p + name] are the block's parameters."""
+    B, L, _ = x.shape
+    g = lambda n: sd.get(p + n)
+    xz = F.linear(x, g("in_proj.weight"), g("in_proj.bias"))                       # :266
+    xs, z = xz.chunk(2, dim=-1)                                                    # :267
+    ED = xs.shape[-1]
+    xs = F.conv1d(xs.transpose(1, 2), g("conv1d.weight"), g("conv1d.bias"), padding=g("conv1d.weight").shape[-1] - 1,
+                  groups=ED)[:, :, :L].transpose(1, 2)                             # :270-272
+    xs = F.silu(xs)                                                                # :274
+    A = -torch.exp(g("A_log").float())                                             # :298
+    D = g("D").float()
+    dbc = F.linear(xs, g("x_proj.weight"))                                         # :301
+    delta, Bm, Cm = torch.split(dbc, [dt_rank, d_state, d_state], dim=-1)          # :302
+    delta = (g("dt_proj.weight") @ delta.transpose(1, 2)).transpose(1, 2)          # :304, :322
+    delta = F.softplus(delta + g("dt_proj.bias"))                                  # :323
+    deltaA = torch.exp(delta.unsqueeze(-1) * A)                                    # :343
+    BX = delta.unsqueeze(-1) * Bm.unsqueeze(2) * xs.unsqueeze(-1)                  # :344-346
+    hs = pscan_forward(deltaA, BX)                                                 # :348
+    y = (hs @ Cm.unsqueeze(-1)).squeeze(3) + D * xs                                # :350-352
+    zs = F.silu(z)                                                                 # :282
+    out = y * zs + xs * (1 - torch.sigmoid(zs)) if use_version == 1 else y * zs    # :283-287
+    return F.linear(out, g("out_proj.weight"), g("out_proj.bias"))                 # :288
+
+
+def mamba_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, n_layers: int, dt_rank: int, d_state: int = 16,
+                  eps: float = 1e-5) -> torch.Tensor:
+    """Mamba.forward over ResidualBlocks (mamba.py:91-98, 144-149): x = mixer(norm(x)) + x."""
+    for l in range(n_layers):
+        p = "layers.%d." % l
+        x = mamba_block_forward(sd, p + "mixer.", rmsnorm(x, sd.get(p + "norm.weight"), eps), dt_rank, d_state) + x
+    return x
+
+
+def bimamba_layer_forward(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, dt_rank: int, d_state: int = 16) -> torch.Tensor:
+    """BiMambaEncoderLayer.forward in eval mode (bimamba.py:64-99), literal: ffn2 reads the forward branch (:91)."""
+    D = x.shape[-1]
+    ln = lambda n, t: F.layer_norm(t, (D,), sd[p + n + ".weight"], sd[p + n + ".bias"], 1e-5)
+    ffn = lambda n, t: F.linear(F.relu(F.linear(t, sd[p + n + ".0.weight"], sd[p + n + ".0.bias"])), sd[p + n + ".3.weight"],
+                                sd[p + n + ".3.bias"])
+    x_f = ln("norm1", mamba_block_forward(sd, p + "mamba_forward.", x, dt_rank, d_state) + x)
+    x_f = ln("norm2", ffn("ffn1", x_f) + x_f)
+    x_b = torch.flip(mamba_block_forward(sd, p + "mamba_backward.", torch.flip(x, dims=[1]), dt_rank, d_state), dims=[1])
+    x_b = ln("norm3", x_b + x)
+    x_b = ln("norm4", ffn("ffn2", x_f) + x_b)
+    return x_f + x_b

@@ -248,6 +248,38 @@ def golden_pscan(ref):
     _save("pscan.pt", dict(cases=cases))
 
 
+def golden_mamba(ref):
+    """MambaBlock (both versions), a 2-layer Mamba stack and a BiMambaEncoderLayer (mamba.py:259-351, bimamba.py:64-99),
+    eval mode, fp32 CPU, regression-model sizes (d_model 128, d_inner 256, d_state 16, argument_generate_funcs.py:87-91)."""
+    out = {}
+    for name, ver in (("block_v0", 0), ("block_v1", 1)):
+        cfg = ref.mamba.MambaConfig(d_model=128, n_layers=1, use_version=ver)
+        m = ref.mamba.MambaBlock(cfg).eval()
+        sd = _load_weights(m, 21 + ver)
+        spec = dict(B=3, L=300, d_model=128, seed=31 + ver, weight_seed=21 + ver, use_version=ver)
+        x = syn.unit_uniform((spec["B"], spec["L"], 128), syn._gen(spec["seed"], "x"))
+        with torch.no_grad():
+            y = m(x)
+        out[name] = dict(spec=spec, weights_checksum=syn.checksum(sd), y=y.clone())
+    cfg = ref.mamba.MambaConfig(d_model=128, n_layers=2)
+    m = ref.mamba.Mamba(cfg).eval()
+    sd = _load_weights(m, 23)
+    spec = dict(B=2, L=77, d_model=128, seed=33, weight_seed=23, n_layers=2)
+    x = syn.unit_uniform((spec["B"], spec["L"], 128), syn._gen(spec["seed"], "x"))
+    with torch.no_grad():
+        y = m(x)
+    out["stack"] = dict(spec=spec, weights_checksum=syn.checksum(sd), y=y.clone())
+    cfg = ref.mamba.MambaConfig(d_model=128, n_layers=1)
+    m = ref.bimamba.BiMambaEncoderLayer(cfg, dim_feedforward=256, dropout=0.2).eval()
+    sd = _load_weights(m, 24)
+    spec = dict(B=2, L=300, d_model=128, d_ff=256, seed=34, weight_seed=24)
+    x = syn.unit_uniform((spec["B"], spec["L"], 128), syn._gen(spec["seed"], "x"))
+    with torch.no_grad():
+        y = m(x)
+    out["bimamba_layer"] = dict(spec=spec, weights_checksum=syn.checksum(sd), y=y.clone())
+    _save("mamba.pt", out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -258,6 +290,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
+                mamba=lambda: golden_mamba(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

@@ -369,3 +369,53 @@ def test_gqa_golden_gpu():
     with pytest.raises(ValueError):
         scaled_dot_product_gqa(torch.zeros(1, 2, 3, 8, device=DEV), torch.zeros(1, 2, 2, 8, device=DEV),
                                torch.zeros(1, 2, 2, 8, device=DEV))
+
+
+# ---------------------------------------------------------------- Mamba block (fused selective scan)
+def test_mamba_golden_gpu():
+    """MambaBlock (both versions), the 2-layer stack and the BiMamba layer on the GPU kernels vs the reference's outputs."""
+    from video2music_b200.mamba import MambaConfig, MambaBlock, Mamba, BiMambaEncoderLayer
+    g = load_golden("mamba.pt")
+    cases = [("block_v0", lambda s: MambaBlock(MambaConfig(d_model=128, n_layers=1, use_version=0))),
+             ("block_v1", lambda s: MambaBlock(MambaConfig(d_model=128, n_layers=1, use_version=1))),
+             ("stack", lambda s: Mamba(MambaConfig(d_model=128, n_layers=2))),
+             ("bimamba_layer", lambda s: BiMambaEncoderLayer(MambaConfig(d_model=128, n_layers=1), dim_feedforward=s["d_ff"]))]
+    for name, make in cases:
+        c = g[name]
+        s = c["spec"]
+        m = make(s)
+        sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["weight_seed"])
+        assert same_checksum(syn.checksum(sd), c["weights_checksum"])
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()
+        x = syn.unit_uniform((s["B"], s["L"], 128), syn._gen(s["seed"], "x")).to(DEV)
+        with torch.no_grad():
+            y = m(x)
+        err = rel_err(y, c["y"])
+        print("mamba %s rel err %.2e" % (name, err))
+        assert err < 1e-4, name
+    with pytest.raises(NotImplementedError):
+        m(x.requires_grad_(True))
+
+
+@pytest.mark.parametrize("B,L", [(64, 300), (8, 4096)])
+def test_selective_scan_fused_equals_pscan_composition(B, L):
+    """BASELINE config 5 sizes: the fused scan (no (B, L, ED, N) tensors) equals exp/mul + the pscan kernel + contraction."""
+    from video2music_b200 import ops
+    ED, N = 256, 16
+    gx = syn._gen(5, "scan")
+    x = syn.unit_uniform((B * L, ED), gx).to(DEV)
+    draw = (syn.unit_uniform((B * L, ED), gx) * 0.5 - 1.0).to(DEV)
+    bias = (syn.unit_uniform((ED,), gx) * 0.1).to(DEV)
+    A_log = torch.log(torch.arange(1, N + 1, dtype=torch.float32)).repeat(ED, 1).to(DEV)
+    bc = syn.unit_uniform((B * L, 2 * N), gx).to(DEV)
+    D = syn.unit_uniform((ED,), gx).to(DEV)
+    y = ops.selective_scan(x, draw, bias, A_log, bc[:, :N], bc[:, N:], D, None, B, L)
+    delta = torch.nn.functional.softplus(draw + bias).view(B, L, ED)
+    A = -torch.exp(A_log)
+    xs = x.view(B, L, ED)
+    dA = torch.exp(delta.unsqueeze(-1) * A)
+    BX = delta.unsqueeze(-1) * bc[:, :N].view(B, L, 1, N) * xs.unsqueeze(-1)
+    hs = ops.pscan_fwd(dA, BX)
+    ref = (hs * bc[:, N:].view(B, L, 1, N)).sum(-1) + D * xs
+    assert rel_err(y.view(B, L, ED), ref) < 2e-5

@@ -142,3 +142,36 @@ def test_pscan_golden():
         gA, gX = O.pscan_backward(A, H, gH)
         assert rel_err(gX, case["gX"]) < 1e-5
         assert rel_err(gA, case["gA"]) < 1e-5 or float(case["gA"].abs().max()) == 0.0
+
+
+def _mamba_sd(shapes, seed):
+    return syn.fill_like_reference_init(shapes, seed=seed)
+
+
+def test_mamba_oracle_matches_reference_golden():
+    """oracle Mamba restatement (mamba.py:259-351, bimamba.py:64-99) vs outputs of the unmodified reference."""
+    from video2music_b200.mamba import MambaConfig, MambaBlock, Mamba, BiMambaEncoderLayer
+    g = load_golden("mamba.pt")
+    for name in ("block_v0", "block_v1"):
+        c = g[name]
+        s = c["spec"]
+        m = MambaBlock(MambaConfig(d_model=128, n_layers=1, use_version=s["use_version"]))
+        sd = _mamba_sd({k: tuple(v.shape) for k, v in m.state_dict().items()}, s["weight_seed"])
+        assert same_checksum(syn.checksum(sd), c["weights_checksum"])
+        x = syn.unit_uniform((s["B"], s["L"], 128), syn._gen(s["seed"], "x"))
+        y = O.mamba_block_forward(sd, "", x, dt_rank=8, use_version=s["use_version"])
+        assert rel_err(y, c["y"]) < 2e-5, name
+    c = g["stack"]
+    s = c["spec"]
+    m = Mamba(MambaConfig(d_model=128, n_layers=2))
+    sd = _mamba_sd({k: tuple(v.shape) for k, v in m.state_dict().items()}, s["weight_seed"])
+    assert same_checksum(syn.checksum(sd), c["weights_checksum"])
+    x = syn.unit_uniform((s["B"], s["L"], 128), syn._gen(s["seed"], "x"))
+    assert rel_err(O.mamba_forward(sd, x, 2, dt_rank=8), c["y"]) < 2e-5
+    c = g["bimamba_layer"]
+    s = c["spec"]
+    m = BiMambaEncoderLayer(MambaConfig(d_model=128, n_layers=1), dim_feedforward=s["d_ff"])
+    sd = _mamba_sd({k: tuple(v.shape) for k, v in m.state_dict().items()}, s["weight_seed"])
+    assert same_checksum(syn.checksum(sd), c["weights_checksum"])
+    x = syn.unit_uniform((s["B"], s["L"], 128), syn._gen(s["seed"], "x"))
+    assert rel_err(O.bimamba_layer_forward(sd, "", x, dt_rank=8), c["y"]) < 2e-5

@@ -220,6 +220,22 @@ int64_t v2m_decode_launches_per_step(const v2m_decode* p) {
   return decode_kernel_launches_per_step(d);
 }
 
+int v2m_mamba_conv_silu(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int32_t B, int32_t L,
+                        int32_t ED, int32_t KW, void* stream) {
+  return mamba_conv_silu(x, ldx, w, bias, y, ldy, B, L, ED, KW, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
+                           const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz, float* out,
+                           int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, void* stream) {
+  return selective_scan_fwd(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, D, z, ldz, out, ldo, B, L, ED, N, plus,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, float eps, void* stream) {
+  return rmsnorm(x, w, y, M, D, eps, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream) {
   return pscan_fwd(A, X, H, B, L, D, N, static_cast<cudaStream_t>(stream));
 }

@@ -166,6 +166,14 @@ int pscan_fwd(const float* A, const float* X, float* H, int B, int L, int D, int
 int pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float* gX, int B, int L, int D, int N,
               cudaStream_t stream);
 
+// ------------------------------------------------------------------ Mamba block (mamba.cu), fp32
+int mamba_conv_silu(const float* x, long long ldx, const float* w, const float* bias, float* y, long long ldy, int B, int L, int ED,
+                    int KW, cudaStream_t stream);
+int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, long long ldd, const float* dt_bias,
+                       const float* A_log, const float* Bm, const float* Cm, long long ldbc, const float* Dp, const float* z,
+                       long long ldz, float* out, long long ldo, int B, int L, int ED, int N, int plus, cudaStream_t stream);
+int rmsnorm(const float* x, const float* w, float* y, int M, int D, float eps, cudaStream_t stream);
+
 // ------------------------------------------------------------------ MoE (moe.cu)
 int moe_route(const float* x, const float* wg, const float* bg, const float* sel_bias, float inv_t_pre, float inv_t_post,
               int tokens, int d, int n_experts, int k, long long* idx_out, float* w_out, float* logits_out,

@@ -231,6 +231,43 @@ def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: floa
     return (dz[:, :N] if (dz is not None and ld != N) else dz), db
 
 
+def mamba_conv_silu(xz: torch.Tensor, ED: int, w: torch.Tensor, bias: Optional[torch.Tensor], B: int, L: int) -> torch.Tensor:
+    """silu(depthwise causal conv1d) of the x half of xz (B*L, >= ED) -> (B*L, ED)   (mamba.py:270-276)."""
+    require_device(xz)
+    assert xz.dtype == torch.float32 and xz.stride(1) == 1 and w.is_contiguous()
+    y = torch.empty((B * L, ED), device=xz.device, dtype=torch.float32)
+    check(load().v2m_mamba_conv_silu(ptr(xz), xz.stride(0), ptr(w), ptr(bias), ptr(y), ED, B, L, ED, w.shape[1], stream()))
+    _lib.count_launches(1)
+    return y
+
+
+def selective_scan(x: torch.Tensor, delta_raw: torch.Tensor, dt_bias: Optional[torch.Tensor], A_log: torch.Tensor,
+                   Bm: torch.Tensor, Cm: torch.Tensor, D: torch.Tensor, z: Optional[torch.Tensor], B: int, L: int,
+                   plus: bool = False) -> torch.Tensor:
+    """Fused selective scan (mamba.py:293-351 + the gating of :281-287): 2-D row-major views (B*L, .) with unit inner
+    stride; Bm / Cm share their leading dimension (slices of the x_proj output)."""
+    require_device(x)
+    ED, N = A_log.shape
+    for t in (x, delta_raw, Bm, Cm) + ((z,) if z is not None else ()):
+        assert t.dtype == torch.float32 and t.stride(1) == 1
+    assert Bm.stride(0) == Cm.stride(0)
+    out = torch.empty((B * L, ED), device=x.device, dtype=torch.float32)
+    check(load().v2m_selective_scan_fwd(ptr(x), x.stride(0), ptr(delta_raw), delta_raw.stride(0), ptr(dt_bias), ptr(A_log.contiguous()),
+                                        ptr(Bm), ptr(Cm), Bm.stride(0), ptr(D), ptr(z), z.stride(0) if z is not None else 0,
+                                        ptr(out), ED, B, L, ED, N, int(plus), stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    require_device(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(load().v2m_rmsnorm(ptr(x), ptr(w), ptr(y), _rows(x), x.shape[-1], eps, stream()))
+    _lib.count_launches(1)
+    return y
+
+
 def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5):
     require_device(x)
     x, dy = x.contiguous(), dy.contiguous()
