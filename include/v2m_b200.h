@@ -181,6 +181,11 @@ typedef struct v2m_decode {
   int32_t* step;
   float* h; void* r; float* qbuf; void* ctx; void* ff; float* logits; float* logits_all;
   void* xn;
+  /* next-token rule: sample 0 = greedy arg-max (beam=1, video_music_transformer.py:1078-1084); 1 = the sampling branch
+   * (:1085-1128): P(N)=0 if max_conseq_N==0, P(prev)=0 after max_conseq_chord equal tokens, inverse-CDF draw with
+   * uniforms[b*cap + t+1]; gen_root / gen_attr of generated positions follow the chord id (closed form of the JSON maps). */
+  int32_t sample, max_conseq_N, max_conseq_chord, pad_;
+  const float* uniforms;
 } v2m_decode;
 int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void* stream);
 /* Same loop as ONE persistent kernel launch (csrc/decode_stream.cu): a cluster of 8 CTAs (one per head) owns up to 8

@@ -222,9 +222,13 @@ def generate_greedy_literal(sd: SD, sem, key, scene, motion, emotion, primer, pr
 
 def generate_greedy_cached(sd: SD, sem, key, scene, motion, emotion, primer, primer_root, primer_attr,
                            target_seq_length: int = 300, num_heads: int = 8, chord_embed: bool = False,
-                           return_logits: bool = False):
+                           return_logits: bool = False, uniforms: Optional[torch.Tensor] = None, max_conseq_N: int = 0,
+                           max_conseq_chord: int = 2, return_root_attr: bool = False):
     """KV-cached, batched restatement of the same greedy loop (what the decode
-    kernels implement).  Mathematically identical to generate_greedy_literal because
+    kernels implement).  With `uniforms` (B, target_seq_length) the next token comes from the SAMPLING branch instead
+    (video_music_transformer.py:1085-1123): softmax over the vocabulary restricted to [:CHORD_END], P(N) = 0 when
+    max_conseq_N == 0, P(previous chord) = 0 after max_conseq_chord equal tokens, one Categorical draw -- stated as the
+    inverse CDF at uniforms[b, t+1] -- and root / attr ids of the drawn chord (closed form of the JSON maps, :1105-1123).  Mathematically identical to generate_greedy_literal because
     the decoder is causal: row t of the prefix forward depends only on rows <= t, and
     Srel[t,j] = q_t . Er[er_len-1-(t-j)] does not depend on the prefix length
     (rpr.py:426-455).  primer* are (B,P) or (P,).  Returns (B, target_seq_length)."""
@@ -284,10 +288,30 @@ def generate_greedy_cached(sd: SD, sem, key, scene, motion, emotion, primer, pri
         if return_logits:
             all_logits.append(logits)
         if t + 1 >= P:
-            gen[:, t + 1] = torch.argmax(logits[:, :CHORD_END], dim=-1)
+            if uniforms is None:
+                gen[:, t + 1] = torch.argmax(logits[:, :CHORD_END], dim=-1)
+            else:
+                probs = torch.softmax(logits, dim=-1)[:, :CHORD_END].clone()                    # :1069
+                if max_conseq_N == 0:
+                    probs[:, 0] = 0.0                                                           # :1090-1091
+                if t + 1 >= max_conseq_chord:                                                   # :1093-1104
+                    prev = gen[:, t]
+                    same = torch.ones(B, dtype=torch.bool)
+                    for k in range(1, max_conseq_chord):
+                        same &= gen[:, t - k] == prev
+                    probs[same, prev[same]] = 0.0
+                cdf = torch.cumsum(probs, dim=-1)
+                target = uniforms[:, t + 1:t + 2] * cdf[:, -1:]
+                nxt = ((cdf > target) & (probs > 0)).float().argmax(dim=-1)
+                gen[:, t + 1] = nxt
+                gen_root[:, t + 1] = torch.where(nxt > 0, (nxt - 1) // 13 + 1, torch.zeros_like(nxt))   # chord_inv/root/attr.json
+                gen_attr[:, t + 1] = torch.where(nxt > 0, (nxt - 1) % 13 + 1, torch.ones_like(nxt))
+    out = (gen,)
     if return_logits:
-        return gen, torch.stack(all_logits, dim=1)
-    return gen
+        out += (torch.stack(all_logits, dim=1),)
+    if return_root_attr:
+        out += (gen_root, gen_attr)
+    return out if len(out) > 1 else gen
 
 
 # --------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import amt_oracle as O
-from oracle.ref_shim import load_reference, reference_available, reference_cwd
+from oracle.ref_shim import REFERENCE_ROOT, load_reference, reference_available, reference_cwd
 from video2music_b200 import synthetic as syn
 
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not mounted")
@@ -61,3 +61,19 @@ def test_generate_live(chord_embed):
         g_c = O.generate_greedy_cached(sd, inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
                                        inp["feature_motion"], inp["feature_emotion"], prim, pr, pa, 20, chord_embed=chord_embed)
     assert torch.equal(g_ref, g_lit) and torch.equal(g_ref, g_c)
+
+
+def test_chord_id_to_root_attr_closed_form():
+    """The sampling branch maps the drawn chord id to (root, attr) through three JSON dictionaries
+    (video_music_transformer.py:1052-1057,1105-1123); our kernels and the oracle use the closed form."""
+    import json
+    import os
+    base = os.path.join(REFERENCE_ROOT, "dataset", "vevo_meta")
+    inv = json.load(open(os.path.join(base, "chord_inv.json")))
+    root = json.load(open(os.path.join(base, "chord_root.json")))
+    attr = json.load(open(os.path.join(base, "chord_attr.json")))
+    for c in range(157):
+        parts = inv[str(c)].split(":")
+        want = (root[parts[0]], 1) if len(parts) == 1 else (root[parts[0]], attr[parts[1]])
+        got = (0, 1) if c == 0 else ((c - 1) // 13 + 1, (c - 1) % 13 + 1)
+        assert got == want, (c, inv[str(c)])

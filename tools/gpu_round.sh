@@ -1,2 +1,2 @@
 set -x
-timeout 300 python -m pytest tests/test_gpu_kernels.py -x -q -k "mamba or selective_scan" -s 2>&1 | tail -12
+timeout 400 python -m pytest tests/test_gpu_amt.py -x -q 2>&1 | tail -5

@@ -58,7 +58,8 @@ class Decode(C.Structure):
                 [("layer", DecLayer * MAX_DEC_LAYERS)] +
                 [(n, vp) for n in ("lnf_g", "lnf_b", "w_out", "b_out", "emb_root", "emb_attr", "emb_chord",
                                    "w_chord", "wc_key", "b_chord", "pe", "key", "gen", "gen_root", "gen_attr",
-                                   "step", "h", "r", "qbuf", "ctx", "ff", "logits", "logits_all", "xn")])
+                                   "step", "h", "r", "qbuf", "ctx", "ff", "logits", "logits_all", "xn")] +
+                [(n, i32) for n in ("sample", "max_conseq_N", "max_conseq_chord", "pad_")] + [("uniforms", vp)])
 
 
 # every symbol include/v2m_b200.h declares (tests check that the library exports all of them)

@@ -20,6 +20,7 @@
 //     async copy each (TMA engine, mbarrier completion).
 #include "common.cuh"
 #include "kernels.h"
+#include "decode_pick.cuh"
 #include <type_traits>
 #include <stdlib.h>
 
@@ -423,27 +424,27 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attn_kernel(const __grid_const
   }
 }
 
-// arg-max over logits[:, :vocab_limit] (softmax is monotone: video_music_transformer.py:1070-1084 with beam=1),
-// first index wins on exact ties; writes gen[:, t+1] and advances the step counter.
+// Next token of every video (decode_pick.cuh: greedy arg-max or the sampling branch with its constraints); writes gen[:, t+1]
+// (and gen_root / gen_attr when sampling, video_music_transformer.py:1105-1123) and advances the step counter.
 __global__ void __launch_bounds__(256) argmax_advance_kernel(const __grid_constant__ DecodeParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_trigger();
   pdl_wait();
   const int t = *p.step;
   for (int b = warp; b < p.B; b += 8) {
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int n = lane; n < p.vocab_limit; n += 32) {
-      const float v = p.logits[(size_t)b * p.vocab + n];
-      if (v > best) { best = v; bi = n; }
+    const long long* g = p.gen + (size_t)b * p.cap;
+    const float u = p.sample ? p.uniforms[(size_t)b * p.cap + min(t + 1, p.cap - 1)] : 0.f;
+    const int bi = pick_token(p.logits + (size_t)b * p.vocab, p.vocab, p.vocab_limit, p.sample, p.max_conseq_N, p.max_conseq_chord,
+                              t, u, [&](int k) { return (int)g[t - k]; }, lane);
+    if (lane == 0 && t + 1 >= p.primer_len && t + 1 < p.cap) {
+      p.gen[(size_t)b * p.cap + t + 1] = bi;
+      if (p.sample) {
+        long long root, attr;
+        chord_root_attr(bi, root, attr);
+        p.gen_root[(size_t)b * p.cap + t + 1] = root;
+        p.gen_attr[(size_t)b * p.cap + t + 1] = attr;
+      }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0 && t + 1 >= p.primer_len && t + 1 < p.cap) p.gen[(size_t)b * p.cap + t + 1] = bi;
   }
   __syncthreads();
   if (threadIdx.x == 0) *p.step = t + 1;
@@ -702,6 +703,7 @@ int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t s
   V2M_REQUIRE(p.E == 512 && p.FF % 512 == 0 && p.FF <= 2048, "decode: d_model must be 512 and dim_feedforward a multiple of 512 (E=%d FF=%d)", p.E, p.FF);
   V2M_REQUIRE(p.cap <= p.er_len, "decode: cap %d exceeds er_len %d (rpr.py:426-450 fails for L > er_len)", p.cap, p.er_len);
   V2M_REQUIRE(p.B >= 1 && n_steps >= 0, "decode: bad B=%d n_steps=%d", p.B, n_steps);
+  V2M_REQUIRE(!p.sample || (p.uniforms && p.max_conseq_chord >= 1), "decode: sampling needs uniforms and max_conseq_chord >= 1");
   if (p.dtype == 0) return decode_run_t<float>(p, n_steps, use_graph, stream);
   if (p.dtype == 1) return decode_run_t<bf16>(p, n_steps, use_graph, stream);
   set_last_error("decode: dtype %d unsupported", p.dtype);

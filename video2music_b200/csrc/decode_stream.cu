@@ -28,6 +28,7 @@
 //     barrier per position, for the logits in global memory, is an mbarrier with remote arrives.)
 #include "common.cuh"
 #include "kernels.h"
+#include "decode_pick.cuh"
 #include <stdlib.h>
 #include <stdio.h>
 
@@ -58,7 +59,7 @@ struct Layout {
   int srel_pitch, nslot, nch_max;
   uint32_t stage_bytes;
 };
-__host__ __device__ inline Layout make_layout(int R, int cap) {
+__host__ __device__ inline Layout make_layout(int R, int cap, int S) {
   Layout L;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 127u) & ~127u; return r; };
@@ -76,10 +77,10 @@ __host__ __device__ inline Layout make_layout(int R, int cap) {
   L.vnew = take(R * DH * 2);
   L.srel_pitch = (cap + 3) & ~3;
   L.srel = take(R * L.srel_pitch * 4);
-  L.nch_max = (cap + KCH - 1) / KCH;
+  L.nch_max = ((cap > S ? cap : S) + KCH - 1) / KCH;   // chunks per video in the longer of the two attention kinds
   L.comb = take(R * L.nch_max * CW * 4);
   L.snew = take(R * 4);
-  L.tok = take(R * 8);
+  L.tok = take(R * 64);               // per video: token, root, attr (int64) + the last 8 tokens (int32)
   o = (o + 1023u) & ~1023u;
   L.ring = o;
   int ns = ((int)SMEM_MAX - (int)o) / SLOT_BYTES;
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
   cx.c = (int)cluster_ctarank();
   cx.row0 = (int)cluster_id() * rows_per_cluster;
   cx.R = min(rows_per_cluster, p.B - cx.row0);
-  cx.L = make_layout(rows_per_cluster, p.cap);
+  cx.L = make_layout(rows_per_cluster, p.cap, p.S);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ds_smem + cx.L.bars);
   cx.rg = Ring{bars, bars + MAX_SLOTS, ds_smem + cx.L.ring, 0u, 0, cx.L.nslot};
   cx.cbar = bars + 2 * MAX_SLOTS;
@@ -663,8 +664,18 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
 
   // ===================================================== consumer warps =====================================================
   cx.ts = ts; cx.ts_cap = ts_cap; cx.ts_n = 0;
+  // per-video token state, identical in every CTA of the cluster: [0] token, [1] root, [2] attr of the current position,
+  // then (int32 view, index 6..13) the tokens of positions t, t-1, ..., t-7 for the repeat constraint
   long long* tok = cx.at<long long>(cx.L.tok);
-  if (tid < cx.R) tok[tid] = p.gen[(size_t)(cx.row0 + tid) * p.cap + t0];
+  if (tid < cx.R) {
+    const size_t row = (size_t)(cx.row0 + tid) * p.cap;
+    long long* ts_ = tok + tid * 8;
+    ts_[0] = p.gen[row + t0];
+    ts_[1] = p.gen_root[row + t0];
+    ts_[2] = p.gen_attr[row + t0];
+    int* hist = reinterpret_cast<int*>(ts_ + 3);
+    for (int k = 0; k < 8; ++k) hist[k] = t0 - k >= 0 ? (int)p.gen[row + t0 - k] : -1;
+  }
   stamp(cx);
 
   for (int step = 0; step < n_steps; ++step) {
@@ -676,12 +687,17 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
       const int b = cx.row0 + warp;
       float v[16];
       if (p.chord_embed) {
-        const float* src = p.emb_chord + (size_t)tok[warp] * E + lane * 16;
+        const float* src = p.emb_chord + (size_t)tok[warp * 8] * E + lane * 16;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(src) + q4); v[4 * q4] = t4.x; v[4 * q4 + 1] = t4.y; v[4 * q4 + 2] = t4.z; v[4 * q4 + 3] = t4.w; }
       } else {
-        const float* sa = p.emb_root + (size_t)p.gen_root[(size_t)b * p.cap + t] * E + lane * 16;
-        const float* sb = p.emb_attr + (size_t)p.gen_attr[(size_t)b * p.cap + t] * E + lane * 16;
+        // primer positions and (greedy mode) the never-updated PAD entries come from the token buffers; sampled positions
+        // carry the root / attribute of the token chosen in the previous step (video_music_transformer.py:1105-1123)
+        const bool own = p.sample && t >= p.primer_len;
+        const long long ir = own ? tok[warp * 8 + 1] : p.gen_root[(size_t)b * p.cap + t];
+        const long long ia = own ? tok[warp * 8 + 2] : p.gen_attr[(size_t)b * p.cap + t];
+        const float* sa = p.emb_root + (size_t)ir * E + lane * 16;
+        const float* sb = p.emb_attr + (size_t)ia * E + lane * 16;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           const float4 x4 = __ldg(reinterpret_cast<const float4*>(sa) + q4), y4 = __ldg(reinterpret_cast<const float4*>(sb) + q4);
@@ -821,28 +837,31 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
     });
     __threadfence();                                      // logits of this CTA visible cluster-wide before the barrier
     cluster_sync_cons(cx);
-    // ---- greedy arg-max over [:vocab_limit] (first index wins on ties), redundantly in every CTA; CTA 0 records it
+    // ---- next token (decode_pick.cuh), computed redundantly and identically in every CTA; CTA 0 records it
     if (warp < cx.R) {
       const int b = cx.row0 + warp;
-      float best = -INFINITY;
-      int bi = 0x7fffffff;
-      for (int n = lane; n < p.vocab_limit; n += 32) {
-        const float v = __ldcg(p.logits + (size_t)b * p.vocab + n);
-        if (v > best) { best = v; bi = n; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-      }
+      long long* ts_ = tok + warp * 8;
+      int* hist = reinterpret_cast<int*>(ts_ + 3);
+      const float u = p.sample ? __ldg(p.uniforms + (size_t)b * p.cap + min(t + 1, p.cap - 1)) : 0.f;
+      int nt = pick_token(p.logits + (size_t)b * p.vocab, p.vocab, p.vocab_limit, p.sample, p.max_conseq_N, p.max_conseq_chord, t, u,
+                          [&](int k) { return hist[k]; }, lane);
+      __syncwarp();
       if (lane == 0 && t + 1 < p.cap) {
+        long long root, attr;
         if (t + 1 >= p.primer_len) {
-          tok[warp] = bi;
-          if (c == 0) p.gen[(size_t)b * p.cap + t + 1] = bi;
+          chord_root_attr(nt, root, attr);
+          if (c == 0) {
+            p.gen[(size_t)b * p.cap + t + 1] = nt;
+            if (p.sample) { p.gen_root[(size_t)b * p.cap + t + 1] = root; p.gen_attr[(size_t)b * p.cap + t + 1] = attr; }
+          }
         } else {
-          tok[warp] = p.gen[(size_t)b * p.cap + t + 1];
+          nt = (int)p.gen[(size_t)b * p.cap + t + 1];
+          root = p.gen_root[(size_t)b * p.cap + t + 1];
+          attr = p.gen_attr[(size_t)b * p.cap + t + 1];
         }
+        ts_[0] = nt; ts_[1] = root; ts_[2] = attr;
+        for (int k = 7; k > 0; --k) hist[k] = hist[k - 1];
+        hist[0] = nt;
       }
     }
     stamp(cx);
@@ -862,6 +881,7 @@ int decode_run_stream(const DecodeParams& p, int t0, int n_steps, unsigned long 
     return kUnsupported;
   for (int l = 0; l < p.n_layers; ++l)
     if (p.layer[l].er_sw == nullptr) return kUnsupported;
+  if (p.sample && (p.max_conseq_chord < 1 || p.max_conseq_chord > 8 || !p.uniforms)) return kUnsupported;
   if (n_steps <= 0) return kOk;
   static int max_clusters[9] = {0};
   static bool attr_set = false;
@@ -874,7 +894,7 @@ int decode_run_stream(const DecodeParams& p, int t0, int n_steps, unsigned long 
   // than fit would still be correct, just run in waves)
   int R_sel = 0;
   for (int R = 1; R <= 8; ++R) {
-    const ds::Layout L = ds::make_layout(R, p.cap);
+    const ds::Layout L = ds::make_layout(R, p.cap, p.S);
     if (L.nslot < 4) break;
     if (max_clusters[R] == 0) {
       cudaLaunchConfig_t cfg = {};
@@ -893,10 +913,10 @@ int decode_run_stream(const DecodeParams& p, int t0, int n_steps, unsigned long 
   }
   if (const char* ov = getenv("V2M_STREAM_ROWS")) {       // measurement / test override
     const int R = atoi(ov);
-    if (R >= 1 && R <= 8 && ds::make_layout(R, p.cap).nslot >= 4) R_sel = R;
+    if (R >= 1 && R <= 8 && ds::make_layout(R, p.cap, p.S).nslot >= 4) R_sel = R;
   }
   if (R_sel == 0) return kUnsupported;
-  const ds::Layout L = ds::make_layout(R_sel, p.cap);
+  const ds::Layout L = ds::make_layout(R_sel, p.cap, p.S);
   const int ncl = (p.B + R_sel - 1) / R_sel;
   if (getenv("V2M_VERBOSE"))
     fprintf(stderr, "v2m: decode stream kernel: %d clusters x 8 CTAs, %d videos per cluster, ring %d x 32 KB, %u B smem (max co-resident %d)\n",

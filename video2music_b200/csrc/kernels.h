@@ -152,6 +152,9 @@ struct DecodeParams {
   float* logits;                  // [B, vocab]
   float* logits_all;              // optional [B, cap, vocab] (tests): row t receives the step-t logits
   void* xn;                       // [B, E]  normalised activations (GEMM operand), dtype T
+  // next-token rule: 0 = greedy arg-max (beam=1), 1 = sampling branch of generate() with its constraints
+  int sample, max_conseq_N, max_conseq_chord, pad_;
+  const float* uniforms;          // [B, cap] uniforms in [0, 1) consumed at position t + 1 (sampling only)
 };
 // Runs `n_steps` decode steps starting at *step (device).  use_graph: capture one step into a CUDA graph and replay.
 int decode_run(const DecodeParams& p, int n_steps, int use_graph, cudaStream_t stream);

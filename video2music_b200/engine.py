@@ -228,7 +228,8 @@ def stream_config_ok(dt, E, H, FF, B) -> bool:
 
 
 def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, primer_root, primer_attr,
-                 target_seq_length: int, want_logits: bool = False, mode: str = "auto") -> DecodeState:
+                 target_seq_length: int, want_logits: bool = False, mode: str = "auto", sample: bool = False,
+                 max_conseq_N: int = 0, max_conseq_chord: int = 2, uniforms: Optional[torch.Tensor] = None) -> DecodeState:
     """Encoder pass + cross-attention K/V caches + decode buffers.
     Replaces the per-step re-forward of generate() (video_music_transformer.py:1069-1071).
     mode "stream" / "kernels" / "auto" picks the decode path (see run_decode); the caches are built for that path only."""
@@ -241,7 +242,7 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     dt = W.dtype
     st = DecodeState()
     if mode == "auto":
-        mode = "stream" if stream_config_ok(dt, E, H, FF, B) else "kernels"
+        mode = "stream" if (stream_config_ok(dt, E, H, FF, B) and (not sample or 1 <= max_conseq_chord <= 8)) else "kernels"
     if mode == "stream" and not stream_config_ok(dt, E, H, FF, B):
         raise RuntimeError("streamed decode needs bf16, d_model 512, 8 heads, dim_feedforward 1024, batch <= 104")
     st.mode = mode
@@ -252,6 +253,15 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     d.B, d.H, d.E, d.FF, d.S, d.cap, d.n_layers = B, H, E, FF, S, cap, NL
     d.vocab, d.vocab_limit = CHORD_SIZE, CHORD_END
     d.chord_embed = int(cfg["chord_embed"])
+    d.sample, d.max_conseq_N, d.max_conseq_chord = int(sample), int(max_conseq_N), int(max_conseq_chord)
+    if sample:
+        # one uniform per (video, position): Categorical(probs).sample() of the reference (:1103-1104) as an inverse-CDF draw
+        if uniforms is None:
+            uniforms = torch.rand((B, cap), device=dev, dtype=torch.float32)
+        assert uniforms.shape == (B, cap) and uniforms.dtype == torch.float32
+        uniforms = uniforms.to(dev).contiguous()
+        st.keep.append(uniforms)
+        d.uniforms = ptr(uniforms)
     if primer.dim() == 1:
         primer, primer_root, primer_attr = (t.view(1, -1).expand(B, -1) for t in (primer, primer_root, primer_attr))
     P = primer.shape[1]

@@ -172,13 +172,19 @@ class VideoMusicTransformer(nn.Module):
     @torch.no_grad()
     def generate(self, feature_semantic_list=[], feature_key=None, feature_scene_offset=None, feature_motion=None,
                  feature_emotion=None, primer=None, primer_root=None, primer_attr=None, target_seq_length=300, beam=0,
-                 beam_chance=1.0, max_conseq_N=0, max_conseq_chord=2, use_graph=True, return_logits=False, decode_mode="auto"):
+                 beam_chance=1.0, max_conseq_N=0, max_conseq_chord=2, use_graph=True, return_logits=False, decode_mode="auto",
+                 uniforms=None):
         assert (not self.training), "Cannot generate while in training mode"
-        if not (beam >= 1 and beam_chance >= 1.0):
-            raise NotImplementedError(
-                "only the deterministic beam branch (beam>=1, beam_chance=1.0; greedy arg-max, "
-                "video_music_transformer.py:1078-1084) runs on device so far; the sampling branch (:1085-1128) "
-                "is SURVEY.md section 8f row 3")
+        # beam >= 1 with beam_chance >= 1: the deterministic branch (:1078-1084) == greedy arg-max for beam == 1;
+        # beam == 0: the sampling branch with its constraints (:1085-1128).  The random mix of both (0 < beam_chance < 1)
+        # and beam > 1 (which only rewrites gen_seq rows of a batch of one) are not reproduced.
+        if beam == 0:
+            sample = True
+        elif beam == 1 and beam_chance >= 1.0:
+            sample = False
+        else:
+            raise NotImplementedError("generate(): beam=0 (sampling branch) and beam=1 with beam_chance=1.0 (greedy) run on "
+                                      "device; beam > 1 / a random mix of branches (video_music_transformer.py:1073-1084) do not")
         dev = self._device()
         sem = feature_semantic_list.to(dev).float()
         B = sem.shape[0]
@@ -188,7 +194,8 @@ class VideoMusicTransformer(nn.Module):
         st = engine.build_decode(self._w(), self._cfg(), sem, key.to(dev), feature_scene_offset.to(dev).float(),
                                  feature_motion.to(dev).float(), feature_emotion.to(dev).float(),
                                  primer.long(), primer_root.long(), primer_attr.long(), target_seq_length,
-                                 want_logits=return_logits, mode=decode_mode)
+                                 want_logits=return_logits, mode=decode_mode, sample=sample, max_conseq_N=max_conseq_N,
+                                 max_conseq_chord=max_conseq_chord, uniforms=uniforms)
         engine.run_decode(st, target_seq_length - 1, use_graph=use_graph)
         gen = st.gen[:, :target_seq_length]
         if return_logits:
