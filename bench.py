@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 BATCH = 64                 # videos per GPU (BASELINE config 2)
 TRAIN_GLOBAL_BATCH = 512   # BASELINE config 3 (split over the ranks: strong scaling)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture, per launch)
-NCU_TRAFFIC_BYTES = {"stream": 116703284000 + 257316352}   # profiles/r01_decode_stream_ncu_full_details.txt
+NCU_TRAFFIC_BYTES = {"stream": 122944729000 + 286507008}   # profiles/r01_decode_stream_ncu_full_details.txt (ncu --set full, per launch)
 SEQ = 300                  # target_seq_length -> 299 generated chord tokens per video
 METRIC = "generate_chord_tokens_per_s"
 UNIT = "tokens/s"
