@@ -203,12 +203,37 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = m < M;
       const float rs = (row_ok && ep.row_scale) ? ep.row_scale[m] : 0.f;
       const size_t res_row = ep.residual ? (size_t)(ep.res_mod > 0 ? m % ep.res_mod : m) * ep.ldr : 0;
+      // The global operands of the epilogue (bias row, bf16 residual rows) do not depend on the accumulators: their loads
+      // are issued BEFORE waiting for the TMEM load, and the residual of the NEXT chunk is fetched while this one is
+      // processed (an L2 round trip per chunk otherwise sits on the critical path of an epilogue-bound tile).
+      const bool pre_res = vec_ok && row_ok && ep.residual && ep.residual_bf16 && k_split == 1;
+      uint4 res_nx[4];
+      auto fetch_res = [&](int cc, uint4* dst) {
+        const int nn = n_blk * BN + cc * 32;
+        if (pre_res && cc < BN / 32 && nn + 32 <= N) {
+          const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.residual) + res_row + nn);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = __ldg(rp + q);
+        }
+      };
+      fetch_res(half, res_nx);
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
-        tmem_ld_wait();
         const int n0 = n_blk * BN + c * 32;
+        const bool fast = vec_ok && n0 + 32 <= N && k_split == 1;
+        float4 bv[8];
+        if (fast && row_ok && ep.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bv[q] = __ldg(bp + q);
+        }
+        uint4 res_cur[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) res_cur[q] = res_nx[q];
+        fetch_res(c + 2, res_nx);
+        tmem_ld_wait();
         if (!row_ok || n0 >= N) continue;
         float v[32];
 #pragma unroll
@@ -223,10 +248,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (vec_ok && n0 + 32 <= N) {
           // ---- fast path: whole chunk in range, every pointer 16-byte aligned -> 128-bit loads / stores only
           if (ep.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 t = __ldg(bp + q);
+              const float4 t = bv[q];
               v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
             }
           }
@@ -249,10 +273,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (ep.residual) {
             if (ep.residual_bf16) {
-              const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.residual) + res_row + n0);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                const uint4 t = __ldg(rp + q);
+                const uint4 t = res_cur[q];
                 float2 f;
                 f = bf16x2_to_f2(t.x); v[8 * q] += f.x; v[8 * q + 1] += f.y;
                 f = bf16x2_to_f2(t.y); v[8 * q + 2] += f.x; v[8 * q + 3] += f.y;
@@ -286,11 +309,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
         } else {
-          // ---- edge path (N tail or unaligned operands): scalar, guarded
-#pragma unroll 1
+          // ---- edge path (N tail or unaligned operands): scalar, guarded.  Fully unrolled: a dynamically indexed v[]
+          // would live in local memory for the fast path as well.
+#pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int n = n0 + i;
-            if (n >= N) break;
+            if (n >= N) continue;
             float x = v[i];
             if (ep.bias) x += __ldg(ep.bias + n);
             if (n < ep.alpha_cols) x *= ep.alpha;
