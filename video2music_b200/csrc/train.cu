@@ -47,9 +47,71 @@ __global__ void __launch_bounds__(256) dy_prep_kernel(const void* __restrict__ d
   }
 }
 
+// bf16 fast path: a thread owns 8 consecutive columns (one 16-byte access per tensor and row), 32 row-lanes per block
+__global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restrict__ dy, long long ld_dy, const bf16* __restrict__ y,
+                                                             long long ld_y, int relu, float alpha, int alpha_cols,
+                                                             bf16* __restrict__ dz, long long ld_dz, float* __restrict__ db, int M,
+                                                             int N) {
+  __shared__ float part[32][8 * 8 + 1];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;            // 8 column groups x 32 row lanes
+  const int n0 = (blockIdx.x * 8 + tx) * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (n0 < N) {
+    float sc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sc[e] = (n0 + e < alpha_cols) ? alpha : 1.f;
+    for (int m = blockIdx.y * 32 + ty; m < M; m += gridDim.y * 32) {
+      const uint4 gq = *reinterpret_cast<const uint4*>(dy + (size_t)m * ld_dy + n0);
+      float g[8];
+      float2 f;
+      f = bf16x2_to_f2(gq.x); g[0] = f.x; g[1] = f.y;   f = bf16x2_to_f2(gq.y); g[2] = f.x; g[3] = f.y;
+      f = bf16x2_to_f2(gq.z); g[4] = f.x; g[5] = f.y;   f = bf16x2_to_f2(gq.w); g[6] = f.x; g[7] = f.y;
+      if (relu) {
+        const uint4 yq = *reinterpret_cast<const uint4*>(y + (size_t)m * ld_y + n0);
+        float yv[8];
+        f = bf16x2_to_f2(yq.x); yv[0] = f.x; yv[1] = f.y;   f = bf16x2_to_f2(yq.y); yv[2] = f.x; yv[3] = f.y;
+        f = bf16x2_to_f2(yq.z); yv[4] = f.x; yv[5] = f.y;   f = bf16x2_to_f2(yq.w); yv[6] = f.x; yv[7] = f.y;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (!(yv[e] > 0.f)) g[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { g[e] *= sc[e]; acc[e] += g[e]; }
+      if (dz) {
+        uint4 o;
+        o.x = f2_to_bf16x2(g[0], g[1]); o.y = f2_to_bf16x2(g[2], g[3]); o.z = f2_to_bf16x2(g[4], g[5]); o.w = f2_to_bf16x2(g[6], g[7]);
+        *reinterpret_cast<uint4*>(dz + (size_t)m * ld_dz + n0) = o;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) part[ty][tx * 8 + e] = acc[e];
+  __syncthreads();
+  if (threadIdx.x < 64 && db) {
+    const int n = blockIdx.x * 64 + threadIdx.x;
+    if (n < N) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) s += part[i][threadIdx.x];
+      atomicAdd(db + n, s);
+    }
+  }
+}
+
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
             int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, cudaStream_t stream) {
   if (M == 0 || N == 0) return kOk;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  if (dy_dtype == 1 && (!dz || dz_dtype == 1) && (!relu || y_dtype == 1) && N % 8 == 0 && ld_dy % 8 == 0 && (!dz || ld_dz % 8 == 0) &&
+      (!relu || ld_y % 8 == 0) && al16(dy) && al16(dz) && (!relu || al16(y))) {
+    int gy2 = (M + 31) / 32;
+    if (gy2 > 148) gy2 = 148;
+    dim3 grid2((N + 63) / 64, gy2);
+    dy_prep_bf16x8_kernel<<<grid2, 256, 0, stream>>>(static_cast<const bf16*>(dy), ld_dy, static_cast<const bf16*>(y), ld_y, relu, alpha,
+                                                     alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N);
+    return check_launch("dy_prep_bf16x8");
+  }
   int gy = (M + 7) / 8;
   if (gy > 148 * 2) gy = 148 * 2;
   dim3 grid((N + 31) / 32, gy);
