@@ -31,7 +31,41 @@ __device__ __forceinline__ void ldsm_x4_t(const bf16* p, uint32_t& r0, uint32_t&
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
 }
+__device__ __forceinline__ void ldsm_x4(const bf16* p, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(smem_u32(p)));
+}
 __device__ __forceinline__ uint32_t lds32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;                         // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// asynchronous version of load_tile (completion: cp_async_wait + __syncthreads)
+__device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, long long ld, int n_valid) {
+  for (int idx = threadIdx.x; idx < 64 * 8; idx += THREADS) {
+    const int r = idx >> 3, c = idx & 7;
+    const bool ok = r < n_valid;
+    cp_async16(dst + r * TP + c * 8, src + (ok ? (long long)r * ld + c * 8 : 0), ok);
+  }
+}
+
+// acc[nt][4] (16 rows x 64 columns = 8 n-tiles) = A (16 x 64, four k-step fragments) * T^T where T holds the n index in
+// its rows and the k index in its columns (K / V tiles: rows = keys, columns = head dims): one ldmatrix.x4 feeds two MMAs.
+__device__ __forceinline__ void mma_a_times_colmajor(float acc[8][4], const uint32_t a[4][4], const bf16* t, int lane) {
+  const int ri = lane & 7, mi = lane >> 3;
+#pragma unroll
+  for (int ntp = 0; ntp < 4; ++ntp) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t r0, r1, r2, r3;
+      ldsm_x4(t + ((2 * ntp + (mi >> 1)) * 8 + ri) * TP + ks * 16 + (mi & 1) * 8, r0, r1, r2, r3);
+      mma16816(acc[2 * ntp], a[ks], r0, r1);
+      mma16816(acc[2 * ntp + 1], a[ks], r2, r3);
+    }
+  }
+}
 
 // 64 rows x 64 bf16 from global (row stride `ld` elements, rows >= n_valid zero-filled) into a pitch-72 tile
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, long long ld, int n_valid) {
@@ -78,9 +112,11 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
   bf16* sdO = sQ + TILE;
   bf16* sK = sdO + TILE;                // first holds the O tile
   bf16* sV = sK + TILE;
+  bf16* sK2 = sV + TILE;                // second K / V buffer (cp.async double buffering)
+  bf16* sV2 = sK2 + TILE;
   // RPR only: Er_rev rows (d -> Er[er_len-1-d]), the Q Er_rev^T table (fp32) and the skewed dS rows (bf16)
   const int QP = ws.Lkp + 4, DP = ws.Lkp + 8;
-  bf16* sEr = sV + TILE;                                   // [Lkp][TP]
+  bf16* sEr = sV2 + TILE;                                  // [Lkp][TP]
   float* sQE = reinterpret_cast<float*>(sEr + (HAS_ER ? ws.Lkp * TP : 0));   // [64][QP]
   bf16* sdQE = reinterpret_cast<bf16*>(sQE + (HAS_ER ? 64 * QP : 0));        // [64][DP]
 
@@ -156,25 +192,30 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
   const int n_jt = p.causal ? min(ws.Lkp / 64, (I0 + 63 + coff) / 64 + 1) : ws.Lkp / 64;
   bf16* Pw = ws.P + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
   bf16* dSw = ws.dS + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
-  for (int jt = 0; jt < n_jt; ++jt) {
+  // K / V tiles are double-buffered with cp.async: tile jt+1 is in flight while tile jt is processed
+  auto issue_kv = [&](int jt) {
     const int J0 = jt * 64;
     const int nk = max(0, min(64, p.Lk - J0));
-    load_tile(sK, Kg + (long long)J0 * p.k_sl, p.k_sl, nk);
-    load_tile(sV, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
+    bf16* kb = (jt & 1) ? sK2 : sK;
+    bf16* vb = (jt & 1) ? sV2 : sV;
+    load_tile_async(kb, Kg + (long long)J0 * p.k_sl, p.k_sl, nk);
+    load_tile_async(vb, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
+    cp_async_commit();
+  };
+  if (n_jt > 0) issue_kv(0);
+  for (int jt = 0; jt < n_jt; ++jt) {
+    const int J0 = jt * 64;
+    const bf16* kb = (jt & 1) ? sK2 : sK;
+    const bf16* vb = (jt & 1) ? sV2 : sV;
+    if (jt + 1 < n_jt) { issue_kv(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) { s[nt][e] = 0.f; dp[nt][e] = 0.f; }
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const bf16* kp = sK + (nt * 8 + g) * TP + ks * 16 + 2 * q;
-        mma16816(s[nt], qa[ks], lds32(kp), lds32(kp + 8));
-        const bf16* vp = sV + (nt * 8 + g) * TP + ks * 16 + 2 * q;
-        mma16816(dp[nt], doa[ks], lds32(vp), lds32(vp + 8));
-      }
-    }
+    mma_a_times_colmajor(s, qa, kb, lane);
+    mma_a_times_colmajor(dp, doa, vb, lane);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -206,8 +247,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
       a[kk][2] = f2_to_bf16x2(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
       a[kk][3] = f2_to_bf16x2(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
     }
-    mma_a_times_rowmajor(dq, a, sK, lane);
-    __syncthreads();
+    mma_a_times_rowmajor(dq, a, kb, lane);
+    __syncthreads();                                       // everyone is done with this buffer before tile jt+2 lands in it
   }
   if (HAS_ER) {
     __syncwarp();
@@ -251,39 +292,42 @@ __device__ __forceinline__ void frag_a_transposed(const bf16* t, int c0, int lan
 // ------------------------------------------------------------------------------------------------ cols kernel
 __global__ void __launch_bounds__(THREADS) attn_bwd_cols_kernel(AttnBwdParams p, Ws ws) {
   extern __shared__ __align__(16) unsigned char abt_smem[];
-  bf16* sP = reinterpret_cast<bf16*>(abt_smem);
-  bf16* sdS = sP + TILE;
-  bf16* sdO = sdS + TILE;
-  bf16* sQ = sdO + TILE;
+  bf16* sP = reinterpret_cast<bf16*>(abt_smem);         // two stages of [P | dS | dO | Q] tiles
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
   const int b = blockIdx.y / p.Hkv, hkv = blockIdx.y % p.Hkv, grp = p.Hq / p.Hkv;
-  const int J0 = blockIdx.x * 64, jt = blockIdx.x;
+  const int J0 = blockIdx.x * 64;
   const int coff = p.Lk - p.Lq;
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
-  for (int hh = 0; hh < grp; ++hh) {
-    const int hq = hkv * grp + hh, bh = b * p.Hq + hq;
-    const bf16* Qg = static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64;
-    const bf16* dOg = static_cast<const bf16*>(p.dO) + (long long)b * p.do_sb + (long long)hq * 64;
-    for (int it = 0; it < ws.Lqp / 64; ++it) {
-      const int I0 = it * 64;
-      if (p.causal && jt > (I0 + 63 + coff) / 64) continue;           // tile never written by the rows kernel (all masked)
-      const int nq = max(0, min(64, p.Lq - I0));
-      load_tile(sP, ws.P + ((long long)bh * ws.Lqp + I0) * ws.Lkp + J0, ws.Lkp, 64);
-      load_tile(sdS, ws.dS + ((long long)bh * ws.Lqp + I0) * ws.Lkp + J0, ws.Lkp, 64);
-      load_tile(sdO, dOg + (long long)I0 * p.do_sl, p.do_sl, nq);
-      load_tile(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
-      __syncthreads();
-      uint32_t a[4][4];
-      frag_a_transposed(sP, w * 16, lane, a);                         // A[m = key][k = query] = P[query][key]
-      mma_a_times_rowmajor(dv, a, sdO, lane);
-      frag_a_transposed(sdS, w * 16, lane, a);
-      mma_a_times_rowmajor(dk, a, sQ, lane);
-      __syncthreads();
-    }
+  // query tiles that the rows kernel wrote for this key tile (causal: the others are fully masked) form a contiguous range;
+  // the (query head of the group, query tile) pairs are walked with cp.async double buffering (4 tiles per stage)
+  const int it_begin = p.causal ? max(0, (J0 - 63 - coff + 63) / 64) : 0;
+  const int n_it = ws.Lqp / 64 - it_begin, total = grp * max(n_it, 0);
+  auto issue = [&](int k) {
+    const int hh = k / n_it, it = it_begin + k % n_it;
+    const int hq = hkv * grp + hh, bh = b * p.Hq + hq, I0 = it * 64;
+    const int nq = max(0, min(64, p.Lq - I0));
+    bf16* base = sP + (k & 1) * 4 * TILE;
+    load_tile_async(base, ws.P + ((long long)bh * ws.Lqp + I0) * ws.Lkp + J0, ws.Lkp, 64);
+    load_tile_async(base + TILE, ws.dS + ((long long)bh * ws.Lqp + I0) * ws.Lkp + J0, ws.Lkp, 64);
+    load_tile_async(base + 2 * TILE, static_cast<const bf16*>(p.dO) + (long long)b * p.do_sb + (long long)hq * 64 + (long long)I0 * p.do_sl, p.do_sl, nq);
+    load_tile_async(base + 3 * TILE, static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64 + (long long)I0 * p.q_sl, p.q_sl, nq);
+    cp_async_commit();
+  };
+  if (total > 0) issue(0);
+  for (int k = 0; k < total; ++k) {
+    if (k + 1 < total) { issue(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const bf16* base = sP + (k & 1) * 4 * TILE;
+    uint32_t a[4][4];
+    frag_a_transposed(base, w * 16, lane, a);                         // A[m = key][k = query] = P[query][key]
+    mma_a_times_rowmajor(dv, a, base + 2 * TILE, lane);
+    frag_a_transposed(base + TILE, w * 16, lane, a);
+    mma_a_times_rowmajor(dk, a, base + 3 * TILE, lane);
+    __syncthreads();
   }
   const int jlo = J0 + w * 16 + g, jhi = jlo + 8;
   bf16* dKg = reinterpret_cast<bf16*>(p.dk) + (long long)b * p.dkv_sb + (long long)hkv * 64;
@@ -375,22 +419,23 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   ws.P = static_cast<bf16*>(ws_ptr);
   ws.dS = ws.P + plane;
   ws.dQE = has_er ? ws.dS + plane : nullptr;
-  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16);
-  const size_t smem_er = tiles4 + (size_t)ws.Lkp * abt::TP * 2 + (size_t)64 * (ws.Lkp + 4) * 4 + (size_t)64 * (ws.Lkp + 8) * 2;
+  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16), tiles6 = 6 * abt::TILE * sizeof(bf16);
+  const size_t smem_er = tiles6 + (size_t)ws.Lkp * abt::TP * 2 + (size_t)64 * (ws.Lkp + 4) * 4 + (size_t)64 * (ws.Lkp + 8) * 2;
   V2M_REQUIRE(!has_er || smem_er <= 227 * 1024, "attn_bwd_tc: L=%d needs %zu B of shared memory with RPR (> 227 KB)", p.Lk, smem_er);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles4);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles6);
+    cudaFuncSetAttribute(abt::attn_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tiles4));
     attr_set = true;
   }
   dim3 grid_r(ws.Lqp / 64, p.B * p.Hq);
   if (has_er) abt::attn_bwd_rows_kernel<true><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
-  else abt::attn_bwd_rows_kernel<false><<<grid_r, abt::THREADS, tiles4, stream>>>(p, ws);
+  else abt::attn_bwd_rows_kernel<false><<<grid_r, abt::THREADS, tiles6, stream>>>(p, ws);
   int rc = check_launch("attn_bwd_rows");
   if (rc) return rc;
   dim3 grid_c(ws.Lkp / 64, p.B * p.Hkv);
-  abt::attn_bwd_cols_kernel<<<grid_c, abt::THREADS, tiles4, stream>>>(p, ws);
+  abt::attn_bwd_cols_kernel<<<grid_c, abt::THREADS, 2 * tiles4, stream>>>(p, ws);
   rc = check_launch("attn_bwd_cols");
   if (rc || !has_er) return rc;
   const int n_split = p.B * p.Hq < 64 ? p.B * p.Hq : 64;
