@@ -349,8 +349,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_cols_kernel(AttnBwdParams p,
 // ------------------------------------------------------------------------------------------------ dEr kernel
 __global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, Ws ws, int n_split) {
   extern __shared__ __align__(16) unsigned char abt_smem[];
-  bf16* sE = reinterpret_cast<bf16*>(abt_smem);          // dQE tile [64 i][64 d]
-  bf16* sQ = sE + TILE;
+  bf16* sE = reinterpret_cast<bf16*>(abt_smem);          // two stages of [dQE tile (64 i x 64 d) | Q tile]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
   const int D0 = blockIdx.x * 64;
   float acc[8][4];
@@ -358,20 +357,27 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, 
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-  for (int bh = blockIdx.y; bh < p.B * p.Hq; bh += n_split) {
+  // (batch*head, query tile) pairs of this split, rows i >= d only, cp.async double buffering (2 tiles per stage)
+  const int it_begin = D0 / 64, n_it = ws.Lqp / 64 - it_begin;
+  const int n_bh = (p.B * p.Hq - (int)blockIdx.y + n_split - 1) / n_split, total = n_bh * n_it;
+  auto issue = [&](int k) {
+    const int bh = blockIdx.y + (k / n_it) * n_split, I0 = (it_begin + k % n_it) * 64;
     const int b = bh / p.Hq, hq = bh % p.Hq;
-    const bf16* Qg = static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64;
-    for (int it = D0 / 64; it < ws.Lqp / 64; ++it) {       // rows i >= d only
-      const int I0 = it * 64;
-      const int nq = max(0, min(64, p.Lq - I0));
-      load_tile(sE, ws.dQE + ((long long)bh * ws.Lqp + I0) * ws.Lkp + D0, ws.Lkp, 64);
-      load_tile(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
-      __syncthreads();
-      uint32_t a[4][4];
-      frag_a_transposed(sE, w * 16, lane, a);               // A[m = d][k = i] = dQE[i][d]
-      mma_a_times_rowmajor(acc, a, sQ, lane);
-      __syncthreads();
-    }
+    const int nq = max(0, min(64, p.Lq - I0));
+    bf16* base = sE + (k & 1) * 2 * TILE;
+    load_tile_async(base, ws.dQE + ((long long)bh * ws.Lqp + I0) * ws.Lkp + D0, ws.Lkp, 64);
+    load_tile_async(base + TILE, static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64 + (long long)I0 * p.q_sl, p.q_sl, nq);
+    cp_async_commit();
+  };
+  if (total > 0) issue(0);
+  for (int k = 0; k < total; ++k) {
+    if (k + 1 < total) { issue(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    const bf16* base = sE + (k & 1) * 2 * TILE;
+    uint32_t a[4][4];
+    frag_a_transposed(base, w * 16, lane, a);                 // A[m = d][k = i] = dQE[i][d]
+    mma_a_times_rowmajor(acc, a, base + TILE, lane);
+    __syncthreads();
   }
   const int dlo = D0 + w * 16 + g, dhi = dlo + 8;
   const int dlim = min(p.Lq, p.er_len);
@@ -438,9 +444,9 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   abt::attn_bwd_cols_kernel<<<grid_c, abt::THREADS, 2 * tiles4, stream>>>(p, ws);
   rc = check_launch("attn_bwd_cols");
   if (rc || !has_er) return rc;
-  const int n_split = p.B * p.Hq < 64 ? p.B * p.Hq : 64;
+  const int n_split = p.B * p.Hq < 148 ? p.B * p.Hq : 148;
   dim3 grid_e(ws.Lkp / 64, n_split);
-  abt::attn_bwd_der_kernel<<<grid_e, abt::THREADS, 2 * abt::TILE * sizeof(bf16), stream>>>(p, ws, n_split);
+  abt::attn_bwd_der_kernel<<<grid_e, abt::THREADS, tiles4, stream>>>(p, ws, n_split);
   return check_launch("attn_bwd_der");
 }
 
