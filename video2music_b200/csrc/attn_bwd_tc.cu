@@ -112,11 +112,14 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
   bf16* sdO = sQ + TILE;
   bf16* sK = sdO + TILE;                // first holds the O tile
   bf16* sV = sK + TILE;
-  bf16* sK2 = sV + TILE;                // second K / V buffer (cp.async double buffering)
-  bf16* sV2 = sK2 + TILE;
+  // second K / V buffer (cp.async double buffering); the RPR variant has no shared memory left for it
+  constexpr bool DBUF = !HAS_ER;
+  bf16* sK2 = DBUF ? sV + TILE : sK;
+  bf16* sV2 = DBUF ? sK2 + TILE : sV;
+  bf16* sStage = sV + (DBUF ? 3 : 1) * TILE;            // per warp: 16 rows of P + 16 rows of dS (pitch TP) on their way to the workspace
   // RPR only: Er_rev rows (d -> Er[er_len-1-d]), the Q Er_rev^T table (fp32) and the skewed dS rows (bf16)
   const int QP = ws.Lkp + 4, DP = ws.Lkp + 8;
-  bf16* sEr = sV2 + TILE;                                  // [Lkp][TP]
+  bf16* sEr = sStage + 2 * TILE;                           // [Lkp][TP]
   float* sQE = reinterpret_cast<float*>(sEr + (HAS_ER ? ws.Lkp * TP : 0));   // [64][QP]
   bf16* sdQE = reinterpret_cast<bf16*>(sQE + (HAS_ER ? 64 * QP : 0));        // [64][DP]
 
@@ -202,12 +205,14 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
     load_tile_async(vb, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
     cp_async_commit();
   };
-  if (n_jt > 0) issue_kv(0);
+  if (DBUF && n_jt > 0) issue_kv(0);
   for (int jt = 0; jt < n_jt; ++jt) {
     const int J0 = jt * 64;
     const bf16* kb = (jt & 1) ? sK2 : sK;
     const bf16* vb = (jt & 1) ? sV2 : sV;
-    if (jt + 1 < n_jt) { issue_kv(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    if (!DBUF) { issue_kv(jt); cp_async_wait<0>(); }
+    else if (jt + 1 < n_jt) { issue_kv(jt + 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
@@ -231,13 +236,24 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
         dp[nt][e] = dsv;
         if (rel) sdQE[(r0 + g + hi * 8) * DP + (i - j)] = __float2bfloat16_rn(dsv);
       }
-      // P and dS tiles for the cols kernel
-      const long long o_lo = (long long)g * ws.Lkp + J0 + nt * 8 + 2 * q, o_hi = o_lo + 8LL * ws.Lkp;
-      *reinterpret_cast<uint32_t*>(Pw + o_lo) = f2_to_bf16x2(s[nt][0], s[nt][1]);
-      *reinterpret_cast<uint32_t*>(Pw + o_hi) = f2_to_bf16x2(s[nt][2], s[nt][3]);
-      *reinterpret_cast<uint32_t*>(dSw + o_lo) = f2_to_bf16x2(dp[nt][0], dp[nt][1]);
-      *reinterpret_cast<uint32_t*>(dSw + o_hi) = f2_to_bf16x2(dp[nt][2], dp[nt][3]);
+      // P and dS fragments -> this warp's staging rows (bf16, pitch 72): written out below as whole 128-byte rows
+      bf16* sp = sStage + (w * 32 + g) * TP + nt * 8 + 2 * q;
+      *reinterpret_cast<uint32_t*>(sp) = f2_to_bf16x2(s[nt][0], s[nt][1]);
+      *reinterpret_cast<uint32_t*>(sp + 8 * TP) = f2_to_bf16x2(s[nt][2], s[nt][3]);
+      *reinterpret_cast<uint32_t*>(sp + 16 * TP) = f2_to_bf16x2(dp[nt][0], dp[nt][1]);
+      *reinterpret_cast<uint32_t*>(sp + 24 * TP) = f2_to_bf16x2(dp[nt][2], dp[nt][3]);
     }
+    __syncwarp();
+    // P and dS tiles for the cols kernel: 16 rows x 128 B each, 16-byte stores, 8 lanes per row
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = it * 32 + lane, r = idx >> 3, c8 = idx & 7;
+      const uint4 pv4 = *reinterpret_cast<const uint4*>(sStage + (w * 32 + r) * TP + c8 * 8);
+      const uint4 dv4 = *reinterpret_cast<const uint4*>(sStage + (w * 32 + 16 + r) * TP + c8 * 8);
+      *reinterpret_cast<uint4*>(Pw + (long long)r * ws.Lkp + J0 + c8 * 8) = pv4;
+      *reinterpret_cast<uint4*>(dSw + (long long)r * ws.Lkp + J0 + c8 * 8) = dv4;
+    }
+    __syncwarp();
     // dQ += dS K_J : the C fragments of two adjacent key tiles form the A fragment of one k-step
     uint32_t a[4][4];
 #pragma unroll
@@ -425,8 +441,8 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   ws.P = static_cast<bf16*>(ws_ptr);
   ws.dS = ws.P + plane;
   ws.dQE = has_er ? ws.dS + plane : nullptr;
-  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16), tiles6 = 6 * abt::TILE * sizeof(bf16);
-  const size_t smem_er = tiles6 + (size_t)ws.Lkp * abt::TP * 2 + (size_t)64 * (ws.Lkp + 4) * 4 + (size_t)64 * (ws.Lkp + 8) * 2;
+  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16), tiles6 = 8 * abt::TILE * sizeof(bf16);
+  const size_t smem_er = 6 * abt::TILE * sizeof(bf16) + (size_t)ws.Lkp * abt::TP * 2 + (size_t)64 * (ws.Lkp + 4) * 4 + (size_t)64 * (ws.Lkp + 8) * 2;
   V2M_REQUIRE(!has_er || smem_er <= 227 * 1024, "attn_bwd_tc: L=%d needs %zu B of shared memory with RPR (> 227 KB)", p.Lk, smem_er);
   static bool attr_set = false;
   if (!attr_set) {
