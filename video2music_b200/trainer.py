@@ -74,14 +74,36 @@ class Trainer:
         self.group = group
         self.step_no = 0
         self.last_parts = None
+        self._copy_stream = None
+
+    def prefetch(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """Starts the host -> device copy of a (pinned) batch on a side stream and returns the device batch; train_step waits
+        for it.  Called for step i+1 before train_step(i), the copy overlaps the compute of step i (the reference's DataLoader
+        does the same job with pin_memory workers, train.py:160-170)."""
+        dev = self.flat.flat_p.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            out = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        out["_ready"] = ev
+        return out
 
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """batch: this rank's shard with the keys of synthetic.make_inputs (run_model_vevo.py:31-45)."""
+        """batch: this rank's shard with the keys of synthetic.make_inputs (run_model_vevo.py:31-45), on the host or a
+        device batch returned by prefetch()."""
         from . import ops
         from .autograd import AmtLossFn
         m = self.model
         dev = self.flat.flat_p.device
-        b = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+        ready = batch.get("_ready")
+        if ready is not None:
+            torch.cuda.current_stream(dev).wait_event(ready)
+            for k, v in batch.items():
+                if k != "_ready":
+                    v.record_stream(torch.cuda.current_stream(dev))
+        b = {k: v.to(dev, non_blocking=True) for k, v in batch.items() if k != "_ready"}
         y = m(b["x"], b["x_root"], b["x_attr"], b["feature_semantic_list"], b["feature_key"], b["feature_scene_offset"],
               b["feature_motion"], b["feature_emotion"])
         loss = AmtLossFn.apply(y, b["tgt"], b["tgt_emotion"], 0.1, 0.4, 0.6)          # run_model_vevo.py:101-119
