@@ -229,6 +229,19 @@ int v2m_moe_route(const float* x, const float* wg, const float* bg, const float*
                   float inv_t_post, int32_t tokens, int32_t d, int32_t n_experts, int32_t k, int64_t* idx_out,
                   float* w_out, float* logits_out, int32_t* hist_out, void* stream);
 
+/* ---- MoE expert dispatch, model/moe.py:191-199 without the per-expert Python loop / torch.where host syncs (fp32).
+ * permute: off[E+1] = exclusive scan of hist; copy (t, r) of token t lands in row perm[t*k+r] of xp (expert-contiguous).
+ * grouped_gemm: C[row] = x_row . W1_e^T + b1_e for the rows of group e (bounds read from off[] on the device; max_rows =
+ *   tokens * k sizes the grid); with Wg != NULL: C = (x W1^T + b1) * silu(x Wg^T + bg)  (GLUExpert, moe.py:44-49).
+ *   W1 / Wg: [E][N][K] stacks (w_gstride elements apart), b1 / bg: [E][N] (b_gstride).
+ * combine: out[t] = sum_r w[t*k+r] * yp[perm[t*k+r]], rank order. */
+int v2m_moe_permute(const float* x, const int64_t* idx, const int32_t* hist, int32_t tokens, int32_t k, int32_t d, int32_t n_experts,
+                    int32_t* off, int32_t* cursor, float* xp, int32_t* perm, void* stream);
+int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const float* b1, const float* Wg, const float* bg,
+                         int64_t w_gstride, int64_t b_gstride, const int32_t* off, int32_t n_experts, int32_t max_rows, float* C,
+                         int32_t ldc, int32_t N, int32_t K, void* stream);
+int v2m_moe_combine(const float* yp, const int32_t* perm, const float* w, float* out, int32_t tokens, int32_t k, int32_t d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,6 +331,33 @@ def test_moe_golden_gpu(shared):
     assert rel_err(y, g["out"]) < 1e-4
 
 
+@pytest.mark.parametrize("tokens,E,k,d,ff", [(203, 6, 2, 64, 80), (1, 4, 4, 32, 48), (1500, 8, 3, 128, 272)])
+def test_moe_dispatch_ragged_groups_vs_oracle(tokens, E, k, d, ff):
+    """Skewed router (one expert takes most tokens, some take none): group sizes are neither equal nor tile multiples."""
+    from video2music_b200 import GLUExpert, MoELayer
+    mod = MoELayer(GLUExpert(d, ff, 0.0), d, n_experts=E, n_experts_per_token=k, dropout=0.0).eval()
+    sd = syn.fill_like_reference_init({n: tuple(v.shape) for n, v in mod.state_dict().items()}, seed=77)
+    sd["gate.bias"] = torch.tensor([3.0, -50.0, 1.0, 0.5] + [0.0] * (E - 4))[:E]      # expert 1 never chosen when k < E
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    x = _u((tokens, 1, d), 5, "x")
+    with torch.no_grad():
+        y = mod(x.to(DEV))
+        y_again = mod(x.to(DEV))
+    ref, idx, _ = O.moe_layer(x, sd, "", E, k)
+    assert torch.equal(mod.last_selected_experts.cpu(), idx)
+    assert rel_err(y, ref) < 1e-4
+    assert torch.equal(y, y_again)                    # row order inside a group is arbitrary, the result is not
+    if k < E:
+        assert int((idx == 1).sum()) == 0
+    # an in-place weight update must invalidate the stacked-weight cache
+    with torch.no_grad():
+        mod.experts[0].linear2.bias.add_(1.0)
+        y2 = mod(x.to(DEV))
+    sd["experts.0.linear2.bias"] = sd["experts.0.linear2.bias"] + 1.0
+    assert rel_err(y2, O.moe_layer(x, sd, "", E, k)[0]) < 1e-4
+
+
 def test_moe_route_ties_and_bias():
     from video2music_b200 import ops
     x = torch.zeros((5, 64), device=DEV)

@@ -236,6 +236,23 @@ int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, 
   return rmsnorm(x, w, y, M, D, eps, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_moe_permute(const float* x, const int64_t* idx, const int32_t* hist, int32_t tokens, int32_t k, int32_t d, int32_t n_experts,
+                    int32_t* off, int32_t* cursor, float* xp, int32_t* perm, void* stream) {
+  return moe_permute(x, reinterpret_cast<const long long*>(idx), hist, tokens, k, d, n_experts, off, cursor, xp, perm,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const float* b1, const float* Wg, const float* bg,
+                         int64_t w_gstride, int64_t b_gstride, const int32_t* off, int32_t n_experts, int32_t max_rows, float* C,
+                         int32_t ldc, int32_t N, int32_t K, void* stream) {
+  return moe_grouped_gemm(A, lda, W1, b1, Wg, bg, w_gstride, b_gstride, off, n_experts, max_rows, C, ldc, N, K,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int v2m_moe_combine(const float* yp, const int32_t* perm, const float* w, float* out, int32_t tokens, int32_t k, int32_t d, void* stream) {
+  return moe_combine(yp, perm, w, out, tokens, k, d, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream) {
   return pscan_fwd(A, X, H, B, L, D, N, static_cast<cudaStream_t>(stream));
 }

@@ -82,7 +82,7 @@ __device__ __forceinline__ int pick_token(const float* logits, int vocab, int vo
 }
 
 // chord id -> (root id, attribute id): dataset/vevo_meta/chord_inv.json + chord_root.json + chord_attr.json of the reference
-// are the closed form below (checked by tests/test_oracle_vs_reference.py); "N" and plain major names get attribute 1
+// are the closed form below (checked against those JSON tables in the CPU tests); "N" and plain major names get attribute 1
 // (video_music_transformer.py:1109-1116).
 __device__ __forceinline__ void chord_root_attr(int c, long long& root, long long& attr) {
   if (c <= 0) { root = 0; attr = 1; return; }

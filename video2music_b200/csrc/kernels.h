@@ -182,4 +182,13 @@ int moe_route(const float* x, const float* wg, const float* bg, const float* sel
               int tokens, int d, int n_experts, int k, long long* idx_out, float* w_out, float* logits_out,
               int* hist_out, cudaStream_t stream);
 
+// Expert dispatch (moe.cu): expert-contiguous token permutation, ragged grouped GEMM with device-side group bounds
+// (optionally the fused SwiGLU pair of GLUExpert), weighted combine in rank order.
+int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int* off,
+                int* cursor, float* xp, int* perm, cudaStream_t stream);
+int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,
+                     long long b_gstride, const int* off, int n_experts, int max_rows, float* C, int ldc, int N, int K,
+                     cudaStream_t stream);
+int moe_combine(const float* yp, const int* perm, const float* w, float* out, int tokens, int k, int d, cudaStream_t stream);
+
 }  // namespace v2m

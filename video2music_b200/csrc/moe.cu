@@ -72,4 +72,158 @@ int moe_route(const float* x, const float* wg, const float* bg, const float* sel
   return check_launch("moe_route");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Expert dispatch without host round trips (the reference loops over experts in Python with torch.where per expert,
+// model/moe.py:192-199):
+//   moe_offsets   : exclusive scan of the router's histogram -> off[E+1]; clears the per-expert cursors
+//   moe_permute   : token copy (t, r) goes to row off[e] + cursor[e]++ of the expert-contiguous matrix xp; perm[t*k+r] = row
+//                   (row order inside a group is arbitrary; every row's result is independent of its position)
+//   moe_grouped_* : C[row] = epi(xp[row] . W_e^T) for the rows of group e = blockIdx.z, with the group bounds read from
+//                   off[] ON THE DEVICE (ragged groups, grid sized for the worst case, surplus CTAs exit at once).
+//                   glu != 0: two weight stacks, C = (x W1^T + b1) * silu(x Wg^T + bg)   (GLUExpert, moe.py:44-49)
+//   moe_combine   : out[t] = sum_r w[t][r] * yp[perm[t*k+r]]  in rank order (deterministic)        (moe.py:196-199)
+__global__ void moe_offsets_kernel(const int* __restrict__ hist, int n_experts, int* __restrict__ off, int* __restrict__ cursor) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < n_experts; ++e) { off[e] = acc; cursor[e] = 0; acc += hist[e]; }
+    off[n_experts] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) moe_permute_kernel(const float* __restrict__ x, const long long* __restrict__ idx,
+                                                          const int* __restrict__ off, int* __restrict__ cursor,
+                                                          float* __restrict__ xp, int* __restrict__ perm, int tokens, int k, int d) {
+  const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (item >= tokens * k) return;
+  const int t = item / k;
+  int row = 0;
+  if (lane == 0) {
+    const int e = (int)idx[item];
+    row = off[e] + atomicAdd(cursor + e, 1);
+    perm[item] = row;
+  }
+  row = __shfl_sync(0xffffffffu, row, 0);
+  const float4* src = reinterpret_cast<const float4*>(x + (size_t)t * d);
+  float4* dst = reinterpret_cast<float4*>(xp + (size_t)row * d);
+  for (int i = lane; i < d / 4; i += 32) dst[i] = src[i];
+}
+
+constexpr int GB = 64, GK = 16;       // 64 x 64 output tile, 256 threads, 4 x 4 outputs each
+template <bool GLU>
+__global__ void __launch_bounds__(256) moe_grouped_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W1,
+                                                               const float* __restrict__ b1, const float* __restrict__ Wg,
+                                                               const float* __restrict__ bg, long long w_gstride,
+                                                               long long b_gstride, const int* __restrict__ off,
+                                                               float* __restrict__ C, int ldc, int N, int K) {
+  __shared__ __align__(16) float As[GK][GB + 4];
+  __shared__ __align__(16) float Bs[GK][GB + 4];
+  __shared__ __align__(16) float Gs[GLU ? GK : 1][GB + 4];
+  const int e = blockIdx.z;
+  const int m_begin = off[e], m_end = off[e + 1];
+  const int m0 = m_begin + blockIdx.y * GB, n0 = blockIdx.x * GB;
+  if (m0 >= m_end) return;
+  const float* W1e = W1 + (size_t)e * w_gstride;
+  const float* Wge = GLU ? Wg + (size_t)e * w_gstride : nullptr;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+  float acc[4][4], accg[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; accg[i][j] = 0.f; }
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va, vg = va;
+    const int gm = m0 + lrow, gn = n0 + lrow, gk = k0 + lk;
+    if (gm < m_end) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk));
+    if (gn < N) {
+      vb = __ldg(reinterpret_cast<const float4*>(W1e + (size_t)gn * K + gk));
+      if (GLU) vg = __ldg(reinterpret_cast<const float4*>(Wge + (size_t)gn * K + gk));
+    }
+    As[lk + 0][lrow] = va.x; As[lk + 1][lrow] = va.y; As[lk + 2][lrow] = va.z; As[lk + 3][lrow] = va.w;
+    Bs[lk + 0][lrow] = vb.x; Bs[lk + 1][lrow] = vb.y; Bs[lk + 2][lrow] = vb.z; Bs[lk + 3][lrow] = vb.w;
+    if (GLU) { Gs[lk + 0][lrow] = vg.x; Gs[lk + 1][lrow] = vg.y; Gs[lk + 2][lrow] = vg.z; Gs[lk + 3][lrow] = vg.w; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      if (GLU) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&Gs[k][tx * 4]);
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) accg[i][j] = fmaf(a[i], gg[j], accg[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= m_end) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (b1 ? b1[(size_t)e * b_gstride + n] : 0.f);
+      if (GLU) {
+        const float gv = accg[i][j] + (bg ? bg[(size_t)e * b_gstride + n] : 0.f);
+        v = v * (gv / (1.f + expf(-gv)));
+      }
+      C[(size_t)m * ldc + n] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) moe_combine_kernel(const float* __restrict__ yp, const int* __restrict__ perm,
+                                                          const float* __restrict__ w, float* __restrict__ out, int tokens, int k, int d) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= tokens) return;
+  for (int i = lane; i < d / 4; i += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < k; ++r) {
+      const float wr = w[(size_t)t * k + r];
+      const float4 v = reinterpret_cast<const float4*>(yp + (size_t)perm[(size_t)t * k + r] * d)[i];
+      acc.x = fmaf(wr, v.x, acc.x); acc.y = fmaf(wr, v.y, acc.y); acc.z = fmaf(wr, v.z, acc.z); acc.w = fmaf(wr, v.w, acc.w);
+    }
+    reinterpret_cast<float4*>(out + (size_t)t * d)[i] = acc;
+  }
+}
+
+int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int* off,
+                int* cursor, float* xp, int* perm, cudaStream_t stream) {
+  V2M_REQUIRE(d % 4 == 0 && n_experts >= 1 && n_experts <= kMaxExperts && k >= 1, "moe_permute: bad dims d=%d E=%d k=%d", d, n_experts, k);
+  moe_offsets_kernel<<<1, 32, 0, stream>>>(hist, n_experts, off, cursor);
+  if (tokens > 0) {
+    const long long warps = (long long)tokens * k;
+    moe_permute_kernel<<<(int)((warps + 7) / 8), 256, 0, stream>>>(x, idx, off, cursor, xp, perm, tokens, k, d);
+  }
+  return check_launch("moe_permute");
+}
+
+int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,
+                     long long b_gstride, const int* off, int n_experts, int max_rows, float* C, int ldc, int N, int K,
+                     cudaStream_t stream) {
+  V2M_REQUIRE(K % 16 == 0 && lda % 4 == 0 && N > 0, "moe_grouped_gemm: K=%d must be a multiple of 16, lda=%d of 4", K, lda);
+  if (max_rows == 0) return kOk;
+  dim3 grid((N + GB - 1) / GB, (max_rows + GB - 1) / GB, n_experts);
+  if (Wg) moe_grouped_gemm_kernel<true><<<grid, 256, 0, stream>>>(A, lda, W1, b1, Wg, bg, w_gstride, b_gstride, off, C, ldc, N, K);
+  else moe_grouped_gemm_kernel<false><<<grid, 256, 0, stream>>>(A, lda, W1, b1, nullptr, nullptr, w_gstride, b_gstride, off, C, ldc, N, K);
+  return check_launch("moe_grouped_gemm");
+}
+
+int moe_combine(const float* yp, const int* perm, const float* w, float* out, int tokens, int k, int d, cudaStream_t stream) {
+  V2M_REQUIRE(d % 4 == 0, "moe_combine: d=%d must be a multiple of 4", d);
+  if (tokens == 0) return kOk;
+  moe_combine_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(yp, perm, w, out, tokens, k, d);
+  return check_launch("moe_combine");
+}
+
 }  // namespace v2m

@@ -2,9 +2,10 @@
 (:202-302), TopKScheduler (:66-82), TemperatureScheduler (:84-97) -- same constructor signatures and
 parameter names (`experts.N.{linear1,linear2,gate}`, `gate`, `shared_expert`, buffer `bias`).
 
-Routing (gate GEMV + top-k + fp32 softmax + expert histogram) is one fused kernel; tokens are then
-grouped by expert and every expert runs as GEMMs over its contiguous token group with the SwiGLU
-gating fused between them (see `_experts_forward`).  The reference's per-expert Python loop with
+Routing (gate GEMV + top-k + fp32 softmax + expert histogram) is one fused kernel; token copies are then
+permuted into expert-contiguous order by a second kernel and all experts run as two ragged grouped GEMMs
+(group bounds read on the device, SwiGLU fused into the first) followed by a weighted combine (see
+`_experts_forward`): five launches per MoE layer and no host synchronisation.  The reference's per-expert Python loop with
 `torch.where` host syncs (moe.py:192-199) is gone; the logging side channels
 (third_party/log_experts.py, log_maxvio.py) are kept as optional callables (`on_route`).
 """
@@ -77,28 +78,30 @@ class TemperatureScheduler(nn.Module):
         return self.t
 
 
+def _stacked(experts):
+    """Expert weights as [E, ...] stacks for the grouped GEMMs, rebuilt only when a parameter changed in place
+    (optimizer step, load_state_dict) or moved."""
+    ps = [p for e in experts for p in (e.linear1.weight, e.linear1.bias, e.gate.weight, e.gate.bias, e.linear2.weight, e.linear2.bias)]
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    cache = getattr(experts, "_v2m_stack", None)
+    if cache is None or cache[0] != key:
+        def st(f):
+            return torch.stack([f(e).detach().float() for e in experts]).contiguous()
+        cache = (key, (st(lambda e: e.linear1.weight), st(lambda e: e.linear1.bias), st(lambda e: e.gate.weight),
+                       st(lambda e: e.gate.bias), st(lambda e: e.linear2.weight), st(lambda e: e.linear2.bias)))
+        object.__setattr__(experts, "_v2m_stack", cache)
+    return cache[1]
+
+
 def _experts_forward(experts, x2: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor) -> torch.Tensor:
     """out[t] = sum_r w[t,r] * expert_{idx[t,r]}(x[t])  (moe.py:191-199).
-    Tokens are permuted into expert-contiguous order (stable counting sort by expert), every expert
-    processes its slice, and the weighted results are combined per token in rank order (deterministic)."""
-    T, k = idx.shape
-    d = x2.shape[1]
-    flat = idx.reshape(-1)
-    order = torch.argsort(flat, stable=True)                 # TODO(round 2): fused permute kernel
-    tok = order // k
-    xp = x2.index_select(0, tok)
-    counts = hist.tolist()
-    yp = torch.empty((T * k, experts[0].linear2.out_features), device=x2.device, dtype=torch.float32)
-    start = 0
-    for i, e in enumerate(experts):
-        n = counts[i]
-        if n:
-            yp[start:start + n] = _glu(e, xp[start:start + n])
-        start += n
-    inv = torch.empty_like(order)
-    inv[order] = torch.arange(order.numel(), device=order.device)
-    y = yp.index_select(0, inv).view(T, k, -1)
-    return (y * w.unsqueeze(-1)).sum(dim=1)
+    Token copies are permuted into expert-contiguous order on the device, the experts run as two ragged grouped GEMMs
+    (SwiGLU fused into the first), and the weighted results are combined per token in rank order (deterministic).
+    No index tensors go through torch and nothing is read back to the host."""
+    if x2.shape[1] % 16 or experts[0].linear1.out_features % 16:
+        raise NotImplementedError("MoE expert GEMMs need d_model and d_ff to be multiples of 16")
+    w1, b1, wg, bg, w2, b2 = _stacked(experts)
+    return ops.moe_experts(x2, idx.reshape(-1, idx.shape[-1]), w.reshape(-1, w.shape[-1]), hist, w1, b1, wg, bg, w2, b2)
 
 
 class MoELayer(nn.Module):

@@ -198,6 +198,32 @@ def moe_route(x: torch.Tensor, wg: torch.Tensor, bg: torch.Tensor, k: int, *, se
     return idx, w, hist, logits
 
 
+def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
+                wg: torch.Tensor, bg: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """out[t] = sum_r w[t,r] * GLUExpert_{idx[t,r]}(x[t])  (model/moe.py:191-199) with stacked expert weights
+    w1/wg [E, ff, d], w2 [E, d_out, ff]: permute -> grouped (x W1^T + b1) * silu(x Wg^T + bg) -> grouped linear2 -> combine.
+    Five launches, group sizes stay on the device (no host sync)."""
+    require_device(x)
+    T, k = idx.shape
+    E, ff, d = w1.shape
+    d_out = w2.shape[1]
+    dev = x.device
+    meta = torch.empty((2 * E + 1 + T * k,), device=dev, dtype=torch.int32)
+    off, cursor, perm = meta[:E + 1], meta[E + 1:2 * E + 1], meta[2 * E + 1:]
+    xp = torch.empty((T * k, d), device=dev, dtype=torch.float32)
+    h = torch.empty((T * k, ff), device=dev, dtype=torch.float32)
+    yp = torch.empty((T * k, d_out), device=dev, dtype=torch.float32)
+    out = torch.empty((T, d_out), device=dev, dtype=torch.float32)
+    lib, st = load(), stream()
+    check(lib.v2m_moe_permute(ptr(x), ptr(idx), ptr(hist), T, k, d, E, ptr(off), ptr(cursor), ptr(xp), ptr(perm), st))
+    check(lib.v2m_moe_grouped_gemm(ptr(xp), d, ptr(w1), ptr(b1), ptr(wg), ptr(bg), ff * d, ff, ptr(off), E, T * k, ptr(h), ff, ff, d, st))
+    check(lib.v2m_moe_grouped_gemm(ptr(h), ff, ptr(w2), ptr(b2), None, None, d_out * ff, d_out, ptr(off), E, T * k, ptr(yp), d_out,
+                                   d_out, ff, st))
+    check(lib.v2m_moe_combine(ptr(yp), ptr(perm), ptr(w), ptr(out), T, k, d_out, st))
+    _lib.count_launches(5)
+    return out
+
+
 # ----------------------------------------------------------------------------- backward-pass kernels
 def gemm_strided(a: torch.Tensor, a_rs: int, a_cs: int, w: torch.Tensor, w_rs: int, w_cs: int, M: int, N: int, K: int,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
