@@ -212,9 +212,11 @@ int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stre
  *       never materialised.  rmsnorm: mamba.py:483-489. */
 int v2m_mamba_conv_silu(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int32_t B, int32_t L,
                         int32_t ED, int32_t KW, void* stream);
+int64_t v2m_selective_scan_workspace(int32_t B, int32_t L, int32_t ED, int32_t N);   /* bytes of `ws` (0 when L <= 64) */
 int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
                            const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz, float* out,
-                           int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, void* stream);
+                           int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, float* ws, int64_t ws_bytes,
+                           void* stream);
 int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, float eps, void* stream);
 
 /* ---- selective scan, model/pscan.py:154-226: H[t] = A[t]*H[t-1] + X[t] over (B,L,D,N) fp32 ---- */
@@ -230,13 +232,23 @@ int v2m_moe_route(const float* x, const float* wg, const float* bg, const float*
                   float* w_out, float* logits_out, int32_t* hist_out, void* stream);
 
 /* ---- MoE expert dispatch, model/moe.py:191-199 without the per-expert Python loop / torch.where host syncs (fp32).
- * permute: off[E+1] = exclusive scan of hist; copy (t, r) of token t lands in row perm[t*k+r] of xp (expert-contiguous).
+ * permute: off[E+1] = exclusive scan of hist rounded up to `align` rows per group; copy (t, r) of token t lands in row
+ *   perm[t*k+r] of xp (expert-contiguous; fp32 or bf16); tile_group may be NULL.
  * grouped_gemm: C[row] = x_row . W1_e^T + b1_e for the rows of group e (bounds read from off[] on the device; max_rows =
  *   tokens * k sizes the grid); with Wg != NULL: C = (x W1^T + b1) * silu(x Wg^T + bg)  (GLUExpert, moe.py:44-49).
  *   W1 / Wg: [E][N][K] stacks (w_gstride elements apart), b1 / bg: [E][N] (b_gstride).
  * combine: out[t] = sum_r w[t*k+r] * yp[perm[t*k+r]], rank order. */
 int v2m_moe_permute(const float* x, const int64_t* idx, const int32_t* hist, int32_t tokens, int32_t k, int32_t d, int32_t n_experts,
-                    int32_t* off, int32_t* cursor, float* xp, int32_t* perm, void* stream);
+                    int32_t align, int32_t* off, int32_t* cursor, void* xp, int32_t xp_dtype, int32_t* perm, int32_t* tile_group,
+                    int32_t n_tiles, void* stream);
+/* Tensor-core expert path (bf16): permute with align = 128 and xp_dtype = V2M_BF16 (groups start on 128-row boundaries,
+ * tile_group[t] = expert of row tile t or -1), then the grouped tcgen05 GEMM: rows of tile t use W rows
+ * [g*N, (g+1)*N) of the stacked weights and bias + g*N.  swiglu_pair: h[m][j] = a[m][j] * silu(a[m][ff+j]) on the
+ * [M, 2 ff] output of the stacked (linear1 | gate) GEMM (moe.py:46-47). */
+int v2m_gemm_bf16_grouped(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
+                          int32_t M_cap, int32_t N, int32_t K, int32_t n_groups, const int32_t* tile_group, const float* bias,
+                          int32_t relu, void* stream);
+int v2m_swiglu_pair_bf16(const void* a, void* h, int64_t M, int32_t ff, void* stream);
 int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const float* b1, const float* Wg, const float* bg,
                          int64_t w_gstride, int64_t b_gstride, const int32_t* off, int32_t n_experts, int32_t max_rows, float* C,
                          int32_t ldc, int32_t N, int32_t K, void* stream);

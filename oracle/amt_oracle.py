@@ -398,6 +398,56 @@ def mhgqa_forward(query, key, value, sd: SD, p: str, query_heads: int, kv_heads:
 
 
 # --------------------------------------------------------------------------
+# Generic layer wrappers (model/custom_transformer.py) -- BASELINE config 4: GQA attention + MoE FFN
+# --------------------------------------------------------------------------
+def _norm_generic(x, sd: SD, p: str, rms: bool):
+    """LayerNorm(eps 1e-5) or the RMSNorm of custom_transformer.py:27-47 (eps 1e-6)."""
+    if rms:
+        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * sd[p + ".weight"]
+    return _ln(x, sd, p)
+
+
+def variant_encoder_layer(x, sd: SD, p: str, hq: int, hk: int, n_experts: int, k: int, shared: bool, pre_norm: bool, rms: bool):
+    """TransformerEncoderLayer(att=MultiheadGQA, ff=MoELayer|SharedMoELayer).forward, custom_transformer.py:1230-1248.
+    attn_mask is passed by the wrapper and ignored by MultiheadGQA (grouped_query_attention.py:339): non-causal."""
+    ff = lambda t: moe_layer(t, sd, p + "ff.", n_experts, k, shared=shared)[0]
+    att = lambda t: mhgqa_forward(t, t, t, sd, p + "self_attn.", hq, hk)
+    if not pre_norm:
+        x = _norm_generic(x + att(x), sd, p + "norm1", rms)
+        return _norm_generic(x + ff(x), sd, p + "norm2", rms)
+    x = x + att(_norm_generic(x, sd, p + "norm1", rms))
+    return x + ff(_norm_generic(x, sd, p + "norm2", rms))
+
+
+def variant_decoder_layer(x, mem, sd: SD, p: str, hq: int, hk: int, n_experts: int, k: int, shared: bool, pre_norm: bool, rms: bool):
+    """TransformerDecoderLayer.forward, custom_transformer.py:1261-1292."""
+    ff = lambda t: moe_layer(t, sd, p + "ff.", n_experts, k, shared=shared)[0]
+    satt = lambda t: mhgqa_forward(t, t, t, sd, p + "self_attn.", hq, hk)
+    catt = lambda t: mhgqa_forward(t, mem, mem, sd, p + "cross_attn.", hq, hk)
+    if not pre_norm:
+        x = _norm_generic(x + satt(x), sd, p + "norm1", rms)
+        x = _norm_generic(x + catt(x), sd, p + "norm2", rms)
+        return _norm_generic(x + ff(x), sd, p + "norm3", rms)
+    x = x + satt(_norm_generic(x, sd, p + "norm1", rms))
+    x = x + catt(_norm_generic(x, sd, p + "norm2", rms))
+    return x + ff(_norm_generic(x, sd, p + "norm3", rms))
+
+
+def variant_stack_forward(sd: SD, src, tgt, n_layers: int, hq: int, hk: int, n_experts: int, k: int, shared: bool,
+                          pre_norm: bool, rms: bool):
+    """TransformerEncoder + TransformerDecoder (custom_transformer.py:1371-1401) over the layers above, each with a
+    final norm; state_dict prefixes `enc.` / `dec.`.  Returns (memory, decoder output)."""
+    m = src
+    for i in range(n_layers):
+        m = variant_encoder_layer(m, sd, "enc.layers.%d." % i, hq, hk, n_experts, k, shared, pre_norm, rms)
+    m = _norm_generic(m, sd, "enc.norm", rms)
+    y = tgt
+    for i in range(n_layers):
+        y = variant_decoder_layer(y, m, sd, "dec.layers.%d." % i, hq, hk, n_experts, k, shared, pre_norm, rms)
+    return m, _norm_generic(y, sd, "dec.norm", rms)
+
+
+# --------------------------------------------------------------------------
 # Selective scan (model/pscan.py)
 # --------------------------------------------------------------------------
 def pscan_forward(A: torch.Tensor, X: torch.Tensor) -> torch.Tensor:

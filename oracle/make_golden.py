@@ -230,6 +230,55 @@ def golden_gqa(ref):
     _save("gqa.pt", out)
 
 
+VARIANT_CASES = [dict(name="post_ln_moe", shared=False, pre_norm=False, rms=False, T=24, S=40, B=1, seed=61),
+                 dict(name="post_ln_sharedmoe_b2", shared=True, pre_norm=False, rms=False, T=24, S=40, B=2, seed=62),
+                 dict(name="pre_rms_moe", shared=False, pre_norm=True, rms=True, T=17, S=33, B=1, seed=63)]
+
+
+def build_variant(ct, gqa, moe, c, d=512, ff=1024, hq=8, hk=2, n_experts=6, k=2, n_layers=2):
+    """BASELINE config 4 from the reference's own blocks: generic wrappers with
+    att=MultiheadGQA(512, 8, kv_heads=2), ff=MoELayer|SharedMoELayer(GLUExpert(512,1024), 6 experts, top-2).
+    `ct`, `gqa`, `moe` are the module namespaces (the reference's here, ours in the tests)."""
+    import torch.nn as nn
+    att = gqa.MultiheadGQA(d, hq, hk, dropout=0.0)
+    cls = moe.SharedMoELayer if c["shared"] else moe.MoELayer
+    ffl = cls(moe.GLUExpert(d, ff, 0.0), d, n_experts=n_experts, n_experts_per_token=k, dropout=0.0)
+    norm = ct.RMSNorm(d) if c["rms"] else nn.LayerNorm(d)
+    enc = ct.TransformerEncoder(ct.TransformerEncoderLayer(att, ffl, pre_norm=c["pre_norm"], norm=norm, dropout=0.0), n_layers, norm)
+    dec = ct.TransformerDecoder(ct.TransformerDecoderLayer(att, att, ffl, pre_norm=c["pre_norm"], norm=norm, dropout=0.0), n_layers,
+                                norm)
+    return nn.ModuleDict(dict(enc=enc, dec=dec)).eval()
+
+
+def golden_variant(ref):
+    """GQA + MoE encoder/decoder stacks assembled from custom_transformer.py:1220-1401 wrappers."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    for c in VARIANT_CASES:
+        torch.manual_seed(0)
+        net = build_variant(ref.custom_transformer, ref.gqa, ref.moe, c)
+        sd = _load_weights(net, c["seed"])
+        src = syn.unit_uniform((c["S"], c["B"], 512), syn._gen(c["seed"], "src"))
+        tgt = syn.unit_uniform((c["T"], c["B"], 512), syn._gen(c["seed"], "tgt"))
+        gaps = []
+
+        def hook(mod, inp, outp):
+            top3 = torch.topk(outp, 3).values
+            gaps.append(float((top3[..., :-1] - top3[..., 1:]).min()))
+        hs = [m.gate.register_forward_hook(hook) for m in net.modules() if isinstance(m, (ref.moe.MoELayer, ref.moe.SharedMoELayer))]
+        mask = torch.triu(torch.full((c["T"], c["T"]), float("-inf")), diagonal=1)
+        with torch.no_grad():
+            mem = net["enc"](src)
+            y = net["dec"](tgt, mem, tgt_mask=mask)          # MultiheadGQA ignores the mask (literal behaviour)
+        for h in hs:
+            h.remove()
+        out[c["name"]] = dict(spec=dict(c), weights_checksum=syn.checksum(sd), memory=mem.clone(), out=y.clone(),
+                              min_rank_gap=min(gaps))
+        print(c["name"], "min gate gap %.2e" % min(gaps))
+    _save("variant.pt", out)
+
+
 def golden_pscan(ref):
     """pscan forward/backward (pscan.py:154-226) incl. a non power-of-two length."""
     cases = []
@@ -290,7 +339,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref),
+                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

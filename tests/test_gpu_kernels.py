@@ -331,6 +331,42 @@ def test_moe_golden_gpu(shared):
     assert rel_err(y, g["out"]) < 1e-4
 
 
+@pytest.mark.parametrize("shared", [False, True])
+def test_moe_golden_gpu_bf16_tensor_core(shared):
+    """Expert GEMMs on the grouped tcgen05 path: routing bit-exact (fp32 router), outputs within the bf16 tolerance."""
+    from video2music_b200 import GLUExpert, MoELayer, SharedMoELayer
+    g = load_golden("moe.pt")["shared_%s" % shared]
+    s = g["spec"]
+    cls = SharedMoELayer if shared else MoELayer
+    mod = cls(GLUExpert(s["d"], s["ff"], 0.0), s["d"], n_experts=s["n_experts"], n_experts_per_token=s["k"], dropout=0.0).eval()
+    mod.load_state_dict(syn.fill_like_reference_init({k: tuple(v.shape) for k, v in mod.state_dict().items()}, seed=s["seed"]))
+    mod = mod.to(DEV)
+    mod.compute_dtype = torch.bfloat16
+    x = _u((s["L"], s["B"], s["d"]), s["x_seed"], "x").to(DEV)
+    with torch.no_grad():
+        y = mod(x)
+    assert torch.equal(mod.last_selected_experts.cpu(), g["selected_experts"])
+    assert rel_err(y, g["out"]) < 2e-2
+
+
+def test_moe_bf16_skewed_groups():
+    """Ragged groups on the tensor-core path (one empty expert, one holding most tokens) vs the fp32 path of the same module."""
+    from video2music_b200 import GLUExpert, MoELayer
+    E, k, d, ff, tokens = 6, 2, 256, 320, 1111
+    mod = MoELayer(GLUExpert(d, ff, 0.0), d, n_experts=E, n_experts_per_token=k, dropout=0.0).eval()
+    sd = syn.fill_like_reference_init({n: tuple(v.shape) for n, v in mod.state_dict().items()}, seed=78)
+    sd["gate.bias"] = torch.tensor([3.0, -50.0, 1.0, 0.5, 0.0, 0.0])
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    x = _u((tokens, 1, d), 6, "x").to(DEV)
+    with torch.no_grad():
+        y32 = mod(x)
+        mod.compute_dtype = torch.bfloat16
+        y16 = mod(x)
+    assert int((mod.last_selected_experts == 1).sum()) == 0
+    assert rel_err(y16, y32) < 2e-2
+
+
 @pytest.mark.parametrize("tokens,E,k,d,ff", [(203, 6, 2, 64, 80), (1, 4, 4, 32, 48), (1500, 8, 3, 128, 272)])
 def test_moe_dispatch_ragged_groups_vs_oracle(tokens, E, k, d, ff):
     """Skewed router (one expert takes most tokens, some take none): group sizes are neither equal nor tile multiples."""
@@ -370,6 +406,27 @@ def test_moe_route_ties_and_bias():
     idx2, w2, _, _ = ops.moe_route(x, wg, bg, 2, sel_bias=torch.tensor([0., 0., 5., 0., 0., 0.], device=DEV))
     assert idx2[0].tolist() == [2, 3]
     assert torch.allclose(w2[0], torch.softmax(torch.tensor([0.1, 0.9]), 0).to(DEV))    # weights from un-biased logits
+
+
+@pytest.mark.parametrize("name", ["post_ln_moe", "post_ln_sharedmoe_b2", "pre_rms_moe"])
+def test_variant_gqa_moe_stack_golden_gpu(name):
+    """BASELINE config 4 through our drop-in wrappers (custom_transformer.py) + MultiheadGQA + (Shared)MoELayer."""
+    from test_oracle import _variant_net
+    g = load_golden("variant.pt")[name]
+    c = g["spec"]
+    net, sd = _variant_net(c)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    net.load_state_dict(sd)
+    net = net.to(DEV)
+    src = _u((c["S"], c["B"], 512), c["seed"], "src").to(DEV)
+    tgt = _u((c["T"], c["B"], 512), c["seed"], "tgt").to(DEV)
+    mask = torch.triu(torch.full((c["T"], c["T"]), float("-inf"), device=DEV), diagonal=1)
+    with torch.no_grad():
+        mem = net["enc"](src)
+        y = net["dec"](tgt, mem, tgt_mask=mask)
+    assert rel_err(mem, g["memory"]) < 1e-4 and rel_err(y, g["out"]) < 1e-4
+    ref_mem, ref_y = O.variant_stack_forward(sd, src.cpu(), tgt.cpu(), 2, 8, 2, 6, 2, c["shared"], c["pre_norm"], c["rms"])
+    assert rel_err(y, ref_y) < 1e-4
 
 
 # ---------------------------------------------------------------- GQA

@@ -131,6 +131,30 @@ def test_gqa_golden():
         assert rel_err(y, case["out"]) < 2e-5
 
 
+def _variant_net(c):
+    import video2music_b200.custom_transformer as ct
+    import video2music_b200.grouped_query_attention as gqa
+    import video2music_b200.moe as moe
+    from oracle.make_golden import build_variant
+    net = build_variant(ct, gqa, moe, c)
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=c["seed"])
+    return net, sd
+
+
+@pytest.mark.parametrize("name", ["post_ln_moe", "post_ln_sharedmoe_b2", "pre_rms_moe"])
+def test_variant_gqa_moe_stack_golden(name):
+    """BASELINE config 4: the reference's generic wrappers around MultiheadGQA + (Shared)MoELayer, 2+2 layers."""
+    g = load_golden("variant.pt")[name]
+    c = g["spec"]
+    _, sd = _variant_net(c)                                   # our modules have the reference's parameter names
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    src = syn.unit_uniform((c["S"], c["B"], 512), syn._gen(c["seed"], "src"))
+    tgt = syn.unit_uniform((c["T"], c["B"], 512), syn._gen(c["seed"], "tgt"))
+    mem, y = O.variant_stack_forward(sd, src, tgt, 2, 8, 2, 6, 2, c["shared"], c["pre_norm"], c["rms"])
+    assert g["min_rank_gap"] > 1e-4
+    assert rel_err(mem, g["memory"]) < 2e-5 and rel_err(y, g["out"]) < 2e-5
+
+
 def test_pscan_golden():
     for case in load_golden("pscan.pt")["cases"]:
         s = case["spec"]

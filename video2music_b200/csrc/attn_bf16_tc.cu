@@ -9,16 +9,20 @@
 //
 // Because L <= 320 the whole score row of a query fits in tensor memory, so the softmax is exact
 // (two passes over TMEM, no online rescaling):
-//   TMEM columns [0,320)    S = Q K^T (fp32), later overwritten in place by P (packed bf16 pairs)
-//   TMEM columns [320,512)  QE = Q Er_band^T, 192 columns at a time (two overlapping halves), later O
+//   TMEM columns [0,320)    S = Q K^T (fp32), rewritten in place as the masked scores; O lands in columns [0,64) at the end
+//   TMEM columns [320,512)  QE = Q Er_band^T, 192 columns at a time (two overlapping halves), later P (packed bf16 pairs)
 // The relative term needs, for query row i and key j, column c = j - i + imax of QE (imax = last row
 // of the tile): a per-row shift.  tcgen05.ld addresses are warp-uniform, so each softmax warp pulls a
 // 64-column window of QE into registers, parks it in its private shared-memory scratch rows and
 // reads it back at the row-dependent offset -- the skew is a shifted read of shared memory
 // (conflict-free: row pitch 68 words).
 //
-// Warp roles (160 threads): warp 0 = TMA producer + single-thread MMA issuer + TMEM allocator,
-// warps 1-4 = softmax/epilogue, one TMEM lane quadrant (32 query rows) each.
+// Warp roles (32 + 128 * AT_NW threads): warp 0 = TMA producer + single-thread MMA issuer + TMEM allocator,
+// warps 1.. = softmax/epilogue.  A warp can only touch the TMEM lane quadrant (warp id % 4), so AT_NW warps share each
+// quadrant (32 query rows) and split its 32-key chunks round-robin; the row max / row sum are exchanged through shared
+// memory behind a named barrier per quadrant.  The softmax warps are the critical path of a tile (one warp per SM
+// sub-partition issues at ~0.24 IPC), hence several of them per sub-partition.  Chunks that lie entirely below the
+// causal diagonal skip the mask / skew predicates, chunks entirely above it are zero-filled without being read.
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda.h>
@@ -30,13 +34,15 @@ constexpr int AT_DH = 64;            // head dim (128-byte swizzled rows)
 constexpr int AT_MAXK = 320;         // keys per row that fit the TMEM plan
 constexpr int AT_QE_COLS = 192;      // width of one QE half
 constexpr int AT_QE_OVERLAP = 128;   // half B starts at band column 128
-constexpr int AT_THREADS = 160;
+constexpr int AT_NW = 2;             // softmax warps per TMEM lane quadrant
+constexpr int AT_THREADS = 32 + 128 * AT_NW;
 constexpr int AT_SCR_PITCH = 68;     // floats; 68 % 32 == 4 -> conflict-free STS.128 and shifted LDS.32
 
 constexpr int AT_SMEM_Q = AT_M * 128;
 constexpr int AT_SMEM_K = AT_MAXK * 128;
-constexpr int AT_SMEM_SCR = 4 * 32 * AT_SCR_PITCH * 4;
-constexpr size_t AT_SMEM = 1024 + AT_SMEM_Q + 3 * AT_SMEM_K + AT_SMEM_SCR + 256;
+constexpr int AT_SMEM_SCR = AT_NW * 4 * 32 * AT_SCR_PITCH * 4;
+constexpr int AT_SMEM_RED = 2 * AT_NW * AT_M * 4;   // row max / row sum exchange
+constexpr size_t AT_SMEM = 1024 + AT_SMEM_Q + 3 * AT_SMEM_K + AT_SMEM_SCR + AT_SMEM_RED + 256;
 
 int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch,
                       long long row_pitch, long long batch_pitch, int box_rows, int swap);
@@ -60,15 +66,16 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   unsigned char* sV = sK + AT_SMEM_K;
   unsigned char* sE = sV + AT_SMEM_K;
   float* scr = reinterpret_cast<float*>(sE + AT_SMEM_K);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(scr) + AT_SMEM_SCR);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scr) + AT_SMEM_SCR);   // [2][AT_NW][AT_M]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + AT_SMEM_RED);
   uint64_t* bar_qk = bars + 0;     // Q and K tiles landed
   uint64_t* bar_e = bars + 1;      // Er band landed
   uint64_t* bar_v = bars + 2;      // V tile landed
   uint64_t* bar_s = bars + 3;      // S = Q K^T complete
   uint64_t* bar_qa = bars + 4;     // QE half A complete
-  uint64_t* bar_qa_free = bars + 5;  // all softmax warps are done with half A (count 4)
+  uint64_t* bar_qa_free = bars + 5;  // all softmax warps are done with half A (count 4 * AT_NW)
   uint64_t* bar_qb = bars + 6;     // QE half B complete
-  uint64_t* bar_p = bars + 7;      // P written to TMEM by all softmax warps (count 4)
+  uint64_t* bar_p = bars + 7;      // P written to TMEM by all softmax warps (count 4 * AT_NW)
   uint64_t* bar_o = bars + 8;      // O = P V complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
@@ -90,7 +97,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int qe_rows = need_b ? AT_QE_OVERLAP + AT_QE_COLS : AT_QE_COLS;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(bars + i, (i == 5 || i == 7) ? 4u : 1u);
+    for (int i = 0; i < 9; ++i) mbar_init(bars + i, (i == 5 || i == 7) ? 4u * AT_NW : 1u);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     if (a.has_er) tma_prefetch_desc(&tmE);
@@ -100,7 +107,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t T_S = tmem, T_QE = tmem + AT_MAXK, T_O = tmem + AT_MAXK, T_P = tmem;
+  // P goes where QE was (free once the quadrant's warps have left pass A) and O over the first S columns (all read by the
+  // time P is complete): with several warps per quadrant P chunk c would otherwise overwrite S chunk c/2 of another warp.
+  const uint32_t T_S = tmem, T_QE = tmem + AT_MAXK, T_O = tmem, T_P = tmem + AT_MAXK;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -163,17 +172,24 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // ================= softmax / epilogue warps =================
     const int quad = warp & 3;                                   // TMEM lane quadrant of this warp
+    const int sub = (warp - 1) >> 2;                             // which of the AT_NW warps of the quadrant
     const int u = lane;
-    const int i = i0 + quad * 32 + u;                            // my query row
+    const int row = quad * 32 + u;
+    const int i = i0 + row;                                      // my query row
     const bool row_ok = i < a.Lq;
     const int jlim = row_ok ? (a.causal ? min(a.Lk, i + coff + 1) : a.Lk) : 0;   // keys [0, jlim) are visible
-    const int wlast = min(imax, i0 + quad * 32 + 31);            // last valid row of this warp
-    const int wjlim = (i0 + quad * 32 <= imax) ? (a.causal ? min(a.Lk, wlast + coff + 1) : a.Lk) : 0;
+    const int wfirst = i0 + quad * 32;                           // first row of this quadrant
+    const int wlast = min(imax, wfirst + 31);                    // last valid row of this quadrant
+    const bool quad_ok = wfirst <= imax;
+    const int wjlim = quad_ok ? (a.causal ? min(a.Lk, wlast + coff + 1) : a.Lk) : 0;     // widest row of the quadrant
+    const int wjmin = (quad_ok && wfirst + 31 <= imax) ? (a.causal ? min(a.Lk, wfirst + coff + 1) : a.Lk) : 0;  // narrowest
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float* my_scr = scr + (size_t)(quad * 32 + u) * AT_SCR_PITCH;
-    const int nchunks = (nk16 + 31) / 32;
+    float* my_scr = scr + (size_t)((sub * 4 + quad) * 32 + u) * AT_SCR_PITCH;
+    const int nchunks = (nk16 + 31) / 32;                        // chunks the P V product reads
+    const int live = min(nchunks, (wjlim + 31) / 32);            // chunks with at least one visible key for this quadrant
     const int base_w = imax - i0 - quad * 32 - 31;               // window start (band column) for key chunk j0 is j0 + base_w
     const float LOG2E = 1.4426950408889634f;
+    const uint32_t bar_id = 1 + quad;                            // named barrier of this quadrant's AT_NW warps
 
     mbar_wait(bar_s, 0);
     tc_fence_after();
@@ -189,10 +205,10 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(bar_qb, 0);
         tc_fence_after();
       }
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = sub; c < live; c += AT_NW) {
         const int j0 = c * 32;
         const int start = j0 + base_w;                           // un-clamped window start
-        const bool rel_chunk = a.has_er && (j0 < wjlim) && (j0 <= wlast);   // chunk holds some (i, j<=i) of this warp
+        const bool rel_chunk = a.has_er && (j0 <= wlast);        // chunk holds some (i, j<=i) of this quadrant
         const bool in_a = !need_b || !rel_chunk || start <= AT_QE_OVERLAP;
         if ((phase == 0) != in_a) continue;
         uint32_t r[32];
@@ -209,40 +225,61 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             *reinterpret_cast<uint4*>(my_scr + q4 * 4) = make_uint4(w[q4 * 4], w[q4 * 4 + 1], w[q4 * 4 + 2], w[q4 * 4 + 3]);
           // band column of (i, j) is j - i + imax; offset inside the window = that - cs
           const int off = j0 - i + imax - cs;                    // in [0, 63 - k] for every (i, j <= i) that is needed
+          if (j0 + 31 <= wfirst) {                               // whole chunk at or below the diagonal for every row
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
-            const float rel = my_scr[min(max(off + k, 0), 63)];  // clamped reads only hit masked / invalid entries
-            if (j0 + k <= i) r[k] = __float_as_uint(__uint_as_float(r[k]) + rel);
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + my_scr[off + k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float rel = my_scr[min(max(off + k, 0), 63)];  // clamped reads only hit masked / invalid entries
+              if (j0 + k <= i) r[k] = __float_as_uint(__uint_as_float(r[k]) + rel);
+            }
           }
         } else {
           tmem_ld_wait();
         }
+        if (j0 + 32 <= wjmin) {                                  // every key of the chunk is visible to every row
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          float s = __uint_as_float(r[k]);
-          s = (j0 + k < jlim) ? s : -INFINITY;
-          mx = fmaxf(mx, s);
-          r[k] = __float_as_uint(s);
+          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            float sv = __uint_as_float(r[k]);
+            sv = (j0 + k < jlim) ? sv : -INFINITY;
+            mx = fmaxf(mx, sv);
+            r[k] = __float_as_uint(sv);
+          }
         }
         tmem_st_32x32(T_S + lane_off + j0, r);
       }
     }
     tmem_st_wait();
+    if (AT_NW > 1) {                                             // row max over the warps of the quadrant; also orders
+      red[sub * AT_M + row] = mx;                                // every QE read of the quadrant before the P writes
+      named_bar_sync(bar_id, 32 * AT_NW);
+#pragma unroll
+      for (int w2 = 0; w2 < AT_NW; ++w2) mx = fmaxf(mx, red[w2 * AT_M + row]);
+    }
     // ---- pass B: p = exp(s - max), row sum, P (bf16 pairs) written over S
     const float mneg = (mx == -INFINITY) ? 0.f : mx * LOG2E;
     float sum = 0.f;
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = sub; c < nchunks; c += AT_NW) {
       const int j0 = c * 32;
-      uint32_t r[32];
-      tmem_ld_32x32(T_S + lane_off + j0, r);
-      tmem_ld_wait();
       uint32_t pk[16];
+      if (c < live) {
+        uint32_t r[32];
+        tmem_ld_32x32(T_S + lane_off + j0, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float p0 = exp2f(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
-        const float p1 = exp2f(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
-        sum += p0 + p1;
-        pk[k] = f2_to_bf16x2(p0, p1);
+        for (int k = 0; k < 16; ++k) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
+          sum += p0 + p1;
+          pk[k] = f2_to_bf16x2(p0, p1);
+        }
+      } else {                                                   // above the diagonal for the whole quadrant: P = 0
+#pragma unroll
+        for (int k = 0; k < 16; ++k) pk[k] = 0u;
       }
       tmem_st_32x16(T_P + lane_off + c * 16, pk);
     }
@@ -250,18 +287,29 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
-    // ---- epilogue: O / sum -> bf16 -> global
+    if (AT_NW > 1) {                                             // row sum over the warps of the quadrant
+      red[(AT_NW + sub) * AT_M + row] = sum;
+      named_bar_sync(bar_id, 32 * AT_NW);
+      sum = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < AT_NW; ++w2) sum += red[(AT_NW + w2) * AT_M + row];
+    }
+    // ---- epilogue: O / sum -> bf16 -> global; the warps of a quadrant split the 64 columns
+    constexpr int OC = AT_DH / AT_NW;
     mbar_wait(bar_o, 0);
     tc_fence_after();
-    uint32_t o[64];
-    tmem_ld_32x32(T_O + lane_off, o);
-    tmem_ld_32x32(T_O + lane_off + 32, o + 32);
+    uint32_t o[OC];
+#pragma unroll
+    for (int c32 = 0; c32 < OC; c32 += 32) {
+      if (OC - c32 >= 32) tmem_ld_32x32(T_O + lane_off + sub * OC + c32, o + c32);
+      else tmem_ld_32x16(T_O + lane_off + sub * OC + c32, o + c32);
+    }
     tmem_ld_wait();
     if (row_ok) {
       const float inv = 1.f / sum;
-      bf16* dst = static_cast<bf16*>(a.o) + (size_t)b * a.o_sb + (size_t)i * a.o_sl + (size_t)hq * AT_DH;
+      bf16* dst = static_cast<bf16*>(a.o) + (size_t)b * a.o_sb + (size_t)i * a.o_sl + (size_t)hq * AT_DH + sub * OC;
 #pragma unroll
-      for (int g8 = 0; g8 < 8; ++g8) {
+      for (int g8 = 0; g8 < OC / 8; ++g8) {
         uint4 v;
         v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]) * inv, __uint_as_float(o[g8 * 8 + 1]) * inv);
         v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]) * inv, __uint_as_float(o[g8 * 8 + 3]) * inv);
@@ -269,7 +317,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         v.w = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 6]) * inv, __uint_as_float(o[g8 * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(dst + g8 * 8) = v;
       }
-      if (a.lse) a.lse[(size_t)bh * a.Lq + i] = mx + logf(sum);
+      if (a.lse && sub == 0) a.lse[(size_t)bh * a.Lq + i] = mx + logf(sum);
     }
   }
   tc_fence_before();

@@ -225,10 +225,13 @@ int v2m_mamba_conv_silu(const float* x, int64_t ldx, const float* w, const float
   return mamba_conv_silu(x, ldx, w, bias, y, ldy, B, L, ED, KW, static_cast<cudaStream_t>(stream));
 }
 
+int64_t v2m_selective_scan_workspace(int32_t B, int32_t L, int32_t ED, int32_t N) { return selective_scan_workspace(B, L, ED, N); }
+
 int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
                            const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz, float* out,
-                           int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, void* stream) {
-  return selective_scan_fwd(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, D, z, ldz, out, ldo, B, L, ED, N, plus,
+                           int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, float* ws, int64_t ws_bytes,
+                           void* stream) {
+  return selective_scan_fwd(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, D, z, ldz, out, ldo, B, L, ED, N, plus, ws, ws_bytes,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -237,9 +240,21 @@ int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, 
 }
 
 int v2m_moe_permute(const float* x, const int64_t* idx, const int32_t* hist, int32_t tokens, int32_t k, int32_t d, int32_t n_experts,
-                    int32_t* off, int32_t* cursor, float* xp, int32_t* perm, void* stream) {
-  return moe_permute(x, reinterpret_cast<const long long*>(idx), hist, tokens, k, d, n_experts, off, cursor, xp, perm,
-                     static_cast<cudaStream_t>(stream));
+                    int32_t align, int32_t* off, int32_t* cursor, void* xp, int32_t xp_dtype, int32_t* perm, int32_t* tile_group,
+                    int32_t n_tiles, void* stream) {
+  return moe_permute(x, reinterpret_cast<const long long*>(idx), hist, tokens, k, d, n_experts, align, off, cursor, xp,
+                     xp_dtype == V2M_BF16, perm, tile_group, n_tiles, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_gemm_bf16_grouped(const void* A, int32_t lda, const void* W, int32_t ldw, void* C, int32_t ldc, int32_t out_dtype,
+                          int32_t M_cap, int32_t N, int32_t K, int32_t n_groups, const int32_t* tile_group, const float* bias,
+                          int32_t relu, void* stream) {
+  return gemm_bf16_tc_grouped(A, lda, W, ldw, C, ldc, out_dtype == V2M_BF16, M_cap, N, K, n_groups, tile_group, bias, relu,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int v2m_swiglu_pair_bf16(const void* a, void* h, int64_t M, int32_t ff, void* stream) {
+  return swiglu_pair_bf16(a, h, M, ff, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const float* b1, const float* Wg, const float* bg,

@@ -96,7 +96,11 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long lo
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
-                    int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split) {
+                    int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split,
+                    const int* __restrict__ tile_group) {
+  // tile_group != null: grouped (ragged) GEMM for the MoE experts.  Rows of A are expert-contiguous with every group
+  // starting on a 128-row boundary; tile_group[m_blk] names the group of a row tile (-1: unused tile, skipped by all three
+  // roles), whose weights are rows [g*N, (g+1)*N) of the stacked W and whose bias is ep.bias + g*N.
   // k_split > 1: a work item is (output tile, K slice); partial sums are added to the zero-initialised fp32 C with
   // red.global (small outputs with a long K, e.g. dW = dY^T X over all tokens, would otherwise keep a handful of SMs busy)
   using Cfg = GemmCfg<BN>;
@@ -136,6 +140,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int tile = item / k_split, ks = item - tile * k_split;
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
         const int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+        int g = 0;
+        if (tile_group) { g = tile_group[m_blk]; if (g < 0) continue; }
+        const int b_row = g * N + n_blk * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
@@ -151,7 +158,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int c = 0; c < BN / 64; ++c)
               tma_load_2d(sa + Cfg::kABytes + c * 8192, &tmB, n_blk * BN + c * 64, kb * GK, full_bar + stage);
           } else {
-            tma_load_2d(sa + Cfg::kABytes, &tmB, kb * GK, n_blk * BN, full_bar + stage);
+            tma_load_2d(sa + Cfg::kABytes, &tmB, kb * GK, b_row, full_bar + stage);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -165,6 +172,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int ks = item % k_split;
       const int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+      if (tile_group && tile_group[(item / k_split) / n_tiles] < 0) continue;
       mbar_wait(tempty_bar + acc, acc_phase ^ 1);
       tc_fence_after();
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -198,6 +206,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int tile = item / k_split;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m = m_blk * GM + quad * 32 + lane;
+      const float* bias = ep.bias;
+      if (tile_group) {
+        const int g = tile_group[m_blk];
+        if (g < 0) continue;
+        if (bias) bias += (size_t)g * N;
+      }
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const bool row_ok = m < M;
@@ -224,8 +238,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n0 = n_blk * BN + c * 32;
         const bool fast = vec_ok && n0 + 32 <= N && k_split == 1;
         float4 bv[8];
-        if (fast && row_ok && ep.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0);
+        if (fast && row_ok && bias) {
+          const float4* bp = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
           for (int q = 0; q < 8; ++q) bv[q] = __ldg(bp + q);
         }
@@ -247,7 +261,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (vec_ok && n0 + 32 <= N) {
           // ---- fast path: whole chunk in range, every pointer 16-byte aligned -> 128-bit loads / stores only
-          if (ep.bias) {
+          if (bias) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float4 t = bv[q];
@@ -316,7 +330,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int n = n0 + i;
             if (n >= N) continue;
             float x = v[i];
-            if (ep.bias) x += __ldg(ep.bias + n);
+            if (bias) x += __ldg(bias + n);
             if (n < ep.alpha_cols) x *= ep.alpha;
             if (ep.relu) x = fmaxf(x, 0.f);
             if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
@@ -342,7 +356,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
-                       const GemmEpilogue& ep, cudaStream_t stream, bool allow_split) {
+                       const GemmEpilogue& ep, cudaStream_t stream, bool allow_split, const int* tile_group = nullptr) {
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -370,7 +384,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   }
   const int items = tiles * k_split;
   const int grid = items < num_sms ? items : num_sms;
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split);
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split, tile_group);
   return check_launch("gemm_bf16_tc");
 }
 
@@ -406,6 +420,28 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
   if (a_mn && b_mn) return V2M_GO(128, true, true);
   return V2M_GO(128, true, false);
 #undef V2M_GO
+}
+
+// Grouped GEMM over expert-contiguous rows (see the kernel comment): A [M_cap, K], W [n_groups * N, K] stacked, bias [n_groups * N],
+// tile_group [ceil(M_cap / 128)] on the device.  Bias and ReLU are the only epilogue operations.
+int gemm_bf16_tc_grouped(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M_cap, int N, int K,
+                         int n_groups, const int* tile_group, const float* bias, int relu, cudaStream_t stream) {
+  V2M_REQUIRE(M_cap >= 0 && N > 0 && K > 0 && n_groups > 0 && tile_group, "gemm_bf16_tc_grouped: bad arguments");
+  V2M_REQUIRE(N % 128 == 0, "gemm_bf16_tc_grouped: N=%d must be a multiple of 128 (a weight tile must not straddle two experts)", N);
+  if (M_cap == 0) return kOk;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, A, M_cap, K, lda, GM);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, W, (long long)n_groups * N, K, ldw, bn);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  ep.bias = bias;
+  ep.relu = relu;
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const int vec_ok = al16(bias) && al16(C) && ((long long)ldc * (out_bf16 ? 2 : 4)) % 16 == 0;
+  if (bn == 256) return launch_gemm<256, false, false>(tmA, tmB, C, ldc, out_bf16, vec_ok, M_cap, N, K, ep, stream, false, tile_group);
+  return launch_gemm<128, false, false>(tmA, tmB, C, ldc, out_bf16, vec_ok, M_cap, N, K, ep, stream, false, tile_group);
 }
 
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,

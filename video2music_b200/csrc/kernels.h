@@ -172,9 +172,11 @@ int pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float*
 // ------------------------------------------------------------------ Mamba block (mamba.cu), fp32
 int mamba_conv_silu(const float* x, long long ldx, const float* w, const float* bias, float* y, long long ldy, int B, int L, int ED,
                     int KW, cudaStream_t stream);
+long long selective_scan_workspace(int B, int L, int ED, int N);
 int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, long long ldd, const float* dt_bias,
                        const float* A_log, const float* Bm, const float* Cm, long long ldbc, const float* Dp, const float* z,
-                       long long ldz, float* out, long long ldo, int B, int L, int ED, int N, int plus, cudaStream_t stream);
+                       long long ldz, float* out, long long ldo, int B, int L, int ED, int N, int plus, float* ws,
+                       long long ws_bytes, cudaStream_t stream);
 int rmsnorm(const float* x, const float* w, float* y, int M, int D, float eps, cudaStream_t stream);
 
 // ------------------------------------------------------------------ MoE (moe.cu)
@@ -184,8 +186,11 @@ int moe_route(const float* x, const float* wg, const float* bg, const float* sel
 
 // Expert dispatch (moe.cu): expert-contiguous token permutation, ragged grouped GEMM with device-side group bounds
 // (optionally the fused SwiGLU pair of GLUExpert), weighted combine in rank order.
-int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int* off,
-                int* cursor, float* xp, int* perm, cudaStream_t stream);
+int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int align, int* off,
+                int* cursor, void* xp, int xp_bf16, int* perm, int* tile_group, int n_tiles, cudaStream_t stream);
+int swiglu_pair_bf16(const void* a, void* h, long long M, int ff, cudaStream_t stream);
+int gemm_bf16_tc_grouped(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M_cap, int N, int K,
+                         int n_groups, const int* tile_group, const float* bias, int relu, cudaStream_t stream);
 int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,
                      long long b_gstride, const int* off, int n_experts, int max_rows, float* C, int ldc, int N, int K,
                      cudaStream_t stream);

@@ -83,17 +83,34 @@ int moe_route(const float* x, const float* wg, const float* bg, const float* sel
 //                   off[] ON THE DEVICE (ragged groups, grid sized for the worst case, surplus CTAs exit at once).
 //                   glu != 0: two weight stacks, C = (x W1^T + b1) * silu(x Wg^T + bg)   (GLUExpert, moe.py:44-49)
 //   moe_combine   : out[t] = sum_r w[t][r] * yp[perm[t*k+r]]  in rank order (deterministic)        (moe.py:196-199)
-__global__ void moe_offsets_kernel(const int* __restrict__ hist, int n_experts, int* __restrict__ off, int* __restrict__ cursor) {
+// align > 1 (tensor-core path): every group starts on an `align`-row boundary and tile_group[t] names the group that owns
+// row tile t of `align` rows (-1 for the unused tail), which is all the grouped tcgen05 GEMM needs to pick its weight tile.
+__global__ void moe_offsets_kernel(const int* __restrict__ hist, int n_experts, int align, int* __restrict__ off,
+                                   int* __restrict__ cursor, int* __restrict__ tile_group, int n_tiles) {
+  __shared__ int s_off[kMaxExperts + 1];
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int e = 0; e < n_experts; ++e) { off[e] = acc; cursor[e] = 0; acc += hist[e]; }
-    off[n_experts] = acc;
+    for (int e = 0; e < n_experts; ++e) {
+      off[e] = acc; s_off[e] = acc; cursor[e] = 0;
+      acc += (hist[e] + align - 1) / align * align;
+    }
+    off[n_experts] = acc; s_off[n_experts] = acc;
   }
+  __syncthreads();
+  if (tile_group)
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+      const int r = t * align;
+      int g = -1;
+      for (int e = 0; e < n_experts; ++e)
+        if (r >= s_off[e] && r < s_off[e] + hist[e]) g = e;
+      tile_group[t] = g;
+    }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) moe_permute_kernel(const float* __restrict__ x, const long long* __restrict__ idx,
                                                           const int* __restrict__ off, int* __restrict__ cursor,
-                                                          float* __restrict__ xp, int* __restrict__ perm, int tokens, int k, int d) {
+                                                          T* __restrict__ xp, int* __restrict__ perm, int tokens, int k, int d) {
   const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (item >= tokens * k) return;
   const int t = item / k;
@@ -105,8 +122,35 @@ __global__ void __launch_bounds__(256) moe_permute_kernel(const float* __restric
   }
   row = __shfl_sync(0xffffffffu, row, 0);
   const float4* src = reinterpret_cast<const float4*>(x + (size_t)t * d);
-  float4* dst = reinterpret_cast<float4*>(xp + (size_t)row * d);
-  for (int i = lane; i < d / 4; i += 32) dst[i] = src[i];
+  if (sizeof(T) == 4) {
+    float4* dst = reinterpret_cast<float4*>(xp + (size_t)row * d);
+    for (int i = lane; i < d / 4; i += 32) dst[i] = src[i];
+  } else {
+    uint2* dst = reinterpret_cast<uint2*>(xp + (size_t)row * d);
+    for (int i = lane; i < d / 4; i += 32) {
+      const float4 v = src[i];
+      dst[i] = make_uint2(f2_to_bf16x2(v.x, v.y), f2_to_bf16x2(v.z, v.w));
+    }
+  }
+}
+
+// h[m][j] = a[m][j] * silu(a[m][ff + j]) over the [M, 2 ff] bf16 output of the stacked (linear1 | gate) GEMM  (moe.py:46-47)
+__global__ void __launch_bounds__(256) swiglu_pair_bf16_kernel(const bf16* __restrict__ a, bf16* __restrict__ h, long long M, int ff) {
+  const long long n8 = M * (ff / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / (ff / 8);
+    const int j = (int)(i - m * (ff / 8)) * 8;
+    const uint4 va = *reinterpret_cast<const uint4*>(a + m * 2 * ff + j);
+    const uint4 vg = *reinterpret_cast<const uint4*>(a + m * 2 * ff + ff + j);
+    const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ug[4] = {vg.x, vg.y, vg.z, vg.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 fa = bf16x2_to_f2(ua[q]), fg = bf16x2_to_f2(ug[q]);
+      o[q] = f2_to_bf16x2(fa.x * (fg.x / (1.f + expf(-fg.x))), fa.y * (fg.y / (1.f + expf(-fg.y))));
+    }
+    *reinterpret_cast<uint4*>(h + m * ff + j) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 
 constexpr int GB = 64, GK = 16;       // 64 x 64 output tile, 256 threads, 4 x 4 outputs each
@@ -197,15 +241,26 @@ __global__ void __launch_bounds__(256) moe_combine_kernel(const float* __restric
   }
 }
 
-int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int* off,
-                int* cursor, float* xp, int* perm, cudaStream_t stream) {
-  V2M_REQUIRE(d % 4 == 0 && n_experts >= 1 && n_experts <= kMaxExperts && k >= 1, "moe_permute: bad dims d=%d E=%d k=%d", d, n_experts, k);
-  moe_offsets_kernel<<<1, 32, 0, stream>>>(hist, n_experts, off, cursor);
+int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int align, int* off,
+                int* cursor, void* xp, int xp_bf16, int* perm, int* tile_group, int n_tiles, cudaStream_t stream) {
+  V2M_REQUIRE(d % 4 == 0 && n_experts >= 1 && n_experts <= kMaxExperts && k >= 1 && align >= 1, "moe_permute: bad dims d=%d E=%d k=%d",
+              d, n_experts, k);
+  moe_offsets_kernel<<<1, 256, 0, stream>>>(hist, n_experts, align, off, cursor, tile_group, n_tiles);
   if (tokens > 0) {
     const long long warps = (long long)tokens * k;
-    moe_permute_kernel<<<(int)((warps + 7) / 8), 256, 0, stream>>>(x, idx, off, cursor, xp, perm, tokens, k, d);
+    const int grid = (int)((warps + 7) / 8);
+    if (xp_bf16) moe_permute_kernel<bf16><<<grid, 256, 0, stream>>>(x, idx, off, cursor, static_cast<bf16*>(xp), perm, tokens, k, d);
+    else moe_permute_kernel<float><<<grid, 256, 0, stream>>>(x, idx, off, cursor, static_cast<float*>(xp), perm, tokens, k, d);
   }
   return check_launch("moe_permute");
+}
+
+int swiglu_pair_bf16(const void* a, void* h, long long M, int ff, cudaStream_t stream) {
+  V2M_REQUIRE(ff % 8 == 0, "swiglu_pair: ff=%d must be a multiple of 8", ff);
+  if (M == 0) return kOk;
+  const long long want = (M * (ff / 8) + 255) / 256;
+  swiglu_pair_bf16_kernel<<<(int)(want < 148 * 8 ? want : 148 * 8), 256, 0, stream>>>(static_cast<const bf16*>(a), static_cast<bf16*>(h), M, ff);
+  return check_launch("swiglu_pair_bf16");
 }
 
 int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,

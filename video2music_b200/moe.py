@@ -5,7 +5,11 @@ parameter names (`experts.N.{linear1,linear2,gate}`, `gate`, `shared_expert`, bu
 Routing (gate GEMV + top-k + fp32 softmax + expert histogram) is one fused kernel; token copies are then
 permuted into expert-contiguous order by a second kernel and all experts run as two ragged grouped GEMMs
 (group bounds read on the device, SwiGLU fused into the first) followed by a weighted combine (see
-`_experts_forward`): five launches per MoE layer and no host synchronisation.  The reference's per-expert Python loop with
+`_experts_forward`): five launches per MoE layer and no host synchronisation.
+
+`module.compute_dtype = torch.bfloat16` moves the expert GEMMs to the tcgen05 tensor-core path (grouped GEMM over
+128-row aligned expert groups, bf16 operands, fp32 accumulation); the router always runs in fp32, so the routing indices
+stay bit-exact.  The reference's per-expert Python loop with
 `torch.where` host syncs (moe.py:192-199) is gone; the logging side channels
 (third_party/log_experts.py, log_maxvio.py) are kept as optional callables (`on_route`).
 """
@@ -93,13 +97,46 @@ def _stacked(experts):
     return cache[1]
 
 
-def _experts_forward(experts, x2: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor) -> torch.Tensor:
+def _stacked_bf16(experts):
+    """bf16 stacks for the tensor-core path: (linear1 | gate) weights as one [E, 2 ff, d] operand, linear2 as [E, d, ff];
+    biases stay fp32."""
+    ps = [p for e in experts for p in (e.linear1.weight, e.linear1.bias, e.gate.weight, e.gate.bias, e.linear2.weight, e.linear2.bias)]
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    holder = experts if isinstance(experts, nn.Module) else experts[0]      # a single (shared) expert caches on itself
+    cache = getattr(holder, "_v2m_stack_bf16", None)
+    if cache is None or cache[0] != key:
+        w1g = torch.stack([torch.cat([e.linear1.weight.detach(), e.gate.weight.detach()], 0) for e in experts]).bfloat16().contiguous()
+        b1g = torch.stack([torch.cat([e.linear1.bias.detach(), e.gate.bias.detach()], 0) for e in experts]).float().contiguous()
+        w2 = torch.stack([e.linear2.weight.detach() for e in experts]).bfloat16().contiguous()
+        b2 = torch.stack([e.linear2.bias.detach() for e in experts]).float().contiguous()
+        cache = (key, (w1g, b1g, w2, b2))
+        object.__setattr__(holder, "_v2m_stack_bf16", cache)
+    return cache[1]
+
+
+def _tc_ok(d: int, ff: int, d_out: int) -> bool:
+    return d % 64 == 0 and ff % 64 == 0 and d_out % 128 == 0
+
+
+def _glu_bf16(e: GLUExpert, x2: torch.Tensor) -> torch.Tensor:
+    """One expert over all tokens (the shared expert) on the tcgen05 GEMM: stacked (linear1 | gate) projection, SwiGLU, linear2."""
+    w1g, b1g, w2, b2 = _stacked_bf16([e])
+    a = ops.linear(ops.cast_2d(x2, torch.bfloat16), w1g[0], b1g[0], out_dtype=torch.bfloat16)
+    return ops.linear(ops.swiglu_pair(a), w2[0], b2[0], out_dtype=torch.float32)
+
+
+def _experts_forward(experts, x2: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor,
+                     dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """out[t] = sum_r w[t,r] * expert_{idx[t,r]}(x[t])  (moe.py:191-199).
     Token copies are permuted into expert-contiguous order on the device, the experts run as two ragged grouped GEMMs
     (SwiGLU fused into the first), and the weighted results are combined per token in rank order (deterministic).
     No index tensors go through torch and nothing is read back to the host."""
     if x2.shape[1] % 16 or experts[0].linear1.out_features % 16:
         raise NotImplementedError("MoE expert GEMMs need d_model and d_ff to be multiples of 16")
+    if dtype == torch.bfloat16:
+        if not _tc_ok(x2.shape[1], experts[0].linear1.out_features, experts[0].linear2.out_features):
+            raise NotImplementedError("bf16 MoE experts need d_model % 128 == 0 and d_ff % 64 == 0")
+        return ops.moe_experts_bf16(x2, idx.reshape(-1, idx.shape[-1]), w.reshape(-1, w.shape[-1]), hist, *_stacked_bf16(experts))
     w1, b1, wg, bg, w2, b2 = _stacked(experts)
     return ops.moe_experts(x2, idx.reshape(-1, idx.shape[-1]), w.reshape(-1, w.shape[-1]), hist, w1, b1, wg, bg, w2, b2)
 
@@ -140,7 +177,7 @@ class MoELayer(nn.Module):
         self.last_selected_experts = idx.view(shp[:-1] + (k,))
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)
-        return _experts_forward(self.experts, x2, idx, w, hist).view(shp)
+        return _experts_forward(self.experts, x2, idx, w, hist, getattr(self, "compute_dtype", torch.float32)).view(shp)
 
 
 class SharedMoELayer(nn.Module):
@@ -193,6 +230,7 @@ class SharedMoELayer(nn.Module):
         self.last_selected_experts = idx.view(shp[:-1] + (k,))
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)
-        out = _experts_forward(self.experts, x2, idx, w, hist)
-        shared = _glu(self.shared_expert, x2)                            # moe.py:301
+        dt = getattr(self, "compute_dtype", torch.float32)
+        out = _experts_forward(self.experts, x2, idx, w, hist, dt)
+        shared = _glu_bf16(self.shared_expert, x2) if dt == torch.bfloat16 else _glu(self.shared_expert, x2)   # moe.py:301
         return ops.axpy(out, shared, 1.0 / k).view(shp[:-1] + (self.d_model,))

@@ -215,13 +215,55 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch
     yp = torch.empty((T * k, d_out), device=dev, dtype=torch.float32)
     out = torch.empty((T, d_out), device=dev, dtype=torch.float32)
     lib, st = load(), stream()
-    check(lib.v2m_moe_permute(ptr(x), ptr(idx), ptr(hist), T, k, d, E, ptr(off), ptr(cursor), ptr(xp), ptr(perm), st))
+    check(lib.v2m_moe_permute(ptr(x), ptr(idx), ptr(hist), T, k, d, E, 1, ptr(off), ptr(cursor), ptr(xp), dtype_code(xp.dtype), ptr(perm),
+                              None, 0, st))
     check(lib.v2m_moe_grouped_gemm(ptr(xp), d, ptr(w1), ptr(b1), ptr(wg), ptr(bg), ff * d, ff, ptr(off), E, T * k, ptr(h), ff, ff, d, st))
     check(lib.v2m_moe_grouped_gemm(ptr(h), ff, ptr(w2), ptr(b2), None, None, d_out * ff, d_out, ptr(off), E, T * k, ptr(yp), d_out,
                                    d_out, ff, st))
     check(lib.v2m_moe_combine(ptr(yp), ptr(perm), ptr(w), ptr(out), T, k, d_out, st))
     _lib.count_launches(5)
     return out
+
+
+def moe_experts_bf16(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor, w1g: torch.Tensor, b1g: torch.Tensor,
+                     w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """Tensor-core expert path: x fp32 (T, d) is permuted into bf16 expert-contiguous rows with 128-row aligned groups, the
+    experts run as two grouped tcgen05 GEMMs (stacked bf16 weights w1g [E, 2 ff, d] = linear1 | gate, w2 [E, d_out, ff];
+    fp32 biases) with the SwiGLU between them, and the fp32 results are combined with the fp32 router weights."""
+    require_device(x)
+    T, k = idx.shape
+    E, ff2, d = w1g.shape
+    ff, d_out = ff2 // 2, w2.shape[1]
+    dev = x.device
+    m_cap = (T * k + E * 127 + 127) // 128 * 128
+    n_tiles = m_cap // 128
+    meta = torch.empty((2 * E + 1 + T * k + n_tiles,), device=dev, dtype=torch.int32)
+    off, cursor, perm, tile_group = meta[:E + 1], meta[E + 1:2 * E + 1], meta[2 * E + 1:2 * E + 1 + T * k], meta[2 * E + 1 + T * k:]
+    xp = torch.zeros((m_cap, d), device=dev, dtype=torch.bfloat16)
+    a = torch.empty((m_cap, ff2), device=dev, dtype=torch.bfloat16)
+    h = torch.empty((m_cap, ff), device=dev, dtype=torch.bfloat16)
+    yp = torch.empty((m_cap, d_out), device=dev, dtype=torch.float32)
+    out = torch.empty((T, d_out), device=dev, dtype=torch.float32)
+    lib, st = load(), stream()
+    check(lib.v2m_moe_permute(ptr(x), ptr(idx), ptr(hist), T, k, d, E, 128, ptr(off), ptr(cursor), ptr(xp), dtype_code(xp.dtype), ptr(perm),
+                              ptr(tile_group), n_tiles, st))
+    check(lib.v2m_gemm_bf16_grouped(ptr(xp), d, ptr(w1g), d, ptr(a), ff2, dtype_code(a.dtype), m_cap, ff2, d, E, ptr(tile_group), ptr(b1g), 0, st))
+    check(lib.v2m_swiglu_pair_bf16(ptr(a), ptr(h), m_cap, ff, st))
+    check(lib.v2m_gemm_bf16_grouped(ptr(h), ff, ptr(w2), ff, ptr(yp), d_out, dtype_code(yp.dtype), m_cap, d_out, ff, E, ptr(tile_group), ptr(b2), 0, st))
+    check(lib.v2m_moe_combine(ptr(yp), ptr(perm), ptr(w), ptr(out), T, k, d_out, st))
+    _lib.count_launches(7)
+    return out
+
+
+def swiglu_pair(a: torch.Tensor) -> torch.Tensor:
+    """(M, 2 ff) bf16 -> (M, ff) bf16: a[:, :ff] * silu(a[:, ff:])."""
+    require_device(a)
+    assert a.dtype == torch.bfloat16 and a.is_contiguous()
+    M, ff = a.shape[0], a.shape[1] // 2
+    h = torch.empty((M, ff), device=a.device, dtype=torch.bfloat16)
+    check(load().v2m_swiglu_pair_bf16(ptr(a), ptr(h), M, ff, stream()))
+    _lib.count_launches(1)
+    return h
 
 
 # ----------------------------------------------------------------------------- backward-pass kernels
@@ -278,10 +320,13 @@ def selective_scan(x: torch.Tensor, delta_raw: torch.Tensor, dt_bias: Optional[t
         assert t.dtype == torch.float32 and t.stride(1) == 1
     assert Bm.stride(0) == Cm.stride(0)
     out = torch.empty((B * L, ED), device=x.device, dtype=torch.float32)
-    check(load().v2m_selective_scan_fwd(ptr(x), x.stride(0), ptr(delta_raw), delta_raw.stride(0), ptr(dt_bias), ptr(A_log.contiguous()),
-                                        ptr(Bm), ptr(Cm), Bm.stride(0), ptr(D), ptr(z), z.stride(0) if z is not None else 0,
-                                        ptr(out), ED, B, L, ED, N, int(plus), stream()))
-    _lib.count_launches(1)
+    lib = load()
+    ws_bytes = int(lib.v2m_selective_scan_workspace(B, L, ED, N))
+    ws = torch.empty((ws_bytes // 4,), device=x.device, dtype=torch.float32) if ws_bytes else None
+    check(lib.v2m_selective_scan_fwd(ptr(x), x.stride(0), ptr(delta_raw), delta_raw.stride(0), ptr(dt_bias), ptr(A_log.contiguous()),
+                                     ptr(Bm), ptr(Cm), Bm.stride(0), ptr(D), ptr(z), z.stride(0) if z is not None else 0,
+                                     ptr(out), ED, B, L, ED, N, int(plus), ptr(ws), ws_bytes, stream()))
+    _lib.count_launches(3 if ws_bytes else 1)
     return out
 
 
