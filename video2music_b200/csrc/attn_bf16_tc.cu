@@ -17,6 +17,11 @@
 // reads it back at the row-dependent offset -- the skew is a shifted read of shared memory
 // (conflict-free: row pitch 68 words).
 //
+// Persistent: one CTA per SM walks the (video, head, query tile) items with stride gridDim.x.  The shared-memory
+// operands of item n+1 are fetched as soon as the tensor core has consumed those of item n (Q, K, Er band right after
+// the S / QE products, V after P V), so TMA latency, TMEM allocation and CTA launch are off the per-tile critical path;
+// the next S product only waits for the epilogue warps to have pulled O out of tensor memory (bar_epi).
+//
 // Warp roles (32 + 128 * AT_NW threads): warp 0 = TMA producer + single-thread MMA issuer + TMEM allocator,
 // warps 1.. = softmax/epilogue.  A warp can only touch the TMEM lane quadrant (warp id % 4), so AT_NW warps share each
 // quadrant (32 query rows) and split its 32-key chunks round-robin; the row max / row sum are exchanged through shared
@@ -53,6 +58,7 @@ struct AttnTcArgs {
   float* lse;
   int B, Hq, Hkv, Lq, Lk, causal, has_er, er_len;
   int swap;   // tensor maps are (col, batch, row) instead of (col, row, batch): sequence-first layouts
+  int n_q_tiles, n_items;   // work items = (video, head) x 128-row query tiles; CTAs walk them with stride gridDim.x
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -77,27 +83,33 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bar_qb = bars + 6;     // QE half B complete
   uint64_t* bar_p = bars + 7;      // P written to TMEM by all softmax warps (count 4 * AT_NW)
   uint64_t* bar_o = bars + 8;      // O = P V complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* bar_epi = bars + 9;    // O pulled out of TMEM by all softmax warps (count 4 * AT_NW): next item may overwrite S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   auto tma3 = [&](void* dst, const CUtensorMap* tm, int col, int row, int batch, uint64_t* bar) {
     if (a.swap) tma_load_3d(dst, tm, col, batch, row, bar);
     else tma_load_3d(dst, tm, col, row, batch, bar);
   };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.y, b = bh / a.Hq, hq = bh % a.Hq, hkv = hq / (a.Hq / a.Hkv);
-  const int i0 = blockIdx.x * AT_M;
-  const int imax = min(i0 + AT_M - 1, a.Lq - 1);
   const int coff = a.Lk - a.Lq;
-  const int nk = a.causal ? min(a.Lk, imax + coff + 1) : a.Lk;         // keys this tile needs
-  const int nk16 = (nk + 15) & ~15;
-  const int nk64 = (nk + 63) & ~63;
-  // band column c <-> Er row e_base + c, needed c in [0, imax]
-  const int e_base = a.er_len - 1 - imax;
-  const bool need_b = a.has_er && (imax >= AT_QE_COLS);               // widest window start is clamped to 128 in half A
-  const int qe_rows = need_b ? AT_QE_OVERLAP + AT_QE_COLS : AT_QE_COLS;
+  struct Item { int b, hq, hkv, bh, i0, imax, nk, nk16, nk64, e_base, qe_rows; bool need_b; };
+  auto make_item = [&](int item) {
+    Item t;
+    t.bh = item / a.n_q_tiles;
+    t.b = t.bh / a.Hq; t.hq = t.bh % a.Hq; t.hkv = t.hq / (a.Hq / a.Hkv);
+    t.i0 = (item - t.bh * a.n_q_tiles) * AT_M;
+    t.imax = min(t.i0 + AT_M - 1, a.Lq - 1);
+    t.nk = a.causal ? min(a.Lk, t.imax + coff + 1) : a.Lk;            // keys this tile needs
+    t.nk16 = (t.nk + 15) & ~15;
+    t.nk64 = (t.nk + 63) & ~63;
+    t.e_base = a.er_len - 1 - t.imax;                                  // band column c <-> Er row e_base + c, needed c in [0, imax]
+    t.need_b = a.has_er && (t.imax >= AT_QE_COLS);                     // widest window start is clamped to 128 in half A
+    t.qe_rows = t.need_b ? AT_QE_OVERLAP + AT_QE_COLS : AT_QE_COLS;
+    return t;
+  };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 9; ++i) mbar_init(bars + i, (i == 5 || i == 7) ? 4u * AT_NW : 1u);
+    for (int i = 0; i < 10; ++i) mbar_init(bars + i, (i == 5 || i == 7 || i == 9) ? 4u * AT_NW : 1u);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     if (a.has_er) tma_prefetch_desc(&tmE);
@@ -113,60 +125,87 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA: Q + K, Er band, V (64-row boxes) ----------------
-      mbar_arrive_expect_tx(bar_qk, AT_SMEM_Q + nk64 * 128);
-      tma3(sQ, &tmQ, hq * AT_DH, i0, b, bar_qk);
-      tma3(sQ + 64 * 128, &tmQ, hq * AT_DH, i0 + 64, b, bar_qk);
-      for (int r = 0; r < nk64; r += 64) tma3(sK + r * 128, &tmK, hkv * AT_DH, r, b, bar_qk);
-      if (a.has_er) {
-        mbar_arrive_expect_tx(bar_e, qe_rows * 128);
-        for (int r = 0; r < qe_rows; r += 64) tma_load_2d(sE + r * 128, &tmE, 0, e_base + r, bar_e);
-      }
-      mbar_arrive_expect_tx(bar_v, nk64 * 128);
-      for (int r = 0; r < nk64; r += 64) tma3(sV + r * 128, &tmV, hkv * AT_DH, r, b, bar_v);
-
-      // ---------------- MMA issue ----------------
+      auto load_qke = [&](const Item& t) {                             // Q + K, Er band (64-row boxes)
+        mbar_arrive_expect_tx(bar_qk, AT_SMEM_Q + t.nk64 * 128);
+        tma3(sQ, &tmQ, t.hq * AT_DH, t.i0, t.b, bar_qk);
+        tma3(sQ + 64 * 128, &tmQ, t.hq * AT_DH, t.i0 + 64, t.b, bar_qk);
+        for (int r = 0; r < t.nk64; r += 64) tma3(sK + r * 128, &tmK, t.hkv * AT_DH, r, t.b, bar_qk);
+        if (a.has_er) {
+          mbar_arrive_expect_tx(bar_e, t.qe_rows * 128);
+          for (int r = 0; r < t.qe_rows; r += 64) tma_load_2d(sE + r * 128, &tmE, 0, t.e_base + r, bar_e);
+        }
+      };
+      auto load_v = [&](const Item& t) {
+        mbar_arrive_expect_tx(bar_v, t.nk64 * 128);
+        for (int r = 0; r < t.nk64; r += 64) tma3(sV + r * 128, &tmV, t.hkv * AT_DH, r, t.b, bar_v);
+      };
       const uint32_t q_addr = smem_u32(sQ), k_addr = smem_u32(sK), v_addr = smem_u32(sV), e_addr = smem_u32(sE);
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
-      for (int n0 = 0; n0 < nk16; n0 += 256) {                         // S[:, n0:n0+n] = Q K[n0:n0+n]^T
-        const int n = min(256, nk16 - n0);
-        const uint32_t idesc = make_idesc_bf16(AT_M, n, 0, 0);
-#pragma unroll
-        for (int k = 0; k < AT_DH / 16; ++k)
-          umma_bf16_ss(T_S + n0, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                       make_smem_desc_sw128(k_addr + n0 * 128 + k * 32, 16, 1024), idesc, k != 0);
+      uint32_t par = 0, parb = 0;                                      // phase of the once-per-item barriers / of the half-B pair
+      if ((int)blockIdx.x < a.n_items) {
+        const Item first = make_item(blockIdx.x);
+        load_qke(first);
+        load_v(first);
       }
-      umma_commit(bar_s);
-      if (a.has_er) {
-        const uint32_t idesc = make_idesc_bf16(AT_M, AT_QE_COLS, 0, 0);
-        mbar_wait(bar_e, 0);
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const Item t = make_item(item);
+        const bool has_next = item + (int)gridDim.x < a.n_items;
+        // ---------------- MMA issue ----------------
+        mbar_wait(bar_qk, par);
         tc_fence_after();
+        for (int n0 = 0; n0 < t.nk16; n0 += 256) {                     // S[:, n0:n0+n] = Q K[n0:n0+n]^T
+          const int n = min(256, t.nk16 - n0);
+          const uint32_t idesc = make_idesc_bf16(AT_M, n, 0, 0);
 #pragma unroll
-        for (int k = 0; k < AT_DH / 16; ++k)
-          umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                       make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc, k != 0);
-        umma_commit(bar_qa);
-        if (need_b) {
-          mbar_wait(bar_qa_free, 0);
+          for (int k = 0; k < AT_DH / 16; ++k)
+            umma_bf16_ss(T_S + n0, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         make_smem_desc_sw128(k_addr + n0 * 128 + k * 32, 16, 1024), idesc, k != 0);
+        }
+        umma_commit(bar_s);
+        if (a.has_er) {
+          const uint32_t idesc = make_idesc_bf16(AT_M, AT_QE_COLS, 0, 0);
+          mbar_wait(bar_e, par);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < AT_DH / 16; ++k)
             umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         make_smem_desc_sw128(e_addr + AT_QE_OVERLAP * 128 + k * 32, 16, 1024), idesc, k != 0);
-          umma_commit(bar_qb);
+                         make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc, k != 0);
+          umma_commit(bar_qa);
+          if (t.need_b) {
+            mbar_wait(bar_qa_free, parb);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < AT_DH / 16; ++k)
+              umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           make_smem_desc_sw128(e_addr + AT_QE_OVERLAP * 128 + k * 32, 16, 1024), idesc, k != 0);
+            umma_commit(bar_qb);
+          }
         }
+        // the products above are the last readers of sQ / sK / sE: once they have retired, fetch the next item's operands
+        if (has_next) {
+          if (t.need_b) mbar_wait(bar_qb, parb);
+          else if (a.has_er) mbar_wait(bar_qa, par);
+          else mbar_wait(bar_s, par);
+          load_qke(make_item(item + gridDim.x));
+        }
+        // O = P V : A = P from TMEM (bf16 pairs, 8 columns per k16), B = V (d contiguous -> MN-major)
+        mbar_wait(bar_v, par);
+        mbar_wait(bar_p, par);
+        tc_fence_after();
+        {
+          const uint32_t idesc = make_idesc_bf16(AT_M, AT_DH, 0, 1);
+          for (int k = 0; k < t.nk16 / 16; ++k)
+            umma_bf16_ts(T_O, T_P + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc, k != 0);
+        }
+        umma_commit(bar_o);
+        if (has_next) {
+          mbar_wait(bar_o, par);                                       // P V retired: sV is free
+          load_v(make_item(item + gridDim.x));
+          mbar_wait(bar_epi, par);                                     // O is out of TMEM: the next S may overwrite it
+          tc_fence_after();
+        }
+        par ^= 1;
+        if (t.need_b) parb ^= 1;
       }
-      // O = P V : A = P from TMEM (bf16 pairs, 8 columns per k16), B = V (d contiguous -> MN-major)
-      mbar_wait(bar_v, 0);
-      mbar_wait(bar_p, 0);
-      tc_fence_after();
-      {
-        const uint32_t idesc = make_idesc_bf16(AT_M, AT_DH, 0, 1);
-        for (int k = 0; k < nk16 / 16; ++k)
-          umma_bf16_ts(T_O, T_P + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc, k != 0);
-      }
-      umma_commit(bar_o);
     }
     __syncwarp();
   } else {
@@ -175,6 +214,15 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int sub = (warp - 1) >> 2;                             // which of the AT_NW warps of the quadrant
     const int u = lane;
     const int row = quad * 32 + u;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float* my_scr = scr + (size_t)((sub * 4 + quad) * 32 + u) * AT_SCR_PITCH;
+    const float LOG2E = 1.4426950408889634f;
+    const uint32_t bar_id = 1 + quad;                            // named barrier of this quadrant's AT_NW warps
+    uint32_t par = 0, parb = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const Item t = make_item(item);
+    const int i0 = t.i0, imax = t.imax, nk16 = t.nk16, b = t.b, hq = t.hq, bh = t.bh;
+    const bool need_b = t.need_b;
     const int i = i0 + row;                                      // my query row
     const bool row_ok = i < a.Lq;
     const int jlim = row_ok ? (a.causal ? min(a.Lk, i + coff + 1) : a.Lk) : 0;   // keys [0, jlim) are visible
@@ -183,26 +231,22 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const bool quad_ok = wfirst <= imax;
     const int wjlim = quad_ok ? (a.causal ? min(a.Lk, wlast + coff + 1) : a.Lk) : 0;     // widest row of the quadrant
     const int wjmin = (quad_ok && wfirst + 31 <= imax) ? (a.causal ? min(a.Lk, wfirst + coff + 1) : a.Lk) : 0;  // narrowest
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float* my_scr = scr + (size_t)((sub * 4 + quad) * 32 + u) * AT_SCR_PITCH;
     const int nchunks = (nk16 + 31) / 32;                        // chunks the P V product reads
     const int live = min(nchunks, (wjlim + 31) / 32);            // chunks with at least one visible key for this quadrant
     const int base_w = imax - i0 - quad * 32 - 31;               // window start (band column) for key chunk j0 is j0 + base_w
-    const float LOG2E = 1.4426950408889634f;
-    const uint32_t bar_id = 1 + quad;                            // named barrier of this quadrant's AT_NW warps
 
-    mbar_wait(bar_s, 0);
+    mbar_wait(bar_s, par);
     tc_fence_after();
     float mx = -INFINITY;
     // ---- pass A: s = S + Srel, mask, running max, s written back to TMEM
     for (int phase = 0; phase < 2; ++phase) {
-      if (phase == 0 && a.has_er) { mbar_wait(bar_qa, 0); tc_fence_after(); }
+      if (phase == 0 && a.has_er) { mbar_wait(bar_qa, par); tc_fence_after(); }
       if (phase == 1) {
         if (!need_b) break;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_qa_free);
-        mbar_wait(bar_qb, 0);
+        mbar_wait(bar_qb, parb);
         tc_fence_after();
       }
       for (int c = sub; c < live; c += AT_NW) {
@@ -296,7 +340,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     // ---- epilogue: O / sum -> bf16 -> global; the warps of a quadrant split the 64 columns
     constexpr int OC = AT_DH / AT_NW;
-    mbar_wait(bar_o, 0);
+    mbar_wait(bar_o, par);
     tc_fence_after();
     uint32_t o[OC];
 #pragma unroll
@@ -305,6 +349,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       else tmem_ld_32x16(T_O + lane_off + sub * OC + c32, o + c32);
     }
     tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_epi);                         // the stores below overlap the next item's products
     if (row_ok) {
       const float inv = 1.f / sum;
       bf16* dst = static_cast<bf16*>(a.o) + (size_t)b * a.o_sb + (size_t)i * a.o_sl + (size_t)hq * AT_DH + sub * OC;
@@ -319,6 +366,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       if (a.lse && sub == 0) a.lse[(size_t)bh * a.Lq + i] = mx + logf(sum);
     }
+    par ^= 1;
+    if (need_b) parb ^= 1;
+    }  // items
   }
   tc_fence_before();
   __syncthreads();
@@ -360,8 +410,17 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) { set_last_error("attn_fwd_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
     attr = true;
   }
-  dim3 grid((p.Lq + AT_M - 1) / AT_M, p.B * p.Hq);
-  attn_bf16_tc_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, tmE, a);
+  a.n_q_tiles = (p.Lq + AT_M - 1) / AT_M;
+  const long long items = (long long)a.n_q_tiles * p.B * p.Hq;
+  V2M_REQUIRE(items < (1ll << 31), "attn_fwd_bf16_tc: too many tiles");
+  a.n_items = (int)items;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  attn_bf16_tc_kernel<<<a.n_items < num_sms ? a.n_items : num_sms, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, tmE, a);
   return check_launch("attn_fwd_bf16_tc");
 }
 
