@@ -106,7 +106,7 @@ struct Ws {          // workspace views (bf16), padded to multiples of 64 in bot
 
 // ------------------------------------------------------------------------------------------------ rows kernel
 template <bool HAS_ER>
-__global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
+__global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
   extern __shared__ __align__(16) unsigned char abt_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(abt_smem);
   bf16* sdO = sQ + TILE;
@@ -133,20 +133,37 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
   const bf16* Og = static_cast<const bf16*>(p.o) + (long long)b * p.o_sb + (long long)hq * 64;
   const bf16* dOg = static_cast<const bf16*>(p.dO) + (long long)b * p.do_sb + (long long)hq * 64;
   const int nq = max(0, min(64, p.Lq - I0));
-  load_tile(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
-  load_tile(sdO, dOg + (long long)I0 * p.do_sl, p.do_sl, nq);
-  load_tile(sK, Og + (long long)I0 * p.o_sl, p.o_sl, nq);
+  const int n_jt = p.causal ? min(ws.Lkp / 64, (I0 + 63 + coff) / 64 + 1) : ws.Lkp / 64;
+  // K / V tiles are double-buffered with cp.async: tile jt+1 is in flight while tile jt is processed
+  auto issue_kv = [&](int jt) {
+    const int J0 = jt * 64;
+    const int nk = max(0, min(64, p.Lk - J0));
+    bf16* kb = (jt & 1) ? sK2 : sK;
+    bf16* vb = (jt & 1) ? sV2 : sV;
+    load_tile_async(kb, Kg + (long long)J0 * p.k_sl, p.k_sl, nk);
+    load_tile_async(vb, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
+    cp_async_commit();
+  };
+  // Prologue: Q, dO, O (and the reversed Er rows) are fetched asynchronously and together -- with two CTAs per SM a chain of
+  // synchronous tile loads was a third of the kernel's stall samples.  The O tile borrows a K buffer that is not needed yet.
+  bf16* sO = DBUF ? sK2 : sK;
+  load_tile_async(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
+  load_tile_async(sdO, dOg + (long long)I0 * p.do_sl, p.do_sl, nq);
+  load_tile_async(sO, Og + (long long)I0 * p.o_sl, p.o_sl, nq);
   const int dmax = min(ws.Lkp, I0 + 64);                   // distances d = i - j < dmax are needed (multiple of 64)
   if (HAS_ER) {
     const bf16* Er = static_cast<const bf16*>(p.Er);
     for (int idx = tid; idx < dmax * 8; idx += THREADS) {
       const int d = idx >> 3, c = idx & 7;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (d < p.er_len && d < p.Lq) v = *reinterpret_cast<const uint4*>(Er + (long long)(p.er_len - 1 - d) * 64 + c * 8);
-      *reinterpret_cast<uint4*>(sEr + d * TP + c * 8) = v;
+      const bool ok = d < p.er_len && d < p.Lq;
+      cp_async16(sEr + d * TP + c * 8, Er + (ok ? (long long)(p.er_len - 1 - d) * 64 + c * 8 : 0), ok);
     }
-    for (int idx = tid; idx < 64 * DP / 8; idx += THREADS) reinterpret_cast<uint4*>(sdQE)[idx] = make_uint4(0u, 0u, 0u, 0u);
   }
+  cp_async_commit();
+  if (DBUF) issue_kv(0);
+  if (HAS_ER)
+    for (int idx = tid; idx < 64 * DP / 8; idx += THREADS) reinterpret_cast<uint4*>(sdQE)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  if (DBUF) cp_async_wait<1>(); else cp_async_wait<0>();
   __syncthreads();
 
   const int r0 = w * 16;
@@ -157,7 +174,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
     frag_a(sQ, r0, ks, g, q, qa[ks]);
     frag_a(sdO, r0, ks, g, q, doa[ks]);
     uint32_t oa[4];
-    frag_a(sK, r0, ks, g, q, oa);
+    frag_a(sO, r0, ks, g, q, oa);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float2 x = bf16x2_to_f2(doa[ks][e]), y = bf16x2_to_f2(oa[e]);
@@ -192,20 +209,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_rows_kernel(AttnBwdParams p,
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dq[nt][e] = 0.f;
-  const int n_jt = p.causal ? min(ws.Lkp / 64, (I0 + 63 + coff) / 64 + 1) : ws.Lkp / 64;
   bf16* Pw = ws.P + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
   bf16* dSw = ws.dS + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
-  // K / V tiles are double-buffered with cp.async: tile jt+1 is in flight while tile jt is processed
-  auto issue_kv = [&](int jt) {
-    const int J0 = jt * 64;
-    const int nk = max(0, min(64, p.Lk - J0));
-    bf16* kb = (jt & 1) ? sK2 : sK;
-    bf16* vb = (jt & 1) ? sV2 : sV;
-    load_tile_async(kb, Kg + (long long)J0 * p.k_sl, p.k_sl, nk);
-    load_tile_async(vb, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
-    cp_async_commit();
-  };
-  if (DBUF && n_jt > 0) issue_kv(0);
   for (int jt = 0; jt < n_jt; ++jt) {
     const int J0 = jt * 64;
     const bf16* kb = (jt & 1) ? sK2 : sK;
