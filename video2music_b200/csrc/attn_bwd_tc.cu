@@ -3,12 +3,13 @@
 // which the reference obtains from autograd over the materialised (B*H, L, L) tensors.  Same math as the exact SIMT
 // kernel in attn_bwd.cu (see the formulas there); three kernels, no atomics except the final dEr reduction:
 //   rows kernel : one CTA = (batch, head) x 64 query rows, one warp = 16 rows (P and dS never leave the registers of the
-//                 warp that owns the rows).  Recomputes S = Q K^T (+ Srel read from a per-CTA Q Er_rev^T table), P, dP = dO V^T,
-//                 dS = P o (dP - D); accumulates dQ = dS K (+ dQE Er_rev) in registers; writes the P and dS tiles (bf16) and,
-//                 for RPR, the skewed dS rows dQE[i][d] = dS[i][i-d] to a workspace.
+//                 warp that owns the rows).  Recomputes S = Q K^T (+ Srel from a per-key-tile Q Er_band^T product), P,
+//                 dP = dO V^T, dS = P o (dP - D); accumulates dQ = dS K (+ skewed dS . Er_band) in registers; writes the
+//                 P and dS tiles (bf16) to a workspace.
 //   cols kernel : one CTA = (batch, kv head) x 64 keys: dV = P^T dO, dK = dS^T Q from the workspace tiles (operands
 //                 transposed on the fly by ldmatrix.trans), summed over the query heads of the group (GQA).
-//   dEr kernel  : dEr[er_len-1-d] = sum_{b,h,i} dQE[i][d] q_i, split over (batch, head) groups, one fp32 atomic per output.
+//   dEr kernel  : dEr[er_len-1-d] = sum_{b,h,i} dS[i][i-d] q_i read skewed from the dS workspace, split over (batch, head)
+//                 groups, one fp32 atomic per output.
 // Shared-memory tiles are 64 x 64 bf16 with a pitch of 72 elements: ldmatrix and 32-bit fragment loads are conflict-free.
 #include "common.cuh"
 #include "kernels.h"
@@ -105,23 +106,31 @@ struct Ws {          // workspace views (bf16), padded to multiples of 64 in bot
 };
 
 // ------------------------------------------------------------------------------------------------ rows kernel
+// RPR (HAS_ER): the relative term needs, for this warp's 16 rows and the 64 keys of tile J0, the distances
+// d = i - j in [dhi - 78, dhi], dhi = (I0 + r0 + 15) - J0: an 80-wide band of Er rows.  Band column e <-> d = dhi - e <-> row
+// k0 + e of the shared-memory Er slice (ascending Er rows), and element (row r, key column c) of the tile sits at e = 15 - r + c.
+//   * QE band  = q (16 x 64) . Er_band^T (80 rows): 40 MMAs per tile, parked as fp32 in the warp's scratch and read back
+//     skewed when the scores are formed;
+//   * dQ      += dS_skewed (16 x 80) . Er_band: the A fragments are read straight out of the staged dS rows (the same
+//     bf16 tile that goes to the workspace) at column c = e - 15 + r, zero outside the tile / above the diagonal.
+// No per-CTA (64 x L) tables: 105 KB of shared memory for L = 320, two CTAs per SM (the table version had one).  dEr is
+// computed by the dEr kernel from the dS workspace itself.
+constexpr int QB = 88;                 // fp32 pitch of the QE band scratch (16 rows x 80 columns)
+constexpr int WBUF = 16 * QB * 4;      // per-warp scratch bytes: QE band (fp32), later the staged P / dS rows (2 x 16 x TP bf16)
+
 template <bool HAS_ER>
-__global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
+__global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
   extern __shared__ __align__(16) unsigned char abt_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(abt_smem);
   bf16* sdO = sQ + TILE;
-  bf16* sK = sdO + TILE;                // first holds the O tile
+  bf16* sK = sdO + TILE;                // first holds the O tile (RPR variant)
   bf16* sV = sK + TILE;
-  // second K / V buffer (cp.async double buffering); the RPR variant has no shared memory left for it
+  // second K / V buffer (cp.async double buffering); the RPR variant spends the shared memory on occupancy instead
   constexpr bool DBUF = !HAS_ER;
   bf16* sK2 = DBUF ? sV + TILE : sK;
   bf16* sV2 = DBUF ? sK2 + TILE : sV;
-  bf16* sStage = sV + (DBUF ? 3 : 1) * TILE;            // per warp: 16 rows of P + 16 rows of dS (pitch TP) on their way to the workspace
-  // RPR only: Er_rev rows (d -> Er[er_len-1-d]), the Q Er_rev^T table (fp32) and the skewed dS rows (bf16)
-  const int QP = ws.Lkp + 4, DP = ws.Lkp + 8;
-  bf16* sEr = sStage + 2 * TILE;                           // [Lkp][TP]
-  float* sQE = reinterpret_cast<float*>(sEr + (HAS_ER ? ws.Lkp * TP : 0));   // [64][QP]
-  bf16* sdQE = reinterpret_cast<bf16*>(sQE + (HAS_ER ? 64 * QP : 0));        // [64][DP]
+  unsigned char* sWarp = reinterpret_cast<unsigned char*>(sV + (DBUF ? 3 : 1) * TILE);   // 4 x WBUF
+  bf16* sEr = reinterpret_cast<bf16*>(sWarp + 4 * WBUF);     // RPR only: [I0 + 64][TP], row k <-> distance d = I0 + 63 - k
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
   const int bh = blockIdx.y, b = bh / p.Hq, hq = bh % p.Hq, hkv = hq / (p.Hq / p.Hkv);
@@ -144,25 +153,23 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
     load_tile_async(vb, Vg + (long long)J0 * p.v_sl, p.v_sl, nk);
     cp_async_commit();
   };
-  // Prologue: Q, dO, O (and the reversed Er rows) are fetched asynchronously and together -- with two CTAs per SM a chain of
-  // synchronous tile loads was a third of the kernel's stall samples.  The O tile borrows a K buffer that is not needed yet.
+  // Prologue: Q, dO, O (and the Er slice) are fetched asynchronously and together -- a chain of synchronous tile loads
+  // was a third of the kernel's stall samples.  The O tile borrows a K buffer that is not needed yet.
   bf16* sO = DBUF ? sK2 : sK;
   load_tile_async(sQ, Qg + (long long)I0 * p.q_sl, p.q_sl, nq);
   load_tile_async(sdO, dOg + (long long)I0 * p.do_sl, p.do_sl, nq);
   load_tile_async(sO, Og + (long long)I0 * p.o_sl, p.o_sl, nq);
-  const int dmax = min(ws.Lkp, I0 + 64);                   // distances d = i - j < dmax are needed (multiple of 64)
+  const int er_rows = min(ws.Lkp, I0 + 64);                 // distances d = i - j <= I0 + 63 can occur in this row tile
   if (HAS_ER) {
     const bf16* Er = static_cast<const bf16*>(p.Er);
-    for (int idx = tid; idx < dmax * 8; idx += THREADS) {
-      const int d = idx >> 3, c = idx & 7;
-      const bool ok = d < p.er_len && d < p.Lq;
-      cp_async16(sEr + d * TP + c * 8, Er + (ok ? (long long)(p.er_len - 1 - d) * 64 + c * 8 : 0), ok);
+    for (int idx = tid; idx < er_rows * 8; idx += THREADS) {
+      const int k = idx >> 3, c = idx & 7, d = I0 + 63 - k;
+      const bool ok = d < p.er_len && d < p.Lq;              // other distances never meet a valid (i, j <= i): zero rows
+      cp_async16(sEr + k * TP + c * 8, Er + (ok ? (long long)(p.er_len - 1 - d) * 64 + c * 8 : 0), ok);
     }
   }
   cp_async_commit();
   if (DBUF) issue_kv(0);
-  if (HAS_ER)
-    for (int idx = tid; idx < 64 * DP / 8; idx += THREADS) reinterpret_cast<uint4*>(sdQE)[idx] = make_uint4(0u, 0u, 0u, 0u);
   if (DBUF) cp_async_wait<1>(); else cp_async_wait<0>();
   __syncthreads();
 
@@ -187,21 +194,6 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
   const int ilo = I0 + r0 + g, ihi = ilo + 8;
   const float lse_lo = ilo < p.Lq ? p.lse[(long long)bh * p.Lq + ilo] : 0.f;
   const float lse_hi = ihi < p.Lq ? p.lse[(long long)bh * p.Lq + ihi] : 0.f;
-
-  if (HAS_ER) {
-    // QE[i][d] = q_i . Er_rev[d] for this warp's 16 rows (only the warp itself reads them back)
-    for (int nt = 0; nt < dmax / 8; ++nt) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const bf16* bp = sEr + (nt * 8 + g) * TP + ks * 16 + 2 * q;
-        mma16816(c, qa[ks], lds32(bp), lds32(bp + 8));
-      }
-      float* dst = sQE + (r0 + g) * QP + nt * 8 + 2 * q;
-      dst[0] = c[0]; dst[1] = c[1];
-      dst[8 * QP] = c[2]; dst[8 * QP + 1] = c[3];
-    }
-  }
   __syncthreads();                                         // the O tile is no longer needed: K / V tiles go there
 
   float dq[8][4];
@@ -211,6 +203,9 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
     for (int e = 0; e < 4; ++e) dq[nt][e] = 0.f;
   bf16* Pw = ws.P + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
   bf16* dSw = ws.dS + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
+  float* wQE = reinterpret_cast<float*>(sWarp + w * WBUF);            // [16][QB] fp32 QE band ...
+  bf16* wSt = reinterpret_cast<bf16*>(sWarp + w * WBUF);              // ... then 16 rows of P + 16 rows of dS (pitch TP)
+  const int ri = lane & 7, mi = lane >> 3;
   for (int jt = 0; jt < n_jt; ++jt) {
     const int J0 = jt * 64;
     const bf16* kb = (jt & 1) ? sK2 : sK;
@@ -219,6 +214,23 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
     else if (jt + 1 < n_jt) { issue_kv(jt + 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
+    const int dhi = I0 + r0 + 15 - J0;                       // largest distance of this warp's rows in this key tile
+    const bool rel_tile = HAS_ER && dhi >= 0;                // some (i, j <= i) in the tile
+    const int k0 = 48 - r0 + J0;                             // Er slice row of band column 0 (>= 0)
+    if (rel_tile) {
+      // QE band: 10 n-tiles of 8 band columns
+#pragma unroll
+      for (int nt = 0; nt < 10; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const bf16* bp = sEr + min(k0 + nt * 8 + g, er_rows - 1) * TP + 2 * q;   // clamped rows are above the diagonal (unused)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma16816(c, qa[ks], lds32(bp + ks * 16), lds32(bp + ks * 16 + 8));
+        float* dst = wQE + g * QB + nt * 8 + 2 * q;
+        *reinterpret_cast<float2*>(dst) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(dst + 8 * QB) = make_float2(c[2], c[3]);
+      }
+      __syncwarp();
+    }
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -230,19 +242,21 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int hi = e >> 1, i = hi ? ihi : ilo, j = J0 + nt * 8 + 2 * q + (e & 1);
+        const int hi = e >> 1, i = hi ? ihi : ilo, c = nt * 8 + 2 * q + (e & 1), j = J0 + c;
         const bool valid = i < p.Lq && j < p.Lk && (!p.causal || j <= i + coff);
         float sc = s[nt][e];
         const bool rel = HAS_ER && valid && j <= i;            // _skew contributes only for j <= i (rpr.py:439-455)
-        if (rel) sc += sQE[(r0 + g + hi * 8) * QP + (i - j)];
+        if (rel) sc += wQE[(g + hi * 8) * QB + 15 - (g + hi * 8) + c];
         const float pv = valid ? __expf(sc - (hi ? lse_hi : lse_lo)) : 0.f;
-        const float dsv = pv * (dp[nt][e] - (hi ? Dhi : Dlo));
         s[nt][e] = pv;
-        dp[nt][e] = dsv;
-        if (rel) sdQE[(r0 + g + hi * 8) * DP + (i - j)] = __float2bfloat16_rn(dsv);
+        dp[nt][e] = pv * (dp[nt][e] - (hi ? Dhi : Dlo));
       }
-      // P and dS fragments -> this warp's staging rows (bf16, pitch 72): written out below as whole 128-byte rows
-      bf16* sp = sStage + (w * 32 + g) * TP + nt * 8 + 2 * q;
+    }
+    if (rel_tile) __syncwarp();                                // every lane has read its QE values: the scratch becomes the stage
+    // P and dS fragments -> this warp's staging rows (bf16, pitch 72): written out below as whole 128-byte rows
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      bf16* sp = wSt + g * TP + nt * 8 + 2 * q;
       *reinterpret_cast<uint32_t*>(sp) = f2_to_bf16x2(s[nt][0], s[nt][1]);
       *reinterpret_cast<uint32_t*>(sp + 8 * TP) = f2_to_bf16x2(s[nt][2], s[nt][3]);
       *reinterpret_cast<uint32_t*>(sp + 16 * TP) = f2_to_bf16x2(dp[nt][0], dp[nt][1]);
@@ -253,12 +267,11 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int idx = it * 32 + lane, r = idx >> 3, c8 = idx & 7;
-      const uint4 pv4 = *reinterpret_cast<const uint4*>(sStage + (w * 32 + r) * TP + c8 * 8);
-      const uint4 dv4 = *reinterpret_cast<const uint4*>(sStage + (w * 32 + 16 + r) * TP + c8 * 8);
+      const uint4 pv4 = *reinterpret_cast<const uint4*>(wSt + r * TP + c8 * 8);
+      const uint4 dv4 = *reinterpret_cast<const uint4*>(wSt + (16 + r) * TP + c8 * 8);
       *reinterpret_cast<uint4*>(Pw + (long long)r * ws.Lkp + J0 + c8 * 8) = pv4;
       *reinterpret_cast<uint4*>(dSw + (long long)r * ws.Lkp + J0 + c8 * 8) = dv4;
     }
-    __syncwarp();
     // dQ += dS K_J : the C fragments of two adjacent key tiles form the A fragment of one k-step
     uint32_t a[4][4];
 #pragma unroll
@@ -269,29 +282,31 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 1 : 3) attn_bwd_rows_kernel(
       a[kk][3] = f2_to_bf16x2(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
     }
     mma_a_times_rowmajor(dq, a, kb, lane);
-    __syncthreads();                                       // everyone is done with this buffer before tile jt+2 lands in it
-  }
-  if (HAS_ER) {
-    __syncwarp();
-    // skewed dS rows of this warp -> workspace (for the dEr kernel), then dQ += dQE Er_rev
-    bf16* dQEw = ws.dQE + ((long long)bh * ws.Lqp + I0 + r0) * ws.Lkp;
-    for (int idx = lane; idx < 16 * (ws.Lkp / 8); idx += 32) {
-      const int r = idx / (ws.Lkp / 8), c = idx % (ws.Lkp / 8);
-      *reinterpret_cast<uint4*>(dQEw + (long long)r * ws.Lkp + c * 8) = *reinterpret_cast<const uint4*>(sdQE + (r0 + r) * DP + c * 8);
-    }
-    const int ri = lane & 7, mi = lane >> 3;
-    for (int ks = 0; ks < dmax / 16; ++ks) {
-      uint32_t af[4];
-      const bf16* ap = sdQE + (r0 + g) * DP + ks * 16 + 2 * q;
-      af[0] = lds32(ap); af[1] = lds32(ap + 8 * DP); af[2] = lds32(ap + 8); af[3] = lds32(ap + 8 * DP + 8);
+    if (rel_tile) {
+      // dQ += dS_skewed . Er_band : A[r][e] = dS[r][c = e - 15 + r] for 0 <= c < 64 and e <= dhi (j <= i), else 0
+      const unsigned short* dsr = reinterpret_cast<const unsigned short*>(wSt + 16 * TP);
+      auto skew2 = [&](int r, int e) -> uint32_t {             // band columns e, e + 1 of row r, packed
+        const int c = e - 15 + r;
+        const uint32_t lo = (c >= 0 && c < 64 && e <= dhi) ? dsr[r * TP + c] : 0u;
+        const uint32_t hi = (c + 1 >= 0 && c + 1 < 64 && e + 1 <= dhi) ? dsr[r * TP + c + 1] : 0u;
+        return lo | (hi << 16);
+      };
 #pragma unroll
-      for (int ntp = 0; ntp < 4; ++ntp) {
-        uint32_t x0, x1, x2, x3;
-        ldsm_x4_t(sEr + (ks * 16 + (mi & 1) * 8 + ri) * TP + (2 * ntp + (mi >> 1)) * 8, x0, x1, x2, x3);
-        mma16816(dq[2 * ntp], af, x0, x1);
-        mma16816(dq[2 * ntp + 1], af, x2, x3);
+      for (int ks = 0; ks < 5; ++ks) {
+        uint32_t af[4];
+        const int e0 = ks * 16 + 2 * q;
+        af[0] = skew2(g, e0); af[1] = skew2(g + 8, e0); af[2] = skew2(g, e0 + 8); af[3] = skew2(g + 8, e0 + 8);
+        const int kr = min(k0 + ks * 16 + (mi & 1) * 8 + ri, er_rows - 1);
+#pragma unroll
+        for (int ntp = 0; ntp < 4; ++ntp) {
+          uint32_t x0, x1, x2, x3;
+          ldsm_x4_t(sEr + kr * TP + (2 * ntp + (mi >> 1)) * 8, x0, x1, x2, x3);
+          mma16816(dq[2 * ntp], af, x0, x1);
+          mma16816(dq[2 * ntp + 1], af, x2, x3);
+        }
       }
     }
+    __syncthreads();                                       // everyone is done with this buffer before the next tile lands in it
   }
   bf16* dQg = static_cast<bf16*>(p.dq) + (long long)b * p.dq_sb + (long long)hq * 64;
 #pragma unroll
@@ -368,9 +383,14 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_cols_kernel(AttnBwdParams p,
 }
 
 // ------------------------------------------------------------------------------------------------ dEr kernel
+// dEr[er_len-1-d] = sum_{b,h,i} dS[i][i-d] q_i.  For the distance block [D0, D0+64) and the query tile I0 the needed keys
+// j = i - d lie in the two dS tiles starting at I0 - D0 - 64 and I0 - D0: both go to shared memory side by side
+// ([64 rows][128 columns], pitch TP2) and the A operand A[m = d][k = i] = T[i][i - d + 64] is gathered with 16-bit loads.
+constexpr int TP2 = 136;
 __global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, Ws ws, int n_split) {
   extern __shared__ __align__(16) unsigned char abt_smem[];
-  bf16* sE = reinterpret_cast<bf16*>(abt_smem);          // two stages of [dQE tile (64 i x 64 d) | Q tile]
+  constexpr int STAGE = 64 * TP2 + TILE;                  // elements: [dS pair | Q tile]
+  bf16* sE = reinterpret_cast<bf16*>(abt_smem);           // two stages
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
   const int D0 = blockIdx.x * 64;
   float acc[8][4];
@@ -378,26 +398,41 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, 
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-  // (batch*head, query tile) pairs of this split, rows i >= d only, cp.async double buffering (2 tiles per stage)
+  // (batch*head, query tile) pairs of this split, rows i >= d only, cp.async double buffering
   const int it_begin = D0 / 64, n_it = ws.Lqp / 64 - it_begin;
   const int n_bh = (p.B * p.Hq - (int)blockIdx.y + n_split - 1) / n_split, total = n_bh * n_it;
   auto issue = [&](int k) {
     const int bh = blockIdx.y + (k / n_it) * n_split, I0 = (it_begin + k % n_it) * 64;
     const int b = bh / p.Hq, hq = bh % p.Hq;
     const int nq = max(0, min(64, p.Lq - I0));
-    bf16* base = sE + (k & 1) * 2 * TILE;
-    load_tile_async(base, ws.dQE + ((long long)bh * ws.Lqp + I0) * ws.Lkp + D0, ws.Lkp, 64);
-    load_tile_async(base + TILE, static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64 + (long long)I0 * p.q_sl, p.q_sl, nq);
+    bf16* base = sE + (k & 1) * STAGE;
+    const int Ja = I0 - D0 - 64;                           // multiple of 64; negative only when I0 == D0 (keys j < 0: zeros)
+    const bf16* src = ws.dS + ((long long)bh * ws.Lqp + I0) * ws.Lkp;
+    for (int idx = threadIdx.x; idx < 64 * 16; idx += THREADS) {
+      const int r = idx >> 4, c = idx & 15;                // 16 chunks of 8 columns per row
+      const bool ok = Ja >= 0 || c >= 8;
+      cp_async16(base + r * TP2 + c * 8, src + (ok ? (long long)r * ws.Lkp + Ja + c * 8 : 0), ok);
+    }
+    load_tile_async(base + 64 * TP2, static_cast<const bf16*>(p.q) + (long long)b * p.q_sb + (long long)hq * 64 + (long long)I0 * p.q_sl, p.q_sl, nq);
     cp_async_commit();
   };
   if (total > 0) issue(0);
   for (int k = 0; k < total; ++k) {
     if (k + 1 < total) { issue(k + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    const bf16* base = sE + (k & 1) * 2 * TILE;
+    const unsigned short* T = reinterpret_cast<const unsigned short*>(sE + (k & 1) * STAGE);
     uint32_t a[4][4];
-    frag_a_transposed(base, w * 16, lane, a);                 // A[m = d][k = i] = dQE[i][d]
-    mma_a_times_rowmajor(acc, a, base + TILE, lane);
+    const int m_lo = w * 16 + g, m_hi = m_lo + 8;           // distance rows of this thread's fragments
+    auto pair = [&](int m, int kk) -> uint32_t {            // A[m][kk], A[m][kk+1] packed
+      const uint32_t lo = T[kk * TP2 + kk - m + 64], hi = T[(kk + 1) * TP2 + kk + 1 - m + 64];
+      return lo | (hi << 16);
+    };
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int kk = ks * 16 + 2 * q;
+      a[ks][0] = pair(m_lo, kk); a[ks][1] = pair(m_hi, kk); a[ks][2] = pair(m_lo, kk + 8); a[ks][3] = pair(m_hi, kk + 8);
+    }
+    mma_a_times_rowmajor(acc, a, sE + (k & 1) * STAGE + 64 * TP2, lane);
     __syncthreads();
   }
   const int dlo = D0 + w * 16 + g, dhi = dlo + 8;
@@ -421,7 +456,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, 
 // Workspace bytes attn_bwd_tc needs for these dimensions.
 long long attn_bwd_tc_workspace(int B, int Hq, int Lq, int Lk, int has_er) {
   const long long Lqp = (Lq + 63) / 64 * 64, Lkp = (Lk + 63) / 64 * 64;
-  return (long long)B * Hq * Lqp * Lkp * 2 * (has_er ? 3 : 2);
+  (void)has_er;
+  return (long long)B * Hq * Lqp * Lkp * 2 * 2;            // P and dS planes (bf16)
 }
 
 // bf16 only, head_dim 64.  p.dk / p.dv are BF16 outputs here (written once, no accumulation; strides dkv_sb / dkv_sl in
@@ -445,20 +481,23 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   const long long plane = (long long)p.B * p.Hq * ws.Lqp * ws.Lkp;
   ws.P = static_cast<bf16*>(ws_ptr);
   ws.dS = ws.P + plane;
-  ws.dQE = has_er ? ws.dS + plane : nullptr;
-  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16), tiles6 = 8 * abt::TILE * sizeof(bf16);
-  const size_t smem_er = 6 * abt::TILE * sizeof(bf16) + (size_t)ws.Lkp * abt::TP * 2 + (size_t)64 * (ws.Lkp + 4) * 4 + (size_t)64 * (ws.Lkp + 8) * 2;
+  ws.dQE = nullptr;
+  const size_t tiles4 = 4 * abt::TILE * sizeof(bf16);
+  const size_t smem_plain = 6 * abt::TILE * sizeof(bf16) + 4 * abt::WBUF;
+  const size_t smem_er = 4 * abt::TILE * sizeof(bf16) + 4 * abt::WBUF + (size_t)ws.Lkp * abt::TP * 2;
+  const size_t smem_der = 2 * (64 * abt::TP2 + abt::TILE) * sizeof(bf16);
   V2M_REQUIRE(!has_er || smem_er <= 227 * 1024, "attn_bwd_tc: L=%d needs %zu B of shared memory with RPR (> 227 KB)", p.Lk, smem_er);
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles6);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
     cudaFuncSetAttribute(abt::attn_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tiles4));
+    cudaFuncSetAttribute(abt::attn_bwd_der_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der);
     attr_set = true;
   }
   dim3 grid_r(ws.Lqp / 64, p.B * p.Hq);
   if (has_er) abt::attn_bwd_rows_kernel<true><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
-  else abt::attn_bwd_rows_kernel<false><<<grid_r, abt::THREADS, tiles6, stream>>>(p, ws);
+  else abt::attn_bwd_rows_kernel<false><<<grid_r, abt::THREADS, smem_plain, stream>>>(p, ws);
   int rc = check_launch("attn_bwd_rows");
   if (rc) return rc;
   dim3 grid_c(ws.Lkp / 64, p.B * p.Hkv);
@@ -467,7 +506,7 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   if (rc || !has_er) return rc;
   const int n_split = p.B * p.Hq < 148 ? p.B * p.Hq : 148;
   dim3 grid_e(ws.Lkp / 64, n_split);
-  abt::attn_bwd_der_kernel<<<grid_e, abt::THREADS, tiles4, stream>>>(p, ws, n_split);
+  abt::attn_bwd_der_kernel<<<grid_e, abt::THREADS, smem_der, stream>>>(p, ws, n_split);
   return check_launch("attn_bwd_der");
 }
 

@@ -83,11 +83,27 @@ class Trainer:
         dev = self.flat.flat_p.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(self._copy_stream):
-            out = {k: v.to(dev, non_blocking=True) for k, v in batch.items()}
+            self._slots = [None, None]          # two persistent device batches (no allocator traffic in the steady state)
+            self._slot_free = [None, None]      # event: the step that last read the slot has finished
+            self._slot_i = 0
+        i = self._slot_i
+        self._slot_i ^= 1
+        cs = self._copy_stream
+        slot = self._slots[i]
+        if slot is None or any(k not in slot or slot[k].shape != v.shape or slot[k].dtype != v.dtype for k, v in batch.items()):
+            slot = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in batch.items()}
+            self._slots[i] = slot
+            cs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cs):
+            if self._slot_free[i] is not None:
+                cs.wait_event(self._slot_free[i])
+            for k, v in batch.items():
+                slot[k].copy_(v, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(self._copy_stream)
+            ev.record(cs)
+        out = dict(slot)
         out["_ready"] = ev
+        out["_slot"] = i
         return out
 
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -97,13 +113,10 @@ class Trainer:
         from .autograd import AmtLossFn
         m = self.model
         dev = self.flat.flat_p.device
-        ready = batch.get("_ready")
+        ready, slot_i = batch.get("_ready"), batch.get("_slot")
         if ready is not None:
             torch.cuda.current_stream(dev).wait_event(ready)
-            for k, v in batch.items():
-                if k != "_ready":
-                    v.record_stream(torch.cuda.current_stream(dev))
-        b = {k: v.to(dev, non_blocking=True) for k, v in batch.items() if k != "_ready"}
+        b = {k: v.to(dev, non_blocking=True) for k, v in batch.items() if not k.startswith("_")}
         y = m(b["x"], b["x_root"], b["x_attr"], b["feature_semantic_list"], b["feature_key"], b["feature_scene_offset"],
               b["feature_motion"], b["feature_emotion"])
         loss = AmtLossFn.apply(y, b["tgt"], b["tgt_emotion"], 0.1, 0.4, 0.6)          # run_model_vevo.py:101-119
@@ -114,4 +127,8 @@ class Trainer:
         ops.adam_step(self.flat.flat_p, self.flat.flat_g, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps,
                       self.step_no, grad_scale=scale)
         self.flat.flat_g.zero_()
+        if slot_i is not None:                  # the prefetch slot may be overwritten once this step has run
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._slot_free[slot_i] = ev
         return loss.detach()
