@@ -285,26 +285,35 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(
     if (rel_tile) {
       // dQ += dS_skewed . Er_band : A[r][e] = dS[r][c = e - 15 + r] for 0 <= c < 64 and e <= dhi (j <= i), else 0
       const unsigned short* dsr = reinterpret_cast<const unsigned short*>(wSt + 16 * TP);
-      auto skew2 = [&](int r, int e) -> uint32_t {             // band columns e, e + 1 of row r, packed
+      // chk_c: band columns 16..63 always fall inside the tile (c = e - 15 + r in [1, 63]); chk_d: only the tile on the
+      // diagonal has band columns beyond dhi.  Both are resolved at compile time / per warp.
+      auto skew2 = [&](int r, int e, bool chk_c, bool chk_d) -> uint32_t {   // band columns e, e + 1 of row r, packed
         const int c = e - 15 + r;
-        const uint32_t lo = (c >= 0 && c < 64 && e <= dhi) ? dsr[r * TP + c] : 0u;
-        const uint32_t hi = (c + 1 >= 0 && c + 1 < 64 && e + 1 <= dhi) ? dsr[r * TP + c + 1] : 0u;
+        const bool ok_lo = (!chk_c || (c >= 0 && c < 64)) && (!chk_d || e <= dhi);
+        const bool ok_hi = (!chk_c || (c + 1 >= 0 && c + 1 < 64)) && (!chk_d || e + 1 <= dhi);
+        const uint32_t lo = ok_lo ? dsr[r * TP + c] : 0u;
+        const uint32_t hi = ok_hi ? dsr[r * TP + c + 1] : 0u;
         return lo | (hi << 16);
       };
+      auto band = [&](bool chk_d) {
 #pragma unroll
-      for (int ks = 0; ks < 5; ++ks) {
-        uint32_t af[4];
-        const int e0 = ks * 16 + 2 * q;
-        af[0] = skew2(g, e0); af[1] = skew2(g + 8, e0); af[2] = skew2(g, e0 + 8); af[3] = skew2(g + 8, e0 + 8);
-        const int kr = min(k0 + ks * 16 + (mi & 1) * 8 + ri, er_rows - 1);
+        for (int ks = 0; ks < 5; ++ks) {
+          uint32_t af[4];
+          const int e0 = ks * 16 + 2 * q;
+          const bool chk_c = ks == 0 || ks == 4;
+          af[0] = skew2(g, e0, chk_c, chk_d); af[1] = skew2(g + 8, e0, chk_c, chk_d);
+          af[2] = skew2(g, e0 + 8, chk_c, chk_d); af[3] = skew2(g + 8, e0 + 8, chk_c, chk_d);
+          const int kr = min(k0 + ks * 16 + (mi & 1) * 8 + ri, er_rows - 1);
 #pragma unroll
-        for (int ntp = 0; ntp < 4; ++ntp) {
-          uint32_t x0, x1, x2, x3;
-          ldsm_x4_t(sEr + kr * TP + (2 * ntp + (mi >> 1)) * 8, x0, x1, x2, x3);
-          mma16816(dq[2 * ntp], af, x0, x1);
-          mma16816(dq[2 * ntp + 1], af, x2, x3);
+          for (int ntp = 0; ntp < 4; ++ntp) {
+            uint32_t x0, x1, x2, x3;
+            ldsm_x4_t(sEr + kr * TP + (2 * ntp + (mi >> 1)) * 8, x0, x1, x2, x3);
+            mma16816(dq[2 * ntp], af, x0, x1);
+            mma16816(dq[2 * ntp + 1], af, x2, x3);
+          }
         }
-      }
+      };
+      if (dhi >= 79) band(false); else band(true);
     }
     __syncthreads();                                       // everyone is done with this buffer before the next tile lands in it
   }
