@@ -28,7 +28,9 @@ template <int BN> struct GemmCfg {
   static constexpr int kBBytes = BN * GK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;      // two accumulator stages
-  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kBarBytes = 1024;        // barriers + TMEM slot (keeps the staging buffers 1024-byte aligned)
+  static constexpr int kStoreBytes = 8 * 2 * 2048;   // per epilogue warp: two 32 x 32 bf16 boxes on their way out through TMA
+  static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + kBarBytes + kStoreBytes;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -61,6 +63,21 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, long lo
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
+  return kOk;
+}
+
+// Store-side map of a bf16 row-major [rows, cols] matrix: box = 32 rows x 32 columns (64-byte rows, 64B swizzle).
+static int make_tmap_store_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return kCudaError; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(store) failed (%d)", (int)r); return kCudaError; }
   return kOk;
 }
 
@@ -97,7 +114,10 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
                     int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split,
-                    const int* __restrict__ tile_group) {
+                    const int* __restrict__ tile_group, const __grid_constant__ CUtensorMap tmC, int tma_out) {
+  // tma_out: plain bf16 row-major C with 16-byte aligned rows.  Each epilogue warp packs its 32 x 32 chunk into a private
+  // swizzled shared-memory box and one lane hands it to the TMA engine: the per-thread row stores (32 rows x 16 B per
+  // instruction) were 40 % of the time of a K = 512 GEMM.
   // tile_group != null: grouped (ragged) GEMM for the MoE experts.  Rows of A are expert-contiguous with every group
   // starting on a 128-row boundary; tile_group[m_blk] names the group of a row tile (-1: unused tile, skipped by all three
   // roles), whose weights are rows [g*N, (g+1)*N) of the stacked W and whose bias is ep.bias + g*N.
@@ -120,6 +140,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (tma_out) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
@@ -201,6 +222,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================= epilogue: 8 warps, two per TMEM lane quadrant, alternating 32-column chunks ============
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;          // which chunks of the tile this warp drains
+    unsigned char* stage = smem + (size_t)Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 4) * 4096;
+    uint32_t n_store = 0;                      // boxes this warp has sent (selects the staging buffer)
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int tile = item / k_split;
@@ -248,7 +271,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int q = 0; q < 4; ++q) res_cur[q] = res_nx[q];
         fetch_res(c + 2, res_nx);
         tmem_ld_wait();
-        if (!row_ok || n0 >= N) continue;
+        const bool tma_chunk = tma_out && fast;                // warp-uniform
+        if ((!row_ok && !tma_chunk) || n0 >= N) continue;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -261,6 +285,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (vec_ok && n0 + 32 <= N) {
           // ---- fast path: whole chunk in range, every pointer 16-byte aligned -> 128-bit loads / stores only
+          if (row_ok) {                                          // rows past M only exist on the TMA-store path (clipped there)
           if (bias) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -305,8 +330,29 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               }
             }
           }
+          }
           const long long o = epi_out_index(ep, m, n0, ldc);     // 32 columns never straddle a head (dh % 32 == 0)
-          if (out_bf16) {
+          if (tma_chunk) {
+            unsigned char* buf = stage + (n_store & 1) * 2048;
+            if (lane == 0) tma_store_wait_read<1>();             // the box sent two chunks ago has left this buffer
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                        // row = lane, 16-byte chunk q at its 64B-swizzled place
+              uint4 pk;
+              pk.x = f2_to_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+              pk.y = f2_to_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+              pk.z = f2_to_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+              pk.w = f2_to_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pk;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmC, buf, n0, m_blk * GM + quad * 32);   // rows >= M are clipped by the tensor map
+              tma_store_commit();
+            }
+            ++n_store;
+          } else if (out_bf16) {
             uint4* dst = reinterpret_cast<uint4*>(static_cast<bf16*>(C) + o);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -348,6 +394,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(tempty_bar + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (tma_out && lane == 0) tma_store_wait_read<0>();      // shared memory must outlive the reads of the last boxes
   }
   tc_fence_before();
   __syncthreads();
@@ -357,6 +404,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
                        const GemmEpilogue& ep, cudaStream_t stream, bool allow_split, const int* tile_group = nullptr) {
+  // TMA-store epilogue for plain bf16 outputs (the store map only exists in that case; otherwise it aliases tmA, unused)
+  CUtensorMap tmC = tmA;
+  int tma_out = 0;
+  if (out_bf16 && vec_ok && !ep.head_scatter && make_tmap_store_bf16(&tmC, C, M, N, ldc) == kOk) tma_out = 1;
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -384,7 +435,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   }
   const int items = tiles * k_split;
   const int grid = items < num_sms ? items : num_sms;
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split, tile_group);
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out);
   return check_launch("gemm_bf16_tc");
 }
 
