@@ -125,6 +125,11 @@ int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld
                   void* stream);
 /* 0.4*CrossEntropy(label_smoothing, ignore_index) + 0.6*BCEWithLogits (run_model_vevo.py:101-119, train.py:222,233):
  * scratch3 = [sum CE over valid rows, sum BCE over elements, #valid rows]; dlogits = d(total loss)/d(logits).      */
+/* Evaluation metrics, dataset/vevo_dataset.py:653-701 (compute_vevo_accuracy, compute_hits_k) for a whole batch in one
+ * launch: counters[5] (int32, device) = {rows with tgt != pad, argmax hits, hits@k0, hits@k1, hits@k2}; ties go to the
+ * lower class index. */
+int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t Cn, int64_t pad, int32_t k0, int32_t k1, int32_t k2,
+                    int32_t* counters, void* stream);
 int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
                  float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream);
 /* torch.optim.Adam step on flat fp32 buffers (train.py:238). grad_scale multiplies g first (1/world_size after all-reduce). */

@@ -532,3 +532,49 @@ def bimamba_layer_forward(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, 
     x_b = ln("norm3", x_b + x)
     x_b = ln("norm4", ffn("ffn2", x_f) + x_b)
     return x_f + x_b
+
+
+def bimamba_v1_layer_forward(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, dt_rank: int, norm_first: bool,
+                             moe: Optional[dict] = None, d_state: int = 16) -> torch.Tensor:
+    """BiMambaEncoderLayer_V1.forward (bimamba.py:136-191), eval mode.  moe = dict(n_experts, k, shared) when the
+    feed-forward is a (Shared)MoELayer, None for Linear-ReLU-Linear (`ffn.0`, `ffn.3`)."""
+    mb = lambda name, t: mamba_block_forward(sd, p + name + ".", t, dt_rank, d_state, use_version=1)
+    ln = lambda name, t: F.layer_norm(t, (t.shape[-1],), sd[p + name + ".weight"], sd[p + name + ".bias"], 1e-5)
+
+    def ffn(t):
+        if moe is None:
+            h = F.relu(F.linear(t, sd[p + "ffn.0.weight"], sd[p + "ffn.0.bias"]))
+            return F.linear(h, sd[p + "ffn.3.weight"], sd[p + "ffn.3.bias"])
+        return moe_layer(t, sd, p + "ffn.", moe["n_experts"], moe["k"], shared=moe["shared"])[0]
+    x_flip = torch.flip(x, dims=[1])
+    if norm_first:
+        x_f = x + mb("mamba_forward", ln("norm1", x))
+        x_b = x + torch.flip(mb("mamba_backward", ln("norm2", x_flip)), dims=[1])
+        x = x_f + x_b
+        return x + ffn(ln("norm3", x))
+    x_f = ln("norm1", mb("mamba_forward", x) + x)
+    x_b = ln("norm2", torch.flip(mb("mamba_backward", x_flip), dims=[1]) + x)
+    x = x_f + x_b
+    return ln("norm3", ffn(x) + x)
+
+
+# --------------------------------------------------------------------------
+# Evaluation metrics (dataset/vevo_dataset.py)
+# --------------------------------------------------------------------------
+def vevo_accuracy(out: torch.Tensor, tgt: torch.Tensor, pad: int = 158) -> float:
+    """compute_vevo_accuracy, vevo_dataset.py:653-673."""
+    pred = torch.argmax(torch.softmax(out, dim=-1), dim=-1).flatten()
+    t = tgt.flatten()
+    m = t != pad
+    if int(m.sum()) == 0:
+        return 1.0
+    return float((pred[m] == t[m]).sum()) / int(m.sum())
+
+
+def hits_k(out: torch.Tensor, tgt: torch.Tensor, k: int, pad: int = 158) -> float:
+    """compute_hits_k, vevo_dataset.py:675-701 (vectorised: target among the top-k classes of each non-pad row)."""
+    top = torch.topk(torch.softmax(out, dim=-1), k, dim=-1).indices.reshape(-1, k)
+    t = tgt.flatten()
+    m = t != pad
+    hit = (top == t.unsqueeze(1)).any(dim=1) & m
+    return float(hit.sum()) / max(int(m.sum()), 1)

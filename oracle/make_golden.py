@@ -279,6 +279,24 @@ def golden_variant(ref):
     _save("variant.pt", out)
 
 
+def golden_metrics(ref):
+    """compute_vevo_accuracy / compute_hits_k of the reference (dataset/vevo_dataset.py:653-701) on seeded logits."""
+    import importlib
+    with reference_cwd():
+        vd = importlib.import_module("dataset.vevo_dataset")
+    cases = []
+    for seed, pad_from in ((71, 299), (72, 200), (73, 0)):
+        g = syn._gen(seed, "metrics")
+        out = syn.unit_uniform((1, 299, 159), g) * 3.0
+        tgt = (torch.rand((1, 299), generator=g) * 157).long()
+        out[0, torch.arange(0, 299, 3), tgt[0, ::3]] += 4.0            # make a third of the rows correct
+        tgt[0, pad_from:] = 158
+        acc = vd.compute_vevo_accuracy(out, tgt)
+        cases.append(dict(seed=seed, pad_from=pad_from, acc=float(acc), hits=[float(vd.compute_hits_k(out, tgt, k)) if pad_from > 0 else None
+                                                                            for k in (1, 3, 5)]))
+    _save("metrics.pt", dict(cases=cases))
+
+
 def golden_pscan(ref):
     """pscan forward/backward (pscan.py:154-226) incl. a non power-of-two length."""
     cases = []
@@ -326,6 +344,19 @@ def golden_mamba(ref):
     with torch.no_grad():
         y = m(x)
     out["bimamba_layer"] = dict(spec=spec, weights_checksum=syn.checksum(sd), y=y.clone())
+    # Bi-Mamba+ layers (bimamba.py:101-191): plain FFN post-norm, MoE feed-forward norm_first
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    for name, norm_first, use_moe in (("bimamba_v1_ffn", False, False), ("bimamba_v1_moe", True, True)):
+        cfg = ref.mamba.MambaConfig(d_model=128, n_layers=1, use_version=1)
+        moe = ref.moe.MoELayer(ref.moe.GLUExpert(128, 256, 0.0), 128, n_experts=6, n_experts_per_token=2, dropout=0.0) if use_moe else None
+        m = ref.bimamba.BiMambaEncoderLayer_V1(cfg, dim_feedforward=256, dropout=0.2, moe_layer=moe, norm_first=norm_first).eval()
+        sd = _load_weights(m, 25 + use_moe)
+        spec = dict(B=2, L=150, d_model=128, d_ff=256, seed=35 + use_moe, weight_seed=25 + use_moe, norm_first=norm_first, moe=use_moe)
+        x = syn.unit_uniform((spec["B"], spec["L"], 128), syn._gen(spec["seed"], "x"))
+        with torch.no_grad():
+            y = m(x)
+        out[name] = dict(spec=spec, weights_checksum=syn.checksum(sd), y=y.clone())
     _save("mamba.pt", out)
 
 
@@ -339,7 +370,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref),
+                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

@@ -456,6 +456,9 @@ def test_gqa_golden_gpu():
 
 
 # ---------------------------------------------------------------- Mamba block (fused selective scan)
+from test_oracle import _bimamba_v1  # noqa: E402
+
+
 def test_mamba_golden_gpu():
     """MambaBlock (both versions), the 2-layer stack and the BiMamba layer on the GPU kernels vs the reference's outputs."""
     from video2music_b200.mamba import MambaConfig, MambaBlock, Mamba, BiMambaEncoderLayer
@@ -463,7 +466,8 @@ def test_mamba_golden_gpu():
     cases = [("block_v0", lambda s: MambaBlock(MambaConfig(d_model=128, n_layers=1, use_version=0))),
              ("block_v1", lambda s: MambaBlock(MambaConfig(d_model=128, n_layers=1, use_version=1))),
              ("stack", lambda s: Mamba(MambaConfig(d_model=128, n_layers=2))),
-             ("bimamba_layer", lambda s: BiMambaEncoderLayer(MambaConfig(d_model=128, n_layers=1), dim_feedforward=s["d_ff"]))]
+             ("bimamba_layer", lambda s: BiMambaEncoderLayer(MambaConfig(d_model=128, n_layers=1), dim_feedforward=s["d_ff"])),
+             ("bimamba_v1_ffn", _bimamba_v1), ("bimamba_v1_moe", _bimamba_v1)]       # Bi-Mamba+ (bimamba.py:101-191)
     for name, make in cases:
         c = g[name]
         s = c["spec"]
@@ -503,3 +507,25 @@ def test_selective_scan_fused_equals_pscan_composition(B, L):
     hs = ops.pscan_fwd(dA, BX)
     ref = (hs * bc[:, N:].view(B, L, 1, N)).sum(-1) + D * xs
     assert rel_err(y.view(B, L, ED), ref) < 2e-5
+
+
+# ---------------------------------------------------------------- evaluation metrics
+def test_amt_metrics_kernel_vs_reference_golden_and_oracle():
+    from test_oracle import _metrics_case
+    from video2music_b200 import ops
+    for c in load_golden("metrics.pt")["cases"]:
+        out, tgt = _metrics_case(c)
+        cnt = ops.amt_metrics(out.to(DEV), tgt.to(DEV)).tolist()
+        n_valid = int((tgt != 158).sum())
+        assert cnt[0] == n_valid
+        if n_valid == 0:
+            continue
+        assert abs(cnt[1] / n_valid - c["acc"]) < 1e-6
+        for i, h in enumerate(c["hits"]):
+            assert abs(cnt[2 + i] / n_valid - h) < 1e-6
+    # a batch with exact ties: the lower class index wins, as torch.argmax / topk on equal values
+    out = torch.zeros((2, 7, 159))
+    tgt = torch.tensor([[0, 1, 2, 3, 4, 158, 158], [158, 0, 0, 0, 0, 0, 5]])
+    cnt = ops.amt_metrics(out.to(DEV), tgt.to(DEV), ks=(1, 3, 5)).tolist()
+    assert cnt == [11, 6, 6, 8, 10]
+    assert abs(O.vevo_accuracy(out, tgt) - 6 / 11) < 1e-6

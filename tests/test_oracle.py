@@ -172,6 +172,13 @@ def _mamba_sd(shapes, seed):
     return syn.fill_like_reference_init(shapes, seed=seed)
 
 
+def _bimamba_v1(s):
+    from video2music_b200 import BiMambaEncoderLayer_V1, GLUExpert, MambaConfig, MoELayer
+    moe = MoELayer(GLUExpert(128, 256, 0.0), 128, n_experts=6, n_experts_per_token=2, dropout=0.0) if s["moe"] else None
+    return BiMambaEncoderLayer_V1(MambaConfig(d_model=128, n_layers=1, use_version=1), dim_feedforward=s["d_ff"], moe_layer=moe,
+                                  norm_first=s["norm_first"])
+
+
 def test_mamba_oracle_matches_reference_golden():
     """oracle Mamba restatement (mamba.py:259-351, bimamba.py:64-99) vs outputs of the unmodified reference."""
     from video2music_b200.mamba import MambaConfig, MambaBlock, Mamba, BiMambaEncoderLayer
@@ -199,3 +206,31 @@ def test_mamba_oracle_matches_reference_golden():
     assert same_checksum(syn.checksum(sd), c["weights_checksum"])
     x = syn.unit_uniform((s["B"], s["L"], 128), syn._gen(s["seed"], "x"))
     assert rel_err(O.bimamba_layer_forward(sd, "", x, dt_rank=8), c["y"]) < 2e-5
+    for name in ("bimamba_v1_ffn", "bimamba_v1_moe"):
+        c = g[name]
+        s = c["spec"]
+        m = _bimamba_v1(s)
+        sd = _mamba_sd({k: tuple(v.shape) for k, v in m.state_dict().items()}, s["weight_seed"])
+        assert same_checksum(syn.checksum(sd), c["weights_checksum"])
+        x = syn.unit_uniform((s["B"], s["L"], 128), syn._gen(s["seed"], "x"))
+        y = O.bimamba_v1_layer_forward(sd, "", x, 8, s["norm_first"], dict(n_experts=6, k=2, shared=False) if s["moe"] else None)
+        assert rel_err(y, c["y"]) < 2e-5, name
+
+
+def _metrics_case(c):
+    g = syn._gen(c["seed"], "metrics")
+    out = syn.unit_uniform((1, 299, 159), g) * 3.0
+    tgt = (torch.rand((1, 299), generator=g) * 157).long()
+    out[0, torch.arange(0, 299, 3), tgt[0, ::3]] += 4.0
+    tgt[0, c["pad_from"]:] = 158
+    return out, tgt
+
+
+def test_metrics_oracle_matches_reference_golden():
+    """compute_vevo_accuracy / compute_hits_k (dataset/vevo_dataset.py:653-701) restated vs the reference's values."""
+    for c in load_golden("metrics.pt")["cases"]:
+        out, tgt = _metrics_case(c)
+        assert abs(O.vevo_accuracy(out, tgt) - c["acc"]) < 1e-6
+        for k, h in zip((1, 3, 5), c["hits"]):
+            if h is not None:
+                assert abs(O.hits_k(out, tgt, k) - h) < 1e-6

@@ -144,6 +144,11 @@ int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld
   return embed_bwd(reinterpret_cast<const long long*>(idx), d, d_dtype, ld_d, dtable, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t Cn, int64_t pad, int32_t k0, int32_t k1, int32_t k2,
+                    int32_t* counters, void* stream) {
+  return amt_metrics(logits, reinterpret_cast<const long long*>(tgt), R, Cn, pad, k0, k1, k2, counters, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
                  float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream) {
   return amt_loss(logits, reinterpret_cast<const long long*>(tgt), tgt_emotion, R, Cn, ignore, smooth, w_ce, w_bce, scratch3,

@@ -196,4 +196,8 @@ int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, 
                      cudaStream_t stream);
 int moe_combine(const float* yp, const int* perm, const float* w, float* out, int tokens, int k, int d, cudaStream_t stream);
 
+// accuracy / hits@k counters of the evaluation loop (train.cu)
+int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long long pad, int k0, int k1, int k2, int* counters,
+                cudaStream_t stream);
+
 }  // namespace v2m

@@ -397,4 +397,42 @@ int adam_step(float* p, const float* g, float* m, float* v, long long n, float l
   return check_launch("adam_step");
 }
 
+// Evaluation metrics of the run loop (dataset/vevo_dataset.py:653-701: compute_vevo_accuracy, compute_hits_k), which the
+// reference evaluates with a Python loop and one .item() per token: one warp per (video, position) row ranks the target's
+// logit (softmax is monotonic, so logits are ranked directly).  rank = number of classes that beat the target, with the
+// lower index winning ties (the order torch.argmax / torch.topk return on equal values).  Padded targets are skipped.
+// counters: [0] valid rows, [1] rank == 0 (accuracy), [2 + i] rank < ks[i] (hits@k), int32, zeroed here.
+__global__ void __launch_bounds__(256) amt_metrics_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt, int R,
+                                                          int Cn, long long pad, int k0, int k1, int k2, int* __restrict__ counters) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const long long t = tgt[row];
+  if (t == pad || t < 0 || t >= Cn) return;
+  const float* lr = logits + (long long)row * Cn;
+  const float lt = lr[t];
+  int beat = 0;
+  for (int c = lane; c < Cn; c += 32) {
+    const float v = lr[c];
+    beat += (v > lt || (v == lt && c < (int)t)) ? 1 : 0;
+  }
+  beat = warp_sum_int(beat);
+  if (lane == 0) {
+    atomicAdd(counters + 0, 1);
+    if (beat == 0) atomicAdd(counters + 1, 1);
+    if (beat < k0) atomicAdd(counters + 2, 1);
+    if (beat < k1) atomicAdd(counters + 3, 1);
+    if (beat < k2) atomicAdd(counters + 4, 1);
+  }
+}
+
+int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long long pad, int k0, int k1, int k2, int* counters,
+                cudaStream_t stream) {
+  V2M_REQUIRE(R >= 0 && Cn > 0 && counters, "amt_metrics: bad arguments");
+  cudaError_t e = cudaMemsetAsync(counters, 0, 5 * sizeof(int), stream);
+  if (e != cudaSuccess) { set_last_error("amt_metrics: %s", cudaGetErrorString(e)); return kCudaError; }
+  if (R == 0) return kOk;
+  amt_metrics_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, tgt, R, Cn, pad, k0, k1, k2, counters);
+  return check_launch("amt_metrics");
+}
+
 }  // namespace v2m

@@ -11,6 +11,8 @@ import math
 from dataclasses import dataclass
 from typing import Union
 
+import copy
+
 import torch
 import torch.nn as nn
 
@@ -191,13 +193,56 @@ class BiMambaEncoderLayer(nn.Module):
         return ops.axpy(x_f.contiguous(), x_b.contiguous(), 1.0)
 
 
+def _norm_only(norm: nn.LayerNorm, a):
+    shp = a.shape
+    return ops.layernorm(a.reshape(-1, shp[-1]).contiguous(), norm.weight.detach(), norm.bias.detach(), eps=norm.eps).view(shp)
+
+
+class BiMambaEncoderLayer_V1(nn.Module):
+    """Bi-Mamba+ layer, bimamba.py:101-191: two mamba+ blocks (forward / flipped sequence), one feed-forward that is either
+    Linear-ReLU-Linear or a deep copy of the caller's MoE layer, post-norm or norm_first."""
+
+    def __init__(self, config: MambaConfig, dim_feedforward=1024, dropout=0.2, moe_layer=None, norm_first=False):
+        super().__init__()
+        assert config.use_version == 1, "use_version should be 1 to use Mamba+"
+        self.config = config
+        self.mamba_forward = MambaBlock(config)
+        self.mamba_backward = MambaBlock(config)
+        self.d_ff = dim_feedforward
+        self.dropout = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(config.d_model)
+        self.norm2 = nn.LayerNorm(config.d_model)
+        self.norm3 = nn.LayerNorm(config.d_model)
+        self.norm_first = norm_first
+        self.ffn = _FFN(config.d_model, dim_feedforward, dropout) if moe_layer is None else copy.deepcopy(moe_layer)
+
+    def forward(self, x):
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not built; use eval() or dropout=0")
+        _no_grad_only(x)
+        x = x.float().contiguous()
+        x_flip = torch.flip(x, dims=[1])
+        if self.norm_first:                                                      # bimamba.py:141-165
+            x_f = ops.axpy(x, self.mamba_forward(_norm_only(self.norm1, x)).contiguous(), 1.0)
+            x_b = torch.flip(self.mamba_backward(_norm_only(self.norm2, x_flip)), dims=[1]).contiguous()
+            x_b = ops.axpy(x, x_b, 1.0)
+            x = ops.axpy(x_f, x_b, 1.0)
+            return ops.axpy(x, self.ffn(_norm_only(self.norm3, x)).float().contiguous(), 1.0)
+        x_f = _add_norm(self.norm1, self.mamba_forward(x), x)                    # :168-189
+        x_b = _add_norm(self.norm2, torch.flip(self.mamba_backward(x_flip), dims=[1]), x)
+        x = ops.axpy(x_f.contiguous(), x_b.contiguous(), 1.0)
+        return _add_norm(self.norm3, self.ffn(x).float(), x)
+
+
 class BiMambaEncoder(nn.Module):
     def __init__(self, config: MambaConfig, dim_feedforward=1024, n_encoder_layers=2, dropout=0.2, moe_layer=None, norm_first=False):
         super().__init__()
-        if config.use_version != 0:
-            raise NotImplementedError("BiMambaEncoderLayer_V1 (mamba+ with MoE, bimamba.py:101-191) is not built yet")
         self.n_encoder_layers = n_encoder_layers
-        self.layers = nn.ModuleList([BiMambaEncoderLayer(config, dim_feedforward, dropout) for _ in range(n_encoder_layers)])
+        if config.use_version == 0:                                              # bimamba.py:15-19
+            self.layers = nn.ModuleList([BiMambaEncoderLayer(config, dim_feedforward, dropout) for _ in range(n_encoder_layers)])
+        else:
+            self.layers = nn.ModuleList([BiMambaEncoderLayer_V1(config, dim_feedforward, dropout, moe_layer=moe_layer,
+                                                                norm_first=norm_first) for _ in range(n_encoder_layers)])
         self.norm_first = norm_first
         if norm_first:
             self.norm = nn.LayerNorm(config.d_model)

@@ -379,6 +379,21 @@ def amt_loss(logits: torch.Tensor, tgt: torch.Tensor, tgt_emotion: torch.Tensor,
     return scratch, dl
 
 
+def amt_metrics(logits: torch.Tensor, tgt: torch.Tensor, pad: int = 158, ks=(1, 3, 5)) -> torch.Tensor:
+    """int32 device counters [valid, argmax hits, hits@ks[0], hits@ks[1], hits@ks[2]] over all (video, position) rows
+    (compute_vevo_accuracy / compute_hits_k, dataset/vevo_dataset.py:653-701); accuracy = c[1] / c[0], hits@k = c[2+i] / c[0]."""
+    require_device(logits)
+    logits = logits.float().contiguous()
+    Cn = logits.shape[-1]
+    R = logits.numel() // Cn
+    tgt = tgt.contiguous().view(-1)
+    assert tgt.numel() == R and tgt.dtype == torch.int64 and len(ks) == 3
+    counters = torch.empty((5,), device=logits.device, dtype=torch.int32)
+    check(load().v2m_amt_metrics(ptr(logits), ptr(tgt), R, Cn, pad, int(ks[0]), int(ks[1]), int(ks[2]), ptr(counters), stream()))
+    _lib.count_launches(1)
+    return counters
+
+
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, b1: float, b2: float, eps: float,
               step: int, grad_scale: float = 1.0) -> None:
     require_device(p)
