@@ -29,7 +29,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 BATCH = 64                 # videos per GPU (BASELINE config 2)
-TRAIN_GLOBAL_BATCH = 512   # BASELINE config 3 (split over the ranks: strong scaling)
+TRAIN_GLOBAL_BATCH = 512
+TRAIN_DROPOUT = 0.1            # argument_funcs.py default of train.py; all dropout sites run fused in the bf16 kernels   # BASELINE config 3 (split over the ranks: strong scaling)
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture, per launch)
 NCU_TRAFFIC_BYTES = {"stream": 122944729000 + 286507008}   # profiles/r01_decode_stream_ncu_full_details.txt (ncu --set full, per launch)
 SEQ = 300                  # target_seq_length -> 299 generated chord tokens per video
@@ -109,7 +110,7 @@ def train_leg(args, dev, rank, world, dtype):
     from video2music_b200 import VideoMusicTransformer, _lib
     from video2music_b200 import synthetic as syn
     from video2music_b200.trainer import Trainer, shard_range
-    m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0)
+    m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=TRAIN_DROPOUT)     # the reference's training default
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     m.load_state_dict(syn.fill_like_reference_init(shapes, seed=1), strict=False)
     m = m.to(dev).train().set_compute_dtype(dtype)
@@ -141,7 +142,7 @@ def train_leg(args, dev, rank, world, dtype):
         ms = float(t[0])
     flops = 69.4e9 * TRAIN_GLOBAL_BATCH                 # 3 x 23.14 GF per sample
     return {"metric": "train_samples_per_s", "value": TRAIN_GLOBAL_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
-            "global_batch": TRAIN_GLOBAL_BATCH, "per_gpu_batch": b1 - b0, "scaling": "strong", "steps": args.train_steps,
+            "global_batch": TRAIN_GLOBAL_BATCH, "per_gpu_batch": b1 - b0, "dropout": TRAIN_DROPOUT, "scaling": "strong", "steps": args.train_steps,
             "loss": lossv, "tflops": flops / (ms * 1e-3) / 1e12, "launches_per_step": _lib.launches() // args.train_steps,
             "collective": "NCCL all-reduce of the flat fp32 gradient buffer (130 MB)" if world > 1 else "none (1 rank)",
             "timed": "e2e: every step copies its batch from pinned host memory (side stream, overlapped with the previous step), loss read back at the end",

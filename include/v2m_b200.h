@@ -61,6 +61,13 @@ typedef struct v2m_epilogue {
   int32_t residual_bf16;
   int32_t head_scatter, S, H, dh, cap, pos0;
   int64_t part_stride;
+  /* Training-time inverted dropout fused into the epilogue (nn.Dropout after a linear layer, rpr.py:58-69 and the stock
+   * encoder layer; PositionalEncoding dropout, positional_encoding.py:21-23).  drop_scale = 1/(1-p), 0 = off; element (m, n)
+   * is kept iff mix(drop_seed, m, n) >= drop_thresh = p * 2^32 (stateless: v2m_dy_prep recomputes the same mask);
+   * drop_after_res: y = drop(acc + residual) instead of drop(acc) + residual.  bf16 tensor-core path only. */
+  float drop_scale;
+  uint32_t drop_thresh, drop_seed;
+  int32_t drop_after_res;
 } v2m_epilogue;
 
 /* fp32 SIMT GEMM (exact path, batch-invariant summation order). */
@@ -90,6 +97,7 @@ typedef struct v2m_attn {
   const void* Er; int32_t er_len;
   float q_scale;
   float* lse; float* p_out;
+  float drop_scale; uint32_t drop_thresh, drop_seed;   /* dropout of the probabilities (training, bf16 path): see v2m_epilogue */
 } v2m_attn;
 int v2m_attn_fwd(const v2m_attn* p, int32_t dtype, void* stream);
 
@@ -107,6 +115,7 @@ typedef struct v2m_attn_bwd_t {
   int64_t q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl, do_sb, do_sl, dq_sb, dq_sl, dkv_sb, dkv_sl;
   int32_t B, Hq, Hkv, Lq, Lk, dh, causal, er_len, dtype;
   float q_scale;
+  float drop_scale; uint32_t drop_thresh, drop_seed;   /* the forward's probability dropout (v2m_attn_bwd_tc only) */
 } v2m_attn_bwd_t;
 int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);
 /* Tensor-core attention backward (bf16, head_dim 64, q pre-scaled: q_scale must be 1): same gradients as v2m_attn_bwd from
@@ -115,10 +124,11 @@ int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);
  * ws: v2m_attn_bwd_tc_workspace(B, Hq, Lq, Lk, has_er) bytes of device scratch (P, dS and skewed dS tiles, bf16). */
 int64_t v2m_attn_bwd_tc_workspace(int32_t B, int32_t Hq, int32_t Lq, int32_t Lk, int32_t has_er);
 int v2m_attn_bwd_tc(const v2m_attn_bwd_t* a, void* ws, int64_t ws_bytes, void* stream);
-/* dz = dy * relu'(y) * (n < alpha_cols ? alpha : 1), db[n] += sum_m dz[m][n]: gradient of the fused linear epilogue. */
+/* dz = dy * relu'(y) * (n < alpha_cols ? alpha : 1) * dropmask(m, n), db[n] += sum_m dz[m][n]: gradient of the fused linear
+ * epilogue (drop_scale = 0: no dropout; otherwise the mask of v2m_epilogue with the same seed / threshold). */
 int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
                 float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
-                void* stream);
+                float drop_scale, uint32_t drop_thresh, uint32_t drop_seed, void* stream);
 int v2m_layernorm_bwd(const void* x, int32_t x_dtype, const float* gamma, const void* dy, int32_t dy_dtype, void* dx,
                       int32_t dx_dtype, float* dgamma, float* dbeta, int32_t M, int32_t D, float eps, void* stream);
 int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld_d, float* dtable, int32_t rows, int32_t D,

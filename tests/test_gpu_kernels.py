@@ -529,3 +529,102 @@ def test_amt_metrics_kernel_vs_reference_golden_and_oracle():
     cnt = ops.amt_metrics(out.to(DEV), tgt.to(DEV), ks=(1, 3, 5)).tolist()
     assert cnt == [11, 6, 6, 8, 10]
     assert abs(O.vevo_accuracy(out, tgt) - 6 / 11) < 1e-6
+
+
+# ---------------------------------------------------------------- fused dropout (training)
+def test_linear_fused_dropout_forward_backward():
+    """Dropout fused into the GEMM epilogue (both placements) and re-derived by dy_prep in backward, against torch with the
+    SAME mask (read back through a GEMM with zero weights and unit bias)."""
+    from video2music_b200 import ops
+    from video2music_b200.autograd import LinearFn
+    bf = torch.bfloat16
+    M, K, N, pdrop, seed = 333, 512, 384, 0.1, 12345
+    x = _u((M, K), 41, "x").to(bf)
+    w = (_u((N, K), 41, "w") * 0.05).to(bf)
+    b = _u((N,), 41, "b") * 0.1
+    r = _u((M, N), 41, "r").to(bf)
+    dy = _u((M, N), 41, "dy").to(bf)
+    xd, wd, bd, rd = x.to(DEV), w.to(DEV), b.to(DEV), r.to(DEV)
+    ones = torch.ones((N,), device=DEV)
+    m1 = ops.linear(torch.zeros_like(xd), wd, ones, dropout=(pdrop, seed, False)).float().cpu()
+    mask = (m1 > 0).float()
+    keep = float(mask.mean())
+    assert abs(keep - (1 - pdrop)) < 0.01 and torch.allclose(m1[m1 > 0], torch.tensor(1 / (1 - pdrop)), rtol=1e-2)
+    m2 = ops.linear(torch.zeros_like(xd), wd, ones, dropout=(pdrop, seed, False)).float().cpu()
+    m3 = ops.linear(torch.zeros_like(xd), wd, ones, dropout=(pdrop, seed + 1, False)).float().cpu()
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    scale = 1 / (1 - pdrop)
+    # the three placements of the model: sub-layer output before the residual add, FFN hidden layer (ReLU, no residual),
+    # positional-encoding dropout after the (constant) residual
+    for after_res, relu, with_res in ((False, False, True), (False, True, False), (True, False, True)):
+        xf, wf, bfp, rf = (t.float().clone().requires_grad_(True) for t in (x, w, b, r))    # fresh leaves every case
+        z = xf @ wf.t() + bfp
+        if relu:
+            z = torch.relu(z)
+        rterm = rf if with_res else 0.0
+        ref = (z + rterm) * mask * scale if after_res else z * mask * scale + rterm
+        ref.backward(dy.float())
+        xg, wg, bg, rg = (t.detach().clone().requires_grad_(True) for t in (xd, wd.float(), bd, rd))
+        res = None if not with_res else (rd if after_res else rg)
+        y = LinearFn.apply(xg, wg, bg, wd, K, relu, 1.0, 0, res, 0, bf, (pdrop, seed, after_res))
+        assert rel_err(y.float(), ref) < 2e-2
+        y.backward(dy.to(DEV))
+        assert rel_err(xg.grad.float(), xf.grad) < 2e-2 and rel_err(wg.grad, wf.grad) < 2e-2 and rel_err(bg.grad, bfp.grad) < 2e-2
+        if with_res and not after_res:
+            assert rel_err(rg.grad.float(), rf.grad) < 2e-2
+
+
+@pytest.mark.parametrize("L,S,er_len,causal", [(150, 150, 160, True), (99, 140, 0, False)])
+def test_attention_probability_dropout_forward_backward(L, S, er_len, causal):
+    """Dropout of the attention probabilities inside the fused forward kernel and the backward rows kernel, against torch
+    autograd with the SAME mask (recovered by attending with q = k = 0 over one-hot V blocks)."""
+    from video2music_b200 import ops
+    B, H, dh, bf, pdrop, seed = 2, 4, 64, torch.bfloat16, 0.1, 777
+    scale = 1 / (1 - pdrop)
+    q = (_u((B, L, H, dh), 51, "q") * 0.3).to(bf)
+    k, v = _u((B, S, H, dh), 51, "k").to(bf), _u((B, S, H, dh), 51, "v").to(bf)
+    dO = _u((B, L, H, dh), 51, "do").to(bf)
+    Er = _u((er_len, dh), 51, "er").to(bf) if er_len else None
+    qs, ks = (L * H * dh, H * dh), (S * H * dh, H * dh)
+
+    def fwd(qq, kk, vv, er, lse=None):
+        out = torch.zeros((B, L, H, dh), device=DEV, dtype=bf)
+        ops.attention(qq, kk, vv, out, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=qs, k_strides=ks, v_strides=ks, o_strides=qs,
+                      causal=causal, Er=er, lse=lse, dropout=(pdrop, seed))
+        return out
+    # mask recovery: uniform probabilities, V = one-hot column blocks
+    mask = torch.zeros((B, H, L, S))
+    z_q, z_k = torch.zeros_like(q).to(DEV), torch.zeros_like(k).to(DEV)
+    for blk in range((S + dh - 1) // dh):
+        vv = torch.zeros((B, S, H, dh))
+        for d in range(dh):
+            if blk * dh + d < S:
+                vv[:, blk * dh + d, :, d] = 1.0
+        o = fwd(z_q, z_k, vv.to(bf).to(DEV), None).float().cpu()        # (B, L, H, dh): P_drop[i, blk*dh + d]
+        n = min(dh, S - blk * dh)
+        mask[:, :, :, blk * dh:blk * dh + n] = (o.permute(0, 2, 1, 3)[..., :n] > 0).float()
+    vis = torch.ones((L, S)) if not causal else torch.tril(torch.ones((L, S)), diagonal=S - L)
+    keep = float((mask * vis).sum() / (vis.sum() * B * H))
+    assert abs(keep - (1 - pdrop)) < 0.01
+    # reference with the explicit mask
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    erf = Er.float().requires_grad_(True) if er_len else None
+    _, pref = _attn_ref(qf.permute(0, 2, 1, 3), kf.permute(0, 2, 1, 3), vf.permute(0, 2, 1, 3), erf, causal)
+    ref = torch.einsum("bhls,bhsd->bhld", pref * mask * scale, vf.permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    ref.backward(dO.float())
+    qd, kd, vd, dOd = q.to(DEV), k.to(DEV), v.to(DEV), dO.to(DEV)
+    erd = Er.to(DEV) if er_len else None
+    lse = torch.zeros((B * H, L), device=DEV)
+    out = fwd(qd, kd, vd, erd, lse)
+    assert rel_err(out.float(), ref) < 2e-2
+    dq, dk, dv = torch.full_like(qd, float("nan")), torch.full_like(kd, float("nan")), torch.full_like(vd, float("nan"))
+    der = torch.zeros((er_len, dh), device=DEV) if er_len else None
+    ops.attention_bwd(qd, kd, vd, out, dOd, lse, erd, dq, dk, dv, der, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=qs,
+                      k_strides=ks, v_strides=ks, o_strides=qs, do_strides=qs, dq_strides=qs, dkv_strides=ks, causal=causal,
+                      tensor_core=True, dropout=(pdrop, seed))
+    errs = {"dq": rel_err(dq.float().cpu(), qf.grad), "dk": rel_err(dk.float().cpu(), kf.grad), "dv": rel_err(dv.float().cpu(), vf.grad)}
+    if er_len:
+        errs["dEr"] = rel_err(der.cpu(), erf.grad)
+    print("attention dropout rel errs", {n: "%.2e" % e for n, e in errs.items()})
+    for n, e in errs.items():
+        assert e < 2e-2, n

@@ -76,3 +76,40 @@ def test_train_step_bf16_close_to_reference():
         e = rel_err(params[name].grad, gref)
         print("bf16 grad %-55s rel err %.3e" % (name, e))
         assert e < 0.15, name
+
+
+def test_train_steps_with_dropout():
+    """dropout = 0.1 (the reference's default, train.py / argument_funcs.py): every nn.Dropout site of the graph runs fused in
+    the bf16 kernels.  Checks: training-mode outputs differ from eval, masks change between calls but are reproducible under
+    the same torch seed, the loss goes down over a few steps, and eval() is unaffected."""
+    import torch
+    from video2music_b200 import VideoMusicTransformer, synthetic as syn
+    from video2music_b200.trainer import Trainer
+    dev = torch.device("cuda", 0)
+
+    def make():
+        torch.manual_seed(5)
+        m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.1)
+        m.load_state_dict(syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=1), strict=False)
+        return m.to(dev).train().set_compute_dtype(torch.bfloat16)
+    inp = {k: v.to(dev) for k, v in syn.make_inputs(4, 99, 60, 40, 0).items()}
+    args = [inp[k] for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                             "feature_motion", "feature_emotion")]
+    m = make()
+    y1 = m(*args).detach()
+    y2 = m(*args).detach()
+    assert torch.isfinite(y1).all() and not torch.equal(y1, y2)          # a new mask per call
+    m_again = make()
+    assert torch.equal(m_again(*args).detach(), y1)                      # same torch seed, same call index: same masks
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(*args), m(*args)
+    assert torch.equal(e1, e2) and not torch.allclose(e1, y1, atol=1e-3)
+    m.train()
+    tr = Trainer(m, lr=1e-3)
+    losses = [float(tr.train_step(inp)) for _ in range(8)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    m32 = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.1).to(dev).train()
+    import pytest
+    with pytest.raises(NotImplementedError):
+        m32(*args)

@@ -1,7 +1,6 @@
 #!/bin/bash
-# scratch script for one gpurun call (overwritten per call)
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "mamba or metrics or moe" > gpurun_out/new_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/new_tests.log
-tail -6 gpurun_out/new_tests.log
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "dropout" > gpurun_out/drop_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/drop_tests.log
+tail -12 gpurun_out/drop_tests.log | cut -c1-300

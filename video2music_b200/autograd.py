@@ -37,14 +37,20 @@ def _gemm_dw(dz: torch.Tensor, x: torch.Tensor, K: int) -> torch.Tensor:
 
 
 class LinearFn(torch.autograd.Function):
-    """y = relu?((x @ w[:, :K].T + b) * alpha_n) + residual.   x (M, >=K) compute dtype; w, b fp32 masters."""
+    """y = drop?(relu?((x @ w[:, :K].T + b) * alpha_n)) + residual.   x (M, >=K) compute dtype; w, b fp32 masters.
+    dropout = None or (p, seed, after_residual): mask fused into the GEMM epilogue, recomputed by dy_prep in backward."""
 
     @staticmethod
-    def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype):
+    def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype, dropout=None):
+        if dropout is not None and dropout[0] <= 0.0:
+            dropout = None
+        # drop(acc + residual) is only used for the constant positional-encoding rows (no gradient flows to the residual)
+        assert not (dropout is not None and dropout[2] and residual is not None and residual.requires_grad)
         y = ops.linear(x, wc, b, k=K, relu=relu, alpha=alpha, alpha_cols=alpha_cols, residual=residual, res_mod=res_mod,
-                       out_dtype=out_dtype)
+                       out_dtype=out_dtype, dropout=dropout)
         ctx.save_for_backward(x, wc, y if relu else None)
         ctx.meta = (K, relu, alpha, alpha_cols, residual is not None and res_mod == 0, b is not None, tuple(w.shape), x.dtype)
+        ctx.dropout = dropout
         return y
 
     @staticmethod
@@ -52,8 +58,8 @@ class LinearFn(torch.autograd.Function):
         x, wc, y = ctx.saved_tensors
         K, relu, alpha, alpha_cols, res_grad, has_b, wshape, cdt = ctx.meta
         dy = dy.contiguous()
-        plain = (not relu) and alpha_cols == 0 and dy.dtype == cdt
-        dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain)
+        plain = (not relu) and alpha_cols == 0 and dy.dtype == cdt and ctx.dropout is None
+        dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain, dropout=ctx.dropout)
         if plain:
             dz = dy
         dx = _gemm_dx(dz, wc, K) if ctx.needs_input_grad[0] else None
@@ -65,14 +71,16 @@ class LinearFn(torch.autograd.Function):
         if dw.shape[1] != wshape[1]:
             dw = dw[:, :wshape[1]].contiguous()
         dres = dy if res_grad else None
-        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None
+        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None
 
 
 class AttnSelfFn(torch.autograd.Function):
     """ctx[M,E] = attention over the fused qkv [M, 3E] (q pre-scaled by the projection epilogue), optional Er, causal."""
 
     @staticmethod
-    def forward(ctx, qkv, er, erc, B, L, H, causal):
+    def forward(ctx, qkv, er, erc, B, L, H, causal, dropout=None):
+        if dropout is not None and dropout[0] <= 0.0:
+            dropout = None
         E = qkv.shape[1] // 3
         dh = E // H
         out = torch.empty((B * L, E), device=qkv.device, dtype=qkv.dtype)
@@ -80,9 +88,10 @@ class AttnSelfFn(torch.autograd.Function):
         ld = qkv.stride(0)
         ops.attention(qkv, qkv[:, E:], qkv[:, 2 * E:], out, B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh,
                       q_strides=(L * ld, ld), k_strides=(L * ld, ld), v_strides=(L * ld, ld), o_strides=(L * E, E),
-                      causal=causal, Er=erc, lse=lse)
+                      causal=causal, Er=erc, lse=lse, dropout=dropout)
         ctx.save_for_backward(qkv, out, lse, erc)
         ctx.meta = (B, L, H, causal, er is not None)
+        ctx.dropout = dropout
         return out
 
     @staticmethod
@@ -96,7 +105,7 @@ class AttnSelfFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         der = torch.zeros(erc.shape, device=qkv.device, dtype=F32) if has_er else None
         common = dict(B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=(L * ld, ld), k_strides=(L * ld, ld), v_strides=(L * ld, ld),
-                      o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld), causal=causal)
+                      o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld), causal=causal, dropout=ctx.dropout)
         if qkv.dtype == BF16 and dh == 64:
             # tensor-core kernels write dK / dV straight into the fused gradient (bf16), no fp32 staging
             ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dqkv[:, E:],
@@ -106,22 +115,26 @@ class AttnSelfFn(torch.autograd.Function):
             ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dkv32, dkv32[:, E:],
                               der, dkv_strides=(L * 2 * E, 2 * E), **common)
             dqkv[:, E:] = dkv32                                           # fp32 accumulators -> gradient dtype
-        return dqkv, der, None, None, None, None, None
+        return dqkv, der, None, None, None, None, None, None
 
 
 class AttnCrossFn(torch.autograd.Function):
     """ctx[Mq,E] = attention of q [B*T, E] (pre-scaled) over kv [B*S, 2E] (non-causal, no Er)."""
 
     @staticmethod
-    def forward(ctx, q, kv, B, T, S, H):
+    def forward(ctx, q, kv, B, T, S, H, dropout=None):
+        if dropout is not None and dropout[0] <= 0.0:
+            dropout = None
         E = q.shape[1]
         dh = E // H
         out = torch.empty((B * T, E), device=q.device, dtype=q.dtype)
         lse = torch.empty((B * H, T), device=q.device, dtype=F32)
         ops.attention(q, kv, kv[:, E:], out, B=B, Hq=H, Hkv=H, Lq=T, Lk=S, dh=dh, q_strides=(T * E, E),
-                      k_strides=(S * 2 * E, 2 * E), v_strides=(S * 2 * E, 2 * E), o_strides=(T * E, E), causal=False, lse=lse)
+                      k_strides=(S * 2 * E, 2 * E), v_strides=(S * 2 * E, 2 * E), o_strides=(T * E, E), causal=False, lse=lse,
+                      dropout=dropout)
         ctx.save_for_backward(q, kv, out, lse)
         ctx.meta = (B, T, S, H)
+        ctx.dropout = dropout
         return out
 
     @staticmethod
@@ -134,14 +147,14 @@ class AttnCrossFn(torch.autograd.Function):
         dq = torch.empty_like(q)
         common = dict(B=B, Hq=H, Hkv=H, Lq=T, Lk=S, dh=dh, q_strides=(T * E, E), k_strides=(S * 2 * E, 2 * E),
                       v_strides=(S * 2 * E, 2 * E), o_strides=(T * E, E), do_strides=(T * E, E), dq_strides=(T * E, E),
-                      dkv_strides=(S * 2 * E, 2 * E), causal=False)
+                      dkv_strides=(S * 2 * E, 2 * E), causal=False, dropout=ctx.dropout)
         if q.dtype == BF16 and dh == 64:
             dkv = torch.empty_like(kv)
             ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv, dkv[:, E:], None, tensor_core=True, **common)
-            return dq, dkv, None, None, None, None
+            return dq, dkv, None, None, None, None, None
         dkv32 = torch.zeros((B * S, 2 * E), device=q.device, dtype=F32)
         ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv32, dkv32[:, E:], None, **common)
-        return dq, dkv32.to(kv.dtype) if kv.dtype != F32 else dkv32, None, None, None, None
+        return dq, dkv32.to(kv.dtype) if kv.dtype != F32 else dkv32, None, None, None, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -207,7 +220,7 @@ class AmtLossFn(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------------------------- model forward
 def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, residual=None, res_mod=0, rows=None,
-         out_dtype=None):
+         out_dtype=None, dropout=None):
     w = W._sd[wname]
     b = W._sd[bname] if bname is not None else None
     if rows is not None:
@@ -216,15 +229,32 @@ def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, res
         w_v, b_v = w, b
     wc = W.w(wname, rows=rows)
     K = K if K is not None else w.shape[1]
-    return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype)
+    return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype, dropout)
 
 
 def _ln(W, name, x):
     return LayerNormFn.apply(x, W._sd[name + ".weight"], W._sd[name + ".bias"], 1e-5)
 
 
-def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emotion, mask: bool = True) -> torch.Tensor:
-    """Differentiable VideoMusicTransformer.forward (video_music_transformer.py:978-1044), dropout-free."""
+def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emotion, mask: bool = True, dropout_p: float = 0.0,
+                         seed: int = 0) -> torch.Tensor:
+    """Differentiable VideoMusicTransformer.forward (video_music_transformer.py:978-1044).
+    dropout_p > 0 (training, bf16): every nn.Dropout of the reference graph -- positional encodings
+    (positional_encoding.py:23), attention probabilities (rpr.py:407 and the stock MultiheadAttention), sub-layer outputs
+    before the residual adds and the FFN hidden layer (rpr.py:58-69, nn.TransformerEncoderLayer) -- is fused into the kernel
+    that produces the tensor; each site gets its own seed derived from `seed`.  The masks come from a stateless integer
+    hash, not from torch's Philox stream, so individual draws differ from the reference's for the same torch seed."""
+    site = [0]
+
+    def dr(after_res=False):                       # (p, seed, after_residual) of the next dropout site, None when off
+        if dropout_p <= 0.0:
+            return None
+        site[0] += 1
+        return (dropout_p, (seed * 0x9E3779B1 + site[0] * 0x85EBCA6B) & 0xFFFFFFFF, after_res)
+
+    def dra():                                     # attention-probability site: (p, seed)
+        d = dr()
+        return None if d is None else d[:2]
     W = model._w()
     W.refresh()
     cfg = model._cfg()
@@ -239,15 +269,15 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     vf_dim = sd["Linear_vis.weight"].shape[1]
     vin = ops.concat_features(sem, scene, motion, emotion, dt, vf_dim if dt == F32 else _pad8(vf_dim))
     pe_v = sd["positional_encoding_video.pe"].view(-1, E)
-    xv = _lin(W, vin, "Linear_vis.weight", "Linear_vis.bias", K=vf_dim, residual=pe_v, res_mod=S)
+    xv = _lin(W, vin, "Linear_vis.weight", "Linear_vis.bias", K=vf_dim, residual=pe_v, res_mod=S, dropout=dr(True))
     for l in range(NL):
         p = "transformer.encoder.layers.%d." % l
         qkv = _lin(W, xv, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E)
-        a = AttnSelfFn.apply(qkv, None, None, B, S, H, False)
-        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv)
+        a = AttnSelfFn.apply(qkv, None, None, B, S, H, False, dra())
+        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv, dropout=dr())
         xv = _ln(W, p + "norm1", r)
-        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True)
-        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv)
+        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=dr())
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv, dropout=dr())
         xv = _ln(W, p + "norm2", r)
     mem = _ln(W, "transformer.encoder.norm", xv)
     # ---- chord stream
@@ -258,23 +288,23 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
         xin = EmbedKeyFn.apply(x_root.reshape(-1), sd["embedding_root.weight"], x_attr.reshape(-1), sd["embedding_attr.weight"],
                                key_rows, dt)
     pe_c = sd["positional_encoding.pe"].view(-1, E)
-    xf = _lin(W, xin, "Linear_chord.weight", "Linear_chord.bias", K=E + 1, residual=pe_c, res_mod=T)
+    xf = _lin(W, xin, "Linear_chord.weight", "Linear_chord.bias", K=E + 1, residual=pe_c, res_mod=T, dropout=dr(True))
     for l in range(NL):
         p = "transformer.decoder.layers.%d." % l
         er = sd.get(p + "self_attn.Er")
         erc = W.table(p + "self_attn.Er") if er is not None else None
         qkv = _lin(W, xf, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E)
-        a = AttnSelfFn.apply(qkv, er, erc, B, T, H, bool(mask))
-        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xf)
+        a = AttnSelfFn.apply(qkv, er, erc, B, T, H, bool(mask), dra())
+        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xf, dropout=dr())
         xf = _ln(W, p + "norm1", r)
         q = _lin(W, xf, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(0, E), alpha=scal,
                  alpha_cols=E)
         kv = _lin(W, mem, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(E, 3 * E))
-        a = AttnCrossFn.apply(q, kv, B, T, S, H)
-        r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf)
+        a = AttnCrossFn.apply(q, kv, B, T, S, H, dra())
+        r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf, dropout=dr())
         xf = _ln(W, p + "norm2", r)
-        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True)
-        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf)
+        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=dr())
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf, dropout=dr())
         xf = _ln(W, p + "norm3", r)
     xf = _ln(W, "transformer.decoder.norm", xf)
     y = _lin(W, xf, "Wout.weight", "Wout.bias", out_dtype=F32)

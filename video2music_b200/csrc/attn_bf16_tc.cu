@@ -58,6 +58,7 @@ struct AttnTcArgs {
   float* lse;
   int B, Hq, Hkv, Lq, Lk, causal, has_er, er_len;
   int swap;   // tensor maps are (col, batch, row) instead of (col, row, batch): sequence-first layouts
+  float drop_scale; unsigned int drop_thresh, drop_seed;   // probability dropout (training), 0 = off
   int n_q_tiles, n_items;   // work items = (video, head) x 128-row query tiles; CTAs walk them with stride gridDim.x
 };
 
@@ -316,9 +317,14 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
+          float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
+          float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
           sum += p0 + p1;
+          if (a.drop_scale != 0.f) {                           // dropout acts on the normalised probabilities: O stays / sum
+            const uint32_t rr = (uint32_t)bh * (uint32_t)a.Lq + (uint32_t)i;
+            p0 = drop_keep(a.drop_seed, rr, j0 + 2 * k, a.drop_thresh) ? p0 * a.drop_scale : 0.f;
+            p1 = drop_keep(a.drop_seed, rr, j0 + 2 * k + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f;
+          }
           pk[k] = f2_to_bf16x2(p0, p1);
         }
       } else {                                                   // above the diagonal for the whole quadrant: P = 0
@@ -404,6 +410,7 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
   a.o = p.o; a.o_sb = p.o_sb; a.o_sl = p.o_sl; a.lse = p.lse;
   a.B = p.B; a.Hq = p.Hq; a.Hkv = p.Hkv; a.Lq = p.Lq; a.Lk = p.Lk; a.causal = p.causal;
   a.has_er = p.Er != nullptr; a.er_len = p.er_len; a.swap = swap;
+  a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);

@@ -248,8 +248,12 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(
         const bool rel = HAS_ER && valid && j <= i;            // _skew contributes only for j <= i (rpr.py:439-455)
         if (rel) sc += wQE[(g + hi * 8) * QB + 15 - (g + hi * 8) + c];
         const float pv = valid ? __expf(sc - (hi ? lse_hi : lse_lo)) : 0.f;
-        s[nt][e] = pv;
-        dp[nt][e] = pv * (dp[nt][e] - (hi ? Dhi : Dlo));
+        // forward dropout of the probabilities: O = (P o M) V, so dV needs P o M and dP = (dO V^T) o M; D = rowsum(dO o O) as is
+        float mk = 1.f;
+        if (p.drop_scale != 0.f)
+          mk = drop_keep(p.drop_seed, (uint32_t)bh * (uint32_t)p.Lq + (uint32_t)i, (uint32_t)j, p.drop_thresh) ? p.drop_scale : 0.f;
+        s[nt][e] = pv * mk;
+        dp[nt][e] = pv * (dp[nt][e] * mk - (hi ? Dhi : Dlo));
       }
     }
     if (rel_tile) __syncwarp();                                // every lane has read its QE values: the scratch becomes the stage

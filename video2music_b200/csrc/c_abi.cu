@@ -35,6 +35,7 @@ static GemmEpilogue to_ep(const v2m_epilogue* e) {
   g.alpha = e->alpha; g.alpha_cols = e->alpha_cols; g.relu = e->relu; g.residual_bf16 = e->residual_bf16;
   g.head_scatter = e->head_scatter; g.S = e->S; g.H = e->H; g.dh = e->dh; g.cap = e->cap; g.pos0 = e->pos0;
   g.part_stride = e->part_stride;
+  g.drop_scale = e->drop_scale; g.drop_thresh = e->drop_thresh; g.drop_seed = e->drop_seed; g.drop_after_res = e->drop_after_res;
   return g;
 }
 
@@ -72,6 +73,7 @@ int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float
                  int32_t K, const v2m_epilogue* ep, void* stream) {
   GemmEpilogue g = to_ep(ep);
   V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32: bf16 residual not supported on the fp32 path");
+  V2M_REQUIRE(g.drop_scale == 0.f, "v2m_gemm_f32: fused dropout exists on the bf16 tensor-core path only");
   return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream));
 }
 
@@ -79,6 +81,7 @@ int v2m_gemm_f32_strided(const float* A, int32_t a_rs, int32_t a_cs, const float
                          int32_t ldc, int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
   GemmEpilogue g = to_ep(ep);
   V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32_strided: bf16 residual not supported on the fp32 path");
+  V2M_REQUIRE(g.drop_scale == 0.f, "v2m_gemm_f32_strided: fused dropout exists on the bf16 tensor-core path only");
   return gemm_f32(A, a_rs, W, w_rs, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream), a_cs, w_cs);
 }
 
@@ -102,6 +105,8 @@ int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {
   p.B = a->B; p.Hq = a->Hq; p.Hkv = a->Hkv; p.Lq = a->Lq; p.Lk = a->Lk; p.dh = a->dh;
   p.causal = a->causal; p.Er = a->Er; p.er_len = a->er_len; p.q_scale = a->q_scale;
   p.lse = a->lse; p.p_out = a->p_out;
+  p.drop_scale = a->drop_scale; p.drop_thresh = a->drop_thresh; p.drop_seed = a->drop_seed;
+  V2M_REQUIRE(dtype == V2M_BF16 || p.drop_scale == 0.f, "v2m_attn_fwd: probability dropout exists on the bf16 path only");
   if (dtype == V2M_F32) return attn_fwd_f32(p, static_cast<cudaStream_t>(stream));
   if (dtype == V2M_BF16) return attn_fwd_bf16_tc(p, static_cast<cudaStream_t>(stream));
   set_last_error("v2m_attn_fwd: dtype %d unsupported", dtype);
@@ -113,6 +118,7 @@ int v2m_attn_bwd(const v2m_attn_bwd_t* a, void* stream) {
   static_assert(sizeof(v2m_attn_bwd_t) == sizeof(AttnBwdParams), "v2m_attn_bwd_t must mirror AttnBwdParams");
   AttnBwdParams p;
   memcpy(&p, a, sizeof(p));
+  V2M_REQUIRE(p.drop_scale == 0.f, "v2m_attn_bwd: probability dropout exists on the tensor-core path only");
   return attn_bwd(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -129,9 +135,9 @@ int v2m_attn_bwd_tc(const v2m_attn_bwd_t* a, void* ws, int64_t ws_bytes, void* s
 
 int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
                 float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
-                void* stream) {
-  return dy_prep(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz, db, M, N,
-                 static_cast<cudaStream_t>(stream));
+                float drop_scale, uint32_t drop_thresh, uint32_t drop_seed, void* stream) {
+  return dy_prep(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz, db, M, N, drop_scale, drop_thresh,
+                 drop_seed, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_layernorm_bwd(const void* x, int32_t x_dtype, const float* gamma, const void* dy, int32_t dy_dtype, void* dx,

@@ -35,6 +35,16 @@ int check_launch(const char* what);
   } while (0)
 
 // ---- small device utilities ------------------------------------------------------------------
+// Dropout masks are a stateless function of (seed, row, column): the forward kernel and the backward kernel that needs the
+// same mask recompute it instead of storing it (lowbias32-style integer mix).  keep <=> hash >= thresh, thresh = p * 2^32.
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t row, uint32_t col, uint32_t thresh) {
+  uint32_t h = seed ^ (row * 0x9E3779B1u);
+  h ^= col * 0x85EBCA77u + 0x165667B1u;
+  h ^= h >> 16; h *= 0x7FEB352Du;
+  h ^= h >> 15; h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h >= thresh;
+}
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -310,6 +310,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               v[4 * q + 2] = fmaf(rs, t.z, v[4 * q + 2]); v[4 * q + 3] = fmaf(rs, t.w, v[4 * q + 3]);
             }
           }
+          if (ep.drop_scale != 0.f && !ep.drop_after_res) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = drop_keep(ep.drop_seed, m, n0 + i, ep.drop_thresh) ? v[i] * ep.drop_scale : 0.f;
+          }
           if (ep.residual) {
             if (ep.residual_bf16) {
 #pragma unroll
@@ -329,6 +333,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
               }
             }
+          }
+          if (ep.drop_scale != 0.f && ep.drop_after_res) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = drop_keep(ep.drop_seed, m, n0 + i, ep.drop_thresh) ? v[i] * ep.drop_scale : 0.f;
           }
           }
           const long long o = epi_out_index(ep, m, n0, ldc);     // 32 columns never straddle a head (dh % 32 == 0)
@@ -380,9 +388,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (n < ep.alpha_cols) x *= ep.alpha;
             if (ep.relu) x = fmaxf(x, 0.f);
             if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
+            if (ep.drop_scale != 0.f && !ep.drop_after_res) x = drop_keep(ep.drop_seed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
             if (ep.residual)
               x += ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
                                     : __ldg(ep.residual + res_row + n);
+            if (ep.drop_scale != 0.f && ep.drop_after_res) x = drop_keep(ep.drop_seed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
             const long long o = epi_out_index(ep, m, n, ldc);
             if (out_bf16) static_cast<bf16*>(C)[o] = __float2bfloat16_rn(x);
             else static_cast<float*>(C)[o] = x;
@@ -458,7 +468,8 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
   if (ep.head_scatter) vec_ok = vec_ok && ep.dh % 32 == 0 && ((long long)ep.part_stride * osz) % 16 == 0;
   else vec_ok = vec_ok && ((long long)ldc * osz) % 16 == 0;
   // split-K only for plain fp32 outputs (no epilogue operation commutes with partial sums except the identity)
-  const bool allow_split = !out_bf16 && !ep.bias && !ep.residual && !ep.row_scale && !ep.relu && ep.alpha_cols == 0 && !ep.head_scatter;
+  const bool allow_split = !out_bf16 && !ep.bias && !ep.residual && !ep.row_scale && !ep.relu && ep.alpha_cols == 0 && !ep.head_scatter &&
+                           ep.drop_scale == 0.f;
 #define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split)
   if (bn == 256) {
     if (!a_mn && !b_mn) return V2M_GO(256, false, false);

@@ -25,6 +25,12 @@ struct GemmEpilogue {
   int head_scatter = 0;
   int S = 0, H = 0, dh = 0, cap = 0, pos0 = 0;
   long long part_stride = 0;
+  // Inverted dropout fused into the epilogue (training): element (m, n) is kept iff drop_keep(drop_seed, m, n, drop_thresh)
+  // and scaled by drop_scale = 1 / (1 - p); drop_scale == 0 disables it.  drop_after_res: y = drop(acc + residual) (the
+  // positional-encoding dropout) instead of y = drop(acc) + residual (sub-layer dropout before the residual add).
+  float drop_scale = 0.f;
+  unsigned int drop_thresh = 0, drop_seed = 0;
+  int drop_after_res = 0;
 };
 
 #ifdef __CUDACC__
@@ -63,6 +69,10 @@ struct AttnParams {
   float q_scale;           // multiplies q on load (1.0 when the projection epilogue already scaled it)
   float* lse;              // optional [B*Hq, Lq] log-sum-exp (for backward)
   float* p_out;            // optional [B*Hq, Lq, Lk] probabilities (need_weights=True)
+  // training: inverted dropout of the probabilities (rpr.py:407, F.multi_head_attention_forward): element (b*Hq+h, i, j) is kept
+  // iff drop_keep(drop_seed, (b*Hq+h)*Lq + i, j, drop_thresh), scaled by drop_scale = 1/(1-p); 0 = off.  bf16 path only.
+  float drop_scale = 0.f;
+  unsigned int drop_thresh = 0, drop_seed = 0;
 };
 int attn_fwd_f32(const AttnParams& p, cudaStream_t stream);
 int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream);
@@ -73,6 +83,8 @@ struct AttnBwdParams {
   long long q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl, do_sb, do_sl, dq_sb, dq_sl, dkv_sb, dkv_sl;
   int B, Hq, Hkv, Lq, Lk, dh, causal, er_len, dtype;
   float q_scale;
+  float drop_scale;                 // the forward's probability dropout (same mask function), 0 = off; tensor-core path only
+  unsigned int drop_thresh, drop_seed;
 };
 int attn_bwd(const AttnBwdParams& p, cudaStream_t stream);
 // Tensor-core variant (bf16, head_dim 64, q pre-scaled): p.dk / p.dv are BF16 outputs written once (no accumulation),
@@ -81,7 +93,8 @@ long long attn_bwd_tc_workspace(int B, int Hq, int Lq, int Lk, int has_er);
 int attn_bwd_tc(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStream_t stream);
 
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
-            int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, cudaStream_t stream);
+            int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, float drop_scale, unsigned int drop_thresh,
+            unsigned int drop_seed, cudaStream_t stream);
 int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy, int dy_dtype, void* dx, int dx_dtype,
                   float* dgamma, float* dbeta, int M, int D, float eps, cudaStream_t stream);
 int embed_bwd(const long long* idx, const void* d, int d_dtype, long long ld_d, float* dtable, int rows, int D,

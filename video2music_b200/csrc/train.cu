@@ -22,7 +22,8 @@ __device__ __forceinline__ void st_any(void* p, int dtype, size_t i, float v) {
 __global__ void __launch_bounds__(256) dy_prep_kernel(const void* __restrict__ dy, int dy_dtype, long long ld_dy,
                                                       const void* __restrict__ y, int y_dtype, long long ld_y, int relu,
                                                       float alpha, int alpha_cols, void* __restrict__ dz, int dz_dtype,
-                                                      long long ld_dz, float* __restrict__ db, int M, int N) {
+                                                      long long ld_dz, float* __restrict__ db, int M, int N, float drop_scale,
+                                                      unsigned int drop_thresh, unsigned int drop_seed) {
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256) dy_prep_kernel(const void* __restrict__ d
       float g = ld_any(dy, dy_dtype, (size_t)m * ld_dy + n);
       if (relu && !(ld_any(y, y_dtype, (size_t)m * ld_y + n) > 0.f)) g = 0.f;
       g *= sc;
+      if (drop_scale != 0.f) g = drop_keep(drop_seed, m, n, drop_thresh) ? g * drop_scale : 0.f;   // mask of the forward epilogue
       if (dz) st_any(dz, dz_dtype, (size_t)m * ld_dz + n, g);
       acc += g;
     }
@@ -51,7 +53,8 @@ __global__ void __launch_bounds__(256) dy_prep_kernel(const void* __restrict__ d
 __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restrict__ dy, long long ld_dy, const bf16* __restrict__ y,
                                                              long long ld_y, int relu, float alpha, int alpha_cols,
                                                              bf16* __restrict__ dz, long long ld_dz, float* __restrict__ db, int M,
-                                                             int N) {
+                                                             int N, float drop_scale, unsigned int drop_thresh,
+                                                             unsigned int drop_seed) {
   __shared__ float part[32][8 * 8 + 1];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;            // 8 column groups x 32 row lanes
   const int n0 = (blockIdx.x * 8 + tx) * 8;
@@ -77,7 +80,11 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
         for (int e = 0; e < 8; ++e) if (!(yv[e] > 0.f)) g[e] = 0.f;
       }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { g[e] *= sc[e]; acc[e] += g[e]; }
+      for (int e = 0; e < 8; ++e) {
+        g[e] *= sc[e];
+        if (drop_scale != 0.f) g[e] = drop_keep(drop_seed, m, n0 + e, drop_thresh) ? g[e] * drop_scale : 0.f;
+        acc[e] += g[e];
+      }
       if (dz) {
         uint4 o;
         o.x = f2_to_bf16x2(g[0], g[1]); o.y = f2_to_bf16x2(g[2], g[3]); o.z = f2_to_bf16x2(g[4], g[5]); o.w = f2_to_bf16x2(g[6], g[7]);
@@ -100,7 +107,8 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
 }
 
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
-            int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, cudaStream_t stream) {
+            int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, float drop_scale, unsigned int drop_thresh,
+            unsigned int drop_seed, cudaStream_t stream) {
   if (M == 0 || N == 0) return kOk;
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (dy_dtype == 1 && (!dz || dz_dtype == 1) && (!relu || y_dtype == 1) && N % 8 == 0 && ld_dy % 8 == 0 && (!dz || ld_dz % 8 == 0) &&
@@ -109,14 +117,14 @@ int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_
     if (gy2 > 148) gy2 = 148;
     dim3 grid2((N + 63) / 64, gy2);
     dy_prep_bf16x8_kernel<<<grid2, 256, 0, stream>>>(static_cast<const bf16*>(dy), ld_dy, static_cast<const bf16*>(y), ld_y, relu, alpha,
-                                                     alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N);
+                                                     alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N, drop_scale, drop_thresh, drop_seed);
     return check_launch("dy_prep_bf16x8");
   }
   int gy = (M + 7) / 8;
   if (gy > 148 * 2) gy = 148 * 2;
   dim3 grid((N + 31) / 32, gy);
   dy_prep_kernel<<<grid, 256, 0, stream>>>(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz,
-                                          db, M, N);
+                                          db, M, N, drop_scale, drop_thresh, drop_seed);
   return check_launch("dy_prep");
 }
 

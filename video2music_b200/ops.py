@@ -16,14 +16,22 @@ def _rows(t: torch.Tensor) -> int:
     return t.numel() // t.shape[-1]
 
 
+def drop_args(p: float, seed: int):
+    """(scale, threshold, seed) of the stateless dropout mask shared by the forward and backward kernels: an element is kept
+    iff mix(seed, row, col) >= p * 2^32 and scaled by 1 / (1 - p)."""
+    assert 0.0 < p < 1.0
+    return 1.0 / (1.0 - p), min(int(p * 4294967296.0), 4294967295), int(seed) & 0xFFFFFFFF
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, k: Optional[int] = None,
            relu: bool = False, alpha: float = 1.0, alpha_cols: int = 0,
            residual: Optional[torch.Tensor] = None, res_mod: int = 0,
            row_scale: Optional[torch.Tensor] = None, col_vec: Optional[torch.Tensor] = None,
            out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
-           head_scatter: Optional[dict] = None) -> torch.Tensor:
+           head_scatter: Optional[dict] = None, dropout: Optional[tuple] = None) -> torch.Tensor:
     """y = epilogue(x @ w[:, :k].T).  x (M, >=k) and w (N, >=k) are row-major 2-D tensors of the same
-    dtype (fp32 -> SIMT exact GEMM, bf16 -> tcgen05 GEMM); leading dims are taken from the strides."""
+    dtype (fp32 -> SIMT exact GEMM, bf16 -> tcgen05 GEMM); leading dims are taken from the strides.
+    dropout = (p, seed, after_residual): inverted dropout fused into the epilogue (bf16 path), see drop_args()."""
     require_device(x)
     assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
     assert x.dtype == w.dtype, (x.dtype, w.dtype)
@@ -41,6 +49,9 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         ep.residual_bf16 = int(residual.dtype == torch.bfloat16)
     if row_scale is not None:
         ep.row_scale, ep.col_vec = ptr(row_scale), ptr(col_vec)
+    if dropout is not None and dropout[0] > 0.0:
+        ep.drop_scale, ep.drop_thresh, ep.drop_seed = drop_args(dropout[0], dropout[1])
+        ep.drop_after_res = int(bool(dropout[2]))
     if head_scatter is not None:
         assert out is not None
         ep.head_scatter = 1
@@ -65,7 +76,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, Hq: int, Hkv: int,
               Lq: int, Lk: int, dh: int, q_strides, k_strides, v_strides, o_strides, causal: bool,
               Er: Optional[torch.Tensor] = None, q_scale: float = 1.0, lse: Optional[torch.Tensor] = None,
-              p_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              p_out: Optional[torch.Tensor] = None, dropout: Optional[tuple] = None) -> torch.Tensor:
     """softmax(q k^T + skew(q Er^T) + causal) v.  *_strides = (batch stride, row stride) in elements;
     q/k/v/out may be column slices of wider matrices (head h starts at column h*dh of the given pointer)."""
     require_device(q)
@@ -82,6 +93,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
         a.Er, a.er_len = ptr(Er), Er.shape[0]
     a.q_scale = q_scale
     a.lse, a.p_out = ptr(lse), ptr(p_out)
+    if dropout is not None and dropout[0] > 0.0:                 # (p, seed): dropout of the probabilities, bf16 path
+        a.drop_scale, a.drop_thresh, a.drop_seed = drop_args(dropout[0], dropout[1])
     check(load().v2m_attn_fwd(C.byref(a), dtype_code(q.dtype), stream()))
     _lib.count_launches(1)
     return out
@@ -282,8 +295,9 @@ def gemm_strided(a: torch.Tensor, a_rs: int, a_cs: int, w: torch.Tensor, w_rs: i
 
 
 def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: float, alpha_cols: int, out_dtype: torch.dtype,
-            want_dz: bool = True):
-    """dz = dy * relu'(y) * alpha_n ; db = column sums of dz.  Returns (dz or None, db fp32 [N])."""
+            want_dz: bool = True, dropout: Optional[tuple] = None):
+    """dz = dy * relu'(y) * alpha_n * dropmask ; db = column sums of dz.  Returns (dz or None, db fp32 [N]).
+    dropout = (p, seed) of the forward epilogue whose mask is recomputed here."""
     require_device(dy)
     assert dy.dim() == 2 and dy.stride(1) == 1
     M, N = dy.shape
@@ -294,7 +308,8 @@ def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: floa
     db = torch.zeros((N,), device=dy.device, dtype=torch.float32)
     check(load().v2m_dy_prep(ptr(dy), dtype_code(dy.dtype), dy.stride(0), ptr(y), dtype_code(y.dtype) if y is not None else 0,
                              y.stride(0) if y is not None else 0, int(relu), alpha, alpha_cols, ptr(dz),
-                             dtype_code(out_dtype), ld, ptr(db), M, N, stream()))
+                             dtype_code(out_dtype), ld, ptr(db), M, N, *(drop_args(*dropout[:2]) if dropout and dropout[0] > 0 else (0.0, 0, 0)),
+                             stream()))
     _lib.count_launches(1)
     return (dz[:, :N] if (dz is not None and ld != N) else dz), db
 
@@ -403,7 +418,7 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 
 
 def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_strides,
-                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False):
+                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False, dropout=None):
     """tensor_core=True (bf16, head_dim 64): dk / dv are bf16 outputs written once by the mma.sync kernels of
     csrc/attn_bwd_tc.cu; otherwise dk / dv are zeroed fp32 buffers the exact SIMT kernel accumulates into."""
     require_device(q)
@@ -416,6 +431,8 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
     a.er_len = Er.shape[0] if Er is not None else 0
     a.dtype = dtype_code(q.dtype)
     a.q_scale = q_scale
+    if dropout is not None and dropout[0] > 0.0:                 # the forward's (p, seed)
+        a.drop_scale, a.drop_thresh, a.drop_seed = drop_args(dropout[0], dropout[1])
     if tensor_core:
         n = int(load().v2m_attn_bwd_tc_workspace(B, Hq, Lq, Lk, int(Er is not None)))
         ws = torch.empty(n, dtype=torch.uint8, device=q.device)

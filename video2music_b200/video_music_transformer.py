@@ -154,14 +154,22 @@ class VideoMusicTransformer(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x, x_root, x_attr, feature_semantic_list, feature_key, feature_scene_offset, feature_motion,
                 feature_emotion, mask=True):
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built yet (use dropout=0.0)")
+        drop = float(self.dropout) if self.training else 0.0
+        grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if drop > 0 and not (grad and self._w().dtype == torch.bfloat16):
+            raise NotImplementedError("dropout > 0 in training mode runs on the bf16 autograd path only "
+                                      "(set_compute_dtype(torch.bfloat16), gradients enabled), or use dropout=0.0 / eval()")
         dev = self._device()
         args = [t.to(dev) for t in (x, x_root, x_attr, feature_semantic_list, feature_key, feature_scene_offset,
                                     feature_motion, feature_emotion)]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if grad:
             from .autograd import amt_forward_autograd
-            y = amt_forward_autograd(self, *args, mask=mask is True)
+            seed = 0
+            if drop > 0:                      # a fresh mask per forward call, reproducible under torch.manual_seed
+                self._drop_calls = getattr(self, "_drop_calls", 0) + 1
+                rank = torch.distributed.get_rank() if torch.distributed.is_available() and torch.distributed.is_initialized() else 0
+                seed = (torch.initial_seed() * 1000003 + self._drop_calls * 7919 + rank * 104729) & 0xFFFFFFFF
+            y = amt_forward_autograd(self, *args, mask=mask is True, dropout_p=drop, seed=seed)
         else:
             y = engine.amt_forward(self._w(), self._cfg(), *args, mask=mask is True)
         if IS_SEPERATED:
