@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace v2m {
 
@@ -39,15 +40,17 @@ constexpr int AT_DH = 64;            // head dim (128-byte swizzled rows)
 constexpr int AT_MAXK = 320;         // keys per row that fit the TMEM plan
 constexpr int AT_QE_COLS = 192;      // width of one QE half
 constexpr int AT_QE_OVERLAP = 128;   // half B starts at band column 128
-constexpr int AT_NW = 2;             // softmax warps per TMEM lane quadrant
-constexpr int AT_THREADS = 32 + 128 * AT_NW;
+// softmax warps per TMEM lane quadrant: 2 with RPR (each needs a 8.7 KB skew scratch), 4 without (encoder / cross attention)
+constexpr int at_threads(int nw) { return 32 + 128 * nw; }
 constexpr int AT_SCR_PITCH = 68;     // floats; 68 % 32 == 4 -> conflict-free STS.128 and shifted LDS.32
 
 constexpr int AT_SMEM_Q = AT_M * 128;
 constexpr int AT_SMEM_K = AT_MAXK * 128;
-constexpr int AT_SMEM_SCR = AT_NW * 4 * 32 * AT_SCR_PITCH * 4;
-constexpr int AT_SMEM_RED = 2 * AT_NW * AT_M * 4;   // row max / row sum exchange
-constexpr size_t AT_SMEM = 1024 + AT_SMEM_Q + 3 * AT_SMEM_K + AT_SMEM_SCR + AT_SMEM_RED + 256;
+constexpr int at_smem_scr(int nw, bool er) { return er ? nw * 4 * 32 * AT_SCR_PITCH * 4 : 0; }
+constexpr int at_smem_red(int nw) { return 2 * nw * AT_M * 4; }   // row max / row sum exchange
+constexpr size_t at_smem(int nw, bool er) {
+  return 1024 + AT_SMEM_Q + (er ? 3 : 2) * AT_SMEM_K + at_smem_scr(nw, er) + at_smem_red(nw) + 256;
+}
 
 int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch,
                       long long row_pitch, long long batch_pitch, int box_rows, int swap);
@@ -62,7 +65,8 @@ struct AttnTcArgs {
   int n_q_tiles, n_items;   // work items = (video, head) x 128-row query tiles; CTAs walk them with stride gridDim.x
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+template <int AT_NW, bool HAS_ER, bool DROP>
+__global__ void __launch_bounds__(at_threads(AT_NW), 1)
 attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmE,
                     const __grid_constant__ AttnTcArgs a) {
@@ -72,9 +76,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   unsigned char* sK = sQ + AT_SMEM_Q;
   unsigned char* sV = sK + AT_SMEM_K;
   unsigned char* sE = sV + AT_SMEM_K;
-  float* scr = reinterpret_cast<float*>(sE + AT_SMEM_K);
-  float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scr) + AT_SMEM_SCR);   // [2][AT_NW][AT_M]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + AT_SMEM_RED);
+  float* scr = reinterpret_cast<float*>(sE + (HAS_ER ? AT_SMEM_K : 0));   // no Er buffer / skew scratch without RPR
+  float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scr) + at_smem_scr(AT_NW, HAS_ER));   // [2][AT_NW][AT_M]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(red) + at_smem_red(AT_NW));
   uint64_t* bar_qk = bars + 0;     // Q and K tiles landed
   uint64_t* bar_e = bars + 1;      // Er band landed
   uint64_t* bar_v = bars + 2;      // V tile landed
@@ -104,7 +108,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     t.nk16 = (t.nk + 15) & ~15;
     t.nk64 = (t.nk + 63) & ~63;
     t.e_base = a.er_len - 1 - t.imax;                                  // band column c <-> Er row e_base + c, needed c in [0, imax]
-    t.need_b = a.has_er && (t.imax >= AT_QE_COLS);                     // widest window start is clamped to 128 in half A
+    t.need_b = HAS_ER && (t.imax >= AT_QE_COLS);                     // widest window start is clamped to 128 in half A
     t.qe_rows = t.need_b ? AT_QE_OVERLAP + AT_QE_COLS : AT_QE_COLS;
     return t;
   };
@@ -113,7 +117,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < 10; ++i) mbar_init(bars + i, (i == 5 || i == 7 || i == 9) ? 4u * AT_NW : 1u);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    if (a.has_er) tma_prefetch_desc(&tmE);
+    if (HAS_ER) tma_prefetch_desc(&tmE);
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -131,7 +135,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma3(sQ, &tmQ, t.hq * AT_DH, t.i0, t.b, bar_qk);
         tma3(sQ + 64 * 128, &tmQ, t.hq * AT_DH, t.i0 + 64, t.b, bar_qk);
         for (int r = 0; r < t.nk64; r += 64) tma3(sK + r * 128, &tmK, t.hkv * AT_DH, r, t.b, bar_qk);
-        if (a.has_er) {
+        if (HAS_ER) {
           mbar_arrive_expect_tx(bar_e, t.qe_rows * 128);
           for (int r = 0; r < t.qe_rows; r += 64) tma_load_2d(sE + r * 128, &tmE, 0, t.e_base + r, bar_e);
         }
@@ -162,7 +166,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                          make_smem_desc_sw128(k_addr + n0 * 128 + k * 32, 16, 1024), idesc, k != 0);
         }
         umma_commit(bar_s);
-        if (a.has_er) {
+        if (HAS_ER) {
           const uint32_t idesc = make_idesc_bf16(AT_M, AT_QE_COLS, 0, 0);
           mbar_wait(bar_e, par);
           tc_fence_after();
@@ -184,7 +188,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // the products above are the last readers of sQ / sK / sE: once they have retired, fetch the next item's operands
         if (has_next) {
           if (t.need_b) mbar_wait(bar_qb, parb);
-          else if (a.has_er) mbar_wait(bar_qa, par);
+          else if (HAS_ER) mbar_wait(bar_qa, par);
           else mbar_wait(bar_s, par);
           load_qke(make_item(item + gridDim.x));
         }
@@ -241,7 +245,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float mx = -INFINITY;
     // ---- pass A: s = S + Srel, mask, running max, s written back to TMEM
     for (int phase = 0; phase < 2; ++phase) {
-      if (phase == 0 && a.has_er) { mbar_wait(bar_qa, par); tc_fence_after(); }
+      if (phase == 0 && HAS_ER) { mbar_wait(bar_qa, par); tc_fence_after(); }
       if (phase == 1) {
         if (!need_b) break;
         tc_fence_before();
@@ -253,7 +257,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int c = sub; c < live; c += AT_NW) {
         const int j0 = c * 32;
         const int start = j0 + base_w;                           // un-clamped window start
-        const bool rel_chunk = a.has_er && (j0 <= wlast);        // chunk holds some (i, j<=i) of this quadrant
+        const bool rel_chunk = HAS_ER && (j0 <= wlast);        // chunk holds some (i, j<=i) of this quadrant
         const bool in_a = !need_b || !rel_chunk || start <= AT_QE_OVERLAP;
         if ((phase == 0) != in_a) continue;
         uint32_t r[32];
@@ -283,10 +287,12 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         } else {
           tmem_ld_wait();
         }
+        bool modified = rel_chunk;                               // scores that changed go back to TMEM for pass B
         if (j0 + 32 <= wjmin) {                                  // every key of the chunk is visible to every row
 #pragma unroll
           for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
         } else {
+          modified = true;
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             float sv = __uint_as_float(r[k]);
@@ -295,7 +301,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             r[k] = __float_as_uint(sv);
           }
         }
-        tmem_st_32x32(T_S + lane_off + j0, r);
+        if (modified) tmem_st_32x32(T_S + lane_off + j0, r);
       }
     }
     tmem_st_wait();
@@ -320,7 +326,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
           float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
           sum += p0 + p1;
-          if (a.drop_scale != 0.f) {                           // dropout acts on the normalised probabilities: O stays / sum
+          if (DROP) {                                          // dropout acts on the normalised probabilities: O stays / sum
             const uint32_t rr = (uint32_t)bh * (uint32_t)a.Lq + (uint32_t)i;
             p0 = drop_keep(a.drop_seed, rr, j0 + 2 * k, a.drop_thresh) ? p0 * a.drop_scale : 0.f;
             p1 = drop_keep(a.drop_seed, rr, j0 + 2 * k + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f;
@@ -412,8 +418,16 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
   a.has_er = p.Er != nullptr; a.er_len = p.er_len; a.swap = swap;
   a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed;
   static bool attr = false;
+  static int nw_plain = 4;                 // softmax warps per quadrant without RPR (V2M_ATTN_NW=2 for A/B measurements)
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AT_SMEM);
+    if (const char* e = getenv("V2M_ATTN_NW")) nw_plain = atoi(e) == 2 ? 2 : 4;
+    cudaError_t e = cudaSuccess;
+#define V2M_ATTR(NW, ER, DR)                                                                                                      \
+    if (e == cudaSuccess)                                                                                                          \
+      e = cudaFuncSetAttribute(attn_bf16_tc_kernel<NW, ER, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_smem(NW, ER))
+    V2M_ATTR(2, true, false); V2M_ATTR(2, true, true); V2M_ATTR(4, false, false); V2M_ATTR(4, false, true);
+    V2M_ATTR(2, false, false); V2M_ATTR(2, false, true);
+#undef V2M_ATTR
     if (e != cudaSuccess) { set_last_error("attn_fwd_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
     attr = true;
   }
@@ -427,7 +441,13 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  attn_bf16_tc_kernel<<<a.n_items < num_sms ? a.n_items : num_sms, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, tmE, a);
+  const int grid = a.n_items < num_sms ? a.n_items : num_sms;
+  const bool drop = a.drop_scale != 0.f;
+#define V2M_GO(NW, ER, DR) attn_bf16_tc_kernel<NW, ER, DR><<<grid, at_threads(NW), at_smem(NW, ER), stream>>>(tmQ, tmK, tmV, tmE, a)
+  if (a.has_er) { if (drop) V2M_GO(2, true, true); else V2M_GO(2, true, false); }
+  else if (nw_plain == 4) { if (drop) V2M_GO(4, false, true); else V2M_GO(4, false, false); }
+  else { if (drop) V2M_GO(2, false, true); else V2M_GO(2, false, false); }
+#undef V2M_GO
   return check_launch("attn_fwd_bf16_tc");
 }
 

@@ -118,7 +118,7 @@ struct Ws {          // workspace views (bf16), padded to multiples of 64 in bot
 constexpr int QB = 88;                 // fp32 pitch of the QE band scratch (16 rows x 80 columns)
 constexpr int WBUF = 16 * QB * 4;      // per-warp scratch bytes: QE band (fp32), later the staged P / dS rows (2 x 16 x TP bf16)
 
-template <bool HAS_ER>
+template <bool HAS_ER, bool DROP>
 __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
   extern __shared__ __align__(16) unsigned char abt_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(abt_smem);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(
         const float pv = valid ? __expf(sc - (hi ? lse_hi : lse_lo)) : 0.f;
         // forward dropout of the probabilities: O = (P o M) V, so dV needs P o M and dP = (dO V^T) o M; D = rowsum(dO o O) as is
         float mk = 1.f;
-        if (p.drop_scale != 0.f)
+        if (DROP)
           mk = drop_keep(p.drop_seed, (uint32_t)bh * (uint32_t)p.Lq + (uint32_t)i, (uint32_t)j, p.drop_thresh) ? p.drop_scale : 0.f;
         s[nt][e] = pv * mk;
         dp[nt][e] = pv * (dp[nt][e] * mk - (hi ? Dhi : Dlo));
@@ -502,15 +502,23 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   V2M_REQUIRE(!has_er || smem_er <= 227 * 1024, "attn_bwd_tc: L=%d needs %zu B of shared memory with RPR (> 227 KB)", p.Lk, smem_er);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
+    cudaFuncSetAttribute(abt::attn_bwd_rows_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plain);
     cudaFuncSetAttribute(abt::attn_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tiles4));
     cudaFuncSetAttribute(abt::attn_bwd_der_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_der);
     attr_set = true;
   }
   dim3 grid_r(ws.Lqp / 64, p.B * p.Hq);
-  if (has_er) abt::attn_bwd_rows_kernel<true><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
-  else abt::attn_bwd_rows_kernel<false><<<grid_r, abt::THREADS, smem_plain, stream>>>(p, ws);
+  const bool drop = p.drop_scale != 0.f;
+  if (has_er) {
+    if (drop) abt::attn_bwd_rows_kernel<true, true><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
+    else abt::attn_bwd_rows_kernel<true, false><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
+  } else {
+    if (drop) abt::attn_bwd_rows_kernel<false, true><<<grid_r, abt::THREADS, smem_plain, stream>>>(p, ws);
+    else abt::attn_bwd_rows_kernel<false, false><<<grid_r, abt::THREADS, smem_plain, stream>>>(p, ws);
+  }
   int rc = check_launch("attn_bwd_rows");
   if (rc) return rc;
   dim3 grid_c(ws.Lkp / 64, p.B * p.Hkv);
