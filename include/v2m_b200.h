@@ -63,7 +63,8 @@ typedef struct v2m_epilogue {
   int64_t part_stride;
   /* Training-time inverted dropout fused into the epilogue (nn.Dropout after a linear layer, rpr.py:58-69 and the stock
    * encoder layer; PositionalEncoding dropout, positional_encoding.py:21-23).  drop_scale = 1/(1-p), 0 = off; element (m, n)
-   * is kept iff mix(drop_seed, m, n) >= drop_thresh = p * 2^32 (stateless: v2m_dy_prep recomputes the same mask);
+   * is kept iff byte (n & 3) of mix(drop_seed, m, n / 4) >= drop_thresh = round(p * 256), drop_scale = 256 / (256 - drop_thresh)
+   * (stateless: v2m_dy_prep recomputes the same mask);
    * drop_after_res: y = drop(acc + residual) instead of drop(acc) + residual.  bf16 tensor-core path only. */
   float drop_scale;
   uint32_t drop_thresh, drop_seed;

@@ -328,8 +328,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           sum += p0 + p1;
           if (DROP) {                                          // dropout acts on the normalised probabilities: O stays / sum
             const uint32_t rr = (uint32_t)bh * (uint32_t)a.Lq + (uint32_t)i;
-            p0 = drop_keep(a.drop_seed, rr, j0 + 2 * k, a.drop_thresh) ? p0 * a.drop_scale : 0.f;
-            p1 = drop_keep(a.drop_seed, rr, j0 + 2 * k + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f;
+            const uint32_t hh = drop_hash4(a.drop_seed, rr, (j0 >> 2) + (k >> 1));   // columns j0 + 2k, +1 (j0 % 32 == 0); CSE'd per two k
+            p0 = drop_keep_byte(hh, 2 * k, a.drop_thresh) ? p0 * a.drop_scale : 0.f;
+            p1 = drop_keep_byte(hh, 2 * k + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f;
           }
           pk[k] = f2_to_bf16x2(p0, p1);
         }

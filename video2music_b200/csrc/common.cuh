@@ -36,14 +36,22 @@ int check_launch(const char* what);
 
 // ---- small device utilities ------------------------------------------------------------------
 // Dropout masks are a stateless function of (seed, row, column): the forward kernel and the backward kernel that needs the
-// same mask recompute it instead of storing it (lowbias32-style integer mix).  keep <=> hash >= thresh, thresh = p * 2^32.
-__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t row, uint32_t col, uint32_t thresh) {
+// same mask recompute it instead of storing it.  One 32-bit hash (lowbias32-style integer mix) of (seed, row, column / 4)
+// serves four neighbouring columns, one byte each: keep <=> byte >= thresh8, thresh8 = round(p * 256) -- the drop
+// probability is quantised to 1/256 and the kept values are scaled by 256 / (256 - thresh8).
+__device__ __forceinline__ uint32_t drop_hash4(uint32_t seed, uint32_t row, uint32_t col4) {
   uint32_t h = seed ^ (row * 0x9E3779B1u);
-  h ^= col * 0x85EBCA77u + 0x165667B1u;
+  h ^= col4 * 0x85EBCA77u + 0x165667B1u;
   h ^= h >> 16; h *= 0x7FEB352Du;
   h ^= h >> 15; h *= 0x846CA68Bu;
   h ^= h >> 16;
-  return h >= thresh;
+  return h;
+}
+__device__ __forceinline__ bool drop_keep_byte(uint32_t h, uint32_t col, uint32_t thresh8) {
+  return ((h >> ((col & 3u) * 8u)) & 0xFFu) >= thresh8;
+}
+__device__ __forceinline__ bool drop_keep(uint32_t seed, uint32_t row, uint32_t col, uint32_t thresh8) {
+  return drop_keep_byte(drop_hash4(seed, row, col >> 2), col, thresh8);
 }
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll

@@ -312,7 +312,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (ep.drop_scale != 0.f && !ep.drop_after_res) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = drop_keep(ep.drop_seed, m, n0 + i, ep.drop_thresh) ? v[i] * ep.drop_scale : 0.f;
+            for (int i4 = 0; i4 < 8; ++i4) {                     // one hash per four columns (n0 is a multiple of 32)
+              const uint32_t h = drop_hash4(ep.drop_seed, m, (n0 >> 2) + i4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[4 * i4 + e] = drop_keep_byte(h, e, ep.drop_thresh) ? v[4 * i4 + e] * ep.drop_scale : 0.f;
+            }
           }
           if (ep.residual) {
             if (ep.residual_bf16) {
@@ -336,7 +340,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (ep.drop_scale != 0.f && ep.drop_after_res) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = drop_keep(ep.drop_seed, m, n0 + i, ep.drop_thresh) ? v[i] * ep.drop_scale : 0.f;
+            for (int i4 = 0; i4 < 8; ++i4) {                     // one hash per four columns (n0 is a multiple of 32)
+              const uint32_t h = drop_hash4(ep.drop_seed, m, (n0 >> 2) + i4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[4 * i4 + e] = drop_keep_byte(h, e, ep.drop_thresh) ? v[4 * i4 + e] * ep.drop_scale : 0.f;
+            }
           }
           }
           const long long o = epi_out_index(ep, m, n0, ldc);     // 32 columns never straddle a head (dh % 32 == 0)

@@ -26,7 +26,7 @@ struct GemmEpilogue {
   int S = 0, H = 0, dh = 0, cap = 0, pos0 = 0;
   long long part_stride = 0;
   // Inverted dropout fused into the epilogue (training): element (m, n) is kept iff drop_keep(drop_seed, m, n, drop_thresh)
-  // and scaled by drop_scale = 1 / (1 - p); drop_scale == 0 disables it.  drop_after_res: y = drop(acc + residual) (the
+  // (thresh = round(p * 256), one hash byte per element) and scaled by drop_scale = 256 / (256 - thresh); 0 disables it.  drop_after_res: y = drop(acc + residual) (the
   // positional-encoding dropout) instead of y = drop(acc) + residual (sub-layer dropout before the residual add).
   float drop_scale = 0.f;
   unsigned int drop_thresh = 0, drop_seed = 0;

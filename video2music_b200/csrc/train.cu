@@ -79,10 +79,12 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
 #pragma unroll
         for (int e = 0; e < 8; ++e) if (!(yv[e] > 0.f)) g[e] = 0.f;
       }
+      uint32_t hd[2] = {0u, 0u};
+      if (drop_scale != 0.f) { hd[0] = drop_hash4(drop_seed, m, n0 >> 2); hd[1] = drop_hash4(drop_seed, m, (n0 >> 2) + 1); }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         g[e] *= sc[e];
-        if (drop_scale != 0.f) g[e] = drop_keep(drop_seed, m, n0 + e, drop_thresh) ? g[e] * drop_scale : 0.f;
+        if (drop_scale != 0.f) g[e] = drop_keep_byte(hd[e >> 2], e, drop_thresh) ? g[e] * drop_scale : 0.f;
         acc[e] += g[e];
       }
       if (dz) {

@@ -17,10 +17,12 @@ def _rows(t: torch.Tensor) -> int:
 
 
 def drop_args(p: float, seed: int):
-    """(scale, threshold, seed) of the stateless dropout mask shared by the forward and backward kernels: an element is kept
-    iff mix(seed, row, col) >= p * 2^32 and scaled by 1 / (1 - p)."""
+    """(scale, threshold, seed) of the stateless dropout mask shared by the forward and backward kernels: one hash byte per
+    element, kept iff byte >= round(p * 256); the drop probability is therefore quantised to 1/256 (0.1 -> 26/256) and the
+    kept values are scaled by 256 / (256 - threshold)."""
     assert 0.0 < p < 1.0
-    return 1.0 / (1.0 - p), min(int(p * 4294967296.0), 4294967295), int(seed) & 0xFFFFFFFF
+    t = min(max(int(round(p * 256.0)), 1), 255)
+    return 256.0 / (256.0 - t), t, int(seed) & 0xFFFFFFFF
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, k: Optional[int] = None,
