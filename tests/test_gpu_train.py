@@ -113,3 +113,31 @@ def test_train_steps_with_dropout():
     import pytest
     with pytest.raises(NotImplementedError):
         m32(*args)
+
+
+def test_optimizer_steps_reach_the_bf16_operands():
+    """Three Adam steps with a large fixed lr: the bf16 path (which multiplies with cached bf16 copies of the fp32 masters) must
+    end up where the fp32 path does -- the copies have to be re-derived after every in-place optimiser update."""
+    from video2music_b200 import VideoMusicTransformer
+    from video2music_b200.trainer import Trainer
+    inp = {k: v.to(DEV) for k, v in syn.make_inputs(4, 77, 50, 40, 0).items()}
+    args = [inp[k] for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                             "feature_motion", "feature_emotion")]
+    outs = {}
+    for dt in (torch.float32, torch.bfloat16):
+        m, _ = _model(3, dt)
+        with torch.no_grad():
+            m.eval()
+            y0 = m(*args).float().clone()
+            m.train()
+        tr = Trainer(m, lr=2e-3)
+        for _ in range(3):
+            tr.train_step(inp)
+        with torch.no_grad():
+            m.eval()
+            outs[dt] = (y0, m(*args).float().clone())
+    moved32 = rel_err(outs[torch.float32][1], outs[torch.float32][0])
+    moved16 = rel_err(outs[torch.bfloat16][1], outs[torch.bfloat16][0])
+    assert moved32 > 0.05 and moved16 > 0.05                      # the updates are visible in the next forward
+    # and both precisions moved to the same place (closer to each other than to the starting point)
+    assert rel_err(outs[torch.bfloat16][1], outs[torch.float32][1]) < 0.5 * moved32

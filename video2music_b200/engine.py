@@ -48,6 +48,11 @@ class AMTWeights:
         if versions != self._versions:
             self._sd, self._cache, self._versions = sd, {}, versions
 
+    def invalidate(self) -> None:
+        """Drops the compute-dtype copies: for in-place updates that bypass torch's version counters (the fused Adam kernel
+        writes the flat parameter buffer through a raw pointer)."""
+        self._versions = None
+
     def has(self, name: str) -> bool:
         return name in self._sd
 

@@ -127,6 +127,8 @@ class Trainer:
         ops.adam_step(self.flat.flat_p, self.flat.flat_g, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps,
                       self.step_no, grad_scale=scale)
         self.flat.flat_g.zero_()
+        for w in getattr(m, "_weights", {}).values():    # the kernel updated the masters behind torch's back: re-derive the
+            w.invalidate()                                # bf16 operand copies on the next forward
         if slot_i is not None:                  # the prefetch slot may be overwritten once this step has run
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
