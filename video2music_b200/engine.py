@@ -39,6 +39,7 @@ class AMTWeights:
         self._sd: Dict[str, torch.Tensor] = {}
         self._cache: Dict[str, torch.Tensor] = {}
         self._versions = None
+        self.flat16: Optional[Dict[str, torch.Tensor]] = None    # trainer-owned bf16 mirror: name -> view (see trainer.Trainer)
         self.refresh()
 
     def refresh(self) -> None:
@@ -46,6 +47,8 @@ class AMTWeights:
         sd.update(dict(self.module.named_buffers()))
         versions = tuple((k, v._version, v.data_ptr()) for k, v in sd.items())
         if versions != self._versions:
+            if self._versions is not None:     # changed through torch (load_state_dict, another optimiser): the trainer's
+                self.flat16 = None             # bf16 mirror no longer matches; it is handed back at its next step
             self._sd, self._cache, self._versions = sd, {}, versions
 
     def invalidate(self) -> None:
@@ -62,6 +65,10 @@ class AMTWeights:
 
     def w(self, name: str, rows: Optional[slice] = None, cols: Optional[int] = None) -> torch.Tensor:
         """Matrix [N, K] in the compute dtype (row slice / leading `cols` columns optional)."""
+        if self.dtype == torch.bfloat16 and self.flat16 is not None and cols is None:
+            t = self.flat16.get(name)
+            if t is not None and t.shape[1] % 8 == 0:              # 16-byte row pitch: usable by TMA as it is
+                return t[rows] if rows is not None else t
         key = "%s|%s|%s" % (name, rows, cols)
         t = self._cache.get(key)
         if t is None:
@@ -87,6 +94,8 @@ class AMTWeights:
 
     def table(self, name: str) -> torch.Tensor:
         """Vector-like tensor converted to the compute dtype (Er)."""
+        if self.dtype == torch.bfloat16 and self.flat16 is not None and name in self.flat16:
+            return self.flat16[name]
         key = "%s|tab" % name
         t = self._cache.get(key)
         if t is None:

@@ -155,6 +155,15 @@ def cast_2d(src: torch.Tensor, dst_dtype: torch.dtype, ld_dst: Optional[int] = N
     return dst
 
 
+def cast_into(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[r, c] = src[r, c] converted to dst's dtype (same 2-D shape, unit inner strides)."""
+    require_device(src)
+    assert src.dim() == 2 and dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    check(load().v2m_cast_2d(ptr(src), dtype_code(src.dtype), src.stride(0), ptr(dst), dtype_code(dst.dtype), dst.stride(0), src.shape[0],
+                             src.shape[1], 0, stream()))
+    _lib.count_launches(1)
+
+
 def _binary(a: torch.Tensor, b: torch.Tensor, mode: int, alpha: float) -> torch.Tensor:
     require_device(a)
     a, b = a.contiguous(), b.contiguous()

@@ -46,19 +46,25 @@ class FlatParams:
     """Re-homes every parameter of `model` into one contiguous fp32 buffer (and its gradient into another)."""
 
     def __init__(self, model: torch.nn.Module):
-        params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
         self.params = params
-        n = sum(p.numel() for p in params)
-        dev = params[0].device
-        self.flat_p = torch.empty(n, device=dev, dtype=torch.float32)
-        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
-        off = 0
+        # every parameter starts on a 16-byte boundary of the bf16 mirror (TMA operands), the total is a multiple of 512
+        offs, off = [], 0
         for p in params:
+            offs.append(off)
+            off += (p.numel() + 7) // 8 * 8
+        n = (off + 511) // 512 * 512
+        dev = params[0].device
+        self.flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.offsets = {}
+        for (name, p), o in zip(named, offs):
             k = p.numel()
-            self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
-            p.data = self.flat_p[off:off + k].view(p.shape)
-            p.grad = self.flat_g[off:off + k].view(p.shape)
-            off += k
+            self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[o:o + k].view(p.shape)
+            p.grad = self.flat_g[o:o + k].view(p.shape)
+            self.offsets[name] = (o, tuple(p.shape))
         self.numel = n
 
 
@@ -75,6 +81,21 @@ class Trainer:
         self.step_no = 0
         self.last_parts = None
         self._copy_stream = None
+        # bf16 mirror of the flat parameter buffer: ONE cast kernel per optimiser step instead of one per weight matrix;
+        # the model's bf16 operands are views into it (engine.AMTWeights.flat16)
+        self.flat16 = None
+        if self.flat.flat_p.is_cuda:
+            self.flat16 = torch.empty(self.flat.numel, device=self.flat.flat_p.device, dtype=torch.bfloat16)
+            self._views16 = {name: self.flat16[o:o + math.prod(shp)].view(shp) for name, (o, shp) in self.flat.offsets.items()}
+            self._mirror()
+
+    def _mirror(self) -> None:
+        """flat fp32 masters -> flat bf16 mirror, and hand the views to the model's weight resolvers."""
+        from . import ops
+        ops.cast_into(self.flat.flat_p.view(-1, 512), self.flat16.view(-1, 512))
+        for w in getattr(self.model, "_weights", {}).values():
+            w.flat16 = self._views16
+            w.invalidate()
 
     def prefetch(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Starts the host -> device copy of a (pinned) batch on a side stream and returns the device batch; train_step waits
@@ -127,8 +148,11 @@ class Trainer:
         ops.adam_step(self.flat.flat_p, self.flat.flat_g, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps,
                       self.step_no, grad_scale=scale)
         self.flat.flat_g.zero_()
-        for w in getattr(m, "_weights", {}).values():    # the kernel updated the masters behind torch's back: re-derive the
-            w.invalidate()                                # bf16 operand copies on the next forward
+        if self.flat16 is not None:                       # the kernel updated the masters behind torch's back: refresh the bf16
+            self._mirror()                                # mirror and drop the per-weight copies
+        else:
+            for w in getattr(m, "_weights", {}).values():
+                w.invalidate()
         if slot_i is not None:                  # the prefetch slot may be overwritten once this step has run
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
