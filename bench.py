@@ -114,11 +114,11 @@ def train_leg(args, dev, rank, world, dtype):
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
     m.load_state_dict(syn.fill_like_reference_init(shapes, seed=1), strict=False)
     m = m.to(dev).train().set_compute_dtype(dtype)
-    tr = Trainer(m)
+    tr = Trainer(m, use_graph=True)                     # the step is replayed from one CUDA graph after two eager steps
     b0, b1 = shard_range(TRAIN_GLOBAL_BATCH, rank, world)
     inp = syn.make_inputs(b1 - b0, 4321 + rank, SEQ - 1, 300, 0)
     host = {k: v.pin_memory() for k, v in inp.items()}
-    for _ in range(2):
+    for _ in range(4):                                  # two eager steps, the capture, one replay
         tr.train_step(host)
     if world > 1:
         dist.barrier()
@@ -143,7 +143,7 @@ def train_leg(args, dev, rank, world, dtype):
     flops = 69.4e9 * TRAIN_GLOBAL_BATCH                 # 3 x 23.14 GF per sample
     return {"metric": "train_samples_per_s", "value": TRAIN_GLOBAL_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
             "global_batch": TRAIN_GLOBAL_BATCH, "per_gpu_batch": b1 - b0, "dropout": TRAIN_DROPOUT, "scaling": "strong", "steps": args.train_steps,
-            "loss": lossv, "tflops": flops / (ms * 1e-3) / 1e12, "launches_per_step": _lib.launches() // args.train_steps,
+            "loss": lossv, "tflops": flops / (ms * 1e-3) / 1e12, "launches_per_step": tr.launches_per_step or _lib.launches() // args.train_steps, "cuda_graph": tr._graph is not None,
             "collective": "NCCL all-reduce of the flat fp32 gradient buffer (130 MB)" if world > 1 else "none (1 rank)",
             "timed": "e2e: every step copies its batch from pinned host memory (side stream, overlapped with the previous step), loss read back at the end",
             "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values())}

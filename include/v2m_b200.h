@@ -69,6 +69,7 @@ typedef struct v2m_epilogue {
   float drop_scale;
   uint32_t drop_thresh, drop_seed;
   int32_t drop_after_res;
+  const uint32_t* drop_seed_dev;   /* optional device counter added to drop_seed: fresh masks when a CUDA graph is replayed */
 } v2m_epilogue;
 
 /* fp32 SIMT GEMM (exact path, batch-invariant summation order). */
@@ -99,6 +100,7 @@ typedef struct v2m_attn {
   float q_scale;
   float* lse; float* p_out;
   float drop_scale; uint32_t drop_thresh, drop_seed;   /* dropout of the probabilities (training, bf16 path): see v2m_epilogue */
+  const uint32_t* drop_seed_dev;
 } v2m_attn;
 int v2m_attn_fwd(const v2m_attn* p, int32_t dtype, void* stream);
 
@@ -117,6 +119,7 @@ typedef struct v2m_attn_bwd_t {
   int32_t B, Hq, Hkv, Lq, Lk, dh, causal, er_len, dtype;
   float q_scale;
   float drop_scale; uint32_t drop_thresh, drop_seed;   /* the forward's probability dropout (v2m_attn_bwd_tc only) */
+  const uint32_t* drop_seed_dev;
 } v2m_attn_bwd_t;
 int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);
 /* Tensor-core attention backward (bf16, head_dim 64, q pre-scaled: q_scale must be 1): same gradients as v2m_attn_bwd from
@@ -129,7 +132,7 @@ int v2m_attn_bwd_tc(const v2m_attn_bwd_t* a, void* ws, int64_t ws_bytes, void* s
  * epilogue (drop_scale = 0: no dropout; otherwise the mask of v2m_epilogue with the same seed / threshold). */
 int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
                 float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
-                float drop_scale, uint32_t drop_thresh, uint32_t drop_seed, void* stream);
+                float drop_scale, uint32_t drop_thresh, uint32_t drop_seed, const uint32_t* drop_seed_dev, void* stream);
 int v2m_layernorm_bwd(const void* x, int32_t x_dtype, const float* gamma, const void* dy, int32_t dy_dtype, void* dx,
                       int32_t dx_dtype, float* dgamma, float* dbeta, int32_t M, int32_t D, float eps, void* stream);
 int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld_d, float* dtable, int32_t rows, int32_t D,
@@ -144,8 +147,10 @@ int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t 
 int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
                  float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream);
 /* torch.optim.Adam step on flat fp32 buffers (train.py:238). grad_scale multiplies g first (1/world_size after all-reduce). */
-int v2m_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
-                  float grad_scale, void* stream);
+/* dyn (optional, device {lr, 1-b1^t, 1-b2^t}) overrides the scalar arguments at run time (CUDA-graph replay with a schedule);
+ * p16 (optional) receives the bf16 mirror of the updated parameters; zero_grad clears g; ctr (optional) += 1 per call. */
+int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
+                  float grad_scale, const float* dyn, void* p16, int32_t zero_grad, uint32_t* ctr, void* stream);
 
 /* ---- residual + LayerNorm (rpr.py:59-69; nn.LayerNorm eps) ------------------------------------ */
 int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma,

@@ -141,3 +141,31 @@ def test_optimizer_steps_reach_the_bf16_operands():
     assert moved32 > 0.05 and moved16 > 0.05                      # the updates are visible in the next forward
     # and both precisions moved to the same place (closer to each other than to the starting point)
     assert rel_err(outs[torch.bfloat16][1], outs[torch.float32][1]) < 0.5 * moved32
+
+
+def test_graphed_train_step_equals_eager_and_keeps_dropout_fresh():
+    """Trainer(use_graph=True): the replayed CUDA graph of the whole step walks the same trajectory as eager steps (learning
+    rate schedule and Adam bias corrections come from device memory), and with dropout the masks change from replay to replay
+    (device-side seed counter) although the host-side seeds are frozen into the graph."""
+    from video2music_b200.trainer import Trainer
+    inp = {k: v.to(DEV) for k, v in syn.make_inputs(4, 78, 50, 40, 0).items()}
+    losses, finals = {}, {}
+    for graph in (False, True):
+        m, _ = _model(4, torch.bfloat16)
+        tr = Trainer(m, warmup=400, use_graph=graph)               # Noam schedule: lr = 5.5e-6 * step, different every step
+        init = tr.flat.flat_p.clone()
+        losses[graph] = [float(tr.train_step(inp)) for _ in range(7)]
+        finals[graph] = tr.flat.flat_p.clone()
+        assert (tr._graph is not None) == graph
+    print("eager", losses[False], "graph", losses[True])
+    assert max(abs(a - b) for a, b in zip(losses[False], losses[True])) < 5e-3 * abs(losses[False][0])
+    moved = float((finals[False] - init).norm())
+    assert moved > 0 and float((finals[True] - finals[False]).norm()) < 0.1 * moved
+    # dropout under replay: frozen weights (lr = 0), same batch -> the loss only moves if the masks do
+    from video2music_b200 import VideoMusicTransformer
+    m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.2)
+    m.load_state_dict(syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=4), strict=False)
+    m = m.to(DEV).train().set_compute_dtype(torch.bfloat16)
+    tr = Trainer(m, lr=0.0, use_graph=True)
+    ls = [float(tr.train_step(inp)) for _ in range(6)]
+    assert tr._graph is not None and len(set(ls[3:])) == len(ls[3:])      # three replays, three different losses

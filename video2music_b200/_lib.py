@@ -26,7 +26,7 @@ class Epilogue(C.Structure):
                 ("alpha", C.c_float), ("alpha_cols", i32), ("relu", i32), ("residual_bf16", i32),
                 ("head_scatter", i32), ("S", i32), ("H", i32), ("dh", i32), ("cap", i32), ("pos0", i32),
                 ("part_stride", i64), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32),
-                ("drop_after_res", i32)]
+                ("drop_after_res", i32), ("drop_seed_dev", vp)]
 
 
 class Attn(C.Structure):
@@ -35,7 +35,8 @@ class Attn(C.Structure):
                 ("v_sb", i64), ("v_sl", i64), ("o_sb", i64), ("o_sl", i64),
                 ("B", i32), ("Hq", i32), ("Hkv", i32), ("Lq", i32), ("Lk", i32), ("dh", i32),
                 ("causal", i32), ("Er", vp), ("er_len", i32), ("q_scale", C.c_float),
-                ("lse", vp), ("p_out", vp), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32)]
+                ("lse", vp), ("p_out", vp), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32),
+                ("drop_seed_dev", vp)]
 
 
 class AttnBwd(C.Structure):
@@ -43,7 +44,8 @@ class AttnBwd(C.Structure):
                 [(n, i64) for n in ("q_sb", "q_sl", "k_sb", "k_sl", "v_sb", "v_sl", "o_sb", "o_sl", "do_sb", "do_sl",
                                     "dq_sb", "dq_sl", "dkv_sb", "dkv_sl")] +
                 [(n, i32) for n in ("B", "Hq", "Hkv", "Lq", "Lk", "dh", "causal", "er_len", "dtype")] +
-                [("q_scale", C.c_float), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32)])
+                [("q_scale", C.c_float), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32),
+                ("drop_seed_dev", vp)])
 
 
 class DecLayer(C.Structure):
@@ -99,12 +101,12 @@ def load() -> C.CDLL:
     lib.v2m_attn_bwd_tc.argtypes = [C.POINTER(AttnBwd), vp, i64, vp]
     lib.v2m_attn_bwd_tc_workspace.argtypes = [i32, i32, i32, i32, i32]
     lib.v2m_attn_bwd_tc_workspace.restype = i64
-    lib.v2m_dy_prep.argtypes = [vp, i32, i64, vp, i32, i64, i32, C.c_float, i32, vp, i32, i64, vp, i32, i32, C.c_float, C.c_uint32, C.c_uint32, vp]
+    lib.v2m_dy_prep.argtypes = [vp, i32, i64, vp, i32, i64, i32, C.c_float, i32, vp, i32, i64, vp, i32, i32, C.c_float, C.c_uint32, C.c_uint32, vp, vp]
     lib.v2m_layernorm_bwd.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, C.c_float, vp]
     lib.v2m_embed_bwd.argtypes = [vp, vp, i32, i64, vp, i32, i32, vp]
     lib.v2m_amt_metrics.argtypes = [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp]
     lib.v2m_amt_loss.argtypes = [vp, vp, vp, i32, i32, i64, C.c_float, C.c_float, C.c_float, vp, vp, vp]
-    lib.v2m_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp]
+    lib.v2m_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp, vp, i32, vp, vp]
     lib.v2m_layernorm.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, C.c_float, vp]
     lib.v2m_embed_sum.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.v2m_concat_features.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp]

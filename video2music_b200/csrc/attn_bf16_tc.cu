@@ -62,6 +62,7 @@ struct AttnTcArgs {
   int B, Hq, Hkv, Lq, Lk, causal, has_er, er_len;
   int swap;   // tensor maps are (col, batch, row) instead of (col, row, batch): sequence-first layouts
   float drop_scale; unsigned int drop_thresh, drop_seed;   // probability dropout (training), 0 = off
+  const unsigned int* drop_seed_dev;
   int n_q_tiles, n_items;   // work items = (video, head) x 128-row query tiles; CTAs walk them with stride gridDim.x
 };
 
@@ -224,6 +225,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float LOG2E = 1.4426950408889634f;
     const uint32_t bar_id = 1 + quad;                            // named barrier of this quadrant's AT_NW warps
     uint32_t par = 0, parb = 0;
+    const uint32_t dseed = DROP ? a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0u) : 0u;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const Item t = make_item(item);
     const int i0 = t.i0, imax = t.imax, nk16 = t.nk16, b = t.b, hq = t.hq, bh = t.bh;
@@ -328,7 +330,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           sum += p0 + p1;
           if (DROP) {                                          // dropout acts on the normalised probabilities: O stays / sum
             const uint32_t rr = (uint32_t)bh * (uint32_t)a.Lq + (uint32_t)i;
-            const uint32_t hh = drop_hash4(a.drop_seed, rr, (j0 >> 2) + (k >> 1));   // columns j0 + 2k, +1 (j0 % 32 == 0); CSE'd per two k
+            const uint32_t hh = drop_hash4(dseed, rr, (j0 >> 2) + (k >> 1));   // columns j0 + 2k, +1 (j0 % 32 == 0); CSE'd per two k
             p0 = drop_keep_byte(hh, 2 * k, a.drop_thresh) ? p0 * a.drop_scale : 0.f;
             p1 = drop_keep_byte(hh, 2 * k + 1, a.drop_thresh) ? p1 * a.drop_scale : 0.f;
           }
@@ -417,7 +419,7 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
   a.o = p.o; a.o_sb = p.o_sb; a.o_sl = p.o_sl; a.lse = p.lse;
   a.B = p.B; a.Hq = p.Hq; a.Hkv = p.Hkv; a.Lq = p.Lq; a.Lk = p.Lk; a.causal = p.causal;
   a.has_er = p.Er != nullptr; a.er_len = p.er_len; a.swap = swap;
-  a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed;
+  a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed; a.drop_seed_dev = p.drop_seed_dev;
   static bool attr = false;
   static int nw_plain = 4;                 // softmax warps per quadrant without RPR (V2M_ATTN_NW=2 for A/B measurements)
   if (!attr) {

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(
   __syncthreads();
 
   const int r0 = w * 16;
+  const uint32_t dseed = DROP ? p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0u) : 0u;
   uint32_t qa[4][4], doa[4][4];
   float Dlo = 0.f, Dhi = 0.f;
 #pragma unroll
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(
         // forward dropout of the probabilities: O = (P o M) V, so dV needs P o M and dP = (dO V^T) o M; D = rowsum(dO o O) as is
         float mk = 1.f;
         if (DROP)                                              // j and j ^ 1 share one hash (the compiler merges the two calls)
-          mk = drop_keep_byte(drop_hash4(p.drop_seed, (uint32_t)bh * (uint32_t)p.Lq + (uint32_t)i, (uint32_t)j >> 2), (uint32_t)j,
+          mk = drop_keep_byte(drop_hash4(dseed, (uint32_t)bh * (uint32_t)p.Lq + (uint32_t)i, (uint32_t)j >> 2), (uint32_t)j,
                               p.drop_thresh) ? p.drop_scale : 0.f;
         s[nt][e] = pv * mk;
         dp[nt][e] = pv * (dp[nt][e] * mk - (hi ? Dhi : Dlo));

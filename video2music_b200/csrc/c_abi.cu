@@ -36,6 +36,7 @@ static GemmEpilogue to_ep(const v2m_epilogue* e) {
   g.head_scatter = e->head_scatter; g.S = e->S; g.H = e->H; g.dh = e->dh; g.cap = e->cap; g.pos0 = e->pos0;
   g.part_stride = e->part_stride;
   g.drop_scale = e->drop_scale; g.drop_thresh = e->drop_thresh; g.drop_seed = e->drop_seed; g.drop_after_res = e->drop_after_res;
+  g.drop_seed_dev = e->drop_seed_dev;
   return g;
 }
 
@@ -105,7 +106,7 @@ int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {
   p.B = a->B; p.Hq = a->Hq; p.Hkv = a->Hkv; p.Lq = a->Lq; p.Lk = a->Lk; p.dh = a->dh;
   p.causal = a->causal; p.Er = a->Er; p.er_len = a->er_len; p.q_scale = a->q_scale;
   p.lse = a->lse; p.p_out = a->p_out;
-  p.drop_scale = a->drop_scale; p.drop_thresh = a->drop_thresh; p.drop_seed = a->drop_seed;
+  p.drop_scale = a->drop_scale; p.drop_thresh = a->drop_thresh; p.drop_seed = a->drop_seed; p.drop_seed_dev = a->drop_seed_dev;
   V2M_REQUIRE(dtype == V2M_BF16 || p.drop_scale == 0.f, "v2m_attn_fwd: probability dropout exists on the bf16 path only");
   if (dtype == V2M_F32) return attn_fwd_f32(p, static_cast<cudaStream_t>(stream));
   if (dtype == V2M_BF16) return attn_fwd_bf16_tc(p, static_cast<cudaStream_t>(stream));
@@ -135,9 +136,9 @@ int v2m_attn_bwd_tc(const v2m_attn_bwd_t* a, void* ws, int64_t ws_bytes, void* s
 
 int v2m_dy_prep(const void* dy, int32_t dy_dtype, int64_t ld_dy, const void* y, int32_t y_dtype, int64_t ld_y, int32_t relu,
                 float alpha, int32_t alpha_cols, void* dz, int32_t dz_dtype, int64_t ld_dz, float* db, int32_t M, int32_t N,
-                float drop_scale, uint32_t drop_thresh, uint32_t drop_seed, void* stream) {
+                float drop_scale, uint32_t drop_thresh, uint32_t drop_seed, const uint32_t* drop_seed_dev, void* stream) {
   return dy_prep(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz, db, M, N, drop_scale, drop_thresh,
-                 drop_seed, static_cast<cudaStream_t>(stream));
+                 drop_seed, drop_seed_dev, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_layernorm_bwd(const void* x, int32_t x_dtype, const float* gamma, const void* dy, int32_t dy_dtype, void* dx,
@@ -161,9 +162,9 @@ int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emoti
                   dlogits, static_cast<cudaStream_t>(stream));
 }
 
-int v2m_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
-                  float grad_scale, void* stream) {
-  return adam_step(p, g, m, v, n, lr, b1, b2, eps, step, grad_scale, static_cast<cudaStream_t>(stream));
+int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
+                  float grad_scale, const float* dyn, void* p16, int32_t zero_grad, uint32_t* ctr, void* stream) {
+  return adam_step(p, g, m, v, n, lr, b1, b2, eps, step, grad_scale, dyn, p16, zero_grad, ctr, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma, const float* beta,

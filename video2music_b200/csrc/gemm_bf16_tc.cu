@@ -224,6 +224,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int half = (warp - 4) >> 2;          // which chunks of the tile this warp drains
     unsigned char* stage = smem + (size_t)Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 4) * 4096;
     uint32_t n_store = 0;                      // boxes this warp has sent (selects the staging buffer)
+    const uint32_t dseed = ep.drop_seed + (ep.drop_seed_dev ? *ep.drop_seed_dev : 0u);
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int tile = item / k_split;
@@ -313,7 +314,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ep.drop_scale != 0.f && !ep.drop_after_res) {
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {                     // one hash per four columns (n0 is a multiple of 32)
-              const uint32_t h = drop_hash4(ep.drop_seed, m, (n0 >> 2) + i4);
+              const uint32_t h = drop_hash4(dseed, m, (n0 >> 2) + i4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[4 * i4 + e] = drop_keep_byte(h, e, ep.drop_thresh) ? v[4 * i4 + e] * ep.drop_scale : 0.f;
             }
@@ -341,7 +342,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ep.drop_scale != 0.f && ep.drop_after_res) {
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {                     // one hash per four columns (n0 is a multiple of 32)
-              const uint32_t h = drop_hash4(ep.drop_seed, m, (n0 >> 2) + i4);
+              const uint32_t h = drop_hash4(dseed, m, (n0 >> 2) + i4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[4 * i4 + e] = drop_keep_byte(h, e, ep.drop_thresh) ? v[4 * i4 + e] * ep.drop_scale : 0.f;
             }
@@ -396,11 +397,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (n < ep.alpha_cols) x *= ep.alpha;
             if (ep.relu) x = fmaxf(x, 0.f);
             if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
-            if (ep.drop_scale != 0.f && !ep.drop_after_res) x = drop_keep(ep.drop_seed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
+            if (ep.drop_scale != 0.f && !ep.drop_after_res) x = drop_keep(dseed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
             if (ep.residual)
               x += ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
                                     : __ldg(ep.residual + res_row + n);
-            if (ep.drop_scale != 0.f && ep.drop_after_res) x = drop_keep(ep.drop_seed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
+            if (ep.drop_scale != 0.f && ep.drop_after_res) x = drop_keep(dseed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
             const long long o = epi_out_index(ep, m, n, ldc);
             if (out_bf16) static_cast<bf16*>(C)[o] = __float2bfloat16_rn(x);
             else static_cast<float*>(C)[o] = x;

@@ -31,6 +31,7 @@ struct GemmEpilogue {
   float drop_scale = 0.f;
   unsigned int drop_thresh = 0, drop_seed = 0;
   int drop_after_res = 0;
+  const unsigned int* drop_seed_dev = nullptr;   // optional device counter added to drop_seed (CUDA-graph replays need fresh masks)
 };
 
 #ifdef __CUDACC__
@@ -73,6 +74,7 @@ struct AttnParams {
   // iff drop_keep(drop_seed, (b*Hq+h)*Lq + i, j, drop_thresh), scaled by drop_scale = 1/(1-p); 0 = off.  bf16 path only.
   float drop_scale = 0.f;
   unsigned int drop_thresh = 0, drop_seed = 0;
+  const unsigned int* drop_seed_dev = nullptr;   // optional device counter added to drop_seed
 };
 int attn_fwd_f32(const AttnParams& p, cudaStream_t stream);
 int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream);
@@ -85,6 +87,7 @@ struct AttnBwdParams {
   float q_scale;
   float drop_scale;                 // the forward's probability dropout (same mask function), 0 = off; tensor-core path only
   unsigned int drop_thresh, drop_seed;
+  const unsigned int* drop_seed_dev;   // optional device counter added to drop_seed
 };
 int attn_bwd(const AttnBwdParams& p, cudaStream_t stream);
 // Tensor-core variant (bf16, head_dim 64, q pre-scaled): p.dk / p.dv are BF16 outputs written once (no accumulation),
@@ -94,15 +97,15 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStream
 
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
             int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, float drop_scale, unsigned int drop_thresh,
-            unsigned int drop_seed, cudaStream_t stream);
+            unsigned int drop_seed, const unsigned int* drop_seed_dev, cudaStream_t stream);
 int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy, int dy_dtype, void* dx, int dx_dtype,
                   float* dgamma, float* dbeta, int M, int D, float eps, cudaStream_t stream);
 int embed_bwd(const long long* idx, const void* d, int d_dtype, long long ld_d, float* dtable, int rows, int D,
               cudaStream_t stream);
 int amt_loss(const float* logits, const long long* tgt, const float* tgt_emotion, int R, int Cn, long long ignore, float smooth,
              float w_ce, float w_bce, float* scratch3, float* dlogits, cudaStream_t stream);
-int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
-              float grad_scale, cudaStream_t stream);
+int adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+              float grad_scale, const float* dyn, void* p16, int zero_grad, unsigned int* ctr, cudaStream_t stream);
 
 // y = LayerNorm(x (+ res)) * gamma + beta over the last dim D (eps 1e-5 like nn.LayerNorm).
 // dtype codes: 0 = fp32, 1 = bf16.  y2 (optional) receives a second copy in dtype y2_dtype.

@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(256) dy_prep_kernel(const void* __restrict__ d
                                                       const void* __restrict__ y, int y_dtype, long long ld_y, int relu,
                                                       float alpha, int alpha_cols, void* __restrict__ dz, int dz_dtype,
                                                       long long ld_dz, float* __restrict__ db, int M, int N, float drop_scale,
-                                                      unsigned int drop_thresh, unsigned int drop_seed) {
+                                                      unsigned int drop_thresh, unsigned int drop_seed,
+                                                      const unsigned int* __restrict__ drop_seed_dev) {
+  if (drop_seed_dev) drop_seed += *drop_seed_dev;
   __shared__ float part[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
                                                              long long ld_y, int relu, float alpha, int alpha_cols,
                                                              bf16* __restrict__ dz, long long ld_dz, float* __restrict__ db, int M,
                                                              int N, float drop_scale, unsigned int drop_thresh,
-                                                             unsigned int drop_seed) {
+                                                             unsigned int drop_seed, const unsigned int* __restrict__ drop_seed_dev) {
+  if (drop_seed_dev) drop_seed += *drop_seed_dev;
   __shared__ float part[32][8 * 8 + 1];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;            // 8 column groups x 32 row lanes
   const int n0 = (blockIdx.x * 8 + tx) * 8;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
 
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
             int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, float drop_scale, unsigned int drop_thresh,
-            unsigned int drop_seed, cudaStream_t stream) {
+            unsigned int drop_seed, const unsigned int* drop_seed_dev, cudaStream_t stream) {
   if (M == 0 || N == 0) return kOk;
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (dy_dtype == 1 && (!dz || dz_dtype == 1) && (!relu || y_dtype == 1) && N % 8 == 0 && ld_dy % 8 == 0 && (!dz || ld_dz % 8 == 0) &&
@@ -119,14 +122,14 @@ int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_
     if (gy2 > 148) gy2 = 148;
     dim3 grid2((N + 63) / 64, gy2);
     dy_prep_bf16x8_kernel<<<grid2, 256, 0, stream>>>(static_cast<const bf16*>(dy), ld_dy, static_cast<const bf16*>(y), ld_y, relu, alpha,
-                                                     alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N, drop_scale, drop_thresh, drop_seed);
+                                                     alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N, drop_scale, drop_thresh, drop_seed, drop_seed_dev);
     return check_launch("dy_prep_bf16x8");
   }
   int gy = (M + 7) / 8;
   if (gy > 148 * 2) gy = 148 * 2;
   dim3 grid((N + 31) / 32, gy);
   dy_prep_kernel<<<grid, 256, 0, stream>>>(dy, dy_dtype, ld_dy, y, y_dtype, ld_y, relu, alpha, alpha_cols, dz, dz_dtype, ld_dz,
-                                          db, M, N, drop_scale, drop_thresh, drop_seed);
+                                          db, M, N, drop_scale, drop_thresh, drop_seed, drop_seed_dev);
   return check_launch("dy_prep");
 }
 
@@ -386,24 +389,35 @@ int amt_loss(const float* logits, const long long* tgt, const float* tgt_emotion
 }
 
 // ---- Adam (train.py:238: betas (0.9, 0.98), eps 1e-9 per constants.py:89-91; torch.optim.Adam semantics) --------
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale) {
+// dyn (optional, device): {lr, 1 - b1^t, 1 - b2^t} read at run time, so that a CUDA graph of the whole training step can be
+// replayed with a changing learning-rate schedule.  Fused extras: p16 (optional) receives the bf16 mirror of the updated
+// parameters, zero_grad clears the gradient buffer for the next step, ctr (optional) is a device step counter that the
+// dropout kernels add to their seeds.
+__global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale,
+                            const float* __restrict__ dyn, bf16* __restrict__ p16, int zero_grad, unsigned int* __restrict__ ctr) {
+  if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    const float pi = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    p[i] = pi;
+    if (p16) p16[i] = __float2bfloat16_rn(pi);
+    if (zero_grad) g[i] = 0.f;
   }
+  if (ctr && blockIdx.x == 0 && threadIdx.x == 0) *ctr += 1u;
 }
 
-int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
-              float grad_scale, cudaStream_t stream) {
+int adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+              float grad_scale, const float* dyn, void* p16, int zero_grad, unsigned int* ctr, cudaStream_t stream) {
   if (n == 0) return kOk;
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   const long long want = (n + 255) / 256;
-  adam_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale);
+  adam_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale, dyn,
+                                                                            static_cast<bf16*>(p16), zero_grad, ctr);
   return check_launch("adam_step");
 }
 

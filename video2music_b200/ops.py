@@ -16,6 +16,11 @@ def _rows(t: torch.Tensor) -> int:
     return t.numel() // t.shape[-1]
 
 
+# Optional device counter (uint32 viewed as int32 tensor of one element) that every dropout kernel adds to its seed: set by the
+# trainer when the training step is replayed from a CUDA graph, where the host-side seeds are frozen into the graph.
+DROP_SEED_DEV: Optional[torch.Tensor] = None
+
+
 def drop_args(p: float, seed: int):
     """(scale, threshold, seed) of the stateless dropout mask shared by the forward and backward kernels: one hash byte per
     element, kept iff byte >= round(p * 256); the drop probability is therefore quantised to 1/256 (0.1 -> 26/256) and the
@@ -54,6 +59,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if dropout is not None and dropout[0] > 0.0:
         ep.drop_scale, ep.drop_thresh, ep.drop_seed = drop_args(dropout[0], dropout[1])
         ep.drop_after_res = int(bool(dropout[2]))
+        ep.drop_seed_dev = ptr(DROP_SEED_DEV)
     if head_scatter is not None:
         assert out is not None
         ep.head_scatter = 1
@@ -97,6 +103,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     a.lse, a.p_out = ptr(lse), ptr(p_out)
     if dropout is not None and dropout[0] > 0.0:                 # (p, seed): dropout of the probabilities, bf16 path
         a.drop_scale, a.drop_thresh, a.drop_seed = drop_args(dropout[0], dropout[1])
+        a.drop_seed_dev = ptr(DROP_SEED_DEV)
     check(load().v2m_attn_fwd(C.byref(a), dtype_code(q.dtype), stream()))
     _lib.count_launches(1)
     return out
@@ -320,7 +327,7 @@ def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: floa
     check(load().v2m_dy_prep(ptr(dy), dtype_code(dy.dtype), dy.stride(0), ptr(y), dtype_code(y.dtype) if y is not None else 0,
                              y.stride(0) if y is not None else 0, int(relu), alpha, alpha_cols, ptr(dz),
                              dtype_code(out_dtype), ld, ptr(db), M, N, *(drop_args(*dropout[:2]) if dropout and dropout[0] > 0 else (0.0, 0, 0)),
-                             stream()))
+                             ptr(DROP_SEED_DEV) if dropout and dropout[0] > 0 else None, stream()))
     _lib.count_launches(1)
     return (dz[:, :N] if (dz is not None and ld != N) else dz), db
 
@@ -421,10 +428,14 @@ def amt_metrics(logits: torch.Tensor, tgt: torch.Tensor, pad: int = 158, ks=(1, 
 
 
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, b1: float, b2: float, eps: float,
-              step: int, grad_scale: float = 1.0) -> None:
+              step: int, grad_scale: float = 1.0, *, dyn: Optional[torch.Tensor] = None, p16: Optional[torch.Tensor] = None,
+              zero_grad: bool = False, counter: Optional[torch.Tensor] = None) -> None:
+    """torch.optim.Adam semantics on flat buffers.  dyn (device fp32 [lr, 1-b1^t, 1-b2^t]) replaces the scalar lr / step at run
+    time; p16: bf16 mirror of the updated parameters; zero_grad clears g; counter (device, 4 bytes) is incremented."""
     require_device(p)
     assert p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32
-    check(load().v2m_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, b1, b2, eps, step, grad_scale, stream()))
+    check(load().v2m_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, b1, b2, eps, step, grad_scale, ptr(dyn), ptr(p16),
+                               int(zero_grad), ptr(counter), stream()))
     _lib.count_launches(1)
 
 
@@ -444,6 +455,7 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
     a.q_scale = q_scale
     if dropout is not None and dropout[0] > 0.0:                 # the forward's (p, seed)
         a.drop_scale, a.drop_thresh, a.drop_seed = drop_args(dropout[0], dropout[1])
+        a.drop_seed_dev = ptr(DROP_SEED_DEV)
     if tensor_core:
         n = int(load().v2m_attn_bwd_tc_workspace(B, Hq, Lq, Lk, int(Er is not None)))
         ws = torch.empty(n, dtype=torch.uint8, device=q.device)

@@ -70,7 +70,11 @@ class FlatParams:
 
 class Trainer:
     def __init__(self, model, lr: Optional[float] = None, betas=(0.9, 0.98), eps: float = 1e-9, warmup: int = 4000,
-                 group=None):
+                 group=None, use_graph: bool = False):
+        """use_graph: after two eager steps the whole step (forward, loss, backward, all-reduce, Adam) is captured into ONE
+        CUDA graph and replayed -- ~400 launches per step otherwise keep the host busier than a small per-GPU batch keeps the
+        GPU (strong scaling over 8 GPUs).  Needs fixed batch shapes; the learning rate, Adam's bias corrections and the
+        dropout seeds are read from device memory so that they keep changing across replays."""
         from .autograd import AmtLossFn  # noqa: F401  (fail early if the extension is missing)
         self.model = model
         self.flat = FlatParams(model)
@@ -88,14 +92,48 @@ class Trainer:
             self.flat16 = torch.empty(self.flat.numel, device=self.flat.flat_p.device, dtype=torch.bfloat16)
             self._views16 = {name: self.flat16[o:o + math.prod(shp)].view(shp) for name, (o, shp) in self.flat.offsets.items()}
             self._mirror()
+        self.use_graph = bool(use_graph) and self.flat.flat_p.is_cuda
+        self._graph = None
+        self._static = None
+        self._static_loss = None
+        self.launches_per_step = None
+        if self.use_graph:
+            from . import ops
+            dev = self.flat.flat_p.device
+            self._dyn = torch.zeros(3, device=dev, dtype=torch.float32)       # lr, 1 - b1^t, 1 - b2^t
+            self._ctr = torch.zeros(1, device=dev, dtype=torch.int32)         # step counter added to the dropout seeds
+            ops.DROP_SEED_DEV = self._ctr
 
     def _mirror(self) -> None:
         """flat fp32 masters -> flat bf16 mirror, and hand the views to the model's weight resolvers."""
         from . import ops
         ops.cast_into(self.flat.flat_p.view(-1, 512), self.flat16.view(-1, 512))
+        self._handoff()
+
+    def _handoff(self) -> None:
         for w in getattr(self.model, "_weights", {}).values():
-            w.flat16 = self._views16
-            w.invalidate()
+            if self.flat16 is not None:
+                w.flat16 = self._views16
+            w.invalidate()                      # per-weight copies (odd leading dimensions) are re-derived on the next forward
+
+    def _lr(self) -> float:
+        return self.lr if self.lr is not None else noam_lr(self.step_no, self.model.d_model, self.warmup)
+
+    def _step_body(self, b: Dict[str, torch.Tensor], dyn: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """forward + loss + backward + the one exchange step + Adam (which also writes the bf16 mirror of the parameters and
+        clears the gradients) -- everything the GPU does in one iteration, enqueued on the current stream."""
+        from . import ops
+        from .autograd import AmtLossFn
+        m = self.model
+        y = m(b["x"], b["x_root"], b["x_attr"], b["feature_semantic_list"], b["feature_key"], b["feature_scene_offset"],
+              b["feature_motion"], b["feature_emotion"])
+        loss = AmtLossFn.apply(y, b["tgt"], b["tgt_emotion"], 0.1, 0.4, 0.6)          # run_model_vevo.py:101-119
+        loss.backward()                                                                  # accumulates into flat_g views
+        scale = allreduce_mean_(self.flat.flat_g, self.group)                            # the one exchange step
+        ops.adam_step(self.flat.flat_p, self.flat.flat_g, self.m, self.v, self._lr(), self.betas[0], self.betas[1], self.eps,
+                      max(self.step_no, 1), grad_scale=scale, dyn=dyn, p16=self.flat16, zero_grad=True,
+                      counter=self._ctr if self.use_graph else None)
+        return loss.detach()
 
     def prefetch(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """Starts the host -> device copy of a (pinned) batch on a side stream and returns the device batch; train_step waits
@@ -138,21 +176,27 @@ class Trainer:
         if ready is not None:
             torch.cuda.current_stream(dev).wait_event(ready)
         b = {k: v.to(dev, non_blocking=True) for k, v in batch.items() if not k.startswith("_")}
-        y = m(b["x"], b["x_root"], b["x_attr"], b["feature_semantic_list"], b["feature_key"], b["feature_scene_offset"],
-              b["feature_motion"], b["feature_emotion"])
-        loss = AmtLossFn.apply(y, b["tgt"], b["tgt_emotion"], 0.1, 0.4, 0.6)          # run_model_vevo.py:101-119
-        loss.backward()                                                                  # accumulates into flat_g views
-        scale = allreduce_mean_(self.flat.flat_g, self.group)                            # the one exchange step
         self.step_no += 1
-        lr = self.lr if self.lr is not None else noam_lr(self.step_no, m.d_model, self.warmup)
-        ops.adam_step(self.flat.flat_p, self.flat.flat_g, self.m, self.v, lr, self.betas[0], self.betas[1], self.eps,
-                      self.step_no, grad_scale=scale)
-        self.flat.flat_g.zero_()
-        if self.flat16 is not None:                       # the kernel updated the masters behind torch's back: refresh the bf16
-            self._mirror()                                # mirror and drop the per-weight copies
+        if not self.use_graph or self.step_no <= 2:
+            loss = self._step_body(b)
         else:
-            for w in getattr(m, "_weights", {}).values():
-                w.invalidate()
+            if self._static is None:
+                self._static = {k: torch.empty_like(v) for k, v in b.items()}
+            for k, v in b.items():
+                self._static[k].copy_(v, non_blocking=True)
+            b1, b2 = self.betas
+            self._dyn.copy_(torch.tensor([self._lr(), 1.0 - b1 ** self.step_no, 1.0 - b2 ** self.step_no], dtype=torch.float32))
+            if self._graph is None:
+                from . import _lib
+                torch.cuda.synchronize(dev)
+                n0 = _lib.launches()
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._static_loss = self._step_body(self._static, dyn=self._dyn)
+                self.launches_per_step = _lib.launches() - n0
+            self._graph.replay()
+            loss = self._static_loss
+        self._handoff()
         if slot_i is not None:                  # the prefetch slot may be overwritten once this step has run
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
