@@ -2,12 +2,16 @@
 # scratch script for one gpurun call (overwritten per call)
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/gpu_tests.log
-tail -4 gpurun_out/gpu_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
-tail -2 gpurun_out/smoke.log
-timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
-echo "bench exit $?"; python -c "
-import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches']); print(d['train'])"
-tail -3 gpurun_out/bench.err
+NCU="ncu --set full --clock-control none --import-source on"
+cap() {  # name regex skip [batch]
+  timeout 400 $NCU -k regex:$2 --launch-skip $3 --launch-count 1 -o gpurun_out/ncu2_$1 -f python tools/prof_kernels.py ${4:-512} > gpurun_out/ncu2_$1.log 2>&1
+  echo "ncu $1 exit $?"
+}
+cap gemm_inproj gemm_bf16_tc_kernel 2
+cap attn_self attn_bf16_tc_kernel 2
+cap attn_cross attn_bf16_tc_kernel 9
+cap selscan "selective_scan_fwd_kernel" 7 64
+timeout 600 $NCU -k regex:attn_bwd_rows_kernel --launch-skip 54 --launch-count 2 -o gpurun_out/ncu2_bwd_rows -f python tools/train_time.py 512 bf16 1 > gpurun_out/ncu2_bwd_rows.log 2>&1
+echo "ncu rows exit $?"
+timeout 300 python tools/prof_kernels.py 512 > gpurun_out/kernels_live3.txt 2>&1
+cat gpurun_out/kernels_live3.txt
