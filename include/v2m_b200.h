@@ -275,6 +275,11 @@ int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const flo
                          int32_t ldc, int32_t N, int32_t K, void* stream);
 int v2m_moe_combine(const float* yp, const int32_t* perm, const float* w, float* out, int32_t tokens, int32_t k, int32_t d, void* stream);
 
+/* ---- RoPE of the V2/V3 attention, custom_transformer.py:1044-1053 + rotate_operation.py:117-165, fp32 --------------
+ * x, y: the (len, B, H*dh) projection as stored; cache: RotaryPositionalEmbeddings.cache[:len] ([len][H*dh/2][2] cos, sin).
+ * Literal semantics: x is viewed as [H][len][B][dh] and the cache as [H][len][dh/2][2] without any transposition. */
+int v2m_rope_quirk(const float* x, const float* cache, float* y, int32_t len, int32_t B, int32_t H, int32_t dh, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -578,3 +578,49 @@ def hits_k(out: torch.Tensor, tgt: torch.Tensor, k: int, pad: int = 158) -> floa
     m = t != pad
     hit = (top == t.unsqueeze(1)).any(dim=1) & m
     return float(hit.sum()) / max(int(m.sum()), 1)
+
+
+# --------------------------------------------------------------------------
+# V2 / V3 attention: nn.MultiheadAttention + RoPE (model/custom_transformer.py:51-321, 864-1218; rotate_operation.py)
+# --------------------------------------------------------------------------
+def rope_cache(dim: int, max_seq_len: int, base: int = 10000) -> torch.Tensor:
+    """RotaryPositionalEmbeddings._rope_init / build_rope_cache (rotate_operation.py:89-110): [max_seq_len, dim/2, 2]."""
+    theta = 1.0 / (base ** (torch.arange(0, dim, 2)[: (dim // 2)].float() / dim))
+    idx_theta = torch.einsum("i, j -> ij", torch.arange(max_seq_len, dtype=theta.dtype), theta).float()
+    return torch.stack([torch.cos(idx_theta), torch.sin(idx_theta)], dim=-1)
+
+
+def rope_literal(x: torch.Tensor, cache: torch.Tensor) -> torch.Tensor:
+    """RotaryPositionalEmbeddings.forward (rotate_operation.py:112-165) on the [n_heads, len, bsz, head_dim] VIEW that
+    custom_multi_head_attention_forward hands it (custom_transformer.py:1044-1050)."""
+    seq_len = x.size(1)
+    rc = cache[:seq_len]
+    xs = x.float().reshape(*x.shape[:-1], -1, 2)
+    rc = rc.view(-1, xs.size(1), 1, xs.size(3), 2)[:xs.size(0)]
+    out = torch.stack([xs[..., 0] * rc[..., 0] - xs[..., 1] * rc[..., 1], xs[..., 1] * rc[..., 0] + xs[..., 0] * rc[..., 1]], -1)
+    return out.flatten(3).type_as(x)
+
+
+def custom_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache: Optional[torch.Tensor], causal: bool):
+    """custom_multi_head_attention_forward (custom_transformer.py:864-1218), eval, no padding masks: returns
+    (output (L,B,E), head-averaged weights (B,L,S))."""
+    L, B, E = query.shape
+    S = key.shape[0]
+    dh = E // num_heads
+    w, b = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+    q = F.linear(query, w[:E], b[:E])
+    k = F.linear(key, w[E:2 * E], b[E:2 * E])
+    v = F.linear(value, w[2 * E:], b[2 * E:])
+    if cache is not None:
+        q = rope_literal(q.contiguous().view(num_heads, L, B, dh), cache).view(L, B, E)
+        k = rope_literal(k.contiguous().view(num_heads, S, B, dh), cache).view(S, B, E)
+    q = q.contiguous().view(L, B * num_heads, dh).transpose(0, 1) * (dh ** -0.5)
+    k = k.contiguous().view(S, B * num_heads, dh).transpose(0, 1)
+    v = v.contiguous().view(S, B * num_heads, dh).transpose(0, 1)
+    a = torch.bmm(q, k.transpose(1, 2))
+    if causal:
+        a = a + torch.triu(torch.full((L, S), float("-inf")), diagonal=1)
+    a = torch.softmax(a, dim=-1)
+    o = torch.bmm(a, v).transpose(0, 1).contiguous().view(L * B, E)
+    o = F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"]).view(L, B, E)
+    return o, a.view(B, num_heads, L, S).mean(dim=1)

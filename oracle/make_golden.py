@@ -297,6 +297,27 @@ def golden_metrics(ref):
     _save("metrics.pt", dict(cases=cases))
 
 
+def golden_custom_mha(ref):
+    """CustomMultiheadAttention with RoPE (custom_transformer.py:51-321; V2 models: RotaryPositionalEmbeddings(d_model,
+    max_sequence_video), video_music_transformer.py:379) and without, self (causal mask) and cross attention."""
+    import importlib
+    rot = importlib.import_module("model.rotate_operation")
+    out = []
+    for (L, S, B, rope, causal, self_att, seed) in [(40, 40, 2, True, True, True, 81), (24, 36, 3, True, False, False, 82),
+                                                    (300, 300, 1, True, True, True, 83), (17, 17, 2, False, False, True, 84)]:
+        torch.manual_seed(0)
+        m = ref.custom_transformer.CustomMultiheadAttention(512, 8, 0.0, RoPE=rot.RotaryPositionalEmbeddings(512, 300) if rope else None).eval()
+        sd = _load_weights(m, seed)
+        xq = syn.unit_uniform((L, B, 512), syn._gen(seed, "xq"))
+        xk = xq if self_att else syn.unit_uniform((S, B, 512), syn._gen(seed, "xk"))
+        mask = torch.triu(torch.full((L, L), float("-inf")), diagonal=1) if causal else None
+        with torch.no_grad():
+            y, w = m(xq, xk, xk, attn_mask=mask)
+        out.append(dict(spec=dict(L=L, S=S, B=B, rope=rope, causal=causal, self_att=self_att, seed=seed),
+                        weights_checksum=syn.checksum(sd), y=y.clone(), w_mean=w.mean(dim=0).clone()))
+    _save("custom_mha.pt", dict(cases=out))
+
+
 def golden_pscan(ref):
     """pscan forward/backward (pscan.py:154-226) incl. a non power-of-two length."""
     cases = []
@@ -370,7 +391,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref),
+                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

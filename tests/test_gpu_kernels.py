@@ -628,3 +628,21 @@ def test_attention_probability_dropout_forward_backward(L, S, er_len, causal):
     print("attention dropout rel errs", {n: "%.2e" % e for n, e in errs.items()})
     for n, e in errs.items():
         assert e < 2e-2, n
+
+
+# ---------------------------------------------------------------- V2 / V3 attention (nn.MultiheadAttention + RoPE)
+def test_custom_mha_rope_golden_gpu():
+    from test_oracle import _custom_mha_case
+    for c in load_golden("custom_mha.pt")["cases"]:
+        s = c["spec"]
+        m, sd, xq, xk = _custom_mha_case(c)
+        m.load_state_dict(sd)
+        m = m.to(DEV)
+        mask = torch.triu(torch.full((s["L"], s["L"]), float("-inf"), device=DEV), diagonal=1) if s["causal"] else None
+        xqd = xq.to(DEV)
+        xkd = xqd if s["self_att"] else xk.to(DEV)
+        with torch.no_grad():
+            y, w = m(xqd, xkd, xkd, attn_mask=mask)
+            y2, w2 = m(xqd, xkd, xkd, attn_mask=mask, need_weights=False)
+        assert rel_err(y, c["y"]) < 1e-4 and rel_err(w.mean(dim=0), c["w_mean"]) < 1e-4, s
+        assert w2 is None and torch.equal(y, y2)

@@ -234,3 +234,25 @@ def test_metrics_oracle_matches_reference_golden():
         for k, h in zip((1, 3, 5), c["hits"]):
             if h is not None:
                 assert abs(O.hits_k(out, tgt, k) - h) < 1e-6
+
+
+def _custom_mha_case(c):
+    from video2music_b200 import CustomMultiheadAttention, RotaryPositionalEmbeddings
+    s = c["spec"]
+    m = CustomMultiheadAttention(512, 8, 0.0, RoPE=RotaryPositionalEmbeddings(512, 300) if s["rope"] else None).eval()
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["seed"])
+    xq = syn.unit_uniform((s["L"], s["B"], 512), syn._gen(s["seed"], "xq"))
+    xk = xq if s["self_att"] else syn.unit_uniform((s["S"], s["B"], 512), syn._gen(s["seed"], "xk"))
+    return m, sd, xq, xk
+
+
+def test_custom_mha_rope_oracle_matches_reference_golden():
+    """nn.MultiheadAttention + the reference's literal RoPE reinterpretation (custom_transformer.py:1044-1053) restated."""
+    for c in load_golden("custom_mha.pt")["cases"]:
+        s = c["spec"]
+        m, sd, xq, xk = _custom_mha_case(c)
+        assert same_checksum(syn.checksum(sd), c["weights_checksum"])
+        if s["rope"]:
+            assert torch.equal(m.RoPE.cache, O.rope_cache(512, 300))
+        y, w = O.custom_mha_forward(xq, xk, xk, sd, "", 8, O.rope_cache(512, 300) if s["rope"] else None, s["causal"])
+        assert rel_err(y, c["y"]) < 2e-5 and rel_err(w.mean(dim=0), c["w_mean"]) < 2e-5

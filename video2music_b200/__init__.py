@@ -10,7 +10,8 @@ from .pscan import pscan  # noqa: F401
 from .moe import GLUExpert, MoELayer, SharedMoELayer, TopKScheduler, TemperatureScheduler  # noqa: F401
 from .grouped_query_attention import MultiheadGQA, scaled_dot_product_gqa  # noqa: F401
 from .custom_transformer import (TransformerEncoderLayer, TransformerDecoderLayer, TransformerEncoder,  # noqa: F401
-                                 TransformerDecoder, TransformerEncoderShorter, TransformerDecoderShorter)
+                                 TransformerDecoder, TransformerEncoderShorter, TransformerDecoderShorter,
+                                 CustomMultiheadAttention, RotaryPositionalEmbeddings)
 from .mamba import MambaConfig, MambaBlock, ResidualBlock, Mamba, RMSNorm, BiMambaEncoderLayer, BiMambaEncoderLayer_V1, BiMambaEncoder  # noqa: F401
 
 __version__ = "0.1.0"

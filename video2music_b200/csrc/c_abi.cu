@@ -192,6 +192,10 @@ int v2m_cast_2d(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, i
                       static_cast<cudaStream_t>(stream));
 }
 
+int v2m_rope_quirk(const float* x, const float* cache, float* y, int32_t len, int32_t B, int32_t H, int32_t dh, void* stream) {
+  return rope_quirk(x, cache, y, len, B, H, dh, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_binary_f32(const float* a, const float* b, float* out, int64_t n, int32_t mode, float alpha, void* stream) {
   return binary_op(a, b, out, n, mode, alpha, static_cast<cudaStream_t>(stream));
 }

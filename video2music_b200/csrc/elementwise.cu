@@ -250,4 +250,29 @@ int binary_op(const float* a, const float* b, float* out, long long n, int mode,
   return check_launch("binary_op");
 }
 
+// RoPE exactly as the reference's V2 attention applies it (custom_transformer.py:1044-1053 + rotate_operation.py:117-165):
+// the (len, B, E) projection is REINTERPRETED (.view, no transpose) as [H][len][B][dh], the rotation cache [len][E/2][2] is
+// reinterpreted as [H][len][dh/2][2], and pair j of element (h', l', b', .) is rotated by cache entry (h'*len + l')*(dh/2) + j.
+// One thread per (even, odd) pair.
+__global__ void __launch_bounds__(256) rope_quirk_kernel(const float* __restrict__ x, const float2* __restrict__ cache,
+                                                         float* __restrict__ y, long long n_pairs, int len, int B, int dh2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % dh2);
+    const long long r = i / dh2;                    // (h' * len + l') * B + b'
+    const long long hl = r / B;
+    const float2 cs = cache[hl * dh2 + j];
+    const float2 v = reinterpret_cast<const float2*>(x)[i];
+    reinterpret_cast<float2*>(y)[i] = make_float2(v.x * cs.x - v.y * cs.y, v.y * cs.x + v.x * cs.y);
+  }
+}
+
+int rope_quirk(const float* x, const float* cache, float* y, int len, int B, int H, int dh, cudaStream_t stream) {
+  V2M_REQUIRE(len > 0 && B > 0 && H > 0 && dh > 0 && dh % 2 == 0, "rope_quirk: bad dims len=%d B=%d H=%d dh=%d", len, B, H, dh);
+  const long long n_pairs = (long long)len * B * H * (dh / 2);
+  const long long want = (n_pairs + 255) / 256;
+  rope_quirk_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(x, reinterpret_cast<const float2*>(cache), y, n_pairs,
+                                                                                 len, B, dh / 2);
+  return check_launch("rope_quirk");
+}
+
 }  // namespace v2m

@@ -216,4 +216,7 @@ int moe_combine(const float* yp, const int* perm, const float* w, float* out, in
 int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long long pad, int k0, int k1, int k2, int* counters,
                 cudaStream_t stream);
 
+// RoPE with the reference's reinterpretations (elementwise.cu)
+int rope_quirk(const float* x, const float* cache, float* y, int len, int B, int H, int dh, cudaStream_t stream);
+
 }  // namespace v2m

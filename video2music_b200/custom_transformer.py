@@ -21,6 +21,80 @@ from . import ops
 from .rpr import _get_clones
 
 
+class RotaryPositionalEmbeddings(nn.Module):
+    """Rotation cache of rotate_operation.py:53-113 (theta_i = base^(-2i/dim), cache[pos][i] = (cos, sin)(pos * theta_i));
+    buffers are non-persistent as in the reference.  Applying it is `ops.rope_quirk` (see CustomMultiheadAttention)."""
+
+    def __init__(self, dim: int, max_seq_len: int = 4096, base: int = 10_000) -> None:
+        super().__init__()
+        self.dim, self.base, self.max_seq_len = dim, base, max_seq_len
+        theta = 1.0 / (base ** (torch.arange(0, dim, 2)[: (dim // 2)].float() / dim))
+        self.register_buffer("theta", theta, persistent=False)
+        idx_theta = torch.einsum("i, j -> ij", torch.arange(max_seq_len, dtype=theta.dtype), theta).float()
+        self.register_buffer("cache", torch.stack([torch.cos(idx_theta), torch.sin(idx_theta)], dim=-1), persistent=False)
+
+
+class CustomMultiheadAttention(nn.Module):
+    """Drop-in for custom_transformer.py:51-321 (nn.MultiheadAttention + optional RoPE, the attention of the V2 / V3 model
+    zoo): packed in-projection, RoPE on q and k with the reference's literal reinterpretations (:1044-1053), scaled
+    dot-product attention (causal float mask or none), out-projection.  fp32, inference (inputs are detached).
+    Same parameter names (`in_proj_weight`, `in_proj_bias`, `out_proj.weight`, `out_proj.bias`)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0., bias=True, add_bias_kv=False, add_zero_attn=False, kdim=None, vdim=None,
+                 batch_first=False, device=None, dtype=None, RoPE=None) -> None:
+        super().__init__()
+        if embed_dim <= 0 or num_heads <= 0:
+            raise ValueError(f"embed_dim and num_heads must be greater than 0, got embed_dim={embed_dim} and num_heads={num_heads} instead")
+        if add_bias_kv or add_zero_attn or batch_first or (kdim not in (None, embed_dim)) or (vdim not in (None, embed_dim)) or not bias:
+            raise NotImplementedError("add_bias_kv / add_zero_attn / batch_first / kdim / vdim / bias=False are never used by the reference's models")
+        self.embed_dim, self.num_heads, self.dropout, self.batch_first = embed_dim, num_heads, dropout, False
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        self.RoPE = deepcopy(RoPE)
+        self.in_proj_weight = nn.Parameter(torch.empty((3 * embed_dim, embed_dim)))
+        self.in_proj_bias = nn.Parameter(torch.empty(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=True)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.in_proj_bias, 0.)
+        nn.init.constant_(self.out_proj.bias, 0.)
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None, average_attn_weights=True,
+                is_causal=False):
+        from .rpr import is_causal_mask
+        if key_padding_mask is not None:
+            raise NotImplementedError("key_padding_mask is not used by the reference's models")
+        if self.training and self.dropout > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not built for this module")
+        L, B, E = query.shape
+        S = key.shape[0]
+        H, dh = self.num_heads, self.head_dim
+        causal = is_causal_mask(attn_mask, L) if attn_mask is not None else False
+        w, b = self.in_proj_weight.detach(), self.in_proj_bias.detach()
+        flat = lambda t: t.detach().reshape(-1, E).float().contiguous()
+        if key is query and value is query:                                            # packed self-attention projection
+            qkv = ops.linear(flat(query), w, b)
+            q, k, v = qkv[:, :E].contiguous(), qkv[:, E:2 * E].contiguous(), qkv[:, 2 * E:]
+        else:
+            q = ops.linear(flat(query), w[:E], b[:E])
+            kv = ops.linear(flat(key), w[E:], b[E:]) if key is value else None
+            k = kv[:, :E].contiguous() if kv is not None else ops.linear(flat(key), w[E:2 * E], b[E:2 * E])
+            v = kv[:, E:] if kv is not None else ops.linear(flat(value), w[2 * E:], b[2 * E:])
+        if self.RoPE is not None:                                                       # custom_transformer.py:1047-1050
+            cache = self.RoPE.cache
+            q = ops.rope_quirk(q, cache[:L].contiguous(), B, H)
+            k = ops.rope_quirk(k, cache[:S].contiguous(), B, H)
+        out = torch.empty((L * B, E), device=q.device, dtype=torch.float32)             # rows (l, b): sequence-first strides
+        p_out = torch.empty((B * H, L, S), device=q.device, dtype=torch.float32) if need_weights else None
+        ops.attention(q, k, v, out, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=(q.stride(0), B * q.stride(0)),
+                      k_strides=(k.stride(0), B * k.stride(0)), v_strides=(v.stride(0), B * v.stride(0)), o_strides=(E, B * E),
+                      causal=causal, q_scale=float(dh) ** -0.5, p_out=p_out)
+        y = ops.linear(out, self.out_proj.weight.detach(), self.out_proj.bias.detach()).view(L, B, E)
+        if not need_weights:
+            return y, None
+        wts = p_out.view(B, H, L, S)
+        return y, (wts.mean(dim=1) if average_attn_weights else wts)
+
+
 class RMSNorm(nn.Module):
     """x * rsqrt(mean(x^2) + eps) * weight, eps 1e-6 by default (custom_transformer.py:27-47)."""
 

@@ -162,6 +162,20 @@ def cast_2d(src: torch.Tensor, dst_dtype: torch.dtype, ld_dst: Optional[int] = N
     return dst
 
 
+def rope_quirk(x: torch.Tensor, cache: torch.Tensor, B: int, H: int) -> torch.Tensor:
+    """RoPE of the reference's V2 attention on a (len*B, E) fp32 projection (rows ordered (l, b)); cache = the first len
+    positions of RotaryPositionalEmbeddings.cache, contiguous [len, E/2, 2]."""
+    require_device(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and cache.dtype == torch.float32 and cache.is_contiguous()
+    E = x.shape[1]
+    length = x.shape[0] // B
+    assert cache.shape[0] == length and cache.shape[1] * 2 == E
+    y = torch.empty_like(x)
+    check(load().v2m_rope_quirk(ptr(x), ptr(cache), ptr(y), length, B, H, E // H, stream()))
+    _lib.count_launches(1)
+    return y
+
+
 def cast_into(src: torch.Tensor, dst: torch.Tensor) -> None:
     """dst[r, c] = src[r, c] converted to dst's dtype (same 2-D shape, unit inner strides)."""
     require_device(src)
