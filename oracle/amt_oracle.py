@@ -624,3 +624,43 @@ def custom_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache:
     o = torch.bmm(a, v).transpose(0, 1).contiguous().view(L * B, E)
     o = F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"]).view(L, B, E)
     return o, a.view(B, num_heads, L, S).mean(dim=1)
+
+
+def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,
+               version: str = "2.2", max_seq_video: int = 300, mask: bool = True) -> torch.Tensor:
+    """VideoMusicTransformer_V2.forward (video_music_transformer.py:437-520), eval, versions 2.0 / 2.1 / 2.2: three shallow
+    layers (CustomMultiheadAttention [+ RoPE] + GLUExpert) and n_layers - 3 deep layers (SharedMoELayer, 6 experts, top-2) in
+    both stacks (:399-416), post-norm LayerNorm wrappers (custom_transformer.py:1220-1292), final norms, Wout."""
+    B, T = x_root.shape
+    E = sd["Wout.weight"].shape[1]
+    emb = sd["embedding_root.weight"][x_root] + sd["embedding_attr.weight"][x_attr]
+    keycol = key.reshape(B, -1)[:, :1].float().expand(B, T).unsqueeze(-1)
+    xf = F.linear(torch.cat([emb, keycol], dim=-1), sd["Linear_chord.weight"], sd["Linear_chord.bias"]).permute(1, 0, 2)
+    vf = F.linear(video_features(sem, scene, motion, emotion), sd["Linear_vis.weight"], sd["Linear_vis.bias"]).permute(1, 0, 2)
+    S = vf.shape[0]
+    cache = None
+    if version == "2.0":
+        xf = xf + sd["positional_embedding.weight"][:T].unsqueeze(1)
+        vf = vf + sd["positional_embedding_video.weight"][:S].unsqueeze(1)
+    else:
+        cache = rope_cache(E, max_seq_video)
+    ln = lambda t, p: _ln(t, sd, p)
+
+    def ff(t, p, l):
+        if l < 3:
+            return glu_expert(t, sd, p + "ff.")
+        return moe_layer(t, sd, p + "ff.", 6, 2, shared=True)[0]
+    m = vf
+    for l in range(n_layers):
+        p = "transformer.encoder.layers.%d." % l
+        m = ln(m + custom_mha_forward(m, m, m, sd, p + "self_attn.", num_heads, cache, False)[0], p + "norm1")
+        m = ln(m + ff(m, p, l), p + "norm2")
+    m = ln(m, "transformer.encoder.norm")
+    y = xf
+    for l in range(n_layers):
+        p = "transformer.decoder.layers.%d." % l
+        y = ln(y + custom_mha_forward(y, y, y, sd, p + "self_attn.", num_heads, cache, bool(mask))[0], p + "norm1")
+        y = ln(y + custom_mha_forward(y, m, m, sd, p + "cross_attn.", num_heads, cache, False)[0], p + "norm2")
+        y = ln(y + ff(y, p, l), p + "norm3")
+    y = ln(y, "transformer.decoder.norm")
+    return F.linear(y.permute(1, 0, 2), sd["Wout.weight"], sd["Wout.bias"])

@@ -318,6 +318,35 @@ def golden_custom_mha(ref):
     _save("custom_mha.pt", dict(cases=out))
 
 
+def golden_v2(ref):
+    """VideoMusicTransformer_V2 '2.2' (the shipped inference default, argument_generate_funcs.py:82) and '2.0': logits of an
+    eval forward and a short generate(beam=1) of the unmodified reference."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    for ver, seed in (("2.2", 91), ("2.0", 92)):
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()), reference_cwd():
+            m = ref.vmt.VideoMusicTransformer_V2(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
+        sd = _load_weights(m, seed)
+        inp = syn.make_inputs(2, seed, 24, 40, 0)
+        args = [inp[k] for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                                 "feature_motion", "feature_emotion")]
+        with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+            y = m(*args)
+            one = [t[:1] for t in args]
+            prim = inp["x"][0, :3]
+            with reference_cwd():
+                g = m.generate(one[3], one[4][0], one[5], one[6], one[7], primer=prim, primer_root=inp["x_root"][0, :3],
+                               primer_attr=inp["x_attr"][0, :3], target_seq_length=14, beam=1, beam_chance=1.0)
+        top2 = torch.topk(torch.softmax(y, -1)[..., :157], 2).values
+        out[ver] = dict(spec=dict(version=ver, seed=seed, B=2, T=24, S=40, n_params=sum(p.numel() for p in m.parameters()),
+                                  n_keys=len(sd)), weights_checksum=syn.checksum(sd), logits=y.clone(), generated=g.clone(),
+                        keys=sorted(sd.keys())[:5])
+        print(ver, "params", out[ver]["spec"]["n_params"], "keys", len(sd), "generated", g.tolist(), "min top-2 gap %.2e" % float((top2[..., 0] - top2[..., 1]).min()))
+    _save("v2.pt", out)
+
+
 def golden_pscan(ref):
     """pscan forward/backward (pscan.py:154-226) incl. a non power-of-two length."""
     cases = []
@@ -391,7 +420,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref),
+                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

@@ -231,3 +231,28 @@ def test_generate_sampling_branch(dtype, mode, chord_embed):
     g2 = m.generate(inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"], inp["feature_motion"],
                     inp["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=T, beam=0, decode_mode=mode)
     assert torch.equal(g1, g2)
+
+
+@pytest.mark.parametrize("ver", ["2.2", "2.0"])
+def test_v2_model_forward_and_generate_vs_reference_golden(ver):
+    """VideoMusicTransformer_V2 ('2.2' = the reference's shipped inference default): logits of the eval forward and the tokens
+    of generate(beam=1) (literal loop: one full forward per token) against the unmodified reference."""
+    from test_oracle import _v2_case
+    g, m, sd, inp = _v2_case(ver)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    args = [inp[k] for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                             "feature_motion", "feature_emotion")]
+    with torch.no_grad():
+        y = m(*args)
+    assert rel_err(y, g["logits"]) < 1e-4
+    one = [t[:1] for t in args]
+    gen = m.generate(one[3], one[4][0], one[5], one[6], one[7], primer=inp["x"][0, :3], primer_root=inp["x_root"][0, :3],
+                     primer_attr=inp["x_attr"][0, :3], target_seq_length=14, beam=1, beam_chance=1.0)
+    assert torch.equal(gen.cpu(), g["generated"])
+    # sampling branch: constraints hold, tokens stay in range, root / attribute follow the token
+    u = torch.linspace(0.05, 0.95, 14)
+    smp = m.generate(one[3], one[4][0], one[5], one[6], one[7], primer=inp["x"][0, :3], primer_root=inp["x_root"][0, :3],
+                     primer_attr=inp["x_attr"][0, :3], target_seq_length=14, beam=0, uniforms=u.to(DEV)).cpu()[0]
+    assert smp.shape[0] == 14 and int(smp[3:].min()) >= 1 and int(smp.max()) < 157          # "N" is never drawn
+    assert all(not (smp[i] == smp[i - 1] == smp[i - 2]) for i in range(5, 14))             # no three equal chords in a row

@@ -1,0 +1,153 @@
+"""Drop-in for `VideoMusicTransformer_V2` (model/video_music_transformer.py:317-610), the reference's shipped inference
+default (version '2.2', argument_generate_funcs.py:82): root + attribute embeddings and the key column through
+`Linear_chord`, the concatenated per-second video features through `Linear_vis`, then an encoder / decoder built from the
+generic wrappers of custom_transformer.py -- three "shallow" layers (CustomMultiheadAttention with RoPE + GLUExpert) followed
+by `n_layers - 3` "deep" layers whose feed-forward is a SharedMoELayer (6 experts, top-2) -- and `Wout`.
+
+Same constructor signature, attribute and `state_dict` names (`transformer.encoder.layers.N.self_attn.in_proj_weight`,
+`...ff.experts.M.linear1.weight`, ...), so a reference checkpoint loads.  Inference only: eval-mode forward and `generate`
+(the literal loop of the reference: one full forward per generated token, batch of one).  Versions '2.0' (learned positional
+embeddings), '2.1' and '2.2' are built; '2.3' needs efficient_kan (out of scope), `scene_embed`, `dropTokenRate` > 0 in
+training and the logging side channel `get_highest_emotion_indices` are not reproduced.
+"""
+import copy
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .custom_transformer import (CustomMultiheadAttention, RotaryPositionalEmbeddings, TransformerDecoderLayer,
+                                 TransformerDecoderShorter, TransformerEncoderLayer, TransformerEncoderShorter)
+from .moe import GLUExpert, SharedMoELayer, TopKScheduler
+from .video_music_transformer import CHORD_ATTR_SIZE, CHORD_END, CHORD_PAD, CHORD_ROOT_SIZE, CHORD_SIZE
+
+CHORD_ROOT_PAD, CHORD_ATTR_PAD = 14, 15            # utilities/constants.py
+
+
+def chord_root_attr(c: int):
+    """chord id -> (root id, attribute id): closed form of dataset/vevo_meta/chord_inv.json + chord_root.json + chord_attr.json
+    (video_music_transformer.py:585-600; checked against the JSON tables in tests/test_oracle_vs_reference.py)."""
+    return (0, 1) if c <= 0 else ((c - 1) // 13 + 1, (c - 1) % 13 + 1)
+
+
+class _Transformer(nn.Module):
+    """Parameter layout of nn.Transformer(custom_encoder=..., custom_decoder=...): `encoder.*`, `decoder.*`."""
+
+    def __init__(self, encoder, decoder):
+        super().__init__()
+        self.encoder, self.decoder = encoder, decoder
+
+    def forward(self, src, tgt, tgt_mask=None):
+        return self.decoder(tgt, self.encoder(src), tgt_mask=tgt_mask)
+
+
+class VideoMusicTransformer_V2(nn.Module):
+    def __init__(self, version_name='2.0', n_layers=6, num_heads=8, d_model=512, dim_feedforward=1024, dropout=0.1,
+                 max_sequence_midi=2048, max_sequence_video=300, max_sequence_chord=300, total_vf_dim=0, rms_norm=False,
+                 scene_embed=False, chord_embed=False, dropTokenRate=0.0, balancing=False):
+        super().__init__()
+        if version_name not in ('2.0', '2.1', '2.2'):
+            raise NotImplementedError("version %r (2.3 needs efficient_kan: out of scope)" % (version_name,))
+        if scene_embed or chord_embed:
+            raise NotImplementedError("scene_embed / chord_embed are not built for the V2 model")
+        self.nlayers, self.nhead, self.d_model, self.d_ff, self.dropout = n_layers, num_heads, d_model, dim_feedforward, dropout
+        self.max_seq_midi, self.max_seq_video, self.max_seq_chord = max_sequence_midi, max_sequence_video, max_sequence_chord
+        self.scene_embed, self.dropTokenRate, self.chord_embed, self.version_name = scene_embed, dropTokenRate, chord_embed, version_name
+        self.embedding = nn.Embedding(CHORD_SIZE, d_model)
+        self.embedding_root = nn.Embedding(CHORD_ROOT_SIZE, d_model)
+        self.embedding_attr = nn.Embedding(CHORD_ATTR_SIZE, d_model)
+        self.total_vf_dim = total_vf_dim
+        self.Linear_vis = nn.Linear(total_vf_dim, d_model)
+        self.Linear_chord = nn.Linear(d_model + 1, d_model)
+        self.condition_linear = nn.Linear(1, d_model)
+        norm = nn.LayerNorm(d_model)
+        RoPE = None
+        if version_name == '2.0':
+            self.positional_embedding = nn.Embedding(max_sequence_chord, d_model)
+            self.positional_embedding_video = nn.Embedding(max_sequence_video, d_model)
+        else:
+            RoPE = RotaryPositionalEmbeddings(d_model, max_sequence_video)       # video_music_transformer.py:379
+        self.n_experts, self.n_experts_per_token = 6, 2
+        expert = GLUExpert(d_model, dim_feedforward, dropout)
+        att = CustomMultiheadAttention(d_model, num_heads, dropout, RoPE=RoPE)
+        topk = None if version_name == '2.2' else TopKScheduler(n_experts=6, min_n_experts_per_token=2, update_step=32)
+        moelayer = SharedMoELayer(expert=expert, d_model=d_model, n_experts=6, n_experts_per_token=2, dropout=dropout,
+                                  balancing=balancing, topk_scheduler=topk, temperature_scheduler=None, use_KAN=False)
+        swiglu = GLUExpert(d_model, dim_feedforward, dropout)
+        mk_e = lambda ff: TransformerEncoderLayer(att, ff, pre_norm=False, norm=norm, dropout=dropout)
+        mk_d = lambda ff: TransformerDecoderLayer(att, att, ff, pre_norm=False, norm=norm, dropout=dropout)
+        rate = 3
+        enc = nn.ModuleList([copy.deepcopy(mk_e(swiglu)) for _ in range(rate)] + [copy.deepcopy(mk_e(moelayer)) for _ in range(n_layers - rate)])
+        dec = nn.ModuleList([copy.deepcopy(mk_d(swiglu)) for _ in range(rate)] + [copy.deepcopy(mk_d(moelayer)) for _ in range(n_layers - rate)])
+        self.transformer = _Transformer(TransformerEncoderShorter(enc, norm), TransformerDecoderShorter(dec, norm))
+        self.Wout = nn.Linear(d_model, CHORD_SIZE)
+        self.softmax = nn.Softmax(dim=-1)
+
+    # ------------------------------------------------------------------ forward (video_music_transformer.py:437-520)
+    def forward(self, x, x_root, x_attr, feature_semantic_list, feature_key, feature_scene_offset, feature_motion, feature_emotion,
+                mask=True):
+        if self.training:
+            raise NotImplementedError("the V2 model runs inference only (eval()); training is built for the base AMT")
+        dev = self.Wout.weight.device
+        x_root, x_attr, sem, key, scene, motion, emotion = (t.to(dev) for t in (x_root, x_attr, feature_semantic_list, feature_key,
+                                                                                feature_scene_offset, feature_motion, feature_emotion))
+        B, T = x_root.shape
+        S, E = sem.shape[1], self.d_model
+        # chords, sequence-first rows (t, b): (emb_root + emb_attr | key) -> Linear_chord; the key column is a rank-1 epilogue term
+        xin = ops.embed_sum(x_root.t().reshape(-1), self.embedding_root.weight.detach(), x_attr.t().reshape(-1),
+                            self.embedding_attr.weight.detach(), torch.float32)
+        key_rows = key.reshape(B, -1)[:, 0].float().unsqueeze(0).expand(T, B).reshape(-1).contiguous()
+        wc = self.Linear_chord.weight.detach()
+        xf = ops.linear(xin, wc, self.Linear_chord.bias.detach(), k=E, row_scale=key_rows, col_vec=wc[:, E].contiguous())
+        # video features, rows (s, b)
+        tr = lambda t: t.transpose(0, 1).contiguous()
+        vin = ops.concat_features(tr(sem), tr(scene), tr(motion), tr(emotion), torch.float32, self.total_vf_dim)
+        vf = ops.linear(vin, self.Linear_vis.weight.detach(), self.Linear_vis.bias.detach())
+        if self.version_name == '2.0':                                          # learned positions (:496-505)
+            xf = ops.axpy(xf.view(T, B, E), self.positional_embedding.weight.detach()[:T].unsqueeze(1).expand(T, B, E).contiguous(), 1.0)
+            vf = ops.axpy(vf.view(S, B, E), self.positional_embedding_video.weight.detach()[:S].unsqueeze(1).expand(S, B, E).contiguous(), 1.0)
+        tgt_mask = torch.triu(torch.full((T, T), float("-inf"), device=dev), diagonal=1) if mask is True else None
+        out = self.transformer(src=vf.view(S, B, E), tgt=xf.view(T, B, E), tgt_mask=tgt_mask)      # (T, B, E)
+        y = ops.linear(out.reshape(T * B, E).contiguous(), self.Wout.weight.detach(), self.Wout.bias.detach())
+        return y.view(T, B, CHORD_SIZE).permute(1, 0, 2).contiguous()
+
+    # ------------------------------------------------------------------ generate (video_music_transformer.py:522-610)
+    @torch.no_grad()
+    def generate(self, feature_semantic_list=[], feature_key=None, feature_scene_offset=None, feature_motion=None,
+                 feature_emotion=None, primer=None, primer_root=None, primer_attr=None, target_seq_length=300, beam=0,
+                 beam_chance=1.0, max_conseq_N=0, max_conseq_chord=2, temperature=1.0, uniforms: Optional[torch.Tensor] = None):
+        """The reference's loop: batch of one, one full forward per token.  beam=1 (beam_chance >= 1): arg-max over the first
+        157 classes, root / attribute inputs of generated positions stay PAD (literal); beam=0: the sampling branch with its
+        no-"N" / no-repeat constraints, drawn by inverse CDF from `uniforms` (or torch.rand), root / attribute updated."""
+        assert (not self.training), "Cannot generate while in training mode"
+        if not (beam == 0 or (beam == 1 and beam_chance >= 1.0)):
+            raise NotImplementedError("beam > 1 / 0 < beam_chance < 1 are not reproduced")
+        dev = self.Wout.weight.device
+        gen = torch.full((1, target_seq_length), CHORD_PAD, dtype=torch.long, device=dev)
+        gen_root = torch.full((1, target_seq_length), CHORD_ROOT_PAD, dtype=torch.long, device=dev)
+        gen_attr = torch.full((1, target_seq_length), CHORD_ATTR_PAD, dtype=torch.long, device=dev)
+        n0 = len(primer)
+        gen[..., :n0], gen_root[..., :n0], gen_attr[..., :n0] = primer.long().to(dev), primer_root.long().to(dev), primer_attr.long().to(dev)
+        if beam == 0 and uniforms is None:
+            uniforms = torch.rand(target_seq_length, device=dev)
+        cur = n0
+        while cur < target_seq_length:
+            logits = self.forward(gen[..., :cur], gen_root[..., :cur], gen_attr[..., :cur], feature_semantic_list, feature_key,
+                                  feature_scene_offset, feature_motion, feature_emotion)
+            probs = torch.softmax(logits[0, cur - 1] / temperature, dim=-1)[:CHORD_END]
+            if beam == 1:
+                gen[0, cur] = int(torch.argmax(probs))
+            else:
+                probs = probs.clone()
+                if max_conseq_N == 0:
+                    probs[0] = 0.0
+                if cur >= max_conseq_chord and bool((gen[0, cur - max_conseq_chord:cur] == gen[0, cur - 1]).all()):
+                    probs[int(gen[0, cur - 1])] = 0.0
+                cdf = torch.cumsum(probs / probs.sum(), dim=0)
+                tok = min(int((cdf <= float(uniforms[cur])).sum()), CHORD_END - 1)
+                gen[0, cur] = tok
+                r, a = chord_root_attr(tok)
+                gen_root[0, cur], gen_attr[0, cur] = r, a
+            cur += 1
+        return gen[:, :cur]
