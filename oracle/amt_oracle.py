@@ -626,11 +626,12 @@ def custom_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache:
     return o, a.view(B, num_heads, L, S).mean(dim=1)
 
 
-def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,
-               version: str = "2.2", max_seq_video: int = 300, mask: bool = True) -> torch.Tensor:
-    """VideoMusicTransformer_V2.forward (video_music_transformer.py:437-520), eval, versions 2.0 / 2.1 / 2.2: three shallow
-    layers (CustomMultiheadAttention [+ RoPE] + GLUExpert) and n_layers - 3 deep layers (SharedMoELayer, 6 experts, top-2) in
-    both stacks (:399-416), post-norm LayerNorm wrappers (custom_transformer.py:1220-1292), final norms, Wout."""
+def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int, num_heads: int, ff_kind,
+                rope: bool, pos_tables: bool, rms: bool = False, max_seq_video: int = 300, mask: bool = True) -> torch.Tensor:
+    """Shared body of VideoMusicTransformer_V1.forward / _V2.forward (video_music_transformer.py:141-225, 437-520), eval:
+    embeddings + key column -> Linear_chord, video features -> Linear_vis, learned position tables or RoPE inside the
+    attention, post-norm wrappers (custom_transformer.py:1220-1292) with feed-forward ff_kind(layer) in {"glu", "moe",
+    "shared"}, final norms, Wout."""
     B, T = x_root.shape
     E = sd["Wout.weight"].shape[1]
     emb = sd["embedding_root.weight"][x_root] + sd["embedding_attr.weight"][x_attr]
@@ -638,18 +639,17 @@ def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layer
     xf = F.linear(torch.cat([emb, keycol], dim=-1), sd["Linear_chord.weight"], sd["Linear_chord.bias"]).permute(1, 0, 2)
     vf = F.linear(video_features(sem, scene, motion, emotion), sd["Linear_vis.weight"], sd["Linear_vis.bias"]).permute(1, 0, 2)
     S = vf.shape[0]
-    cache = None
-    if version == "2.0":
+    if pos_tables:
         xf = xf + sd["positional_embedding.weight"][:T].unsqueeze(1)
         vf = vf + sd["positional_embedding_video.weight"][:S].unsqueeze(1)
-    else:
-        cache = rope_cache(E, max_seq_video)
-    ln = lambda t, p: _ln(t, sd, p)
+    cache = rope_cache(E, max_seq_video) if rope else None
+    ln = lambda t, p: _norm_generic(t, sd, p, rms)
 
     def ff(t, p, l):
-        if l < 3:
+        kind = ff_kind(l)
+        if kind == "glu":
             return glu_expert(t, sd, p + "ff.")
-        return moe_layer(t, sd, p + "ff.", 6, 2, shared=True)[0]
+        return moe_layer(t, sd, p + "ff.", 6, 2, shared=(kind == "shared"))[0]
     m = vf
     for l in range(n_layers):
         p = "transformer.encoder.layers.%d." % l
@@ -664,3 +664,18 @@ def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layer
         y = ln(y + ff(y, p, l), p + "norm3")
     y = ln(y, "transformer.decoder.norm")
     return F.linear(y.permute(1, 0, 2), sd["Wout.weight"], sd["Wout.bias"])
+
+
+def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,
+               version: str = "2.2", max_seq_video: int = 300, mask: bool = True) -> torch.Tensor:
+    """VideoMusicTransformer_V2 (versions 2.0 / 2.1 / 2.2): three shallow layers (GLUExpert) then SharedMoELayer layers (:399-416)."""
+    return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads,
+                       lambda l: "glu" if l < 3 else "shared", rope=version != "2.0", pos_tables=version == "2.0",
+                       max_seq_video=max_seq_video, mask=mask)
+
+
+def v1_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,
+               version: str = "1.1", rms: bool = False, mask: bool = True) -> torch.Tensor:
+    """VideoMusicTransformer_V1 versions 1.1 (MoELayer) / 1.3 (SharedMoELayer): video_music_transformer.py:77-118."""
+    return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads,
+                       lambda l: "moe" if version == "1.1" else "shared", rope=False, pos_tables=True, rms=rms, mask=mask)

@@ -233,7 +233,7 @@ def test_generate_sampling_branch(dtype, mode, chord_embed):
     assert torch.equal(g1, g2)
 
 
-@pytest.mark.parametrize("ver", ["2.2", "2.0"])
+@pytest.mark.parametrize("ver", ["2.2", "2.0", "1.1", "1.3rms"])
 def test_v2_model_forward_and_generate_vs_reference_golden(ver):
     """VideoMusicTransformer_V2 ('2.2' = the reference's shipped inference default): logits of the eval forward and the tokens
     of generate(beam=1) (literal loop: one full forward per token) against the unmodified reference."""

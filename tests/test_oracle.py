@@ -259,22 +259,26 @@ def test_custom_mha_rope_oracle_matches_reference_golden():
 
 
 def _v2_case(ver):
-    from video2music_b200 import VideoMusicTransformer_V2
+    from video2music_b200 import VideoMusicTransformer_V1, VideoMusicTransformer_V2
     g = load_golden("v2.pt")[ver]
     s = g["spec"]
-    m = VideoMusicTransformer_V2(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
+    if ver.startswith("2"):
+        m = VideoMusicTransformer_V2(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
+    else:
+        m = VideoMusicTransformer_V1(version_name=ver[:3], total_vf_dim=syn.vf_dim(0), dropout=0.1, rms_norm=ver.endswith("rms")).eval()
     sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["seed"])
     inp = syn.make_inputs(s["B"], s["seed"], s["T"], s["S"], 0)
     return g, m, sd, inp
 
 
-@pytest.mark.parametrize("ver", ["2.2", "2.0"])
+@pytest.mark.parametrize("ver", ["2.2", "2.0", "1.1", "1.3rms"])
 def test_v2_model_oracle_matches_reference_golden(ver):
     """VideoMusicTransformer_V2 (video_music_transformer.py:317-520): same parameter set as the reference (count, names) and
     the oracle's restatement of its forward reproduces the reference's logits."""
     g, m, sd, inp = _v2_case(ver)
     assert sum(p.numel() for p in m.parameters()) == g["spec"]["n_params"] and len(sd) == g["spec"]["n_keys"]
     assert sorted(sd.keys())[:5] == g["keys"] and same_checksum(syn.checksum(sd), g["weights_checksum"])
-    y = O.v2_forward(sd, inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
-                     inp["feature_motion"], inp["feature_emotion"], version=ver)
+    a = (sd, inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+         inp["feature_motion"], inp["feature_emotion"])
+    y = O.v2_forward(*a, version=ver) if ver.startswith("2") else O.v1_forward(*a, version=ver[:3], rms=ver.endswith("rms"))
     assert rel_err(y, g["logits"]) < 5e-5

@@ -42,7 +42,25 @@ class _Transformer(nn.Module):
         return self.decoder(tgt, self.encoder(src), tgt_mask=tgt_mask)
 
 
-class VideoMusicTransformer_V2(nn.Module):
+class _ZooModel(nn.Module):
+    """forward / generate shared by the V1 and V2 classes (their bodies are the same in the reference up to the positional
+    scheme: learned position tables in V1 and V2 '2.0', RoPE inside the attention otherwise)."""
+
+    def _embeddings(self, d_model, total_vf_dim, max_sequence_chord, max_sequence_video, pos_tables: bool):
+        self.embedding = nn.Embedding(CHORD_SIZE, d_model)
+        self.embedding_root = nn.Embedding(CHORD_ROOT_SIZE, d_model)
+        self.embedding_attr = nn.Embedding(CHORD_ATTR_SIZE, d_model)
+        self.total_vf_dim = total_vf_dim
+        self.Linear_vis = nn.Linear(total_vf_dim, d_model)
+        self.Linear_chord = nn.Linear(d_model + 1, d_model)
+        if pos_tables:
+            self.positional_embedding = nn.Embedding(max_sequence_chord, d_model)
+            self.positional_embedding_video = nn.Embedding(max_sequence_video, d_model)
+        self.condition_linear = nn.Linear(1, d_model)
+        self._pos_tables = pos_tables
+
+
+class VideoMusicTransformer_V2(_ZooModel):
     def __init__(self, version_name='2.0', n_layers=6, num_heads=8, d_model=512, dim_feedforward=1024, dropout=0.1,
                  max_sequence_midi=2048, max_sequence_video=300, max_sequence_chord=300, total_vf_dim=0, rms_norm=False,
                  scene_embed=False, chord_embed=False, dropTokenRate=0.0, balancing=False):
@@ -54,20 +72,9 @@ class VideoMusicTransformer_V2(nn.Module):
         self.nlayers, self.nhead, self.d_model, self.d_ff, self.dropout = n_layers, num_heads, d_model, dim_feedforward, dropout
         self.max_seq_midi, self.max_seq_video, self.max_seq_chord = max_sequence_midi, max_sequence_video, max_sequence_chord
         self.scene_embed, self.dropTokenRate, self.chord_embed, self.version_name = scene_embed, dropTokenRate, chord_embed, version_name
-        self.embedding = nn.Embedding(CHORD_SIZE, d_model)
-        self.embedding_root = nn.Embedding(CHORD_ROOT_SIZE, d_model)
-        self.embedding_attr = nn.Embedding(CHORD_ATTR_SIZE, d_model)
-        self.total_vf_dim = total_vf_dim
-        self.Linear_vis = nn.Linear(total_vf_dim, d_model)
-        self.Linear_chord = nn.Linear(d_model + 1, d_model)
-        self.condition_linear = nn.Linear(1, d_model)
+        self._embeddings(d_model, total_vf_dim, max_sequence_chord, max_sequence_video, pos_tables=version_name == '2.0')
         norm = nn.LayerNorm(d_model)
-        RoPE = None
-        if version_name == '2.0':
-            self.positional_embedding = nn.Embedding(max_sequence_chord, d_model)
-            self.positional_embedding_video = nn.Embedding(max_sequence_video, d_model)
-        else:
-            RoPE = RotaryPositionalEmbeddings(d_model, max_sequence_video)       # video_music_transformer.py:379
+        RoPE = None if version_name == '2.0' else RotaryPositionalEmbeddings(d_model, max_sequence_video)   # :379
         self.n_experts, self.n_experts_per_token = 6, 2
         expert = GLUExpert(d_model, dim_feedforward, dropout)
         att = CustomMultiheadAttention(d_model, num_heads, dropout, RoPE=RoPE)
@@ -104,7 +111,7 @@ class VideoMusicTransformer_V2(nn.Module):
         tr = lambda t: t.transpose(0, 1).contiguous()
         vin = ops.concat_features(tr(sem), tr(scene), tr(motion), tr(emotion), torch.float32, self.total_vf_dim)
         vf = ops.linear(vin, self.Linear_vis.weight.detach(), self.Linear_vis.bias.detach())
-        if self.version_name == '2.0':                                          # learned positions (:496-505)
+        if self._pos_tables:                                                    # learned positions (:496-505, :196-201)
             xf = ops.axpy(xf.view(T, B, E), self.positional_embedding.weight.detach()[:T].unsqueeze(1).expand(T, B, E).contiguous(), 1.0)
             vf = ops.axpy(vf.view(S, B, E), self.positional_embedding_video.weight.detach()[:S].unsqueeze(1).expand(S, B, E).contiguous(), 1.0)
         tgt_mask = torch.triu(torch.full((T, T), float("-inf"), device=dev), diagonal=1) if mask is True else None
@@ -151,3 +158,42 @@ class VideoMusicTransformer_V2(nn.Module):
                 gen_root[0, cur], gen_attr[0, cur] = r, a
             cur += 1
         return gen[:, :cur]
+
+
+class VideoMusicTransformer_V1(_ZooModel):
+    """Drop-in for `VideoMusicTransformer_V1` (model/video_music_transformer.py:22-315), versions '1.1' (MoELayer) and '1.3'
+    (SharedMoELayer): stock multi-head attention, GLU experts (6, top-2) in every layer of both stacks, learned position tables,
+    LayerNorm or RMSNorm (`rms_norm`).  The versions with nn.Sequential SiLU experts or RoPE ('1.0', '1.2.x', '1.3.3', '1.3.4')
+    are not built.  Inference only."""
+
+    def __init__(self, version_name='1.1', n_layers=6, num_heads=8, d_model=512, dim_feedforward=1024, dropout=0.1,
+                 max_sequence_midi=2048, max_sequence_video=300, max_sequence_chord=300, total_vf_dim=0, rms_norm=False,
+                 scene_embed=False, chord_embed=False, dropTokenRate=0.0):
+        super().__init__()
+        if version_name not in ('1.1', '1.3'):
+            raise NotImplementedError("version %r (built: '1.1', '1.3')" % (version_name,))
+        if scene_embed or chord_embed:
+            raise NotImplementedError("scene_embed / chord_embed are not built for the V1 model")
+        from .custom_transformer import RMSNorm, TransformerDecoder, TransformerEncoder
+        from .moe import MoELayer
+        self.nlayers, self.nhead, self.d_model, self.d_ff, self.dropout = n_layers, num_heads, d_model, dim_feedforward, dropout
+        self.max_seq_midi, self.max_seq_video, self.max_seq_chord = max_sequence_midi, max_sequence_video, max_sequence_chord
+        self.scene_embed, self.dropTokenRate, self.chord_embed, self.version_name = scene_embed, dropTokenRate, chord_embed, version_name
+        self._embeddings(d_model, total_vf_dim, max_sequence_chord, max_sequence_video, pos_tables=True)
+        norm = RMSNorm(d_model) if rms_norm else nn.LayerNorm(d_model)
+        self.n_experts, self.n_experts_per_token = 6, 2
+        expert = GLUExpert(d_model, dim_feedforward, dropout)
+        att = CustomMultiheadAttention(d_model, num_heads, dropout)             # == nn.MultiheadAttention (same parameters)
+        if version_name == '1.1':
+            moelayer = MoELayer(expert, d_model, 6, 2, dropout)
+        else:
+            moelayer = SharedMoELayer(expert, d_model, n_experts=6, n_experts_per_token=2, balancing=False, dropout=dropout)
+        encoder = TransformerEncoder(TransformerEncoderLayer(att, moelayer, pre_norm=False, norm=norm, dropout=dropout), n_layers, norm)
+        decoder = TransformerDecoder(TransformerDecoderLayer(att, att, moelayer, pre_norm=False, norm=norm, dropout=dropout), n_layers, norm)
+        self.transformer = _Transformer(encoder, decoder)
+        self.Wout = nn.Linear(d_model, CHORD_SIZE)
+        self.softmax = nn.Softmax(dim=-1)
+
+
+_ZooModel.forward = VideoMusicTransformer_V2.forward
+_ZooModel.generate = VideoMusicTransformer_V2.generate
