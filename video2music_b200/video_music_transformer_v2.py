@@ -27,7 +27,7 @@ CHORD_ROOT_PAD, CHORD_ATTR_PAD = 14, 15            # utilities/constants.py
 
 def chord_root_attr(c: int):
     """chord id -> (root id, attribute id): closed form of dataset/vevo_meta/chord_inv.json + chord_root.json + chord_attr.json
-    (video_music_transformer.py:585-600; checked against the JSON tables in tests/test_oracle_vs_reference.py)."""
+    (video_music_transformer.py:585-600; checked against those JSON tables in the CPU tests)."""
     return (0, 1) if c <= 0 else ((c - 1) // 13 + 1, (c - 1) % 13 + 1)
 
 
