@@ -626,8 +626,40 @@ def custom_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache:
     return o, a.view(B, num_heads, L, S).mean(dim=1)
 
 
+def diff_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache: Optional[torch.Tensor], causal: bool, depth: int):
+    """DifferentialMultiheadAttention.forward (custom_transformer.py:763-830), eval: literal views included."""
+    import math
+    L, B, E = query.shape
+    S = key.shape[0]
+    dh = E // num_heads
+    k = F.linear(key, sd[p + "k_proj.weight"])
+    q = F.linear(query, sd[p + "q_proj.weight"])
+    v = F.linear(value, sd[p + "v_proj.weight"])
+    q = q.contiguous().view(2 * num_heads, L, B, dh)
+    k = k.contiguous().view(2 * num_heads, S, B, dh)
+    if cache is not None:
+        q, k = rope_literal(q, cache), rope_literal(k, cache)
+    q = q.view(B, L, 2 * num_heads, dh).transpose(1, 2) * (dh ** -0.5)
+    k = k.view(B, S, 2 * num_heads, dh).transpose(1, 2)
+    v = v.contiguous().view(B, S, num_heads, dh).transpose(1, 2)
+    a = torch.matmul(q, k.transpose(-1, -2))
+    if causal:
+        a = a + torch.triu(torch.full((L, S), float("-inf")), diagonal=1 + S - L)
+    a = torch.softmax(a, dim=-1)
+    lam_init = 0.8 - 0.6 * math.exp(-0.3 * depth)
+    lam = torch.exp(torch.sum(sd[p + "lambda_q1"] * sd[p + "lambda_k1"])) - torch.exp(torch.sum(sd[p + "lambda_q2"] * sd[p + "lambda_k2"])) \
+        + lam_init
+    a = a.view(B, num_heads, 2, L, S)
+    a = a[:, :, 0] - lam * a[:, :, 1]
+    o = torch.matmul(a, v)                                                            # (B, H, L, dh)
+    o = o * torch.rsqrt(o.pow(2).mean(-1, keepdim=True) + 1e-5) * sd[p + "subln.weight"]
+    o = (o * (1 - lam_init)).contiguous().view(L, B, E)
+    return F.linear(o, sd[p + "out_proj.weight"])
+
+
 def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int, num_heads: int, ff_kind,
-                rope: bool, pos_tables: bool, rms: bool = False, max_seq_video: int = 300, mask: bool = True) -> torch.Tensor:
+                rope: bool, pos_tables: bool, rms: bool = False, max_seq_video: int = 300, mask: bool = True,
+                rope_dim: Optional[int] = None, diff_enc: bool = False, diff_dec: bool = False, pre_norm: bool = False) -> torch.Tensor:
     """Shared body of VideoMusicTransformer_V1.forward / _V2.forward (video_music_transformer.py:141-225, 437-520), eval:
     embeddings + key column -> Linear_chord, video features -> Linear_vis, learned position tables or RoPE inside the
     attention, post-norm wrappers (custom_transformer.py:1220-1292) with feed-forward ff_kind(layer) in {"glu", "moe",
@@ -642,8 +674,13 @@ def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_laye
     if pos_tables:
         xf = xf + sd["positional_embedding.weight"][:T].unsqueeze(1)
         vf = vf + sd["positional_embedding_video.weight"][:S].unsqueeze(1)
-    cache = rope_cache(E, max_seq_video) if rope else None
+    cache = rope_cache(rope_dim or E, max_seq_video) if rope else None
     ln = lambda t, p: _norm_generic(t, sd, p, rms)
+
+    def att(qx, kx, p, causal, diff, depth):
+        if diff:
+            return diff_mha_forward(qx, kx, kx, sd, p, num_heads, cache, causal, depth)
+        return custom_mha_forward(qx, kx, kx, sd, p, num_heads, cache, causal)[0]
 
     def ff(t, p, l):
         kind = ff_kind(l)
@@ -653,15 +690,26 @@ def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_laye
     m = vf
     for l in range(n_layers):
         p = "transformer.encoder.layers.%d." % l
-        m = ln(m + custom_mha_forward(m, m, m, sd, p + "self_attn.", num_heads, cache, False)[0], p + "norm1")
-        m = ln(m + ff(m, p, l), p + "norm2")
+        if not pre_norm:
+            m = ln(m + att(m, m, p + "self_attn.", False, diff_enc, l), p + "norm1")
+            m = ln(m + ff(m, p, l), p + "norm2")
+        else:                                                               # custom_transformer.py:1239-1247
+            t = ln(m, p + "norm1")
+            m = m + att(t, t, p + "self_attn.", False, diff_enc, l)
+            m = m + ff(ln(m, p + "norm2"), p, l)
     m = ln(m, "transformer.encoder.norm")
     y = xf
     for l in range(n_layers):
         p = "transformer.decoder.layers.%d." % l
-        y = ln(y + custom_mha_forward(y, y, y, sd, p + "self_attn.", num_heads, cache, bool(mask))[0], p + "norm1")
-        y = ln(y + custom_mha_forward(y, m, m, sd, p + "cross_attn.", num_heads, cache, False)[0], p + "norm2")
-        y = ln(y + ff(y, p, l), p + "norm3")
+        if not pre_norm:
+            y = ln(y + att(y, y, p + "self_attn.", bool(mask), diff_dec, l), p + "norm1")
+            y = ln(y + att(y, m, p + "cross_attn.", False, diff_dec, l), p + "norm2")
+            y = ln(y + ff(y, p, l), p + "norm3")
+        else:                                                               # :1278-1291
+            t = ln(y, p + "norm1")
+            y = y + att(t, t, p + "self_attn.", bool(mask), diff_dec, l)
+            y = y + att(ln(y, p + "norm2"), m, p + "cross_attn.", False, diff_dec, l)
+            y = y + ff(ln(y, p + "norm3"), p, l)
     y = ln(y, "transformer.decoder.norm")
     return F.linear(y.permute(1, 0, 2), sd["Wout.weight"], sd["Wout.bias"])
 
@@ -679,3 +727,13 @@ def v1_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layer
     """VideoMusicTransformer_V1 versions 1.1 (MoELayer) / 1.3 (SharedMoELayer): video_music_transformer.py:77-118."""
     return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads,
                        lambda l: "moe" if version == "1.1" else "shared", rope=False, pos_tables=True, rms=rms, mask=mask)
+
+
+def v3_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,
+               version: str = "3.0", mask: bool = True) -> torch.Tensor:
+    """VideoMusicTransformer_V3 (video_music_transformer.py:611-760): RMSNorm, RoPE cache of dimension 2 * d_model, differential
+    attention in the decoder (all versions) and in the encoder (3.1, 3.2), three GLU layers then SharedMoE layers, pre-norm for
+    3.2.  The cross-attention of a differential layer carries the decoder mask?  No: memory_mask is None (:1271)."""
+    return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads, lambda l: "glu" if l < 3 else "shared",
+                       rope=True, pos_tables=False, rms=True, mask=mask, rope_dim=2 * sd["Wout.weight"].shape[1],
+                       diff_enc=version != "3.0", diff_dec=True, pre_norm=version == "3.2")

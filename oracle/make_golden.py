@@ -324,11 +324,13 @@ def golden_v2(ref):
     import third_party.log_maxvio as lm
     lm.is_logging = False
     out = {}
-    for ver, seed in (("2.2", 91), ("2.0", 92), ("1.1", 93), ("1.3rms", 94)):
+    for ver, seed in (("2.2", 91), ("2.0", 92), ("1.1", 93), ("1.3rms", 94), ("3.0", 95), ("3.1", 96), ("3.2", 97)):
         torch.manual_seed(0)
         with contextlib.redirect_stdout(io.StringIO()), reference_cwd():
             if ver.startswith("2"):
                 m = ref.vmt.VideoMusicTransformer_V2(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
+            elif ver.startswith("3"):
+                m = ref.vmt.VideoMusicTransformer_V3(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
             else:
                 m = ref.vmt.VideoMusicTransformer_V1(version_name=ver[:3], total_vf_dim=syn.vf_dim(0), dropout=0.1,
                                                      rms_norm=ver.endswith("rms")).eval()

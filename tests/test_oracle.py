@@ -259,11 +259,13 @@ def test_custom_mha_rope_oracle_matches_reference_golden():
 
 
 def _v2_case(ver):
-    from video2music_b200 import VideoMusicTransformer_V1, VideoMusicTransformer_V2
+    from video2music_b200 import VideoMusicTransformer_V1, VideoMusicTransformer_V2, VideoMusicTransformer_V3
     g = load_golden("v2.pt")[ver]
     s = g["spec"]
     if ver.startswith("2"):
         m = VideoMusicTransformer_V2(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
+    elif ver.startswith("3"):
+        m = VideoMusicTransformer_V3(version_name=ver, total_vf_dim=syn.vf_dim(0), dropout=0.1).eval()
     else:
         m = VideoMusicTransformer_V1(version_name=ver[:3], total_vf_dim=syn.vf_dim(0), dropout=0.1, rms_norm=ver.endswith("rms")).eval()
     sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["seed"])
@@ -271,7 +273,7 @@ def _v2_case(ver):
     return g, m, sd, inp
 
 
-@pytest.mark.parametrize("ver", ["2.2", "2.0", "1.1", "1.3rms"])
+@pytest.mark.parametrize("ver", ["2.2", "2.0", "1.1", "1.3rms", "3.0", "3.1", "3.2"])
 def test_v2_model_oracle_matches_reference_golden(ver):
     """VideoMusicTransformer_V2 (video_music_transformer.py:317-520): same parameter set as the reference (count, names) and
     the oracle's restatement of its forward reproduces the reference's logits."""
@@ -280,5 +282,10 @@ def test_v2_model_oracle_matches_reference_golden(ver):
     assert sorted(sd.keys())[:5] == g["keys"] and same_checksum(syn.checksum(sd), g["weights_checksum"])
     a = (sd, inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
          inp["feature_motion"], inp["feature_emotion"])
-    y = O.v2_forward(*a, version=ver) if ver.startswith("2") else O.v1_forward(*a, version=ver[:3], rms=ver.endswith("rms"))
+    if ver.startswith("2"):
+        y = O.v2_forward(*a, version=ver)
+    elif ver.startswith("3"):
+        y = O.v3_forward(*a, version=ver)
+    else:
+        y = O.v1_forward(*a, version=ver[:3], rms=ver.endswith("rms"))
     assert rel_err(y, g["logits"]) < 5e-5

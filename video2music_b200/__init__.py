@@ -11,8 +11,8 @@ from .moe import GLUExpert, MoELayer, SharedMoELayer, TopKScheduler, Temperature
 from .grouped_query_attention import MultiheadGQA, scaled_dot_product_gqa  # noqa: F401
 from .custom_transformer import (TransformerEncoderLayer, TransformerDecoderLayer, TransformerEncoder,  # noqa: F401
                                  TransformerDecoder, TransformerEncoderShorter, TransformerDecoderShorter,
-                                 CustomMultiheadAttention, RotaryPositionalEmbeddings)
-from .video_music_transformer_v2 import VideoMusicTransformer_V1, VideoMusicTransformer_V2  # noqa: F401
+                                 CustomMultiheadAttention, DifferentialMultiheadAttention, RotaryPositionalEmbeddings)
+from .video_music_transformer_v2 import VideoMusicTransformer_V1, VideoMusicTransformer_V2, VideoMusicTransformer_V3  # noqa: F401
 from .mamba import MambaConfig, MambaBlock, ResidualBlock, Mamba, RMSNorm, BiMambaEncoderLayer, BiMambaEncoderLayer_V1, BiMambaEncoder  # noqa: F401
 
 __version__ = "0.1.0"

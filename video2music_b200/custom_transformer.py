@@ -12,6 +12,7 @@ caller plugs in (MultiheadGQA, MultiheadAttentionRPR, MoELayer, SharedMoELayer, 
 residual add and the normalisation run as one kernel of ours.  Inference only (inputs are detached);
 training goes through `autograd.py` for the base AMT.  The RoSC layers (:1294-1369) are out of scope.
 """
+import math
 from copy import deepcopy
 
 import torch
@@ -93,6 +94,81 @@ class CustomMultiheadAttention(nn.Module):
             return y, None
         wts = p_out.view(B, H, L, S)
         return y, (wts.mean(dim=1) if average_attn_weights else wts)
+
+
+def lambda_init_fn(depth):
+    return 0.8 - 0.6 * math.exp(-0.3 * depth)                 # custom_transformer.py:607-608
+
+
+class DifferentialMultiheadAttention(nn.Module):
+    """Drop-in for custom_transformer.py:610-832 (Differential Transformer attention of the V3 models), inference.
+    q, k are projected to 2 * num_heads heads, v to num_heads heads; head pair (2h, 2h+1) gives
+        softmax(q_2h k_2h^T) v_h - lambda * softmax(q_2h+1 k_2h+1^T) v_h,
+    followed by a per-head RMSNorm (`subln`), the factor (1 - lambda_init) and the bias-free out-projection.
+    Literal layout behaviour kept: RoPE on the [2H, len, B, dh] VIEW of the projections (:777-784), then the same memory
+    viewed batch-first as [B, len, 2H, dh] (:786-788), and the (B, H, L, dh) result viewed as (L, B, E) (:824)."""
+
+    def __init__(self, embed_dim, num_heads, dropout=0., batch_first=False, device=None, dtype=None, RoPE=None, depth=2) -> None:
+        super().__init__()
+        if embed_dim <= 0 or num_heads <= 0:
+            raise ValueError(f"embed_dim and num_heads must be greater than 0, got embed_dim={embed_dim} and num_heads={num_heads} instead")
+        if batch_first:
+            raise NotImplementedError("batch_first is never used by the reference's models")
+        self.embed_dim, self.num_heads, self.batch_first = embed_dim, num_heads, False
+        self.dropout = nn.Dropout(dropout)
+        self.head_dim = embed_dim // num_heads
+        self.scaling = self.head_dim ** -0.5
+        self.RoPE = deepcopy(RoPE)
+        self.k_proj = nn.Linear(embed_dim, embed_dim * 2, bias=False)
+        self.q_proj = nn.Linear(embed_dim, embed_dim * 2, bias=False)
+        self.v_proj = nn.Linear(embed_dim, embed_dim, bias=False)
+        self.out_proj = nn.Linear(embed_dim, embed_dim, bias=False)
+        for lin in (self.k_proj, self.q_proj, self.v_proj, self.out_proj):
+            nn.init.xavier_uniform_(lin.weight)
+        self.lambda_init = lambda_init_fn(depth)
+        for n in ("lambda_q1", "lambda_k1", "lambda_q2", "lambda_k2"):
+            setattr(self, n, nn.Parameter(torch.zeros(self.head_dim, dtype=torch.float32).normal_(mean=0, std=0.1)))
+        self.subln = RMSNorm(self.head_dim, eps=1e-5, elementwise_affine=True)
+        self._lam = None
+
+    def _lambda_full(self) -> float:
+        ps = (self.lambda_q1, self.lambda_k1, self.lambda_q2, self.lambda_k2)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if self._lam is None or self._lam[0] != key:                     # four 64-vectors: evaluated on the host, cached
+            q1, k1, q2, k2 = (p.detach().float().cpu() for p in ps)
+            lam = float(torch.exp(torch.sum(q1 * k1)) - torch.exp(torch.sum(q2 * k2))) + self.lambda_init
+            self._lam = (key, lam)
+        return self._lam[1]
+
+    def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None, average_attn_weights=True,
+                is_causal=False):
+        if key_padding_mask is not None:
+            raise NotImplementedError("key_padding_mask is not used by the reference's models")
+        L, B, E = query.shape
+        S = key.shape[0]
+        H, dh = self.num_heads, self.head_dim
+        flat = lambda t: t.detach().reshape(-1, E).float().contiguous()
+        q = ops.linear(flat(query), self.q_proj.weight.detach())          # (L*B, 2E), rows (l, b)
+        k = ops.linear(flat(key), self.k_proj.weight.detach())
+        v = ops.linear(flat(value), self.v_proj.weight.detach())          # (S*B, E)
+        if self.RoPE is not None:
+            q = ops.rope_quirk(q, self.RoPE.cache[:L].contiguous(), B, 2 * H)
+            k = ops.rope_quirk(k, self.RoPE.cache[:S].contiguous(), B, 2 * H)
+        # the same memory, now read batch-first as [B, len, 2H, dh]; even / odd heads are split into two operands
+        q5, k5 = q.view(B, L, H, 2, dh), k.view(B, S, H, 2, dh)
+        causal = attn_mask is not None                                    # any mask means the causal one here (:801-809)
+        outs = []
+        for i in (0, 1):
+            qi, ki = q5[:, :, :, i].contiguous(), k5[:, :, :, i].contiguous()         # (B, len, H, dh)
+            o = torch.empty((B, L, H, dh), device=q.device, dtype=torch.float32)
+            ops.attention(qi, ki, v, o, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=(L * E, E), k_strides=(S * E, E),
+                          v_strides=(S * E, E), o_strides=(L * E, E), causal=causal, q_scale=self.scaling)
+            outs.append(o)
+        diff = ops.axpy(outs[0], outs[1], -self._lambda_full())            # a1 v - lambda a2 v
+        w = (self.subln.weight.detach() * (1.0 - self.lambda_init)).contiguous()
+        attn = ops.rmsnorm(diff.view(-1, dh), w, self.subln.eps).view(B, L, H, dh)
+        attn = attn.permute(0, 2, 1, 3).contiguous().view(L * B, E)        # (B, H, L, dh) memory read as (L, B, E) rows (:824)
+        return ops.linear(attn, self.out_proj.weight.detach()).view(L, B, E), None
 
 
 class RMSNorm(nn.Module):

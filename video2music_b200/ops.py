@@ -169,7 +169,9 @@ def rope_quirk(x: torch.Tensor, cache: torch.Tensor, B: int, H: int) -> torch.Te
     assert x.dtype == torch.float32 and x.is_contiguous() and cache.dtype == torch.float32 and cache.is_contiguous()
     E = x.shape[1]
     length = x.shape[0] // B
-    assert cache.shape[0] == length and cache.shape[1] * 2 == E
+    # a wider cache (RotaryPositionalEmbeddings(2 * d_model) feeding a d_model-wide projection in the V3 encoder) is viewed the
+    # same way by the reference ([-1, len, 1, dh/2, 2], first H slabs): only its first H * len * dh/2 entries are used
+    assert cache.shape[0] == length and cache.shape[1] * 2 >= E
     y = torch.empty_like(x)
     check(load().v2m_rope_quirk(ptr(x), ptr(cache), ptr(y), length, B, H, E // H, stream()))
     _lib.count_launches(1)

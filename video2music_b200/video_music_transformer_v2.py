@@ -195,5 +195,44 @@ class VideoMusicTransformer_V1(_ZooModel):
         self.softmax = nn.Softmax(dim=-1)
 
 
+class VideoMusicTransformer_V3(_ZooModel):
+    """Drop-in for `VideoMusicTransformer_V3` (model/video_music_transformer.py:611-905), versions '3.0', '3.1', '3.2': RMSNorm,
+    a RoPE cache of dimension 2 * d_model, DifferentialMultiheadAttention (depth = layer index) in every decoder layer and --
+    for 3.1 / 3.2 -- in the encoder ('3.0' keeps CustomMultiheadAttention there), three GLUExpert layers then SharedMoELayer
+    layers (balancing buffers registered as in the reference), pre-norm wrappers for '3.2'.  Inference only."""
+
+    def __init__(self, version_name='3.0', n_layers=6, num_heads=8, d_model=512, dim_feedforward=1024, dropout=0.1,
+                 max_sequence_midi=2048, max_sequence_video=300, max_sequence_chord=300, total_vf_dim=0, rms_norm=False,
+                 scene_embed=False, chord_embed=False, dropTokenRate=0.0):
+        super().__init__()
+        if version_name not in ('3.0', '3.1', '3.2'):
+            raise NotImplementedError("version %r (built: '3.0', '3.1', '3.2')" % (version_name,))
+        if scene_embed or chord_embed:
+            raise NotImplementedError("scene_embed / chord_embed are not built for the V3 model")
+        from .custom_transformer import DifferentialMultiheadAttention, RMSNorm
+        self.nlayers, self.nhead, self.d_model, self.d_ff, self.dropout = n_layers, num_heads, d_model, dim_feedforward, dropout
+        self.max_seq_midi, self.max_seq_video, self.max_seq_chord = max_sequence_midi, max_sequence_video, max_sequence_chord
+        self.scene_embed, self.dropTokenRate, self.chord_embed, self.version_name = scene_embed, dropTokenRate, chord_embed, version_name
+        self._embeddings(d_model, total_vf_dim, max_sequence_chord, max_sequence_video, pos_tables=False)
+        RoPE = RotaryPositionalEmbeddings(d_model * 2, max_sequence_video)      # video_music_transformer.py:662
+        norm = RMSNorm(d_model, elementwise_affine=True)
+        self.n_experts, self.n_experts_per_token = 6, 2
+        expert = GLUExpert(d_model, dim_feedforward, dropout)
+        moelayer = SharedMoELayer(expert=expert, d_model=d_model, n_experts=6, n_experts_per_token=2, dropout=dropout, balancing=True,
+                                  topk_scheduler=None, temperature_scheduler=None, use_KAN=False)
+        swiglu = GLUExpert(d_model, dim_feedforward, dropout)
+        att = CustomMultiheadAttention(d_model, num_heads, dropout=dropout, RoPE=RoPE)
+        difatt = [DifferentialMultiheadAttention(d_model, num_heads, dropout=dropout, RoPE=RoPE, depth=d) for d in range(n_layers)]
+        rate, pre_norm = 3, version_name == '3.2'
+        ffs = [swiglu] * rate + [moelayer] * (n_layers - rate)
+        enc_att = [att] * n_layers if version_name == '3.0' else difatt
+        enc = nn.ModuleList([TransformerEncoderLayer(enc_att[i], ffs[i], pre_norm=pre_norm, norm=norm, dropout=dropout) for i in range(n_layers)])
+        dec = nn.ModuleList([TransformerDecoderLayer(difatt[i], difatt[i], ffs[i], pre_norm=pre_norm, norm=norm, dropout=dropout)
+                             for i in range(n_layers)])
+        self.transformer = _Transformer(TransformerEncoderShorter(enc, norm), TransformerDecoderShorter(dec, norm))
+        self.Wout = nn.Linear(d_model, CHORD_SIZE)
+        self.softmax = nn.Softmax(dim=-1)
+
+
 _ZooModel.forward = VideoMusicTransformer_V2.forward
 _ZooModel.generate = VideoMusicTransformer_V2.generate
