@@ -166,7 +166,8 @@ int v2m_concat_features(const float* sem, int32_t sem_dim, const float* scene, c
 int v2m_cast_2d(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst,
                 int32_t rows, int32_t cols, int32_t zero_pad, void* stream);
 
-/* mode 0: out = a * silu(b) (GLUExpert gating, moe.py:47); mode 1: out = a + alpha*b (shared expert, moe.py:301) */
+/* mode 0: out = a * silu(b) (GLUExpert gating, moe.py:47); mode 1: out = a + alpha*b (shared expert, moe.py:301);
+ * mode 2: out = sigmoid(a) (instrument classifier head, video_regression.py:197-200; b is read but unused) */
 int v2m_binary_f32(const float* a, const float* b, float* out, int64_t n, int32_t mode, float alpha, void* stream);
 
 /* ---- KV-cached greedy decode (replaces the re-forward loop of VideoMusicTransformer.generate,

@@ -512,11 +512,11 @@ def mamba_block_forward(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, dt
 
 
 def mamba_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, n_layers: int, dt_rank: int, d_state: int = 16,
-                  eps: float = 1e-5) -> torch.Tensor:
+                  eps: float = 1e-5, use_version: int = 0) -> torch.Tensor:
     """Mamba.forward over ResidualBlocks (mamba.py:91-98, 144-149): x = mixer(norm(x)) + x."""
     for l in range(n_layers):
         p = "layers.%d." % l
-        x = mamba_block_forward(sd, p + "mixer.", rmsnorm(x, sd.get(p + "norm.weight"), eps), dt_rank, d_state) + x
+        x = mamba_block_forward(sd, p + "mixer.", rmsnorm(x, sd.get(p + "norm.weight"), eps), dt_rank, d_state, use_version=use_version) + x
     return x
 
 
@@ -737,3 +737,19 @@ def v3_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layer
     return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads, lambda l: "glu" if l < 3 else "shared",
                        rope=True, pos_tables=False, rms=True, mask=mask, rope_dim=2 * sd["Wout.weight"].shape[1],
                        diff_enc=version != "3.0", diff_dec=True, pre_norm=version == "3.2")
+
+
+def video_regression_forward(sd: SD, sem, emotion, reg_model: str, n_layers: int, dt_rank: int):
+    """VideoRegression.forward (video_regression.py:208-245) for regModel "mamba" / "mamba+" (Mamba stack) and "bimamba+"
+    (BiMambaEncoder of Bi-Mamba+ layers with the FFN feed-forward): returns (loudness / note density (B,L,2), instruments)."""
+    vf = F.linear(torch.cat([sem.float(), emotion.float()], dim=-1), sd["in_proj.0.weight"], sd["in_proj.0.bias"])
+    if reg_model in ("mamba", "mamba+"):
+        msd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+        out = mamba_forward(msd, vf, n_layers, dt_rank, use_version=1 if reg_model == "mamba+" else 0)
+    elif reg_model == "bimamba+":
+        out = vf
+        for i in range(n_layers):
+            out = bimamba_v1_layer_forward(sd, "model.layers.%d." % i, out, dt_rank, norm_first=False)
+    else:
+        raise NotImplementedError(reg_model)
+    return F.linear(out, sd["regressor.weight"], sd["regressor.bias"]), torch.sigmoid(F.linear(out, sd["classifier.0.weight"], sd["classifier.0.bias"]))

@@ -353,6 +353,29 @@ def golden_v2(ref):
     _save("v2.pt", out)
 
 
+def golden_regression(ref):
+    """VideoRegression (video_regression.py:103-245) with the generate-time defaults of BASELINE config 5
+    (argument_generate_funcs.py:87-91: n_layers 6, d_model 128, d_hidden 256, total_vf_dim 774), Mamba-family backbones."""
+    import importlib
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    vr = importlib.import_module("model.video_regression")
+    out = {}
+    for reg, seed in (("mamba", 101), ("mamba+", 102), ("bimamba+", 103), ("sharedmoe_bimamba+", 104)):
+        torch.manual_seed(0)
+        m = vr.VideoRegression(n_layers=6, d_model=128, d_hidden=256, dropout=0.1, total_vf_dim=774, regModel=reg).eval()
+        sd = _load_weights(m, seed)
+        B, L = 2, 300
+        sem = syn.unit_uniform((B, L, 768), syn._gen(seed, "sem"))
+        emo = torch.softmax(syn.unit_uniform((B, L, 6), syn._gen(seed, "emo")), dim=-1)
+        z = torch.zeros((B, L))
+        with torch.no_grad():
+            ln, inst = m(sem, z, z, emo)
+        out[reg] = dict(spec=dict(reg=reg, seed=seed, B=B, L=L, n_keys=len(sd)), weights_checksum=syn.checksum(sd), ln=ln.clone(), inst=inst.clone())
+        print(reg, "keys", len(sd), float(ln.abs().max()), float(inst.mean()))
+    _save("regression.pt", out)
+
+
 def golden_pscan(ref):
     """pscan forward/backward (pscan.py:154-226) incl. a non power-of-two length."""
     cases = []
@@ -426,7 +449,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref),
+                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

@@ -100,7 +100,9 @@ def load_reference():
     mpl = _stub("matplotlib")
     plt = _stub("matplotlib.pyplot")
     mpl.pyplot = plt
-    _stub("minGRU_pytorch", minGRU=object)
+    mg = _stub("minGRU_pytorch", minGRU=object)
+    mg.__path__ = []                                          # model/minGRULM.py:6 imports the submodule minGRU_pytorch.minGRU
+    mg.minGRU = _stub("minGRU_pytorch.minGRU", minGRU=object)
 
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)

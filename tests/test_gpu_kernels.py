@@ -367,7 +367,7 @@ def test_moe_bf16_skewed_groups():
     assert rel_err(y16, y32) < 2e-2
 
 
-@pytest.mark.parametrize("tokens,E,k,d,ff", [(203, 6, 2, 64, 80), (1, 4, 4, 32, 48), (1500, 8, 3, 128, 272)])
+@pytest.mark.parametrize("tokens,E,k,d,ff", [(203, 6, 2, 64, 80), (1, 4, 4, 32, 48), (1500, 8, 3, 128, 272), (300, 6, 2, 128, 257)])
 def test_moe_dispatch_ragged_groups_vs_oracle(tokens, E, k, d, ff):
     """Skewed router (one expert takes most tokens, some take none): group sizes are neither equal nor tile multiples."""
     from video2music_b200 import GLUExpert, MoELayer
@@ -646,3 +646,19 @@ def test_custom_mha_rope_golden_gpu():
             y2, w2 = m(xqd, xkd, xkd, attn_mask=mask, need_weights=False)
         assert rel_err(y, c["y"]) < 1e-4 and rel_err(w.mean(dim=0), c["w_mean"]) < 1e-4, s
         assert w2 is None and torch.equal(y, y2)
+
+
+# ---------------------------------------------------------------- VideoRegression (BASELINE config 5)
+@pytest.mark.parametrize("reg", ["mamba", "mamba+", "bimamba+", "sharedmoe_bimamba+"])
+def test_video_regression_golden_gpu(reg):
+    """Loudness / note-density regressor and instrument classifier over the Mamba-family backbones (n_layers 6, d_model 128,
+    d_hidden 256, total_vf_dim 774, L = 300) against the unmodified reference."""
+    from test_oracle import _regression_case
+    g, m, sd, sem, emo = _regression_case(reg)
+    assert len(sd) == g["spec"]["n_keys"] and same_checksum(syn.checksum(sd), g["weights_checksum"])
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    z = torch.zeros(sem.shape[:2])
+    with torch.no_grad():
+        ln, inst = m(sem.to(DEV), z, z, emo.to(DEV))
+    assert rel_err(ln, g["ln"]) < 1e-4 and rel_err(inst, g["inst"]) < 1e-4

@@ -289,3 +289,23 @@ def test_v2_model_oracle_matches_reference_golden(ver):
     else:
         y = O.v1_forward(*a, version=ver[:3], rms=ver.endswith("rms"))
     assert rel_err(y, g["logits"]) < 5e-5
+
+
+def _regression_case(reg):
+    from video2music_b200 import VideoRegression
+    g = load_golden("regression.pt")[reg]
+    s = g["spec"]
+    m = VideoRegression(n_layers=6, d_model=128, d_hidden=256, dropout=0.1, total_vf_dim=774, regModel=reg).eval()
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["seed"])
+    sem = syn.unit_uniform((s["B"], s["L"], 768), syn._gen(s["seed"], "sem"))
+    emo = torch.softmax(syn.unit_uniform((s["B"], s["L"], 6), syn._gen(s["seed"], "emo")), dim=-1)
+    return g, m, sd, sem, emo
+
+
+@pytest.mark.parametrize("reg", ["mamba", "mamba+", "bimamba+"])
+def test_video_regression_oracle_matches_reference_golden(reg):
+    """VideoRegression (video_regression.py:208-245) with the Mamba-family backbones of BASELINE config 5."""
+    g, m, sd, sem, emo = _regression_case(reg)
+    assert len(sd) == g["spec"]["n_keys"] and same_checksum(syn.checksum(sd), g["weights_checksum"])
+    ln, inst = O.video_regression_forward(sd, sem, emo, reg, 6, dt_rank=8)
+    assert rel_err(ln, g["ln"]) < 5e-5 and rel_err(inst, g["inst"]) < 5e-5

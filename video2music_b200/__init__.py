@@ -15,4 +15,6 @@ from .custom_transformer import (TransformerEncoderLayer, TransformerDecoderLaye
 from .video_music_transformer_v2 import VideoMusicTransformer_V1, VideoMusicTransformer_V2, VideoMusicTransformer_V3  # noqa: F401
 from .mamba import MambaConfig, MambaBlock, ResidualBlock, Mamba, RMSNorm, BiMambaEncoderLayer, BiMambaEncoderLayer_V1, BiMambaEncoder  # noqa: F401
 
+from .video_regression import VideoRegression  # noqa: F401
+
 __version__ = "0.1.0"

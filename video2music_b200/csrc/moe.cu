@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256) swiglu_pair_bf16_kernel(const bf16* __res
 }
 
 constexpr int GB = 64, GK = 16;       // 64 x 64 output tile, 256 threads, 4 x 4 outputs each
-template <bool GLU>
+template <bool GLU, bool VEC>
 __global__ void __launch_bounds__(256) moe_grouped_gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W1,
                                                                const float* __restrict__ b1, const float* __restrict__ Wg,
                                                                const float* __restrict__ bg, long long w_gstride,
@@ -179,10 +179,25 @@ __global__ void __launch_bounds__(256) moe_grouped_gemm_kernel(const float* __re
   for (int k0 = 0; k0 < K; k0 += GK) {
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va, vg = va;
     const int gm = m0 + lrow, gn = n0 + lrow, gk = k0 + lk;
-    if (gm < m_end) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk));
-    if (gn < N) {
-      vb = __ldg(reinterpret_cast<const float4*>(W1e + (size_t)gn * K + gk));
-      if (GLU) vg = __ldg(reinterpret_cast<const float4*>(Wge + (size_t)gn * K + gk));
+    if (VEC) {
+      if (gm < m_end) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk));
+      if (gn < N) {
+        vb = __ldg(reinterpret_cast<const float4*>(W1e + (size_t)gn * K + gk));
+        if (GLU) vg = __ldg(reinterpret_cast<const float4*>(Wge + (size_t)gn * K + gk));
+      }
+    } else {                                        // odd K / leading dimensions (d_ff = 2 d_model + 1 experts): guarded scalars
+      float ta[4] = {0.f, 0.f, 0.f, 0.f}, tb[4] = {0.f, 0.f, 0.f, 0.f}, tg[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (gk + i < K) {
+          if (gm < m_end) ta[i] = __ldg(A + (size_t)gm * lda + gk + i);
+          if (gn < N) {
+            tb[i] = __ldg(W1e + (size_t)gn * K + gk + i);
+            if (GLU) tg[i] = __ldg(Wge + (size_t)gn * K + gk + i);
+          }
+        }
+      }
+      va = make_float4(ta[0], ta[1], ta[2], ta[3]); vb = make_float4(tb[0], tb[1], tb[2], tb[3]); vg = make_float4(tg[0], tg[1], tg[2], tg[3]);
     }
     As[lk + 0][lrow] = va.x; As[lk + 1][lrow] = va.y; As[lk + 2][lrow] = va.z; As[lk + 3][lrow] = va.w;
     Bs[lk + 0][lrow] = vb.x; Bs[lk + 1][lrow] = vb.y; Bs[lk + 2][lrow] = vb.z; Bs[lk + 3][lrow] = vb.w;
@@ -266,11 +281,15 @@ int swiglu_pair_bf16(const void* a, void* h, long long M, int ff, cudaStream_t s
 int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,
                      long long b_gstride, const int* off, int n_experts, int max_rows, float* C, int ldc, int N, int K,
                      cudaStream_t stream) {
-  V2M_REQUIRE(K % 16 == 0 && lda % 4 == 0 && N > 0, "moe_grouped_gemm: K=%d must be a multiple of 16, lda=%d of 4", K, lda);
+  V2M_REQUIRE(K > 0 && N > 0, "moe_grouped_gemm: bad dims N=%d K=%d", N, K);
   if (max_rows == 0) return kOk;
   dim3 grid((N + GB - 1) / GB, (max_rows + GB - 1) / GB, n_experts);
-  if (Wg) moe_grouped_gemm_kernel<true><<<grid, 256, 0, stream>>>(A, lda, W1, b1, Wg, bg, w_gstride, b_gstride, off, C, ldc, N, K);
-  else moe_grouped_gemm_kernel<false><<<grid, 256, 0, stream>>>(A, lda, W1, b1, nullptr, nullptr, w_gstride, b_gstride, off, C, ldc, N, K);
+  auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+  const bool vec = K % 16 == 0 && lda % 4 == 0 && al16(A) && al16(W1) && al16(Wg) && w_gstride % 4 == 0;
+#define V2M_GG(GLU, VEC) moe_grouped_gemm_kernel<GLU, VEC><<<grid, 256, 0, stream>>>(A, lda, W1, b1, Wg, bg, w_gstride, b_gstride, off, C, ldc, N, K)
+  if (Wg) { if (vec) V2M_GG(true, true); else V2M_GG(true, false); }
+  else { if (vec) V2M_GG(false, true); else V2M_GG(false, false); }
+#undef V2M_GG
   return check_launch("moe_grouped_gemm");
 }
 

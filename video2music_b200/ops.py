@@ -202,6 +202,11 @@ def swiglu(a: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return _binary(a, g, 0, 0.0)
 
 
+def sigmoid(a: torch.Tensor) -> torch.Tensor:
+    """1 / (1 + exp(-a))  (video_regression.py:197-200)."""
+    return _binary(a, a, 2, 0.0)
+
+
 def axpy(a: torch.Tensor, b: torch.Tensor, alpha: float) -> torch.Tensor:
     """a + alpha * b  (moe.py:301)."""
     return _binary(a, b, 1, alpha)
