@@ -102,7 +102,6 @@ class Trainer:
             dev = self.flat.flat_p.device
             self._dyn = torch.zeros(3, device=dev, dtype=torch.float32)       # lr, 1 - b1^t, 1 - b2^t
             self._ctr = torch.zeros(1, device=dev, dtype=torch.int32)         # step counter added to the dropout seeds
-            ops.DROP_SEED_DEV = self._ctr
 
     def _mirror(self) -> None:
         """flat fp32 masters -> flat bf16 mirror, and hand the views to the model's weight resolvers."""
@@ -177,6 +176,22 @@ class Trainer:
             torch.cuda.current_stream(dev).wait_event(ready)
         b = {k: v.to(dev, non_blocking=True) for k, v in batch.items() if not k.startswith("_")}
         self.step_no += 1
+        from . import ops
+        prev_seed_dev = ops.DROP_SEED_DEV
+        if self.use_graph:
+            ops.DROP_SEED_DEV = self._ctr        # only while this trainer's kernels are being enqueued / captured
+        try:
+            loss = self._run_step(b, dev)
+        finally:
+            ops.DROP_SEED_DEV = prev_seed_dev
+        self._handoff()
+        if slot_i is not None:                  # the prefetch slot may be overwritten once this step has run
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._slot_free[slot_i] = ev
+        return loss.detach()
+
+    def _run_step(self, b: Dict[str, torch.Tensor], dev) -> torch.Tensor:
         if not self.use_graph or self.step_no <= 2:
             loss = self._step_body(b)
         else:
@@ -196,9 +211,4 @@ class Trainer:
                 self.launches_per_step = _lib.launches() - n0
             self._graph.replay()
             loss = self._static_loss
-        self._handoff()
-        if slot_i is not None:                  # the prefetch slot may be overwritten once this step has run
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            self._slot_free[slot_i] = ev
-        return loss.detach()
+        return loss
