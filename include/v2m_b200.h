@@ -240,6 +240,9 @@ int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, 
                            int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, float* ws, int64_t ws_bytes,
                            void* stream);
 int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, float eps, void* stream);
+/* gradient of v2m_rmsnorm (autograd over custom_transformer.py:27-47 / mamba.py:483-489): dx [M][D]; dw [D] is accumulated
+ * into a caller-zeroed buffer (may be NULL). */
+int v2m_rmsnorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int32_t M, int32_t D, float eps, void* stream);
 
 /* ---- selective scan, model/pscan.py:154-226: H[t] = A[t]*H[t-1] + X[t] over (B,L,D,N) fp32 ---- */
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream);
@@ -275,6 +278,19 @@ int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const flo
                          int64_t w_gstride, int64_t b_gstride, const int32_t* off, int32_t n_experts, int32_t max_rows, float* C,
                          int32_t ldc, int32_t N, int32_t K, void* stream);
 int v2m_moe_combine(const float* yp, const int32_t* perm, const float* w, float* out, int32_t tokens, int32_t k, int32_t d, void* stream);
+
+/* ---- MoE backward (fp32): what torch autograd derives from model/moe.py:180-199 (topk values -> softmax -> weighted
+ * index_put of the expert outputs) and GLUExpert.forward (moe.py:44-49).
+ * combine_bwd: dyp[perm[t*k+r]] = w[t,r] * dout[t];  dw[t,r] = <dout[t], yp[perm[t*k+r]]>;  dlogits [tokens][n_experts] =
+ *   scale * softmax-backward of dw scattered to the selected experts (zero elsewhere); scale = inv_t_pre * inv_t_post.
+ * swiglu_bwd: h = a * silu(g): dag[m][0:ff] = dh * silu(g), dag[m][ff:2ff] = dh * a * silu'(g)   (dag is [M][2 ff]).
+ * grouped_dw: dW[e][n][j] = sum over the rows m of group e (off[e] <= m < off[e+1]) of dY[m][n] * X[m][j]; db[e][n] = sum_m dY[m][n]
+ *   (db may be NULL).  dX of a grouped linear is v2m_moe_grouped_gemm over the transposed weight stack. */
+int v2m_moe_combine_bwd(const float* dout, const float* yp, const int32_t* perm, const float* w, const int64_t* idx, float scale,
+                        int32_t tokens, int32_t k, int32_t d, int32_t n_experts, float* dyp, float* dlogits, void* stream);
+int v2m_swiglu_bwd(const float* a, const float* g, const float* dh, float* dag, int64_t M, int32_t ff, void* stream);
+int v2m_moe_grouped_dw(const float* dY, int32_t ldy, const float* X, int32_t ldx, const int32_t* off, int32_t n_experts, float* dW,
+                       float* db, int32_t N, int32_t K, void* stream);
 
 /* ---- RoPE of the V2/V3 attention, custom_transformer.py:1044-1053 + rotate_operation.py:117-165, fp32 --------------
  * x, y: the (len, B, H*dh) projection as stored; cache: RotaryPositionalEmbeddings.cache[:len] ([len][H*dh/2][2] cos, sin).

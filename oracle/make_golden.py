@@ -279,6 +279,65 @@ def golden_variant(ref):
     _save("variant.pt", out)
 
 
+MOE_TRAIN_KEEP = ("gate.weight", "gate.bias", "experts.0.gate.bias", "experts.2.linear2.bias", "experts.5.linear1.bias")
+
+
+def golden_moe_train(ref):
+    """Gradients of MoELayer / SharedMoELayer in train() mode (dropout 0) that torch autograd derives from moe.py:167-302:
+    loss = sum(y * r); d loss / d x, d / d gate (through the softmax over the top-k logits), d / d experts."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    for shared in (False, True):
+        torch.manual_seed(0)
+        exp = ref.moe.GLUExpert(512, 1024, 0.0)
+        cls = ref.moe.SharedMoELayer if shared else ref.moe.MoELayer
+        mod = cls(exp, 512, n_experts=6, n_experts_per_token=2, dropout=0.0).train()
+        sd = _load_weights(mod, 71 + shared)
+        x = syn.unit_uniform((23, 3, 512), syn._gen(71, "x")).requires_grad_(True)
+        r = syn.unit_uniform((23, 3, 512), syn._gen(71, "r"))
+        y = mod(x)
+        loss = (y * r).sum()
+        loss.backward()
+        with torch.no_grad():
+            logits = mod.gate(x)
+            idx = torch.topk(logits, 2).indices
+            top3 = torch.topk(logits, 3).values
+        norms = {n: float(p.grad.double().norm()) for n, p in mod.named_parameters() if p.grad is not None}
+        grads = {n: p.grad.clone() for n, p in mod.named_parameters() if n in MOE_TRAIN_KEEP}
+        out["shared_%s" % shared] = dict(spec=dict(L=23, B=3, d=512, ff=1024, n_experts=6, k=2, seed=71 + shared, x_seed=71),
+                                         weights_checksum=syn.checksum(sd), out=y.detach().clone(), loss=float(loss.detach()),
+                                         selected_experts=idx.clone(), dx=x.grad.clone(), grad_norms=norms, grads=grads,
+                                         min_rank_gap=float((top3[..., :-1] - top3[..., 1:]).min()))
+    _save("moe_train.pt", out)
+
+
+def golden_variant_train(ref):
+    """One backward pass through the GQA + MoE stacks of golden_variant (train() mode, dropout 0): loss = sum(y * r)."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    for c in VARIANT_CASES:
+        torch.manual_seed(0)
+        net = build_variant(ref.custom_transformer, ref.gqa, ref.moe, c).train()
+        sd = _load_weights(net, c["seed"])
+        src = syn.unit_uniform((c["S"], c["B"], 512), syn._gen(c["seed"], "src")).requires_grad_(True)
+        tgt = syn.unit_uniform((c["T"], c["B"], 512), syn._gen(c["seed"], "tgt")).requires_grad_(True)
+        r = syn.unit_uniform((c["T"], c["B"], 512), syn._gen(c["seed"], "r"))
+        mask = torch.triu(torch.full((c["T"], c["T"]), float("-inf")), diagonal=1)
+        y = net["dec"](tgt, net["enc"](src), tgt_mask=mask)
+        loss = (y * r).sum()
+        loss.backward()
+        norms = {n: float(p.grad.double().norm()) for n, p in net.named_parameters() if p.grad is not None}
+        keep = ("enc.layers.0.self_attn.k_proj.weight", "dec.layers.1.ff.gate.weight", "dec.norm.weight",
+                "dec.layers.0.cross_attn.norm.bias", "enc.layers.1.ff.experts.3.linear2.bias")
+        grads = {n: p.grad.clone() for n, p in net.named_parameters() if n in keep}
+        out[c["name"]] = dict(spec=dict(c), weights_checksum=syn.checksum(sd), out=y.detach().clone(), loss=float(loss.detach()),
+                              d_src=src.grad.clone(), d_tgt=tgt.grad.clone(), grad_norms=norms, grads=grads)
+        print(c["name"], "loss %.6f, %d parameter gradients" % (float(loss), len(norms)))
+    _save("variant_train.pt", out)
+
+
 def golden_metrics(ref):
     """compute_vevo_accuracy / compute_hits_k of the reference (dataset/vevo_dataset.py:653-701) on seeded logits."""
     import importlib
@@ -449,7 +508,8 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
+                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
+                variant_train=lambda: golden_variant_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

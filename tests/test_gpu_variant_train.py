@@ -1,0 +1,149 @@
+"""GPU parity of the MoE / GQA / generic-wrapper backward passes (BASELINE config 4 training) against the gradients the
+UNMODIFIED reference gets from torch autograd (tests/golden/moe_train.pt, variant_train.pt; oracle/make_golden.py), plus
+kernel-level checks of the new backward kernels against float64 torch on ragged / empty / odd-sized cases."""
+import pytest
+import torch
+
+from conftest import load_golden, rel_err, same_checksum
+from oracle import amt_oracle as O
+from video2music_b200 import synthetic as syn
+from test_oracle import _check_grads, _variant_net
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _u(shape, seed, name="t"):
+    return syn.unit_uniform(shape, syn._gen(seed, name))
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_moe_train_golden_gpu(shared):
+    from video2music_b200 import GLUExpert, MoELayer, SharedMoELayer
+    g = load_golden("moe_train.pt")["shared_%s" % shared]
+    s = g["spec"]
+    cls = SharedMoELayer if shared else MoELayer
+    mod = cls(GLUExpert(s["d"], s["ff"], 0.0), s["d"], n_experts=s["n_experts"], n_experts_per_token=s["k"], dropout=0.0).train()
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in mod.state_dict().items()}, seed=s["seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    x = _u((s["L"], s["B"], s["d"]), s["x_seed"], "x").to(DEV).requires_grad_(True)
+    r = _u((s["L"], s["B"], s["d"]), s["x_seed"], "r").to(DEV)
+    y = mod(x)
+    (y * r).sum().backward()
+    assert g["min_rank_gap"] > 1e-4
+    assert torch.equal(mod.last_selected_experts.cpu(), g["selected_experts"])          # routing indices bit-exact
+    assert rel_err(y, g["out"]) < 1e-4 and rel_err(x.grad, g["dx"]) < 1e-4
+    _check_grads({n: p.grad for n, p in mod.named_parameters()}, g, 1e-4)
+    # eval-mode forward under no_grad (fused SwiGLU path) gives the same output as the training-mode forward
+    with torch.no_grad():
+        assert rel_err(mod.eval()(x), y) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["post_ln_moe", "post_ln_sharedmoe_b2", "pre_rms_moe"])
+def test_variant_train_golden_gpu(name):
+    """Backward through 2 encoder + 2 decoder layers of MultiheadGQA(8 q heads, 2 kv heads) + (Shared)MoELayer inside the
+    generic post-/pre-norm wrappers: every parameter gradient norm and the input gradients equal the reference's autograd."""
+    g = load_golden("variant_train.pt")[name]
+    c = g["spec"]
+    net, sd = _variant_net(c)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    net.load_state_dict(sd)
+    net = net.to(DEV).train()
+    src = _u((c["S"], c["B"], 512), c["seed"], "src").to(DEV).requires_grad_(True)
+    tgt = _u((c["T"], c["B"], 512), c["seed"], "tgt").to(DEV).requires_grad_(True)
+    r = _u((c["T"], c["B"], 512), c["seed"], "r").to(DEV)
+    y = net["dec"](tgt, net["enc"](src))
+    loss = (y * r).sum()
+    loss.backward()
+    assert rel_err(y, g["out"]) < 1e-4
+    assert abs(float(loss.detach()) - g["loss"]) < 1e-4 * max(abs(g["loss"]), 1.0)
+    assert rel_err(src.grad, g["d_src"]) < 2e-4 and rel_err(tgt.grad, g["d_tgt"]) < 2e-4
+    grads = {n: p.grad for n, p in net.named_parameters() if p.grad is not None}
+    _check_grads(grads, g, 2e-4)
+    # experts that received no token: None in the reference, exact zeros here (the grouped kernels write empty groups)
+    for n in set(grads) - set(g["grad_norms"]):
+        assert ".experts." in n and float(grads[n].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("b,n,s,hq,hk,causal", [(2, 33, 33, 8, 2, True), (3, 20, 45, 8, 4, False), (1, 70, 70, 8, 1, True)])
+def test_gqa_function_backward_vs_oracle(b, n, s, hq, hk, causal):
+    from video2music_b200 import scaled_dot_product_gqa
+    q, k, v = _u((b, n, hq, 64), 5, "q"), _u((b, s, hk, 64), 5, "k"), _u((b, s, hk, 64), 5, "v")
+    r = _u((n, b, hq, 64), 5, "r")
+    ref_in = [t.clone().requires_grad_(True) for t in (q, k, v)]
+    (O.sdp_gqa(*ref_in, is_causal=causal) * r).sum().backward()
+    ours = [t.to(DEV).requires_grad_(True) for t in (q, k, v)]
+    out, _ = scaled_dot_product_gqa(*ours, num_heads=hq, is_causal=True if causal else None)
+    (out * r.to(DEV)).sum().backward()
+    for a, bb in zip(ours, ref_in):
+        assert rel_err(a.grad, bb.grad) < 2e-5
+
+
+@pytest.mark.parametrize("rows,E,N,K", [([5, 0, 130, 17], 4, 96, 80), ([0, 0, 3], 3, 70, 33), ([64, 64], 2, 64, 64)])
+def test_moe_grouped_dw_ragged(rows, E, N, K):
+    """dW_e = dY_e^T X_e, db_e = column sums over ragged (and empty) groups, sizes that are not tile multiples."""
+    from video2music_b200 import ops
+    from video2music_b200._lib import load, check
+    M = sum(rows)
+    dY, X = _u((M, N), 9, "dy").to(DEV), _u((M, K), 9, "x").to(DEV)
+    off = torch.tensor([0] + list(torch.tensor(rows).cumsum(0)), dtype=torch.int32, device=DEV)
+    dW = torch.full((E, N, K), float("nan"), device=DEV)
+    db = torch.full((E, N), float("nan"), device=DEV)
+    check(load().v2m_moe_grouped_dw(ops.ptr(dY), N, ops.ptr(X), K, ops.ptr(off), E, ops.ptr(dW), ops.ptr(db), N, K, ops.stream()))
+    o = off.tolist()
+    for e in range(E):
+        ye, xe = dY[o[e]:o[e + 1]].double(), X[o[e]:o[e + 1]].double()
+        ref = ye.T @ xe
+        assert float((dW[e].double() - ref).abs().max()) <= 1e-5 * max(float(ref.abs().max()), 1.0)
+        assert float((db[e].double() - ye.sum(0)).abs().max()) <= 1e-5 * max(float(ye.sum(0).abs().max()), 1.0)
+
+
+def test_swiglu_and_rmsnorm_backward_kernels():
+    from video2music_b200 import ops
+    a, g, dh = (_u((37, 50), 11, n) * 4 - 2 for n in "agd")
+    ar, gr = a.double().requires_grad_(True), g.double().requires_grad_(True)
+    (ar * torch.nn.functional.silu(gr)).backward(dh.double())
+    dag = ops.swiglu_bwd(a.to(DEV), g.to(DEV), dh.to(DEV))
+    assert rel_err(dag[:, :50], ar.grad) < 1e-5 and rel_err(dag[:, 50:], gr.grad) < 1e-5
+    for D, has_w in ((512, True), (100, True), (64, False)):
+        x, dy, w = _u((29, D), 12, "x") - 0.5, _u((29, D), 12, "dy") - 0.5, _u((D,), 12, "w") + 0.5
+        xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+        y = xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-6) * (wr if has_w else 1.0)
+        y.backward(dy.double())
+        dx, dw = ops.rmsnorm_bwd(x.to(DEV), w.to(DEV) if has_w else None, dy.to(DEV), 1e-6)
+        assert rel_err(dx, xr.grad) < 1e-5
+        if has_w:
+            assert rel_err(dw, wr.grad) < 1e-5
+        else:
+            assert dw is None
+
+
+def test_moe_backward_skewed_routing_vs_oracle():
+    """All tokens routed to two experts (four empty groups), k = 3 of 5 in a second case: gradients equal the oracle's autograd."""
+    from video2music_b200 import GLUExpert, MoELayer
+    for (E, k, d, ff, T, skew) in ((6, 2, 64, 96, 150, True), (5, 3, 128, 64, 77, False)):
+        mod = MoELayer(GLUExpert(d, ff, 0.0), d, n_experts=E, n_experts_per_token=k, dropout=0.0).train()
+        sd = syn.fill_like_reference_init({n: tuple(v.shape) for n, v in mod.state_dict().items()}, seed=81)
+        if skew:
+            sd["gate.bias"] = torch.tensor([9.0, -9.0, -9.0, 7.0, -9.0, -9.0])
+        mod.load_state_dict(sd)
+        mod = mod.to(DEV)
+        x = _u((T, 1, d), 82, "x")
+        r = _u((T, 1, d), 82, "r")
+        leaf = {n: v.clone().requires_grad_(True) for n, v in sd.items()}
+        xr = x.clone().requires_grad_(True)
+        ref, idx, _ = O.moe_layer(xr, leaf, "", E, k)
+        (ref * r).sum().backward()
+        xg = x.to(DEV).requires_grad_(True)
+        y = mod(xg)
+        (y * r.to(DEV)).sum().backward()
+        assert torch.equal(mod.last_selected_experts.cpu(), idx)
+        assert rel_err(y, ref) < 1e-4 and rel_err(xg.grad, xr.grad) < 1e-4
+        for n, p in mod.named_parameters():
+            rg = leaf[n].grad
+            if rg is None:
+                assert float(p.grad.abs().max()) == 0.0, n
+            else:
+                assert float((p.grad.cpu().double() - rg.double()).abs().max()) <= 1e-4 * max(float(rg.abs().max()), 1e-3), n

@@ -155,6 +155,55 @@ def test_variant_gqa_moe_stack_golden(name):
     assert rel_err(mem, g["memory"]) < 2e-5 and rel_err(y, g["out"]) < 2e-5
 
 
+def _leaf_sd(sd):
+    return {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+def _check_grads(named_grads, g, tol):
+    """All gradient norms within tol (relative) and the stored full gradients within tol of the reference's."""
+    floor = 1e-3 * max(g["grad_norms"].values())     # k_proj.bias gradients are rounding noise (softmax is shift-invariant)
+    for n, ref_norm in g["grad_norms"].items():
+        got = float(named_grads[n].double().norm())
+        assert abs(got - ref_norm) <= tol * max(ref_norm, floor), (n, got, ref_norm)
+    for n, ref in g["grads"].items():
+        assert rel_err(named_grads[n], ref) < tol, n
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_moe_train_golden(shared):
+    """Oracle MoE gradients (torch autograd over the restatement) == the reference's (moe.py:167-302 in train mode)."""
+    g = load_golden("moe_train.pt")["shared_%s" % shared]
+    spec = g["spec"]
+    sd = _moe_sd(spec, shared)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    sd = _leaf_sd(sd)
+    x = syn.unit_uniform((spec["L"], spec["B"], spec["d"]), syn._gen(spec["x_seed"], "x")).requires_grad_(True)
+    r = syn.unit_uniform((spec["L"], spec["B"], spec["d"]), syn._gen(spec["x_seed"], "r"))
+    out, idx, _ = O.moe_layer(x, sd, "", spec["n_experts"], spec["k"], shared=shared)
+    (out * r).sum().backward()
+    assert g["min_rank_gap"] > 1e-4 and torch.equal(idx, g["selected_experts"])
+    assert rel_err(out, g["out"]) < 2e-5 and rel_err(x.grad, g["dx"]) < 2e-5
+    _check_grads({k: v.grad for k, v in sd.items()}, g, 2e-5)
+
+
+@pytest.mark.parametrize("name", ["post_ln_moe", "post_ln_sharedmoe_b2", "pre_rms_moe"])
+def test_variant_train_golden(name):
+    """BASELINE config 4 training: gradients of the oracle's GQA + MoE stack == the reference's autograd."""
+    g = load_golden("variant_train.pt")[name]
+    c = g["spec"]
+    _, sd = _variant_net(c)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    sd = _leaf_sd(sd)
+    src = syn.unit_uniform((c["S"], c["B"], 512), syn._gen(c["seed"], "src")).requires_grad_(True)
+    tgt = syn.unit_uniform((c["T"], c["B"], 512), syn._gen(c["seed"], "tgt")).requires_grad_(True)
+    r = syn.unit_uniform((c["T"], c["B"], 512), syn._gen(c["seed"], "r"))
+    _, y = O.variant_stack_forward(sd, src, tgt, 2, 8, 2, 6, 2, c["shared"], c["pre_norm"], c["rms"])
+    (y * r).sum().backward()
+    assert rel_err(y, g["out"]) < 2e-5
+    assert rel_err(src.grad, g["d_src"]) < 5e-5 and rel_err(tgt.grad, g["d_tgt"]) < 5e-5
+    _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 5e-5)
+
+
 def test_pscan_golden():
     for case in load_golden("pscan.pt")["cases"]:
         s = case["spec"]

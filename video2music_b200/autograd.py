@@ -311,6 +311,153 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     return y.view(B, T, -1)
 
 
+# ----------------------------------------------------------------------------------------------- variant blocks (fp32)
+# Autograd through the MoE / GQA / generic-wrapper blocks (BASELINE config 4): forward AND backward are our kernels; the
+# reference gets these gradients from torch autograd over model/moe.py, model/grouped_query_attention.py and
+# model/custom_transformer.py:1220-1292.
+
+def tracking(*things) -> bool:
+    """True when a backward pass may be asked for: grad mode on and any tensor / module parameter requires grad."""
+    if not torch.is_grad_enabled():
+        return False
+    for t in things:
+        if isinstance(t, torch.Tensor):
+            if t.requires_grad:
+                return True
+        elif isinstance(t, torch.nn.Module):
+            if any(p.requires_grad for p in t.parameters()):
+                return True
+    return False
+
+
+def rows_f32(x: torch.Tensor) -> torch.Tensor:
+    """(..., d) -> contiguous fp32 (rows, d), staying in the autograd graph (view bookkeeping only)."""
+    return x.reshape(-1, x.shape[-1]).float().contiguous()
+
+
+def linear_fn(x2: torch.Tensor, lin: torch.nn.Linear, relu: bool = False) -> torch.Tensor:
+    """nn.Linear on (rows, d) fp32 through LinearFn."""
+    return LinearFn.apply(x2, lin.weight, lin.bias, lin.weight, x2.shape[1], relu, 1.0, 0, None, 0, F32, None)
+
+
+class AddFn(torch.autograd.Function):
+    """a + alpha * b."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha):
+        ctx.alpha = alpha
+        return ops.axpy(a, b, alpha)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        return g, (g if ctx.alpha == 1.0 else ops.axpy(g, g, ctx.alpha - 1.0)), None
+
+
+class SwigluFn(torch.autograd.Function):
+    """a * silu(g)  (GLUExpert, moe.py:46-47)."""
+
+    @staticmethod
+    def forward(ctx, a, g):
+        ctx.save_for_backward(a, g)
+        return ops.swiglu(a, g)
+
+    @staticmethod
+    def backward(ctx, dh):
+        a, g = ctx.saved_tensors
+        dag = ops.swiglu_bwd(a, g, dh)
+        ff = a.shape[1]
+        return dag[:, :ff], dag[:, ff:]
+
+
+class RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        ctx.save_for_backward(x, w)
+        ctx.eps = eps
+        return ops.rmsnorm(x, w, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx, dw = ops.rmsnorm_bwd(x, w, dy, ctx.eps)
+        return dx, dw, None
+
+
+def glu_expert_fn(e, x2: torch.Tensor) -> torch.Tensor:
+    """GLUExpert.forward (moe.py:44-49) on (rows, d) with gradients: three LinearFn GEMMs around SwigluFn."""
+    return linear_fn(SwigluFn.apply(linear_fn(x2, e.linear1), linear_fn(x2, e.gate)), e.linear2)
+
+
+class MoEExpertsFn(torch.autograd.Function):
+    """out[t] = sum_r softmax(top-k gate logits)[t,r] * expert_{idx[t,r]}(x[t])  (moe.py:180-199 / 244-299).
+    The routing (idx, w, hist) is computed by the fused router outside; its gradient (softmax over the selected logits ->
+    gate weight / bias / x) is produced here.  params = the experts' (linear1.weight, linear1.bias, gate.weight, gate.bias,
+    linear2.weight, linear2.bias) in expert order; `stacks` = their [E, ...] copies."""
+
+    @staticmethod
+    def forward(ctx, x2, gate_w, gate_b, idx, w, hist, scale, stacks, *params):
+        w1, b1, wg, bg, w2, b2 = stacks
+        out, saved = ops.moe_experts_fwd_saved(x2, idx, w, hist, w1, b1, wg, bg, w2, b2)
+        ctx.save_for_backward(x2, gate_w, idx, w, w1, wg, w2, *saved)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, gate_w, idx, w, w1, wg, w2, *saved = ctx.saved_tensors
+        E, ff, d = w1.shape
+        w1g_t = torch.cat([w1, wg], 1).transpose(1, 2).contiguous()          # [E, d, 2 ff]
+        w2_t = w2.transpose(1, 2).contiguous()                               # [E, ff, d_out]
+        dx_e, dlogits, dW1g, db1g, dW2, db2 = ops.moe_experts_bwd(dout, tuple(saved), idx, w, ctx.scale, w1g_t, w2_t, E)
+        dgate_w = _gemm_dw(dlogits, x2, d)
+        _, dgate_b = ops.dy_prep(dlogits, None, False, 1.0, 0, F32, want_dz=False)
+        dx = ops.axpy(dx_e, _gemm_dx(dlogits, gate_w.detach().contiguous(), d), 1.0)
+        grads = []
+        for e in range(E):
+            grads += [dW1g[e, :ff], db1g[e, :ff], dW1g[e, ff:], db1g[e, ff:], dW2[e], db2[e]]
+        return (dx, dgate_w, dgate_b, None, None, None, None, None, *grads)
+
+
+def moe_experts_fn(experts, gate, x2, idx, w, hist, scale, stacks):
+    params = [p for e in experts for p in (e.linear1.weight, e.linear1.bias, e.gate.weight, e.gate.bias, e.linear2.weight, e.linear2.bias)]
+    k = idx.shape[-1]
+    return MoEExpertsFn.apply(x2, gate.weight, gate.bias, idx.reshape(-1, k), w.reshape(-1, k), hist, scale, stacks, *params)
+
+
+class GqaAttnFn(torch.autograd.Function):
+    """scaled_dot_product_gqa (grouped_query_attention.py:19-170): q (b,n,hq,d), k/v (b,s,hk,d) contiguous fp32 ->
+    out (n,b,hq,d) (sequence-first, :159); query head h*g+gi reads kv head h."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, causal, q_scale):
+        b, n, hq, d = q.shape
+        s, hk = k.shape[1], k.shape[2]
+        out = torch.empty((n, b, hq, d), device=q.device, dtype=q.dtype)
+        lse = torch.empty((b * hq, n), device=q.device, dtype=F32)
+        ops.attention(q, k, v, out, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d, q_strides=(n * hq * d, hq * d),
+                      k_strides=(s * hk * d, hk * d), v_strides=(s * hk * d, hk * d), o_strides=(hq * d, b * hq * d),
+                      causal=causal, q_scale=q_scale, lse=lse)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.meta = (causal, q_scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        causal, q_scale = ctx.meta
+        b, n, hq, d = q.shape
+        s, hk = k.shape[1], k.shape[2]
+        dout = dout.contiguous()
+        dq = torch.empty_like(q)
+        dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+        ops.attention_bwd(q, k, v, out, dout, lse, None, dq, dk, dv, None, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d,
+                          q_strides=(n * hq * d, hq * d), k_strides=(s * hk * d, hk * d), v_strides=(s * hk * d, hk * d),
+                          o_strides=(hq * d, b * hq * d), do_strides=(hq * d, b * hq * d), dq_strides=(n * hq * d, hq * d),
+                          dkv_strides=(s * hk * d, hk * d), causal=causal, q_scale=q_scale)
+        return dq, dk, dv, None, None
+
+
 def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
     raise NotImplementedError("module-level autograd for MultiheadAttentionRPR: train through VideoMusicTransformer "
                               "(video2music_b200.autograd.amt_forward_autograd) or call under torch.no_grad()")

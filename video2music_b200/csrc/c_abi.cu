@@ -255,6 +255,10 @@ int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, 
   return rmsnorm(x, w, y, M, D, eps, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_rmsnorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int32_t M, int32_t D, float eps, void* stream) {
+  return rmsnorm_bwd(x, w, dy, dx, dw, M, D, eps, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_moe_permute(const float* x, const int64_t* idx, const int32_t* hist, int32_t tokens, int32_t k, int32_t d, int32_t n_experts,
                     int32_t align, int32_t* off, int32_t* cursor, void* xp, int32_t xp_dtype, int32_t* perm, int32_t* tile_group,
                     int32_t n_tiles, void* stream) {
@@ -282,6 +286,21 @@ int v2m_moe_grouped_gemm(const float* A, int32_t lda, const float* W1, const flo
 
 int v2m_moe_combine(const float* yp, const int32_t* perm, const float* w, float* out, int32_t tokens, int32_t k, int32_t d, void* stream) {
   return moe_combine(yp, perm, w, out, tokens, k, d, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_moe_combine_bwd(const float* dout, const float* yp, const int32_t* perm, const float* w, const int64_t* idx, float scale,
+                        int32_t tokens, int32_t k, int32_t d, int32_t n_experts, float* dyp, float* dlogits, void* stream) {
+  return moe_combine_bwd(dout, yp, perm, w, reinterpret_cast<const long long*>(idx), scale, tokens, k, d, n_experts, dyp, dlogits,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int v2m_swiglu_bwd(const float* a, const float* g, const float* dh, float* dag, int64_t M, int32_t ff, void* stream) {
+  return swiglu_bwd(a, g, dh, dag, M, ff, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_moe_grouped_dw(const float* dY, int32_t ldy, const float* X, int32_t ldx, const int32_t* off, int32_t n_experts, float* dW,
+                       float* db, int32_t N, int32_t K, void* stream) {
+  return moe_grouped_dw(dY, ldy, X, ldx, off, n_experts, dW, db, N, K, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream) {

@@ -194,6 +194,7 @@ int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, lo
                        long long ldz, float* out, long long ldo, int B, int L, int ED, int N, int plus, float* ws,
                        long long ws_bytes, cudaStream_t stream);
 int rmsnorm(const float* x, const float* w, float* y, int M, int D, float eps, cudaStream_t stream);
+int rmsnorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int M, int D, float eps, cudaStream_t stream);
 
 // ------------------------------------------------------------------ MoE (moe.cu)
 int moe_route(const float* x, const float* wg, const float* bg, const float* sel_bias, float inv_t_pre, float inv_t_post,
@@ -211,6 +212,12 @@ int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, 
                      long long b_gstride, const int* off, int n_experts, int max_rows, float* C, int ldc, int N, int K,
                      cudaStream_t stream);
 int moe_combine(const float* yp, const int* perm, const float* w, float* out, int tokens, int k, int d, cudaStream_t stream);
+// backward of the dispatch: combine / softmax-over-top-k, SwiGLU, per-expert weight gradients over the ragged groups
+int moe_combine_bwd(const float* dout, const float* yp, const int* perm, const float* w, const long long* idx, float scale, int tokens,
+                    int k, int d, int n_experts, float* dyp, float* dlogits, cudaStream_t stream);
+int swiglu_bwd(const float* a, const float* g, const float* dh, float* dag, long long M, int ff, cudaStream_t stream);
+int moe_grouped_dw(const float* dY, int ldy, const float* X, int ldx, const int* off, int n_experts, float* dW, float* db, int N, int K,
+                   cudaStream_t stream);
 
 // accuracy / hits@k counters of the evaluation loop (train.cu)
 int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long long pad, int k0, int k1, int k2, int* counters,

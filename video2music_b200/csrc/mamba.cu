@@ -186,4 +186,34 @@ int rmsnorm(const float* x, const float* w, float* y, int M, int D, float eps, c
   return check_launch("rmsnorm");
 }
 
+// backward of rmsnorm: with r = rsqrt(mean(x^2) + eps), g = w o dy:  dx = r g - x r^3 mean(g o x);  dw += dy o x r  (fp32 atomics
+// into a caller-zeroed buffer, rows folded per CTA first).  One warp per row, 8 rows per CTA.
+__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ dy, float* __restrict__ dx, float* __restrict__ dw,
+                                                          int M, int D, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (long long)row * D;
+  const float* gr = dy + (long long)row * D;
+  float sq = 0.f, dot = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float xv = xr[d];
+    sq = fmaf(xv, xv, sq);
+    dot = fmaf(gr[d] * (w ? w[d] : 1.f), xv, dot);
+  }
+  const float r = rsqrtf(warp_sum(sq) / (float)D + eps);
+  const float c = warp_sum(dot) * r * r * r / (float)D;
+  for (int d = lane; d < D; d += 32) {
+    const float xv = xr[d], gv = gr[d];
+    dx[(long long)row * D + d] = r * gv * (w ? w[d] : 1.f) - xv * c;
+    if (dw) atomicAdd(dw + d, gv * xv * r);
+  }
+}
+
+int rmsnorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int M, int D, float eps, cudaStream_t stream) {
+  if (M == 0) return kOk;
+  rmsnorm_bwd_kernel<<<(M + 7) / 8, 256, 0, stream>>>(x, w, dy, dx, dw, M, D, eps);
+  return check_launch("rmsnorm_bwd");
+}
+
 }  // namespace v2m

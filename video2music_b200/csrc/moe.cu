@@ -256,6 +256,117 @@ __global__ void __launch_bounds__(256) moe_combine_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Backward of the expert dispatch (the reference gets these from autograd over the per-expert index_put / where loop,
+// model/moe.py:190-199):
+//   moe_combine_bwd : dyp[perm[t,r]] = w[t,r] * dout[t];  dw[t,r] = <dout[t], yp[perm[t,r]]>;  softmax-over-top-k backward
+//                     scattered into the dense gate-logit gradient: dlogits[t, idx[t,r]] = scale * w_r (dw_r - sum_s w_s dw_s)
+//   swiglu_bwd      : h = a * silu(g)  ->  dag[:, :ff] = dh * silu(g),  dag[:, ff:] = dh * a * sig(g) (1 + g (1 - sig(g)))
+//   moe_grouped_dw  : dW_e[n][j] = sum_{rows m of group e} dY[m][n] * X[m][j],  db_e[n] = sum_m dY[m][n]   (ragged groups, bounds
+//                     read from off[] on the device; an empty group writes zeros)
+__global__ void __launch_bounds__(256) moe_combine_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ yp,
+                                                              const int* __restrict__ perm, const float* __restrict__ w,
+                                                              const long long* __restrict__ idx, float scale, int tokens, int k, int d,
+                                                              int n_experts, float* __restrict__ dyp, float* __restrict__ dlogits) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= tokens) return;
+  const float4* g4 = reinterpret_cast<const float4*>(dout + (size_t)t * d);
+  float dw[kMaxExperts];
+#pragma unroll
+  for (int r = 0; r < kMaxExperts; ++r) {
+    dw[r] = 0.f;
+    if (r < k) {
+      const int row = perm[(size_t)t * k + r];
+      const float wr = w[(size_t)t * k + r];
+      const float4* y4 = reinterpret_cast<const float4*>(yp + (size_t)row * d);
+      float4* o4 = reinterpret_cast<float4*>(dyp + (size_t)row * d);
+      float acc = 0.f;
+      for (int i = lane; i < d / 4; i += 32) {
+        const float4 g = g4[i], y = y4[i];
+        acc = fmaf(g.x, y.x, acc); acc = fmaf(g.y, y.y, acc); acc = fmaf(g.z, y.z, acc); acc = fmaf(g.w, y.w, acc);
+        o4[i] = make_float4(wr * g.x, wr * g.y, wr * g.z, wr * g.w);
+      }
+      dw[r] = warp_sum(acc);
+    }
+  }
+  if (lane != 0) return;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMaxExperts; ++r)
+    if (r < k) s = fmaf(w[(size_t)t * k + r], dw[r], s);
+  for (int e = 0; e < n_experts; ++e) dlogits[(size_t)t * n_experts + e] = 0.f;
+#pragma unroll
+  for (int r = 0; r < kMaxExperts; ++r)
+    if (r < k) dlogits[(size_t)t * n_experts + (int)idx[(size_t)t * k + r]] = scale * w[(size_t)t * k + r] * (dw[r] - s);
+}
+
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const float* __restrict__ a, const float* __restrict__ g,
+                                                         const float* __restrict__ dh, float* __restrict__ dag, long long M, int ff) {
+  const long long n = M * ff;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / ff;
+    const int j = (int)(i - m * ff);
+    const float gv = g[i], av = a[i], dv = dh[i];
+    const float sg = 1.f / (1.f + expf(-gv));
+    dag[m * 2 * ff + j] = dv * gv * sg;
+    dag[m * 2 * ff + ff + j] = dv * av * sg * (1.f + gv * (1.f - sg));
+  }
+}
+
+__global__ void __launch_bounds__(256) moe_grouped_dw_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx,
+                                                             const int* __restrict__ off, float* __restrict__ dW, float* __restrict__ db,
+                                                             int N, int K) {
+  __shared__ __align__(16) float Ys[GK][GB + 4];
+  __shared__ __align__(16) float Xs[GK][GB + 4];
+  const int e = blockIdx.z;
+  const int m_begin = off[e], m_end = off[e + 1];
+  const int n0 = blockIdx.y * GB, k0 = blockIdx.x * GB;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lm = tid >> 4, lc = (tid & 15) * 4;          // loader: row lm of the 16-row chunk, 4 consecutive columns
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bacc = 0.f;
+  for (int m0 = m_begin; m0 < m_end; m0 += GK) {
+    const int m = m0 + lm;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int n = n0 + lc + c, kk = k0 + lc + c;
+      Ys[lm][lc + c] = (m < m_end && n < N) ? __ldg(dY + (size_t)m * ldy + n) : 0.f;
+      Xs[lm][lc + c] = (m < m_end && kk < K) ? __ldg(X + (size_t)m * ldx + kk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < GK; ++r) {
+      const float4 y4 = *reinterpret_cast<const float4*>(&Ys[r][ty * 4]);
+      const float4 x4 = *reinterpret_cast<const float4*>(&Xs[r][tx * 4]);
+      const float y[4] = {y4.x, y4.y, y4.z, y4.w}, x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(y[i], x[j], acc[i][j]);
+    }
+    if (db && blockIdx.x == 0 && tid < GB) {
+#pragma unroll
+      for (int r = 0; r < GK; ++r) bacc += Ys[r][tid];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = k0 + tx * 4 + j;
+      if (kk < K) dW[((size_t)e * N + n) * K + kk] = acc[i][j];
+    }
+  }
+  if (db && blockIdx.x == 0 && tid < GB && n0 + tid < N) db[(size_t)e * N + n0 + tid] = bacc;
+}
+
 int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int align, int* off,
                 int* cursor, void* xp, int xp_bf16, int* perm, int* tile_group, int n_tiles, cudaStream_t stream) {
   V2M_REQUIRE(d % 4 == 0 && n_experts >= 1 && n_experts <= kMaxExperts && k >= 1 && align >= 1, "moe_permute: bad dims d=%d E=%d k=%d",
@@ -298,6 +409,31 @@ int moe_combine(const float* yp, const int* perm, const float* w, float* out, in
   if (tokens == 0) return kOk;
   moe_combine_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(yp, perm, w, out, tokens, k, d);
   return check_launch("moe_combine");
+}
+
+int moe_combine_bwd(const float* dout, const float* yp, const int* perm, const float* w, const long long* idx, float scale, int tokens,
+                    int k, int d, int n_experts, float* dyp, float* dlogits, cudaStream_t stream) {
+  V2M_REQUIRE(d % 4 == 0 && k >= 1 && k <= kMaxExperts && n_experts >= k && n_experts <= kMaxExperts,
+              "moe_combine_bwd: bad dims d=%d k=%d E=%d", d, k, n_experts);
+  if (tokens == 0) return kOk;
+  moe_combine_bwd_kernel<<<(tokens + 7) / 8, 256, 0, stream>>>(dout, yp, perm, w, idx, scale, tokens, k, d, n_experts, dyp, dlogits);
+  return check_launch("moe_combine_bwd");
+}
+
+int swiglu_bwd(const float* a, const float* g, const float* dh, float* dag, long long M, int ff, cudaStream_t stream) {
+  V2M_REQUIRE(ff > 0, "swiglu_bwd: ff=%d", ff);
+  if (M == 0) return kOk;
+  const long long want = (M * ff + 255) / 256;
+  swiglu_bwd_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(a, g, dh, dag, M, ff);
+  return check_launch("swiglu_bwd");
+}
+
+int moe_grouped_dw(const float* dY, int ldy, const float* X, int ldx, const int* off, int n_experts, float* dW, float* db, int N, int K,
+                   cudaStream_t stream) {
+  V2M_REQUIRE(K > 0 && N > 0 && n_experts >= 1, "moe_grouped_dw: bad dims N=%d K=%d E=%d", N, K, n_experts);
+  dim3 grid((K + GB - 1) / GB, (N + GB - 1) / GB, n_experts);
+  moe_grouped_dw_kernel<<<grid, 256, 0, stream>>>(dY, ldy, X, ldx, off, dW, db, N, K);
+  return check_launch("moe_grouped_dw");
 }
 
 }  // namespace v2m

@@ -9,8 +9,9 @@ BASELINE config 4 (grouped-query attention + MoE FFN) are assembled from:
 Same constructor signatures and attribute names (`self_attn`, `cross_attn`, `ff`, `norm1..3`, `layers`,
 `norm`), so a reference checkpoint loads.  The attention and feed-forward sub-modules are whatever the
 caller plugs in (MultiheadGQA, MultiheadAttentionRPR, MoELayer, SharedMoELayer, GLUExpert ...); the
-residual add and the normalisation run as one kernel of ours.  Inference only (inputs are detached);
-training goes through `autograd.py` for the base AMT.  The RoSC layers (:1294-1369) are out of scope.
+residual add and the normalisation run as one kernel of ours.  The generic wrappers, RMSNorm, MultiheadGQA and the MoE
+layers also train (fp32): with grad mode on they chain the autograd Functions of `autograd.py`, whose forward and backward
+are our kernels (BASELINE config 4).  CustomMultiheadAttention / DifferentialMultiheadAttention: inference only.  The RoSC layers (:1294-1369) are out of scope.
 """
 import math
 from copy import deepcopy
@@ -185,6 +186,9 @@ class RMSNorm(nn.Module):
             self.register_parameter("weight", None)
 
     def forward(self, x):
+        from . import autograd as ag
+        if ag.tracking(x, self):
+            return ag.RMSNormFn.apply(x.float().contiguous(), self.weight, self.eps).type_as(x)
         w = self.weight.detach() if self.weight is not None else None
         return ops.rmsnorm(x.detach().float(), w, self.eps).type_as(x)
 
@@ -193,7 +197,18 @@ class RMSNorm(nn.Module):
 
 
 def _norm(norm, x, res=None):
-    """norm(x + res): one fused kernel for LayerNorm, add + RMSNorm kernels otherwise."""
+    """norm(x + res): one fused kernel for LayerNorm, add + RMSNorm kernels otherwise.  With gradients being tracked the
+    same kernels run inside autograd Functions (add, then the norm with its backward kernel)."""
+    from . import autograd as ag
+    if ag.tracking(x, res, norm):
+        x = x.float().contiguous()
+        if res is not None:
+            x = ag.AddFn.apply(x, res.float().contiguous(), 1.0)
+        if isinstance(norm, nn.LayerNorm):
+            return ag.LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+        if isinstance(norm, RMSNorm):
+            return ag.RMSNormFn.apply(x, norm.weight, norm.eps)
+        raise NotImplementedError("norm layer %s (LayerNorm and RMSNorm are built)" % type(norm).__name__)
     x = x.detach().float().contiguous()
     if isinstance(norm, nn.LayerNorm):
         return ops.layernorm(x, norm.weight.detach(), norm.bias.detach(), res=None if res is None else res.detach().float().contiguous(),
@@ -207,6 +222,9 @@ def _norm(norm, x, res=None):
 
 
 def _add(x, y):
+    from . import autograd as ag
+    if ag.tracking(x, y):
+        return ag.AddFn.apply(x.float().contiguous(), y.float().contiguous(), 1.0)
     return ops.axpy(x.detach().float().contiguous(), y.detach().float().contiguous(), 1.0)
 
 

@@ -33,6 +33,9 @@ def scaled_dot_product_gqa(query, key, value, num_heads=None, dropout: float = 0
     if scale is None:
         scale = d ** 0.5
     dt = query.dtype
+    from . import autograd as ag
+    if ag.tracking(query, key, value) and dt == torch.float32:             # gradients through our attention backward kernel
+        return ag.GqaAttnFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), bool(is_causal), 1.0 / scale), None
     q, k, v = (t.detach().contiguous() for t in (query, key, value))
     out = torch.empty((n, b, hq, d), device=q.device, dtype=dt)          # sequence-first, :159
     ops.attention(q, k, v, out, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d,
@@ -89,7 +92,12 @@ class MultiheadGQA(nn.Module):
         H, Hk = self.query_heads, self.kv_heads
         dh = E // H
 
+        from . import autograd as ag
+        track = ag.tracking(query, key, value, self)
+
         def lin(m, x):
+            if track:
+                return ag.linear_fn(ag.rows_f32(x), m)
             x2 = x.detach().reshape(-1, x.shape[-1]).float().contiguous()
             return ops.linear(x2, m.weight.detach(), m.bias.detach() if m.bias is not None else None, k=x2.shape[1])
 
@@ -100,6 +108,11 @@ class MultiheadGQA(nn.Module):
         v4 = v.view(bsz, src_len, Hk, dh)
         x, _ = scaled_dot_product_gqa(q4, k4, v4, num_heads=H, is_causal=True if is_causal else None)
         x = x.reshape(x.shape[0], x.shape[1], H * dh)                   # labelled "b n (h d)" by the reference (:343)
+        if track:
+            x2 = x.reshape(-1, E)
+            if self.layer_norm:
+                x2 = ag.LayerNormFn.apply(x2.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
+            return ag.linear_fn(x2, self.out_proj).view(x.shape[0], x.shape[1], E), None
         if self.layer_norm:
             x = ops.layernorm(x.contiguous(), self.norm.weight.detach(), self.norm.bias.detach(), eps=self.norm.eps)
         y = ops.linear(x.reshape(-1, E), self.out_proj.weight.detach(),

@@ -7,6 +7,10 @@ permuted into expert-contiguous order by a second kernel and all experts run as 
 (group bounds read on the device, SwiGLU fused into the first) followed by a weighted combine (see
 `_experts_forward`): five launches per MoE layer and no host synchronisation.
 
+Training: when grad mode is on and the input or a parameter requires grad, the layers run through
+`autograd.MoEExpertsFn` (fp32): permute, grouped GEMMs, SwiGLU, combine and the softmax-over-top-k router gradient are all
+our kernels in both directions (`csrc/moe.cu`: combine_bwd, swiglu_bwd, grouped_dw); dropout must be 0.
+
 `module.compute_dtype = torch.bfloat16` moves the expert GEMMs to the tcgen05 tensor-core path (grouped GEMM over
 128-row aligned expert groups, bf16 operands, fp32 accumulation); the router always runs in fp32, so the routing indices
 stay bit-exact.  The reference's per-expert Python loop with
@@ -36,6 +40,9 @@ class GLUExpert(nn.Module):
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in training mode is not built yet")
         shp = x.shape
+        from . import autograd as ag
+        if ag.tracking(x, self):                                          # training: forward and backward on our kernels
+            return ag.glu_expert_fn(self, ag.rows_f32(x)).view(shp[:-1] + (self.linear2.out_features,))
         x2 = x.detach().reshape(-1, shp[-1]).float().contiguous()
         return _glu(self, x2).view(shp[:-1] + (self.linear2.out_features,))
 
@@ -175,6 +182,9 @@ class MoELayer(nn.Module):
         self.last_selected_experts = idx.view(shp[:-1] + (k,))
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)
+        from . import autograd as ag
+        if ag.tracking(x, self) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:180-199
+            return ag.moe_experts_fn(self.experts, self.gate, ag.rows_f32(x), idx, w, hist, 1.0 / t, _stacked(self.experts)).view(shp)
         return _experts_forward(self.experts, x2, idx, w, hist, getattr(self, "compute_dtype", torch.float32)).view(shp)
 
 
@@ -224,10 +234,16 @@ class SharedMoELayer(nn.Module):
                                         inv_t_post=1.0 / t)
         if self.balancing and self.training:                             # moe.py:270-279
             c = hist.to(self.bias.dtype)
-            self.bias += self.update_rate * (c.mean() - c).unsqueeze(1)
+            with torch.no_grad():
+                self.bias += self.update_rate * (c.mean() - c).unsqueeze(1)
         self.last_selected_experts = idx.view(shp[:-1] + (k,))
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)
+        from . import autograd as ag
+        if ag.tracking(x, self) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:244-301
+            xr = ag.rows_f32(x)
+            out = ag.moe_experts_fn(self.experts, self.gate, xr, idx, w, hist, 1.0 / t, _stacked(self.experts))
+            return ag.AddFn.apply(out, ag.glu_expert_fn(self.shared_expert, xr), 1.0 / k).view(shp[:-1] + (self.d_model,))
         dt = getattr(self, "compute_dtype", torch.float32)
         out = _experts_forward(self.experts, x2, idx, w, hist, dt)
         shared = _glu_bf16(self.shared_expert, x2) if dt == torch.bfloat16 else _glu(self.shared_expert, x2)   # moe.py:301

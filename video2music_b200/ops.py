@@ -307,6 +307,75 @@ def moe_experts_bf16(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: 
     return out
 
 
+def moe_experts_fwd_saved(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
+                          wg: torch.Tensor, bg: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor):
+    """Training-mode forward of `moe_experts`: same result, but the two halves of the SwiGLU pair are kept (a = x W1^T + b1,
+    g = x Wg^T + bg) together with the permuted input, the hidden rows and the per-row expert outputs, which the backward
+    needs.  Returns (out, saved) with saved = (xp, a, g, h, yp, perm, off)."""
+    require_device(x)
+    T, k = idx.shape
+    E, ff, d = w1.shape
+    d_out = w2.shape[1]
+    dev = x.device
+    meta = torch.empty((2 * E + 1 + T * k,), device=dev, dtype=torch.int32)
+    off, cursor, perm = meta[:E + 1], meta[E + 1:2 * E + 1], meta[2 * E + 1:]
+    f32 = dict(device=dev, dtype=torch.float32)
+    xp, a, g = torch.empty((T * k, d), **f32), torch.empty((T * k, ff), **f32), torch.empty((T * k, ff), **f32)
+    yp, out = torch.empty((T * k, d_out), **f32), torch.empty((T, d_out), **f32)
+    lib, st = load(), stream()
+    check(lib.v2m_moe_permute(ptr(x), ptr(idx), ptr(hist), T, k, d, E, 1, ptr(off), ptr(cursor), ptr(xp), dtype_code(xp.dtype), ptr(perm),
+                              None, 0, st))
+    check(lib.v2m_moe_grouped_gemm(ptr(xp), d, ptr(w1), ptr(b1), None, None, ff * d, ff, ptr(off), E, T * k, ptr(a), ff, ff, d, st))
+    check(lib.v2m_moe_grouped_gemm(ptr(xp), d, ptr(wg), ptr(bg), None, None, ff * d, ff, ptr(off), E, T * k, ptr(g), ff, ff, d, st))
+    _lib.count_launches(4)
+    h = swiglu(a, g)
+    check(lib.v2m_moe_grouped_gemm(ptr(h), ff, ptr(w2), ptr(b2), None, None, d_out * ff, d_out, ptr(off), E, T * k, ptr(yp), d_out,
+                                   d_out, ff, st))
+    check(lib.v2m_moe_combine(ptr(yp), ptr(perm), ptr(w), ptr(out), T, k, d_out, st))
+    _lib.count_launches(2)
+    return out, (xp, a, g, h, yp, perm, off)
+
+
+def moe_experts_bwd(dout: torch.Tensor, saved, idx: torch.Tensor, w: torch.Tensor, scale: float, w1g_t: torch.Tensor,
+                    w2_t: torch.Tensor, n_experts: int):
+    """Backward of `moe_experts_fwd_saved`.  w1g_t [E, d, 2 ff] = (linear1 | gate) weights transposed, w2_t [E, ff, d_out].
+    Returns (dx_experts (T, d), dlogits (T, E), dW1g (E, 2 ff, d), db1g (E, 2 ff), dW2 (E, d_out, ff), db2 (E, d_out))."""
+    require_device(dout)
+    xp, a, g, h, yp, perm, off = saved
+    T, k = idx.shape
+    E = n_experts
+    M, d = xp.shape
+    ff, d_out = a.shape[1], yp.shape[1]
+    f32 = dict(device=dout.device, dtype=torch.float32)
+    dout = dout.contiguous()
+    dyp, dlogits = torch.empty((M, d_out), **f32), torch.empty((T, E), **f32)
+    dh, dag, dxp, dx = torch.empty((M, ff), **f32), torch.empty((M, 2 * ff), **f32), torch.empty((M, d), **f32), torch.empty((T, d), **f32)
+    dW2, db2 = torch.empty((E, d_out, ff), **f32), torch.empty((E, d_out), **f32)
+    dW1g, db1g = torch.empty((E, 2 * ff, d), **f32), torch.empty((E, 2 * ff), **f32)
+    ones = torch.ones((T, k), **f32)
+    lib, st = load(), stream()
+    check(lib.v2m_moe_combine_bwd(ptr(dout), ptr(yp), ptr(perm), ptr(w), ptr(idx), scale, T, k, d_out, E, ptr(dyp), ptr(dlogits), st))
+    check(lib.v2m_moe_grouped_dw(ptr(dyp), d_out, ptr(h), ff, ptr(off), E, ptr(dW2), ptr(db2), d_out, ff, st))
+    check(lib.v2m_moe_grouped_gemm(ptr(dyp), d_out, ptr(w2_t), None, None, None, ff * d_out, 0, ptr(off), E, M, ptr(dh), ff, ff, d_out, st))
+    check(lib.v2m_swiglu_bwd(ptr(a), ptr(g), ptr(dh), ptr(dag), M, ff, st))
+    check(lib.v2m_moe_grouped_dw(ptr(dag), 2 * ff, ptr(xp), d, ptr(off), E, ptr(dW1g), ptr(db1g), 2 * ff, d, st))
+    check(lib.v2m_moe_grouped_gemm(ptr(dag), 2 * ff, ptr(w1g_t), None, None, None, d * 2 * ff, 0, ptr(off), E, M, ptr(dxp), d, d, 2 * ff, st))
+    check(lib.v2m_moe_combine(ptr(dxp), ptr(perm), ptr(ones), ptr(dx), T, k, d, st))
+    _lib.count_launches(7)
+    return dx, dlogits, dW1g, db1g, dW2, db2
+
+
+def swiglu_bwd(a: torch.Tensor, g: torch.Tensor, dh: torch.Tensor) -> torch.Tensor:
+    """Gradient of h = a * silu(g) as one [M, 2 ff] matrix (da | dg)."""
+    require_device(a)
+    a, g, dh = a.contiguous(), g.contiguous(), dh.contiguous()
+    M, ff = a.shape
+    dag = torch.empty((M, 2 * ff), device=a.device, dtype=torch.float32)
+    check(load().v2m_swiglu_bwd(ptr(a), ptr(g), ptr(dh), ptr(dag), M, ff, stream()))
+    _lib.count_launches(1)
+    return dag
+
+
 def swiglu_pair(a: torch.Tensor) -> torch.Tensor:
     """(M, 2 ff) bf16 -> (M, ff) bf16: a[:, :ff] * silu(a[:, ff:])."""
     require_device(a)
@@ -391,6 +460,18 @@ def rmsnorm(x: torch.Tensor, w: Optional[torch.Tensor], eps: float = 1e-5) -> to
     check(load().v2m_rmsnorm(ptr(x), ptr(w), ptr(y), _rows(x), x.shape[-1], eps, stream()))
     _lib.count_launches(1)
     return y
+
+
+def rmsnorm_bwd(x: torch.Tensor, w: Optional[torch.Tensor], dy: torch.Tensor, eps: float = 1e-5):
+    """(dx, dw or None) of rmsnorm."""
+    require_device(x)
+    x, dy = x.contiguous(), dy.contiguous()
+    D = x.shape[-1]
+    dx = torch.empty_like(x)
+    dw = torch.zeros((D,), device=x.device, dtype=torch.float32) if w is not None else None
+    check(load().v2m_rmsnorm_bwd(ptr(x), ptr(w), ptr(dy), ptr(dx), ptr(dw), _rows(x), D, eps, stream()))
+    _lib.count_launches(1)
+    return dx, dw
 
 
 def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5):
