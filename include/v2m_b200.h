@@ -239,6 +239,20 @@ int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, 
                            const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz, float* out,
                            int64_t ldo, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, float* ws, int64_t ws_bytes,
                            void* stream);
+/* Backward of the two kernels above (what torch autograd derives from mamba.py:270-276 and from the materialised
+ * deltaA / BX / pscan graph of mamba.py:333-351, pscan.py:196-226).
+ * scan_bwd: `hs` = state workspace of v2m_selective_scan_bwd_workspace() bytes ([B][L][N][ED] fp32, recomputed inside);
+ *   writes dx, ddelta_raw, dz (dz may be NULL when z is NULL); ADDS into the caller-zeroed dBm / dCm rows ([B*L][N] with
+ *   leading dimension lddbc), dA_log [ED][N], dD [ED], ddt_bias [ED] (may be NULL).
+ * conv_bwd: writes dx (the (B, L, lddx) view of the conv input gradient), ADDS into caller-zeroed dw [ED][KW], dbias [ED]. */
+int64_t v2m_selective_scan_bwd_workspace(int32_t B, int32_t L, int32_t ED, int32_t N);
+int v2m_selective_scan_bwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
+                           const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz,
+                           const float* dout, int64_t ldo, float* hs, int64_t hs_bytes, float* dx, int64_t lddx, float* ddelta_raw,
+                           int64_t lddd, float* dBm, float* dCm, int64_t lddbc, float* dz, int64_t lddz, float* dA_log, float* dD,
+                           float* ddt_bias, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, void* stream);
+int v2m_mamba_conv_silu_bwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* dy, int64_t ldy, float* dx,
+                            int64_t lddx, float* dw, float* dbias, int32_t B, int32_t L, int32_t ED, int32_t KW, void* stream);
 int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, float eps, void* stream);
 /* gradient of v2m_rmsnorm (autograd over custom_transformer.py:27-47 / mamba.py:483-489): dx [M][D]; dw [D] is accumulated
  * into a caller-zeroed buffer (may be NULL). */

@@ -498,6 +498,52 @@ def golden_mamba(ref):
     _save("mamba.pt", out)
 
 
+MAMBA_TRAIN_CASES = [dict(name="block_v0", kind="block", ver=0, B=2, L=130, wseed=91, seed=191),
+                     dict(name="block_v1", kind="block", ver=1, B=2, L=77, wseed=92, seed=192),
+                     dict(name="stack", kind="stack", ver=0, B=2, L=70, wseed=93, seed=193),
+                     dict(name="bimamba_layer", kind="bi", ver=0, B=2, L=90, wseed=94, seed=194),
+                     dict(name="bimamba_v1_ffn", kind="bi_v1", ver=1, B=2, L=66, wseed=95, seed=195, norm_first=False, moe=False),
+                     dict(name="bimamba_v1_moe", kind="bi_v1", ver=1, B=1, L=100, wseed=96, seed=196, norm_first=True, moe=True)]
+
+
+def build_mamba_case(mamba, bimamba, moe, c):
+    """The module of one MAMBA_TRAIN_CASES entry from the given namespaces (the reference's here, ours in the tests);
+    regression-model sizes (d_model 128, d_inner 256, d_state 16), dropout 0."""
+    cfg = mamba.MambaConfig(d_model=128, n_layers=2 if c["kind"] == "stack" else 1, use_version=c["ver"])
+    if c["kind"] == "block":
+        return mamba.MambaBlock(cfg)
+    if c["kind"] == "stack":
+        return mamba.Mamba(cfg)
+    if c["kind"] == "bi":
+        return bimamba.BiMambaEncoderLayer(cfg, dim_feedforward=256, dropout=0.0)
+    ml = moe.MoELayer(moe.GLUExpert(128, 256, 0.0), 128, n_experts=6, n_experts_per_token=2, dropout=0.0) if c["moe"] else None
+    return bimamba.BiMambaEncoderLayer_V1(cfg, dim_feedforward=256, dropout=0.0, moe_layer=ml, norm_first=c["norm_first"])
+
+
+def golden_mamba_train(ref):
+    """Gradients of the Mamba-family blocks in train() mode (pscan path of the reference, mamba.py:333-351 + pscan.py autograd):
+    loss = sum(y * r); every parameter gradient norm, a few full gradients and d loss / d x."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    for c in MAMBA_TRAIN_CASES:
+        torch.manual_seed(0)
+        m = build_mamba_case(ref.mamba, ref.bimamba, ref.moe, c).train()
+        sd = _load_weights(m, c["wseed"])
+        x = syn.unit_uniform((c["B"], c["L"], 128), syn._gen(c["seed"], "x")).requires_grad_(True)
+        r = syn.unit_uniform((c["B"], c["L"], 128), syn._gen(c["seed"], "r"))
+        y = m(x)
+        loss = (y * r).sum()
+        loss.backward()
+        norms = {n: float(p.grad.double().norm()) for n, p in m.named_parameters() if p.grad is not None}
+        keep = [n for n in norms if n.endswith(("A_log", ".D", "conv1d.weight", "dt_proj.bias", "x_proj.weight")) or n in ("A_log", "D")]
+        grads = {n: m.get_parameter(n).grad.clone() for n in keep[:6]}
+        out[c["name"]] = dict(spec=dict(c), weights_checksum=syn.checksum(sd), y=y.detach().clone(), loss=float(loss.detach()),
+                              dx=x.grad.clone(), grad_norms=norms, grads=grads)
+        print(c["name"], "loss %.6f, %d parameter gradients, kept %s" % (float(loss.detach()), len(norms), list(grads)))
+    _save("mamba_train.pt", out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -509,7 +555,7 @@ def main():
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
                 mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
-                variant_train=lambda: golden_variant_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
+                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

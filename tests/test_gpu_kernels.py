@@ -482,8 +482,6 @@ def test_mamba_golden_gpu():
         err = rel_err(y, c["y"])
         print("mamba %s rel err %.2e" % (name, err))
         assert err < 1e-4, name
-    with pytest.raises(NotImplementedError):
-        m(x.requires_grad_(True))
 
 
 @pytest.mark.parametrize("B,L", [(64, 300), (8, 4096)])

@@ -204,6 +204,41 @@ def test_variant_train_golden(name):
     _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 5e-5)
 
 
+def _mamba_train_module(c):
+    import video2music_b200.mamba as mamba
+    import video2music_b200.moe as moe
+    from oracle.make_golden import build_mamba_case
+    m = build_mamba_case(mamba, mamba, moe, c)
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=c["wseed"])
+    return m, sd
+
+
+def _mamba_oracle_forward(c, sd, x):
+    if c["kind"] == "block":
+        return O.mamba_block_forward(sd, "", x, dt_rank=8, use_version=c["ver"])
+    if c["kind"] == "stack":
+        return O.mamba_forward(sd, x, 2, dt_rank=8)
+    if c["kind"] == "bi":
+        return O.bimamba_layer_forward(sd, "", x, dt_rank=8)
+    return O.bimamba_v1_layer_forward(sd, "", x, 8, c["norm_first"], dict(n_experts=6, k=2, shared=False) if c["moe"] else None)
+
+
+@pytest.mark.parametrize("name", ["block_v0", "block_v1", "stack", "bimamba_layer", "bimamba_v1_ffn", "bimamba_v1_moe"])
+def test_mamba_train_golden(name):
+    """Oracle Mamba-family gradients (autograd over the restatement) == the reference's (pscan path, train mode)."""
+    g = load_golden("mamba_train.pt")[name]
+    c = g["spec"]
+    _, sd = _mamba_train_module(c)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    sd = _leaf_sd(sd)
+    x = syn.unit_uniform((c["B"], c["L"], 128), syn._gen(c["seed"], "x")).requires_grad_(True)
+    r = syn.unit_uniform((c["B"], c["L"], 128), syn._gen(c["seed"], "r"))
+    y = _mamba_oracle_forward(c, sd, x)
+    (y * r).sum().backward()
+    assert rel_err(y, g["y"]) < 2e-5 and rel_err(x.grad, g["dx"]) < 5e-5
+    _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 5e-5)
+
+
 def test_pscan_golden():
     for case in load_golden("pscan.pt")["cases"]:
         s = case["spec"]

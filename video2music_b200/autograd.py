@@ -458,6 +458,44 @@ class GqaAttnFn(torch.autograd.Function):
         return dq, dk, dv, None, None
 
 
+class MambaCoreFn(torch.autograd.Function):
+    """xz (B*L, 2 ED) = in_proj output (x | z)  ->  y (B*L, ED): depthwise conv + SiLU of the x half, x_proj, dt_proj and the
+    fused selective scan gated by the z half (mamba.py:264-351).  Backward: selective_scan_bwd (states recomputed, no
+    (B, L, ED, N) autograd graph), four strided GEMMs for the two small projections, conv/SiLU backward."""
+
+    @staticmethod
+    def forward(ctx, xz, conv_w, conv_b, xproj_w, dtproj_w, dt_bias, A_log, D, B, L, plus):
+        ED, N = A_log.shape
+        R = dtproj_w.shape[1]
+        xc = ops.mamba_conv_silu(xz, ED, conv_w.contiguous(), conv_b, B, L)
+        dbc = ops.linear(xc, xproj_w.contiguous())
+        draw = ops.linear(dbc[:, :R], dtproj_w.contiguous())
+        y = ops.selective_scan(xc, draw, dt_bias, A_log, dbc[:, R:R + N], dbc[:, R + N:], D, xz[:, ED:], B, L, plus=plus)
+        ctx.save_for_backward(xz, conv_w, conv_b, xproj_w, dtproj_w, dt_bias, A_log, D, xc, dbc, draw)
+        ctx.meta = (B, L, plus)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xz, conv_w, conv_b, xproj_w, dtproj_w, dt_bias, A_log, D, xc, dbc, draw = ctx.saved_tensors
+        B, L, plus = ctx.meta
+        ED, N = A_log.shape
+        R = dtproj_w.shape[1]
+        M, P = xc.shape[0], dbc.shape[1]
+        dy = dy.contiguous()
+        dxz = torch.empty_like(xz)
+        ddbc = torch.zeros_like(dbc)
+        dxc, ddraw, dA_log, dD, ddtb = ops.selective_scan_bwd(xc, draw, dt_bias, A_log, dbc[:, R:R + N], dbc[:, R + N:], D, xz[:, ED:],
+                                                              dy, ddbc[:, R:R + N], ddbc[:, R + N:], dxz[:, ED:], B, L, plus=plus)
+        wdt, wx = dtproj_w.contiguous(), xproj_w.contiguous()
+        ops.gemm_strided(ddraw, ED, 1, wdt, 1, R, M, R, ED, out=ddbc[:, :R])                  # d(dbc[:, :R]) = ddraw @ Wdt
+        dwdt = ops.gemm_strided(ddraw, 1, ED, dbc, 1, P, ED, R, M)                            # ddraw^T @ dbc[:, :R]
+        dxc = ops.axpy(dxc, ops.gemm_strided(ddbc, P, 1, wx, 1, ED, M, ED, P), 1.0)           # + ddbc @ Wx
+        dwx = ops.gemm_strided(ddbc, 1, P, xc, 1, ED, P, ED, M)                               # ddbc^T @ xc
+        dconv_w, dconv_b = ops.mamba_conv_silu_bwd(xz, ED, conv_w.contiguous(), conv_b, dxc, dxz, B, L)
+        return dxz, dconv_w, dconv_b, dwx, dwdt, ddtb, dA_log, dD, None, None, None
+
+
 def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
     raise NotImplementedError("module-level autograd for MultiheadAttentionRPR: train through VideoMusicTransformer "
                               "(video2music_b200.autograd.amt_forward_autograd) or call under torch.no_grad()")

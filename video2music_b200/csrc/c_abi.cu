@@ -255,6 +255,23 @@ int v2m_rmsnorm(const float* x, const float* w, float* y, int32_t M, int32_t D, 
   return rmsnorm(x, w, y, M, D, eps, static_cast<cudaStream_t>(stream));
 }
 
+int64_t v2m_selective_scan_bwd_workspace(int32_t B, int32_t L, int32_t ED, int32_t N) { return selective_scan_bwd_workspace(B, L, ED, N); }
+
+int v2m_selective_scan_bwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
+                           const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz,
+                           const float* dout, int64_t ldo, float* hs, int64_t hs_bytes, float* dx, int64_t lddx, float* ddelta_raw,
+                           int64_t lddd, float* dBm, float* dCm, int64_t lddbc, float* dz, int64_t lddz, float* dA_log, float* dD,
+                           float* ddt_bias, int32_t B, int32_t L, int32_t ED, int32_t N, int32_t plus, void* stream) {
+  return selective_scan_bwd(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, D, z, ldz, dout, ldo, hs, hs_bytes, dx, lddx,
+                            ddelta_raw, lddd, dBm, dCm, lddbc, dz, lddz, dA_log, dD, ddt_bias, B, L, ED, N, plus,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int v2m_mamba_conv_silu_bwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* dy, int64_t ldy, float* dx,
+                            int64_t lddx, float* dw, float* dbias, int32_t B, int32_t L, int32_t ED, int32_t KW, void* stream) {
+  return mamba_conv_silu_bwd(x, ldx, w, bias, dy, ldy, dx, lddx, dw, dbias, B, L, ED, KW, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_rmsnorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int32_t M, int32_t D, float eps, void* stream) {
   return rmsnorm_bwd(x, w, dy, dx, dw, M, D, eps, static_cast<cudaStream_t>(stream));
 }

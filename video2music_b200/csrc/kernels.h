@@ -194,6 +194,14 @@ int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, lo
                        long long ldz, float* out, long long ldo, int B, int L, int ED, int N, int plus, float* ws,
                        long long ws_bytes, cudaStream_t stream);
 int rmsnorm(const float* x, const float* w, float* y, int M, int D, float eps, cudaStream_t stream);
+long long selective_scan_bwd_workspace(int B, int L, int ED, int N);
+int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, long long ldd, const float* dt_bias, const float* A_log,
+                       const float* Bm, const float* Cm, long long ldbc, const float* Dp, const float* z, long long ldz,
+                       const float* dout, long long ldo, float* hs, long long hs_bytes, float* dx, long long lddx, float* ddraw,
+                       long long lddd, float* dBm, float* dCm, long long lddbc, float* dz, long long lddz, float* dA_log, float* dD,
+                       float* ddt_bias, int B, int L, int ED, int N, int plus, cudaStream_t stream);
+int mamba_conv_silu_bwd(const float* x, long long ldx, const float* w, const float* bias, const float* dy, long long ldy, float* dx,
+                        long long lddx, float* dw, float* dbias, int B, int L, int ED, int KW, cudaStream_t stream);
 int rmsnorm_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw, int M, int D, float eps, cudaStream_t stream);
 
 // ------------------------------------------------------------------ MoE (moe.cu)

@@ -168,6 +168,189 @@ int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, lo
   return check_launch("selective_scan_fwd");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Backward of the fused selective scan (exact fp32 training path; the reference differentiates the materialised
+// deltaA / BX tensors and the pscan through torch autograd, mamba.py:333-351 + pscan.py:196-226).
+// Thread <-> (video, channel), one CTA = 128 channels of one video, all walking L in lockstep:
+//   sweep 1 (l = 0 .. L-1)   recompute the states and store them, Hs[b][l][n][c] (channel fastest: coalesced)
+//   sweep 2 (l = L-1 .. 0)   gh_n = dL/dh_l[n] carried in registers; per step
+//        y  = sum_n h_n C_n + D x;  out = y silu(z) (+ x (1 - sigmoid(silu(z))) for mamba+)
+//        dC_n = dy h_n;  gh_n += dy C_n;  with a_n = exp(delta A_n):  d delta += gh_n (A_n a_n h_{l-1,n} + B_n x),
+//        dA_n += gh_n h_{l-1,n} delta a_n,  dB_n = gh_n delta x,  dx += gh_n delta B_n,  gh_n *= a_n
+//        d delta_raw = d delta * softplus'(delta_raw + dt_bias)
+//   dB / dC are sums over the channels: the CTA folds its 128 channels through shared memory (2 N = 32 values per step) and
+//   adds them to the caller-zeroed gradient rows; dA_log (= dA * A), dD, d dt_bias are accumulated per thread and added once.
+template <int N>
+__global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __restrict__ x, long long ldx,
+                                                                 const float* __restrict__ delta_raw, long long ldd,
+                                                                 const float* __restrict__ dt_bias, const float* __restrict__ A_log,
+                                                                 const float* __restrict__ Bm, const float* __restrict__ Cm,
+                                                                 long long ldbc, const float* __restrict__ Dp,
+                                                                 const float* __restrict__ z, long long ldz,
+                                                                 const float* __restrict__ dout, long long ldo, float* __restrict__ Hs,
+                                                                 float* __restrict__ dx, long long lddx, float* __restrict__ ddraw,
+                                                                 long long lddd, float* __restrict__ dBm, float* __restrict__ dCm,
+                                                                 long long lddbc, float* __restrict__ dz, long long lddz,
+                                                                 float* __restrict__ dA_log, float* __restrict__ dD,
+                                                                 float* __restrict__ ddt_bias, int L, int ED, int plus) {
+  static_assert(2 * N == 32, "the channel fold maps 2 N values onto the 32 lanes of a warp");
+  __shared__ float red[2 * N][129];
+  const int tid = threadIdx.x, c = blockIdx.x * 128 + tid, b = blockIdx.y;
+  const bool act = c < ED;
+  const int cc = act ? c : ED - 1;                     // inactive lanes read a valid channel and contribute nothing
+  float A[N], A2[N], h[N], gh[N], gA[N];
+#pragma unroll
+  for (int n = 0; n < N; ++n) {
+    A[n] = -expf(A_log[(long long)cc * N + n]);
+    A2[n] = A[n] * 1.4426950408889634f;
+    h[n] = 0.f; gh[n] = 0.f; gA[n] = 0.f;
+  }
+  const float Dc = Dp[cc], db = dt_bias ? dt_bias[cc] : 0.f;
+  for (int l = 0; l < L; ++l) {
+    const long long row = (long long)b * L + l;
+    const float xv = x[row * ldx + cc];
+    const float dl = softplus_f(delta_raw[row * ldd + cc] + db);
+    const float dxv = dl * xv;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      h[n] = fmaf(ex2_approx(dl * A2[n]), h[n], dxv * __ldg(Bm + row * ldbc + n));
+      if (act) Hs[(row * N + n) * ED + c] = h[n];
+    }
+  }
+  float gD = 0.f, gdb = 0.f;
+  for (int l = L - 1; l >= 0; --l) {
+    const long long row = (long long)b * L + l;
+    const float xv = x[row * ldx + cc];
+    const float raw = delta_raw[row * ldd + cc] + db;
+    const float dl = softplus_f(raw);
+    const float g = act ? dout[row * ldo + c] : 0.f;
+    float y = Dc * xv;
+#pragma unroll
+    for (int n = 0; n < N; ++n) y = fmaf(h[n], __ldg(Cm + row * ldbc + n), y);
+    float dy = g, dzv = 0.f, dxv = 0.f;
+    if (z) {
+      const float zv = z[row * ldz + cc];
+      const float sg = 1.f / (1.f + expf(-zv));
+      const float sl = zv * sg, dsl = sg * (1.f + zv * (1.f - sg));
+      dy = g * sl;
+      dzv = g * y * dsl;
+      if (plus) {
+        const float s2 = 1.f / (1.f + expf(-sl));
+        dxv = g * (1.f - s2);
+        dzv -= g * xv * s2 * (1.f - s2) * dsl;
+      }
+    }
+    dxv = fmaf(dy, Dc, dxv);
+    gD = fmaf(dy, xv, gD);
+    float ddl = 0.f;
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+      const float Bv = __ldg(Bm + row * ldbc + n), Cv = __ldg(Cm + row * ldbc + n);
+      const float hp = (l > 0) ? Hs[((row - 1) * N + n) * ED + cc] : 0.f;
+      const float a = ex2_approx(dl * A2[n]);
+      red[N + n][tid] = act ? dy * h[n] : 0.f;                     // dC_n
+      gh[n] = fmaf(dy, Cv, gh[n]);
+      const float t = gh[n] * hp;
+      ddl = fmaf(t, A[n] * a, ddl);
+      ddl = fmaf(gh[n] * Bv, xv, ddl);
+      gA[n] = fmaf(t, dl * a, gA[n]);
+      red[n][tid] = act ? gh[n] * dl * xv : 0.f;                   // dB_n
+      dxv = fmaf(gh[n] * dl, Bv, dxv);
+      gh[n] *= a;
+      h[n] = hp;
+    }
+    const float ddr = ddl * (raw > 20.f ? 1.f : 1.f / (1.f + expf(-raw)));
+    gdb += ddr;
+    if (act) {
+      dx[row * lddx + c] = dxv;
+      ddraw[row * lddd + c] = ddr;
+      if (dz) dz[row * lddz + c] = dzv;
+    }
+    __syncthreads();
+    {
+      const int v = tid & 31, q = tid >> 5;
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += red[v][q * 32 + j];
+      atomicAdd((v < N ? dBm + row * lddbc + v : dCm + row * lddbc + (v - N)), sum);
+    }
+    __syncthreads();
+  }
+  if (act) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) atomicAdd(dA_log + (long long)c * N + n, gA[n] * A[n]);
+    atomicAdd(dD + c, gD);
+    if (ddt_bias) atomicAdd(ddt_bias + c, gdb);
+  }
+}
+
+long long selective_scan_bwd_workspace(int B, int L, int ED, int N) { return (long long)B * L * ED * N * (long long)sizeof(float); }
+
+int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, long long ldd, const float* dt_bias, const float* A_log,
+                       const float* Bm, const float* Cm, long long ldbc, const float* Dp, const float* z, long long ldz,
+                       const float* dout, long long ldo, float* hs, long long hs_bytes, float* dx, long long lddx, float* ddraw,
+                       long long lddd, float* dBm, float* dCm, long long lddbc, float* dz, long long lddz, float* dA_log, float* dD,
+                       float* ddt_bias, int B, int L, int ED, int N, int plus, cudaStream_t stream) {
+  V2M_REQUIRE(B > 0 && L > 0 && ED > 0, "selective_scan_bwd: bad dims B=%d L=%d ED=%d", B, L, ED);
+  V2M_REQUIRE(N == 16, "selective_scan_bwd: d_state %d unsupported (16)", N);
+  V2M_REQUIRE(hs && hs_bytes >= selective_scan_bwd_workspace(B, L, ED, N), "selective_scan_bwd: state workspace of %lld bytes needed",
+              selective_scan_bwd_workspace(B, L, ED, N));
+  V2M_REQUIRE(B <= 65535, "selective_scan_bwd: B=%d too large for the grid", B);
+  selective_scan_bwd_kernel<16><<<dim3((ED + 127) / 128, B), 128, 0, stream>>>(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z,
+                                                                              ldz, dout, ldo, hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc,
+                                                                              dz, lddz, dA_log, dD, ddt_bias, L, ED, plus);
+  return check_launch("selective_scan_bwd");
+}
+
+// Backward of mamba_conv_silu: thread <-> (video, channel) walking L with a KW-wide sliding window of inputs and of pending
+// input gradients (position p collects from the outputs p .. p+KW-1); dw / dbias are summed per thread and added once
+// (caller-zeroed buffers).
+template <int KW>
+__global__ void __launch_bounds__(128) mamba_conv_silu_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, const float* __restrict__ dy,
+                                                                  long long ldy, float* __restrict__ dx, long long lddx,
+                                                                  float* __restrict__ dw, float* __restrict__ dbias, int L, int ED) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= ED) return;
+  float wk[KW], win[KW], acc[KW], gw[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) { wk[k] = w[c * KW + k]; win[k] = 0.f; acc[k] = 0.f; gw[k] = 0.f; }
+  const float bs = bias ? bias[c] : 0.f;
+  float gb = 0.f;
+  for (int l = 0; l < L; ++l) {
+    const long long row = (long long)b * L + l;
+#pragma unroll
+    for (int k = 0; k < KW - 1; ++k) { win[k] = win[k + 1]; acc[k] = acc[k + 1]; }
+    win[KW - 1] = x[row * ldx + c];
+    acc[KW - 1] = 0.f;
+    float pre = bs;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) pre = fmaf(wk[k], win[k], pre);
+    const float sg = 1.f / (1.f + expf(-pre));
+    const float dpre = dy[row * ldy + c] * sg * (1.f + pre * (1.f - sg));
+    gb += dpre;
+#pragma unroll
+    for (int k = 0; k < KW; ++k) { gw[k] = fmaf(dpre, win[k], gw[k]); acc[k] = fmaf(wk[k], dpre, acc[k]); }
+    if (l - (KW - 1) >= 0) dx[(row - (KW - 1)) * lddx + c] = acc[0];
+  }
+#pragma unroll
+  for (int k = 1; k < KW; ++k) {
+    const int pos = L - 1 - (KW - 1) + k;
+    if (pos >= 0) dx[((long long)b * L + pos) * lddx + c] = acc[k];
+  }
+#pragma unroll
+  for (int k = 0; k < KW; ++k) atomicAdd(dw + c * KW + k, gw[k]);
+  if (dbias) atomicAdd(dbias + c, gb);
+}
+
+int mamba_conv_silu_bwd(const float* x, long long ldx, const float* w, const float* bias, const float* dy, long long ldy, float* dx,
+                        long long lddx, float* dw, float* dbias, int B, int L, int ED, int KW, cudaStream_t stream) {
+  V2M_REQUIRE(B > 0 && L > 0 && ED > 0 && B <= 65535, "mamba_conv_silu_bwd: bad dims B=%d L=%d ED=%d", B, L, ED);
+  V2M_REQUIRE(KW == 4, "mamba_conv_silu_bwd: d_conv %d unsupported (4)", KW);
+  mamba_conv_silu_bwd_kernel<4><<<dim3((ED + 127) / 128, B), 128, 0, stream>>>(x, ldx, w, bias, dy, ldy, dx, lddx, dw, dbias, L, ED);
+  return check_launch("mamba_conv_silu_bwd");
+}
+
 // y = x * rsqrt(mean(x^2) + eps) * w   (mamba.py:483-489); one warp per row
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                                       int M, int D, float eps) {

@@ -4,8 +4,10 @@ Class names, constructor arguments, parameter names and shapes follow the refere
 checkpoint works: MambaConfig (mamba.py:36-79), RMSNorm (:472-489), MambaBlock (:161-257), ResidualBlock (:137-159),
 Mamba (:81-104), BiMambaEncoderLayer / BiMambaEncoder (bimamba.py:9-99).  The forward pass (mamba.py:259-351) runs as
 GEMMs (in_proj, x_proj, dt_proj, out_proj) + a depthwise conv/SiLU kernel + ONE fused selective-scan kernel that never
-materialises the (B, L, ED, N) tensors of `selective_scan` (:333-351).  fp32, inference (no autograd through the fused
-scan; training the scan goes through video2music_b200.pscan as in the reference's pscan mode).
+materialises the (B, L, ED, N) tensors of `selective_scan` (:333-351).  fp32.  With grad mode on (input or parameters
+requiring grad) the same kernels run inside autograd Functions (`autograd.MambaCoreFn`: fused-scan backward with recomputed
+states, conv/SiLU backward; LinearFn / LayerNormFn / RMSNormFn around it), so Mamba, Mamba+ and the Bi-Mamba layers train;
+dropout must be 0.  The stand-alone differentiable scan is video2music_b200.pscan (model/pscan.py:228).
 """
 import math
 from dataclasses import dataclass
@@ -53,10 +55,9 @@ class MambaConfig:
             self.mup_width_mult = self.d_model / self.mup_base_width
 
 
-def _no_grad_only(*tensors):
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
-        raise NotImplementedError("the fused Mamba forward is inference-only: call it under torch.no_grad() "
-                                  "(the differentiable scan is video2music_b200.pscan, model/pscan.py:228)")
+def _ag():
+    from . import autograd
+    return autograd
 
 
 class RMSNorm(nn.Module):
@@ -68,7 +69,8 @@ class RMSNorm(nn.Module):
             self.weight = nn.Parameter(torch.ones(d_model))
 
     def forward(self, x):
-        _no_grad_only(x)
+        if _ag().tracking(x, self):
+            return _ag().RMSNormFn.apply(x.float().contiguous(), None if self.use_mup else self.weight, self.eps)
         return ops.rmsnorm(x.float(), None if self.use_mup else self.weight.detach(), self.eps)
 
 
@@ -107,10 +109,15 @@ class MambaBlock(nn.Module):
 
     def forward(self, x):
         """x (B, L, D) -> (B, L, D)   (mamba.py:259-291; dropout is defined but never applied by the reference forward)."""
-        _no_grad_only(x)
         cfg = self.config
         B, L, D = x.shape
         ED, N, R = cfg.d_inner, cfg.d_state, cfg.dt_rank
+        ag = _ag()
+        if ag.tracking(x, self):                                   # training: same kernels inside autograd Functions
+            xz = ag.linear_fn(ag.rows_f32(x), self.in_proj)
+            y = ag.MambaCoreFn.apply(xz, self.conv1d.weight.reshape(ED, -1), self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                     self.dt_proj.bias, self.A_log, self.D, B, L, cfg.use_version == 1)
+            return ag.linear_fn(y, self.out_proj).view(B, L, D)
         x2 = x.reshape(B * L, D).float().contiguous()
         det = lambda p: None if p is None else p.detach()
         xz = ops.linear(x2, det(self.in_proj.weight), det(self.in_proj.bias))                       # (B*L, 2ED): x | z
@@ -152,13 +159,27 @@ class _FFN(nn.Sequential):
 
     def forward(self, x):
         shp = x.shape
+        ag = _ag()
+        if ag.tracking(x, self):
+            return ag.linear_fn(ag.linear_fn(ag.rows_f32(x), self[0], relu=True), self[3]).view(shp)
         x2 = x.reshape(-1, shp[-1]).float().contiguous()
         h = ops.linear(x2, self[0].weight.detach(), self[0].bias.detach(), relu=True)
         return ops.linear(h, self[3].weight.detach(), self[3].bias.detach()).view(shp)
 
 
+def _sum(a, b):
+    """a + b (one kernel; inside an autograd Function when gradients are tracked)."""
+    ag = _ag()
+    if ag.tracking(a, b):
+        return ag.AddFn.apply(a.float().contiguous(), b.float().contiguous(), 1.0)
+    return ops.axpy(a.float().contiguous(), b.float().contiguous(), 1.0)
+
+
 def _add_norm(norm: nn.LayerNorm, a, b):
     shp = a.shape
+    ag = _ag()
+    if ag.tracking(a, b, norm):
+        return ag.LayerNormFn.apply(ag.AddFn.apply(ag.rows_f32(a), ag.rows_f32(b), 1.0), norm.weight, norm.bias, norm.eps).view(shp)
     return ops.layernorm(a.reshape(-1, shp[-1]).contiguous(), norm.weight.detach(), norm.bias.detach(),
                          res=b.reshape(-1, shp[-1]).contiguous(), eps=norm.eps).view(shp)
 
@@ -190,11 +211,14 @@ class BiMambaEncoderLayer(nn.Module):
         x_b = torch.flip(self.mamba_backward(x_flip), dims=[1])
         x_b = _add_norm(self.norm3, x_b, x)
         x_b = _add_norm(self.norm4, self.ffn2(x_f), x_b)
-        return ops.axpy(x_f.contiguous(), x_b.contiguous(), 1.0)
+        return _sum(x_f, x_b)
 
 
 def _norm_only(norm: nn.LayerNorm, a):
     shp = a.shape
+    ag = _ag()
+    if ag.tracking(a, norm):
+        return ag.LayerNormFn.apply(ag.rows_f32(a), norm.weight, norm.bias, norm.eps).view(shp)
     return ops.layernorm(a.reshape(-1, shp[-1]).contiguous(), norm.weight.detach(), norm.bias.detach(), eps=norm.eps).view(shp)
 
 
@@ -219,18 +243,17 @@ class BiMambaEncoderLayer_V1(nn.Module):
     def forward(self, x):
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("dropout > 0 in training mode is not built; use eval() or dropout=0")
-        _no_grad_only(x)
         x = x.float().contiguous()
         x_flip = torch.flip(x, dims=[1])
         if self.norm_first:                                                      # bimamba.py:141-165
-            x_f = ops.axpy(x, self.mamba_forward(_norm_only(self.norm1, x)).contiguous(), 1.0)
-            x_b = torch.flip(self.mamba_backward(_norm_only(self.norm2, x_flip)), dims=[1]).contiguous()
-            x_b = ops.axpy(x, x_b, 1.0)
-            x = ops.axpy(x_f, x_b, 1.0)
-            return ops.axpy(x, self.ffn(_norm_only(self.norm3, x)).float().contiguous(), 1.0)
+            x_f = _sum(x, self.mamba_forward(_norm_only(self.norm1, x)))
+            x_b = torch.flip(self.mamba_backward(_norm_only(self.norm2, x_flip)), dims=[1])
+            x_b = _sum(x, x_b)
+            x = _sum(x_f, x_b)
+            return _sum(x, self.ffn(_norm_only(self.norm3, x)))
         x_f = _add_norm(self.norm1, self.mamba_forward(x), x)                    # :168-189
         x_b = _add_norm(self.norm2, torch.flip(self.mamba_backward(x_flip), dims=[1]), x)
-        x = ops.axpy(x_f.contiguous(), x_b.contiguous(), 1.0)
+        x = _sum(x_f, x_b)
         return _add_norm(self.norm3, self.ffn(x).float(), x)
 
 
@@ -251,7 +274,5 @@ class BiMambaEncoder(nn.Module):
         for i in range(self.n_encoder_layers):
             x = self.layers[i](x)
         if self.norm_first:
-            shp = x.shape
-            x = ops.layernorm(x.reshape(-1, shp[-1]).contiguous(), self.norm.weight.detach(), self.norm.bias.detach(),
-                              eps=self.norm.eps).view(shp)
+            x = _norm_only(self.norm, x)
         return x

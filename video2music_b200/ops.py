@@ -453,6 +453,46 @@ def selective_scan(x: torch.Tensor, delta_raw: torch.Tensor, dt_bias: Optional[t
     return out
 
 
+def mamba_conv_silu_bwd(xz: torch.Tensor, ED: int, w: torch.Tensor, bias: Optional[torch.Tensor], dy: torch.Tensor, dxz: torch.Tensor,
+                        B: int, L: int):
+    """Backward of mamba_conv_silu: writes the input gradient into the first ED columns of dxz (B*L, >= ED); returns
+    (dw (ED, KW), dbias (ED) or None)."""
+    require_device(xz)
+    assert xz.stride(1) == 1 and dy.stride(1) == 1 and dxz.stride(1) == 1 and w.is_contiguous()
+    dw = torch.zeros_like(w)
+    dbias = torch.zeros((ED,), device=xz.device, dtype=torch.float32) if bias is not None else None
+    check(load().v2m_mamba_conv_silu_bwd(ptr(xz), xz.stride(0), ptr(w), ptr(bias), ptr(dy), dy.stride(0), ptr(dxz), dxz.stride(0), ptr(dw),
+                                         ptr(dbias), B, L, ED, w.shape[1], stream()))
+    _lib.count_launches(1)
+    return dw, dbias
+
+
+def selective_scan_bwd(x: torch.Tensor, delta_raw: torch.Tensor, dt_bias: Optional[torch.Tensor], A_log: torch.Tensor, Bm: torch.Tensor,
+                       Cm: torch.Tensor, D: torch.Tensor, z: Optional[torch.Tensor], dout: torch.Tensor, dBm: torch.Tensor,
+                       dCm: torch.Tensor, dz: Optional[torch.Tensor], B: int, L: int, plus: bool = False):
+    """Backward of selective_scan.  dBm / dCm: zeroed (B*L, N) views (slices of the x_proj output gradient) that receive the
+    channel sums; dz: (B*L, ED) view that receives the gate gradient.  Returns (dx, ddelta_raw, dA_log, dD, ddt_bias)."""
+    require_device(x)
+    ED, N = A_log.shape
+    for t in (x, delta_raw, Bm, Cm, dout, dBm, dCm) + ((z, dz) if z is not None else ()):
+        assert t.dtype == torch.float32 and t.stride(1) == 1
+    assert Bm.stride(0) == Cm.stride(0) and dBm.stride(0) == dCm.stride(0)
+    f32 = dict(device=x.device, dtype=torch.float32)
+    dx, ddraw = torch.empty((B * L, ED), **f32), torch.empty((B * L, ED), **f32)
+    dA_log, dD = torch.zeros((ED, N), **f32), torch.zeros((ED,), **f32)
+    ddtb = torch.zeros((ED,), **f32) if dt_bias is not None else None
+    lib = load()
+    hs_bytes = int(lib.v2m_selective_scan_bwd_workspace(B, L, ED, N))
+    hs = torch.empty((hs_bytes // 4,), **f32)
+    check(lib.v2m_selective_scan_bwd(ptr(x), x.stride(0), ptr(delta_raw), delta_raw.stride(0), ptr(dt_bias), ptr(A_log.contiguous()),
+                                     ptr(Bm), ptr(Cm), Bm.stride(0), ptr(D), ptr(z), z.stride(0) if z is not None else 0,
+                                     ptr(dout), dout.stride(0), ptr(hs), hs_bytes, ptr(dx), ED, ptr(ddraw), ED, ptr(dBm), ptr(dCm),
+                                     dBm.stride(0), ptr(dz), dz.stride(0) if dz is not None else 0, ptr(dA_log), ptr(dD), ptr(ddtb),
+                                     B, L, ED, N, int(plus), stream()))
+    _lib.count_launches(1)
+    return dx, ddraw, dA_log, dD, ddtb
+
+
 def rmsnorm(x: torch.Tensor, w: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
     require_device(x)
     x = x.contiguous()
