@@ -167,7 +167,8 @@ int v2m_cast_2d(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, i
                 int32_t rows, int32_t cols, int32_t zero_pad, void* stream);
 
 /* mode 0: out = a * silu(b) (GLUExpert gating, moe.py:47); mode 1: out = a + alpha*b (shared expert, moe.py:301);
- * mode 2: out = sigmoid(a) (instrument classifier head, video_regression.py:197-200; b is read but unused) */
+ * mode 2: out = sigmoid(a) (instrument classifier head, video_regression.py:197-200; b is read but unused);
+ * mode 3: out = a * b * (1 - b) (gradient of mode 2: a = upstream gradient, b = the sigmoid output) */
 int v2m_binary_f32(const float* a, const float* b, float* out, int64_t n, int32_t mode, float alpha, void* stream);
 
 /* ---- KV-cached greedy decode (replaces the re-forward loop of VideoMusicTransformer.generate,

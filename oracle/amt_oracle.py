@@ -741,15 +741,16 @@ def v3_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layer
 
 def video_regression_forward(sd: SD, sem, emotion, reg_model: str, n_layers: int, dt_rank: int):
     """VideoRegression.forward (video_regression.py:208-245) for regModel "mamba" / "mamba+" (Mamba stack) and "bimamba+"
-    (BiMambaEncoder of Bi-Mamba+ layers with the FFN feed-forward): returns (loudness / note density (B,L,2), instruments)."""
+    (BiMambaEncoder of Bi-Mamba+ layers with the FFN feed-forward) and "moe_bimamba+" / "sharedmoe_bimamba+" (MoE feed-forward): returns (loudness / note density (B,L,2), instruments)."""
     vf = F.linear(torch.cat([sem.float(), emotion.float()], dim=-1), sd["in_proj.0.weight"], sd["in_proj.0.bias"])
     if reg_model in ("mamba", "mamba+"):
         msd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
         out = mamba_forward(msd, vf, n_layers, dt_rank, use_version=1 if reg_model == "mamba+" else 0)
-    elif reg_model == "bimamba+":
+    elif reg_model in ("bimamba+", "moe_bimamba+", "sharedmoe_bimamba+"):              # video_regression.py:158-186
+        moe = None if reg_model == "bimamba+" else dict(n_experts=6, k=2, shared=reg_model.startswith("shared"))
         out = vf
         for i in range(n_layers):
-            out = bimamba_v1_layer_forward(sd, "model.layers.%d." % i, out, dt_rank, norm_first=False)
+            out = bimamba_v1_layer_forward(sd, "model.layers.%d." % i, out, dt_rank, norm_first=False, moe=moe)
     else:
         raise NotImplementedError(reg_model)
     return F.linear(out, sd["regressor.weight"], sd["regressor.bias"]), torch.sigmoid(F.linear(out, sd["classifier.0.weight"], sd["classifier.0.bias"]))

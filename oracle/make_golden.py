@@ -544,6 +544,45 @@ def golden_mamba_train(ref):
     _save("mamba_train.pt", out)
 
 
+REGRESSION_TRAIN_CASES = [("mamba+", 111), ("bimamba+", 112), ("sharedmoe_bimamba+", 113)]
+
+
+def regression_train_targets(seed, B, L):
+    """Synthetic (loudness, note density) and instrument targets of the regression training loss."""
+    return syn.unit_uniform((B, L, 2), syn._gen(seed, "t_ln")), (syn.unit_uniform((B, L, 40), syn._gen(seed, "t_inst")) > 0.7).float()
+
+
+def golden_regression_train(ref):
+    """One backward pass of VideoRegression training (utilities/run_model_regression.py:39: MSE(ln_nd) + BCE(instruments)),
+    2 layers, dropout 0, train() mode."""
+    import importlib
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    vr = importlib.import_module("model.video_regression")
+    out = {}
+    for reg, seed in REGRESSION_TRAIN_CASES:
+        torch.manual_seed(0)
+        m = vr.VideoRegression(n_layers=2, d_model=128, d_hidden=256, dropout=0.0, total_vf_dim=774, regModel=reg).train()
+        for mod in m.modules():                      # the experts are built with GLUExpert's default dropout 0.1 (video_regression.py:176)
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        sd = _load_weights(m, seed)
+        B, L = 2, 120
+        sem = syn.unit_uniform((B, L, 768), syn._gen(seed, "sem"))
+        emo = torch.softmax(syn.unit_uniform((B, L, 6), syn._gen(seed, "emo")), dim=-1)
+        t_ln, t_inst = regression_train_targets(seed, B, L)
+        z = torch.zeros((B, L))
+        ln, inst = m(sem, z, z, emo)
+        loss = torch.nn.functional.mse_loss(ln, t_ln) + torch.nn.functional.binary_cross_entropy(inst, t_inst)
+        loss.backward()
+        norms = {n: float(p.grad.double().norm()) for n, p in m.named_parameters() if p.grad is not None}
+        grads = {n: m.get_parameter(n).grad.clone() for n in ("regressor.weight", "classifier.0.bias", "in_proj.0.bias")}
+        out[reg] = dict(spec=dict(reg=reg, seed=seed, B=B, L=L, n_layers=2), weights_checksum=syn.checksum(sd), ln=ln.detach().clone(),
+                        inst=inst.detach().clone(), loss=float(loss.detach()), grad_norms=norms, grads=grads)
+        print(reg, "loss %.6f, %d parameter gradients" % (float(loss.detach()), len(norms)))
+    _save("regression_train.pt", out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -555,7 +594,7 @@ def main():
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
                 mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
-                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
+                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

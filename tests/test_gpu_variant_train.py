@@ -223,3 +223,22 @@ def test_selective_scan_and_conv_backward_kernels_vs_autograd(B, L, ED, plus):
     assert rel_err(ddbc[:, R:], dbc_r.grad[:, R:]) < tol and float(ddbc[:, :R].abs().max()) == 0.0
     assert rel_err(dxz, xz_r.grad) < tol                       # x half through conv backward, z half from the gate
     assert rel_err(dcw, cw_r.grad) < tol and rel_err(dcb, cb_r.grad) < tol
+
+
+# ---------------------------------------------------------------- VideoRegression training step (BASELINE config 5 model)
+@pytest.mark.parametrize("reg", ["mamba+", "bimamba+", "sharedmoe_bimamba+"])
+def test_video_regression_train_golden_gpu(reg):
+    """One training step's gradients of VideoRegression (MSE + BCE loss of utilities/run_model_regression.py:39 applied to our
+    outputs) equal the reference's for the Mamba+, Bi-Mamba+ and SharedMoE Bi-Mamba+ backbones (odd d_ff = 257 experts)."""
+    from test_oracle import _regression_train_case, regression_loss
+    g, m, sd, sem, emo, (t_ln, t_inst) = _regression_train_case(reg)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    z = torch.zeros(sem.shape[:2], device=DEV)
+    ln, inst = m(sem.to(DEV), z, z, emo.to(DEV))
+    loss = regression_loss(ln, inst, t_ln.to(DEV), t_inst.to(DEV))
+    loss.backward()
+    assert rel_err(ln, g["ln"]) < 1e-4 and rel_err(inst, g["inst"]) < 1e-4
+    assert abs(float(loss.detach()) - g["loss"]) < 1e-4 * abs(g["loss"])
+    _check_grads({n: p.grad for n, p in m.named_parameters() if p.grad is not None}, g, 3e-4)

@@ -239,6 +239,39 @@ def test_mamba_train_golden(name):
     _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 5e-5)
 
 
+def _regression_train_case(reg):
+    from video2music_b200 import VideoRegression
+    from oracle.make_golden import regression_train_targets
+    g = load_golden("regression_train.pt")[reg]
+    s = g["spec"]
+    m = VideoRegression(n_layers=s["n_layers"], d_model=128, d_hidden=256, dropout=0.0, total_vf_dim=774, regModel=reg).train()
+    for mod in m.modules():                          # GLUExpert's default dropout 0.1 (video_regression.py:176), zeroed as in the golden
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["seed"])
+    sem = syn.unit_uniform((s["B"], s["L"], 768), syn._gen(s["seed"], "sem"))
+    emo = torch.softmax(syn.unit_uniform((s["B"], s["L"], 6), syn._gen(s["seed"], "emo")), dim=-1)
+    return g, m, sd, sem, emo, regression_train_targets(s["seed"], s["B"], s["L"])
+
+
+def regression_loss(ln, inst, t_ln, t_inst):
+    """utilities/run_model_regression.py:39."""
+    return torch.nn.functional.mse_loss(ln, t_ln) + torch.nn.functional.binary_cross_entropy(inst, t_inst)
+
+
+@pytest.mark.parametrize("reg", ["mamba+", "bimamba+", "sharedmoe_bimamba+"])
+def test_video_regression_train_golden(reg):
+    """Oracle gradients of one VideoRegression training step == the reference's."""
+    g, m, sd, sem, emo, (t_ln, t_inst) = _regression_train_case(reg)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    sd = _leaf_sd(sd)
+    ln, inst = O.video_regression_forward(sd, sem, emo, reg, g["spec"]["n_layers"], dt_rank=8)
+    loss = regression_loss(ln, inst, t_ln, t_inst)
+    loss.backward()
+    assert rel_err(ln, g["ln"]) < 5e-5 and rel_err(inst, g["inst"]) < 5e-5 and abs(float(loss.detach()) - g["loss"]) < 1e-5 * abs(g["loss"])
+    _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 1e-4)
+
+
 def test_pscan_golden():
     for case in load_golden("pscan.pt")["cases"]:
         s = case["spec"]

@@ -370,6 +370,19 @@ class SwigluFn(torch.autograd.Function):
         return dag[:, :ff], dag[:, ff:]
 
 
+class SigmoidFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a):
+        s = ops.sigmoid(a)
+        ctx.save_for_backward(s)
+        return s
+
+    @staticmethod
+    def backward(ctx, dy):
+        (s,) = ctx.saved_tensors
+        return ops.sigmoid_bwd(dy.contiguous(), s)
+
+
 class RMSNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, eps):

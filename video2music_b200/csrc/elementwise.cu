@@ -238,7 +238,8 @@ __global__ void binary_kernel(const float* __restrict__ a, const float* __restri
                               long long n, int mode, float alpha) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float x = a[i], y = b[i];
-    out[i] = mode == 0 ? x * (y / (1.f + expf(-y))) : mode == 1 ? fmaf(alpha, y, x) : 1.f / (1.f + expf(-x));   // 2: sigmoid(a)
+    out[i] = mode == 0 ? x * (y / (1.f + expf(-y))) : mode == 1 ? fmaf(alpha, y, x) : mode == 2 ? 1.f / (1.f + expf(-x))   // 2: sigmoid(a)
+                                                                                 : x * y * (1.f - y);       // 3: sigmoid backward, a = dy, b = sigmoid
   }
 }
 

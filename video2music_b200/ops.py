@@ -207,6 +207,11 @@ def sigmoid(a: torch.Tensor) -> torch.Tensor:
     return _binary(a, a, 2, 0.0)
 
 
+def sigmoid_bwd(dy: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """dy * s * (1 - s): gradient of sigmoid given its output."""
+    return _binary(dy, s, 3, 0.0)
+
+
 def axpy(a: torch.Tensor, b: torch.Tensor, alpha: float) -> torch.Tensor:
     """a + alpha * b  (moe.py:301)."""
     return _binary(a, b, 1, alpha)

@@ -2,7 +2,8 @@
 regModel in {"mamba", "mamba+", "bimamba", "bimamba+", "moe_bimamba+", "sharedmoe_bimamba+"} -- the loudness / note-density
 regressor and instrument classifier that `video2music.py:613,651` runs next to the chord transformer.  Same constructor
 signature and parameter names (`in_proj.0`, `model.*`, `regressor`, `classifier.0`).  The LSTM / GRU / CNN-GRU / minGRU /
-moemamba backbones are outside the hot path (not built).  Inference only."""
+moemamba backbones are outside the hot path (not built).  Trains in fp32 with dropout 0 (gradients through the autograd
+Functions of `autograd.py`: every forward and backward kernel is ours)."""
 import torch
 import torch.nn as nn
 
@@ -43,17 +44,25 @@ class VideoRegression(nn.Module):
         self.classifier = nn.Sequential(nn.Linear(d_model, INSTRUMENT_SIZE), nn.Sigmoid())
 
     def get_feature(self, feature_semantic_list, feature_scene_offset, feature_motion, feature_emotion):
-        if self.training:
-            raise NotImplementedError("VideoRegression runs inference only (eval())")
+        if self.training and self.dropout_layer.p > 0:
+            raise NotImplementedError("dropout > 0 in training mode is not built; use eval() or dropout=0")
         dev = self.regressor.weight.device
         vf = torch.cat([feature_semantic_list.float().to(dev), feature_emotion.float().to(dev)], dim=-1)   # :211-213
         B, L, F = vf.shape
+        from . import autograd as ag
+        if ag.tracking(vf, self):
+            return self.model(ag.linear_fn(vf.reshape(B * L, F).contiguous(), self.in_proj[0]).view(B, L, self.d_model))
         x = ops.linear(vf.reshape(B * L, F).contiguous(), self.in_proj[0].weight.detach(), self.in_proj[0].bias.detach())
         return self.model(x.view(B, L, self.d_model))
 
     def forward(self, feature_semantic_list, feature_scene_offset, feature_motion, feature_emotion):
         out = self.get_feature(feature_semantic_list, feature_scene_offset, feature_motion, feature_emotion)
         B, L, E = out.shape
+        from . import autograd as ag
+        if ag.tracking(out, self):
+            o2 = ag.rows_f32(out)
+            return (ag.linear_fn(o2, self.regressor).view(B, L, 2),
+                    ag.SigmoidFn.apply(ag.linear_fn(o2, self.classifier[0])).view(B, L, INSTRUMENT_SIZE))
         o2 = out.reshape(B * L, E).float().contiguous()
         ln = ops.linear(o2, self.regressor.weight.detach(), self.regressor.bias.detach()).view(B, L, 2)
         inst = ops.sigmoid(ops.linear(o2, self.classifier[0].weight.detach(), self.classifier[0].bias.detach())).view(B, L, INSTRUMENT_SIZE)
