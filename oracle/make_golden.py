@@ -583,6 +583,31 @@ def golden_regression_train(ref):
     _save("regression_train.pt", out)
 
 
+def golden_rpr_train(ref):
+    """Gradients of TransformerDecoderLayerRPR and a 2-layer TransformerDecoderRPR (rpr.py:18-70) in train() mode, dropout 0:
+    loss = sum(y * r)."""
+    out = {}
+    for name, n_layers in (("layer", 1), ("decoder", 2)):
+        torch.manual_seed(0)
+        layer = ref.rpr.TransformerDecoderLayerRPR(256, 4, 512, 0.0, er_len=80)
+        m = (layer if n_layers == 1 else ref.rpr.TransformerDecoderRPR(layer, n_layers, torch.nn.LayerNorm(256))).train()
+        seed = 121 + n_layers
+        sd = _load_weights(m, seed)
+        tgt = syn.unit_uniform((50, 3, 256), syn._gen(seed, "tgt")).requires_grad_(True)
+        mem = syn.unit_uniform((70, 3, 256), syn._gen(seed, "mem")).requires_grad_(True)
+        r = syn.unit_uniform((50, 3, 256), syn._gen(seed, "r"))
+        mask = torch.triu(torch.full((50, 50), float("-inf")), diagonal=1)
+        y = m(tgt, mem, tgt_mask=mask)
+        (y * r).sum().backward()
+        norms = {n: float(p.grad.double().norm()) for n, p in m.named_parameters() if p.grad is not None}
+        keep = [n for n in norms if n.endswith(("self_attn.Er", "norm2.weight", "multihead_attn.in_proj_bias"))][:4]
+        out[name] = dict(spec=dict(T=50, S=70, B=3, E=256, H=4, ff=512, er_len=80, seed=seed, n_layers=n_layers),
+                         weights_checksum=syn.checksum(sd), out=y.detach().clone(), d_tgt=tgt.grad.clone(), d_mem=mem.grad.clone(),
+                         grad_norms=norms, grads={n: m.get_parameter(n).grad.clone() for n in keep})
+        print(name, len(norms), "parameter gradients, kept", keep)
+    _save("rpr_train.pt", out)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -594,7 +619,7 @@ def main():
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
                 mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
-                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
+                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), rpr_train=lambda: golden_rpr_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

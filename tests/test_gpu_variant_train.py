@@ -242,3 +242,42 @@ def test_video_regression_train_golden_gpu(reg):
     assert rel_err(ln, g["ln"]) < 1e-4 and rel_err(inst, g["inst"]) < 1e-4
     assert abs(float(loss.detach()) - g["loss"]) < 1e-4 * abs(g["loss"])
     _check_grads({n: p.grad for n, p in m.named_parameters() if p.grad is not None}, g, 3e-4)
+
+
+# ---------------------------------------------------------------- RPR attention module / decoder layer, stand-alone training
+def test_rpr_module_backward_golden_gpu():
+    """MultiheadAttentionRPR called as a module with gradients (rpr.py:170-198): d/dx, d/dEr, d/d in_proj against the reference."""
+    from video2music_b200 import MultiheadAttentionRPR
+    for case in load_golden("rpr_attention.pt")["cases"]:
+        s = case["spec"]
+        mod = MultiheadAttentionRPR(s["E"], s["H"], dropout=0.0, er_len=s["er_len"]).eval()
+        mod.load_state_dict(syn.fill_like_reference_init({k: tuple(v.shape) for k, v in mod.state_dict().items()}, seed=s["seed"]))
+        mod = mod.to(DEV)
+        x = _u((s["L"], s["B"], s["E"]), s["seed"], "x").to(DEV).requires_grad_(True)
+        gy = _u((s["L"], s["B"], s["E"]), s["seed"], "gy").to(DEV)
+        mask = torch.triu(torch.full((s["L"], s["L"]), float("-inf"), device=DEV), diagonal=1)
+        out, w = mod(x, x, x, attn_mask=mask)
+        (out * gy).sum().backward()
+        assert rel_err(out, case["out"]) < 1e-4
+        if case["weights_mean"] is not None:
+            assert rel_err(w, case["weights_mean"]) < 1e-4
+        assert rel_err(x.grad, case["grad_x"]) < 2e-4 and rel_err(mod.Er.grad, case["grad_Er"]) < 2e-4
+        assert rel_err(mod.in_proj_bias.grad, case["grad_in_proj_bias"]) < 2e-4
+        n = float(mod.in_proj_weight.grad.double().norm())
+        assert abs(n - case["grad_in_proj_weight_norm"]) < 2e-4 * case["grad_in_proj_weight_norm"]
+
+
+@pytest.mark.parametrize("name", ["layer", "decoder"])
+def test_rpr_decoder_train_golden_gpu(name):
+    from test_oracle import _rpr_train_module
+    g, m, sd, tgt, mem, r = _rpr_train_module(name)
+    s = g["spec"]
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    tgt, mem = tgt.to(DEV).requires_grad_(True), mem.to(DEV).requires_grad_(True)
+    mask = torch.triu(torch.full((s["T"], s["T"]), float("-inf"), device=DEV), diagonal=1)
+    y = m(tgt, mem, tgt_mask=mask)
+    (y * r.to(DEV)).sum().backward()
+    assert rel_err(y, g["out"]) < 1e-4 and rel_err(tgt.grad, g["d_tgt"]) < 2e-4 and rel_err(mem.grad, g["d_mem"]) < 2e-4
+    _check_grads({n: p.grad for n, p in m.named_parameters() if p.grad is not None}, g, 2e-4)

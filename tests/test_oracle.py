@@ -272,6 +272,40 @@ def test_video_regression_train_golden(reg):
     _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 1e-4)
 
 
+def _rpr_train_module(name):
+    from video2music_b200 import TransformerDecoderLayerRPR, TransformerDecoderRPR
+    g = load_golden("rpr_train.pt")[name]
+    s = g["spec"]
+    layer = TransformerDecoderLayerRPR(s["E"], s["H"], s["ff"], 0.0, er_len=s["er_len"])
+    m = layer if s["n_layers"] == 1 else TransformerDecoderRPR(layer, s["n_layers"], torch.nn.LayerNorm(s["E"]))
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["seed"])
+    tgt = syn.unit_uniform((s["T"], s["B"], s["E"]), syn._gen(s["seed"], "tgt"))
+    mem = syn.unit_uniform((s["S"], s["B"], s["E"]), syn._gen(s["seed"], "mem"))
+    r = syn.unit_uniform((s["T"], s["B"], s["E"]), syn._gen(s["seed"], "r"))
+    return g, m.train(), sd, tgt, mem, r
+
+
+@pytest.mark.parametrize("name", ["layer", "decoder"])
+def test_rpr_decoder_train_golden(name):
+    """Oracle gradients of TransformerDecoderLayerRPR / a 2-layer TransformerDecoderRPR == the reference's autograd."""
+    g, _, sd, tgt, mem, r = _rpr_train_module(name)
+    s = g["spec"]
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    sd = _leaf_sd(sd)
+    tgt.requires_grad_(True), mem.requires_grad_(True)
+    mask = torch.triu(torch.full((s["T"], s["T"]), float("-inf")), diagonal=1)
+    if s["n_layers"] == 1:
+        y = O.decoder_layer_rpr(tgt, mem, sd, "", s["H"], mask)
+    else:
+        y = tgt
+        for i in range(s["n_layers"]):
+            y = O.decoder_layer_rpr(y, mem, sd, "layers.%d." % i, s["H"], mask)
+        y = torch.nn.functional.layer_norm(y, (s["E"],), sd["norm.weight"], sd["norm.bias"])
+    (y * r).sum().backward()
+    assert rel_err(y, g["out"]) < 2e-5 and rel_err(tgt.grad, g["d_tgt"]) < 5e-5 and rel_err(mem.grad, g["d_mem"]) < 5e-5
+    _check_grads({k: v.grad for k, v in sd.items() if v.grad is not None}, g, 5e-5)
+
+
 def test_pscan_golden():
     for case in load_golden("pscan.pt")["cases"]:
         s = case["spec"]

@@ -509,6 +509,68 @@ class MambaCoreFn(torch.autograd.Function):
         return dxz, dconv_w, dconv_b, dwx, dwdt, ddtb, dA_log, dD, None, None, None
 
 
+class AttnRowsFn(torch.autograd.Function):
+    """Attention over separate q (rows_q, E), k, v (rows_k, E) fp32 projections with explicit (batch, row) strides -- the
+    (L, B, E) module layout has rows ordered (l, b).  q arrives pre-scaled.  Optional Er (RPR skew) and causal mask; with
+    need_p the per-head probabilities (B*H, Lq, Lk) are returned as a second, non-differentiable output."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, er, B, Lq, Lk, H, causal, qs, ks, need_p):
+        E = q.shape[1]
+        out = torch.empty_like(q)
+        lse = torch.empty((B * H, Lq), device=q.device, dtype=F32)
+        p_out = torch.empty((B * H, Lq, Lk), device=q.device, dtype=F32) if need_p else None
+        ops.attention(q, k, v, out, B=B, Hq=H, Hkv=H, Lq=Lq, Lk=Lk, dh=E // H, q_strides=qs, k_strides=ks, v_strides=ks, o_strides=qs,
+                      causal=causal, Er=er, lse=lse, p_out=p_out)
+        ctx.save_for_backward(q, k, v, out, lse, er)
+        ctx.meta = (B, Lq, Lk, H, causal, qs, ks)
+        if need_p:
+            ctx.mark_non_differentiable(p_out)
+            return out, p_out
+        return out, None
+
+    @staticmethod
+    def backward(ctx, dout, _dp):
+        q, k, v, out, lse, er = ctx.saved_tensors
+        B, Lq, Lk, H, causal, qs, ks = ctx.meta
+        E = q.shape[1]
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.zeros_like(k), torch.zeros_like(v)
+        der = torch.zeros_like(er) if er is not None else None
+        ops.attention_bwd(q, k, v, out, dout, lse, er, dq, dk, dv, der, B=B, Hq=H, Hkv=H, Lq=Lq, Lk=Lk, dh=E // H, q_strides=qs,
+                          k_strides=ks, v_strides=ks, o_strides=qs, do_strides=qs, dq_strides=qs, dkv_strides=ks, causal=causal)
+        return dq, dk, dv, der, None, None, None, None, None, None, None, None
+
+
 def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
-    raise NotImplementedError("module-level autograd for MultiheadAttentionRPR: train through VideoMusicTransformer "
-                              "(video2music_b200.autograd.amt_forward_autograd) or call under torch.no_grad()")
+    """MultiheadAttentionRPR.forward (rpr.py:170-198 -> multi_head_attention_forward_rpr :201-424) with gradients, fp32:
+    three projection GEMMs (q pre-scaled in the epilogue), AttnRowsFn (fused RPR attention forward / backward), out-projection."""
+    from .rpr import is_causal_mask
+    L, B, E = query.shape
+    S = key.shape[0]
+    H = module.num_heads
+    assert E == module.embed_dim and key.shape == value.shape
+    assert key is value or torch.equal(key, value), "separate key / value tensors are not on the AMT path"
+    if getattr(module, "compute_dtype", F32) != F32:
+        raise NotImplementedError("module-level autograd runs on the fp32 path; bf16 training goes through VideoMusicTransformer "
+                                  "(amt_forward_autograd)")
+    causal = is_causal_mask(attn_mask, L)
+    W, bias = module.in_proj_weight, module.in_proj_bias
+    xq = rows_f32(query)
+    xk = xq if key is query else rows_f32(key)
+
+    def proj(x, lo, alpha=1.0, alpha_cols=0):
+        w = W[lo:lo + E]
+        return LinearFn.apply(x, w, None if bias is None else bias[lo:lo + E], w, E, False, alpha, alpha_cols, None, 0, F32, None)
+
+    q = proj(xq, 0, float(E // H) ** -0.5, E)                                    # rpr.py:328 scaling
+    k, v = proj(xk, E), proj(xk, 2 * E)
+    er = None
+    if module.Er is not None:
+        if L != S or L > module.Er.shape[0]:
+            raise RuntimeError("RPR attention needs len_q == len_k <= er_len (got %d, %d, er_len %d); the reference "
+                               "fails in _skew for longer inputs (rpr.py:426-450)" % (L, S, module.Er.shape[0]))
+        er = module.Er
+    ctxv, p = AttnRowsFn.apply(q, k, v, er, B, L, S, H, causal, (E, B * E), (E, B * E), bool(need_weights))
+    out = linear_fn(ctxv, module.out_proj).view(L, B, E)
+    return out, (p.view(B, H, L, S).sum(dim=1) / H if need_weights else None)           # rpr.py:419-422

@@ -217,6 +217,18 @@ class TransformerDecoderLayerRPR(nn.Module):
         self.self_attn.compute_dtype = dt
         self.multihead_attn.compute_dtype = dt
         L, B, E = tgt.shape
+        from . import autograd as ag
+        if ag.tracking(tgt, memory, self):                       # stand-alone training of the layer (fp32): autograd Functions
+            if dt != torch.float32:
+                raise NotImplementedError("module-level autograd runs on the fp32 path; bf16 training goes through "
+                                          "VideoMusicTransformer (autograd.amt_forward_autograd)")
+            add_ln = lambda x, y, n: ag.LayerNormFn.apply(ag.AddFn.apply(ag.rows_f32(x), ag.rows_f32(y), 1.0), n.weight, n.bias, n.eps)
+            tgt2 = self.self_attn(tgt, tgt, tgt, attn_mask=tgt_mask, need_weights=False)[0]
+            x = add_ln(tgt, tgt2, self.norm1)
+            tgt2 = self.multihead_attn(x.view(L, B, E), memory, memory, need_weights=False)[0]
+            x = add_ln(x, tgt2, self.norm2)
+            r = ag.AddFn.apply(x, ag.linear_fn(ag.linear_fn(x, self.linear1, relu=True), self.linear2), 1.0)
+            return ag.LayerNormFn.apply(r, self.norm3.weight, self.norm3.bias, self.norm3.eps).view(L, B, E)
         tgt2 = self.self_attn(tgt, tgt, tgt, attn_mask=tgt_mask, need_weights=False)[0]                 # rpr.py:56-57
         tgt = self._add_ln(tgt, tgt2, self.norm1)                                                        # :58-59
         tgt2 = self.multihead_attn(tgt, memory, memory, need_weights=False)[0]                           # :62-63
@@ -244,5 +256,8 @@ class TransformerDecoderRPR(nn.Module):
             output = mod(output, memory, tgt_mask=tgt_mask, memory_mask=memory_mask,
                          tgt_key_padding_mask=tgt_key_padding_mask, memory_key_padding_mask=memory_key_padding_mask)
         if self.norm is not None:
+            from . import autograd as ag
+            if ag.tracking(output, self.norm):
+                return ag.LayerNormFn.apply(output.float().contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
             output = ops.layernorm(output.contiguous(), self.norm.weight.detach(), self.norm.bias.detach(), eps=self.norm.eps)
         return output
