@@ -149,6 +149,62 @@ def train_leg(args, dev, rank, world, dtype):
             "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values())}
 
 
+def variants_leg(dev):
+    """BASELINE configs 4 and 5 (extra key "variants"; fp32 exact training path, dropout 0, synthetic inputs, CUDA events):
+    one forward + backward of (a) a 6-layer encoder of MultiheadGQA(8 q / 2 kv heads) + MoELayer(6 experts, top-2) blocks,
+    (b) VideoRegression with the Bi-Mamba+ backbone at 64 videos x 300 s, (c) a Mamba block at the 4096-token stress shape."""
+    import torch.nn as nn
+    from video2music_b200 import (GLUExpert, MoELayer, MultiheadGQA, TransformerEncoder, TransformerEncoderLayer, VideoRegression)
+    from video2music_b200.mamba import MambaBlock, MambaConfig
+
+    def timed(fn, reps=3):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def step(net, fwd):
+        def f():
+            net.zero_grad(set_to_none=True)
+            fwd().sum().backward()
+        return f
+
+    g = torch.Generator().manual_seed(11)
+    out = {}
+    torch.manual_seed(0)
+    layer = TransformerEncoderLayer(MultiheadGQA(512, 8, 2, dropout=0.0), MoELayer(GLUExpert(512, 1024, 0.0), 512, n_experts=6,
+                                    n_experts_per_token=2, dropout=0.0), pre_norm=False, norm=nn.LayerNorm(512), dropout=0.0)
+    enc = TransformerEncoder(layer, 6, nn.LayerNorm(512)).to(dev).train()
+    src = torch.randn(300, 8, 512, generator=g).to(dev)
+    ms = timed(step(enc, lambda: enc(src)))
+    out["gqa_moe_encoder_train"] = {"ms_per_step": ms, "samples_per_s": 8 / (ms * 1e-3), "shape": "6 layers, 8 videos x 300 tokens, d 512, "
+                                    "8 q / 2 kv heads, 6 experts top-2 ff 1024", "dtype": "f32"}
+    del enc, layer
+    reg = VideoRegression(n_layers=6, d_model=128, d_hidden=256, dropout=0.0, total_vf_dim=774, regModel="bimamba+").to(dev).train()
+    sem, emo = torch.randn(64, 300, 768, generator=g).to(dev), torch.softmax(torch.randn(64, 300, 6, generator=g), -1).to(dev)
+    zz = torch.zeros(64, 300, device=dev)
+
+    def reg_fwd():
+        ln, inst = reg(sem, zz, zz, emo)
+        return ln.sum() + inst.sum()
+    ms = timed(step(reg, reg_fwd))
+    out["video_regression_bimamba_plus_train"] = {"ms_per_step": ms, "samples_per_s": 64 / (ms * 1e-3),
+                                                  "shape": "6 Bi-Mamba+ layers, 64 videos x 300 s, d_model 128, d_inner 256, d_state 16", "dtype": "f32"}
+    del reg
+    blk = MambaBlock(MambaConfig(d_model=128, n_layers=1)).to(dev).train()
+    xb = torch.randn(8, 4096, 128, generator=g).to(dev)
+    ms = timed(step(blk, lambda: blk(xb)))
+    out["mamba_block_train_L4096"] = {"ms_per_step": ms, "tokens_per_s": 8 * 4096 / (ms * 1e-3), "shape": "8 x 4096 tokens, d_model 128, "
+                                      "d_inner 256, d_state 16", "dtype": "f32"}
+    return out
+
+
 def reference_arm(args):
     """The reference's algorithm on the host cores (oracle port, literal re-forward loop, batch 1)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -204,6 +260,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE config 3)")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-variants", action="store_true", help="skip the GQA+MoE / Mamba training timings (BASELINE configs 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -327,6 +384,11 @@ def main():
     }
     if train is not None:
         out["train"] = train
+    if rank == 0 and world == 1 and not args.no_variants:
+        try:
+            out["variants"] = variants_leg(dev)
+        except Exception as e:                                   # the headline line must survive a failure of the extra leg
+            out["variants"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import amt_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)

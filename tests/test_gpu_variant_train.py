@@ -261,7 +261,10 @@ def test_rpr_module_backward_golden_gpu():
         assert rel_err(out, case["out"]) < 1e-4
         if case["weights_mean"] is not None:
             assert rel_err(w, case["weights_mean"]) < 1e-4
-        assert rel_err(x.grad, case["grad_x"]) < 2e-4 and rel_err(mod.Er.grad, case["grad_Er"]) < 2e-4
+        assert rel_err(x.grad, case["grad_x"]) < 2e-4
+        # L = 1: softmax over one key, the reference's dEr is exactly 0 and ours is rounding noise -> absolute floor
+        d_er = float((mod.Er.grad.cpu().double() - case["grad_Er"].double()).abs().max())
+        assert d_er <= 2e-4 * max(float(case["grad_Er"].abs().max()), 1e-2)
         assert rel_err(mod.in_proj_bias.grad, case["grad_in_proj_bias"]) < 2e-4
         n = float(mod.in_proj_weight.grad.double().norm())
         assert abs(n - case["grad_in_proj_weight_norm"]) < 2e-4 * case["grad_in_proj_weight_norm"]

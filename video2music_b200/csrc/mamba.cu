@@ -171,33 +171,44 @@ int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, lo
 // ---------------------------------------------------------------------------------------------------------------------------
 // Backward of the fused selective scan (exact fp32 training path; the reference differentiates the materialised
 // deltaA / BX tensors and the pscan through torch autograd, mamba.py:333-351 + pscan.py:196-226).
-// Thread <-> (video, channel), one CTA = 128 channels of one video, all walking L in lockstep:
-//   sweep 1 (l = 0 .. L-1)   recompute the states and store them, Hs[b][l][n][c] (channel fastest: coalesced)
-//   sweep 2 (l = L-1 .. 0)   gh_n = dL/dh_l[n] carried in registers; per step
-//        y  = sum_n h_n C_n + D x;  out = y silu(z) (+ x (1 - sigmoid(silu(z))) for mamba+)
-//        dC_n = dy h_n;  gh_n += dy C_n;  with a_n = exp(delta A_n):  d delta += gh_n (A_n a_n h_{l-1,n} + B_n x),
-//        dA_n += gh_n h_{l-1,n} delta a_n,  dB_n = gh_n delta x,  dx += gh_n delta B_n,  gh_n *= a_n
-//        d delta_raw = d delta * softplus'(delta_raw + dt_bias)
+// Like the forward, L is cut into chunks of kScanChunk steps so that (video, channel, chunk) triples fill the GPU:
+//   forward pass 0 + carry (the kernels above)            -> true state at every chunk start                          (wsf)
+//   bwd pass 0   thread = (channel, chunk >= 1, video)    reverse sweep of the chunk from gh = 0: the gradient its own outputs
+//                send to the state before the chunk, and sum(delta) of the chunk                                      (wsg)
+//   bwd carry    thread = (channel, state, video)         G[ch-1] = exp(A_n sum_delta[ch]) G[ch] + local[ch], last chunk first:
+//                G[ch] = dL/dh arriving at the END of chunk ch from all later chunks (in place)
+//   bwd pass 1   thread = (channel, chunk, video), one CTA = 128 channels of one (video, chunk) walking in lockstep:
+//        sweep 1 (l0 .. l1-1)   recompute the states from the chunk-start state, store them, Hs[b][l][n][c]
+//        sweep 2 (l1-1 .. l0)   gh_n = dL/dh_l[n] carried in registers, starting from G[ch]; per step
+//            y  = sum_n h_n C_n + D x;  out = y silu(z) (+ x (1 - sigmoid(silu(z))) for mamba+)
+//            dC_n = dy h_n;  gh_n += dy C_n;  with a_n = exp(delta A_n):  d delta += gh_n (A_n a_n h_{l-1,n} + B_n x),
+//            dA_n += gh_n h_{l-1,n} delta a_n,  dB_n = gh_n delta x,  dx += gh_n delta B_n,  gh_n *= a_n
+//            d delta_raw = d delta * softplus'(delta_raw + dt_bias)
 //   dB / dC are sums over the channels: the CTA folds its 128 channels through shared memory (2 N = 32 values per step) and
 //   adds them to the caller-zeroed gradient rows; dA_log (= dA * A), dD, d dt_bias are accumulated per thread and added once.
-template <int N>
+// wsf / wsg layout [B][n_chunks-1][N+1][ED] (row N = sum(delta)); wsg entry ch-1 belongs to chunk ch before the carry and holds
+// G[ch-1] after it.
+template <int N, int PASS>
 __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __restrict__ x, long long ldx,
                                                                  const float* __restrict__ delta_raw, long long ldd,
                                                                  const float* __restrict__ dt_bias, const float* __restrict__ A_log,
                                                                  const float* __restrict__ Bm, const float* __restrict__ Cm,
                                                                  long long ldbc, const float* __restrict__ Dp,
                                                                  const float* __restrict__ z, long long ldz,
-                                                                 const float* __restrict__ dout, long long ldo, float* __restrict__ Hs,
-                                                                 float* __restrict__ dx, long long lddx, float* __restrict__ ddraw,
-                                                                 long long lddd, float* __restrict__ dBm, float* __restrict__ dCm,
-                                                                 long long lddbc, float* __restrict__ dz, long long lddz,
-                                                                 float* __restrict__ dA_log, float* __restrict__ dD,
-                                                                 float* __restrict__ ddt_bias, int L, int ED, int plus) {
+                                                                 const float* __restrict__ dout, long long ldo,
+                                                                 const float* __restrict__ wsf, float* __restrict__ wsg,
+                                                                 float* __restrict__ Hs, float* __restrict__ dx, long long lddx,
+                                                                 float* __restrict__ ddraw, long long lddd, float* __restrict__ dBm,
+                                                                 float* __restrict__ dCm, long long lddbc, float* __restrict__ dz,
+                                                                 long long lddz, float* __restrict__ dA_log, float* __restrict__ dD,
+                                                                 float* __restrict__ ddt_bias, int L, int ED, int n_chunks, int plus) {
   static_assert(2 * N == 32, "the channel fold maps 2 N values onto the 32 lanes of a warp");
-  __shared__ float red[2 * N][129];
-  const int tid = threadIdx.x, c = blockIdx.x * 128 + tid, b = blockIdx.y;
+  __shared__ float red[PASS == 1 ? 2 * N : 1][129];
+  const int tid = threadIdx.x, c = blockIdx.x * 128 + tid, b = blockIdx.z;
+  const int ch = PASS == 0 ? blockIdx.y + 1 : blockIdx.y;            // pass 0 skips chunk 0 (nobody needs its start gradient)
   const bool act = c < ED;
-  const int cc = act ? c : ED - 1;                     // inactive lanes read a valid channel and contribute nothing
+  const int cc = act ? c : ED - 1;                                   // inactive lanes read a valid channel and contribute nothing
+  const int l0 = ch * kScanChunk, l1 = min(L, l0 + kScanChunk);
   float A[N], A2[N], h[N], gh[N], gA[N];
 #pragma unroll
   for (int n = 0; n < N; ++n) {
@@ -206,7 +217,39 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
     h[n] = 0.f; gh[n] = 0.f; gA[n] = 0.f;
   }
   const float Dc = Dp[cc], db = dt_bias ? dt_bias[cc] : 0.f;
-  for (int l = 0; l < L; ++l) {
+  if (PASS == 0) {
+    float dsum = 0.f;
+    for (int l = l1 - 1; l >= l0; --l) {
+      const long long row = (long long)b * L + l;
+      const float dl = softplus_f(delta_raw[row * ldd + cc] + db);
+      float dy = dout[row * ldo + cc];
+      if (z) {
+        const float zv = z[row * ldz + cc];
+        dy *= zv / (1.f + expf(-zv));
+      }
+      dsum += dl;
+#pragma unroll
+      for (int n = 0; n < N; ++n) gh[n] = fmaf(dy, __ldg(Cm + row * ldbc + n), gh[n]) * ex2_approx(dl * A2[n]);
+    }
+    if (act) {
+      float* w = wsg + ((long long)b * (n_chunks - 1) + (ch - 1)) * (N + 1) * ED + c;
+#pragma unroll
+      for (int n = 0; n < N; ++n) w[(long long)n * ED] = gh[n];
+      w[(long long)N * ED] = dsum;
+    }
+    return;
+  }
+  const float* h0 = ch > 0 ? wsf + ((long long)b * (n_chunks - 1) + (ch - 1)) * (N + 1) * ED + cc : nullptr;   // chunk-start state
+  if (ch > 0) {
+#pragma unroll
+    for (int n = 0; n < N; ++n) h[n] = h0[(long long)n * ED];
+  }
+  if (ch < n_chunks - 1) {
+    const float* w = wsg + ((long long)b * (n_chunks - 1) + ch) * (N + 1) * ED + cc;
+#pragma unroll
+    for (int n = 0; n < N; ++n) gh[n] = w[(long long)n * ED];
+  }
+  for (int l = l0; l < l1; ++l) {
     const long long row = (long long)b * L + l;
     const float xv = x[row * ldx + cc];
     const float dl = softplus_f(delta_raw[row * ldd + cc] + db);
@@ -218,7 +261,7 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
     }
   }
   float gD = 0.f, gdb = 0.f;
-  for (int l = L - 1; l >= 0; --l) {
+  for (int l = l1 - 1; l >= l0; --l) {
     const long long row = (long long)b * L + l;
     const float xv = x[row * ldx + cc];
     const float raw = delta_raw[row * ldd + cc] + db;
@@ -246,7 +289,7 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       const float Bv = __ldg(Bm + row * ldbc + n), Cv = __ldg(Cm + row * ldbc + n);
-      const float hp = (l > 0) ? Hs[((row - 1) * N + n) * ED + cc] : 0.f;
+      const float hp = (l > l0) ? Hs[((row - 1) * N + n) * ED + cc] : (ch > 0 ? h0[(long long)n * ED] : 0.f);
       const float a = ex2_approx(dl * A2[n]);
       red[N + n][tid] = act ? dy * h[n] : 0.f;                     // dC_n
       gh[n] = fmaf(dy, Cv, gh[n]);
@@ -284,7 +327,24 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
   }
 }
 
-long long selective_scan_bwd_workspace(int B, int L, int ED, int N) { return (long long)B * L * ED * N * (long long)sizeof(float); }
+// G[ch-1] = exp(A_n sum_delta[ch]) G[ch] + local[ch] for ch = n_chunks-1 .. 1, in place (entry ch-1 of wsg), G[n_chunks-1] = 0
+template <int N>
+__global__ void __launch_bounds__(128) selective_scan_bwd_carry_kernel(const float* __restrict__ A_log, float* __restrict__ wsg, int ED,
+                                                                       int n_chunks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y, b = blockIdx.z;
+  if (c >= ED) return;
+  const float A2 = -expf(A_log[(long long)c * N + n]) * 1.4426950408889634f;
+  float G = 0.f;
+  for (int ch = n_chunks - 1; ch >= 1; --ch) {
+    float* w = wsg + ((long long)b * (n_chunks - 1) + (ch - 1)) * (N + 1) * ED + c;
+    G = fmaf(ex2_approx(A2 * w[(long long)N * ED]), G, w[(long long)n * ED]);
+    w[(long long)n * ED] = G;
+  }
+}
+
+long long selective_scan_bwd_workspace(int B, int L, int ED, int N) {
+  return (long long)B * L * ED * N * (long long)sizeof(float) + 2 * selective_scan_workspace(B, L, ED, N);
+}
 
 int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, long long ldd, const float* dt_bias, const float* A_log,
                        const float* Bm, const float* Cm, long long ldbc, const float* Dp, const float* z, long long ldz,
@@ -293,12 +353,28 @@ int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, lo
                        float* ddt_bias, int B, int L, int ED, int N, int plus, cudaStream_t stream) {
   V2M_REQUIRE(B > 0 && L > 0 && ED > 0, "selective_scan_bwd: bad dims B=%d L=%d ED=%d", B, L, ED);
   V2M_REQUIRE(N == 16, "selective_scan_bwd: d_state %d unsupported (16)", N);
-  V2M_REQUIRE(hs && hs_bytes >= selective_scan_bwd_workspace(B, L, ED, N), "selective_scan_bwd: state workspace of %lld bytes needed",
+  V2M_REQUIRE(hs && hs_bytes >= selective_scan_bwd_workspace(B, L, ED, N), "selective_scan_bwd: workspace of %lld bytes needed",
               selective_scan_bwd_workspace(B, L, ED, N));
-  V2M_REQUIRE(B <= 65535, "selective_scan_bwd: B=%d too large for the grid", B);
-  selective_scan_bwd_kernel<16><<<dim3((ED + 127) / 128, B), 128, 0, stream>>>(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z,
-                                                                              ldz, dout, ldo, hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc,
-                                                                              dz, lddz, dA_log, dD, ddt_bias, L, ED, plus);
+  const int n_chunks = (L + kScanChunk - 1) / kScanChunk;
+  V2M_REQUIRE(n_chunks <= 65535 && B <= 65535, "selective_scan_bwd: L=%d / B=%d too large for the grid", L, B);
+  const long long ws_floats = selective_scan_workspace(B, L, ED, N) / (long long)sizeof(float);
+  float* wsf = hs;                         // chunk-start states (forward pass 0 + carry)
+  float* wsg = hs + ws_floats;             // chunk-end gradients
+  float* Hs = hs + 2 * ws_floats;          // all states
+  const int gx = (ED + 127) / 128;
+  if (n_chunks > 1) {
+    selective_scan_fwd_kernel<16, 0, false><<<dim3(gx, n_chunks - 1, B), 128, 0, stream>>>(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm,
+                                                                                           ldbc, Dp, z, ldz, nullptr, 0, wsf, L, ED,
+                                                                                           n_chunks, plus);
+    selective_scan_carry_kernel<16><<<dim3(gx, 16, B), 128, 0, stream>>>(A_log, wsf, ED, n_chunks);
+    selective_scan_bwd_kernel<16, 0><<<dim3(gx, n_chunks - 1, B), 128, 0, stream>>>(
+        x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z, ldz, dout, ldo, wsf, wsg, Hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc,
+        dz, lddz, dA_log, dD, ddt_bias, L, ED, n_chunks, plus);
+    selective_scan_bwd_carry_kernel<16><<<dim3(gx, 16, B), 128, 0, stream>>>(A_log, wsg, ED, n_chunks);
+  }
+  selective_scan_bwd_kernel<16, 1><<<dim3(gx, n_chunks, B), 128, 0, stream>>>(
+      x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z, ldz, dout, ldo, wsf, wsg, Hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc, dz,
+      lddz, dA_log, dD, ddt_bias, L, ED, n_chunks, plus);
   return check_launch("selective_scan_bwd");
 }
 
