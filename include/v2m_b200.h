@@ -306,6 +306,10 @@ int v2m_moe_combine_bwd(const float* dout, const float* yp, const int32_t* perm,
 int v2m_swiglu_bwd(const float* a, const float* g, const float* dh, float* dag, int64_t M, int32_t ff, void* stream);
 int v2m_moe_grouped_dw(const float* dY, int32_t ldy, const float* X, int32_t ldx, const int32_t* off, int32_t n_experts, float* dW,
                        float* db, int32_t N, int32_t K, void* stream);
+/* Weight gradient of one dense fp32 layer (autograd of F.linear): dW [N][K] = dY[rows][N]^T X[rows][K], db [N] = column sums of
+ * dY (may be NULL).  Rows are split over the GPU and summed with fp32 atomics (the outputs are cleared inside). */
+int v2m_dw_f32(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t rows, float* dW, float* db, int32_t N, int32_t K,
+               void* stream);
 
 /* ---- RoPE of the V2/V3 attention, custom_transformer.py:1044-1053 + rotate_operation.py:117-165, fp32 --------------
  * x, y: the (len, B, H*dh) projection as stored; cache: RotaryPositionalEmbeddings.cache[:len] ([len][H*dh/2][2] cos, sin).

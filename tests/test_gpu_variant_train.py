@@ -284,3 +284,16 @@ def test_rpr_decoder_train_golden_gpu(name):
     (y * r.to(DEV)).sum().backward()
     assert rel_err(y, g["out"]) < 1e-4 and rel_err(tgt.grad, g["d_tgt"]) < 2e-4 and rel_err(mem.grad, g["d_mem"]) < 2e-4
     _check_grads({n: p.grad for n, p in m.named_parameters() if p.grad is not None}, g, 2e-4)
+
+
+@pytest.mark.parametrize("M,N,K,ldx", [(19200, 512, 128, 128), (1000, 6, 512, 512), (77, 159, 512, 520), (0, 8, 8, 8), (300, 40, 33, 40),
+                                       (5000, 1024, 512, 512)])
+def test_dw_f32_split_rows(M, N, K, ldx):
+    """fp32 weight gradient of a dense layer: dW = dz^T x[:, :K] with the rows split over the GPU (atomic partial sums)."""
+    from video2music_b200 import ops
+    dz = (_u((max(M, 1), N), 21, "dz") - 0.5)[:M].to(DEV)
+    x = (_u((max(M, 1), ldx), 21, "x") - 0.5)[:M].to(DEV)
+    dw = ops.dw_f32(dz, x, K)
+    ref = dz.double().T @ x[:, :K].double()
+    assert dw.shape == (N, K)
+    assert float((dw.double() - ref).abs().max()) <= 2e-5 * max(float(ref.abs().max()), 1.0)

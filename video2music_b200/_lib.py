@@ -70,7 +70,7 @@ EXPORTS = [
     "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_attn_bwd_tc", "v2m_attn_bwd_tc_workspace", "v2m_dy_prep",
     "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_amt_metrics", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
-    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_rope_quirk", "v2m_mamba_conv_silu", "v2m_selective_scan_fwd", "v2m_selective_scan_workspace", "v2m_selective_scan_bwd_workspace", "v2m_selective_scan_bwd", "v2m_mamba_conv_silu_bwd", "v2m_rmsnorm", "v2m_rmsnorm_bwd", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route", "v2m_moe_permute", "v2m_moe_grouped_gemm", "v2m_gemm_bf16_grouped", "v2m_swiglu_pair_bf16", "v2m_moe_combine", "v2m_moe_combine_bwd", "v2m_swiglu_bwd", "v2m_moe_grouped_dw",
+    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_rope_quirk", "v2m_mamba_conv_silu", "v2m_selective_scan_fwd", "v2m_selective_scan_workspace", "v2m_selective_scan_bwd_workspace", "v2m_selective_scan_bwd", "v2m_mamba_conv_silu_bwd", "v2m_rmsnorm", "v2m_rmsnorm_bwd", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route", "v2m_moe_permute", "v2m_moe_grouped_gemm", "v2m_gemm_bf16_grouped", "v2m_swiglu_pair_bf16", "v2m_moe_combine", "v2m_moe_combine_bwd", "v2m_swiglu_bwd", "v2m_moe_grouped_dw", "v2m_dw_f32",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -139,6 +139,7 @@ def load() -> C.CDLL:
     lib.v2m_moe_combine_bwd.argtypes = [vp, vp, vp, vp, vp, C.c_float, i32, i32, i32, i32, vp, vp, vp]
     lib.v2m_swiglu_bwd.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     lib.v2m_moe_grouped_dw.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, vp]
+    lib.v2m_dw_f32.argtypes = [vp, i32, vp, i32, i32, vp, vp, i32, i32, vp]
     lib.v2m_moe_route.argtypes = [vp, vp, vp, vp, C.c_float, C.c_float, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     for which, cls in enumerate((Epilogue, Attn, DecLayer, Decode, AttnBwd)):
         if lib.v2m_struct_size(which) != C.sizeof(cls):

@@ -32,7 +32,7 @@ def _gemm_dw(dz: torch.Tensor, x: torch.Tensor, K: int) -> torch.Tensor:
     """dW[N,K] = dz[M,N]^T @ x[M,K]   (both operands read transposed in place), fp32 result."""
     M, N = dz.shape
     if dz.dtype == F32:
-        return ops.gemm_strided(dz, 1, dz.stride(0), x, 1, x.stride(0), N, K, M)
+        return ops.dw_f32(dz, x, K)
     return ops.linear_general(dz, x, a_mn=True, b_mn=True, M=N, N=K, K=M, out_dtype=F32)
 
 
@@ -502,9 +502,9 @@ class MambaCoreFn(torch.autograd.Function):
                                                               dy, ddbc[:, R:R + N], ddbc[:, R + N:], dxz[:, ED:], B, L, plus=plus)
         wdt, wx = dtproj_w.contiguous(), xproj_w.contiguous()
         ops.gemm_strided(ddraw, ED, 1, wdt, 1, R, M, R, ED, out=ddbc[:, :R])                  # d(dbc[:, :R]) = ddraw @ Wdt
-        dwdt = ops.gemm_strided(ddraw, 1, ED, dbc, 1, P, ED, R, M)                            # ddraw^T @ dbc[:, :R]
+        dwdt = _gemm_dw(ddraw, dbc, R)                                                        # ddraw^T @ dbc[:, :R]
         dxc = ops.axpy(dxc, ops.gemm_strided(ddbc, P, 1, wx, 1, ED, M, ED, P), 1.0)           # + ddbc @ Wx
-        dwx = ops.gemm_strided(ddbc, 1, P, xc, 1, ED, P, ED, M)                               # ddbc^T @ xc
+        dwx = _gemm_dw(ddbc, xc, ED)                                                          # ddbc^T @ xc
         dconv_w, dconv_b = ops.mamba_conv_silu_bwd(xz, ED, conv_w.contiguous(), conv_b, dxc, dxz, B, L)
         return dxz, dconv_w, dconv_b, dwx, dwdt, ddtb, dA_log, dD, None, None, None
 

@@ -320,6 +320,11 @@ int v2m_moe_grouped_dw(const float* dY, int32_t ldy, const float* X, int32_t ldx
   return moe_grouped_dw(dY, ldy, X, ldx, off, n_experts, dW, db, N, K, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_dw_f32(const float* dY, int32_t ldy, const float* X, int32_t ldx, int32_t rows, float* dW, float* db, int32_t N, int32_t K,
+               void* stream) {
+  return dw_f32(dY, ldy, X, ldx, rows, dW, db, N, K, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_pscan_fwd(const float* A, const float* X, float* H, int32_t B, int32_t L, int32_t D, int32_t N, void* stream) {
   return pscan_fwd(A, X, H, B, L, D, N, static_cast<cudaStream_t>(stream));
 }

@@ -226,6 +226,7 @@ int moe_combine_bwd(const float* dout, const float* yp, const int* perm, const f
 int swiglu_bwd(const float* a, const float* g, const float* dh, float* dag, long long M, int ff, cudaStream_t stream);
 int moe_grouped_dw(const float* dY, int ldy, const float* X, int ldx, const int* off, int n_experts, float* dW, float* db, int N, int K,
                    cudaStream_t stream);
+int dw_f32(const float* dY, int ldy, const float* X, int ldx, int rows, float* dW, float* db, int N, int K, cudaStream_t stream);
 
 // accuracy / hits@k counters of the evaluation loop (train.cu)
 int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long long pad, int k0, int k1, int k2, int* counters,

@@ -378,22 +378,33 @@ int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, lo
   return check_launch("selective_scan_bwd");
 }
 
-// Backward of mamba_conv_silu: thread <-> (video, channel) walking L with a KW-wide sliding window of inputs and of pending
-// input gradients (position p collects from the outputs p .. p+KW-1); dw / dbias are summed per thread and added once
+// Backward of mamba_conv_silu: thread <-> (channel, chunk of kScanChunk steps, video).  The thread walks its chunk plus a
+// (KW-1)-step halo on the right with a KW-wide sliding window of inputs (primed with the KW-1 inputs before the chunk) and of
+// pending input gradients: position p collects w[k] * dpre from the outputs p .. p+KW-1, so every position of the chunk is
+// complete once the halo has been visited; contributions that fall before the chunk belong to the previous chunk's thread
+// (which recomputes them in its own halo).  dw / dbias are summed over the chunk's own outputs per thread and added once
 // (caller-zeroed buffers).
 template <int KW>
 __global__ void __launch_bounds__(128) mamba_conv_silu_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
                                                                   const float* __restrict__ bias, const float* __restrict__ dy,
                                                                   long long ldy, float* __restrict__ dx, long long lddx,
                                                                   float* __restrict__ dw, float* __restrict__ dbias, int L, int ED) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y, b = blockIdx.z;
   if (c >= ED) return;
+  const int l0 = ch * kScanChunk, l1 = min(L, l0 + kScanChunk), lh = min(L, l1 + KW - 1);
   float wk[KW], win[KW], acc[KW], gw[KW];
 #pragma unroll
-  for (int k = 0; k < KW; ++k) { wk[k] = w[c * KW + k]; win[k] = 0.f; acc[k] = 0.f; gw[k] = 0.f; }
+  for (int k = 0; k < KW; ++k) { wk[k] = w[c * KW + k]; acc[k] = 0.f; gw[k] = 0.f; }
+  // window before the first step: win[k] will hold x[l - (KW-1) + k] after the shift at step l
+#pragma unroll
+  for (int k = 1; k < KW; ++k) {
+    const int ls = l0 - KW + k;                                      // becomes win[k-1] at step l0
+    win[k] = ls >= 0 ? x[((long long)b * L + ls) * ldx + c] : 0.f;
+  }
+  win[0] = 0.f;
   const float bs = bias ? bias[c] : 0.f;
   float gb = 0.f;
-  for (int l = 0; l < L; ++l) {
+  for (int l = l0; l < lh; ++l) {
     const long long row = (long long)b * L + l;
 #pragma unroll
     for (int k = 0; k < KW - 1; ++k) { win[k] = win[k + 1]; acc[k] = acc[k + 1]; }
@@ -404,15 +415,21 @@ __global__ void __launch_bounds__(128) mamba_conv_silu_bwd_kernel(const float* _
     for (int k = 0; k < KW; ++k) pre = fmaf(wk[k], win[k], pre);
     const float sg = 1.f / (1.f + expf(-pre));
     const float dpre = dy[row * ldy + c] * sg * (1.f + pre * (1.f - sg));
-    gb += dpre;
+    if (l < l1) {                                                    // own outputs only: the halo belongs to the next chunk
+      gb += dpre;
 #pragma unroll
-    for (int k = 0; k < KW; ++k) { gw[k] = fmaf(dpre, win[k], gw[k]); acc[k] = fmaf(wk[k], dpre, acc[k]); }
-    if (l - (KW - 1) >= 0) dx[(row - (KW - 1)) * lddx + c] = acc[0];
+      for (int k = 0; k < KW; ++k) gw[k] = fmaf(dpre, win[k], gw[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < KW; ++k) acc[k] = fmaf(wk[k], dpre, acc[k]);
+    const int p = l - (KW - 1);                                      // acc[0] is complete now
+    if (p >= l0 && p < l1) dx[(row - (KW - 1)) * lddx + c] = acc[0];
   }
+  // positions whose later outputs do not exist (end of the sequence): acc[k] belongs to position lh - 1 - (KW-1) + k
 #pragma unroll
   for (int k = 1; k < KW; ++k) {
-    const int pos = L - 1 - (KW - 1) + k;
-    if (pos >= 0) dx[((long long)b * L + pos) * lddx + c] = acc[k];
+    const int p = lh - 1 - (KW - 1) + k;
+    if (p >= l0 && p < l1) dx[((long long)b * L + p) * lddx + c] = acc[k];
   }
 #pragma unroll
   for (int k = 0; k < KW; ++k) atomicAdd(dw + c * KW + k, gw[k]);
@@ -423,7 +440,9 @@ int mamba_conv_silu_bwd(const float* x, long long ldx, const float* w, const flo
                         long long lddx, float* dw, float* dbias, int B, int L, int ED, int KW, cudaStream_t stream) {
   V2M_REQUIRE(B > 0 && L > 0 && ED > 0 && B <= 65535, "mamba_conv_silu_bwd: bad dims B=%d L=%d ED=%d", B, L, ED);
   V2M_REQUIRE(KW == 4, "mamba_conv_silu_bwd: d_conv %d unsupported (4)", KW);
-  mamba_conv_silu_bwd_kernel<4><<<dim3((ED + 127) / 128, B), 128, 0, stream>>>(x, ldx, w, bias, dy, ldy, dx, lddx, dw, dbias, L, ED);
+  const int n_chunks = (L + kScanChunk - 1) / kScanChunk;
+  V2M_REQUIRE(n_chunks <= 65535, "mamba_conv_silu_bwd: L=%d too large for the grid", L);
+  mamba_conv_silu_bwd_kernel<4><<<dim3((ED + 127) / 128, n_chunks, B), 128, 0, stream>>>(x, ldx, w, bias, dy, ldy, dx, lddx, dw, dbias, L, ED);
   return check_launch("mamba_conv_silu_bwd");
 }
 

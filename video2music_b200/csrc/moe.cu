@@ -314,12 +314,19 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const float* __restrict
 }
 
 __global__ void __launch_bounds__(256) moe_grouped_dw_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx,
-                                                             const int* __restrict__ off, float* __restrict__ dW, float* __restrict__ db,
-                                                             int N, int K) {
+                                                             const int* __restrict__ off, int total_rows, int splits,
+                                                             float* __restrict__ dW, float* __restrict__ db, int N, int K) {
+  // off == NULL: one group of total_rows rows.  splits > 1: the rows of a group are cut into `splits` ranges (blockIdx.z = e *
+  // splits + s) whose partial sums are ADDED into the caller-zeroed outputs (split-K for tall, narrow weight gradients).
   __shared__ __align__(16) float Ys[GK][GB + 4];
   __shared__ __align__(16) float Xs[GK][GB + 4];
-  const int e = blockIdx.z;
-  const int m_begin = off[e], m_end = off[e + 1];
+  const int e = blockIdx.z / splits;
+  int m_begin = off ? off[e] : 0, m_end = off ? off[e + 1] : total_rows;
+  if (splits > 1) {
+    const int per = ((m_end - m_begin + splits - 1) / splits + GK - 1) / GK * GK;
+    m_begin += (blockIdx.z % splits) * per;
+    m_end = min(m_end, m_begin + per);
+  }
   const int n0 = blockIdx.y * GB, k0 = blockIdx.x * GB;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int lm = tid >> 4, lc = (tid & 15) * 4;          // loader: row lm of the 16-row chunk, 4 consecutive columns
@@ -361,10 +368,16 @@ __global__ void __launch_bounds__(256) moe_grouped_dw_kernel(const float* __rest
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int kk = k0 + tx * 4 + j;
-      if (kk < K) dW[((size_t)e * N + n) * K + kk] = acc[i][j];
+      if (kk < K) {
+        if (splits > 1) atomicAdd(dW + ((size_t)e * N + n) * K + kk, acc[i][j]);
+        else dW[((size_t)e * N + n) * K + kk] = acc[i][j];
+      }
     }
   }
-  if (db && blockIdx.x == 0 && tid < GB && n0 + tid < N) db[(size_t)e * N + n0 + tid] = bacc;
+  if (db && blockIdx.x == 0 && tid < GB && n0 + tid < N) {
+    if (splits > 1) atomicAdd(db + (size_t)e * N + n0 + tid, bacc);
+    else db[(size_t)e * N + n0 + tid] = bacc;
+  }
 }
 
 int moe_permute(const float* x, const long long* idx, const int* hist, int tokens, int k, int d, int n_experts, int align, int* off,
@@ -432,8 +445,26 @@ int moe_grouped_dw(const float* dY, int ldy, const float* X, int ldx, const int*
                    cudaStream_t stream) {
   V2M_REQUIRE(K > 0 && N > 0 && n_experts >= 1, "moe_grouped_dw: bad dims N=%d K=%d E=%d", N, K, n_experts);
   dim3 grid((K + GB - 1) / GB, (N + GB - 1) / GB, n_experts);
-  moe_grouped_dw_kernel<<<grid, 256, 0, stream>>>(dY, ldy, X, ldx, off, dW, db, N, K);
+  moe_grouped_dw_kernel<<<grid, 256, 0, stream>>>(dY, ldy, X, ldx, off, 0, 1, dW, db, N, K);
   return check_launch("moe_grouped_dw");
+}
+
+// dW[N][K] = dY[rows][N]^T X[rows][K] (+ db[N] = column sums of dY) for ONE dense layer on the fp32 path: the same tile kernel
+// (operands read along their contiguous dimension), rows split over enough CTAs to fill the GPU, partial sums added atomically.
+int dw_f32(const float* dY, int ldy, const float* X, int ldx, int rows, float* dW, float* db, int N, int K, cudaStream_t stream) {
+  V2M_REQUIRE(K > 0 && N > 0 && rows >= 0, "dw_f32: bad dims N=%d K=%d rows=%d", N, K, rows);
+  const int tiles = ((K + GB - 1) / GB) * ((N + GB - 1) / GB);
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int max_splits = (rows + 255) / 256;                       // at least 256 rows per split
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 1) {
+    cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)N * K, stream);
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, stream);
+  }
+  dim3 grid((K + GB - 1) / GB, (N + GB - 1) / GB, splits);
+  moe_grouped_dw_kernel<<<grid, 256, 0, stream>>>(dY, ldy, X, ldx, nullptr, rows, splits, dW, db, N, K);
+  return check_launch("dw_f32");
 }
 
 }  // namespace v2m

@@ -370,6 +370,17 @@ def moe_experts_bwd(dout: torch.Tensor, saved, idx: torch.Tensor, w: torch.Tenso
     return dx, dlogits, dW1g, db1g, dW2, db2
 
 
+def dw_f32(dz: torch.Tensor, x: torch.Tensor, K: int) -> torch.Tensor:
+    """fp32 weight gradient dW[N, K] = dz[M, N]^T x[M, :K] (row-major operands with unit inner stride), rows split over the GPU."""
+    require_device(dz)
+    assert dz.dtype == x.dtype == torch.float32 and dz.stride(1) == 1 and x.stride(1) == 1 and x.shape[1] >= K
+    M, N = dz.shape
+    dw = torch.empty((N, K), device=dz.device, dtype=torch.float32)
+    check(load().v2m_dw_f32(ptr(dz), dz.stride(0), ptr(x), x.stride(0), M, ptr(dw), None, N, K, stream()))
+    _lib.count_launches(1)
+    return dw
+
+
 def swiglu_bwd(a: torch.Tensor, g: torch.Tensor, dh: torch.Tensor) -> torch.Tensor:
     """Gradient of h = a * silu(g) as one [M, 2 ff] matrix (da | dg)."""
     require_device(a)
