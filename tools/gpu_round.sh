@@ -2,8 +2,12 @@
 # scratch script for one gpurun call (overwritten per call)
 cd /root/repo
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_variant_train.py tests/test_gpu_train.py -q -m gpu > gpurun_out/variant_train_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/variant_train_tests.log
-tail -30 gpurun_out/variant_train_tests.log | cut -c1-600
-timeout 200 python tools/prof_train_variants.py > gpurun_out/prof_train_variants.log 2>&1
-echo "prof exit $?"; tail -14 gpurun_out/prof_train_variants.log | cut -c1-200
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/gpu_tests.log
+tail -4 gpurun_out/gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
+tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"; python -c "
+import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['gpu_launches']); print(d['train']['value'], d['train']['ms_per_step'], d['train']['cuda_graph']); print(json.dumps(d.get('variants'))[:900])"
+tail -3 gpurun_out/bench.err
