@@ -65,13 +65,16 @@ def golden_forward(ref):
     _save("amt_forward_small.pt", dict(spec=spec2, weights_checksum=syn.checksum(sd2), logits=y2.contiguous()))
 
 
-def golden_train(ref):
-    """One training step's loss and gradients (run_model_vevo.py:84-121), dropout 0, fp32 CPU."""
-    spec = dict(batch=2, tgt_len=64, src_len=300, motion_type=0, input_seed=4321, weight_seed=3)
+def _train_step_record(ref, spec, keep, pad_tail=False):
+    """One training step of the unmodified reference (run_model_vevo.py:84-121): loss, every parameter's gradient norm
+    and the gradients named in `keep`.  `pad_tail`: the last positions of each target row are CHORD_PAD (158), which
+    CrossEntropyLoss(ignore_index) drops (train.py:222) -- the ragged-target case of the data loader."""
     with contextlib.redirect_stdout(io.StringIO()), reference_cwd():
-        m = ref.vmt.VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0).train()
-    sd = _load_weights(m, 3)
-    inp = syn.make_inputs(2, 4321, 64, 300, 0)
+        m = ref.vmt.VideoMusicTransformer(total_vf_dim=syn.vf_dim(spec["motion_type"]), rpr=True, dropout=0.0).train()
+    sd = _load_weights(m, spec["weight_seed"])
+    inp = syn.make_inputs(spec["batch"], spec["input_seed"], spec["tgt_len"], spec["src_len"], spec["motion_type"])
+    if pad_tail:
+        inp["tgt"] = syn.pad_targets(inp["tgt"], spec["input_seed"])
     y = m(inp["x"], inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"],
           inp["feature_scene_offset"], inp["feature_motion"], inp["feature_emotion"])
     ce = torch.nn.CrossEntropyLoss(ignore_index=158, label_smoothing=0.1)          # train.py:222
@@ -82,18 +85,45 @@ def golden_train(ref):
     total.backward()
     grads = {}
     norms = {}
-    keep = ("transformer.decoder.layers.0.self_attn.Er", "transformer.decoder.layers.5.self_attn.Er",
-            "Wout.bias", "transformer.decoder.layers.3.norm2.weight", "embedding_root.weight",
-            "transformer.encoder.layers.0.self_attn.in_proj_bias", "Linear_chord.bias")
     for n, p in m.named_parameters():
         if p.grad is None:
             continue
         norms[n] = float(p.grad.double().norm())
         if n in keep:
             grads[n] = p.grad.clone()
-    _save("amt_train_step.pt", dict(spec=spec, weights_checksum=syn.checksum(sd), logits=y.detach().clone(),
-                                    loss=float(total), loss_chord=float(loss_chord), loss_emotion=float(loss_emotion),
-                                    grad_norms=norms, grads=grads))
+    return dict(spec=spec, weights_checksum=syn.checksum(sd), logits=y.detach().clone(),
+                loss=float(total), loss_chord=float(loss_chord), loss_emotion=float(loss_emotion),
+                grad_norms=norms, grads=grads, pad_tail=pad_tail)
+
+
+TRAIN_KEEP = ("transformer.decoder.layers.0.self_attn.Er", "transformer.decoder.layers.5.self_attn.Er",
+              "Wout.bias", "transformer.decoder.layers.3.norm2.weight", "embedding_root.weight",
+              "transformer.encoder.layers.0.self_attn.in_proj_bias", "Linear_chord.bias")
+
+
+def golden_train(ref):
+    """One training step's loss and gradients (run_model_vevo.py:84-121), dropout 0, fp32 CPU; small shape."""
+    spec = dict(batch=2, tgt_len=64, src_len=300, motion_type=0, input_seed=4321, weight_seed=3)
+    _save("amt_train_step.pt", _train_step_record(ref, spec, TRAIN_KEEP))
+
+
+def golden_train_full(ref):
+    """BASELINE config 3 at the real sequence shape: B=4, T=299, S=300 (multi-tile attention backward, the whole Er band,
+    the T=299 tails), once with PAD-free targets and once with ragged PAD tails.  Logits are stored for video 0 only."""
+    keep = TRAIN_KEEP + ("transformer.decoder.layers.2.self_attn.in_proj_weight",
+                         "transformer.decoder.layers.4.multihead_attn.in_proj_bias",
+                         "transformer.decoder.layers.1.self_attn.Er")
+    out = {}
+    for name, pad in (("full", False), ("ragged", True)):
+        spec = dict(batch=4, tgt_len=299, src_len=300, motion_type=0, input_seed=2025 + pad, weight_seed=11)
+        r = _train_step_record(ref, spec, keep, pad_tail=pad)
+        r["logits"] = r["logits"][:1].clone()
+        # the 1536x512 in_proj gradient is 3 MB: keep every 8th row
+        k = "transformer.decoder.layers.2.self_attn.in_proj_weight"
+        r["grads"][k] = r["grads"][k][::8].clone()
+        out[name] = r
+        print(name, "loss", r["loss"], len(r["grad_norms"]), "gradient norms")
+    _save("amt_train_step_full.pt", out)
 
 
 def golden_generate(ref, n_videos):
@@ -616,7 +646,7 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = load_reference()
     torch.set_num_threads(os.cpu_count())
-    jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), rpr=lambda: golden_rpr(ref),
+    jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), train_full=lambda: golden_train_full(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
                 mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
                 variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), rpr_train=lambda: golden_rpr_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),

@@ -78,6 +78,62 @@ def test_train_step_bf16_close_to_reference():
         assert e < 0.15, name
 
 
+def _full_case(name, dtype):
+    g = load_golden("amt_train_step_full.pt")[name]
+    s = g["spec"]
+    m, sd = _model(s["weight_seed"], dtype)
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    inp = syn.make_inputs(s["batch"], s["input_seed"], s["tgt_len"], s["src_len"], s["motion_type"])
+    if g["pad_tail"]:
+        inp["tgt"] = syn.pad_targets(inp["tgt"], s["input_seed"])
+    y, loss = _step(m, inp)
+    return g, m, y, loss
+
+
+def _kept(grad, gref):
+    return grad[::8] if grad.shape != gref.shape else grad
+
+
+@pytest.mark.parametrize("name", ["full", "ragged"])
+def test_train_step_fp32_full_shape_vs_reference_golden(name):
+    """BASELINE config 3 at the real sequence shape (B=4, T=299, S=300; multi-tile attention backward, the whole Er band,
+    T=299 tails; PAD-free and ragged PAD-tail targets): fp32 loss and every gradient against the reference's autograd."""
+    g, m, y, loss = _full_case(name, torch.float32)
+    assert rel_err(y[:1], g["logits"]) < 1e-4
+    assert abs(float(loss.detach()) - g["loss"]) < 2e-5 * abs(g["loss"])
+    params = dict(m.named_parameters())
+    errs = {n: abs(float(params[n].grad.double().norm()) - gn) / max(gn, 1e-12) for n, gn in g["grad_norms"].items()}
+    worst = max(errs, key=errs.get)
+    print("fp32 %s: worst gradient-norm error over %d parameters %.2e (%s)" % (name, len(errs), errs[worst], worst))
+    assert errs[worst] < 2e-3
+    for n, gref in g["grads"].items():
+        e = rel_err(_kept(params[n].grad, gref), gref)
+        print("fp32 %s grad %-60s rel err %.2e" % (name, n, e))
+        assert e < 2e-3, n
+    for n, p in params.items():
+        assert (p.grad is not None) == (n in g["grad_norms"]), n
+
+
+@pytest.mark.parametrize("name", ["full", "ragged"])
+def test_train_step_bf16_full_shape_close_to_reference(name):
+    """Same step on the bf16 tensor-core path: every gradient norm within 5 % and every kept gradient (incl. three Er
+    tables) within 5 % of the reference's fp32 autograd (bf16 operands, fp32 accumulation and fp32 gradients)."""
+    g, m, y, loss = _full_case(name, torch.bfloat16)
+    assert rel_err(y[:1], g["logits"]) < 2e-2
+    assert abs(float(loss.detach()) - g["loss"]) < 1e-2 * abs(g["loss"])
+    params = dict(m.named_parameters())
+    errs = {n: abs(float(params[n].grad.double().norm()) - gn) / max(gn, 1e-12) for n, gn in g["grad_norms"].items()}
+    order = sorted(errs, key=errs.get)
+    print("bf16 %s: gradient-norm error median %.4f, worst %.4f (%s), 2nd %.4f (%s)" % (
+        name, errs[order[len(order) // 2]], errs[order[-1]], order[-1], errs[order[-2]], order[-2]))
+    assert errs[order[len(order) // 2]] < 1e-2
+    assert errs[order[-1]] < 5e-2, order[-1]
+    for n, gref in g["grads"].items():
+        e = rel_err(_kept(params[n].grad, gref), gref)
+        print("bf16 %s grad %-55s rel err %.3e" % (name, n, e))
+        assert e < 5e-2, n
+
+
 def test_train_steps_with_dropout():
     """dropout = 0.1 (the reference's default, train.py / argument_funcs.py): every nn.Dropout site of the graph runs fused in
     the bf16 kernels.  Checks: training-mode outputs differ from eval, masks change between calls but are reproducible under

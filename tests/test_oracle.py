@@ -460,3 +460,36 @@ def test_video_regression_oracle_matches_reference_golden(reg):
     assert len(sd) == g["spec"]["n_keys"] and same_checksum(syn.checksum(sd), g["weights_checksum"])
     ln, inst = O.video_regression_forward(sd, sem, emo, reg, 6, dt_rank=8)
     assert rel_err(ln, g["ln"]) < 5e-5 and rel_err(inst, g["inst"]) < 5e-5
+
+
+@pytest.mark.parametrize("name", ["full", "ragged"])
+def test_amt_train_step_full_shape_golden(name):
+    """BASELINE config 3 at the real shape (B=4, T=299, S=300): autograd over the oracle's forward + the loss of
+    run_model_vevo.py:101-119 gives the reference's loss and gradients (PAD-free and ragged PAD-tail targets)."""
+    g = load_golden("amt_train_step_full.pt")[name]
+    s = g["spec"]
+    _, sd = amt_state_dict(syn.vf_dim(s["motion_type"]), s["weight_seed"])
+    assert same_checksum(syn.checksum({k: v for k, v in sd.items() if not k.endswith(".pe")}), g["weights_checksum"])
+    inp = syn.make_inputs(s["batch"], s["input_seed"], s["tgt_len"], s["src_len"], s["motion_type"])
+    if g["pad_tail"]:
+        inp["tgt"] = syn.pad_targets(inp["tgt"], s["input_seed"])
+        assert int((inp["tgt"] == syn.CHORD_PAD).sum()) > 0
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and not k.endswith(".pe")}
+    full = dict(sd)
+    full.update(leaves)
+    y = O.amt_forward(full, inp["x"], inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"],
+                      inp["feature_scene_offset"], inp["feature_motion"], inp["feature_emotion"])
+    assert rel_err(y[:1], g["logits"]) < 5e-5
+    ce = torch.nn.functional.cross_entropy(y.permute(0, 2, 1), inp["tgt"], ignore_index=158, label_smoothing=0.1)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(y, inp["tgt_emotion"])
+    loss = 0.4 * ce + 0.6 * bce
+    assert abs(float(loss) - g["loss"]) < 1e-5 * abs(g["loss"])
+    loss.backward()
+    for n, gn in g["grad_norms"].items():
+        got = float(leaves[n].grad.double().norm())
+        assert abs(got - gn) < 1e-3 * max(gn, 1e-9), n
+    for n, gr in g["grads"].items():
+        mine = leaves[n].grad
+        if mine.shape != gr.shape:
+            mine = mine[::8]
+        assert rel_err(mine, gr) < 1e-3, n

@@ -57,6 +57,18 @@ def make_inputs(batch: int, seed: int = 1234, tgt_len: int = 299, src_len: int =
     return d
 
 
+def pad_targets(tgt: torch.Tensor, seed: int, max_pad: int = 150) -> torch.Tensor:
+    """Ragged targets: the last U(0, max_pad) positions of every row become CHORD_PAD, as the
+    data loader pads short chord sequences (dataset/vevo_dataset.py) and CrossEntropyLoss(ignore_index=158) drops them."""
+    g = _gen(seed, "pad")
+    n = torch.randint(0, min(max_pad, tgt.shape[1] - 1) + 1, (tgt.shape[0],), generator=g)
+    out = tgt.clone()
+    for b in range(tgt.shape[0]):
+        if int(n[b]):
+            out[b, tgt.shape[1] - int(n[b]):] = CHORD_PAD
+    return out
+
+
 def fill_like_reference_init(shapes: Dict[str, Tuple[int, ...]], seed: int = 0,
                              wout_gain: float = 1.0) -> Dict[str, torch.Tensor]:
     """Seeded values for every entry of a state_dict, given only names/shapes.
