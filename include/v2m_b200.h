@@ -145,11 +145,17 @@ int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld
 int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t Cn, int64_t pad, int32_t k0, int32_t k1, int32_t k2,
                     int32_t* counters, void* stream);
 int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
-                 float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream);
-/* torch.optim.Adam step on flat fp32 buffers (train.py:238). grad_scale multiplies g first (1/world_size after all-reduce). */
+                 float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, const float* norm_in, void* stream);
+/* out1[0] = number of targets != ignore (the CE normaliser, nn.CrossEntropyLoss(ignore_index), train.py:222).  A data-parallel
+ * trainer all-reduces it and hands {count / world, global rows / world} back to v2m_amt_loss as norm_in (2 device floats), so
+ * that the mean of the ranks' gradients is the gradient of the reference's single-process global-batch loss. */
+int v2m_count_valid(const int64_t* tgt, int32_t R, int64_t ignore, float* out1, void* stream);
+/* torch.optim.Adam step on flat fp32 buffers (train.py:237-238; eps ADAM_EPSILON = 10e-9 = 1e-8, utilities/constants.py:91).
+ * weight_decay > 0: torch.optim.AdamW's decoupled decay p *= 1 - lr * weight_decay (train.py:239-240, the CLI default optimiser,
+ * utilities/argument_funcs.py:17).  grad_scale multiplies g first (1/world_size after all-reduce). */
 /* dyn (optional, device {lr, 1-b1^t, 1-b2^t}) overrides the scalar arguments at run time (CUDA-graph replay with a schedule);
  * p16 (optional) receives the bf16 mirror of the updated parameters; zero_grad clears g; ctr (optional) += 1 per call. */
-int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
+int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float weight_decay, int32_t step,
                   float grad_scale, const float* dyn, void* p16, int32_t zero_grad, uint32_t* ctr, void* stream);
 
 /* ---- residual + LayerNorm (rpr.py:59-69; nn.LayerNorm eps) ------------------------------------ */

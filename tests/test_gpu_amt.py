@@ -259,3 +259,15 @@ def test_v2_model_forward_and_generate_vs_reference_golden(ver):
                      primer_attr=inp["x_attr"][0, :3], target_seq_length=14, beam=0, uniforms=u.to(DEV)).cpu()[0]
     assert smp.shape[0] == 14 and int(smp[3:].min()) >= 1 and int(smp.max()) < 157          # "N" is never drawn
     assert all(not (smp[i] == smp[i - 1] == smp[i - 2]) for i in range(5, 14))             # no three equal chords in a row
+
+
+def test_generate_without_rpr_raises_a_clear_error():
+    """rpr=False builds the stock decoder (video_music_transformer.py:957-962): forward works, the KV-cached generate() is
+    built for the RPR decoder only and says so (no bare KeyError)."""
+    from video2music_b200 import VideoMusicTransformer
+    m = VideoMusicTransformer(n_layers=1, total_vf_dim=syn.vf_dim(0), rpr=False, max_sequence_chord=32, max_sequence_video=16).to(DEV).eval()
+    inp = syn.make_inputs(1, 3, 8, 16, 0)
+    with pytest.raises(NotImplementedError):
+        m.generate(inp["feature_semantic_list"].to(DEV), inp["feature_key"].to(DEV), inp["feature_scene_offset"].to(DEV),
+                   inp["feature_motion"].to(DEV), inp["feature_emotion"].to(DEV), primer=inp["x"][:, :1].to(DEV),
+                   primer_root=inp["x_root"][:, :1].to(DEV), primer_attr=inp["x_attr"][:, :1].to(DEV), target_seq_length=8, beam=1)

@@ -507,6 +507,55 @@ def test_selective_scan_fused_equals_pscan_composition(B, L):
     assert rel_err(y.view(B, L, ED), ref) < 2e-5
 
 
+@pytest.mark.parametrize("B,L,nvid", [(64, 300, 64), (8, 4096, 2)])
+def test_mamba_block_full_size_vs_oracle(B, L, nvid):
+    """BASELINE config 5 sizes against the ORACLE (O.mamba_block_forward, the sequential restatement of mamba.py:259-351), not
+    against our own pscan kernel: the whole MambaBlock (in_proj, conv, SiLU, x_proj / dt_proj, fused selective scan, gate,
+    out_proj) at (64, 300, 256, 16), and at the (8, 4096) stress shape for `nvid` of the videos (videos are independent;
+    the oracle's (B, L, ED, N) tensors are 0.5 GB per video pair there)."""
+    from video2music_b200.mamba import MambaConfig, MambaBlock
+    for ver in (0, 1):
+        cfg = MambaConfig(d_model=128, n_layers=1, use_version=ver)
+        m = MambaBlock(cfg)
+        sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=21 + ver)
+        m.load_state_dict(sd)
+        m = m.to(DEV).eval()
+        x = syn.unit_uniform((B, L, 128), syn._gen(31, "x"))
+        with torch.no_grad():
+            y = m(x.to(DEV)).cpu()
+            pick = torch.linspace(0, B - 1, nvid).round().long().unique()
+            ref = O.mamba_block_forward(sd, "", x[pick], cfg.dt_rank, cfg.d_state, use_version=ver)
+        err = rel_err(y[pick], ref)
+        print("MambaBlock v%d (%d, %d): %d videos vs oracle, rel err %.2e" % (ver, B, L, len(pick), err))
+        assert err < 1e-4
+
+
+@pytest.mark.parametrize("B,L,nvid", [(64, 300, 8), (8, 4096, 1)])
+def test_selective_scan_full_size_vs_oracle_scan(B, L, nvid):
+    """The fused scan kernel alone at the config-5 sizes against the oracle's sequential scan (O.pscan_forward over
+    exp(delta A), delta B x; mamba.py:343-352) on a sample of the videos."""
+    from video2music_b200 import ops
+    ED, N = 256, 16
+    gx = syn._gen(6, "scan")
+    x = syn.unit_uniform((B * L, ED), gx)
+    draw = syn.unit_uniform((B * L, ED), gx) * 0.5 - 1.0
+    bias = syn.unit_uniform((ED,), gx) * 0.1
+    A_log = torch.log(torch.arange(1, N + 1, dtype=torch.float32)).repeat(ED, 1)
+    bc = syn.unit_uniform((B * L, 2 * N), gx)
+    D = syn.unit_uniform((ED,), gx)
+    y = ops.selective_scan(x.to(DEV), draw.to(DEV), bias.to(DEV), A_log.to(DEV), bc[:, :N].to(DEV), bc[:, N:].to(DEV), D.to(DEV),
+                           None, B, L).view(B, L, ED).cpu()
+    pick = torch.linspace(0, B - 1, nvid).round().long().unique()
+    xs = x.view(B, L, ED)[pick]
+    delta = torch.nn.functional.softplus(draw + bias).view(B, L, ED)[pick]
+    Bm, Cm = bc[:, :N].reshape(B, L, N)[pick], bc[:, N:].reshape(B, L, N)[pick]
+    hs = O.pscan_forward(torch.exp(delta.unsqueeze(-1) * (-torch.exp(A_log))), delta.unsqueeze(-1) * Bm.unsqueeze(2) * xs.unsqueeze(-1))
+    ref = (hs @ Cm.unsqueeze(-1)).squeeze(3) + D * xs
+    err = rel_err(y[pick], ref)
+    print("selective_scan (%d, %d): %d videos vs oracle scan, rel err %.2e" % (B, L, len(pick), err))
+    assert err < 2e-5
+
+
 # ---------------------------------------------------------------- evaluation metrics
 def test_amt_metrics_kernel_vs_reference_golden_and_oracle():
     from test_oracle import _metrics_case

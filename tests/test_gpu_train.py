@@ -225,3 +225,70 @@ def test_graphed_train_step_equals_eager_and_keeps_dropout_fresh():
     tr = Trainer(m, lr=0.0, use_graph=True)
     ls = [float(tr.train_step(inp)) for _ in range(6)]
     assert tr._graph is not None and len(set(ls[3:])) == len(ls[3:])      # three replays, three different losses
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "AdamW"])
+def test_adam_kernel_equals_torch_optim_with_the_reference_constants(optimizer):
+    """Five optimiser steps on a flat buffer against torch.optim.Adam / AdamW with the reference's constants (train.py:237-240:
+    betas (0.9, 0.98), eps ADAM_EPSILON = 10e-9 = 1e-8, utilities/constants.py:89-91; AdamW's default decoupled weight decay
+    0.01) driven by LambdaLR(LrStepTracker.step) (train.py:252, stepped after the optimiser, run_model_vevo.py:121-123):
+    the first update runs with lr = 0, step t with f(t - 1)."""
+    from video2music_b200 import ops
+    from video2music_b200.trainer import noam_lr, scheduled_lr
+    g = syn._gen(9, "adam")
+    n, warm = 4096 + 512, 3
+    p0 = syn.unit_uniform((n,), g)
+    grads = [syn.unit_uniform((n,), g) * (10.0 ** (i - 2)) for i in range(5)]
+    ref_p = torch.nn.Parameter(p0.clone().to(DEV))
+    cls = torch.optim.Adam if optimizer == "Adam" else torch.optim.AdamW
+    opt = cls([ref_p], lr=1.0, betas=(0.9, 0.98), eps=10e-9)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s_: noam_lr(s_, 512, warm))
+    wd = 0.01 if optimizer == "AdamW" else 0.0
+    p, m, v = p0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    p16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    for t, gr in enumerate(grads, start=1):
+        ref_p.grad = gr.clone().to(DEV)
+        opt.step()
+        sched.step()
+        gbuf = (gr * 2.0).to(DEV)                                  # as if summed over 2 ranks: grad_scale = 1/2
+        ops.adam_step(p, gbuf, m, v, scheduled_lr(t, 512, warm), 0.9, 0.98, 1e-8, t, grad_scale=0.5, p16=p16, zero_grad=True,
+                      weight_decay=wd)
+        assert float(gbuf.abs().max()) == 0.0
+        err = rel_err(p, ref_p.detach())
+        print("%s step %d lr %.3e: rel err %.2e" % (optimizer, t, scheduled_lr(t, 512, warm), err))
+        assert err < 2e-6, t
+        assert torch.equal(p16, p.to(torch.bfloat16))
+        if t == 1:
+            assert torch.equal(p.cpu(), p0)                        # lr(0) = 0: the first update moves nothing
+
+
+def test_trainer_defaults_follow_the_reference_constants():
+    from video2music_b200 import VideoMusicTransformer
+    from video2music_b200.trainer import Trainer
+    m = VideoMusicTransformer(n_layers=1, total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0, max_sequence_chord=32,
+                              max_sequence_video=16).to(DEV).train()
+    tr = Trainer(m)
+    assert tr.eps == 1e-8 and tr.betas == (0.9, 0.98) and tr.weight_decay == 0.0
+    tr.step_no = 1
+    assert tr._lr() == 0.0
+    assert Trainer(m, optimizer="AdamW").weight_decay == 0.01
+    with pytest.raises(ValueError):
+        Trainer(m, optimizer="Lion")
+
+
+def test_loss_rejects_bad_targets_loudly():
+    from video2music_b200 import ops
+    y = torch.zeros((4, 159), device=DEV)
+    e = torch.zeros((4, 159), device=DEV)
+    with pytest.raises(TypeError):
+        ops.amt_loss(y, torch.zeros(4, dtype=torch.int32, device=DEV), e)
+    scratch, _ = ops.amt_loss(y, torch.tensor([0, 5, 200, 158], device=DEV), e)       # 200: outside [0, 159), not the pad id
+    assert bool(torch.isnan(scratch[0]))
+    scratch, _ = ops.amt_loss(y, torch.tensor([0, 5, 157, 158], device=DEV), e)
+    assert bool(torch.isfinite(scratch).all()) and float(scratch[2]) == 3.0
+    norm = torch.tensor([6.0, 8.0], device=DEV)                                         # global / world normalisers
+    s2, dl2 = ops.amt_loss(y, torch.tensor([0, 5, 157, 158], device=DEV), e, norm=norm)
+    s1, dl1 = ops.amt_loss(y, torch.tensor([0, 5, 157, 158], device=DEV), e)
+    assert torch.allclose(s1[:2], s2[:2])
+    # CE part scales by 3/6, BCE part by 4/8: with zero logits and zero emotion targets both are exactly halved
+    assert torch.allclose(dl2, dl1 * 0.5, atol=1e-7)

@@ -203,11 +203,13 @@ class AmtLossFn(torch.autograd.Function):
     """total = 0.4 * CE(label_smoothing 0.1, ignore 158) + 0.6 * BCEWithLogits  (run_model_vevo.py:101-119)."""
 
     @staticmethod
-    def forward(ctx, logits, tgt, tgt_emotion, smooth, w_ce, w_bce):
-        scratch, dl = ops.amt_loss(logits, tgt, tgt_emotion, 158, smooth, w_ce, w_bce)
+    def forward(ctx, logits, tgt, tgt_emotion, smooth, w_ce, w_bce, norm=None):
+        """norm (device fp32 [n_valid, rows]): normalisers replacing this batch's own (a data-parallel rank passes
+        global / world: the mean over ranks of the returned loss and of its gradient are then the global-batch ones)."""
+        scratch, dl = ops.amt_loss(logits, tgt, tgt_emotion, 158, smooth, w_ce, w_bce, norm=norm)
         R = logits.numel() // logits.shape[-1]
-        ce = scratch[0] / scratch[2].clamp_min(1.0)
-        bce = scratch[1] / float(R * logits.shape[-1])
+        ce = scratch[0] / (norm[0] if norm is not None else scratch[2]).clamp_min(1.0)
+        bce = scratch[1] / ((norm[1] if norm is not None else float(R)) * logits.shape[-1])
         ctx.save_for_backward(dl)
         ctx.parts = (ce.detach(), bce.detach())
         return w_ce * ce + w_bce * bce
@@ -215,7 +217,7 @@ class AmtLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dl,) = ctx.saved_tensors
-        return dl * g, None, None, None, None, None
+        return dl * g, None, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------- model forward

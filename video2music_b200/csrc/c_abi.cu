@@ -157,14 +157,18 @@ int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t 
 }
 
 int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
-                 float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, void* stream) {
+                 float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, const float* norm_in, void* stream) {
   return amt_loss(logits, reinterpret_cast<const long long*>(tgt), tgt_emotion, R, Cn, ignore, smooth, w_ce, w_bce, scratch3,
-                  dlogits, static_cast<cudaStream_t>(stream));
+                  dlogits, norm_in, static_cast<cudaStream_t>(stream));
 }
 
-int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, int32_t step,
+int v2m_count_valid(const int64_t* tgt, int32_t R, int64_t ignore, float* out1, void* stream) {
+  return count_valid(reinterpret_cast<const long long*>(tgt), R, ignore, out1, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float weight_decay, int32_t step,
                   float grad_scale, const float* dyn, void* p16, int32_t zero_grad, uint32_t* ctr, void* stream) {
-  return adam_step(p, g, m, v, n, lr, b1, b2, eps, step, grad_scale, dyn, p16, zero_grad, ctr, static_cast<cudaStream_t>(stream));
+  return adam_step(p, g, m, v, n, lr, b1, b2, eps, weight_decay, step, grad_scale, dyn, p16, zero_grad, ctr, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma, const float* beta,

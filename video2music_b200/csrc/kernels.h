@@ -103,8 +103,9 @@ int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy
 int embed_bwd(const long long* idx, const void* d, int d_dtype, long long ld_d, float* dtable, int rows, int D,
               cudaStream_t stream);
 int amt_loss(const float* logits, const long long* tgt, const float* tgt_emotion, int R, int Cn, long long ignore, float smooth,
-             float w_ce, float w_bce, float* scratch3, float* dlogits, cudaStream_t stream);
-int adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+             float w_ce, float w_bce, float* scratch3, float* dlogits, const float* norm_in, cudaStream_t stream);
+int count_valid(const long long* tgt, int R, long long ignore, float* out1, cudaStream_t stream);
+int adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float weight_decay, int step,
               float grad_scale, const float* dyn, void* p16, int zero_grad, unsigned int* ctr, cudaStream_t stream);
 
 // y = LayerNorm(x (+ res)) * gamma + beta over the last dim D (eps 1e-5 like nn.LayerNorm).

@@ -330,14 +330,19 @@ __global__ void count_valid_kernel(const long long* __restrict__ tgt, int R, lon
 __global__ void __launch_bounds__(256) amt_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt,
                                                        const float* __restrict__ tgt_emotion, int R, int Cn, long long ignore,
                                                        float smooth, float w_ce, float w_bce, const float* __restrict__ n_valid,
-                                                       float* __restrict__ out, float* __restrict__ dlogits) {
+                                                       const float* __restrict__ bce_rows_p, float* __restrict__ out,
+                                                       float* __restrict__ dlogits) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= R) return;
   const float* x = logits + (size_t)row * Cn;
   const float* e = tgt_emotion + (size_t)row * Cn;
   const long long t = tgt[row];
-  const bool valid = t != ignore;
+  const bool in_range = t >= 0 && t < Cn;
+  const bool valid = t != ignore && in_range;
+  // a label outside [0, Cn) that is not the ignore index: torch's cross_entropy raises; here the loss becomes NaN (loud)
+  // instead of reading x[t] out of bounds
+  if (lane == 0 && t != ignore && !in_range) atomicAdd(out + 0, __int_as_float(0x7fc00000));
   float mx = -INFINITY;
   for (int c = lane; c < Cn; c += 32) mx = fmaxf(mx, x[c]);
   mx = warp_max(mx);
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(256) amt_loss_kernel(const float* __restrict__
   bce = warp_sum(bce);
   const float lse = mx + logf(se);
   const float nv = fmaxf(*n_valid, 1.f);
-  const float inv_bce = 1.f / ((float)R * (float)Cn);
+  const float inv_bce = 1.f / ((bce_rows_p ? *bce_rows_p : (float)R) * (float)Cn);
   if (lane == 0) {
     if (valid) {
       const float nll = lse - x[t];
@@ -377,33 +382,47 @@ __global__ void __launch_bounds__(256) amt_loss_kernel(const float* __restrict__
 }
 
 int amt_loss(const float* logits, const long long* tgt, const float* tgt_emotion, int R, int Cn, long long ignore, float smooth,
-             float w_ce, float w_bce, float* scratch3, float* dlogits, cudaStream_t stream) {
-  // scratch3: [ce_sum, bce_sum, n_valid] (device, zeroed here)
+             float w_ce, float w_bce, float* scratch3, float* dlogits, const float* norm_in, cudaStream_t stream) {
+  // scratch3: [ce_sum, bce_sum, n_valid] (device, zeroed here).  norm_in (optional, device, 2 floats): [the CE normaliser to
+  // use instead of this call's own count of non-ignored targets, the row count the BCE mean divides by instead of R] --
+  // a data-parallel rank passes global_count / world and global_rows / world so that the 1/world mean of the ranks'
+  // gradients is the gradient of the single-process global-batch loss (run_model_vevo.py:101-119).
   if (R == 0) return kOk;
   cudaError_t e = cudaMemsetAsync(scratch3, 0, 3 * sizeof(float), stream);
   if (e != cudaSuccess) { set_last_error("amt_loss: memset: %s", cudaGetErrorString(e)); return kCudaError; }
   count_valid_kernel<<<(R + 255) / 256 < 296 ? (R + 255) / 256 : 296, 256, 0, stream>>>(tgt, R, ignore, scratch3 + 2);
-  amt_loss_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, tgt, tgt_emotion, R, Cn, ignore, smooth, w_ce, w_bce, scratch3 + 2,
-                                                   scratch3, dlogits);
+  amt_loss_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, tgt, tgt_emotion, R, Cn, ignore, smooth, w_ce, w_bce,
+                                                   norm_in ? norm_in : scratch3 + 2, norm_in ? norm_in + 1 : nullptr, scratch3, dlogits);
   return check_launch("amt_loss");
 }
 
-// ---- Adam (train.py:238: betas (0.9, 0.98), eps 1e-9 per constants.py:89-91; torch.optim.Adam semantics) --------
+int count_valid(const long long* tgt, int R, long long ignore, float* out1, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(out1, 0, sizeof(float), stream);
+  if (e != cudaSuccess) { set_last_error("count_valid: memset: %s", cudaGetErrorString(e)); return kCudaError; }
+  if (R == 0) return kOk;
+  count_valid_kernel<<<(R + 255) / 256 < 296 ? (R + 255) / 256 : 296, 256, 0, stream>>>(tgt, R, ignore, out1);
+  return check_launch("count_valid");
+}
+
+// ---- Adam / AdamW (train.py:237-240: betas (0.9, 0.98), eps ADAM_EPSILON = 10e-9 = 1e-8, constants.py:89-91) ----------
+// torch.optim.Adam semantics; weight_decay > 0 adds torch.optim.AdamW's decoupled decay p *= 1 - lr * weight_decay before the
+// update (the reference CLI's default optimiser, argument_funcs.py:17, uses AdamW's default 0.01).
 // dyn (optional, device): {lr, 1 - b1^t, 1 - b2^t} read at run time, so that a CUDA graph of the whole training step can be
 // replayed with a changing learning-rate schedule.  Fused extras: p16 (optional) receives the bf16 mirror of the updated
 // parameters, zero_grad clears the gradient buffer for the next step, ctr (optional) is a device step counter that the
 // dropout kernels add to their seeds.
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2, float grad_scale,
-                            const float* __restrict__ dyn, bf16* __restrict__ p16, int zero_grad, unsigned int* __restrict__ ctr) {
+                            long long n, float lr, float b1, float b2, float eps, float weight_decay, float bc1, float bc2,
+                            float grad_scale, const float* __restrict__ dyn, bf16* __restrict__ p16, int zero_grad, unsigned int* __restrict__ ctr) {
   if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
+  const float decay = 1.f - lr * weight_decay;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    const float pi = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    const float pi = p[i] * decay - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
     p[i] = pi;
     if (p16) p16[i] = __float2bfloat16_rn(pi);
     if (zero_grad) g[i] = 0.f;
@@ -411,12 +430,12 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   if (ctr && blockIdx.x == 0 && threadIdx.x == 0) *ctr += 1u;
 }
 
-int adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, int step,
+int adam_step(float* p, float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, float weight_decay, int step,
               float grad_scale, const float* dyn, void* p16, int zero_grad, unsigned int* ctr, cudaStream_t stream) {
   if (n == 0) return kOk;
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
   const long long want = (n + 255) / 256;
-  adam_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, grad_scale, dyn,
+  adam_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, weight_decay, bc1, bc2, grad_scale, dyn,
                                                                             static_cast<bf16*>(p16), zero_grad, ctr);
   return check_launch("adam_step");
 }

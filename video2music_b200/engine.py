@@ -253,6 +253,11 @@ def build_decode(W: AMTWeights, cfg, sem, key, scene, motion, emotion, primer, p
     E, H, FF, NL = cfg["d_model"], cfg["nhead"], cfg["d_ff"], cfg["n_layers"]
     dh = E // H
     cap = target_seq_length
+    if not W.has("transformer.decoder.layers.0.self_attn.Er"):
+        raise NotImplementedError("KV-cached generate() is built for the RPR decoder (rpr=True, the shipped AMT, "
+                                  "video2music.py:640); this model has no Er tables")
+    if E != 512 or dh != 64:
+        raise NotImplementedError("the decode kernels are built for d_model 512 with head_dim 64 (got d_model %d, %d heads)" % (E, H))
     dt = W.dtype
     st = DecodeState()
     if mode == "auto":

@@ -146,6 +146,21 @@ def _experts_forward(experts, x2: torch.Tensor, idx: torch.Tensor, w: torch.Tens
     return ops.moe_experts(x2, idx.reshape(-1, idx.shape[-1]), w.reshape(-1, w.shape[-1]), hist, w1, b1, wg, bg, w2, b2)
 
 
+def balance_update_(bias: torch.Tensor, hist: torch.Tensor, rate: float, group=None) -> torch.Tensor:
+    """Loss-free load balancing of SharedMoELayer (moe.py:270-279): bias += rate * (mean(c) - c), c = how many token copies
+    each expert received in this batch.  Data parallel (one process per GPU, torch.distributed initialised): the histogram is
+    sum-all-reduced first, so every replica applies the update of the GLOBAL batch and the `bias` buffers stay identical
+    across ranks; the update is linear in c, so this equals the single-process update."""
+    import torch.distributed as dist
+    c = hist.to(bias.dtype)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        c = c.clone()
+        dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    with torch.no_grad():
+        bias += rate * (c.mean() - c).unsqueeze(1)
+    return c
+
+
 class MoELayer(nn.Module):
     def __init__(self, expert, d_model, n_experts=8, n_experts_per_token=2, dropout=0.1, topk_scheduler=None,
                  temperature_scheduler=None):
@@ -233,9 +248,7 @@ class SharedMoELayer(nn.Module):
         idx, w, hist, _ = ops.moe_route(x2, self.gate.weight.detach(), self.gate.bias.detach(), k, sel_bias=sel_bias,
                                         inv_t_post=1.0 / t)
         if self.balancing and self.training:                             # moe.py:270-279
-            c = hist.to(self.bias.dtype)
-            with torch.no_grad():
-                self.bias += self.update_rate * (c.mean() - c).unsqueeze(1)
+            balance_update_(self.bias, hist, self.update_rate, getattr(self, "process_group", None))
         self.last_selected_experts = idx.view(shp[:-1] + (k,))
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)

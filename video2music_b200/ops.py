@@ -554,9 +554,12 @@ def embed_bwd(idx: torch.Tensor, d: torch.Tensor, n_rows_table: int, D: int) -> 
 
 
 def amt_loss(logits: torch.Tensor, tgt: torch.Tensor, tgt_emotion: torch.Tensor, ignore: int = 158, smooth: float = 0.1,
-             w_ce: float = 0.4, w_bce: float = 0.6, want_grad: bool = True):
-    """Returns (scratch [ce_sum, bce_sum, n_valid] on device, dlogits or None)."""
+             w_ce: float = 0.4, w_bce: float = 0.6, want_grad: bool = True, norm: Optional[torch.Tensor] = None):
+    """Returns (scratch [ce_sum, bce_sum, n_valid] on device, dlogits or None).  norm (device fp32 [n_valid, rows])
+    replaces the local normalisers (data-parallel ranks pass global / world, see count_valid)."""
     require_device(logits)
+    if tgt.dtype != torch.int64:
+        raise TypeError("amt_loss: targets must be int64 (got %s)" % tgt.dtype)
     logits = logits.contiguous()
     Cn = logits.shape[-1]
     R = logits.numel() // Cn
@@ -565,9 +568,21 @@ def amt_loss(logits: torch.Tensor, tgt: torch.Tensor, tgt_emotion: torch.Tensor,
     scratch = torch.empty((3,), device=logits.device, dtype=torch.float32)
     dl = torch.empty_like(logits) if want_grad else None
     check(load().v2m_amt_loss(ptr(logits), ptr(tgt), ptr(tgt_emotion), R, Cn, ignore, smooth, w_ce, w_bce, ptr(scratch), ptr(dl),
-                              stream()))
+                              ptr(norm), stream()))
     _lib.count_launches(2)
     return scratch, dl
+
+
+def count_valid(tgt: torch.Tensor, ignore: int = 158) -> torch.Tensor:
+    """Device fp32 scalar: number of targets != ignore (the normaliser of nn.CrossEntropyLoss(ignore_index), train.py:222)."""
+    require_device(tgt)
+    if tgt.dtype != torch.int64:
+        raise TypeError("count_valid: targets must be int64 (got %s)" % tgt.dtype)
+    tgt = tgt.contiguous().view(-1)
+    out = torch.empty((1,), device=tgt.device, dtype=torch.float32)
+    check(load().v2m_count_valid(ptr(tgt), tgt.numel(), ignore, ptr(out), stream()))
+    _lib.count_launches(1)
+    return out
 
 
 def amt_metrics(logits: torch.Tensor, tgt: torch.Tensor, pad: int = 158, ks=(1, 3, 5)) -> torch.Tensor:
@@ -587,12 +602,12 @@ def amt_metrics(logits: torch.Tensor, tgt: torch.Tensor, pad: int = 158, ks=(1, 
 
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, b1: float, b2: float, eps: float,
               step: int, grad_scale: float = 1.0, *, dyn: Optional[torch.Tensor] = None, p16: Optional[torch.Tensor] = None,
-              zero_grad: bool = False, counter: Optional[torch.Tensor] = None) -> None:
-    """torch.optim.Adam semantics on flat buffers.  dyn (device fp32 [lr, 1-b1^t, 1-b2^t]) replaces the scalar lr / step at run
+              zero_grad: bool = False, counter: Optional[torch.Tensor] = None, weight_decay: float = 0.0) -> None:
+    """torch.optim.Adam semantics on flat buffers (weight_decay > 0: torch.optim.AdamW's decoupled decay).  dyn (device fp32 [lr, 1-b1^t, 1-b2^t]) replaces the scalar lr / step at run
     time; p16: bf16 mirror of the updated parameters; zero_grad clears g; counter (device, 4 bytes) is incremented."""
     require_device(p)
     assert p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32
-    check(load().v2m_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, b1, b2, eps, step, grad_scale, ptr(dyn), ptr(p16),
+    check(load().v2m_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, b1, b2, eps, weight_decay, step, grad_scale, ptr(dyn), ptr(p16),
                                int(zero_grad), ptr(counter), stream()))
     _lib.count_launches(1)
 

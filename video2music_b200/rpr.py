@@ -17,6 +17,8 @@ from typing import Optional
 import torch
 import torch.nn as nn
 from torch.nn import Parameter
+import weakref
+
 from torch.nn.init import constant_, xavier_uniform_
 
 from . import ops
@@ -26,25 +28,27 @@ def _get_clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
 
-_mask_cache = {}
+_mask_cache = {}      # id(mask tensor) -> (weakref to it, version, L, verdict); entries die with the tensor
 
 
 def is_causal_mask(attn_mask: Optional[torch.Tensor], L: int) -> bool:
     """True for the float mask of nn.Transformer.generate_square_subsequent_mask (0 on/below the
-    diagonal, -inf above); None -> False; anything else is rejected."""
+    diagonal, -inf above); None -> False; anything else is rejected.
+    The verdict is cached per tensor object (weak reference) and in-place version: a different mask that the caching
+    allocator later places at the same address is a different object and is checked again (the reference rebuilds its
+    mask every forward, video_music_transformer.py:1033, so an address-keyed cache would go stale)."""
     if attn_mask is None:
         return False
-    key = (attn_mask.data_ptr(), tuple(attn_mask.shape), attn_mask._version, str(attn_mask.device))
+    key = id(attn_mask)
     hit = _mask_cache.get(key)
-    if hit is None:
+    if hit is None or hit[0]() is not attn_mask or hit[1] != attn_mask._version or hit[2] != L:
         ok = attn_mask.shape == (L, L)
         if ok:
             ref = torch.triu(torch.full((L, L), float("-inf"), device=attn_mask.device), diagonal=1)
             ok = bool(torch.equal(attn_mask.float(), ref))
-        if len(_mask_cache) > 64:
-            _mask_cache.clear()
-        _mask_cache[key] = hit = ok
-    if not hit:
+        hit = (weakref.ref(attn_mask, lambda _r, k=key: _mask_cache.pop(k, None)), attn_mask._version, L, ok)
+        _mask_cache[key] = hit
+    if not hit[3]:
         raise NotImplementedError("only the causal square-subsequent attn_mask (or None) is supported")
     return True
 
