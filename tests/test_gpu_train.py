@@ -116,8 +116,9 @@ def test_train_step_fp32_full_shape_vs_reference_golden(name):
 
 @pytest.mark.parametrize("name", ["full", "ragged"])
 def test_train_step_bf16_full_shape_close_to_reference(name):
-    """Same step on the bf16 tensor-core path: every gradient norm within 5 % and every kept gradient (incl. three Er
-    tables) within 5 % of the reference's fp32 autograd (bf16 operands, fp32 accumulation and fp32 gradients)."""
+    """Same step on the bf16 tensor-core path: every gradient norm within 2 % (median 0.5 %) and every kept gradient (incl.
+    three Er tables) within 3 % in relative Frobenius norm / 8 % max-elementwise of the reference's fp32 autograd (bf16
+    operands, fp32 accumulation and fp32 gradients)."""
     g, m, y, loss = _full_case(name, torch.bfloat16)
     assert rel_err(y[:1], g["logits"]) < 2e-2
     assert abs(float(loss.detach()) - g["loss"]) < 1e-2 * abs(g["loss"])
@@ -126,12 +127,17 @@ def test_train_step_bf16_full_shape_close_to_reference(name):
     order = sorted(errs, key=errs.get)
     print("bf16 %s: gradient-norm error median %.4f, worst %.4f (%s), 2nd %.4f (%s)" % (
         name, errs[order[len(order) // 2]], errs[order[-1]], order[-1], errs[order[-2]], order[-2]))
-    assert errs[order[len(order) // 2]] < 1e-2
-    assert errs[order[-1]] < 5e-2, order[-1]
+    assert errs[order[len(order) // 2]] < 5e-3
+    assert errs[order[-1]] < 2e-2, order[-1]                 # measured: worst 0.9 % (an Er table), median 0.1 %
     for n, gref in g["grads"].items():
-        e = rel_err(_kept(params[n].grad, gref), gref)
-        print("bf16 %s grad %-55s rel err %.3e" % (name, n, e))
-        assert e < 5e-2, n
+        mine = _kept(params[n].grad, gref).detach().double().cpu()
+        e = rel_err(mine, gref)
+        fro = float((mine - gref.double()).norm() / gref.double().norm())
+        print("bf16 %s grad %-55s max-elementwise %.3e, relative Frobenius %.3e" % (name, n, e, fro))
+        # max |diff| / max |ref| of a sum of ~10^6 bf16-rounded terms: 2-5.5 % measured on the Er tables (the smallest
+        # gradients of the model), <= 3 % elsewhere; the Frobenius error separates rounding noise from a dropped term
+        assert e < 8e-2, n
+        assert fro < 3e-2, n
 
 
 def test_train_steps_with_dropout():
