@@ -31,8 +31,7 @@ sys.path.insert(0, ROOT)
 BATCH = 64                 # videos per GPU (BASELINE config 2)
 TRAIN_GLOBAL_BATCH = 512   # BASELINE config 3 (split over the ranks: strong scaling)
 TRAIN_DROPOUT = 0.2        # train.py's default (utilities/argument_funcs.py:14,52); every dropout site runs fused in the bf16 kernels
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from profiles/ (one ncu --set full capture, per launch)
-NCU_TRAFFIC_BYTES = {"stream": 122944729000 + 286507008}   # profiles/r01_decode_stream_ncu_full_details.txt (ncu --set full, per launch)
+WOUT_GAIN = 4.0            # synthetic weights: Wout scaled x4 so that the greedy arg-max is not decided by rounding noise
 SEQ = 300                  # target_seq_length -> 299 generated chord tokens per video
 METRIC = "generate_chord_tokens_per_s"
 UNIT = "tokens/s"
@@ -44,6 +43,54 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peaks():
+    """(burst, sustained) dense bf16 TFLOP/s: a kernel timed alone is held against the burst figure, a kernel inside a
+    long step against the sustained one."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 1700.0, 1700.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_substr`, parsed from the NEWEST ncu raw-page export
+    under profiles/ (`ncu -i X.ncu-rep --page raw --csv`, kept as profiles/rNN_*_ncu_raw.csv; one `--set full` capture).
+    Returns (bytes or None, file name or None)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_raw.csv")), reverse=True)
+    for f in files:
+        try:
+            rows = list(csv.reader(open(f, newline="")))
+        except OSError:
+            continue
+        hdr = next((r for r in rows if "Kernel Name" in r), None)
+        if hdr is None or "dram__bytes_read.sum" not in hdr:
+            continue
+        units = rows[rows.index(hdr) + 1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        for r in rows[rows.index(hdr) + 2:]:
+            if len(r) > max(kn, rd, wr) and kernel_substr in r[kn]:
+                try:
+                    return int(float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) +
+                               float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0)), os.path.basename(f)
+                except ValueError:
+                    continue
+    return None, None
+
+
+def bench_config():
+    """The workload both arms are timed on (BASELINE config 2)."""
+    return {"workload": "AMT greedy chord generation with KV cache: 64 videos/GPU x 300 positions (299 decoded tokens), "
+                        "6+6 layers, d_model 512, 8 heads, RPR, vf 776, primer length 1, chord_embed",
+            "videos_per_gpu": BATCH, "target_seq_length": SEQ, "sharding": "independent videos per rank, no collective",
+            "weights": "seeded random init at the reference constructor's scales, Wout x %g (wout_gain) so that the greedy "
+                       "arg-max is not decided by rounding noise" % WOUT_GAIN,
+            "l2": "256 MiB written between timed steps (L2 flush); per-step working set 386 MB > L2"}
 
 
 class ClockSampler:
@@ -96,7 +143,7 @@ def make_model(dtype, device, seed=1):
     from video2music_b200 import synthetic as syn
     m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, chord_embed=True)
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
-    m.load_state_dict(syn.fill_like_reference_init(shapes, seed=seed, wout_gain=4.0), strict=False)
+    m.load_state_dict(syn.fill_like_reference_init(shapes, seed=seed, wout_gain=WOUT_GAIN), strict=False)
     sd = {k: v.clone() for k, v in m.state_dict().items()}
     if device is not None:
         m = m.to(device)
@@ -141,10 +188,19 @@ def train_leg(args, dev, rank, world, dtype):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     flops = 69.4e9 * TRAIN_GLOBAL_BATCH                 # 3 x 23.14 GF per sample
-    return {"metric": "train_samples_per_s", "value": TRAIN_GLOBAL_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+    tfl = flops / (ms * 1e-3) / 1e12
+    _, sustained, psrc = tensor_peaks()
+    return {"roofline": {"bound": "tensor", "achieved": tfl / world, "peak": sustained, "unit": "TFLOP/s", "frac": tfl / world / sustained,
+                         "peak_source": psrc + ", sustained cuBLAS bf16 (a kernel timed inside a long step)",
+                         "note": "per GPU: 69.4 GFLOP per sample (3 x the dense forward, SURVEY 8d) x global batch / step time / n_gpus"},
+            "metric": "train_samples_per_s", "value": TRAIN_GLOBAL_BATCH / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
             "global_batch": TRAIN_GLOBAL_BATCH, "per_gpu_batch": b1 - b0, "dropout": TRAIN_DROPOUT, "scaling": "strong", "steps": args.train_steps,
             "loss": lossv, "tflops": flops / (ms * 1e-3) / 1e12, "launches_per_step": tr.launches_per_step or _lib.launches() // args.train_steps, "cuda_graph": tr._graph is not None,
-            "collective": "NCCL all-reduce of the flat fp32 gradient buffer (130 MB)" if world > 1 else "none (1 rank)",
+            "collective": ("NCCL all-reduce of the fp32 gradients in %d buckets launched from backward hooks (overlapped with "
+                           "backward inside the captured graph), 130 MB per step; launch order last step: %s"
+                           % (len(tr.buckets.bounds), tr.buckets.order)) if (world > 1 and tr.buckets is not None)
+            else ("NCCL all-reduce of the flat fp32 gradient buffer (130 MB)" if world > 1 else "none (1 rank)"),
+            "optimizer": "Adam betas (0.9, 0.98) eps 1e-8, LambdaLR(LrStepTracker) schedule (train.py:237-253)",
             "timed": "e2e: every step copies its batch from pinned host memory (side stream, overlapped with the previous step), loss read back at the end",
             "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values())}
 
@@ -205,6 +261,99 @@ def variants_leg(dev):
     return out
 
 
+def kernel_rooflines(dev):
+    """roofline_extra: the other kernels BASELINE.json names, each timed alone in this run (CUDA events on the launching
+    stream, median of 5, L2 flushed between launches) at the BASELINE shapes: fused RPR attention forward and a projection
+    GEMM against the measured bf16 burst peak, pscan forward / backward against the measured HBM copy bandwidth."""
+    from video2music_b200 import ops
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm, hsrc = peaks()
+    burst, _, tsrc = tensor_peaks()
+
+    def timed(fn, reps=5):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    out = []
+    g = torch.Generator(device="cpu").manual_seed(3)
+    B, L, S, H, dh, E = TRAIN_GLOBAL_BATCH, SEQ - 1, 300, 8, 64, 512
+    qkv = (torch.randn(B, L, 3 * E, generator=g) * 0.3).to(dev).bfloat16()
+    Er = (torch.randn(300, dh, generator=g) * 0.3).to(dev).bfloat16()
+    o = torch.empty(B, L, E, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B * H, L, device=dev, dtype=torch.float32)
+    st = (L * 3 * E, 3 * E)
+    ms = timed(lambda: ops.attention(qkv, qkv[:, :, E:], qkv[:, :, 2 * E:], o, B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=st,
+                                     k_strides=st, v_strides=st, o_strides=(L * E, E), causal=True, Er=Er, lse=lse))
+    fl = 6.0 * L * L * dh * B * H                          # QK^T + Q Er^T + P V, dense (SURVEY 8d: 3 * 2 * T^2 * d per layer and sample)
+    out.append({"kernel": "attn_bf16_tc_kernel (fused RPR causal self-attention forward)", "shape": "B=%d H=%d L=%d dh=%d" % (B, H, L, dh),
+                "bound": "tensor", "ms": ms, "achieved": fl / ms / 1e9, "peak": burst, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / burst,
+                "achieved_causal": 0.5 * fl / ms / 1e9, "peak_source": tsrc + ", burst",
+                "note": "achieved = dense-equivalent flops (the causal half the kernel skips is counted); achieved_causal counts only the lower triangle"})
+    kv = (torch.randn(B, S, 2 * E, generator=g) * 0.3).to(dev).bfloat16()
+    sk = (S * 2 * E, 2 * E)
+    ms = timed(lambda: ops.attention(qkv, kv, kv[:, :, E:], o, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=st, k_strides=sk,
+                                     v_strides=sk, o_strides=(L * E, E), causal=False, lse=lse))
+    fl = 4.0 * L * S * dh * B * H
+    out.append({"kernel": "attn_bf16_tc_kernel (cross-attention forward)", "shape": "B=%d H=%d L=%d S=%d dh=%d" % (B, H, L, S, dh),
+                "bound": "tensor", "ms": ms, "achieved": fl / ms / 1e9, "peak": burst, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / burst,
+                "peak_source": tsrc + ", burst"})
+    M = B * L
+    x = qkv.view(M, 3 * E)[:, :E].contiguous()
+    w = (torch.randn(3 * E, E, generator=g) * 0.05).to(dev).bfloat16()
+    bias = torch.randn(3 * E, generator=g).to(dev)
+    ms = timed(lambda: ops.linear(x, w, bias, out_dtype=torch.bfloat16))
+    fl = 2.0 * M * 3 * E * E
+    out.append({"kernel": "gemm_bf16_tc_kernel (in_proj)", "shape": "M=%d N=%d K=%d" % (M, 3 * E, E), "bound": "tensor", "ms": ms,
+                "achieved": fl / ms / 1e9, "peak": burst, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / burst, "peak_source": tsrc + ", burst"})
+    del qkv, kv, o, x
+    for (b_, l_) in ((64, 300), (8, 4096)):
+        A = torch.rand(b_, l_, 256, 16, generator=g).mul_(0.99).to(dev)
+        X = torch.randn(b_, l_, 256, 16, generator=g).to(dev)
+        ms = timed(lambda: ops.pscan_fwd(A, X))
+        by = 3.0 * 4 * A.numel()
+        out.append({"kernel": "pscan_kernel forward", "shape": "(%d,%d,256,16)" % (b_, l_), "bound": "hbm", "ms": ms, "achieved": by / ms / 1e6,
+                    "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm, "peak_source": hsrc, "note": "12 B per element: read A, X, write H"})
+        Hh = ops.pscan_fwd(A, X)
+        ms = timed(lambda: ops.pscan_bwd(A, Hh, X))
+        by = 5.0 * 4 * A.numel()
+        out.append({"kernel": "pscan_kernel backward", "shape": "(%d,%d,256,16)" % (b_, l_), "bound": "hbm", "ms": ms, "achieved": by / ms / 1e6,
+                    "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm, "peak_source": hsrc,
+                    "note": "20 B per element: read gradH, A, H, write gradA, gradX"})
+        del A, X, Hh
+    return out
+
+
+def fp32_leg(dev, devt, prim, pr, pa, l2_flush, steps=2):
+    """Same workload on the fp32 exact path (the one whose greedy tokens are bit-exact against the reference): value_fp32."""
+    model32, _ = make_model(torch.float32, dev)
+
+    def gen32():
+        return model32.generate(devt["feature_semantic_list"], devt["feature_key"], devt["feature_scene_offset"], devt["feature_motion"],
+                                devt["feature_emotion"], primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=SEQ, beam=1,
+                                beam_chance=1.0)
+    gen32()
+    ms = []
+    for _ in range(steps):
+        l2_flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gen32(); e1.record(); e1.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = sum(ms) / len(ms)
+    run_bytes, _ = algorithmic_bytes(BATCH, 300, SEQ, 512, 8, 1024, 6, 159, 4)
+    peak, _ = peaks()
+    val = BATCH * (SEQ - 1) / (t / 1e3)
+    return {"value": val, "unit": UNIT, "ms_per_step": t, "steps": steps, "dtype": "f32",
+            "path": "decode step kernels (skinny_gemm / dec_attn, CUDA graph of 51 launches per position), fp32 prefill",
+            "hbm_floor_tokens_per_s": BATCH * (SEQ - 1) / (run_bytes / (peak * 1e9)), "frac_of_floor": val / (BATCH * (SEQ - 1) / (run_bytes / (peak * 1e9)))}
+
+
 def reference_arm(args):
     """The reference's algorithm on the host cores (oracle port, literal re-forward loop, batch 1)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -224,15 +373,10 @@ def reference_arm(args):
                                       inp["feature_motion"], inp["feature_emotion"], prim, pr, pa, n, chord_embed=True)
         return time.perf_counter() - t0
 
-    # bounded sample: the longest prefix for which (steps + warmup) passes fit in ~150 s
-    t_probe = run(24)
+    # Same target as our arm: 299 greedy tokens (target_seq_length 300).  The bounded sample is ONE video per step (our arm
+    # generates 64 per GPU; the metric is per token, and the reference's loop is batch 1 anyway, generate.py:368-392): one
+    # step is ~5 s on 16 cores, so --steps 20 --warmup 5 ends in ~2.5 minutes.
     seq = SEQ
-    total = args.steps + args.warmup
-    for cand in (300, 200, 128, 64, 32):
-        est = t_probe * (cand / 24.0) ** 1.6
-        seq = cand
-        if est * total <= 150.0:
-            break
     for _ in range(args.warmup):
         run(seq)
     times = [run(seq) for _ in range(args.steps)]
@@ -241,10 +385,11 @@ def reference_arm(args):
     out = {"metric": METRIC, "value": val, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "AMT greedy chord generation, reference algorithm (batch 1, no KV cache, full re-forward per token)",
-                      "videos": 1, "target_seq_length": seq},
+           "config": bench_config(),
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": "1 video x %d greedy tokens, literal re-forward loop" % tokens},
+                            "sample": "1 video x %d greedy tokens per step (same target_seq_length %d as the GPU arm), the "
+                                      "reference's algorithm: batch 1, no KV cache, full re-forward per token "
+                                      "(video_music_transformer.py:1069-1084), oracle port on the host cores" % (tokens, seq)},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -260,6 +405,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE config 3)")
     ap.add_argument("--train-steps", type=int, default=10)
+    ap.add_argument("--no-extra", action="store_true", help="skip the fp32 generation value and the per-kernel roofline_extra list")
     ap.add_argument("--no-variants", action="store_true", help="skip the GQA+MoE / Mamba training timings (BASELINE configs 4, 5)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -363,20 +509,18 @@ def main():
     h2d = sum(host[k].numel() * host[k].element_size() for k in keys)
     kname = "decode_stream_kernel (one launch: 299 positions x 64 videos, 6 layers)" if decode_mode == "stream" else \
         "decode step kernels (skinny_gemm / dec_attn, 70 launches per position)"
+    traffic, traffic_src = ncu_traffic("decode_stream_kernel") if decode_mode == "stream" else (None, None)
     out = {
         "metric": METRIC, "value": tokens / (t_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": "AMT greedy chord generation with KV cache: 64 videos/GPU x 300 positions (299 decoded tokens), "
-                               "6+6 layers, d_model 512, 8 heads, RPR, vf 776, primer length 1, chord_embed",
-                   "videos_per_gpu": BATCH, "target_seq_length": SEQ, "sharding": "independent videos per rank, no collective",
-                   "l2": "256 MiB written between timed steps (L2 flush); per-step working set 386 MB > L2"},
+        "config": bench_config(),
         "e2e": {"value": tokens / (t_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": BATCH * SEQ * 8, "ms_per_step": t_e2e},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": kname, "bound": "hbm", "achieved": run_bytes / (kern_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": run_bytes / (kern_ms * 1e-3) / 1e9 / peak, "traffic": NCU_TRAFFIC_BYTES.get(decode_mode),
+                     "frac": run_bytes / (kern_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "bytes_per_launch": run_bytes, "us_per_launch": kern_ms * 1e3,
                      "note": "algorithmic bytes = SURVEY 8d decode byte floor (weights once per position + every cached K/V "
                              "element once per position) for the 299 positions one launch processes"},
@@ -384,6 +528,15 @@ def main():
     }
     if train is not None:
         out["train"] = train
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            out["value_fp32"] = fp32_leg(dev, devt, prim, pr, pa, l2_flush)
+        except Exception as e:
+            out["value_fp32"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+        try:
+            out["roofline_extra"] = kernel_rooflines(dev)
+        except Exception as e:
+            out["roofline_extra"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     if rank == 0 and world == 1 and not args.no_variants:
         try:
             out["variants"] = variants_leg(dev)

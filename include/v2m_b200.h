@@ -65,7 +65,7 @@ typedef struct v2m_epilogue {
    * encoder layer; PositionalEncoding dropout, positional_encoding.py:21-23).  drop_scale = 1/(1-p), 0 = off; element (m, n)
    * is kept iff byte (n & 3) of mix(drop_seed, m, n / 4) >= drop_thresh = round(p * 256), drop_scale = 256 / (256 - drop_thresh)
    * (stateless: v2m_dy_prep recomputes the same mask);
-   * drop_after_res: y = drop(acc + residual) instead of drop(acc) + residual.  bf16 tensor-core path only. */
+   * drop_after_res: y = drop(acc + residual) instead of drop(acc) + residual.  Both GEMM paths (fp32 SIMT, bf16 tcgen05). */
   float drop_scale;
   uint32_t drop_thresh, drop_seed;
   int32_t drop_after_res;
@@ -99,7 +99,7 @@ typedef struct v2m_attn {
   const void* Er; int32_t er_len;
   float q_scale;
   float* lse; float* p_out;
-  float drop_scale; uint32_t drop_thresh, drop_seed;   /* dropout of the probabilities (training, bf16 path): see v2m_epilogue */
+  float drop_scale; uint32_t drop_thresh, drop_seed;   /* dropout of the probabilities (training, fp32 and bf16 kernels): see v2m_epilogue */
   const uint32_t* drop_seed_dev;
 } v2m_attn;
 int v2m_attn_fwd(const v2m_attn* p, int32_t dtype, void* stream);
@@ -118,7 +118,7 @@ typedef struct v2m_attn_bwd_t {
   int64_t q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl, do_sb, do_sl, dq_sb, dq_sl, dkv_sb, dkv_sl;
   int32_t B, Hq, Hkv, Lq, Lk, dh, causal, er_len, dtype;
   float q_scale;
-  float drop_scale; uint32_t drop_thresh, drop_seed;   /* the forward's probability dropout (v2m_attn_bwd_tc only) */
+  float drop_scale; uint32_t drop_thresh, drop_seed;   /* the forward's probability dropout (v2m_attn_bwd and v2m_attn_bwd_tc) */
   const uint32_t* drop_seed_dev;
 } v2m_attn_bwd_t;
 int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);

@@ -85,7 +85,7 @@ MIRRORS['moe_route'] = moe_route
 
 def _glu(x, w1, b1, wg, bg, w2, b2):
     return (F.linear(x, w1, b1) * F.silu(F.linear(x, wg, bg))) @ w2.t() + b2
-def moe_experts_fwd_saved(x, idx, w, hist, w1, b1, wg, bg, w2, b2):
+def moe_experts_fwd_saved(x, idx, w, hist, w1, b1, wg, bg, w2, b2, drops=None):
     T, k = idx.shape; E = w1.shape[0]
     order = torch.argsort(idx.flatten(), stable=True)          # row -> item
     perm = torch.empty_like(order); perm[order] = torch.arange(T * k)
@@ -99,7 +99,7 @@ def moe_experts_fwd_saved(x, idx, w, hist, w1, b1, wg, bg, w2, b2):
     out = (w.unsqueeze(-1) * yp[perm].view(T, k, -1)).sum(1)
     return out, (xp, a, g, h, yp, perm, off)
 MIRRORS['moe_experts_fwd_saved'] = moe_experts_fwd_saved
-def moe_experts_bwd(dout, saved, idx, w, scale, w1g_t, w2_t, E):
+def moe_experts_bwd(dout, saved, idx, w, scale, w1g_t, w2_t, E, drops=None):
     xp, a, g, h, yp, perm, off = saved
     T, k = idx.shape; M = xp.shape[0]; ff = a.shape[1]
     dyp = torch.empty_like(yp); dw = torch.empty_like(w)

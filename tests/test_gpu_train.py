@@ -172,9 +172,8 @@ def test_train_steps_with_dropout():
     losses = [float(tr.train_step(inp)) for _ in range(8)]
     assert all(l == l for l in losses) and losses[-1] < losses[0]
     m32 = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.1).to(dev).train()
-    import pytest
-    with pytest.raises(NotImplementedError):
-        m32(*args)
+    y32a, y32b = m32(*args).detach(), m32(*args).detach()                # the fp32 exact path draws the same kind of masks
+    assert torch.isfinite(y32a).all() and not torch.equal(y32a, y32b)
 
 
 def test_optimizer_steps_reach_the_bf16_operands():

@@ -399,9 +399,43 @@ class RMSNormFn(torch.autograd.Function):
         return dx, dw, None
 
 
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout in training mode on a (rows, cols) tensor: y = x o mask(seed) * 1/(1-p); the backward applies the same
+    stateless mask to the incoming gradient (nothing is stored)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.ps = (p, seed)
+        return ops.dropout(x, p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(dy.contiguous(), *ctx.ps), None, None
+
+
+def drop_rows(x2: torch.Tensor, drop: torch.nn.Dropout, training: bool) -> torch.Tensor:
+    """`drop(x)` of a reference forward on a 2-D tensor: identity in eval mode or with p = 0."""
+    if not training or drop.p <= 0.0:
+        return x2
+    return DropoutFn.apply(x2.contiguous(), float(drop.p), ops.next_dropout_seed())
+
+
+def drop_any(x: torch.Tensor, drop: torch.nn.Dropout, training: bool) -> torch.Tensor:
+    if not training or drop.p <= 0.0:
+        return x
+    return drop_rows(x.reshape(-1, x.shape[-1]), drop, training).view(x.shape)
+
+
+def has_dropout(module: torch.nn.Module) -> bool:
+    """True when `module` is in training mode and any nn.Dropout inside it has p > 0."""
+    return module.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in module.modules())
+
+
 def glu_expert_fn(e, x2: torch.Tensor) -> torch.Tensor:
-    """GLUExpert.forward (moe.py:44-49) on (rows, d) with gradients: three LinearFn GEMMs around SwigluFn."""
-    return linear_fn(SwigluFn.apply(linear_fn(x2, e.linear1), linear_fn(x2, e.gate)), e.linear2)
+    """GLUExpert.forward (moe.py:44-49) on (rows, d) with gradients: three LinearFn GEMMs around SwigluFn, the expert's
+    dropout on the hidden rows in training mode (moe.py:48)."""
+    h = SwigluFn.apply(linear_fn(x2, e.linear1), linear_fn(x2, e.gate))
+    return linear_fn(drop_rows(h, e.dropout, e.training), e.linear2)
 
 
 class MoEExpertsFn(torch.autograd.Function):
@@ -411,11 +445,12 @@ class MoEExpertsFn(torch.autograd.Function):
     linear2.weight, linear2.bias) in expert order; `stacks` = their [E, ...] copies."""
 
     @staticmethod
-    def forward(ctx, x2, gate_w, gate_b, idx, w, hist, scale, stacks, *params):
+    def forward(ctx, x2, gate_w, gate_b, idx, w, hist, scale, stacks, drops, *params):
         w1, b1, wg, bg, w2, b2 = stacks
-        out, saved = ops.moe_experts_fwd_saved(x2, idx, w, hist, w1, b1, wg, bg, w2, b2)
+        out, saved = ops.moe_experts_fwd_saved(x2, idx, w, hist, w1, b1, wg, bg, w2, b2, drops=drops)
         ctx.save_for_backward(x2, gate_w, idx, w, w1, wg, w2, *saved)
         ctx.scale = scale
+        ctx.drops = drops
         return out
 
     @staticmethod
@@ -424,20 +459,28 @@ class MoEExpertsFn(torch.autograd.Function):
         E, ff, d = w1.shape
         w1g_t = torch.cat([w1, wg], 1).transpose(1, 2).contiguous()          # [E, d, 2 ff]
         w2_t = w2.transpose(1, 2).contiguous()                               # [E, ff, d_out]
-        dx_e, dlogits, dW1g, db1g, dW2, db2 = ops.moe_experts_bwd(dout, tuple(saved), idx, w, ctx.scale, w1g_t, w2_t, E)
+        dx_e, dlogits, dW1g, db1g, dW2, db2 = ops.moe_experts_bwd(dout, tuple(saved), idx, w, ctx.scale, w1g_t, w2_t, E, drops=ctx.drops)
         dgate_w = _gemm_dw(dlogits, x2, d)
         _, dgate_b = ops.dy_prep(dlogits, None, False, 1.0, 0, F32, want_dz=False)
         dx = ops.axpy(dx_e, _gemm_dx(dlogits, gate_w.detach().contiguous(), d), 1.0)
         grads = []
         for e in range(E):
             grads += [dW1g[e, :ff], db1g[e, :ff], dW1g[e, ff:], db1g[e, ff:], dW2[e], db2[e]]
-        return (dx, dgate_w, dgate_b, None, None, None, None, None, *grads)
+        return (dx, dgate_w, dgate_b, None, None, None, None, None, None, *grads)
 
 
-def moe_experts_fn(experts, gate, x2, idx, w, hist, scale, stacks):
+def moe_experts_fn(experts, gate, x2, idx, w, hist, scale, stacks, layer_dropout=None, training=False):
+    """layer_dropout: the MoE layer's nn.Dropout (applied to every expert output row, moe.py:197); the experts' own dropout
+    (hidden rows, moe.py:48) is read from experts[0] (all experts are clones of one GLUExpert)."""
     params = [p for e in experts for p in (e.linear1.weight, e.linear1.bias, e.gate.weight, e.gate.bias, e.linear2.weight, e.linear2.bias)]
     k = idx.shape[-1]
-    return MoEExpertsFn.apply(x2, gate.weight, gate.bias, idx.reshape(-1, k), w.reshape(-1, k), hist, scale, stacks, *params)
+    drops = None
+    if training:
+        p_h = float(experts[0].dropout.p)
+        p_o = float(layer_dropout.p) if layer_dropout is not None else 0.0
+        if p_h > 0 or p_o > 0:
+            drops = (p_h, ops.next_dropout_seed(), p_o, ops.next_dropout_seed())
+    return MoEExpertsFn.apply(x2, gate.weight, gate.bias, idx.reshape(-1, k), w.reshape(-1, k), hist, scale, stacks, drops, *params)
 
 
 class GqaAttnFn(torch.autograd.Function):
@@ -445,16 +488,17 @@ class GqaAttnFn(torch.autograd.Function):
     out (n,b,hq,d) (sequence-first, :159); query head h*g+gi reads kv head h."""
 
     @staticmethod
-    def forward(ctx, q, k, v, causal, q_scale):
+    def forward(ctx, q, k, v, causal, q_scale, dropout=None):
         b, n, hq, d = q.shape
         s, hk = k.shape[1], k.shape[2]
         out = torch.empty((n, b, hq, d), device=q.device, dtype=q.dtype)
         lse = torch.empty((b * hq, n), device=q.device, dtype=F32)
         ops.attention(q, k, v, out, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d, q_strides=(n * hq * d, hq * d),
                       k_strides=(s * hk * d, hk * d), v_strides=(s * hk * d, hk * d), o_strides=(hq * d, b * hq * d),
-                      causal=causal, q_scale=q_scale, lse=lse)
+                      causal=causal, q_scale=q_scale, lse=lse, dropout=dropout)
         ctx.save_for_backward(q, k, v, out, lse)
         ctx.meta = (causal, q_scale)
+        ctx.dropout = dropout
         return out
 
     @staticmethod
@@ -469,8 +513,8 @@ class GqaAttnFn(torch.autograd.Function):
         ops.attention_bwd(q, k, v, out, dout, lse, None, dq, dk, dv, None, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d,
                           q_strides=(n * hq * d, hq * d), k_strides=(s * hk * d, hk * d), v_strides=(s * hk * d, hk * d),
                           o_strides=(hq * d, b * hq * d), do_strides=(hq * d, b * hq * d), dq_strides=(n * hq * d, hq * d),
-                          dkv_strides=(s * hk * d, hk * d), causal=causal, q_scale=q_scale)
-        return dq, dk, dv, None, None
+                          dkv_strides=(s * hk * d, hk * d), causal=causal, q_scale=q_scale, dropout=ctx.dropout)
+        return dq, dk, dv, None, None, None
 
 
 class MambaCoreFn(torch.autograd.Function):
@@ -517,13 +561,14 @@ class AttnRowsFn(torch.autograd.Function):
     need_p the per-head probabilities (B*H, Lq, Lk) are returned as a second, non-differentiable output."""
 
     @staticmethod
-    def forward(ctx, q, k, v, er, B, Lq, Lk, H, causal, qs, ks, need_p):
+    def forward(ctx, q, k, v, er, B, Lq, Lk, H, causal, qs, ks, need_p, dropout=None):
         E = q.shape[1]
+        ctx.dropout = dropout
         out = torch.empty_like(q)
         lse = torch.empty((B * H, Lq), device=q.device, dtype=F32)
         p_out = torch.empty((B * H, Lq, Lk), device=q.device, dtype=F32) if need_p else None
         ops.attention(q, k, v, out, B=B, Hq=H, Hkv=H, Lq=Lq, Lk=Lk, dh=E // H, q_strides=qs, k_strides=ks, v_strides=ks, o_strides=qs,
-                      causal=causal, Er=er, lse=lse, p_out=p_out)
+                      causal=causal, Er=er, lse=lse, p_out=p_out, dropout=dropout)
         ctx.save_for_backward(q, k, v, out, lse, er)
         ctx.meta = (B, Lq, Lk, H, causal, qs, ks)
         if need_p:
@@ -540,8 +585,9 @@ class AttnRowsFn(torch.autograd.Function):
         dq, dk, dv = torch.empty_like(q), torch.zeros_like(k), torch.zeros_like(v)
         der = torch.zeros_like(er) if er is not None else None
         ops.attention_bwd(q, k, v, out, dout, lse, er, dq, dk, dv, der, B=B, Hq=H, Hkv=H, Lq=Lq, Lk=Lk, dh=E // H, q_strides=qs,
-                          k_strides=ks, v_strides=ks, o_strides=qs, do_strides=qs, dq_strides=qs, dkv_strides=ks, causal=causal)
-        return dq, dk, dv, der, None, None, None, None, None, None, None, None
+                          k_strides=ks, v_strides=ks, o_strides=qs, do_strides=qs, dq_strides=qs, dkv_strides=ks, causal=causal,
+                          dropout=ctx.dropout)
+        return dq, dk, dv, der, None, None, None, None, None, None, None, None, None
 
 
 def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
@@ -573,6 +619,7 @@ def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
             raise RuntimeError("RPR attention needs len_q == len_k <= er_len (got %d, %d, er_len %d); the reference "
                                "fails in _skew for longer inputs (rpr.py:426-450)" % (L, S, module.Er.shape[0]))
         er = module.Er
-    ctxv, p = AttnRowsFn.apply(q, k, v, er, B, L, S, H, causal, (E, B * E), (E, B * E), bool(need_weights))
+    drop = (float(module.dropout), ops.next_dropout_seed()) if (module.training and module.dropout > 0) else None   # rpr.py:412
+    ctxv, p = AttnRowsFn.apply(q, k, v, er, B, L, S, H, causal, (E, B * E), (E, B * E), bool(need_weights), drop)
     out = linear_fn(ctxv, module.out_proj).view(L, B, E)
     return out, (p.view(B, H, L, S).sum(dim=1) / H if need_weights else None)           # rpr.py:419-422

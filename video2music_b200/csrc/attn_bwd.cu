@@ -48,6 +48,11 @@ __global__ void __launch_bounds__(BNW * 32) attn_bwd_kernel(AttnBwdParams p, int
   const size_t doo = (size_t)b * p.do_sb + (size_t)hq * DH, dqo = (size_t)b * p.dq_sb + (size_t)hq * DH;
   const bool has_er = p.Er != nullptr;
   const int nr = has_er ? min(i0 + nrows, p.er_len) : 0;          // distances [0, nr) are needed
+  // the forward's probability dropout: same stateless mask (seed, (b*Hq+h)*Lq + i, j).  With Pd = P o M * s:
+  //   dV = Pd^T dO,  dS = P o (M * s * (dO V^T) - D),  D_i = dO_i . O_i  (unchanged, O = Pd V)
+  const bool drop_on = p.drop_scale != 0.f;
+  const uint32_t dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0u);
+  const uint32_t drow0 = (uint32_t)bh * (uint32_t)p.Lq + (uint32_t)i0;
 
   auto load_er = [&]() {
     for (int idx = tid; idx < nr * DH; idx += BNW * 32) {
@@ -145,7 +150,8 @@ __global__ void __launch_bounds__(BNW * 32) attn_bwd_kernel(AttnBwdParams p, int
 #pragma unroll
       for (int e = 0; e < DH / 8; ++e) acc[e] = 0.f;
       for (int i = 0; i < nrows; ++i) {
-        const float pij = Ps[i * lk_pad + j];
+        float pij = Ps[i * lk_pad + j];
+        if (drop_on) pij = drop_keep(dseed, drow0 + (uint32_t)i, (uint32_t)j, p.drop_thresh) ? pij * p.drop_scale : 0.f;   // dV uses the dropped P
 #pragma unroll
         for (int e = 0; e < DH / 8; ++e) acc[e] = fmaf(pij, dOs[i * DH + d0 + e], acc[e]);
       }
@@ -174,7 +180,9 @@ __global__ void __launch_bounds__(BNW * 32) attn_bwd_kernel(AttnBwdParams p, int
 #pragma unroll
     for (int r = 0; r < BRPW; ++r) {
       float* ps = Ps + (r0 + r) * lk_pad + j;
-      *ps = *ps * (acc[r] - Dsh[r0 + r]);
+      float dp = acc[r];                            // d(dropped P); d(P) = mask * scale * it
+      if (drop_on) dp = drop_keep(dseed, drow0 + (uint32_t)(r0 + r), (uint32_t)j, p.drop_thresh) ? dp * p.drop_scale : 0.f;
+      *ps = *ps * (dp - Dsh[r0 + r]);
     }
   }
   __syncthreads();                               // dS complete, V no longer needed -> Er band again

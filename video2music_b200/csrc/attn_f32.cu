@@ -130,7 +130,16 @@ __global__ void __launch_bounds__(NW * 32) attn_f32_kernel(AttnParams p, int lk_
     }
     sum = warp_sum(sum);
     const float inv = lim > 0 ? 1.f / sum : 0.f;
-    for (int j = lane; j < nk; j += 32) pr[j] = (j < lim) ? pr[j] * inv : 0.f;
+    if (p.drop_scale != 0.f) {
+      // training: inverted dropout of the probabilities (rpr.py:407 / F.multi_head_attention_forward): the same stateless
+      // mask (seed, (b*Hq+h)*Lq + i, j) as the tensor-core kernels; the returned weights are the dropped ones, as in torch
+      const uint32_t dseed = p.drop_seed + (p.drop_seed_dev ? *p.drop_seed_dev : 0u);
+      const uint32_t drow = (uint32_t)bh * (uint32_t)p.Lq + (uint32_t)i;
+      for (int j = lane; j < nk; j += 32)
+        pr[j] = (j < lim && drop_keep(dseed, drow, (uint32_t)j, p.drop_thresh)) ? pr[j] * inv * p.drop_scale : 0.f;
+    } else {
+      for (int j = lane; j < nk; j += 32) pr[j] = (j < lim) ? pr[j] * inv : 0.f;
+    }
     if (p.lse && lane == 0 && i < p.Lq) p.lse[(size_t)bh * p.Lq + i] = mx + logf(sum);
     if (p.p_out && i < p.Lq) {
       float* po = p.p_out + ((size_t)bh * p.Lq + i) * p.Lk;

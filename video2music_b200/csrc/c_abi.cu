@@ -74,7 +74,6 @@ int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float
                  int32_t K, const v2m_epilogue* ep, void* stream) {
   GemmEpilogue g = to_ep(ep);
   V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32: bf16 residual not supported on the fp32 path");
-  V2M_REQUIRE(g.drop_scale == 0.f, "v2m_gemm_f32: fused dropout exists on the bf16 tensor-core path only");
   return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream));
 }
 
@@ -82,7 +81,6 @@ int v2m_gemm_f32_strided(const float* A, int32_t a_rs, int32_t a_cs, const float
                          int32_t ldc, int32_t M, int32_t N, int32_t K, const v2m_epilogue* ep, void* stream) {
   GemmEpilogue g = to_ep(ep);
   V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32_strided: bf16 residual not supported on the fp32 path");
-  V2M_REQUIRE(g.drop_scale == 0.f, "v2m_gemm_f32_strided: fused dropout exists on the bf16 tensor-core path only");
   return gemm_f32(A, a_rs, W, w_rs, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream), a_cs, w_cs);
 }
 
@@ -107,7 +105,6 @@ int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {
   p.causal = a->causal; p.Er = a->Er; p.er_len = a->er_len; p.q_scale = a->q_scale;
   p.lse = a->lse; p.p_out = a->p_out;
   p.drop_scale = a->drop_scale; p.drop_thresh = a->drop_thresh; p.drop_seed = a->drop_seed; p.drop_seed_dev = a->drop_seed_dev;
-  V2M_REQUIRE(dtype == V2M_BF16 || p.drop_scale == 0.f, "v2m_attn_fwd: probability dropout exists on the bf16 path only");
   if (dtype == V2M_F32) return attn_fwd_f32(p, static_cast<cudaStream_t>(stream));
   if (dtype == V2M_BF16) return attn_fwd_bf16_tc(p, static_cast<cudaStream_t>(stream));
   set_last_error("v2m_attn_fwd: dtype %d unsupported", dtype);
@@ -119,7 +116,6 @@ int v2m_attn_bwd(const v2m_attn_bwd_t* a, void* stream) {
   static_assert(sizeof(v2m_attn_bwd_t) == sizeof(AttnBwdParams), "v2m_attn_bwd_t must mirror AttnBwdParams");
   AttnBwdParams p;
   memcpy(&p, a, sizeof(p));
-  V2M_REQUIRE(p.drop_scale == 0.f, "v2m_attn_bwd: probability dropout exists on the tensor-core path only");
   return attn_bwd(p, static_cast<cudaStream_t>(stream));
 }
 

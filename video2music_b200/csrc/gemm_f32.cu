@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     __syncthreads();
   }
 
+  const uint32_t dseed = ep.drop_seed + (ep.drop_seed_dev ? *ep.drop_seed_dev : 0u);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -89,7 +90,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
       if (n < ep.alpha_cols) v *= ep.alpha;
       if (ep.relu) v = fmaxf(v, 0.f);
       if (ep.row_scale) v = fmaf(rs, ep.col_vec[n], v);
+      // training: inverted dropout with the same stateless mask as the bf16 epilogue (dy_prep recomputes it in backward)
+      if (ep.drop_scale != 0.f && !ep.drop_after_res) v = drop_keep(dseed, m, n, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
       if (res) v += res[n];  // fp32 path: residual is always fp32
+      if (ep.drop_scale != 0.f && ep.drop_after_res) v = drop_keep(dseed, m, n, ep.drop_thresh) ? v * ep.drop_scale : 0.f;
       C[epi_out_index(ep, m, n, ldc)] = v;
     }
   }

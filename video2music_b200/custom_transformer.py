@@ -65,8 +65,7 @@ class CustomMultiheadAttention(nn.Module):
         from .rpr import is_causal_mask
         if key_padding_mask is not None:
             raise NotImplementedError("key_padding_mask is not used by the reference's models")
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built for this module")
+        drop = (float(self.dropout), ops.next_dropout_seed()) if (self.training and self.dropout > 0) else None
         L, B, E = query.shape
         S = key.shape[0]
         H, dh = self.num_heads, self.head_dim
@@ -89,7 +88,7 @@ class CustomMultiheadAttention(nn.Module):
         p_out = torch.empty((B * H, L, S), device=q.device, dtype=torch.float32) if need_weights else None
         ops.attention(q, k, v, out, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=(q.stride(0), B * q.stride(0)),
                       k_strides=(k.stride(0), B * k.stride(0)), v_strides=(v.stride(0), B * v.stride(0)), o_strides=(E, B * E),
-                      causal=causal, q_scale=float(dh) ** -0.5, p_out=p_out)
+                      causal=causal, q_scale=float(dh) ** -0.5, p_out=p_out, dropout=drop)   # F.multi_head_attention_forward's dropout_p
         y = ops.linear(out, self.out_proj.weight.detach(), self.out_proj.bias.detach()).view(L, B, E)
         if not need_weights:
             return y, None

@@ -19,8 +19,8 @@ def scaled_dot_product_gqa(query, key, value, num_heads=None, dropout: float = 0
     elif not query.ndim == key.ndim == value.ndim == 4:
         raise ValueError(f"Expected query, key, and value to be 4-dimensional, but got shapes "
                          f"{query.shape}, {key.shape}, and {value.shape}.")
-    if attn_mask is not None or key_padding_mask is not None or need_weights or dropout > 0.0:
-        raise NotImplementedError("attn_mask / key_padding_mask / need_weights / dropout are never used by the reference's "
+    if attn_mask is not None or key_padding_mask is not None or need_weights:
+        raise NotImplementedError("attn_mask / key_padding_mask / need_weights are never used by the reference's "
                                   "callers (grouped_query_attention.py:333-342)")
     b, n, hq, d = query.shape
     bk, s, hk, dk = key.shape
@@ -34,8 +34,13 @@ def scaled_dot_product_gqa(query, key, value, num_heads=None, dropout: float = 0
         scale = d ** 0.5
     dt = query.dtype
     from . import autograd as ag
-    if ag.tracking(query, key, value) and dt == torch.float32:             # gradients through our attention backward kernel
-        return ag.GqaAttnFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), bool(is_causal), 1.0 / scale), None
+    # dropout > 0: F.dropout(attention, p) with its default training=True, i.e. ALWAYS applied (grouped_query_attention.py:152-153;
+    # MultiheadGQA never passes it, :333-342)
+    drop = (float(dropout), ops.next_dropout_seed()) if dropout > 0.0 else None
+    if (ag.tracking(query, key, value) or drop is not None) and dt == torch.float32:   # gradients through our attention backward kernel
+        return ag.GqaAttnFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), bool(is_causal), 1.0 / scale, drop), None
+    if drop is not None:
+        raise NotImplementedError("scaled_dot_product_gqa: dropout > 0 is built on the fp32 path")
     q, k, v = (t.detach().contiguous() for t in (query, key, value))
     out = torch.empty((n, b, hq, d), device=q.device, dtype=dt)          # sequence-first, :159
     ops.attention(q, k, v, out, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d,

@@ -160,8 +160,9 @@ class _FFN(nn.Sequential):
     def forward(self, x):
         shp = x.shape
         ag = _ag()
-        if ag.tracking(x, self):
-            return ag.linear_fn(ag.linear_fn(ag.rows_f32(x), self[0], relu=True), self[3]).view(shp)
+        drop = self.training and self[2].p > 0
+        if ag.tracking(x, self) or drop:
+            return ag.linear_fn(ag.drop_rows(ag.linear_fn(ag.rows_f32(x), self[0], relu=True), self[2], self.training), self[3]).view(shp)
         x2 = x.reshape(-1, shp[-1]).float().contiguous()
         h = ops.linear(x2, self[0].weight.detach(), self[0].bias.detach(), relu=True)
         return ops.linear(h, self[3].weight.detach(), self[3].bias.detach()).view(shp)
@@ -202,15 +203,14 @@ class BiMambaEncoderLayer(nn.Module):
         self.ffn2 = _FFN(config.d_model, dim_feedforward, dropout)
 
     def forward(self, x):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built; use eval() or dropout=0")
         x = x.float()
+        dr = lambda t: _ag().drop_any(t, self.dropout, self.training)            # self.dropout(.) of bimamba.py:73,79,87,93
         x_flip = torch.flip(x, dims=[1])
-        x_f = _add_norm(self.norm1, self.mamba_forward(x), x)
-        x_f = _add_norm(self.norm2, self.ffn1(x_f), x_f)
+        x_f = _add_norm(self.norm1, dr(self.mamba_forward(x)), x)
+        x_f = _add_norm(self.norm2, dr(self.ffn1(x_f)), x_f)
         x_b = torch.flip(self.mamba_backward(x_flip), dims=[1])
-        x_b = _add_norm(self.norm3, x_b, x)
-        x_b = _add_norm(self.norm4, self.ffn2(x_f), x_b)
+        x_b = _add_norm(self.norm3, dr(x_b), x)
+        x_b = _add_norm(self.norm4, dr(self.ffn2(x_f)), x_b)
         return _sum(x_f, x_b)
 
 
@@ -241,20 +241,19 @@ class BiMambaEncoderLayer_V1(nn.Module):
         self.ffn = _FFN(config.d_model, dim_feedforward, dropout) if moe_layer is None else copy.deepcopy(moe_layer)
 
     def forward(self, x):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built; use eval() or dropout=0")
         x = x.float().contiguous()
+        dr = lambda t: _ag().drop_any(t, self.dropout, self.training)            # self.dropout(.) of bimamba.py:142,151,162,170,178,188
         x_flip = torch.flip(x, dims=[1])
         if self.norm_first:                                                      # bimamba.py:141-165
-            x_f = _sum(x, self.mamba_forward(_norm_only(self.norm1, x)))
-            x_b = torch.flip(self.mamba_backward(_norm_only(self.norm2, x_flip)), dims=[1])
+            x_f = _sum(x, dr(self.mamba_forward(_norm_only(self.norm1, x))))
+            x_b = dr(torch.flip(self.mamba_backward(_norm_only(self.norm2, x_flip)), dims=[1]))
             x_b = _sum(x, x_b)
             x = _sum(x_f, x_b)
-            return _sum(x, self.ffn(_norm_only(self.norm3, x)))
-        x_f = _add_norm(self.norm1, self.mamba_forward(x), x)                    # :168-189
-        x_b = _add_norm(self.norm2, torch.flip(self.mamba_backward(x_flip), dims=[1]), x)
+            return _sum(x, dr(self.ffn(_norm_only(self.norm3, x)).float()))
+        x_f = _add_norm(self.norm1, dr(self.mamba_forward(x)), x)                # :168-189
+        x_b = _add_norm(self.norm2, dr(torch.flip(self.mamba_backward(x_flip), dims=[1])), x)
         x = _sum(x_f, x_b)
-        return _add_norm(self.norm3, self.ffn(x).float(), x)
+        return _add_norm(self.norm3, dr(self.ffn(x).float()), x)
 
 
 class BiMambaEncoder(nn.Module):

@@ -36,12 +36,13 @@ class GLUExpert(nn.Module):
         self.dropout = nn.Dropout(dropout)
 
     def forward(self, x):
-        """x (..., d) -> linear2((linear1 x) * silu(gate x))  (moe.py:44-49), eval semantics."""
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built yet")
+        """x (..., d) -> linear2(dropout((linear1 x) * silu(gate x)))  (moe.py:44-49)."""
         shp = x.shape
         from . import autograd as ag
-        if ag.tracking(x, self):                                          # training: forward and backward on our kernels
+        drop = self.training and self.dropout.p > 0
+        if drop and getattr(self, "compute_dtype", torch.float32) != torch.float32:
+            raise NotImplementedError("training-mode dropout of GLUExpert is built on the fp32 path")
+        if ag.tracking(x, self) or drop:                                  # training: forward and backward on our kernels
             return ag.glu_expert_fn(self, ag.rows_f32(x)).view(shp[:-1] + (self.linear2.out_features,))
         x2 = x.detach().reshape(-1, shp[-1]).float().contiguous()
         return _glu(self, x2).view(shp[:-1] + (self.linear2.out_features,))
@@ -179,8 +180,6 @@ class MoELayer(nn.Module):
         self.last_selected_experts = None
 
     def forward(self, x):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built yet")
         if hasattr(self, "topk_scheduler") and self.training:            # moe.py:168-172
             self.topk_scheduler.step()
             k = self.topk_scheduler.getK()
@@ -198,8 +197,12 @@ class MoELayer(nn.Module):
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)
         from . import autograd as ag
-        if ag.tracking(x, self) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:180-199
-            return ag.moe_experts_fn(self.experts, self.gate, ag.rows_f32(x), idx, w, hist, 1.0 / t, _stacked(self.experts)).view(shp)
+        drop = ag.has_dropout(self)                                      # nn.Dropout sites of moe.py:48,197 in training mode
+        if drop and getattr(self, "compute_dtype", torch.float32) != torch.float32:
+            raise NotImplementedError("training-mode dropout of the MoE layers is built on the fp32 path")
+        if (ag.tracking(x, self) or drop) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:180-199
+            return ag.moe_experts_fn(self.experts, self.gate, ag.rows_f32(x), idx, w, hist, 1.0 / t, _stacked(self.experts),
+                                     layer_dropout=self.dropout, training=self.training).view(shp)
         return _experts_forward(self.experts, x2, idx, w, hist, getattr(self, "compute_dtype", torch.float32)).view(shp)
 
 
@@ -228,8 +231,6 @@ class SharedMoELayer(nn.Module):
         self.last_selected_experts = None
 
     def forward(self, x):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built yet")
         if hasattr(self, "topk_scheduler") and self.training:            # moe.py:232-236
             self.topk_scheduler.step()
             k = self.topk_scheduler.getK()
@@ -253,9 +254,13 @@ class SharedMoELayer(nn.Module):
         if self.on_route is not None:
             self.on_route(self.last_selected_experts, hist, self.training)
         from . import autograd as ag
-        if ag.tracking(x, self) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:244-301
+        drop = ag.has_dropout(self)                                      # nn.Dropout sites of moe.py:48,295 in training mode
+        if drop and getattr(self, "compute_dtype", torch.float32) != torch.float32:
+            raise NotImplementedError("training-mode dropout of the MoE layers is built on the fp32 path")
+        if (ag.tracking(x, self) or drop) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:244-301
             xr = ag.rows_f32(x)
-            out = ag.moe_experts_fn(self.experts, self.gate, xr, idx, w, hist, 1.0 / t, _stacked(self.experts))
+            out = ag.moe_experts_fn(self.experts, self.gate, xr, idx, w, hist, 1.0 / t, _stacked(self.experts),
+                                    layer_dropout=self.dropout, training=self.training)
             return ag.AddFn.apply(out, ag.glu_expert_fn(self.shared_expert, xr), 1.0 / k).view(shp[:-1] + (self.d_model,))
         dt = getattr(self, "compute_dtype", torch.float32)
         out = _experts_forward(self.experts, x2, idx, w, hist, dt)

@@ -30,6 +30,49 @@ def drop_args(p: float, seed: int):
     return 256.0 / (256.0 - t), t, int(seed) & 0xFFFFFFFF
 
 
+_drop_state = {"calls": 0, "fixed": None}
+
+
+def next_dropout_seed() -> int:
+    """Seed of the next dropout site of a module forward: a new mask per site and per call, reproducible under
+    torch.manual_seed (the draws are a stateless hash, not torch's Philox stream), different on every rank."""
+    import torch.distributed as dist
+    st = _drop_state
+    st["calls"] += 1
+    base = st["fixed"] if st["fixed"] is not None else torch.initial_seed()
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    return (base * 1000003 + st["calls"] * 7919 + rank * 104729) & 0xFFFFFFFF
+
+
+class fixed_dropout_seed:
+    """with fixed_dropout_seed(s): ...  -- the dropout sites inside draw seeds from (s, site index), the site index
+    restarting at every entry: two forwards under the same `s` see identical masks (tests, finite differences)."""
+
+    def __init__(self, seed: int):
+        self.seed = int(seed)
+
+    def __enter__(self):
+        self.prev = dict(_drop_state)
+        _drop_state["fixed"], _drop_state["calls"] = self.seed, 0
+        return self
+
+    def __exit__(self, *exc):
+        _drop_state.update(self.prev)
+        return False
+
+
+def dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+    """Inverted dropout of a 2-D fp32 / bf16 tensor: element (r, c) is kept iff drop_keep(seed, r, c) (the mask of the GEMM
+    epilogues and of dy_prep, see drop_args) and scaled by 256 / (256 - round(256 p)).  The same call on the incoming gradient
+    is the backward.  nn.Dropout in training mode (moe.py:48,197; bimamba.py:50-98; video_regression.py:203)."""
+    if p <= 0.0:
+        return x
+    assert x.dim() == 2
+    x = x if x.stride(1) == 1 else x.contiguous()
+    dz, _ = dy_prep(x, None, False, 1.0, 0, x.dtype, want_dz=True, dropout=(p, seed))
+    return dz
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, k: Optional[int] = None,
            relu: bool = False, alpha: float = 1.0, alpha_cols: int = 0,
            residual: Optional[torch.Tensor] = None, res_mod: int = 0,
@@ -38,7 +81,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            head_scatter: Optional[dict] = None, dropout: Optional[tuple] = None) -> torch.Tensor:
     """y = epilogue(x @ w[:, :k].T).  x (M, >=k) and w (N, >=k) are row-major 2-D tensors of the same
     dtype (fp32 -> SIMT exact GEMM, bf16 -> tcgen05 GEMM); leading dims are taken from the strides.
-    dropout = (p, seed, after_residual): inverted dropout fused into the epilogue (bf16 path), see drop_args()."""
+    dropout = (p, seed, after_residual): inverted dropout fused into the epilogue (both paths), see drop_args()."""
     require_device(x)
     assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
     assert x.dtype == w.dtype, (x.dtype, w.dtype)
@@ -313,10 +356,12 @@ def moe_experts_bf16(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: 
 
 
 def moe_experts_fwd_saved(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
-                          wg: torch.Tensor, bg: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor):
+                          wg: torch.Tensor, bg: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, drops=None):
     """Training-mode forward of `moe_experts`: same result, but the two halves of the SwiGLU pair are kept (a = x W1^T + b1,
     g = x Wg^T + bg) together with the permuted input, the hidden rows and the per-row expert outputs, which the backward
-    needs.  Returns (out, saved) with saved = (xp, a, g, h, yp, perm, off)."""
+    needs.  Returns (out, saved) with saved = (xp, a, g, h, yp, perm, off).
+    drops = (p_hidden, seed_hidden, p_out, seed_out): GLUExpert's dropout of the hidden rows (moe.py:48) and the layer's dropout
+    of each expert output row (moe.py:197) in training mode, masks over (permuted row, column); h and yp are saved dropped."""
     require_device(x)
     T, k = idx.shape
     E, ff, d = w1.shape
@@ -334,15 +379,19 @@ def moe_experts_fwd_saved(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, h
     check(lib.v2m_moe_grouped_gemm(ptr(xp), d, ptr(wg), ptr(bg), None, None, ff * d, ff, ptr(off), E, T * k, ptr(g), ff, ff, d, st))
     _lib.count_launches(4)
     h = swiglu(a, g)
+    if drops is not None and drops[0] > 0.0:
+        h = dropout(h, drops[0], drops[1])
     check(lib.v2m_moe_grouped_gemm(ptr(h), ff, ptr(w2), ptr(b2), None, None, d_out * ff, d_out, ptr(off), E, T * k, ptr(yp), d_out,
                                    d_out, ff, st))
+    if drops is not None and drops[2] > 0.0:
+        yp = dropout(yp, drops[2], drops[3])
     check(lib.v2m_moe_combine(ptr(yp), ptr(perm), ptr(w), ptr(out), T, k, d_out, st))
     _lib.count_launches(2)
     return out, (xp, a, g, h, yp, perm, off)
 
 
 def moe_experts_bwd(dout: torch.Tensor, saved, idx: torch.Tensor, w: torch.Tensor, scale: float, w1g_t: torch.Tensor,
-                    w2_t: torch.Tensor, n_experts: int):
+                    w2_t: torch.Tensor, n_experts: int, drops=None):
     """Backward of `moe_experts_fwd_saved`.  w1g_t [E, d, 2 ff] = (linear1 | gate) weights transposed, w2_t [E, ff, d_out].
     Returns (dx_experts (T, d), dlogits (T, E), dW1g (E, 2 ff, d), db1g (E, 2 ff), dW2 (E, d_out, ff), db2 (E, d_out))."""
     require_device(dout)
@@ -360,8 +409,12 @@ def moe_experts_bwd(dout: torch.Tensor, saved, idx: torch.Tensor, w: torch.Tenso
     ones = torch.ones((T, k), **f32)
     lib, st = load(), stream()
     check(lib.v2m_moe_combine_bwd(ptr(dout), ptr(yp), ptr(perm), ptr(w), ptr(idx), scale, T, k, d_out, E, ptr(dyp), ptr(dlogits), st))
+    if drops is not None and drops[2] > 0.0:                      # gradient of the dropped expert output -> of the GEMM output
+        dyp = dropout(dyp, drops[2], drops[3])
     check(lib.v2m_moe_grouped_dw(ptr(dyp), d_out, ptr(h), ff, ptr(off), E, ptr(dW2), ptr(db2), d_out, ff, st))
     check(lib.v2m_moe_grouped_gemm(ptr(dyp), d_out, ptr(w2_t), None, None, None, ff * d_out, 0, ptr(off), E, M, ptr(dh), ff, ff, d_out, st))
+    if drops is not None and drops[0] > 0.0:                      # ... of the dropped hidden rows -> of the SwiGLU output
+        dh = dropout(dh, drops[0], drops[1])
     check(lib.v2m_swiglu_bwd(ptr(a), ptr(g), ptr(dh), ptr(dag), M, ff, st))
     check(lib.v2m_moe_grouped_dw(ptr(dag), 2 * ff, ptr(xp), d, ptr(off), E, ptr(dW1g), ptr(db1g), 2 * ff, d, st))
     check(lib.v2m_moe_grouped_gemm(ptr(dag), 2 * ff, ptr(w1g_t), None, None, None, d * 2 * ff, 0, ptr(off), E, M, ptr(dxp), d, d, 2 * ff, st))

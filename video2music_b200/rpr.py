@@ -125,9 +125,11 @@ class MultiheadAttentionRPR(nn.Module):
     def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None, **kwargs):
         if key_padding_mask is not None:
             raise NotImplementedError("key_padding_mask is not used by the AMT path (rpr.py:55-57 passes None)")
-        if self.training and self.dropout > 0:
-            raise NotImplementedError("attention dropout > 0 in training mode is not built yet")
-        if torch.is_grad_enabled() and (query.requires_grad or self.in_proj_weight.requires_grad):
+        drop = self.training and self.dropout > 0            # dropout of the probabilities (rpr.py:412), training mode
+        if drop and _compute_dtype(self) != torch.float32:
+            raise NotImplementedError("module-level attention dropout runs on the fp32 path; bf16 training with dropout goes "
+                                      "through VideoMusicTransformer (autograd.amt_forward_autograd)")
+        if drop or (torch.is_grad_enabled() and (query.requires_grad or self.in_proj_weight.requires_grad)):
             from .autograd import mha_rpr_autograd
             return mha_rpr_autograd(self, query, key, value, need_weights, attn_mask)
         return self._forward_impl(query, key, value, need_weights, attn_mask)
@@ -215,23 +217,23 @@ class TransformerDecoderLayerRPR(nn.Module):
                 memory_key_padding_mask=None, **kwargs):
         if memory_mask is not None or tgt_key_padding_mask is not None or memory_key_padding_mask is not None:
             raise NotImplementedError("memory_mask / key padding masks are not used by the AMT path")
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built yet")
         dt = _compute_dtype(self)
         self.self_attn.compute_dtype = dt
         self.multihead_attn.compute_dtype = dt
         L, B, E = tgt.shape
         from . import autograd as ag
-        if ag.tracking(tgt, memory, self):                       # stand-alone training of the layer (fp32): autograd Functions
+        if ag.tracking(tgt, memory, self) or ag.has_dropout(self):     # stand-alone training of the layer (fp32): autograd Functions
             if dt != torch.float32:
                 raise NotImplementedError("module-level autograd runs on the fp32 path; bf16 training goes through "
                                           "VideoMusicTransformer (autograd.amt_forward_autograd)")
             add_ln = lambda x, y, n: ag.LayerNormFn.apply(ag.AddFn.apply(ag.rows_f32(x), ag.rows_f32(y), 1.0), n.weight, n.bias, n.eps)
+            tr = self.training
             tgt2 = self.self_attn(tgt, tgt, tgt, attn_mask=tgt_mask, need_weights=False)[0]
-            x = add_ln(tgt, tgt2, self.norm1)
+            x = add_ln(tgt, ag.drop_any(tgt2, self.dropout1, tr), self.norm1)                        # rpr.py:59
             tgt2 = self.multihead_attn(x.view(L, B, E), memory, memory, need_weights=False)[0]
-            x = add_ln(x, tgt2, self.norm2)
-            r = ag.AddFn.apply(x, ag.linear_fn(ag.linear_fn(x, self.linear1, relu=True), self.linear2), 1.0)
+            x = add_ln(x, ag.drop_any(tgt2, self.dropout2, tr), self.norm2)                           # :65
+            hdn = ag.drop_rows(ag.linear_fn(x, self.linear1, relu=True), self.dropout, tr)            # :67
+            r = ag.AddFn.apply(x, ag.drop_rows(ag.linear_fn(hdn, self.linear2), self.dropout3, tr), 1.0)   # :68
             return ag.LayerNormFn.apply(r, self.norm3.weight, self.norm3.bias, self.norm3.eps).view(L, B, E)
         tgt2 = self.self_attn(tgt, tgt, tgt, attn_mask=tgt_mask, need_weights=False)[0]                 # rpr.py:56-57
         tgt = self._add_ln(tgt, tgt2, self.norm1)                                                        # :58-59

@@ -156,13 +156,10 @@ class VideoMusicTransformer(nn.Module):
                 feature_emotion, mask=True):
         drop = float(self.dropout) if self.training else 0.0
         grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if drop > 0 and not (grad and self._w().dtype == torch.bfloat16):
-            raise NotImplementedError("dropout > 0 in training mode runs on the bf16 autograd path only "
-                                      "(set_compute_dtype(torch.bfloat16), gradients enabled), or use dropout=0.0 / eval()")
         dev = self._device()
         args = [t.to(dev) for t in (x, x_root, x_attr, feature_semantic_list, feature_key, feature_scene_offset,
                                     feature_motion, feature_emotion)]
-        if grad:
+        if grad or drop > 0:                  # training mode with dropout draws masks with or without gradients
             from .autograd import amt_forward_autograd
             seed = 0
             if drop > 0:                      # a fresh mask per forward call, reproducible under torch.manual_seed

@@ -44,14 +44,13 @@ class VideoRegression(nn.Module):
         self.classifier = nn.Sequential(nn.Linear(d_model, INSTRUMENT_SIZE), nn.Sigmoid())
 
     def get_feature(self, feature_semantic_list, feature_scene_offset, feature_motion, feature_emotion):
-        if self.training and self.dropout_layer.p > 0:
-            raise NotImplementedError("dropout > 0 in training mode is not built; use eval() or dropout=0")
         dev = self.regressor.weight.device
         vf = torch.cat([feature_semantic_list.float().to(dev), feature_emotion.float().to(dev)], dim=-1)   # :211-213
         B, L, F = vf.shape
         from . import autograd as ag
-        if ag.tracking(vf, self):
-            return self.model(ag.linear_fn(vf.reshape(B * L, F).contiguous(), self.in_proj[0]).view(B, L, self.d_model))
+        if ag.tracking(vf, self) or ag.has_dropout(self):
+            x = ag.drop_rows(ag.linear_fn(vf.reshape(B * L, F).contiguous(), self.in_proj[0]), self.in_proj[1], self.training)   # :203
+            return self.model(x.view(B, L, self.d_model))
         x = ops.linear(vf.reshape(B * L, F).contiguous(), self.in_proj[0].weight.detach(), self.in_proj[0].bias.detach())
         return self.model(x.view(B, L, self.d_model))
 
