@@ -241,6 +241,16 @@ int v2m_decode_probe(const v2m_decode* p, int32_t kind, int32_t reps, void* stre
  *       never materialised.  rmsnorm: mamba.py:483-489. */
 int v2m_mamba_conv_silu(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy, int32_t B, int32_t L,
                         int32_t ED, int32_t KW, void* stream);
+/* Recurrent single-token step, MambaBlock.step / ssm_step (mamba.py:407-470): one new token per video against the cache
+ * (h (B, ED, N) or NULL = zeros, inputs (B, ED, KW-1)).  step_conv: xs = silu(conv1d([in_old | x_new])[KW-1]) with x_new =
+ * xz[b*ldxz + e], in_new = the window shifted by one (mamba.py:419-425,435).  step_ssm: delta = softplus(dt_proj(dbc[:, :R])),
+ * h_new = exp(delta A) h_old + delta B x, y = h_new C + D x, out = y * silu(z) with dbc (B, R + 2N) = x_proj(xs) (mamba.py:437-465,
+ * 427-430).  Neither kernel writes to its inputs. */
+int v2m_mamba_step_conv(const float* xz, int64_t ldxz, const float* in_old, const float* w, const float* bias, float* xs, float* in_new,
+                        int32_t B, int32_t ED, int32_t KW, void* stream);
+int v2m_mamba_step_ssm(const float* xs, const float* dbc, int64_t lddbc, const float* dtw, const float* dtb, const float* A_log,
+                       const float* D, const float* z, int64_t ldz, const float* h_old, float* h_new, float* out, int32_t B, int32_t ED,
+                       int32_t N, int32_t R, void* stream);
 int64_t v2m_selective_scan_workspace(int32_t B, int32_t L, int32_t ED, int32_t N);   /* bytes of `ws` (0 when L <= 64) */
 int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,
                            const float* Bm, const float* Cm, int64_t ldbc, const float* D, const float* z, int64_t ldz, float* out,

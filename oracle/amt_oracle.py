@@ -511,6 +511,42 @@ def mamba_block_forward(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, dt
     return F.linear(out, g("out_proj.weight"), g("out_proj.bias"))                 # :288
 
 
+def mamba_block_step(sd: Dict[str, torch.Tensor], p: str, x: torch.Tensor, cache, dt_rank: int, d_state: int = 16):
+    """MambaBlock.step + ssm_step (mamba.py:407-470): one token x (B, D) against cache = (h (B, ED, N) or None, inputs (B, ED,
+    d_conv - 1)); returns (output (B, D), new cache).  The gate is y * silu(z) whatever use_version (:430)."""
+    g = lambda n: sd.get(p + n)
+    h, inputs = cache
+    xz = F.linear(x, g("in_proj.weight"), g("in_proj.bias"))                       # :417
+    xs, z = xz.chunk(2, dim=1)                                                     # :418
+    ED = xs.shape[1]
+    w = g("conv1d.weight")                                                         # (ED, 1, d_conv)
+    window = torch.cat([inputs, xs.unsqueeze(2)], dim=2)                           # :421-422
+    xc = F.conv1d(window, w, g("conv1d.bias"), padding=w.shape[-1] - 1, groups=ED)[:, :, w.shape[-1] - 1]
+    xc = F.silu(xc)                                                                # :424
+    A = -torch.exp(g("A_log").float())                                             # :443
+    dbc = F.linear(xc, g("x_proj.weight"))                                         # :446
+    delta, Bm, Cm = torch.split(dbc, [dt_rank, d_state, d_state], dim=-1)          # :448
+    delta = F.softplus(F.linear(delta, g("dt_proj.weight"), g("dt_proj.bias")))    # :450
+    dA = torch.exp(delta.unsqueeze(-1) * A)                                        # :452
+    BX = delta.unsqueeze(-1) * Bm.unsqueeze(1) * xc.unsqueeze(-1)                  # :453-455
+    if h is None:
+        h = torch.zeros(x.shape[0], ED, d_state)                                   # :457-458
+    h = dA * h + BX                                                                # :460
+    y = (h @ Cm.unsqueeze(-1)).squeeze(2) + g("D").float() * xc                    # :462-464
+    out = F.linear(y * F.silu(z), g("out_proj.weight"), g("out_proj.bias"))        # :428-431
+    return out, (h, torch.cat([inputs[:, :, 1:], xs.unsqueeze(2)], dim=2))         # :434-435
+
+
+def mamba_step(sd: Dict[str, torch.Tensor], x: torch.Tensor, caches, n_layers: int, dt_rank: int, d_state: int = 16, eps: float = 1e-5):
+    """Mamba.step over ResidualBlock.step (mamba.py:100-108,151-159): x = mixer.step(norm(x)) + x per layer."""
+    caches = list(caches)
+    for l in range(n_layers):
+        p = "layers.%d." % l
+        y, caches[l] = mamba_block_step(sd, p + "mixer.", rmsnorm(x, sd.get(p + "norm.weight"), eps), caches[l], dt_rank, d_state)
+        x = y + x
+    return x, caches
+
+
 def mamba_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, n_layers: int, dt_rank: int, d_state: int = 16,
                   eps: float = 1e-5, use_version: int = 0) -> torch.Tensor:
     """Mamba.forward over ResidualBlocks (mamba.py:91-98, 144-149): x = mixer(norm(x)) + x."""

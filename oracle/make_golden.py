@@ -528,6 +528,33 @@ def golden_mamba(ref):
     _save("mamba.pt", out)
 
 
+def golden_mamba_step(ref):
+    """Recurrent single-token inference (MambaBlock.step / ResidualBlock.step / Mamba.step, mamba.py:100-108,151-159,407-470):
+    T tokens fed one by one from the empty cache (None, zeros); outputs of every step and the final cache.  Also stored: the
+    same tokens through forward() -- for use_version 0 the two agree (the reference's own consistency), for use_version 1
+    they differ because step() ignores the mamba+ gate (mamba.py:430 vs :283-287)."""
+    out = {}
+    for name, ver, layers in (("block_v0", 0, 0), ("block_v1", 1, 0), ("stack", 0, 2)):
+        cfg = ref.mamba.MambaConfig(d_model=128, n_layers=max(layers, 1), use_version=ver)
+        m = (ref.mamba.Mamba(cfg) if layers else ref.mamba.MambaBlock(cfg)).eval()
+        sd = _load_weights(m, 41 + ver + layers)
+        spec = dict(B=3, T=20, d_model=128, seed=51 + ver + layers, weight_seed=41 + ver + layers, use_version=ver, n_layers=layers)
+        x = syn.unit_uniform((spec["B"], spec["T"], 128), syn._gen(spec["seed"], "x"))
+        empty = lambda: (None, torch.zeros(spec["B"], cfg.d_inner, cfg.d_conv - 1))
+        cache = [empty() for _ in range(layers)] if layers else empty()
+        ys = []
+        with torch.no_grad():
+            for t in range(spec["T"]):
+                y, cache = m.step(x[:, t], cache)
+                ys.append(y.clone())
+            full = m(x)
+        last = cache[-1] if layers else cache
+        out[name] = dict(spec=spec, weights_checksum=syn.checksum(sd), y=torch.stack(ys, 1), y_forward=full.clone(),
+                         h=last[0].clone(), inputs=last[1].clone())
+        print(name, "step vs forward max diff %.2e" % float((out[name]["y"] - full).abs().max()))
+    _save("mamba_step.pt", out)
+
+
 MAMBA_TRAIN_CASES = [dict(name="block_v0", kind="block", ver=0, B=2, L=130, wseed=91, seed=191),
                      dict(name="block_v1", kind="block", ver=1, B=2, L=77, wseed=92, seed=192),
                      dict(name="stack", kind="stack", ver=0, B=2, L=70, wseed=93, seed=193),
@@ -648,7 +675,7 @@ def main():
     torch.set_num_threads(os.cpu_count())
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), train_full=lambda: golden_train_full(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
-                mamba=lambda: golden_mamba(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
+                mamba=lambda: golden_mamba(ref), mamba_step=lambda: golden_mamba_step(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
                 variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), rpr_train=lambda: golden_rpr_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))

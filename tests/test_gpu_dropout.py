@@ -95,9 +95,9 @@ def test_attention_fp32_probability_dropout_forward_backward(case):
         P = torch.softmax(qr.permute(0, 2, 1, 3) @ kk.transpose(-1, -2) * d ** -0.5, -1) * m
         ref = (P @ vv).permute(2, 0, 1, 3)                                   # (n, b, hq, d)
         ref.backward(dy.double())
-        assert rel_err(out, ref) < 1e-5
+        assert rel_err(out, ref) < 5e-5
         for mine, theirs in ((qd.grad, qr.grad), (kd.grad, kr.grad), (vd.grad, vr.grad)):
-            assert rel_err(mine, theirs) < 2e-5
+            assert rel_err(mine, theirs) < 1e-4
         return
     B, H, E = 2, 4, 256
     L, S, causal, with_er = (41, 41, True, True) if case == "rpr_causal" else (29, 53, False, False)
@@ -122,12 +122,12 @@ def test_attention_fp32_probability_dropout_forward_backward(case):
     P = torch.softmax(sc, -1) * m
     ref = (P @ vh).permute(2, 0, 1, 3).reshape(L * B, E)
     ref.backward(dy.double())
-    assert rel_err(out, ref) < 1e-5
-    assert rel_err(pw.view(B, H, L, S), P) < 1e-5                           # the weights come back dropped, as in torch
+    assert rel_err(out, ref) < 5e-5                                          # fp32 kernels against float64 torch
+    assert rel_err(pw.view(B, H, L, S), P) < 5e-5                           # the weights come back dropped, as in torch
     for mine, theirs in ((qd.grad, qr.grad), (kd.grad, kr.grad), (vd.grad, vr.grad)):
-        assert rel_err(mine, theirs) < 2e-5
+        assert rel_err(mine, theirs) < 1e-4
     if with_er:
-        assert rel_err(erd.grad, err.grad) < 2e-5
+        assert rel_err(erd.grad, err.grad) < 1e-4
 
 
 @pytest.mark.parametrize("shared", [False, True])

@@ -556,6 +556,40 @@ def test_selective_scan_full_size_vs_oracle_scan(B, L, nvid):
     assert err < 2e-5
 
 
+@pytest.mark.parametrize("name", ["block_v0", "block_v1", "stack"])
+def test_mamba_step_golden_gpu(name):
+    """MambaBlock.step / Mamba.step on the GPU step kernels against the unmodified reference (mamba_step.pt): every step's
+    output, the final cache, the caller's cache left untouched, and (use_version 0) agreement with our own forward()."""
+    from video2music_b200.mamba import MambaConfig, MambaBlock, Mamba
+    g = load_golden("mamba_step.pt")[name]
+    s = g["spec"]
+    cfg = MambaConfig(d_model=128, n_layers=max(s["n_layers"], 1), use_version=s["use_version"])
+    m = Mamba(cfg) if s["n_layers"] else MambaBlock(cfg)
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["weight_seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    x = syn.unit_uniform((s["B"], s["T"], 128), syn._gen(s["seed"], "x")).to(DEV)
+    empty = lambda: (None, torch.zeros(s["B"], cfg.d_inner, cfg.d_conv - 1, device=DEV))
+    cache = [empty() for _ in range(s["n_layers"])] if s["n_layers"] else empty()
+    ys = []
+    with torch.no_grad():
+        for t in range(s["T"]):
+            before = cache
+            keep = [c[1].clone() for c in cache] if s["n_layers"] else cache[1].clone()
+            y, cache = m.step(x[:, t], cache)
+            if s["n_layers"]:
+                assert all(torch.equal(b[1], k_) for b, k_ in zip(before, keep))       # the caller's cache is not modified
+            else:
+                assert torch.equal(before[1], keep)
+            ys.append(y)
+        y = torch.stack(ys, 1)
+        last = cache[-1] if s["n_layers"] else cache
+        assert rel_err(y, g["y"]) < 1e-4 and rel_err(last[0], g["h"]) < 1e-4 and rel_err(last[1], g["inputs"]) < 1e-5
+        if s["use_version"] == 0:
+            assert rel_err(m(x), y) < 1e-4                      # recurrent steps == the chunked parallel scan of forward()
+
+
 # ---------------------------------------------------------------- evaluation metrics
 def test_amt_metrics_kernel_vs_reference_golden_and_oracle():
     from test_oracle import _metrics_case

@@ -493,3 +493,38 @@ def test_amt_train_step_full_shape_golden(name):
         if mine.shape != gr.shape:
             mine = mine[::8]
         assert rel_err(mine, gr) < 1e-3, n
+
+
+@pytest.mark.parametrize("name", ["block_v0", "block_v1", "stack"])
+def test_mamba_step_oracle_matches_reference_golden(name):
+    """Recurrent single-token inference (MambaBlock.step / Mamba.step, mamba.py:100-108,407-470): T steps from the empty
+    cache equal the reference's step outputs and final cache; for use_version 0 they also equal forward()."""
+    from video2music_b200.mamba import MambaConfig, MambaBlock, Mamba
+    g = load_golden("mamba_step.pt")[name]
+    s = g["spec"]
+    cfg = MambaConfig(d_model=128, n_layers=max(s["n_layers"], 1), use_version=s["use_version"])
+    m = Mamba(cfg) if s["n_layers"] else MambaBlock(cfg)
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=s["weight_seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    x = syn.unit_uniform((s["B"], s["T"], 128), syn._gen(s["seed"], "x"))
+    empty = lambda: (None, torch.zeros(s["B"], cfg.d_inner, cfg.d_conv - 1))
+    ys = []
+    with torch.no_grad():
+        if s["n_layers"]:
+            caches = [empty() for _ in range(s["n_layers"])]
+            for t in range(s["T"]):
+                y, caches = O.mamba_step(sd, x[:, t], caches, s["n_layers"], cfg.dt_rank, cfg.d_state)
+                ys.append(y)
+            last = caches[-1]
+        else:
+            cache = empty()
+            for t in range(s["T"]):
+                y, cache = O.mamba_block_step(sd, "", x[:, t], cache, cfg.dt_rank, cfg.d_state)
+                ys.append(y)
+            last = cache
+    y = torch.stack(ys, 1)
+    assert rel_err(y, g["y"]) < 1e-5 and rel_err(last[0], g["h"]) < 1e-5 and rel_err(last[1], g["inputs"]) < 1e-6
+    if s["use_version"] == 0:
+        assert rel_err(y, g["y_forward"]) < 1e-5                  # step == forward (the reference's own consistency)
+    else:
+        assert rel_err(g["y"], g["y_forward"]) > 1e-2             # literal: step() ignores the mamba+ gate (mamba.py:430)

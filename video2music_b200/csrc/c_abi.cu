@@ -241,6 +241,19 @@ int v2m_mamba_conv_silu(const float* x, int64_t ldx, const float* w, const float
   return mamba_conv_silu(x, ldx, w, bias, y, ldy, B, L, ED, KW, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_mamba_step_conv(const float* xz, int64_t ldxz, const float* in_old, const float* w, const float* bias, float* xs, float* in_new,
+                        int32_t B, int32_t ED, int32_t KW, void* stream) {
+  V2M_REQUIRE(xz && in_old && w && xs && in_new, "v2m_mamba_step_conv: null pointer");
+  return mamba_step_conv(xz, ldxz, in_old, w, bias, xs, in_new, B, ED, KW, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_mamba_step_ssm(const float* xs, const float* dbc, int64_t lddbc, const float* dtw, const float* dtb, const float* A_log,
+                       const float* D, const float* z, int64_t ldz, const float* h_old, float* h_new, float* out, int32_t B, int32_t ED,
+                       int32_t N, int32_t R, void* stream) {
+  V2M_REQUIRE(xs && dbc && dtw && dtb && A_log && D && z && h_new && out, "v2m_mamba_step_ssm: null pointer");
+  return mamba_step_ssm(xs, dbc, lddbc, dtw, dtb, A_log, D, z, ldz, h_old, h_new, out, B, ED, N, R, static_cast<cudaStream_t>(stream));
+}
+
 int64_t v2m_selective_scan_workspace(int32_t B, int32_t L, int32_t ED, int32_t N) { return selective_scan_workspace(B, L, ED, N); }
 
 int v2m_selective_scan_fwd(const float* x, int64_t ldx, const float* delta_raw, int64_t ldd, const float* dt_bias, const float* A_log,

@@ -187,6 +187,11 @@ int pscan_bwd(const float* A, const float* H, const float* gH, float* gA, float*
               cudaStream_t stream);
 
 // ------------------------------------------------------------------ Mamba block (mamba.cu), fp32
+int mamba_step_conv(const float* xz, long long ldxz, const float* in_old, const float* w, const float* bias, float* xs, float* in_new,
+                    int B, int ED, int KW, cudaStream_t stream);
+int mamba_step_ssm(const float* xs, const float* dbc, long long lddbc, const float* dtw, const float* dtb, const float* A_log,
+                   const float* D, const float* z, long long ldz, const float* h_old, float* h_new, float* out, int B, int ED, int N,
+                   int R, cudaStream_t stream);
 int mamba_conv_silu(const float* x, long long ldx, const float* w, const float* bias, float* y, long long ldy, int B, int L, int ED,
                     int KW, cudaStream_t stream);
 long long selective_scan_workspace(int B, int L, int ED, int N);

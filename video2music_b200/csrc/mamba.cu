@@ -446,6 +446,82 @@ int mamba_conv_silu_bwd(const float* x, long long ldx, const float* w, const flo
   return check_launch("mamba_conv_silu_bwd");
 }
 
+// ---- recurrent single-token step (MambaBlock.step / ssm_step, mamba.py:407-470) -------------------------------------------
+// One new token per video: the cache holds the last KW-1 inputs of the depthwise convolution (B, ED, KW-1) and the SSM
+// state h (B, ED, N).  Two kernels around the three small GEMMs (in_proj, x_proj, out_proj) of the step:
+//   mamba_step_conv : xs = silu(conv1d([inputs | x_new])[KW-1]) and the shifted input window          (mamba.py:419-425,435)
+//   mamba_step_ssm  : delta = softplus(dt_proj(delta_raw)); h = exp(delta A) h + delta B x; y = h C + D x; out = y silu(z)
+// Nothing is modified in place: the caller's cache tensors stay valid, as in the reference (which builds new tensors).
+__global__ void __launch_bounds__(256) mamba_step_conv_kernel(const float* __restrict__ xz, long long ldxz, const float* __restrict__ in_old,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              float* __restrict__ xs, float* __restrict__ in_new, int B, int ED, int KW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * ED) return;
+  const int b = i / ED, e = i - b * ED;
+  const float xn = xz[(long long)b * ldxz + e];
+  const float* io = in_old + (long long)i * (KW - 1);
+  float* in = in_new + (long long)i * (KW - 1);
+  float acc = bias ? bias[e] : 0.f;
+  for (int j = 0; j < KW - 1; ++j) {
+    const float v = io[j];
+    acc = fmaf(w[e * KW + j], v, acc);
+    if (j > 0) in[j - 1] = v;
+  }
+  acc = fmaf(w[e * KW + KW - 1], xn, acc);
+  if (KW > 1) in[KW - 2] = xn;
+  xs[i] = acc / (1.f + expf(-acc));
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) mamba_step_ssm_kernel(const float* __restrict__ xs, const float* __restrict__ dbc, long long lddbc,
+                                                             const float* __restrict__ dtw, const float* __restrict__ dtb,
+                                                             const float* __restrict__ A_log, const float* __restrict__ D,
+                                                             const float* __restrict__ z, long long ldz, const float* __restrict__ h_old,
+                                                             float* __restrict__ h_new, float* __restrict__ out, int B, int ED, int R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * ED) return;
+  const int b = i / ED, e = i - b * ED;
+  const float* row = dbc + (long long)b * lddbc;            // [delta_raw (R) | B (N) | C (N)]
+  float dr = dtb[e];
+  for (int r = 0; r < R; ++r) dr = fmaf(dtw[e * R + r], row[r], dr);
+  const float delta = softplus_f(dr);
+  const float x = xs[i];
+  float y = 0.f;
+#pragma unroll
+  for (int n4 = 0; n4 < N; n4 += 4) {
+    float4 hv = h_old ? *reinterpret_cast<const float4*>(h_old + (long long)i * N + n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 al = *reinterpret_cast<const float4*>(A_log + (long long)e * N + n4);
+    float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+    const float aa[4] = {al.x, al.y, al.z, al.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float dA = expf(delta * -expf(aa[k]));
+      hh[k] = fmaf(dA, hh[k], delta * row[R + n4 + k] * x);
+      y = fmaf(hh[k], row[R + N + n4 + k], y);
+    }
+    *reinterpret_cast<float4*>(h_new + (long long)i * N + n4) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+  }
+  y = fmaf(D[e], x, y);
+  const float zz = z[(long long)b * ldz + e];
+  out[i] = y * (zz / (1.f + expf(-zz)));
+}
+
+int mamba_step_conv(const float* xz, long long ldxz, const float* in_old, const float* w, const float* bias, float* xs, float* in_new,
+                    int B, int ED, int KW, cudaStream_t stream) {
+  V2M_REQUIRE(B > 0 && ED > 0 && KW >= 1 && KW <= 8, "mamba_step_conv: bad dims B=%d ED=%d KW=%d", B, ED, KW);
+  mamba_step_conv_kernel<<<(B * ED + 255) / 256, 256, 0, stream>>>(xz, ldxz, in_old, w, bias, xs, in_new, B, ED, KW);
+  return check_launch("mamba_step_conv");
+}
+
+int mamba_step_ssm(const float* xs, const float* dbc, long long lddbc, const float* dtw, const float* dtb, const float* A_log,
+                   const float* D, const float* z, long long ldz, const float* h_old, float* h_new, float* out, int B, int ED, int N,
+                   int R, cudaStream_t stream) {
+  V2M_REQUIRE(B > 0 && ED > 0 && R >= 1, "mamba_step_ssm: bad dims B=%d ED=%d R=%d", B, ED, R);
+  V2M_REQUIRE(N == 16, "mamba_step_ssm: d_state %d unsupported (16)", N);
+  mamba_step_ssm_kernel<16><<<(B * ED + 127) / 128, 128, 0, stream>>>(xs, dbc, lddbc, dtw, dtb, A_log, D, z, ldz, h_old, h_new, out, B, ED, R);
+  return check_launch("mamba_step_ssm");
+}
+
 // y = x * rsqrt(mean(x^2) + eps) * w   (mamba.py:483-489); one warp per row
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                                       int M, int D, float eps) {

@@ -129,6 +129,22 @@ class MambaBlock(nn.Module):
         return ops.linear(y, det(self.out_proj.weight), det(self.out_proj.bias)).view(B, L, D)
 
 
+    @torch.no_grad()
+    def step(self, x, cache):
+        """Recurrent single-token inference (mamba.py:407-438): x (B, D), cache = (h (B, ED, N) or None, inputs (B, ED,
+        d_conv - 1)) -> (output (B, D), new cache).  Literal: the gate is y * silu(z) for both use_version values (:430), the
+        caller's cache tensors are left untouched.  Five launches: in_proj GEMM, conv window, x_proj GEMM, fused dt_proj +
+        softplus + state update + C contraction + gate, out_proj GEMM."""
+        cfg = self.config
+        h, inputs = cache
+        det = lambda p: None if p is None else p.detach()
+        xz = ops.linear(x.float().contiguous(), det(self.in_proj.weight), det(self.in_proj.bias))          # (B, 2 ED)
+        out, h_new, in_new = ops.mamba_step(xz, cfg.d_inner, det(self.conv1d.weight).reshape(cfg.d_inner, -1), det(self.conv1d.bias),
+                                            det(self.x_proj.weight), det(self.dt_proj.weight), det(self.dt_proj.bias),
+                                            det(self.A_log), det(self.D), h, inputs)
+        return ops.linear(out, det(self.out_proj.weight), det(self.out_proj.bias)), (h_new, in_new)
+
+
 class ResidualBlock(nn.Module):
     def __init__(self, config: MambaConfig):
         super().__init__()
@@ -138,12 +154,24 @@ class ResidualBlock(nn.Module):
     def forward(self, x):
         return self.mixer(self.norm(x)) + x                                                         # mamba.py:144-149
 
+    def step(self, x, cache):
+        """mamba.py:151-159: x (B, D), cache (h, inputs) -> (mixer.step(norm(x)) + x, new cache)."""
+        output, cache = self.mixer.step(self.norm(x), cache)
+        return output + x, cache
+
 
 class Mamba(nn.Module):
     def __init__(self, config: MambaConfig):
         super().__init__()
         self.config = config
         self.layers = nn.ModuleList([ResidualBlock(config) for _ in range(config.n_layers)])
+
+    def step(self, x, caches):
+        """mamba.py:100-108: one token through every layer; caches[i] = (h, inputs) of layer i (a new list is returned)."""
+        caches = list(caches)
+        for i, layer in enumerate(self.layers):
+            x, caches[i] = layer.step(x, caches[i])
+        return x, caches
 
     def forward(self, x):
         for layer in self.layers:

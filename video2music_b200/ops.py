@@ -501,6 +501,34 @@ def mamba_conv_silu(xz: torch.Tensor, ED: int, w: torch.Tensor, bias: Optional[t
     return y
 
 
+def mamba_step(xz: torch.Tensor, ED: int, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], x_proj_w: torch.Tensor,
+               dt_w: torch.Tensor, dt_b: torch.Tensor, A_log: torch.Tensor, D: torch.Tensor, h: Optional[torch.Tensor],
+               inputs: torch.Tensor):
+    """Core of MambaBlock.step (mamba.py:407-470) between in_proj and out_proj: xz (B, 2 ED) = [x | z], cache (h (B, ED, N) or
+    None, inputs (B, ED, d_conv - 1)) -> (gated output (B, ED), new h, new inputs).  The cache tensors are not modified."""
+    require_device(xz)
+    B = xz.shape[0]
+    N, R = A_log.shape[1], dt_w.shape[1]
+    KW = conv_w.shape[1]
+    assert xz.dtype == torch.float32 and xz.stride(1) == 1 and inputs.shape == (B, ED, KW - 1)
+    inputs = inputs.float().contiguous()
+    f32 = dict(device=xz.device, dtype=torch.float32)
+    xs, in_new = torch.empty((B, ED), **f32), torch.empty((B, ED, KW - 1), **f32)
+    check(load().v2m_mamba_step_conv(ptr(xz), xz.stride(0), ptr(inputs), ptr(conv_w.contiguous()), ptr(conv_b), ptr(xs), ptr(in_new),
+                                     B, ED, KW, stream()))
+    _lib.count_launches(1)
+    dbc = linear(xs, x_proj_w)                                                  # (B, R + 2N), mamba.py:445
+    h_new, out = torch.empty((B, ED, N), **f32), torch.empty((B, ED), **f32)
+    if h is not None:
+        h = h.float().contiguous()
+        assert h.shape == (B, ED, N)
+    z = xz[:, ED:]
+    check(load().v2m_mamba_step_ssm(ptr(xs), ptr(dbc), dbc.stride(0), ptr(dt_w.contiguous()), ptr(dt_b), ptr(A_log.contiguous()), ptr(D),
+                                    ptr(z), xz.stride(0), ptr(h), ptr(h_new), ptr(out), B, ED, N, R, stream()))
+    _lib.count_launches(1)
+    return out, h_new, in_new
+
+
 def selective_scan(x: torch.Tensor, delta_raw: torch.Tensor, dt_bias: Optional[torch.Tensor], A_log: torch.Tensor,
                    Bm: torch.Tensor, Cm: torch.Tensor, D: torch.Tensor, z: Optional[torch.Tensor], B: int, L: int,
                    plus: bool = False) -> torch.Tensor:
