@@ -253,6 +253,33 @@ def variants_leg(dev):
     out["video_regression_bimamba_plus_train"] = {"ms_per_step": ms, "samples_per_s": 64 / (ms * 1e-3),
                                                   "shape": "6 Bi-Mamba+ layers, 64 videos x 300 s, d_model 128, d_inner 256, d_state 16", "dtype": "f32"}
     del reg
+    # config 4 generation: KV-cached, batched greedy decode of the GQA (8 q / 2 kv heads) + MoE (6 experts, top-2) shell
+    from video2music_b200 import _lib
+    from video2music_b200 import synthetic as syn
+    from video2music_b200.video_music_transformer_v2 import VideoMusicTransformer_GQA
+    torch.manual_seed(0)
+    gm = VideoMusicTransformer_GQA(total_vf_dim=syn.vf_dim(0)).eval()
+    gm.load_state_dict(syn.fill_like_reference_init({k: tuple(v.shape) for k, v in gm.state_dict().items()}, seed=7))
+    gm = gm.to(dev)
+    gi = syn.make_inputs(BATCH, 1234, SEQ - 1, 300, 0)
+    feats = [gi[k].to(dev) for k in ("feature_semantic_list", "feature_key", "feature_scene_offset", "feature_motion", "feature_emotion")]
+    one = torch.tensor([1])
+    gen_fn = lambda n: gm.generate_cached(*feats, primer=one, primer_root=one, primer_attr=torch.tensor([0]), target_seq_length=n,
+                                          beam=1, beam_chance=1.0)
+    gen_fn(8)
+    torch.cuda.synchronize(dev)
+    n0 = _lib.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gen_fn(SEQ)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["gqa_moe_generate"] = {"tokens_per_s": BATCH * (SEQ - 1) / (ms * 1e-3), "ms_per_generation": ms, "launches": _lib.launches() - n0,
+                               "shape": "%d videos x %d positions, 6 layers, 8 q / 2 kv heads, 6 experts top-2, fp32, KV cache "
+                                        "(self %d MB for 2 kv heads, cross K|V projected once)" % (BATCH, SEQ, 6 * 2 * BATCH * SEQ * 128 * 4 // (1 << 20)),
+                               "dtype": "f32", "note": "the literal loop of the reference re-runs the whole model on the growing prefix for every token, batch 1"}
+    del gm, feats
     blk = MambaBlock(MambaConfig(d_model=128, n_layers=1)).to(dev).train()
     xb = torch.randn(8, 4096, 128, generator=g).to(dev)
     ms = timed(step(blk, lambda: blk(xb)))

@@ -695,7 +695,8 @@ def diff_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache: O
 
 def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int, num_heads: int, ff_kind,
                 rope: bool, pos_tables: bool, rms: bool = False, max_seq_video: int = 300, mask: bool = True,
-                rope_dim: Optional[int] = None, diff_enc: bool = False, diff_dec: bool = False, pre_norm: bool = False) -> torch.Tensor:
+                rope_dim: Optional[int] = None, diff_enc: bool = False, diff_dec: bool = False, pre_norm: bool = False,
+                gqa_kv_heads: int = 0) -> torch.Tensor:
     """Shared body of VideoMusicTransformer_V1.forward / _V2.forward (video_music_transformer.py:141-225, 437-520), eval:
     embeddings + key column -> Linear_chord, video features -> Linear_vis, learned position tables or RoPE inside the
     attention, post-norm wrappers (custom_transformer.py:1220-1292) with feed-forward ff_kind(layer) in {"glu", "moe",
@@ -714,6 +715,8 @@ def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_laye
     ln = lambda t, p: _norm_generic(t, sd, p, rms)
 
     def att(qx, kx, p, causal, diff, depth):
+        if gqa_kv_heads:            # BASELINE config 4: MultiheadGQA in every layer; decoder self-attention causal (is_causal=True)
+            return mhgqa_forward(qx, kx, kx, sd, p, num_heads, gqa_kv_heads, is_causal=causal)
         if diff:
             return diff_mha_forward(qx, kx, kx, sd, p, num_heads, cache, causal, depth)
         return custom_mha_forward(qx, kx, kx, sd, p, num_heads, cache, causal)[0]
@@ -748,6 +751,33 @@ def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_laye
             y = y + ff(ln(y, p + "norm3"), p, l)
     y = ln(y, "transformer.decoder.norm")
     return F.linear(y.permute(1, 0, 2), sd["Wout.weight"], sd["Wout.bias"])
+
+
+def gqa_moe_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8, kv_heads: int = 2,
+                    shared: bool = False, rms: bool = False, pre_norm: bool = False, mask: bool = True) -> torch.Tensor:
+    """BASELINE config 4: the V1 shell (video_music_transformer.py:77-118) over TransformerEncoderLayer /
+    TransformerDecoderLayer(att=MultiheadGQA(d, heads, kv_heads), ff=MoELayer | SharedMoELayer) (custom_transformer.py:1220-1292),
+    decoder self-attention with is_causal=True (grouped_query_attention.py:106-121), everything else non-causal."""
+    return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads,
+                       lambda l: "shared" if shared else "moe", rope=False, pos_tables=True, rms=rms, mask=mask, pre_norm=pre_norm,
+                       gqa_kv_heads=kv_heads)
+
+
+def zoo_generate_greedy_literal(forward, sem, key, scene, motion, emotion, primer, primer_root, primer_attr, target_seq_length: int):
+    """generate(beam=1, beam_chance=1.0) of the V1 / V2 shells (video_music_transformer.py:227-315, 522-610): batch of one, one
+    full forward per token, arg-max over the first 157 classes of softmax(logits[-1]), root / attribute of generated positions
+    stay PAD.  `forward(x_root, x_attr)` -> logits (1, T, 159)."""
+    gen = torch.full((1, target_seq_length), 158, dtype=torch.long)
+    gr = torch.full((1, target_seq_length), 14, dtype=torch.long)
+    ga = torch.full((1, target_seq_length), 15, dtype=torch.long)
+    n0 = len(primer)
+    gen[0, :n0], gr[0, :n0], ga[0, :n0] = primer, primer_root, primer_attr
+    cur = n0
+    while cur < target_seq_length:
+        y = forward(gr[:, :cur], ga[:, :cur])
+        gen[0, cur] = int(torch.argmax(torch.softmax(y[0, cur - 1], -1)[:157]))
+        cur += 1
+    return gen
 
 
 def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,

@@ -1,0 +1,233 @@
+"""KV-cached, batched autoregressive generation for the decoder stacks built from the reference's generic wrappers
+(model/custom_transformer.py:1250-1292,1401-1433) -- BASELINE config 4 "generation".
+
+The reference generates with a batch of one and one FULL forward per token over the growing prefix
+(video_music_transformer.py:227-315 / 522-610): O(n^2) work, nothing reused.  For the stacks whose self-attention is causal the
+keys / values of earlier positions never change, so one position per step is enough:
+
+  * per decoder layer, a self-attention cache K | V of shape (videos, cap, kv_heads * head_dim) -- grouped-query attention
+    (grouped_query_attention.py:172-358) keeps only `kv_heads` heads, i.e. 4x less cache than the 8 query heads at kv_heads = 2;
+  * the cross-attention K | V of the encoder memory, projected once per generation instead of once per token and layer;
+  * one step = one token per video through every layer: q / k / v projection of the new rows, attention of ONE query row per
+    (video, head) over the cached rows (the fp32 attention kernel with Lq = 1), out-projection, the layer's feed-forward
+    (GLUExpert, MoELayer or SharedMoELayer: fused router + permute + grouped expert GEMMs over the B new tokens).
+
+Everything runs on the same fp32 kernels as the full forward, whose per-row arithmetic does not depend on how many rows a
+launch carries (fixed k order in the GEMMs, one warp per softmax row): the greedy tokens are therefore bit-identical to the
+literal re-forward loop (tests/test_gpu_cached_decode.py), which in turn is bit-exact against the unmodified reference for
+the V1 models (tests/golden/v2.pt).
+
+Cacheable attention modules: `CustomMultiheadAttention` without RoPE (V1 '1.1' / '1.3', V2 '2.0'; the RoPE variant rotates a
+(position, head) element by an angle that depends on the CURRENT prefix length, custom_transformer.py:1044-1053, so its keys
+change every step) and `MultiheadGQA` with causal self-attention.
+"""
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .custom_transformer import CustomMultiheadAttention, _norm
+from .grouped_query_attention import MultiheadGQA
+from .video_music_transformer import CHORD_END, CHORD_PAD
+
+CHORD_ROOT_PAD, CHORD_ATTR_PAD = 14, 15            # utilities/constants.py
+
+
+def _kind(att: nn.Module) -> Optional[str]:
+    if isinstance(att, MultiheadGQA):
+        return "gqa"
+    if isinstance(att, CustomMultiheadAttention) and att.RoPE is None:
+        return "mha"
+    return None
+
+
+def cacheable(model: nn.Module) -> bool:
+    """True when `model` (a V1 / V2 / GQA shell: .transformer.decoder.layers of generic TransformerDecoderLayer) can be decoded
+    with a KV cache: learned position tables, cacheable attention modules, causal decoder self-attention."""
+    dec = getattr(getattr(model, "transformer", None), "decoder", None)
+    if dec is None or not getattr(model, "_pos_tables", False):
+        return False
+    for layer in dec.layers:
+        ks, kc = _kind(layer.self_attn), _kind(layer.cross_attn)
+        if ks is None or kc is None:
+            return False
+        if ks == "gqa" and not getattr(layer.self_attn, "force_causal", False):
+            return False                       # the literal GQA module ignores the mask (grouped_query_attention.py:339): not causal
+    return True
+
+
+class _Att:
+    """One attention module of one decoder layer in step form."""
+
+    def __init__(self, att: nn.Module):
+        self.att, self.kind = att, _kind(att)
+        det = lambda p: None if p is None else p.detach()
+        if self.kind == "gqa":
+            self.Hq, self.Hk = att.query_heads, att.kv_heads
+            self.E = att.q_proj.in_features
+            self.dh = self.E // self.Hq
+            self.wq, self.bq = det(att.q_proj.weight), det(att.q_proj.bias)
+            self.wk, self.bk = det(att.k_proj.weight), det(att.k_proj.bias)
+            self.wv, self.bv = det(att.v_proj.weight), det(att.v_proj.bias)
+        else:
+            self.Hq = self.Hk = att.num_heads
+            self.E, self.dh = att.embed_dim, att.head_dim
+            w, b = det(att.in_proj_weight), det(att.in_proj_bias)
+            E = self.E
+            self.wq, self.bq, self.wk, self.bk, self.wv, self.bv = w[:E], b[:E], w[E:2 * E], b[E:2 * E], w[2 * E:], b[2 * E:]
+            self.w_qkv, self.b_qkv, self.w_kv, self.b_kv = w, b, w[E:], b[E:]
+        self.Wk = self.Hk * self.dh                      # cache row width
+        self.q_scale = float(self.dh) ** -0.5            # q / sqrt(d) (grouped_query_attention.py:93-96; F.multi_head_attention_forward)
+
+    def qkv(self, x: torch.Tensor):
+        """q (B, E), k, v (B, Wk) of the new rows x (B, E)."""
+        if self.kind == "mha":                           # packed projection, as the module's self-attention path
+            y = ops.linear(x, self.w_qkv, self.b_qkv)
+            E = self.E
+            return y[:, :E], y[:, E:2 * E], y[:, 2 * E:]
+        return ops.linear(x, self.wq, self.bq), ops.linear(x, self.wk, self.bk), ops.linear(x, self.wv, self.bv)
+
+    def q_only(self, x: torch.Tensor) -> torch.Tensor:
+        return ops.linear(x, self.wq, self.bq)
+
+    def memory_kv(self, mem_rows: torch.Tensor):
+        """K, V (S*B, Wk) of the encoder memory rows (s, b) -- once per generation."""
+        if self.kind == "mha":
+            kv = ops.linear(mem_rows, self.w_kv, self.b_kv)
+            return kv[:, :self.E], kv[:, self.E:]
+        return ops.linear(mem_rows, self.wk, self.bk), ops.linear(mem_rows, self.wv, self.bv)
+
+    def attend(self, q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, n: int, k_strides) -> torch.Tensor:
+        """One query row per (video, head) over n cached rows, then the module's output path."""
+        B, E = q.shape[0], self.E
+        ctx = torch.empty((B, E), device=q.device, dtype=torch.float32)
+        assert V.stride() == K.stride() and q.stride(1) == 1
+        ops.attention(q, K, V, ctx, B=B, Hq=self.Hq, Hkv=self.Hk, Lq=1, Lk=n, dh=self.dh, q_strides=(q.stride(0), q.stride(0)),
+                      k_strides=k_strides, v_strides=k_strides, o_strides=(E, E), causal=False, q_scale=self.q_scale)
+        a = self.att
+        if self.kind == "gqa":
+            if a.layer_norm:                             # grouped_query_attention.py:347-349
+                ctx = ops.layernorm(ctx, a.norm.weight.detach(), a.norm.bias.detach(), eps=a.norm.eps)
+            return ops.linear(ctx, a.out_proj.weight.detach(), None if a.out_proj.bias is None else a.out_proj.bias.detach(), k=E)
+        return ops.linear(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach())
+
+
+class CachedDecoder:
+    """Self-attention caches + projected memory of every decoder layer, and the per-position step."""
+
+    def __init__(self, model: nn.Module, memory: torch.Tensor, cap: int):
+        S, B, E = memory.shape
+        self.model, self.B, self.S, self.E, self.cap = model, B, S, E, cap
+        dec = model.transformer.decoder
+        self.layers = list(dec.layers)
+        self.final_norm = dec.norm
+        mem_rows = memory.reshape(S * B, E).float().contiguous()
+        dev = memory.device
+        self.sa: List[_Att] = [_Att(l.self_attn) for l in self.layers]
+        self.ca: List[_Att] = [_Att(l.cross_attn) for l in self.layers]
+        self.mem_kv = [a.memory_kv(mem_rows) for a in self.ca]
+        self.K = [torch.zeros((B, cap, a.Wk), device=dev, dtype=torch.float32) for a in self.sa]
+        self.V = [torch.zeros((B, cap, a.Wk), device=dev, dtype=torch.float32) for a in self.sa]
+        self.cache_bytes = sum(k.numel() * 8 for k in self.K) + sum(kv[0].numel() * 8 for kv in self.mem_kv)
+
+    def step(self, x: torch.Tensor, t: int) -> torch.Tensor:
+        """x (B, E): embedded token of position t of every video -> decoder output rows (B, E) after the final norm."""
+        B = self.B
+        for i, layer in enumerate(self.layers):
+            sa, ca = self.sa[i], self.ca[i]
+            K, V = self.K[i], self.V[i]
+            mk, mv = self.mem_kv[i]
+
+            def self_att(z):
+                q, k, v = sa.qkv(z)
+                K[:, t].copy_(k)
+                V[:, t].copy_(v)
+                return sa.attend(q, K, V, t + 1, (K.stride(0), K.stride(1)))
+
+            def cross_att(z):
+                # memory rows are ordered (s, b): video b's row s sits at (s * B + b)
+                return ca.attend(ca.q_only(z), mk, mv, self.S, (mk.stride(0), B * mk.stride(0)))
+
+            ff = lambda z: layer.ff(z.view(1, B, self.E)).reshape(B, -1)
+            if not layer.pre_norm:                                           # custom_transformer.py:1263-1277
+                x = _norm(layer.norm1, x, self_att(x))
+                x = _norm(layer.norm2, x, cross_att(x))
+                x = _norm(layer.norm3, x, ff(x))
+            else:                                                            # :1278-1291
+                x = ops.axpy(x, self_att(_norm(layer.norm1, x)), 1.0)
+                x = ops.axpy(x, cross_att(_norm(layer.norm2, x)), 1.0)
+                x = ops.axpy(x, ff(_norm(layer.norm3, x)), 1.0)
+        if self.final_norm is not None:
+            x = _norm(self.final_norm, x)
+        return x
+
+
+@torch.no_grad()
+def generate_cached(model: nn.Module, feature_semantic_list, feature_key, feature_scene_offset, feature_motion, feature_emotion,
+                    primer, primer_root, primer_attr, target_seq_length: int = 300, beam: int = 0, beam_chance: float = 1.0,
+                    max_conseq_N: int = 0, max_conseq_chord: int = 2, temperature: float = 1.0,
+                    uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched `generate` of the V1 / V2 '2.0' / GQA shells (video_music_transformer.py:227-315, 522-610) with a KV cache.
+    Features carry a batch dimension of B videos (the reference: 1); the primer (P,) is shared by all videos or (B, P).
+    beam=1 (beam_chance >= 1): arg-max over the first 157 classes, root / attribute inputs of generated positions stay PAD
+    (literal); beam=0: the sampling branch (no-"N" / no-repeat constraints, inverse-CDF draw from `uniforms` (B, T) or
+    torch.rand), root / attribute updated.  Returns (B, target_seq_length) int64."""
+    assert not model.training, "Cannot generate while in training mode"
+    if not (beam == 0 or (beam == 1 and beam_chance >= 1.0)):
+        raise NotImplementedError("beam > 1 / 0 < beam_chance < 1 are not reproduced")
+    if not cacheable(model):
+        raise NotImplementedError("this model's decoder cannot be decoded with a KV cache (RoPE / differential attention / "
+                                  "non-causal self-attention); use generate()")
+    dev = model.Wout.weight.device
+    sem, key, scene, motion, emotion = (t.to(dev) for t in (feature_semantic_list, feature_key, feature_scene_offset,
+                                                             feature_motion, feature_emotion))
+    B, S, E = sem.shape[0], sem.shape[1], model.d_model
+    T = target_seq_length
+    prim = lambda p: (p.long().to(dev).reshape(1, -1).expand(B, -1) if p.dim() == 1 else p.long().to(dev))
+    primer, primer_root, primer_attr = prim(primer), prim(primer_root), prim(primer_attr)
+    n0 = primer.shape[1]
+    gen = torch.full((B, T), CHORD_PAD, dtype=torch.long, device=dev)
+    gen_root = torch.full((B, T), CHORD_ROOT_PAD, dtype=torch.long, device=dev)
+    gen_attr = torch.full((B, T), CHORD_ATTR_PAD, dtype=torch.long, device=dev)
+    gen[:, :n0], gen_root[:, :n0], gen_attr[:, :n0] = primer, primer_root, primer_attr
+    if beam == 0 and uniforms is None:
+        uniforms = torch.rand((B, T), device=dev)
+    # ---- encoder memory, once (the literal loop recomputes it for every token)
+    tr = lambda t: t.transpose(0, 1).contiguous()
+    vin = ops.concat_features(tr(sem), tr(scene), tr(motion), tr(emotion), torch.float32, model.total_vf_dim)
+    vf = ops.linear(vin, model.Linear_vis.weight.detach(), model.Linear_vis.bias.detach())
+    pos_v = model.positional_embedding_video.weight.detach()[:S].unsqueeze(1).expand(S, B, E).contiguous()
+    vf = ops.axpy(vf.view(S, B, E), pos_v, 1.0)
+    memory = model.transformer.encoder(vf)
+    dec = CachedDecoder(model, memory, T)
+    wc = model.Linear_chord.weight.detach()
+    wkey = wc[:, E].contiguous()
+    key_rows = key.reshape(B, -1)[:, 0].float().contiguous()
+    pos = model.positional_embedding.weight.detach()
+    for t in range(T - 1):                               # the token of position t goes in, the token of position t + 1 comes out
+        xin = ops.embed_sum(gen_root[:, t].contiguous(), model.embedding_root.weight.detach(), gen_attr[:, t].contiguous(),
+                            model.embedding_attr.weight.detach(), torch.float32)
+        x = ops.linear(xin, wc, model.Linear_chord.bias.detach(), k=E, row_scale=key_rows, col_vec=wkey)
+        x = ops.axpy(x, pos[t].unsqueeze(0).expand(B, E).contiguous(), 1.0)
+        h = dec.step(x, t)
+        cur = t + 1
+        if cur < n0:
+            continue                                     # primer positions only fill the caches
+        logits = ops.linear(h, model.Wout.weight.detach(), model.Wout.bias.detach())
+        probs = torch.softmax(logits / temperature, dim=-1)[:, :CHORD_END]
+        if beam == 1:
+            gen[:, cur] = torch.argmax(probs, dim=-1)
+        else:
+            probs = probs.clone()
+            if max_conseq_N == 0:
+                probs[:, 0] = 0.0
+            if cur >= max_conseq_chord:
+                rep = (gen[:, cur - max_conseq_chord:cur] == gen[:, cur - 1:cur]).all(dim=1)
+                probs[rep, gen[rep, cur - 1]] = 0.0
+            cdf = torch.cumsum(probs / probs.sum(dim=1, keepdim=True), dim=1)
+            tok = (cdf <= uniforms[:, cur:cur + 1]).sum(dim=1).clamp_max(CHORD_END - 1)
+            gen[:, cur] = tok
+            gen_root[:, cur] = torch.where(tok <= 0, torch.zeros_like(tok), (tok - 1) // 13 + 1)
+            gen_attr[:, cur] = torch.where(tok <= 0, torch.ones_like(tok), (tok - 1) % 13 + 1)
+    return gen

@@ -111,6 +111,10 @@ class MultiheadGQA(nn.Module):
         q4 = q.view(bsz, tgt_len, H, dh)
         k4 = k.view(bsz, src_len, Hk, dh)
         v4 = v.view(bsz, src_len, Hk, dh)
+        # force_causal (our extension, off by default): the reference's wrappers hand the causal mask over as attn_mask, which
+        # this module drops (grouped_query_attention.py:339 "attn_mask=None"), so a literal GQA decoder sees future positions;
+        # the config-4 shell (VideoMusicTransformer_GQA) turns this on for decoder self-attention
+        is_causal = bool(is_causal) or bool(getattr(self, "force_causal", False))
         x, _ = scaled_dot_product_gqa(q4, k4, v4, num_heads=H, is_causal=True if is_causal else None)
         x = x.reshape(x.shape[0], x.shape[1], H * dh)                   # labelled "b n (h d)" by the reference (:343)
         if track:

@@ -195,6 +195,41 @@ class VideoMusicTransformer_V1(_ZooModel):
         self.softmax = nn.Softmax(dim=-1)
 
 
+class VideoMusicTransformer_GQA(_ZooModel):
+    """BASELINE config 4: the AMT built from the reference's own blocks with grouped-query attention and MoE feed-forwards --
+    `TransformerEncoderLayer / TransformerDecoderLayer(att=MultiheadGQA(d_model, num_heads, kv_heads), ff=MoELayer | SharedMoELayer
+    (GLUExpert, 6 experts, top-2))` (custom_transformer.py:1220-1292, grouped_query_attention.py:172-358, moe.py:150-302) inside
+    the V1 shell (learned position tables, root + attribute embeddings, video_music_transformer.py:77-118).  The reference ships
+    no such class; it is the composition SURVEY.md 8d defines.  One deliberate difference from a literal composition: decoder
+    self-attention is causal (`force_causal`), because MultiheadGQA drops the mask its wrapper passes (see there) -- without
+    it next-chord training would see the future and generation would have no KV cache."""
+
+    def __init__(self, n_layers=6, num_heads=8, kv_heads=2, d_model=512, dim_feedforward=1024, dropout=0.1, max_sequence_video=300,
+                 max_sequence_chord=300, total_vf_dim=0, shared_moe=False, rms_norm=False, pre_norm=False):
+        super().__init__()
+        from .custom_transformer import RMSNorm, TransformerDecoder, TransformerEncoder
+        from .grouped_query_attention import MultiheadGQA
+        from .moe import MoELayer
+        self.nlayers, self.nhead, self.d_model, self.d_ff, self.dropout = n_layers, num_heads, d_model, dim_feedforward, dropout
+        self.max_seq_video, self.max_seq_chord = max_sequence_video, max_sequence_chord
+        self._embeddings(d_model, total_vf_dim, max_sequence_chord, max_sequence_video, pos_tables=True)
+        norm = RMSNorm(d_model) if rms_norm else nn.LayerNorm(d_model)
+        self.n_experts, self.n_experts_per_token = 6, 2
+        expert = GLUExpert(d_model, dim_feedforward, dropout)
+        att = MultiheadGQA(d_model, num_heads, kv_heads, dropout=dropout)
+        if shared_moe:
+            moelayer = SharedMoELayer(expert, d_model, n_experts=6, n_experts_per_token=2, balancing=False, dropout=dropout)
+        else:
+            moelayer = MoELayer(expert, d_model, 6, 2, dropout)
+        encoder = TransformerEncoder(TransformerEncoderLayer(att, moelayer, pre_norm=pre_norm, norm=norm, dropout=dropout), n_layers, norm)
+        decoder = TransformerDecoder(TransformerDecoderLayer(att, att, moelayer, pre_norm=pre_norm, norm=norm, dropout=dropout), n_layers, norm)
+        for layer in decoder.layers:
+            layer.self_attn.force_causal = True
+        self.transformer = _Transformer(encoder, decoder)
+        self.Wout = nn.Linear(d_model, CHORD_SIZE)
+        self.softmax = nn.Softmax(dim=-1)
+
+
 class VideoMusicTransformer_V3(_ZooModel):
     """Drop-in for `VideoMusicTransformer_V3` (model/video_music_transformer.py:611-905), versions '3.0', '3.1', '3.2': RMSNorm,
     a RoPE cache of dimension 2 * d_model, DifferentialMultiheadAttention (depth = layer index) in every decoder layer and --
@@ -236,3 +271,13 @@ class VideoMusicTransformer_V3(_ZooModel):
 
 _ZooModel.forward = VideoMusicTransformer_V2.forward
 _ZooModel.generate = VideoMusicTransformer_V2.generate
+
+
+def _generate_cached(self, *args, **kwargs):
+    """KV-cached, batched generation (cached_decode.generate_cached): same tokens as `generate` video by video for the models
+    whose decoder is cacheable (V1 '1.1' / '1.3', V2 '2.0', the GQA + MoE shell), O(n) instead of O(n^2) per video."""
+    from .cached_decode import generate_cached
+    return generate_cached(self, *args, **kwargs)
+
+
+_ZooModel.generate_cached = _generate_cached
