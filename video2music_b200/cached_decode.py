@@ -199,7 +199,17 @@ def generate_cached(model: nn.Module, feature_semantic_list, feature_key, featur
     vf = ops.linear(vin, model.Linear_vis.weight.detach(), model.Linear_vis.bias.detach())
     pos_v = model.positional_embedding_video.weight.detach()[:S].unsqueeze(1).expand(S, B, E).contiguous()
     vf = ops.axpy(vf.view(S, B, E), pos_v, 1.0)
-    memory = model.transformer.encoder(vf)
+    # the videos of the batch are independent generations: MultiheadGQA's literal (len, batch) -> (batch, len) `.view` would mix
+    # them for B > 1, so the encoder runs in its batch-independent form (identical to the reference for every single video)
+    gqa = [mod for mod in model.transformer.encoder.modules() if isinstance(mod, MultiheadGQA)]
+    prev = [getattr(mod, "batch_independent", False) for mod in gqa]
+    try:
+        for mod in gqa:
+            mod.batch_independent = True
+        memory = model.transformer.encoder(vf)
+    finally:
+        for mod, pv in zip(gqa, prev):
+            mod.batch_independent = pv
     dec = CachedDecoder(model, memory, T)
     wc = model.Linear_chord.weight.detach()
     wkey = wc[:, E].contiguous()

@@ -108,9 +108,17 @@ class MultiheadGQA(nn.Module):
 
         q, k, v = lin(self.q_proj, query), lin(self.k_proj, key), lin(self.v_proj, value)   # :306-308
         # literal `.view(bsz, len, heads*dh)` of the (len, bsz, .) projections (:324-326)
-        q4 = q.view(bsz, tgt_len, H, dh)
-        k4 = k.view(bsz, src_len, Hk, dh)
-        v4 = v.view(bsz, src_len, Hk, dh)
+        if getattr(self, "batch_independent", False) and bsz > 1:
+            # our extension (off by default): every video of the batch is treated as the reference treats a batch of one --
+            # the literal `.view` below interleaves batch and time for bsz > 1, which batched generation of
+            # independent videos must not do.  For bsz == 1 the two are the same tensor.
+            q4 = q.view(tgt_len, bsz, H, dh).transpose(0, 1).contiguous()
+            k4 = k.view(src_len, bsz, Hk, dh).transpose(0, 1).contiguous()
+            v4 = v.view(src_len, bsz, Hk, dh).transpose(0, 1).contiguous()
+        else:
+            q4 = q.view(bsz, tgt_len, H, dh)
+            k4 = k.view(bsz, src_len, Hk, dh)
+            v4 = v.view(bsz, src_len, Hk, dh)
         # force_causal (our extension, off by default): the reference's wrappers hand the causal mask over as attn_mask, which
         # this module drops (grouped_query_attention.py:339 "attn_mask=None"), so a literal GQA decoder sees future positions;
         # the config-4 shell (VideoMusicTransformer_GQA) turns this on for decoder self-attention
