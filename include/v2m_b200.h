@@ -70,6 +70,10 @@ typedef struct v2m_epilogue {
   uint32_t drop_thresh, drop_seed;
   int32_t drop_after_res;
   const uint32_t* drop_seed_dev;   /* optional device counter added to drop_seed: fresh masks when a CUDA graph is replayed */
+  /* bf16 GEMMs with an fp32 output and no other epilogue operation: C += A W^T instead of C = A W^T (coalesced vector
+   * reductions into the caller's buffer) -- weight gradients accumulate straight into the optimiser's gradient buffer. */
+  int32_t accumulate;
+  int32_t pad_;
 } v2m_epilogue;
 
 /* fp32 SIMT GEMM (exact path, batch-invariant summation order). */

@@ -39,21 +39,27 @@ def gemm_strided(a, a_rs, a_cs, w, w_rs, w_cs, M, N, K, out=None):
         out.copy_(r); return out
     return r
 MIRRORS['gemm_strided'] = gemm_strided
-def dy_prep(dy, y, relu, alpha, alpha_cols, out_dtype, want_dz=True, dropout=None):
+def dy_prep(dy, y, relu, alpha, alpha_cols, out_dtype, want_dz=True, dropout=None, db_out=None):
     dz = dy.clone()
     if relu: dz = dz * (y > 0)
     if alpha_cols: dz[:, :alpha_cols] *= alpha
-    return (dz if want_dz else None), dz.sum(0)
+    db = dz.sum(0)
+    if db_out is not None:
+        db_out += db; db = db_out
+    return (dz if want_dz else None), db
 MIRRORS['dy_prep'] = dy_prep
 def layernorm(x, gamma, beta, *, res=None, eps=1e-5, **kw):
     x = x.detach()
     if res is not None: x = x + res.detach()
     return F.layer_norm(x, (x.shape[-1],), gamma.detach(), beta.detach(), eps)
 MIRRORS['layernorm'] = layernorm
-def layernorm_bwd(x, gamma, dy, eps=1e-5):
+def layernorm_bwd(x, gamma, dy, eps=1e-5, dg_out=None, db_out=None):
     x = x.detach().clone().requires_grad_(True); g = gamma.detach().clone().requires_grad_(True); b = torch.zeros_like(g).requires_grad_(True)
     with torch.enable_grad():
         F.layer_norm(x, (x.shape[-1],), g, b, eps).backward(dy)
+    if dg_out is not None:
+        dg_out += g.grad; db_out += b.grad
+        return x.grad, dg_out, db_out
     return x.grad, g.grad, b.grad
 MIRRORS['layernorm_bwd'] = layernorm_bwd
 def rms(x, w, eps): 

@@ -302,3 +302,50 @@ def test_loss_rejects_bad_targets_loudly():
     assert torch.allclose(s1[:2], s2[:2])
     # CE part scales by 3/6, BCE part by 4/8: with zero logits and zero emotion targets both are exactly halved
     assert torch.allclose(dl2, dl1 * 0.5, atol=1e-7)
+
+
+def test_direct_gradient_accumulation_equals_autograd_accumulation():
+    """Trainer-managed parameters: the backward kernels add their results straight into the flat gradient buffer (split-K
+    vector reductions of the dW GEMM, bias / LayerNorm / embedding / Er atomics) instead of producing temporaries that
+    AccumulateGrad adds.  Same gradients as the standard path (fp32 atomics reorder the sums: 1e-5), twice as large after two
+    backward passes without an optimiser step (accumulation semantics), and far fewer launches."""
+    from video2music_b200 import _lib
+    from video2music_b200.trainer import FlatParams
+    inp = syn.make_inputs(3, 55, 70, 48, 0)
+    grads, launches = {}, {}
+    for direct in (False, True):
+        m, _ = _model(6, torch.bfloat16)
+        flat = FlatParams(m, direct=direct)
+        _step(m, inp)                                             # warm the bf16 weight caches
+        flat.flat_g.zero_()
+        torch.cuda.synchronize()
+        _lib.reset_launches()
+        _step(m, inp)
+        launches[direct] = _lib.launches()
+        grads[direct] = flat.flat_g.clone()
+        if direct:
+            _step(m, inp)
+            twice = flat.flat_g.clone()
+    ref, mine = grads[False], grads[True]
+    assert float(ref.abs().max()) > 0
+    assert rel_err(mine, ref) < 1e-4
+    assert float((mine - ref).norm() / ref.norm()) < 1e-5
+    assert float((twice - 2 * mine).norm() / mine.norm()) < 1e-5
+    print("launches through our library per backward+forward: autograd accumulation %d, direct %d" % (launches[False], launches[True]))
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 19136), (1536, 512, 2990), (512, 1024, 640), (160, 776, 4000)])
+def test_gemm_accumulate_mode(M, N, K):
+    """C += A^T-stored x B^T-stored (the dW form: both operands MN-major) through the split-K / accumulate epilogue with
+    coalesced red.global.add.v4.f32: result added to the previous contents of C, row / column tails included."""
+    from video2music_b200 import ops
+    g = syn._gen(12, "acc")
+    a = (syn.unit_uniform((K, M), g) * 0.5).to(torch.bfloat16).to(DEV)        # [K, M]: A stored MN-major
+    b = (syn.unit_uniform((K, N), g) * 0.5).to(torch.bfloat16).to(DEV)        # [K, N]
+    c0 = syn.unit_uniform((M, N), g).to(DEV)
+    ref = c0.double() + a.double().t() @ b.double()
+    c = c0.clone()
+    ops.linear_general(a, b, a_mn=True, b_mn=True, M=M, N=N, K=K, out_dtype=torch.float32, out=c, accumulate=True)
+    assert rel_err(c, ref) < 1e-5
+    plain = ops.linear_general(a, b, a_mn=True, b_mn=True, M=M, N=N, K=K, out_dtype=torch.float32)      # split-K without accumulate
+    assert rel_err(plain, ref - c0.double()) < 1e-5

@@ -37,6 +37,7 @@ static GemmEpilogue to_ep(const v2m_epilogue* e) {
   g.part_stride = e->part_stride;
   g.drop_scale = e->drop_scale; g.drop_thresh = e->drop_thresh; g.drop_seed = e->drop_seed; g.drop_after_res = e->drop_after_res;
   g.drop_seed_dev = e->drop_seed_dev;
+  g.accumulate = e->accumulate;
   return g;
 }
 
@@ -74,6 +75,7 @@ int v2m_gemm_f32(const float* A, int32_t lda, const float* W, int32_t ldw, float
                  int32_t K, const v2m_epilogue* ep, void* stream) {
   GemmEpilogue g = to_ep(ep);
   V2M_REQUIRE(!g.residual_bf16, "v2m_gemm_f32: bf16 residual not supported on the fp32 path");
+  V2M_REQUIRE(!g.accumulate, "v2m_gemm_f32: accumulate exists on the bf16 tensor-core path only");
   return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, g, static_cast<cudaStream_t>(stream));
 }
 

@@ -260,7 +260,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
         const int n0 = n_blk * BN + c * 32;
-        const bool fast = vec_ok && n0 + 32 <= N && k_split == 1;
+        const bool fast = vec_ok && n0 + 32 <= N && k_split == 1 && !ep.accumulate;
         float4 bv[8];
         if (fast && row_ok && bias) {
           const float4* bp = reinterpret_cast<const float4*>(bias + n0);
@@ -273,15 +273,40 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fetch_res(c + 2, res_nx);
         tmem_ld_wait();
         const bool tma_chunk = tma_out && fast;                // warp-uniform
-        if ((!row_ok && !tma_chunk) || n0 >= N) continue;
+        const bool red_chunk = (k_split > 1 || ep.accumulate) && vec_ok && n0 + 32 <= N;   // warp-uniform: all lanes take part in the transpose
+        if ((!row_ok && !tma_chunk && !red_chunk) || n0 >= N) continue;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (k_split > 1) {                                   // partial sum of one K slice (plain fp32 output, no epilogue ops)
-          float* dst = static_cast<float*>(C) + (size_t)m * ldc + n0;
+        if (k_split > 1 || ep.accumulate) {                  // partial sum of one K slice / accumulation into C (plain fp32, no epilogue ops)
+          if (vec_ok && n0 + 32 <= N) {
+            // Coalesced vector reductions: the 32 x 32 chunk (lane = row) is transposed through this warp's staging buffer so
+            // that one red.global.add.v4.f32 instruction covers four whole 128-byte row segments (8 lanes x 16 B each) instead
+            // of 32 scalar atomics scattered over 32 rows: 8 instructions per chunk instead of 32, every one fully coalesced.
+            float* sbuf = reinterpret_cast<float*>(stage);
+            __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + i < N) atomicAdd(dst + i, v[i]);
+            for (int i = 0; i < 32; ++i) sbuf[lane * 32 + (i ^ lane)] = v[i];      // XOR swizzle: conflict-free both ways
+            __syncwarp();
+            const int c0 = (lane & 7) * 4, rsub = lane >> 3;
+#pragma unroll
+            for (int r4 = 0; r4 < 8; ++r4) {
+              const int row = r4 * 4 + rsub;
+              const int mm = m_blk * GM + quad * 32 + row;
+              const float a0 = sbuf[row * 32 + ((c0 + 0) ^ row)], a1 = sbuf[row * 32 + ((c0 + 1) ^ row)];
+              const float a2 = sbuf[row * 32 + ((c0 + 2) ^ row)], a3 = sbuf[row * 32 + ((c0 + 3) ^ row)];
+              if (mm < M) {
+                float* dst = static_cast<float*>(C) + (size_t)mm * ldc + n0 + c0;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+              }
+            }
+            __syncwarp();
+          } else if (row_ok) {
+            float* dst = static_cast<float*>(C) + (size_t)m * ldc + n0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < N) atomicAdd(dst + i, v[i]);
+          }
           continue;
         }
         if (vec_ok && n0 + 32 <= N) {
@@ -448,7 +473,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
     if (k_split > num_kb / 4) k_split = num_kb / 4;           // at least 4 k-blocks per slice
     if (k_split < 1) k_split = 1;
   }
-  if (k_split > 1) {
+  if (k_split > 1 && !ep.accumulate) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
     if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: clearing the split-K output failed: %s", cudaGetErrorString(e)); return kCudaError; }
   }
@@ -479,6 +504,7 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
   // split-K only for plain fp32 outputs (no epilogue operation commutes with partial sums except the identity)
   const bool allow_split = !out_bf16 && !ep.bias && !ep.residual && !ep.row_scale && !ep.relu && ep.alpha_cols == 0 && !ep.head_scatter &&
                            ep.drop_scale == 0.f;
+  V2M_REQUIRE(!ep.accumulate || allow_split, "gemm_bf16_tc: accumulate needs a plain fp32 output (no bias / residual / activation / dropout)");
 #define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split)
   if (bn == 256) {
     if (!a_mn && !b_mn) return V2M_GO(256, false, false);

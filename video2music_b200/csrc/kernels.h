@@ -32,6 +32,9 @@ struct GemmEpilogue {
   unsigned int drop_thresh = 0, drop_seed = 0;
   int drop_after_res = 0;
   const unsigned int* drop_seed_dev = nullptr;   // optional device counter added to drop_seed (CUDA-graph replays need fresh masks)
+  // bf16 GEMM, fp32 output only: C += A W^T (vector reductions into C, which the caller owns and has initialised) instead of
+  // C = A W^T: weight gradients accumulate straight into the optimiser's gradient buffer.  No other epilogue operation.
+  int accumulate = 0;
 };
 
 #ifdef __CUDACC__

@@ -472,7 +472,7 @@ def gemm_strided(a: torch.Tensor, a_rs: int, a_cs: int, w: torch.Tensor, w_rs: i
 
 
 def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: float, alpha_cols: int, out_dtype: torch.dtype,
-            want_dz: bool = True, dropout: Optional[tuple] = None):
+            want_dz: bool = True, dropout: Optional[tuple] = None, db_out: Optional[torch.Tensor] = None):
     """dz = dy * relu'(y) * alpha_n * dropmask ; db = column sums of dz.  Returns (dz or None, db fp32 [N]).
     dropout = (p, seed) of the forward epilogue whose mask is recomputed here."""
     require_device(dy)
@@ -482,7 +482,9 @@ def dy_prep(dy: torch.Tensor, y: Optional[torch.Tensor], relu: bool, alpha: floa
     dz = None
     if want_dz:
         dz = torch.zeros((M, ld), device=dy.device, dtype=out_dtype) if ld != N else torch.empty((M, N), device=dy.device, dtype=out_dtype)
-    db = torch.zeros((N,), device=dy.device, dtype=torch.float32)
+    # db_out: the column sums are ADDED to this caller-owned fp32 buffer (a bias gradient inside the optimiser's buffer)
+    db = torch.zeros((N,), device=dy.device, dtype=torch.float32) if db_out is None else db_out
+    assert db.shape == (N,) and db.dtype == torch.float32 and db.is_contiguous()
     check(load().v2m_dy_prep(ptr(dy), dtype_code(dy.dtype), dy.stride(0), ptr(y), dtype_code(y.dtype) if y is not None else 0,
                              y.stride(0) if y is not None else 0, int(relu), alpha, alpha_cols, ptr(dz),
                              dtype_code(out_dtype), ld, ptr(db), M, N, *(drop_args(*dropout[:2]) if dropout and dropout[0] > 0 else (0.0, 0, 0)),
@@ -611,24 +613,28 @@ def rmsnorm_bwd(x: torch.Tensor, w: Optional[torch.Tensor], dy: torch.Tensor, ep
     return dx, dw
 
 
-def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5):
+def layernorm_bwd(x: torch.Tensor, gamma: torch.Tensor, dy: torch.Tensor, eps: float = 1e-5, dg_out: Optional[torch.Tensor] = None,
+                  db_out: Optional[torch.Tensor] = None):
+    """dg_out / db_out: caller-owned fp32 buffers the affine gradients are ADDED to (instead of fresh zeroed ones)."""
     require_device(x)
     x, dy = x.contiguous(), dy.contiguous()
     D = x.shape[-1]
     M = x.numel() // D
     dx = torch.empty_like(x)
-    dg = torch.zeros((D,), device=x.device, dtype=torch.float32)
-    db = torch.zeros((D,), device=x.device, dtype=torch.float32)
+    dg = torch.zeros((D,), device=x.device, dtype=torch.float32) if dg_out is None else dg_out
+    db = torch.zeros((D,), device=x.device, dtype=torch.float32) if db_out is None else db_out
     check(load().v2m_layernorm_bwd(ptr(x), dtype_code(x.dtype), ptr(gamma), ptr(dy), dtype_code(dy.dtype), ptr(dx),
                                    dtype_code(dx.dtype), ptr(dg), ptr(db), M, D, eps, stream()))
     _lib.count_launches(1)
     return dx, dg, db
 
 
-def embed_bwd(idx: torch.Tensor, d: torch.Tensor, n_rows_table: int, D: int) -> torch.Tensor:
+def embed_bwd(idx: torch.Tensor, d: torch.Tensor, n_rows_table: int, D: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out: caller-owned fp32 (rows, D) buffer the table gradient is ADDED to (instead of a fresh zeroed one)."""
     require_device(d)
     idx = idx.contiguous().view(-1)
-    dt = torch.zeros((n_rows_table, D), device=d.device, dtype=torch.float32)
+    dt = torch.zeros((n_rows_table, D), device=d.device, dtype=torch.float32) if out is None else out
+    assert dt.shape == (n_rows_table, D) and dt.is_contiguous()
     check(load().v2m_embed_bwd(ptr(idx), ptr(d), dtype_code(d.dtype), d.stride(0), ptr(dt), idx.numel(), D, stream()))
     _lib.count_launches(1)
     return dt
@@ -721,13 +727,19 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
 
 
 def linear_general(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool, b_mn: bool, M: int, N: int, K: int,
-                   out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+                   out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """bf16 tcgen05 GEMM C[M,N] = A B^T-style with optionally transposed storage: a is [M,K] (or [K,M] when a_mn),
-    b is [N,K] (or [K,N] when b_mn), both row-major 2-D bf16 tensors (leading dims from the strides)."""
+    b is [N,K] (or [K,N] when b_mn), both row-major 2-D bf16 tensors (leading dims from the strides).
+    accumulate (fp32 `out` given by the caller): out += A B^T through coalesced vector reductions."""
     require_device(a)
     assert a.dtype == b.dtype == torch.bfloat16 and a.stride(1) == 1 and b.stride(1) == 1
-    out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    else:
+        assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == out_dtype
     ep = Epilogue()
+    ep.accumulate = int(accumulate)
     check(load().v2m_gemm_bf16_general(ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), out.stride(0),
                                        dtype_code(out_dtype), M, N, K, C.byref(ep), stream()))
     _lib.count_launches(1)

@@ -103,21 +103,23 @@ class GradBuckets:
         else:
             self.bounds[-1] = (self.bounds[-1][0], flat_g.numel())
         self.bucket_of = [min(b, len(self.bounds) - 1) for b in self.bucket_of]
-        self.expected = None                  # per bucket: number of parameters that receive a gradient
+        self.expected = None                  # per bucket: number of gradient-complete signals per step
         self._seen = [0] * len(self.bounds)
         self._fired = set()
-        self._arrived = set()
         self._work = []
         self.order = []                       # bucket indices in launch order of the last step (diagnostics / tests)
         self.enabled = self.world > 1
         for i, p in enumerate(params):
-            p.register_post_accumulate_grad_hook(self._make_hook(i))
+            hook = self._make_hook(i)
+            p.register_post_accumulate_grad_hook(hook)
+            # backward kernels that add straight into the flat buffer (autograd.direct_grad) bypass AccumulateGrad and its
+            # hook; they call this instead -- once per use of the parameter, the same number of times every step
+            p._v2m_grad_ready = hook
 
     def _make_hook(self, i):
-        def hook(_p):
+        def hook(_p=None):
             if not self.enabled:
                 return
-            self._arrived.add(i)
             b = self.bucket_of[i]
             self._seen[b] += 1
             if self.expected is not None and self._seen[b] == self.expected[b] and b not in self._fired:
@@ -132,7 +134,7 @@ class GradBuckets:
 
     def start(self):
         self._seen = [0] * len(self.bounds)
-        self._fired, self._arrived, self._work, self.order = set(), set(), [], []
+        self._fired, self._work, self.order = set(), [], []
 
     def finish(self) -> float:
         """Waits for the in-flight buckets, reduces the ones that never fired; returns the scale (1 / world) that turns the
@@ -142,10 +144,7 @@ class GradBuckets:
         if self.expected is None:
             # discovery step: one flat all-reduce, remember which parameters produced gradients
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
-            exp = [0] * len(self.bounds)
-            for i in self._arrived:
-                exp[self.bucket_of[i]] += 1
-            self.expected = exp
+            self.expected = list(self._seen)
             self.order = [-1]
             return 1.0 / self.world
         for b in range(len(self.bounds) - 1, -1, -1):
@@ -160,7 +159,9 @@ class GradBuckets:
 class FlatParams:
     """Re-homes every parameter of `model` into one contiguous fp32 buffer (and its gradient into another)."""
 
-    def __init__(self, model: torch.nn.Module):
+    def __init__(self, model: torch.nn.Module, direct: bool = True):
+        """direct: mark the parameters so that the backward kernels accumulate into flat_g directly (autograd.direct_grad);
+        requires that whoever owns the buffers clears flat_g after every optimiser step (Trainer's Adam kernel does)."""
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
         params = [p for _, p in named]
         self.params = params
@@ -180,6 +181,8 @@ class FlatParams:
             self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
             p.data = self.flat_p[o:o + k].view(p.shape)
             p.grad = self.flat_g[o:o + k].view(p.shape)
+            if direct:
+                p._v2m_direct_grad = True
             self.offsets[name] = (o, tuple(p.shape))
         self.numel = n
 
@@ -188,7 +191,7 @@ class Trainer:
     def __init__(self, model, lr: Optional[float] = None, betas=(0.9, 0.98), eps: float = 1e-8, warmup: int = 4000,
                  group=None, use_graph: bool = False, optimizer: str = "Adam", weight_decay: Optional[float] = None,
                  bucket_mb: float = 16.0, overlap: bool = True, broadcast_init: bool = True, global_loss_norm: bool = True,
-                 init_steps: int = 0):
+                 init_steps: int = 0, direct_grads: bool = True):
         """lr None: the reference's schedule (LambdaLR over LrStepTracker, train.py:252; see scheduled_lr), else constant.
         eps: ADAM_EPSILON = 10e-9 = 1e-8 (utilities/constants.py:91).  optimizer: "Adam" (train.py:237-238) or "AdamW"
         (train.py:239-240, the CLI default, argument_funcs.py:17; decoupled weight_decay, torch's default 0.01).
@@ -203,7 +206,7 @@ class Trainer:
         dropout seeds are read from device memory so that they keep changing across replays."""
         from .autograd import AmtLossFn  # noqa: F401  (fail early if the extension is missing)
         self.model = model
-        self.flat = FlatParams(model)
+        self.flat = FlatParams(model, direct=direct_grads)
         self.m = torch.zeros_like(self.flat.flat_p)
         self.v = torch.zeros_like(self.flat.flat_p)
         self.lr, self.betas, self.eps, self.warmup = lr, betas, eps, warmup
