@@ -231,6 +231,17 @@ int v2m_decode_run(const v2m_decode* p, int32_t n_steps, int32_t use_graph, void
  * bf16, d_model 512, 8 heads, dim_feedforward 1024; V2M_UNSUPPORTED otherwise (callers then use v2m_decode_run).
  * timestamps (optional, device, ts_cap entries): globaltimer (ns) at every phase boundary of CTA 0 (measurement aid). */
 int v2m_decode_run_stream(const v2m_decode* p, int32_t t0, int32_t n_steps, uint64_t* timestamps, int32_t ts_cap, void* stream);
+/* bf16 tensor-core TRAINING path of the MoE experts (gradients of moe.py:44-49,191-199; torch autograd in the reference).
+ * kgrouped: C[g] (M x N fp32, stride c_gstride) = A_g^T B_g over the rows [k_off[g], k_off[g+1]) of the row-major bf16 matrices A
+ * [R, M] and B [R, N] -- the ragged dW_e = dY_e^T X_e with the group bounds (multiples of 64: moe_permute's 128-row aligned groups)
+ * read on the device.  swiglu_pair_bwd: gradient of h = a1 * silu(g) w.r.t. the pair matrix a = [a1 | g] (M x 2 ff).
+ * group_colsum: out[g][n] = column sums over group g (expert bias gradients). */
+int v2m_gemm_bf16_kgrouped(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc, int64_t c_gstride, int32_t M,
+                           int32_t N, int32_t R, int32_t n_groups, const int32_t* k_off, void* stream);
+int v2m_swiglu_pair_bwd_bf16(const void* a, const void* dh, void* dag, int64_t M, int32_t ff, void* stream);
+int v2m_moe_group_colsum_bf16(const void* x, int64_t ldx, const int32_t* off, int32_t n_groups, float* out, int32_t N, int32_t rows_hint,
+                              void* stream);
+
 /* out[row] = [k[row] | v[row]] (2 x 64 bf16) with the XOR swizzle above, row = (video*H + head)*S + position. */
 int v2m_kv_interleave(const void* k, const void* v, void* out, int64_t rows, int32_t S, void* stream);
 int64_t v2m_decode_launches_per_step(const v2m_decode* p);

@@ -41,6 +41,62 @@ def test_moe_train_golden_gpu(shared):
         assert rel_err(mod.eval()(x), y) < 1e-5
 
 
+@pytest.mark.parametrize("shared", [False, True])
+def test_moe_train_bf16_tensor_core_vs_reference_golden(shared):
+    """The same MoE / SharedMoE training step on the bf16 tensor-core path (grouped tcgen05 GEMMs forward, grouped dX and
+    K-grouped ragged dW GEMMs backward): routing indices bit-exact (the router stays fp32), output and every gradient within
+    2e-2 of the reference's fp32 autograd (moe_train.pt)."""
+    from video2music_b200 import GLUExpert, MoELayer, SharedMoELayer
+    g = load_golden("moe_train.pt")["shared_%s" % shared]
+    s = g["spec"]
+    cls = SharedMoELayer if shared else MoELayer
+    mod = cls(GLUExpert(s["d"], s["ff"], 0.0), s["d"], n_experts=s["n_experts"], n_experts_per_token=s["k"], dropout=0.0).train()
+    mod.load_state_dict(syn.fill_like_reference_init({k: tuple(v.shape) for k, v in mod.state_dict().items()}, seed=s["seed"]))
+    mod = mod.to(DEV)
+    mod.compute_dtype = torch.bfloat16
+    x = _u((s["L"], s["B"], s["d"]), s["x_seed"], "x").to(DEV).requires_grad_(True)
+    r = _u((s["L"], s["B"], s["d"]), s["x_seed"], "r").to(DEV)
+    y = mod(x)
+    (y * r).sum().backward()
+    assert torch.equal(mod.last_selected_experts.cpu(), g["selected_experts"])
+    assert rel_err(y, g["out"]) < 2e-2 and rel_err(x.grad, g["dx"]) < 2e-2
+    worst = 0.0
+    for n, p in mod.named_parameters():
+        gn = g["grad_norms"].get(n)
+        if gn is None:                                        # expert without tokens: None in the reference, zeros here
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        worst = max(worst, abs(float(p.grad.double().norm()) - gn) / max(gn, 1e-12))
+    print("bf16 MoE (shared=%s): worst gradient-norm error %.3e" % (shared, worst))
+    assert worst < 2e-2
+    for n, gref in g["grads"].items():
+        assert rel_err(dict(mod.named_parameters())[n].grad, gref) < 2e-2, n
+
+
+def test_gemm_kgrouped_ragged_dw():
+    """K-grouped tcgen05 GEMM: dW_e = dY_e^T X_e over 128-row aligned ragged groups (one of them empty) against float64."""
+    from video2music_b200 import ops
+    from video2music_b200._lib import load, check
+    rows = [384, 0, 128, 640, 256, 128]
+    off = [0]
+    for r_ in rows:
+        off.append(off[-1] + r_)
+    R, M, N, E = off[-1], 512, 1024, len(rows)
+    dy = (_u((R, M), 3, "dy") - 0.5).to(torch.bfloat16).to(DEV)
+    xx = (_u((R, N), 3, "x") - 0.5).to(torch.bfloat16).to(DEV)
+    offd = torch.tensor(off, dtype=torch.int32, device=DEV)
+    out = torch.full((E, M, N), float("nan"), device=DEV)
+    check(load().v2m_gemm_bf16_kgrouped(ops.ptr(dy), M, ops.ptr(xx), N, ops.ptr(out), N, M * N, M, N, R, E, ops.ptr(offd), ops.stream()))
+    for e in range(E):
+        ref = dy[off[e]:off[e + 1]].double().t() @ xx[off[e]:off[e + 1]].double()
+        assert float((out[e].double() - ref).abs().max()) <= 1e-3 * max(float(ref.abs().max()), 1.0), e
+    cs = torch.empty((E, M), device=DEV)
+    check(load().v2m_moe_group_colsum_bf16(ops.ptr(dy), M, ops.ptr(offd), E, ops.ptr(cs), M, R, ops.stream()))
+    for e in range(E):
+        ref = dy[off[e]:off[e + 1]].double().sum(0)
+        assert float((cs[e].double() - ref).abs().max()) <= 1e-3 * max(float(ref.abs().max()), 1.0), e
+
+
 @pytest.mark.parametrize("name", ["post_ln_moe", "post_ln_sharedmoe_b2", "pre_rms_moe"])
 def test_variant_train_golden_gpu(name):
     """Backward through 2 encoder + 2 decoder layers of MultiheadGQA(8 q heads, 2 kv heads) + (Shared)MoELayer inside the

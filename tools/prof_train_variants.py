@@ -41,6 +41,21 @@ def moe_step():
 
 
 timed("MoE fp32 forward + backward %d tokens" % T, moe_step, flops=3 * 2.0 * 2 * T * 3 * d * ff)
+moe.compute_dtype = torch.bfloat16
+timed("MoE bf16 tensor-core forward + backward %d tokens" % T, moe_step, flops=3 * 2.0 * 2 * T * 3 * d * ff)
+from video2music_b200 import SharedMoELayer
+smoe = SharedMoELayer(GLUExpert(d, ff, 0.0), d, n_experts=6, n_experts_per_token=2, dropout=0.0).to(dev).train()
+smoe.compute_dtype = torch.bfloat16
+
+
+def smoe_step():
+    smoe.zero_grad(set_to_none=True)
+    xg.grad = None
+    smoe(xg).sum().backward()
+
+
+timed("SharedMoE bf16 tensor-core forward + backward %d tokens" % T, smoe_step, flops=3 * 2.0 * 3 * T * 3 * d * ff)
+moe.compute_dtype = torch.float32
 # ---- fused selective scan forward / backward and conv backward (BASELINE config 5 shapes)
 ED, N, R = 256, 16, 8
 for (B, L) in [(64, 300), (8, 4096)]:

@@ -70,7 +70,7 @@ EXPORTS = [
     "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_attn_bwd_tc", "v2m_attn_bwd_tc_workspace", "v2m_dy_prep",
     "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_count_valid", "v2m_amt_metrics", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
-    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_rope_quirk", "v2m_mamba_conv_silu", "v2m_mamba_step_conv", "v2m_mamba_step_ssm", "v2m_selective_scan_fwd", "v2m_selective_scan_workspace", "v2m_selective_scan_bwd_workspace", "v2m_selective_scan_bwd", "v2m_mamba_conv_silu_bwd", "v2m_rmsnorm", "v2m_rmsnorm_bwd", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route", "v2m_moe_permute", "v2m_moe_grouped_gemm", "v2m_gemm_bf16_grouped", "v2m_swiglu_pair_bf16", "v2m_moe_combine", "v2m_moe_combine_bwd", "v2m_swiglu_bwd", "v2m_moe_grouped_dw", "v2m_dw_f32",
+    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_rope_quirk", "v2m_mamba_conv_silu", "v2m_mamba_step_conv", "v2m_mamba_step_ssm", "v2m_selective_scan_fwd", "v2m_selective_scan_workspace", "v2m_selective_scan_bwd_workspace", "v2m_selective_scan_bwd", "v2m_mamba_conv_silu_bwd", "v2m_rmsnorm", "v2m_rmsnorm_bwd", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route", "v2m_moe_permute", "v2m_moe_grouped_gemm", "v2m_gemm_bf16_grouped", "v2m_gemm_bf16_kgrouped", "v2m_swiglu_pair_bwd_bf16", "v2m_moe_group_colsum_bf16", "v2m_swiglu_pair_bf16", "v2m_moe_combine", "v2m_moe_combine_bwd", "v2m_swiglu_bwd", "v2m_moe_grouped_dw", "v2m_dw_f32",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -116,6 +116,9 @@ def load() -> C.CDLL:
     lib.v2m_binary_f32.argtypes = [vp, vp, vp, i64, i32, C.c_float, vp]
     lib.v2m_mamba_step_conv.argtypes = [vp, i64, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.v2m_mamba_step_ssm.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.v2m_gemm_bf16_kgrouped.argtypes = [vp, i32, vp, i32, vp, i32, i64, i32, i32, i32, i32, vp, vp]
+    lib.v2m_swiglu_pair_bwd_bf16.argtypes = [vp, vp, vp, i64, i32, vp]
+    lib.v2m_moe_group_colsum_bf16.argtypes = [vp, i64, vp, i32, vp, i32, i32, vp]
     lib.v2m_decode_run.argtypes = [C.POINTER(Decode), i32, i32, vp]
     lib.v2m_decode_run_stream.argtypes = [C.POINTER(Decode), i32, i32, vp, i32, vp]
     lib.v2m_kv_interleave.argtypes = [vp, vp, vp, i64, i32, vp]

@@ -542,6 +542,75 @@ class MoEExpertsFn(torch.autograd.Function):
         return (dx, dgate_w, dgate_b, None, None, None, None, None, None, *grads)
 
 
+class MoEExpertsBf16Fn(torch.autograd.Function):
+    """MoEExpertsFn on the bf16 tensor-core path: forward = the grouped tcgen05 GEMMs of the inference path with their
+    intermediates kept, backward = grouped GEMMs against the transposed weight stacks (dX) and K-grouped GEMMs over the ragged
+    expert groups (dW), all bf16 operands with fp32 accumulation; routing weights, the combine and every gradient that
+    reaches a parameter stay fp32.  stacks16 = (w1g bf16 [E, 2 ff, d], b1g fp32, w2 bf16 [E, d_out, ff], b2 fp32)."""
+
+    @staticmethod
+    def forward(ctx, x2, gate_w, gate_b, idx, w, hist, scale, stacks16, *params):
+        w1g, b1g, w2, b2 = stacks16
+        out, saved = ops.moe_experts_bf16_fwd_saved(x2, idx, w, hist, w1g, b1g, w2, b2)
+        ctx.save_for_backward(x2, gate_w, idx, w, w1g, w2, *saved)
+        ctx.scale = scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, gate_w, idx, w, w1g, w2, *saved = ctx.saved_tensors
+        E, ff2, d = w1g.shape
+        ff = ff2 // 2
+        w1g_t = w1g.transpose(1, 2).contiguous()                             # bf16 [E, d, 2 ff]
+        w2_t = w2.transpose(1, 2).contiguous()                               # bf16 [E, ff, d_out]
+        dx_e, dlogits, dW1g, db1g, dW2, db2 = ops.moe_experts_bf16_bwd(dout, tuple(saved), idx, w, ctx.scale, w1g_t, w2_t, E)
+        dgate_w = _gemm_dw(dlogits, x2, d)                                   # the router stays fp32 (6 columns)
+        _, dgate_b = ops.dy_prep(dlogits, None, False, 1.0, 0, F32, want_dz=False)
+        dx = ops.axpy(dx_e, _gemm_dx(dlogits, gate_w.detach().contiguous(), d), 1.0)
+        grads = []
+        for e in range(E):
+            grads += [dW1g[e, :ff], db1g[e, :ff], dW1g[e, ff:], db1g[e, ff:], dW2[e], db2[e]]
+        return (dx, dgate_w, dgate_b, None, None, None, None, None, *grads)
+
+
+class GluBf16Fn(torch.autograd.Function):
+    """One GLUExpert over all rows (the shared expert, moe.py:301) on the tcgen05 GEMMs with gradients: x fp32 (rows, d) ->
+    linear2((linear1 x) * silu(gate x)) fp32; stacks16 as above with E = 1."""
+
+    @staticmethod
+    def forward(ctx, x2, stacks16, w1, b1, wg, bg, w2p, b2p):
+        w1g, b1g, w2, b2 = stacks16
+        x16 = ops.cast_2d(x2, BF16)
+        a = ops.linear(x16, w1g[0], b1g[0], out_dtype=BF16)
+        h = ops.swiglu_pair(a)
+        ctx.save_for_backward(x16, a, h, w1g, w2)
+        return ops.linear(h, w2[0], b2[0], out_dtype=F32)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, a, h, w1g, w2 = ctx.saved_tensors
+        ff = h.shape[1]
+        d = x16.shape[1]
+        dy16, db2 = ops.dy_prep(dy.contiguous(), None, False, 1.0, 0, BF16, want_dz=True)
+        dW2 = _gemm_dw(dy16, h, ff)
+        dh = _gemm_dx(dy16, w2[0], ff)
+        dag = ops.swiglu_pair_bwd(a, dh.contiguous())
+        _, db1g = ops.dy_prep(dag, None, False, 1.0, 0, BF16, want_dz=False)
+        dW1g = _gemm_dw(dag, x16, d)
+        dx = _gemm_dx(dag, w1g[0], d).float()
+        return dx, None, dW1g[:ff], db1g[:ff], dW1g[ff:], db1g[ff:], dW2, db2
+
+
+def glu_expert_bf16_fn(e, x2: torch.Tensor, stacks16) -> torch.Tensor:
+    return GluBf16Fn.apply(x2, stacks16, e.linear1.weight, e.linear1.bias, e.gate.weight, e.gate.bias, e.linear2.weight, e.linear2.bias)
+
+
+def moe_experts_bf16_fn(experts, gate, x2, idx, w, hist, scale, stacks16):
+    params = [p for e in experts for p in (e.linear1.weight, e.linear1.bias, e.gate.weight, e.gate.bias, e.linear2.weight, e.linear2.bias)]
+    k = idx.shape[-1]
+    return MoEExpertsBf16Fn.apply(x2, gate.weight, gate.bias, idx.reshape(-1, k), w.reshape(-1, k), hist, scale, stacks16, *params)
+
+
 def moe_experts_fn(experts, gate, x2, idx, w, hist, scale, stacks, layer_dropout=None, training=False):
     """layer_dropout: the MoE layer's nn.Dropout (applied to every expert output row, moe.py:197); the experts' own dropout
     (hidden rows, moe.py:48) is read from experts[0] (all experts are clones of one GLUExpert)."""

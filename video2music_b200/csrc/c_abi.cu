@@ -220,6 +220,22 @@ int v2m_decode_run_stream(const v2m_decode* p, int32_t t0, int32_t n_steps, uint
   return rc;
 }
 
+int v2m_gemm_bf16_kgrouped(const void* A, int32_t lda, const void* B, int32_t ldb, float* C, int32_t ldc, int64_t c_gstride, int32_t M,
+                           int32_t N, int32_t R, int32_t n_groups, const int32_t* k_off, void* stream) {
+  V2M_REQUIRE(A && B && C && k_off, "v2m_gemm_bf16_kgrouped: null pointer");
+  return gemm_bf16_tc_kgrouped(A, lda, B, ldb, C, ldc, c_gstride, M, N, R, n_groups, k_off, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_swiglu_pair_bwd_bf16(const void* a, const void* dh, void* dag, int64_t M, int32_t ff, void* stream) {
+  V2M_REQUIRE(a && dh && dag, "v2m_swiglu_pair_bwd_bf16: null pointer");
+  return swiglu_pair_bwd_bf16(a, dh, dag, M, ff, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_moe_group_colsum_bf16(const void* x, int64_t ldx, const int32_t* off, int32_t n_groups, float* out, int32_t N, int32_t rows_hint,
+                              void* stream) {
+  return moe_group_colsum_bf16(x, ldx, off, n_groups, out, N, rows_hint, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_kv_interleave(const void* k, const void* v, void* out, int64_t rows, int32_t S, void* stream) {
   V2M_REQUIRE(k && v && out, "v2m_kv_interleave: null pointer");
   return kv_interleave(k, v, out, rows, S, static_cast<cudaStream_t>(stream));

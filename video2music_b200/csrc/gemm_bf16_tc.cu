@@ -114,7 +114,12 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
                     int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split,
-                    const int* __restrict__ tile_group, const __grid_constant__ CUtensorMap tmC, int tma_out) {
+                    const int* __restrict__ tile_group, const __grid_constant__ CUtensorMap tmC, int tma_out,
+                    const int* __restrict__ k_off, long long c_gstride) {
+  // k_off != null ("K-grouped", the ragged dW of the MoE experts: dW_e = dY_e^T X_e over the rows of group e): k_split is the
+  // number of groups, work item (tile, g) multiplies over the K range [k_off[g], k_off[g+1]) (multiples of 64, read on the
+  // device: group sizes never visit the host) and adds its tile to C + g * c_gstride (zero-initialised by the launcher);
+  // empty groups are skipped by all three roles.
   // tma_out: plain bf16 row-major C with 16-byte aligned rows.  Each epilogue warp packs its 32 x 32 chunk into a private
   // swizzled shared-memory box and one lane hands it to the TMA engine: the per-thread row stores (32 rows x 16 B per
   // instruction) were 40 % of the time of a K = 512 GEMM.
@@ -160,7 +165,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
         const int tile = item / k_split, ks = item - tile * k_split;
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+        int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+        if (k_off) { kb0 = k_off[ks] / GK; kb1 = k_off[ks + 1] / GK; if (kb0 >= kb1) continue; }
         int g = 0;
         if (tile_group) { g = tile_group[m_blk]; if (g < 0) continue; }
         const int b_row = g * N + n_blk * BN;
@@ -192,7 +198,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int ks = item % k_split;
-      const int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+      int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
+      if (k_off) { kb0 = k_off[ks] / GK; kb1 = k_off[ks + 1] / GK; if (kb0 >= kb1) continue; }
       if (tile_group && tile_group[(item / k_split) / n_tiles] < 0) continue;
       mbar_wait(tempty_bar + acc, acc_phase ^ 1);
       tc_fence_after();
@@ -230,6 +237,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int tile = item / k_split;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int m = m_blk * GM + quad * 32 + lane;
+      size_t c_goff = 0;
+      if (k_off) {
+        const int ks = item - tile * k_split;
+        if (k_off[ks] / GK >= k_off[ks + 1] / GK) continue;
+        c_goff = (size_t)ks * (size_t)c_gstride;
+      }
       const float* bias = ep.bias;
       if (tile_group) {
         const int g = tile_group[m_blk];
@@ -260,7 +273,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
         const int n0 = n_blk * BN + c * 32;
-        const bool fast = vec_ok && n0 + 32 <= N && k_split == 1 && !ep.accumulate;
+        const bool fast = vec_ok && n0 + 32 <= N && k_split == 1 && !ep.accumulate && !k_off;
         float4 bv[8];
         if (fast && row_ok && bias) {
           const float4* bp = reinterpret_cast<const float4*>(bias + n0);
@@ -273,12 +286,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fetch_res(c + 2, res_nx);
         tmem_ld_wait();
         const bool tma_chunk = tma_out && fast;                // warp-uniform
-        const bool red_chunk = (k_split > 1 || ep.accumulate) && vec_ok && n0 + 32 <= N;   // warp-uniform: all lanes take part in the transpose
+        const bool red_chunk = (k_split > 1 || ep.accumulate || k_off) && vec_ok && n0 + 32 <= N;   // warp-uniform: all lanes take part in the transpose
         if ((!row_ok && !tma_chunk && !red_chunk) || n0 >= N) continue;
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (k_split > 1 || ep.accumulate) {                  // partial sum of one K slice / accumulation into C (plain fp32, no epilogue ops)
+        if (k_split > 1 || ep.accumulate || k_off) {          // partial sum of one K slice / accumulation into C (plain fp32, no epilogue ops)
           if (vec_ok && n0 + 32 <= N) {
             // Coalesced vector reductions: the 32 x 32 chunk (lane = row) is transposed through this warp's staging buffer so
             // that one red.global.add.v4.f32 instruction covers four whole 128-byte row segments (8 lanes x 16 B each) instead
@@ -296,13 +309,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               const float a0 = sbuf[row * 32 + ((c0 + 0) ^ row)], a1 = sbuf[row * 32 + ((c0 + 1) ^ row)];
               const float a2 = sbuf[row * 32 + ((c0 + 2) ^ row)], a3 = sbuf[row * 32 + ((c0 + 3) ^ row)];
               if (mm < M) {
-                float* dst = static_cast<float*>(C) + (size_t)mm * ldc + n0 + c0;
+                float* dst = static_cast<float*>(C) + c_goff + (size_t)mm * ldc + n0 + c0;
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
               }
             }
             __syncwarp();
           } else if (row_ok) {
-            float* dst = static_cast<float*>(C) + (size_t)m * ldc + n0;
+            float* dst = static_cast<float*>(C) + c_goff + (size_t)m * ldc + n0;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (n0 + i < N) atomicAdd(dst + i, v[i]);
@@ -447,7 +460,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
-                       const GemmEpilogue& ep, cudaStream_t stream, bool allow_split, const int* tile_group = nullptr) {
+                       const GemmEpilogue& ep, cudaStream_t stream, bool allow_split, const int* tile_group = nullptr,
+                       const int* k_off = nullptr, int n_kgroups = 0, long long c_gstride = 0) {
   // TMA-store epilogue for plain bf16 outputs (the store map only exists in that case; otherwise it aliases tmA, unused)
   CUtensorMap tmC = tmA;
   int tma_out = 0;
@@ -473,13 +487,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
     if (k_split > num_kb / 4) k_split = num_kb / 4;           // at least 4 k-blocks per slice
     if (k_split < 1) k_split = 1;
   }
-  if (k_split > 1 && !ep.accumulate) {
+  if (k_off) k_split = n_kgroups;                            // K-grouped: one K range per group, outputs C + g * c_gstride (cleared by the caller)
+  if (k_split > 1 && !ep.accumulate && !k_off) {
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
     if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: clearing the split-K output failed: %s", cudaGetErrorString(e)); return kCudaError; }
   }
   const int items = tiles * k_split;
   const int grid = items < num_sms ? items : num_sms;
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out);
+  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out,
+                                                                                  k_off, c_gstride);
   return check_launch("gemm_bf16_tc");
 }
 
@@ -539,6 +555,27 @@ int gemm_bf16_tc_grouped(const void* A, int lda, const void* W, int ldw, void* C
   const int vec_ok = al16(bias) && al16(C) && ((long long)ldc * (out_bf16 ? 2 : 4)) % 16 == 0;
   if (bn == 256) return launch_gemm<256, false, false>(tmA, tmB, C, ldc, out_bf16, vec_ok, M_cap, N, K, ep, stream, false, tile_group);
   return launch_gemm<128, false, false>(tmA, tmB, C, ldc, out_bf16, vec_ok, M_cap, N, K, ep, stream, false, tile_group);
+}
+
+// K-grouped dW: C[g] (M x N fp32, group stride c_gstride elements) = A[rows of group g]^T B[rows of group g], both operands
+// stored row-major over the rows ([R, M] and [R, N] bf16: "MN-major"), group g = rows [k_off[g], k_off[g+1]) with every bound a
+// multiple of 64 (the 128-row aligned expert groups of moe_permute; padding rows are zero in at least one operand).
+int gemm_bf16_tc_kgrouped(const void* A, int lda, const void* B, int ldb, float* C, int ldc, long long c_gstride, int M, int N,
+                          int R, int n_groups, const int* k_off, cudaStream_t stream) {
+  V2M_REQUIRE(M > 0 && N > 0 && R >= 0 && n_groups > 0 && k_off, "gemm_bf16_tc_kgrouped: bad arguments");
+  cudaError_t e = cudaMemsetAsync(C, 0, (size_t)n_groups * (size_t)c_gstride * 4, stream);
+  if (e != cudaSuccess) { set_last_error("gemm_bf16_tc_kgrouped: clearing the output failed: %s", cudaGetErrorString(e)); return kCudaError; }
+  if (R == 0) return kOk;
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, A, R, M, lda, 64);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tmB, B, R, N, ldb, 64);
+  if (rc) return rc;
+  GemmEpilogue ep;
+  const int vec_ok = reinterpret_cast<uintptr_t>(C) % 16 == 0 && ((long long)ldc * 4) % 16 == 0 && (c_gstride * 4) % 16 == 0;
+  if (bn == 256) return launch_gemm<256, true, true>(tmA, tmB, C, ldc, 0, vec_ok, M, N, R, ep, stream, false, nullptr, k_off, n_groups, c_gstride);
+  return launch_gemm<128, true, true>(tmA, tmB, C, ldc, 0, vec_ok, M, N, R, ep, stream, false, nullptr, k_off, n_groups, c_gstride);
 }
 
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,

@@ -57,6 +57,10 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc
 int gemm_bf16_tc(const void* A, int lda, const void* W, int ldw, void* C, int ldc, int out_bf16, int M, int N, int K,
                  const GemmEpilogue& ep, cudaStream_t stream);
 
+int swiglu_pair_bwd_bf16(const void* a, const void* dh, void* dag, long long M, int ff, cudaStream_t stream);
+int moe_group_colsum_bf16(const void* x, long long ldx, const int* off, int n_groups, float* out, int N, int rows_hint, cudaStream_t stream);
+int gemm_bf16_tc_kgrouped(const void* A, int lda, const void* B, int ldb, float* C, int ldc, long long c_gstride, int M, int N,
+                          int R, int n_groups, const int* k_off, cudaStream_t stream);
 // General form: a_mn / b_mn != 0 means the operand is stored transposed ([K, M] resp. [K, N] row-major).
 int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ldw, int b_mn, void* C, int ldc, int out_bf16,
                          int M, int N, int K, const GemmEpilogue& ep, cudaStream_t stream);

@@ -73,6 +73,69 @@ int moe_route(const float* x, const float* wg, const float* bg, const float* sel
 }
 
 
+// ---- bf16 tensor-core training path of the experts (gradients of moe.py:44-49,191-199 on the grouped tcgen05 GEMMs) ----------
+// swiglu_pair_bwd: a [M, 2 ff] = (x W1^T + b1 | x Wg^T + bg) as written by the grouped GEMM, dh [M, ff] -> dag [M, 2 ff]:
+//   d a1 = dh * silu(g),  d g = dh * a1 * sigmoid(g) * (1 + g * (1 - sigmoid(g)))
+__global__ void __launch_bounds__(256) swiglu_pair_bwd_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ dh,
+                                                                   bf16* __restrict__ dag, long long M, int ff) {
+  const long long n2 = M * (long long)(ff / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (ff / 2);
+    const int c = (int)(i - r * (ff / 2)) * 2;
+    const float2 a1 = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(a + r * 2 * ff + c));
+    const float2 g = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(a + r * 2 * ff + ff + c));
+    const float2 d = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(dh + r * ff + c));
+    const float s0 = 1.f / (1.f + expf(-g.x)), s1 = 1.f / (1.f + expf(-g.y));
+    *reinterpret_cast<uint32_t*>(dag + r * 2 * ff + c) = f2_to_bf16x2(d.x * g.x * s0, d.y * g.y * s1);
+    *reinterpret_cast<uint32_t*>(dag + r * 2 * ff + ff + c) =
+        f2_to_bf16x2(d.x * a1.x * s0 * (1.f + g.x * (1.f - s0)), d.y * a1.y * s1 * (1.f + g.y * (1.f - s1)));
+  }
+}
+
+int swiglu_pair_bwd_bf16(const void* a, const void* dh, void* dag, long long M, int ff, cudaStream_t stream) {
+  V2M_REQUIRE(ff > 0 && ff % 2 == 0, "swiglu_pair_bwd_bf16: ff=%d must be even", ff);
+  if (M == 0) return kOk;
+  const long long want = (M * (ff / 2) + 255) / 256;
+  swiglu_pair_bwd_bf16_kernel<<<(int)(want < 148 * 16 ? want : 148 * 16), 256, 0, stream>>>(static_cast<const bf16*>(a), static_cast<const bf16*>(dh),
+                                                                                            static_cast<bf16*>(dag), M, ff);
+  return check_launch("swiglu_pair_bwd_bf16");
+}
+
+// out[g][n] = sum over the rows of group g of x[row][n] (bias gradients of the experts): grid (column blocks of 64, row
+// splits, groups), group bounds read on the device, partial sums added to the zero-initialised output.
+__global__ void __launch_bounds__(256) moe_group_colsum_bf16_kernel(const bf16* __restrict__ x, long long ldx, const int* __restrict__ off,
+                                                                    float* __restrict__ out, int N) {
+  const int g = blockIdx.z;
+  const int r0 = off[g], r1 = off[g + 1];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;           // 32 column pairs x 8 row lanes
+  const int n = blockIdx.x * 64 + 2 * cx;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = r0 + blockIdx.y * 8 + ry; r < r1 && n < N; r += gridDim.y * 8) {
+    const float2 v = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(x + (long long)r * ldx + n));
+    s0 += v.x; s1 += v.y;
+  }
+  __shared__ float part[8][66];
+  part[ry][2 * cx] = s0; part[ry][2 * cx + 1] = s1;
+  __syncthreads();
+  if (ry == 0) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a0 += part[i][2 * cx]; a1 += part[i][2 * cx + 1]; }
+    if (n < N && a0 != 0.f) atomicAdd(out + (long long)g * N + n, a0);
+    if (n + 1 < N && a1 != 0.f) atomicAdd(out + (long long)g * N + n + 1, a1);
+  }
+}
+
+int moe_group_colsum_bf16(const void* x, long long ldx, const int* off, int n_groups, float* out, int N, int rows_hint, cudaStream_t stream) {
+  V2M_REQUIRE(N > 0 && N % 2 == 0 && n_groups > 0 && off && out, "moe_group_colsum_bf16: bad arguments");
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)n_groups * N * 4, stream);
+  if (e != cudaSuccess) { set_last_error("moe_group_colsum_bf16: memset: %s", cudaGetErrorString(e)); return kCudaError; }
+  int splits = (rows_hint / n_groups + 255) / 256;
+  splits = splits < 1 ? 1 : (splits > 32 ? 32 : splits);
+  moe_group_colsum_bf16_kernel<<<dim3((N + 63) / 64, splits, n_groups), 256, 0, stream>>>(static_cast<const bf16*>(x), ldx, off, out, N);
+  return check_launch("moe_group_colsum_bf16");
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Expert dispatch without host round trips (the reference loops over experts in Python with torch.where per expert,
 // model/moe.py:192-199):

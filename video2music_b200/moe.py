@@ -203,6 +203,9 @@ class MoELayer(nn.Module):
         if (ag.tracking(x, self) or drop) and getattr(self, "compute_dtype", torch.float32) == torch.float32:   # gradients of moe.py:180-199
             return ag.moe_experts_fn(self.experts, self.gate, ag.rows_f32(x), idx, w, hist, 1.0 / t, _stacked(self.experts),
                                      layer_dropout=self.dropout, training=self.training).view(shp)
+        if ag.tracking(x, self) and _tc_ok(shp[-1], self.experts[0].linear1.out_features, self.experts[0].linear2.out_features):
+            # bf16 compute dtype with gradients: forward and backward on the grouped tcgen05 GEMMs
+            return ag.moe_experts_bf16_fn(self.experts, self.gate, ag.rows_f32(x), idx, w, hist, 1.0 / t, _stacked_bf16(self.experts)).view(shp)
         return _experts_forward(self.experts, x2, idx, w, hist, getattr(self, "compute_dtype", torch.float32)).view(shp)
 
 
@@ -263,6 +266,11 @@ class SharedMoELayer(nn.Module):
                                     layer_dropout=self.dropout, training=self.training)
             return ag.AddFn.apply(out, ag.glu_expert_fn(self.shared_expert, xr), 1.0 / k).view(shp[:-1] + (self.d_model,))
         dt = getattr(self, "compute_dtype", torch.float32)
+        if ag.tracking(x, self) and _tc_ok(shp[-1], self.experts[0].linear1.out_features, self.experts[0].linear2.out_features):
+            xr = ag.rows_f32(x)                                          # bf16 compute dtype with gradients: tensor-core training path
+            out = ag.moe_experts_bf16_fn(self.experts, self.gate, xr, idx, w, hist, 1.0 / t, _stacked_bf16(self.experts))
+            shared = ag.glu_expert_bf16_fn(self.shared_expert, xr, _stacked_bf16([self.shared_expert]))
+            return ag.AddFn.apply(out, shared, 1.0 / k).view(shp[:-1] + (self.d_model,))
         out = _experts_forward(self.experts, x2, idx, w, hist, dt)
         shared = _glu_bf16(self.shared_expert, x2) if dt == torch.bfloat16 else _glu(self.shared_expert, x2)   # moe.py:301
         return ops.axpy(out, shared, 1.0 / k).view(shp[:-1] + (self.d_model,))

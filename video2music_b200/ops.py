@@ -355,6 +355,90 @@ def moe_experts_bf16(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: 
     return out
 
 
+def _moe_bf16_forward(x, idx, w, hist, w1g, b1g, w2, b2):
+    T, k = idx.shape
+    E, ff2, d = w1g.shape
+    ff, d_out = ff2 // 2, w2.shape[1]
+    dev = x.device
+    m_cap = (T * k + E * 127 + 127) // 128 * 128
+    n_tiles = m_cap // 128
+    meta = torch.empty((2 * E + 1 + T * k + n_tiles,), device=dev, dtype=torch.int32)
+    off, cursor, perm, tile_group = meta[:E + 1], meta[E + 1:2 * E + 1], meta[2 * E + 1:2 * E + 1 + T * k], meta[2 * E + 1 + T * k:]
+    xp = torch.zeros((m_cap, d), device=dev, dtype=torch.bfloat16)
+    a = torch.empty((m_cap, ff2), device=dev, dtype=torch.bfloat16)
+    h = torch.empty((m_cap, ff), device=dev, dtype=torch.bfloat16)
+    yp = torch.empty((m_cap, d_out), device=dev, dtype=torch.float32)
+    out = torch.empty((T, d_out), device=dev, dtype=torch.float32)
+    lib, st = load(), stream()
+    check(lib.v2m_moe_permute(ptr(x), ptr(idx), ptr(hist), T, k, d, E, 128, ptr(off), ptr(cursor), ptr(xp), dtype_code(xp.dtype), ptr(perm),
+                              ptr(tile_group), n_tiles, st))
+    check(lib.v2m_gemm_bf16_grouped(ptr(xp), d, ptr(w1g), d, ptr(a), ff2, dtype_code(a.dtype), m_cap, ff2, d, E, ptr(tile_group), ptr(b1g), 0, st))
+    check(lib.v2m_swiglu_pair_bf16(ptr(a), ptr(h), m_cap, ff, st))
+    check(lib.v2m_gemm_bf16_grouped(ptr(h), ff, ptr(w2), ff, ptr(yp), d_out, dtype_code(yp.dtype), m_cap, d_out, ff, E, ptr(tile_group), ptr(b2), 0, st))
+    check(lib.v2m_moe_combine(ptr(yp), ptr(perm), ptr(w), ptr(out), T, k, d_out, st))
+    _lib.count_launches(7)
+    return out, (xp, a, h, yp, perm, off, tile_group)
+
+
+def moe_experts_bf16_fwd_saved(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor, w1g: torch.Tensor,
+                               b1g: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor):
+    """Training-mode forward of `moe_experts_bf16` (same launches): returns (out, saved) with saved = (xp bf16 (m_cap, d), a bf16
+    (m_cap, 2 ff) = [linear1 | gate] pre-activations, h bf16, yp fp32, perm, off (128-row aligned group starts), tile_group)."""
+    require_device(x)
+    return _moe_bf16_forward(x, idx, w, hist, w1g, b1g, w2, b2)
+
+
+def moe_experts_bf16_bwd(dout: torch.Tensor, saved, idx: torch.Tensor, w: torch.Tensor, scale: float, w1g_t: torch.Tensor,
+                         w2_t: torch.Tensor, n_experts: int):
+    """Backward of the bf16 expert path on the tensor cores.  w1g_t bf16 [E, d, 2 ff] and w2_t bf16 [E, ff, d_out] are the
+    transposed weight stacks (the dX products are grouped GEMMs against them); the ragged weight gradients dW_e = dY_e^T X_e
+    are K-grouped tcgen05 GEMMs with the group bounds read on the device.  Returns (dx_experts fp32 (T, d), dlogits (T, E),
+    dW1g fp32 (E, 2 ff, d), db1g (E, 2 ff), dW2 (E, d_out, ff), db2 (E, d_out))."""
+    require_device(dout)
+    xp, a, h, yp, perm, off, tile_group = saved
+    T, k = idx.shape
+    E = n_experts
+    m_cap, d = xp.shape
+    ff, d_out = h.shape[1], yp.shape[1]
+    dev = dout.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    bf = dict(device=dev, dtype=torch.bfloat16)
+    dout = dout.float().contiguous()
+    dyp32, dlogits = torch.zeros((m_cap, d_out), **f32), torch.empty((T, E), **f32)      # padding rows of every group stay zero
+    lib, st = load(), stream()
+    check(lib.v2m_moe_combine_bwd(ptr(dout), ptr(yp), ptr(perm), ptr(w), ptr(idx), scale, T, k, d_out, E, ptr(dyp32), ptr(dlogits), st))
+    _lib.count_launches(1)
+    dyp = cast_2d(dyp32, torch.bfloat16)
+    dW2, db2 = torch.empty((E, d_out, ff), **f32), torch.empty((E, d_out), **f32)
+    dW1g, db1g = torch.empty((E, 2 * ff, d), **f32), torch.empty((E, 2 * ff), **f32)
+    dh, dag = torch.empty((m_cap, ff), **bf), torch.empty((m_cap, 2 * ff), **bf)
+    dxp, dx = torch.empty((m_cap, d), **f32), torch.empty((T, d), **f32)
+    ones = torch.ones((T, k), **f32)
+    check(lib.v2m_gemm_bf16_kgrouped(ptr(dyp), dyp.stride(0), ptr(h), ff, ptr(dW2), ff, d_out * ff, d_out, ff, m_cap, E, ptr(off), st))
+    check(lib.v2m_moe_group_colsum_bf16(ptr(dyp), dyp.stride(0), ptr(off), E, ptr(db2), d_out, m_cap, st))
+    check(lib.v2m_gemm_bf16_grouped(ptr(dyp), dyp.stride(0), ptr(w2_t), d_out, ptr(dh), ff, dtype_code(dh.dtype), m_cap, ff, d_out, E,
+                                    ptr(tile_group), None, 0, st))
+    check(lib.v2m_swiglu_pair_bwd_bf16(ptr(a), ptr(dh), ptr(dag), m_cap, ff, st))
+    check(lib.v2m_gemm_bf16_kgrouped(ptr(dag), 2 * ff, ptr(xp), d, ptr(dW1g), d, 2 * ff * d, 2 * ff, d, m_cap, E, ptr(off), st))
+    check(lib.v2m_moe_group_colsum_bf16(ptr(dag), 2 * ff, ptr(off), E, ptr(db1g), 2 * ff, m_cap, st))
+    check(lib.v2m_gemm_bf16_grouped(ptr(dag), 2 * ff, ptr(w1g_t), 2 * ff, ptr(dxp), d, dtype_code(dxp.dtype), m_cap, d, 2 * ff, E,
+                                    ptr(tile_group), None, 0, st))
+    check(lib.v2m_moe_combine(ptr(dxp), ptr(perm), ptr(ones), ptr(dx), T, k, d, st))
+    _lib.count_launches(12)
+    return dx, dlogits, dW1g, db1g, dW2, db2
+
+
+def swiglu_pair_bwd(a: torch.Tensor, dh: torch.Tensor) -> torch.Tensor:
+    """Gradient of h = a[:, :ff] * silu(a[:, ff:]) w.r.t. the bf16 pair matrix a (M, 2 ff): (M, 2 ff) bf16."""
+    require_device(a)
+    assert a.dtype == dh.dtype == torch.bfloat16 and a.is_contiguous() and dh.is_contiguous()
+    M, ff = dh.shape
+    dag = torch.empty_like(a)
+    check(load().v2m_swiglu_pair_bwd_bf16(ptr(a), ptr(dh), ptr(dag), M, ff, stream()))
+    _lib.count_launches(1)
+    return dag
+
+
 def moe_experts_fwd_saved(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, hist: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
                           wg: torch.Tensor, bg: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, drops=None):
     """Training-mode forward of `moe_experts`: same result, but the two halves of the SwiGLU pair are kept (a = x W1^T + b1,
