@@ -241,6 +241,12 @@ def variants_leg(dev):
     ms = timed(step(enc, lambda: enc(src)))
     out["gqa_moe_encoder_train"] = {"ms_per_step": ms, "samples_per_s": 8 / (ms * 1e-3), "shape": "6 layers, 8 videos x 300 tokens, d 512, "
                                     "8 q / 2 kv heads, 6 experts top-2 ff 1024", "dtype": "f32"}
+    for mod in enc.modules():
+        if isinstance(mod, MoELayer):
+            mod.compute_dtype = torch.bfloat16                  # experts on the grouped tcgen05 GEMMs (forward and backward)
+    ms = timed(step(enc, lambda: enc(src)))
+    out["gqa_moe_encoder_train_moe_bf16"] = {"ms_per_step": ms, "samples_per_s": 8 / (ms * 1e-3), "shape": out["gqa_moe_encoder_train"]["shape"],
+                                             "dtype": "bf16 experts (grouped tcgen05 GEMMs, K-grouped ragged dW), fp32 GQA attention / router / norms"}
     del enc, layer
     reg = VideoRegression(n_layers=6, d_model=128, d_hidden=256, dropout=0.0, total_vf_dim=774, regModel="bimamba+").to(dev).train()
     sem, emo = torch.randn(64, 300, 768, generator=g).to(dev), torch.softmax(torch.randn(64, 300, 6, generator=g), -1).to(dev)

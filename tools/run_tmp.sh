@@ -1,2 +1,2 @@
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_train_b64_launches_b.csv python tools/train_time.py 64 bf16 1 > /dev/null 2>&1
-python tools/ncu_summary.py gpurun_out/r2_train_b64_launches_b.csv > gpurun_out/r2_train_b64_summary_b.txt 2>&1
+python -m pytest tests/test_gpu_variant_train.py -m gpu -q -s -k "bf16 or kgrouped" 2>&1 | tail -25 > gpurun_out/r2_moe16_tests.log
+python tools/prof_train_variants.py 2>&1 | head -8 > gpurun_out/r2_moe16_timing.txt
