@@ -139,6 +139,15 @@ def test_attention_f32(B, H, L, S, dh, er_len, causal):
     (2, 4, 4, 150, 150, 160, False),     # RPR without a mask
     (2, 8, 2, 130, 170, 0, False),       # grouped-query (Hkv < Hq), ragged
     (1, 2, 2, 1, 1, 16, True),
+    # stock attentions -> the single-kernel tcgen05 backward (csrc/attn_bwd_tc5.cu): tails, exact tile multiples, the
+    # largest supported lengths, odd / even numbers of query blocks, more (video, head) items than SMs
+    (3, 4, 4, 37, 53, 0, False),
+    (1, 2, 2, 64, 128, 0, False),
+    (2, 4, 4, 65, 129, 0, False),
+    (2, 4, 4, 320, 320, 0, False),
+    (2, 2, 2, 257, 200, 0, False),
+    (20, 8, 8, 100, 90, 0, False),
+    (1, 1, 1, 1, 1, 0, False),
 ])
 def test_attention_bwd_tensor_core(B, Hq, Hkv, L, S, er_len, causal):
     """mma.sync attention backward (csrc/attn_bwd_tc.cu) against torch autograd over the oracle's arithmetic (the
@@ -655,7 +664,7 @@ def test_linear_fused_dropout_forward_backward():
             assert rel_err(rg.grad.float(), rf.grad) < 2e-2
 
 
-@pytest.mark.parametrize("L,S,er_len,causal", [(150, 150, 160, True), (99, 140, 0, False)])
+@pytest.mark.parametrize("L,S,er_len,causal", [(150, 150, 160, True), (99, 140, 0, False), (299, 300, 0, False)])
 def test_attention_probability_dropout_forward_backward(L, S, er_len, causal):
     """Dropout of the attention probabilities inside the fused forward kernel and the backward rows kernel, against torch
     autograd with the SAME mask (recovered by attending with q = k = 0 over one-hot V blocks)."""

@@ -490,6 +490,8 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   V2M_REQUIRE(p.dq_sl % 2 == 0 && p.dkv_sl % 2 == 0 && p.dq_sb % 2 == 0 && p.dkv_sb % 2 == 0, "attn_bwd_tc: odd gradient strides");
   const long long need = attn_bwd_tc_workspace(p.B, p.Hq, p.Lq, p.Lk, has_er);
   V2M_REQUIRE(ws_ptr && ws_bytes >= need, "attn_bwd_tc: workspace of %lld B needed, %lld given", need, ws_bytes);
+  // stock attentions (encoder self-attention, decoder cross-attention): one tcgen05 kernel, nothing through HBM
+  if (attn_bwd_tc5_supported(p)) return attn_bwd_tc5(p, ws_ptr, ws_bytes, stream);
   abt::Ws ws;
   ws.Lqp = (p.Lq + 63) / 64 * 64;
   ws.Lkp = (p.Lk + 63) / 64 * 64;

@@ -1,0 +1,379 @@
+// Attention backward on tcgen05 / TMEM / TMA (bf16 operands, fp32 accumulate, sm_100a) -- the stock attentions of the AMT
+// (encoder self-attention and decoder cross-attention: no relative term, no mask), i.e. the gradient torch autograd derives
+// for F.multi_head_attention_forward (model/rpr.py:42,62-63; nn.TransformerEncoderLayer):
+//
+//   P = exp(Q K^T - lse),  Pd = dropout(P),  D_i = dO_i . O_i,  dS = P o (dropout'(dO V^T) - D)
+//   dV = Pd^T dO,   dK = dS^T Q,   dQ = dS K
+//
+// One CTA owns one (video, head): Q, K, V, dO of the whole problem (L <= 320) are resident in shared memory, every product
+// runs on the tensor core and NOTHING goes through HBM between them (the mma.sync kernels of attn_bwd_tc.cu write the P and dS
+// tiles -- 1.8 GB per launch at B = 512 -- to a workspace for a second kernel).
+//
+// Orientation: keys on the TMEM lanes.  For key tile j (128 keys) and query block i (64 queries):
+//   S^T  = K_j Q_i^T          [128 x 64]   TMEM cols [  0, 64)      A = K_j (K-major), B = Q_i (K-major)
+//   dP^T = V_j dO_i^T         [128 x 64]   TMEM cols [ 64,128)
+//   the 8 softmax warps (two per lane quadrant, 32 query columns each) turn them into P^T (dropped) and dS^T, bf16, written
+//   to shared memory as [128 keys x 64 queries] tiles in the 128-byte-swizzled operand layout;
+//   dV_j += P^T dO_i          TMEM cols [128,192)   A = P^T tile (K-major),  B = dO_i (MN-major: [queries x dims])
+//   dK_j += dS^T Q_i          TMEM cols [192,256)   A = dS^T tile (K-major), B = Q_i  (MN-major)
+//   dQ_I += dS_I K_j          TMEM cols [256,448)   for the pair I = (i-1, i) of query blocks: A = the two dS^T tiles read as
+//                                                  an MN-major operand (M = 128 queries, K = 128 keys), B = K_j (MN-major)
+// dQ accumulates over the key tiles in TMEM (3 x 64 columns), dK / dV leave after each key tile.
+// An odd last query block issues its dQ product with a stale second half: only accumulator rows >= Lq see it, and those
+// are never stored.  Keys >= Lk (zero rows of K / V) are masked in P^T and dS^T.
+//
+// Pipeline per step n = (j, i):   issuer: S^T / dP^T of step n+1 are issued as soon as the softmax warps have pulled step n
+// out of TMEM (bar_sfree); the three accumulating products of step n follow when the tiles are in shared memory (bar_pds)
+// and free them again when they retire (bar_tfree).
+#include "common.cuh"
+#include "kernels.h"
+#include <cuda.h>
+#include <cstdlib>
+
+namespace v2m {
+
+int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long long rows, long long batch,
+                      long long row_pitch, long long batch_pitch, int box_rows, int swap);
+
+namespace ab5 {
+
+constexpr int DH = 64;
+constexpr int MAXL = 320;                 // queries / keys per (video, head)
+constexpr int QROWS = 320, KROWS = 384;   // rows held in shared memory (keys padded to whole 128-row tiles, zero rows)
+constexpr int SM_Q = QROWS * 128, SM_K = KROWS * 128, SM_TILE = 128 * 128;
+constexpr int NW = 2;                     // softmax warps per TMEM lane quadrant
+constexpr int THREADS = 32 + 128 * NW;
+constexpr size_t SMEM = 1024 + 2 * SM_Q + 2 * SM_K + 3 * SM_TILE + 256;
+
+struct Args {
+  const float* lse; const float* delta;
+  void* dq; void* dk; void* dv;
+  long long dq_sb, dq_sl, dkv_sb, dkv_sl;
+  int B, H, Lq, Lk, swap;
+  float drop_scale; unsigned int drop_thresh, drop_seed; const unsigned int* drop_seed_dev;
+};
+
+// delta[bh][i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per row)
+__global__ void __launch_bounds__(256) delta_kernel(const bf16* __restrict__ o, long long o_sb, long long o_sl, const bf16* __restrict__ dO,
+                                                    long long do_sb, long long do_sl, float* __restrict__ delta, int B, int H, int Lq) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * H * Lq) return;
+  const int i = (int)(row % Lq);
+  const long long bh = row / Lq;
+  const int h = (int)(bh % H);
+  const long long b = bh / H;
+  const float2 a = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(o + b * o_sb + (long long)i * o_sl + h * DH + 2 * lane));
+  const float2 g = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(dO + b * do_sb + (long long)i * do_sl + h * DH + 2 * lane));
+  float s = a.x * g.x + a.y * g.y;
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o_);
+  if (lane == 0) delta[row] = s;
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ Args a) {
+  extern __shared__ unsigned char ab5_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ab5_smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;
+  unsigned char* sDO = sQ + SM_Q;
+  unsigned char* sK = sDO + SM_Q;
+  unsigned char* sV = sK + SM_K;
+  unsigned char* sP = sV + SM_K;            // P^T tile
+  unsigned char* sDS = sP + SM_TILE;        // two dS^T tiles (even / odd query block of a pair)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * SM_TILE);
+  uint64_t* bar_ld = bars + 0;       // operands of the item landed
+  uint64_t* bar_s = bars + 1;        // S^T and dP^T of a step complete
+  uint64_t* bar_sfree = bars + 2;    // all softmax warps have pulled them out of TMEM (count 4 * NW)
+  uint64_t* bar_pds = bars + 3;      // P^T / dS^T tiles written (count 4 * NW)
+  uint64_t* bar_tfree = bars + 4;    // the accumulating products of a step have retired: tiles (and, after a key tile, dV / dK) final
+  uint64_t* bar_kvfree = bars + 5;   // dV / dK pulled out of TMEM (count 4 * NW)
+  uint64_t* bar_qfree = bars + 6;    // dQ pulled out of TMEM (count 4 * NW): next item may start
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nqb = (a.Lq + 63) / 64;          // query blocks of 64
+  const int nkt = (a.Lk + 127) / 128;        // key tiles of 128
+  const int nq64 = nqb, nk64 = (a.Lk + 63) / 64;
+  const int n_items = a.B * a.H;
+  const int steps = nkt * nqb;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 4 * NW); mbar_init(bar_pds, 4 * NW);
+    mbar_init(bar_tfree, 1); mbar_init(bar_kvfree, 4 * NW); mbar_init(bar_qfree, 4 * NW);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  // rows of K / V beyond the loaded boxes are read by the MN-major dQ product (times dS = 0): they must be finite
+  for (int i = threadIdx.x; i < 2 * SM_K / 16; i += THREADS) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t T_S = tmem, T_DP = tmem + 64, T_DV = tmem + 128, T_DK = tmem + 192, T_DQ = tmem + 256;
+
+  auto tma3 = [&](void* dst, const CUtensorMap* tm, int col, int row, int batch, uint64_t* bar) {
+    if (a.swap) tma_load_3d(dst, tm, col, batch, row, bar);
+    else tma_load_3d(dst, tm, col, row, batch, bar);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);      // S^T, dP^T: both operands K-major
+      const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);     // dV, dK: A K-major tile, B MN-major
+      const uint32_t idesc_q = make_idesc_bf16(128, 64, 1, 1);      // dQ: A = dS^T tiles read MN-major, B = K_j MN-major
+      uint32_t ph_ld = 0, ph_sfree = 0, ph_pds = 0, ph_kvfree = 0, ph_qfree = 0;
+      auto issue_s = [&](int n) {                                    // S^T and dP^T of step n
+        const int j = n / nqb, i = n - j * nqb;
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16_ss(T_S, make_smem_desc_sw128(k_addr + j * SM_TILE + k * 32, 16, 1024),
+                       make_smem_desc_sw128(q_addr + i * 8192 + k * 32, 16, 1024), idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16_ss(T_DP, make_smem_desc_sw128(v_addr + j * SM_TILE + k * 32, 16, 1024),
+                       make_smem_desc_sw128(do_addr + i * 8192 + k * 32, 16, 1024), idesc_s, k != 0);
+        umma_commit(bar_s);
+      };
+      bool first_item = true;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / a.H, h = item - b * a.H;
+        if (!first_item) {                                           // dQ of the previous item is out of TMEM, its products retired
+          mbar_wait(bar_qfree, ph_qfree); ph_qfree ^= 1;
+          tc_fence_after();
+        }
+        first_item = false;
+        mbar_arrive_expect_tx(bar_ld, (uint32_t)(2 * nq64 + 2 * nk64) * 8192u);
+        for (int r = 0; r < nq64; ++r) {
+          tma3(sQ + r * 8192, &tmQ, h * DH, r * 64, b, bar_ld);
+          tma3(sDO + r * 8192, &tmDO, h * DH, r * 64, b, bar_ld);
+        }
+        for (int r = 0; r < nk64; ++r) {
+          tma3(sK + r * 8192, &tmK, h * DH, r * 64, b, bar_ld);
+          tma3(sV + r * 8192, &tmV, h * DH, r * 64, b, bar_ld);
+        }
+        mbar_wait(bar_ld, ph_ld); ph_ld ^= 1;
+        tc_fence_after();
+        issue_s(0);
+        for (int n = 0; n < steps; ++n) {
+          const int j = n / nqb, i = n - j * nqb;
+          mbar_wait(bar_sfree, ph_sfree); ph_sfree ^= 1;             // step n is in the warps' registers
+          tc_fence_after();
+          if (n + 1 < steps) issue_s(n + 1);
+          if (i == 0 && j > 0) {                                     // dV / dK of the previous key tile are out of TMEM
+            mbar_wait(bar_kvfree, ph_kvfree); ph_kvfree ^= 1;
+            tc_fence_after();
+          }
+          mbar_wait(bar_pds, ph_pds); ph_pds ^= 1;                   // P^T and dS^T[i & 1] are in shared memory
+          tc_fence_after();
+          const uint32_t ds_i = ds_addr + (i & 1) * SM_TILE;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                              // K = 64 queries
+            umma_bf16_ss(T_DV, make_smem_desc_sw128(p_addr + k * 32, 16, 1024),
+                         make_smem_desc_sw128(do_addr + i * 8192 + k * 2048, 1024, 1024), idesc_kv, (i | k) != 0);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_ss(T_DK, make_smem_desc_sw128(ds_i + k * 32, 16, 1024),
+                         make_smem_desc_sw128(q_addr + i * 8192 + k * 2048, 1024, 1024), idesc_kv, (i | k) != 0);
+          }
+          if ((i & 1) || i == nqb - 1) {                             // pair complete (or odd last block: stale second half)
+            const int I = i >> 1;
+            const uint32_t a_base = ds_addr;                         // chunk 0 = even block, chunk 1 = odd block
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                            // K = 128 keys
+              umma_bf16_ss(T_DQ + I * 64, make_smem_desc_sw128(a_base + k * 2048, SM_TILE, 1024),
+                           make_smem_desc_sw128(k_addr + j * SM_TILE + k * 2048, 1024, 1024), idesc_q, (j | k) != 0);
+            }
+          }
+          umma_commit(bar_tfree);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= softmax warps =================
+    const int quad = warp & 3;
+    const int sub = (warp - 1) >> 2;                                 // which 32 query columns of the block
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int r = quad * 32 + lane;                                  // key row inside the tile == TMEM lane
+    const float LOG2E = 1.4426950408889634f;
+    uint32_t ph_s = 0, ph_tfree = 0;
+    const uint32_t dseed = DROP ? a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0u) : 0u;
+    unsigned char* my_p = sP + r * 128;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / a.H, h = item - b * a.H;
+      const float* lse = a.lse + (size_t)item * a.Lq;
+      const float* delta = a.delta + (size_t)item * a.Lq;
+      for (int n = 0; n < steps; ++n) {
+        const int j = n / nqb, i = n - j * nqb;
+        const int key = j * 128 + r;
+        const bool key_ok = key < a.Lk;
+        const int q0 = i * 64 + sub * 32;                            // first query column of this warp
+        // per-column constants, fetched before the wait (L1 broadcast loads)
+        mbar_wait(bar_s, ph_s); ph_s ^= 1;
+        tc_fence_after();
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(T_S + lane_off + sub * 32, s);
+        tmem_ld_32x32(T_DP + lane_off + sub * 32, dp);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sfree);
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int qi = q0 + c + e;
+            const bool ok = key_ok && qi < a.Lq;
+            const float l2 = ok ? __ldg(lse + qi) * LOG2E : 0.f;
+            const float dl = ok ? __ldg(delta + qi) : 0.f;
+            float p = ok ? ex2_approx(fmaf(__uint_as_float(s[c + e]), LOG2E, -l2)) : 0.f;
+            float g = __uint_as_float(dp[c + e]);
+            float pd = p;
+            if (DROP) {
+              const bool keep = drop_keep(dseed, (uint32_t)item * (uint32_t)a.Lq + (uint32_t)qi, (uint32_t)key, a.drop_thresh);
+              pd = keep ? p * a.drop_scale : 0.f;
+              g = keep ? g * a.drop_scale : 0.f;
+            }
+            pv[e] = pd;
+            dv[e] = p * (g - dl);
+          }
+          pk[c >> 1] = f2_to_bf16x2(pv[0], pv[1]);
+          dk_[c >> 1] = f2_to_bf16x2(dv[0], dv[1]);
+        }
+        if (i > 0) {                                                 // products of step n-1 have retired: the tiles are free
+          mbar_wait(bar_tfree, ph_tfree); ph_tfree ^= 1;             // (i == 0: the end-of-key-tile wait below already saw them)
+        }
+        unsigned char* my_ds = sDS + (i & 1) * SM_TILE + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {                             // this warp's 64 bytes of row r: chunks sub*4 .. sub*4+3
+          const int ch = ((sub * 4 + q4) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(my_p + ch) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(my_ds + ch) = make_uint4(dk_[4 * q4], dk_[4 * q4 + 1], dk_[4 * q4 + 2], dk_[4 * q4 + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_pds);
+        if (i == nqb - 1) {
+          // ---- dV_j / dK_j complete once this step's products retire: pull them out, store bf16 rows
+          mbar_wait(bar_tfree, ph_tfree); ph_tfree ^= 1;
+          tc_fence_after();
+          uint32_t o[32];
+#pragma unroll
+          for (int which = 0; which < 2; ++which) {
+            tmem_ld_32x32((which ? T_DK : T_DV) + lane_off + sub * 32, o);
+            tmem_ld_wait();
+            if (key_ok) {
+              bf16* dst = static_cast<bf16*>(which ? a.dk : a.dv) + (size_t)b * a.dkv_sb + (size_t)key * a.dkv_sl + (size_t)h * DH + sub * 32;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                uint4 v;
+                v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]), __uint_as_float(o[g8 * 8 + 1]));
+                v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]), __uint_as_float(o[g8 * 8 + 3]));
+                v.z = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 4]), __uint_as_float(o[g8 * 8 + 5]));
+                v.w = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 6]), __uint_as_float(o[g8 * 8 + 7]));
+                *reinterpret_cast<uint4*>(dst + g8 * 8) = v;
+              }
+            }
+          }
+          if (j == nkt - 1) {
+            // ---- dQ complete: accumulator I holds queries [128 I, 128 I + 128) on the lanes
+            for (int I = 0; I < (nqb + 1) / 2; ++I) {
+              tmem_ld_32x32(T_DQ + I * 64 + lane_off + sub * 32, o);
+              tmem_ld_wait();
+              const int qi = I * 128 + r;
+              if (qi < a.Lq) {
+                bf16* dst = static_cast<bf16*>(a.dq) + (size_t)b * a.dq_sb + (size_t)qi * a.dq_sl + (size_t)h * DH + sub * 32;
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                  uint4 v;
+                  v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]), __uint_as_float(o[g8 * 8 + 1]));
+                  v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]), __uint_as_float(o[g8 * 8 + 3]));
+                  v.z = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 4]), __uint_as_float(o[g8 * 8 + 5]));
+                  v.w = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 6]), __uint_as_float(o[g8 * 8 + 7]));
+                  *reinterpret_cast<uint4*>(dst + g8 * 8) = v;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (j == nkt - 1) mbar_arrive(bar_qfree); else mbar_arrive(bar_kvfree); }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace ab5
+
+// Workspace: delta (fp32, B * H * Lq).
+long long attn_bwd_tc5_workspace(int B, int H, int Lq) { return (long long)B * H * Lq * 4; }
+
+bool attn_bwd_tc5_supported(const AttnBwdParams& p) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("V2M_ATTN_BWD_TC5");
+    enabled = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return enabled && p.dtype == 1 && p.dh == 64 && !p.Er && !p.causal && p.Hq == p.Hkv && p.Lq <= ab5::MAXL && p.Lk <= ab5::MAXL &&
+         p.q_scale == 1.0f && p.dq_sl % 8 == 0 && p.dq_sb % 8 == 0 && p.dkv_sl % 8 == 0 && p.dkv_sb % 8 == 0 &&
+         reinterpret_cast<uintptr_t>(p.dq) % 16 == 0 && reinterpret_cast<uintptr_t>(p.dk) % 16 == 0 && reinterpret_cast<uintptr_t>(p.dv) % 16 == 0;
+}
+
+int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStream_t stream) {
+  V2M_REQUIRE(attn_bwd_tc5_supported(p), "attn_bwd_tc5: configuration not covered");
+  V2M_REQUIRE(ws && ws_bytes >= attn_bwd_tc5_workspace(p.B, p.Hq, p.Lq), "attn_bwd_tc5: workspace too small");
+  float* delta = static_cast<float*>(ws);
+  const long long rows = (long long)p.B * p.Hq * p.Lq;
+  ab5::delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(static_cast<const bf16*>(p.o), p.o_sb, p.o_sl,
+                                                                          static_cast<const bf16*>(p.dO), p.do_sb, p.do_sl, delta, p.B, p.Hq, p.Lq);
+  int rc = check_launch("attn_bwd_tc5 delta");
+  if (rc) return rc;
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  const int swap = p.B > 1 && p.q_sl > p.q_sb;
+  V2M_REQUIRE(p.B == 1 || ((p.k_sl > p.k_sb) == (swap != 0) && (p.v_sl > p.v_sb) == (swap != 0) && (p.do_sl > p.do_sb) == (swap != 0)),
+              "attn_bwd_tc5: q, k, v, dO must share one layout family (batch-first or sequence-first)");
+  if ((rc = make_tmap_3d_bf16(&tmQ, p.q, (long long)p.Hq * 64, p.Lq, p.B, p.q_sl, p.q_sb, 64, swap))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tmK, p.k, (long long)p.Hkv * 64, p.Lk, p.B, p.k_sl, p.k_sb, 64, swap))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tmV, p.v, (long long)p.Hkv * 64, p.Lk, p.B, p.v_sl, p.v_sb, 64, swap))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tmDO, p.dO, (long long)p.Hq * 64, p.Lq, p.B, p.do_sl, p.do_sb, 64, swap))) return rc;
+  ab5::Args a;
+  a.lse = p.lse; a.delta = delta;
+  a.dq = p.dq; a.dk = p.dk; a.dv = p.dv;
+  a.dq_sb = p.dq_sb; a.dq_sl = p.dq_sl; a.dkv_sb = p.dkv_sb; a.dkv_sl = p.dkv_sl;
+  a.B = p.B; a.H = p.Hq; a.Lq = p.Lq; a.Lk = p.Lk; a.swap = swap;
+  a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed; a.drop_seed_dev = p.drop_seed_dev;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
+    if (e != cudaSuccess) { set_last_error("attn_bwd_tc5: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
+    attr = true;
+  }
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int items = p.B * p.Hq;
+  const int grid = items < num_sms ? items : num_sms;
+  if (a.drop_scale != 0.f) ab5::attn_bwd_tc5_kernel<true><<<grid, ab5::THREADS, ab5::SMEM, stream>>>(tmQ, tmK, tmV, tmDO, a);
+  else ab5::attn_bwd_tc5_kernel<false><<<grid, ab5::THREADS, ab5::SMEM, stream>>>(tmQ, tmK, tmV, tmDO, a);
+  return check_launch("attn_bwd_tc5");
+}
+
+}  // namespace v2m

@@ -101,6 +101,9 @@ int attn_bwd(const AttnBwdParams& p, cudaStream_t stream);
 // p.dEr fp32 zeroed by the caller; ws = attn_bwd_tc_workspace() bytes of device scratch (P, dS and skewed-dS tiles).
 long long attn_bwd_tc_workspace(int B, int Hq, int Lq, int Lk, int has_er);
 int attn_bwd_tc(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStream_t stream);
+// tcgen05 / TMEM single-kernel backward of the stock attentions (no Er, no mask, Lq, Lk <= 320): csrc/attn_bwd_tc5.cu
+bool attn_bwd_tc5_supported(const AttnBwdParams& p);
+int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStream_t stream);
 
 int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_dtype, long long ld_y, int relu, float alpha,
             int alpha_cols, void* dz, int dz_dtype, long long ld_dz, float* db, int M, int N, float drop_scale, unsigned int drop_thresh,
