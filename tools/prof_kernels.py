@@ -54,6 +54,26 @@ sk = (S * 2 * E, 2 * E)
 timed("attn_bf16_tc cross B=%d L=%d S=%d" % (B, L, S),
       lambda: ops.attention(qkv, kv, kv[:, :, E:], out, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=st, k_strides=sk, v_strides=sk,
                             o_strides=(L * E, E), causal=False, lse=lse), flops=4.0 * L * S * dh * B * H)
+# ---- attention backward (tensor-core paths): RPR causal self-attention, encoder self-attention, cross-attention
+dO = (torch.randn(B, L, E, generator=g) * 0.3).to(dev).bfloat16()
+dqkv = torch.empty_like(qkv)
+der = torch.zeros(300, dh, device=dev)
+ops.attention(qkv, qkv[:, :, E:], qkv[:, :, 2 * E:], out, B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=st, k_strides=st, v_strides=st,
+              o_strides=(L * E, E), causal=True, Er=Er, lse=lse)
+timed("attn_bwd RPR causal self B=%d L=%d" % (B, L),
+      lambda: ops.attention_bwd(qkv, qkv[:, :, E:], qkv[:, :, 2 * E:], out, dO, lse, Er, dqkv, dqkv[:, :, E:], dqkv[:, :, 2 * E:], der,
+                                B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=st, k_strides=st, v_strides=st, o_strides=(L * E, E),
+                                do_strides=(L * E, E), dq_strides=st, dkv_strides=st, causal=True, tensor_core=True),
+      flops=10.0 * L * L * dh * B * H)
+ops.attention(qkv, kv, kv[:, :, E:], out, B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=st, k_strides=sk, v_strides=sk,
+              o_strides=(L * E, E), causal=False, lse=lse)
+dkv = torch.empty_like(kv)
+for drop in (None, (0.2, 99)):
+    timed("attn_bwd cross B=%d L=%d S=%d%s" % (B, L, S, " dropout 0.2" if drop else ""),
+          lambda: ops.attention_bwd(qkv, kv, kv[:, :, E:], out, dO, lse, None, dqkv, dkv, dkv[:, :, E:], None,
+                                    B=B, Hq=H, Hkv=H, Lq=L, Lk=S, dh=dh, q_strides=st, k_strides=sk, v_strides=sk, o_strides=(L * E, E),
+                                    do_strides=(L * E, E), dq_strides=st, dkv_strides=sk, causal=False, tensor_core=True, dropout=drop),
+          flops=10.0 * L * S * dh * B * H)
 # ---- pscan and the fused selective scan (BASELINE config 5)
 for (b_, l_) in [(64, 300), (8, 4096)]:
     A = torch.rand(b_, l_, 256, 16, generator=g).mul_(0.99).to(dev)

@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_variant_train.py -m gpu -q -s -k "bf16 or kgrouped" 2>&1 | tail -25 > gpurun_out/r2_moe16_tests.log
-python tools/prof_train_variants.py 2>&1 | head -8 > gpurun_out/r2_moe16_timing.txt
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention_bwd_tensor_core or probability_dropout" 2>&1 | tail -4 > gpurun_out/r2_tc5_tests.log
+python tools/prof_kernels.py 512 2>&1 | grep -E "attn_bwd" > gpurun_out/r2_tc5_kernels.txt

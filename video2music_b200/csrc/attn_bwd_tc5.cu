@@ -91,7 +91,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* bar_tfree = bars + 4;    // the accumulating products of a step have retired: tiles (and, after a key tile, dV / dK) final
   uint64_t* bar_kvfree = bars + 5;   // dV / dK pulled out of TMEM (count 4 * NW)
   uint64_t* bar_qfree = bars + 6;    // dQ pulled out of TMEM (count 4 * NW): next item may start
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_done = bars + 7;     // all products of the item retired (issuer only): the operand buffers may be reloaded
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqb = (a.Lq + 63) / 64;          // query blocks of 64
@@ -102,7 +103,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(bar_ld, 1); mbar_init(bar_s, 1); mbar_init(bar_sfree, 4 * NW); mbar_init(bar_pds, 4 * NW);
-    mbar_init(bar_tfree, 1); mbar_init(bar_kvfree, 4 * NW); mbar_init(bar_qfree, 4 * NW);
+    mbar_init(bar_tfree, 1); mbar_init(bar_kvfree, 4 * NW); mbar_init(bar_qfree, 4 * NW); mbar_init(bar_done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
   }
@@ -128,7 +129,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);      // S^T, dP^T: both operands K-major
       const uint32_t idesc_kv = make_idesc_bf16(128, 64, 0, 1);     // dV, dK: A K-major tile, B MN-major
       const uint32_t idesc_q = make_idesc_bf16(128, 64, 1, 1);      // dQ: A = dS^T tiles read MN-major, B = K_j MN-major
-      uint32_t ph_ld = 0, ph_sfree = 0, ph_pds = 0, ph_kvfree = 0, ph_qfree = 0;
+      uint32_t ph_ld = 0, ph_sfree = 0, ph_pds = 0, ph_kvfree = 0, ph_qfree = 0, ph_done = 0;
       auto issue_s = [&](int n) {                                    // S^T and dP^T of step n
         const int j = n / nqb, i = n - j * nqb;
 #pragma unroll
@@ -144,11 +145,9 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       bool first_item = true;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int b = item / a.H, h = item - b * a.H;
-        if (!first_item) {                                           // dQ of the previous item is out of TMEM, its products retired
-          mbar_wait(bar_qfree, ph_qfree); ph_qfree ^= 1;
-          tc_fence_after();
-        }
-        first_item = false;
+        // every product of the previous item has retired (its last commit): the operand buffers may be overwritten while the
+        // softmax warps are still storing that item's dQ
+        if (!first_item) { mbar_wait(bar_done, ph_done); ph_done ^= 1; }
         mbar_arrive_expect_tx(bar_ld, (uint32_t)(2 * nq64 + 2 * nk64) * 8192u);
         for (int r = 0; r < nq64; ++r) {
           tma3(sQ + r * 8192, &tmQ, h * DH, r * 64, b, bar_ld);
@@ -158,6 +157,11 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma3(sK + r * 8192, &tmK, h * DH, r * 64, b, bar_ld);
           tma3(sV + r * 8192, &tmV, h * DH, r * 64, b, bar_ld);
         }
+        if (!first_item) {                                           // dQ of the previous item is out of TMEM (the stores of the
+          mbar_wait(bar_qfree, ph_qfree); ph_qfree ^= 1;             // epilogue overlapped the loads above)
+          tc_fence_after();
+        }
+        first_item = false;
         mbar_wait(bar_ld, ph_ld); ph_ld ^= 1;
         tc_fence_after();
         issue_s(0);
@@ -193,6 +197,7 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
           umma_commit(bar_tfree);
+          if (n == steps - 1) umma_commit(bar_done);                 // every product of the item has retired: operands may be replaced
         }
       }
     }
@@ -211,12 +216,19 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int b = item / a.H, h = item - b * a.H;
       const float* lse = a.lse + (size_t)item * a.Lq;
       const float* delta = a.delta + (size_t)item * a.Lq;
-      for (int n = 0; n < steps; ++n) {
-        const int j = n / nqb, i = n - j * nqb;
+      int j = 0, i = 0;
+      for (int n = 0; n < steps; ++n, ++i) {
+        if (i == nqb) { i = 0; ++j; }
         const int key = j * 128 + r;
         const bool key_ok = key < a.Lk;
         const int q0 = i * 64 + sub * 32;                            // first query column of this warp
-        // per-column constants, fetched before the wait (L1 broadcast loads)
+        // per-column constants: lane c fetches those of column q0 + c BEFORE the wait (global latency off the critical path) and
+        // the loop below broadcasts them with shuffles.  Queries >= Lq: lse = +inf -> P = 0, dS = 0 (their Q / dO rows are zero).
+        // Keys >= Lk need no mask: their K / V rows are zero, so P^T and dS^T stay finite and only touch dV / dK rows that are
+        // never stored, while dQ sees them multiplied by K = 0.
+        const int qc = q0 + lane;
+        const float my_l2 = qc < a.Lq ? __ldg(lse + qc) * LOG2E : INFINITY;
+        const float my_dl = qc < a.Lq ? __ldg(delta + qc) : 0.f;
         mbar_wait(bar_s, ph_s); ph_s ^= 1;
         tc_fence_after();
         uint32_t s[32], dp[32];
@@ -233,10 +245,9 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int qi = q0 + c + e;
-            const bool ok = key_ok && qi < a.Lq;
-            const float l2 = ok ? __ldg(lse + qi) * LOG2E : 0.f;
-            const float dl = ok ? __ldg(delta + qi) : 0.f;
-            float p = ok ? ex2_approx(fmaf(__uint_as_float(s[c + e]), LOG2E, -l2)) : 0.f;
+            const float l2 = __shfl_sync(0xffffffffu, my_l2, c + e);
+            const float dl = __shfl_sync(0xffffffffu, my_dl, c + e);
+            float p = ex2_approx(fmaf(__uint_as_float(s[c + e]), LOG2E, -l2));
             float g = __uint_as_float(dp[c + e]);
             float pd = p;
             if (DROP) {
