@@ -41,8 +41,7 @@ constexpr int DH = 64;
 constexpr int MAXL = 320;                 // queries / keys per (video, head)
 constexpr int QROWS = 320, KROWS = 384;   // rows held in shared memory (keys padded to whole 128-row tiles, zero rows)
 constexpr int SM_Q = QROWS * 128, SM_K = KROWS * 128, SM_TILE = 128 * 128;
-constexpr int NW = 2;                     // softmax warps per TMEM lane quadrant
-constexpr int THREADS = 32 + 128 * NW;
+constexpr int threads(int nw) { return 32 + 128 * nw; }   // nw = softmax warps per TMEM lane quadrant (64 / nw query columns each)
 constexpr size_t SMEM = 1024 + 2 * SM_Q + 2 * SM_K + 3 * SM_TILE + 256;
 
 struct Args {
@@ -71,8 +70,8 @@ __global__ void __launch_bounds__(256) delta_kernel(const bf16* __restrict__ o, 
   if (lane == 0) delta[row] = s;
 }
 
-template <bool DROP>
-__global__ void __launch_bounds__(THREADS, 1)
+template <bool DROP, int NW>
+__global__ void __launch_bounds__(threads(NW), 1)
 attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ Args a) {
   extern __shared__ unsigned char ab5_smem_raw[];
@@ -108,6 +107,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
   }
   // rows of K / V beyond the loaded boxes are read by the MN-major dQ product (times dS = 0): they must be finite
+  constexpr int THREADS = threads(NW);
+  constexpr int CW = 64 / NW;               // query columns per softmax warp
   for (int i = threadIdx.x; i < 2 * SM_K / 16; i += THREADS) reinterpret_cast<uint4*>(sK)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -205,42 +206,51 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // ================= softmax warps =================
     const int quad = warp & 3;
-    const int sub = (warp - 1) >> 2;                                 // which 32 query columns of the block
+    const int sub = (warp - 1) >> 2;                                 // which CW query columns of the block
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const int r = quad * 32 + lane;                                  // key row inside the tile == TMEM lane
     const float LOG2E = 1.4426950408889634f;
     uint32_t ph_s = 0, ph_tfree = 0;
     const uint32_t dseed = DROP ? a.drop_seed + (a.drop_seed_dev ? *a.drop_seed_dev : 0u) : 0u;
     unsigned char* my_p = sP + r * 128;
+    auto ld_cols = [&](uint32_t taddr, uint32_t* dst) {
+      if (CW == 32) tmem_ld_32x32(taddr, dst); else tmem_ld_32x16(taddr, dst);
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / a.H, h = item - b * a.H;
       const float* lse = a.lse + (size_t)item * a.Lq;
       const float* delta = a.delta + (size_t)item * a.Lq;
+      // per-column constants: lane c (< CW) holds those of column q0 + c and the loop below broadcasts them with shuffles; the
+      // values of the NEXT step are fetched while this one is being processed (global latency off the critical path).
+      // Queries >= Lq: lse = +inf -> P = 0, dS = 0 (their Q / dO rows are zero).  Keys >= Lk need no mask: their K / V rows are
+      // zero, so P^T and dS^T stay finite and only touch dV / dK rows that are never stored, while dQ sees them times K = 0.
+      auto fetch = [&](int ii, float& l2, float& dl) {
+        const int qc = ii * 64 + sub * CW + (lane & (CW - 1));
+        l2 = qc < a.Lq ? __ldg(lse + qc) * LOG2E : INFINITY;
+        dl = qc < a.Lq ? __ldg(delta + qc) : 0.f;
+      };
+      float my_l2, my_dl;
+      fetch(0, my_l2, my_dl);
       int j = 0, i = 0;
       for (int n = 0; n < steps; ++n, ++i) {
         if (i == nqb) { i = 0; ++j; }
         const int key = j * 128 + r;
         const bool key_ok = key < a.Lk;
-        const int q0 = i * 64 + sub * 32;                            // first query column of this warp
-        // per-column constants: lane c fetches those of column q0 + c BEFORE the wait (global latency off the critical path) and
-        // the loop below broadcasts them with shuffles.  Queries >= Lq: lse = +inf -> P = 0, dS = 0 (their Q / dO rows are zero).
-        // Keys >= Lk need no mask: their K / V rows are zero, so P^T and dS^T stay finite and only touch dV / dK rows that are
-        // never stored, while dQ sees them multiplied by K = 0.
-        const int qc = q0 + lane;
-        const float my_l2 = qc < a.Lq ? __ldg(lse + qc) * LOG2E : INFINITY;
-        const float my_dl = qc < a.Lq ? __ldg(delta + qc) : 0.f;
+        const int q0 = i * 64 + sub * CW;                            // first query column of this warp
         mbar_wait(bar_s, ph_s); ph_s ^= 1;
         tc_fence_after();
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(T_S + lane_off + sub * 32, s);
-        tmem_ld_32x32(T_DP + lane_off + sub * 32, dp);
+        uint32_t s[CW], dp[CW];
+        ld_cols(T_S + lane_off + sub * CW, s);
+        ld_cols(T_DP + lane_off + sub * CW, dp);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_sfree);
-        uint32_t pk[16], dk_[16];
+        float nx_l2, nx_dl;
+        fetch(i + 1 == nqb ? 0 : i + 1, nx_l2, nx_dl);
+        uint32_t pk[CW / 2], dk_[CW / 2];
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
+        for (int c = 0; c < CW; c += 2) {
           float pv[2], dv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -261,13 +271,14 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           pk[c >> 1] = f2_to_bf16x2(pv[0], pv[1]);
           dk_[c >> 1] = f2_to_bf16x2(dv[0], dv[1]);
         }
+        my_l2 = nx_l2; my_dl = nx_dl;
         if (i > 0) {                                                 // products of step n-1 have retired: the tiles are free
           mbar_wait(bar_tfree, ph_tfree); ph_tfree ^= 1;             // (i == 0: the end-of-key-tile wait below already saw them)
         }
         unsigned char* my_ds = sDS + (i & 1) * SM_TILE + r * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {                             // this warp's 64 bytes of row r: chunks sub*4 .. sub*4+3
-          const int ch = ((sub * 4 + q4) ^ (r & 7)) << 4;
+        for (int q4 = 0; q4 < CW / 8; ++q4) {                        // this warp's CW * 2 bytes of row r: 16-byte chunks sub*CW/8 ..
+          const int ch = ((sub * (CW / 8) + q4) ^ (r & 7)) << 4;
           *reinterpret_cast<uint4*>(my_p + ch) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
           *reinterpret_cast<uint4*>(my_ds + ch) = make_uint4(dk_[4 * q4], dk_[4 * q4 + 1], dk_[4 * q4 + 2], dk_[4 * q4 + 3]);
         }
@@ -278,15 +289,15 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // ---- dV_j / dK_j complete once this step's products retire: pull them out, store bf16 rows
           mbar_wait(bar_tfree, ph_tfree); ph_tfree ^= 1;
           tc_fence_after();
-          uint32_t o[32];
+          uint32_t o[CW];
 #pragma unroll
           for (int which = 0; which < 2; ++which) {
-            tmem_ld_32x32((which ? T_DK : T_DV) + lane_off + sub * 32, o);
+            ld_cols((which ? T_DK : T_DV) + lane_off + sub * CW, o);
             tmem_ld_wait();
             if (key_ok) {
-              bf16* dst = static_cast<bf16*>(which ? a.dk : a.dv) + (size_t)b * a.dkv_sb + (size_t)key * a.dkv_sl + (size_t)h * DH + sub * 32;
+              bf16* dst = static_cast<bf16*>(which ? a.dk : a.dv) + (size_t)b * a.dkv_sb + (size_t)key * a.dkv_sl + (size_t)h * DH + sub * CW;
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {
+              for (int g8 = 0; g8 < CW / 8; ++g8) {
                 uint4 v;
                 v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]), __uint_as_float(o[g8 * 8 + 1]));
                 v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]), __uint_as_float(o[g8 * 8 + 3]));
@@ -299,13 +310,13 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (j == nkt - 1) {
             // ---- dQ complete: accumulator I holds queries [128 I, 128 I + 128) on the lanes
             for (int I = 0; I < (nqb + 1) / 2; ++I) {
-              tmem_ld_32x32(T_DQ + I * 64 + lane_off + sub * 32, o);
+              ld_cols(T_DQ + I * 64 + lane_off + sub * CW, o);
               tmem_ld_wait();
               const int qi = I * 128 + r;
               if (qi < a.Lq) {
-                bf16* dst = static_cast<bf16*>(a.dq) + (size_t)b * a.dq_sb + (size_t)qi * a.dq_sl + (size_t)h * DH + sub * 32;
+                bf16* dst = static_cast<bf16*>(a.dq) + (size_t)b * a.dq_sb + (size_t)qi * a.dq_sl + (size_t)h * DH + sub * CW;
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
+                for (int g8 = 0; g8 < CW / 8; ++g8) {
                   uint4 v;
                   v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]), __uint_as_float(o[g8 * 8 + 1]));
                   v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]), __uint_as_float(o[g8 * 8 + 3]));
@@ -368,9 +379,13 @@ int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStrea
   a.B = p.B; a.H = p.Hq; a.Lq = p.Lq; a.Lk = p.Lk; a.swap = swap;
   a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed; a.drop_seed_dev = p.drop_seed_dev;
   static bool attr = false;
+  static int nw = 2;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
+    if (const char* ev = getenv("V2M_TC5_NW")) nw = atoi(ev) == 4 ? 4 : 2;       // A/B switch: softmax warps per lane quadrant
+    cudaError_t e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ab5::attn_bwd_tc5_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ab5::SMEM);
     if (e != cudaSuccess) { set_last_error("attn_bwd_tc5: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
     attr = true;
   }
@@ -382,8 +397,11 @@ int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStrea
   }
   const int items = p.B * p.Hq;
   const int grid = items < num_sms ? items : num_sms;
-  if (a.drop_scale != 0.f) ab5::attn_bwd_tc5_kernel<true><<<grid, ab5::THREADS, ab5::SMEM, stream>>>(tmQ, tmK, tmV, tmDO, a);
-  else ab5::attn_bwd_tc5_kernel<false><<<grid, ab5::THREADS, ab5::SMEM, stream>>>(tmQ, tmK, tmV, tmDO, a);
+  const bool drop = a.drop_scale != 0.f;
+#define V2M_GO(DR, NW_) ab5::attn_bwd_tc5_kernel<DR, NW_><<<grid, ab5::threads(NW_), ab5::SMEM, stream>>>(tmQ, tmK, tmV, tmDO, a)
+  if (nw == 4) { if (drop) V2M_GO(true, 4); else V2M_GO(false, 4); }
+  else { if (drop) V2M_GO(true, 2); else V2M_GO(false, 2); }
+#undef V2M_GO
   return check_launch("attn_bwd_tc5");
 }
 
