@@ -1,4 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention_bwd_tensor_core or probability_dropout" 2>&1 | tail -3 > gpurun_out/r2_tc5_tests.log
-V2M_TC5_NW=4 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "attention_bwd_tensor_core or probability_dropout" 2>&1 | tail -3 >> gpurun_out/r2_tc5_tests.log
-python tools/prof_kernels.py 512 2>&1 | grep -E "attn_bwd cross" > gpurun_out/r2_tc5_kernels.txt
-V2M_TC5_NW=4 python tools/prof_kernels.py 512 2>&1 | grep -E "attn_bwd cross" >> gpurun_out/r2_tc5_kernels.txt
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_train.py -m gpu -q -x 2>&1 | tail -3 > gpurun_out/r2_t.log
+for b in 64 512; do python tools/train_time.py $b bf16 5; done > gpurun_out/r2_train_scaling_1gpu_d.txt 2>&1

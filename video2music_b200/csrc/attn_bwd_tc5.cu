@@ -52,22 +52,34 @@ struct Args {
   float drop_scale; unsigned int drop_thresh, drop_seed; const unsigned int* drop_seed_dev;
 };
 
-// delta[bh][i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per row)
+// delta[bh][i] = sum_d dO[b,i,h,d] * O[b,i,h,d]: eight lanes per (video, position, head) row of 64 dims (one 16-byte load of
+// each operand per lane); consecutive lane groups take consecutive heads of the same position, so a warp reads 512 contiguous
+// bytes of O and of dO.
 __global__ void __launch_bounds__(256) delta_kernel(const bf16* __restrict__ o, long long o_sb, long long o_sl, const bf16* __restrict__ dO,
                                                     long long do_sb, long long do_sl, float* __restrict__ delta, int B, int H, int Lq) {
-  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= (long long)B * H * Lq) return;
-  const int i = (int)(row % Lq);
-  const long long bh = row / Lq;
-  const int h = (int)(bh % H);
-  const long long b = bh / H;
-  const float2 a = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(o + b * o_sb + (long long)i * o_sl + h * DH + 2 * lane));
-  const float2 g = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(dO + b * do_sb + (long long)i * do_sl + h * DH + 2 * lane));
-  float s = a.x * g.x + a.y * g.y;
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;        // (b, i, h) with h fastest
+  const int sub = threadIdx.x & 7;
+  const bool ok = grp < (long long)B * H * Lq;
+  float s = 0.f;
+  long long b = 0; int i = 0, h = 0;
+  if (ok) {
+    h = (int)(grp % H);
+    const long long bi = grp / H;
+    i = (int)(bi % Lq);
+    b = bi / Lq;
+    const uint4 a = *reinterpret_cast<const uint4*>(o + b * o_sb + (long long)i * o_sl + h * DH + 8 * sub);
+    const uint4 g = *reinterpret_cast<const uint4*>(dO + b * do_sb + (long long)i * do_sl + h * DH + 8 * sub);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-  for (int o_ = 16; o_ > 0; o_ >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o_);
-  if (lane == 0) delta[row] = s;
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = bf16x2_to_f2(aw[e]), y = bf16x2_to_f2(gw[e]);
+      s = fmaf(x.x, y.x, fmaf(x.y, y.y, s));
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && sub == 0) delta[((size_t)b * H + h) * Lq + i] = s;
 }
 
 template <bool DROP, int NW>
@@ -360,7 +372,7 @@ int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStrea
   V2M_REQUIRE(ws && ws_bytes >= attn_bwd_tc5_workspace(p.B, p.Hq, p.Lq), "attn_bwd_tc5: workspace too small");
   float* delta = static_cast<float*>(ws);
   const long long rows = (long long)p.B * p.Hq * p.Lq;
-  ab5::delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, stream>>>(static_cast<const bf16*>(p.o), p.o_sb, p.o_sl,
+  ab5::delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, stream>>>(static_cast<const bf16*>(p.o), p.o_sb, p.o_sl,
                                                                           static_cast<const bf16*>(p.dO), p.do_sb, p.do_sl, delta, p.B, p.Hq, p.Lq);
   int rc = check_launch("attn_bwd_tc5 delta");
   if (rc) return rc;

@@ -68,7 +68,28 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
     float sc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) sc[e] = (n0 + e < alpha_cols) ? alpha : 1.f;
-    for (int m = blockIdx.y * 32 + ty; m < M; m += gridDim.y * 32) {
+    // db-only calls (no dz, no ReLU mask, no dropout: the plain linear layers, two thirds of all calls) only sum columns:
+    // four independent 16-byte loads per thread and iteration keep the memory pipe busy
+    int m = blockIdx.y * 32 + ty;
+    if (!dz && !relu && drop_scale == 0.f) {
+      const int stride = gridDim.y * 32;
+      for (; m + 3 * stride < M; m += 4 * stride) {
+        uint4 q4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q4[u] = *reinterpret_cast<const uint4*>(dy + (size_t)(m + u * stride) * ld_dy + n0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w[4] = {q4[u].x, q4[u].y, q4[u].z, q4[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = bf16x2_to_f2(w[e]);
+            acc[2 * e] = fmaf(f2.x, sc[2 * e], acc[2 * e]);
+            acc[2 * e + 1] = fmaf(f2.y, sc[2 * e + 1], acc[2 * e + 1]);
+          }
+        }
+      }
+    }
+    for (; m < M; m += gridDim.y * 32) {
       const uint4 gq = *reinterpret_cast<const uint4*>(dy + (size_t)m * ld_dy + n0);
       float g[8];
       float2 f;
