@@ -503,7 +503,18 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
                          int M, int N, int K, const GemmEpilogue& ep, cudaStream_t stream) {
   V2M_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm_bf16_tc: bad dims M=%d N=%d K=%d", M, N, K);
   if (M == 0) return kOk;
-  const int bn = (N % 256 == 0) ? 256 : 128;
+  int bn = (N % 256 == 0) ? 256 : 128;
+  if (bn == 256) {
+    // Wave quantisation: the persistent grid hands every SM ceil(tiles / SMs) tiles.  When 128 x 256 tiles leave most SMs idle
+    // in the last round (e.g. M = 19136 = 150 row tiles on 148 SMs with N = 512: 300 tiles, 3 rounds for 2.03 rounds of
+    // work) the 128 x 128 tiling wastes less, although a narrow tile costs a little more than half a wide one.
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const long long mt = (M + GM - 1) / GM;
+    const long long t256 = mt * (N / 256), t128 = mt * (N / 128);
+    const double c256 = (double)((t256 + sms - 1) / sms), c128 = 0.56 * (double)((t128 + sms - 1) / sms);
+    if (t256 > sms && c128 < 0.93 * c256) bn = 128;           // (small outputs keep the wide tile: they are split along K)
+  }
   CUtensorMap tmA, tmB;
   // K-major operand: [rows = M|N, cols = K], box (rows x 64 k);  MN-major operand: [rows = K, cols = M|N], box (64 k x 64)
   int rc = a_mn ? make_tmap_2d_bf16(&tmA, A, K, M, lda, 64) : make_tmap_2d_bf16(&tmA, A, M, K, lda, GM);
