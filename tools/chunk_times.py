@@ -7,7 +7,8 @@ from video2music_b200 import engine, synthetic as syn
 pos = 150
 dev = torch.device("cuda", 0)
 model, _ = bench.make_model(torch.bfloat16, dev)
-inp = syn.make_inputs(64, 1234, 299, 300, 0)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+inp = syn.make_inputs(B, 1234, 299, 300, 0)
 d = {k: v.to(dev) for k, v in inp.items()}
 prim, pr, pa = torch.tensor([1]), torch.tensor([1]), torch.tensor([0])
 st = engine.build_decode(model._w(), model._cfg(), d["feature_semantic_list"], d["feature_key"].reshape(-1),
