@@ -105,6 +105,8 @@ typedef struct v2m_attn {
   float* lse; float* p_out;
   float drop_scale; uint32_t drop_thresh, drop_seed;   /* dropout of the probabilities (training, fp32 and bf16 kernels): see v2m_epilogue */
   const uint32_t* drop_seed_dev;
+  const int32_t* lk_dev;   /* optional device word (fp32 kernel, no Er / p_out): only the first min(Lk, *lk_dev) keys exist -- one captured
+                              CUDA graph then serves every position of a KV-cached generation (cached_decode.py)             */
 } v2m_attn;
 int v2m_attn_fwd(const v2m_attn* p, int32_t dtype, void* stream);
 
@@ -148,6 +150,12 @@ int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld
  * lower class index. */
 int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t Cn, int64_t pad, int32_t k0, int32_t k1, int32_t k2,
                     int32_t* counters, void* stream);
+/* Emotion correspondence of the evaluation loop (compute_vevo_correspondence, dataset/vevo_dataset.py:747-810; called at
+ * utilities/run_model_vevo.py:307,415 with EMOTION_THRESHOLD = 0.8): logits [R, Cn], tgt_emotion [R, Ce] (columns 0..13 = chord
+ * qualities, last column = padding flag), tgt_emotion_prob [R]; counters (int32[2], zeroed by the call) = {pt, right}:
+ * correspondence = right / pt, -1 when pt == 0.  chord_end = 157: END / PAD predictions are never right.                      */
+int v2m_amt_correspondence(const float* logits, const float* tgt_emotion, const float* tgt_emotion_prob, int32_t R, int32_t Cn, int32_t Ce,
+                           float threshold, int32_t chord_end, int32_t* counters, void* stream);
 int v2m_amt_loss(const float* logits, const int64_t* tgt, const float* tgt_emotion, int32_t R, int32_t Cn, int64_t ignore,
                  float smooth, float w_ce, float w_bce, float* scratch3, float* dlogits, const float* norm_in, void* stream);
 /* out1[0] = number of targets != ignore (the CE normaliser, nn.CrossEntropyLoss(ignore_index), train.py:222).  A data-parallel
@@ -161,6 +169,21 @@ int v2m_count_valid(const int64_t* tgt, int32_t R, int64_t ignore, float* out1, 
  * p16 (optional) receives the bf16 mirror of the updated parameters; zero_grad clears g; ctr (optional) += 1 per call. */
 int v2m_adam_step(float* p, float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float weight_decay, int32_t step,
                   float grad_scale, const float* dyn, void* p16, int32_t zero_grad, uint32_t* ctr, void* stream);
+
+/* ---- one generation step of the generic decoder stacks (BASELINE config 4: grouped-query attention + MoE feed-forward) ----------
+ * The reference generates with one FULL forward per token (video_music_transformer.py:227-315); the KV-cached step
+ * (video2music_b200/cached_decode.py) pushes ONE new row per video through the layers, so its linear layers have M <= 64 rows.
+ * v2m_step_linear_f32: y[M,N] = act(x[M,K] W[N,K]^T + bias[n] + row_scale[m] * col_vec[n]) -- F.linear of
+ *   grouped_query_attention.py:306-309,350-356, custom_transformer.py (in_proj / out_proj), video_music_transformer.py:240-262
+ *   (Linear_chord with its key column, Wout); fixed k order, result independent of M.
+ * v2m_step_attn_f32: o[b, hq*64:] = softmax(q_scale * q[b, hq] . K[b, :n, hkv]) V[b, :n, hkv], hkv = hq / (Hq / Hkv), one query row
+ *   per (video, query head) over the first n = min(n_max, *n_dev) cached rows (n_dev optional, device word: the launch is the same
+ *   for every position, so a generation replays ONE captured CUDA graph); element (b, j, h, d) of a cache is k[b*kv_sb + j*kv_sl + h*64 + d]
+ *   -- scaled_dot_product_gqa (grouped_query_attention.py:93-159) and F.multi_head_attention_forward with a single query.     */
+int v2m_step_linear_f32(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, const float* row_scale,
+                        const float* col_vec, float* y, int64_t ldy, int32_t M, int32_t N, int32_t K, int32_t relu, void* stream);
+int v2m_step_attn_f32(const float* q, int64_t q_sb, const float* k, const float* v, int64_t kv_sb, int64_t kv_sl, float* o, int64_t o_sb,
+                      int32_t B, int32_t Hq, int32_t Hkv, int32_t dh, int32_t n_max, const int32_t* n_dev, float q_scale, void* stream);
 
 /* ---- residual + LayerNorm (rpr.py:59-69; nn.LayerNorm eps) ------------------------------------ */
 int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_dtype, const float* gamma,

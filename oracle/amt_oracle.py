@@ -616,6 +616,28 @@ def hits_k(out: torch.Tensor, tgt: torch.Tensor, k: int, pad: int = 158) -> floa
     return float(hit.sum()) / max(int(m.sum()), 1)
 
 
+def vevo_correspondence(out: torch.Tensor, tgt_emotion: torch.Tensor, tgt_emotion_prob: torch.Tensor, threshold: float):
+    """compute_vevo_correspondence, vevo_dataset.py:747-810, position by position as the reference loops (the chord_inv /
+    chord_attr JSON lookups :775-790 reduce to quality = 1 for chord 0 and (c - 1) % 13 + 1 otherwise; checked against the
+    reference's tables by oracle/make_golden.py).  Returns (value, pt, right)."""
+    emo = tgt_emotion.reshape(-1, tgt_emotion.shape[-1])
+    prob = tgt_emotion_prob.reshape(-1)
+    pred = torch.argmax(torch.softmax(out, dim=-1), dim=-1).flatten()
+    if emo.shape[0] == 0:
+        return 1.0, 0, 0
+    pt = right = 0
+    for i in range(pred.numel()):
+        if emo[i, -1] == 1 or bool(torch.all(emo[i, :14] == 0)) or prob[i] < threshold:      # :781-783
+            continue
+        pt += 1
+        c = int(pred[i])
+        if c != 157 and c != 158:                                                                 # CHORD_END / CHORD_PAD, :786
+            quality = 1 if c == 0 else (c - 1) % 13 + 1
+            if emo[i, quality] == 1:
+                right += 1
+    return (-1 if pt == 0 else right / pt), pt, right
+
+
 # --------------------------------------------------------------------------
 # V2 / V3 attention: nn.MultiheadAttention + RoPE (model/custom_transformer.py:51-321, 864-1218; rotate_operation.py)
 # --------------------------------------------------------------------------

@@ -383,7 +383,38 @@ def golden_metrics(ref):
         acc = vd.compute_vevo_accuracy(out, tgt)
         cases.append(dict(seed=seed, pad_from=pad_from, acc=float(acc), hits=[float(vd.compute_hits_k(out, tgt, k)) if pad_from > 0 else None
                                                                             for k in (1, 3, 5)]))
-    _save("metrics.pt", dict(cases=cases))
+    # compute_vevo_correspondence (:747-810) on seeded emotion rows: quality columns ~ Bernoulli(0.3), some rows all-zero, some
+    # flagged as padding, probabilities around the 0.8 threshold; the closed form of its JSON lookups is checked on the way
+    import json, os
+    with reference_cwd():
+        inv = json.load(open(os.path.join("dataset", "vevo_meta", "chord_inv.json")))
+        attr = json.load(open(os.path.join("dataset", "vevo_meta", "chord_attr.json")))
+    for k, name in inv.items():
+        parts = name.split(":")
+        assert (1 if len(parts) == 1 else attr[parts[1]]) == (1 if int(k) == 0 else (int(k) - 1) % 13 + 1), (k, name)
+    cor = []
+    for seed, thr in ((81, 0.8), (82, 0.8), (83, 0.5), (84, 2.0)):
+        out, emo, prob = correspondence_case(seed)
+        with reference_cwd():
+            v = vd.compute_vevo_correspondence(out, torch.zeros((1, 299), dtype=torch.long), emo, prob, thr)
+        cor.append(dict(seed=seed, thr=thr, value=float(v)))
+        print("correspondence seed %d thr %.1f: %.6f" % (seed, thr, float(v)))
+    _save("metrics.pt", dict(cases=cases, correspondence=cor))
+
+
+def correspondence_case(seed):
+    """Seeded inputs of the correspondence goldens (also used by the tests): logits (1, 299, 159), tgt_emotion (1, 299, 159),
+    tgt_emotion_prob (1, 299)."""
+    g = syn._gen(seed, "correspondence")
+    out = syn.unit_uniform((1, 299, 159), g) * 3.0
+    emo = torch.zeros((1, 299, 159))
+    emo[0, :, :14] = (torch.rand((299, 14), generator=g) < 0.3).float()
+    emo[0, torch.arange(0, 299, 7), :14] = 0.0                       # rows without any quality
+    emo[0, 250:, -1] = 1.0                                           # padding tail
+    out[0, torch.arange(0, 299, 5), 157] += 9.0                      # END predictions: counted, never right
+    out[0, torch.arange(1, 299, 11), 0] += 9.0                       # "N": quality 1 by the reference's literal rule
+    prob = 0.6 + 0.4 * torch.rand((1, 299), generator=g)
+    return out, emo, prob
 
 
 def golden_custom_mha(ref):

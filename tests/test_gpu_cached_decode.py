@@ -73,6 +73,9 @@ def test_cached_generate_gqa_moe_equals_literal_loop_and_oracle(shared, rms, pre
     feats = [inp[k].to(DEV) for k in KEYS]
     prim, pr, pa = inp["x"][0, :2], inp["x_root"][0, :2], inp["x_attr"][0, :2]
     out = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=16, beam=1, beam_chance=1.0)
+    eager = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=16, beam=1, beam_chance=1.0,
+                              use_graph=False)
+    assert torch.equal(out, eager)                                      # one captured CUDA graph per position == eager launches
     for b in range(B):
         one = [t[b:b + 1] for t in feats]
         lit = m.generate(one[0], one[1][0], one[2], one[3], one[4], primer=prim, primer_root=pr, primer_attr=pa,
@@ -100,7 +103,7 @@ def test_cached_generate_sampling_branch_and_errors():
     prim, pr, pa = torch.tensor([1]), torch.tensor([1]), torch.tensor([0])
     u = torch.rand((4, 40), generator=torch.Generator().manual_seed(3)).to(DEV)
     a = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=40, beam=0, uniforms=u)
-    b = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=40, beam=0, uniforms=u)
+    b = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=40, beam=0, uniforms=u, use_graph=False)
     assert torch.equal(a, b) and a.shape == (4, 40)
     assert int((a[:, 1:] == 0).sum()) == 0 and int(a.max()) < 157
     same3 = (a[:, 2:] == a[:, 1:-1]) & (a[:, 1:-1] == a[:, :-2])

@@ -621,6 +621,29 @@ def test_amt_metrics_kernel_vs_reference_golden_and_oracle():
     assert abs(O.vevo_accuracy(out, tgt) - 6 / 11) < 1e-6
 
 
+def test_amt_correspondence_kernel_vs_reference_golden_and_oracle():
+    """Emotion correspondence of the evaluation loop (dataset/vevo_dataset.py:747-810) in one launch: equal to the reference's own
+    values (golden) and to the oracle's counters; a batch of several videos is the sum over its rows."""
+    from test_oracle import _correspondence_case as correspondence_case
+    from video2music_b200 import ops
+    outs, emos, probs, tot = [], [], [], [0, 0]
+    for c in load_golden("metrics.pt")["correspondence"]:
+        out, emo, prob = correspondence_case(c["seed"])
+        v = ops.compute_vevo_correspondence(out.to(DEV), None, emo.to(DEV), prob.to(DEV), c["thr"])
+        assert abs(v - c["value"]) < 1e-6, (c, v)
+        _, pt, right = O.vevo_correspondence(out, emo, prob, c["thr"])
+        assert ops.amt_correspondence(out.to(DEV), emo.to(DEV), prob.to(DEV), c["thr"]).tolist() == [pt, right]
+        if c["thr"] == 0.8:
+            outs.append(out); emos.append(emo); probs.append(prob)
+            tot[0] += pt; tot[1] += right
+    cnt = ops.amt_correspondence(torch.cat(outs).to(DEV), torch.cat(emos).to(DEV), torch.cat(probs).to(DEV), 0.8).tolist()
+    assert cnt == tot and tot[0] > 0
+    # arg-max ties: the lower chord id wins (torch.argmax), here chord 0 ("N" -> quality 1)
+    out = torch.zeros((1, 3, 159)); emo = torch.zeros((1, 3, 159)); emo[0, :, 1] = 1.0; emo[0, 2, 1] = 0.0; emo[0, 2, 5] = 1.0
+    assert ops.amt_correspondence(out.to(DEV), emo.to(DEV), torch.ones((1, 3), device=DEV), 0.8).tolist() == [3, 2]
+    assert ops.compute_vevo_correspondence(out.to(DEV), None, emo[:, :0].to(DEV), torch.ones((1, 0), device=DEV), 0.8) == 1.0
+
+
 # ---------------------------------------------------------------- fused dropout (training)
 def test_linear_fused_dropout_forward_backward():
     """Dropout fused into the GEMM epilogue (both placements) and re-derived by dy_prep in backward, against torch with the

@@ -387,6 +387,35 @@ def test_metrics_oracle_matches_reference_golden():
                 assert abs(O.hits_k(out, tgt, k) - h) < 1e-6
 
 
+def _correspondence_case(seed):
+    """The seeded inputs oracle/make_golden.py::correspondence_case fed to the reference (kept in step with it)."""
+    g = syn._gen(seed, "correspondence")
+    out = syn.unit_uniform((1, 299, 159), g) * 3.0
+    emo = torch.zeros((1, 299, 159))
+    emo[0, :, :14] = (torch.rand((299, 14), generator=g) < 0.3).float()
+    emo[0, torch.arange(0, 299, 7), :14] = 0.0
+    emo[0, 250:, -1] = 1.0
+    out[0, torch.arange(0, 299, 5), 157] += 9.0
+    out[0, torch.arange(1, 299, 11), 0] += 9.0
+    prob = 0.6 + 0.4 * torch.rand((1, 299), generator=g)
+    return out, emo, prob
+
+
+def test_correspondence_oracle_matches_reference_golden():
+    """compute_vevo_correspondence (dataset/vevo_dataset.py:747-810) restated vs the values the reference's own function returned
+    (its JSON chord tables included) on the seeded cases of oracle/make_golden.py."""
+    correspondence_case = _correspondence_case
+    cases = load_golden("metrics.pt")["correspondence"]
+    assert len(cases) == 4
+    seen = set()
+    for c in cases:
+        out, emo, prob = correspondence_case(c["seed"])
+        v, pt, right = O.vevo_correspondence(out, emo, prob, c["thr"])
+        assert abs(v - c["value"]) < 1e-6, (c, v)
+        seen.add(v == -1)
+    assert seen == {True, False}                       # both the "no position qualifies" (-1) and the regular branch are pinned
+
+
 def _custom_mha_case(c):
     from video2music_b200 import CustomMultiheadAttention, RotaryPositionalEmbeddings
     s = c["spec"]

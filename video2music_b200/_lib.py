@@ -36,7 +36,7 @@ class Attn(C.Structure):
                 ("B", i32), ("Hq", i32), ("Hkv", i32), ("Lq", i32), ("Lk", i32), ("dh", i32),
                 ("causal", i32), ("Er", vp), ("er_len", i32), ("q_scale", C.c_float),
                 ("lse", vp), ("p_out", vp), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32),
-                ("drop_seed_dev", vp)]
+                ("drop_seed_dev", vp), ("lk_dev", vp)]
 
 
 class AttnBwd(C.Structure):
@@ -68,9 +68,9 @@ class Decode(C.Structure):
 # every symbol include/v2m_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "v2m_abi_version", "v2m_last_error", "v2m_struct_size", "v2m_device_ok", "v2m_gemm_f32", "v2m_gemm_f32_strided", "v2m_gemm_bf16", "v2m_gemm_bf16_general", "v2m_attn_fwd", "v2m_attn_bwd", "v2m_attn_bwd_tc", "v2m_attn_bwd_tc_workspace", "v2m_dy_prep",
-    "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_count_valid", "v2m_amt_metrics", "v2m_adam_step",
+    "v2m_layernorm_bwd", "v2m_embed_bwd", "v2m_amt_loss", "v2m_count_valid", "v2m_amt_metrics", "v2m_amt_correspondence", "v2m_adam_step",
     "v2m_layernorm", "v2m_embed_sum", "v2m_concat_features", "v2m_cast_2d", "v2m_decode_run",
-    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_rope_quirk", "v2m_mamba_conv_silu", "v2m_mamba_step_conv", "v2m_mamba_step_ssm", "v2m_selective_scan_fwd", "v2m_selective_scan_workspace", "v2m_selective_scan_bwd_workspace", "v2m_selective_scan_bwd", "v2m_mamba_conv_silu_bwd", "v2m_rmsnorm", "v2m_rmsnorm_bwd", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route", "v2m_moe_permute", "v2m_moe_grouped_gemm", "v2m_gemm_bf16_grouped", "v2m_gemm_bf16_kgrouped", "v2m_swiglu_pair_bwd_bf16", "v2m_moe_group_colsum_bf16", "v2m_swiglu_pair_bf16", "v2m_moe_combine", "v2m_moe_combine_bwd", "v2m_swiglu_bwd", "v2m_moe_grouped_dw", "v2m_dw_f32",
+    "v2m_decode_run_stream", "v2m_kv_interleave", "v2m_decode_launches_per_step", "v2m_decode_probe", "v2m_binary_f32", "v2m_rope_quirk", "v2m_mamba_conv_silu", "v2m_mamba_step_conv", "v2m_mamba_step_ssm", "v2m_selective_scan_fwd", "v2m_selective_scan_workspace", "v2m_selective_scan_bwd_workspace", "v2m_selective_scan_bwd", "v2m_mamba_conv_silu_bwd", "v2m_rmsnorm", "v2m_rmsnorm_bwd", "v2m_pscan_fwd", "v2m_pscan_bwd", "v2m_moe_route", "v2m_moe_permute", "v2m_moe_grouped_gemm", "v2m_gemm_bf16_grouped", "v2m_gemm_bf16_kgrouped", "v2m_swiglu_pair_bwd_bf16", "v2m_moe_group_colsum_bf16", "v2m_swiglu_pair_bf16", "v2m_moe_combine", "v2m_moe_combine_bwd", "v2m_swiglu_bwd", "v2m_moe_grouped_dw", "v2m_dw_f32", "v2m_step_linear_f32", "v2m_step_attn_f32",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -106,10 +106,13 @@ def load() -> C.CDLL:
     lib.v2m_embed_bwd.argtypes = [vp, vp, i32, i64, vp, i32, i32, vp]
     lib.v2m_rope_quirk.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.v2m_amt_metrics.argtypes = [vp, vp, i32, i32, i64, i32, i32, i32, vp, vp]
+    lib.v2m_amt_correspondence.argtypes = [vp, vp, vp, i32, i32, i32, C.c_float, i32, vp, vp]
     lib.v2m_amt_loss.argtypes = [vp, vp, vp, i32, i32, i64, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
     lib.v2m_count_valid.argtypes = [vp, i32, i64, vp, vp]
     lib.v2m_adam_step.argtypes = [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i32, C.c_float, vp, vp, i32, vp, vp]
     lib.v2m_layernorm.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32, vp, i32, i32, i32, C.c_float, vp]
+    lib.v2m_step_linear_f32.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.v2m_step_attn_f32.argtypes = [vp, i64, vp, vp, i64, i64, vp, i64, i32, i32, i32, i32, i32, vp, C.c_float, vp]
     lib.v2m_embed_sum.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.v2m_concat_features.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, i32, i32, i32, vp]
     lib.v2m_cast_2d.argtypes = [vp, i32, i64, vp, i32, i64, i32, i32, i32, vp]

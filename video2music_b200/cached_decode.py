@@ -12,10 +12,10 @@ keys / values of earlier positions never change, so one position per step is eno
     (video, head) over the cached rows (the fp32 attention kernel with Lq = 1), out-projection, the layer's feed-forward
     (GLUExpert, MoELayer or SharedMoELayer: fused router + permute + grouped expert GEMMs over the B new tokens).
 
-Everything runs on the same fp32 kernels as the full forward, whose per-row arithmetic does not depend on how many rows a
-launch carries (fixed k order in the GEMMs, one warp per softmax row): the greedy tokens are therefore bit-identical to the
-literal re-forward loop (tests/test_gpu_cached_decode.py), which in turn is bit-exact against the unmodified reference for
-the V1 models (tests/golden/v2.pt).
+The step runs in fp32 on kernels made for a handful of rows (csrc/step_f32.cu: the linear layers as weight streams over the whole
+chip, one query row per (video, head) over the cache; fixed summation orders, results independent of the batch size) plus the
+MoE kernels of the full forward; the greedy tokens equal those of the literal re-forward loop (tests/test_gpu_cached_decode.py),
+which in turn equals the unmodified reference's generate() for the V1 models (tests/golden/v2.pt).
 
 Cacheable attention modules: `CustomMultiheadAttention` without RoPE (V1 '1.1' / '1.3', V2 '2.0'; the RoPE variant rotates a
 (position, head) element by an angle that depends on the CURRENT prefix length, custom_transformer.py:1044-1053, so its keys
@@ -70,6 +70,10 @@ class _Att:
             self.wq, self.bq = det(att.q_proj.weight), det(att.q_proj.bias)
             self.wk, self.bk = det(att.k_proj.weight), det(att.k_proj.bias)
             self.wv, self.bv = det(att.v_proj.weight), det(att.v_proj.bias)
+            if self.bq is not None and self.bk is not None and self.bv is not None:
+                # one launch for the three projections of a step (rows of the stacked weight keep their own k order)
+                self.w_qkv = torch.cat([self.wq, self.wk, self.wv], 0).contiguous()
+                self.b_qkv = torch.cat([self.bq, self.bk, self.bv], 0).contiguous()
         else:
             self.Hq = self.Hk = att.num_heads
             self.E, self.dh = att.embed_dim, att.head_dim
@@ -83,13 +87,17 @@ class _Att:
     def qkv(self, x: torch.Tensor):
         """q (B, E), k, v (B, Wk) of the new rows x (B, E)."""
         if self.kind == "mha":                           # packed projection, as the module's self-attention path
-            y = ops.linear(x, self.w_qkv, self.b_qkv)
+            y = ops.step_linear(x, self.w_qkv, self.b_qkv)
             E = self.E
             return y[:, :E], y[:, E:2 * E], y[:, 2 * E:]
-        return ops.linear(x, self.wq, self.bq), ops.linear(x, self.wk, self.bk), ops.linear(x, self.wv, self.bv)
+        if getattr(self, "w_qkv", None) is not None:
+            y = ops.step_linear(x, self.w_qkv, self.b_qkv)
+            E, W = self.E, self.Hk * self.dh
+            return y[:, :E], y[:, E:E + W], y[:, E + W:]
+        return ops.step_linear(x, self.wq, self.bq), ops.step_linear(x, self.wk, self.bk), ops.step_linear(x, self.wv, self.bv)
 
     def q_only(self, x: torch.Tensor) -> torch.Tensor:
-        return ops.linear(x, self.wq, self.bq)
+        return ops.step_linear(x, self.wq, self.bq)
 
     def memory_kv(self, mem_rows: torch.Tensor):
         """K, V (S*B, Wk) of the encoder memory rows (s, b) -- once per generation."""
@@ -98,19 +106,24 @@ class _Att:
             return kv[:, :self.E], kv[:, self.E:]
         return ops.linear(mem_rows, self.wk, self.bk), ops.linear(mem_rows, self.wv, self.bv)
 
-    def attend(self, q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, n: int, k_strides) -> torch.Tensor:
-        """One query row per (video, head) over n cached rows, then the module's output path."""
+    def attend(self, q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, n: int, k_strides, n_dev=None) -> torch.Tensor:
+        """One query row per (video, head) over the first n cached rows (n_dev: the count lives in an int32 device word and n is
+        the capacity -- the launch is then the same for every position), then the module's output path."""
         B, E = q.shape[0], self.E
-        ctx = torch.empty((B, E), device=q.device, dtype=torch.float32)
         assert V.stride() == K.stride() and q.stride(1) == 1
-        ops.attention(q, K, V, ctx, B=B, Hq=self.Hq, Hkv=self.Hk, Lq=1, Lk=n, dh=self.dh, q_strides=(q.stride(0), q.stride(0)),
-                      k_strides=k_strides, v_strides=k_strides, o_strides=(E, E), causal=False, q_scale=self.q_scale)
+        if self.dh == 64:                                # one query row per (video, head): csrc/step_f32.cu
+            ctx = ops.step_attention(q, K, V, Hq=self.Hq, Hkv=self.Hk, dh=64, n_max=n, kv_strides=k_strides, n_dev=n_dev,
+                                     q_scale=self.q_scale)
+        else:
+            ctx = torch.empty((B, E), device=q.device, dtype=torch.float32)
+            ops.attention(q, K, V, ctx, B=B, Hq=self.Hq, Hkv=self.Hk, Lq=1, Lk=n, dh=self.dh, q_strides=(q.stride(0), q.stride(0)),
+                          k_strides=k_strides, v_strides=k_strides, o_strides=(E, E), causal=False, q_scale=self.q_scale, lk_dev=n_dev)
         a = self.att
         if self.kind == "gqa":
             if a.layer_norm:                             # grouped_query_attention.py:347-349
                 ctx = ops.layernorm(ctx, a.norm.weight.detach(), a.norm.bias.detach(), eps=a.norm.eps)
-            return ops.linear(ctx, a.out_proj.weight.detach(), None if a.out_proj.bias is None else a.out_proj.bias.detach(), k=E)
-        return ops.linear(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach())
+            return ops.step_linear(ctx, a.out_proj.weight.detach(), None if a.out_proj.bias is None else a.out_proj.bias.detach(), k=E)
+        return ops.step_linear(ctx, a.out_proj.weight.detach(), a.out_proj.bias.detach())
 
 
 class CachedDecoder:
@@ -131,8 +144,10 @@ class CachedDecoder:
         self.V = [torch.zeros((B, cap, a.Wk), device=dev, dtype=torch.float32) for a in self.sa]
         self.cache_bytes = sum(k.numel() * 8 for k in self.K) + sum(kv[0].numel() * 8 for kv in self.mem_kv)
 
-    def step(self, x: torch.Tensor, t: int) -> torch.Tensor:
-        """x (B, E): embedded token of position t of every video -> decoder output rows (B, E) after the final norm."""
+    def step(self, x: torch.Tensor, t: torch.Tensor, n_keys: torch.Tensor) -> torch.Tensor:
+        """x (B, E): embedded token of position t of every video -> decoder output rows (B, E) after the final norm.
+        t: int64 device tensor (1,), n_keys = t + 1 as an int32 device tensor (1,): the position never reaches the host, so the
+        launches of a step are the same for every position (one CUDA graph, replayed)."""
         B = self.B
         for i, layer in enumerate(self.layers):
             sa, ca = self.sa[i], self.ca[i]
@@ -141,9 +156,9 @@ class CachedDecoder:
 
             def self_att(z):
                 q, k, v = sa.qkv(z)
-                K[:, t].copy_(k)
-                V[:, t].copy_(v)
-                return sa.attend(q, K, V, t + 1, (K.stride(0), K.stride(1)))
+                K.index_copy_(1, t, k.unsqueeze(1))
+                V.index_copy_(1, t, v.unsqueeze(1))
+                return sa.attend(q, K, V, self.cap, (K.stride(0), K.stride(1)), n_dev=n_keys)
 
             def cross_att(z):
                 # memory rows are ordered (s, b): video b's row s sits at (s * B + b)
@@ -167,12 +182,15 @@ class CachedDecoder:
 def generate_cached(model: nn.Module, feature_semantic_list, feature_key, feature_scene_offset, feature_motion, feature_emotion,
                     primer, primer_root, primer_attr, target_seq_length: int = 300, beam: int = 0, beam_chance: float = 1.0,
                     max_conseq_N: int = 0, max_conseq_chord: int = 2, temperature: float = 1.0,
-                    uniforms: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    uniforms: Optional[torch.Tensor] = None, use_graph: Optional[bool] = None) -> torch.Tensor:
     """Batched `generate` of the V1 / V2 '2.0' / GQA shells (video_music_transformer.py:227-315, 522-610) with a KV cache.
     Features carry a batch dimension of B videos (the reference: 1); the primer (P,) is shared by all videos or (B, P).
     beam=1 (beam_chance >= 1): arg-max over the first 157 classes, root / attribute inputs of generated positions stay PAD
     (literal); beam=0: the sampling branch (no-"N" / no-repeat constraints, inverse-CDF draw from `uniforms` (B, T) or
-    torch.rand), root / attribute updated.  Returns (B, target_seq_length) int64."""
+    torch.rand), root / attribute updated.  Returns (B, target_seq_length) int64.
+    The position is a device word (caches are written with index_copy_, the attention kernel reads its key count from it), so
+    one position is ONE CUDA graph captured after the first step and replayed (use_graph; default: on unless a module carries
+    a Python-side temperature scheduler, which advances per call, moe.py:238-242)."""
     assert not model.training, "Cannot generate while in training mode"
     if not (beam == 0 or (beam == 1 and beam_chance >= 1.0)):
         raise NotImplementedError("beam > 1 / 0 < beam_chance < 1 are not reproduced")
@@ -213,31 +231,72 @@ def generate_cached(model: nn.Module, feature_semantic_list, feature_key, featur
     dec = CachedDecoder(model, memory, T)
     wc = model.Linear_chord.weight.detach()
     wkey = wc[:, E].contiguous()
+    wc_main = wc[:, :E].contiguous()                     # 16-byte aligned rows for the step kernel (the weight has 513 columns)
     key_rows = key.reshape(B, -1)[:, 0].float().contiguous()
     pos = model.positional_embedding.weight.detach()
-    for t in range(T - 1):                               # the token of position t goes in, the token of position t + 1 comes out
-        xin = ops.embed_sum(gen_root[:, t].contiguous(), model.embedding_root.weight.detach(), gen_attr[:, t].contiguous(),
-                            model.embedding_attr.weight.detach(), torch.float32)
-        x = ops.linear(xin, wc, model.Linear_chord.bias.detach(), k=E, row_scale=key_rows, col_vec=wkey)
-        x = ops.axpy(x, pos[t].unsqueeze(0).expand(B, E).contiguous(), 1.0)
-        h = dec.step(x, t)
-        cur = t + 1
-        if cur < n0:
-            continue                                     # primer positions only fill the caches
-        logits = ops.linear(h, model.Wout.weight.detach(), model.Wout.bias.detach())
+    emb_root, emb_attr = model.embedding_root.weight.detach(), model.embedding_attr.weight.detach()
+    w_out, b_out = model.Wout.weight.detach(), model.Wout.bias.detach()
+    b_chord = model.Linear_chord.bias.detach()
+    # the position lives on the device: t (int64, index of the token that goes in), n_keys = t + 1 (int32, rows of the caches)
+    t_dev = torch.zeros(1, dtype=torch.long, device=dev)
+    n_keys = torch.ones(1, dtype=torch.int32, device=dev)
+    ar_back = torch.arange(1, max(1, max_conseq_chord) + 1, device=dev).view(1, -1)     # 1 .. max_conseq_chord
+
+    def step():
+        """Token of position t in, token of position t + 1 out; then t += 1.  No host-visible value depends on t."""
+        col = t_dev.view(1, 1).expand(B, 1)
+        xin = ops.embed_sum(gen_root.gather(1, col).view(B), emb_root, gen_attr.gather(1, col).view(B), emb_attr, torch.float32)
+        x = ops.step_linear(xin, wc_main, b_chord, k=E, row_scale=key_rows, col_vec=wkey)
+        x = ops.axpy(x, pos.index_select(0, t_dev).expand(B, E).contiguous(), 1.0)
+        h = dec.step(x, t_dev, n_keys)
+        cur = col + 1                                    # (B, 1)
+        logits = ops.step_linear(h, w_out, b_out)
         probs = torch.softmax(logits / temperature, dim=-1)[:, :CHORD_END]
+        old = gen.gather(1, cur)
+        in_primer = cur < n0                             # primer positions only fill the caches
         if beam == 1:
-            gen[:, cur] = torch.argmax(probs, dim=-1)
+            tok = torch.argmax(probs, dim=-1, keepdim=True)
         else:
             probs = probs.clone()
             if max_conseq_N == 0:
                 probs[:, 0] = 0.0
-            if cur >= max_conseq_chord:
-                rep = (gen[:, cur - max_conseq_chord:cur] == gen[:, cur - 1:cur]).all(dim=1)
-                probs[rep, gen[rep, cur - 1]] = 0.0
+            # the last max_conseq_chord tokens all equal the previous one -> it may not be drawn again
+            back = (cur - ar_back).clamp_min(0)          # (B, max_conseq_chord)
+            prev = gen.gather(1, cur - 1)
+            rep = (gen.gather(1, back) == prev).all(dim=1, keepdim=True) & (cur >= max_conseq_chord)
+            probs.scatter_(1, prev.clamp(0, CHORD_END - 1), torch.where(rep & (prev < CHORD_END), torch.zeros_like(probs[:, :1]),
+                                                                      probs.gather(1, prev.clamp(0, CHORD_END - 1))))
             cdf = torch.cumsum(probs / probs.sum(dim=1, keepdim=True), dim=1)
-            tok = (cdf <= uniforms[:, cur:cur + 1]).sum(dim=1).clamp_max(CHORD_END - 1)
-            gen[:, cur] = tok
-            gen_root[:, cur] = torch.where(tok <= 0, torch.zeros_like(tok), (tok - 1) // 13 + 1)
-            gen_attr[:, cur] = torch.where(tok <= 0, torch.ones_like(tok), (tok - 1) % 13 + 1)
+            tok = (cdf <= uniforms.gather(1, cur)).sum(dim=1, keepdim=True).clamp_max(CHORD_END - 1)
+            root = torch.where(tok <= 0, torch.zeros_like(tok), (tok - 1) // 13 + 1)
+            attr = torch.where(tok <= 0, torch.ones_like(tok), (tok - 1) % 13 + 1)
+            gen_root.scatter_(1, cur, torch.where(in_primer, gen_root.gather(1, cur), root))
+            gen_attr.scatter_(1, cur, torch.where(in_primer, gen_attr.gather(1, cur), attr))
+        gen.scatter_(1, cur, torch.where(in_primer, old, tok))
+        t_dev.add_(1)
+        n_keys.add_(1)
+
+    n_steps = T - 1
+    if use_graph is None:                                # Python-side schedulers that advance in eval mode cannot be replayed
+        use_graph = not any(hasattr(mod, "temperature_scheduler") for mod in model.modules())
+    if not use_graph or n_steps < 3:
+        for _ in range(n_steps):
+            step()
+        return gen
+    # one eager step (allocator / caches warm), then the step is captured once and replayed for every remaining position
+    from . import _lib
+    step()
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(device=dev)
+    graph = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        n_before = _lib.launches()
+        with torch.cuda.graph(graph, stream=side):
+            step()
+        per_step = _lib.launches() - n_before
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for _ in range(n_steps - 1):
+        graph.replay()
+    _lib.count_launches(per_step * (n_steps - 2))        # the capture counted one step
     return gen

@@ -399,6 +399,7 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
   V2M_REQUIRE(!p.causal || p.Lk >= p.Lq, "attn_fwd_bf16_tc: causal needs Lk >= Lq");
   V2M_REQUIRE(p.q_scale == 1.0f, "attn_fwd_bf16_tc: q must be pre-scaled (fold the scale into the projection epilogue)");
   V2M_REQUIRE(p.p_out == nullptr, "attn_fwd_bf16_tc: need_weights output is only available on the fp32 path");
+  V2M_REQUIRE(p.lk_dev == nullptr, "attn_fwd_bf16_tc: a device-side key count is only available on the fp32 path");
   V2M_REQUIRE(p.o_sl % 8 == 0 && p.o_sb % 8 == 0 && reinterpret_cast<uintptr_t>(p.o) % 16 == 0,
               "attn_fwd_bf16_tc: output must be 16-byte aligned");
   CUtensorMap tmQ, tmK, tmV, tmE;

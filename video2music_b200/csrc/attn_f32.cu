@@ -34,8 +34,9 @@ __global__ void __launch_bounds__(NW * 32) attn_f32_kernel(AttnParams p, int lk_
   const int i0 = blockIdx.x * RB;
   const int nrows = min(RB, p.Lq - i0);
   // causal: query i sees keys j <= i + (Lk - Lq)   (Lq == Lk for self-attention)
-  const int coff = p.Lk - p.Lq;
-  const int nk = p.causal ? min(p.Lk, i0 + nrows + coff) : p.Lk;   // keys needed by this CTA
+  const int Lk = p.lk_dev ? min(p.Lk, __ldg(p.lk_dev)) : p.Lk;     // keys that exist (device-side count: graph replays)
+  const int coff = Lk - p.Lq;
+  const int nk = p.causal ? min(Lk, i0 + nrows + coff) : Lk;       // keys needed by this CTA
 
   const float* q = static_cast<const float*>(p.q) + (size_t)b * p.q_sb + (size_t)hq * DH;
   const float* k = static_cast<const float*>(p.k) + (size_t)b * p.k_sb + (size_t)hkv * DH;
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(NW * 32) attn_f32_kernel(AttnParams p, int lk_
   for (int r = 0; r < RPW; ++r) {
     const int i = i0 + r0 + r;
     float* pr = Ps + (r0 + r) * lk_pad;
-    const int lim = (i < p.Lq) ? (p.causal ? min(p.Lk, i + coff + 1) : p.Lk) : 0;   // keys [0, lim)
+    const int lim = (i < p.Lq) ? (p.causal ? min(Lk, i + coff + 1) : Lk) : 0;   // keys [0, lim)
     float mx = -INFINITY;
     for (int j = lane; j < lim; j += 32) mx = fmaxf(mx, pr[j]);
     mx = warp_max(mx);
@@ -203,6 +204,7 @@ int attn_fwd_f32(const AttnParams& p, cudaStream_t stream) {
   V2M_REQUIRE(p.Lq > 0 && p.Lk > 0, "attn_fwd_f32: empty sequence Lq=%d Lk=%d", p.Lq, p.Lk);
   V2M_REQUIRE(!p.Er || (p.Lq == p.Lk && p.Lq <= p.er_len), "attn_fwd_f32: RPR needs Lq == Lk <= er_len (%d, %d, %d)",
               p.Lq, p.Lk, p.er_len);
+  V2M_REQUIRE(!p.lk_dev || (!p.Er && !p.p_out), "attn_fwd_f32: a device-side key count excludes Er and need_weights");
   switch (p.dh) {
     case 32: return launch<32>(p, stream);
     case 64: return launch<64>(p, stream);

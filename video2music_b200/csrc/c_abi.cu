@@ -107,6 +107,7 @@ int v2m_attn_fwd(const v2m_attn* a, int32_t dtype, void* stream) {
   p.causal = a->causal; p.Er = a->Er; p.er_len = a->er_len; p.q_scale = a->q_scale;
   p.lse = a->lse; p.p_out = a->p_out;
   p.drop_scale = a->drop_scale; p.drop_thresh = a->drop_thresh; p.drop_seed = a->drop_seed; p.drop_seed_dev = a->drop_seed_dev;
+  p.lk_dev = a->lk_dev;
   if (dtype == V2M_F32) return attn_fwd_f32(p, static_cast<cudaStream_t>(stream));
   if (dtype == V2M_BF16) return attn_fwd_bf16_tc(p, static_cast<cudaStream_t>(stream));
   set_last_error("v2m_attn_fwd: dtype %d unsupported", dtype);
@@ -149,6 +150,11 @@ int v2m_embed_bwd(const int64_t* idx, const void* d, int32_t d_dtype, int64_t ld
   return embed_bwd(reinterpret_cast<const long long*>(idx), d, d_dtype, ld_d, dtable, rows, D, static_cast<cudaStream_t>(stream));
 }
 
+int v2m_amt_correspondence(const float* logits, const float* tgt_emotion, const float* tgt_emotion_prob, int32_t R, int32_t Cn, int32_t Ce,
+                           float threshold, int32_t chord_end, int32_t* counters, void* stream) {
+  return amt_correspondence(logits, tgt_emotion, tgt_emotion_prob, R, Cn, Ce, threshold, chord_end, counters, static_cast<cudaStream_t>(stream));
+}
+
 int v2m_amt_metrics(const float* logits, const int64_t* tgt, int32_t R, int32_t Cn, int64_t pad, int32_t k0, int32_t k1, int32_t k2,
                     int32_t* counters, void* stream) {
   return amt_metrics(logits, reinterpret_cast<const long long*>(tgt), R, Cn, pad, k0, k1, k2, counters, static_cast<cudaStream_t>(stream));
@@ -173,6 +179,16 @@ int v2m_layernorm(const void* x, int32_t x_dtype, const void* res, int32_t res_d
                   void* y, int32_t y_dtype, void* y2, int32_t y2_dtype, int32_t M, int32_t D, float eps, void* stream) {
   return layernorm(x, x_dtype, res, res_dtype, gamma, beta, y, y_dtype, y2, y2_dtype, M, D, eps,
                    static_cast<cudaStream_t>(stream));
+}
+
+int v2m_step_linear_f32(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, const float* row_scale,
+                        const float* col_vec, float* y, int64_t ldy, int32_t M, int32_t N, int32_t K, int32_t relu, void* stream) {
+  return step_linear_f32(x, ldx, W, ldw, bias, row_scale, col_vec, y, ldy, M, N, K, relu, static_cast<cudaStream_t>(stream));
+}
+
+int v2m_step_attn_f32(const float* q, int64_t q_sb, const float* k, const float* v, int64_t kv_sb, int64_t kv_sl, float* o, int64_t o_sb,
+                      int32_t B, int32_t Hq, int32_t Hkv, int32_t dh, int32_t n_max, const int32_t* n_dev, float q_scale, void* stream) {
+  return step_attn_f32(q, q_sb, k, v, kv_sb, kv_sl, o, o_sb, B, Hq, Hkv, dh, n_max, n_dev, q_scale, static_cast<cudaStream_t>(stream));
 }
 
 int v2m_embed_sum(const int64_t* idx_a, const float* table_a, const int64_t* idx_b, const float* table_b, void* out,

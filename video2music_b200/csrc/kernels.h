@@ -82,6 +82,9 @@ struct AttnParams {
   float drop_scale = 0.f;
   unsigned int drop_thresh = 0, drop_seed = 0;
   const unsigned int* drop_seed_dev = nullptr;   // optional device counter added to drop_seed
+  // optional device word: only the first min(Lk, *lk_dev) keys exist (fp32 kernel).  Lets ONE captured CUDA graph be replayed
+  // for every position of a KV-cached generation: the cache grows, the launch parameters do not.
+  const int* lk_dev = nullptr;
 };
 int attn_fwd_f32(const AttnParams& p, cudaStream_t stream);
 int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream);
@@ -209,6 +212,13 @@ int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, lo
                        const float* A_log, const float* Bm, const float* Cm, long long ldbc, const float* Dp, const float* z,
                        long long ldz, float* out, long long ldo, int B, int L, int ED, int N, int plus, float* ws,
                        long long ws_bytes, cudaStream_t stream);
+// one generation step of the generic decoder stacks (csrc/step_f32.cu): M <= 64 new rows per launch, one query row per (video, head)
+int step_linear_f32(const float* x, long long ldx, const float* W, long long ldw, const float* bias, const float* row_scale,
+                    const float* col_vec, float* y, long long ldy, int M, int N, int K, int relu, cudaStream_t stream);
+int step_moe_gemm_f32(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,
+                      long long b_gstride, const int* off, int n_experts, float* C, int ldc, int N, int K, cudaStream_t stream);
+int step_attn_f32(const float* q, long long q_sb, const float* k, const float* v, long long kv_sb, long long kv_sl, float* o, long long o_sb,
+                  int B, int Hq, int Hkv, int dh, int n_max, const int* n_dev, float q_scale, cudaStream_t stream);
 int rmsnorm(const float* x, const float* w, float* y, int M, int D, float eps, cudaStream_t stream);
 long long selective_scan_bwd_workspace(int B, int L, int ED, int N);
 int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, long long ldd, const float* dt_bias, const float* A_log,
@@ -245,6 +255,8 @@ int moe_grouped_dw(const float* dY, int ldy, const float* X, int ldx, const int*
 int dw_f32(const float* dY, int ldy, const float* X, int ldx, int rows, float* dW, float* db, int N, int K, cudaStream_t stream);
 
 // accuracy / hits@k counters of the evaluation loop (train.cu)
+int amt_correspondence(const float* logits, const float* emo, const float* prob, int R, int Cn, int Ce, float thr, int chord_end,
+                       int* counters, cudaStream_t stream);
 int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long long pad, int k0, int k1, int k2, int* counters,
                 cudaStream_t stream);
 

@@ -473,6 +473,8 @@ int moe_grouped_gemm(const float* A, int lda, const float* W1, const float* b1, 
   dim3 grid((N + GB - 1) / GB, (max_rows + GB - 1) / GB, n_experts);
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   const bool vec = K % 16 == 0 && lda % 4 == 0 && al16(A) && al16(W1) && al16(Wg) && w_gstride % 4 == 0;
+  // a generation step (one token per video): weight-streaming kernel over the whole chip instead of mostly empty 64 x 64 tiles
+  if (vec && max_rows <= 256) return step_moe_gemm_f32(A, lda, W1, b1, Wg, bg, w_gstride, b_gstride, off, n_experts, C, ldc, N, K, stream);
 #define V2M_GG(GLU, VEC) moe_grouped_gemm_kernel<GLU, VEC><<<grid, 256, 0, stream>>>(A, lda, W1, b1, Wg, bg, w_gstride, b_gstride, off, C, ldc, N, K)
   if (Wg) { if (vec) V2M_GG(true, true); else V2M_GG(true, false); }
   else { if (vec) V2M_GG(false, true); else V2M_GG(false, false); }

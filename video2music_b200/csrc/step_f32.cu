@@ -1,0 +1,243 @@
+// fp32 kernels of ONE generation step of the generic decoder stacks (BASELINE config 4: grouped-query attention + MoE feed-forward,
+// cached_decode.py): the batch is one new token per video (M <= 64 rows), so a linear layer is a weight stream and the attention is one
+// query row per (video, head) over the cached keys / values.  The tiled GEMM / attention kernels of the full forward run these shapes
+// on 4..12 CTAs (93 us per launch measured); here every launch covers the chip and is bound by its weight / cache bytes.
+//
+//   step_gemm_f32_kernel   : y[M,N] = act(x[M,K] W[N,K]^T + bias[n] + row_scale[m] col_vec[n])   (F.linear at
+//                            custom_transformer.py:1044-1053 / grouped_query_attention.py:306-356 / video_music_transformer.py:240-262)
+//                            and, per expert group, the GLU expert GEMMs of the MoE feed-forward (moe.py:44-49);
+//                            CTA = 8 output features x 64 rows, activations in registers, weights as broadcast loads, fixed k order.
+//   step_attn_f32_kernel   : o = softmax(q K^T * scale) V for ONE query row per (video, query head) over the first n cached rows,
+//                            n read from a device word (the launch is identical for every position -> one CUDA graph per
+//                            generation); kv head = query head / (Hq / Hkv)  (grouped_query_attention.py:99-159 with one query).
+// Both use a fixed summation order: results do not depend on the batch size or on n_max.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace v2m {
+
+namespace stp {
+
+constexpr int THREADS = 256;
+constexpr int NT = 8;          // output features per CTA
+constexpr int MT = 64;         // rows (videos) per CTA
+
+// thread = (row r of the 64-row block, k quarter kq): the thread's 128 activations of a 512-wide k block live in REGISTERS (32
+// independent 16-byte loads, issued together: one memory latency), the weights of the CTA's NT features are broadcast loads
+// (all lanes of a warp share kq, hence the address), the four k quarters meet in shared memory and are added in a fixed order.
+// No staging of the activations in shared memory and no barrier inside the k loop.
+struct StepGemm {
+  const float* A; long long lda;
+  const float* W1; const float* b1; const float* Wg; const float* bg;
+  long long ldw, w_gstride, b_gstride;
+  const int* off;            // row ranges of the groups (experts); null: one group = rows [0, M)
+  const float* row_scale; const float* col_vec;
+  float* C; long long ldc;
+  int M, N, K, relu;
+};
+
+template <bool GLU>
+__global__ void __launch_bounds__(THREADS) step_gemm_f32_kernel(const __grid_constant__ StepGemm p) {
+  constexpr int NT = GLU ? stp::NT / 2 : stp::NT;                // features per CTA: eight accumulator chains either way
+  constexpr int NV = GLU ? 2 * NT : NT;
+  __shared__ float red[3][MT][NV + 1];
+  const int tid = threadIdx.x, r = tid & 63, kq = tid >> 6;
+  const int e = blockIdx.y;
+  const int r_begin = p.off ? p.off[e] : 0, r_end = p.off ? p.off[e + 1] : p.M;
+  if (r_begin >= r_end) return;                                  // group without rows (uniform over the CTA)
+  const int n0 = blockIdx.x * NT;
+  const float* W1e = p.W1 + (size_t)e * p.w_gstride;
+  const float* Wge = GLU ? p.Wg + (size_t)e * p.w_gstride : nullptr;
+  for (int row0 = r_begin; row0 < r_end; row0 += MT) {
+    const int m = row0 + r;
+    const bool ok = m < r_end;
+    const bool warp_ok = row0 + (r & ~31) < r_end;               // a warp whose 32 rows are all beyond the group skips the k loop
+    float acc[NT], gac[NT];
+#pragma unroll
+    for (int nn = 0; nn < NT; ++nn) { acc[nn] = 0.f; gac[nn] = 0.f; }
+    for (int kb = 0; warp_ok && kb < p.K; kb += 512) {
+      const int k0 = kb + kq * 128;
+      const int nv = max(0, min(32, (p.K - k0) >> 2));           // 16-byte chunks of this thread's slice inside K
+      float4 xr[32];
+      const float4* xs = reinterpret_cast<const float4*>(p.A + (size_t)(ok ? m : r_begin) * p.lda + k0);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xr[i] = (ok && i < nv) ? __ldg(xs + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int nn = 0; nn < NT; ++nn) {
+        const int n = min(n0 + nn, p.N - 1);
+        const float4* w = reinterpret_cast<const float4*>(W1e + (size_t)n * p.ldw + k0);
+        const float4* wg = GLU ? reinterpret_cast<const float4*>(Wge + (size_t)n * p.ldw + k0) : w;
+        float a = acc[nn], g = gac[nn];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i < nv) {
+            const float4 u = __ldg(w + i);
+            a = fmaf(xr[i].x, u.x, a); a = fmaf(xr[i].y, u.y, a); a = fmaf(xr[i].z, u.z, a); a = fmaf(xr[i].w, u.w, a);
+            if (GLU) {
+              const float4 h = __ldg(wg + i);
+              g = fmaf(xr[i].x, h.x, g); g = fmaf(xr[i].y, h.y, g); g = fmaf(xr[i].z, h.z, g); g = fmaf(xr[i].w, h.w, g);
+            }
+          }
+        }
+        acc[nn] = a;
+        gac[nn] = g;
+      }
+    }
+    if (row0 > r_begin) __syncthreads();                         // the previous block's partials have been read
+    if (kq > 0) {
+#pragma unroll
+      for (int nn = 0; nn < NT; ++nn) {
+        red[kq - 1][r][nn] = acc[nn];
+        if (GLU) red[kq - 1][r][NT + nn] = gac[nn];
+      }
+    }
+    __syncthreads();
+    if (kq == 0 && ok) {
+      const float rs = p.row_scale ? p.row_scale[m] : 0.f;
+#pragma unroll
+      for (int nn = 0; nn < NT; ++nn) {
+        const int n = n0 + nn;
+        if (n < p.N) {
+          float v = ((acc[nn] + red[0][r][nn]) + red[1][r][nn]) + red[2][r][nn];
+          if (p.b1) v += p.b1[(size_t)e * p.b_gstride + n];
+          if (GLU) {
+            const float gv = (((gac[nn] + red[0][r][NT + nn]) + red[1][r][NT + nn]) + red[2][r][NT + nn]) + p.bg[(size_t)e * p.b_gstride + n];
+            v = v * (gv / (1.f + expf(-gv)));
+          }
+          if (p.row_scale) v = fmaf(rs, p.col_vec[n], v);
+          if (p.relu) v = fmaxf(v, 0.f);
+          p.C[(size_t)m * p.ldc + n] = v;
+        }
+      }
+    }
+  }
+}
+
+constexpr int ATH = 128;       // threads of the attention CTA (4 warps)
+
+// grid = B * Hq.  Shared memory: q[64] | sc[n_max] | part[8][64] | red[8]
+__global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restrict__ q, long long q_sb, const float* __restrict__ Kc,
+                                                            const float* __restrict__ Vc, long long kv_sb, long long kv_sl,
+                                                            float* __restrict__ o, long long o_sb, int Hq, int Hkv, int n_max,
+                                                            const int* __restrict__ n_dev, float q_scale) {
+  extern __shared__ __align__(16) float sa_smem[];
+  float* qs = sa_smem;
+  float* sc = qs + 64;
+  float* part = sc + ((n_max + 3) & ~3);
+  float* red = part + 8 * 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / Hq, hq = blockIdx.x % Hq, hkv = hq / (Hq / Hkv);
+  const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
+  const float* kb = Kc + (size_t)b * kv_sb + (size_t)hkv * 64;
+  const float* vb = Vc + (size_t)b * kv_sb + (size_t)hkv * 64;
+  if (tid < 64) qs[tid] = q[(size_t)b * q_sb + (size_t)hq * 64 + tid] * q_scale;
+  __syncthreads();
+  // ---- scores: warp w takes keys w, w + 4, ...; a lane holds two dims of the row (256 contiguous bytes per warp and key);
+  // eight keys of the warp in flight per iteration
+  const float2 qq = *reinterpret_cast<const float2*>(qs + 2 * lane);
+  float mx = -INFINITY;
+  for (int j0 = warp; j0 < n; j0 += 32) {
+    float s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + 4 * u;
+      float2 kk = make_float2(0.f, 0.f);
+      if (j < n) kk = __ldg(reinterpret_cast<const float2*>(kb + (size_t)j * kv_sl) + lane);
+      s[u] = fmaf(qq.x, kk.x, qq.y * kk.y);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + 4 * u;
+      if (j < n) { if (lane == 0) sc[j] = s[u]; mx = fmaxf(mx, s[u]); }
+    }
+  }
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  // ---- p = exp(s - max) (kept un-normalised), row sum in a fixed order: lane-strided partials, shuffle tree, warps 0..3
+  float sum = 0.f;
+  for (int j = tid; j < n; j += ATH) {
+    const float p = __expf(sc[j] - mx);
+    sc[j] = p;
+    sum += p;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if (lane == 0) red[4 + warp] = sum;
+  __syncthreads();
+  const float total = (red[4] + red[5]) + (red[6] + red[7]);
+  // ---- o[d] = sum_j p_j V[j][d]: thread = (key group g of 8, four dims d4); keys g, g + 8, ... with four 16-byte loads in
+  // flight, the eight partial rows meet in shared memory and are added in a fixed order
+  const int d4 = tid & 15, g = tid >> 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = g; j0 < n; j0 += 32) {
+    float4 vv[4];
+    float pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 8 * u;
+      vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pp[u] = 0.f;
+      if (j < n) { vv[u] = __ldg(reinterpret_cast<const float4*>(vb + (size_t)j * kv_sl) + d4); pp[u] = sc[j]; }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc.x = fmaf(pp[u], vv[u].x, acc.x); acc.y = fmaf(pp[u], vv[u].y, acc.y);
+      acc.z = fmaf(pp[u], vv[u].z, acc.z); acc.w = fmaf(pp[u], vv[u].w, acc.w);
+    }
+  }
+  reinterpret_cast<float4*>(part)[g * 16 + d4] = acc;
+  __syncthreads();
+  if (tid < 64) {
+    float v = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < 8; ++gg) v += part[gg * 64 + tid];
+    o[(size_t)b * o_sb + (size_t)hq * 64 + tid] = v / total;
+  }
+}
+
+}  // namespace stp
+
+int step_linear_f32(const float* x, long long ldx, const float* W, long long ldw, const float* bias, const float* row_scale,
+                    const float* col_vec, float* y, long long ldy, int M, int N, int K, int relu, cudaStream_t stream) {
+  V2M_REQUIRE(M > 0 && N > 0 && K > 0, "step_linear_f32: empty problem %d x %d x %d", M, N, K);
+  V2M_REQUIRE(K % 4 == 0 && ldw % 4 == 0 && ldx % 4 == 0 && reinterpret_cast<uintptr_t>(W) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0,
+              "step_linear_f32: rows must be 16-byte aligned (K %d, ldx %lld, ldw %lld)", K, ldx, ldw);
+  V2M_REQUIRE((row_scale == nullptr) == (col_vec == nullptr), "step_linear_f32: row_scale and col_vec come together");
+  stp::StepGemm p{x, ldx, W, bias, nullptr, nullptr, ldw, 0, 0, nullptr, row_scale, col_vec, y, ldy, M, N, K, relu};
+  stp::step_gemm_f32_kernel<false><<<dim3((N + stp::NT - 1) / stp::NT, 1), stp::THREADS, 0, stream>>>(p);
+  return check_launch("step_linear_f32");
+}
+
+int step_attn_f32(const float* q, long long q_sb, const float* k, const float* v, long long kv_sb, long long kv_sl, float* o, long long o_sb,
+                  int B, int Hq, int Hkv, int dh, int n_max, const int* n_dev, float q_scale, cudaStream_t stream) {
+  V2M_REQUIRE(dh == 64, "step_attn_f32: head_dim %d unsupported (64)", dh);
+  V2M_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && n_max > 0, "step_attn_f32: bad shape B=%d Hq=%d Hkv=%d n=%d", B, Hq, Hkv, n_max);
+  V2M_REQUIRE(kv_sl % 4 == 0 && kv_sb % 4 == 0 && reinterpret_cast<uintptr_t>(k) % 16 == 0 && reinterpret_cast<uintptr_t>(v) % 16 == 0,
+              "step_attn_f32: cache rows must be 16-byte aligned");
+  const size_t smem = sizeof(float) * (64 + ((n_max + 3) & ~3) + 8 * 64 + 8);
+  V2M_REQUIRE(smem <= 48 * 1024, "step_attn_f32: n_max %d too large", n_max);
+  stp::step_attn_f32_kernel<<<B * Hq, stp::ATH, smem, stream>>>(q, q_sb, k, v, kv_sb, kv_sl, o, o_sb, Hq, Hkv, n_max, n_dev, q_scale);
+  return check_launch("step_attn_f32");
+}
+
+// Small-row variant of moe_grouped_gemm (moe.cu calls it when a launch carries at most a few hundred token copies): rows
+// [off[e], off[e+1]) of A belong to expert e, C = A W_e^T + b_e, or with the gate stack C = (A W1_e^T + b1_e) * silu(A Wg_e^T + bg_e)
+// (GLUExpert, moe.py:44-49); K % 4 == 0 and 16-byte aligned rows are the caller's `vec` condition.  The expert weights (226 MB per
+// position for 6 layers x 6 experts) are read once per launch.
+int step_moe_gemm_f32(const float* A, int lda, const float* W1, const float* b1, const float* Wg, const float* bg, long long w_gstride,
+                      long long b_gstride, const int* off, int n_experts, float* C, int ldc, int N, int K, cudaStream_t stream) {
+  stp::StepGemm p{A, lda, W1, b1, Wg, bg, K, w_gstride, b_gstride, off, nullptr, nullptr, C, ldc, 0, N, K, 0};
+  const int nt = Wg ? stp::NT / 2 : stp::NT;
+  dim3 grid((N + nt - 1) / nt, n_experts);
+  if (Wg) stp::step_gemm_f32_kernel<true><<<grid, stp::THREADS, 0, stream>>>(p);
+  else stp::step_gemm_f32_kernel<false><<<grid, stp::THREADS, 0, stream>>>(p);
+  return check_launch("step_moe_gemm_f32");
+}
+
+}  // namespace v2m

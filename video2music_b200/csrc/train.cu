@@ -499,4 +499,51 @@ int amt_metrics(const float* logits, const long long* tgt, int R, int Cn, long l
   return check_launch("amt_metrics");
 }
 
+// Emotion-correspondence metric of the evaluation loop (dataset/vevo_dataset.py:747-810: compute_vevo_correspondence), which the
+// reference evaluates with a Python loop, one .item() per position and five JSON files per call: a position counts (pt) when its
+// emotion row is not padding (last column != 1), has at least one of the 14 chord qualities set and comes with probability >=
+// threshold; it is right when the quality of the arg-max chord is one of the set qualities.  Chord id c -> quality: the
+// chord_inv / chord_attr tables reduce to 1 ("maj") for c == 0 ("N" has no ':' either, literal) and (c - 1) % 13 + 1 otherwise;
+// END (157) / PAD (158) predictions count in pt but are never right.  One warp per position; lower index wins arg-max ties.
+// counters: [0] pt, [1] right (int32, zeroed here).
+__global__ void __launch_bounds__(256) amt_correspondence_kernel(const float* __restrict__ logits, const float* __restrict__ emo,
+                                                                 const float* __restrict__ prob, int R, int Cn, int Ce, float thr,
+                                                                 int chord_end, int* __restrict__ counters) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= R) return;
+  const float* er = emo + (long long)row * Ce;
+  const float q = lane < 14 ? er[lane] : 0.f;
+  const bool any_q = __any_sync(0xffffffffu, lane < 14 && q != 0.f);
+  if (er[Ce - 1] == 1.f || !any_q || prob[row] < thr) return;           // warp-uniform
+  const float* lr = logits + (long long)row * Cn;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = lane; c < Cn; c += 32) {
+    const float v = lr[c];
+    if (v > best) { best = v; arg = c; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, off);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  const int quality = arg == 0 ? 1 : (arg - 1) % 13 + 1;
+  const float hit = __shfl_sync(0xffffffffu, q, quality);
+  if (lane == 0) {
+    atomicAdd(counters + 0, 1);
+    if (arg < chord_end && hit == 1.f) atomicAdd(counters + 1, 1);
+  }
+}
+
+int amt_correspondence(const float* logits, const float* emo, const float* prob, int R, int Cn, int Ce, float thr, int chord_end,
+                       int* counters, cudaStream_t stream) {
+  V2M_REQUIRE(R >= 0 && Cn > 0 && Ce >= 14 && counters, "amt_correspondence: bad arguments (Ce = %d needs the 14 quality columns)", Ce);
+  cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(int), stream);
+  if (e != cudaSuccess) { set_last_error("amt_correspondence: %s", cudaGetErrorString(e)); return kCudaError; }
+  if (R == 0) return kOk;
+  amt_correspondence_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, emo, prob, R, Cn, Ce, thr, chord_end, counters);
+  return check_launch("amt_correspondence");
+}
+
 }  // namespace v2m

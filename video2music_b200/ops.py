@@ -127,9 +127,11 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, B: int, Hq: int, Hkv: int,
               Lq: int, Lk: int, dh: int, q_strides, k_strides, v_strides, o_strides, causal: bool,
               Er: Optional[torch.Tensor] = None, q_scale: float = 1.0, lse: Optional[torch.Tensor] = None,
-              p_out: Optional[torch.Tensor] = None, dropout: Optional[tuple] = None) -> torch.Tensor:
+              p_out: Optional[torch.Tensor] = None, dropout: Optional[tuple] = None,
+              lk_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T + skew(q Er^T) + causal) v.  *_strides = (batch stride, row stride) in elements;
-    q/k/v/out may be column slices of wider matrices (head h starts at column h*dh of the given pointer)."""
+    q/k/v/out may be column slices of wider matrices (head h starts at column h*dh of the given pointer).
+    lk_dev (int32 device scalar, fp32 path): only the first min(Lk, lk_dev) keys exist (graph-replayed cached decode)."""
     require_device(q)
     a = Attn()
     a.q, a.k, a.v, a.o = ptr(q), ptr(k), ptr(v), ptr(out)
@@ -147,7 +149,41 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     if dropout is not None and dropout[0] > 0.0:                 # (p, seed): dropout of the probabilities, bf16 path
         a.drop_scale, a.drop_thresh, a.drop_seed = drop_args(dropout[0], dropout[1])
         a.drop_seed_dev = ptr(DROP_SEED_DEV)
+    if lk_dev is not None:
+        assert lk_dev.dtype == torch.int32 and lk_dev.is_cuda and q.dtype == torch.float32
+        a.lk_dev = ptr(lk_dev)
     check(load().v2m_attn_fwd(C.byref(a), dtype_code(q.dtype), stream()))
+    _lib.count_launches(1)
+    return out
+
+
+def step_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, k: Optional[int] = None, relu: bool = False,
+                row_scale: Optional[torch.Tensor] = None, col_vec: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 y = act(x @ w[:, :k].T + bias + row_scale[:, None] * col_vec[None, :]) for the few rows of one generation step
+    (csrc/step_f32.cu: a weight stream over the whole chip instead of one 128-row GEMM tile)."""
+    require_device(x)
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1 and x.dtype == w.dtype == torch.float32
+    M, N = x.shape[0], w.shape[0]
+    K = k if k is not None else min(x.shape[1], w.shape[1])
+    y = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    check(load().v2m_step_linear_f32(ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(row_scale), ptr(col_vec), ptr(y), N,
+                                     M, N, K, int(relu), stream()))
+    _lib.count_launches(1)
+    return y
+
+
+def step_attention(q: torch.Tensor, K: torch.Tensor, V: torch.Tensor, *, Hq: int, Hkv: int, dh: int, n_max: int, kv_strides,
+                   n_dev: Optional[torch.Tensor] = None, q_scale: float = 1.0) -> torch.Tensor:
+    """One query row per (video, query head) over the first n cached rows: q (B, Hq*dh) fp32, K / V caches addressed as
+    [b*kv_strides[0] + j*kv_strides[1] + h*dh + d]; n = min(n_max, n_dev) with n_dev an int32 device scalar (optional)."""
+    require_device(q)
+    assert q.dtype == K.dtype == V.dtype == torch.float32 and q.dim() == 2 and q.stride(1) == 1
+    B = q.shape[0]
+    out = torch.empty((B, Hq * dh), device=q.device, dtype=torch.float32)
+    if n_dev is not None:
+        assert n_dev.dtype == torch.int32 and n_dev.is_cuda
+    check(load().v2m_step_attn_f32(ptr(q), q.stride(0), ptr(K), ptr(V), kv_strides[0], kv_strides[1], ptr(out), Hq * dh, B, Hq, Hkv, dh,
+                                   n_max, ptr(n_dev), q_scale, stream()))
     _lib.count_launches(1)
     return out
 
@@ -769,6 +805,35 @@ def amt_metrics(logits: torch.Tensor, tgt: torch.Tensor, pad: int = 158, ks=(1, 
     check(load().v2m_amt_metrics(ptr(logits), ptr(tgt), R, Cn, pad, int(ks[0]), int(ks[1]), int(ks[2]), ptr(counters), stream()))
     _lib.count_launches(1)
     return counters
+
+
+def amt_correspondence(logits: torch.Tensor, tgt_emotion: torch.Tensor, tgt_emotion_prob: torch.Tensor, threshold: float = 0.8,
+                       chord_end: int = 157) -> torch.Tensor:
+    """int32 device counters [pt, right] of compute_vevo_correspondence (dataset/vevo_dataset.py:747-810) over all rows:
+    logits (..., Cn), tgt_emotion (..., Ce) with the 14 chord-quality columns first and the padding flag last, tgt_emotion_prob (...).
+    correspondence = right / pt (the reference returns -1 when pt == 0); `compute_vevo_correspondence` below wraps it."""
+    require_device(logits)
+    logits = logits.float().contiguous()
+    Cn = logits.shape[-1]
+    R = logits.numel() // Cn
+    emo = tgt_emotion.float().contiguous()
+    Ce = emo.shape[-1]
+    prob = tgt_emotion_prob.float().contiguous().view(-1)
+    assert emo.numel() == R * Ce and prob.numel() == R, (emo.shape, prob.shape, R)
+    counters = torch.empty((2,), device=logits.device, dtype=torch.int32)
+    check(load().v2m_amt_correspondence(ptr(logits), ptr(emo), ptr(prob), R, Cn, Ce, float(threshold), chord_end, ptr(counters), stream()))
+    _lib.count_launches(1)
+    return counters
+
+
+def compute_vevo_correspondence(out: torch.Tensor, tgt: torch.Tensor, tgt_emotion: torch.Tensor, tgt_emotion_prob: torch.Tensor,
+                                emotion_threshold: float) -> float:
+    """Same signature and return convention as the reference's function (dataset/vevo_dataset.py:747): 1.0 for an empty batch,
+    -1 when no position qualifies, else right / pt.  `tgt` is unused there as well."""
+    if tgt_emotion.numel() == 0:
+        return 1.0
+    pt, right = amt_correspondence(out, tgt_emotion, tgt_emotion_prob, emotion_threshold).tolist()
+    return -1 if pt == 0 else right / pt
 
 
 def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, lr: float, b1: float, b2: float, eps: float,
