@@ -50,8 +50,8 @@ template <> struct SkinnyCfg<bf16> {
   static size_t smem(int K) { return (size_t)MT * a_stride(K) * 2 + 8 * MT * NT * 4 + 16; }
 };
 template <> struct SkinnyCfg<float> {
-  static __host__ __device__ int a_stride(int) { return F32_KCHUNK + 1; }
-  static size_t smem(int) { return (size_t)MT * (F32_KCHUNK + 1) * 4; }
+  static __host__ __device__ int a_stride(int) { return 0; }
+  static size_t smem(int) { return 16; }                                           // registers only
 };
 
 __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -250,37 +250,66 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_gemm_kernel(const __grid_co
       skinny_epilogue<T>(p, a, row0 + o / NT, n0 + o % NT, s, t);
     }
   } else {
-    float* As = reinterpret_cast<float*>(smem_raw);
-    const int AS = F32_KCHUNK + 1;
-    const int row = tid & 63, cp = tid >> 6;
-    const float* w0 = static_cast<const float*>(a.W) + (size_t)min(n0 + 2 * cp, a.N - 1) * K;
-    const float* w1 = static_cast<const float*>(a.W) + (size_t)min(n0 + 2 * cp + 1, a.N - 1) * K;
-    float acc0 = 0.f, acc1 = 0.f;
+    // fp32 (exact path): warp = 8 video rows, lane = a k slice (16 of every 512 k: four 16-byte chunks, 128 apart), so that the
+    // activation and weight loads are coalesced 512-byte requests (staging 64 rows through shared memory and reading the
+    // weights as broadcast loads kept the load/store unit busy for ~40 us per launch); 8 rows x 8 features = 64 accumulators
+    // per lane, whose 32 lane partials meet in a transpose-reduce butterfly (fixed order) that leaves lane l with the sum of
+    // (row l / 8, feature l % 8).  No shared memory, no barrier.
+    float acc[8][NT];
+#pragma unroll
+    for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+      for (int c = 0; c < NT; ++c) acc[rr][c] = 0.f;
+    const int rw = row0 + 8 * warp;
     pdl_wait();
     const int t = *p.step;
-    for (int kc0 = 0; kc0 < K; kc0 += F32_KCHUNK) {
-      const int kc = min(F32_KCHUNK, K - kc0);
-      if (kc0 > 0) __syncthreads();
-      for (int r = warp; r < MT; r += SK_THREADS / 32) {       // coalesced row copies, 16 loads in flight per lane
-        const bool ok = row0 + r < p.B;
-        const float* src = static_cast<const float*>(a.a_src) + (size_t)(row0 + r) * K + kc0;
-#pragma unroll 16
-        for (int k = lane; k < kc; k += 32) As[(size_t)r * AS + k] = ok ? src[k] : 0.f;
+    if (rw < p.B) {
+      for (int kb = 0; kb < K; kb += 512) {
+        float4 xr[8][4];
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          const bool ok = rw + rr < p.B;
+          const float* xs = static_cast<const float*>(a.a_src) + (size_t)(ok ? rw + rr : 0) * K + kb + 4 * lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            xr[rr][j] = (ok && kb + 128 * j + 4 * lane < K) ? __ldg(reinterpret_cast<const float4*>(xs + 128 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < NT; ++c) {
+          const float* ws = static_cast<const float*>(a.W) + (size_t)min(n0 + c, a.N - 1) * K + kb + 4 * lane;
+          float4 wv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            wv[j] = (kb + 128 * j + 4 * lane < K) ? __ldg(reinterpret_cast<const float4*>(ws + 128 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            float s = acc[rr][c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              s = fmaf(xr[rr][j].x, wv[j].x, s); s = fmaf(xr[rr][j].y, wv[j].y, s);
+              s = fmaf(xr[rr][j].z, wv[j].z, s); s = fmaf(xr[rr][j].w, wv[j].w, s);
+            }
+            acc[rr][c] = s;
+          }
+        }
       }
-      __syncthreads();
-      const float* ar = As + (size_t)row * AS;
-      for (int k = 0; k < kc; k += 4) {
-        const float4 x0 = __ldg(reinterpret_cast<const float4*>(w0 + kc0 + k));
-        const float4 x1 = __ldg(reinterpret_cast<const float4*>(w1 + kc0 + k));
-        const float a0 = ar[k], a1 = ar[k + 1], a2 = ar[k + 2], a3 = ar[k + 3];
-        acc0 = fmaf(a0, x0.x, acc0); acc1 = fmaf(a0, x1.x, acc1);
-        acc0 = fmaf(a1, x0.y, acc0); acc1 = fmaf(a1, x1.y, acc1);
-        acc0 = fmaf(a2, x0.z, acc0); acc1 = fmaf(a2, x1.z, acc1);
-        acc0 = fmaf(a3, x0.w, acc0); acc1 = fmaf(a3, x1.w, acc1);
+#pragma unroll
+      for (int g2 = 0; g2 < 2; ++g2) {                           // rows 4 g2 .. 4 g2 + 3 of the warp: 32 sums -> one per lane
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = acc[4 * g2 + (i >> 3)][i & 7];
+#pragma unroll
+        for (int h = 16; h >= 1; h >>= 1) {
+          const bool up = (lane & h) != 0;
+#pragma unroll
+          for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+          }
+        }
+        skinny_epilogue<T>(p, a, rw + 4 * g2 + (lane >> 3), n0 + (lane & 7), v[0], t);
       }
     }
-    skinny_epilogue<T>(p, a, row0 + row, n0 + 2 * cp, acc0, t);
-    skinny_epilogue<T>(p, a, row0 + row, n0 + 2 * cp + 1, acc1, t);
   }
 }
 

@@ -22,10 +22,11 @@ constexpr int THREADS = 256;
 constexpr int NT = 8;          // output features per CTA
 constexpr int MT = 64;         // rows (videos) per CTA
 
-// thread = (row r of the 64-row block, k quarter kq): the thread's 128 activations of a 512-wide k block live in REGISTERS (32
-// independent 16-byte loads, issued together: one memory latency), the weights of the CTA's NT features are broadcast loads
-// (all lanes of a warp share kq, hence the address), the four k quarters meet in shared memory and are added in a fixed order.
-// No staging of the activations in shared memory and no barrier inside the k loop.
+// warp = 8 rows, lane = a k slice (16 of every 512 k: four 16-byte chunks, 128 apart): activation and weight loads are coalesced
+// 512-byte requests (a broadcast or row-strided 16-byte load costs the load/store unit the same as a full request and was the
+// bound of the first two versions: 12.5 us per 64 x 512 x 512 launch), 64 accumulators per lane (8 rows x 8 feature columns), and
+// the 32 lane partials of each accumulator meet in a transpose-reduce butterfly (31 shuffles per 32 values, fixed order) that
+// leaves lane l with the total of (row l / 8, column l % 8).  No shared memory, no barrier.
 struct StepGemm {
   const float* A; long long lda;
   const float* W1; const float* b1; const float* Wg; const float* bg;
@@ -36,78 +37,84 @@ struct StepGemm {
   int M, N, K, relu;
 };
 
+// v[0..31] (one partial per lane of 32 different sums) -> lane l returns sum #l over all lanes
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
+  }
+  return v[0];
+}
+
 template <bool GLU>
 __global__ void __launch_bounds__(THREADS) step_gemm_f32_kernel(const __grid_constant__ StepGemm p) {
-  constexpr int NT = GLU ? stp::NT / 2 : stp::NT;                // features per CTA: eight accumulator chains either way
-  constexpr int NV = GLU ? 2 * NT : NT;
-  __shared__ float red[3][MT][NV + 1];
-  const int tid = threadIdx.x, r = tid & 63, kq = tid >> 6;
+  constexpr int NF = GLU ? 4 : 8;                                // features per CTA; 8 accumulator columns either way
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int e = blockIdx.y;
   const int r_begin = p.off ? p.off[e] : 0, r_end = p.off ? p.off[e + 1] : p.M;
-  if (r_begin >= r_end) return;                                  // group without rows (uniform over the CTA)
-  const int n0 = blockIdx.x * NT;
+  const int n0 = blockIdx.x * NF;
   const float* W1e = p.W1 + (size_t)e * p.w_gstride;
   const float* Wge = GLU ? p.Wg + (size_t)e * p.w_gstride : nullptr;
-  for (int row0 = r_begin; row0 < r_end; row0 += MT) {
-    const int m = row0 + r;
-    const bool ok = m < r_end;
-    const bool warp_ok = row0 + (r & ~31) < r_end;               // a warp whose 32 rows are all beyond the group skips the k loop
-    float acc[NT], gac[NT];
+  for (int rw = r_begin + 8 * warp; rw < r_end; rw += MT) {      // this warp's 8 rows of every 64-row block
+    float acc[8][8];
 #pragma unroll
-    for (int nn = 0; nn < NT; ++nn) { acc[nn] = 0.f; gac[nn] = 0.f; }
-    for (int kb = 0; warp_ok && kb < p.K; kb += 512) {
-      const int k0 = kb + kq * 128;
-      const int nv = max(0, min(32, (p.K - k0) >> 2));           // 16-byte chunks of this thread's slice inside K
-      float4 xr[32];
-      const float4* xs = reinterpret_cast<const float4*>(p.A + (size_t)(ok ? m : r_begin) * p.lda + k0);
+    for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) xr[i] = (ok && i < nv) ? __ldg(xs + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 8; ++c) acc[rr][c] = 0.f;
+    for (int kb = 0; kb < p.K; kb += 512) {
+      float4 xr[8][4];
 #pragma unroll
-      for (int nn = 0; nn < NT; ++nn) {
-        const int n = min(n0 + nn, p.N - 1);
-        const float4* w = reinterpret_cast<const float4*>(W1e + (size_t)n * p.ldw + k0);
-        const float4* wg = GLU ? reinterpret_cast<const float4*>(Wge + (size_t)n * p.ldw + k0) : w;
-        float a = acc[nn], g = gac[nn];
+      for (int rr = 0; rr < 8; ++rr) {
+        const bool ok = rw + rr < r_end;
+        const float* xs = p.A + (size_t)(ok ? rw + rr : r_begin) * p.lda + kb + 4 * lane;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i < nv) {
-            const float4 u = __ldg(w + i);
-            a = fmaf(xr[i].x, u.x, a); a = fmaf(xr[i].y, u.y, a); a = fmaf(xr[i].z, u.z, a); a = fmaf(xr[i].w, u.w, a);
-            if (GLU) {
-              const float4 h = __ldg(wg + i);
-              g = fmaf(xr[i].x, h.x, g); g = fmaf(xr[i].y, h.y, g); g = fmaf(xr[i].z, h.z, g); g = fmaf(xr[i].w, h.w, g);
-            }
+        for (int j = 0; j < 4; ++j)
+          xr[rr][j] = (ok && kb + 128 * j + 4 * lane < p.K) ? __ldg(reinterpret_cast<const float4*>(xs + 128 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int n = min(n0 + (GLU ? (c & 3) : c), p.N - 1);
+        const float* ws = ((GLU && c >= 4) ? Wge : W1e) + (size_t)n * p.ldw + kb + 4 * lane;
+        float4 wv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          wv[j] = (kb + 128 * j + 4 * lane < p.K) ? __ldg(reinterpret_cast<const float4*>(ws + 128 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+          float a = acc[rr][c];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a = fmaf(xr[rr][j].x, wv[j].x, a); a = fmaf(xr[rr][j].y, wv[j].y, a);
+            a = fmaf(xr[rr][j].z, wv[j].z, a); a = fmaf(xr[rr][j].w, wv[j].w, a);
           }
+          acc[rr][c] = a;
         }
-        acc[nn] = a;
-        gac[nn] = g;
       }
     }
-    if (row0 > r_begin) __syncthreads();                         // the previous block's partials have been read
-    if (kq > 0) {
 #pragma unroll
-      for (int nn = 0; nn < NT; ++nn) {
-        red[kq - 1][r][nn] = acc[nn];
-        if (GLU) red[kq - 1][r][NT + nn] = gac[nn];
-      }
-    }
-    __syncthreads();
-    if (kq == 0 && ok) {
-      const float rs = p.row_scale ? p.row_scale[m] : 0.f;
+    for (int g = 0; g < 2; ++g) {                                  // rows 4g .. 4g + 3 of the warp: 32 sums -> one per lane
+      float v[32];
 #pragma unroll
-      for (int nn = 0; nn < NT; ++nn) {
-        const int n = n0 + nn;
-        if (n < p.N) {
-          float v = ((acc[nn] + red[0][r][nn]) + red[1][r][nn]) + red[2][r][nn];
-          if (p.b1) v += p.b1[(size_t)e * p.b_gstride + n];
-          if (GLU) {
-            const float gv = (((gac[nn] + red[0][r][NT + nn]) + red[1][r][NT + nn]) + red[2][r][NT + nn]) + p.bg[(size_t)e * p.b_gstride + n];
-            v = v * (gv / (1.f + expf(-gv)));
-          }
-          if (p.row_scale) v = fmaf(rs, p.col_vec[n], v);
-          if (p.relu) v = fmaxf(v, 0.f);
-          p.C[(size_t)m * p.ldc + n] = v;
+      for (int i = 0; i < 32; ++i) v[i] = acc[4 * g + (i >> 3)][i & 7];
+      float tot = transpose_reduce32(v, lane);
+      const int m = rw + 4 * g + (lane >> 3), c = lane & 7;
+      float gate = 0.f;
+      if (GLU) gate = __shfl_down_sync(0xffffffffu, tot, 4);       // column c + 4 = the gate sum of feature c
+      const int n = n0 + c;
+      if (m < r_end && c < NF && n < p.N) {
+        if (p.b1) tot += p.b1[(size_t)e * p.b_gstride + n];
+        if (GLU) {
+          const float gv = gate + p.bg[(size_t)e * p.b_gstride + n];
+          tot = tot * (gv / (1.f + expf(-gv)));
         }
+        if (p.row_scale) tot = fmaf(p.row_scale[m], p.col_vec[n], tot);
+        if (p.relu) tot = fmaxf(tot, 0.f);
+        p.C[(size_t)m * p.ldc + n] = tot;
       }
     }
   }
