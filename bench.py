@@ -284,7 +284,9 @@ def variants_leg(dev):
     out["gqa_moe_generate"] = {"tokens_per_s": BATCH * (SEQ - 1) / (ms * 1e-3), "ms_per_generation": ms, "launches": _lib.launches() - n0,
                                "shape": "%d videos x %d positions, 6 layers, 8 q / 2 kv heads, 6 experts top-2, fp32, KV cache "
                                         "(self %d MB for 2 kv heads, cross K|V projected once)" % (BATCH, SEQ, 6 * 2 * BATCH * SEQ * 128 * 4 // (1 << 20)),
-                               "dtype": "f32", "note": "the literal loop of the reference re-runs the whole model on the growing prefix for every token, batch 1"}
+                               "dtype": "f32", "cuda_graph": True,
+                               "note": "one position = ONE captured CUDA graph replayed 298 times (device-side position; step kernels of csrc/step_f32.cu); "
+                                       "the literal loop of the reference re-runs the whole model on the growing prefix for every token, batch 1"}
     del gm, feats
     blk = MambaBlock(MambaConfig(d_model=128, n_layers=1)).to(dev).train()
     xb = torch.randn(8, 4096, 128, generator=g).to(dev)
@@ -383,7 +385,7 @@ def fp32_leg(dev, devt, prim, pr, pa, l2_flush, steps=2):
     peak, _ = peaks()
     val = BATCH * (SEQ - 1) / (t / 1e3)
     return {"value": val, "unit": UNIT, "ms_per_step": t, "steps": steps, "dtype": "f32",
-            "path": "decode step kernels (skinny_gemm / dec_attn, CUDA graph of 51 launches per position), fp32 prefill",
+            "path": "decode step kernels (skinny_gemm with coalesced loads + transpose-reduce / dec_attn, CUDA graph of 51 launches per position), fp32 prefill",
             "hbm_floor_tokens_per_s": BATCH * (SEQ - 1) / (run_bytes / (peak * 1e9)), "frac_of_floor": val / (BATCH * (SEQ - 1) / (run_bytes / (peak * 1e9)))}
 
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd /root/repo
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_amt.py -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r2m_tests.log
-cat gpurun_out/r2m_tests.log
-timeout 600 python tools/scratch/fp32_gen_time.py 2>&1 | tail -3 | tee gpurun_out/r2m_fp32.log
+make -C video2music_b200/csrc clean > /dev/null; make -j8 -C video2music_b200/csrc EXTRA=-DV2M_CHUNK_STAMPS > /dev/null 2>&1 || exit 1
+python tools/chunk_times.py 5 2>&1 | tail -2 > gpurun_out/r2o_chunks_b5.txt
+python tools/chunk_times.py 64 2>&1 | tail -2 > gpurun_out/r2o_chunks_b64.txt
+cat gpurun_out/r2o_chunks_b5.txt gpurun_out/r2o_chunks_b64.txt
