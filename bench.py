@@ -272,7 +272,7 @@ def variants_leg(dev):
     one = torch.tensor([1])
     gen_fn = lambda n: gm.generate_cached(*feats, primer=one, primer_root=one, primer_attr=torch.tensor([0]), target_seq_length=n,
                                           beam=1, beam_chance=1.0)
-    gen_fn(8)
+    gen_fn(SEQ)                                          # first generation of a configuration: captures the per-position CUDA graph
     torch.cuda.synchronize(dev)
     n0 = _lib.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

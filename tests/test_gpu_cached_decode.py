@@ -76,6 +76,11 @@ def test_cached_generate_gqa_moe_equals_literal_loop_and_oracle(shared, rms, pre
     eager = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=16, beam=1, beam_chance=1.0,
                               use_graph=False)
     assert torch.equal(out, eager)                                      # one captured CUDA graph per position == eager launches
+    again = m.generate_cached(*feats, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=16, beam=1, beam_chance=1.0)
+    assert torch.equal(out, again)                                      # second call: same session, graph replayed without capture
+    other = [t.flip(0) for t in feats]                                  # other videos through the same captured graph
+    out2 = m.generate_cached(*other, primer=prim, primer_root=pr, primer_attr=pa, target_seq_length=16, beam=1, beam_chance=1.0)
+    assert torch.equal(out2, out.flip(0))
     for b in range(B):
         one = [t[b:b + 1] for t in feats]
         lit = m.generate(one[0], one[1][0], one[2], one[3], one[4], primer=prim, primer_root=pr, primer_attr=pa,

@@ -21,6 +21,7 @@ Cacheable attention modules: `CustomMultiheadAttention` without RoPE (V1 '1.1' /
 (position, head) element by an angle that depends on the CURRENT prefix length, custom_transformer.py:1044-1053, so its keys
 change every step) and `MultiheadGQA` with causal self-attention.
 """
+import weakref
 from typing import List, Optional
 
 import torch
@@ -144,6 +145,17 @@ class CachedDecoder:
         self.V = [torch.zeros((B, cap, a.Wk), device=dev, dtype=torch.float32) for a in self.sa]
         self.cache_bytes = sum(k.numel() * 8 for k in self.K) + sum(kv[0].numel() * 8 for kv in self.mem_kv)
 
+    def load_memory(self, memory: torch.Tensor) -> None:
+        """New encoder memory into the SAME cross-attention K | V buffers (a captured graph keeps reading them); the self-attention
+        caches need no reset: only their first n_keys rows are ever read."""
+        S, B, E = memory.shape
+        assert (S, B, E) == (self.S, self.B, self.E)
+        mem_rows = memory.reshape(S * B, E).float().contiguous()
+        for a, (k, v) in zip(self.ca, self.mem_kv):
+            nk, nv = a.memory_kv(mem_rows)
+            k.copy_(nk)
+            v.copy_(nv)
+
     def step(self, x: torch.Tensor, t: torch.Tensor, n_keys: torch.Tensor) -> torch.Tensor:
         """x (B, E): embedded token of position t of every video -> decoder output rows (B, E) after the final norm.
         t: int64 device tensor (1,), n_keys = t + 1 as an int32 device tensor (1,): the position never reaches the host, so the
@@ -190,7 +202,8 @@ def generate_cached(model: nn.Module, feature_semantic_list, feature_key, featur
     torch.rand), root / attribute updated.  Returns (B, target_seq_length) int64.
     The position is a device word (caches are written with index_copy_, the attention kernel reads its key count from it), so
     one position is ONE CUDA graph captured after the first step and replayed (use_graph; default: on unless a module carries
-    a Python-side temperature scheduler, which advances per call, moe.py:238-242)."""
+    a Python-side temperature scheduler, which advances per call, moe.py:238-242).  The buffers and the graph of a configuration
+    (batch, lengths, options, parameter versions) are kept with the model (weakly) and reused by later calls."""
     assert not model.training, "Cannot generate while in training mode"
     if not (beam == 0 or (beam == 1 and beam_chance >= 1.0)):
         raise NotImplementedError("beam > 1 / 0 < beam_chance < 1 are not reproduced")
@@ -205,10 +218,6 @@ def generate_cached(model: nn.Module, feature_semantic_list, feature_key, featur
     prim = lambda p: (p.long().to(dev).reshape(1, -1).expand(B, -1) if p.dim() == 1 else p.long().to(dev))
     primer, primer_root, primer_attr = prim(primer), prim(primer_root), prim(primer_attr)
     n0 = primer.shape[1]
-    gen = torch.full((B, T), CHORD_PAD, dtype=torch.long, device=dev)
-    gen_root = torch.full((B, T), CHORD_ROOT_PAD, dtype=torch.long, device=dev)
-    gen_attr = torch.full((B, T), CHORD_ATTR_PAD, dtype=torch.long, device=dev)
-    gen[:, :n0], gen_root[:, :n0], gen_attr[:, :n0] = primer, primer_root, primer_attr
     if beam == 0 and uniforms is None:
         uniforms = torch.rand((B, T), device=dev)
     # ---- encoder memory, once (the literal loop recomputes it for every token)
@@ -228,75 +237,119 @@ def generate_cached(model: nn.Module, feature_semantic_list, feature_key, featur
     finally:
         for mod, pv in zip(gqa, prev):
             mod.batch_independent = pv
-    dec = CachedDecoder(model, memory, T)
-    wc = model.Linear_chord.weight.detach()
-    wkey = wc[:, E].contiguous()
-    wc_main = wc[:, :E].contiguous()                     # 16-byte aligned rows for the step kernel (the weight has 513 columns)
+    if use_graph is None:                                # Python-side schedulers that advance in eval mode cannot be replayed
+        use_graph = not any(hasattr(mod, "temperature_scheduler") for mod in model.modules())
     key_rows = key.reshape(B, -1)[:, 0].float().contiguous()
-    pos = model.positional_embedding.weight.detach()
-    emb_root, emb_attr = model.embedding_root.weight.detach(), model.embedding_attr.weight.detach()
-    w_out, b_out = model.Wout.weight.detach(), model.Wout.bias.detach()
-    b_chord = model.Linear_chord.bias.detach()
-    # the position lives on the device: t (int64, index of the token that goes in), n_keys = t + 1 (int32, rows of the caches)
-    t_dev = torch.zeros(1, dtype=torch.long, device=dev)
-    n_keys = torch.ones(1, dtype=torch.int32, device=dev)
-    ar_back = torch.arange(1, max(1, max_conseq_chord) + 1, device=dev).view(1, -1)     # 1 .. max_conseq_chord
+    cfg = (B, S, T, n0, beam, max_conseq_N, max_conseq_chord, float(temperature), bool(use_graph), str(dev),
+           tuple((p.data_ptr(), p._version) for p in model.parameters()))
+    sessions = _SESSIONS.setdefault(model, {})
+    sess = sessions.get(cfg)
+    if sess is None:
+        sessions.clear()                                 # one live session per model: its buffers are the KV caches
+        sess = sessions[cfg] = _GenSession(model, memory, T, n0, beam, max_conseq_N, max_conseq_chord, float(temperature))
+    else:
+        sess.dec.load_memory(memory)
+    return sess.run(primer, primer_root, primer_attr, key_rows, uniforms, use_graph)
 
-    def step():
+
+_SESSIONS = weakref.WeakKeyDictionary()      # model -> {configuration: _GenSession}; not part of the module's state (deepcopy-safe)
+
+
+class _GenSession:
+    """Persistent buffers of one generation configuration (token arrays, position words, KV caches, projected memory) and the
+    CUDA graph of one position captured over them: the first generation captures, later ones only replay."""
+
+    def __init__(self, model, memory, T, n0, beam, max_conseq_N, max_conseq_chord, temperature):
+        S, B, E = memory.shape
+        dev = memory.device
+        self.model, self.B, self.T, self.E, self.n0 = model, B, T, E, n0
+        self.beam, self.max_conseq_N, self.max_conseq_chord, self.temperature = beam, max_conseq_N, max_conseq_chord, temperature
+        self.dec = CachedDecoder(model, memory, T)
+        self.gen = torch.empty((B, T), dtype=torch.long, device=dev)
+        self.gen_root, self.gen_attr = torch.empty_like(self.gen), torch.empty_like(self.gen)
+        self.uniforms = torch.zeros((B, T), device=dev)
+        self.key_rows = torch.zeros((B,), device=dev)
+        # the position lives on the device: t (int64, index of the token that goes in), n_keys = t + 1 (int32, rows of the caches)
+        self.t_dev = torch.zeros(1, dtype=torch.long, device=dev)
+        self.n_keys = torch.ones(1, dtype=torch.int32, device=dev)
+        self.ar_back = torch.arange(1, max(1, max_conseq_chord) + 1, device=dev).view(1, -1)     # 1 .. max_conseq_chord
+        wc = model.Linear_chord.weight.detach()
+        self.wkey = wc[:, E].contiguous()
+        self.wc_main = wc[:, :E].contiguous()            # 16-byte aligned rows for the step kernel (the weight has 513 columns)
+        self.graph, self.per_step = None, 0
+
+    def step(self):
         """Token of position t in, token of position t + 1 out; then t += 1.  No host-visible value depends on t."""
+        m, B, E = self.model, self.B, self.E
+        gen, gen_root, gen_attr, t_dev = self.gen, self.gen_root, self.gen_attr, self.t_dev
         col = t_dev.view(1, 1).expand(B, 1)
-        xin = ops.embed_sum(gen_root.gather(1, col).view(B), emb_root, gen_attr.gather(1, col).view(B), emb_attr, torch.float32)
-        x = ops.step_linear(xin, wc_main, b_chord, k=E, row_scale=key_rows, col_vec=wkey)
-        x = ops.axpy(x, pos.index_select(0, t_dev).expand(B, E).contiguous(), 1.0)
-        h = dec.step(x, t_dev, n_keys)
+        xin = ops.embed_sum(gen_root.gather(1, col).view(B), m.embedding_root.weight.detach(), gen_attr.gather(1, col).view(B),
+                            m.embedding_attr.weight.detach(), torch.float32)
+        x = ops.step_linear(xin, self.wc_main, m.Linear_chord.bias.detach(), k=E, row_scale=self.key_rows, col_vec=self.wkey)
+        x = ops.axpy(x, m.positional_embedding.weight.detach().index_select(0, t_dev).expand(B, E).contiguous(), 1.0)
+        h = self.dec.step(x, t_dev, self.n_keys)
         cur = col + 1                                    # (B, 1)
-        logits = ops.step_linear(h, w_out, b_out)
-        probs = torch.softmax(logits / temperature, dim=-1)[:, :CHORD_END]
+        logits = ops.step_linear(h, m.Wout.weight.detach(), m.Wout.bias.detach())
+        probs = torch.softmax(logits / self.temperature, dim=-1)[:, :CHORD_END]
         old = gen.gather(1, cur)
-        in_primer = cur < n0                             # primer positions only fill the caches
-        if beam == 1:
+        in_primer = cur < self.n0                        # primer positions only fill the caches
+        if self.beam == 1:
             tok = torch.argmax(probs, dim=-1, keepdim=True)
         else:
             probs = probs.clone()
-            if max_conseq_N == 0:
+            if self.max_conseq_N == 0:
                 probs[:, 0] = 0.0
             # the last max_conseq_chord tokens all equal the previous one -> it may not be drawn again
-            back = (cur - ar_back).clamp_min(0)          # (B, max_conseq_chord)
+            back = (cur - self.ar_back).clamp_min(0)     # (B, max_conseq_chord)
             prev = gen.gather(1, cur - 1)
-            rep = (gen.gather(1, back) == prev).all(dim=1, keepdim=True) & (cur >= max_conseq_chord)
-            probs.scatter_(1, prev.clamp(0, CHORD_END - 1), torch.where(rep & (prev < CHORD_END), torch.zeros_like(probs[:, :1]),
-                                                                      probs.gather(1, prev.clamp(0, CHORD_END - 1))))
+            rep = (gen.gather(1, back) == prev).all(dim=1, keepdim=True) & (cur >= self.max_conseq_chord)
+            pidx = prev.clamp(0, CHORD_END - 1)
+            probs.scatter_(1, pidx, torch.where(rep & (prev < CHORD_END), torch.zeros_like(probs[:, :1]), probs.gather(1, pidx)))
             cdf = torch.cumsum(probs / probs.sum(dim=1, keepdim=True), dim=1)
-            tok = (cdf <= uniforms.gather(1, cur)).sum(dim=1, keepdim=True).clamp_max(CHORD_END - 1)
+            tok = (cdf <= self.uniforms.gather(1, cur)).sum(dim=1, keepdim=True).clamp_max(CHORD_END - 1)
             root = torch.where(tok <= 0, torch.zeros_like(tok), (tok - 1) // 13 + 1)
             attr = torch.where(tok <= 0, torch.ones_like(tok), (tok - 1) % 13 + 1)
             gen_root.scatter_(1, cur, torch.where(in_primer, gen_root.gather(1, cur), root))
             gen_attr.scatter_(1, cur, torch.where(in_primer, gen_attr.gather(1, cur), attr))
         gen.scatter_(1, cur, torch.where(in_primer, old, tok))
         t_dev.add_(1)
-        n_keys.add_(1)
+        self.n_keys.add_(1)
 
-    n_steps = T - 1
-    if use_graph is None:                                # Python-side schedulers that advance in eval mode cannot be replayed
-        use_graph = not any(hasattr(mod, "temperature_scheduler") for mod in model.modules())
-    if not use_graph or n_steps < 3:
-        for _ in range(n_steps):
-            step()
-        return gen
-    # one eager step (allocator / caches warm), then the step is captured once and replayed for every remaining position
-    from . import _lib
-    step()
-    torch.cuda.synchronize(dev)
-    side = torch.cuda.Stream(device=dev)
-    graph = torch.cuda.CUDAGraph()
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        n_before = _lib.launches()
-        with torch.cuda.graph(graph, stream=side):
-            step()
-        per_step = _lib.launches() - n_before
-    torch.cuda.current_stream(dev).wait_stream(side)
-    for _ in range(n_steps - 1):
-        graph.replay()
-    _lib.count_launches(per_step * (n_steps - 2))        # the capture counted one step
-    return gen
+    def run(self, primer, primer_root, primer_attr, key_rows, uniforms, use_graph) -> torch.Tensor:
+        from . import _lib
+        n0, T = self.n0, self.T
+        dev = self.gen.device
+        self.gen.fill_(CHORD_PAD); self.gen_root.fill_(CHORD_ROOT_PAD); self.gen_attr.fill_(CHORD_ATTR_PAD)
+        self.gen[:, :n0], self.gen_root[:, :n0], self.gen_attr[:, :n0] = primer, primer_root, primer_attr
+        self.key_rows.copy_(key_rows)
+        if uniforms is not None:
+            self.uniforms.copy_(uniforms)
+        self.t_dev.zero_()
+        self.n_keys.fill_(1)
+        n_steps = T - 1
+        if not use_graph or n_steps < 3:
+            for _ in range(n_steps):
+                self.step()
+            return self.gen.clone()
+        done = 0
+        if self.graph is None:
+            # one eager step (allocator / weight stacks warm), then the step is captured once; every later position -- and every
+            # later generation of this configuration -- replays it
+            self.step()
+            done = 1
+            torch.cuda.synchronize(dev)
+            side = torch.cuda.Stream(device=dev)
+            graph = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                n_before = _lib.launches()
+                with torch.cuda.graph(graph, stream=side):
+                    self.step()
+                self.per_step = _lib.launches() - n_before
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = graph
+            _lib.count_launches(-self.per_step)          # the capture enqueued nothing
+        for _ in range(n_steps - done):
+            self.graph.replay()
+        _lib.count_launches(self.per_step * (n_steps - done))
+        return self.gen.clone()
