@@ -644,6 +644,69 @@ def test_amt_correspondence_kernel_vs_reference_golden_and_oracle():
     assert ops.compute_vevo_correspondence(out.to(DEV), None, emo[:, :0].to(DEV), torch.ones((1, 0), device=DEV), 0.8) == 1.0
 
 
+# ---------------------------------------------------------------- kernels of one generation step (csrc/step_f32.cu)
+@pytest.mark.parametrize("M,N,K", [(1, 159, 512), (3, 512, 512), (64, 1536, 512), (64, 512, 1024), (70, 128, 516), (130, 24, 64)])
+def test_step_linear_vs_float64_and_batch_invariance(M, N, K):
+    """The few-row linear layer of a KV-cached generation step: against a float64 reference (bias, ReLU, the rank-1
+    row_scale x col_vec term of Linear_chord), ragged M / N / K tails, and bit-identical rows whatever the batch size."""
+    from video2music_b200 import ops
+    x, w, b = _u((M, K), 11, "x"), _u((N, K), 11, "w") * 0.1, _u((N,), 11, "b")
+    rs, cv = _u((M,), 11, "rs"), _u((N,), 11, "cv")
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    ref = x.double() @ w.double().t() + b.double()
+    y = ops.step_linear(xd, wd, bd)
+    assert rel_err(y, ref.float()) < 2e-6
+    y2 = ops.step_linear(xd, wd, bd, relu=True, row_scale=rs.to(DEV), col_vec=cv.to(DEV))
+    assert rel_err(y2, torch.relu(ref + rs.double()[:, None] * cv.double()[None, :]).float()) < 2e-6
+    assert rel_err(ops.step_linear(xd, wd, None), (ref - b.double()).float()) < 2e-6
+    one = ops.step_linear(xd[M - 1:].contiguous(), wd, bd)
+    assert torch.equal(one[0], y[M - 1])                                   # fixed summation order: no dependence on the row count
+    wide = torch.cat([w, _u((N, 4), 12, "pad")], 1).to(DEV)               # leading dimension > K (k = K of a wider weight)
+    assert torch.equal(ops.step_linear(xd, wide, bd, k=K), y)
+    assert rel_err(y, ops.linear(xd, wd, bd)) < 2e-6                       # the tiled fp32 GEMM of the full forward
+
+
+@pytest.mark.parametrize("Hq,Hkv,n", [(8, 8, 1), (8, 2, 77), (8, 2, 300), (4, 1, 129)])
+def test_step_attention_vs_float64(Hq, Hkv, n):
+    """One query row per (video, head) over the first n cached rows (n from a device word): against float64 softmax attention;
+    rows beyond n are never read (NaN there), grouped heads share their kv head, slices of wider rows as caches."""
+    from video2music_b200 import ops
+    B, dh, cap = 5, 64, 304
+    q = _u((B, Hq * dh), 21, "q")
+    kv = _u((B, cap, 2 * Hkv * dh), 21, "kv")                              # K | V side by side: row stride 2 Hkv dh
+    kv[:, n:] = float("nan")
+    qd, kvd = q.to(DEV), kv.to(DEV)
+    K, V = kvd[:, :, :Hkv * dh], kvd[:, :, Hkv * dh:]
+    nd = torch.tensor([n], dtype=torch.int32, device=DEV)
+    out = ops.step_attention(qd, K, V, Hq=Hq, Hkv=Hkv, dh=dh, n_max=cap, kv_strides=(K.stride(0), K.stride(1)), n_dev=nd, q_scale=0.125)
+    qh = q.double().view(B, Hq, dh) * 0.125
+    kh = kv[:, :n, :Hkv * dh].double().view(B, n, Hkv, dh).repeat_interleave(Hq // Hkv, dim=2)
+    vh = kv[:, :n, Hkv * dh:].double().view(B, n, Hkv, dh).repeat_interleave(Hq // Hkv, dim=2)
+    p = torch.softmax(torch.einsum("bhd,bnhd->bhn", qh, kh), dim=-1)
+    ref = torch.einsum("bhn,bnhd->bhd", p, vh).reshape(B, Hq * dh)
+    assert torch.isfinite(out).all() and rel_err(out, ref.float()) < 2e-6
+    out_h = ops.step_attention(qd, K, V, Hq=Hq, Hkv=Hkv, dh=dh, n_max=n, kv_strides=(K.stride(0), K.stride(1)), q_scale=0.125)
+    assert torch.equal(out, out_h)                                         # host-side count == device-side count
+
+
+def test_moe_experts_small_batch_kernel_equals_tiled_kernel():
+    """A generation step carries a few token copies per expert: moe_grouped_gemm then runs on the weight-streaming kernel of
+    step_f32.cu (<= 256 copies); same outputs as the tiled kernel that the same tokens get inside a larger batch."""
+    from video2music_b200 import GLUExpert, MoELayer
+    E, k, d, ff = 6, 2, 512, 1024
+    mod = MoELayer(GLUExpert(d, ff, 0.0), d, n_experts=E, n_experts_per_token=k, dropout=0.0).eval()
+    sd = syn.fill_like_reference_init({n: tuple(v.shape) for n, v in mod.state_dict().items()}, seed=79)
+    sd["gate.bias"] = torch.tensor([2.0, -50.0, 1.0, 0.5, 0.0, 0.0])      # one expert without tokens
+    mod.load_state_dict(sd)
+    mod = mod.to(DEV)
+    x = _u((300, 1, d), 7, "x").to(DEV)
+    with torch.no_grad():
+        big = mod(x)                                                        # 600 copies: tiled kernel
+        for m in (1, 64, 128):                                              # 2 .. 256 copies: step kernel
+            small = mod(x[:m].contiguous())
+            assert rel_err(small, big[:m]) < 1e-5, m
+
+
 # ---------------------------------------------------------------- fused dropout (training)
 def test_linear_fused_dropout_forward_backward():
     """Dropout fused into the GEMM epilogue (both placements) and re-derived by dy_prep in backward, against torch with the
