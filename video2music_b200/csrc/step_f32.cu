@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(THREADS) step_gemm_f32_kernel(const __grid_con
   }
 }
 
-constexpr int ATH = 128;       // threads of the attention CTA (4 warps)
+constexpr int ATH = 256;       // threads of the attention CTA (8 warps)
 
-// grid = B * Hq.  Shared memory: q[64] | sc[n_max] | part[8][64] | red[8]
+// grid = B * Hq.  Shared memory: q[64] | sc[n_max] | part[16][64] | red[16]
 __global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restrict__ q, long long q_sb, const float* __restrict__ Kc,
                                                             const float* __restrict__ Vc, long long kv_sb, long long kv_sl,
                                                             float* __restrict__ o, long long o_sb, int Hq, int Hkv, int n_max,
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restr
   float* qs = sa_smem;
   float* sc = qs + 64;
   float* part = sc + ((n_max + 3) & ~3);
-  float* red = part + 8 * 64;
+  float* red = part + 16 * 64;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / Hq, hq = blockIdx.x % Hq, hkv = hq / (Hq / Hkv);
   const int n = n_dev ? min(n_max, __ldg(n_dev)) : n_max;
@@ -139,15 +139,15 @@ __global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restr
   const float* vb = Vc + (size_t)b * kv_sb + (size_t)hkv * 64;
   if (tid < 64) qs[tid] = q[(size_t)b * q_sb + (size_t)hq * 64 + tid] * q_scale;
   __syncthreads();
-  // ---- scores: warp w takes keys w, w + 4, ...; a lane holds two dims of the row (256 contiguous bytes per warp and key);
+  // ---- scores: warp w takes keys w, w + 8, ...; a lane holds two dims of the row (256 contiguous bytes per warp and key);
   // eight keys of the warp in flight per iteration
   const float2 qq = *reinterpret_cast<const float2*>(qs + 2 * lane);
   float mx = -INFINITY;
-  for (int j0 = warp; j0 < n; j0 += 32) {
+  for (int j0 = warp; j0 < n; j0 += 64) {
     float s[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int j = j0 + 4 * u;
+      const int j = j0 + 8 * u;
       float2 kk = make_float2(0.f, 0.f);
       if (j < n) kk = __ldg(reinterpret_cast<const float2*>(kb + (size_t)j * kv_sl) + lane);
       s[u] = fmaf(qq.x, kk.x, qq.y * kk.y);
@@ -159,14 +159,14 @@ __global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restr
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int j = j0 + 4 * u;
+      const int j = j0 + 8 * u;
       if (j < n) { if (lane == 0) sc[j] = s[u]; mx = fmaxf(mx, s[u]); }
     }
   }
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  // ---- p = exp(s - max) (kept un-normalised), row sum in a fixed order: lane-strided partials, shuffle tree, warps 0..3
+  mx = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+  // ---- p = exp(s - max) (kept un-normalised), row sum in a fixed order: lane-strided partials, shuffle tree, warps 0..7
   float sum = 0.f;
   for (int j = tid; j < n; j += ATH) {
     const float p = __expf(sc[j] - mx);
@@ -175,19 +175,19 @@ __global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restr
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-  if (lane == 0) red[4 + warp] = sum;
+  if (lane == 0) red[8 + warp] = sum;
   __syncthreads();
-  const float total = (red[4] + red[5]) + (red[6] + red[7]);
-  // ---- o[d] = sum_j p_j V[j][d]: thread = (key group g of 8, four dims d4); keys g, g + 8, ... with four 16-byte loads in
-  // flight, the eight partial rows meet in shared memory and are added in a fixed order
+  const float total = ((red[8] + red[9]) + (red[10] + red[11])) + ((red[12] + red[13]) + (red[14] + red[15]));
+  // ---- o[d] = sum_j p_j V[j][d]: thread = (key group g of 16, four dims d4); keys g, g + 16, ... with four 16-byte loads in
+  // flight, the sixteen partial rows meet in shared memory and are added in a fixed order
   const int d4 = tid & 15, g = tid >> 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int j0 = g; j0 < n; j0 += 32) {
+  for (int j0 = g; j0 < n; j0 += 64) {
     float4 vv[4];
     float pp[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int j = j0 + 8 * u;
+      const int j = j0 + 16 * u;
       vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       pp[u] = 0.f;
       if (j < n) { vv[u] = __ldg(reinterpret_cast<const float4*>(vb + (size_t)j * kv_sl) + d4); pp[u] = sc[j]; }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(ATH) step_attn_f32_kernel(const float* __restr
   if (tid < 64) {
     float v = 0.f;
 #pragma unroll
-    for (int gg = 0; gg < 8; ++gg) v += part[gg * 64 + tid];
+    for (int gg = 0; gg < 16; ++gg) v += part[gg * 64 + tid];
     o[(size_t)b * o_sb + (size_t)hq * 64 + tid] = v / total;
   }
 }
@@ -227,7 +227,7 @@ int step_attn_f32(const float* q, long long q_sb, const float* k, const float* v
   V2M_REQUIRE(B > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0 && n_max > 0, "step_attn_f32: bad shape B=%d Hq=%d Hkv=%d n=%d", B, Hq, Hkv, n_max);
   V2M_REQUIRE(kv_sl % 4 == 0 && kv_sb % 4 == 0 && reinterpret_cast<uintptr_t>(k) % 16 == 0 && reinterpret_cast<uintptr_t>(v) % 16 == 0,
               "step_attn_f32: cache rows must be 16-byte aligned");
-  const size_t smem = sizeof(float) * (64 + ((n_max + 3) & ~3) + 8 * 64 + 8);
+  const size_t smem = sizeof(float) * (64 + ((n_max + 3) & ~3) + 16 * 64 + 16);
   V2M_REQUIRE(smem <= 48 * 1024, "step_attn_f32: n_max %d too large", n_max);
   stp::step_attn_f32_kernel<<<B * Hq, stp::ATH, smem, stream>>>(q, q_sb, k, v, kv_sb, kv_sl, o, o_sb, Hq, Hkv, n_max, n_dev, q_scale);
   return check_launch("step_attn_f32");
