@@ -247,7 +247,24 @@ def variants_leg(dev):
     ms = timed(step(enc, lambda: enc(src)))
     out["gqa_moe_encoder_train_moe_bf16"] = {"ms_per_step": ms, "samples_per_s": 8 / (ms * 1e-3), "shape": out["gqa_moe_encoder_train"]["shape"],
                                              "dtype": "bf16 experts (grouped tcgen05 GEMMs, K-grouped ragged dW), fp32 GQA attention / router / norms"}
-    del enc, layer
+    for mod in enc.modules():
+        if isinstance(mod, MultiheadGQA):
+            mod.compute_dtype = torch.bfloat16                  # projections on the tcgen05 GEMM, tcgen05 attention forward, tensor-core backward
+    ms = timed(step(enc, lambda: enc(src)))
+    bf16_desc = "bf16 GQA attention (tcgen05 projections + forward, tensor-core backward) and bf16 experts; fp32 master weights, router, residual stream"
+    out["gqa_moe_encoder_train_bf16"] = {"ms_per_step": ms, "samples_per_s": 8 / (ms * 1e-3), "shape": out["gqa_moe_encoder_train"]["shape"],
+                                         "dtype": bf16_desc, "note": "8 videos: bound by the ~900 eager launches of the step"}
+    src64 = torch.randn(300, 64, 512, generator=g).to(dev)
+    ms = timed(step(enc, lambda: enc(src64)))
+    out["gqa_moe_encoder_train_bf16_b64"] = {"ms_per_step": ms, "samples_per_s": 64 / (ms * 1e-3), "shape": "6 layers, 64 videos x 300 tokens, d 512, "
+                                             "8 q / 2 kv heads, 6 experts top-2 ff 1024", "dtype": bf16_desc}
+    for mod in enc.modules():
+        if isinstance(mod, (MoELayer, MultiheadGQA)):
+            mod.compute_dtype = torch.float32
+    ms = timed(step(enc, lambda: enc(src64)))
+    out["gqa_moe_encoder_train_b64"] = {"ms_per_step": ms, "samples_per_s": 64 / (ms * 1e-3), "shape": out["gqa_moe_encoder_train_bf16_b64"]["shape"],
+                                        "dtype": "f32"}
+    del enc, layer, src64
     reg = VideoRegression(n_layers=6, d_model=128, d_hidden=256, dropout=0.0, total_vf_dim=774, regModel="bimamba+").to(dev).train()
     sem, emo = torch.randn(64, 300, 768, generator=g).to(dev), torch.softmax(torch.randn(64, 300, 6, generator=g), -1).to(dev)
     zz = torch.zeros(64, 300, device=dev)

@@ -415,6 +415,25 @@ def linear_fn(x2: torch.Tensor, lin: torch.nn.Linear, relu: bool = False) -> tor
     return LinearFn.apply(x2, lin.weight, lin.bias, lin.weight, x2.shape[1], relu, 1.0, 0, None, 0, F32, None)
 
 
+def weight_bf16(lin: torch.nn.Linear) -> torch.Tensor:
+    """bf16 copy of an nn.Linear weight for the tensor-core GEMMs, cached on the module and refreshed when the fp32 master changes."""
+    w = lin.weight
+    key = (w.data_ptr(), w._version)
+    hit = lin.__dict__.get("_v2m_w16")
+    if hit is None or hit[0] != key:
+        hit = (key, w.detach().to(BF16).contiguous())
+        lin.__dict__["_v2m_w16"] = hit
+    return hit[1]
+
+
+def linear_bf16_fn(x16: torch.Tensor, lin: torch.nn.Linear, *, alpha: float = 1.0, out_dtype=BF16) -> torch.Tensor:
+    """nn.Linear on (rows, d) bf16 rows on the tcgen05 GEMM (fp32 master weights and gradients); alpha scales every output column
+    (the 1 / sqrt(head_dim) of the query projection)."""
+    N = lin.weight.shape[0]
+    return LinearFn.apply(x16, lin.weight, lin.bias, weight_bf16(lin), x16.shape[1], False, alpha, N if alpha != 1.0 else 0, None, 0,
+                          out_dtype, None)
+
+
 class AddFn(torch.autograd.Function):
     """a + alpha * b."""
 
@@ -631,8 +650,10 @@ class GqaAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, causal, q_scale, dropout=None):
+        """bf16 tensors (head_dim 64, q pre-scaled: q_scale == 1) run on the tcgen05 forward and the tensor-core backward."""
         b, n, hq, d = q.shape
         s, hk = k.shape[1], k.shape[2]
+        assert q.dtype == F32 or (d == 64 and q_scale == 1.0), "bf16 grouped-query attention needs head_dim 64 and pre-scaled queries"
         out = torch.empty((n, b, hq, d), device=q.device, dtype=q.dtype)
         lse = torch.empty((b * hq, n), device=q.device, dtype=F32)
         ops.attention(q, k, v, out, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d, q_strides=(n * hq * d, hq * d),
@@ -651,11 +672,12 @@ class GqaAttnFn(torch.autograd.Function):
         s, hk = k.shape[1], k.shape[2]
         dout = dout.contiguous()
         dq = torch.empty_like(q)
-        dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+        tc = q.dtype == BF16                                               # tensor-core kernels write bf16 dK / dV once (summed over the group)
+        dk, dv = (torch.empty_like(k), torch.empty_like(v)) if tc else (torch.zeros_like(k), torch.zeros_like(v))
         ops.attention_bwd(q, k, v, out, dout, lse, None, dq, dk, dv, None, B=b, Hq=hq, Hkv=hk, Lq=n, Lk=s, dh=d,
                           q_strides=(n * hq * d, hq * d), k_strides=(s * hk * d, hk * d), v_strides=(s * hk * d, hk * d),
                           o_strides=(hq * d, b * hq * d), do_strides=(hq * d, b * hq * d), dq_strides=(n * hq * d, hq * d),
-                          dkv_strides=(s * hk * d, hk * d), causal=causal, q_scale=q_scale, dropout=ctx.dropout)
+                          dkv_strides=(s * hk * d, hk * d), causal=causal, q_scale=q_scale, dropout=ctx.dropout, tensor_core=tc)
         return dq, dk, dv, None, None, None
 
 

@@ -39,6 +39,9 @@ def scaled_dot_product_gqa(query, key, value, num_heads=None, dropout: float = 0
     drop = (float(dropout), ops.next_dropout_seed()) if dropout > 0.0 else None
     if (ag.tracking(query, key, value) or drop is not None) and dt == torch.float32:   # gradients through our attention backward kernel
         return ag.GqaAttnFn.apply(query.contiguous(), key.contiguous(), value.contiguous(), bool(is_causal), 1.0 / scale, drop), None
+    if ag.tracking(query, key, value) and drop is None and dt == torch.bfloat16 and d == 64:
+        # tensor-core path: the kernels want pre-scaled queries (the scaling stays in the autograd graph)
+        return ag.GqaAttnFn.apply((query * (1.0 / scale)).contiguous(), key.contiguous(), value.contiguous(), bool(is_causal), 1.0, None), None
     if drop is not None:
         raise NotImplementedError("scaled_dot_product_gqa: dropout > 0 is built on the fp32 path")
     q, k, v = (t.detach().contiguous() for t in (query, key, value))
@@ -106,6 +109,27 @@ class MultiheadGQA(nn.Module):
             x2 = x.detach().reshape(-1, x.shape[-1]).float().contiguous()
             return ops.linear(x2, m.weight.detach(), m.bias.detach() if m.bias is not None else None, k=x2.shape[1])
 
+        bf16 = torch.bfloat16
+        tc = (track and getattr(self, "compute_dtype", torch.float32) == bf16 and dh == 64 and E % 8 == 0
+              and not getattr(self, "batch_independent", False))
+        if tc:
+            # tensor-core training path (compute_dtype = bf16; fp32 master weights, fp32 gradients): projections on the tcgen05 GEMM
+            # with the 1 / sqrt(d) of scaled_dot_product_gqa (:93-96) folded into the query projection, tcgen05 attention forward,
+            # tensor-core attention backward (dK / dV summed over the query heads of a group), bf16 LayerNorm, fp32 output
+            rows16 = lambda x: ag.rows_f32(x).to(bf16)
+            xq = rows16(query)
+            same = key is query and value is query
+            xk, xv = (xq, xq) if same else (rows16(key), rows16(value))
+            q = ag.linear_bf16_fn(xq, self.q_proj, alpha=float(dh) ** -0.5)
+            k, v = ag.linear_bf16_fn(xk, self.k_proj), ag.linear_bf16_fn(xv, self.v_proj)
+            q4, k4, v4 = q.view(bsz, tgt_len, H, dh), k.view(bsz, src_len, Hk, dh), v.view(bsz, src_len, Hk, dh)   # literal .view, :324-326
+            causal = bool(is_causal) or bool(getattr(self, "force_causal", False))
+            x = ag.GqaAttnFn.apply(q4, k4, v4, causal, 1.0, None)          # (n, b, hq, d), :159
+            x2 = x.reshape(-1, E)
+            if self.layer_norm:
+                x2 = ag.LayerNormFn.apply(x2.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
+            y = ag.linear_bf16_fn(x2, self.out_proj, out_dtype=torch.float32)
+            return y.view(x.shape[0], x.shape[1], E), None
         q, k, v = lin(self.q_proj, query), lin(self.k_proj, key), lin(self.v_proj, value)   # :306-308
         # literal `.view(bsz, len, heads*dh)` of the (len, bsz, .) projections (:324-326)
         if getattr(self, "batch_independent", False) and bsz > 1:
