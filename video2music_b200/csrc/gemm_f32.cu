@@ -29,35 +29,48 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 
   const int lrow = tid >> 2;         // 0..63
   const int lk = (tid & 3) * 4;      // 0,4,8,12
+  // global -> register loads of one k tile (two rows of A and of W per thread); issued for tile k0 + BK BEFORE the FMAs of
+  // tile k0, so the memory latency hides behind the arithmetic (same k order and same products as a plain loop: the results
+  // are bit-identical, only the waiting moved)
+  float4 va[2], vb[2];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = lrow + 64 * i;
+      va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vb[i] = va[i];
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + lk;
+      if (ALIGNED) {
+        if (gm < M && gk < K) va[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk));
+        if (gn < N && gk < K) vb[i] = __ldg(reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk));
+      } else {
+        if (gm < M) {
+          const float* p = A + (size_t)gm * lda + (size_t)gk * a_cs;      // element (m, k) at m*lda + k*a_cs
+          if (gk + 0 < K) va[i].x = __ldg(p);
+          if (gk + 1 < K) va[i].y = __ldg(p + (size_t)a_cs);
+          if (gk + 2 < K) va[i].z = __ldg(p + 2 * (size_t)a_cs);
+          if (gk + 3 < K) va[i].w = __ldg(p + 3 * (size_t)a_cs);
+        }
+        if (gn < N) {
+          const float* p = W + (size_t)gn * ldw + (size_t)gk * w_cs;
+          if (gk + 0 < K) vb[i].x = __ldg(p);
+          if (gk + 1 < K) vb[i].y = __ldg(p + (size_t)w_cs);
+          if (gk + 2 < K) vb[i].z = __ldg(p + 2 * (size_t)w_cs);
+          if (gk + 3 < K) vb[i].w = __ldg(p + 3 * (size_t)w_cs);
+        }
+      }
+    }
+  };
+  load_tile(0);
   for (int k0 = 0; k0 < K; k0 += BK) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int r = lrow + 64 * i;
-      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-      const int gm = m0 + r, gn = n0 + r, gk = k0 + lk;
-      if (ALIGNED) {
-        if (gm < M && gk < K) va = __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk));
-        if (gn < N && gk < K) vb = __ldg(reinterpret_cast<const float4*>(W + (size_t)gn * ldw + gk));
-      } else {
-        if (gm < M) {
-          const float* p = A + (size_t)gm * lda + (size_t)gk * a_cs;      // element (m, k) at m*lda + k*a_cs
-          if (gk + 0 < K) va.x = __ldg(p);
-          if (gk + 1 < K) va.y = __ldg(p + (size_t)a_cs);
-          if (gk + 2 < K) va.z = __ldg(p + 2 * (size_t)a_cs);
-          if (gk + 3 < K) va.w = __ldg(p + 3 * (size_t)a_cs);
-        }
-        if (gn < N) {
-          const float* p = W + (size_t)gn * ldw + (size_t)gk * w_cs;
-          if (gk + 0 < K) vb.x = __ldg(p);
-          if (gk + 1 < K) vb.y = __ldg(p + (size_t)w_cs);
-          if (gk + 2 < K) vb.z = __ldg(p + 2 * (size_t)w_cs);
-          if (gk + 3 < K) vb.w = __ldg(p + 3 * (size_t)w_cs);
-        }
-      }
-      As[lk + 0][r] = va.x; As[lk + 1][r] = va.y; As[lk + 2][r] = va.z; As[lk + 3][r] = va.w;
-      Bs[lk + 0][r] = vb.x; Bs[lk + 1][r] = vb.y; Bs[lk + 2][r] = vb.z; Bs[lk + 3][r] = vb.w;
+      As[lk + 0][r] = va[i].x; As[lk + 1][r] = va[i].y; As[lk + 2][r] = va[i].z; As[lk + 3][r] = va[i].w;
+      Bs[lk + 0][r] = vb[i].x; Bs[lk + 1][r] = vb[i].y; Bs[lk + 2][r] = vb[i].z; Bs[lk + 3][r] = vb[i].w;
     }
     __syncthreads();
+    if (k0 + BK < K) load_tile(k0 + BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);

@@ -184,8 +184,8 @@ int selective_scan_fwd(const float* x, long long ldx, const float* delta_raw, lo
 //            dC_n = dy h_n;  gh_n += dy C_n;  with a_n = exp(delta A_n):  d delta += gh_n (A_n a_n h_{l-1,n} + B_n x),
 //            dA_n += gh_n h_{l-1,n} delta a_n,  dB_n = gh_n delta x,  dx += gh_n delta B_n,  gh_n *= a_n
 //            d delta_raw = d delta * softplus'(delta_raw + dt_bias)
-//   dB / dC are sums over the channels: the CTA folds its 128 channels through shared memory (2 N = 32 values per step) and
-//   adds them to the caller-zeroed gradient rows; dA_log (= dA * A), dD, d dt_bias are accumulated per thread and added once.
+//   dB / dC are sums over the channels: every warp folds its 32 channels with a transpose-reduce butterfly (2 N = 32 values per
+//   step) and adds them to the caller-zeroed gradient rows; dA_log (= dA * A), dD, d dt_bias are accumulated per thread and added once.
 // wsf / wsg layout [B][n_chunks-1][N+1][ED] (row N = sum(delta)); wsg entry ch-1 belongs to chunk ch before the carry and holds
 // G[ch-1] after it.
 template <int N, int PASS>
@@ -203,8 +203,10 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
                                                                  long long lddz, float* __restrict__ dA_log, float* __restrict__ dD,
                                                                  float* __restrict__ ddt_bias, int L, int ED, int n_chunks, int plus) {
   static_assert(2 * N == 32, "the channel fold maps 2 N values onto the 32 lanes of a warp");
-  __shared__ float red[PASS == 1 ? 2 * N : 1][129];
-  const int tid = threadIdx.x, c = blockIdx.x * 128 + tid, b = blockIdx.z;
+  // B | C rows of the chunk (shared by every channel): staged once per CTA and read as shared-memory broadcasts -- per-lane
+  // broadcast loads from global memory cost the load/store unit one request per value and step
+  __shared__ __align__(16) float sBC[PASS == 1 ? kScanChunk : 1][2 * N];
+  const int tid = threadIdx.x, lane = tid & 31, c = blockIdx.x * 128 + tid, b = blockIdx.z;
   const int ch = PASS == 0 ? blockIdx.y + 1 : blockIdx.y;            // pass 0 skips chunk 0 (nobody needs its start gradient)
   const bool act = c < ED;
   const int cc = act ? c : ED - 1;                                   // inactive lanes read a valid channel and contribute nothing
@@ -239,6 +241,12 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
     }
     return;
   }
+  for (int i = tid; i < (l1 - l0) * 2 * N; i += 128) {
+    const int li = i / (2 * N), v = i % (2 * N);
+    const long long row = (long long)b * L + l0 + li;
+    sBC[li][v] = v < N ? Bm[row * ldbc + v] : Cm[row * ldbc + (v - N)];
+  }
+  __syncthreads();
   const float* h0 = ch > 0 ? wsf + ((long long)b * (n_chunks - 1) + (ch - 1)) * (N + 1) * ED + cc : nullptr;   // chunk-start state
   if (ch > 0) {
 #pragma unroll
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
     const float dxv = dl * xv;
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      h[n] = fmaf(ex2_approx(dl * A2[n]), h[n], dxv * __ldg(Bm + row * ldbc + n));
+      h[n] = fmaf(ex2_approx(dl * A2[n]), h[n], dxv * sBC[l - l0][n]);
       if (act) Hs[(row * N + n) * ED + c] = h[n];
     }
   }
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
     const float g = act ? dout[row * ldo + c] : 0.f;
     float y = Dc * xv;
 #pragma unroll
-    for (int n = 0; n < N; ++n) y = fmaf(h[n], __ldg(Cm + row * ldbc + n), y);
+    for (int n = 0; n < N; ++n) y = fmaf(h[n], sBC[l - l0][N + n], y);
     float dy = g, dzv = 0.f, dxv = 0.f;
     if (z) {
       const float zv = z[row * ldz + cc];
@@ -286,18 +294,19 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
     dxv = fmaf(dy, Dc, dxv);
     gD = fmaf(dy, xv, gD);
     float ddl = 0.f;
+    float fold[2 * N];                                             // this channel's dB_n | dC_n of the step
 #pragma unroll
     for (int n = 0; n < N; ++n) {
-      const float Bv = __ldg(Bm + row * ldbc + n), Cv = __ldg(Cm + row * ldbc + n);
+      const float Bv = sBC[l - l0][n], Cv = sBC[l - l0][N + n];
       const float hp = (l > l0) ? Hs[((row - 1) * N + n) * ED + cc] : (ch > 0 ? h0[(long long)n * ED] : 0.f);
       const float a = ex2_approx(dl * A2[n]);
-      red[N + n][tid] = act ? dy * h[n] : 0.f;                     // dC_n
+      fold[N + n] = act ? dy * h[n] : 0.f;                         // dC_n
       gh[n] = fmaf(dy, Cv, gh[n]);
       const float t = gh[n] * hp;
       ddl = fmaf(t, A[n] * a, ddl);
       ddl = fmaf(gh[n] * Bv, xv, ddl);
       gA[n] = fmaf(t, dl * a, gA[n]);
-      red[n][tid] = act ? gh[n] * dl * xv : 0.f;                   // dB_n
+      fold[n] = act ? gh[n] * dl * xv : 0.f;                       // dB_n
       dxv = fmaf(gh[n] * dl, Bv, dxv);
       gh[n] *= a;
       h[n] = hp;
@@ -309,15 +318,10 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
       ddraw[row * lddd + c] = ddr;
       if (dz) dz[row * lddz + c] = dzv;
     }
-    __syncthreads();
-    {
-      const int v = tid & 31, q = tid >> 5;
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) sum += red[v][q * 32 + j];
-      atomicAdd((v < N ? dBm + row * lddbc + v : dCm + row * lddbc + (v - N)), sum);
-    }
-    __syncthreads();
+    // dB / dC are sums over the channels: the 32 channels of a warp meet in a transpose-reduce butterfly (lane v ends with sum
+    // #v), one reduction per warp and value -- no shared memory and no CTA barrier inside the sweep, warps run independently
+    const float sum = warp_transpose_reduce32(fold, lane);
+    atomicAdd((lane < N ? dBm + row * lddbc + lane : dCm + row * lddbc + (lane - N)), sum);
   }
   if (act) {
 #pragma unroll

@@ -37,20 +37,6 @@ struct StepGemm {
   int M, N, K, relu;
 };
 
-// v[0..31] (one partial per lane of 32 different sums) -> lane l returns sum #l over all lanes
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
-#pragma unroll
-    for (int i = 0; i < h; ++i) {
-      const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-    }
-  }
-  return v[0];
-}
-
 template <bool GLU>
 __global__ void __launch_bounds__(THREADS) step_gemm_f32_kernel(const __grid_constant__ StepGemm p) {
   constexpr int NF = GLU ? 4 : 8;                                // features per CTA; 8 accumulator columns either way
@@ -101,7 +87,7 @@ __global__ void __launch_bounds__(THREADS) step_gemm_f32_kernel(const __grid_con
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = acc[4 * g + (i >> 3)][i & 7];
-      float tot = transpose_reduce32(v, lane);
+      float tot = warp_transpose_reduce32(v, lane);
       const int m = rw + 4 * g + (lane >> 3), c = lane & 7;
       float gate = 0.f;
       if (GLU) gate = __shfl_down_sync(0xffffffffu, tot, 4);       // column c + 4 = the gate sum of feature c
