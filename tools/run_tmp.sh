@@ -1,6 +1,8 @@
 #!/bin/bash
 cd /root/repo
-timeout 1500 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_amt.py -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/r3b_tests.log
-python tools/scratch/step_kernels_time.py 2>&1 | grep "tiled" | tee gpurun_out/r3b_times.txt
-python tools/scratch/cfg5_train_step.py 2>&1 | tail -1 | tee -a gpurun_out/r3b_times.txt
-python tools/scratch/cfg4_train_step.py 64 f32 2>&1 | tail -1 | tee -a gpurun_out/r3b_times.txt
+make -C video2music_b200/csrc clean > /dev/null; make -j8 -C video2music_b200/csrc EXTRA=-DV2M_EXP_NOATTN > /dev/null 2>&1 || { echo build failed; exit 1; }
+for R in 5 8; do
+  V2M_STREAM_ROWS=$R python tools/stream_exp.py 64 100 100 2>&1 | tail -1
+done | tee gpurun_out/r3d_noattn.txt
+V2M_STREAM_ROWS=8 python tools/stream_exp.py 8 100 100 2>&1 | tail -1 | tee -a gpurun_out/r3d_noattn.txt
+V2M_STREAM_ROWS=5 python tools/stream_exp.py 5 100 100 2>&1 | tail -1 | tee -a gpurun_out/r3d_noattn.txt

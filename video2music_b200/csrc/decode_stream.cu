@@ -386,7 +386,11 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
   const int ri = lane & 7, mi = lane >> 3;             // ldmatrix: this lane addresses row ri of 8x8 matrix mi
   cons_sync();                                         // q_s / knew / vnew written
   ++cx.ph; mark(cx.ph * 1000 + (is_self ? 200 : 300));
+#ifdef V2M_EXP_NOATTN
+  if (false) {                                         // timing experiment: the linear chain + exchanges alone (wrong results)
+#else
   if (is_self) {
+#endif
     if (warp < cx.R) {                                 // score of position t itself (distance 0: Er[er_len-1])
       const DecLayer& Ld = p.layer[layer];
       const float2 kn = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(cx.at<bf16>(cx.L.knew) + warp * DH + 2 * lane));
@@ -439,7 +443,11 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
   }
   // a chunk is processed by the warp whose index equals its ring slot: that warp then meets every use of the slot during
   // the phase in order and can never be two uses ahead of it (the parity waits cannot tell use k from use k+2)
+#ifdef V2M_EXP_NOATTN
+  const int total = 0;
+#else
   const int total = cx.R * nch;
+#endif
   for (int i = 0; i < total; ++i) {
     uint32_t my_par;
     const int my_slot = cx.rg.next(my_par);            // ring state in step in every warp
@@ -550,7 +558,12 @@ __device__ __forceinline__ void attention_phase(Ctx& cx, const DecodeParams& p, 
       Lt = fmaf(cb[ci * CW + 1], f, Lt);
       ov = fmaf(cb[ci * CW + 4 + d], f, ov);
     }
+#ifdef V2M_EXP_NOATTN
+    st[r * CP + d] = __float2bfloat16_rn(0.01f * (float)(d & 7));
+    (void)ov; (void)Lt;
+#else
     st[r * CP + d] = __float2bfloat16_rn(ov / Lt);
+#endif
   }
   gather(cx, 0, cx.L.ctxg, (uint32_t)cx.R * CP * 2);
   mark(cx.ph * 1000 + (is_self ? 250 : 350));
@@ -637,6 +650,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
           tiles512(Ld.w_qkv, 32 + c * 4, 4);
           tiles512(Ld.w_qkv, 64 + c * 4, 4);
           // Er rows [er_len-1-t, er_len-1) from the copy swizzled for that start row, then the cached self K|V rows
+#ifndef V2M_EXP_NOATTN
           const int start = p.er_len - 1 - t;
           const char* er = static_cast<const char*>(Ld.er_sw) + ((size_t)(start & 7) * p.er_len + start) * (DH * 2);
           for (int r0 = 0; r0 < t; r0 += ECH) rg.put(id, er + (size_t)r0 * DH * 2, (uint32_t)min(ECH, t - r0) * DH * 2);
@@ -645,13 +659,16 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
               const size_t off = ((((size_t)(cx.row0 + r)) * hb + c) * p.cap + r0) * (2 * DH);
               rg.put(id, static_cast<const bf16*>(Ld.self_k) + off, (uint32_t)min(KCH, t - r0) * 2 * DH * 2);
             }
+#endif
           tiles512(Ld.w_so, c * 4, 4);
           tiles512(Ld.w_cq, c * 4, 4);
+#ifndef V2M_EXP_NOATTN
           for (int r = 0; r < cx.R; ++r)
             for (int r0 = 0; r0 < p.S; r0 += KCH) {
               const size_t off = ((((size_t)(cx.row0 + r)) * hb + c) * p.S + r0) * (2 * DH);
               rg.put(id, static_cast<const bf16*>(Ld.cross_k) + off, (uint32_t)min(KCH, p.S - r0) * 2 * DH * 2);
             }
+#endif
           tiles512(Ld.w_co, c * 4, 4);
           tiles512(Ld.w_f1, c * 8, 8);
           for (int i = 0; i < 4; ++i) rg.put(id, static_cast<const char*>(Ld.w_f2) + (size_t)(c * 4 + i) * SLOT_BYTES, SLOT_BYTES);
