@@ -286,3 +286,42 @@ MIRRORS['mamba_conv_silu_bwd'] = mamba_conv_silu_bwd
 MIRRORS['sigmoid'] = lambda a: torch.sigmoid(a.detach())
 MIRRORS['sigmoid_bwd'] = lambda dy, s: dy * s * (1 - s)
 MIRRORS['dw_f32'] = lambda dz, x, K: dz.detach().t() @ x.detach()[:, :K]
+
+
+# ---- inference ops of the KV-cached generation of the generic decoder stacks (video2music_b200/cached_decode.py): the plain definition of
+# each op, so that the HOST side of the generation loop (position kept in a tensor, caches written with index_copy_, token bookkeeping
+# with gather / scatter, primer handling, sampling constraints) runs on a CPU box
+def concat_features(sem, scene, motion, emotion, out_dtype, ld_out):
+    rows = sem.shape[0] * sem.shape[1]
+    mo = motion.float().reshape(rows, -1)
+    parts = [sem.float().reshape(rows, -1), scene.float().reshape(rows, 1), mo, emotion.float().reshape(rows, -1)]
+    cat = torch.cat(parts, 1)
+    out = torch.zeros((rows, ld_out), dtype=out_dtype)
+    out[:, :cat.shape[1]] = cat
+    return out
+MIRRORS['concat_features'] = concat_features
+def embed_sum(idx_a, table_a, idx_b, table_b, out_dtype):
+    y = table_a.detach()[idx_a.reshape(-1)]
+    if idx_b is not None: y = y + table_b.detach()[idx_b.reshape(-1)]
+    return y.to(out_dtype)
+MIRRORS['embed_sum'] = embed_sum
+def step_linear(x, w, bias=None, *, k=None, relu=False, row_scale=None, col_vec=None):
+    K = k if k is not None else min(x.shape[1], w.shape[1])
+    y = x[:, :K] @ w[:, :K].t()
+    if bias is not None: y = y + bias
+    if row_scale is not None: y = y + row_scale[:, None] * col_vec[None, :]
+    return y.relu() if relu else y
+MIRRORS['step_linear'] = step_linear
+def step_attention(q, K, V, *, Hq, Hkv, dh, n_max, kv_strides, n_dev=None, q_scale=1.0):
+    B = q.shape[0]
+    n = n_max if n_dev is None else min(n_max, int(n_dev))
+    out = torch.empty((B, Hq * dh))
+    for b in range(B):
+        for h in range(Hq):
+            off = K.storage_offset() + b * kv_strides[0] + (h // (Hq // Hkv)) * dh
+            Kh = torch.as_strided(K, (n, dh), (kv_strides[1], 1), off)
+            Vh = torch.as_strided(V, (n, dh), (kv_strides[1], 1), V.storage_offset() + b * kv_strides[0] + (h // (Hq // Hkv)) * dh)
+            p = torch.softmax((q[b, h * dh:(h + 1) * dh] * q_scale) @ Kh.t(), -1)
+            out[b, h * dh:(h + 1) * dh] = p @ Vh
+    return out
+MIRRORS['step_attention'] = step_attention
