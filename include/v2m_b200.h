@@ -73,6 +73,11 @@ typedef struct v2m_epilogue {
   /* bf16 GEMMs with an fp32 output and no other epilogue operation: C += A W^T instead of C = A W^T (coalesced vector
    * reductions into the caller's buffer) -- weight gradients accumulate straight into the optimiser's gradient buffer. */
   int32_t accumulate;
+  /* bf16 GEMMs: `residual` (bf16) is a GATE instead of an addend: C = residual[m][n] > 0 ? acc * gate_scale : 0 -- the backward of
+   * relu(linear1(x)) followed by dropout (rpr.py:67, nn.TransformerEncoderLayer) applied by the dX GEMM of linear2: the gate is the
+   * saved hidden activation, gate_scale the dropout scale 1 / (1 - p) (1 without dropout). */
+  int32_t residual_gate;
+  float gate_scale;
   int32_t pad_;
 } v2m_epilogue;
 

@@ -26,7 +26,8 @@ class Epilogue(C.Structure):
                 ("alpha", C.c_float), ("alpha_cols", i32), ("relu", i32), ("residual_bf16", i32),
                 ("head_scatter", i32), ("S", i32), ("H", i32), ("dh", i32), ("cap", i32), ("pos0", i32),
                 ("part_stride", i64), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32),
-                ("drop_after_res", i32), ("drop_seed_dev", vp), ("accumulate", i32), ("pad_", i32)]
+                ("drop_after_res", i32), ("drop_seed_dev", vp), ("accumulate", i32), ("residual_gate", i32), ("gate_scale", C.c_float),
+                ("pad_", i32)]
 
 
 class Attn(C.Structure):

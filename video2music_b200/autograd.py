@@ -60,12 +60,19 @@ class LinearFn(torch.autograd.Function):
     dropout = None or (p, seed, after_residual): mask fused into the GEMM epilogue, recomputed by dy_prep in backward."""
 
     @staticmethod
-    def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype, dropout=None, owner=None):
+    def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype, dropout=None, owner=None,
+                in_gate_scale=None, pre_gated=False):
         """owner = (weight parameter, bias parameter or None, row slice or None): the parameters `w` / `b` are (views of), for
-        direct gradient accumulation (see direct_grad)."""
+        direct gradient accumulation (see direct_grad).
+        in_gate_scale (bf16 path): x is the output of a relu (+ fused dropout of that scale) LinearFn built with pre_gated=True;
+        this layer's dX GEMM applies that activation's backward in its epilogue (dx = x > 0 ? dx * scale : 0), so the layer
+        below needs no pass over dy / y / dz (its backward then only sums the bias gradient)."""
         if dropout is not None and dropout[0] <= 0.0:
             dropout = None
         ctx.owner = owner
+        ctx.in_gate_scale = in_gate_scale if x.dtype == BF16 else None
+        ctx.pre_gated = bool(pre_gated) and x.dtype == BF16
+        assert not ctx.pre_gated or (relu and alpha_cols == 0)
         # drop(acc + residual) is only used for the constant positional-encoding rows (no gradient flows to the residual)
         assert not (dropout is not None and dropout[2] and residual is not None and residual.requires_grad)
         y = ops.linear(x, wc, b, k=K, relu=relu, alpha=alpha, alpha_cols=alpha_cols, residual=residual, res_mod=res_mod,
@@ -80,7 +87,7 @@ class LinearFn(torch.autograd.Function):
         x, wc, y = ctx.saved_tensors
         K, relu, alpha, alpha_cols, res_grad, has_b, wshape, cdt = ctx.meta
         dy = dy.contiguous()
-        plain = (not relu) and alpha_cols == 0 and dy.dtype == cdt and ctx.dropout is None
+        plain = ((not relu) and alpha_cols == 0 and dy.dtype == cdt and ctx.dropout is None) or (ctx.pre_gated and dy.dtype == cdt)
         wp, bp, rows = ctx.owner if ctx.owner is not None else (None, None, None)
         gw, gb = direct_grad(wp), direct_grad(bp) if has_b else None
         if gw is not None and rows is not None:
@@ -90,10 +97,19 @@ class LinearFn(torch.autograd.Function):
         direct_w = gw is not None and cdt == BF16 and tuple(gw.shape) == (wshape[0], K) and gw.stride(1) == 1 and (gw.stride(0) * 4) % 16 == 0 \
             and gw.data_ptr() % 16 == 0
         direct_b = gb is not None and gb.is_contiguous()
-        dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain, dropout=ctx.dropout, db_out=gb if direct_b else None)
+        if ctx.pre_gated and plain:                                          # relu' and the dropout mask were applied by the consumer's dX GEMM
+            dz, db = ops.dy_prep(dy, None, False, 1.0, 0, cdt, want_dz=False, dropout=None, db_out=gb if direct_b else None)
+        else:
+            dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain, dropout=ctx.dropout, db_out=gb if direct_b else None)
         if plain:
             dz = dy
-        dx = _gemm_dx(dz, wc, K) if ctx.needs_input_grad[0] else None
+        if not ctx.needs_input_grad[0]:
+            dx = None
+        elif ctx.in_gate_scale is not None and cdt == BF16:
+            M_, N_ = dz.shape
+            dx = ops.linear_general(dz, wc, a_mn=False, b_mn=True, M=M_, N=K, K=N_, out_dtype=BF16, gate=x[:, :K], gate_scale=ctx.in_gate_scale)
+        else:
+            dx = _gemm_dx(dz, wc, K)
         if dx is not None and dx.shape[1] != x.shape[1]:                     # x carries zero padding columns
             full = torch.zeros_like(x)
             full[:, :K] = dx
@@ -113,7 +129,7 @@ class LinearFn(torch.autograd.Function):
         if direct_b and bp is not wp:
             grad_ready(bp)
         dres = dy if res_grad else None
-        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None, None
+        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None, None, None, None
 
 
 class AttnSelfFn(torch.autograd.Function):
@@ -293,7 +309,7 @@ class AmtLossFn(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------------------------- model forward
 def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, residual=None, res_mod=0, rows=None,
-         out_dtype=None, dropout=None):
+         out_dtype=None, dropout=None, in_gate_scale=None, pre_gated=False):
     w = W._sd[wname]
     b = W._sd[bname] if bname is not None else None
     if rows is not None:
@@ -302,7 +318,8 @@ def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, res
         w_v, b_v = w, b
     wc = W.w(wname, rows=rows)
     K = K if K is not None else w.shape[1]
-    return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype, dropout, (w, b, rows))
+    return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype, dropout, (w, b, rows),
+                          in_gate_scale, pre_gated)
 
 
 def _ln(W, name, x):
@@ -339,6 +356,7 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     dh = E // H
     scal = float(dh) ** -0.5
     sd = W._sd
+    fuse_gate = dt == BF16                           # ReLU / dropout backward of the FFN fused into the next layer's dX GEMM
     # ---- video stream
     vf_dim = sd["Linear_vis.weight"].shape[1]
     vin = ops.concat_features(sem, scene, motion, emotion, dt, vf_dim if dt == F32 else _pad8(vf_dim))
@@ -350,8 +368,10 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
         a = AttnSelfFn.apply(qkv, None, None, B, S, H, False, dra())
         r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv, dropout=dr())
         xv = _ln(W, p + "norm1", r)
-        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=dr())
-        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv, dropout=dr())
+        d1 = dr()                                    # relu' and this dropout's mask are applied by linear2's dX GEMM (bf16 path)
+        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=d1, pre_gated=fuse_gate)
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv, dropout=dr(),
+                 in_gate_scale=(ops.drop_args(*d1[:2])[0] if d1 is not None else 1.0) if fuse_gate else None)
         xv = _ln(W, p + "norm2", r)
     mem = _ln(W, "transformer.encoder.norm", xv)
     # ---- chord stream
@@ -378,8 +398,10 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
         a = AttnCrossFn.apply(q, kv, B, T, S, H, dra())
         r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf, dropout=dr())
         xf = _ln(W, p + "norm2", r)
-        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=dr())
-        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf, dropout=dr())
+        d1 = dr()                                    # relu' and this dropout's mask are applied by linear2's dX GEMM (bf16 path)
+        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=d1, pre_gated=fuse_gate)
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf, dropout=dr(),
+                 in_gate_scale=(ops.drop_args(*d1[:2])[0] if d1 is not None else 1.0) if fuse_gate else None)
         xf = _ln(W, p + "norm3", r)
     xf = _ln(W, "transformer.decoder.norm", xf)
     y = _lin(W, xf, "Wout.weight", "Wout.bias", out_dtype=F32)

@@ -38,6 +38,7 @@ static GemmEpilogue to_ep(const v2m_epilogue* e) {
   g.drop_scale = e->drop_scale; g.drop_thresh = e->drop_thresh; g.drop_seed = e->drop_seed; g.drop_after_res = e->drop_after_res;
   g.drop_seed_dev = e->drop_seed_dev;
   g.accumulate = e->accumulate;
+  g.residual_gate = e->residual_gate; g.gate_scale = e->gate_scale;
   return g;
 }
 

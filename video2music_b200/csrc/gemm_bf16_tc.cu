@@ -362,11 +362,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint4 t = res_cur[q];
-                float2 f;
-                f = bf16x2_to_f2(t.x); v[8 * q] += f.x; v[8 * q + 1] += f.y;
-                f = bf16x2_to_f2(t.y); v[8 * q + 2] += f.x; v[8 * q + 3] += f.y;
-                f = bf16x2_to_f2(t.z); v[8 * q + 4] += f.x; v[8 * q + 5] += f.y;
-                f = bf16x2_to_f2(t.w); v[8 * q + 6] += f.x; v[8 * q + 7] += f.y;
+                const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = bf16x2_to_f2(tw[e]);
+                  if (ep.residual_gate) {                         // backward of ReLU (+ dropout) of the layer below, see kernels.h
+                    v[8 * q + 2 * e] = f.x > 0.f ? v[8 * q + 2 * e] * ep.gate_scale : 0.f;
+                    v[8 * q + 2 * e + 1] = f.y > 0.f ? v[8 * q + 2 * e + 1] * ep.gate_scale : 0.f;
+                  } else {
+                    v[8 * q + 2 * e] += f.x; v[8 * q + 2 * e + 1] += f.y;
+                  }
+                }
               }
             } else {
               const float4* rp = reinterpret_cast<const float4*>(ep.residual + res_row + n0);
@@ -436,9 +442,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (ep.relu) x = fmaxf(x, 0.f);
             if (ep.row_scale) x = fmaf(rs, __ldg(ep.col_vec + n), x);
             if (ep.drop_scale != 0.f && !ep.drop_after_res) x = drop_keep(dseed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
-            if (ep.residual)
-              x += ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
-                                    : __ldg(ep.residual + res_row + n);
+            if (ep.residual) {
+              const float rv = ep.residual_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(ep.residual)[res_row + n])
+                                                : __ldg(ep.residual + res_row + n);
+              x = ep.residual_gate ? (rv > 0.f ? x * ep.gate_scale : 0.f) : x + rv;
+            }
             if (ep.drop_scale != 0.f && ep.drop_after_res) x = drop_keep(dseed, m, n, ep.drop_thresh) ? x * ep.drop_scale : 0.f;
             const long long o = epi_out_index(ep, m, n, ldc);
             if (out_bf16) static_cast<bf16*>(C)[o] = __float2bfloat16_rn(x);
@@ -532,6 +540,7 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
   const bool allow_split = !out_bf16 && !ep.bias && !ep.residual && !ep.row_scale && !ep.relu && ep.alpha_cols == 0 && !ep.head_scatter &&
                            ep.drop_scale == 0.f;
   V2M_REQUIRE(!ep.accumulate || allow_split, "gemm_bf16_tc: accumulate needs a plain fp32 output (no bias / residual / activation / dropout)");
+  V2M_REQUIRE(!ep.residual_gate || (ep.residual && ep.residual_bf16), "gemm_bf16_tc: the gate operand is a bf16 matrix");
 #define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split)
   if (bn == 256) {
     if (!a_mn && !b_mn) return V2M_GO(256, false, false);

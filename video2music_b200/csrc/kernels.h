@@ -35,6 +35,11 @@ struct GemmEpilogue {
   // bf16 GEMM, fp32 output only: C += A W^T (vector reductions into C, which the caller owns and has initialised) instead of
   // C = A W^T: weight gradients accumulate straight into the optimiser's gradient buffer.  No other epilogue operation.
   int accumulate = 0;
+  // bf16 GEMM: the (bf16) `residual` operand is a GATE instead of an addend: C = residual[m][n] > 0 ? acc * gate_scale : 0.  The dX
+  // GEMM of the layer that FOLLOWS a ReLU (+ fused dropout) applies that activation's backward in its epilogue: the gate is the
+  // saved activation output (positive exactly where the ReLU was active and the element was kept), gate_scale the dropout scale.
+  int residual_gate = 0;
+  float gate_scale = 1.f;
 };
 
 #ifdef __CUDACC__
