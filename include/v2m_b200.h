@@ -131,6 +131,7 @@ typedef struct v2m_attn_bwd_t {
   float q_scale;
   float drop_scale; uint32_t drop_thresh, drop_seed;   /* the forward's probability dropout (v2m_attn_bwd and v2m_attn_bwd_tc) */
   const uint32_t* drop_seed_dev;
+  float dq_scale;   /* dq is stored times dq_scale (0 = 1): backward of a query scaling applied by the projection's epilogue */
 } v2m_attn_bwd_t;
 int v2m_attn_bwd(const v2m_attn_bwd_t* p, void* stream);
 /* Tensor-core attention backward (bf16, head_dim 64, q pre-scaled: q_scale must be 1): same gradients as v2m_attn_bwd from

@@ -150,7 +150,7 @@ def attention(q, k, v, out, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_s
             torch.as_strided(out, (Lq, dh), (o_strides[1], 1), b * o_strides[0] + h * dh).copy_(O)
     return out
 MIRRORS['attention'] = attention
-def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False, dropout=None):
+def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_strides, o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False, dropout=None, dq_scale=1.0):
     G = Hq // Hkv
     for b in range(B):
         for h in range(Hq):
@@ -164,7 +164,7 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
                 if causal: S = S + torch.triu(torch.full((Lq, Lk), float("-inf")), 1)
                 (torch.softmax(S, -1) @ V).backward(dOo)
                 if Er is not None: dEr.add_(Erl.grad)
-            torch.as_strided(dq, (Lq, dh), (dq_strides[1], 1), b * dq_strides[0] + h * dh).copy_(Q.grad)
+            torch.as_strided(dq, (Lq, dh), (dq_strides[1], 1), b * dq_strides[0] + h * dh).copy_(Q.grad * dq_scale)
             torch.as_strided(dk, (Lk, dh), (dkv_strides[1], 1), b * dkv_strides[0] + (h // G) * dh).add_(K.grad)
             torch.as_strided(dv, (Lk, dh), (dkv_strides[1], 1), b * dkv_strides[0] + (h // G) * dh).add_(V.grad)
 MIRRORS['attention_bwd'] = attention_bwd

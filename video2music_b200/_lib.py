@@ -46,7 +46,7 @@ class AttnBwd(C.Structure):
                                     "dq_sb", "dq_sl", "dkv_sb", "dkv_sl")] +
                 [(n, i32) for n in ("B", "Hq", "Hkv", "Lq", "Lk", "dh", "causal", "er_len", "dtype")] +
                 [("q_scale", C.c_float), ("drop_scale", C.c_float), ("drop_thresh", C.c_uint32), ("drop_seed", C.c_uint32),
-                ("drop_seed_dev", vp)])
+                ("drop_seed_dev", vp), ("dq_scale", C.c_float)])
 
 
 class DecLayer(C.Structure):

@@ -61,7 +61,7 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype, dropout=None, owner=None,
-                in_gate_scale=None, pre_gated=False):
+                in_gate_scale=None, pre_gated=False, pre_scaled=False):
         """owner = (weight parameter, bias parameter or None, row slice or None): the parameters `w` / `b` are (views of), for
         direct gradient accumulation (see direct_grad).
         in_gate_scale (bf16 path): x is the output of a relu (+ fused dropout of that scale) LinearFn built with pre_gated=True;
@@ -73,6 +73,9 @@ class LinearFn(torch.autograd.Function):
         ctx.in_gate_scale = in_gate_scale if x.dtype == BF16 else None
         ctx.pre_gated = bool(pre_gated) and x.dtype == BF16
         assert not ctx.pre_gated or (relu and alpha_cols == 0)
+        # pre_scaled: the consumer (attention backward, dq_scale) already multiplied the gradient of the alpha-scaled columns by alpha
+        ctx.pre_scaled = bool(pre_scaled)
+        assert not ctx.pre_scaled or (not relu and dropout is None)
         # drop(acc + residual) is only used for the constant positional-encoding rows (no gradient flows to the residual)
         assert not (dropout is not None and dropout[2] and residual is not None and residual.requires_grad)
         y = ops.linear(x, wc, b, k=K, relu=relu, alpha=alpha, alpha_cols=alpha_cols, residual=residual, res_mod=res_mod,
@@ -87,7 +90,7 @@ class LinearFn(torch.autograd.Function):
         x, wc, y = ctx.saved_tensors
         K, relu, alpha, alpha_cols, res_grad, has_b, wshape, cdt = ctx.meta
         dy = dy.contiguous()
-        plain = ((not relu) and alpha_cols == 0 and dy.dtype == cdt and ctx.dropout is None) or (ctx.pre_gated and dy.dtype == cdt)
+        plain = ((not relu) and (alpha_cols == 0 or ctx.pre_scaled) and dy.dtype == cdt and ctx.dropout is None) or (ctx.pre_gated and dy.dtype == cdt)
         wp, bp, rows = ctx.owner if ctx.owner is not None else (None, None, None)
         gw, gb = direct_grad(wp), direct_grad(bp) if has_b else None
         if gw is not None and rows is not None:
@@ -97,7 +100,7 @@ class LinearFn(torch.autograd.Function):
         direct_w = gw is not None and cdt == BF16 and tuple(gw.shape) == (wshape[0], K) and gw.stride(1) == 1 and (gw.stride(0) * 4) % 16 == 0 \
             and gw.data_ptr() % 16 == 0
         direct_b = gb is not None and gb.is_contiguous()
-        if ctx.pre_gated and plain:                                          # relu' and the dropout mask were applied by the consumer's dX GEMM
+        if (ctx.pre_gated or ctx.pre_scaled) and plain:                      # relu' / dropout mask / column scaling were applied by the consumer
             dz, db = ops.dy_prep(dy, None, False, 1.0, 0, cdt, want_dz=False, dropout=None, db_out=gb if direct_b else None)
         else:
             dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain, dropout=ctx.dropout, db_out=gb if direct_b else None)
@@ -129,17 +132,20 @@ class LinearFn(torch.autograd.Function):
         if direct_b and bp is not wp:
             grad_ready(bp)
         dres = dy if res_grad else None
-        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None, None, None, None
+        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None, None, None, None, None
 
 
 class AttnSelfFn(torch.autograd.Function):
     """ctx[M,E] = attention over the fused qkv [M, 3E] (q pre-scaled by the projection epilogue), optional Er, causal."""
 
     @staticmethod
-    def forward(ctx, qkv, er, erc, B, L, H, causal, dropout=None, er_owner=None):
+    def forward(ctx, qkv, er, erc, B, L, H, causal, dropout=None, er_owner=None, dq_scale=1.0):
+        """dq_scale: the q gradient is stored times dq_scale (the in-projection that produced qkv was built with pre_scaled=True: the
+        backward of its 1 / sqrt(d) column scaling is applied here, for free, instead of by a pass over the whole gradient)."""
         if dropout is not None and dropout[0] <= 0.0:
             dropout = None
         ctx.er_owner = er_owner           # the Er parameter, for direct gradient accumulation
+        ctx.dq_scale = dq_scale
         E = qkv.shape[1] // 3
         dh = E // H
         out = torch.empty((B * L, E), device=qkv.device, dtype=qkv.dtype)
@@ -166,7 +172,8 @@ class AttnSelfFn(torch.autograd.Function):
         direct_er = ger is not None and ger.is_contiguous() and tuple(ger.shape) == tuple(erc.shape)
         der = (ger if direct_er else torch.zeros(erc.shape, device=qkv.device, dtype=F32)) if has_er else None
         common = dict(B=B, Hq=H, Hkv=H, Lq=L, Lk=L, dh=dh, q_strides=(L * ld, ld), k_strides=(L * ld, ld), v_strides=(L * ld, ld),
-                      o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld), causal=causal, dropout=ctx.dropout)
+                      o_strides=(L * E, E), do_strides=(L * E, E), dq_strides=(L * ld, ld), causal=causal, dropout=ctx.dropout,
+                      dq_scale=ctx.dq_scale)
         if qkv.dtype == BF16 and dh == 64:
             # tensor-core kernels write dK / dV straight into the fused gradient (bf16), no fp32 staging
             ops.attention_bwd(qkv, qkv[:, E:], qkv[:, 2 * E:], out, dout, lse, erc if has_er else None, dqkv, dqkv[:, E:],
@@ -179,16 +186,17 @@ class AttnSelfFn(torch.autograd.Function):
         if has_er and direct_er:
             grad_ready(ctx.er_owner)
             der = None
-        return dqkv, der, None, None, None, None, None, None, None
+        return dqkv, der, None, None, None, None, None, None, None, None
 
 
 class AttnCrossFn(torch.autograd.Function):
     """ctx[Mq,E] = attention of q [B*T, E] (pre-scaled) over kv [B*S, 2E] (non-causal, no Er)."""
 
     @staticmethod
-    def forward(ctx, q, kv, B, T, S, H, dropout=None):
+    def forward(ctx, q, kv, B, T, S, H, dropout=None, dq_scale=1.0):
         if dropout is not None and dropout[0] <= 0.0:
             dropout = None
+        ctx.dq_scale = dq_scale
         E = q.shape[1]
         dh = E // H
         out = torch.empty((B * T, E), device=q.device, dtype=q.dtype)
@@ -211,14 +219,14 @@ class AttnCrossFn(torch.autograd.Function):
         dq = torch.empty_like(q)
         common = dict(B=B, Hq=H, Hkv=H, Lq=T, Lk=S, dh=dh, q_strides=(T * E, E), k_strides=(S * 2 * E, 2 * E),
                       v_strides=(S * 2 * E, 2 * E), o_strides=(T * E, E), do_strides=(T * E, E), dq_strides=(T * E, E),
-                      dkv_strides=(S * 2 * E, 2 * E), causal=False, dropout=ctx.dropout)
+                      dkv_strides=(S * 2 * E, 2 * E), causal=False, dropout=ctx.dropout, dq_scale=ctx.dq_scale)
         if q.dtype == BF16 and dh == 64:
             dkv = torch.empty_like(kv)
             ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv, dkv[:, E:], None, tensor_core=True, **common)
-            return dq, dkv, None, None, None, None, None
+            return dq, dkv, None, None, None, None, None, None
         dkv32 = torch.zeros((B * S, 2 * E), device=q.device, dtype=F32)
         ops.attention_bwd(q, kv, kv[:, E:], out, dout, lse, None, dq, dkv32, dkv32[:, E:], None, **common)
-        return dq, dkv32.to(kv.dtype) if kv.dtype != F32 else dkv32, None, None, None, None, None
+        return dq, dkv32.to(kv.dtype) if kv.dtype != F32 else dkv32, None, None, None, None, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -309,7 +317,7 @@ class AmtLossFn(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------------------------- model forward
 def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, residual=None, res_mod=0, rows=None,
-         out_dtype=None, dropout=None, in_gate_scale=None, pre_gated=False):
+         out_dtype=None, dropout=None, in_gate_scale=None, pre_gated=False, pre_scaled=False):
     w = W._sd[wname]
     b = W._sd[bname] if bname is not None else None
     if rows is not None:
@@ -319,7 +327,7 @@ def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, res
     wc = W.w(wname, rows=rows)
     K = K if K is not None else w.shape[1]
     return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype, dropout, (w, b, rows),
-                          in_gate_scale, pre_gated)
+                          in_gate_scale, pre_gated, pre_scaled)
 
 
 def _ln(W, name, x):
@@ -357,6 +365,7 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     scal = float(dh) ** -0.5
     sd = W._sd
     fuse_gate = dt == BF16                           # ReLU / dropout backward of the FFN fused into the next layer's dX GEMM
+    fuse_q = True                                    # backward of the 1 / sqrt(d) of the query columns applied by the attention backward
     # ---- video stream
     vf_dim = sd["Linear_vis.weight"].shape[1]
     vin = ops.concat_features(sem, scene, motion, emotion, dt, vf_dim if dt == F32 else _pad8(vf_dim))
@@ -364,8 +373,8 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     xv = _lin(W, vin, "Linear_vis.weight", "Linear_vis.bias", K=vf_dim, residual=pe_v, res_mod=S, dropout=dr(True))
     for l in range(NL):
         p = "transformer.encoder.layers.%d." % l
-        qkv = _lin(W, xv, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E)
-        a = AttnSelfFn.apply(qkv, None, None, B, S, H, False, dra())
+        qkv = _lin(W, xv, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E, pre_scaled=fuse_q)
+        a = AttnSelfFn.apply(qkv, None, None, B, S, H, False, dra(), None, scal if fuse_q else 1.0)
         r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv, dropout=dr())
         xv = _ln(W, p + "norm1", r)
         d1 = dr()                                    # relu' and this dropout's mask are applied by linear2's dX GEMM (bf16 path)
@@ -388,14 +397,14 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
         p = "transformer.decoder.layers.%d." % l
         er = sd.get(p + "self_attn.Er")
         erc = W.table(p + "self_attn.Er") if er is not None else None
-        qkv = _lin(W, xf, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E)
-        a = AttnSelfFn.apply(qkv, er, erc, B, T, H, bool(mask), dra(), er)
+        qkv = _lin(W, xf, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E, pre_scaled=fuse_q)
+        a = AttnSelfFn.apply(qkv, er, erc, B, T, H, bool(mask), dra(), er, scal if fuse_q else 1.0)
         r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xf, dropout=dr())
         xf = _ln(W, p + "norm1", r)
         q = _lin(W, xf, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(0, E), alpha=scal,
-                 alpha_cols=E)
+                 alpha_cols=E, pre_scaled=fuse_q)
         kv = _lin(W, mem, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(E, 3 * E))
-        a = AttnCrossFn.apply(q, kv, B, T, S, H, dra())
+        a = AttnCrossFn.apply(q, kv, B, T, S, H, dra(), scal if fuse_q else 1.0)
         r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf, dropout=dr())
         xf = _ln(W, p + "norm2", r)
         d1 = dr()                                    # relu' and this dropout's mask are applied by linear2's dX GEMM (bf16 path)

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(BNW * 32) attn_bwd_kernel(AttnBwdParams p, int
       const int i = i0 + r0 + r;
       if (i < p.Lq) {
 #pragma unroll
-        for (int c = 0; c < DPL; ++c) stT(p.dq, dt, dqo + (size_t)i * p.dq_sl + lane + 32 * c, dq[r][c] * p.q_scale);
+        for (int c = 0; c < DPL; ++c) stT(p.dq, dt, dqo + (size_t)i * p.dq_sl + lane + 32 * c, dq[r][c] * p.q_scale * (p.dq_scale == 0.f ? 1.f : p.dq_scale));
       }
     }
   }

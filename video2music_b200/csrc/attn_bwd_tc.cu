@@ -324,10 +324,11 @@ __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(
     __syncthreads();                                       // everyone is done with this buffer before the next tile lands in it
   }
   bf16* dQg = static_cast<bf16*>(p.dq) + (long long)b * p.dq_sb + (long long)hq * 64;
+  const float dqs = p.q_scale * (p.dq_scale == 0.f ? 1.f : p.dq_scale);
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
-    if (ilo < p.Lq) *reinterpret_cast<uint32_t*>(dQg + (long long)ilo * p.dq_sl + nt * 8 + 2 * q) = f2_to_bf16x2(dq[nt][0] * p.q_scale, dq[nt][1] * p.q_scale);
-    if (ihi < p.Lq) *reinterpret_cast<uint32_t*>(dQg + (long long)ihi * p.dq_sl + nt * 8 + 2 * q) = f2_to_bf16x2(dq[nt][2] * p.q_scale, dq[nt][3] * p.q_scale);
+    if (ilo < p.Lq) *reinterpret_cast<uint32_t*>(dQg + (long long)ilo * p.dq_sl + nt * 8 + 2 * q) = f2_to_bf16x2(dq[nt][0] * dqs, dq[nt][1] * dqs);
+    if (ihi < p.Lq) *reinterpret_cast<uint32_t*>(dQg + (long long)ihi * p.dq_sl + nt * 8 + 2 * q) = f2_to_bf16x2(dq[nt][2] * dqs, dq[nt][3] * dqs);
   }
 }
 

@@ -50,6 +50,7 @@ struct Args {
   long long dq_sb, dq_sl, dkv_sb, dkv_sl;
   int B, H, Lq, Lk, swap;
   float drop_scale; unsigned int drop_thresh, drop_seed; const unsigned int* drop_seed_dev;
+  float dq_scale;
 };
 
 // delta[bh][i] = sum_d dO[b,i,h,d] * O[b,i,h,d]: eight lanes per (video, position, head) row of 64 dims (one 16-byte load of
@@ -327,13 +328,14 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               const int qi = I * 128 + r;
               if (qi < a.Lq) {
                 bf16* dst = static_cast<bf16*>(a.dq) + (size_t)b * a.dq_sb + (size_t)qi * a.dq_sl + (size_t)h * DH + sub * CW;
+                const float qs = a.dq_scale;
 #pragma unroll
                 for (int g8 = 0; g8 < CW / 8; ++g8) {
                   uint4 v;
-                  v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]), __uint_as_float(o[g8 * 8 + 1]));
-                  v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]), __uint_as_float(o[g8 * 8 + 3]));
-                  v.z = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 4]), __uint_as_float(o[g8 * 8 + 5]));
-                  v.w = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 6]), __uint_as_float(o[g8 * 8 + 7]));
+                  v.x = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 0]) * qs, __uint_as_float(o[g8 * 8 + 1]) * qs);
+                  v.y = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 2]) * qs, __uint_as_float(o[g8 * 8 + 3]) * qs);
+                  v.z = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 4]) * qs, __uint_as_float(o[g8 * 8 + 5]) * qs);
+                  v.w = f2_to_bf16x2(__uint_as_float(o[g8 * 8 + 6]) * qs, __uint_as_float(o[g8 * 8 + 7]) * qs);
                   *reinterpret_cast<uint4*>(dst + g8 * 8) = v;
                 }
               }
@@ -390,6 +392,7 @@ int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStrea
   a.dq_sb = p.dq_sb; a.dq_sl = p.dq_sl; a.dkv_sb = p.dkv_sb; a.dkv_sl = p.dkv_sl;
   a.B = p.B; a.H = p.Hq; a.Lq = p.Lq; a.Lk = p.Lk; a.swap = swap;
   a.drop_scale = p.drop_scale; a.drop_thresh = p.drop_thresh; a.drop_seed = p.drop_seed; a.drop_seed_dev = p.drop_seed_dev;
+  a.dq_scale = p.dq_scale == 0.f ? 1.f : p.dq_scale;
   static bool attr = false;
   static int nw = 2;
   if (!attr) {

@@ -103,6 +103,9 @@ struct AttnBwdParams {
   float drop_scale;                 // the forward's probability dropout (same mask function), 0 = off; tensor-core path only
   unsigned int drop_thresh, drop_seed;
   const unsigned int* drop_seed_dev;   // optional device counter added to drop_seed
+  // dq is stored times dq_scale (0 = 1): the backward of the 1 / sqrt(d) that the query projection's epilogue applied in the forward,
+  // so that the projection's own backward needs no pass that rescales its incoming gradient
+  float dq_scale;
 };
 int attn_bwd(const AttnBwdParams& p, cudaStream_t stream);
 // Tensor-core variant (bf16, head_dim 64, q pre-scaled): p.dk / p.dv are BF16 outputs written once (no accumulation),

@@ -849,7 +849,7 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
 
 
 def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, Lk, dh, q_strides, k_strides, v_strides,
-                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False, dropout=None):
+                  o_strides, do_strides, dq_strides, dkv_strides, causal, q_scale=1.0, tensor_core=False, dropout=None, dq_scale=1.0):
     """tensor_core=True (bf16, head_dim 64): dk / dv are bf16 outputs written once by the mma.sync kernels of
     csrc/attn_bwd_tc.cu; otherwise dk / dv are zeroed fp32 buffers the exact SIMT kernel accumulates into."""
     require_device(q)
@@ -862,6 +862,7 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
     a.er_len = Er.shape[0] if Er is not None else 0
     a.dtype = dtype_code(q.dtype)
     a.q_scale = q_scale
+    a.dq_scale = dq_scale                                        # dq stored times dq_scale (backward of a query scaling applied upstream)
     if dropout is not None and dropout[0] > 0.0:                 # the forward's (p, seed)
         a.drop_scale, a.drop_thresh, a.drop_seed = drop_args(dropout[0], dropout[1])
         a.drop_seed_dev = ptr(DROP_SEED_DEV)
