@@ -61,7 +61,7 @@ class LinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype, dropout=None, owner=None,
-                in_gate_scale=None, pre_gated=False, pre_scaled=False):
+                in_gate_scale=None, pre_gated=False, pre_scaled=False, in_link=None, res_link=None):
         """owner = (weight parameter, bias parameter or None, row slice or None): the parameters `w` / `b` are (views of), for
         direct gradient accumulation (see direct_grad).
         in_gate_scale (bf16 path): x is the output of a relu (+ fused dropout of that scale) LinearFn built with pre_gated=True;
@@ -76,6 +76,12 @@ class LinearFn(torch.autograd.Function):
         # pre_scaled: the consumer (attention backward, dq_scale) already multiplied the gradient of the alpha-scaled columns by alpha
         ctx.pre_scaled = bool(pre_scaled)
         assert not ctx.pre_scaled or (not relu and dropout is None)
+        # Residual link of a sub-layer (bf16 path): its input x feeds the first linear (in_link) and the residual add of the last one
+        # (res_link, the same dict).  The last linear's backward -- which always runs first -- leaves the residual-branch gradient
+        # in the dict instead of returning it, and the first linear's dX GEMM adds it in its epilogue: autograd no longer sums
+        # the two branches with a separate pass over three activation-sized tensors per sub-layer.
+        ctx.in_link = in_link if x.dtype == BF16 else None
+        ctx.res_link = res_link if (x.dtype == BF16 and residual is not None and res_mod == 0 and residual.dtype == BF16) else None
         # drop(acc + residual) is only used for the constant positional-encoding rows (no gradient flows to the residual)
         assert not (dropout is not None and dropout[2] and residual is not None and residual.requires_grad)
         y = ops.linear(x, wc, b, k=K, relu=relu, alpha=alpha, alpha_cols=alpha_cols, residual=residual, res_mod=res_mod,
@@ -106,13 +112,21 @@ class LinearFn(torch.autograd.Function):
             dz, db = ops.dy_prep(dy, y, relu, alpha, alpha_cols, cdt, want_dz=not plain, dropout=ctx.dropout, db_out=gb if direct_b else None)
         if plain:
             dz = dy
+        extra = ctx.in_link.pop("dres", None) if ctx.in_link is not None else None    # residual-branch gradient of this sub-layer
         if not ctx.needs_input_grad[0]:
+            assert extra is None, "a linked residual gradient needs the gradient of the sub-layer input"
             dx = None
+        elif extra is not None and cdt == BF16 and extra.shape == (dz.shape[0], K) and x.shape[1] == K:
+            M_, N_ = dz.shape
+            dx = ops.linear_general(dz, wc, a_mn=False, b_mn=True, M=M_, N=K, K=N_, out_dtype=BF16, residual=extra)
+            extra = None
         elif ctx.in_gate_scale is not None and cdt == BF16:
             M_, N_ = dz.shape
             dx = ops.linear_general(dz, wc, a_mn=False, b_mn=True, M=M_, N=K, K=N_, out_dtype=BF16, gate=x[:, :K], gate_scale=ctx.in_gate_scale)
         else:
             dx = _gemm_dx(dz, wc, K)
+        if extra is not None:                                                # not fusable: plain sum
+            dx = dx + extra.to(dx.dtype)
         if dx is not None and dx.shape[1] != x.shape[1]:                     # x carries zero padding columns
             full = torch.zeros_like(x)
             full[:, :K] = dx
@@ -132,7 +146,10 @@ class LinearFn(torch.autograd.Function):
         if direct_b and bp is not wp:
             grad_ready(bp)
         dres = dy if res_grad else None
-        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None, None, None, None, None
+        if dres is not None and ctx.res_link is not None and ctx.res_link.get("armed"):
+            ctx.res_link["dres"] = dres                                      # picked up by the sub-layer's first linear (see forward)
+            dres = None
+        return dx, dw, (db if has_b else None), None, None, None, None, None, dres, None, None, None, None, None, None, None, None, None
 
 
 class AttnSelfFn(torch.autograd.Function):
@@ -317,7 +334,7 @@ class AmtLossFn(torch.autograd.Function):
 
 # ----------------------------------------------------------------------------------------------- model forward
 def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, residual=None, res_mod=0, rows=None,
-         out_dtype=None, dropout=None, in_gate_scale=None, pre_gated=False, pre_scaled=False):
+         out_dtype=None, dropout=None, in_gate_scale=None, pre_gated=False, pre_scaled=False, in_link=None, res_link=None):
     w = W._sd[wname]
     b = W._sd[bname] if bname is not None else None
     if rows is not None:
@@ -327,7 +344,7 @@ def _lin(W, x, wname, bname, *, K=None, relu=False, alpha=1.0, alpha_cols=0, res
     wc = W.w(wname, rows=rows)
     K = K if K is not None else w.shape[1]
     return LinearFn.apply(x, w_v, b_v, wc, K, relu, alpha, alpha_cols, residual, res_mod, out_dtype or x.dtype, dropout, (w, b, rows),
-                          in_gate_scale, pre_gated, pre_scaled)
+                          in_gate_scale, pre_gated, pre_scaled, in_link, res_link)
 
 
 def _ln(W, name, x):
@@ -366,6 +383,7 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     sd = W._sd
     fuse_gate = dt == BF16                           # ReLU / dropout backward of the FFN fused into the next layer's dX GEMM
     fuse_q = True                                    # backward of the 1 / sqrt(d) of the query columns applied by the attention backward
+    link = (lambda: {"armed": True}) if dt == BF16 else (lambda: None)   # residual links of the sub-layers (see LinearFn.forward)
     # ---- video stream
     vf_dim = sd["Linear_vis.weight"].shape[1]
     vin = ops.concat_features(sem, scene, motion, emotion, dt, vf_dim if dt == F32 else _pad8(vf_dim))
@@ -373,13 +391,15 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
     xv = _lin(W, vin, "Linear_vis.weight", "Linear_vis.bias", K=vf_dim, residual=pe_v, res_mod=S, dropout=dr(True))
     for l in range(NL):
         p = "transformer.encoder.layers.%d." % l
-        qkv = _lin(W, xv, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E, pre_scaled=fuse_q)
+        lk = link()
+        qkv = _lin(W, xv, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E, pre_scaled=fuse_q, in_link=lk)
         a = AttnSelfFn.apply(qkv, None, None, B, S, H, False, dra(), None, scal if fuse_q else 1.0)
-        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv, dropout=dr())
+        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xv, dropout=dr(), res_link=lk)
         xv = _ln(W, p + "norm1", r)
         d1 = dr()                                    # relu' and this dropout's mask are applied by linear2's dX GEMM (bf16 path)
-        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=d1, pre_gated=fuse_gate)
-        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv, dropout=dr(),
+        lk = link()
+        hdn = _lin(W, xv, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=d1, pre_gated=fuse_gate, in_link=lk)
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xv, dropout=dr(), res_link=lk,
                  in_gate_scale=(ops.drop_args(*d1[:2])[0] if d1 is not None else 1.0) if fuse_gate else None)
         xv = _ln(W, p + "norm2", r)
     mem = _ln(W, "transformer.encoder.norm", xv)
@@ -397,19 +417,22 @@ def amt_forward_autograd(model, x, x_root, x_attr, sem, key, scene, motion, emot
         p = "transformer.decoder.layers.%d." % l
         er = sd.get(p + "self_attn.Er")
         erc = W.table(p + "self_attn.Er") if er is not None else None
-        qkv = _lin(W, xf, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E, pre_scaled=fuse_q)
+        lk = link()
+        qkv = _lin(W, xf, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", alpha=scal, alpha_cols=E, pre_scaled=fuse_q, in_link=lk)
         a = AttnSelfFn.apply(qkv, er, erc, B, T, H, bool(mask), dra(), er, scal if fuse_q else 1.0)
-        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xf, dropout=dr())
+        r = _lin(W, a, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", residual=xf, dropout=dr(), res_link=lk)
         xf = _ln(W, p + "norm1", r)
+        lk = link()
         q = _lin(W, xf, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(0, E), alpha=scal,
-                 alpha_cols=E, pre_scaled=fuse_q)
+                 alpha_cols=E, pre_scaled=fuse_q, in_link=lk)
         kv = _lin(W, mem, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", rows=slice(E, 3 * E))
         a = AttnCrossFn.apply(q, kv, B, T, S, H, dra(), scal if fuse_q else 1.0)
-        r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf, dropout=dr())
+        r = _lin(W, a, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", residual=xf, dropout=dr(), res_link=lk)
         xf = _ln(W, p + "norm2", r)
         d1 = dr()                                    # relu' and this dropout's mask are applied by linear2's dX GEMM (bf16 path)
-        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=d1, pre_gated=fuse_gate)
-        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf, dropout=dr(),
+        lk = link()
+        hdn = _lin(W, xf, p + "linear1.weight", p + "linear1.bias", relu=True, dropout=d1, pre_gated=fuse_gate, in_link=lk)
+        r = _lin(W, hdn, p + "linear2.weight", p + "linear2.bias", residual=xf, dropout=dr(), res_link=lk,
                  in_gate_scale=(ops.drop_args(*d1[:2])[0] if d1 is not None else 1.0) if fuse_gate else None)
         xf = _ln(W, p + "norm3", r)
     xf = _ln(W, "transformer.decoder.norm", xf)

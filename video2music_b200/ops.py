@@ -878,7 +878,7 @@ def attention_bwd(q, k, v, o, dO, lse, Er, dq, dk, dv, dEr, *, B, Hq, Hkv, Lq, L
 
 def linear_general(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool, b_mn: bool, M: int, N: int, K: int,
                    out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None, accumulate: bool = False,
-                   gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0) -> torch.Tensor:
+                   gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """bf16 tcgen05 GEMM C[M,N] = A B^T-style with optionally transposed storage: a is [M,K] (or [K,M] when a_mn),
     b is [N,K] (or [K,N] when b_mn), both row-major 2-D bf16 tensors (leading dims from the strides).
     accumulate (fp32 `out` given by the caller): out += A B^T through coalesced vector reductions."""
@@ -891,6 +891,9 @@ def linear_general(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool, b_mn: bool, 
         assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype == out_dtype
     ep = Epilogue()
     ep.accumulate = int(accumulate)
+    if residual is not None:                     # C = acc + residual (bf16): the residual-branch gradient joins the dX GEMM
+        assert gate is None and residual.dtype == torch.bfloat16 and residual.shape == (M, N) and residual.stride(1) == 1 and not accumulate
+        ep.residual, ep.ldr, ep.residual_bf16 = ptr(residual), residual.stride(0), 1
     if gate is not None:                         # C = gate > 0 ? acc * gate_scale : 0 (ReLU / dropout backward fused into the dX GEMM)
         assert gate.dtype == torch.bfloat16 and gate.shape == (M, N) and gate.stride(1) == 1 and not accumulate
         ep.residual, ep.ldr, ep.residual_bf16, ep.residual_gate, ep.gate_scale = ptr(gate), gate.stride(0), 1, 1, float(gate_scale)
