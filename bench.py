@@ -275,6 +275,14 @@ def variants_leg(dev):
     ms = timed(step(reg, reg_fwd))
     out["video_regression_bimamba_plus_train"] = {"ms_per_step": ms, "samples_per_s": 64 / (ms * 1e-3),
                                                   "shape": "6 Bi-Mamba+ layers, 64 videos x 300 s, d_model 128, d_inner 256, d_state 16", "dtype": "f32"}
+    from video2music_b200.mamba import MambaBlock, _FFN
+    for mod in reg.modules():
+        if isinstance(mod, (MambaBlock, _FFN)):
+            mod.compute_dtype = torch.bfloat16                  # in_proj / out_proj / feed-forward on the tcgen05 GEMM
+    ms = timed(step(reg, reg_fwd))
+    out["video_regression_bimamba_plus_train_bf16"] = {"ms_per_step": ms, "samples_per_s": 64 / (ms * 1e-3),
+                                                       "shape": out["video_regression_bimamba_plus_train"]["shape"],
+                                                       "dtype": "bf16 wide projections and feed-forward (tcgen05 GEMMs); conv, scan, x_proj / dt_proj, master weights fp32"}
     del reg
     # config 4 generation: KV-cached, batched greedy decode of the GQA (8 q / 2 kv heads) + MoE (6 experts, top-2) shell
     from video2music_b200 import _lib

@@ -1,5 +1,4 @@
 #!/bin/bash
 cd /root/repo
-timeout 1500 python -m pytest tests/test_gpu_train.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r3j_tests.log
-python tools/train_time.py 512 bf16 3 2>&1 | tail -1 | tee gpurun_out/r3j_train.txt
-python tools/train_time.py 64 bf16 5 2>&1 | tail -1 | tee -a gpurun_out/r3j_train.txt
+timeout 900 python -m pytest tests/test_gpu_variant_train.py -m gpu -q -s -k "bf16_projections" > gpurun_out/r3l_tests_full.log 2>&1
+grep -n "bf16 Mamba projections\|passed\|failed" gpurun_out/r3l_tests_full.log

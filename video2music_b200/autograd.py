@@ -480,12 +480,17 @@ def weight_bf16(lin: torch.nn.Linear) -> torch.Tensor:
     return hit[1]
 
 
-def linear_bf16_fn(x16: torch.Tensor, lin: torch.nn.Linear, *, alpha: float = 1.0, out_dtype=BF16) -> torch.Tensor:
+def linear_bf16_fn(x16: torch.Tensor, lin: torch.nn.Linear, *, alpha: float = 1.0, out_dtype=BF16, relu: bool = False) -> torch.Tensor:
     """nn.Linear on (rows, d) bf16 rows on the tcgen05 GEMM (fp32 master weights and gradients); alpha scales every output column
     (the 1 / sqrt(head_dim) of the query projection)."""
     N = lin.weight.shape[0]
-    return LinearFn.apply(x16, lin.weight, lin.bias, weight_bf16(lin), x16.shape[1], False, alpha, N if alpha != 1.0 else 0, None, 0,
+    return LinearFn.apply(x16, lin.weight, lin.bias, weight_bf16(lin), x16.shape[1], relu, alpha, N if alpha != 1.0 else 0, None, 0,
                           out_dtype, None)
+
+
+def bf16_ok(*lins) -> bool:
+    """Shapes the tcgen05 GEMM takes for forward, dX and dW of these nn.Linear layers (16-byte rows: multiples of 8 both ways)."""
+    return all(l.weight.shape[0] % 8 == 0 and l.weight.shape[1] % 8 == 0 for l in lins)
 
 
 class AddFn(torch.autograd.Function):

@@ -114,9 +114,17 @@ class MambaBlock(nn.Module):
         ED, N, R = cfg.d_inner, cfg.d_state, cfg.dt_rank
         ag = _ag()
         if ag.tracking(x, self):                                   # training: same kernels inside autograd Functions
-            xz = ag.linear_fn(ag.rows_f32(x), self.in_proj)
+            # compute_dtype = bf16: the two wide projections (in_proj, out_proj: ~85 % of the block's GEMM flops) run on the tcgen05
+            # GEMM with bf16 operands; conv, the small x_proj / dt_proj, the scan, master weights and gradients stay fp32
+            tc = getattr(self, "compute_dtype", torch.float32) == torch.bfloat16 and ag.bf16_ok(self.in_proj, self.out_proj)
+            if tc:
+                xz = ag.linear_bf16_fn(ag.rows_f32(x).to(torch.bfloat16), self.in_proj, out_dtype=torch.float32)
+            else:
+                xz = ag.linear_fn(ag.rows_f32(x), self.in_proj)
             y = ag.MambaCoreFn.apply(xz, self.conv1d.weight.reshape(ED, -1), self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
                                      self.dt_proj.bias, self.A_log, self.D, B, L, cfg.use_version == 1)
+            if tc:
+                return ag.linear_bf16_fn(y.to(torch.bfloat16), self.out_proj, out_dtype=torch.float32).view(B, L, D)
             return ag.linear_fn(y, self.out_proj).view(B, L, D)
         x2 = x.reshape(B * L, D).float().contiguous()
         det = lambda p: None if p is None else p.detach()
@@ -190,6 +198,11 @@ class _FFN(nn.Sequential):
         ag = _ag()
         drop = self.training and self[2].p > 0
         if ag.tracking(x, self) or drop:
+            if getattr(self, "compute_dtype", torch.float32) == torch.bfloat16 and ag.bf16_ok(self[0], self[3]):   # tensor-core path
+                h = ag.linear_bf16_fn(ag.rows_f32(x).to(torch.bfloat16), self[0], relu=True, out_dtype=torch.float32 if drop else torch.bfloat16)
+                if drop:                                       # the element-wise dropout op is fp32
+                    h = ag.drop_rows(h, self[2], self.training).to(torch.bfloat16)
+                return ag.linear_bf16_fn(h, self[3], out_dtype=torch.float32).view(shp)
             return ag.linear_fn(ag.drop_rows(ag.linear_fn(ag.rows_f32(x), self[0], relu=True), self[2], self.training), self[3]).view(shp)
         x2 = x.reshape(-1, shp[-1]).float().contiguous()
         h = ops.linear(x2, self[0].weight.detach(), self[0].bias.detach(), relu=True)
