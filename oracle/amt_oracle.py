@@ -718,7 +718,7 @@ def diff_mha_forward(query, key, value, sd: SD, p: str, num_heads: int, cache: O
 def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int, num_heads: int, ff_kind,
                 rope: bool, pos_tables: bool, rms: bool = False, max_seq_video: int = 300, mask: bool = True,
                 rope_dim: Optional[int] = None, diff_enc: bool = False, diff_dec: bool = False, pre_norm: bool = False,
-                gqa_kv_heads: int = 0) -> torch.Tensor:
+                gqa_kv_heads: int = 0, moe_k: int = 2) -> torch.Tensor:
     """Shared body of VideoMusicTransformer_V1.forward / _V2.forward (video_music_transformer.py:141-225, 437-520), eval:
     embeddings + key column -> Linear_chord, video features -> Linear_vis, learned position tables or RoPE inside the
     attention, post-norm wrappers (custom_transformer.py:1220-1292) with feed-forward ff_kind(layer) in {"glu", "moe",
@@ -747,7 +747,7 @@ def zoo_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_laye
         kind = ff_kind(l)
         if kind == "glu":
             return glu_expert(t, sd, p + "ff.")
-        return moe_layer(t, sd, p + "ff.", 6, 2, shared=(kind == "shared"))[0]
+        return moe_layer(t, sd, p + "ff.", 6, moe_k, shared=(kind == "shared"))[0]   # moe_k: the top-k scheduler's k in train() mode
     m = vf
     for l in range(n_layers):
         p = "transformer.encoder.layers.%d." % l
@@ -803,11 +803,13 @@ def zoo_generate_greedy_literal(forward, sem, key, scene, motion, emotion, prime
 
 
 def v2_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,
-               version: str = "2.2", max_seq_video: int = 300, mask: bool = True) -> torch.Tensor:
-    """VideoMusicTransformer_V2 (versions 2.0 / 2.1 / 2.2): three shallow layers (GLUExpert) then SharedMoELayer layers (:399-416)."""
+               version: str = "2.2", max_seq_video: int = 300, mask: bool = True, moe_k: int = 2) -> torch.Tensor:
+    """VideoMusicTransformer_V2 (versions 2.0 / 2.1 / 2.2): three shallow layers (GLUExpert) then SharedMoELayer layers (:399-416).
+    moe_k: experts per token -- 2 in eval mode; in train() mode versions 2.0 / 2.1 take it from their TopKScheduler (moe.py:66-82,
+    232-236: 6 for the first 31 forward calls)."""
     return zoo_forward(sd, x_root, x_attr, sem, key, scene, motion, emotion, n_layers, num_heads,
                        lambda l: "glu" if l < 3 else "shared", rope=version != "2.0", pos_tables=version == "2.0",
-                       max_seq_video=max_seq_video, mask=mask)
+                       max_seq_video=max_seq_video, mask=mask, moe_k=moe_k)
 
 
 def v1_forward(sd: SD, x_root, x_attr, sem, key, scene, motion, emotion, n_layers: int = 6, num_heads: int = 8,

@@ -473,6 +473,43 @@ def golden_v2(ref):
     _save("v2.pt", out)
 
 
+def golden_zoo_train(ref):
+    """One training step (train() mode, dropout 0, torch autograd) of the unmodified reference's model zoo: V2 '2.2' (RoPE + GLU / SharedMoE
+    feed-forwards, the shipped default), V2 '2.0' (position tables, top-k scheduler stepping), V1 '1.1' (MoE everywhere) and V3 '3.1'
+    (differential attention): logits, loss = sum(y * r), every parameter-gradient norm and a few whole gradients."""
+    import third_party.log_maxvio as lm
+    lm.is_logging = False
+    out = {}
+    keep_of = {"2": ("transformer.decoder.layers.0.self_attn.in_proj_bias", "transformer.encoder.layers.3.ff.gate.weight", "Linear_chord.bias",
+                     "embedding_attr.weight", "transformer.decoder.layers.3.ff.shared_expert.linear2.bias", "transformer.decoder.layers.1.norm2.weight"),
+               "1": ("transformer.decoder.layers.1.cross_attn.in_proj_bias", "transformer.encoder.layers.0.ff.gate.weight", "embedding_attr.weight",
+                     "Wout.bias", "transformer.decoder.layers.0.ff.experts.2.linear1.bias"),
+               "3": ("transformer.decoder.layers.1.self_attn.lambda_q1", "transformer.decoder.layers.0.self_attn.subln.weight",
+                     "transformer.decoder.layers.2.self_attn.lambda_k2", "Linear_vis.bias", "transformer.decoder.norm.weight")}
+    for ver, seed, nl in (("2.2", 191, 4), ("2.0", 192, 4), ("1.1", 193, 2), ("3.1", 196, 3)):
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()), reference_cwd():
+            cls = {"2": ref.vmt.VideoMusicTransformer_V2, "1": ref.vmt.VideoMusicTransformer_V1, "3": ref.vmt.VideoMusicTransformer_V3}[ver[0]]
+            m = cls(version_name=ver, n_layers=nl, total_vf_dim=syn.vf_dim(0), dropout=0.0).train()
+        sd = _load_weights(m, seed)
+        B, T, S = 2, 20, 24
+        inp = syn.make_inputs(B, seed, T, S, 0)
+        args = [inp[k] for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                                 "feature_motion", "feature_emotion")]
+        r = syn.unit_uniform((B, T, 159), syn._gen(seed, "r"))
+        with contextlib.redirect_stdout(io.StringIO()):
+            y = m(*args)
+            loss = (y * r).sum()
+            loss.backward()
+        norms = {n: float(p.grad.double().norm()) for n, p in m.named_parameters() if p.grad is not None}
+        keep = [n for n in keep_of[ver[0]] if n in norms]
+        grads = {n: p.grad.clone() for n, p in m.named_parameters() if n in keep}
+        out[ver] = dict(spec=dict(version=ver, seed=seed, n_layers=nl, B=B, T=T, S=S), weights_checksum=syn.checksum(sd), logits=y.detach().clone(),
+                        loss=float(loss.detach()), grad_norms=norms, grads=grads)
+        print(ver, "loss %.6f, %d parameter gradients, kept %s" % (float(loss), len(norms), keep))
+    _save("zoo_train.pt", out)
+
+
 def golden_regression(ref):
     """VideoRegression (video_regression.py:103-245) with the generate-time defaults of BASELINE config 5
     (argument_generate_funcs.py:87-91: n_layers 6, d_model 128, d_hidden 256, total_vf_dim 774), Mamba-family backbones."""
@@ -707,7 +744,7 @@ def main():
     jobs = dict(forward=lambda: golden_forward(ref), train=lambda: golden_train(ref), train_full=lambda: golden_train_full(ref), rpr=lambda: golden_rpr(ref),
                 moe=lambda: golden_moe(ref), gqa=lambda: golden_gqa(ref), pscan=lambda: golden_pscan(ref),
                 mamba=lambda: golden_mamba(ref), mamba_step=lambda: golden_mamba_step(ref), variant=lambda: golden_variant(ref), moe_train=lambda: golden_moe_train(ref),
-                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), rpr_train=lambda: golden_rpr_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
+                variant_train=lambda: golden_variant_train(ref), mamba_train=lambda: golden_mamba_train(ref), rpr_train=lambda: golden_rpr_train(ref), regression_train=lambda: golden_regression_train(ref), metrics=lambda: golden_metrics(ref), zoo_train=lambda: golden_zoo_train(ref), custom_mha=lambda: golden_custom_mha(ref), v2=lambda: golden_v2(ref), regression=lambda: golden_regression(ref),
                 generate=lambda: golden_generate(ref, args.gen_videos),
                 primed=lambda: golden_generate_primed(ref))
     for name, fn in jobs.items():

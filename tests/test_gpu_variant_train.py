@@ -490,3 +490,35 @@ def test_mamba_train_bf16_projections_vs_fp32_path(name):
         name, rel_err(h[0], f[0]), rel_err(h[1], f[1]), ", ".join("%s %.1e" % (n, e) for e, n in errs[:4])))
     # the input gradient of the first positions collects the whole reverse scan: bf16 rounding of the projections is amplified there
     assert rel_err(h[0], f[0]) < 2e-2 and rel_err(h[1], f[1]) < 1e-1 and worst < 2.5e-1
+
+
+@pytest.mark.parametrize("ver", ["2.2", "2.0", "1.1", "3.1"])
+def test_zoo_model_train_step_vs_reference_golden(ver):
+    """One training step of the model zoo (train() mode, dropout 0) against the UNMODIFIED reference's torch autograd
+    (tests/golden/zoo_train.pt): V2 '2.2' (RoPE with the literal reinterpretation + GLU / SharedMoE feed-forwards), V2 '2.0' (position
+    tables, the top-k scheduler stepping), V1 '1.1' (MoE in every layer) and V3 '3.1' (differential attention): logits, loss, every
+    parameter-gradient norm and the stored gradients."""
+    from video2music_b200 import VideoMusicTransformer_V1, VideoMusicTransformer_V2, VideoMusicTransformer_V3
+    g = load_golden("zoo_train.pt")[ver]
+    c = g["spec"]
+    cls = {"2": VideoMusicTransformer_V2, "1": VideoMusicTransformer_V1, "3": VideoMusicTransformer_V3}[ver[0]]
+    m = cls(version_name=ver, n_layers=c["n_layers"], total_vf_dim=syn.vf_dim(0), dropout=0.0).train()
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=c["seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    inp = syn.make_inputs(c["B"], c["seed"], c["T"], c["S"], 0)
+    args = [inp[k].to(DEV) for k in ("x", "x_root", "x_attr", "feature_semantic_list", "feature_key", "feature_scene_offset",
+                                     "feature_motion", "feature_emotion")]
+    r = _u((c["B"], c["T"], 159), c["seed"], "r").to(DEV)
+    y = m(*args)
+    loss = (y * r).sum()
+    loss.backward()
+    assert rel_err(y, g["logits"]) < 2e-4
+    assert abs(float(loss.detach()) - g["loss"]) < 2e-4 * max(abs(g["loss"]), 1.0)
+    grads = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    missing = set(g["grad_norms"]) - set(grads)
+    assert not missing, sorted(missing)[:5]
+    _check_grads(grads, g, 5e-4)
+    for n in set(grads) - set(g["grad_norms"]):              # experts without tokens: None in the reference, exact zeros here
+        assert ".experts." in n and float(grads[n].abs().max()) == 0.0, n

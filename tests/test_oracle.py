@@ -557,3 +557,32 @@ def test_mamba_step_oracle_matches_reference_golden(name):
         assert rel_err(y, g["y_forward"]) < 1e-5                  # step == forward (the reference's own consistency)
     else:
         assert rel_err(g["y"], g["y_forward"]) > 1e-2             # literal: step() ignores the mamba+ gate (mamba.py:430)
+
+
+@pytest.mark.parametrize("ver", ["2.2", "2.0", "1.1", "3.1"])
+def test_zoo_train_oracle_matches_reference_golden(ver):
+    """torch autograd over the oracle's restatement of the model zoo == the reference's own training-step gradients
+    (tests/golden/zoo_train.pt: train() mode, dropout 0): logits, loss, every parameter-gradient norm, the stored gradients."""
+    g = load_golden("zoo_train.pt")[ver]
+    c = g["spec"]
+    from video2music_b200 import VideoMusicTransformer_V1, VideoMusicTransformer_V2, VideoMusicTransformer_V3
+    cls = {"2": VideoMusicTransformer_V2, "1": VideoMusicTransformer_V1, "3": VideoMusicTransformer_V3}[ver[0]]
+    m = cls(version_name=ver, n_layers=c["n_layers"], total_vf_dim=syn.vf_dim(0), dropout=0.0)
+    sd = syn.fill_like_reference_init({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=c["seed"])
+    assert same_checksum(syn.checksum(sd), g["weights_checksum"])
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    inp = syn.make_inputs(c["B"], c["seed"], c["T"], c["S"], 0)
+    a = (leaf, inp["x_root"], inp["x_attr"], inp["feature_semantic_list"], inp["feature_key"], inp["feature_scene_offset"],
+         inp["feature_motion"], inp["feature_emotion"])
+    if ver[0] == "2":
+        y = O.v2_forward(*a, n_layers=c["n_layers"], version=ver, moe_k=6 if ver == "2.0" else 2)   # first scheduler step: k = 6
+    elif ver[0] == "3":
+        y = O.v3_forward(*a, n_layers=c["n_layers"], version=ver)
+    else:
+        y = O.v1_forward(*a, n_layers=c["n_layers"], version=ver)
+    r = syn.unit_uniform((c["B"], c["T"], 159), syn._gen(c["seed"], "r"))
+    loss = (y * r).sum()
+    loss.backward()
+    assert rel_err(y, g["logits"]) < 5e-5 and abs(float(loss) - g["loss"]) < 1e-4 * max(abs(g["loss"]), 1.0)
+    grads = {n: v.grad for n, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad and v.grad is not None}
+    _check_grads(grads, g, 2e-4)

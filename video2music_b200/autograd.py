@@ -550,6 +550,24 @@ class RMSNormFn(torch.autograd.Function):
         return dx, dw, None
 
 
+class RopeQuirkFn(torch.autograd.Function):
+    """RoPE of the V2 / V3 attention with the reference's literal reinterpretation (custom_transformer.py:1044-1053; ops.rope_quirk): a
+    rotation of every (even, odd) pair by a cache entry, so the backward is the same kernel with the sines negated."""
+
+    @staticmethod
+    def forward(ctx, x, cache, B, H):
+        ctx.save_for_backward(cache)
+        ctx.meta = (B, H)
+        return ops.rope_quirk(x.contiguous(), cache, B, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (cache,) = ctx.saved_tensors
+        inv = cache.clone()
+        inv[..., 1].neg_()
+        return ops.rope_quirk(dy.contiguous(), inv, *ctx.meta), None, None, None
+
+
 class DropoutFn(torch.autograd.Function):
     """nn.Dropout in training mode on a (rows, cols) tensor: y = x o mask(seed) * 1/(1-p); the backward applies the same
     stateless mask to the incoming gradient (nothing is stored)."""
@@ -846,3 +864,72 @@ def mha_rpr_autograd(module, query, key, value, need_weights, attn_mask):
     ctxv, p = AttnRowsFn.apply(q, k, v, er, B, L, S, H, causal, (E, B * E), (E, B * E), bool(need_weights), drop)
     out = linear_fn(ctxv, module.out_proj).view(L, B, E)
     return out, (p.view(B, H, L, S).sum(dim=1) / H if need_weights else None)           # rpr.py:419-422
+
+
+def custom_mha_autograd(module, query, key, value, need_weights, attn_mask, average_attn_weights):
+    """CustomMultiheadAttention.forward (custom_transformer.py:51-321 -> custom_multi_head_attention_forward :864-1218) with gradients,
+    fp32: projections (q pre-scaled in the epilogue: the scaling commutes with the rotation), RoPE with the literal reinterpretation,
+    AttnRowsFn, out-projection.  Training of the V1 / V2 model zoo."""
+    from .rpr import is_causal_mask
+    L, B, E = query.shape
+    S = key.shape[0]
+    H, dh = module.num_heads, module.head_dim
+    causal = is_causal_mask(attn_mask, L) if attn_mask is not None else False
+    W, bias = module.in_proj_weight, module.in_proj_bias
+    xq = rows_f32(query)
+    xk = xq if key is query else rows_f32(key)
+    xv = xk if value is key else rows_f32(value)
+
+    def proj(x, lo, alpha=1.0, alpha_cols=0):
+        w = W[lo:lo + E]
+        return LinearFn.apply(x, w, bias[lo:lo + E], w, E, False, alpha, alpha_cols, None, 0, F32, None)
+
+    q = proj(xq, 0, float(dh) ** -0.5, E)
+    k, v = proj(xk, E), proj(xv, 2 * E)
+    if module.RoPE is not None:                                                       # custom_transformer.py:1047-1050
+        cache = module.RoPE.cache
+        q = RopeQuirkFn.apply(q, cache[:L].contiguous(), B, H)
+        k = RopeQuirkFn.apply(k, cache[:S].contiguous(), B, H)
+    drop = (float(module.dropout), ops.next_dropout_seed()) if (module.training and module.dropout > 0) else None
+    ctxv, p = AttnRowsFn.apply(q, k, v, None, B, L, S, H, causal, (E, B * E), (E, B * E), bool(need_weights), drop)
+    out = linear_fn(ctxv, module.out_proj).view(L, B, E)
+    if not need_weights:
+        return out, None
+    wts = p.view(B, H, L, S)
+    return out, (wts.mean(dim=1) if average_attn_weights else wts)
+
+
+def diff_mha_autograd(module, query, key, value, attn_mask):
+    """DifferentialMultiheadAttention.forward (custom_transformer.py:610-832) with gradients, fp32: two attentions over the even / odd
+    half-heads sharing the values (AttnRowsFn on the literal batch-first re-view of the projections), their difference weighted by
+    the differentiable lambda, per-head RMSNorm scaled by (1 - lambda_init), the literal (B, H, L, d) -> (L, B, E) re-view, out-projection."""
+    L, B, E = query.shape
+    S = key.shape[0]
+    H, dh = module.num_heads, module.head_dim
+    if module.training and module.dropout.p > 0:
+        raise NotImplementedError("DifferentialMultiheadAttention trains with dropout 0 (its attention-weight dropout is not built)")
+    xq = rows_f32(query)
+    xk = xq if key is query else rows_f32(key)
+    xv = xk if value is key else rows_f32(value)
+    wq, wk = module.q_proj.weight, module.k_proj.weight
+    q = LinearFn.apply(xq, wq, None, wq, E, False, float(module.scaling), 2 * E, None, 0, F32, None)      # (L*B, 2E), pre-scaled
+    k = linear_fn(xk, module.k_proj)
+    v = linear_fn(xv, module.v_proj)                                                  # (S*B, E)
+    if module.RoPE is not None:
+        q = RopeQuirkFn.apply(q, module.RoPE.cache[:L].contiguous(), B, 2 * H)
+        k = RopeQuirkFn.apply(k, module.RoPE.cache[:S].contiguous(), B, 2 * H)
+    q5, k5 = q.view(B, L, H, 2, dh), k.view(B, S, H, 2, dh)                           # the same memory read batch-first (:786-788)
+    causal = attn_mask is not None
+    outs = []
+    for i in (0, 1):
+        qi = q5[:, :, :, i].contiguous().view(B * L, E)
+        ki = k5[:, :, :, i].contiguous().view(B * S, E)
+        o, _ = AttnRowsFn.apply(qi, ki, v, None, B, L, S, H, causal, (L * E, E), (S * E, E), False, None)
+        outs.append(o)
+    lam = (torch.exp(torch.sum(module.lambda_q1 * module.lambda_k1)) - torch.exp(torch.sum(module.lambda_q2 * module.lambda_k2))
+           + module.lambda_init)                                                      # :811-813, differentiable
+    diff = outs[0] - lam * outs[1]
+    w = module.subln.weight * (1.0 - module.lambda_init)
+    attn = RMSNormFn.apply(diff.view(-1, dh).contiguous(), w.contiguous(), module.subln.eps).view(B, L, H, dh)
+    attn = attn.permute(0, 2, 1, 3).contiguous().view(L * B, E)                       # (B, H, L, d) memory read as (L, B, E) rows (:824)
+    return linear_fn(attn, module.out_proj).view(L, B, E), None

@@ -39,7 +39,8 @@ class RotaryPositionalEmbeddings(nn.Module):
 class CustomMultiheadAttention(nn.Module):
     """Drop-in for custom_transformer.py:51-321 (nn.MultiheadAttention + optional RoPE, the attention of the V2 / V3 model
     zoo): packed in-projection, RoPE on q and k with the reference's literal reinterpretations (:1044-1053), scaled
-    dot-product attention (causal float mask or none), out-projection.  fp32, inference (inputs are detached).
+    dot-product attention (causal float mask or none), out-projection.  fp32; with gradients being tracked the same kernels run
+    inside autograd Functions (autograd.custom_mha_autograd: RoPE backward = the rotation with negated sines).
     Same parameter names (`in_proj_weight`, `in_proj_bias`, `out_proj.weight`, `out_proj.bias`)."""
 
     def __init__(self, embed_dim, num_heads, dropout=0., bias=True, add_bias_kv=False, add_zero_attn=False, kdim=None, vdim=None,
@@ -65,6 +66,9 @@ class CustomMultiheadAttention(nn.Module):
         from .rpr import is_causal_mask
         if key_padding_mask is not None:
             raise NotImplementedError("key_padding_mask is not used by the reference's models")
+        from . import autograd as ag
+        if ag.tracking(query, key, value, self):                                        # training: the same kernels inside autograd Functions
+            return ag.custom_mha_autograd(self, query, key, value, need_weights, attn_mask, average_attn_weights)
         drop = (float(self.dropout), ops.next_dropout_seed()) if (self.training and self.dropout > 0) else None
         L, B, E = query.shape
         S = key.shape[0]
@@ -101,7 +105,8 @@ def lambda_init_fn(depth):
 
 
 class DifferentialMultiheadAttention(nn.Module):
-    """Drop-in for custom_transformer.py:610-832 (Differential Transformer attention of the V3 models), inference.
+    """Drop-in for custom_transformer.py:610-832 (Differential Transformer attention of the V3 models), inference and fp32
+    training (autograd.diff_mha_autograd).
     q, k are projected to 2 * num_heads heads, v to num_heads heads; head pair (2h, 2h+1) gives
         softmax(q_2h k_2h^T) v_h - lambda * softmax(q_2h+1 k_2h+1^T) v_h,
     followed by a per-head RMSNorm (`subln`), the factor (1 - lambda_init) and the bias-free out-projection.
@@ -144,6 +149,9 @@ class DifferentialMultiheadAttention(nn.Module):
                 is_causal=False):
         if key_padding_mask is not None:
             raise NotImplementedError("key_padding_mask is not used by the reference's models")
+        from . import autograd as ag
+        if ag.tracking(query, key, value, self):                          # training: the same kernels inside autograd Functions
+            return ag.diff_mha_autograd(self, query, key, value, attn_mask)
         L, B, E = query.shape
         S = key.shape[0]
         H, dh = self.num_heads, self.head_dim

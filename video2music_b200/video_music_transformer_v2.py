@@ -94,13 +94,33 @@ class VideoMusicTransformer_V2(_ZooModel):
     # ------------------------------------------------------------------ forward (video_music_transformer.py:437-520)
     def forward(self, x, x_root, x_attr, feature_semantic_list, feature_key, feature_scene_offset, feature_motion, feature_emotion,
                 mask=True):
-        if self.training:
-            raise NotImplementedError("the V2 model runs inference only (eval()); training is built for the base AMT")
         dev = self.Wout.weight.device
         x_root, x_attr, sem, key, scene, motion, emotion = (t.to(dev) for t in (x_root, x_attr, feature_semantic_list, feature_key,
                                                                                 feature_scene_offset, feature_motion, feature_emotion))
         B, T = x_root.shape
         S, E = sem.shape[1], self.d_model
+        from . import autograd as ag
+        if ag.tracking(self):
+            # training (fp32): the same kernels inside autograd Functions -- embeddings + key column, Linear_chord / Linear_vis / Wout
+            # through LinearFn, learned position tables, and the attention / feed-forward modules' own training paths
+            if getattr(self, "dropTokenRate", 0.0) != 0.0:
+                raise NotImplementedError("dropTokenRate > 0 (video_music_transformer.py:486-491) is not built")
+            F32 = torch.float32
+            key_rows = key.reshape(B, -1)[:, 0].float().unsqueeze(0).expand(T, B).reshape(-1).contiguous()
+            xin = ag.EmbedKeyFn.apply(x_root.t().reshape(-1).contiguous(), self.embedding_root.weight, x_attr.t().reshape(-1).contiguous(),
+                                      self.embedding_attr.weight, key_rows, F32)                    # (T*B, pad8(E + 1)): [emb | key | 0]
+            wc = self.Linear_chord.weight
+            xf = ag.LinearFn.apply(xin, wc, self.Linear_chord.bias, wc, E + 1, False, 1.0, 0, None, 0, F32, None)
+            tr = lambda t: t.transpose(0, 1).contiguous()
+            vin = ops.concat_features(tr(sem), tr(scene), tr(motion), tr(emotion), F32, self.total_vf_dim)
+            vf = ag.linear_fn(vin, self.Linear_vis)
+            if self._pos_tables:                                                # learned positions (:496-505, :196-201)
+                xf = xf.view(T, B, E) + self.positional_embedding.weight[:T].unsqueeze(1)
+                vf = vf.view(S, B, E) + self.positional_embedding_video.weight[:S].unsqueeze(1)
+            tgt_mask = torch.triu(torch.full((T, T), float("-inf"), device=dev), diagonal=1) if mask is True else None
+            out = self.transformer(src=vf.reshape(S, B, E), tgt=xf.reshape(T, B, E), tgt_mask=tgt_mask)
+            y = ag.linear_fn(out.reshape(T * B, E).contiguous(), self.Wout)
+            return y.view(T, B, CHORD_SIZE).permute(1, 0, 2).contiguous()
         # chords, sequence-first rows (t, b): (emb_root + emb_attr | key) -> Linear_chord; the key column is a rank-1 epilogue term
         xin = ops.embed_sum(x_root.t().reshape(-1), self.embedding_root.weight.detach(), x_attr.t().reshape(-1),
                             self.embedding_attr.weight.detach(), torch.float32)
@@ -164,7 +184,7 @@ class VideoMusicTransformer_V1(_ZooModel):
     """Drop-in for `VideoMusicTransformer_V1` (model/video_music_transformer.py:22-315), versions '1.1' (MoELayer) and '1.3'
     (SharedMoELayer): stock multi-head attention, GLU experts (6, top-2) in every layer of both stacks, learned position tables,
     LayerNorm or RMSNorm (`rms_norm`).  The versions with nn.Sequential SiLU experts or RoPE ('1.0', '1.2.x', '1.3.3', '1.3.4')
-    are not built.  Inference only."""
+    are not built.  Inference and (fp32, autograd over the same kernels) training."""
 
     def __init__(self, version_name='1.1', n_layers=6, num_heads=8, d_model=512, dim_feedforward=1024, dropout=0.1,
                  max_sequence_midi=2048, max_sequence_video=300, max_sequence_chord=300, total_vf_dim=0, rms_norm=False,
@@ -234,7 +254,7 @@ class VideoMusicTransformer_V3(_ZooModel):
     """Drop-in for `VideoMusicTransformer_V3` (model/video_music_transformer.py:611-905), versions '3.0', '3.1', '3.2': RMSNorm,
     a RoPE cache of dimension 2 * d_model, DifferentialMultiheadAttention (depth = layer index) in every decoder layer and --
     for 3.1 / 3.2 -- in the encoder ('3.0' keeps CustomMultiheadAttention there), three GLUExpert layers then SharedMoELayer
-    layers (balancing buffers registered as in the reference), pre-norm wrappers for '3.2'.  Inference only."""
+    layers (balancing buffers registered as in the reference), pre-norm wrappers for '3.2'.  Inference and fp32 training (dropout 0 in the differential attention)."""
 
     def __init__(self, version_name='3.0', n_layers=6, num_heads=8, d_model=512, dim_feedforward=1024, dropout=0.1,
                  max_sequence_midi=2048, max_sequence_video=300, max_sequence_chord=300, total_vf_dim=0, rms_norm=False,
