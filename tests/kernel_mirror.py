@@ -325,3 +325,21 @@ def step_attention(q, K, V, *, Hq, Hkv, dh, n_max, kv_strides, n_dev=None, q_sca
             out[b, h * dh:(h + 1) * dh] = p @ Vh
     return out
 MIRRORS['step_attention'] = step_attention
+
+
+# ---- model zoo training (V1 / V2 / V3): RoPE with the literal reinterpretation, embedding backward
+def rope_quirk(x, cache, B, H):
+    """csrc/elementwise.cu rope_quirk_kernel: the (len*B, E) rows are read as [H][len][B][dh] and the cache [len][E/2][2] as
+    [H][len][dh/2][2]; pair j of element (h', l', b') is rotated by cache entry (h'*len + l')*(dh/2) + j."""
+    E = x.shape[1]
+    length, dh2 = x.shape[0] // B, E // H // 2
+    xp = x.detach().reshape(H, length, B, dh2, 2)
+    cs = cache.reshape(-1, 2)[:H * length * dh2].reshape(H, length, 1, dh2, 2)
+    y = torch.stack([xp[..., 0] * cs[..., 0] - xp[..., 1] * cs[..., 1], xp[..., 1] * cs[..., 0] + xp[..., 0] * cs[..., 1]], -1)
+    return y.reshape(x.shape).contiguous()
+MIRRORS['rope_quirk'] = rope_quirk
+def embed_bwd(idx, d, n_rows_table, D, out=None):
+    dt = torch.zeros((n_rows_table, D)) if out is None else out
+    dt.index_add_(0, idx.reshape(-1), d[:, :D].float())
+    return dt
+MIRRORS['embed_bwd'] = embed_bwd

@@ -53,6 +53,13 @@ def test_rpr_module_and_decoder_gradients_host(mirrored):
     T.test_rpr_decoder_train_golden_gpu("decoder")
 
 
+@pytest.mark.parametrize("ver", ["2.2", "1.1", "3.1"])
+def test_zoo_model_training_host(mirrored, ver):
+    """Host side of the model-zoo training paths (custom / differential attention autograd, RoPE backward, embeddings, position tables)
+    against the unmodified reference's gradients (tests/golden/zoo_train.pt), ops replaced by the CPU mirrors."""
+    T.test_zoo_model_train_step_vs_reference_golden(ver)
+
+
 def test_mirrors_are_not_installed_outside_the_fixture():
     """The product path has no CPU fallback: without the fixture the same call raises."""
     import torch
