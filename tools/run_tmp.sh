@@ -1,5 +1,8 @@
 #!/bin/bash
 cd /root/repo
-timeout 600 python -m pytest tests/test_gpu_amt.py -m gpu -x -q -k "stream" 2>&1 | tail -3 | tee gpurun_out/r3o_tests.log
-timeout 300 python tools/stream_exp.py 64 100 100 2>&1 | tail -1 | tee gpurun_out/r3o_exp.log
-timeout 300 python tools/stream_exp.py 64 250 49 2>&1 | tail -1 | tee -a gpurun_out/r3o_exp.log
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_cached_decode.py -m gpu -x -q -k "step_ or small_batch or correspondence or cached_generate_gqa" > gpurun_out/r3p_memcheck.log 2>&1
+echo "memcheck exit $?" >> gpurun_out/r3p_memcheck.log
+grep -c "Invalid\|out of bounds" gpurun_out/r3p_memcheck.log; tail -6 gpurun_out/r3p_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "step_attention" > gpurun_out/r3p_racecheck.log 2>&1
+echo "racecheck exit $?" >> gpurun_out/r3p_racecheck.log
+tail -4 gpurun_out/r3p_racecheck.log
