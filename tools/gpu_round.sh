@@ -2,10 +2,10 @@
 # scratch script for one gpurun call (overwritten per call): full validation = GPU tests, smoke, bench
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r3e_gpu_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/r3e_gpu_tests.log
-tail -4 gpurun_out/r3e_gpu_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r3e_smoke.log 2>&1
-tail -2 gpurun_out/r3e_smoke.log
-timeout 900 python bench.py > gpurun_out/r3e_bench.json 2> gpurun_out/r3e_bench.err
-echo "bench exit $?"; tail -3 gpurun_out/r3e_bench.err
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r3q_gpu_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/r3q_gpu_tests.log
+tail -4 gpurun_out/r3q_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r3q_smoke.log 2>&1
+tail -2 gpurun_out/r3q_smoke.log
+timeout 900 python bench.py > gpurun_out/r3q_bench.json 2> gpurun_out/r3q_bench.err
+echo "bench exit $?"; tail -3 gpurun_out/r3q_bench.err
