@@ -1,11 +1,12 @@
 #!/bin/bash
-# scratch script for one gpurun call (overwritten per call): full validation = GPU tests, smoke, bench
+# scratch script for one gpurun call (overwritten per call)
 cd /root/repo
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r3q_gpu_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/r3q_gpu_tests.log
-tail -4 gpurun_out/r3q_gpu_tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r3q_smoke.log 2>&1
-tail -2 gpurun_out/r3q_smoke.log
-timeout 900 python bench.py > gpurun_out/r3q_bench.json 2> gpurun_out/r3q_bench.err
-echo "bench exit $?"; tail -3 gpurun_out/r3q_bench.err
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -m gpu -k "pscan or scan" > gpurun_out/r4_pscan_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/r4_pscan_tests.log
+tail -5 gpurun_out/r4_pscan_tests.log
+( timeout 120 python tools/scratch/pscan_ab.py
+  V2M_PSCAN_CPI=32 timeout 120 python tools/scratch/pscan_ab.py
+  V2M_PSCAN_CPI=64 timeout 120 python tools/scratch/pscan_ab.py
+  V2M_PSCAN_CPI=32 V2M_PSCAN_LC=64 timeout 120 python tools/scratch/pscan_ab.py ) > gpurun_out/r4_pscan_ab2.txt 2>&1
+cat gpurun_out/r4_pscan_ab2.txt
