@@ -378,12 +378,12 @@ def kernel_rooflines(dev):
         X = torch.randn(b_, l_, 256, 16, generator=g).to(dev)
         ms = timed(lambda: ops.pscan_fwd(A, X))
         by = 3.0 * 4 * A.numel()
-        out.append({"kernel": "pscan_kernel forward", "shape": "(%d,%d,256,16)" % (b_, l_), "bound": "hbm", "ms": ms, "achieved": by / ms / 1e6,
+        out.append({"kernel": "pscan_tma_kernel forward", "shape": "(%d,%d,256,16)" % (b_, l_), "bound": "hbm", "ms": ms, "achieved": by / ms / 1e6,
                     "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm, "peak_source": hsrc, "note": "12 B per element: read A, X, write H"})
         Hh = ops.pscan_fwd(A, X)
         ms = timed(lambda: ops.pscan_bwd(A, Hh, X))
         by = 5.0 * 4 * A.numel()
-        out.append({"kernel": "pscan_kernel backward", "shape": "(%d,%d,256,16)" % (b_, l_), "bound": "hbm", "ms": ms, "achieved": by / ms / 1e6,
+        out.append({"kernel": "pscan_tma_kernel backward", "shape": "(%d,%d,256,16)" % (b_, l_), "bound": "hbm", "ms": ms, "achieved": by / ms / 1e6,
                     "peak": hbm, "unit": "GB/s", "frac": by / ms / 1e6 / hbm, "peak_source": hsrc,
                     "note": "20 B per element: read gradH, A, H, write gradA, gradX"})
         del A, X, Hh

@@ -8,5 +8,5 @@ tail -5 gpurun_out/r4_pscan_tests.log
 ( timeout 120 python tools/scratch/pscan_ab.py
   V2M_PSCAN_CPI=32 timeout 120 python tools/scratch/pscan_ab.py
   V2M_PSCAN_CPI=64 timeout 120 python tools/scratch/pscan_ab.py
-  V2M_PSCAN_CPI=32 V2M_PSCAN_LC=64 timeout 120 python tools/scratch/pscan_ab.py ) > gpurun_out/r4_pscan_ab2.txt 2>&1
-cat gpurun_out/r4_pscan_ab2.txt
+  V2M_PSCAN_CPI=32 V2M_PSCAN_LC=64 timeout 120 python tools/scratch/pscan_ab.py ) > gpurun_out/r4_pscan_ab3.txt 2>&1
+cat gpurun_out/r4_pscan_ab3.txt

@@ -245,7 +245,7 @@ pscan_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      : "memory");
         tma_store_commit();
         if (q > 0) {                             // the store of chunk q-1 has read its stage: hand it back to the loaders
-          tma_store_wait_read<1>();
+          tma_store_wait_read<1>();              // (waiting for the newest store instead, or freeing the A buffer at `done`, measured slower)
           mbar_arrive(empty + (q - 1) % S);
         }
       }
