@@ -7,6 +7,7 @@
 // mamba_ssm hook (mamba.py:308-317).  Thread <-> (batch, channel); a warp reads 128 contiguous bytes per tensor and step.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace v2m {
 
@@ -76,10 +77,23 @@ __global__ void __launch_bounds__(128) selective_scan_fwd_kernel(const float* __
   }
   const float Dc = Dp[c], db = dt_bias ? dt_bias[c] : 0.f;
   float dsum = 0.f;
-  for (int l = l0; l < l1; ++l) {
+  // the steps are sequential, their inputs are not: the loads of 4 steps are issued together (one memory latency per 4 steps)
+  for (int lg = l0; lg < l1; lg += 4) {
+  float xq[4], dq[4], zq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const long long row = (long long)b * L + min(lg + j, l1 - 1);
+    xq[j] = x[row * ldx + c];
+    dq[j] = delta_raw[row * ldd + c];
+    zq[j] = (PASS == 1 && z) ? z[row * ldz + c] : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int l = lg + j;
+    if (l >= l1) break;
     const long long row = (long long)b * L + l;
-    const float xv = x[row * ldx + c];
-    const float dl = softplus_f(delta_raw[row * ldd + c] + db);
+    const float xv = xq[j];
+    const float dl = softplus_f(dq[j] + db);
     const float dx = dl * xv;
     float Bv[N], Cv[N];                    // the step's B and C rows are the same for every channel: broadcast loads
     if (VEC) {
@@ -109,13 +123,14 @@ __global__ void __launch_bounds__(128) selective_scan_fwd_kernel(const float* __
       y = fmaf(Dc, xv, y);
       float o = y;
       if (z) {
-        const float zv = z[row * ldz + c];
+        const float zv = zq[j];
         const float sg = 1.f / (1.f + expf(-zv));
         o = y * (zv * sg);
         if (plus) o = fmaf(xv, 1.f - 1.f / (1.f + expf(-(zv * sg))), o);     // x * (1 - sigmoid(silu(z)))
       }
       out[row * ldo + c] = o;
     }
+  }
   }
   if (PASS == 0) {
     float* w = ws + ((long long)b * (n_chunks - 1) + ch) * (N + 1) * ED + c;
@@ -221,17 +236,30 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
   const float Dc = Dp[cc], db = dt_bias ? dt_bias[cc] : 0.f;
   if (PASS == 0) {
     float dsum = 0.f;
-    for (int l = l1 - 1; l >= l0; --l) {
-      const long long row = (long long)b * L + l;
-      const float dl = softplus_f(delta_raw[row * ldd + cc] + db);
-      float dy = dout[row * ldo + cc];
-      if (z) {
-        const float zv = z[row * ldz + cc];
-        dy *= zv / (1.f + expf(-zv));
-      }
-      dsum += dl;
+    for (int lg = l1 - 1; lg >= l0; lg -= 4) {                         // loads of 4 steps issued together
+      float dq[4], gq[4], zq[4];
 #pragma unroll
-      for (int n = 0; n < N; ++n) gh[n] = fmaf(dy, __ldg(Cm + row * ldbc + n), gh[n]) * ex2_approx(dl * A2[n]);
+      for (int j = 0; j < 4; ++j) {
+        const long long row = (long long)b * L + max(lg - j, l0);
+        dq[j] = delta_raw[row * ldd + cc];
+        gq[j] = dout[row * ldo + cc];
+        zq[j] = z ? z[row * ldz + cc] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int l = lg - j;
+        if (l < l0) break;
+        const long long row = (long long)b * L + l;
+        const float dl = softplus_f(dq[j] + db);
+        float dy = gq[j];
+        if (z) {
+          const float zv = zq[j];
+          dy *= zv / (1.f + expf(-zv));
+        }
+        dsum += dl;
+#pragma unroll
+        for (int n = 0; n < N; ++n) gh[n] = fmaf(dy, __ldg(Cm + row * ldbc + n), gh[n]) * ex2_approx(dl * A2[n]);
+      }
     }
     if (act) {
       float* w = wsg + ((long long)b * (n_chunks - 1) + (ch - 1)) * (N + 1) * ED + c;
@@ -331,6 +359,185 @@ __global__ void __launch_bounds__(128) selective_scan_bwd_kernel(const float* __
   }
 }
 
+// bwd pass 1, second version (the one that runs; the kernel above with PASS == 1 is kept for A/B runs, V2M_SCAN_BWD_OLD=1):
+// thread = (channel, STATE), CTA = 16 channels x 16 states of one (video, chunk).  One state per thread means the whole history of
+// the chunk (64 values) fits in REGISTERS: the recomputed states never go to memory (the first version wrote and re-read
+// 2 x 64 B per (token, channel) through HBM and waited for a dependent global load in every step of both sweeps).  Everything a
+// step needs that depends on (step, channel) only -- delta = softplus(.), x, dy = g silu(z), softplus', the z / "mamba+" terms -- is
+// computed ONCE per (step, channel) by the staging phase (not once per state) and parked in shared memory together with the
+// chunk's B | C rows, so the two sweeps touch shared memory and registers only.  Sums over the states (d delta, dx, y) are
+// 16-lane butterflies; dB / dC (sums over channels) are folded over the warp's two channels by one shuffle, over the CTA's 16
+// channels by shared-memory reductions, and leave as one global reduction per (step, state) and CTA.
+template <int N>
+__global__ void __launch_bounds__(256, 2) selective_scan_bwd_state_kernel(
+    const float* __restrict__ x, long long ldx, const float* __restrict__ delta_raw, long long ldd, const float* __restrict__ dt_bias,
+    const float* __restrict__ A_log, const float* __restrict__ Bm, const float* __restrict__ Cm, long long ldbc,
+    const float* __restrict__ Dp, const float* __restrict__ z, long long ldz, const float* __restrict__ dout, long long ldo,
+    const float* __restrict__ wsf, const float* __restrict__ wsg, float* __restrict__ dx, long long lddx, float* __restrict__ ddraw,
+    long long lddd, float* __restrict__ dBm, float* __restrict__ dCm, long long lddbc, float* __restrict__ dz, long long lddz,
+    float* __restrict__ dA_log, float* __restrict__ dD, float* __restrict__ ddt_bias, int L, int ED, int n_chunks, int plus) {
+  static_assert(N == 16, "lane = 16 x (channel & 1) + state");
+  constexpr int CH = kScanChunk, CC = 16;                            // steps per chunk, channels per CTA
+  // [array][step][channel | state].  The three per-(step, channel) outputs have the form  out = M * (sum over the states) + Q  with
+  // M and Q known at staging time:  d delta_raw = softplus' * sum,   dx = 1 * sum + dx0,   dz = gz * sum_y + (gz D x + dz0);
+  // the lane that ends up with the sum (states 0 / 4 / 8 of the channel) applies its (M, Q) pair and parks the result over M.
+  __shared__ __align__(16) float sm[11][CH][CC];
+  float (*sB)[CC] = sm[0], (*sC)[CC] = sm[1], (*s_dl)[CC] = sm[2], (*s_x)[CC] = sm[3], (*s_dy)[CC] = sm[4];
+  float (*sM)[CH][CC] = &sm[5], (*sQ)[CH][CC] = &sm[8];              // role 0: d delta_raw, 1: dx, 2: dz
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = tid & 15, cl = tid >> 4, ch = blockIdx.y, b = blockIdx.z;
+  const int c = blockIdx.x * CC + cl;
+  const bool act = c < ED;
+  const int cc = act ? c : ED - 1;
+  const int l0 = ch * CH, len = min(L, l0 + CH) - l0;
+  // ---- staging: one (step, channel) element per thread and round (all loads first); B | C rows
+  {
+    const int scl = tid & 15, sc = blockIdx.x * CC + scl;
+    const bool sact = sc < ED;
+    const float Dc = sact ? Dp[sc] : 0.f, db = (dt_bias && sact) ? dt_bias[sc] : 0.f;
+    float vx[CH / 16], vr[CH / 16], vg[CH / 16], vz[CH / 16];
+#pragma unroll
+    for (int k = 0; k < CH / 16; ++k) {
+      const int li = (tid >> 4) + 16 * k;
+      const bool ok = li < len && sact;
+      const long long row = (long long)b * L + l0 + (ok ? li : 0);
+      const int scc = sact ? sc : 0;
+      vx[k] = ok ? x[row * ldx + scc] : 0.f;
+      vr[k] = ok ? delta_raw[row * ldd + scc] : 0.f;
+      vg[k] = ok ? dout[row * ldo + scc] : 0.f;
+      vz[k] = (ok && z) ? z[row * ldz + scc] : 0.f;
+    }
+    for (int i = tid; i < CH * N; i += 256) {
+      const int li = i / N, v = i % N;
+      const long long row = (long long)b * L + l0 + li;
+      sB[li][v] = li < len ? Bm[row * ldbc + v] : 0.f;
+      sC[li][v] = li < len ? Cm[row * ldbc + v] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < CH / 16; ++k) {
+      const int li = (tid >> 4) + 16 * k;
+      float dl = 0.f, xv = 0.f, dy = 0.f, spd = 0.f, gz = 0.f, dx0 = 0.f, dz0 = 0.f;
+      if (li < len && sact) {
+        xv = vx[k];
+        const float raw = vr[k] + db;
+        dl = softplus_f(raw);
+        spd = raw > 20.f ? 1.f : 1.f / (1.f + expf(-raw));
+        const float g = vg[k];
+        dy = g;
+        if (z) {
+          const float zv = vz[k];
+          const float sg = 1.f / (1.f + expf(-zv));
+          const float sl = zv * sg, dsl = sg * (1.f + zv * (1.f - sg));
+          dy = g * sl;
+          gz = g * dsl;
+          if (plus) {
+            const float s2 = 1.f / (1.f + expf(-sl));
+            dx0 = g * (1.f - s2);
+            dz0 = -g * xv * s2 * (1.f - s2) * dsl;
+          }
+        }
+        dx0 = fmaf(dy, Dc, dx0);
+      }
+      s_dl[li][scl] = dl; s_x[li][scl] = xv; s_dy[li][scl] = dy;
+      sM[0][li][scl] = spd; sQ[0][li][scl] = 0.f;
+      sM[1][li][scl] = 1.f; sQ[1][li][scl] = dx0;
+      sM[2][li][scl] = gz;  sQ[2][li][scl] = fmaf(gz, Dc * xv, dz0);
+    }
+  }
+  const float A = -expf(A_log[(long long)cc * N + n]), A2 = A * 1.4426950408889634f;
+  const float h0 = (ch > 0) ? wsf[(((long long)b * (n_chunks - 1) + (ch - 1)) * (N + 1) + n) * ED + cc] : 0.f;
+  float gh = (ch < n_chunks - 1) ? wsg[(((long long)b * (n_chunks - 1) + ch) * (N + 1) + n) * ED + cc] : 0.f;
+  if (!act) gh = 0.f;
+  __syncthreads();
+  // ---- sweep 1: the states of the chunk, kept in registers
+  float hist[CH];
+  {
+    float h = h0;
+#pragma unroll
+    for (int l = 0; l < CH; ++l) {
+      const float dl = s_dl[l][cl];
+      h = fmaf(ex2_approx(dl * A2), h, dl * s_x[l][cl] * sB[l][n]);   // steps past the chunk's end: dl = 0, x = 0 -> h unchanged
+      hist[l] = h;
+    }
+  }
+  // ---- sweep 2: last step first.  s_acc[warp][l][lane]: this warp's two-channel sum of dB_n (lanes 0..15) | dC_n (lanes 16..31)
+  // of step l (shared memory: 64 more live registers per thread would halve the occupancy)
+  extern __shared__ float s_acc[];                                   // [8 warps][CH steps][32 lanes]
+  float* my_acc = s_acc + (size_t)warp * CH * 32 + lane;
+  float gA = 0.f, gD = 0.f, gdb = 0.f;
+  const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, up = (lane & 16) != 0;
+  const int role = n >> 2;                                           // lanes with state 0 / 4 / 8 end up with the three sums
+  const bool writer = (n & 3) == 0 && n < 12;
+  float* pM = &sM[writer ? role : 0][0][cl];
+  const float* pQ = &sQ[writer ? role : 0][0][cl];
+#pragma unroll
+  for (int l = CH - 1; l >= 0; --l) {
+    if (l < len) {                                                   // uniform over the CTA
+      if ((l & 7) == 7) asm volatile("" ::: "memory");              // keeps the unrolled steps from being interleaved too far (registers)
+      const float dl = s_dl[l][cl], xv = s_x[l][cl], dy = s_dy[l][cl];
+      const float Bv = sB[l][n], Cv = sC[l][n];
+      const float hl = hist[l], hp = l > 0 ? hist[l > 0 ? l - 1 : 0] : h0;
+      const float a = ex2_approx(dl * A2);
+      gh = fmaf(dy, Cv, gh);
+      const float t = gh * hp;
+      const float p_ddl = fmaf(t, A * a, gh * Bv * xv);
+      gA = fmaf(t, dl * a, gA);
+      const float p_dx = gh * dl * Bv;
+      const float p_y = hl * Cv;
+      const float dBc = gh * dl * xv, dCc = dy * hl;
+      gh *= a;
+      gD = fmaf(dy, xv, gD);
+      // sums over the 16 states of a channel as a transpose-reduce: 5 shuffles for the three sums (instead of 12); they end in
+      // the lanes with state bits (b3, b2) = (0, 0): d delta, (0, 1): dx, (1, x): y
+      const float g0 = __shfl_xor_sync(0xffffffffu, b3 ? p_ddl : p_y, 8);
+      const float g1 = __shfl_xor_sync(0xffffffffu, p_dx, 8);
+      const float k0 = (b3 ? p_y : p_ddl) + g0;                      // b3: y          else: d delta
+      const float k1 = p_dx + g1;                                    //                else: dx
+      float r = (b3 ? k0 : (b2 ? k1 : k0)) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : (b2 ? k0 : k1), 4);
+      r += __shfl_xor_sync(0xffffffffu, r, 2);
+      r += __shfl_xor_sync(0xffffffffu, r, 1);
+      // dB | dC over the two channels of the warp: one exchange, lanes 0..15 keep dB, lanes 16..31 keep dC
+      my_acc[l * 32] = (up ? dCc : dBc) + __shfl_xor_sync(0xffffffffu, up ? dBc : dCc, 16);
+      if (writer) {
+        const float o = fmaf(pM[l * CC], r, pQ[l * CC]);
+        gdb += o;                                                    // meaningful in the role-0 lane only
+        pM[l * CC] = o;                                              // outputs parked in place, written coalesced below
+      }
+    }
+  }
+  if (act) {
+    atomicAdd(dA_log + (long long)c * N + n, gA * A);
+    if (n == 0) {
+      atomicAdd(dD + c, gD);
+      if (ddt_bias) atomicAdd(ddt_bias + c, gdb);
+    }
+  }
+  __syncthreads();
+  {
+    const int scl = tid & 15, sc = blockIdx.x * CC + scl;
+    if (sc < ED) {
+#pragma unroll
+      for (int k = 0; k < CH / 16; ++k) {
+        const int li = (tid >> 4) + 16 * k;
+        if (li < len) {
+          const long long row = (long long)b * L + l0 + li;
+          ddraw[row * lddd + sc] = sM[0][li][scl];
+          dx[row * lddx + sc] = sM[1][li][scl];
+          if (dz) dz[row * lddz + sc] = sM[2][li][scl];
+        }
+      }
+    }
+  }
+  // ---- dB | dC over the CTA's 16 channels (8 warps), then one global reduction per (step, state) and CTA
+  for (int i = tid; i < len * 32; i += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_acc[(size_t)w * CH * 32 + i];
+    const int li = i >> 5, v = i & 31;
+    const long long row = (long long)b * L + l0 + li;
+    atomicAdd(v < N ? dBm + row * lddbc + v : dCm + row * lddbc + (v - N), s);
+  }
+}
+
 // G[ch-1] = exp(A_n sum_delta[ch]) G[ch] + local[ch] for ch = n_chunks-1 .. 1, in place (entry ch-1 of wsg), G[n_chunks-1] = 0
 template <int N>
 __global__ void __launch_bounds__(128) selective_scan_bwd_carry_kernel(const float* __restrict__ A_log, float* __restrict__ wsg, int ED,
@@ -367,18 +574,40 @@ int selective_scan_bwd(const float* x, long long ldx, const float* delta_raw, lo
   float* Hs = hs + 2 * ws_floats;          // all states
   const int gx = (ED + 127) / 128;
   if (n_chunks > 1) {
-    selective_scan_fwd_kernel<16, 0, false><<<dim3(gx, n_chunks - 1, B), 128, 0, stream>>>(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm,
-                                                                                           ldbc, Dp, z, ldz, nullptr, 0, wsf, L, ED,
-                                                                                           n_chunks, plus);
+    const bool vec = ldbc % 4 == 0 && reinterpret_cast<uintptr_t>(Bm) % 16 == 0 && reinterpret_cast<uintptr_t>(Cm) % 16 == 0;
+    if (vec)
+      selective_scan_fwd_kernel<16, 0, true><<<dim3(gx, n_chunks - 1, B), 128, 0, stream>>>(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm,
+                                                                                            ldbc, Dp, z, ldz, nullptr, 0, wsf, L, ED,
+                                                                                            n_chunks, plus);
+    else
+      selective_scan_fwd_kernel<16, 0, false><<<dim3(gx, n_chunks - 1, B), 128, 0, stream>>>(x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm,
+                                                                                             ldbc, Dp, z, ldz, nullptr, 0, wsf, L, ED,
+                                                                                             n_chunks, plus);
     selective_scan_carry_kernel<16><<<dim3(gx, 16, B), 128, 0, stream>>>(A_log, wsf, ED, n_chunks);
     selective_scan_bwd_kernel<16, 0><<<dim3(gx, n_chunks - 1, B), 128, 0, stream>>>(
         x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z, ldz, dout, ldo, wsf, wsg, Hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc,
         dz, lddz, dA_log, dD, ddt_bias, L, ED, n_chunks, plus);
     selective_scan_bwd_carry_kernel<16><<<dim3(gx, 16, B), 128, 0, stream>>>(A_log, wsg, ED, n_chunks);
   }
-  selective_scan_bwd_kernel<16, 1><<<dim3(gx, n_chunks, B), 128, 0, stream>>>(
-      x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z, ldz, dout, ldo, wsf, wsg, Hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc, dz,
-      lddz, dA_log, dD, ddt_bias, L, ED, n_chunks, plus);
+  static int use_old = -1;
+  if (use_old < 0) { const char* e = getenv("V2M_SCAN_BWD_OLD"); use_old = (e && atoi(e) == 1) ? 1 : 0; }
+  if (use_old)
+    selective_scan_bwd_kernel<16, 1><<<dim3(gx, n_chunks, B), 128, 0, stream>>>(
+        x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z, ldz, dout, ldo, wsf, wsg, Hs, dx, lddx, ddraw, lddd, dBm, dCm, lddbc, dz,
+        lddz, dA_log, dD, ddt_bias, L, ED, n_chunks, plus);
+  {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(selective_scan_bwd_state_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           8 * kScanChunk * 32 * 4);
+      if (e != cudaSuccess) { set_last_error("selective_scan_bwd: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
+      attr = true;
+    }
+  }
+  if (!use_old)
+    selective_scan_bwd_state_kernel<16><<<dim3((ED + 15) / 16, n_chunks, B), 256, 8 * kScanChunk * 32 * 4, stream>>>(
+        x, ldx, delta_raw, ldd, dt_bias, A_log, Bm, Cm, ldbc, Dp, z, ldz, dout, ldo, wsf, wsg, dx, lddx, ddraw, lddd, dBm, dCm, lddbc, dz,
+        lddz, dA_log, dD, ddt_bias, L, ED, n_chunks, plus);
   return check_launch("selective_scan_bwd");
 }
 
