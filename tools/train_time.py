@@ -12,7 +12,7 @@ m = VideoMusicTransformer(total_vf_dim=syn.vf_dim(0), rpr=True, dropout=0.0)
 shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
 m.load_state_dict(syn.fill_like_reference_init(shapes, seed=1), strict=False)
 m = m.to(dev).train().set_compute_dtype(dt)
-tr = Trainer(m)
+tr = Trainer(m, use_graph=os.environ.get("V2M_TRAIN_GRAPH") == "1")
 inp = syn.make_inputs(B, 1234, 299, 300, 0)
 b = {k: v.to(dev) for k, v in inp.items()}
 for _ in range(3):

@@ -125,6 +125,8 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  grid_dep_launch();
+  grid_dep_wait();                                             // the prologue above overlapped the previous kernel's tail
   // P goes where QE was (free once the quadrant's warps have left pass A) and O over the first S columns (all read by the
   // time P is complete): with several warps per quadrant P chunk c would otherwise overwrite S chunk c/2 of another warp.
   const uint32_t T_S = tmem, T_QE = tmem + AT_MAXK, T_O = tmem, T_P = tmem + AT_MAXK;
@@ -447,7 +449,7 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
   }
   const int grid = a.n_items < num_sms ? a.n_items : num_sms;
   const bool drop = a.drop_scale != 0.f;
-#define V2M_GO(NW, ER, DR) attn_bf16_tc_kernel<NW, ER, DR><<<grid, at_threads(NW), at_smem(NW, ER), stream>>>(tmQ, tmK, tmV, tmE, a)
+#define V2M_GO(NW, ER, DR) launch_dep(attn_bf16_tc_kernel<NW, ER, DR>, dim3(grid), dim3(at_threads(NW)), at_smem(NW, ER), stream, tmQ, tmK, tmV, tmE, a)
   if (a.has_er) { if (drop) V2M_GO(2, true, true); else V2M_GO(2, true, false); }
   else if (nw_plain == 4) { if (drop) V2M_GO(4, false, true); else V2M_GO(4, false, false); }
   else { if (drop) V2M_GO(2, false, true); else V2M_GO(2, false, false); }

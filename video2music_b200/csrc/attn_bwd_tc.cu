@@ -120,6 +120,8 @@ constexpr int WBUF = 16 * QB * 4;      // per-warp scratch bytes: QE band (fp32)
 
 template <bool HAS_ER, bool DROP>
 __global__ void __launch_bounds__(THREADS, HAS_ER ? 2 : 3) attn_bwd_rows_kernel(AttnBwdParams p, Ws ws) {
+  v2m::grid_dep_launch();
+  v2m::grid_dep_wait();
   extern __shared__ __align__(16) unsigned char abt_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(abt_smem);
   bf16* sdO = sQ + TILE;
@@ -343,6 +345,8 @@ __device__ __forceinline__ void frag_a_transposed(const bf16* t, int c0, int lan
 
 // ------------------------------------------------------------------------------------------------ cols kernel
 __global__ void __launch_bounds__(THREADS) attn_bwd_cols_kernel(AttnBwdParams p, Ws ws) {
+  v2m::grid_dep_launch();
+  v2m::grid_dep_wait();
   extern __shared__ __align__(16) unsigned char abt_smem[];
   bf16* sP = reinterpret_cast<bf16*>(abt_smem);         // two stages of [P | dS | dO | Q] tiles
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -404,6 +408,8 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_cols_kernel(AttnBwdParams p,
 // ([64 rows][128 columns], pitch TP2) and the A operand A[m = d][k = i] = T[i][i - d + 64] is gathered with 16-bit loads.
 constexpr int TP2 = 136;
 __global__ void __launch_bounds__(THREADS) attn_bwd_der_kernel(AttnBwdParams p, Ws ws, int n_split) {
+  v2m::grid_dep_launch();
+  v2m::grid_dep_wait();
   extern __shared__ __align__(16) unsigned char abt_smem[];
   constexpr int STAGE = 64 * TP2 + TILE;                  // elements: [dS pair | Q tile]
   bf16* sE = reinterpret_cast<bf16*>(abt_smem);           // two stages
@@ -518,21 +524,21 @@ int attn_bwd_tc(const AttnBwdParams& p, void* ws_ptr, long long ws_bytes, cudaSt
   dim3 grid_r(ws.Lqp / 64, p.B * p.Hq);
   const bool drop = p.drop_scale != 0.f;
   if (has_er) {
-    if (drop) abt::attn_bwd_rows_kernel<true, true><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
-    else abt::attn_bwd_rows_kernel<true, false><<<grid_r, abt::THREADS, smem_er, stream>>>(p, ws);
+    if (drop) launch_dep(abt::attn_bwd_rows_kernel<true, true>, grid_r, dim3(abt::THREADS), smem_er, stream, p, ws);
+    else launch_dep(abt::attn_bwd_rows_kernel<true, false>, grid_r, dim3(abt::THREADS), smem_er, stream, p, ws);
   } else {
-    if (drop) abt::attn_bwd_rows_kernel<false, true><<<grid_r, abt::THREADS, smem_plain, stream>>>(p, ws);
-    else abt::attn_bwd_rows_kernel<false, false><<<grid_r, abt::THREADS, smem_plain, stream>>>(p, ws);
+    if (drop) launch_dep(abt::attn_bwd_rows_kernel<false, true>, grid_r, dim3(abt::THREADS), smem_plain, stream, p, ws);
+    else launch_dep(abt::attn_bwd_rows_kernel<false, false>, grid_r, dim3(abt::THREADS), smem_plain, stream, p, ws);
   }
   int rc = check_launch("attn_bwd_rows");
   if (rc) return rc;
   dim3 grid_c(ws.Lkp / 64, p.B * p.Hkv);
-  abt::attn_bwd_cols_kernel<<<grid_c, abt::THREADS, 2 * tiles4, stream>>>(p, ws);
+  launch_dep(abt::attn_bwd_cols_kernel, grid_c, dim3(abt::THREADS), 2 * tiles4, stream, p, ws);
   rc = check_launch("attn_bwd_cols");
   if (rc || !has_er) return rc;
   const int n_split = p.B * p.Hq < 148 ? p.B * p.Hq : 148;
   dim3 grid_e(ws.Lkp / 64, n_split);
-  abt::attn_bwd_der_kernel<<<grid_e, abt::THREADS, smem_der, stream>>>(p, ws, n_split);
+  launch_dep(abt::attn_bwd_der_kernel, grid_e, dim3(abt::THREADS), smem_der, stream, p, ws, n_split);
   return check_launch("attn_bwd_der");
 }
 

@@ -58,6 +58,8 @@ struct Args {
 // bytes of O and of dO.
 __global__ void __launch_bounds__(256) delta_kernel(const bf16* __restrict__ o, long long o_sb, long long o_sl, const bf16* __restrict__ dO,
                                                     long long do_sb, long long do_sl, float* __restrict__ delta, int B, int H, int Lq) {
+  grid_dep_launch();
+  grid_dep_wait();
   const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;        // (b, i, h) with h fastest
   const int sub = threadIdx.x & 7;
   const bool ok = grp < (long long)B * H * Lq;
@@ -129,6 +131,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  grid_dep_launch();
+  grid_dep_wait();                                             // the prologue above overlapped the previous kernel's tail
   const uint32_t T_S = tmem, T_DP = tmem + 64, T_DV = tmem + 128, T_DK = tmem + 192, T_DQ = tmem + 256;
 
   auto tma3 = [&](void* dst, const CUtensorMap* tm, int col, int row, int batch, uint64_t* bar) {
@@ -374,8 +378,8 @@ int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStrea
   V2M_REQUIRE(ws && ws_bytes >= attn_bwd_tc5_workspace(p.B, p.Hq, p.Lq), "attn_bwd_tc5: workspace too small");
   float* delta = static_cast<float*>(ws);
   const long long rows = (long long)p.B * p.Hq * p.Lq;
-  ab5::delta_kernel<<<(unsigned)((rows * 8 + 255) / 256), 256, 0, stream>>>(static_cast<const bf16*>(p.o), p.o_sb, p.o_sl,
-                                                                          static_cast<const bf16*>(p.dO), p.do_sb, p.do_sl, delta, p.B, p.Hq, p.Lq);
+  launch_dep(ab5::delta_kernel, dim3((unsigned)((rows * 8 + 255) / 256)), dim3(256), 0, stream, static_cast<const bf16*>(p.o), p.o_sb, p.o_sl,
+             static_cast<const bf16*>(p.dO), p.do_sb, p.do_sl, delta, p.B, p.Hq, p.Lq);
   int rc = check_launch("attn_bwd_tc5 delta");
   if (rc) return rc;
   CUtensorMap tmQ, tmK, tmV, tmDO;
@@ -413,7 +417,7 @@ int attn_bwd_tc5(const AttnBwdParams& p, void* ws, long long ws_bytes, cudaStrea
   const int items = p.B * p.Hq;
   const int grid = items < num_sms ? items : num_sms;
   const bool drop = a.drop_scale != 0.f;
-#define V2M_GO(DR, NW_) ab5::attn_bwd_tc5_kernel<DR, NW_><<<grid, ab5::threads(NW_), ab5::SMEM, stream>>>(tmQ, tmK, tmV, tmDO, a)
+#define V2M_GO(DR, NW_) launch_dep(ab5::attn_bwd_tc5_kernel<DR, NW_>, dim3(grid), dim3(ab5::threads(NW_)), ab5::SMEM, stream, tmQ, tmK, tmV, tmDO, a)
   if (nw == 4) { if (drop) V2M_GO(true, 4); else V2M_GO(false, 4); }
   else { if (drop) V2M_GO(true, 2); else V2M_GO(false, 2); }
 #undef V2M_GO

@@ -4,6 +4,7 @@
 #include "../../include/v2m_b200.h"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace v2m {
 
@@ -14,6 +15,12 @@ void set_last_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool dep_launch_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("V2M_PDL"); on = (e && e[0] == '1') ? 1 : 0; }   // opt-in: see the note in common.cuh
+  return on != 0;
 }
 
 int check_launch(const char* what) {

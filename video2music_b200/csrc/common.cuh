@@ -34,6 +34,33 @@ int check_launch(const char* what);
     }                                                  \
   } while (0)
 
+// ---- programmatic dependent launch (training / forward chain) ---------------------------------
+// A kernel launched through launch_dep() may be scheduled while its predecessor in the stream is still draining: its CTAs start
+// on SMs the predecessor has left, run their prologue (barrier init, TMEM allocation, descriptor prefetch) and block in
+// grid_dep_wait() until the predecessor has completed and flushed -- launch latency and the predecessor's tail are hidden.
+// Rules: grid_dep_wait() precedes EVERY global-memory access except kernel parameters; grid_dep_launch() (early trigger) may be
+// called at the very top because dependents guard themselves.  Without the launch attribute both are no-ops.
+// Measured on the training step (profiles/r02_train_pdl_ab.txt): eager launches 13.58 -> 13.15 ms at 64 videos (launch gaps
+// hidden), but NO gain when the step is replayed from a CUDA graph (12.5 ms either way; 77.0 vs 79.6 ms at 512 videos), which
+// is how the trainer runs -- so the attribute is opt-in (V2M_PDL=1) and the default launch is a plain one.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool dep_launch_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_dep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = dep_launch_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- small device utilities ------------------------------------------------------------------
 // Dropout masks are a stateless function of (seed, row, column): the forward kernel and the backward kernel that needs the
 // same mask recompute it instead of storing it.  One 32-bit hash (lowbias32-style integer mix) of (seed, row, column / 4)

@@ -91,6 +91,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm512_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            T* __restrict__ y, int M, float eps) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = gridDim.x * 8;
   float g[16], b[16];
   ld16(gamma + lane * 16, g);
@@ -128,11 +130,11 @@ int layernorm(const void* x, int x_dtype, const void* res, int res_dtype, const 
     int grid = (M + 7) / 8;
     if (grid > 148 * 8) grid = 148 * 8;
     if (x_dtype == 0)
-      layernorm512_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<const float*>(res), gamma, beta,
-                                                           static_cast<float*>(y), M, eps);
+      launch_dep(layernorm512_kernel<float>, dim3(grid), dim3(256), 0, stream, static_cast<const float*>(x), static_cast<const float*>(res), gamma, beta,
+                 static_cast<float*>(y), M, eps);
     else
-      layernorm512_kernel<bf16><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(res), gamma, beta,
-                                                          static_cast<bf16*>(y), M, eps);
+      launch_dep(layernorm512_kernel<bf16>, dim3(grid), dim3(256), 0, stream, static_cast<const bf16*>(x), static_cast<const bf16*>(res), gamma, beta,
+                 static_cast<bf16*>(y), M, eps);
     return check_launch("layernorm512");
   }
   const int rows_per_block = 8;

@@ -157,6 +157,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dep_launch();                                       // the next kernel of the chain may start its own prologue
+  grid_dep_wait();                                         // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -502,8 +504,9 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   }
   const int items = tiles * k_split;
   const int grid = items < num_sms ? items : num_sms;
-  gemm_bf16_tc_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmem, stream>>>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out,
-                                                                                  k_off, c_gstride);
+  cudaError_t le = launch_dep(gemm_bf16_tc_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, C, ldc, out_bf16,
+                              vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out, k_off, c_gstride);
+  if (le != cudaSuccess) { set_last_error("gemm_bf16_tc: %s", cudaGetErrorString(le)); return kCudaError; }
   return check_launch("gemm_bf16_tc");
 }
 

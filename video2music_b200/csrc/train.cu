@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(256) dy_prep_bf16x8_kernel(const bf16* __restr
                                                              bf16* __restrict__ dz, long long ld_dz, float* __restrict__ db, int M,
                                                              int N, float drop_scale, unsigned int drop_thresh,
                                                              unsigned int drop_seed, const unsigned int* __restrict__ drop_seed_dev) {
+  grid_dep_launch();
+  grid_dep_wait();
   if (drop_seed_dev) drop_seed += *drop_seed_dev;
   __shared__ float part[32][8 * 8 + 1];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;            // 8 column groups x 32 row lanes
@@ -142,8 +144,8 @@ int dy_prep(const void* dy, int dy_dtype, long long ld_dy, const void* y, int y_
     int gy2 = (M + 31) / 32;
     if (gy2 > 148) gy2 = 148;
     dim3 grid2((N + 63) / 64, gy2);
-    dy_prep_bf16x8_kernel<<<grid2, 256, 0, stream>>>(static_cast<const bf16*>(dy), ld_dy, static_cast<const bf16*>(y), ld_y, relu, alpha,
-                                                     alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N, drop_scale, drop_thresh, drop_seed, drop_seed_dev);
+    launch_dep(dy_prep_bf16x8_kernel, grid2, dim3(256), 0, stream, static_cast<const bf16*>(dy), ld_dy, static_cast<const bf16*>(y), ld_y, relu, alpha,
+               alpha_cols, static_cast<bf16*>(dz), ld_dz, db, M, N, drop_scale, drop_thresh, drop_seed, drop_seed_dev);
     return check_launch("dy_prep_bf16x8");
   }
   int gy = (M + 7) / 8;
@@ -248,6 +250,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm512_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                                const T* __restrict__ dy, T* __restrict__ dx,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, int M, float eps) {
+  grid_dep_launch();
+  grid_dep_wait();
   __shared__ float sacc[2 * 512];
   for (int i = threadIdx.x; i < 2 * 512; i += 256) sacc[i] = 0.f;
   __syncthreads();
@@ -307,11 +311,11 @@ int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy
     int g2 = (M + 7) / 8;
     if (g2 > 148 * 2) g2 = 148 * 2;
     if (x_dtype == 0)
-      layernorm512_bwd_kernel<float><<<g2, 256, 0, stream>>>(static_cast<const float*>(x), gamma, static_cast<const float*>(dy),
-                                                             static_cast<float*>(dx), dgamma, dbeta, M, eps);
+      launch_dep(layernorm512_bwd_kernel<float>, dim3(g2), dim3(256), 0, stream, static_cast<const float*>(x), gamma, static_cast<const float*>(dy),
+                 static_cast<float*>(dx), dgamma, dbeta, M, eps);
     else
-      layernorm512_bwd_kernel<bf16><<<g2, 256, 0, stream>>>(static_cast<const bf16*>(x), gamma, static_cast<const bf16*>(dy),
-                                                            static_cast<bf16*>(dx), dgamma, dbeta, M, eps);
+      launch_dep(layernorm512_bwd_kernel<bf16>, dim3(g2), dim3(256), 0, stream, static_cast<const bf16*>(x), gamma, static_cast<const bf16*>(dy),
+                 static_cast<bf16*>(dx), dgamma, dbeta, M, eps);
     return check_launch("layernorm512_bwd");
   }
   int grid = (M + 7) / 8;
@@ -341,6 +345,8 @@ int embed_bwd(const long long* idx, const void* d, int d_dtype, long long ld_d, 
 // One warp per row.  out[0] += CE row sum (valid rows), out[1] += BCE element sum; n_valid is a device scalar
 // (count of tgt != ignore) produced by count_valid_kernel.  dlogits gets the already weighted and normalised gradient.
 __global__ void count_valid_kernel(const long long* __restrict__ tgt, int R, long long ignore, float* __restrict__ n_valid) {
+  grid_dep_launch();
+  grid_dep_wait();
   int c = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) c += (tgt[i] != ignore);
 #pragma unroll
@@ -353,6 +359,8 @@ __global__ void __launch_bounds__(256) amt_loss_kernel(const float* __restrict__
                                                        float smooth, float w_ce, float w_bce, const float* __restrict__ n_valid,
                                                        const float* __restrict__ bce_rows_p, float* __restrict__ out,
                                                        float* __restrict__ dlogits) {
+  grid_dep_launch();
+  grid_dep_wait();
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= R) return;
@@ -435,6 +443,8 @@ int count_valid(const long long* tgt, int R, long long ignore, float* out1, cuda
 __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, float lr, float b1, float b2, float eps, float weight_decay, float bc1, float bc2,
                             float grad_scale, const float* __restrict__ dyn, bf16* __restrict__ p16, int zero_grad, unsigned int* __restrict__ ctr) {
+  grid_dep_launch();
+  grid_dep_wait();
   if (dyn) { lr = dyn[0]; bc1 = dyn[1]; bc2 = dyn[2]; }
   const float decay = 1.f - lr * weight_decay;
   // 16-byte path (every buffer 16-byte aligned: the trainer's flat buffers): four elements per thread and access -- the kernel is a
