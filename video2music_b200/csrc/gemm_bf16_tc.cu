@@ -15,6 +15,7 @@
 // Ragged edges: TMA zero-fills out-of-bounds rows/columns (M, N, K tails), stores are guarded.
 #include "common.cuh"
 #include "kernels.h"
+#include <cstdlib>
 #include <cuda.h>
 
 namespace v2m {
@@ -115,7 +116,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
                     int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split,
                     const int* __restrict__ tile_group, const __grid_constant__ CUtensorMap tmC, int tma_out,
-                    const int* __restrict__ k_off, long long c_gstride) {
+                    const int* __restrict__ k_off, long long c_gstride, const __grid_constant__ CUtensorMap tmBs, int tail_first) {
+  // tail_first >= 0 (plain GEMMs only: k_split == 1, no groups): the big tiles [tail_first, tiles) -- the ones that would make up
+  // a mostly idle last round of the persistent grid (M = 19136 gives 150 row tiles on 148 SMs: 300 tiles = 2.03 rounds at
+  // N = 512) -- are cut into BN / 64 sub-tiles of 128 x 64 each, so that round costs a quarter of a tile per SM instead of a
+  // whole one.  Sub-tiles load 64 rows of B (tmBs: the same matrix with a 64-row box), multiply with N = 64 into the first
+  // columns of the accumulator stage and drain two 32-column chunks.
   // k_off != null ("K-grouped", the ragged dW of the MoE experts: dW_e = dY_e^T X_e over the rows of group e): k_split is the
   // number of groups, work item (tile, g) multiplies over the K range [k_off[g], k_off[g+1]) (multiples of 64, read on the
   // device: group sizes never visit the host) and adds its tile to C + g * c_gstride (zero-initialised by the launcher);
@@ -140,7 +146,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + GM - 1) / GM, n_tiles = (N + BN - 1) / BN;
   const int num_kb = (K + GK - 1) / GK;
-  const int num_tiles = m_tiles * n_tiles * k_split;       // work items
+  constexpr int SUB = BN / 64;                             // sub-tiles per tail tile
+  const int big_tiles = m_tiles * n_tiles;
+  const int num_tiles = tail_first >= 0 ? tail_first + (big_tiles - tail_first) * SUB : big_tiles * k_split;       // work items
+  // work item -> (row tile, first column, width); k_split == 1 whenever tail_first >= 0
+  auto decode = [&](int tile, int& m_blk, int& n_base, int& bn) {
+    if (tail_first >= 0 && tile >= tail_first) {
+      const int j = tile - tail_first, t = tail_first + j / SUB;
+      m_blk = t / n_tiles; n_base = (t % n_tiles) * BN + (j % SUB) * 64; bn = 64;
+    } else {
+      m_blk = tile / n_tiles; n_base = (tile % n_tiles) * BN; bn = BN;
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -166,16 +183,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
         const int tile = item / k_split, ks = item - tile * k_split;
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        int m_blk, n_base, bn;
+        decode(tile, m_blk, n_base, bn);
         int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
         if (k_off) { kb0 = k_off[ks] / GK; kb1 = k_off[ks + 1] / GK; if (kb0 >= kb1) continue; }
         int g = 0;
         if (tile_group) { g = tile_group[m_blk]; if (g < 0) continue; }
-        const int b_row = g * N + n_blk * BN;
+        const int b_row = g * N + n_base;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+          mbar_arrive_expect_tx(full_bar + stage, Cfg::kABytes + bn * GK * 2);
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < GM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m_blk * GM + c * 64, kb * GK, full_bar + stage);
@@ -185,9 +203,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sa + Cfg::kABytes + c * 8192, &tmB, n_blk * BN + c * 64, kb * GK, full_bar + stage);
+              if (c * 64 < bn) tma_load_2d(sa + Cfg::kABytes + c * 8192, &tmB, n_base + c * 64, kb * GK, full_bar + stage);
           } else {
-            tma_load_2d(sa + Cfg::kABytes, &tmB, kb * GK, b_row, full_bar + stage);
+            tma_load_2d(sa + Cfg::kABytes, bn == BN ? &tmB : &tmBs, kb * GK, b_row, full_bar + stage);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -195,11 +213,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    constexpr uint32_t idesc = make_idesc_bf16(GM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc_full = make_idesc_bf16(GM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc_sub = make_idesc_bf16(GM, 64, A_MN ? 1 : 0, B_MN ? 1 : 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int ks = item % k_split;
+      const uint32_t idesc = (tail_first >= 0 && item >= tail_first) ? idesc_sub : idesc_full;
       int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
       if (k_off) { kb0 = k_off[ks] / GK; kb1 = k_off[ks + 1] / GK; if (kb0 >= kb1) continue; }
       if (tile_group && tile_group[(item / k_split) / n_tiles] < 0) continue;
@@ -237,7 +257,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
       const int tile = item / k_split;
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      int m_blk, n_base, bn;
+      decode(tile, m_blk, n_base, bn);
       const int m = m_blk * GM + quad * 32 + lane;
       size_t c_goff = 0;
       if (k_off) {
@@ -262,8 +283,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool pre_res = vec_ok && row_ok && ep.residual && ep.residual_bf16 && k_split == 1;
       uint4 res_nx[4];
       auto fetch_res = [&](int cc, uint4* dst) {
-        const int nn = n_blk * BN + cc * 32;
-        if (pre_res && cc < BN / 32 && nn + 32 <= N) {
+        const int nn = n_base + cc * 32;
+        if (pre_res && cc < bn / 32 && nn + 32 <= N) {
           const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(ep.residual) + res_row + nn);
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = __ldg(rp + q);
@@ -271,10 +292,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       };
       fetch_res(half, res_nx);
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < bn / 32; c += 2) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
-        const int n0 = n_blk * BN + c * 32;
+        const int n0 = n_base + c * 32;
         const bool fast = vec_ok && n0 + 32 <= N && k_split == 1 && !ep.accumulate && !k_off;
         float4 bv[8];
         if (fast && row_ok && bias) {
@@ -471,7 +492,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
                        const GemmEpilogue& ep, cudaStream_t stream, bool allow_split, const int* tile_group = nullptr,
-                       const int* k_off = nullptr, int n_kgroups = 0, long long c_gstride = 0) {
+                       const int* k_off = nullptr, int n_kgroups = 0, long long c_gstride = 0, const CUtensorMap* tmB_sub = nullptr) {
   // TMA-store epilogue for plain bf16 outputs (the store map only exists in that case; otherwise it aliases tmA, unused)
   CUtensorMap tmC = tmA;
   int tma_out = 0;
@@ -502,10 +523,22 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
     if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: clearing the split-K output failed: %s", cudaGetErrorString(e)); return kCudaError; }
   }
-  const int items = tiles * k_split;
+  // Tail sub-tiles (see the kernel): when the last round of the persistent grid would hold only a few 128 x BN tiles, those are
+  // cut into 128 x 64 pieces that spread over the SMs.  V2M_GEMM_TAIL=0 turns it off (A/B runs).
+  static int tail_on = -1;
+  if (tail_on < 0) { const char* e = getenv("V2M_GEMM_TAIL"); tail_on = (e && e[0] == '0') ? 0 : 1; }
+  int tail_first = -1;
+  int items = tiles * k_split;
+  if (tail_on && BN == 256 && k_split == 1 && !tile_group && !k_off && tmB_sub && tiles > num_sms) {
+    const int r = tiles % num_sms;
+    if (r > 0 && r * (BN / 64) <= num_sms) {
+      tail_first = tiles - r;
+      items = tail_first + r * (BN / 64);
+    }
+  }
   const int grid = items < num_sms ? items : num_sms;
   cudaError_t le = launch_dep(gemm_bf16_tc_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, C, ldc, out_bf16,
-                              vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out, k_off, c_gstride);
+                              vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out, k_off, c_gstride, tmB_sub ? *tmB_sub : tmB, tail_first);
   if (le != cudaSuccess) { set_last_error("gemm_bf16_tc: %s", cudaGetErrorString(le)); return kCudaError; }
   return check_launch("gemm_bf16_tc");
 }
@@ -544,7 +577,10 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
                            ep.drop_scale == 0.f;
   V2M_REQUIRE(!ep.accumulate || allow_split, "gemm_bf16_tc: accumulate needs a plain fp32 output (no bias / residual / activation / dropout)");
   V2M_REQUIRE(!ep.residual_gate || (ep.residual && ep.residual_bf16), "gemm_bf16_tc: the gate operand is a bf16 matrix");
-#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split)
+  // 64-row box over the same B operand for the tail sub-tiles (the MN-major operand is fetched in 64-column boxes anyway)
+  CUtensorMap tmBs = tmB;
+  if (bn == 256 && !b_mn && (rc = make_tmap_2d_bf16(&tmBs, W, N, K, ldw, 64))) return rc;
+#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split, nullptr, nullptr, 0, 0, &tmBs)
   if (bn == 256) {
     if (!a_mn && !b_mn) return V2M_GO(256, false, false);
     if (!a_mn && b_mn) return V2M_GO(256, false, true);
