@@ -246,24 +246,59 @@ __device__ __forceinline__ void lnb_st16(float* p, const float* v) {
   for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(p)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 
+// raw (unconverted) 16-element slices: what the prefetch of the next row holds in registers
+template <typename T> struct LnbRaw;
+template <> struct LnbRaw<bf16> { uint4 a, b; };
+template <> struct LnbRaw<float> { float4 q[4]; };
+__device__ __forceinline__ void lnb_raw_ld(const bf16* p, LnbRaw<bf16>& r) {
+  r.a = *reinterpret_cast<const uint4*>(p); r.b = *reinterpret_cast<const uint4*>(p + 8);
+}
+__device__ __forceinline__ void lnb_raw_ld(const float* p, LnbRaw<float>& r) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) r.q[q] = reinterpret_cast<const float4*>(p)[q];
+}
+__device__ __forceinline__ void lnb_cvt(const LnbRaw<bf16>& r, float* v) {
+  float2 f;
+  f = bf16x2_to_f2(r.a.x); v[0] = f.x; v[1] = f.y;   f = bf16x2_to_f2(r.a.y); v[2] = f.x; v[3] = f.y;
+  f = bf16x2_to_f2(r.a.z); v[4] = f.x; v[5] = f.y;   f = bf16x2_to_f2(r.a.w); v[6] = f.x; v[7] = f.y;
+  f = bf16x2_to_f2(r.b.x); v[8] = f.x; v[9] = f.y;   f = bf16x2_to_f2(r.b.y); v[10] = f.x; v[11] = f.y;
+  f = bf16x2_to_f2(r.b.z); v[12] = f.x; v[13] = f.y; f = bf16x2_to_f2(r.b.w); v[14] = f.x; v[15] = f.y;
+}
+__device__ __forceinline__ void lnb_cvt(const LnbRaw<float>& r, float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { v[4 * q] = r.q[q].x; v[4 * q + 1] = r.q[q].y; v[4 * q + 2] = r.q[q].z; v[4 * q + 3] = r.q[q].w; }
+}
+
+// The rows of a warp are independent: the NEXT row's x / dy slices are fetched (raw, 8 registers each in bf16) before the
+// current row's reductions, so the four dependent warp sums of a row overlap the memory latency of the next one.  The
+// per-CTA fold of dgamma / dbeta goes through per-warp shared-memory rows (shared-memory float atomics are CAS loops).
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm512_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                                const T* __restrict__ dy, T* __restrict__ dx,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, int M, float eps) {
   grid_dep_launch();
   grid_dep_wait();
-  __shared__ float sacc[2 * 512];
-  for (int i = threadIdx.x; i < 2 * 512; i += 256) sacc[i] = 0.f;
-  __syncthreads();
+  __shared__ float sacc[8][2 * 512];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = gridDim.x * 8;
   float gm[16], dg[16], db[16];
   lnb_ld16(gamma + lane * 16, gm);
 #pragma unroll
   for (int e = 0; e < 16; ++e) { dg[e] = 0.f; db[e] = 0.f; }
-  for (int row = blockIdx.x * 8 + warp; row < M; row += nw) {
+  int row = blockIdx.x * 8 + warp;
+  LnbRaw<T> rx, rg;
+  if (row < M) {
+    lnb_raw_ld(x + (size_t)row * 512 + lane * 16, rx);
+    lnb_raw_ld(dy + (size_t)row * 512 + lane * 16, rg);
+  }
+  while (row < M) {
     float xv[16], gv[16];
-    lnb_ld16(x + (size_t)row * 512 + lane * 16, xv);
-    lnb_ld16(dy + (size_t)row * 512 + lane * 16, gv);
+    lnb_cvt(rx, xv);
+    lnb_cvt(rg, gv);
+    const int nrow = row + nw;
+    if (nrow < M) {
+      lnb_raw_ld(x + (size_t)nrow * 512 + lane * 16, rx);
+      lnb_raw_ld(dy + (size_t)nrow * 512 + lane * 16, rg);
+    }
     float sum = 0.f;
 #pragma unroll
     for (int e = 0; e < 16; ++e) sum += xv[e];
@@ -289,16 +324,16 @@ __global__ void __launch_bounds__(256) layernorm512_bwd_kernel(const T* __restri
 #pragma unroll
     for (int e = 0; e < 16; ++e) gv[e] = rstd * (gv[e] - s1 - xv[e] * s2);
     lnb_st16(dx + (size_t)row * 512 + lane * 16, gv);
+    row = nrow;
   }
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    atomicAdd(&sacc[lane * 16 + e], dg[e]);
-    atomicAdd(&sacc[512 + lane * 16 + e], db[e]);
-  }
+  lnb_st16(&sacc[warp][lane * 16], dg);
+  lnb_st16(&sacc[warp][512 + lane * 16], db);
   __syncthreads();
-  for (int i = threadIdx.x; i < 512; i += 256) {
-    atomicAdd(dgamma + i, sacc[i]);
-    atomicAdd(dbeta + i, sacc[512 + i]);
+  for (int i = threadIdx.x; i < 2 * 512; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sacc[w][i];
+    atomicAdd(i < 512 ? dgamma + i : dbeta + (i - 512), t);
   }
 }
 
@@ -309,7 +344,7 @@ int layernorm_bwd(const void* x, int x_dtype, const float* gamma, const void* dy
   auto al16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; };
   if (D == 512 && x_dtype == dy_dtype && x_dtype == dx_dtype && al16(x) && al16(dy) && al16(dx) && al16(gamma)) {
     int g2 = (M + 7) / 8;
-    if (g2 > 148 * 2) g2 = 148 * 2;
+    if (g2 > 148 * 2) g2 = 148 * 2;                       // 2 CTAs per SM, the rest of a warp's rows in its loop
     if (x_dtype == 0)
       launch_dep(layernorm512_bwd_kernel<float>, dim3(g2), dim3(256), 0, stream, static_cast<const float*>(x), gamma, static_cast<const float*>(dy),
                  static_cast<float*>(dx), dgamma, dbeta, M, eps);
