@@ -1,11 +1,11 @@
 #!/bin/bash
-# scratch script for one gpurun call (overwritten per call)
+# scratch script for one gpurun call (overwritten per call): full validation = GPU tests, smoke, bench
 cd /root/repo
 mkdir -p gpurun_out
-export V2M_TRAIN_GRAPH=1
-( timeout 200 python tools/train_time.py 64 bf16 20; timeout 200 python tools/train_time.py 64 bf16 20
-  timeout 200 python tools/train_time.py 512 bf16 5 ) > gpurun_out/r4_train_time_ln.txt 2>&1
-cat gpurun_out/r4_train_time_ln.txt
-timeout 1200 python -m pytest tests/test_gpu_train.py tests/test_gpu_kernels.py -x -q -m gpu > gpurun_out/r4_ln_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/r4_ln_tests.log
-tail -4 gpurun_out/r4_ln_tests.log
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r4_gpu_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/r4_gpu_tests.log
+tail -4 gpurun_out/r4_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r4_smoke.log 2>&1
+tail -2 gpurun_out/r4_smoke.log
+timeout 900 python bench.py > gpurun_out/r4_bench.json 2> gpurun_out/r4_bench.err
+echo "bench exit $?"; tail -3 gpurun_out/r4_bench.err
