@@ -319,6 +319,38 @@ def test_pscan_full_size_properties(B, L, D, N):
     assert rel_err(gX[:1, :, :2], gXs) < 1e-5 and rel_err(gA[:1, :, :2], gAs) < 1e-5
 
 
+@pytest.mark.parametrize("B,L,D,N", [(1, 1, 2, 16), (3, 7, 2, 16), (2, 8, 2, 16), (2, 9, 4, 16), (1, 129, 2, 16), (5, 257, 6, 16),
+                                     (2, 300, 4, 16), (1, 1031, 2, 16), (148, 65, 4, 16), (37, 64, 16, 16)])
+def test_pscan_edge_shapes_vs_oracle(B, L, D, N):
+    """Chunk / item boundaries of the TMA streaming kernel: one step, a single partial chunk, L just over one / two chunks, a ragged
+    last chunk, 32- and 64-channel items, more items than SMs and fewer -- the WHOLE tensors against the sequential oracle."""
+    from video2music_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(11 + L)
+    A = (torch.rand((B, L, D, N), generator=g) * 0.99)
+    X = syn.unit_uniform((B, L, D, N), g)
+    gH = syn.unit_uniform((B, L, D, N), g)
+    H = ops.pscan_fwd(A.to(DEV), X.to(DEV))
+    Hs = O.pscan_forward(A, X)
+    assert rel_err(H, Hs) < 1e-5
+    gA, gX = ops.pscan_bwd(A.to(DEV), H, gH.to(DEV))
+    gAs, gXs = O.pscan_backward(A, Hs, gH)
+    assert rel_err(gX, gXs) < 1e-5
+    assert rel_err(gA, gAs) < 1e-5 if L > 1 else float(gA.abs().max()) == 0.0
+
+
+def test_pscan_unaligned_pointers_take_the_first_kernel():
+    """Views whose storage offset is not a multiple of 16 bytes cannot be described by a tensor map: the register kernel runs."""
+    from video2music_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, L, D, N = 2, 77, 4, 16
+    n = B * L * D * N
+    bufA, bufX = (torch.rand(n + 1, generator=g) * 0.99).to(DEV), syn.unit_uniform((n + 1,), g).to(DEV)
+    A, X = bufA[1:].view(B, L, D, N), bufX[1:].view(B, L, D, N)
+    assert A.data_ptr() % 16 != 0 and A.is_contiguous()
+    H = ops.pscan_fwd(A, X)
+    assert rel_err(H, O.pscan_forward(A.cpu(), X.cpu())) < 1e-5
+
+
 # ---------------------------------------------------------------- MoE
 @pytest.mark.parametrize("shared", [False, True])
 def test_moe_golden_gpu(shared):

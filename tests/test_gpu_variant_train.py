@@ -330,7 +330,7 @@ def test_mamba_train_golden_gpu(name):
         assert rel_err(m.eval()(x), y) < 1e-5
 
 
-@pytest.mark.parametrize("B,L,ED,plus", [(3, 70, 256, False), (2, 33, 100, True), (1, 200, 40, True)])
+@pytest.mark.parametrize("B,L,ED,plus", [(3, 70, 256, False), (2, 33, 100, True), (1, 200, 40, True), (2, 64, 8, False), (1, 129, 24, True)])
 def test_selective_scan_and_conv_backward_kernels_vs_autograd(B, L, ED, plus):
     """Kernel level: fused-scan and conv/SiLU backward against float64 torch autograd of the materialised recurrence
     (channel counts that are not multiples of the 128-thread CTA, strided dB / dC / dz destinations)."""
