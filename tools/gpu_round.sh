@@ -2,6 +2,9 @@
 # scratch script for one gpurun call (overwritten per call)
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_variant_train.py -x -q -m gpu -k "pscan or selective_scan" > gpurun_out/r4_edge_tests.log 2>&1
-echo "tests exit $?" >> gpurun_out/r4_edge_tests.log
-tail -15 gpurun_out/r4_edge_tests.log
+( V2M_GEMM_ROWS=0 timeout 200 python tools/scratch/cfg5_train_step.py bf16; timeout 200 python tools/scratch/cfg5_train_step.py bf16
+  V2M_GEMM_ROWS=0 timeout 200 python tools/scratch/cfg5_train_step.py; timeout 200 python tools/scratch/cfg5_train_step.py ) > gpurun_out/r4_cfg5_rows_ab3.txt 2>&1
+cat gpurun_out/r4_cfg5_rows_ab3.txt
+timeout 900 python -m pytest tests/test_gpu_variant_train.py tests/test_gpu_kernels.py -x -q -m gpu > gpurun_out/r4_rows_tests.log 2>&1
+echo "tests exit $?" >> gpurun_out/r4_rows_tests.log
+tail -4 gpurun_out/r4_rows_tests.log
