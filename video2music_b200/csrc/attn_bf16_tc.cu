@@ -64,6 +64,7 @@ struct AttnTcArgs {
   float drop_scale; unsigned int drop_thresh, drop_seed;   // probability dropout (training), 0 = off
   const unsigned int* drop_seed_dev;
   int n_q_tiles, n_items;   // work items = (video, head) x 128-row query tiles; CTAs walk them with stride gridDim.x
+  int first_rows;           // query rows of tile 0 (the partial tile comes FIRST: see attn_fwd_bf16_tc)
 };
 
 template <int AT_NW, bool HAS_ER, bool DROP>
@@ -103,8 +104,9 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     Item t;
     t.bh = item / a.n_q_tiles;
     t.b = t.bh / a.Hq; t.hq = t.bh % a.Hq; t.hkv = t.hq / (a.Hq / a.Hkv);
-    t.i0 = (item - t.bh * a.n_q_tiles) * AT_M;
-    t.imax = min(t.i0 + AT_M - 1, a.Lq - 1);
+    const int tq = item - t.bh * a.n_q_tiles;
+    t.i0 = tq == 0 ? 0 : a.first_rows + (tq - 1) * AT_M;
+    t.imax = tq == 0 ? a.first_rows - 1 : min(t.i0 + AT_M - 1, a.Lq - 1);
     t.nk = a.causal ? min(a.Lk, t.imax + coff + 1) : a.Lk;            // keys this tile needs
     t.nk16 = (t.nk + 15) & ~15;
     t.nk64 = (t.nk + 63) & ~63;
@@ -233,7 +235,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int i0 = t.i0, imax = t.imax, nk16 = t.nk16, b = t.b, hq = t.hq, bh = t.bh;
     const bool need_b = t.need_b;
     const int i = i0 + row;                                      // my query row
-    const bool row_ok = i < a.Lq;
+    const bool row_ok = i <= imax;                                // (tile 0 may own fewer than 128 rows)
     const int jlim = row_ok ? (a.causal ? min(a.Lk, i + coff + 1) : a.Lk) : 0;   // keys [0, jlim) are visible
     const int wfirst = i0 + quad * 32;                           // first row of this quadrant
     const int wlast = min(imax, wfirst + 31);                    // last valid row of this quadrant
@@ -292,19 +294,21 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_wait();
         }
         bool modified = rel_chunk;                               // scores that changed go back to TMEM for pass B
+        float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};     // four independent chains instead of 32 dependent FMNMX
         if (j0 + 32 <= wjmin) {                                  // every key of the chunk is visible to every row
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
+          for (int k = 0; k < 32; ++k) m4[k & 3] = fmaxf(m4[k & 3], __uint_as_float(r[k]));
         } else {
           modified = true;
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
             float sv = __uint_as_float(r[k]);
             sv = (j0 + k < jlim) ? sv : -INFINITY;
-            mx = fmaxf(mx, sv);
+            m4[k & 3] = fmaxf(m4[k & 3], sv);
             r[k] = __float_as_uint(sv);
           }
         }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         if (modified) tmem_st_32x32(T_S + lane_off + j0, r);
       }
     }
@@ -317,7 +321,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     // ---- pass B: p = exp(s - max), row sum, P (bf16 pairs) written over S
     const float mneg = (mx == -INFINITY) ? 0.f : mx * LOG2E;
-    float sum = 0.f;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};                          // independent partial row sums (short FADD chains)
     for (int c = sub; c < nchunks; c += AT_NW) {
       const int j0 = c * 32;
       uint32_t pk[16];
@@ -329,7 +333,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int k = 0; k < 16; ++k) {
           float p0 = ex2_approx(fmaf(__uint_as_float(r[2 * k]), LOG2E, -mneg));
           float p1 = ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), LOG2E, -mneg));
-          sum += p0 + p1;
+          s4[k & 3] += p0 + p1;
           if (DROP) {                                          // dropout acts on the normalised probabilities: O stays / sum
             const uint32_t rr = (uint32_t)bh * (uint32_t)a.Lq + (uint32_t)i;
             const uint32_t hh = drop_hash4(dseed, rr, (j0 >> 2) + (k >> 1));   // columns j0 + 2k, +1 (j0 % 32 == 0); CSE'd per two k
@@ -348,6 +352,7 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_p);
+    float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     if (AT_NW > 1) {                                             // row sum over the warps of the quadrant
       red[(AT_NW + sub) * AT_M + row] = sum;
       named_bar_sync(bar_id, 32 * AT_NW);
@@ -438,6 +443,13 @@ int attn_fwd_bf16_tc(const AttnParams& p, cudaStream_t stream) {
     attr = true;
   }
   a.n_q_tiles = (p.Lq + AT_M - 1) / AT_M;
+  // Lq % 128 leftover rows: they form tile 0, not the last tile.  Under the causal mask a tile costs what its LONGEST rows
+  // cost (per TMEM lane quadrant: a warp cannot help another quadrant), so at L = 299 the leftover 43 rows are cheap as rows
+  // 0..42 (2 key chunks, one QE half, 48 S columns) and expensive as rows 256..298 (10 chunks, both QE halves, 304 columns):
+  // critical-path chunks per (video, head) 2 + 6 + 10 = 18 instead of 4 + 8 + 10 = 22, and 20 % fewer MMA columns.
+  static int shift_tiles = -1;
+  if (shift_tiles < 0) { const char* e = getenv("V2M_ATTN_SHIFT"); shift_tiles = e ? atoi(e) != 0 : 1; }
+  a.first_rows = shift_tiles ? p.Lq - (a.n_q_tiles - 1) * AT_M : (p.Lq < AT_M ? p.Lq : AT_M);
   const long long items = (long long)a.n_q_tiles * p.B * p.Hq;
   V2M_REQUIRE(items < (1ll << 31), "attn_fwd_bf16_tc: too many tiles");
   a.n_items = (int)items;
