@@ -225,7 +225,8 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int u = lane;
     const int row = quad * 32 + u;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    float* my_scr = scr + (size_t)((sub * 4 + quad) * 32 + u) * AT_SCR_PITCH;
+    const uint32_t my_scr = smem_u32(scr + (size_t)((sub * 4 + quad) * 32 + u) * AT_SCR_PITCH);   // this lane's private row
+    const uint32_t red_a = smem_u32(red);
     const float LOG2E = 1.4426950408889634f;
     const uint32_t bar_id = 1 + quad;                            // named barrier of this quadrant's AT_NW warps
     uint32_t par = 0, parb = 0;
@@ -277,16 +278,16 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_wait();
 #pragma unroll
           for (int q4 = 0; q4 < 16; ++q4)
-            *reinterpret_cast<uint4*>(my_scr + q4 * 4) = make_uint4(w[q4 * 4], w[q4 * 4 + 1], w[q4 * 4 + 2], w[q4 * 4 + 3]);
+            sts_v4(my_scr + q4 * 16, w[q4 * 4], w[q4 * 4 + 1], w[q4 * 4 + 2], w[q4 * 4 + 3]);
           // band column of (i, j) is j - i + imax; offset inside the window = that - cs
           const int off = j0 - i + imax - cs;                    // in [0, 63 - k] for every (i, j <= i) that is needed
           if (j0 + 31 <= wfirst) {                               // whole chunk at or below the diagonal for every row
 #pragma unroll
-            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + my_scr[off + k]);
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) + lds_f32(my_scr + (off + k) * 4));
           } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              const float rel = my_scr[min(max(off + k, 0), 63)];  // clamped reads only hit masked / invalid entries
+              const float rel = lds_f32(my_scr + min(max(off + k, 0), 63) * 4);  // clamped reads only hit masked / invalid entries
               if (j0 + k <= i) r[k] = __float_as_uint(__uint_as_float(r[k]) + rel);
             }
           }
@@ -314,10 +315,10 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     tmem_st_wait();
     if (AT_NW > 1) {                                             // row max over the warps of the quadrant; also orders
-      red[sub * AT_M + row] = mx;                                // every QE read of the quadrant before the P writes
+      sts_f32(red_a + (sub * AT_M + row) * 4, mx);               // every QE read of the quadrant before the P writes
       named_bar_sync(bar_id, 32 * AT_NW);
 #pragma unroll
-      for (int w2 = 0; w2 < AT_NW; ++w2) mx = fmaxf(mx, red[w2 * AT_M + row]);
+      for (int w2 = 0; w2 < AT_NW; ++w2) mx = fmaxf(mx, lds_f32(red_a + (w2 * AT_M + row) * 4));
     }
     // ---- pass B: p = exp(s - max), row sum, P (bf16 pairs) written over S
     const float mneg = (mx == -INFINITY) ? 0.f : mx * LOG2E;
@@ -354,11 +355,11 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (lane == 0) mbar_arrive(bar_p);
     float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     if (AT_NW > 1) {                                             // row sum over the warps of the quadrant
-      red[(AT_NW + sub) * AT_M + row] = sum;
+      sts_f32(red_a + ((AT_NW + sub) * AT_M + row) * 4, sum);
       named_bar_sync(bar_id, 32 * AT_NW);
       sum = 0.f;
 #pragma unroll
-      for (int w2 = 0; w2 < AT_NW; ++w2) sum += red[(AT_NW + w2) * AT_M + row];
+      for (int w2 = 0; w2 < AT_NW; ++w2) sum += lds_f32(red_a + ((AT_NW + w2) * AT_M + row) * 4);
     }
     // ---- epilogue: O / sum -> bf16 -> global; the warps of a quadrant split the 64 columns
     constexpr int OC = AT_DH / AT_NW;

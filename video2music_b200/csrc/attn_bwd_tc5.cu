@@ -296,8 +296,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int q4 = 0; q4 < CW / 8; ++q4) {                        // this warp's CW * 2 bytes of row r: 16-byte chunks sub*CW/8 ..
           const int ch = ((sub * (CW / 8) + q4) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(my_p + ch) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(my_ds + ch) = make_uint4(dk_[4 * q4], dk_[4 * q4 + 1], dk_[4 * q4 + 2], dk_[4 * q4 + 3]);
+          sts_v4(smem_u32(my_p) + ch, pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);          // explicit shared-space
+          sts_v4(smem_u32(my_ds) + ch, dk_[4 * q4], dk_[4 * q4 + 1], dk_[4 * q4 + 2], dk_[4 * q4 + 3]);   // stores (common.cuh)
         }
         fence_proxy_async();
         __syncwarp();

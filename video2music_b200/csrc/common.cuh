@@ -267,6 +267,21 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 // bar.sync on a named barrier (ids 1..15; 0 is __syncthreads) for `count` threads (multiple of 32)
+// The dynamic shared-memory base is re-aligned through an integer cast, after which the compiler no longer knows the address
+// space and emits GENERIC loads / stores (LD.E / ST.E through the local/global queue: 'stall_lg' on every scratch store in
+// the ncu source page).  The skew scratch and the row-statistics exchange therefore use explicit shared-space accesses.
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }

@@ -319,18 +319,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // Coalesced vector reductions: the 32 x 32 chunk (lane = row) is transposed through this warp's staging buffer so
             // that one red.global.add.v4.f32 instruction covers four whole 128-byte row segments (8 lanes x 16 B each) instead
             // of 32 scalar atomics scattered over 32 rows: 8 instructions per chunk instead of 32, every one fully coalesced.
-            float* sbuf = reinterpret_cast<float*>(stage);
+            const uint32_t sbuf = smem_u32(stage);               // explicit shared-space accesses (see common.cuh: sts_f32)
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sbuf[lane * 32 + (i ^ lane)] = v[i];      // XOR swizzle: conflict-free both ways
+            for (int i = 0; i < 32; ++i) sts_f32(sbuf + (lane * 32 + (i ^ lane)) * 4, v[i]);      // XOR swizzle: conflict-free both ways
             __syncwarp();
             const int c0 = (lane & 7) * 4, rsub = lane >> 3;
 #pragma unroll
             for (int r4 = 0; r4 < 8; ++r4) {
               const int row = r4 * 4 + rsub;
               const int mm = m_blk * GM + quad * 32 + row;
-              const float a0 = sbuf[row * 32 + ((c0 + 0) ^ row)], a1 = sbuf[row * 32 + ((c0 + 1) ^ row)];
-              const float a2 = sbuf[row * 32 + ((c0 + 2) ^ row)], a3 = sbuf[row * 32 + ((c0 + 3) ^ row)];
+              const float a0 = lds_f32(sbuf + (row * 32 + ((c0 + 0) ^ row)) * 4), a1 = lds_f32(sbuf + (row * 32 + ((c0 + 1) ^ row)) * 4);
+              const float a2 = lds_f32(sbuf + (row * 32 + ((c0 + 2) ^ row)) * 4), a3 = lds_f32(sbuf + (row * 32 + ((c0 + 3) ^ row)) * 4);
               if (mm < M) {
                 float* dst = static_cast<float*>(C) + c_goff + (size_t)mm * ldc + n0 + c0;
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
@@ -427,7 +427,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               pk.y = f2_to_bf16x2(v[8 * q + 2], v[8 * q + 3]);
               pk.z = f2_to_bf16x2(v[8 * q + 4], v[8 * q + 5]);
               pk.w = f2_to_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+#ifdef V2M_GEMM_GENERIC_STAGE
               *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pk;
+#else
+              sts_v4(smem_u32(buf) + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), pk.x, pk.y, pk.z, pk.w);
+#endif
             }
             fence_proxy_async();
             __syncwarp();
