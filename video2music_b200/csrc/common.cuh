@@ -176,6 +176,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same bounded wait as ONE asm statement (the spin loop is invisible to the compiler's divergence analysis): used by
+// warp-uniform issue loops, where a C++ `while (!try_wait)` makes everything downstream "possibly divergent" and forces
+// tcgen05 operands through ELECT / R2UR waterfalls (see umma_kstep4).
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1, P2;\n\t.reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n"
+      "V2M_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra V2M_DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.gt.u32 P2, cnt, 0x4000000;\n\t"
+      "@P2 trap;\n\t"
+      "bra V2M_WAIT;\n"
+      "V2M_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one elected lane of a converged warp (the predicate ptxas recognises as uniform-safe)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+
 // 1-D bulk copy global -> shared, completion on an mbarrier (bytes multiple of 16, 16B aligned).
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -244,6 +272,99 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// One k-step of a GEMM main loop in ONE asm statement: four K = 16 MMAs (descriptors advanced by a_step / b_step in the
+// 16-byte address field), the commit that frees the shared-memory slot and, on the last k-step of a tile, the commit that hands
+// the accumulator to the epilogue.  Why: tcgen05 operands must sit in uniform registers, and inside `if (lane == 0)` the
+// compiler wraps EVERY asm statement in an ELECT / R2UR x 7 / branch "waterfall" (~25 instructions): with one statement per
+// MMA and per commit the issuing thread spent ~900 clocks per k-step (ncu source page: the MMA warp never waits, it executes
+// its ~130-instruction loop) where the tensor pipe needs 512 -- the issuer, not the pipe, bounded a K = 512 GEMM.
+__device__ __forceinline__ void umma_kstep4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_first,
+                                            uint32_t a_step, uint32_t b_step, uint64_t* bar_empty, uint64_t* bar_tfull,
+                                            uint32_t last) {
+  asm volatile(
+      "{\n\t.reg .pred p, t, r;\n\t.reg .b64 a1, a2, a3, b1, b2, b3, sa, sb;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "setp.ne.b32 r, %9, 0;\n\t"
+      "cvt.u64.u32 sa, %5;\n\tcvt.u64.u32 sb, %6;\n\t"
+      "add.u64 a1, %1, sa;\n\tadd.u64 a2, a1, sa;\n\tadd.u64 a3, a2, sa;\n\t"
+      "add.u64 b1, %2, sb;\n\tadd.u64 b2, b1, sb;\n\tadd.u64 b3, b2, sb;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t"
+      "@r tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(b_step), "r"(smem_u32(bar_empty)),
+        "r"(smem_u32(bar_tfull)), "r"(last) : "memory");
+}
+// the same for a CTA pair (issued by the leader; commits multicast to both CTAs)
+__device__ __forceinline__ void umma_kstep4_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_first,
+                                                 uint32_t a_step, uint32_t b_step, uint64_t* bar_empty, uint64_t* bar_tfull,
+                                                 uint32_t last) {
+  asm volatile(
+      "{\n\t.reg .pred p, t, r;\n\t.reg .b64 a1, a2, a3, b1, b2, b3, sa, sb;\n\t.reg .b16 m;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "setp.ne.b32 r, %9, 0;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "cvt.u64.u32 sa, %5;\n\tcvt.u64.u32 sb, %6;\n\t"
+      "add.u64 a1, %1, sa;\n\tadd.u64 a2, a1, sa;\n\tadd.u64 a3, a2, sa;\n\t"
+      "add.u64 b1, %2, sb;\n\tadd.u64 b2, b1, sb;\n\tadd.u64 b3, b2, sb;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%7], m;\n\t"
+      "@r tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%8], m;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc_first), "r"(a_step), "r"(b_step), "r"(smem_u32(bar_empty)),
+        "r"(smem_u32(bar_tfull)), "r"(last) : "memory");
+}
+
+// ---- CTA pair (cta_group::2): two CTAs of a cluster (one TPC) run ONE M = 256 MMA; each holds its 128 rows of A and D and
+// half of the N rows of B, so a CTA ingests (128 + N/2) x K operand bytes per tile instead of (128 + N) x K.
+__device__ __forceinline__ uint32_t pair_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pair_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pair_mapa(uint32_t addr, uint32_t rank) {     // shared::cluster address of CTA `rank`'s copy
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void pair_mbar_arrive(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {         // the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols));
+}
+// issued by the leader (rank 0) only; the descriptors are CTA-local offsets valid in both CTAs
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in every CTA of `mask` once the MMAs issued so far have retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// TMA tile into THIS CTA's shared memory, bytes counted on the barrier at `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int c0, int c1, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
 
 // 32 lanes x 32 columns of fp32 accumulators -> 32 registers per thread (thread t <-> TMEM lane base+t).

@@ -111,7 +111,14 @@ int make_tmap_3d_bf16(CUtensorMap* tm, const void* base, long long cols, long lo
 // A_MN / B_MN: the operand is stored transposed ([K, M] resp. [K, N] row-major, "MN-major" for the tensor core):
 // TMA fetches 64(k) x 64(m|n) boxes, the smem descriptor walks 8-k-row groups (SBO 1024 B) and 64-wide chunks (LBO 8 KB).
 // This is what lets the backward pass compute dX = dY W and dW = dY^T X without materialising a transpose.
-template <int BN, bool A_MN, bool B_MN>
+// PAIR: the CTA-pair variant (cta_group::2, plain GEMMs with many rounds of tiles only: no K split, groups or tail sub-tiles).
+// A cluster of two CTAs owns a 256 x BN output tile: CTA r holds rows [128 r, 128 r + 128) of A and of the accumulator (its own
+// TMEM) and rows [BN/2 r, BN/2 (r + 1)) of the B tile; the leader (rank 0) issues ONE M = 256 MMA per k-step that reads both
+// CTAs' shared memory.  Per k-step a CTA ingests 16 + 16 KB instead of 16 + 32 KB: the 1-CTA kernel moves 48.7 B/clk/SM from
+// L2 at K = 512 (ncu: l1tex__m_xbar2l1tex_read_bytes 2.82 GB in 240 us) and is bound by that, not by the tensor pipe (54 %).
+// Barriers: both producers' TMA bytes are counted on the LEADER's full barrier (the leader expects the sum); tcgen05.commit
+// multicasts to both CTAs' empty / tmem-full barriers; both CTAs' epilogue warps arrive on the leader's tmem-empty barrier.
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
                     int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split,
@@ -148,10 +155,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_kb = (K + GK - 1) / GK;
   constexpr int SUB = BN / 64;                             // sub-tiles per tail tile
   const int big_tiles = m_tiles * n_tiles;
-  const int num_tiles = tail_first >= 0 ? tail_first + (big_tiles - tail_first) * SUB : big_tiles * k_split;       // work items
+  const uint32_t rank = PAIR ? pair_rank() : 0u;           // CTA of the pair
+  const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cta_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int num_tiles = PAIR ? ((m_tiles + 1) / 2) * n_tiles
+                             : (tail_first >= 0 ? tail_first + (big_tiles - tail_first) * SUB : big_tiles * k_split);       // work items
   // work item -> (row tile, first column, width); k_split == 1 whenever tail_first >= 0
   auto decode = [&](int tile, int& m_blk, int& n_base, int& bn) {
-    if (tail_first >= 0 && tile >= tail_first) {
+    if (PAIR) {
+      m_blk = 2 * (tile / n_tiles) + (int)rank; n_base = (tile % n_tiles) * BN; bn = BN;
+    } else if (tail_first >= 0 && tile >= tail_first) {
       const int j = tile - tail_first, t = tail_first + j / SUB;
       m_blk = t / n_tiles; n_base = (t % n_tiles) * BN + (j % SUB) * 64; bn = 64;
     } else {
@@ -166,12 +178,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, PAIR ? 16 : 8); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 2) { if (PAIR) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot); }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) pair_sync(); else __syncthreads();             // (pair: the peer's barriers are initialised before anybody signals them)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   grid_dep_launch();                                       // the next kernel of the chain may start its own prologue
@@ -181,10 +193,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+      for (int item = cta_id; item < num_tiles; item += cta_stride) {
         const int tile = item / k_split, ks = item - tile * k_split;
         int m_blk, n_base, bn;
         decode(tile, m_blk, n_base, bn);
+        if (PAIR) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar + stage, phase ^ 1);
+            unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
+            const uint32_t fb = pair_mapa(smem_u32(full_bar + stage), 0);       // the leader's barrier counts both CTAs' bytes
+            if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (Cfg::kABytes + (BN / 2) * GK * 2));
+            tma_load_2d_pair(sa, &tmA, kb * GK, m_blk * GM, fb);
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 128; ++c)
+                tma_load_2d_pair(sa + Cfg::kABytes + c * 8192, &tmB, n_base + (int)rank * (BN / 2) + c * 64, kb * GK, fb);
+            } else {
+              tma_load_2d_pair(sa + Cfg::kABytes, &tmBs, kb * GK, n_base + (int)rank * (BN / 2), fb);   // tmBs: BN/2-row box
+            }
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
         if (k_off) { kb0 = k_off[ks] / GK; kb1 = k_off[ks + 1] / GK; if (kb0 >= kb1) continue; }
         int g = 0;
@@ -211,6 +241,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+  } else if (warp == 1 && PAIR) {
+    // ================= MMA issuer of the pair: the leader only =================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GM, BN, 0, B_MN ? 1 : 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = cta_id; item < num_tiles; item += cta_stride) {
+        mbar_wait_u(tempty_bar + acc, acc_phase ^ 1);            // both CTAs' epilogues have drained this accumulator stage
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_u(full_bar + stage, phase);
+          tc_fence_after();
+          if (elect_one()) {                                     // one asm statement per k-step (see umma_kstep4)
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+            const uint32_t b_addr = a_addr + Cfg::kABytes;
+            const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
+            umma_kstep4_pair(tmem_base + acc * BN, da, db, idesc, kb != 0 ? 1u : 0u, 2u, B_MN ? 128u : 2u, empty_bar + stage,
+                             tfull_bar + acc, kb == num_kb - 1 ? 1u : 0u);   // commits reach both CTAs
+          }
+          __syncwarp();
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc_full = make_idesc_bf16(GM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
@@ -223,24 +279,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int kb0 = (int)((long long)ks * num_kb / k_split), kb1 = (int)((long long)(ks + 1) * num_kb / k_split);
       if (k_off) { kb0 = k_off[ks] / GK; kb1 = k_off[ks + 1] / GK; if (kb0 >= kb1) continue; }
       if (tile_group && tile_group[(item / k_split) / n_tiles] < 0) continue;
-      mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+      mbar_wait_u(tempty_bar + acc, acc_phase ^ 1);
       tc_fence_after();
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar + stage, phase);
+        mbar_wait_u(full_bar + stage, phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {                                       // one asm statement per k-step (see umma_kstep4)
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
-#pragma unroll
-          for (int k = 0; k < GK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_base + acc * BN, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar + stage);                    // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar + acc);     // accumulator ready for the epilogue
+          const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
+          // frees the smem slot when these MMAs retire; on the last k-step the accumulator goes to the epilogue
+          umma_kstep4(tmem_base + acc * BN, da, db, idesc, kb != kb0 ? 1u : 0u, A_MN ? 128u : 2u, B_MN ? 128u : 2u, empty_bar + stage,
+                      tfull_bar + acc, kb == kb1 - 1 ? 1u : 0u);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -255,7 +306,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t n_store = 0;                      // boxes this warp has sent (selects the staging buffer)
     const uint32_t dseed = ep.drop_seed + (ep.drop_seed_dev ? *ep.drop_seed_dev : 0u);
     int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+    for (int item = cta_id; item < num_tiles; item += cta_stride) {
       const int tile = item / k_split;
       int m_blk, n_base, bn;
       decode(tile, m_blk, n_base, bn);
@@ -427,11 +478,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               pk.y = f2_to_bf16x2(v[8 * q + 2], v[8 * q + 3]);
               pk.z = f2_to_bf16x2(v[8 * q + 4], v[8 * q + 5]);
               pk.w = f2_to_bf16x2(v[8 * q + 6], v[8 * q + 7]);
-#ifdef V2M_GEMM_GENERIC_STAGE
-              *reinterpret_cast<uint4*>(buf + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = pk;
-#else
               sts_v4(smem_u32(buf) + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4), pk.x, pk.y, pk.z, pk.w);
-#endif
             }
             fence_proxy_async();
             __syncwarp();
@@ -483,20 +530,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (lane == 0) { if (PAIR) pair_mbar_arrive(pair_mapa(smem_u32(tempty_bar + acc), 0)); else mbar_arrive(tempty_bar + acc); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (tma_out && lane == 0) tma_store_wait_read<0>();      // shared memory must outlive the reads of the last boxes
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (PAIR) pair_sync(); else __syncthreads();             // (pair: nobody leaves while the peer may still read its shared memory)
+  if (warp == 2) { if (PAIR) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base); }
 }
 
 template <int BN, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc, int out_bf16, int vec_ok, int M, int N, int K,
                        const GemmEpilogue& ep, cudaStream_t stream, bool allow_split, const int* tile_group = nullptr,
-                       const int* k_off = nullptr, int n_kgroups = 0, long long c_gstride = 0, const CUtensorMap* tmB_sub = nullptr) {
+                       const int* k_off = nullptr, int n_kgroups = 0, long long c_gstride = 0, const CUtensorMap* tmB_sub = nullptr,
+                       const CUtensorMap* tmB_half = nullptr) {
   // TMA-store epilogue for plain bf16 outputs (the store map only exists in that case; otherwise it aliases tmA, unused)
   CUtensorMap tmC = tmA;
   int tma_out = 0;
@@ -504,7 +552,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   using Cfg = GemmCfg<BN>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if constexpr (BN == 256 && !A_MN)
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, A_MN, B_MN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
     if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: smem attribute: %s", cudaGetErrorString(e)); return kCudaError; }
     attr = true;
   }
@@ -527,6 +578,35 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
     cudaError_t e = cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
     if (e != cudaSuccess) { set_last_error("gemm_bf16_tc: clearing the split-K output failed: %s", cudaGetErrorString(e)); return kCudaError; }
   }
+  // CTA pairs (see the kernel): plain GEMMs with at least pair_min_rounds rounds of 256 x BN tiles on the 74 SM pairs -- the
+  // small-batch shapes keep the 1-CTA kernel, whose tail sub-tiles matter more there.  V2M_GEMM_PAIR=0 turns the pair kernel off,
+  // =2 forces it for every eligible shape (tests).
+  if constexpr (BN == 256 && !A_MN) {
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char* e = getenv("V2M_GEMM_PAIR"); pair_mode = e ? atoi(e) : 1; }
+    const int pair_tiles = (((M + GM - 1) / GM + 1) / 2) * ((N + BN - 1) / BN);
+    const int n_pairs = num_sms / 2;
+    const bool eligible = pair_mode > 0 && k_split == 1 && !tile_group && !k_off && (B_MN || tmB_half) && num_sms % 2 == 0;
+    if (eligible && (pair_mode >= 2 || pair_tiles >= 8 * n_pairs)) {
+      const int grid2 = 2 * (pair_tiles < n_pairs ? pair_tiles : n_pairs);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(grid2);
+      cfg.blockDim = dim3(kGemmThreads);
+      cfg.dynamicSmemBytes = Cfg::kSmem;
+      cfg.stream = stream;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = dep_launch_enabled() ? 2 : 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, A_MN, B_MN, true>, tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, 1,
+                                          (const int*)nullptr, tmC, tma_out, (const int*)nullptr, 0ll, B_MN ? tmB : *tmB_half, -1);
+      if (le != cudaSuccess) { set_last_error("gemm_bf16_tc (pair): %s", cudaGetErrorString(le)); return kCudaError; }
+      return check_launch("gemm_bf16_tc (pair)");
+    }
+  }
   // Tail sub-tiles (see the kernel): when the last round of the persistent grid would hold only a few 128 x BN tiles, those are
   // cut into 128 x 64 pieces that spread over the SMs.  V2M_GEMM_TAIL=0 turns it off (A/B runs).
   static int tail_on = -1;
@@ -541,7 +621,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
     }
   }
   const int grid = items < num_sms ? items : num_sms;
-  cudaError_t le = launch_dep(gemm_bf16_tc_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, C, ldc, out_bf16,
+  cudaError_t le = launch_dep(gemm_bf16_tc_kernel<BN, A_MN, B_MN, false>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, C, ldc, out_bf16,
                               vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out, k_off, c_gstride, tmB_sub ? *tmB_sub : tmB, tail_first);
   if (le != cudaSuccess) { set_last_error("gemm_bf16_tc: %s", cudaGetErrorString(le)); return kCudaError; }
   return check_launch("gemm_bf16_tc");
@@ -584,7 +664,11 @@ int gemm_bf16_tc_general(const void* A, int lda, int a_mn, const void* W, int ld
   // 64-row box over the same B operand for the tail sub-tiles (the MN-major operand is fetched in 64-column boxes anyway)
   CUtensorMap tmBs = tmB;
   if (bn == 256 && !b_mn && (rc = make_tmap_2d_bf16(&tmBs, W, N, K, ldw, 64))) return rc;
-#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split, nullptr, nullptr, 0, 0, &tmBs)
+  // 128-row box for the CTA-pair kernel (each CTA of a pair fetches half of the 256 rows of a B tile)
+  CUtensorMap tmBh = tmB;
+  const bool has_half = bn == 256 && !b_mn;
+  if (has_half && (rc = make_tmap_2d_bf16(&tmBh, W, N, K, ldw, 128))) return rc;
+#define V2M_GO(BN_, AM_, BM_) launch_gemm<BN_, AM_, BM_>(tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, stream, allow_split, nullptr, nullptr, 0, 0, &tmBs, has_half ? &tmBh : nullptr)
   if (bn == 256) {
     if (!a_mn && !b_mn) return V2M_GO(256, false, false);
     if (!a_mn && b_mn) return V2M_GO(256, false, true);
