@@ -134,7 +134,11 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t T_S = tmem, T_QE = tmem + AT_MAXK, T_O = tmem, T_P = tmem + AT_MAXK;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp walks the items in convergent code; one elected lane issues the TMA loads and the MMAs.  (Inside an
+    // `if (lane == 0)` region with C++ spin loops the compiler cannot keep the tcgen05 operands in uniform registers and wraps
+    // every MMA in an ELECT / R2UR x 7 / branch waterfall, ~25 instructions each: the ~35 MMAs of an item then cost the issuing
+    // thread more time than the tensor pipe needs, on the critical path of the softmax warps -- see umma_kstep4 in common.cuh.)
+    {
       auto load_qke = [&](const Item& t) {                             // Q + K, Er band (64-row boxes)
         mbar_arrive_expect_tx(bar_qk, AT_SMEM_Q + t.nk64 * 128);
         tma3(sQ, &tmQ, t.hq * AT_DH, t.i0, t.b, bar_qk);
@@ -153,64 +157,79 @@ attn_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t par = 0, parb = 0;                                      // phase of the once-per-item barriers / of the half-B pair
       if ((int)blockIdx.x < a.n_items) {
         const Item first = make_item(blockIdx.x);
-        load_qke(first);
-        load_v(first);
+        if (elect_one()) {
+          load_qke(first);
+          load_v(first);
+        }
+        __syncwarp();
       }
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const Item t = make_item(item);
         const bool has_next = item + (int)gridDim.x < a.n_items;
         // ---------------- MMA issue ----------------
-        mbar_wait(bar_qk, par);
+        mbar_wait_u(bar_qk, par);
         tc_fence_after();
-        for (int n0 = 0; n0 < t.nk16; n0 += 256) {                     // S[:, n0:n0+n] = Q K[n0:n0+n]^T
-          const int n = min(256, t.nk16 - n0);
-          const uint32_t idesc = make_idesc_bf16(AT_M, n, 0, 0);
+        if (elect_one()) {
+          for (int n0 = 0; n0 < t.nk16; n0 += 256) {                   // S[:, n0:n0+n] = Q K[n0:n0+n]^T
+            const int n = min(256, t.nk16 - n0);
+            const uint32_t idesc = make_idesc_bf16(AT_M, n, 0, 0);
 #pragma unroll
-          for (int k = 0; k < AT_DH / 16; ++k)
-            umma_bf16_ss(T_S + n0, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         make_smem_desc_sw128(k_addr + n0 * 128 + k * 32, 16, 1024), idesc, k != 0);
+            for (int k = 0; k < AT_DH / 16; ++k)
+              umma_bf16_ss(T_S + n0, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           make_smem_desc_sw128(k_addr + n0 * 128 + k * 32, 16, 1024), idesc, k != 0);
+          }
+          umma_commit(bar_s);
         }
-        umma_commit(bar_s);
+        __syncwarp();
         if (HAS_ER) {
           const uint32_t idesc = make_idesc_bf16(AT_M, AT_QE_COLS, 0, 0);
-          mbar_wait(bar_e, par);
+          mbar_wait_u(bar_e, par);
           tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < AT_DH / 16; ++k)
-            umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc, k != 0);
-          umma_commit(bar_qa);
-          if (t.need_b) {
-            mbar_wait(bar_qa_free, parb);
-            tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < AT_DH / 16; ++k)
               umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                           make_smem_desc_sw128(e_addr + AT_QE_OVERLAP * 128 + k * 32, 16, 1024), idesc, k != 0);
-            umma_commit(bar_qb);
+                           make_smem_desc_sw128(e_addr + k * 32, 16, 1024), idesc, k != 0);
+            umma_commit(bar_qa);
+          }
+          __syncwarp();
+          if (t.need_b) {
+            mbar_wait_u(bar_qa_free, parb);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < AT_DH / 16; ++k)
+                umma_bf16_ss(T_QE, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                             make_smem_desc_sw128(e_addr + AT_QE_OVERLAP * 128 + k * 32, 16, 1024), idesc, k != 0);
+              umma_commit(bar_qb);
+            }
+            __syncwarp();
           }
         }
         // the products above are the last readers of sQ / sK / sE: once they have retired, fetch the next item's operands
         if (has_next) {
-          if (t.need_b) mbar_wait(bar_qb, parb);
-          else if (HAS_ER) mbar_wait(bar_qa, par);
-          else mbar_wait(bar_s, par);
-          load_qke(make_item(item + gridDim.x));
+          if (t.need_b) mbar_wait_u(bar_qb, parb);
+          else if (HAS_ER) mbar_wait_u(bar_qa, par);
+          else mbar_wait_u(bar_s, par);
+          if (elect_one()) load_qke(make_item(item + gridDim.x));
+          __syncwarp();
         }
         // O = P V : A = P from TMEM (bf16 pairs, 8 columns per k16), B = V (d contiguous -> MN-major)
-        mbar_wait(bar_v, par);
-        mbar_wait(bar_p, par);
+        mbar_wait_u(bar_v, par);
+        mbar_wait_u(bar_p, par);
         tc_fence_after();
-        {
+        if (elect_one()) {
           const uint32_t idesc = make_idesc_bf16(AT_M, AT_DH, 0, 1);
           for (int k = 0; k < t.nk16 / 16; ++k)
             umma_bf16_ts(T_O, T_P + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc, k != 0);
+          umma_commit(bar_o);
         }
-        umma_commit(bar_o);
+        __syncwarp();
         if (has_next) {
-          mbar_wait(bar_o, par);                                       // P V retired: sV is free
-          load_v(make_item(item + gridDim.x));
-          mbar_wait(bar_epi, par);                                     // O is out of TMEM: the next S may overwrite it
+          mbar_wait_u(bar_o, par);                                     // P V retired: sV is free
+          if (elect_one()) load_v(make_item(item + gridDim.x));
+          __syncwarp();
+          mbar_wait_u(bar_epi, par);                                   // O is out of TMEM: the next S may overwrite it
           tc_fence_after();
         }
         par ^= 1;

@@ -68,15 +68,15 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, long long rows, long lo
 }
 
 // Store-side map of a bf16 row-major [rows, cols] matrix: box = 32 rows x 32 columns (64-byte rows, 64B swizzle).
-static int make_tmap_store_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld) {
+static int make_tmap_store_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int wide = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { set_last_error("cuTensorMapEncodeTiled entry point not found"); return kCudaError; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t box[2] = {wide ? 64u : 32u, 32u};            // wide: 32 rows x 64 columns (128-byte rows, 128B swizzle)
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(store) failed (%d)", (int)r); return kCudaError; }
   return kOk;
@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, void* __restrict__ C,
                     int ldc, int out_bf16, int vec_ok, int M, int N, int K, const __grid_constant__ GemmEpilogue ep, int k_split,
                     const int* __restrict__ tile_group, const __grid_constant__ CUtensorMap tmC, int tma_out,
-                    const int* __restrict__ k_off, long long c_gstride, const __grid_constant__ CUtensorMap tmBs, int tail_first) {
+                    const int* __restrict__ k_off, long long c_gstride, const __grid_constant__ CUtensorMap tmBs, int tail_first,
+                    const __grid_constant__ CUtensorMap tmC64) {
   // tail_first >= 0 (plain GEMMs only: k_split == 1, no groups): the big tiles [tail_first, tiles) -- the ones that would make up
   // a mostly idle last round of the persistent grid (M = 19136 gives 150 row tiles on 148 SMs: 300 tiles = 2.03 rounds at
   // N = 512) -- are cut into BN / 64 sub-tiles of 128 x 64 each, so that round costs a quarter of a tile per SM instead of a
@@ -144,7 +145,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using Cfg = GemmCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * Cfg::kStageBytes);
+  // pair: a stage holds A (16 KB) + half of B; the shared memory this frees deepens the ring of outgoing TMA-store boxes
+  constexpr int kStride = PAIR ? Cfg::kABytes + Cfg::kBBytes / 2 : Cfg::kStageBytes;
+  constexpr int NBUF = 2;                                   // staging boxes per epilogue warp
+  // pair + TMA-store epilogue: 32 rows x 64 columns per box (whole 128-byte lines, half as many TMA operations); a warp then
+  // drains PAIRS of adjacent 32-column chunks instead of every other chunk
+  constexpr int BOXB = PAIR ? 4096 : 2048;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)Cfg::kStages * kStride);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -200,7 +207,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (PAIR) {
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(empty_bar + stage, phase ^ 1);
-            unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
+            unsigned char* sa = smem + (size_t)stage * kStride;
             const uint32_t fb = pair_mapa(smem_u32(full_bar + stage), 0);       // the leader's barrier counts both CTAs' bytes
             if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (Cfg::kABytes + (BN / 2) * GK * 2));
             tma_load_2d_pair(sa, &tmA, kb * GK, m_blk * GM, fb);
@@ -222,7 +229,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int b_row = g * N + n_base;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          unsigned char* sa = smem + (size_t)stage * Cfg::kStageBytes;
+          unsigned char* sa = smem + (size_t)stage * kStride;
           mbar_arrive_expect_tx(full_bar + stage, Cfg::kABytes + bn * GK * 2);
           if (A_MN) {
 #pragma unroll
@@ -254,7 +261,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait_u(full_bar + stage, phase);
           tc_fence_after();
           if (elect_one()) {                                     // one asm statement per k-step (see umma_kstep4)
-            const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+            const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStride);
             const uint32_t b_addr = a_addr + Cfg::kABytes;
             const uint64_t da = make_smem_desc_sw128(a_addr, 16, 1024);
             const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
@@ -285,7 +292,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait_u(full_bar + stage, phase);
         tc_fence_after();
         if (elect_one()) {                                       // one asm statement per k-step (see umma_kstep4)
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * Cfg::kStageBytes);
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStride);
           const uint32_t b_addr = a_addr + Cfg::kABytes;
           const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr, 8192, 1024) : make_smem_desc_sw128(a_addr, 16, 1024);
           const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr, 8192, 1024) : make_smem_desc_sw128(b_addr, 16, 1024);
@@ -302,7 +309,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ================= epilogue: 8 warps, two per TMEM lane quadrant, alternating 32-column chunks ============
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = (warp - 4) >> 2;          // which chunks of the tile this warp drains
-    unsigned char* stage = smem + (size_t)Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes + (warp - 4) * 4096;
+    unsigned char* stage = smem + (size_t)Cfg::kStages * kStride + Cfg::kBarBytes + (warp - 4) * (NBUF * BOXB);
     uint32_t n_store = 0;                      // boxes this warp has sent (selects the staging buffer)
     const uint32_t dseed = ep.drop_seed + (ep.drop_seed_dev ? *ep.drop_seed_dev : 0u);
     int acc = 0; uint32_t acc_phase = 0;
@@ -341,9 +348,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int q = 0; q < 4; ++q) dst[q] = __ldg(rp + q);
         }
       };
-      fetch_res(half, res_nx);
+      const bool w64 = PAIR && tma_out;                       // (pair tiles: N % 256 == 0, every chunk takes the same path)
+      auto chunk_of = [&](int t) { return w64 ? 2 * (half + 2 * (t >> 1)) + (t & 1) : half + 2 * t; };
+      fetch_res(chunk_of(0), res_nx);
 #pragma unroll 1
-      for (int c = half; c < bn / 32; c += 2) {
+      for (int t = 0; chunk_of(t) < bn / 32; ++t) {
+        const int c = chunk_of(t);
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + acc * BN + c * 32 + ((uint32_t)(quad * 32) << 16), r);
         const int n0 = n_base + c * 32;
@@ -357,7 +367,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint4 res_cur[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) res_cur[q] = res_nx[q];
-        fetch_res(c + 2, res_nx);
+        fetch_res(chunk_of(t + 1), res_nx);
         tmem_ld_wait();
         const bool tma_chunk = tma_out && fast;                // warp-uniform
         const bool red_chunk = (k_split > 1 || ep.accumulate || k_off) && vec_ok && n0 + 32 <= N;   // warp-uniform: all lanes take part in the transpose
@@ -467,9 +477,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           }
           const long long o = epi_out_index(ep, m, n0, ldc);     // 32 columns never straddle a head (dh % 32 == 0)
-          if (tma_chunk) {
-            unsigned char* buf = stage + (n_store & 1) * 2048;
-            if (lane == 0) tma_store_wait_read<1>();             // the box sent two chunks ago has left this buffer
+          if (tma_chunk && PAIR) {
+            unsigned char* buf = stage + ((n_store >> 1) % NBUF) * BOXB;
+            if ((t & 1) == 0) {
+              if (lane == 0) tma_store_wait_read<NBUF - 1>();    // the box sent NBUF pairs ago has left this buffer
+              __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                        // row = lane (128 B), 16-byte chunk j at its 128B-swizzled place
+              uint4 pk;
+              pk.x = f2_to_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+              pk.y = f2_to_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+              pk.z = f2_to_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+              pk.w = f2_to_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              const int j = (t & 1) * 4 + q;
+              sts_v4(smem_u32(buf) + lane * 128 + ((j ^ (lane & 7)) << 4), pk.x, pk.y, pk.z, pk.w);
+            }
+            if (t & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmC64, buf, n0 - 32, m_blk * GM + quad * 32);   // rows >= M are clipped by the tensor map
+                tma_store_commit();
+              }
+            }
+            ++n_store;
+          } else if (tma_chunk) {
+            unsigned char* buf = stage + (n_store % NBUF) * 2048;
+            if (lane == 0) tma_store_wait_read<NBUF - 1>();      // the box sent NBUF chunks ago has left this buffer
             __syncwarp();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {                        // row = lane, 16-byte chunk q at its 64B-swizzled place
@@ -482,10 +517,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             fence_proxy_async();
             __syncwarp();
+#ifndef V2M_EXP_NOSTORE
             if (lane == 0) {
               tma_store_2d(&tmC, buf, n0, m_blk * GM + quad * 32);   // rows >= M are clipped by the tensor map
               tma_store_commit();
             }
+#endif
             ++n_store;
           } else if (out_bf16) {
             uint4* dst = reinterpret_cast<uint4*>(static_cast<bf16*>(C) + o);
@@ -601,8 +638,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
       at[1].val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = at;
       cfg.numAttrs = dep_launch_enabled() ? 2 : 1;
+      CUtensorMap tmC64 = tmC;
+      if (tma_out && make_tmap_store_bf16(&tmC64, C, M, N, ldc, 1) != kOk) return kCudaError;
       cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, A_MN, B_MN, true>, tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, 1,
-                                          (const int*)nullptr, tmC, tma_out, (const int*)nullptr, 0ll, B_MN ? tmB : *tmB_half, -1);
+                                          (const int*)nullptr, tmC, tma_out, (const int*)nullptr, 0ll, B_MN ? tmB : *tmB_half, -1, tmC64);
       if (le != cudaSuccess) { set_last_error("gemm_bf16_tc (pair): %s", cudaGetErrorString(le)); return kCudaError; }
       return check_launch("gemm_bf16_tc (pair)");
     }
@@ -622,7 +661,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
   }
   const int grid = items < num_sms ? items : num_sms;
   cudaError_t le = launch_dep(gemm_bf16_tc_kernel<BN, A_MN, B_MN, false>, dim3(grid), dim3(kGemmThreads), Cfg::kSmem, stream, tmA, tmB, C, ldc, out_bf16,
-                              vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out, k_off, c_gstride, tmB_sub ? *tmB_sub : tmB, tail_first);
+                              vec_ok, M, N, K, ep, k_split, tile_group, tmC, tma_out, k_off, c_gstride, tmB_sub ? *tmB_sub : tmB, tail_first, tmC);
   if (le != cudaSuccess) { set_last_error("gemm_bf16_tc: %s", cudaGetErrorString(le)); return kCudaError; }
   return check_launch("gemm_bf16_tc");
 }
