@@ -141,7 +141,11 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp walks the steps in convergent code (asm-loop barrier waits); one elected lane issues the TMA loads and the
+    // ~20 MMAs of a 64-query step back to back from uniform registers.  Under `if (lane == 0)` with C++ spin loops every MMA
+    // was wrapped in an ELECT / R2UR x 7 / branch waterfall (~25 instructions): the issuing thread, not the tensor pipe or the
+    // softmax warps, bounded the kernel (see umma_kstep4 in common.cuh).
+    {
       const uint32_t q_addr = smem_u32(sQ), do_addr = smem_u32(sDO), k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);      // S^T, dP^T: both operands K-major
@@ -165,36 +169,44 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int b = item / a.H, h = item - b * a.H;
         // every product of the previous item has retired (its last commit): the operand buffers may be overwritten while the
         // softmax warps are still storing that item's dQ
-        if (!first_item) { mbar_wait(bar_done, ph_done); ph_done ^= 1; }
-        mbar_arrive_expect_tx(bar_ld, (uint32_t)(2 * nq64 + 2 * nk64) * 8192u);
-        for (int r = 0; r < nq64; ++r) {
-          tma3(sQ + r * 8192, &tmQ, h * DH, r * 64, b, bar_ld);
-          tma3(sDO + r * 8192, &tmDO, h * DH, r * 64, b, bar_ld);
+        if (!first_item) { mbar_wait_u(bar_done, ph_done); ph_done ^= 1; }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_ld, (uint32_t)(2 * nq64 + 2 * nk64) * 8192u);
+          for (int r = 0; r < nq64; ++r) {
+            tma3(sQ + r * 8192, &tmQ, h * DH, r * 64, b, bar_ld);
+            tma3(sDO + r * 8192, &tmDO, h * DH, r * 64, b, bar_ld);
+          }
+          for (int r = 0; r < nk64; ++r) {
+            tma3(sK + r * 8192, &tmK, h * DH, r * 64, b, bar_ld);
+            tma3(sV + r * 8192, &tmV, h * DH, r * 64, b, bar_ld);
+          }
         }
-        for (int r = 0; r < nk64; ++r) {
-          tma3(sK + r * 8192, &tmK, h * DH, r * 64, b, bar_ld);
-          tma3(sV + r * 8192, &tmV, h * DH, r * 64, b, bar_ld);
-        }
+        __syncwarp();
         if (!first_item) {                                           // dQ of the previous item is out of TMEM (the stores of the
-          mbar_wait(bar_qfree, ph_qfree); ph_qfree ^= 1;             // epilogue overlapped the loads above)
+          mbar_wait_u(bar_qfree, ph_qfree); ph_qfree ^= 1;             // epilogue overlapped the loads above)
           tc_fence_after();
         }
         first_item = false;
-        mbar_wait(bar_ld, ph_ld); ph_ld ^= 1;
+        mbar_wait_u(bar_ld, ph_ld); ph_ld ^= 1;
         tc_fence_after();
-        issue_s(0);
+        if (elect_one()) issue_s(0);
+        __syncwarp();
         for (int n = 0; n < steps; ++n) {
           const int j = n / nqb, i = n - j * nqb;
-          mbar_wait(bar_sfree, ph_sfree); ph_sfree ^= 1;             // step n is in the warps' registers
+          mbar_wait_u(bar_sfree, ph_sfree); ph_sfree ^= 1;             // step n is in the warps' registers
           tc_fence_after();
-          if (n + 1 < steps) issue_s(n + 1);
+          if (n + 1 < steps) {
+            if (elect_one()) issue_s(n + 1);
+            __syncwarp();
+          }
           if (i == 0 && j > 0) {                                     // dV / dK of the previous key tile are out of TMEM
-            mbar_wait(bar_kvfree, ph_kvfree); ph_kvfree ^= 1;
+            mbar_wait_u(bar_kvfree, ph_kvfree); ph_kvfree ^= 1;
             tc_fence_after();
           }
-          mbar_wait(bar_pds, ph_pds); ph_pds ^= 1;                   // P^T and dS^T[i & 1] are in shared memory
+          mbar_wait_u(bar_pds, ph_pds); ph_pds ^= 1;                   // P^T and dS^T[i & 1] are in shared memory
           tc_fence_after();
           const uint32_t ds_i = ds_addr + (i & 1) * SM_TILE;
+          if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                              // K = 64 queries
             umma_bf16_ss(T_DV, make_smem_desc_sw128(p_addr + k * 32, 16, 1024),
@@ -216,6 +228,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           umma_commit(bar_tfree);
           if (n == steps - 1) umma_commit(bar_done);                 // every product of the item has retired: operands may be replaced
+          }
+          __syncwarp();
         }
       }
     }
