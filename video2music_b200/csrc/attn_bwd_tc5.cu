@@ -280,6 +280,15 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float nx_l2, nx_dl;
         fetch(i + 1 == nqb ? 0 : i + 1, nx_l2, nx_dl);
         uint32_t pk[CW / 2], dk_[CW / 2];
+        // Dropout keep mask = byte (key & 3) of hash(query row, key >> 2): the four lanes of a key quad need the SAME hash for a
+        // given query, so each computes it for a quarter of the queries and the quad exchanges them by shuffle (one hash per
+        // four elements, as in the forward kernel, instead of one per element).
+        uint32_t hq[DROP ? CW / 4 : 1];
+        if (DROP) {
+#pragma unroll
+          for (int c4 = 0; c4 < CW / 4; ++c4)
+            hq[c4] = drop_hash4(dseed, (uint32_t)item * (uint32_t)a.Lq + (uint32_t)(q0 + c4 * 4 + (lane & 3)), (uint32_t)key >> 2);
+        }
 #pragma unroll
         for (int c = 0; c < CW; c += 2) {
           float pv[2], dv[2];
@@ -292,7 +301,8 @@ attn_bwd_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             float g = __uint_as_float(dp[c + e]);
             float pd = p;
             if (DROP) {
-              const bool keep = drop_keep(dseed, (uint32_t)item * (uint32_t)a.Lq + (uint32_t)qi, (uint32_t)key, a.drop_thresh);
+              const uint32_t hh = __shfl_sync(0xffffffffu, hq[(c + e) >> 2], (lane & ~3) | ((c + e) & 3));
+              const bool keep = drop_keep_byte(hh, (uint32_t)key, a.drop_thresh);
               pd = keep ? p * a.drop_scale : 0.f;
               g = keep ? g * a.drop_scale : 0.f;
             }

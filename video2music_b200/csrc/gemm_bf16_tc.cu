@@ -198,7 +198,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    // (whole warp in convergent code, one elected lane issues: the TMA operands stay in uniform registers -- under
+    //  `if (lane == 0)` each of the up to 6 loads of a k-step went through an ELECT / R2UR waterfall, see umma_kstep4)
+    {
       int stage = 0; uint32_t phase = 0;
       for (int item = cta_id; item < num_tiles; item += cta_stride) {
         const int tile = item / k_split, ks = item - tile * k_split;
@@ -206,18 +208,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         decode(tile, m_blk, n_base, bn);
         if (PAIR) {
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(empty_bar + stage, phase ^ 1);
+            mbar_wait_u(empty_bar + stage, phase ^ 1);
             unsigned char* sa = smem + (size_t)stage * kStride;
             const uint32_t fb = pair_mapa(smem_u32(full_bar + stage), 0);       // the leader's barrier counts both CTAs' bytes
-            if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (Cfg::kABytes + (BN / 2) * GK * 2));
-            tma_load_2d_pair(sa, &tmA, kb * GK, m_blk * GM, fb);
-            if (B_MN) {
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(full_bar + stage, 2 * (Cfg::kABytes + (BN / 2) * GK * 2));
+              tma_load_2d_pair(sa, &tmA, kb * GK, m_blk * GM, fb);
+              if (B_MN) {
 #pragma unroll
-              for (int c = 0; c < BN / 128; ++c)
-                tma_load_2d_pair(sa + Cfg::kABytes + c * 8192, &tmB, n_base + (int)rank * (BN / 2) + c * 64, kb * GK, fb);
-            } else {
-              tma_load_2d_pair(sa + Cfg::kABytes, &tmBs, kb * GK, n_base + (int)rank * (BN / 2), fb);   // tmBs: BN/2-row box
+                for (int c = 0; c < BN / 128; ++c)
+                  tma_load_2d_pair(sa + Cfg::kABytes + c * 8192, &tmB, n_base + (int)rank * (BN / 2) + c * 64, kb * GK, fb);
+              } else {
+                tma_load_2d_pair(sa + Cfg::kABytes, &tmBs, kb * GK, n_base + (int)rank * (BN / 2), fb);   // tmBs: BN/2-row box
+              }
             }
+            __syncwarp();
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
           }
           continue;
@@ -228,8 +233,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (tile_group) { g = tile_group[m_blk]; if (g < 0) continue; }
         const int b_row = g * N + n_base;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_wait_u(empty_bar + stage, phase ^ 1);
           unsigned char* sa = smem + (size_t)stage * kStride;
+          if (elect_one()) {
           mbar_arrive_expect_tx(full_bar + stage, Cfg::kABytes + bn * GK * 2);
           if (A_MN) {
 #pragma unroll
@@ -244,6 +250,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           } else {
             tma_load_2d(sa + Cfg::kABytes, bn == BN ? &tmB : &tmBs, kb * GK, b_row, full_bar + stage);
           }
+          }
+          __syncwarp();
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
       }
