@@ -186,9 +186,14 @@ struct Ring {
     uint32_t par;
     const int s = next(par);
     if ((s % NPROD) != id) return;
-    mbar_wait(empty + s, par ^ 1u);
-    mbar_arrive_expect_tx(full + s, bytes);
-    bulk_g2s(slot(s), src, bytes, full + s);
+    // the whole producer warp walks the schedule in convergent code and one elected lane issues: the operands of the bulk copy
+    // stay in uniform registers (under `if (lane == 0)` every copy went through an ELECT / R2UR waterfall, see common.cuh)
+    mbar_wait_u(empty + s, par ^ 1u);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(full + s, bytes);
+      bulk_g2s(slot(s), src, bytes, full + s);
+    }
+    __syncwarp();
   }
 };
 
@@ -633,8 +638,8 @@ __global__ void __launch_bounds__(THREADS, 1) decode_stream_kernel(const __grid_
   const int n_vt = (p.vocab + 15) / 16;
 
   if (warp >= 8) {
-    // ============================== producer warps (lane 0): the whole schedule in consumption order ==============================
-    if (lane == 0) {
+    // ============================== producer warps: the whole schedule in consumption order ==============================
+    {
       Ring& rg = cx.rg;
       const int id = warp - 8;
       auto tiles512 = [&](const void* base_w, int first, int count) {      // two K=512 tiles per copy
