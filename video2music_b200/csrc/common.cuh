@@ -334,8 +334,12 @@ __device__ __forceinline__ uint32_t pair_mapa(uint32_t addr, uint32_t rank) {   
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Relaxed: the arrival only tells the leader's MMA issuer that this warp's tcgen05.ld of the accumulator stage have completed
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it); no memory is published.  A .release.cluster arrive
+// compiles to a cluster-scope memory barrier (ERRBAR) that waited for the warp's outstanding stores: 7.7 % of the pair
+// kernel's stall samples (ncu source page, profiles/r02_final_ncu_key_metrics_s5.txt).
 __device__ __forceinline__ void pair_mbar_arrive(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {         // the same warp of BOTH CTAs
