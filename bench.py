@@ -357,7 +357,7 @@ def kernel_rooflines(dev):
     burst, _, tsrc = tensor_peaks()
 
     def timed(fn, reps=5):
-        for _ in range(2):
+        for _ in range(5):                                 # warm-up (the first kernel follows a different workload: clocks, caches)
             fn()
         ts = []
         for _ in range(reps):

@@ -2,12 +2,11 @@
 # scratch script for one gpurun call (overwritten per call)
 cd /root/repo
 mkdir -p gpurun_out
-( V2M_GEMM_PAIR=2 timeout 120 python tools/scratch/pair_check.py | grep -v " ok$" ) > gpurun_out/r5_pair_check.txt 2>&1
-cat gpurun_out/r5_pair_check.txt | tail -4
-if [ "$(grep -c 'ALL OK' gpurun_out/r5_pair_check.txt)" = "1" ]; then
-  ( echo "== pair kernel, relaxed tmem-empty arrive (default)"; timeout 200 python tools/gemm_bench.py 2>&1 | grep -v Warning | grep 153600
-    echo "== V2M_GEMM_PAIR=0"; V2M_GEMM_PAIR=0 timeout 200 python tools/gemm_bench.py 2>&1 | grep -v Warning | grep 153600 ) > gpurun_out/r5_pair_bench4.txt 2>&1
-  cat gpurun_out/r5_pair_bench4.txt
-  ( V2M_TRAIN_GRAPH=1 timeout 300 python tools/train_time.py 512 bf16 10; V2M_GEMM_PAIR=0 V2M_TRAIN_GRAPH=1 timeout 300 python tools/train_time.py 512 bf16 10 ) 2>&1 | grep "^train" > gpurun_out/r5_train_time6.txt
-  cat gpurun_out/r5_train_time6.txt
-fi
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r5_bench_n8.json 2> gpurun_out/r5_bench_n8.err
+echo "bench n8 exit $?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r5_bench_n8.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'])
+print('train', {k:d['train'].get(k) for k in ('value','ms_per_step','tflops')})
+PY
