@@ -650,8 +650,10 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, 
       if (tma_out && make_tmap_store_bf16(&tmC64, C, M, N, ldc, 1) != kOk) return kCudaError;
       cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, A_MN, B_MN, true>, tmA, tmB, C, ldc, out_bf16, vec_ok, M, N, K, ep, 1,
                                           (const int*)nullptr, tmC, tma_out, (const int*)nullptr, 0ll, B_MN ? tmB : *tmB_half, -1, tmC64);
-      if (le != cudaSuccess) { set_last_error("gemm_bf16_tc (pair): %s", cudaGetErrorString(le)); return kCudaError; }
-      return check_launch("gemm_bf16_tc (pair)");
+      if (le == cudaSuccess) return check_launch("gemm_bf16_tc (pair)");
+      // a device / driver configuration that refuses the 2-CTA cluster launch: the 1-CTA kernel below computes the same result
+      (void)cudaGetLastError();
+      pair_mode = 0;
     }
   }
   // Tail sub-tiles (see the kernel): when the last round of the persistent grid would hold only a few 128 x BN tiles, those are
