@@ -1,7 +1,9 @@
-"""CTA-pair GEMM (V2M_GEMM_PAIR=2 forces it) against torch.matmul: plain / bias+relu / residual / fp32 out / MN-major B (dX)."""
+"""CTA-pair GEMM (V2M_GEMM_PAIR=2 forces it for every eligible shape; the switch is read once per process, hence a script that
+tests/test_gpu_kernels.py runs in a subprocess) against torch.matmul: plain / bias+relu / residual / fp32 out / MN-major B (dX),
+including M tails where the second CTA of the last pair owns no valid row."""
 import os, sys
 os.environ.setdefault("V2M_GEMM_PAIR", "2")
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from video2music_b200 import ops
 torch.manual_seed(0)

@@ -870,3 +870,32 @@ def test_video_regression_golden_gpu(reg):
     with torch.no_grad():
         ln, inst = m(sem.to(DEV), z, z, emo.to(DEV))
     assert rel_err(ln, g["ln"]) < 1e-4 and rel_err(inst, g["inst"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_gemm_cta_pair_kernel_forced_for_every_shape():
+    """The CTA-pair (cta_group::2) variant of the tcgen05 GEMM serves plain GEMMs with many rounds of tiles by default; the
+    switch V2M_GEMM_PAIR=2 (read once per process, hence the subprocess) forces it for every eligible shape: all epilogues,
+    K-major and MN-major B, M tails where the second CTA of the last pair owns no valid row -- against torch.matmul."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, V2M_GEMM_PAIR="2")
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "pair_gemm_check.py")], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_gemm_large_m_default_dispatch_matches_matmul():
+    """BASELINE config 3 shape (512 videos x 299 tokens): the default dispatch (CTA pairs at this size) against torch.matmul."""
+    from video2music_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 512 * 299, 512, 512
+    a = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).to(DEV).bfloat16()
+    b = torch.randn(N, generator=g).to(DEV)
+    y = ops.linear(a, w, b, relu=True, out_dtype=torch.bfloat16)
+    for lo in (0, M // 2 - 64, M - 4096):                  # slices: first tiles, a middle pair, the M tail
+        ref = torch.relu(a[lo:lo + 4096].float() @ w.float().t() + b)
+        assert rel_err(y[lo:lo + 4096].float(), ref) < 2e-2
