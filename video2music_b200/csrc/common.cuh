@@ -274,12 +274,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// One k-step of a GEMM main loop in ONE asm statement: four K = 16 MMAs (descriptors advanced by a_step / b_step in the
-// 16-byte address field), the commit that frees the shared-memory slot and, on the last k-step of a tile, the commit that hands
-// the accumulator to the epilogue.  Why: tcgen05 operands must sit in uniform registers, and inside `if (lane == 0)` the
-// compiler wraps EVERY asm statement in an ELECT / R2UR x 7 / branch "waterfall" (~25 instructions): with one statement per
-// MMA and per commit the issuing thread spent ~900 clocks per k-step (ncu source page: the MMA warp never waits, it executes
-// its ~130-instruction loop) where the tensor pipe needs 512 -- the issuer, not the pipe, bounded a K = 512 GEMM.
+// One k-step of a GEMM main loop: four K = 16 MMAs (descriptors advanced by a_step / b_step in the 16-byte address field), the
+// commit that frees the shared-memory slot and, on the last k-step of a tile, the commit that hands the accumulator to the
+// epilogue.  LEAN ISSUE (session 5 of round 2): tcgen05 / TMA operands must sit in uniform registers.  In code the compiler
+// cannot prove convergent -- `if (lane == 0) { ... }` around C++ `while (!try_wait)` spin loops -- ptxas wraps EVERY such
+// instruction in an ELECT / R2UR x 7 / branch "waterfall" (~25 instructions each, whether or not several share one asm
+// statement): the issuing thread then spent ~900 clocks per k-step where the tensor pipe needs 512 (ncu source page: the MMA
+// warp never waits on a barrier, it executes its ~130-instruction loop).  The cure is control flow, not syntax: the whole warp
+// runs the loop, waits with mbar_wait_u (spin loop inside one asm statement) and issues under elect_one(); the operands are
+// then computed by the uniform datapath and the MMAs leave back to back (~45 instructions per k-step).
 __device__ __forceinline__ void umma_kstep4(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc_first,
                                             uint32_t a_step, uint32_t b_step, uint64_t* bar_empty, uint64_t* bar_tfull,
                                             uint32_t last) {
@@ -349,20 +352,6 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {        
 template <int kCols>
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols));
-}
-// issued by the leader (rank 0) only; the descriptors are CTA-local offsets valid in both CTAs
-__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                                  uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrives on the barrier at this shared-memory offset in every CTA of `mask` once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // TMA tile into THIS CTA's shared memory, bytes counted on the barrier at `bar_cluster_addr` (the leader's)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int c0, int c1, uint32_t bar_cluster_addr) {
