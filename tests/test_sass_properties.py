@@ -41,7 +41,7 @@ def sass():
         if "Function :" in line:
             fn = line.split("Function :")[1].strip()
             per[fn] = {k: 0 for k in PAT}
-        elif fn is not None:
+        elif fn is not None and any(t in line for t in ("UTC", "UTMA", "LDTM", "STTM", "BRA.U", "LD.E", "ST.E", "LDS", "GMMA")):
             for k, p in PAT.items():
                 if p.search(line):
                     per[fn][k] += 1
