@@ -1,12 +1,11 @@
 #!/bin/bash
-# scratch script for one gpurun call (overwritten per call)
+# One gpurun call: full validation (GPU tests, smoke, bench).  Edited per call during development; this is the end-of-round form.
 cd /root/repo
 mkdir -p gpurun_out
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r5_bench_n8.json 2> gpurun_out/r5_bench_n8.err
-echo "bench n8 exit $?"
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r5_bench_n8.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, d['e2e']['value'])
-print('train', {k:d['train'].get(k) for k in ('value','ms_per_step','tflops')})
-PY
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/tests_final.log 2>&1
+echo "tests exit $?" >> gpurun_out/tests_final.log
+tail -3 gpurun_out/tests_final.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1
+tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"
